@@ -1,0 +1,12 @@
+"""daft_b200 -- Daft's columnar hot path (hash / partition / group-by aggregate / hash join / sort /
+filter / project / exchange) as hand-written sm_100a CUDA kernels behind a C ABI.
+
+Public surface: RecordBatch (device-resident), col / lit expressions, ProbeTable, the TPC-H
+generator and query pipelines in daft_b200.tpch, the multi-GPU exchange in daft_b200.exchange.
+"""
+from . import datatypes
+from ._lib import B200Error, init, launch_count, synchronize
+from .expressions import Expression, col, lit
+from .recordbatch import RecordBatch
+
+__all__ = ["RecordBatch", "Expression", "col", "lit", "init", "B200Error", "datatypes", "launch_count", "synchronize"]

@@ -1,0 +1,346 @@
+// extern "C" boundary of libdaftb200.so (declarations + reference citations: include/daft_b200.h).
+// Every entry point converts C++ exceptions into the daft-ext error convention
+// (int status + malloc'd message, src/daft-ext/src/abi/mod.rs:84-107).
+#include "common.h"
+#include "jit.h"
+#include "ops.h"
+
+using namespace b200;
+
+namespace {
+int set_err(char **errmsg, const std::string &msg) {
+    if (errmsg) {
+        char *m = static_cast<char *>(malloc(msg.size() + 1));
+        if (m) memcpy(m, msg.c_str(), msg.size() + 1);
+        *errmsg = m;
+    }
+    return 1;
+}
+template <class F>
+int guard(char **errmsg, F &&f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception &e) {
+        return set_err(errmsg, e.what());
+    } catch (...) {
+        return set_err(errmsg, "unknown error");
+    }
+}
+const Column &col_at(const Batch *b, int32_t i) {
+    if (!b) fail("null batch");
+    if (i < 0 || i >= (int32_t)b->cols.size()) fail("column index out of range");
+    return b->cols[i];
+}
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int b200_abi_version(void) { return DAFT_B200_ABI_VERSION; }
+
+int b200_init(int device_ordinal, char **errmsg) {
+    return guard(errmsg, [&] {
+        Context &c = ctx();
+        if (c.ready && c.device == device_ordinal) return;
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            fail(std::string("daft_b200: no CUDA device available (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+        if (device_ordinal < 0 || device_ordinal >= ndev) fail("daft_b200: device ordinal out of range");
+        B200_CUDA(cudaSetDevice(device_ordinal));
+        cudaDeviceProp prop;
+        B200_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+        if (prop.major < 10) fail("daft_b200: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+        c.sm_count = prop.multiProcessorCount;
+        if (!c.stream) B200_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
+        uint64_t thr = UINT64_MAX;
+        B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        c.device = device_ordinal;
+        c.ready = true;
+    });
+}
+
+void b200_free_string(char *s) { free(s); }
+void *b200_stream(void) { return ctx().stream; }
+int b200_synchronize(char **errmsg) {
+    return guard(errmsg, [&] {
+        require_device();
+        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+int64_t b200_launch_count(void) { return g_launches.load(); }
+
+// device time of the dominant kernel (the fused aggregate) measured with CUDA events on the launching stream
+int b200_kernel_timing(int enable) {
+    jit::enable_kernel_timing(enable != 0);
+    return 0;
+}
+double b200_last_agg_kernel_ms(void) {
+    try {
+        return jit::last_timed_kernel_ms();
+    } catch (...) {
+        return -1.0;
+    }
+}
+
+int b200_set_jit_cache_dir(const char *path, char **errmsg) {
+    return guard(errmsg, [&] { jit::set_cache_dir(path ? path : ""); });
+}
+int b200_precompile(int32_t op, const uint8_t *plan, size_t plan_len, const int32_t *col_dtypes, const uint8_t *col_nullable,
+                    int32_t ncols, char **errmsg) {
+    return guard(errmsg, [&] {
+        std::vector<int32_t> dt(col_dtypes, col_dtypes + ncols);
+        std::vector<uint8_t> nl(col_nullable, col_nullable + ncols);
+        if (op == B200_OP_FILTER) fail("precompile: wrap a FILTER predicate as PROJECT(fill_null(pred,false))");
+        jit::precompile(op, plan, plan_len, dt, nl);
+    });
+}
+
+// ---- batches -------------------------------------------------------------------------------------
+int b200_batch_import(struct ArrowArray *array, struct ArrowSchema *schema, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = import_batch(array, schema); });
+}
+int b200_batch_export(const b200_batch *batch, struct ArrowArray *out_array, struct ArrowSchema *out_schema, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!batch) fail("null batch");
+        export_batch(*batch, out_array, out_schema);
+    });
+}
+int b200_batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t num_rows, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = batch_from_device(cols, ncols, num_rows); });
+}
+int b200_batch_describe(const b200_batch *batch, int32_t col, b200_column_desc *out, char **errmsg) {
+    return guard(errmsg, [&] {
+        const Column &c = col_at(batch, col);
+        out->dtype = c.dtype;
+        out->_reserved = 0;
+        out->length = c.length;
+        out->null_count = c.null_count;
+        out->validity = c.validity ? c.validity->ptr : nullptr;
+        out->offsets = c.offsets ? c.offsets->ptr : nullptr;
+        out->data = c.data ? c.data->ptr : nullptr;
+        out->data_bytes = c.data_bytes;
+        out->name = c.name.c_str();
+    });
+}
+int64_t b200_batch_num_rows(const b200_batch *batch) { return batch ? batch->num_rows : -1; }
+int32_t b200_batch_num_columns(const b200_batch *batch) { return batch ? (int32_t)batch->cols.size() : -1; }
+int64_t b200_batch_size_bytes(const b200_batch *batch) {
+    if (!batch) return -1;
+    int64_t s = 0;
+    for (auto &c : batch->cols) {
+        s += c.data_bytes;
+        if (c.offsets) s += (c.length + 1) * 8;
+        if (c.validity) s += (c.length + 7) / 8;
+    }
+    return s;
+}
+void b200_batch_free(b200_batch *batch) { delete batch; }
+
+int b200_batch_select(const b200_batch *batch, const int32_t *cols, int32_t ncols, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        auto o = std::make_unique<Batch>();
+        o->num_rows = batch->num_rows;
+        for (int i = 0; i < ncols; i++) o->cols.push_back(col_at(batch, cols[i]));
+        *out = o.release();
+    });
+}
+int b200_batch_rename(b200_batch *batch, int32_t col, const char *name, char **errmsg) {
+    return guard(errmsg, [&] {
+        col_at(batch, col);
+        batch->cols[col].name = name ? name : "";
+    });
+}
+int b200_batch_union(const b200_batch *a, const b200_batch *b, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!a || !b) fail("null batch");
+        if (a->num_rows != b->num_rows && !a->cols.empty() && !b->cols.empty()) fail("union: row counts differ");
+        auto o = std::make_unique<Batch>(*a);
+        if (a->cols.empty()) o->num_rows = b->num_rows;
+        for (auto &c : b->cols) o->cols.push_back(c);
+        *out = o.release();
+    });
+}
+int b200_batch_slice(const b200_batch *batch, int64_t start, int64_t end, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!batch) fail("null batch");
+        if (start < 0 || end < start || end > batch->num_rows) fail("slice: bounds out of range");
+        auto o = std::make_unique<Batch>();
+        o->num_rows = end - start;
+        for (auto &c : batch->cols) o->cols.push_back(slice_column(c, start, end));
+        *out = o.release();
+    });
+}
+
+// ---- hashing / partition -----------------------------------------------------------------------------
+int b200_hash_rows(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const b200_batch *seed, b200_batch **out,
+                   char **errmsg) {
+    return guard(errmsg, [&] {
+        require_device();
+        if (!batch) fail("null batch");
+        const uint64_t *sd = nullptr;
+        if (seed) {
+            const Column &s = col_at(seed, 0);
+            if (s.dtype != B200_U64) fail(std::string("seed data type expected to be uint64, got ") + dtype_name(s.dtype));
+            if (s.length != batch->num_rows) fail("seed length does not match array length");
+            if (s.null_count) fail("seed must not contain nulls");
+            sd = as<uint64_t>(s.data);
+        }
+        Buf h = hash_rows(*batch, key_cols, nkeys, sd);
+        auto o = std::make_unique<Batch>();
+        o->num_rows = batch->num_rows;
+        o->cols.push_back(make_u64_column("hash", h, batch->num_rows));
+        *out = o.release();
+    });
+}
+int b200_partition_by_hash(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, int32_t num_partitions,
+                           b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!batch) fail("null batch");
+        std::vector<Batch *> parts = op_partition_by_hash(*batch, key_cols, nkeys, num_partitions);
+        for (int i = 0; i < num_partitions; i++) out[i] = parts[i];
+    });
+}
+
+// ---- filter / project / agg -----------------------------------------------------------------------
+int b200_filter(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = op_filter(*batch, plan, plan_len); });
+}
+int b200_eval_expression_list(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = op_project(*batch, plan, plan_len, nullptr, 0); });
+}
+int b200_agg(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = op_agg(*batch, plan, plan_len); });
+}
+int b200_dedup(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = op_dedup(*batch, key_cols, nkeys); });
+}
+
+// ---- take / concat ----------------------------------------------------------------------------------
+int b200_take(const b200_batch *batch, const b200_batch *indices, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        require_device();
+        const Column &ic = col_at(indices, 0);
+        Buf idx = indices_to_i64(ic);
+        *out = gather_batch(*batch, as<int64_t>(idx), ic.length, ic.null_count > 0);
+        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        require_device();
+        if (n < 1) fail("concat: need at least one batch");
+        auto o = std::make_unique<Batch>();
+        const size_t nc = batches[0]->cols.size();
+        for (int i = 0; i < n; i++) {
+            if (batches[i]->cols.size() != nc) fail("concat: schema mismatch");
+            o->num_rows += batches[i]->num_rows;
+        }
+        for (size_t c = 0; c < nc; c++) {
+            std::vector<const Column *> cs;
+            for (int i = 0; i < n; i++) cs.push_back(&batches[i]->cols[c]);
+            o->cols.push_back(concat_columns(cs));
+        }
+        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+        *out = o.release();
+    });
+}
+
+// ---- sort --------------------------------------------------------------------------------------------
+int b200_argsort(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
+                 const uint8_t *nulls_first, b200_batch **out_indices, char **errmsg) {
+    return guard(errmsg, [&] {
+        Buf idx = op_argsort(*batch, key_cols, nkeys, descending, nulls_first);
+        auto o = std::make_unique<Batch>();
+        o->num_rows = batch->num_rows;
+        o->cols.push_back(make_u64_column("indices", idx, batch->num_rows));
+        *out_indices = o.release();
+    });
+}
+int b200_sort(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
+              const uint8_t *nulls_first, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        Buf idx = op_argsort(*batch, key_cols, nkeys, descending, nulls_first);
+        *out = gather_batch(*batch, as<int64_t>(idx), batch->num_rows, false);
+        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+int b200_top_n(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
+               const uint8_t *nulls_first, int64_t limit, int64_t offset, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        // RecordBatch::top_n = argsort then slice (src/daft-recordbatch/src/ops/sort.rs:47-61)
+        Buf idx = op_argsort(*batch, key_cols, nkeys, descending, nulls_first);
+        const int64_t n = batch->num_rows;
+        const int64_t start = std::min<int64_t>(std::max<int64_t>(offset, 0), n);
+        const int64_t end = std::min<int64_t>(n, start + std::max<int64_t>(limit, 0));
+        *out = gather_batch(*batch, as<int64_t>(idx) + start, end - start, false);
+        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+
+// ---- join --------------------------------------------------------------------------------------------
+int b200_probe_table_create(int32_t nkeys, const uint8_t *null_equals_null, int32_t track_indices, b200_probe_table **out,
+                            char **errmsg) {
+    return guard(errmsg, [&] { *out = probe_table_create(nkeys, null_equals_null, track_indices != 0); });
+}
+int b200_probe_table_add(b200_probe_table *pt, const b200_batch *build_batch, const int32_t *key_cols, char **errmsg) {
+    return guard(errmsg, [&] { probe_table_add(pt, *build_batch, key_cols); });
+}
+int b200_probe_table_build(b200_probe_table *pt, char **errmsg) {
+    return guard(errmsg, [&] { probe_table_build(pt); });
+}
+int64_t b200_probe_table_num_rows(const b200_probe_table *pt) { return probe_table_num_rows(pt); }
+void b200_probe_table_free(b200_probe_table *pt) { probe_table_free(pt); }
+int b200_probe_exists(const b200_probe_table *pt, const b200_batch *probe, const int32_t *key_cols, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = probe_exists(pt, *probe, key_cols); });
+}
+int b200_probe_indices(const b200_probe_table *pt, const b200_batch *probe, const int32_t *key_cols, b200_batch **out,
+                       char **errmsg) {
+    return guard(errmsg, [&] { *out = probe_indices(pt, *probe, key_cols); });
+}
+int b200_join_state_create(const b200_probe_table *pt, b200_join_state **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = join_state_create(pt); });
+}
+void b200_join_state_free(b200_join_state *st) { join_state_free(st); }
+int b200_hash_join_probe(const b200_probe_table *pt, b200_join_state *st, const b200_batch *probe, const int32_t *key_cols,
+                         int32_t join_type, int32_t build_on_left, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = hash_join_probe(pt, st, *probe, key_cols, join_type, build_on_left != 0); });
+}
+int b200_hash_join_finalize(const b200_probe_table *pt, b200_join_state *st, const b200_batch *probe_schema_like,
+                            int32_t build_on_left, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = hash_join_finalize(pt, st, *probe_schema_like, build_on_left != 0); });
+}
+
+// ---- exchange ----------------------------------------------------------------------------------------
+int b200_comm_unique_id(uint8_t *out128, char **errmsg) {
+    return guard(errmsg, [&] { comm_unique_id(out128); });
+}
+int b200_comm_init(const uint8_t *id128, int32_t rank, int32_t world, b200_comm **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = comm_init(id128, rank, world); });
+}
+void b200_comm_free(b200_comm *c) { comm_free(c); }
+int b200_exchange_by_hash(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out,
+                          char **errmsg) {
+    return guard(errmsg, [&] { *out = exchange_by_hash(c, *batch, key_cols, nkeys); });
+}
+int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = all_gather_batches(c, *batch); });
+}
+
+// ---- TPC-H generator -----------------------------------------------------------------------------------
+int b200_tpch_generate(int32_t table, double scale_factor, int64_t row_begin, int64_t row_end, uint64_t seed,
+                       const char *const *columns, int32_t ncolumns, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = tpch_generate(table, scale_factor, row_begin, row_end, seed, columns, ncolumns); });
+}
+int64_t b200_tpch_num_rows(int32_t table, double scale_factor) { return tpch_num_rows(table, scale_factor); }
+int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begin, int64_t row_end, uint64_t seed,
+                            const char *const *columns, int32_t ncolumns, struct ArrowArray *out_array,
+                            struct ArrowSchema *out_schema, char **errmsg) {
+    return guard(errmsg, [&] { tpch_generate_host(table, scale_factor, row_begin, row_end, seed, columns, ncolumns, out_array, out_schema); });
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

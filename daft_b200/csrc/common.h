@@ -1,0 +1,120 @@
+// Internal host-side types of libdaftb200.so: device buffers, columns, batches, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/daft_b200.h"
+
+namespace b200 {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] inline void fail(const std::string &msg) { throw Error(msg); }
+
+#define B200_CUDA(expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            ::b200::fail(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                         std::to_string(__LINE__) + " in " #expr);                                   \
+    } while (0)
+
+// ---- library context -------------------------------------------------------------------------
+struct Context {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    bool ready = false;
+};
+Context &ctx();
+void require_device();  // throws unless b200_init succeeded (no CPU fallback)
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- device memory ---------------------------------------------------------------------------
+// Stream-ordered allocations from the device's default mempool (release threshold = unlimited so
+// freed blocks stay cached in HBM between operators).
+struct DevAlloc {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    bool owned = true;
+    ~DevAlloc();
+};
+using Buf = std::shared_ptr<DevAlloc>;
+Buf dev_alloc(size_t bytes);                    // uninitialised
+Buf dev_alloc_zero(size_t bytes);
+Buf dev_borrow(const void *ptr, size_t bytes);  // non-owning view
+template <typename T>
+inline T *as(const Buf &b) { return b ? reinterpret_cast<T *>(b->ptr) : nullptr; }
+
+// ---- columns / batches -----------------------------------------------------------------------
+inline int dtype_width(int32_t dt) {
+    switch (dt) {
+        case B200_I8: case B200_U8: return 1;
+        case B200_I16: case B200_U16: return 2;
+        case B200_I32: case B200_U32: case B200_F32: case B200_DATE32: return 4;
+        case B200_I64: case B200_U64: case B200_F64: case B200_TIMESTAMP: return 8;
+        default: return 0;
+    }
+}
+inline bool is_string(int32_t dt) { return dt == B200_LARGE_UTF8 || dt == B200_LARGE_BINARY; }
+inline bool is_float(int32_t dt) { return dt == B200_F32 || dt == B200_F64; }
+inline bool is_signed_int(int32_t dt) { return dt >= B200_I8 && dt <= B200_I64; }
+inline bool is_unsigned_int(int32_t dt) { return dt >= B200_U8 && dt <= B200_U64; }
+inline bool is_integer(int32_t dt) { return is_signed_int(dt) || is_unsigned_int(dt); }
+const char *dtype_name(int32_t dt);
+
+struct Column {
+    std::string name;
+    int32_t dtype = B200_NULL;
+    int64_t length = 0;
+    int64_t null_count = 0;  // exact
+    Buf validity;            // null when null_count == 0
+    Buf offsets;             // strings
+    Buf data;
+    int64_t data_bytes = 0;
+    bool nullable() const { return dtype == B200_NULL || null_count > 0; }
+};
+
+}  // namespace b200
+
+struct b200_batch {
+    std::vector<b200::Column> cols;
+    int64_t num_rows = 0;
+};
+
+namespace b200 {
+using Batch = ::b200_batch;
+
+// ---- small device utilities (util.cu) --------------------------------------------------------
+// exclusive scan of int64 `in[n]` -> `out[n]`, returns total via *total_dev (device int64) if non-null
+void exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *total_dev);
+int64_t count_set_bits(const uint8_t *bitmap, int64_t nbits);  // syncs
+int64_t read_i64(const int64_t *dev_ptr);                      // syncs
+void fill_u8(void *ptr, int value, size_t bytes);
+// gather rows of `src` at `idx[n]` (int64, -1 => null row) into a new column
+Column gather_column(const Column &src, const int64_t *idx, int64_t n, bool idx_may_be_negative);
+Batch *gather_batch(const Batch &src, const int64_t *idx, int64_t n, bool idx_may_be_negative);
+Column slice_column(const Column &src, int64_t start, int64_t end);
+Column concat_columns(const std::vector<const Column *> &cols);
+// any integer column -> int64 index buffer (null -> -1)
+Buf indices_to_i64(const Column &c);
+Column make_u64_column(const std::string &name, Buf data, int64_t n);
+
+// ---- hashing (hash.cu) -----------------------------------------------------------------------
+// out[i] = xxh3_64(col[i], seed ? seed[i] : 0) with Daft's null rules
+void hash_column(const Column &c, const uint64_t *seed, uint64_t *out);
+Buf hash_rows(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint64_t *seed);
+
+}  // namespace b200

@@ -1,0 +1,236 @@
+// a12: the repartition exchange as an NCCL all-to-all over NVLink 5 / NVSwitch.
+//
+// Replaces RepartitionSink -> Arrow-IPC spill files -> Arrow Flight do_get
+// (src/daft-local-execution/src/sinks/repartition.rs:100-370, src/daft-shuffles/src/shuffle_cache.rs:36-434,
+// src/daft-shuffles/src/server/flight_server.rs:70-383): no disk, no IPC framing, no driver-side
+// transposition.  Map side = the same hash_rows % world placement as a3 (so results agree with the
+// reference's partitioning), rows gathered destination-contiguous; the G x G row/byte count matrices are
+// all-gathered first, then every column buffer moves with one grouped ncclSend/ncclRecv.
+// One process per GPU; the communicator is created from an id the host broadcasts out of band.
+#include <nccl.h>
+
+#include <algorithm>
+
+#include "common.h"
+#include "kernels.cuh"
+#include "ops.h"
+
+struct b200_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+namespace b200 {
+
+#define B200_NCCL(expr)                                                                                  \
+    do {                                                                                                 \
+        ncclResult_t _r = (expr);                                                                        \
+        if (_r != ncclSuccess) fail(std::string("NCCL error: ") + ncclGetErrorString(_r) + " in " #expr); \
+    } while (0)
+
+void comm_unique_id(uint8_t *out128) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    B200_NCCL(ncclGetUniqueId(&id));
+    memcpy(out128, &id, 128);
+}
+b200_comm *comm_init(const uint8_t *id128, int32_t rank, int32_t world) {
+    require_device();
+    auto c = std::make_unique<b200_comm>();
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    B200_NCCL(ncclCommInitRank(&c->comm, world, id, rank));
+    c->rank = rank;
+    c->world = world;
+    return c.release();
+}
+void comm_free(b200_comm *c) {
+    if (c && c->comm) ncclCommDestroy(c->comm);
+    delete c;
+}
+
+static int egrid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 8)); }
+
+__global__ void bits_to_bytes(const uint8_t *__restrict__ bits, int64_t n, uint8_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = bits == nullptr ? 1 : (uint8_t)bit_at(bits, i);
+}
+__global__ void bytes_to_bits(const uint8_t *__restrict__ bytes, int64_t n, uint32_t *__restrict__ out) {
+    const int64_t n_round = (n + 31) & ~(int64_t)31;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n_round; i += stride) {
+        const unsigned m = __ballot_sync(0xffffffffu, i < n && bytes[i] != 0);
+        if ((threadIdx.x & 31) == 0) out[i >> 5] = m;
+    }
+}
+__global__ void offsets_to_lengths(const int64_t *__restrict__ off, int64_t n, int64_t *__restrict__ len) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) len[i] = off[i + 1] - off[i];
+}
+
+// who sends how much to whom; *_off/_cnt in elements of the buffer being moved
+struct Route {
+    std::vector<int64_t> send_off, send_cnt, recv_off, recv_cnt;
+    int64_t recv_total = 0;
+};
+
+// all ranks learn everybody's send counts: m[src * world + dst]
+static std::vector<int64_t> gather_counts(b200_comm *c, const std::vector<int64_t> &send_cnt) {
+    cudaStream_t st = ctx().stream;
+    const int W = c->world;
+    Buf d_in = dev_alloc((size_t)W * 8), d_out = dev_alloc((size_t)W * W * 8);
+    B200_CUDA(cudaMemcpyAsync(d_in->ptr, send_cnt.data(), (size_t)W * 8, cudaMemcpyHostToDevice, st));
+    B200_NCCL(ncclAllGather(d_in->ptr, d_out->ptr, (size_t)W, ncclInt64, c->comm, st));
+    std::vector<int64_t> m((size_t)W * W);
+    B200_CUDA(cudaMemcpyAsync(m.data(), d_out->ptr, (size_t)W * W * 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return m;
+}
+static Route make_route(b200_comm *c, const std::vector<int64_t> &send_off, const std::vector<int64_t> &send_cnt) {
+    const int W = c->world;
+    Route r;
+    r.send_off = send_off;
+    r.send_cnt = send_cnt;
+    const std::vector<int64_t> m = gather_counts(c, send_cnt);
+    r.recv_off.assign(W, 0);
+    r.recv_cnt.assign(W, 0);
+    for (int src = 0; src < W; src++) {
+        r.recv_cnt[src] = m[(size_t)src * W + c->rank];
+        r.recv_off[src] = r.recv_total;
+        r.recv_total += r.recv_cnt[src];
+    }
+    return r;
+}
+static void move_buffer(b200_comm *c, const Route &r, const void *send, void *recv, size_t elem_bytes) {
+    cudaStream_t st = ctx().stream;
+    B200_NCCL(ncclGroupStart());
+    for (int p = 0; p < c->world; p++) {
+        if (r.send_cnt[p])
+            B200_NCCL(ncclSend((const uint8_t *)send + (size_t)r.send_off[p] * elem_bytes, (size_t)r.send_cnt[p] * elem_bytes, ncclUint8, p,
+                               c->comm, st));
+        if (r.recv_cnt[p])
+            B200_NCCL(ncclRecv((uint8_t *)recv + (size_t)r.recv_off[p] * elem_bytes, (size_t)r.recv_cnt[p] * elem_bytes, ncclUint8, p, c->comm,
+                               st));
+    }
+    B200_NCCL(ncclGroupEnd());
+    count_launch();
+}
+
+// `src` columns are already destination-contiguous (rows [row_route.send_off[p], +send_cnt[p]) go to peer p)
+static Batch *route_batch(b200_comm *c, const Batch &src, const Route &rows) {
+    cudaStream_t st = ctx().stream;
+    const int W = c->world;
+    const int64_t n_out = rows.recv_total, n_in = src.num_rows;
+    auto out = std::make_unique<Batch>();
+    out->num_rows = n_out;
+    for (const Column &col : src.cols) {
+        Column o;
+        o.name = col.name;
+        o.dtype = col.dtype;
+        o.length = n_out;
+        if (col.dtype == B200_NULL) {
+            o.null_count = n_out;
+            out->cols.push_back(std::move(o));
+            continue;
+        }
+        // validity travels one byte per row (bitmaps cannot be cut at arbitrary bit offsets); any rank may have nulls
+        {
+            Buf sb = dev_alloc((size_t)std::max<int64_t>(n_in, 1)), rb = dev_alloc((size_t)std::max<int64_t>(n_out, 1));
+            if (n_in) {
+                bits_to_bytes<<<egrid(n_in), 256, 0, st>>>(col.null_count > 0 ? as<uint8_t>(col.validity) : nullptr, n_in, as<uint8_t>(sb));
+                count_launch();
+            }
+            move_buffer(c, rows, sb->ptr, rb->ptr, 1);
+            o.validity = dev_alloc((size_t)((n_out + 31) / 32 + 1) * 4);
+            if (n_out) {
+                bytes_to_bits<<<egrid(n_out), 256, 0, st>>>(as<uint8_t>(rb), n_out, as<uint32_t>(o.validity));
+                count_launch();
+            }
+            o.null_count = n_out - count_set_bits(as<uint8_t>(o.validity), n_out);
+            if (o.null_count == 0) o.validity.reset();
+        }
+        const int w = dtype_width(col.dtype);
+        if (w) {
+            o.data = dev_alloc((size_t)std::max<int64_t>(n_out, 1) * w);
+            o.data_bytes = n_out * w;
+            move_buffer(c, rows, col.data ? col.data->ptr : nullptr, o.data->ptr, (size_t)w);
+        } else if (col.dtype == B200_BOOL) {
+            Buf sb = dev_alloc((size_t)std::max<int64_t>(n_in, 1)), rb = dev_alloc((size_t)std::max<int64_t>(n_out, 1));
+            if (n_in) {
+                bits_to_bytes<<<egrid(n_in), 256, 0, st>>>(as<uint8_t>(col.data), n_in, as<uint8_t>(sb));
+                count_launch();
+            }
+            move_buffer(c, rows, sb->ptr, rb->ptr, 1);
+            o.data = dev_alloc((size_t)((n_out + 31) / 32 + 1) * 4);
+            o.data_bytes = (n_out + 7) / 8;
+            if (n_out) {
+                bytes_to_bits<<<egrid(n_out), 256, 0, st>>>(as<uint8_t>(rb), n_out, as<uint32_t>(o.data));
+                count_launch();
+            }
+        } else {  // strings: lengths by row route, bytes by a byte route
+            Buf slen = dev_alloc((size_t)std::max<int64_t>(n_in, 1) * 8), rlen = dev_alloc((size_t)(n_out + 1) * 8);
+            if (n_in) {
+                offsets_to_lengths<<<egrid(n_in), 256, 0, st>>>(as<int64_t>(col.offsets), n_in, as<int64_t>(slen));
+                count_launch();
+            }
+            move_buffer(c, rows, slen->ptr, rlen->ptr, 8);
+            o.offsets = dev_alloc((size_t)(n_out + 1) * 8);
+            exclusive_scan_i64(as<int64_t>(rlen), as<int64_t>(o.offsets), n_out, as<int64_t>(o.offsets) + n_out);
+            // byte offsets of each destination's slice on the send side
+            std::vector<int64_t> cut((size_t)W + 1, 0), boff(W), bcnt(W);
+            for (int p = 0; p <= W; p++) {
+                const int64_t row = p < W ? rows.send_off[p] : n_in;
+                if (n_in) B200_CUDA(cudaMemcpyAsync(&cut[p], as<int64_t>(col.offsets) + row, 8, cudaMemcpyDeviceToHost, st));
+            }
+            B200_CUDA(cudaStreamSynchronize(st));
+            for (int p = 0; p < W; p++) {
+                boff[p] = cut[p] - cut[0];
+                const int64_t endrow = rows.send_off[p] + rows.send_cnt[p];
+                int64_t endb = 0;
+                if (n_in) {
+                    B200_CUDA(cudaMemcpyAsync(&endb, as<int64_t>(col.offsets) + endrow, 8, cudaMemcpyDeviceToHost, st));
+                    B200_CUDA(cudaStreamSynchronize(st));
+                }
+                bcnt[p] = endb - cut[p];
+            }
+            const Route br = make_route(c, boff, bcnt);
+            o.data = dev_alloc((size_t)br.recv_total);
+            o.data_bytes = br.recv_total;
+            move_buffer(c, br, col.data ? as<uint8_t>(col.data) + cut[0] : nullptr, o.data->ptr, 1);
+        }
+        out->cols.push_back(std::move(o));
+    }
+    B200_CUDA(cudaStreamSynchronize(st));
+    return out.release();
+}
+
+Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys) {
+    require_device();
+    if (!c) fail("null communicator");
+    const int W = c->world;
+    Buf h = hash_rows(b, key_cols, nkeys, nullptr);
+    std::vector<int64_t> offsets;
+    Buf perm = partition_permutation(as<uint64_t>(h), b.num_rows, W, offsets);
+    std::unique_ptr<Batch> staged(gather_batch(b, as<int64_t>(perm), b.num_rows, false));
+    std::vector<int64_t> soff(W), scnt(W);
+    for (int p = 0; p < W; p++) {
+        soff[p] = offsets[p];
+        scnt[p] = offsets[p + 1] - offsets[p];
+    }
+    const Route rows = make_route(c, soff, scnt);
+    return route_batch(c, *staged, rows);
+}
+
+Batch *all_gather_batches(b200_comm *c, const Batch &b) {
+    require_device();
+    if (!c) fail("null communicator");
+    const int W = c->world;
+    std::vector<int64_t> soff(W, 0), scnt(W, b.num_rows);
+    const Route rows = make_route(c, soff, scnt);
+    return route_batch(c, b, rows);
+}
+
+}  // namespace b200

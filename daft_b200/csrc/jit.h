@@ -1,0 +1,88 @@
+// Host side of the JIT: plan parsing, typed code generation, NVRTC compile + cubin cache.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace b200 {
+namespace jit {
+
+enum PtrKind {
+    P_COL_DATA = 0, P_COL_VALID, P_COL_OFFSETS,
+    P_OUT_DATA, P_OUT_VALID, P_OUT_LEN, P_OUT_OFFSETS,
+    P_TAKE, P_SLOT_HASH, P_SLOT_ROW, P_ACC, P_OVERFLOW
+};
+struct PtrSlot { int kind; int index; };
+enum IntKind { I_N = 0, I_MASK };
+
+struct OutCol {
+    std::string name;
+    int32_t dtype;
+    bool nullable;
+};
+
+enum CellOp { C_ADD_F64 = 0, C_ADD_F32, C_ADD_I64, C_MIN, C_MAX };
+enum AggKind { AGG_COUNT = 0, AGG_SUM, AGG_MIN, AGG_MAX, AGG_MEAN, AGG_ANY_VALUE };
+
+struct AggOut {
+    std::string name;
+    int kind = 0, count_mode = 0;
+    int32_t val_dtype = 0;   // dtype of the (widened) value the cell accumulates
+    int32_t out_dtype = 0;
+    int lane_cell = -1;      // index into lane cells, -1 if none
+    int cnt_cell = -1;       // warp count cell with #valid (or #null for count-null), -1 => use nrows
+    bool child_nullable = false;
+    bool const_zero = false; // count(null) over a non-nullable child
+};
+
+struct Compiled {
+    cudaKernel_t fn = nullptr;
+    cudaLibrary_t lib = nullptr;
+    std::vector<PtrSlot> ptrs;
+    std::vector<int> ints;
+    // project
+    std::vector<OutCol> outs;
+    bool has_string_out = false;
+    bool with_take = false;
+    // agg
+    int nkeys = 0;
+    int G1 = 0, NLANE = 0, NWARP = 0;
+    std::vector<int> lane_cell_ops;
+    std::vector<AggOut> aggs;
+    size_t smem_bytes = 0;
+    std::vector<uint8_t> key_project_plan;
+    int regs = 0;
+    std::string source_path;
+};
+
+// Codegen only (no CUDA needed): returns the CUDA source for the plan; fills `meta` (fn stays null).
+std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
+                     const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta);
+// NVRTC -> cubin (cached on disk); works without a GPU.
+std::vector<char> compile_to_cubin(const std::string &source, std::string *path_out);
+// generate + compile + load; cached per (op, plan, dtypes, nullability, take)
+const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &input, bool with_take);
+void set_cache_dir(const std::string &dir);
+void precompile(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
+                const std::vector<uint8_t> &col_nullable);
+
+// launch helper: fills the parameter block from resolver callbacks
+struct LaunchArgs {
+    std::vector<void *> ptr;
+    std::vector<long long> ival;
+};
+// `timed`: bracket the launch with CUDA events on the library stream when kernel timing is enabled
+void launch(const Compiled &k, const LaunchArgs &a, int grid, int block, size_t smem, int pass, bool timed);
+void enable_kernel_timing(bool on);
+double last_timed_kernel_ms();
+
+}  // namespace jit
+
+// operators built on the JIT (ops_jit.cu)
+Batch *op_project(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n);
+Batch *op_filter(const Batch &in, const uint8_t *plan, size_t len);
+Batch *op_agg(const Batch &in, const uint8_t *plan, size_t len);
+
+}  // namespace b200

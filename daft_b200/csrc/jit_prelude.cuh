@@ -1,0 +1,311 @@
+// Device-side skeletons of the JIT-specialised pipeline kernels (sm_100a).
+//
+// The host (jit.cpp) turns a serialised plan (include/daft_b200.h "plan encoding") into a `Prog`
+// struct -- straight-line, fully typed code for the filter / key / aggregate-input expressions --
+// and instantiates one of the hand-written skeletons below with it:
+//
+//   project_body         Filter/Project (a10/a11): one pass, outputs written at HBM speed,
+//                        bitmaps built with warp ballots, strings in a length pass + copy pass.
+//   agg_body             fused Filter -> Project -> HashAggregate (a4/a6/a10/a11): every input
+//                        column is read exactly once; nothing is materialised.
+//
+// Group-by design (agg_body), replacing the hashbrown raw-entry probe + per-accumulator scatter
+// passes of src/daft-recordbatch/src/ops/inline_agg.rs:748-824,556-565:
+//   * global open-addressing table keyed by the XXH3 row hash (same hash_rows as the reference), slot
+//     claimed with one atomicCAS; equal hashes are verified against the claiming row's key values
+//     (nulls equal, floats by bit pattern == the reference's "hash equal AND comparator" rule);
+//   * accumulators are indexed by table slot, three tiers by where the group lives:
+//       tier 1  the first G1 groups a CTA meets: per-lane private shared-memory cells, plain
+//               read-modify-write, zero atomics, zero bank conflicts (cell address = lane);
+//               counts and first-row tracking are done per warp with ballots;
+//       tier 3  every other group: red.global atomics on the slot's cells.
+//     Low-cardinality aggregates (TPC-H Q1: 4 groups) never leave tier 1; high-cardinality ones
+//     (Q18: one group per order) spread their atomics over millions of addresses.
+//   * first-occurrence group order (inline_agg.rs:804-807) is recovered by tracking min(row) per group.
+#pragma once
+
+#define FULL_MASK 0xffffffffu
+
+namespace b200 {
+namespace jit {
+
+struct Str {
+    const uint8_t *p;
+    int64_t len;
+};
+
+__device__ __forceinline__ bool bit_at(const uint8_t *bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+
+// ---- order-preserving keys for min/max on any numeric type ---------------------------------------
+// floats: all NaN collapse to the largest key (NaN sorts greatest, search_sorted.rs:238-245)
+__device__ __forceinline__ uint64_t ord_f64(double v) {
+    if (v != v) return 0xFFFFFFFFFFFFFFFFULL;
+    uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double unord_f64(uint64_t k) {
+    if (k == 0xFFFFFFFFFFFFFFFFULL) return __longlong_as_double(0x7FF8000000000000LL);
+    uint64_t b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ uint64_t ord_f32(float v) { return ord_f64((double)v); }
+__device__ __forceinline__ uint64_t ord_i64(int64_t v) { return (uint64_t)v ^ 0x8000000000000000ULL; }
+__device__ __forceinline__ uint64_t ord_u64(uint64_t v) { return v; }
+
+// ---- string helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool str_eq(Str a, Str b) {
+    if (a.len != b.len) return false;
+    for (int64_t i = 0; i < a.len; i++)
+        if (a.p[i] != b.p[i]) return false;
+    return true;
+}
+__device__ __forceinline__ int str_cmp(Str a, Str b) {
+    int64_t n = a.len < b.len ? a.len : b.len;
+    for (int64_t i = 0; i < n; i++) {
+        int d = (int)a.p[i] - (int)b.p[i];
+        if (d) return d;
+    }
+    return a.len < b.len ? -1 : (a.len > b.len ? 1 : 0);
+}
+__device__ __forceinline__ bool str_startswith(Str a, Str pat) {
+    if (pat.len > a.len) return false;
+    for (int64_t i = 0; i < pat.len; i++)
+        if (a.p[i] != pat.p[i]) return false;
+    return true;
+}
+__device__ __forceinline__ bool str_endswith(Str a, Str pat) {
+    if (pat.len > a.len) return false;
+    const uint8_t *q = a.p + (a.len - pat.len);
+    for (int64_t i = 0; i < pat.len; i++)
+        if (q[i] != pat.p[i]) return false;
+    return true;
+}
+__device__ __forceinline__ bool str_contains(Str a, Str pat) {
+    if (pat.len == 0) return true;
+    for (int64_t s = 0; s + pat.len <= a.len; s++) {
+        int64_t i = 0;
+        while (i < pat.len && a.p[s + i] == pat.p[i]) i++;
+        if (i == pat.len) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ int64_t str_char_len(Str a) {
+    int64_t c = 0;
+    for (int64_t i = 0; i < a.len; i++) c += (a.p[i] & 0xC0) != 0x80;
+    return c;
+}
+__device__ __forceinline__ Str str_left(Str a, int64_t nchars) {
+    if (nchars <= 0) return Str{a.p, 0};
+    int64_t c = 0, i = 0;
+    for (; i < a.len; i++) {
+        if ((a.p[i] & 0xC0) != 0x80) {
+            if (c == nchars) break;
+            c++;
+        }
+    }
+    return Str{a.p, i};
+}
+
+// ---- civil calendar from days since 1970-01-01 (proleptic Gregorian) --------------------------------
+__device__ __forceinline__ void civil_from_days(int64_t z, int32_t &y, int32_t &m, int32_t &d) {
+    z += 719468;
+    const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+    const uint32_t doe = (uint32_t)(z - era * 146097);
+    const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const int64_t yy = (int64_t)yoe + era * 400;
+    const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const uint32_t mp = (5 * doy + 2) / 153;
+    d = (int32_t)(doy - (153 * mp + 2) / 5 + 1);
+    m = (int32_t)(mp < 10 ? mp + 3 : mp - 9);
+    y = (int32_t)(yy + (m <= 2));
+}
+__device__ __forceinline__ int32_t date_year(int32_t days) { int32_t y, m, d; civil_from_days(days, y, m, d); return y; }
+__device__ __forceinline__ uint32_t date_month(int32_t days) { int32_t y, m, d; civil_from_days(days, y, m, d); return (uint32_t)m; }
+__device__ __forceinline__ uint32_t date_day(int32_t days) { int32_t y, m, d; civil_from_days(days, y, m, d); return (uint32_t)d; }
+__device__ __forceinline__ uint32_t date_dow(int32_t days) {  // Monday = 0
+    int64_t r = ((int64_t)days + 3) % 7;
+    return (uint32_t)(r < 0 ? r + 7 : r);
+}
+
+// ---- integer division helpers (floor semantics; divisor 0 handled by the caller as null) ------------
+template <typename T>
+__device__ __forceinline__ T floor_div_s(T a, T b) {
+    T q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) q--;
+    return q;
+}
+template <typename T>
+__device__ __forceinline__ T floor_mod_s(T a, T b) {
+    T r = a % b;
+    if (r != 0 && ((r < 0) != (b < 0))) r += b;
+    return r;
+}
+
+// ---- kernel parameter block: 8-byte slots the host fills in the order codegen allocated them ---------
+template <int NPTR, int NINT>
+struct Params {
+    void *ptr[NPTR > 0 ? NPTR : 1];
+    long long ival[NINT > 0 ? NINT : 1];
+};
+
+// ======================================================================================================
+// Filter / Project
+// ======================================================================================================
+// Prog provides:
+//   using P = Params<..>;  static constexpr int IV_N (ival slot of the row count), PTR_TAKE (ptr slot of
+//   the optional int64 gather index, -1 if none)
+//   __device__ static void row(const P&, int64_t out_row, int64_t src_row, bool active, int pass)
+// `row` is called by ALL lanes (inactive ones too) because bitmap outputs are built with warp ballots.
+template <class Prog>
+__device__ __forceinline__ void project_body(const typename Prog::P &p, int pass) {
+    const int64_t n = p.ival[Prog::IV_N];
+    const int64_t n_round = (n + 31) & ~(int64_t)31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool active = i < n;
+        int64_t src = i;
+        if (Prog::PTR_TAKE >= 0 && active) src = ((const int64_t *)p.ptr[Prog::PTR_TAKE < 0 ? 0 : Prog::PTR_TAKE])[i];
+        Prog::row(p, i, src, active, pass);
+    }
+}
+
+// ======================================================================================================
+// fused Filter -> Project -> HashAggregate
+// ======================================================================================================
+// Prog provides (all generated):
+//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_SLOT_HASH, PTR_SLOT_ROW, PTR_MINROW, PTR_NROWS,
+//   PTR_OVERFLOW;  NKEYS, G1, NLANE (lane cells), NWARP (warp count cells), U (rows per lane per step)
+//   struct Raw;  struct Keys;  struct Vals;
+//   load(p,row,Raw&) ; bool eval(p,Raw&,Keys&,Vals&) (false = filtered out) ; eval_keys(p,row,Keys&)
+//   uint64 hash(Keys&) ; bool keys_equal(Keys&,Keys&)
+//   lane_init(cell*) ; lane_update(cell* base, Vals&) ; global_update(p, slot, Vals&)
+//   warp_cells(p, Vals&, bool in_group, unsigned long long* wc)  (ballot-based count cells)
+//   flush(...)  (generated reduction of the lane cells)
+constexpr int AGG_WARPS = 8;
+
+template <class Prog>
+__device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, const typename Prog::Keys &k, uint64_t h,
+                                                  int64_t row) {
+    unsigned long long *slot_hash = (unsigned long long *)p.ptr[Prog::PTR_SLOT_HASH];
+    long long *slot_row = (long long *)p.ptr[Prog::PTR_SLOT_ROW];
+    const uint64_t mask = (uint64_t)p.ival[Prog::IV_MASK];
+    if (h == 0) h = 1;  // 0 marks an empty slot; equality is decided by the key comparison anyway
+    uint64_t s = h & mask;
+    for (uint64_t probes = 0; probes <= mask; probes++) {
+        unsigned long long cur = slot_hash[s];  // may be a stale 0 from L1: the CAS below re-reads at L2
+        bool mine = false;
+        if (cur == 0) {
+            unsigned long long prev = atomicCAS(&slot_hash[s], 0ULL, (unsigned long long)h);
+            if (prev == 0) {
+                // claimed: publish the representative row (written before anyone can need it below)
+                *((volatile long long *)&slot_row[s]) = (long long)row;
+                __threadfence();
+                mine = true;
+            }
+            cur = prev == 0 ? h : prev;
+        }
+        if (mine) return (long long)s;
+        if (cur == h) {
+            long long r = slot_row[s];
+            while (r < 0) r = *((volatile long long *)&slot_row[s]);
+            if (r == row) return (long long)s;
+            typename Prog::Keys other;
+            Prog::eval_keys(p, r, other);
+            if (Prog::keys_equal(k, other)) return (long long)s;
+        }
+        s = (s + 1) & mask;
+    }
+    *((int *)p.ptr[Prog::PTR_OVERFLOW]) = 1;  // table full: host retries with a larger table
+    return -1;
+}
+
+template <class Prog>
+__device__ __forceinline__ void agg_body(const typename Prog::P &p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: int s_small[G1] | pad | warp cells [W][G1][NWARP+1] u64 | lane cells [W][G1][NLANE][32] u64
+    constexpr int G1 = Prog::G1, NL = Prog::NLANE, NW = Prog::NWARP;
+    long long *s_small = (long long *)smem_raw;                                  // G1 (slot or -1)
+    unsigned long long *s_wcell = (unsigned long long *)(s_small + G1);          // W*G1*(NW+1); [NW] = min row
+    unsigned long long *s_lcell = s_wcell + AGG_WARPS * G1 * (NW + 1);           // W*G1*NL*32
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < G1) s_small[threadIdx.x] = -1;
+    for (int i = threadIdx.x; i < AGG_WARPS * G1 * (NW + 1); i += blockDim.x)
+        s_wcell[i] = ((i % (NW + 1)) == NW) ? 0xFFFFFFFFFFFFFFFFULL : 0ULL;
+    unsigned long long *my_lcell = s_lcell + (size_t)warp * G1 * NL * 32 + lane;  // cell c of group g: [(g*NL+c)*32]
+    if (NL > 0)
+        for (int g = 0; g < G1; g++) Prog::lane_init(my_lcell + (size_t)g * NL * 32);
+    unsigned long long *my_wcell = s_wcell + (size_t)warp * G1 * (NW + 1);
+    __syncthreads();
+
+    const int64_t n = p.ival[Prog::IV_N];
+    constexpr int U = Prog::U;
+    const int64_t chunk = 32 * U;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
+        const int64_t base = c * chunk;
+        typename Prog::Raw raw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load(p, row, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            typename Prog::Keys keys;
+            typename Prog::Vals vals;
+            bool live = row < n;
+            if (live) live = Prog::eval(p, raw[u], keys, vals);
+            long long slot = -1;
+            if (live) {
+                if (Prog::NKEYS == 0) slot = 0;
+                else slot = agg_find_slot<Prog>(p, keys, Prog::hash(keys), row);
+                if (slot < 0) live = false;
+            }
+            // tier 1 lookup / insert
+            int lid = -1;
+            if (live) {
+#pragma unroll
+                for (int g = 0; g < G1; g++)
+                    if (((volatile long long *)s_small)[g] == slot) lid = g;
+                if (lid < 0) {
+                    for (int g = 0; g < G1; g++) {
+                        long long old = (long long)atomicCAS((unsigned long long *)&s_small[g], (unsigned long long)-1LL,
+                                                             (unsigned long long)slot);
+                        if (old == -1 || old == slot) { lid = g; break; }
+                    }
+                }
+            }
+            if (live && lid >= 0) {
+                if (NL > 0) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals);
+            } else if (live) {
+                Prog::global_update(p, slot, vals, row);
+            }
+            // warp-level cells: row counts / valid counts by ballot, first row by ffs
+#pragma unroll
+            for (int g = 0; g < G1; g++) {
+                const bool in_g = live && lid == g;
+                const unsigned m = __ballot_sync(FULL_MASK, in_g);
+                if (m) {
+                    Prog::warp_cells(vals, in_g, my_wcell + g * (NW + 1), lane);
+                    if (lane == 0) {
+                        unsigned long long first = (unsigned long long)(base + u * 32 + (__ffs(m) - 1));
+                        if (first < my_wcell[g * (NW + 1) + NW]) my_wcell[g * (NW + 1) + NW] = first;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // flush tier 1: warp w reduces groups w, w+W, ... across all warps' private copies
+    for (int g = warp; g < G1; g += AGG_WARPS) {
+        const long long slot = s_small[g];
+        if (slot < 0) continue;
+        Prog::flush(p, slot, s_lcell + (size_t)g * NL * 32, (size_t)G1 * NL * 32, s_wcell + g * (NW + 1), G1 * (NW + 1), lane);
+    }
+}
+
+}  // namespace jit
+}  // namespace b200

@@ -1,0 +1,486 @@
+// a7/a8: hash join build + probe.
+//
+// Replaces ProbeTable / ProbeTableBuilder (src/daft-recordbatch/src/probeable/probe_table.rs:14-213:
+// a sequential hashbrown insert of (table<<36|row) ids into per-key Vec<u64>) and the row-at-a-time
+// GrowableRecordBatch materialisation of src/daft-local-execution/src/join/inner_join.rs:11-85.
+//
+// Build (all on the device, no sequential step):
+//   1. hash_rows over the build keys (the same XXH3 chain the reference uses);
+//   2. stable radix sort of the build row ids by hash -> rows with equal keys are contiguous and in
+//      INSERTION ORDER (the reference's match-list order, probe_table.rs:178-181);
+//   3. run heads (hash[i] != hash[i-1]) are inserted into an open-addressing table of 32-byte slots
+//      {hash, start, count} with one atomicCAS each (distinct hashes -> no duplicates).
+// Probe (two passes: count -> scan -> write, output rows in probe-row order):
+//   slot lookup by hash, then every candidate row of the run is verified against the probe row's key
+//   values: nulls match only where null_equals_null, floats compare with IEEE == (NaN never matches,
+//   nans_equal=false, probe_table.rs:48-51).
+// Left / right / outer joins mark matched build rows in a bitmap (1 = matched; the reference keeps the
+// complement, src/daft-local-execution/src/join/index_bitmap.rs:5-60) that finalize turns into the
+// unmatched-build-rows output.
+#include <algorithm>
+
+#include "common.h"
+#include "kernels.cuh"
+#include "ops.h"
+
+namespace b200 {
+
+constexpr int MAX_JOIN_KEYS = 8;
+
+struct KeyDesc {
+    int32_t dtype;
+    int32_t nulls_equal;
+    const void *data;
+    const uint8_t *validity;
+    const int64_t *offsets;
+};
+struct KeySet {
+    int32_t nkeys;
+    KeyDesc k[MAX_JOIN_KEYS];
+};
+
+struct __align__(32) JoinSlot {
+    unsigned long long hash;  // 0 = empty (hash 0 is remapped to 1; keys are verified anyway)
+    long long start;          // first position in `sorted_rows`
+    long long count;
+    long long pad;
+};
+
+}  // namespace b200
+
+struct b200_probe_table {
+    int32_t nkeys = 0;
+    std::vector<uint8_t> nulls_equal;
+    bool track_indices = true;
+    bool built = false;
+    std::vector<std::unique_ptr<b200::Batch>> pending;  // added tables (shallow copies share device buffers)
+    std::vector<std::vector<int32_t>> pending_keys;
+    std::unique_ptr<b200::Batch> build;                 // concatenated build side (all columns)
+    std::vector<int32_t> key_cols;
+    b200::Buf sorted_rows;                              // build row ids sorted by hash (stable)
+    b200::Buf slots;                                    // JoinSlot[cap]
+    int64_t cap = 0;
+    int64_t num_rows = 0;
+};
+struct b200_join_state {
+    b200::Buf matched;  // bit per build row
+    int64_t n = 0;
+};
+
+namespace b200 {
+
+static int jgrid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 8)); }
+
+static KeySet make_keyset(const Batch &b, const std::vector<int32_t> &cols, const std::vector<uint8_t> &ne) {
+    KeySet ks;
+    ks.nkeys = (int32_t)cols.size();
+    for (size_t i = 0; i < cols.size(); i++) {
+        if (cols[i] < 0 || cols[i] >= (int32_t)b.cols.size()) fail("join: key column index out of range");
+        const Column &c = b.cols[cols[i]];
+        ks.k[i].dtype = c.dtype;
+        ks.k[i].nulls_equal = ne[i];
+        ks.k[i].data = c.data ? c.data->ptr : nullptr;
+        ks.k[i].validity = c.null_count > 0 ? as<uint8_t>(c.validity) : nullptr;
+        ks.k[i].offsets = as<int64_t>(c.offsets);
+    }
+    return ks;
+}
+
+__device__ __forceinline__ bool key_valid(const KeyDesc &k, int64_t r) {
+    if (k.dtype == B200_NULL) return false;
+    return k.validity == nullptr || bit_at(k.validity, r);
+}
+// build_is_equal (src/daft-core/src/array/ops/arrow/comparison.rs:58-83)
+__device__ __forceinline__ bool keys_match(const KeySet &a, int64_t i, const KeySet &b, int64_t j) {
+    for (int k = 0; k < a.nkeys; k++) {
+        const KeyDesc &x = a.k[k], &y = b.k[k];
+        const bool vx = key_valid(x, i), vy = key_valid(y, j);
+        if (vx != vy) return false;
+        if (!vx) {
+            if (!x.nulls_equal) return false;
+            continue;
+        }
+        bool eq;
+        switch (x.dtype) {
+            case B200_BOOL: eq = bit_at((const uint8_t *)x.data, i) == bit_at((const uint8_t *)y.data, j); break;
+            case B200_I8: case B200_U8: eq = ((const uint8_t *)x.data)[i] == ((const uint8_t *)y.data)[j]; break;
+            case B200_I16: case B200_U16: eq = ((const uint16_t *)x.data)[i] == ((const uint16_t *)y.data)[j]; break;
+            case B200_I32: case B200_U32: case B200_DATE32: eq = ((const uint32_t *)x.data)[i] == ((const uint32_t *)y.data)[j]; break;
+            case B200_I64: case B200_U64: case B200_TIMESTAMP: eq = ((const uint64_t *)x.data)[i] == ((const uint64_t *)y.data)[j]; break;
+            case B200_F32: eq = ((const float *)x.data)[i] == ((const float *)y.data)[j]; break;
+            case B200_F64: eq = ((const double *)x.data)[i] == ((const double *)y.data)[j]; break;
+            case B200_LARGE_UTF8: case B200_LARGE_BINARY: {
+                const int64_t oa = x.offsets[i], la = x.offsets[i + 1] - oa, ob = y.offsets[j], lb = y.offsets[j + 1] - ob;
+                eq = la == lb;
+                const uint8_t *pa = (const uint8_t *)x.data + oa, *pb = (const uint8_t *)y.data + ob;
+                for (int64_t t = 0; eq && t < la; t++) eq = pa[t] == pb[t];
+                break;
+            }
+            default: eq = false;
+        }
+        if (!eq) return false;
+    }
+    return true;
+}
+
+// ---- build ---------------------------------------------------------------------------------------
+__global__ void count_run_heads(const uint64_t *__restrict__ sorted_hash, int64_t n, unsigned long long *__restrict__ nheads) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t c = 0;
+    for (; i < n; i += stride) c += (i == 0 || sorted_hash[i] != sorted_hash[i - 1]);
+    c = block_reduce_sum_i64<256>(c);
+    if (threadIdx.x == 0 && c) atomicAdd(nheads, (unsigned long long)c);
+}
+__global__ void insert_runs(const uint64_t *__restrict__ sorted_hash, int64_t n, JoinSlot *__restrict__ slots, uint64_t mask) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const uint64_t hraw = sorted_hash[i];
+        if (i != 0 && hraw == sorted_hash[i - 1]) continue;
+        const unsigned long long h = hraw ? hraw : 1ULL;
+        uint64_t s = h & mask;
+        for (;;) {
+            const unsigned long long prev = atomicCAS(&slots[s].hash, 0ULL, h);
+            if (prev == 0ULL) {
+                slots[s].start = i;
+                break;
+            }
+            s = (s + 1) & mask;  // distinct run heads never share a hash, except raw 0 vs raw 1 (verified by keys)
+        }
+    }
+}
+// run length = distance to the next head; heads write their own count (one thread per row, cheap scan-free form)
+__global__ void fill_run_counts(const uint64_t *__restrict__ sorted_hash, int64_t n, JoinSlot *__restrict__ slots, uint64_t mask) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const uint64_t hraw = sorted_hash[i];
+        const bool last = (i == n - 1) || sorted_hash[i + 1] != hraw;
+        if (!last) continue;
+        // find this run's slot and store end - start
+        const unsigned long long h = hraw ? hraw : 1ULL;
+        uint64_t s = h & mask;
+        for (;;) {
+            if (slots[s].hash == h) {
+                const long long st = slots[s].start;
+                if (sorted_hash[st] == hraw) {  // raw 0 and raw 1 both map to h == 1: pick the right run
+                    slots[s].count = i + 1 - st;
+                    break;
+                }
+            }
+            s = (s + 1) & mask;
+        }
+    }
+}
+
+// ---- probe -----------------------------------------------------------------------------------------
+// mode 0: count matches per probe row;  mode 1: write pairs at out_off[row]
+template <int MODE>
+__global__ void __launch_bounds__(256) probe_kernel(const uint64_t *__restrict__ probe_hash, int64_t n_probe, KeySet bk, KeySet pk,
+                                                     const JoinSlot *__restrict__ slots, uint64_t mask,
+                                                     const int64_t *__restrict__ sorted_rows, int keep_unmatched_probe,
+                                                     int64_t *__restrict__ counts, const int64_t *__restrict__ out_off,
+                                                     int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build,
+                                                     unsigned int *__restrict__ matched_bits) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n_probe; i += stride) {
+        const uint64_t hraw = probe_hash[i];
+        const unsigned long long h = hraw ? hraw : 1ULL;
+        uint64_t s = h & mask;
+        int64_t nmatch = 0;
+        int64_t o = MODE == 1 ? out_off[i] : 0;
+        for (;;) {
+            const JoinSlot e = slots[s];
+            if (e.hash == 0ULL) break;
+            if (e.hash == h) {
+                for (long long t = 0; t < e.count; t++) {
+                    const int64_t br = sorted_rows[e.start + t];
+                    if (keys_match(bk, br, pk, i)) {
+                        if (MODE == 1) {
+                            out_probe[o + nmatch] = i;
+                            out_build[o + nmatch] = br;
+                            if (matched_bits) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
+                        }
+                        nmatch++;
+                    }
+                }
+                // keep scanning only for the raw-0 / raw-1 alias; a second slot with the same h is otherwise impossible
+                if (h != 1ULL) break;
+            }
+            s = (s + 1) & mask;
+        }
+        if (MODE == 0) {
+            counts[i] = (nmatch == 0 && keep_unmatched_probe) ? 1 : nmatch;
+        } else if (nmatch == 0 && keep_unmatched_probe) {
+            out_probe[o] = i;
+            out_build[o] = -1;
+        }
+    }
+}
+
+__global__ void exists_kernel(const uint64_t *__restrict__ probe_hash, int64_t n_probe, KeySet bk, KeySet pk,
+                              const JoinSlot *__restrict__ slots, uint64_t mask, const int64_t *__restrict__ sorted_rows,
+                              uint32_t *__restrict__ out_bits) {
+    const int64_t n_round = (n_probe + 31) & ~(int64_t)31;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n_round; i += stride) {
+        bool found = false;
+        if (i < n_probe) {
+            const uint64_t hraw = probe_hash[i];
+            const unsigned long long h = hraw ? hraw : 1ULL;
+            uint64_t s = h & mask;
+            for (;;) {
+                const JoinSlot e = slots[s];
+                if (e.hash == 0ULL) break;
+                if (e.hash == h) {
+                    for (long long t = 0; t < e.count && !found; t++) found = keys_match(bk, sorted_rows[e.start + t], pk, i);
+                    if (found || h != 1ULL) break;
+                }
+                s = (s + 1) & mask;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, found);
+        if ((threadIdx.x & 31) == 0) out_bits[i >> 5] = m;
+    }
+}
+
+// ---- host --------------------------------------------------------------------------------------------
+b200_probe_table *probe_table_create(int32_t nkeys, const uint8_t *null_equals_null, bool track_indices) {
+    if (nkeys < 1 || nkeys > MAX_JOIN_KEYS) fail("join: between 1 and 8 key columns are supported");
+    auto *pt = new b200_probe_table;
+    pt->nkeys = nkeys;
+    pt->nulls_equal.assign((size_t)nkeys, 0);
+    if (null_equals_null)
+        for (int i = 0; i < nkeys; i++) pt->nulls_equal[i] = null_equals_null[i] ? 1 : 0;
+    pt->track_indices = track_indices;
+    return pt;
+}
+
+void probe_table_add(b200_probe_table *pt, const Batch &build, const int32_t *key_cols) {
+    if (!pt) fail("null probe table");
+    if (pt->built) fail("probe table already built");
+    pt->pending.push_back(std::make_unique<Batch>(build));
+    pt->pending_keys.emplace_back(key_cols, key_cols + pt->nkeys);
+    if (pt->pending_keys.back() != pt->pending_keys.front()) fail("join: all build tables must use the same key columns");
+}
+
+void probe_table_build(b200_probe_table *pt) {
+    require_device();
+    if (!pt) fail("null probe table");
+    if (pt->built) return;
+    if (pt->pending.empty()) fail("join: probe table has no build tables");
+    cudaStream_t st = ctx().stream;
+    if (pt->pending.size() == 1) {
+        pt->build = std::move(pt->pending[0]);
+    } else {
+        auto b = std::make_unique<Batch>();
+        const size_t nc = pt->pending[0]->cols.size();
+        for (auto &p : pt->pending) {
+            if (p->cols.size() != nc) fail("join: build tables have different schemas");
+            b->num_rows += p->num_rows;
+        }
+        for (size_t c = 0; c < nc; c++) {
+            std::vector<const Column *> cs;
+            for (auto &p : pt->pending) cs.push_back(&p->cols[c]);
+            b->cols.push_back(concat_columns(cs));
+        }
+        pt->build = std::move(b);
+    }
+    pt->key_cols = pt->pending_keys[0];
+    pt->pending.clear();
+    const Batch &b = *pt->build;
+    const int64_t n = b.num_rows;
+    pt->num_rows = n;
+    // reference limits (probe_table.rs:22-25,128-129) are 2^36 rows per table; ours is the same order
+    Buf hashes = hash_rows(b, pt->key_cols.data(), pt->nkeys, nullptr);
+    Buf rows = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+    int64_t nheads = 0;
+    if (n > 0) {
+        fill_iota(as<int64_t>(rows), n);
+        radix_sort_pairs(hashes, rows, n, 0, 64, false);
+        Buf nh = dev_alloc_zero(8);
+        count_run_heads<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), n, as<unsigned long long>(nh));
+        count_launch();
+        nheads = read_i64(as<int64_t>(nh));
+    }
+    int64_t cap = 64;
+    while ((double)cap * 0.7 < (double)nheads) cap <<= 1;
+    pt->cap = cap;
+    pt->slots = dev_alloc_zero((size_t)cap * sizeof(JoinSlot));
+    if (n > 0) {
+        insert_runs<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), n, as<JoinSlot>(pt->slots), (uint64_t)cap - 1);
+        count_launch();
+        fill_run_counts<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), n, as<JoinSlot>(pt->slots), (uint64_t)cap - 1);
+        count_launch();
+    }
+    pt->sorted_rows = rows;
+    B200_CUDA(cudaStreamSynchronize(st));
+    pt->built = true;
+}
+
+int64_t probe_table_num_rows(const b200_probe_table *pt) { return pt ? pt->num_rows : -1; }
+void probe_table_free(b200_probe_table *pt) { delete pt; }
+
+static void check_probe(const b200_probe_table *pt, const Batch &probe, const int32_t *key_cols) {
+    if (!pt || !pt->built) fail("join: probe table is not built");
+    for (int k = 0; k < pt->nkeys; k++) {
+        if (key_cols[k] < 0 || key_cols[k] >= (int32_t)probe.cols.size()) fail("join: probe key column index out of range");
+        const int32_t a = pt->build->cols[pt->key_cols[k]].dtype, b = probe.cols[key_cols[k]].dtype;
+        // join keys must have identical dtypes: the same number hashes differently as Int32 vs Int64
+        // (src/daft-local-execution/src/pipeline.rs:1215-1221)
+        if (a != b) fail(std::string("join: key dtype mismatch ") + dtype_name(a) + " vs " + dtype_name(b));
+    }
+}
+
+Batch *probe_exists(const b200_probe_table *pt, const Batch &probe, const int32_t *key_cols) {
+    require_device();
+    check_probe(pt, probe, key_cols);
+    const int64_t n = probe.num_rows;
+    std::vector<int32_t> pk(key_cols, key_cols + pt->nkeys);
+    Buf h = hash_rows(probe, key_cols, pt->nkeys, nullptr);
+    Column c;
+    c.name = "exists";
+    c.dtype = B200_BOOL;
+    c.length = n;
+    c.data = dev_alloc((size_t)((n + 31) / 32 + 1) * 4);
+    c.data_bytes = (n + 7) / 8;
+    if (n > 0) {
+        exists_kernel<<<jgrid(n), 256, 0, ctx().stream>>>(as<uint64_t>(h), n, make_keyset(*pt->build, pt->key_cols, pt->nulls_equal),
+                                                           make_keyset(probe, pk, pt->nulls_equal), as<JoinSlot>(pt->slots),
+                                                           (uint64_t)pt->cap - 1, as<int64_t>(pt->sorted_rows), as<uint32_t>(c.data));
+        count_launch();
+    }
+    auto out = std::make_unique<Batch>();
+    out->num_rows = n;
+    out->cols.push_back(std::move(c));
+    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    return out.release();
+}
+
+// (probe_idx, build_idx) pairs; build_idx = -1 for a kept unmatched probe row
+static void probe_pairs(const b200_probe_table *pt, const Batch &probe, const int32_t *key_cols, bool keep_unmatched_probe,
+                        unsigned int *matched_bits, Buf &out_probe, Buf &out_build, int64_t &total) {
+    check_probe(pt, probe, key_cols);
+    cudaStream_t st = ctx().stream;
+    const int64_t n = probe.num_rows;
+    std::vector<int32_t> pk(key_cols, key_cols + pt->nkeys);
+    total = 0;
+    if (n == 0) {
+        out_probe = dev_alloc(8);
+        out_build = dev_alloc(8);
+        return;
+    }
+    Buf h = hash_rows(probe, key_cols, pt->nkeys, nullptr);
+    const KeySet bk = make_keyset(*pt->build, pt->key_cols, pt->nulls_equal), pks = make_keyset(probe, pk, pt->nulls_equal);
+    Buf counts = dev_alloc((size_t)(n + 1) * 8), offs = dev_alloc((size_t)(n + 1) * 8);
+    probe_kernel<0><<<jgrid(n), 256, 0, st>>>(as<uint64_t>(h), n, bk, pks, as<JoinSlot>(pt->slots), (uint64_t)pt->cap - 1,
+                                               as<int64_t>(pt->sorted_rows), keep_unmatched_probe ? 1 : 0, as<int64_t>(counts), nullptr,
+                                               nullptr, nullptr, nullptr);
+    count_launch();
+    exclusive_scan_i64(as<int64_t>(counts), as<int64_t>(offs), n, as<int64_t>(offs) + n);
+    total = read_i64(as<int64_t>(offs) + n);
+    out_probe = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
+    out_build = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
+    if (total > 0) {
+        probe_kernel<1><<<jgrid(n), 256, 0, st>>>(as<uint64_t>(h), n, bk, pks, as<JoinSlot>(pt->slots), (uint64_t)pt->cap - 1,
+                                                   as<int64_t>(pt->sorted_rows), keep_unmatched_probe ? 1 : 0, nullptr, as<int64_t>(offs),
+                                                   as<int64_t>(out_probe), as<int64_t>(out_build), matched_bits);
+        count_launch();
+    }
+    B200_CUDA(cudaGetLastError());
+}
+
+Batch *probe_indices(const b200_probe_table *pt, const Batch &probe, const int32_t *key_cols) {
+    require_device();
+    Buf pi, bi;
+    int64_t total = 0;
+    probe_pairs(pt, probe, key_cols, false, nullptr, pi, bi, total);
+    auto out = std::make_unique<Batch>();
+    out->num_rows = total;
+    out->cols.push_back(make_u64_column("probe_idx", pi, total));
+    out->cols.push_back(make_u64_column("build_idx", bi, total));
+    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    return out.release();
+}
+
+b200_join_state *join_state_create(const b200_probe_table *pt) {
+    require_device();
+    if (!pt || !pt->built) fail("join: probe table is not built");
+    auto *s = new b200_join_state;
+    s->n = pt->num_rows;
+    s->matched = dev_alloc_zero((size_t)((s->n + 31) / 32 + 1) * 4);
+    return s;
+}
+void join_state_free(b200_join_state *st) { delete st; }
+
+static void append_cols(Batch &dst, std::unique_ptr<Batch> src) {
+    for (auto &c : src->cols) dst.cols.push_back(std::move(c));
+}
+
+Batch *hash_join_probe(const b200_probe_table *pt, b200_join_state *st, const Batch &probe, const int32_t *key_cols,
+                       int32_t join_type, bool build_on_left) {
+    require_device();
+    if (!pt || !pt->built) fail("join: probe table is not built");
+    const bool probe_is_left = !build_on_left;
+    if (join_type == B200_JOIN_SEMI || join_type == B200_JOIN_ANTI) {
+        // probe side = left side (anti_semi_join.rs); output = probe columns of rows that (do not) find a match
+        if (!probe_is_left) fail("semi/anti join with the build side on the left must use probe_exists + finalize on the host");
+        std::unique_ptr<Batch> ex(probe_exists(pt, probe, key_cols));
+        const int64_t n = probe.num_rows;
+        // reuse the filter machinery: bitmap -> indices
+        int64_t total = 0;
+        Buf idx = bitmap_select(as<uint32_t>(ex->cols[0].data), n, join_type == B200_JOIN_ANTI, &total);
+        Batch *out = gather_batch(probe, as<int64_t>(idx), total, false);
+        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+        return out;
+    }
+    const bool keep_probe = join_type == B200_JOIN_OUTER || (join_type == B200_JOIN_LEFT && probe_is_left) ||
+                            (join_type == B200_JOIN_RIGHT && !probe_is_left);
+    const bool keep_build = join_type == B200_JOIN_OUTER || (join_type == B200_JOIN_LEFT && !probe_is_left) ||
+                            (join_type == B200_JOIN_RIGHT && probe_is_left);
+    if (keep_build && !st) fail("join: this join type needs a b200_join_state to track matched build rows");
+    Buf pi, bi;
+    int64_t total = 0;
+    probe_pairs(pt, probe, key_cols, keep_probe, keep_build ? as<unsigned int>(st->matched) : nullptr, pi, bi, total);
+    std::unique_ptr<Batch> pcols(gather_batch(probe, as<int64_t>(pi), total, false));
+    std::unique_ptr<Batch> bcols(gather_batch(*pt->build, as<int64_t>(bi), total, keep_probe));
+    auto out = std::make_unique<Batch>();
+    out->num_rows = total;
+    if (build_on_left) {
+        append_cols(*out, std::move(bcols));
+        append_cols(*out, std::move(pcols));
+    } else {
+        append_cols(*out, std::move(pcols));
+        append_cols(*out, std::move(bcols));
+    }
+    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    return out.release();
+}
+
+Batch *hash_join_finalize(const b200_probe_table *pt, b200_join_state *st, const Batch &probe_like, bool build_on_left) {
+    require_device();
+    if (!pt || !pt->built || !st) fail("join finalize: need a built probe table and a join state");
+    int64_t total = 0;
+    Buf idx = bitmap_select(as<uint32_t>(st->matched), st->n, true, &total);
+    std::unique_ptr<Batch> bcols(gather_batch(*pt->build, as<int64_t>(idx), total, false));
+    // null-extended probe side
+    Buf neg = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
+    fill_u8(neg->ptr, 0xFF, (size_t)total * 8);
+    std::unique_ptr<Batch> pcols(gather_batch(probe_like, as<int64_t>(neg), total, true));
+    auto out = std::make_unique<Batch>();
+    out->num_rows = total;
+    if (build_on_left) {
+        append_cols(*out, std::move(bcols));
+        append_cols(*out, std::move(pcols));
+    } else {
+        append_cols(*out, std::move(pcols));
+        append_cols(*out, std::move(bcols));
+    }
+    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    return out.release();
+}
+
+}  // namespace b200

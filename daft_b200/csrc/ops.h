@@ -1,0 +1,69 @@
+// Operators implemented ahead of time (fixed-function kernels): sort, partition, join, exchange, generator.
+#pragma once
+#include "common.h"
+
+struct b200_probe_table;
+struct b200_join_state;
+struct b200_comm;
+
+namespace b200 {
+
+// batch.cu
+struct HostCol {
+    std::string name;
+    int32_t dtype;
+    int64_t length;
+    void *data;        // malloc'd, ownership moves into the exported ArrowArray
+    int64_t *offsets;  // malloc'd or null
+    int64_t data_bytes;
+};
+void export_host_columns(std::vector<HostCol> &cols, int64_t num_rows, ArrowArray *out_array, ArrowSchema *out_schema);
+Batch *import_batch(ArrowArray *array, ArrowSchema *schema);
+void export_batch(const Batch &b, ArrowArray *out_array, ArrowSchema *out_schema);
+Batch *batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t num_rows);
+
+// sort.cu -- stable LSD radix sort of (u64 key, i64 payload) pairs and everything built on it
+// sorts in place logically: on return keys/vals hold the sorted sequence (buffers may be swapped)
+void radix_sort_pairs(Buf &keys, Buf &vals, int64_t n, int begin_bit, int end_bit, bool descending);
+void fill_iota(int64_t *out, int64_t n);
+Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending, const uint8_t *nulls_first);
+Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng);
+
+// ops_jit.cu: ascending indices of the set (or, inverted, clear) bits among the first n bits
+Buf bitmap_select(const uint32_t *words, int64_t n, bool invert, int64_t *count_out);
+
+// partition.cu
+// stable partition of rows by pid = hash % P: returns row permutation and fills host offsets[P+1]
+Buf partition_permutation(const uint64_t *hashes, int64_t n, int32_t P, std::vector<int64_t> &offsets);
+std::vector<Batch *> op_partition_by_hash(const Batch &b, const int32_t *key_cols, int32_t nkeys, int32_t P);
+Batch *op_dedup(const Batch &b, const int32_t *key_cols, int32_t nkeys);
+
+// join.cu
+b200_probe_table *probe_table_create(int32_t nkeys, const uint8_t *null_equals_null, bool track_indices);
+void probe_table_add(b200_probe_table *pt, const Batch &build, const int32_t *key_cols);
+void probe_table_build(b200_probe_table *pt);
+int64_t probe_table_num_rows(const b200_probe_table *pt);
+void probe_table_free(b200_probe_table *pt);
+Batch *probe_exists(const b200_probe_table *pt, const Batch &probe, const int32_t *key_cols);
+Batch *probe_indices(const b200_probe_table *pt, const Batch &probe, const int32_t *key_cols);
+b200_join_state *join_state_create(const b200_probe_table *pt);
+void join_state_free(b200_join_state *st);
+Batch *hash_join_probe(const b200_probe_table *pt, b200_join_state *st, const Batch &probe, const int32_t *key_cols,
+                       int32_t join_type, bool build_on_left);
+Batch *hash_join_finalize(const b200_probe_table *pt, b200_join_state *st, const Batch &probe_like, bool build_on_left);
+
+// exchange.cu
+void comm_unique_id(uint8_t *out128);
+b200_comm *comm_init(const uint8_t *id128, int32_t rank, int32_t world);
+void comm_free(b200_comm *c);
+Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys);
+Batch *all_gather_batches(b200_comm *c, const Batch &b);
+
+// tpch_gen.cu
+Batch *tpch_generate(int32_t table, double sf, int64_t row_begin, int64_t row_end, uint64_t seed, const char *const *columns,
+                     int32_t ncolumns);
+int64_t tpch_num_rows(int32_t table, double sf);
+void tpch_generate_host(int32_t table, double sf, int64_t row_begin, int64_t row_end, uint64_t seed, const char *const *columns,
+                        int32_t ncolumns, ArrowArray *out_array, ArrowSchema *out_schema);
+
+}  // namespace b200

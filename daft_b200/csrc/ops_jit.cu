@@ -1,0 +1,386 @@
+// Host orchestration of the JIT-specialised operators: Project, Filter, fused HashAggregate.
+#include <algorithm>
+
+#include "common.h"
+#include "jit.h"
+#include "kernels.cuh"
+#include "ops.h"
+
+namespace b200 {
+
+using jit::Compiled;
+using jit::LaunchArgs;
+
+static int stream_grid(int64_t n, int threads, int per_sm) {
+    int64_t g = (n + threads - 1) / threads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)ctx().sm_count * per_sm));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Project (RecordBatch::eval_expression_list, src/daft-recordbatch/src/lib.rs:1603-1631)
+// optional take_idx: evaluate the expressions at rows take_idx[i] (negative -> null row)
+// ------------------------------------------------------------------------------------------------
+Batch *op_project(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n) {
+    require_device();
+    const bool with_take = take_idx != nullptr;
+    const Compiled &k = jit::get(B200_OP_PROJECT, plan, len, in, with_take);
+    const int64_t n = with_take ? take_n : in.num_rows;
+    auto out = std::make_unique<Batch>();
+    out->num_rows = n;
+    const size_t nout = k.outs.size();
+    std::vector<Buf> lens(nout);
+    for (size_t i = 0; i < nout; i++) {
+        Column c;
+        c.name = k.outs[i].name;
+        c.dtype = k.outs[i].dtype;
+        c.length = n;
+        if (c.dtype == B200_NULL) {
+            c.null_count = n;
+        } else {
+            if (k.outs[i].nullable) c.validity = dev_alloc((size_t)((n + 31) / 32) * 4);
+            int w = dtype_width(c.dtype);
+            if (w) {
+                c.data = dev_alloc((size_t)n * w);
+                c.data_bytes = n * w;
+            } else if (c.dtype == B200_BOOL) {
+                c.data = dev_alloc((size_t)((n + 31) / 32) * 4);
+                c.data_bytes = (n + 7) / 8;
+            } else {
+                lens[i] = dev_alloc((size_t)(n + 1) * 8);
+                c.offsets = dev_alloc((size_t)(n + 1) * 8);
+            }
+        }
+        out->cols.push_back(std::move(c));
+    }
+    auto fill = [&](LaunchArgs &a) {
+        a.ptr.assign(k.ptrs.size(), nullptr);
+        a.ival.assign(k.ints.size(), 0);
+        for (size_t s = 0; s < k.ptrs.size(); s++) {
+            const auto &ps = k.ptrs[s];
+            switch (ps.kind) {
+                case jit::P_COL_DATA: a.ptr[s] = in.cols[ps.index].data ? in.cols[ps.index].data->ptr : nullptr; break;
+                case jit::P_COL_VALID: a.ptr[s] = in.cols[ps.index].validity ? in.cols[ps.index].validity->ptr : nullptr; break;
+                case jit::P_COL_OFFSETS: a.ptr[s] = in.cols[ps.index].offsets ? in.cols[ps.index].offsets->ptr : nullptr; break;
+                case jit::P_OUT_DATA: a.ptr[s] = out->cols[ps.index].data ? out->cols[ps.index].data->ptr : nullptr; break;
+                case jit::P_OUT_VALID: a.ptr[s] = out->cols[ps.index].validity ? out->cols[ps.index].validity->ptr : nullptr; break;
+                case jit::P_OUT_LEN: a.ptr[s] = lens[ps.index] ? lens[ps.index]->ptr : nullptr; break;
+                case jit::P_OUT_OFFSETS: a.ptr[s] = out->cols[ps.index].offsets ? out->cols[ps.index].offsets->ptr : nullptr; break;
+                case jit::P_TAKE: a.ptr[s] = const_cast<int64_t *>(take_idx); break;
+                default: fail("project: unexpected parameter kind");
+            }
+        }
+        for (size_t s = 0; s < k.ints.size(); s++)
+            if (k.ints[s] == jit::I_N) a.ival[s] = n;
+    };
+    if (n > 0) {
+        LaunchArgs a;
+        fill(a);
+        const int grid = stream_grid(n, 256, 8);
+        jit::launch(k, a, grid, 256, 0, 0, false);
+        if (k.has_string_out) {
+            for (size_t i = 0; i < nout; i++) {
+                Column &c = out->cols[i];
+                if (!is_string(c.dtype)) continue;
+                exclusive_scan_i64(as<int64_t>(lens[i]), as<int64_t>(c.offsets), n, as<int64_t>(c.offsets) + n);
+                int64_t total = read_i64(as<int64_t>(c.offsets) + n);
+                c.data = dev_alloc((size_t)total);
+                c.data_bytes = total;
+            }
+            LaunchArgs a2;
+            fill(a2);
+            jit::launch(k, a2, grid, 256, 0, 1, false);
+        }
+    } else {
+        for (auto &c : out->cols)
+            if (is_string(c.dtype)) {
+                fill_u8(c.offsets->ptr, 0, 8);
+                c.data = dev_alloc(0);
+            }
+    }
+    for (size_t i = 0; i < nout; i++) {
+        Column &c = out->cols[i];
+        if (c.dtype != B200_NULL && c.validity) {
+            c.null_count = n - count_set_bits(as<uint8_t>(c.validity), n);
+            if (c.null_count == 0) c.validity.reset();
+        }
+    }
+    return out.release();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Filter (RecordBatch::filter, lib.rs:520-570): predicate -> bitmap -> row indices -> gather
+// ------------------------------------------------------------------------------------------------
+__global__ void word_popc(const uint32_t *__restrict__ words, int64_t nwords, int64_t nbits, uint32_t flip, int64_t *__restrict__ counts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nwords; i += stride) {
+        uint32_t w = words[i] ^ flip;
+        if (i == nwords - 1 && (nbits & 31)) w &= (1u << (nbits & 31)) - 1u;
+        counts[i] = __popc(w);
+    }
+}
+__global__ void expand_bits(const uint32_t *__restrict__ words, int64_t nwords, int64_t nbits, uint32_t flip,
+                            const int64_t *__restrict__ offsets, int64_t *__restrict__ out_idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nwords; i += stride) {
+        uint32_t w = words[i] ^ flip;
+        if (i == nwords - 1 && (nbits & 31)) w &= (1u << (nbits & 31)) - 1u;
+        int64_t o = offsets[i];
+        while (w) {
+            int b = __ffs(w) - 1;
+            out_idx[o++] = i * 32 + b;
+            w &= w - 1;
+        }
+    }
+}
+
+Buf bitmap_select(const uint32_t *words, int64_t n, bool invert, int64_t *count_out) {
+    const int64_t nwords = (n + 31) / 32;
+    const uint32_t flip = invert ? 0xFFFFFFFFu : 0u;
+    Buf counts = dev_alloc((size_t)(nwords + 1) * 8), offs = dev_alloc((size_t)(nwords + 1) * 8);
+    cudaStream_t st = ctx().stream;
+    const int grid = stream_grid(nwords, 256, 8);
+    word_popc<<<grid, 256, 0, st>>>(words, nwords, n, flip, as<int64_t>(counts));
+    count_launch();
+    exclusive_scan_i64(as<int64_t>(counts), as<int64_t>(offs), nwords, as<int64_t>(offs) + nwords);
+    const int64_t total = read_i64(as<int64_t>(offs) + nwords);
+    Buf idx = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
+    if (total) {
+        expand_bits<<<grid, 256, 0, st>>>(words, nwords, n, flip, as<int64_t>(offs), as<int64_t>(idx));
+        count_launch();
+    }
+    *count_out = total;
+    return idx;
+}
+
+Batch *op_filter(const Batch &in, const uint8_t *plan, size_t len) {
+    require_device();
+    // wrap the predicate as a one-expression PROJECT plan: fill_null(pred, false) so that null drops the row
+    std::vector<uint8_t> proj;
+    auto put32 = [&](uint32_t v) { proj.insert(proj.end(), (uint8_t *)&v, (uint8_t *)&v + 4); };
+    put32(1);
+    put32(4);
+    proj.insert(proj.end(), {'m', 'a', 's', 'k'});
+    proj.push_back(8);  // FILL_NULL
+    proj.insert(proj.end(), plan, plan + len);
+    proj.push_back(1);  // LIT
+    proj.push_back(B200_BOOL);
+    proj.push_back(0);
+    int64_t z = 0;
+    proj.insert(proj.end(), (uint8_t *)&z, (uint8_t *)&z + 8);
+    std::unique_ptr<Batch> mask(op_project(in, proj.data(), proj.size(), nullptr, 0));
+    const Column &m = mask->cols[0];
+    if (m.dtype != B200_BOOL) fail("filter: predicate must be boolean, got " + std::string(dtype_name(m.dtype)));
+    const int64_t n = in.num_rows;
+    if (n == 0) return gather_batch(in, nullptr, 0, false);
+    int64_t total = 0;
+    Buf idx = bitmap_select(as<uint32_t>(m.data), n, false, &total);
+    return gather_batch(in, as<int64_t>(idx), total, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused HashAggregate
+// ------------------------------------------------------------------------------------------------
+__global__ void compact_slots(const unsigned long long *__restrict__ slot_hash, const unsigned long long *__restrict__ nrows,
+                              int64_t cap, int ungrouped, unsigned long long *counter, int64_t *__restrict__ out_slot) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < cap; i += stride) {
+        bool used = ungrouped ? (i == 0) : (slot_hash[i] != 0 && nrows[i] != 0);
+        if (used) out_slot[atomicAdd(counter, 1ULL)] = i;
+    }
+}
+
+__global__ void gather_u64(const unsigned long long *__restrict__ src, const int64_t *__restrict__ idx, int64_t n,
+                           unsigned long long *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+// cell (8-byte) -> typed output value
+__global__ void finalize_agg(int kind, int32_t val_dtype, int32_t out_dtype, const unsigned long long *__restrict__ cell,
+                             const unsigned long long *__restrict__ cnt, int cnt_is_valid_count, int const_zero,
+                             const int64_t *__restrict__ slots, int64_t ng, void *__restrict__ out,
+                             uint32_t *__restrict__ out_valid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t g_round = (ng + 31) & ~(int64_t)31;
+    if (i >= g_round) return;
+    bool valid = false;
+    if (i < ng) {
+        const int64_t s = slots[i];
+        const unsigned long long c = cell ? cell[s] : 0ULL;
+        const unsigned long long n = cnt ? cnt[s] : 0ULL;
+        valid = true;
+        if (kind == jit::AGG_COUNT) {
+            ((unsigned long long *)out)[i] = const_zero ? 0ULL : n;
+        } else {
+            if (cnt_is_valid_count) valid = n > 0;
+            if (kind == jit::AGG_MEAN) {
+                double sum;
+                if (val_dtype == B200_F64) sum = __longlong_as_double((long long)c);
+                else if (val_dtype == B200_F32) sum = (double)__int_as_float((int)c);
+                else if (val_dtype == B200_U64) sum = (double)c;
+                else sum = (double)(long long)c;
+                ((double *)out)[i] = valid ? sum / (double)n : 0.0;
+            } else if (kind == jit::AGG_SUM) {
+                if (val_dtype == B200_F32) ((float *)out)[i] = valid ? __int_as_float((int)c) : 0.f;
+                else ((unsigned long long *)out)[i] = valid ? c : 0ULL;  // f64 bits / i64 / u64
+            } else {  // min / max: decode the order-preserving key
+                unsigned long long v = c;
+                switch (out_dtype) {
+                    case B200_F64: {
+                        double d = (c == 0xFFFFFFFFFFFFFFFFULL) ? __longlong_as_double(0x7FF8000000000000LL)
+                                                                 : __longlong_as_double((long long)((c >> 63) ? (c & 0x7FFFFFFFFFFFFFFFULL) : ~c));
+                        ((double *)out)[i] = valid ? d : 0.0;
+                        break;
+                    }
+                    case B200_F32: {
+                        double d = (c == 0xFFFFFFFFFFFFFFFFULL) ? __longlong_as_double(0x7FF8000000000000LL)
+                                                                 : __longlong_as_double((long long)((c >> 63) ? (c & 0x7FFFFFFFFFFFFFFFULL) : ~c));
+                        ((float *)out)[i] = valid ? (float)d : 0.f;
+                        break;
+                    }
+                    case B200_I8: ((int8_t *)out)[i] = valid ? (int8_t)(long long)(v ^ 0x8000000000000000ULL) : 0; break;
+                    case B200_I16: ((int16_t *)out)[i] = valid ? (int16_t)(long long)(v ^ 0x8000000000000000ULL) : 0; break;
+                    case B200_I32: case B200_DATE32: ((int32_t *)out)[i] = valid ? (int32_t)(long long)(v ^ 0x8000000000000000ULL) : 0; break;
+                    case B200_I64: case B200_TIMESTAMP: ((long long *)out)[i] = valid ? (long long)(v ^ 0x8000000000000000ULL) : 0; break;
+                    case B200_U8: ((uint8_t *)out)[i] = valid ? (uint8_t)v : 0; break;
+                    case B200_U16: ((uint16_t *)out)[i] = valid ? (uint16_t)v : 0; break;
+                    case B200_U32: ((uint32_t *)out)[i] = valid ? (uint32_t)v : 0; break;
+                    default: ((unsigned long long *)out)[i] = valid ? v : 0ULL; break;
+                }
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (out_valid && (threadIdx.x & 31) == 0) out_valid[i >> 5] = m;
+}
+
+Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng);  // sort.cu
+
+Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *first_rows, int64_t *ngroups) {
+    require_device();
+    const Compiled &k = jit::get(B200_OP_AGG, plan, len, in, false);
+    cudaStream_t st = ctx().stream;
+    const int64_t n = in.num_rows;
+    const int ncells = k.NLANE + k.NWARP + 1;  // lane cells, count cells (+nrows inside NWARP), min row
+    const int cell_nrows = k.NLANE + k.NWARP - 1, cell_minrow = k.NLANE + k.NWARP;
+
+    // table capacity: grow on overflow (the group count is unknown up front; the reference's
+    // GroupedAggregateSink samples the first morsel for the same reason, grouped_aggregate.rs:205-245)
+    int64_t cap = 1;
+    if (k.nkeys > 0) {
+        cap = 1 << 16;
+        while (cap < 2 * std::min<int64_t>(n, 1 << 15)) cap <<= 1;
+    }
+    Buf slot_hash, slot_row, acc, overflow = dev_alloc_zero(8);
+    for (int attempt = 0;; attempt++) {
+        slot_hash = dev_alloc_zero((size_t)cap * 8);
+        slot_row = dev_alloc((size_t)cap * 8);
+        fill_u8(slot_row->ptr, 0xFF, (size_t)cap * 8);
+        acc = dev_alloc((size_t)ncells * cap * 8);
+        for (int c = 0; c < ncells; c++) {
+            int fillv = 0;
+            if (c < k.NLANE && k.lane_cell_ops[c] == jit::C_MIN) fillv = 0xFF;
+            if (c == cell_minrow) fillv = 0xFF;
+            fill_u8(as<uint8_t>(acc) + (size_t)c * cap * 8, fillv, (size_t)cap * 8);
+        }
+        fill_u8(overflow->ptr, 0, 8);
+        if (n > 0) {
+            LaunchArgs a;
+            a.ptr.assign(k.ptrs.size(), nullptr);
+            a.ival.assign(k.ints.size(), 0);
+            for (size_t s = 0; s < k.ptrs.size(); s++) {
+                const auto &ps = k.ptrs[s];
+                switch (ps.kind) {
+                    case jit::P_COL_DATA: a.ptr[s] = in.cols[ps.index].data ? in.cols[ps.index].data->ptr : nullptr; break;
+                    case jit::P_COL_VALID: a.ptr[s] = in.cols[ps.index].validity ? in.cols[ps.index].validity->ptr : nullptr; break;
+                    case jit::P_COL_OFFSETS: a.ptr[s] = in.cols[ps.index].offsets ? in.cols[ps.index].offsets->ptr : nullptr; break;
+                    case jit::P_SLOT_HASH: a.ptr[s] = slot_hash->ptr; break;
+                    case jit::P_SLOT_ROW: a.ptr[s] = slot_row->ptr; break;
+                    case jit::P_OVERFLOW: a.ptr[s] = overflow->ptr; break;
+                    case jit::P_ACC: a.ptr[s] = as<uint8_t>(acc) + (size_t)ps.index * cap * 8; break;
+                    default: fail("agg: unexpected parameter kind");
+                }
+            }
+            for (size_t s = 0; s < k.ints.size(); s++) a.ival[s] = k.ints[s] == jit::I_N ? n : (cap - 1);
+            int occ = 0;
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k.fn, 256, k.smem_bytes));
+            occ = std::max(1, occ);
+            const int64_t chunks = (n + 127) / 128;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 7) / 8, (int64_t)ctx().sm_count * occ));
+            jit::launch(k, a, grid, 256, k.smem_bytes, 0, true);
+        }
+        int ovf = 0;
+        if (k.nkeys > 0 && n > 0) {
+            B200_CUDA(cudaMemcpyAsync(&ovf, overflow->ptr, 4, cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+        }
+        if (!ovf) break;
+        if (attempt > 12) fail("agg: hash table overflow after repeated growth");
+        cap <<= 2;
+    }
+
+    // ---- compact occupied slots, order groups by first occurrence
+    const unsigned long long *nrows_cell = as<unsigned long long>(acc) + (size_t)cell_nrows * cap;
+    Buf counter = dev_alloc_zero(8);
+    Buf slots = dev_alloc((size_t)std::max<int64_t>(cap, 1) * 8);
+    compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(as<unsigned long long>(slot_hash), nrows_cell, cap, k.nkeys == 0,
+                                                             as<unsigned long long>(counter), as<int64_t>(slots));
+    count_launch();
+    const int64_t ng = read_i64(as<int64_t>(counter));
+    Buf minrow = dev_alloc((size_t)std::max<int64_t>(ng, 1) * 8);
+    if (ng > 0) {
+        gather_u64<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(as<unsigned long long>(acc) + (size_t)cell_minrow * cap,
+                                                                  as<int64_t>(slots), ng, as<unsigned long long>(minrow));
+        count_launch();
+        if (k.nkeys > 0 && ng > 1) {
+            slots = sort_slots_by_minrow(slots, minrow, ng);  // also permutes `minrow` in place
+        }
+    }
+
+    // ---- output: key columns = key expressions evaluated at each group's first row, then agg columns
+    std::unique_ptr<Batch> out;
+    if (k.nkeys > 0) {
+        out.reset(op_project(in, k.key_project_plan.data(), k.key_project_plan.size(), as<int64_t>(minrow), ng));
+        // first rows are real rows: drop the "take may produce nulls" pessimism
+    } else {
+        out = std::make_unique<Batch>();
+        out->num_rows = ng;
+    }
+    for (const auto &ag : k.aggs) {
+        Column c;
+        c.name = ag.name;
+        c.dtype = ag.out_dtype;
+        c.length = ng;
+        const int w = dtype_width(c.dtype);
+        c.data = dev_alloc((size_t)std::max<int64_t>(ng, 1) * w);
+        c.data_bytes = ng * w;
+        const bool may_null = ag.kind != jit::AGG_COUNT && (ag.child_nullable || k.nkeys == 0);
+        if (may_null) c.validity = dev_alloc((size_t)((ng + 31) / 32 + 1) * 4);
+        const unsigned long long *cell = ag.lane_cell >= 0 ? as<unsigned long long>(acc) + (size_t)ag.lane_cell * cap : nullptr;
+        const unsigned long long *cnt = ag.cnt_cell >= 0 ? as<unsigned long long>(acc) + (size_t)(k.NLANE + ag.cnt_cell) * cap : nrows_cell;
+        // an ungrouped aggregate over zero rows still yields one row: sums null, counts 0
+        const int cnt_is_valid = (ag.kind != jit::AGG_COUNT) ? 1 : 0;
+        if (ng > 0) {
+            finalize_agg<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(ag.kind, ag.val_dtype, ag.out_dtype, cell, cnt, cnt_is_valid,
+                                                                        ag.const_zero ? 1 : 0, as<int64_t>(slots), ng, c.data->ptr,
+                                                                        as<uint32_t>(c.validity));
+            count_launch();
+        }
+        if (c.validity) {
+            c.null_count = ng - count_set_bits(as<uint8_t>(c.validity), ng);
+            if (c.null_count == 0) c.validity.reset();
+        }
+        out->cols.push_back(std::move(c));
+    }
+    B200_CUDA(cudaStreamSynchronize(st));  // `acc` and friends are released after this point
+    if (first_rows) *first_rows = minrow;
+    if (ngroups) *ngroups = ng;
+    return out.release();
+}
+
+Batch *op_agg(const Batch &in, const uint8_t *plan, size_t len) { return op_agg_first_rows(in, plan, len, nullptr, nullptr); }
+
+}  // namespace b200

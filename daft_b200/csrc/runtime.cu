@@ -1,0 +1,462 @@
+// Library context, stream-ordered device memory, and the small fixed-function kernels every
+// operator leans on: exclusive scan, bit counting, row gather (take), slice, concat.
+#include "common.h"
+#include "kernels.cuh"
+
+namespace b200 {
+
+std::atomic<int64_t> g_launches{0};
+
+Context &ctx() {
+    static Context c;
+    return c;
+}
+
+void require_device() {
+    if (!ctx().ready) fail("daft_b200: no CUDA device initialised (call b200_init); there is no CPU fallback");
+}
+
+const char *dtype_name(int32_t dt) {
+    static const char *names[] = {"null", "bool", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32",
+                                  "uint64", "float32", "float64", "date32", "timestamp", "large_utf8", "large_binary"};
+    return (dt >= 0 && dt < 16) ? names[dt] : "?";
+}
+
+DevAlloc::~DevAlloc() {
+    if (owned && ptr) cudaFreeAsync(ptr, ctx().stream);
+}
+
+Buf dev_alloc(size_t bytes) {
+    require_device();
+    auto a = std::make_shared<DevAlloc>();
+    a->bytes = bytes;
+    // +16 B slack: word-granular readers (unaligned string loads, bitmap words) may touch the tail
+    B200_CUDA(cudaMallocAsync(&a->ptr, bytes + 16, ctx().stream));
+    return a;
+}
+Buf dev_alloc_zero(size_t bytes) {
+    Buf b = dev_alloc(bytes);
+    B200_CUDA(cudaMemsetAsync(b->ptr, 0, bytes + 16, ctx().stream));
+    return b;
+}
+Buf dev_borrow(const void *ptr, size_t bytes) {
+    auto a = std::make_shared<DevAlloc>();
+    a->ptr = const_cast<void *>(ptr);
+    a->bytes = bytes;
+    a->owned = false;
+    return a;
+}
+void fill_u8(void *ptr, int value, size_t bytes) {
+    if (bytes) B200_CUDA(cudaMemsetAsync(ptr, value, bytes, ctx().stream));
+}
+
+int64_t read_i64(const int64_t *dev_ptr) {
+    int64_t v = 0;
+    B200_CUDA(cudaMemcpyAsync(&v, dev_ptr, 8, cudaMemcpyDeviceToHost, ctx().stream));
+    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan (int64): reduce-then-scan, 2048 items per CTA, recursive on the CTA sums
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const int64_t *__restrict__ in, int64_t n,
+                                                                int64_t *__restrict__ tile_sums) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int64_t i = base + k * SCAN_THREADS + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    s = block_reduce_sum_i64<SCAN_THREADS>(s);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles(const int64_t *__restrict__ in, int64_t n,
+                                                            const int64_t *__restrict__ tile_offsets,
+                                                            int64_t *__restrict__ out, int64_t *total) {
+    __shared__ int64_t warp_tot[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int64_t v[SCAN_ITEMS];
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int64_t i = base + k;
+        v[k] = i < n ? in[i] : 0;
+        s += v[k];
+    }
+    // exclusive scan of per-thread sums across the CTA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    int64_t woff = 0;
+    for (int w = 0; w < warp; w++) woff += warp_tot[w];
+    int64_t run = (tile_offsets ? tile_offsets[blockIdx.x] : 0) + woff + inc - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int64_t i = base + k;
+        if (i < n) out[i] = run;
+        run += v[k];
+    }
+    if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) *total = run;
+}
+
+void exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *total_dev) {
+    cudaStream_t st = ctx().stream;
+    if (n <= 0) {
+        if (total_dev) B200_CUDA(cudaMemsetAsync(total_dev, 0, 8, st));
+        return;
+    }
+    int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles == 1) {
+        scan_tiles<<<1, SCAN_THREADS, 0, st>>>(in, n, nullptr, out, total_dev);
+        count_launch();
+        return;
+    }
+    Buf sums = dev_alloc(tiles * 8), offs = dev_alloc(tiles * 8);
+    scan_tile_sums<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, as<int64_t>(sums));
+    count_launch();
+    exclusive_scan_i64(as<int64_t>(sums), as<int64_t>(offs), tiles, nullptr);
+    scan_tiles<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, as<int64_t>(offs), out, total_dev);
+    count_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void popcount_kernel(const uint32_t *__restrict__ words, int64_t nwords, int tail_bits,
+                                unsigned long long *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t s = 0;
+    for (; i < nwords; i += stride) {
+        uint32_t w = words[i];
+        if (i == nwords - 1 && tail_bits) w &= (1u << tail_bits) - 1u;
+        s += __popc(w);
+    }
+    s = block_reduce_sum_i64<256>(s);
+    if (threadIdx.x == 0 && s) atomicAdd(out, (unsigned long long)s);
+}
+
+int64_t count_set_bits(const uint8_t *bitmap, int64_t nbits) {
+    if (nbits <= 0) return 0;
+    Buf out = dev_alloc_zero(8);
+    int64_t nwords = (nbits + 31) / 32;
+    int grid = (int)std::min<int64_t>((nwords + 255) / 256, ctx().sm_count * 8);
+    popcount_kernel<<<grid, 256, 0, ctx().stream>>>(reinterpret_cast<const uint32_t *>(bitmap), nwords, (int)(nbits & 31),
+                                                    as<unsigned long long>(out));
+    count_launch();
+    return read_i64(as<int64_t>(out));
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather (RecordBatch::take; src/daft-recordbatch/src/lib.rs take + growable/ in the reference)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gather_fixed(const T *__restrict__ src, const int64_t *__restrict__ idx, int64_t n, T *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int64_t j = idx[i];
+        out[i] = j >= 0 ? src[j] : T(0);
+    }
+}
+
+// out bit i = (idx[i] >= 0) && bit(src, idx[i]);  src == nullptr means "all ones"
+__global__ void gather_bits(const uint8_t *__restrict__ src, const int64_t *__restrict__ idx, int64_t n,
+                            uint32_t *__restrict__ out_words) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (n + 31) & ~int64_t(31);
+    for (; i < n_round; i += stride) {
+        bool bit = false;
+        if (i < n) {
+            int64_t j = idx[i];
+            bit = j >= 0 && (src == nullptr || ((src[j >> 3] >> (j & 7)) & 1));
+        }
+        uint32_t w = __ballot_sync(0xffffffffu, bit);
+        if ((threadIdx.x & 31) == 0) out_words[i >> 5] = w;
+    }
+}
+
+__global__ void gather_str_len(const int64_t *__restrict__ offsets, const int64_t *__restrict__ idx, int64_t n,
+                               int64_t *__restrict__ len) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int64_t j = idx[i];
+        len[i] = j >= 0 ? offsets[j + 1] - offsets[j] : 0;
+    }
+}
+// 8 lanes cooperate on one row so that long strings still copy with some parallelism
+__global__ void gather_str_copy(const int64_t *__restrict__ src_off, const uint8_t *__restrict__ src,
+                                const int64_t *__restrict__ idx, int64_t n, const int64_t *__restrict__ out_off,
+                                uint8_t *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    const int sub = (int)(t & 7);
+    for (int64_t i = t >> 3; i < n; i += stride) {
+        int64_t j = idx[i];
+        if (j < 0) continue;
+        int64_t s = src_off[j], len = src_off[j + 1] - s, d = out_off[i];
+        for (int64_t k = sub; k < len; k += 8) out[d + k] = src[s + k];
+    }
+}
+
+static int grid_for(int64_t n, int threads = 256) {
+    int64_t g = (n + threads - 1) / threads;
+    int64_t cap = (int64_t)ctx().sm_count * 16;
+    return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+
+Column gather_column(const Column &src, const int64_t *idx, int64_t n, bool idx_may_be_negative) {
+    cudaStream_t st = ctx().stream;
+    Column out;
+    out.name = src.name;
+    out.dtype = src.dtype;
+    out.length = n;
+    if (src.dtype == B200_NULL) {
+        out.null_count = n;
+        return out;
+    }
+    const bool need_validity = src.null_count > 0 || idx_may_be_negative;
+    if (need_validity && n > 0) {
+        out.validity = dev_alloc(((n + 31) / 32) * 4);
+        gather_bits<<<grid_for(n), 256, 0, st>>>(as<uint8_t>(src.validity), idx, n, as<uint32_t>(out.validity));
+        count_launch();
+        out.null_count = n - count_set_bits(as<uint8_t>(out.validity), n);
+        if (out.null_count == 0) out.validity.reset();
+    }
+    int w = dtype_width(src.dtype);
+    if (w) {
+        out.data = dev_alloc((size_t)n * w);
+        out.data_bytes = n * w;
+        if (n) {
+            int g = grid_for(n);
+            switch (w) {
+                case 1: gather_fixed<uint8_t><<<g, 256, 0, st>>>(as<uint8_t>(src.data), idx, n, as<uint8_t>(out.data)); break;
+                case 2: gather_fixed<uint16_t><<<g, 256, 0, st>>>(as<uint16_t>(src.data), idx, n, as<uint16_t>(out.data)); break;
+                case 4: gather_fixed<uint32_t><<<g, 256, 0, st>>>(as<uint32_t>(src.data), idx, n, as<uint32_t>(out.data)); break;
+                default: gather_fixed<uint64_t><<<g, 256, 0, st>>>(as<uint64_t>(src.data), idx, n, as<uint64_t>(out.data)); break;
+            }
+            count_launch();
+        }
+    } else if (src.dtype == B200_BOOL) {
+        out.data = dev_alloc(((n + 31) / 32) * 4);
+        out.data_bytes = (n + 7) / 8;
+        if (n) {
+            gather_bits<<<grid_for(n), 256, 0, st>>>(as<uint8_t>(src.data), idx, n, as<uint32_t>(out.data));
+            count_launch();
+        }
+    } else if (is_string(src.dtype)) {
+        Buf len = dev_alloc((size_t)(n + 1) * 8);
+        out.offsets = dev_alloc((size_t)(n + 1) * 8);
+        if (n) {
+            gather_str_len<<<grid_for(n), 256, 0, st>>>(as<int64_t>(src.offsets), idx, n, as<int64_t>(len));
+            count_launch();
+        }
+        exclusive_scan_i64(as<int64_t>(len), as<int64_t>(out.offsets), n, as<int64_t>(out.offsets) + n);
+        int64_t total = read_i64(as<int64_t>(out.offsets) + n);
+        out.data = dev_alloc((size_t)total);
+        out.data_bytes = total;
+        if (n && total) {
+            gather_str_copy<<<grid_for(n * 8), 256, 0, st>>>(as<int64_t>(src.offsets), as<uint8_t>(src.data), idx, n,
+                                                              as<int64_t>(out.offsets), as<uint8_t>(out.data));
+            count_launch();
+        }
+    } else {
+        fail(std::string("gather: unsupported dtype ") + dtype_name(src.dtype));
+    }
+    return out;
+}
+
+Batch *gather_batch(const Batch &src, const int64_t *idx, int64_t n, bool idx_may_be_negative) {
+    auto out = std::make_unique<Batch>();
+    out->num_rows = n;
+    for (auto &c : src.cols) out->cols.push_back(gather_column(c, idx, n, idx_may_be_negative));
+    return out.release();
+}
+
+// ------------------------------------------------------------------------------------------------
+// index column (any integer dtype, nullable) -> int64 with null -> -1
+template <typename T>
+__global__ void widen_indices(const T *__restrict__ src, const uint8_t *__restrict__ validity, int64_t n,
+                              int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        bool ok = validity == nullptr || ((validity[i >> 3] >> (i & 7)) & 1);
+        out[i] = ok ? (int64_t)src[i] : -1;
+    }
+}
+
+Buf indices_to_i64(const Column &c) {
+    const int64_t n = c.length;
+    cudaStream_t st = ctx().stream;
+    if ((c.dtype == B200_I64 || c.dtype == B200_U64) && c.null_count == 0) return c.data;
+    Buf out = dev_alloc((size_t)n * 8);
+    if (n == 0) return out;
+    const uint8_t *v = c.null_count ? as<uint8_t>(c.validity) : nullptr;
+    int g = grid_for(n);
+    switch (c.dtype) {
+        case B200_I8: widen_indices<int8_t><<<g, 256, 0, st>>>(as<int8_t>(c.data), v, n, as<int64_t>(out)); break;
+        case B200_I16: widen_indices<int16_t><<<g, 256, 0, st>>>(as<int16_t>(c.data), v, n, as<int64_t>(out)); break;
+        case B200_I32: widen_indices<int32_t><<<g, 256, 0, st>>>(as<int32_t>(c.data), v, n, as<int64_t>(out)); break;
+        case B200_I64: widen_indices<int64_t><<<g, 256, 0, st>>>(as<int64_t>(c.data), v, n, as<int64_t>(out)); break;
+        case B200_U8: widen_indices<uint8_t><<<g, 256, 0, st>>>(as<uint8_t>(c.data), v, n, as<int64_t>(out)); break;
+        case B200_U16: widen_indices<uint16_t><<<g, 256, 0, st>>>(as<uint16_t>(c.data), v, n, as<int64_t>(out)); break;
+        case B200_U32: widen_indices<uint32_t><<<g, 256, 0, st>>>(as<uint32_t>(c.data), v, n, as<int64_t>(out)); break;
+        case B200_U64: widen_indices<uint64_t><<<g, 256, 0, st>>>(as<uint64_t>(c.data), v, n, as<int64_t>(out)); break;
+        default: fail(std::string("take: indices must be an integer column, got ") + dtype_name(c.dtype));
+    }
+    count_launch();
+    return out;
+}
+
+Column make_u64_column(const std::string &name, Buf data, int64_t n) {
+    Column c;
+    c.name = name;
+    c.dtype = B200_U64;
+    c.length = n;
+    c.data = std::move(data);
+    c.data_bytes = n * 8;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// slice / concat
+// ------------------------------------------------------------------------------------------------
+__global__ void iota_i64(int64_t *out, int64_t n, int64_t start) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = start + i;
+}
+
+Column slice_column(const Column &src, int64_t start, int64_t end) {
+    // byte-aligned fixed-width slices without nulls are views; everything else goes through gather
+    const int64_t n = end - start;
+    int w = dtype_width(src.dtype);
+    if (w && src.null_count == 0) {
+        Column out = src;
+        out.length = n;
+        out.data = dev_borrow(as<uint8_t>(src.data) + start * w, (size_t)n * w);
+        // keep the parent alive
+        auto parent = src.data;
+        out.data = Buf(out.data.get(), [parent, keep = out.data](DevAlloc *) {});
+        out.data_bytes = n * w;
+        return out;
+    }
+    Buf idx = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+    if (n) {
+        iota_i64<<<grid_for(n), 256, 0, ctx().stream>>>(as<int64_t>(idx), n, start);
+        count_launch();
+    }
+    return gather_column(src, as<int64_t>(idx), n, false);
+}
+
+__global__ void shift_offsets(const int64_t *__restrict__ src, int64_t n, int64_t delta, int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = src[i] - src[0] + delta;
+}
+// copy `nbits` bits from src (bit 0 aligned) into dst starting at bit `dst_bit`; src==nullptr -> ones.
+// One thread per destination byte: each output byte is owned by exactly one (part, thread) pair only
+// when parts are byte aligned, so the host runs parts one after another on the same stream and the
+// kernel ORs into bytes that straddle a boundary.
+__global__ void copy_bits(const uint8_t *__restrict__ src, int64_t nbits, uint8_t *__restrict__ dst, int64_t dst_bit) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // bit index within part, step 1 (simple, rarely hot)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nbits; i += stride) {
+        bool bit = src == nullptr || ((src[i >> 3] >> (i & 7)) & 1);
+        if (bit) {
+            int64_t d = dst_bit + i;
+            atomicOr(reinterpret_cast<unsigned int *>(dst) + (d >> 5), 1u << (d & 31));
+        }
+    }
+}
+
+Column concat_columns(const std::vector<const Column *> &cols) {
+    cudaStream_t st = ctx().stream;
+    Column out;
+    out.name = cols[0]->name;
+    out.dtype = cols[0]->dtype;
+    int64_t n = 0, nulls = 0, bytes = 0;
+    for (auto *c : cols) {
+        if (c->dtype != out.dtype) fail("concat: dtype mismatch in column " + out.name);
+        n += c->length;
+        nulls += c->null_count;
+        bytes += c->data_bytes;
+    }
+    out.length = n;
+    out.null_count = nulls;
+    if (out.dtype == B200_NULL) return out;
+    if (nulls > 0) {
+        out.validity = dev_alloc_zero(((n + 31) / 32) * 4);
+        int64_t pos = 0;
+        for (auto *c : cols) {
+            if (c->length) {
+                copy_bits<<<grid_for(c->length), 256, 0, st>>>(c->null_count ? as<uint8_t>(c->validity) : nullptr, c->length,
+                                                                as<uint8_t>(out.validity), pos);
+                count_launch();
+            }
+            pos += c->length;
+        }
+    }
+    int w = dtype_width(out.dtype);
+    if (w) {
+        out.data = dev_alloc((size_t)n * w);
+        out.data_bytes = n * w;
+        int64_t pos = 0;
+        for (auto *c : cols) {
+            if (c->length)
+                B200_CUDA(cudaMemcpyAsync(as<uint8_t>(out.data) + pos * w, as<uint8_t>(c->data), (size_t)c->length * w,
+                                          cudaMemcpyDeviceToDevice, st));
+            pos += c->length;
+        }
+    } else if (out.dtype == B200_BOOL) {
+        out.data = dev_alloc_zero(((n + 31) / 32) * 4);
+        out.data_bytes = (n + 7) / 8;
+        int64_t pos = 0;
+        for (auto *c : cols) {
+            if (c->length) {
+                copy_bits<<<grid_for(c->length), 256, 0, st>>>(as<uint8_t>(c->data), c->length, as<uint8_t>(out.data), pos);
+                count_launch();
+            }
+            pos += c->length;
+        }
+    } else if (is_string(out.dtype)) {
+        out.offsets = dev_alloc((size_t)(n + 1) * 8);
+        out.data = dev_alloc((size_t)bytes);
+        out.data_bytes = bytes;
+        int64_t pos = 0, bpos = 0;
+        for (auto *c : cols) {
+            if (c->length) {
+                shift_offsets<<<grid_for(c->length), 256, 0, st>>>(as<int64_t>(c->offsets), c->length, bpos,
+                                                                    as<int64_t>(out.offsets) + pos);
+                count_launch();
+                // data of a (possibly sliced) column starts at offsets[0]; data_bytes counts from there
+                if (c->data_bytes)
+                    B200_CUDA(cudaMemcpyAsync(as<uint8_t>(out.data) + bpos, as<uint8_t>(c->data), (size_t)c->data_bytes,
+                                              cudaMemcpyDeviceToDevice, st));
+            }
+            pos += c->length;
+            bpos += c->data_bytes;
+        }
+        B200_CUDA(cudaMemcpyAsync(as<int64_t>(out.offsets) + n, &bytes, 8, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaStreamSynchronize(st));  // `bytes` is a stack variable
+    } else {
+        fail(std::string("concat: unsupported dtype ") + dtype_name(out.dtype));
+    }
+    return out;
+}
+
+}  // namespace b200

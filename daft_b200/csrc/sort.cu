@@ -1,0 +1,292 @@
+// a9: argsort / sort / top-N as a stable LSD radix sort (replaces the single-threaded comparator
+// sort of src/daft-core/src/array/ops/arrow/sort/primitive/common.rs:24-141).
+//
+// Every sort key column is first mapped to an order-preserving u64 ("ordered key"): integers are
+// biased, floats are canonicalised (-0.0 -> +0.0, every NaN -> one value above +inf, matching
+// cmp_float at src/daft-core/src/kernels/search_sorted.rs:238-245), strings are sorted byte position
+// by byte position with a 9-bit digit (0 = past the end).  Multi-key sorts run the keys from last to
+// first; because each pass is stable the result is exactly the stable sort under the reference's
+// comparator (the reference sort is unstable, so any tie order is admissible).
+//
+// Per pass: shared-memory histogram -> scan over (digit, CTA) -> stable scatter using
+// warp match_any ranks.  HBM traffic per pass = 16 B read (hist pass reads keys only: 8 B) + 16 B
+// written per row; passes whose digit is constant over the whole input are skipped.
+#include <algorithm>
+
+#include "common.h"
+#include "kernels.cuh"
+#include "ops.h"
+
+namespace b200 {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+template <int BITS>
+__global__ void __launch_bounds__(RS_THREADS) radix_hist(const uint64_t *__restrict__ keys, int64_t n, int64_t chunk, int shift,
+                                                          uint32_t xor_mask, int64_t *__restrict__ hist /* [digit][block] */,
+                                                          unsigned long long *__restrict__ totals) {
+    constexpr int R = 1 << BITS;
+    __shared__ unsigned int s_cnt[R];
+    for (int i = threadIdx.x; i < R; i += RS_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
+    for (int64_t i = begin + threadIdx.x; i < end; i += RS_THREADS) {
+        uint32_t d = ((uint32_t)(keys[i] >> shift) & (R - 1)) ^ xor_mask;
+        atomicAdd(&s_cnt[d], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R; i += RS_THREADS) {
+        hist[(int64_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
+        if (s_cnt[i]) atomicAdd(&totals[i], (unsigned long long)s_cnt[i]);
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint64_t *__restrict__ keys, const int64_t *__restrict__ vals,
+                                                             int64_t n, int64_t chunk, int shift, uint32_t xor_mask,
+                                                             const int64_t *__restrict__ base /* scanned hist */,
+                                                             uint64_t *__restrict__ keys_out, int64_t *__restrict__ vals_out) {
+    constexpr int R = 1 << BITS;
+    __shared__ int64_t s_base[R];                 // next output position per digit for this CTA
+    __shared__ unsigned int s_wcnt[RS_WARPS][R];  // per-warp digit counts -> exclusive prefix over warps
+    __shared__ unsigned int s_tile[R];            // digit totals of the current sub-tile
+    for (int i = threadIdx.x; i < R; i += RS_THREADS) s_base[i] = base[(int64_t)i * gridDim.x + blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
+    for (int64_t t0 = begin; t0 < end; t0 += RS_THREADS) {
+        for (int i = threadIdx.x; i < RS_WARPS * R; i += RS_THREADS) (&s_wcnt[0][0])[i] = 0;
+        __syncthreads();
+        const int64_t i = t0 + threadIdx.x;
+        const bool valid = i < end;
+        uint64_t k = 0;
+        int64_t v = 0;
+        uint32_t d = 0xFFFFFFFFu;  // out-of-range lanes only match each other
+        if (valid) {
+            k = keys[i];
+            v = vals[i];
+            d = ((uint32_t)(k >> shift) & (R - 1)) ^ xor_mask;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));  // stable: lower lanes (earlier rows) first
+        if (valid && rank == 0) s_wcnt[warp][d] = __popc(peers);
+        __syncthreads();
+        for (int dd = threadIdx.x; dd < R; dd += RS_THREADS) {
+            unsigned int run = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) {
+                const unsigned int c = s_wcnt[w][dd];
+                s_wcnt[w][dd] = run;
+                run += c;
+            }
+            s_tile[dd] = run;
+        }
+        __syncthreads();
+        if (valid) {
+            const int64_t pos = s_base[d] + (int64_t)s_wcnt[warp][d] + rank;
+            keys_out[pos] = k;
+            vals_out[pos] = v;
+        }
+        __syncthreads();
+        for (int dd = threadIdx.x; dd < R; dd += RS_THREADS) s_base[dd] += s_tile[dd];
+        // the zero-fill + barrier at the top of the next iteration orders this update before its use
+    }
+}
+
+template <int BITS>
+static void radix_pass(const uint64_t *kin, const int64_t *vin, uint64_t *kout, int64_t *vout, int64_t n, int shift,
+                       bool invert, bool *skipped) {
+    constexpr int R = 1 << BITS;
+    cudaStream_t st = ctx().stream;
+    int64_t nblocks = std::min<int64_t>((n + 2047) / 2048, (int64_t)ctx().sm_count * 8);
+    nblocks = std::max<int64_t>(nblocks, 1);
+    int64_t chunk = (n + nblocks - 1) / nblocks;
+    chunk = (chunk + RS_THREADS - 1) / RS_THREADS * RS_THREADS;
+    nblocks = (n + chunk - 1) / chunk;
+    Buf hist = dev_alloc((size_t)R * nblocks * 8), base = dev_alloc((size_t)R * nblocks * 8), totals = dev_alloc_zero((size_t)R * 8);
+    const uint32_t xm = invert ? (uint32_t)(R - 1) : 0u;
+    radix_hist<BITS><<<(unsigned)nblocks, RS_THREADS, 0, st>>>(kin, n, chunk, shift, xm, as<int64_t>(hist), as<unsigned long long>(totals));
+    count_launch();
+    std::vector<unsigned long long> tot(R);
+    B200_CUDA(cudaMemcpyAsync(tot.data(), totals->ptr, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < R; i++)
+        if (tot[i] == (unsigned long long)n) {
+            *skipped = true;  // constant digit: the pass would be the identity permutation
+            return;
+        }
+    *skipped = false;
+    exclusive_scan_i64(as<int64_t>(hist), as<int64_t>(base), (int64_t)R * nblocks, nullptr);
+    radix_scatter<BITS><<<(unsigned)nblocks, RS_THREADS, 0, st>>>(kin, vin, n, chunk, shift, xm, as<int64_t>(base), kout, vout);
+    count_launch();
+    B200_CUDA(cudaGetLastError());
+}
+
+void radix_sort_pairs(Buf &keys, Buf &vals, int64_t n, int begin_bit, int end_bit, bool descending) {
+    if (n <= 1) return;
+    Buf k2 = dev_alloc((size_t)n * 8), v2 = dev_alloc((size_t)n * 8);
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        bool skipped = false;
+        radix_pass<8>(as<uint64_t>(keys), as<int64_t>(vals), as<uint64_t>(k2), as<int64_t>(v2), n, shift, descending, &skipped);
+        if (!skipped) {
+            std::swap(keys, k2);
+            std::swap(vals, v2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ordered keys
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t ordered_f64(double v) {
+    if (v != v) return 0xFFFFFFFFFFFFFFFFULL;   // all NaN equal, greatest
+    v = v + 0.0;                                 // -0.0 -> +0.0 (equal under the reference comparator)
+    uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+// out[i] = ordered key of src[idx[i]] (0 when null); nullflag[i] = 1 when null
+__global__ void make_ordered_keys(int32_t dtype, const void *__restrict__ data, const uint8_t *__restrict__ validity,
+                                  const int64_t *__restrict__ idx, int64_t n, uint64_t *__restrict__ out,
+                                  uint64_t *__restrict__ nullflag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t r = idx[i];
+        const bool ok = validity == nullptr || bit_at(validity, r);
+        uint64_t k = 0;
+        if (ok) {
+            switch (dtype) {
+                case B200_BOOL: k = bit_at((const uint8_t *)data, r); break;
+                case B200_I8: k = (uint64_t)((int64_t)((const int8_t *)data)[r]) ^ 0x8000000000000000ULL; break;
+                case B200_I16: k = (uint64_t)((int64_t)((const int16_t *)data)[r]) ^ 0x8000000000000000ULL; break;
+                case B200_I32: case B200_DATE32: k = (uint64_t)((int64_t)((const int32_t *)data)[r]) ^ 0x8000000000000000ULL; break;
+                case B200_I64: case B200_TIMESTAMP: k = (uint64_t)(((const int64_t *)data)[r]) ^ 0x8000000000000000ULL; break;
+                case B200_U8: k = ((const uint8_t *)data)[r]; break;
+                case B200_U16: k = ((const uint16_t *)data)[r]; break;
+                case B200_U32: k = ((const uint32_t *)data)[r]; break;
+                case B200_U64: k = ((const uint64_t *)data)[r]; break;
+                case B200_F32: k = ordered_f64((double)((const float *)data)[r]); break;
+                case B200_F64: k = ordered_f64(((const double *)data)[r]); break;
+                default: break;
+            }
+        }
+        out[i] = k;
+        if (nullflag) nullflag[i] = ok ? 0 : 1;
+    }
+}
+
+// string digit at byte position `pos`: 0 past the end (or null), byte+1 otherwise
+__global__ void make_string_digit(const int64_t *__restrict__ offsets, const uint8_t *__restrict__ bytes,
+                                  const uint8_t *__restrict__ validity, const int64_t *__restrict__ idx, int64_t n, int64_t pos,
+                                  uint64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t r = idx[i];
+        uint64_t d = 0;
+        if (validity == nullptr || bit_at(validity, r)) {
+            const int64_t o = offsets[r], len = offsets[r + 1] - o;
+            if (pos < len) d = (uint64_t)bytes[o + pos] + 1;
+        }
+        out[i] = d;
+    }
+}
+__global__ void make_null_flag(const uint8_t *__restrict__ validity, const int64_t *__restrict__ idx, int64_t n, uint64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = bit_at(validity, idx[i]) ? 0 : 1;
+}
+__global__ void max_str_len(const int64_t *__restrict__ offsets, int64_t n, unsigned long long *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long m = 0;
+    for (; i < n; i += stride) m = max(m, (unsigned long long)(offsets[i + 1] - offsets[i]));
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+__global__ void iota_kernel(int64_t *out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = i;
+}
+
+void fill_iota(int64_t *out, int64_t n) {
+    if (n <= 0) return;
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 8));
+    iota_kernel<<<g, 256, 0, ctx().stream>>>(out, n);
+    count_launch();
+}
+
+static int sgrid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 8)); }
+
+static int key_bits(int32_t dt) {
+    switch (dt) {
+        case B200_BOOL: return 8;
+        case B200_U8: return 8;
+        case B200_U16: return 16;
+        case B200_U32: return 32;
+        default: return 64;  // signed ints carry the bias in bit 63; floats use all 64
+    }
+}
+
+Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending, const uint8_t *nulls_first) {
+    require_device();
+    if (nkeys < 1) fail("argsort: need at least one sort key");
+    const int64_t n = b.num_rows;
+    cudaStream_t st = ctx().stream;
+    Buf idx = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+    if (n == 0) return idx;
+    iota_kernel<<<sgrid(n), 256, 0, st>>>(as<int64_t>(idx), n);
+    count_launch();
+    if (n == 1) return idx;
+    Buf keys = dev_alloc((size_t)n * 8);
+    for (int k = nkeys - 1; k >= 0; k--) {
+        const int32_t ci = key_cols[k];
+        if (ci < 0 || ci >= (int32_t)b.cols.size()) fail("argsort: key column index out of range");
+        const Column &c = b.cols[ci];
+        const bool desc = descending && descending[k];
+        const bool nf = nulls_first ? nulls_first[k] != 0 : desc;
+        if (c.dtype == B200_NULL) continue;  // every row ties
+        const uint8_t *validity = c.null_count > 0 ? as<uint8_t>(c.validity) : nullptr;
+        if (is_string(c.dtype)) {
+            Buf ml = dev_alloc_zero(8);
+            max_str_len<<<sgrid(n), 256, 0, st>>>(as<int64_t>(c.offsets), c.length, as<unsigned long long>(ml));
+            count_launch();
+            const int64_t maxlen = read_i64(as<int64_t>(ml));
+            for (int64_t pos = maxlen - 1; pos >= 0; pos--) {
+                make_string_digit<<<sgrid(n), 256, 0, st>>>(as<int64_t>(c.offsets), as<uint8_t>(c.data), validity, as<int64_t>(idx), n,
+                                                             pos, as<uint64_t>(keys));
+                count_launch();
+                // 9-bit digit = two 8-bit passes over bits [0,16)
+                radix_sort_pairs(keys, idx, n, 0, 16, desc);
+            }
+        } else {
+            make_ordered_keys<<<sgrid(n), 256, 0, st>>>(c.dtype, c.data ? c.data->ptr : nullptr, validity, as<int64_t>(idx), n,
+                                                         as<uint64_t>(keys), nullptr);
+            count_launch();
+            radix_sort_pairs(keys, idx, n, 0, key_bits(c.dtype), desc);
+        }
+        if (validity) {
+            make_null_flag<<<sgrid(n), 256, 0, st>>>(validity, as<int64_t>(idx), n, as<uint64_t>(keys));
+            count_launch();
+            // nulls_first: nulls (flag 1) must sort first -> descending on the flag
+            radix_sort_pairs(keys, idx, n, 0, 8, nf);
+        }
+    }
+    B200_CUDA(cudaStreamSynchronize(st));
+    return idx;
+}
+
+// group slots ordered by their first row (first-occurrence group order, inline_agg.rs:804-807)
+Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng) {
+    if (ng <= 1) return slots;
+    // minrow < 2^40 in practice; skipped passes make the high bytes free
+    Buf keys = minrow;
+    radix_sort_pairs(keys, slots, ng, 0, 64, false);
+    if (keys.get() != minrow.get())
+        B200_CUDA(cudaMemcpyAsync(minrow->ptr, keys->ptr, (size_t)ng * 8, cudaMemcpyDeviceToDevice, ctx().stream));
+    return slots;
+}
+
+}  // namespace b200

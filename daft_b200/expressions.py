@@ -1,0 +1,334 @@
+"""Expression trees (host side) and their serialisation to the C-ABI plan encoding.
+
+Mirrors the slice of the reference's DSL the hot path needs (daft.col / daft.lit / Expression
+operators, daft/expressions/expressions.py; Expr enum src/daft-dsl/src/expr/mod.rs).  Expressions are
+pure data: resolving names to column indices, inserting the supertype casts the reference decides at
+plan time, and encoding to bytes happen in `bind()`; evaluation happens in CUDA (libdaftb200.so).
+"""
+from __future__ import annotations
+
+import datetime
+import struct
+from typing import Any, Sequence
+
+from . import datatypes as dt
+
+# plan tags / op codes: include/daft_b200.h "expression / plan encoding"
+T_COL, T_LIT, T_BINARY, T_UNARY, T_CAST, T_IF_ELSE, T_IS_IN, T_BETWEEN, T_FILL_NULL, T_FUNCTION = range(10)
+BINOPS = {"add": 0, "sub": 1, "mul": 2, "true_div": 3, "floor_div": 4, "mod": 5, "lt": 6, "le": 7, "eq": 8, "ne": 9,
+          "ge": 10, "gt": 11, "and": 12, "or": 13, "xor": 14, "eq_null_safe": 15, "shl": 16, "shr": 17}
+UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
+FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
+         "day_of_week": 8}
+AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5}
+COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
+_CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
+_ARITH = ("add", "sub", "mul", "floor_div", "mod")
+
+_EPOCH = datetime.date(1970, 1, 1)
+
+
+class Expression:
+    """A node of the expression tree.  kind in {col, lit, binary, unary, cast, if_else, is_in, between,
+    fill_null, function, alias, agg}."""
+
+    __slots__ = ("kind", "op", "args", "value", "dtype", "_name")
+
+    def __init__(self, kind, op=None, args=(), value=None, dtype=None, name=None):
+        self.kind, self.op, self.args, self.value, self.dtype, self._name = kind, op, tuple(args), value, dtype, name
+
+    # ---- naming (Expr::name: the left-most column name, or the alias) ----
+    def name(self) -> str:
+        if self.kind == "alias":
+            return self._name
+        if self.kind == "col":
+            return self.value
+        if self.kind == "lit":
+            return "literal"
+        if self.kind == "is_in" or self.kind == "between" or self.kind == "fill_null":
+            return self.args[0].name()
+        if self.kind == "if_else":
+            return self.args[1].name()
+        return self.args[0].name() if self.args else "expr"
+
+    def alias(self, name: str) -> "Expression":
+        return Expression("alias", args=(self,), name=name)
+
+    # ---- operators ----
+    def _bin(self, op, other, reverse=False):
+        o = _to_expr(other)
+        return Expression("binary", op, (o, self) if reverse else (self, o))
+
+    def __add__(self, o): return self._bin("add", o)
+    def __radd__(self, o): return self._bin("add", o, True)
+    def __sub__(self, o): return self._bin("sub", o)
+    def __rsub__(self, o): return self._bin("sub", o, True)
+    def __mul__(self, o): return self._bin("mul", o)
+    def __rmul__(self, o): return self._bin("mul", o, True)
+    def __truediv__(self, o): return self._bin("true_div", o)
+    def __rtruediv__(self, o): return self._bin("true_div", o, True)
+    def __floordiv__(self, o): return self._bin("floor_div", o)
+    def __mod__(self, o): return self._bin("mod", o)
+    def __lt__(self, o): return self._bin("lt", o)
+    def __le__(self, o): return self._bin("le", o)
+    def __eq__(self, o): return self._bin("eq", o)  # type: ignore[override]
+    def __ne__(self, o): return self._bin("ne", o)  # type: ignore[override]
+    def __ge__(self, o): return self._bin("ge", o)
+    def __gt__(self, o): return self._bin("gt", o)
+    def __and__(self, o): return self._bin("and", o)
+    def __rand__(self, o): return self._bin("and", o, True)
+    def __or__(self, o): return self._bin("or", o)
+    def __ror__(self, o): return self._bin("or", o, True)
+    def __xor__(self, o): return self._bin("xor", o)
+    def __lshift__(self, o): return self._bin("shl", o)
+    def __rshift__(self, o): return self._bin("shr", o)
+    def __invert__(self): return Expression("unary", "not", (self,))
+    def __neg__(self): return Expression("unary", "neg", (self,))
+    def __abs__(self): return Expression("unary", "abs", (self,))
+    def __hash__(self): return id(self)
+    def __bool__(self): raise ValueError("Expressions are lazy; use & | ~ instead of and/or/not")
+
+    def eq_null_safe(self, o): return self._bin("eq_null_safe", o)
+    def abs(self): return Expression("unary", "abs", (self,))
+    def is_null(self): return Expression("unary", "is_null", (self,))
+    def not_null(self): return Expression("unary", "not_null", (self,))
+    def cast(self, dtype) -> "Expression":
+        code = dtype if isinstance(dtype, int) else dt.from_arrow(dtype)
+        return Expression("cast", args=(self,), dtype=code)
+    def if_else(self, if_true, if_false): return Expression("if_else", args=(self, _to_expr(if_true), _to_expr(if_false)))
+    def is_in(self, items: Sequence[Any]): return Expression("is_in", args=(self, *[_to_expr(i) for i in items]))
+    def between(self, lower, upper): return Expression("between", args=(self, _to_expr(lower), _to_expr(upper)))
+    def fill_null(self, fill): return Expression("fill_null", args=(self, _to_expr(fill)))
+
+    # temporal / string namespaces, flattened
+    def year(self): return Expression("function", "year", (self,))
+    def month(self): return Expression("function", "month", (self,))
+    def day(self): return Expression("function", "day", (self,))
+    def day_of_week(self): return Expression("function", "day_of_week", (self,))
+    def length(self): return Expression("function", "utf8_length", (self,))
+    def startswith(self, pat): return Expression("function", "startswith", (self, _to_expr(pat)))
+    def endswith(self, pat): return Expression("function", "endswith", (self, _to_expr(pat)))
+    def contains(self, pat): return Expression("function", "contains", (self, _to_expr(pat)))
+    def left(self, n): return Expression("function", "left", (self, _to_expr(n)))
+
+    # ---- aggregations (AggExpr, src/daft-dsl/src/expr/mod.rs) ----
+    def _agg(self, kind, mode="valid"): return Expression("agg", kind, (self,), value=mode)
+    def sum(self): return self._agg("sum")
+    def mean(self): return self._agg("mean")
+    def avg(self): return self._agg("mean")
+    def min(self): return self._agg("min")
+    def max(self): return self._agg("max")
+    def count(self, mode: str = "valid"): return self._agg("count", mode)
+
+    def __repr__(self):
+        if self.kind == "col": return f"col({self.value})"
+        if self.kind == "lit": return f"lit({self.value!r})"
+        if self.kind == "alias": return f"{self.args[0]!r}.alias({self._name})"
+        return f"{self.kind}:{self.op}({', '.join(map(repr, self.args))})"
+
+
+def col(name: str) -> Expression:
+    return Expression("col", value=name)
+
+
+def lit(value: Any, dtype: int | None = None) -> Expression:
+    return Expression("lit", value=value, dtype=dtype)
+
+
+def _to_expr(x) -> Expression:
+    return x if isinstance(x, Expression) else lit(x)
+
+
+def _lit_dtype(v) -> int:
+    """Literal typing of daft.lit (src/daft-dsl/src/lit): Python int -> Int32 when it fits, else Int64."""
+    if v is None: return dt.NULL
+    if isinstance(v, bool): return dt.BOOL
+    if isinstance(v, int): return dt.I32 if -2**31 <= v < 2**31 else (dt.I64 if v < 2**63 else dt.U64)
+    if isinstance(v, float): return dt.F64
+    if isinstance(v, str): return dt.LARGE_UTF8
+    if isinstance(v, bytes): return dt.LARGE_BINARY
+    if isinstance(v, datetime.datetime): return dt.TIMESTAMP
+    if isinstance(v, datetime.date): return dt.DATE32
+    raise TypeError(f"unsupported literal {v!r}")
+
+
+# ------------------------------------------------------------------------------------------------
+# binding: names -> indices, dtype inference, supertype casts, encoding
+# ------------------------------------------------------------------------------------------------
+class Bound:
+    """A typed, index-resolved node ready for encoding."""
+    __slots__ = ("tag", "op", "dtype", "kids", "col", "value")
+
+    def __init__(self, tag, dtype, op=0, kids=(), col=-1, value=None):
+        self.tag, self.dtype, self.op, self.kids, self.col, self.value = tag, dtype, op, list(kids), col, value
+
+
+def _cast(b: Bound, to: int) -> Bound:
+    if b.dtype == to:
+        return b
+    if b.tag == T_LIT and b.value is not None and b.dtype != dt.NULL:
+        # fold casts of literals so that `col(i64) < 5` compares against an Int64 immediate
+        v = b.value
+        if dt.is_float(to): v = float(v)
+        elif dt.is_integer(to) and isinstance(v, float) and v == int(v): v = int(v)
+        elif dt.is_integer(to) and isinstance(v, float): return Bound(T_CAST, to, kids=[b])
+        return Bound(T_LIT, to, value=v)
+    return Bound(T_CAST, to, kids=[b])
+
+
+def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
+    k = e.kind
+    if k == "alias":
+        return bind(e.args[0], names, dtypes)
+    if k == "col":
+        try:
+            i = list(names).index(e.value)
+        except ValueError:
+            raise KeyError(f"column {e.value!r} not found in {list(names)}") from None
+        return Bound(T_COL, dtypes[i], col=i)
+    if k == "lit":
+        d = e.dtype if e.dtype is not None else _lit_dtype(e.value)
+        return Bound(T_LIT, d, value=e.value)
+    if k == "binary":
+        l, r = bind(e.args[0], names, dtypes), bind(e.args[1], names, dtypes)
+        op = e.op
+        if op == "true_div":
+            return Bound(T_BINARY, dt.F64, BINOPS[op], [_cast(l, dt.F64), _cast(r, dt.F64)])
+        if op in ("and", "or", "xor"):
+            if dt.is_integer(l.dtype) and dt.is_integer(r.dtype):
+                raise NotImplementedError("bitwise and/or/xor on integers")
+            return Bound(T_BINARY, dt.BOOL, BINOPS[op], [_cast(l, dt.BOOL) if l.dtype == dt.NULL else l,
+                                                          _cast(r, dt.BOOL) if r.dtype == dt.NULL else r])
+        if op in ("shl", "shr"):
+            return Bound(T_BINARY, l.dtype, BINOPS[op], [l, _cast(r, l.dtype)])
+        st = dt.supertype(l.dtype, r.dtype)
+        l, r = _cast(l, st), _cast(r, st)
+        if op in _CMP:
+            return Bound(T_BINARY, dt.BOOL, BINOPS[op], [l, r])
+        if op in _ARITH:
+            if not dt.is_numeric(st):
+                raise TypeError(f"cannot apply {op} to {dt.NAMES[st]}")
+            return Bound(T_BINARY, st, BINOPS[op], [l, r])
+        raise ValueError(op)
+    if k == "unary":
+        c = bind(e.args[0], names, dtypes)
+        if e.op in ("is_null", "not_null", "not"):
+            return Bound(T_UNARY, dt.BOOL, UNOPS[e.op], [c])
+        return Bound(T_UNARY, c.dtype, UNOPS[e.op], [c])
+    if k == "cast":
+        return _cast(bind(e.args[0], names, dtypes), e.dtype)
+    if k == "if_else":
+        p, a, b = (bind(x, names, dtypes) for x in e.args)
+        st = dt.supertype(a.dtype, b.dtype)
+        return Bound(T_IF_ELSE, st, kids=[p, _cast(a, st), _cast(b, st)])
+    if k == "is_in":
+        c = bind(e.args[0], names, dtypes)
+        items = [bind(x, names, dtypes) for x in e.args[1:]]
+        st = c.dtype
+        for it in items:
+            st = dt.supertype(st, it.dtype)
+        return Bound(T_IS_IN, dt.BOOL, kids=[_cast(c, st)] + [_cast(it, st) for it in items])
+    if k == "between":
+        c, lo, hi = (bind(x, names, dtypes) for x in e.args)
+        st = dt.supertype(dt.supertype(c.dtype, lo.dtype), hi.dtype)
+        return Bound(T_BETWEEN, dt.BOOL, kids=[_cast(c, st), _cast(lo, st), _cast(hi, st)])
+    if k == "fill_null":
+        c, f = bind(e.args[0], names, dtypes), bind(e.args[1], names, dtypes)
+        st = dt.supertype(c.dtype, f.dtype)
+        return Bound(T_FILL_NULL, st, kids=[_cast(c, st), _cast(f, st)])
+    if k == "function":
+        kids = [bind(x, names, dtypes) for x in e.args]
+        out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,
+               "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8}[e.op]
+        if e.op == "left":
+            kids[1] = _cast(kids[1], dt.I64)
+        return Bound(T_FUNCTION, out, FUNCS[e.op], kids)
+    if k == "agg":
+        raise ValueError("aggregation expressions are only valid inside agg()")
+    raise ValueError(k)
+
+
+def _enc_str(s: bytes) -> bytes:
+    return struct.pack("<I", len(s)) + s
+
+
+def encode(b: Bound) -> bytes:
+    if b.tag == T_COL:
+        return struct.pack("<BI", T_COL, b.col)
+    if b.tag == T_LIT:
+        v, d = b.value, b.dtype
+        isnull = v is None or d == dt.NULL
+        head = struct.pack("<BBB", T_LIT, d, 1 if isnull else 0)
+        if dt.is_string(d):
+            raw = b"" if isnull else (v.encode() if isinstance(v, str) else bytes(v))
+            return head + _enc_str(raw)
+        if isnull:
+            return head + struct.pack("<q", 0)
+        if d in (dt.F32, dt.F64):
+            return head + struct.pack("<d", float(v))
+        if d == dt.DATE32:
+            days = (v - _EPOCH).days if isinstance(v, datetime.date) else int(v)
+            return head + struct.pack("<q", days)
+        if d == dt.TIMESTAMP:
+            if isinstance(v, datetime.datetime):
+                v = int((v - datetime.datetime(1970, 1, 1)).total_seconds() * 1_000_000)
+            return head + struct.pack("<q", int(v))
+        if d == dt.U64:
+            return head + struct.pack("<Q", int(v))
+        return head + struct.pack("<q", int(v))
+    if b.tag in (T_BINARY, T_UNARY):
+        return struct.pack("<BB", b.tag, b.op) + b"".join(encode(k) for k in b.kids)
+    if b.tag == T_CAST:
+        return struct.pack("<BB", T_CAST, b.dtype) + encode(b.kids[0])
+    if b.tag in (T_IF_ELSE, T_BETWEEN, T_FILL_NULL):
+        return struct.pack("<B", b.tag) + b"".join(encode(k) for k in b.kids)
+    if b.tag == T_IS_IN:
+        return struct.pack("<B", T_IS_IN) + encode(b.kids[0]) + struct.pack("<I", len(b.kids) - 1) + b"".join(encode(k) for k in b.kids[1:])
+    if b.tag == T_FUNCTION:
+        return struct.pack("<BBB", T_FUNCTION, b.op, len(b.kids)) + b"".join(encode(k) for k in b.kids)
+    raise ValueError(b.tag)
+
+
+def encode_project(exprs: Sequence[Expression], names, dtypes) -> tuple[bytes, list[str], list[int]]:
+    out = struct.pack("<I", len(exprs))
+    onames, odt = [], []
+    for e in exprs:
+        b = bind(e, names, dtypes)
+        out += _enc_str(e.name().encode()) + encode(b)
+        onames.append(e.name())
+        odt.append(b.dtype)
+    return out, onames, odt
+
+
+def encode_filter(exprs: Sequence[Expression], names, dtypes) -> bytes:
+    """Conjuncts are AND-ed (RecordBatch::filter, src/daft-recordbatch/src/lib.rs:520-541)."""
+    pred = exprs[0]
+    for e in exprs[1:]:
+        pred = pred & e
+    b = bind(pred, names, dtypes)
+    if b.dtype != dt.BOOL:
+        raise ValueError(f"filter predicate must be boolean, got {dt.NAMES[b.dtype]}")
+    return encode(b)
+
+
+def encode_agg(to_agg: Sequence[Expression], group_by: Sequence[Expression], names, dtypes,
+               predicate: Sequence[Expression] | None = None) -> bytes:
+    out = b""
+    if predicate:
+        out += b"\x01" + encode_filter(predicate, names, dtypes)
+    else:
+        out += b"\x00"
+    out += struct.pack("<I", len(group_by))
+    for g in group_by:
+        out += _enc_str(g.name().encode()) + encode(bind(g, names, dtypes))
+    out += struct.pack("<I", len(to_agg))
+    for a in to_agg:
+        name = a.name()
+        inner = a
+        while inner.kind == "alias":
+            inner = inner.args[0]
+        if inner.kind != "agg":
+            raise ValueError(f"expected an aggregation expression, got {a!r}")
+        out += struct.pack("<BB", AGG_KINDS[inner.op], COUNT_MODES[inner.value]) + _enc_str(name.encode())
+        out += encode(bind(inner.args[0], names, dtypes))
+    return out

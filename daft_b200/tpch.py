@@ -1,0 +1,171 @@
+"""Synthetic TPC-H tables (generated in HBM or on the host by the same counter-based generator) and the
+benchmark queries expressed against the RecordBatch operator surface.
+
+Query shapes follow the reference's DataFrame forms in benchmarking/tpch/answers.py (q1 :12-32,
+q5 :124-143, q6 :146-155); the data generator is daft_b200/csrc/tpch_gen.cu.
+"""
+from __future__ import annotations
+
+import ctypes
+import datetime
+from typing import Sequence
+
+import pyarrow as pa
+
+from . import _lib
+from .expressions import col, lit
+from .recordbatch import RecordBatch
+
+TABLES = {"lineitem": 0, "orders": 1, "customer": 2, "supplier": 3, "nation": 4, "region": 5}
+DEFAULT_SEED = 20260921
+
+Q1_COLUMNS = ["L_QUANTITY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_TAX", "L_RETURNFLAG", "L_LINESTATUS", "L_SHIPDATE"]
+# bytes per row of the Arrow layout the reference holds for Q1's 7 columns:
+# 2 x (8 B offset + 1 B) + i64 + 3 x f64 + date32
+Q1_BYTES_PER_ROW = 54
+
+
+def num_rows(table: str, sf: float) -> int:
+    return int(_lib.lib().b200_tpch_num_rows(ctypes.c_int32(TABLES[table]), ctypes.c_double(sf)))
+
+
+def _names(columns: Sequence[str] | None):
+    if not columns:
+        return None, 0
+    arr = (ctypes.c_char_p * len(columns))(*[c.encode() for c in columns])
+    return arr, len(columns)
+
+
+def generate(table: str, sf: float, columns: Sequence[str] | None = None, row_begin: int = 0, row_end: int = -1,
+             seed: int = DEFAULT_SEED) -> RecordBatch:
+    """Rows [row_begin, row_end) of `table` generated straight into HBM."""
+    _lib.ensure_init()
+    arr, n = _names(columns)
+    out = ctypes.c_void_p()
+    _lib.call("b200_tpch_generate", ctypes.c_int32(TABLES[table]), ctypes.c_double(sf), ctypes.c_int64(row_begin),
+              ctypes.c_int64(row_end), ctypes.c_uint64(seed), arr, ctypes.c_int32(n), ctypes.byref(out))
+    return RecordBatch._wrap(out)
+
+
+def generate_host(table: str, sf: float, columns: Sequence[str] | None = None, row_begin: int = 0, row_end: int = -1,
+                  seed: int = DEFAULT_SEED) -> pa.Table:
+    """Same rows, generated on the host cores into Arrow buffers (no GPU needed)."""
+    arr, n = _names(columns)
+    c_arr, c_sch = _lib.ArrowArray(), _lib.ArrowSchema()
+    _lib.call("b200_tpch_generate_host", ctypes.c_int32(TABLES[table]), ctypes.c_double(sf), ctypes.c_int64(row_begin),
+              ctypes.c_int64(row_end), ctypes.c_uint64(seed), arr, ctypes.c_int32(n), ctypes.byref(c_arr), ctypes.byref(c_sch))
+    rb = pa.RecordBatch._import_from_c(ctypes.addressof(c_arr), ctypes.addressof(c_sch))
+    return pa.Table.from_batches([rb])
+
+
+# ------------------------------------------------------------------------------------------------
+# Q1 (benchmarking/tpch/answers.py:12-32)
+# ------------------------------------------------------------------------------------------------
+def q1_exprs():
+    disc_price = col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))
+    charge = disc_price * (1 + col("L_TAX"))
+    predicate = [col("L_SHIPDATE") <= datetime.date(1998, 9, 2)]
+    group_by = [col("L_RETURNFLAG"), col("L_LINESTATUS")]
+    aggs = [
+        col("L_QUANTITY").sum().alias("sum_qty"),
+        col("L_EXTENDEDPRICE").sum().alias("sum_base_price"),
+        disc_price.sum().alias("sum_disc_price"),
+        charge.sum().alias("sum_charge"),
+        col("L_QUANTITY").mean().alias("avg_qty"),
+        col("L_EXTENDEDPRICE").mean().alias("avg_price"),
+        col("L_DISCOUNT").mean().alias("avg_disc"),
+        col("L_QUANTITY").count().alias("count_order"),
+    ]
+    return predicate, group_by, aggs
+
+
+def q1_partial_exprs():
+    """First stage of the two-stage rewrite (src/daft-local-plan/src/agg.rs:107-166): Mean -> Sum + Count."""
+    disc_price = col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))
+    charge = disc_price * (1 + col("L_TAX"))
+    predicate = [col("L_SHIPDATE") <= datetime.date(1998, 9, 2)]
+    group_by = [col("L_RETURNFLAG"), col("L_LINESTATUS")]
+    aggs = [
+        col("L_QUANTITY").sum().alias("sum_qty"),
+        col("L_EXTENDEDPRICE").sum().alias("sum_base_price"),
+        disc_price.sum().alias("sum_disc_price"),
+        charge.sum().alias("sum_charge"),
+        col("L_DISCOUNT").sum().alias("sum_disc"),
+        col("L_QUANTITY").count().alias("count_qty"),
+        col("L_EXTENDEDPRICE").count().alias("count_price"),
+        col("L_DISCOUNT").count().alias("count_disc"),
+    ]
+    return predicate, group_by, aggs
+
+
+def q1_final_exprs():
+    """Second stage + final projection: Sum of partial sums/counts, merge_mean = sum / count
+    (src/daft-dsl/src/functions/agg/mod.rs:29-53)."""
+    group_by = [col("L_RETURNFLAG"), col("L_LINESTATUS")]
+    aggs = [col(n).sum().alias(n) for n in ("sum_qty", "sum_base_price", "sum_disc_price", "sum_charge", "sum_disc",
+                                            "count_qty", "count_price", "count_disc")]
+    project = [
+        col("L_RETURNFLAG"), col("L_LINESTATUS"), col("sum_qty"), col("sum_base_price"), col("sum_disc_price"),
+        col("sum_charge"),
+        (col("sum_qty") / col("count_qty")).alias("avg_qty"),
+        (col("sum_base_price") / col("count_price")).alias("avg_price"),
+        (col("sum_disc") / col("count_disc")).alias("avg_disc"),
+        col("count_qty").alias("count_order"),
+    ]
+    return group_by, aggs, project
+
+
+def q1(lineitem: RecordBatch) -> RecordBatch:
+    """Filter -> Project -> HashAggregate fused into one kernel, then the 4-row sort."""
+    predicate, group_by, aggs = q1_exprs()
+    out = lineitem.agg(aggs, group_by, predicate=predicate)
+    return out.sort([col("L_RETURNFLAG"), col("L_LINESTATUS")])
+
+
+def q1_partial(lineitem: RecordBatch) -> RecordBatch:
+    predicate, group_by, aggs = q1_partial_exprs()
+    return lineitem.agg(aggs, group_by, predicate=predicate)
+
+
+def q1_final(partials: RecordBatch) -> RecordBatch:
+    group_by, aggs, project = q1_final_exprs()
+    return partials.agg(aggs, group_by).eval_expression_list(project).sort([col("L_RETURNFLAG"), col("L_LINESTATUS")])
+
+
+# ------------------------------------------------------------------------------------------------
+# Q6 (answers.py:146-155): pure scan + ungrouped aggregate
+# ------------------------------------------------------------------------------------------------
+def q6(lineitem: RecordBatch) -> RecordBatch:
+    pred = [
+        col("L_SHIPDATE") >= datetime.date(1994, 1, 1), col("L_SHIPDATE") < datetime.date(1995, 1, 1),
+        col("L_DISCOUNT") >= 0.05, col("L_DISCOUNT") <= 0.07, col("L_QUANTITY") < 24,
+    ]
+    return lineitem.agg([(col("L_EXTENDEDPRICE") * col("L_DISCOUNT")).sum().alias("revenue")], [], predicate=pred)
+
+
+# ------------------------------------------------------------------------------------------------
+# Q5 (answers.py:124-143): region -> nation -> supplier/customer -> orders -> lineitem, 2-key last join
+# ------------------------------------------------------------------------------------------------
+Q5_COLUMNS = {
+    "lineitem": ["L_ORDERKEY", "L_SUPPKEY", "L_EXTENDEDPRICE", "L_DISCOUNT"],
+    "orders": ["O_ORDERKEY", "O_CUSTKEY", "O_ORDERDATE"],
+    "customer": ["C_CUSTKEY", "C_NATIONKEY"],
+    "supplier": ["S_SUPPKEY", "S_NATIONKEY"],
+    "nation": ["N_NATIONKEY", "N_REGIONKEY", "N_NAME"],
+    "region": ["R_REGIONKEY", "R_NAME"],
+}
+
+
+def q5(t: dict[str, RecordBatch]) -> RecordBatch:
+    region = t["region"].filter([col("R_NAME") == "ASIA"])
+    orders = t["orders"].filter([col("O_ORDERDATE") >= datetime.date(1994, 1, 1), col("O_ORDERDATE") < datetime.date(1995, 1, 1)])
+    j = region.hash_join(t["nation"], [col("R_REGIONKEY")], [col("N_REGIONKEY")])
+    j = j.hash_join(t["supplier"], [col("N_NATIONKEY")], [col("S_NATIONKEY")])
+    # probe the big table against the small build side: lineitem x (asia suppliers)
+    j = t["lineitem"].hash_join(j.eval_expression_list([col("N_NAME"), col("S_SUPPKEY"), col("S_NATIONKEY")]),
+                                [col("L_SUPPKEY")], [col("S_SUPPKEY")])
+    j = j.eval_expression_list([col("N_NAME"), col("L_ORDERKEY"), col("S_NATIONKEY"), col("L_EXTENDEDPRICE"), col("L_DISCOUNT")])
+    j = j.hash_join(orders.eval_expression_list([col("O_ORDERKEY"), col("O_CUSTKEY")]), [col("L_ORDERKEY")], [col("O_ORDERKEY")])
+    j = j.hash_join(t["customer"], [col("O_CUSTKEY"), col("S_NATIONKEY")], [col("C_CUSTKEY"), col("C_NATIONKEY")])
+    out = j.agg([(col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))).sum().alias("revenue")], [col("N_NAME")])
+    return out.sort([col("revenue")], descending=True)

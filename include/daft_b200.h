@@ -1,0 +1,279 @@
+/*
+ * daft_b200.h -- C ABI of libdaftb200.so: Daft's columnar hot path (hash / partition /
+ * group-by aggregate / hash join / sort / filter / project / exchange) as sm_100a CUDA
+ * kernels over GPU-resident Arrow buffers.
+ *
+ * Conventions are the reference's own stable C ABI (src/daft-ext/src/abi/mod.rs:20-113):
+ *   - every call returns int, 0 = ok; on error a malloc'd NUL-terminated message is
+ *     written to *errmsg and must be released with b200_free_string (abi/mod.rs:50-53);
+ *   - data crosses the boundary as Arrow C Data Interface ArrowArray/ArrowSchema pairs
+ *     (abi/arrow.rs); inputs are MOVED into the callee (their release callback is called
+ *     by this library), outputs carry this library's release callbacks;
+ *   - stateful objects are opaque handles with explicit *_free (ctx + fini in the
+ *     reference's vtables, abi/mod.rs:66,107);
+ *   - handles are not thread-safe for concurrent mutation; read-only sharing of a
+ *     finished b200_probe_table across probe threads is allowed (Probeable is Send+Sync,
+ *     src/daft-recordbatch/src/probeable/mod.rs:33-85).
+ *
+ * There is NO CPU fallback behind any entry point: without a CUDA device every operator
+ * returns an error.
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   b200_hash_rows            RecordBatch::hash_rows          src/daft-recordbatch/src/ops/hash.rs:14-26
+ *                             kernels::hashing::hash          src/daft-core/src/kernels/hashing.rs:304-445
+ *   b200_partition_by_hash    RecordBatch::partition_by_hash  src/daft-recordbatch/src/ops/partition.rs:51-70
+ *   b200_agg                  RecordBatch::agg / agg_groupby_inline
+ *                                                             src/daft-recordbatch/src/ops/agg.rs:35-88,
+ *                                                             src/daft-recordbatch/src/ops/inline_agg.rs:862-928
+ *                             (+ the Filter/Project feeding it, fused)
+ *   b200_filter               RecordBatch::filter             src/daft-recordbatch/src/lib.rs:520-570
+ *   b200_eval_expression_list RecordBatch::eval_expression_list src/daft-recordbatch/src/lib.rs:1603-1631
+ *   b200_take / b200_concat   RecordBatch::take / concat      src/daft-recordbatch/src/lib.rs
+ *   b200_argsort/sort/top_n   RecordBatch::argsort/sort/top_n src/daft-recordbatch/src/ops/sort.rs:7-61
+ *   b200_probe_table_*        ProbeableBuilder::{add_table,build}, Probeable::{probe_indices,probe_exists}
+ *                                                             src/daft-recordbatch/src/probeable/mod.rs:33-126,
+ *                                                             probe_table.rs:56-213
+ *   b200_hash_join_probe/finalize  probe_inner / probe_left_right / probe_outer / probe_anti_semi + finalize_*
+ *                                                             src/daft-local-execution/src/join/ (all files)
+ *   b200_exchange_*           RepartitionSink + Flight shuffle src/daft-local-execution/src/sinks/repartition.rs:100-370,
+ *                                                             src/daft-shuffles/src/ (all files)
+ */
+#ifndef DAFT_B200_H
+#define DAFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAFT_B200_ABI_VERSION 1
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowSchema {
+    const char *format;
+    const char *name;
+    const char *metadata;
+    int64_t flags;
+    int64_t n_children;
+    struct ArrowSchema **children;
+    struct ArrowSchema *dictionary;
+    void (*release)(struct ArrowSchema *);
+    void *private_data;
+};
+struct ArrowArray {
+    int64_t length;
+    int64_t null_count;
+    int64_t offset;
+    int64_t n_buffers;
+    int64_t n_children;
+    const void **buffers;
+    struct ArrowArray **children;
+    struct ArrowArray *dictionary;
+    void (*release)(struct ArrowArray *);
+    void *private_data;
+};
+#endif
+
+/* ---- physical dtypes held on the device (Daft `as_physical` view) ---- */
+typedef enum {
+    B200_NULL = 0,
+    B200_BOOL = 1, /* Arrow bitmap */
+    B200_I8 = 2, B200_I16 = 3, B200_I32 = 4, B200_I64 = 5,
+    B200_U8 = 6, B200_U16 = 7, B200_U32 = 8, B200_U64 = 9,
+    B200_F32 = 10, B200_F64 = 11,
+    B200_DATE32 = 12,       /* days since epoch, physical i32 */
+    B200_TIMESTAMP = 13,    /* no tz, physical i64 */
+    B200_LARGE_UTF8 = 14,   /* i64 offsets -- Daft always holds strings as Large */
+    B200_LARGE_BINARY = 15
+} b200_dtype;
+
+/* One column as raw DEVICE pointers (Arrow layout).  Used to wrap buffers that already
+ * live in HBM (b200_batch_from_device) and to look inside a batch (b200_batch_describe). */
+typedef struct {
+    int32_t dtype;           /* b200_dtype */
+    int32_t _reserved;
+    int64_t length;
+    int64_t null_count;
+    const void *validity;    /* device; Arrow LSB bitmap, NULL = no nulls */
+    const void *offsets;     /* device; int64[length+1] for LARGE_UTF8/LARGE_BINARY, else NULL */
+    const void *data;        /* device; values / bitmap (BOOL) / bytes */
+    int64_t data_bytes;      /* size of `data` in bytes */
+    const char *name;        /* UTF-8, borrowed */
+} b200_column_desc;
+
+typedef struct b200_batch b200_batch;             /* device-resident RecordBatch */
+typedef struct b200_probe_table b200_probe_table; /* join build side: hash table + build batches */
+typedef struct b200_join_state b200_join_state;   /* per-join matched-build-row bitmap (outer/left/right) */
+
+/* ---- library ---- */
+int b200_abi_version(void);
+int b200_init(int device_ordinal, char **errmsg);  /* selects the device, creates the library stream + pool */
+void b200_free_string(char *s);
+void *b200_stream(void);                           /* cudaStream_t all operators are enqueued on */
+int b200_synchronize(char **errmsg);
+/* number of kernel launches issued by this library since load (bench.py "gpu_launches") */
+int64_t b200_launch_count(void);
+/* bench support: when enabled, the fused-aggregate kernel launch is bracketed by CUDA events on the library
+ * stream; b200_last_agg_kernel_ms returns the duration of the most recent one (-1 if none). */
+int b200_kernel_timing(int enable);
+double b200_last_agg_kernel_ms(void);
+/* JIT cache: directory holding generated .cu/.cubin (default <lib dir>/_jitcache) */
+int b200_set_jit_cache_dir(const char *path, char **errmsg);
+/* compile (no launch) the kernels a plan needs -- usable without a GPU (build check) */
+int b200_precompile(int32_t op, const uint8_t *plan, size_t plan_len, const int32_t *col_dtypes,
+                    const uint8_t *col_nullable, int32_t ncols, char **errmsg);
+
+/* ---- batches ---- */
+/* HOST -> device.  `array` must be a struct array (one child per column), as produced by
+ * RecordBatch export; it is moved (released by this call).  Utf8/Binary are widened to Large. */
+int b200_batch_import(struct ArrowArray *array, struct ArrowSchema *schema, b200_batch **out, char **errmsg);
+/* device -> HOST; out_array/out_schema get this library's release callbacks. */
+int b200_batch_export(const b200_batch *batch, struct ArrowArray *out_array, struct ArrowSchema *out_schema,
+                      char **errmsg);
+/* wrap existing DEVICE buffers without copying (borrowed; caller keeps them alive). */
+int b200_batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t num_rows, b200_batch **out,
+                           char **errmsg);
+int b200_batch_describe(const b200_batch *batch, int32_t col, b200_column_desc *out, char **errmsg);
+int64_t b200_batch_num_rows(const b200_batch *batch);
+int32_t b200_batch_num_columns(const b200_batch *batch);
+int64_t b200_batch_size_bytes(const b200_batch *batch);
+void b200_batch_free(b200_batch *batch);
+/* columns by index -> new batch sharing the same device buffers */
+int b200_batch_select(const b200_batch *batch, const int32_t *cols, int32_t ncols, b200_batch **out, char **errmsg);
+int b200_batch_rename(b200_batch *batch, int32_t col, const char *name, char **errmsg);
+/* horizontal union of columns (RecordBatch::union) */
+int b200_batch_union(const b200_batch *a, const b200_batch *b, b200_batch **out, char **errmsg);
+int b200_batch_slice(const b200_batch *batch, int64_t start, int64_t end, b200_batch **out, char **errmsg);
+
+/* ---- a1/a2: hashing ---- */
+/* out: one UInt64 column "hash", no nulls.  seed: optional batch whose column 0 is UInt64[n]. */
+int b200_hash_rows(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const b200_batch *seed,
+                   b200_batch **out, char **errmsg);
+
+/* ---- a3: hash partition ---- */
+/* out[0..P): rows with hash_rows(keys) % P == p, input order preserved inside a partition. */
+int b200_partition_by_hash(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys,
+                           int32_t num_partitions, b200_batch **out, char **errmsg);
+
+/* ---- a10/a11: filter / project.  `plan` = serialised expression program (see below). ---- */
+int b200_filter(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg);
+int b200_eval_expression_list(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out,
+                              char **errmsg);
+
+/* ---- a4/a5/a6: grouped / ungrouped aggregate with the filter + projections fused in ---- */
+int b200_agg(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg);
+/* a13: distinct rows over key columns (first occurrence kept, first-occurrence order) */
+int b200_dedup(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out, char **errmsg);
+
+/* ---- take / concat ---- */
+/* indices: column 0 of `indices`, any integer dtype; null index -> null row. */
+int b200_take(const b200_batch *batch, const b200_batch *indices, b200_batch **out, char **errmsg);
+int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, char **errmsg);
+
+/* ---- a9: sort ---- */
+int b200_argsort(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
+                 const uint8_t *nulls_first, b200_batch **out_indices /* UInt64 */, char **errmsg);
+int b200_sort(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
+              const uint8_t *nulls_first, b200_batch **out, char **errmsg);
+int b200_top_n(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
+               const uint8_t *nulls_first, int64_t limit, int64_t offset, b200_batch **out, char **errmsg);
+
+/* ---- a7/a8: hash join ---- */
+typedef enum { B200_JOIN_INNER = 0, B200_JOIN_LEFT = 1, B200_JOIN_RIGHT = 2, B200_JOIN_OUTER = 3,
+               B200_JOIN_SEMI = 4, B200_JOIN_ANTI = 5 } b200_join_type;
+
+/* ProbeableBuilder: create -> add_table* -> build.  `key_cols` index into each added batch. */
+int b200_probe_table_create(int32_t nkeys, const uint8_t *null_equals_null /* nkeys or NULL */,
+                            int32_t track_indices, b200_probe_table **out, char **errmsg);
+int b200_probe_table_add(b200_probe_table *pt, const b200_batch *build_batch, const int32_t *key_cols,
+                         char **errmsg);
+int b200_probe_table_build(b200_probe_table *pt, char **errmsg);
+int64_t b200_probe_table_num_rows(const b200_probe_table *pt);
+void b200_probe_table_free(b200_probe_table *pt);
+/* Probeable::probe_exists -> Boolean column; Probeable::probe_indices -> (probe_idx, build_idx) UInt64 pairs
+ * in probe-row order, matches of one probe row in build insertion order. */
+int b200_probe_exists(const b200_probe_table *pt, const b200_batch *probe, const int32_t *key_cols,
+                      b200_batch **out, char **errmsg);
+int b200_probe_indices(const b200_probe_table *pt, const b200_batch *probe, const int32_t *key_cols,
+                       b200_batch **out, char **errmsg);
+/* One probe batch through the join operator.  Output columns: probe-side columns `probe_out_cols`
+ * and build-side columns `build_out_cols` gathered per match, build side first iff build_on_left. */
+int b200_join_state_create(const b200_probe_table *pt, b200_join_state **out, char **errmsg);
+void b200_join_state_free(b200_join_state *st);
+int b200_hash_join_probe(const b200_probe_table *pt, b200_join_state *st /* NULL for inner/semi/anti */,
+                         const b200_batch *probe, const int32_t *key_cols, int32_t join_type,
+                         int32_t build_on_left, b200_batch **out, char **errmsg);
+/* unmatched build rows (left/right/outer builds), null-extended on the probe side whose schema is taken
+ * from `probe_schema_like` (a batch with the probe-side columns; may have 0 rows). */
+int b200_hash_join_finalize(const b200_probe_table *pt, b200_join_state *st, const b200_batch *probe_schema_like,
+                            int32_t build_on_left, b200_batch **out, char **errmsg);
+
+/* ---- a12: exchange (hash repartition over NCCL; one process per GPU) ---- */
+typedef struct b200_comm b200_comm;
+int b200_comm_unique_id(uint8_t *out128, char **errmsg); /* rank 0: ncclGetUniqueId, 128 bytes */
+int b200_comm_init(const uint8_t *id128, int32_t rank, int32_t world, b200_comm **out, char **errmsg);
+void b200_comm_free(b200_comm *c);
+/* hash-partition `batch` into `world` pieces and all-to-all them; out = this rank's piece. */
+int b200_exchange_by_hash(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys,
+                          b200_batch **out, char **errmsg);
+/* every rank receives the concatenation of all ranks' batches in rank order (broadcast join / partial-agg merge) */
+int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, char **errmsg);
+
+/* ---- synthetic TPC-H tables generated straight into HBM (bench / tests) ---- */
+typedef enum { B200_TPCH_LINEITEM = 0, B200_TPCH_ORDERS = 1, B200_TPCH_CUSTOMER = 2, B200_TPCH_SUPPLIER = 3,
+               B200_TPCH_NATION = 4, B200_TPCH_REGION = 5 } b200_tpch_table;
+/* rows [row_begin,row_end) of `table` at `scale_factor`; columns selected by name list (NULL = all implemented). */
+int b200_tpch_generate(int32_t table, double scale_factor, int64_t row_begin, int64_t row_end, uint64_t seed,
+                       const char *const *columns, int32_t ncolumns, b200_batch **out, char **errmsg);
+int64_t b200_tpch_num_rows(int32_t table, double scale_factor);
+/* same generator on the host (fills caller-provided host buffers through Arrow export) */
+int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begin, int64_t row_end, uint64_t seed,
+                            const char *const *columns, int32_t ncolumns, struct ArrowArray *out_array,
+                            struct ArrowSchema *out_schema, char **errmsg);
+
+/*
+ * ---- expression / plan encoding (little-endian byte stream) ----
+ *
+ * This is the serialised form of the plan-node parameters the reference hands its operators
+ * (src/daft-local-plan/src/plan.rs: Project:1884, Filter:1921, UnGroupedAggregate:2030,
+ * HashAggregate:2040-2047) with BoundExpr column references already resolved to indices.
+ *
+ *   str    := u32 len, bytes
+ *   node   := u8 tag, payload
+ *     0 COL      u32 column_index
+ *     1 LIT      u8 dtype, u8 is_null, (BOOL/ints: i64 | F32/F64: f64 | DATE32/TIMESTAMP: i64 | UTF8/BINARY: str)
+ *     2 BINARY   u8 op, node lhs, node rhs
+ *     3 UNARY    u8 op, node child
+ *     4 CAST     u8 dtype, node child
+ *     5 IF_ELSE  node predicate, node if_true, node if_false
+ *     6 IS_IN    node child, u32 n, n x node(LIT)
+ *     7 BETWEEN  node child, node lower, node upper
+ *     8 FILL_NULL node child, node fill
+ *     9 FUNCTION u8 fn, u8 nargs, nargs x node
+ *   binary ops (src/daft-dsl Operator, evaluated at src/daft-recordbatch/src/lib.rs:1376-1400):
+ *     0 add 1 sub 2 mul 3 true_div 4 floor_div 5 mod 6 lt 7 le 8 eq 9 ne 10 ge 11 gt 12 and 13 or 14 xor
+ *     15 eq_null_safe 16 shift_left 17 shift_right
+ *   unary ops: 0 not 1 negate 2 is_null 3 not_null 4 abs
+ *   functions: 0 year 1 month 2 day 3 utf8_length 4 utf8_startswith 5 utf8_endswith 6 utf8_contains
+ *              7 utf8_left 8 day_of_week
+ *   Operands of a binary op must already have identical dtypes (the host inserts the supertype
+ *   casts the reference decides at plan time); true_div requires F64 operands.
+ *
+ *   PROJECT plan := u32 nexprs, nexprs x (str name, node)
+ *   FILTER  plan := node predicate               (conjuncts already AND-ed, lib.rs:520-541)
+ *   AGG     plan := u8 has_filter, [node filter], u32 nkeys, nkeys x (str name, node),
+ *                   u32 naggs, naggs x (u8 kind, u8 count_mode, str name, node child)
+ *     agg kinds: 0 count 1 sum 2 min 3 max 4 mean 5 any_value;  count modes: 0 all 1 valid 2 null
+ */
+#define B200_OP_PROJECT 0
+#define B200_OP_FILTER 1
+#define B200_OP_AGG 2
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAFT_B200_H */

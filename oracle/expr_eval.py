@@ -1,0 +1,233 @@
+"""CPU oracle for Filter / Project: column-at-a-time numpy evaluation of daft_b200 Expression trees.
+
+TEST INFRASTRUCTURE ONLY (see oracle/oracle.py).  Follows the reference's tree-walking interpreter
+(src/daft-recordbatch/src/lib.rs:1280-1400): every AST node materialises a full column (values +
+validity mask); binary operands are first cast to their supertype; IEEE f64 arithmetic is elementwise
+(numpy float64 == Rust f64, no fused multiply-add), so results are bit-exact comparable.
+"""
+from __future__ import annotations
+
+import datetime
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+
+from daft_b200 import datatypes as dt
+from daft_b200.expressions import Bound, Expression, bind, T_COL, T_LIT, T_BINARY, T_UNARY, T_CAST, T_IF_ELSE, T_IS_IN, \
+    T_BETWEEN, T_FILL_NULL, T_FUNCTION, BINOPS, UNOPS, FUNCS
+
+_NP = {dt.BOOL: np.bool_, dt.I8: np.int8, dt.I16: np.int16, dt.I32: np.int32, dt.I64: np.int64, dt.U8: np.uint8,
+       dt.U16: np.uint16, dt.U32: np.uint32, dt.U64: np.uint64, dt.F32: np.float32, dt.F64: np.float64,
+       dt.DATE32: np.int32, dt.TIMESTAMP: np.int64, dt.NULL: np.bool_}
+_BIN = {v: k for k, v in BINOPS.items()}
+_UN = {v: k for k, v in UNOPS.items()}
+_FN = {v: k for k, v in FUNCS.items()}
+
+
+def _col_to_np(arr: pa.Array, code: int):
+    n = len(arr)
+    valid = np.ones(n, dtype=bool) if arr.null_count == 0 else np.asarray(arr.is_valid())
+    if code == dt.NULL:
+        return np.zeros(n, dtype=bool), np.zeros(n, dtype=bool)
+    if dt.is_string(code):
+        vals = np.array([x if x is not None else (b"" if code == dt.LARGE_BINARY else "") for x in arr.to_pylist()], dtype=object)
+        if code == dt.LARGE_UTF8:
+            vals = np.array([v.encode() if isinstance(v, str) else v for v in vals], dtype=object)
+        return vals, valid
+    if code == dt.DATE32:
+        vals = np.asarray(arr.cast(pa.int32()).fill_null(0))
+    elif code == dt.TIMESTAMP:
+        vals = np.asarray(arr.cast(pa.int64()).fill_null(0))
+    elif code == dt.BOOL:
+        vals = np.asarray(arr.fill_null(False))
+    else:
+        vals = np.asarray(arr.fill_null(0))
+    return vals.astype(_NP[code], copy=False), valid
+
+
+def _lit_np(b: Bound, n: int):
+    v, d = b.value, b.dtype
+    if v is None or d == dt.NULL:
+        if dt.is_string(d):
+            return np.array([b""] * n, dtype=object), np.zeros(n, dtype=bool)
+        return np.zeros(n, dtype=_NP.get(d, np.bool_)), np.zeros(n, dtype=bool)
+    if dt.is_string(d):
+        raw = v.encode() if isinstance(v, str) else bytes(v)
+        return np.array([raw] * n, dtype=object), np.ones(n, dtype=bool)
+    if d == dt.DATE32 and isinstance(v, datetime.date):
+        v = (v - datetime.date(1970, 1, 1)).days
+    if d == dt.TIMESTAMP and isinstance(v, datetime.datetime):
+        v = int((v - datetime.datetime(1970, 1, 1)).total_seconds() * 1_000_000)
+    return np.full(n, v, dtype=_NP[d]), np.ones(n, dtype=bool)
+
+
+def _civil(days: np.ndarray):
+    z = days.astype(np.int64) + 719468
+    era = np.where(z >= 0, z, z - 146096) // 146097
+    doe = z - era * 146097
+    yoe = (doe - doe // 1460 + doe // 36524 - doe // 146096) // 365
+    y = yoe + era * 400
+    doy = doe - (365 * yoe + yoe // 4 - yoe // 100)
+    mp = (5 * doy + 2) // 153
+    d = doy - (153 * mp + 2) // 5 + 1
+    m = np.where(mp < 10, mp + 3, mp - 9)
+    return y + (m <= 2), m, d
+
+
+def _eval(b: Bound, cols, n: int):
+    if b.tag == T_COL:
+        return cols[b.col]
+    if b.tag == T_LIT:
+        return _lit_np(b, n)
+    kids = [_eval(k, cols, n) for k in b.kids]
+    with np.errstate(all="ignore"):
+        if b.tag == T_BINARY:
+            (a, ka), (c, kc) = kids
+            op = _BIN[b.op]
+            t = b.kids[0].dtype if b.kids[0].dtype != dt.NULL else b.kids[1].dtype
+            both = ka & kc
+            if op in ("add", "sub", "mul"):
+                f = {"add": np.add, "sub": np.subtract, "mul": np.multiply}[op]
+                return f(a, c), both
+            if op == "true_div":
+                return a / c, both
+            if op in ("floor_div", "mod"):
+                if dt.is_float(t):
+                    q = np.floor(a / c)
+                    return (q if op == "floor_div" else a - q * c), both
+                ok = both & (c != 0)
+                cs = np.where(c == 0, 1, c)
+                r = (a // cs) if op == "floor_div" else (a % cs)
+                return np.where(ok, r, 0).astype(a.dtype), ok
+            if op in ("lt", "le", "ge", "gt", "eq", "ne"):
+                f = {"lt": np.less, "le": np.less_equal, "ge": np.greater_equal, "gt": np.greater, "eq": np.equal, "ne": np.not_equal}[op]
+                return np.asarray(f(a, c), dtype=bool), both
+            if op == "eq_null_safe":
+                return np.where(both, np.asarray(a == c, dtype=bool), ka == kc), np.ones(n, dtype=bool)
+            if op == "and":  # Kleene, src/daft-core/src/array/ops/comparison.rs:725-786
+                va, vc = ka & a.astype(bool), kc & c.astype(bool)
+                return va & vc, both | (ka & ~a.astype(bool)) | (kc & ~c.astype(bool))
+            if op == "or":
+                va, vc = ka & a.astype(bool), kc & c.astype(bool)
+                return va | vc, both | va | vc
+            if op == "xor":
+                return a.astype(bool) != c.astype(bool), both
+            if op == "shl":
+                return np.left_shift(a, c), both
+            if op == "shr":
+                return np.right_shift(a, c), both
+        if b.tag == T_UNARY:
+            (a, ka), = kids
+            op = _UN[b.op]
+            if op == "not": return ~a.astype(bool), ka
+            if op == "neg": return (0 - a).astype(a.dtype), ka
+            if op == "abs": return np.abs(a), ka
+            if op == "is_null": return ~ka, np.ones(n, dtype=bool)
+            if op == "not_null": return ka.copy(), np.ones(n, dtype=bool)
+        if b.tag == T_CAST:
+            (a, ka), = kids
+            src = b.kids[0].dtype
+            if src == dt.NULL:
+                return np.zeros(n, dtype=_NP[b.dtype]) if not dt.is_string(b.dtype) else np.array([b""] * n, dtype=object), np.zeros(n, dtype=bool)
+            if dt.is_string(b.dtype):
+                return a, ka
+            if b.dtype == dt.BOOL:
+                return a != 0, ka
+            return a.astype(_NP[b.dtype]), ka
+        if b.tag == T_IF_ELSE:
+            (p, kp), (x, kx), (y, ky) = kids
+            s = kp & p.astype(bool)
+            return np.where(s, x, y), kp & np.where(s, kx, ky)
+        if b.tag == T_IS_IN:
+            (a, ka) = kids[0]
+            r = np.zeros(n, dtype=bool)
+            for (v, kv), kb in zip(kids[1:], b.kids[1:]):
+                if kb.value is None or kb.dtype == dt.NULL:
+                    continue
+                r |= np.asarray(a == v, dtype=bool)
+            return r, ka
+        if b.tag == T_BETWEEN:
+            (a, ka), (lo, kl), (hi, kh) = kids
+            return np.asarray((a >= lo) & (a <= hi), dtype=bool), ka & kl & kh
+        if b.tag == T_FILL_NULL:
+            (a, ka), (f, kf) = kids
+            return np.where(ka, a, f), ka | kf
+        if b.tag == T_FUNCTION:
+            fn = _FN[b.op]
+            allk = np.ones(n, dtype=bool)
+            for _, kk in kids:
+                allk &= kk
+            a = kids[0][0]
+            if fn in ("year", "month", "day"):
+                y, m, d = _civil(a)
+                return {"year": y.astype(np.int32), "month": m.astype(np.uint32), "day": d.astype(np.uint32)}[fn], allk
+            if fn == "day_of_week":
+                return ((a.astype(np.int64) + 3) % 7).astype(np.uint32), allk
+            if fn == "utf8_length":
+                return np.array([len(x.decode("utf-8", "ignore")) for x in a], dtype=np.uint64), allk
+            pat = kids[1][0]
+            if fn == "startswith": return np.array([x.startswith(p) for x, p in zip(a, pat)], dtype=bool), allk
+            if fn == "endswith": return np.array([x.endswith(p) for x, p in zip(a, pat)], dtype=bool), allk
+            if fn == "contains": return np.array([p in x for x, p in zip(a, pat)], dtype=bool), allk
+            if fn == "left":
+                return np.array([x.decode("utf-8", "ignore")[:max(int(k), 0)].encode() for x, k in zip(a, pat)], dtype=object), allk
+    raise NotImplementedError(b.tag)
+
+
+def _to_arrow(vals, valid, code: int) -> pa.Array:
+    mask = None if valid.all() else ~valid
+    if code == dt.NULL:
+        return pa.nulls(len(vals))
+    if code == dt.LARGE_UTF8:
+        return pa.array([v.decode() if k else None for v, k in zip(vals, valid)], type=pa.large_utf8())
+    if code == dt.LARGE_BINARY:
+        return pa.array([bytes(v) if k else None for v, k in zip(vals, valid)], type=pa.large_binary())
+    if code == dt.DATE32:
+        return pa.array(np.asarray(vals, dtype=np.int32), mask=mask).cast(pa.date32())
+    if code == dt.TIMESTAMP:
+        return pa.array(np.asarray(vals, dtype=np.int64), mask=mask).cast(pa.timestamp("us"))
+    return pa.array(np.asarray(vals, dtype=_NP[code]), type=dt.to_arrow(code), mask=mask)
+
+
+class _LazyCols:
+    """Columns are converted to numpy only when an expression actually references them."""
+
+    def __init__(self, tbl: pa.Table, codes):
+        self.tbl, self.codes, self.cache = tbl, codes, {}
+
+    def __getitem__(self, i):
+        if i not in self.cache:
+            c = self.tbl.column(i)
+            c = c.combine_chunks() if c.num_chunks != 1 else c.chunk(0)
+            self.cache[i] = _col_to_np(c, self.codes[i])
+        return self.cache[i]
+
+
+def _table_cols(tbl: pa.Table):
+    names = tbl.column_names
+    codes = [dt.from_arrow(f.type) for f in tbl.schema]
+    return names, codes, _LazyCols(tbl, codes)
+
+
+def eval_expression(tbl: pa.Table, e: Expression) -> pa.Array:
+    names, codes, cols = _table_cols(tbl)
+    b = bind(e, names, codes)
+    if b.tag == T_COL:  # bare column reference: no copy (Expr::Column, lib.rs:1290)
+        c = tbl.column(b.col)
+        return c.combine_chunks() if c.num_chunks != 1 else c.chunk(0)
+    vals, valid = _eval(b, cols, tbl.num_rows)
+    return _to_arrow(vals, valid, b.dtype)
+
+
+def eval_expression_list(tbl: pa.Table, exprs) -> pa.Table:
+    return pa.table([eval_expression(tbl, e) for e in exprs], names=[e.name() for e in exprs])
+
+
+def filter(tbl: pa.Table, exprs) -> pa.Table:
+    """RecordBatch::filter: AND of predicates, null => drop (lib.rs:520-563)."""
+    pred = exprs[0]
+    for e in exprs[1:]:
+        pred = pred & e
+    mask = eval_expression(tbl, pred)
+    return tbl.filter(pc.fill_null(mask, False))

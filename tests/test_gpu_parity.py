@@ -1,0 +1,302 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded Arrow inputs.
+
+Shapes follow the reference's kernel-level tests: tests/recordbatch/test_hash.py, test_table_aggs.py,
+test_joins.py, test_sorting.py, test_partitioning.py, test_filter.py, tests/series/test_hash.py.
+Bar: bit-exact for hashes / indices / keys / integer aggregates / filter+project outputs; 1e-9 relative
+for float sums (north_star allows 1e-6).
+"""
+import datetime
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from helpers import assert_tables_equal, oracle_agg, random_table
+from oracle import expr_eval as E
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def RB(gpu, tbl):
+    return gpu.RecordBatch.from_arrow_table(tbl)
+
+
+# ---------------------------------------------------------------------------------------------- roundtrip
+def test_roundtrip_all_dtypes(gpu):
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 31, 32, 33, 1000):
+        tbl = random_table(rng, n)
+        got = RB(gpu, tbl).to_arrow_table()
+        assert_tables_equal(got, tbl)
+
+
+def test_roundtrip_sliced_and_small_offsets(gpu):
+    tbl = pa.table({"a": pa.array([1, None, 3, 4, 5], type=pa.int32()), "s": pa.array(["x", None, "zz", "", "w"]),
+                    "b": pa.array([True, False, None, True, False])})
+    sl = tbl.slice(1, 3)
+    got = RB(gpu, sl).to_arrow_table()
+    assert_tables_equal(got, sl.combine_chunks())
+
+
+# ---------------------------------------------------------------------------------------------- hashing
+def test_hash_goldens(gpu):
+    # tests/recordbatch/test_hash.py:15-18
+    rb = RB(gpu, pa.table({"utf8": ["foo", "bar"], "int": pa.array([1, None], type=pa.int64())}))
+    assert rb.hash_rows([gpu.col("utf8")]).to_pydict()["hash"] == [12352915711150947722, 15304296276065178466]
+    assert rb.hash_rows([gpu.col("int")]).to_pydict()["hash"] == [3439722301264460078, 3244421341483603138]
+    # :30-33 seed = 42
+    seed = RB(gpu, pa.table({"s": pa.array([42, 42], type=pa.uint64())}))
+    assert rb.hash_rows([gpu.col("utf8")], seed=seed).to_pydict()["hash"] == [15221504070560512414, 2671805001252040144]
+    assert rb.hash_rows([gpu.col("int")], seed=seed).to_pydict()["hash"] == [16405722695416140795, 3244421341483603138]
+    # :45 per-row seeds
+    seed2 = RB(gpu, pa.table({"s": pa.array([1, 1000], type=pa.uint64())}))
+    assert rb.hash_rows([gpu.col("utf8")], seed=seed2).to_pydict()["hash"] == [6076897603942036120, 15438169081903732554]
+
+
+@pytest.mark.parametrize("n", [0, 1, 257, 5000])
+def test_hash_every_dtype_matches_oracle(gpu, n):
+    rng = np.random.default_rng(n)
+    tbl = random_table(rng, n)
+    rb = RB(gpu, tbl)
+    for name in tbl.column_names:
+        got = np.array(rb.hash_rows([gpu.col(name)]).to_pydict()["hash"], dtype=np.uint64)
+        want = O.hash_column(tbl.column(name))
+        assert (got == want).all(), name
+    # chained multi-column hash (RecordBatch::hash_rows)
+    keys = ["i64", "s", "b", "f64", "d", "u8"]
+    got = np.array(rb.hash_rows([gpu.col(k) for k in keys]).to_pydict()["hash"], dtype=np.uint64)
+    assert (got == O.hash_rows([tbl.column(k) for k in keys])).all()
+
+
+def test_hash_string_length_classes(gpu):
+    import xxhash
+    rng = np.random.default_rng(5)
+    lens = list(range(0, 260)) + [511, 512, 1023, 1024, 1025, 2048, 4100]
+    vals = [bytes(rng.integers(0, 256, l, dtype=np.uint8)) for l in lens]
+    tbl = pa.table({"b": pa.array(vals, type=pa.large_binary())})
+    got = RB(gpu, tbl).hash_rows([gpu.col("b")]).to_pydict()["hash"]
+    assert got == [xxhash.xxh3_64_intdigest(v) for v in vals]
+    seeds = [int(x) for x in rng.integers(0, 2**63, len(vals), dtype=np.uint64)]
+    seed = RB(gpu, pa.table({"s": pa.array(seeds, type=pa.uint64())}))
+    got = RB(gpu, tbl).hash_rows([gpu.col("b")], seed=seed).to_pydict()["hash"]
+    assert got == [xxhash.xxh3_64_intdigest(v, s) for v, s in zip(vals, seeds)]
+
+
+def test_hash_null_array(gpu):
+    tbl = pa.table({"n": pa.nulls(5)})
+    got = RB(gpu, tbl).hash_rows([gpu.col("n")]).to_pydict()["hash"]
+    assert got == [3244421341483603138] * 5
+
+
+# ---------------------------------------------------------------------------------------------- project / filter
+def exprs_under_test(c, lit):
+    return [
+        (c("i64") + c("i32")).alias("e0"), (c("f64") * (1 - c("f32"))).alias("e1"), (c("i32") / c("u8")).alias("e2"),
+        (c("i64") // c("i16")).alias("e3"), (c("i64") % 7).alias("e4"), (c("f64") <= 0.5).alias("e5"),
+        ((c("b") & (c("i8") > 0)) | c("f64").is_null()).alias("e6"), (~c("b")).alias("e7"), (-c("i32")).alias("e8"),
+        c("i32").cast(pa.float64()).alias("e9"), c("i16").cast(pa.int64()).alias("e10"),
+        (c("i32") > 0).if_else(c("i64"), c("u32")).alias("e11"), c("u16").is_in([1, 2, 3, 69]).alias("e12"),
+        c("i32").between(-10, 500).alias("e13"), c("i64").fill_null(-1).alias("e14"), c("d").year().alias("e15"),
+        c("d").month().alias("e16"), c("d").day().alias("e17"), (c("d") < datetime.date(1995, 6, 17)).alias("e18"),
+        c("s").startswith("TPC").alias("e19"), c("s").endswith("d").alias("e20"), c("s").contains("lo w").alias("e21"),
+        c("s").length().alias("e22"), (c("s") == "bb").alias("e23"), c("s").is_in(["a", "ccc", "zz"]).alias("e24"),
+        c("s").alias("e25"), c("s").left(3).alias("e26"), (c("s") < "c").alias("e27"), c("b").alias("e28"),
+        c("i8").eq_null_safe(c("i8")).alias("e29"), abs(c("i16")).alias("e30"), (c("u64") + 1).alias("e31"),
+        lit(7).alias("e32"), lit(None).alias("e33"), (c("f32") + c("f32")).alias("e34"), c("d").alias("e35"),
+        (c("b") ^ c("b")).alias("e36"),
+    ]
+
+
+@pytest.mark.parametrize("n,nulls", [(0, 0.1), (1, 0.0), (100, 0.3), (4097, 0.1), (4097, 0.0)])
+def test_project_matches_oracle(gpu, n, nulls):
+    rng = np.random.default_rng(n + 7)
+    tbl = random_table(rng, n, nulls)
+    exprs = exprs_under_test(gpu.col, gpu.lit)
+    got = RB(gpu, tbl).eval_expression_list(exprs).to_arrow_table()
+    want = E.eval_expression_list(tbl, exprs)
+    assert_tables_equal(got, want)  # bit-exact, floats included (same op order, no FMA)
+
+
+@pytest.mark.parametrize("n", [0, 5, 1000, 10007])
+def test_filter_matches_oracle(gpu, n):
+    rng = np.random.default_rng(n)
+    tbl = random_table(rng, n)
+    c = gpu.col
+    for pred in ([c("i32") > 0], [c("b")], [c("f64") < 0.0, c("s") != "a"], [c("i64").is_null() | (c("u8") == 3)],
+                 [c("i32") > 5000], [c("d") <= datetime.date(1998, 9, 2)]):
+        got = RB(gpu, tbl).filter(pred).to_arrow_table()
+        want = E.filter(tbl, pred)
+        assert_tables_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------- aggregate
+@pytest.mark.parametrize("n,nulls", [(0, 0.1), (1, 0.0), (1000, 0.2), (20000, 0.0), (20000, 0.3)])
+def test_groupby_inline_aggs(gpu, n, nulls):
+    rng = np.random.default_rng(n + 11)
+    tbl = random_table(rng, n, nulls)
+    c = gpu.col
+    aggs = [c("i32").sum().alias("s_i32"), c("u16").sum().alias("s_u16"), c("f64").sum().alias("s_f64"), c("f32").sum().alias("s_f32"),
+            c("i8").min().alias("mn_i8"), c("i64").max().alias("mx_i64"), c("u64").min().alias("mn_u64"), c("f64").min().alias("mn_f64"),
+            c("f64").max().alias("mx_f64"), c("d").max().alias("mx_d"), c("i32").count().alias("c_valid"), c("i32").count("all").alias("c_all"),
+            c("i32").count("null").alias("c_null"), c("f64").mean().alias("avg_f64"), c("i16").mean().alias("avg_i16"),
+            (c("f64") * (1 - c("f32").cast(pa.float64()))).sum().alias("s_expr")]
+    for gb in ([c("k")], [c("s")], [c("b"), c("u8")], [c("i8"), c("s"), c("d")], [c("f64")], [(c("k") % 3).alias("k3")]):
+        got = RB(gpu, tbl).agg(aggs, gb).to_arrow_table()
+        want = oracle_agg(tbl, aggs, gb)
+        # group order: first occurrence on both sides (inline_agg.rs:804-807)
+        assert_tables_equal(got, want, float_rtol=1e-9)
+
+
+def test_ungrouped_and_fused_predicate(gpu):
+    rng = np.random.default_rng(3)
+    tbl = random_table(rng, 5000, 0.1)
+    c = gpu.col
+    aggs = [c("i64").sum().alias("s"), c("f64").mean().alias("m"), c("u8").max().alias("mx"), c("s").count().alias("cnt")]
+    got = RB(gpu, tbl).agg(aggs, []).to_arrow_table()
+    assert_tables_equal(got, oracle_agg(tbl, aggs, []), float_rtol=1e-9)
+    pred = [c("i32") > 0, c("b")]
+    got = RB(gpu, tbl).agg(aggs, [c("k")], predicate=pred).to_arrow_table()
+    assert_tables_equal(got, oracle_agg(tbl, aggs, [c("k")], predicate=pred), float_rtol=1e-9)
+    # everything filtered out: ungrouped still yields one row (sum null, count 0)
+    got = RB(gpu, tbl).agg(aggs, [], predicate=[c("i32") > 10**6]).to_arrow_table()
+    assert_tables_equal(got, oracle_agg(tbl, aggs, [], predicate=[c("i32") > 10**6]))
+
+
+def test_groupby_high_cardinality(gpu):
+    rng = np.random.default_rng(9)
+    n = 300_000
+    tbl = pa.table({"k": pa.array(rng.integers(0, 200_000, n).astype(np.int64)), "v": pa.array(rng.integers(0, 1000, n).astype(np.int64)),
+                    "f": pa.array(rng.random(n))})
+    c = gpu.col
+    aggs = [c("v").sum().alias("sv"), c("v").count().alias("cv"), c("f").sum().alias("sf"), c("v").min().alias("mn")]
+    got = RB(gpu, tbl).agg(aggs, [c("k")]).to_arrow_table()
+    assert_tables_equal(got, oracle_agg(tbl, aggs, [c("k")]), float_rtol=1e-9)
+
+
+def test_groupby_null_and_nan_keys(gpu):
+    # inline_agg.rs:1094-1617 behaviours: null key is a group; all-null group sums to null; NaN keys group together
+    tbl = pa.table({"k": pa.array([1, None, 1, None, 2], type=pa.int64()), "v": pa.array([None, None, 3, None, None], type=pa.int64()),
+                    "f": pa.array([float("nan"), 1.0, float("nan"), 1.0, 2.0])})
+    c = gpu.col
+    got = RB(gpu, tbl).agg([c("v").sum().alias("s"), c("v").count().alias("c"), c("v").min().alias("m")], [c("k")]).to_pydict()
+    assert got == {"k": [1, None, 2], "s": [3, None, None], "c": [1, 0, 0], "m": [3, None, None]}
+    got = RB(gpu, tbl).agg([c("k").count("all").alias("n")], [c("f")]).to_arrow_table()
+    assert got.column("n").to_pylist() == [2, 2, 1]
+
+
+def test_dedup(gpu):
+    rng = np.random.default_rng(2)
+    tbl = random_table(rng, 3000, 0.2)
+    c = gpu.col
+    got = RB(gpu, tbl).dedup([c("u8"), c("b")]).to_arrow_table()
+    _, first, _ = O.group_ids([tbl.column("u8"), tbl.column("b")])
+    assert_tables_equal(got, tbl.take(pa.array(first.astype(np.int64))))
+
+
+# ---------------------------------------------------------------------------------------------- sort
+@pytest.mark.parametrize("n", [0, 1, 2, 1000, 50000])
+def test_argsort_single_keys(gpu, n):
+    rng = np.random.default_rng(n + 1)
+    tbl = random_table(rng, n, 0.15)
+    if n > 10:
+        f = tbl.column("f64").to_pylist()
+        f[3], f[5], f[7] = float("nan"), -0.0, 0.0
+        tbl = tbl.set_column(tbl.column_names.index("f64"), "f64", pa.array(f))
+    rb = RB(gpu, tbl)
+    for name in ["i8", "i16", "i32", "i64", "u8", "u16", "u32", "u64", "f32", "f64", "b", "d", "s"]:
+        for desc in (False, True):
+            for nf in (False, True):
+                got = rb.argsort([gpu.col(name)], descending=desc, nulls_first=nf).to_pydict()["indices"]
+                want = O.argsort([tbl.column(name)], [desc], [nf])
+                assert got == want.tolist(), (name, desc, nf)
+
+
+def test_sort_multikey(gpu):
+    rng = np.random.default_rng(17)
+    tbl = random_table(rng, 20000, 0.1)
+    c = gpu.col
+    for keys, desc, nf in [(["u8", "s"], [False, True], [False, True]), (["b", "i8", "f32"], [True, False, True], [True, True, False]),
+                           (["k", "d", "i64"], [False, False, False], None)]:
+        got = RB(gpu, tbl).sort([c(k) for k in keys], descending=desc, nulls_first=nf).to_arrow_table()
+        want = O.sort(tbl, keys, desc, nf if nf is not None else desc)
+        assert_tables_equal(got, want)
+    got = RB(gpu, tbl).top_n([c("i64")], 10, descending=True, nulls_first=False, offset=5).to_arrow_table()
+    assert_tables_equal(got, O.sort(tbl, ["i64"], [True], [False]).slice(5, 10))
+
+
+def test_sort_by_expression(gpu):
+    tbl = pa.table({"a": [3, 1, 2, None], "b": [1.0, 5.0, -1.0, 0.0]})
+    c = gpu.col
+    got = RB(gpu, tbl).sort([(c("a") * -1).alias("neg")]).to_pydict()
+    assert got == {"a": [3, 2, 1, None], "b": [1.0, -1.0, 5.0, 0.0]}
+
+
+# ---------------------------------------------------------------------------------------------- partition / take / concat
+@pytest.mark.parametrize("P", [1, 2, 7, 64, 300])
+def test_partition_by_hash(gpu, P):
+    rng = np.random.default_rng(P)
+    tbl = random_table(rng, 5000, 0.1)
+    c = gpu.col
+    for keys in (["i64"], ["s", "u8"]):
+        got = RB(gpu, tbl).partition_by_hash([c(k) for k in keys], P)
+        want = O.partition_by_hash(tbl, keys, P)
+        assert len(got) == P
+        for g, w in zip(got, want):
+            assert_tables_equal(g.to_arrow_table(), w)  # placement and in-partition order are exact
+
+
+def test_take_and_concat_and_slice(gpu):
+    rng = np.random.default_rng(4)
+    tbl = random_table(rng, 1000, 0.2)
+    idx = rng.integers(0, 1000, 500)
+    got = RB(gpu, tbl).take(pa.array(idx, type=pa.int64())).to_arrow_table()
+    assert_tables_equal(got, tbl.take(pa.array(idx)))
+    got = RB(gpu, tbl).take(pa.array([0, None, 5], type=pa.int32())).to_arrow_table()
+    assert_tables_equal(got, tbl.take(pa.array([0, None, 5])))
+    a, b = tbl.slice(0, 300), tbl.slice(300, 700)
+    got = gpu.RecordBatch.concat([RB(gpu, a), RB(gpu, b), RB(gpu, tbl.slice(0, 0))]).to_arrow_table()
+    assert_tables_equal(got, tbl)
+    got = RB(gpu, tbl).slice(17, 333).to_arrow_table()
+    assert_tables_equal(got, tbl.slice(17, 333 - 17))
+
+
+# ---------------------------------------------------------------------------------------------- join
+def join_tables(rng, nl, nr, key_range, nulls=0.1):
+    def keycol(n):
+        return pa.array(rng.integers(0, key_range, n).astype(np.int64), mask=(rng.random(n) < nulls) if nulls else None)
+    words = ["a", "bb", "ccc", ""]
+    left = pa.table({"k": keycol(nl), "ks": pa.array([words[i] for i in rng.integers(0, 4, nl)], type=pa.large_utf8()),
+                     "lv": pa.array(rng.random(nl)), "li": pa.array(np.arange(nl))})
+    right = pa.table({"k": keycol(nr), "ks": pa.array([words[i] for i in rng.integers(0, 4, nr)], type=pa.large_utf8()),
+                      "rv": pa.array(rng.integers(0, 100, nr).astype(np.int32)), "ri": pa.array(np.arange(nr))})
+    return left, right
+
+
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer", "semi", "anti"])
+@pytest.mark.parametrize("nl,nr,kr", [(0, 10, 5), (10, 0, 5), (1000, 300, 100), (3000, 5000, 20000)])
+def test_hash_join_matches_oracle(gpu, how, nl, nr, kr):
+    rng = np.random.default_rng(nl * 7 + nr)
+    left, right = join_tables(rng, nl, nr, kr)
+    c = gpu.col
+    for on in (["k"], ["k", "ks"]):
+        got = RB(gpu, left).hash_join(RB(gpu, right), [c(k) for k in on], [c(k) for k in on], how=how).to_arrow_table()
+        rsel = right if len(on) == 2 else right.rename_columns(["k", "right.ks", "rv", "ri"])
+        want = O.hash_join(left, rsel, on, on, how)
+        if how in ("semi", "anti"):
+            want = want.select(left.column_names)
+        # row order: probe-row order with matches in build insertion order, unmatched build rows last
+        assert_tables_equal(got, want)
+
+
+def test_join_null_safe_and_float_keys(gpu):
+    left = pa.table({"a": pa.array([1, None, 3], type=pa.int64()), "f": pa.array([0.0, float("nan"), 1.5]), "x": [10, 20, 30]})
+    right = pa.table({"a": pa.array([None, 1, 1], type=pa.int64()), "f": pa.array([-0.0, float("nan"), 1.5]), "y": [1, 2, 3]})
+    c = gpu.col
+    rl, rr = RB(gpu, left), RB(gpu, right)
+    got = rl.hash_join(rr, [c("a")], [c("a")]).to_pydict()
+    assert got["a"] == [1, 1] and got["y"] == [2, 3]
+    got = rl.hash_join(rr, [c("a")], [c("a")], null_equals_null=[True]).to_pydict()
+    assert got["a"] == [1, 1, None] and got["y"] == [2, 3, 1]
+    got = rl.hash_join(rr, [c("f")], [c("f")]).to_pydict()   # NaN never matches; +0.0 vs -0.0 hash differently
+    assert got["x"] == [30] and got["y"] == [3]

