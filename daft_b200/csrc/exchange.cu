@@ -7,6 +7,7 @@
 // reference's partitioning), rows gathered destination-contiguous; the G x G row/byte count matrices are
 // all-gathered first, then every column buffer moves with one grouped ncclSend/ncclRecv.
 // One process per GPU; the communicator is created from an id the host broadcasts out of band.
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -22,16 +23,59 @@ struct b200_comm {
 
 namespace b200 {
 
+// NCCL is bound at first use with dlopen, not at link time: a process that also hosts PyTorch must share
+// PyTorch's libnccl.so.2 (same SONAME, possibly newer than the system copy), and processes that never
+// exchange data should not load NCCL at all.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    const char *(*GetErrorString)(ncclResult_t);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+};
+static NcclApi &nccl() {
+    static NcclApi api = [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // already in the process (e.g. PyTorch's)
+        if (!h) {
+            const char *p = getenv("B200_NCCL_LIB");
+            if (p && *p) h = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+        }
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) fail(std::string("cannot load libnccl.so.2: ") + dlerror());
+        NcclApi a;
+        auto sym = [&](const char *n) {
+            void *f = dlsym(h, n);
+            if (!f) fail(std::string("libnccl.so.2 lacks ") + n);
+            return f;
+        };
+        a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+        a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+        a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+        a.Send = (decltype(a.Send))sym("ncclSend");
+        a.Recv = (decltype(a.Recv))sym("ncclRecv");
+        a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+        return a;
+    }();
+    return api;
+}
+
 #define B200_NCCL(expr)                                                                                  \
     do {                                                                                                 \
         ncclResult_t _r = (expr);                                                                        \
-        if (_r != ncclSuccess) fail(std::string("NCCL error: ") + ncclGetErrorString(_r) + " in " #expr); \
+        if (_r != ncclSuccess) fail(std::string("NCCL error: ") + nccl().GetErrorString(_r) + " in " #expr); \
     } while (0)
 
 void comm_unique_id(uint8_t *out128) {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     ncclUniqueId id;
-    B200_NCCL(ncclGetUniqueId(&id));
+    B200_NCCL(nccl().GetUniqueId(&id));
     memcpy(out128, &id, 128);
 }
 b200_comm *comm_init(const uint8_t *id128, int32_t rank, int32_t world) {
@@ -39,13 +83,13 @@ b200_comm *comm_init(const uint8_t *id128, int32_t rank, int32_t world) {
     auto c = std::make_unique<b200_comm>();
     ncclUniqueId id;
     memcpy(&id, id128, 128);
-    B200_NCCL(ncclCommInitRank(&c->comm, world, id, rank));
+    B200_NCCL(nccl().CommInitRank(&c->comm, world, id, rank));
     c->rank = rank;
     c->world = world;
     return c.release();
 }
 void comm_free(b200_comm *c) {
-    if (c && c->comm) ncclCommDestroy(c->comm);
+    if (c && c->comm) nccl().CommDestroy(c->comm);
     delete c;
 }
 
@@ -83,7 +127,7 @@ static std::vector<int64_t> gather_counts(b200_comm *c, const std::vector<int64_
     const int W = c->world;
     Buf d_in = dev_alloc((size_t)W * 8), d_out = dev_alloc((size_t)W * W * 8);
     B200_CUDA(cudaMemcpyAsync(d_in->ptr, send_cnt.data(), (size_t)W * 8, cudaMemcpyHostToDevice, st));
-    B200_NCCL(ncclAllGather(d_in->ptr, d_out->ptr, (size_t)W, ncclInt64, c->comm, st));
+    B200_NCCL(nccl().AllGather(d_in->ptr, d_out->ptr, (size_t)W, ncclInt64, c->comm, st));
     std::vector<int64_t> m((size_t)W * W);
     B200_CUDA(cudaMemcpyAsync(m.data(), d_out->ptr, (size_t)W * W * 8, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
@@ -106,16 +150,16 @@ static Route make_route(b200_comm *c, const std::vector<int64_t> &send_off, cons
 }
 static void move_buffer(b200_comm *c, const Route &r, const void *send, void *recv, size_t elem_bytes) {
     cudaStream_t st = ctx().stream;
-    B200_NCCL(ncclGroupStart());
+    B200_NCCL(nccl().GroupStart());
     for (int p = 0; p < c->world; p++) {
         if (r.send_cnt[p])
-            B200_NCCL(ncclSend((const uint8_t *)send + (size_t)r.send_off[p] * elem_bytes, (size_t)r.send_cnt[p] * elem_bytes, ncclUint8, p,
+            B200_NCCL(nccl().Send((const uint8_t *)send + (size_t)r.send_off[p] * elem_bytes, (size_t)r.send_cnt[p] * elem_bytes, ncclUint8, p,
                                c->comm, st));
         if (r.recv_cnt[p])
-            B200_NCCL(ncclRecv((uint8_t *)recv + (size_t)r.recv_off[p] * elem_bytes, (size_t)r.recv_cnt[p] * elem_bytes, ncclUint8, p, c->comm,
+            B200_NCCL(nccl().Recv((uint8_t *)recv + (size_t)r.recv_off[p] * elem_bytes, (size_t)r.recv_cnt[p] * elem_bytes, ncclUint8, p, c->comm,
                                st));
     }
-    B200_NCCL(ncclGroupEnd());
+    B200_NCCL(nccl().GroupEnd());
     count_launch();
 }
 

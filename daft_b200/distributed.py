@@ -1,0 +1,97 @@
+"""Multi-GPU host logic: one process per GPU (torch.distributed for rendezvous/plumbing, NCCL for data).
+
+Replaces the Flotilla shapes the hot path needs (src/daft-distributed/src/pipeline_node/aggregate.rs:281-340,
+shuffles/repartition.rs:26-167): scan partitions = contiguous row ranges per rank; low-cardinality
+aggregates exchange only their tiny partial results; high-cardinality group-bys and joins hash-repartition
+their inputs with the NCCL all-to-all in libdaftb200 (b200_exchange_by_hash), whose placement is the
+same hash_rows % world as the reference's partition_by_hash.
+"""
+from __future__ import annotations
+
+import ctypes
+import io
+from typing import Callable, Sequence
+
+import pyarrow as pa
+
+
+def shard_rows(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous scan partition of rank `rank`: sizes differ by at most one row."""
+    base, rem = divmod(n_total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def _to_ipc(tbl: pa.Table) -> bytes:
+    sink = io.BytesIO()
+    with pa.ipc.new_stream(sink, tbl.schema) as w:
+        w.write_table(tbl)
+    return sink.getvalue()
+
+
+def _from_ipc(b: bytes) -> pa.Table:
+    return pa.ipc.open_stream(io.BytesIO(b)).read_all()
+
+
+def gather_tables(tbl: pa.Table, group=None) -> pa.Table:
+    """Every rank receives the concatenation (rank order) of all ranks' small host tables
+    (partial aggregates, top-N candidates).  Works on any torch.distributed backend (nccl or gloo)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return tbl
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, _to_ipc(tbl), group=group)
+    return pa.concat_tables([_from_ipc(p) for p in parts])
+
+
+def two_stage_aggregate(partial: Callable[[], pa.Table], final: Callable[[pa.Table], pa.Table], group=None) -> pa.Table:
+    """partial aggregate per rank -> all-gather of the partials -> identical final merge on every rank
+    (populate_aggregation_stages, src/daft-local-plan/src/agg.rs:13-25)."""
+    return final(gather_tables(partial(), group))
+
+
+class Communicator:
+    """NCCL communicator owned by libdaftb200 (b200_comm): rank 0 creates the unique id, torch.distributed
+    broadcasts it (out-of-band rendezvous only), every rank calls ncclCommInitRank."""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        _lib.ensure_init()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ident = [None]
+        if self.rank == 0:
+            buf = (ctypes.c_uint8 * 128)()
+            _lib.call("b200_comm_unique_id", buf)
+            ident[0] = bytes(buf)
+        dist.broadcast_object_list(ident, src=0, group=group)
+        self._h = ctypes.c_void_p()
+        arr = (ctypes.c_uint8 * 128).from_buffer_copy(ident[0])
+        _lib.call("b200_comm_init", arr, ctypes.c_int32(self.rank), ctypes.c_int32(self.world), ctypes.byref(self._h))
+
+    def __del__(self):
+        try:
+            from . import _lib
+            if self._h and self._h.value:
+                _lib.lib().b200_comm_free(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    def exchange_by_hash(self, batch, exprs: Sequence):
+        """Hash-repartition `batch` across the ranks: this rank receives every row whose
+        hash_rows(exprs) % world == rank, in (source rank, source row) order."""
+        from . import _lib
+        from .recordbatch import RecordBatch, _i32
+        both, idx = batch._resolve_keys(exprs)
+        out = ctypes.c_void_p()
+        _lib.call("b200_exchange_by_hash", self._h, both._h, _i32(idx), ctypes.c_int32(len(idx)), ctypes.byref(out))
+        return RecordBatch._wrap(out).select_columns(list(range(batch.num_columns())))
+
+    def all_gather(self, batch):
+        from . import _lib
+        from .recordbatch import RecordBatch
+        out = ctypes.c_void_p()
+        _lib.call("b200_all_gather", self._h, batch._h, ctypes.byref(out))
+        return RecordBatch._wrap(out)

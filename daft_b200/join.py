@@ -124,7 +124,8 @@ def hash_join(left: RecordBatch, right: RecordBatch, left_on: Sequence[Expressio
         return joined.select_columns(list(range(left.num_columns())))
     if st is not None:
         fin = ctypes.c_void_p()
-        _lib.call("b200_hash_join_finalize", pt._h, st._h, probe.slice(0, 0)._h, ctypes.c_int32(1 if build_on_left else 0), ctypes.byref(fin))
+        probe_like = probe.slice(0, 0)  # keep the handle alive across the call
+        _lib.call("b200_hash_join_finalize", pt._h, st._h, probe_like._h, ctypes.c_int32(1 if build_on_left else 0), ctypes.byref(fin))
         joined = RecordBatch.concat([joined, RecordBatch._wrap(fin)])
     # joined columns: [left_aug..., right_aug...]
     nl, nr = laug.num_columns(), raug.num_columns()

@@ -1,0 +1,80 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, refuses to run without a GPU (no CPU fallback), and the JIT code generator + NVRTC work offline."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from daft_b200 import _lib, datatypes as dt
+from daft_b200.expressions import col, encode_agg, encode_project, lit
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "daft_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    declared = header_symbols()
+    assert len(declared) >= 50
+    for s in declared:
+        assert hasattr(L, s), f"libdaftb200.so does not export {s}"
+    assert sorted(_lib.SYMBOLS) == declared
+    assert L.b200_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.B200Error, match="no CUDA device|CUDA"):
+        _lib.init(0)
+    # every operator refuses as well
+    out = ctypes.c_void_p()
+    with pytest.raises(_lib.B200Error, match="no CPU fallback|CUDA"):
+        _lib.call("b200_tpch_generate", ctypes.c_int32(0), ctypes.c_double(0.001), ctypes.c_int64(0), ctypes.c_int64(-1),
+                  ctypes.c_uint64(1), None, ctypes.c_int32(0), ctypes.byref(out))
+
+
+def test_error_convention_message_and_free():
+    # bad plan bytes -> nonzero status + malloc'd message (daft-ext convention, abi/mod.rs:84-107)
+    err = ctypes.c_void_p()
+    rc = _lib.lib().b200_precompile(ctypes.c_int32(0), b"\xff\xff", ctypes.c_size_t(2), (ctypes.c_int32 * 1)(dt.I64),
+                                    (ctypes.c_uint8 * 1)(0), ctypes.c_int32(1), ctypes.byref(err))
+    assert rc != 0 and err.value
+    assert b"plan" in ctypes.string_at(err.value)
+    _lib.lib().b200_free_string(err)
+
+
+def test_codegen_and_nvrtc_offline(tmp_path):
+    _lib.call("b200_set_jit_cache_dir", str(tmp_path).encode())
+    names, dts = ["a", "b", "s"], [dt.I64, dt.F64, dt.LARGE_UTF8]
+    plan, onames, odt = encode_project([(col("a") + 1).alias("x"), (col("b") * 2.0 > 1).alias("y"), col("s").left(2).alias("z")], names, dts)
+    assert onames == ["x", "y", "z"] and odt == [dt.I64, dt.BOOL, dt.LARGE_UTF8]
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 0, 1), ctypes.c_int32(3))
+    plan = encode_agg([col("b").sum().alias("sb"), col("a").max().alias("ma"), col("a").count().alias("n")], [col("s"), col("a") % 3], names, dts,
+                      [col("b") > lit(0.5)])
+    _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))
+    files = os.listdir(tmp_path)
+    assert any(f.endswith(".cubin") for f in files) and any(f.endswith(".cu") for f in files)
+    src = open(os.path.join(tmp_path, next(f for f in files if f.endswith(".cu")))).read()
+    assert "b200_k" in src and "xxh" in src
+    _lib.call("b200_set_jit_cache_dir", os.path.join(os.path.dirname(_lib.LIB_PATH), "_jitcache").encode())
+
+
+def test_host_generator_is_deterministic_and_shaped():
+    from daft_b200 import tpch
+    a = tpch.generate_host("lineitem", 0.01, tpch.Q1_COLUMNS)
+    b = tpch.generate_host("lineitem", 0.01, tpch.Q1_COLUMNS, 100, 200)
+    assert a.slice(100, 100).equals(b)
+    assert set(a.column("L_RETURNFLAG").to_pylist()) <= {"A", "N", "R"} and set(a.column("L_LINESTATUS").to_pylist()) == {"O", "F"}
+    q = a.column("L_QUANTITY").to_pylist()
+    assert min(q) >= 1 and max(q) <= 50
+    assert tpch.num_rows("lineitem", 10) == 59986052 and tpch.num_rows("lineitem", 100) == 600037902
+    n = tpch.generate_host("nation", 1)
+    assert n.num_rows == 25 and n.column("N_NAME").to_pylist()[8] == "INDIA"
