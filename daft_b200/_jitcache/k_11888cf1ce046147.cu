@@ -321,6 +321,37 @@ __device__ __forceinline__ uint64_t ord_i64(int64_t v) { return (uint64_t)v ^ 0x
 __device__ __forceinline__ uint64_t ord_u64(uint64_t v) { return v; }
 
 // ---- string helpers ---------------------------------------------------------------------------------
+// first min(len, 8) bytes of a string packed little-endian into a register (zero padded): short keys
+// (TPC-H flags, codes) are then hashed and compared without touching memory again
+__device__ __forceinline__ uint64_t str_pack8(Str a) {
+    if (a.len <= 0) return 0ULL;
+    // one or two aligned 8-byte words (never leaves the allocation: the words contain bytes of the string)
+    const uintptr_t addr = (uintptr_t)a.p;
+    const uint64_t *w = (const uint64_t *)(addr & ~(uintptr_t)7);
+    const int sh = (int)(addr & 7) * 8;
+    const int nbits = (a.len < 8 ? (int)a.len : 8) * 8;
+    uint64_t v = w[0] >> sh;
+    if (sh + nbits > 64) v |= w[1] << (64 - sh);
+    if (nbits < 64) v &= (1ULL << nbits) - 1ULL;
+    return v;
+}
+__device__ __forceinline__ uint64_t hash_str_packed(Str a, uint64_t pk, uint64_t seed) {
+    const int64_t len = a.len;
+    if (len <= 8) {
+        if (len == 0) return xxh::hash_empty(seed);
+        if (len <= 3)
+            return xxh::hash_1to3((uint32_t)(pk & 0xff), (uint32_t)((pk >> (8 * (len >> 1))) & 0xff),
+                                  (uint32_t)((pk >> (8 * (len - 1))) & 0xff), (uint32_t)len, seed);
+        return xxh::hash_4to8((uint32_t)pk, (uint32_t)(pk >> (8 * (len - 4))), (uint32_t)len, seed);
+    }
+    return xxh::hash_bytes(a.p, len, seed);
+}
+__device__ __forceinline__ bool str_eq_packed(Str a, uint64_t pa, Str b, uint64_t pb) {
+    if (a.len != b.len || pa != pb) return false;
+    for (int64_t i = 8; i < a.len; i++)
+        if (a.p[i] != b.p[i]) return false;
+    return true;
+}
 __device__ __forceinline__ bool str_eq(Str a, Str b) {
     if (a.len != b.len) return false;
     for (int64_t i = 0; i < a.len; i++)
@@ -441,14 +472,13 @@ __device__ __forceinline__ void project_body(const typename Prog::P &p, int pass
 // fused Filter -> Project -> HashAggregate
 // ======================================================================================================
 // Prog provides (all generated):
-//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_SLOT_HASH, PTR_SLOT_ROW, PTR_MINROW, PTR_NROWS,
-//   PTR_OVERFLOW;  NKEYS, G1, NLANE (lane cells), NWARP (warp count cells), U (rows per lane per step)
+//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_SLOT_HASH, PTR_SLOT_ROW, PTR_OVERFLOW;
+//   NKEYS, G1, NLANE (lane cells incl. row count + first row), NWARP (ballot count cells), U, MINB
 //   struct Raw;  struct Keys;  struct Vals;
 //   load(p,row,Raw&) ; bool eval(p,Raw&,Keys&,Vals&) (false = filtered out) ; eval_keys(p,row,Keys&)
 //   uint64 hash(Keys&) ; bool keys_equal(Keys&,Keys&)
-//   lane_init(cell*) ; lane_update(cell* base, Vals&) ; global_update(p, slot, Vals&)
-//   warp_cells(p, Vals&, bool in_group, unsigned long long* wc)  (ballot-based count cells)
-//   flush(...)  (generated reduction of the lane cells)
+//   lane_init(cell*) ; lane_update(cell*, Vals&, row) ; global_update(p, slot, Vals&, row)
+//   warp_cells(Vals&, in_group, wcell*, lane) ; flush(...)
 constexpr int AGG_WARPS = 8;
 
 template <class Prog>
@@ -487,23 +517,49 @@ __device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, co
     return -1;
 }
 
+// Rare path, kept out of line so that its registers (XXH3, CAS loops) do not burden the streaming loop:
+// find/claim the group's global slot, try to adopt it into the CTA's tier 1, otherwise update it globally.
+// Returns the tier-1 index (>= 0), -2 when the row was accumulated globally, -1 when the table is full.
+template <class Prog>
+__device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const typename Prog::Keys &keys,
+                                                const typename Prog::Vals &vals, int64_t row, unsigned long long fp,
+                                                long long *s_slot, unsigned long long *s_fp, typename Prog::Keys *s_keys) {
+    const long long slot = agg_find_slot<Prog>(p, keys, Prog::hash(keys), row);
+    if (slot < 0) return -1;
+    for (int g = 0; g < Prog::G1; g++) {
+        const long long old = (long long)atomicCAS((unsigned long long *)&s_slot[g], (unsigned long long)-1LL, (unsigned long long)slot);
+        if (old == -1) {  // this lane owns entry g: publish the key values, then the fingerprint
+            s_keys[g] = keys;
+            __threadfence_block();
+            ((volatile unsigned long long *)s_fp)[g] = fp;
+            return g;
+        }
+        if (old == slot) return g;
+    }
+    Prog::global_update(p, slot, vals, row);
+    return -2;
+}
+
 template <class Prog>
 __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: int s_small[G1] | pad | warp cells [W][G1][NWARP+1] u64 | lane cells [W][G1][NLANE][32] u64
-    constexpr int G1 = Prog::G1, NL = Prog::NLANE, NW = Prog::NWARP;
-    long long *s_small = (long long *)smem_raw;                                  // G1 (slot or -1)
-    unsigned long long *s_wcell = (unsigned long long *)(s_small + G1);          // W*G1*(NW+1); [NW] = min row
-    unsigned long long *s_lcell = s_wcell + AGG_WARPS * G1 * (NW + 1);           // W*G1*NL*32
+    constexpr int G1 = Prog::G1, NL = Prog::NLANE, NW = Prog::NWARP, NWS = NW > 0 ? NW : 1;
+    // layout: lane cells [W][G1][NL][32] u64 | warp cells [W][G1][NW] u64 | s_fp[G1] | s_slot[G1] | s_keys[G1]
+    unsigned long long *s_lcell = (unsigned long long *)smem_raw;
+    unsigned long long *s_wcell = s_lcell + (size_t)AGG_WARPS * G1 * NL * 32;
+    unsigned long long *s_fp = s_wcell + AGG_WARPS * G1 * NWS;  // key fingerprint of a published entry, 0 = empty
+    long long *s_slot = (long long *)(s_fp + G1);
+    typename Prog::Keys *s_keys = (typename Prog::Keys *)(s_slot + G1);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < G1) s_small[threadIdx.x] = -1;
-    for (int i = threadIdx.x; i < AGG_WARPS * G1 * (NW + 1); i += blockDim.x)
-        s_wcell[i] = ((i % (NW + 1)) == NW) ? 0xFFFFFFFFFFFFFFFFULL : 0ULL;
+    if (threadIdx.x < G1) {
+        s_slot[threadIdx.x] = Prog::NKEYS == 0 ? 0 : -1;
+        s_fp[threadIdx.x] = Prog::NKEYS == 0 ? 1ULL : 0ULL;
+    }
+    for (int i = threadIdx.x; i < AGG_WARPS * G1 * NWS; i += blockDim.x) s_wcell[i] = 0ULL;
     unsigned long long *my_lcell = s_lcell + (size_t)warp * G1 * NL * 32 + lane;  // cell c of group g: [(g*NL+c)*32]
-    if (NL > 0)
-        for (int g = 0; g < G1; g++) Prog::lane_init(my_lcell + (size_t)g * NL * 32);
-    unsigned long long *my_wcell = s_wcell + (size_t)warp * G1 * (NW + 1);
+    for (int g = 0; g < G1; g++) Prog::lane_init(my_lcell + (size_t)g * NL * 32);
+    unsigned long long *my_wcell = s_wcell + (size_t)warp * G1 * NWS;
     __syncthreads();
 
     const int64_t n = p.ival[Prog::IV_N];
@@ -511,6 +567,11 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     const int64_t chunk = 32 * U;
     const int64_t nchunks = (n + chunk - 1) / chunk;
     const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+    // register copy of the tier-1 fingerprints (entries only ever go from 0 to their final value, so a stale
+    // copy can only miss an entry -> slow path -> refresh)
+    unsigned long long tfp[G1];
+#pragma unroll
+    for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
     for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
         const int64_t base = c * chunk;
         typename Prog::Raw raw[U];
@@ -520,48 +581,43 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
             if (row < n) Prog::load(p, row, raw[u]);
         }
 #pragma unroll
+        for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load2(p, raw[u]);
+        }
+#pragma unroll
         for (int u = 0; u < U; u++) {
             const int64_t row = base + u * 32 + lane;
             typename Prog::Keys keys;
             typename Prog::Vals vals;
             bool live = row < n;
             if (live) live = Prog::eval(p, raw[u], keys, vals);
-            long long slot = -1;
-            if (live) {
-                if (Prog::NKEYS == 0) slot = 0;
-                else slot = agg_find_slot<Prog>(p, keys, Prog::hash(keys), row);
-                if (slot < 0) live = false;
-            }
-            // tier 1 lookup / insert
+            // tier 1: the CTA's first G1 groups, matched by a fingerprint of the key VALUES (registers only),
+            // then verified once against the published key (no xxh3, no global memory on this path)
+            unsigned long long fp = 0ULL;
+            if (live) fp = Prog::NKEYS > 0 ? (Prog::fingerprint(keys) | 1ULL) : 1ULL;
             int lid = -1;
-            if (live) {
 #pragma unroll
-                for (int g = 0; g < G1; g++)
-                    if (((volatile long long *)s_small)[g] == slot) lid = g;
-                if (lid < 0) {
-                    for (int g = 0; g < G1; g++) {
-                        long long old = (long long)atomicCAS((unsigned long long *)&s_small[g], (unsigned long long)-1LL,
-                                                             (unsigned long long)slot);
-                        if (old == -1 || old == slot) { lid = g; break; }
-                    }
-                }
+            for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
+            if (Prog::NKEYS > 0 && live && lid >= 0) {
+                if (!Prog::keys_equal(keys, s_keys[lid])) lid = -1;
             }
-            if (live && lid >= 0) {
-                if (NL > 0) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals);
-            } else if (live) {
-                Prog::global_update(p, slot, vals, row);
-            }
-            // warp-level cells: row counts / valid counts by ballot, first row by ffs
+            if (live && lid < 0) {  // rare: first rows of a CTA, or a group beyond tier 1
+                // copies made HERE so that only this rare branch spills the key/value registers to the stack
+                const typename Prog::Keys kcopy = keys;
+                const typename Prog::Vals vcopy = vals;
+                const long long r = agg_slow_path<Prog>(p, kcopy, vcopy, row, fp, s_slot, s_fp, s_keys);
+                if (r >= 0) lid = (int)r;
+                else live = false;  // accumulated globally (or table overflow)
 #pragma unroll
-            for (int g = 0; g < G1; g++) {
-                const bool in_g = live && lid == g;
-                const unsigned m = __ballot_sync(FULL_MASK, in_g);
-                if (m) {
-                    Prog::warp_cells(vals, in_g, my_wcell + g * (NW + 1), lane);
-                    if (lane == 0) {
-                        unsigned long long first = (unsigned long long)(base + u * 32 + (__ffs(m) - 1));
-                        if (first < my_wcell[g * (NW + 1) + NW]) my_wcell[g * (NW + 1) + NW] = first;
-                    }
+                for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
+            }
+            if (live) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals, row);
+            if (NW > 0) {  // valid / null counts of nullable inputs: one ballot per tier-1 group
+#pragma unroll
+                for (int g = 0; g < G1; g++) {
+                    const bool in_g = live && lid == g;
+                    if (__any_sync(FULL_MASK, in_g)) Prog::warp_cells(vals, in_g, my_wcell + g * NW, lane);
                 }
             }
         }
@@ -569,9 +625,9 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     __syncthreads();
     // flush tier 1: warp w reduces groups w, w+W, ... across all warps' private copies
     for (int g = warp; g < G1; g += AGG_WARPS) {
-        const long long slot = s_small[g];
+        const long long slot = s_slot[g];
         if (slot < 0) continue;
-        Prog::flush(p, slot, s_lcell + (size_t)g * NL * 32, (size_t)G1 * NL * 32, s_wcell + g * (NW + 1), G1 * (NW + 1), lane);
+        Prog::flush(p, slot, s_lcell + (size_t)g * NL * 32, (size_t)G1 * NL * 32, s_wcell + g * NWS, (size_t)G1 * NWS, lane);
     }
 }
 
@@ -583,10 +639,10 @@ using namespace b200::jit;
 struct Prog {
   typedef Params<25, 2> P;
   static constexpr int IV_N = 0, IV_MASK = 1, PTR_SLOT_HASH = 0, PTR_SLOT_ROW = 1, PTR_OVERFLOW = 2;
-  static constexpr int NKEYS = 2, G1 = 3, NLANE = 8, NWARP = 1, U = 4;
+  static constexpr int NKEYS = 2, G1 = 3, NLANE = 10, NWARP = 0, U = 1;
   struct Raw {
-    int64_t o0a, o0b;
-    int64_t o1a, o1b;
+    int64_t o0a, o0b; uint64_t pk0;
+    int64_t o1a, o1b; uint64_t pk1;
     int64_t c2;
     double c3;
     double c4;
@@ -599,7 +655,9 @@ struct Prog {
   };
   struct Keys {
     Str v0; bool k0;
+    uint64_t p0;
     Str v1; bool k1;
+    uint64_t p1;
     int pad_;
   };
   struct Vals {
@@ -615,23 +673,29 @@ struct Prog {
   };
   __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {
     { const int64_t* of_ = (const int64_t*)p.ptr[13]; r.o0a = of_[row]; r.o0b = of_[row + 1]; }
-    { const int64_t* of_ = (const int64_t*)p.ptr[14]; r.o1a = of_[row]; r.o1b = of_[row + 1]; }
-    r.c2 = ((const int64_t*)p.ptr[15])[row];
-    r.c3 = ((const double*)p.ptr[16])[row];
-    r.c4 = ((const double*)p.ptr[17])[row];
-    r.c5 = ((const double*)p.ptr[18])[row];
-    r.c6 = ((const double*)p.ptr[19])[row];
-    r.c7 = ((const uint64_t*)p.ptr[20])[row];
-    r.c8 = ((const uint64_t*)p.ptr[21])[row];
-    r.c9 = ((const uint64_t*)p.ptr[22])[row];
+    { const int64_t* of_ = (const int64_t*)p.ptr[15]; r.o1a = of_[row]; r.o1b = of_[row + 1]; }
+    r.c2 = ((const int64_t*)p.ptr[17])[row];
+    r.c3 = ((const double*)p.ptr[18])[row];
+    r.c4 = ((const double*)p.ptr[19])[row];
+    r.c5 = ((const double*)p.ptr[20])[row];
+    r.c6 = ((const double*)p.ptr[21])[row];
+    r.c7 = ((const uint64_t*)p.ptr[22])[row];
+    r.c8 = ((const uint64_t*)p.ptr[23])[row];
+    r.c9 = ((const uint64_t*)p.ptr[24])[row];
+  }
+  __device__ __forceinline__ static void load2(const P& p, Raw& r) {
+    r.pk0 = str_pack8(Str{(const uint8_t*)p.ptr[14] + r.o0a, r.o0b - r.o0a});
+    r.pk1 = str_pack8(Str{(const uint8_t*)p.ptr[16] + r.o1a, r.o1b - r.o1a});
   }
   __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {
-    const Str v0{(const uint8_t*)p.ptr[23] + r.o0a, r.o0b - r.o0a};
+    const Str v0{(const uint8_t*)p.ptr[14] + r.o0a, r.o0b - r.o0a};
     const bool k0 = true;
     keys.v0 = v0; keys.k0 = k0;
-    const Str v1{(const uint8_t*)p.ptr[24] + r.o1a, r.o1b - r.o1a};
+    keys.p0 = keys.k0 ? r.pk0 : 0ULL;
+    const Str v1{(const uint8_t*)p.ptr[16] + r.o1a, r.o1b - r.o1a};
     const bool k1 = true;
     keys.v1 = v1; keys.k1 = k1;
+    keys.p1 = keys.k1 ? r.pk1 : 0ULL;
     const int64_t v2 = r.c2; const bool k2 = true;
     vals.a0 = (int64_t)v2; vals.k0 = k2;
     const double v3 = r.c3; const bool k3 = true;
@@ -654,21 +718,29 @@ struct Prog {
     const bool rowok = true;
     const bool k0 = rowok;
     Str v0{(const uint8_t*)0, 0};
-    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[13]; const int64_t a_ = of_[row]; v0.p = (const uint8_t*)p.ptr[23] + a_; v0.len = of_[row + 1] - a_; }
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[13]; const int64_t a_ = of_[row]; v0.p = (const uint8_t*)p.ptr[14] + a_; v0.len = of_[row + 1] - a_; }
     keys.v0 = v0; keys.k0 = k0;
+    keys.p0 = keys.k0 ? str_pack8(keys.v0) : 0ULL;
     const bool k1 = rowok;
     Str v1{(const uint8_t*)0, 0};
-    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[14]; const int64_t a_ = of_[row]; v1.p = (const uint8_t*)p.ptr[24] + a_; v1.len = of_[row + 1] - a_; }
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[15]; const int64_t a_ = of_[row]; v1.p = (const uint8_t*)p.ptr[16] + a_; v1.len = of_[row + 1] - a_; }
     keys.v1 = v1; keys.k1 = k1;
+    keys.p1 = keys.k1 ? str_pack8(keys.v1) : 0ULL;
   }
   __device__ __forceinline__ static uint64_t hash(const Keys& k) {
     uint64_t h = 0;
-    h = (k.k0 ? xxh::hash_bytes(k.v0.p, k.v0.len, 0ULL) : xxh::hash_empty(0ULL));
-    h = (k.k1 ? xxh::hash_bytes(k.v1.p, k.v1.len, h) : xxh::hash_empty(h));
+    h = (k.k0 ? hash_str_packed(k.v0, k.p0, 0ULL) : xxh::hash_empty(0ULL));
+    h = (k.k1 ? hash_str_packed(k.v1, k.p1, h) : xxh::hash_empty(h));
     return h;
   }
   __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {
-    return true && (a.k0 == b.k0) && (!a.k0 || str_eq(a.v0, b.v0)) && (a.k1 == b.k1) && (!a.k1 || str_eq(a.v1, b.v1));
+    return true && (a.k0 == b.k0) && (!a.k0 || str_eq_packed(a.v0, a.p0, b.v0, b.p0)) && (a.k1 == b.k1) && (!a.k1 || str_eq_packed(a.v1, a.p1, b.v1, b.p1));
+  }
+  __device__ __forceinline__ static uint64_t fingerprint(const Keys& k) {
+    uint64_t f = 0x9E3779B97F4A7C15ULL;
+    f = (f ^ (k.k0 ? (k.p0 ^ ((uint64_t)k.v0.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    f = (f ^ (k.k1 ? (k.p1 ^ ((uint64_t)k.v1.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    return f;
   }
   __device__ __forceinline__ static void lane_init(unsigned long long* cells) {
     cells[0] = 0ULL;
@@ -679,8 +751,10 @@ struct Prog {
     cells[160] = 0ULL;
     cells[192] = 0ULL;
     cells[224] = 0ULL;
+    cells[256] = 0ULL;
+    cells[288] = 0xFFFFFFFFFFFFFFFFULL;
   }
-  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v) {
+  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v, const int64_t row) {
     if (v.k0) cells[0] += (unsigned long long)v.a0;
     if (v.k1) cells[32] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[32]) + v.a1);
     if (v.k2) cells[64] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[64]) + v.a2);
@@ -689,6 +763,8 @@ struct Prog {
     if (v.k5) cells[160] += (unsigned long long)v.a5;
     if (v.k6) cells[192] += (unsigned long long)v.a6;
     if (v.k7) cells[224] += (unsigned long long)v.a7;
+    cells[256] += 1ULL;
+    if ((unsigned long long)row < cells[288]) cells[288] = (unsigned long long)row;
   }
   __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {
     if (v.k0) atomicAdd(((unsigned long long*)p.ptr[3]) + slot, (unsigned long long)v.a0);
@@ -703,7 +779,6 @@ struct Prog {
     atomicMin(((unsigned long long*)p.ptr[12]) + slot, (unsigned long long)row);
   }
   __device__ __forceinline__ static void warp_cells(const Vals& v, const bool in_g, unsigned long long* wcell, const int lane) {
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g); if (lane == 0) wcell[0] += __popc(m_); }
   }
   __device__ __forceinline__ static void flush(const P& p, const long long slot, const unsigned long long* lcell, const size_t lstride,
                                                const unsigned long long* wcell, const size_t wstride, const int lane) {
@@ -747,12 +822,12 @@ struct Prog {
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
       if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[10]) + slot, a_);
     }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 0] : 0ULL;
+    { unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 256 + lane];
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
       if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[11]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 1] : 0xFFFFFFFFFFFFFFFFULL;
+    { unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 288 + lane]; a_ = t_ < a_ ? t_ : a_; }
       for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }
       if (lane == 0) atomicMin(((unsigned long long*)p.ptr[12]) + slot, a_); }
   }
 };
-extern "C" __global__ void __launch_bounds__(256) b200_k(const Prog::P p) { agg_body<Prog>(p); }
+extern "C" __global__ void __launch_bounds__(256, 3) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }

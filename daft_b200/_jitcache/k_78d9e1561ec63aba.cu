@@ -321,6 +321,37 @@ __device__ __forceinline__ uint64_t ord_i64(int64_t v) { return (uint64_t)v ^ 0x
 __device__ __forceinline__ uint64_t ord_u64(uint64_t v) { return v; }
 
 // ---- string helpers ---------------------------------------------------------------------------------
+// first min(len, 8) bytes of a string packed little-endian into a register (zero padded): short keys
+// (TPC-H flags, codes) are then hashed and compared without touching memory again
+__device__ __forceinline__ uint64_t str_pack8(Str a) {
+    if (a.len <= 0) return 0ULL;
+    // one or two aligned 8-byte words (never leaves the allocation: the words contain bytes of the string)
+    const uintptr_t addr = (uintptr_t)a.p;
+    const uint64_t *w = (const uint64_t *)(addr & ~(uintptr_t)7);
+    const int sh = (int)(addr & 7) * 8;
+    const int nbits = (a.len < 8 ? (int)a.len : 8) * 8;
+    uint64_t v = w[0] >> sh;
+    if (sh + nbits > 64) v |= w[1] << (64 - sh);
+    if (nbits < 64) v &= (1ULL << nbits) - 1ULL;
+    return v;
+}
+__device__ __forceinline__ uint64_t hash_str_packed(Str a, uint64_t pk, uint64_t seed) {
+    const int64_t len = a.len;
+    if (len <= 8) {
+        if (len == 0) return xxh::hash_empty(seed);
+        if (len <= 3)
+            return xxh::hash_1to3((uint32_t)(pk & 0xff), (uint32_t)((pk >> (8 * (len >> 1))) & 0xff),
+                                  (uint32_t)((pk >> (8 * (len - 1))) & 0xff), (uint32_t)len, seed);
+        return xxh::hash_4to8((uint32_t)pk, (uint32_t)(pk >> (8 * (len - 4))), (uint32_t)len, seed);
+    }
+    return xxh::hash_bytes(a.p, len, seed);
+}
+__device__ __forceinline__ bool str_eq_packed(Str a, uint64_t pa, Str b, uint64_t pb) {
+    if (a.len != b.len || pa != pb) return false;
+    for (int64_t i = 8; i < a.len; i++)
+        if (a.p[i] != b.p[i]) return false;
+    return true;
+}
 __device__ __forceinline__ bool str_eq(Str a, Str b) {
     if (a.len != b.len) return false;
     for (int64_t i = 0; i < a.len; i++)
@@ -441,14 +472,13 @@ __device__ __forceinline__ void project_body(const typename Prog::P &p, int pass
 // fused Filter -> Project -> HashAggregate
 // ======================================================================================================
 // Prog provides (all generated):
-//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_SLOT_HASH, PTR_SLOT_ROW, PTR_MINROW, PTR_NROWS,
-//   PTR_OVERFLOW;  NKEYS, G1, NLANE (lane cells), NWARP (warp count cells), U (rows per lane per step)
+//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_SLOT_HASH, PTR_SLOT_ROW, PTR_OVERFLOW;
+//   NKEYS, G1, NLANE (lane cells incl. row count + first row), NWARP (ballot count cells), U, MINB
 //   struct Raw;  struct Keys;  struct Vals;
 //   load(p,row,Raw&) ; bool eval(p,Raw&,Keys&,Vals&) (false = filtered out) ; eval_keys(p,row,Keys&)
 //   uint64 hash(Keys&) ; bool keys_equal(Keys&,Keys&)
-//   lane_init(cell*) ; lane_update(cell* base, Vals&) ; global_update(p, slot, Vals&)
-//   warp_cells(p, Vals&, bool in_group, unsigned long long* wc)  (ballot-based count cells)
-//   flush(...)  (generated reduction of the lane cells)
+//   lane_init(cell*) ; lane_update(cell*, Vals&, row) ; global_update(p, slot, Vals&, row)
+//   warp_cells(Vals&, in_group, wcell*, lane) ; flush(...)
 constexpr int AGG_WARPS = 8;
 
 template <class Prog>
@@ -487,23 +517,49 @@ __device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, co
     return -1;
 }
 
+// Rare path, kept out of line so that its registers (XXH3, CAS loops) do not burden the streaming loop:
+// find/claim the group's global slot, try to adopt it into the CTA's tier 1, otherwise update it globally.
+// Returns the tier-1 index (>= 0), -2 when the row was accumulated globally, -1 when the table is full.
+template <class Prog>
+__device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const typename Prog::Keys &keys,
+                                                const typename Prog::Vals &vals, int64_t row, unsigned long long fp,
+                                                long long *s_slot, unsigned long long *s_fp, typename Prog::Keys *s_keys) {
+    const long long slot = agg_find_slot<Prog>(p, keys, Prog::hash(keys), row);
+    if (slot < 0) return -1;
+    for (int g = 0; g < Prog::G1; g++) {
+        const long long old = (long long)atomicCAS((unsigned long long *)&s_slot[g], (unsigned long long)-1LL, (unsigned long long)slot);
+        if (old == -1) {  // this lane owns entry g: publish the key values, then the fingerprint
+            s_keys[g] = keys;
+            __threadfence_block();
+            ((volatile unsigned long long *)s_fp)[g] = fp;
+            return g;
+        }
+        if (old == slot) return g;
+    }
+    Prog::global_update(p, slot, vals, row);
+    return -2;
+}
+
 template <class Prog>
 __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: int s_small[G1] | pad | warp cells [W][G1][NWARP+1] u64 | lane cells [W][G1][NLANE][32] u64
-    constexpr int G1 = Prog::G1, NL = Prog::NLANE, NW = Prog::NWARP;
-    long long *s_small = (long long *)smem_raw;                                  // G1 (slot or -1)
-    unsigned long long *s_wcell = (unsigned long long *)(s_small + G1);          // W*G1*(NW+1); [NW] = min row
-    unsigned long long *s_lcell = s_wcell + AGG_WARPS * G1 * (NW + 1);           // W*G1*NL*32
+    constexpr int G1 = Prog::G1, NL = Prog::NLANE, NW = Prog::NWARP, NWS = NW > 0 ? NW : 1;
+    // layout: lane cells [W][G1][NL][32] u64 | warp cells [W][G1][NW] u64 | s_fp[G1] | s_slot[G1] | s_keys[G1]
+    unsigned long long *s_lcell = (unsigned long long *)smem_raw;
+    unsigned long long *s_wcell = s_lcell + (size_t)AGG_WARPS * G1 * NL * 32;
+    unsigned long long *s_fp = s_wcell + AGG_WARPS * G1 * NWS;  // key fingerprint of a published entry, 0 = empty
+    long long *s_slot = (long long *)(s_fp + G1);
+    typename Prog::Keys *s_keys = (typename Prog::Keys *)(s_slot + G1);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < G1) s_small[threadIdx.x] = -1;
-    for (int i = threadIdx.x; i < AGG_WARPS * G1 * (NW + 1); i += blockDim.x)
-        s_wcell[i] = ((i % (NW + 1)) == NW) ? 0xFFFFFFFFFFFFFFFFULL : 0ULL;
+    if (threadIdx.x < G1) {
+        s_slot[threadIdx.x] = Prog::NKEYS == 0 ? 0 : -1;
+        s_fp[threadIdx.x] = Prog::NKEYS == 0 ? 1ULL : 0ULL;
+    }
+    for (int i = threadIdx.x; i < AGG_WARPS * G1 * NWS; i += blockDim.x) s_wcell[i] = 0ULL;
     unsigned long long *my_lcell = s_lcell + (size_t)warp * G1 * NL * 32 + lane;  // cell c of group g: [(g*NL+c)*32]
-    if (NL > 0)
-        for (int g = 0; g < G1; g++) Prog::lane_init(my_lcell + (size_t)g * NL * 32);
-    unsigned long long *my_wcell = s_wcell + (size_t)warp * G1 * (NW + 1);
+    for (int g = 0; g < G1; g++) Prog::lane_init(my_lcell + (size_t)g * NL * 32);
+    unsigned long long *my_wcell = s_wcell + (size_t)warp * G1 * NWS;
     __syncthreads();
 
     const int64_t n = p.ival[Prog::IV_N];
@@ -511,6 +567,11 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     const int64_t chunk = 32 * U;
     const int64_t nchunks = (n + chunk - 1) / chunk;
     const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+    // register copy of the tier-1 fingerprints (entries only ever go from 0 to their final value, so a stale
+    // copy can only miss an entry -> slow path -> refresh)
+    unsigned long long tfp[G1];
+#pragma unroll
+    for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
     for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
         const int64_t base = c * chunk;
         typename Prog::Raw raw[U];
@@ -520,48 +581,43 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
             if (row < n) Prog::load(p, row, raw[u]);
         }
 #pragma unroll
+        for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load2(p, raw[u]);
+        }
+#pragma unroll
         for (int u = 0; u < U; u++) {
             const int64_t row = base + u * 32 + lane;
             typename Prog::Keys keys;
             typename Prog::Vals vals;
             bool live = row < n;
             if (live) live = Prog::eval(p, raw[u], keys, vals);
-            long long slot = -1;
-            if (live) {
-                if (Prog::NKEYS == 0) slot = 0;
-                else slot = agg_find_slot<Prog>(p, keys, Prog::hash(keys), row);
-                if (slot < 0) live = false;
-            }
-            // tier 1 lookup / insert
+            // tier 1: the CTA's first G1 groups, matched by a fingerprint of the key VALUES (registers only),
+            // then verified once against the published key (no xxh3, no global memory on this path)
+            unsigned long long fp = 0ULL;
+            if (live) fp = Prog::NKEYS > 0 ? (Prog::fingerprint(keys) | 1ULL) : 1ULL;
             int lid = -1;
-            if (live) {
 #pragma unroll
-                for (int g = 0; g < G1; g++)
-                    if (((volatile long long *)s_small)[g] == slot) lid = g;
-                if (lid < 0) {
-                    for (int g = 0; g < G1; g++) {
-                        long long old = (long long)atomicCAS((unsigned long long *)&s_small[g], (unsigned long long)-1LL,
-                                                             (unsigned long long)slot);
-                        if (old == -1 || old == slot) { lid = g; break; }
-                    }
-                }
+            for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
+            if (Prog::NKEYS > 0 && live && lid >= 0) {
+                if (!Prog::keys_equal(keys, s_keys[lid])) lid = -1;
             }
-            if (live && lid >= 0) {
-                if (NL > 0) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals);
-            } else if (live) {
-                Prog::global_update(p, slot, vals, row);
-            }
-            // warp-level cells: row counts / valid counts by ballot, first row by ffs
+            if (live && lid < 0) {  // rare: first rows of a CTA, or a group beyond tier 1
+                // copies made HERE so that only this rare branch spills the key/value registers to the stack
+                const typename Prog::Keys kcopy = keys;
+                const typename Prog::Vals vcopy = vals;
+                const long long r = agg_slow_path<Prog>(p, kcopy, vcopy, row, fp, s_slot, s_fp, s_keys);
+                if (r >= 0) lid = (int)r;
+                else live = false;  // accumulated globally (or table overflow)
 #pragma unroll
-            for (int g = 0; g < G1; g++) {
-                const bool in_g = live && lid == g;
-                const unsigned m = __ballot_sync(FULL_MASK, in_g);
-                if (m) {
-                    Prog::warp_cells(vals, in_g, my_wcell + g * (NW + 1), lane);
-                    if (lane == 0) {
-                        unsigned long long first = (unsigned long long)(base + u * 32 + (__ffs(m) - 1));
-                        if (first < my_wcell[g * (NW + 1) + NW]) my_wcell[g * (NW + 1) + NW] = first;
-                    }
+                for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
+            }
+            if (live) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals, row);
+            if (NW > 0) {  // valid / null counts of nullable inputs: one ballot per tier-1 group
+#pragma unroll
+                for (int g = 0; g < G1; g++) {
+                    const bool in_g = live && lid == g;
+                    if (__any_sync(FULL_MASK, in_g)) Prog::warp_cells(vals, in_g, my_wcell + g * NW, lane);
                 }
             }
         }
@@ -569,9 +625,9 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     __syncthreads();
     // flush tier 1: warp w reduces groups w, w+W, ... across all warps' private copies
     for (int g = warp; g < G1; g += AGG_WARPS) {
-        const long long slot = s_small[g];
+        const long long slot = s_slot[g];
         if (slot < 0) continue;
-        Prog::flush(p, slot, s_lcell + (size_t)g * NL * 32, (size_t)G1 * NL * 32, s_wcell + g * (NW + 1), G1 * (NW + 1), lane);
+        Prog::flush(p, slot, s_lcell + (size_t)g * NL * 32, (size_t)G1 * NL * 32, s_wcell + g * NWS, (size_t)G1 * NWS, lane);
     }
 }
 
@@ -581,187 +637,137 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
 using namespace b200;
 using namespace b200::jit;
 struct Prog {
-  typedef Params<49, 2> P;
+  typedef Params<19, 2> P;
   static constexpr int IV_N = 0, IV_MASK = 1, PTR_SLOT_HASH = 0, PTR_SLOT_ROW = 1, PTR_OVERFLOW = 2;
-  static constexpr int NKEYS = 1, G1 = 2, NLANE = 12, NWARP = 13, U = 4;
+  static constexpr int NKEYS = 2, G1 = 4, NLANE = 7, NWARP = 0, U = 1;
   struct Raw {
-    bool k13;
-    int64_t c13;
-    bool k2;
-    int32_t c2;
-    bool k5;
-    uint16_t c5;
-    bool k9;
-    double c9;
-    bool k8;
-    float c8;
-    bool k0;
-    int8_t c0;
-    bool k3;
-    int64_t c3;
-    bool k7;
-    uint64_t c7;
-    bool k11;
-    int32_t c11;
-    bool k1;
-    int16_t c1;
+    int32_t c6;
+    int64_t o4a, o4b; uint64_t pk4;
+    int64_t o5a, o5b; uint64_t pk5;
+    int64_t c0;
+    double c1;
+    double c2;
+    double c3;
     int pad_;
   };
   struct Keys {
-    int64_t v0; bool k0;
+    Str v0; bool k0;
+    uint64_t p0;
+    Str v1; bool k1;
+    uint64_t p1;
     int pad_;
   };
   struct Vals {
     int64_t a0; bool k0;
-    uint64_t a1; bool k1;
+    double a1; bool k1;
     double a2; bool k2;
-    float a3; bool k3;
-    int8_t a4; bool k4;
-    int64_t a5; bool k5;
-    uint64_t a6; bool k6;
-    int32_t a7; bool k7;
-    int32_t a8; bool k8;
-    int64_t a9; bool k9;
-    double a10; bool k10;
+    double a3; bool k3;
+    double a4; bool k4;
     int pad_;
   };
   __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {
-    r.k13 = bit_at((const uint8_t*)p.ptr[29], row);
-    r.c13 = ((const int64_t*)p.ptr[30])[row];
-    r.k2 = bit_at((const uint8_t*)p.ptr[31], row);
-    r.c2 = ((const int32_t*)p.ptr[32])[row];
-    r.k5 = bit_at((const uint8_t*)p.ptr[33], row);
-    r.c5 = ((const uint16_t*)p.ptr[34])[row];
-    r.k9 = bit_at((const uint8_t*)p.ptr[35], row);
-    r.c9 = ((const double*)p.ptr[36])[row];
-    r.k8 = bit_at((const uint8_t*)p.ptr[37], row);
-    r.c8 = ((const float*)p.ptr[38])[row];
-    r.k0 = bit_at((const uint8_t*)p.ptr[39], row);
-    r.c0 = ((const int8_t*)p.ptr[40])[row];
-    r.k3 = bit_at((const uint8_t*)p.ptr[41], row);
-    r.c3 = ((const int64_t*)p.ptr[42])[row];
-    r.k7 = bit_at((const uint8_t*)p.ptr[43], row);
-    r.c7 = ((const uint64_t*)p.ptr[44])[row];
-    r.k11 = bit_at((const uint8_t*)p.ptr[45], row);
-    r.c11 = ((const int32_t*)p.ptr[46])[row];
-    r.k1 = bit_at((const uint8_t*)p.ptr[47], row);
-    r.c1 = ((const int16_t*)p.ptr[48])[row];
+    r.c6 = ((const int32_t*)p.ptr[10])[row];
+    { const int64_t* of_ = (const int64_t*)p.ptr[11]; r.o4a = of_[row]; r.o4b = of_[row + 1]; }
+    { const int64_t* of_ = (const int64_t*)p.ptr[13]; r.o5a = of_[row]; r.o5b = of_[row + 1]; }
+    r.c0 = ((const int64_t*)p.ptr[15])[row];
+    r.c1 = ((const double*)p.ptr[16])[row];
+    r.c2 = ((const double*)p.ptr[17])[row];
+    r.c3 = ((const double*)p.ptr[18])[row];
+  }
+  __device__ __forceinline__ static void load2(const P& p, Raw& r) {
+    r.pk4 = str_pack8(Str{(const uint8_t*)p.ptr[12] + r.o4a, r.o4b - r.o4a});
+    r.pk5 = str_pack8(Str{(const uint8_t*)p.ptr[14] + r.o5a, r.o5b - r.o5a});
   }
   __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {
-    const int64_t v0 = r.c13; const bool k0 = r.k13;
-    keys.v0 = v0; keys.k0 = k0;
-    const int32_t v1 = r.c2; const bool k1 = r.k2;
-    vals.a0 = (int64_t)v1; vals.k0 = k1;
-    const uint16_t v2 = r.c5; const bool k2 = r.k5;
-    vals.a1 = (uint64_t)v2; vals.k1 = k2;
-    const double v3 = r.c9; const bool k3 = r.k9;
-    vals.a2 = (double)v3; vals.k2 = k3;
-    const float v4 = r.c8; const bool k4 = r.k8;
-    vals.a3 = (float)v4; vals.k3 = k4;
-    const int8_t v5 = r.c0; const bool k5 = r.k0;
-    vals.a4 = (int8_t)v5; vals.k4 = k5;
-    const int64_t v6 = r.c3; const bool k6 = r.k3;
-    vals.a5 = (int64_t)v6; vals.k5 = k6;
-    const uint64_t v7 = r.c7; const bool k7 = r.k7;
-    vals.a6 = (uint64_t)v7; vals.k6 = k7;
-    const int32_t v10 = r.c11; const bool k10 = r.k11;
-    vals.a7 = (int32_t)v10; vals.k7 = k10;
-    vals.a8 = (int32_t)v1; vals.k8 = k1;
-    const int16_t v15 = r.c1; const bool k15 = r.k1;
-    vals.a9 = (int64_t)v15; vals.k9 = k15;
-    const double v17 = __longlong_as_double(4607182418800017408LL); const bool k17 = true;
-    const double v19 = (double)v4; const bool k19 = k4;
-    const double v20 = v17 - v19;
-    const bool k20 = k17 && k19;
-    const double v21 = v3 * v20;
-    const bool k21 = k3 && k20;
-    vals.a10 = (double)v21; vals.k10 = k21;
+    const int32_t v0 = r.c6; const bool k0 = true;
+    const int32_t v1 = (int32_t)(10471LL); const bool k1 = true;
+    const bool v2 = v0 <= v1;
+    const bool k2 = k0 && k1;
+    if (!(k2 && v2)) return false;
+    const Str v3{(const uint8_t*)p.ptr[12] + r.o4a, r.o4b - r.o4a};
+    const bool k3 = true;
+    keys.v0 = v3; keys.k0 = k3;
+    keys.p0 = keys.k0 ? r.pk4 : 0ULL;
+    const Str v4{(const uint8_t*)p.ptr[14] + r.o5a, r.o5b - r.o5a};
+    const bool k4 = true;
+    keys.v1 = v4; keys.k1 = k4;
+    keys.p1 = keys.k1 ? r.pk5 : 0ULL;
+    const int64_t v5 = r.c0; const bool k5 = true;
+    vals.a0 = (int64_t)v5; vals.k0 = k5;
+    const double v6 = r.c1; const bool k6 = true;
+    vals.a1 = (double)v6; vals.k1 = k6;
+    const double v8 = __longlong_as_double(4607182418800017408LL); const bool k8 = true;
+    const double v9 = r.c2; const bool k9 = true;
+    const double v10 = v8 - v9;
+    const bool k10 = k8 && k9;
+    const double v11 = v6 * v10;
+    const bool k11 = k6 && k10;
+    vals.a2 = (double)v11; vals.k2 = k11;
+    const double v18 = r.c3; const bool k18 = true;
+    const double v19 = v8 + v18;
+    const bool k19 = k8 && k18;
+    const double v20 = v11 * v19;
+    const bool k20 = k11 && k19;
+    vals.a3 = (double)v20; vals.k3 = k20;
+    vals.a4 = (double)v9; vals.k4 = k9;
     return true;
   }
   __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {
     const bool rowok = true;
-    const bool k0 = rowok && bit_at((const uint8_t*)p.ptr[29], row);
-    const int64_t v0 = rowok ? ((const int64_t*)p.ptr[30])[row] : (int64_t)0;
-    keys.v0 = v0; keys.k0 = k0;
+    const bool k3 = rowok;
+    Str v3{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[11]; const int64_t a_ = of_[row]; v3.p = (const uint8_t*)p.ptr[12] + a_; v3.len = of_[row + 1] - a_; }
+    keys.v0 = v3; keys.k0 = k3;
+    keys.p0 = keys.k0 ? str_pack8(keys.v0) : 0ULL;
+    const bool k4 = rowok;
+    Str v4{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[13]; const int64_t a_ = of_[row]; v4.p = (const uint8_t*)p.ptr[14] + a_; v4.len = of_[row + 1] - a_; }
+    keys.v1 = v4; keys.k1 = k4;
+    keys.p1 = keys.k1 ? str_pack8(keys.v1) : 0ULL;
   }
   __device__ __forceinline__ static uint64_t hash(const Keys& k) {
     uint64_t h = 0;
-    h = (k.k0 ? xxh::hash_u64((uint64_t)k.v0, 0ULL) : 0x2D06800538D394C2ULL);
+    h = (k.k0 ? hash_str_packed(k.v0, k.p0, 0ULL) : xxh::hash_empty(0ULL));
+    h = (k.k1 ? hash_str_packed(k.v1, k.p1, h) : xxh::hash_empty(h));
     return h;
   }
   __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {
-    return true && (a.k0 == b.k0) && (!a.k0 || (a.v0 == b.v0));
+    return true && (a.k0 == b.k0) && (!a.k0 || str_eq_packed(a.v0, a.p0, b.v0, b.p0)) && (a.k1 == b.k1) && (!a.k1 || str_eq_packed(a.v1, a.p1, b.v1, b.p1));
+  }
+  __device__ __forceinline__ static uint64_t fingerprint(const Keys& k) {
+    uint64_t f = 0x9E3779B97F4A7C15ULL;
+    f = (f ^ (k.k0 ? (k.p0 ^ ((uint64_t)k.v0.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    f = (f ^ (k.k1 ? (k.p1 ^ ((uint64_t)k.v1.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    return f;
   }
   __device__ __forceinline__ static void lane_init(unsigned long long* cells) {
     cells[0] = 0ULL;
     cells[32] = 0ULL;
     cells[64] = 0ULL;
     cells[96] = 0ULL;
-    cells[128] = 0xFFFFFFFFFFFFFFFFULL;
+    cells[128] = 0ULL;
     cells[160] = 0ULL;
     cells[192] = 0xFFFFFFFFFFFFFFFFULL;
-    cells[224] = 0xFFFFFFFFFFFFFFFFULL;
-    cells[256] = 0ULL;
-    cells[288] = 0ULL;
-    cells[320] = 0ULL;
-    cells[352] = 0ULL;
   }
-  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v) {
+  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v, const int64_t row) {
     if (v.k0) cells[0] += (unsigned long long)v.a0;
-    if (v.k1) cells[32] += (unsigned long long)v.a1;
+    if (v.k1) cells[32] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[32]) + v.a1);
     if (v.k2) cells[64] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[64]) + v.a2);
-    if (v.k3) cells[96] = (unsigned long long)(unsigned)__float_as_int(__int_as_float((int)cells[96]) + v.a3);
-    if (v.k4) { const unsigned long long o_ = ord_i64((int64_t)v.a4); if (o_ < cells[128]) cells[128] = o_; }
-    if (v.k5) { const unsigned long long o_ = ord_i64((int64_t)v.a5); if (o_ > cells[160]) cells[160] = o_; }
-    if (v.k6) { const unsigned long long o_ = ord_u64((uint64_t)v.a6); if (o_ < cells[192]) cells[192] = o_; }
-    if (v.k2) { const unsigned long long o_ = ord_f64(v.a2); if (o_ < cells[224]) cells[224] = o_; }
-    if (v.k2) { const unsigned long long o_ = ord_f64(v.a2); if (o_ > cells[256]) cells[256] = o_; }
-    if (v.k7) { const unsigned long long o_ = ord_i64((int64_t)v.a7); if (o_ > cells[288]) cells[288] = o_; }
-    if (v.k9) cells[320] += (unsigned long long)v.a9;
-    if (v.k10) cells[352] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[352]) + v.a10);
+    if (v.k3) cells[96] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[96]) + v.a3);
+    if (v.k4) cells[128] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[128]) + v.a4);
+    cells[160] += 1ULL;
+    if ((unsigned long long)row < cells[192]) cells[192] = (unsigned long long)row;
   }
   __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {
     if (v.k0) atomicAdd(((unsigned long long*)p.ptr[3]) + slot, (unsigned long long)v.a0);
-    if (v.k1) atomicAdd(((unsigned long long*)p.ptr[4]) + slot, (unsigned long long)v.a1);
+    if (v.k1) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), v.a1);
     if (v.k2) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), v.a2);
-    if (v.k3) atomicAdd((float*)(((unsigned long long*)p.ptr[6]) + slot), v.a3);
-    if (v.k4) atomicMin(((unsigned long long*)p.ptr[7]) + slot, (unsigned long long)ord_i64((int64_t)v.a4));
-    if (v.k5) atomicMax(((unsigned long long*)p.ptr[8]) + slot, (unsigned long long)ord_i64((int64_t)v.a5));
-    if (v.k6) atomicMin(((unsigned long long*)p.ptr[9]) + slot, (unsigned long long)ord_u64((uint64_t)v.a6));
-    if (v.k2) atomicMin(((unsigned long long*)p.ptr[10]) + slot, (unsigned long long)ord_f64(v.a2));
-    if (v.k2) atomicMax(((unsigned long long*)p.ptr[11]) + slot, (unsigned long long)ord_f64(v.a2));
-    if (v.k7) atomicMax(((unsigned long long*)p.ptr[12]) + slot, (unsigned long long)ord_i64((int64_t)v.a7));
-    if (v.k9) atomicAdd(((unsigned long long*)p.ptr[13]) + slot, (unsigned long long)v.a9);
-    if (v.k10) atomicAdd((double*)(((unsigned long long*)p.ptr[14]) + slot), v.a10);
-    if (v.k0) atomicAdd(((unsigned long long*)p.ptr[15]) + slot, 1ULL);
-    if (v.k1) atomicAdd(((unsigned long long*)p.ptr[16]) + slot, 1ULL);
-    if (v.k2) atomicAdd(((unsigned long long*)p.ptr[17]) + slot, 1ULL);
-    if (v.k3) atomicAdd(((unsigned long long*)p.ptr[18]) + slot, 1ULL);
-    if (v.k4) atomicAdd(((unsigned long long*)p.ptr[19]) + slot, 1ULL);
-    if (v.k5) atomicAdd(((unsigned long long*)p.ptr[20]) + slot, 1ULL);
-    if (v.k6) atomicAdd(((unsigned long long*)p.ptr[21]) + slot, 1ULL);
-    if (v.k7) atomicAdd(((unsigned long long*)p.ptr[22]) + slot, 1ULL);
-    if (v.k8) atomicAdd(((unsigned long long*)p.ptr[23]) + slot, 1ULL);
-    if (!v.k8) atomicAdd(((unsigned long long*)p.ptr[24]) + slot, 1ULL);
-    if (v.k9) atomicAdd(((unsigned long long*)p.ptr[25]) + slot, 1ULL);
-    if (v.k10) atomicAdd(((unsigned long long*)p.ptr[26]) + slot, 1ULL);
-    atomicAdd(((unsigned long long*)p.ptr[27]) + slot, 1ULL);
-    atomicMin(((unsigned long long*)p.ptr[28]) + slot, (unsigned long long)row);
+    if (v.k3) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), v.a3);
+    if (v.k4) atomicAdd((double*)(((unsigned long long*)p.ptr[7]) + slot), v.a4);
+    atomicAdd(((unsigned long long*)p.ptr[8]) + slot, 1ULL);
+    atomicMin(((unsigned long long*)p.ptr[9]) + slot, (unsigned long long)row);
   }
   __device__ __forceinline__ static void warp_cells(const Vals& v, const bool in_g, unsigned long long* wcell, const int lane) {
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k0); if (lane == 0) wcell[0] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k1); if (lane == 0) wcell[1] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k2); if (lane == 0) wcell[2] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k3); if (lane == 0) wcell[3] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k4); if (lane == 0) wcell[4] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k5); if (lane == 0) wcell[5] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k6); if (lane == 0) wcell[6] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k7); if (lane == 0) wcell[7] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k8); if (lane == 0) wcell[8] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && !v.k8); if (lane == 0) wcell[9] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k9); if (lane == 0) wcell[10] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && v.k10); if (lane == 0) wcell[11] += __popc(m_); }
-    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g); if (lane == 0) wcell[12] += __popc(m_); }
   }
   __device__ __forceinline__ static void flush(const P& p, const long long slot, const unsigned long long* lcell, const size_t lstride,
                                                const unsigned long long* wcell, const size_t wstride, const int lane) {
@@ -771,9 +777,9 @@ struct Prog {
       if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[3]) + slot, a_);
     }
     {
-      unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 32 + lane];
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 32 + lane]);
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[4]) + slot, a_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), a_);
     }
     {
       double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 64 + lane]);
@@ -781,92 +787,21 @@ struct Prog {
       if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), a_);
     }
     {
-      float a_ = 0.f; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __int_as_float((int)lcell[(size_t)w_ * lstride + 96 + lane]);
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 96 + lane]);
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0) atomicAdd((float*)(((unsigned long long*)p.ptr[6]) + slot), a_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), a_);
     }
     {
-      unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 128 + lane]; a_ = t_ < a_ ? t_ : a_; }
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 128 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[7]) + slot), a_);
+    }
+    { unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 160 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[8]) + slot, a_); }
+    { unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 192 + lane]; a_ = t_ < a_ ? t_ : a_; }
       for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }
-      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[7]) + slot, a_);
-    }
-    {
-      unsigned long long a_ = 0ULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 160 + lane]; a_ = t_ > a_ ? t_ : a_; }
-      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ > a_ ? t_ : a_; }
-      if (lane == 0) atomicMax(((unsigned long long*)p.ptr[8]) + slot, a_);
-    }
-    {
-      unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 192 + lane]; a_ = t_ < a_ ? t_ : a_; }
-      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }
-      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[9]) + slot, a_);
-    }
-    {
-      unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 224 + lane]; a_ = t_ < a_ ? t_ : a_; }
-      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }
-      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[10]) + slot, a_);
-    }
-    {
-      unsigned long long a_ = 0ULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 256 + lane]; a_ = t_ > a_ ? t_ : a_; }
-      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ > a_ ? t_ : a_; }
-      if (lane == 0) atomicMax(((unsigned long long*)p.ptr[11]) + slot, a_);
-    }
-    {
-      unsigned long long a_ = 0ULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 288 + lane]; a_ = t_ > a_ ? t_ : a_; }
-      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ > a_ ? t_ : a_; }
-      if (lane == 0) atomicMax(((unsigned long long*)p.ptr[12]) + slot, a_);
-    }
-    {
-      unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 320 + lane];
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[13]) + slot, a_);
-    }
-    {
-      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 352 + lane]);
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[14]) + slot), a_);
-    }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 0] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[15]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 1] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[16]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 2] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[17]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 3] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[18]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 4] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[19]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 5] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[20]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 6] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[21]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 7] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[22]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 8] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[23]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 9] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[24]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 10] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[25]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 11] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[26]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 12] : 0ULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[27]) + slot, a_); }
-    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + 13] : 0xFFFFFFFFFFFFFFFFULL;
-      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }
-      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[28]) + slot, a_); }
+      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[9]) + slot, a_); }
   }
 };
-extern "C" __global__ void __launch_bounds__(256) b200_k(const Prog::P p) { agg_body<Prog>(p); }
+extern "C" __global__ void __launch_bounds__(256, 3) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }

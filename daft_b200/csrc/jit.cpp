@@ -603,7 +603,7 @@ static std::string gen_project(Reader &r, Ast &ast, Compiled &meta, bool with_ta
     o << "  __device__ __forceinline__ static void row(const P& p, const int64_t out_row, const int64_t row, const bool active, const int pass) {\n";
     o << body.str();
     o << "  }\n};\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(256) b200_k(const Prog::P p, int pass) { project_body<Prog>(p, pass); }\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(256) b200_project_k(const __grid_constant__ Prog::P p, int pass) { project_body<Prog>(p, pass); }\n";
     return o.str();
 }
 
@@ -755,29 +755,36 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         }
         meta.aggs.push_back(o);
     }
-    const int NL = (int)lane_cells.size(), NW = (int)warp_cells.size();
-    meta.NLANE = NL;
+    // lane cells = value cells, then the group's row count and its first row; warp cells = ballot counts
+    const int NL = (int)lane_cells.size(), NW = (int)warp_cells.size(), NLT = NL + 2;
+    meta.NLANE = NLT;
     meta.NWARP = NW;
     for (auto &c : lane_cells) meta.lane_cell_ops.push_back(c.op);
-    int G1 = NL ? (48 * 1024) / (8 * NL * 256) : 8;
+    meta.lane_cell_ops.push_back(C_ADD_I64);  // row count
+    meta.lane_cell_ops.push_back(C_MIN);      // first row
+    int G1 = (60 * 1024) / (8 * NLT * 256);
     G1 = std::max(1, std::min(8, G1));
     if (nkeys == 0) G1 = 1;
     meta.G1 = G1;
-    meta.smem_bytes = 8 * (size_t)G1 + 8 * (size_t)8 * G1 * (NW + 1) + 8 * (size_t)8 * G1 * NL * 32;
+    auto env_int = [](const char *name, int dflt) {
+        const char *v = getenv(name);
+        return v && *v ? atoi(v) : dflt;
+    };
+    const int MINB = std::max(1, std::min(8, env_int("B200_AGG_MINB", 3)));
 
     const int iv_n = cg.int_slot(I_N), iv_mask = cg.int_slot(I_MASK);
     const int p_hash = cg.ptr_slot(P_SLOT_HASH, 0), p_row = cg.ptr_slot(P_SLOT_ROW, 0), p_ovf = cg.ptr_slot(P_OVERFLOW, 0);
-    // global cells: [0,NL) lane cells, [NL,NL+NW) warp cells, NL+NW = nrows, NL+NW+1 = min row
-    const int cell_nrows = NL + NW, cell_minrow = NL + NW + 1;
-    std::vector<int> p_acc(NL + NW + 2);
-    for (int i = 0; i < NL + NW + 2; i++) p_acc[i] = cg.ptr_slot(P_ACC, i);
+    // global cells: [0,NL) value cells, NL = row count, NL+1 = first row, [NL+2, NL+2+NW) ballot count cells
+    const int cell_nrows = NL, cell_minrow = NL + 1;
+    std::vector<int> p_acc(NLT + NW);
+    for (int i = 0; i < NLT + NW; i++) p_acc[i] = cg.ptr_slot(P_ACC, i);
 
     // ---- columns referenced anywhere -> Raw struct
     std::vector<int> cols;
     if (filter_root >= 0) collect_cols(ast, filter_root, cols);
     for (int k : key_roots) collect_cols(ast, k, cols);
     for (int v : val_roots) collect_cols(ast, v, cols);
-    std::ostringstream raw, load;
+    std::ostringstream raw, load, load2;
     size_t raw_bytes = 0;
     for (int c : cols) {
         const int32_t dt = (*ast.col_dtypes)[c];
@@ -789,9 +796,11 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
             raw_bytes += 4;
         }
         if (is_string(dt)) {
-            raw << "    int64_t o" << c << "a, o" << c << "b;\n";
+            raw << "    int64_t o" << c << "a, o" << c << "b; uint64_t pk" << c << ";\n";
             load << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
-            raw_bytes += 16;
+            // second load phase: the first <= 8 bytes of the value (depends on the offsets of phase one)
+            load2 << "    r.pk" << c << " = str_pack8(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, r.o" << c << "b - r.o" << c << "a});\n";
+            raw_bytes += 24;
         } else if (dt == B200_BOOL) {
             raw << "    bool c" << c << ";\n";
             load << "    r.c" << c << " = bit_at((const uint8_t*)" << cg.P(P_COL_DATA, c) << ", row);\n";
@@ -802,13 +811,14 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
             raw_bytes += std::max(4, dtype_width(dt));
         }
     }
-    const int U = raw_bytes <= 96 ? 4 : (raw_bytes <= 192 ? 2 : 1);
+    const int U = std::max(1, std::min(8, env_int("B200_AGG_U", 1)));
 
     // ---- Keys / Vals structs
     std::ostringstream keys_s, vals_s;
     for (uint32_t i = 0; i < nkeys; i++) {
         const Node &n = ast.nodes[key_roots[i]];
         keys_s << "    " << ctype(n.dtype) << " v" << i << "; bool k" << i << ";\n";
+        if (is_string(n.dtype)) keys_s << "    uint64_t p" << i << ";\n";
     }
     for (size_t i = 0; i < val_roots.size(); i++) vals_s << "    " << ctype(val_dtypes[i]) << " a" << i << "; bool k" << i << ";\n";
 
@@ -823,6 +833,13 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         for (uint32_t i = 0; i < nkeys; i++) {
             int id = eg.emit(key_roots[i]);
             ev << "    keys.v" << i << " = " << eg.v(id) << "; keys.k" << i << " = " << eg.k(id) << ";\n";
+            if (is_string(ast.nodes[key_roots[i]].dtype)) {
+                const Node &kn = ast.nodes[key_roots[i]];
+                if (kn.tag == T_COL)  // prefix already fetched by load2()
+                    ev << "    keys.p" << i << " = keys.k" << i << " ? r.pk" << kn.col << " : 0ULL;\n";
+                else
+                    ev << "    keys.p" << i << " = keys.k" << i << " ? str_pack8(keys.v" << i << ") : 0ULL;\n";
+            }
         }
         for (size_t i = 0; i < val_roots.size(); i++) {
             int id = eg.emit(val_roots[i]);
@@ -840,6 +857,8 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         for (uint32_t i = 0; i < nkeys; i++) {
             int id = eg.emit(key_roots[i]);
             ek << "    keys.v" << i << " = " << eg.v(id) << "; keys.k" << i << " = " << eg.k(id) << ";\n";
+            if (is_string(ast.nodes[key_roots[i]].dtype))
+                ek << "    keys.p" << i << " = keys.k" << i << " ? str_pack8(keys.v" << i << ") : 0ULL;\n";
         }
     }
     // ---- hash / equality
@@ -847,16 +866,38 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     hs << "    uint64_t h = 0;\n";
     for (uint32_t i = 0; i < nkeys; i++) {
         const Node &n = ast.nodes[key_roots[i]];
-        hs << "    h = " << hash_expr(n.dtype, "k.v" + std::to_string(i), "k.k" + std::to_string(i), i == 0 ? "0ULL" : "h") << ";\n";
+        if (is_string(n.dtype))
+            hs << "    h = (k.k" << i << " ? hash_str_packed(k.v" << i << ", k.p" << i << ", " << (i == 0 ? "0ULL" : "h") << ") : xxh::hash_empty("
+               << (i == 0 ? "0ULL" : "h") << "));\n";
+        else
+            hs << "    h = " << hash_expr(n.dtype, "k.v" + std::to_string(i), "k.k" + std::to_string(i), i == 0 ? "0ULL" : "h") << ";\n";
     }
     hs << "    return h;\n";
     eq << "    return true";
     for (uint32_t i = 0; i < nkeys; i++) {
         const Node &n = ast.nodes[key_roots[i]];
         const std::string si = std::to_string(i);
-        eq << " && (a.k" << si << " == b.k" << si << ") && (!a.k" << si << " || " << bits_equal(n.dtype, "a.v" + si, "b.v" + si) << ")";
+        if (is_string(n.dtype))
+            eq << " && (a.k" << si << " == b.k" << si << ") && (!a.k" << si << " || str_eq_packed(a.v" << si << ", a.p" << si << ", b.v" << si << ", b.p" << si << "))";
+        else
+            eq << " && (a.k" << si << " == b.k" << si << ") && (!a.k" << si << " || " << bits_equal(n.dtype, "a.v" + si, "b.v" + si) << ")";
     }
     eq << ";\n";
+    // cheap 64-bit fingerprint of the key values for the tier-1 lookup (a pre-filter only: keys_equal decides)
+    std::ostringstream fps;
+    fps << "    uint64_t f = 0x9E3779B97F4A7C15ULL;\n";
+    for (uint32_t i = 0; i < nkeys; i++) {
+        const Node &n = ast.nodes[key_roots[i]];
+        const std::string si = std::to_string(i);
+        std::string bits;
+        if (is_string(n.dtype)) bits = "(k.p" + si + " ^ ((uint64_t)k.v" + si + ".len << 56))";
+        else if (n.dtype == B200_F64) bits = "(uint64_t)__double_as_longlong(k.v" + si + ")";
+        else if (n.dtype == B200_F32) bits = "(uint64_t)(uint32_t)__float_as_int(k.v" + si + ")";
+        else if (n.dtype == B200_NULL) bits = "0ULL";
+        else bits = "(uint64_t)k.v" + si;
+        fps << "    f = (f ^ (k.k" << si << " ? " << bits << " : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;\n";
+    }
+    fps << "    return f;\n";
 
     // ---- lane cells: init / update / global update / flush
     std::ostringstream li, lu, gu, wc, fl;
@@ -924,28 +965,32 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         }
         fl << "    }\n";
     }
-    // warp cells: tier-1 ballots, global atomics, flush
-    // my_wcell layout per group: [0,NW) count cells, [NW] min row; nrows is tracked in an extra slot appended by codegen:
-    // we keep nrows as warp cell index NW_ROWS = NW (shifting min row to NW+1) -- see NWARP below.
+    // row count and first row: two more lane cells (plain read-modify-write, no ballots)
+    {
+        const std::string cn = "cells[" + std::to_string(NL * 32) + "]", cm = "cells[" + std::to_string((NL + 1) * 32) + "]";
+        li << "    " << cn << " = 0ULL;\n    " << cm << " = 0xFFFFFFFFFFFFFFFFULL;\n";
+        lu << "    " << cn << " += 1ULL;\n    if ((unsigned long long)row < " << cm << ") " << cm << " = (unsigned long long)row;\n";
+        gu << "    atomicAdd(((unsigned long long*)p.ptr[" << p_acc[cell_nrows] << "]) + slot, 1ULL);\n";
+        gu << "    atomicMin(((unsigned long long*)p.ptr[" << p_acc[cell_minrow] << "]) + slot, (unsigned long long)row);\n";
+        fl << "    { unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + " << NL * 32 << " + lane];\n";
+        fl << "      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);\n";
+        fl << "      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[" << p_acc[cell_nrows] << "]) + slot, a_); }\n";
+        fl << "    { unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + "
+           << (NL + 1) * 32 << " + lane]; a_ = t_ < a_ ? t_ : a_; }\n";
+        fl << "      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }\n";
+        fl << "      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[" << p_acc[cell_minrow] << "]) + slot, a_); }\n";
+    }
+    // ballot count cells (valid / null counts of nullable aggregate inputs)
     for (int c = 0; c < NW; c++) {
         const WarpCell &w = warp_cells[c];
         const std::string vk = "v.k" + std::to_string(w.val_slot);
         const std::string cond = w.count_nulls ? "!" + vk : vk;
         wc << "    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && " << cond << "); if (lane == 0) wcell[" << c << "] += __popc(m_); }\n";
-        gu << "    if (" << cond << ") atomicAdd(((unsigned long long*)p.ptr[" << p_acc[NL + c] << "]) + slot, 1ULL);\n";
-    }
-    wc << "    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g); if (lane == 0) wcell[" << NW << "] += __popc(m_); }\n";
-    gu << "    atomicAdd(((unsigned long long*)p.ptr[" << p_acc[cell_nrows] << "]) + slot, 1ULL);\n";
-    gu << "    atomicMin(((unsigned long long*)p.ptr[" << p_acc[cell_minrow] << "]) + slot, (unsigned long long)row);\n";
-    // flush of warp cells: lanes 0..7 read one warp each
-    for (int c = 0; c <= NW; c++) {
+        gu << "    if (" << cond << ") atomicAdd(((unsigned long long*)p.ptr[" << p_acc[NLT + c] << "]) + slot, 1ULL);\n";
         fl << "    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + " << c << "] : 0ULL;\n";
         fl << "      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);\n";
-        fl << "      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[" << p_acc[c < NW ? NL + c : cell_nrows] << "]) + slot, a_); }\n";
+        fl << "      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[" << p_acc[NLT + c] << "]) + slot, a_); }\n";
     }
-    fl << "    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + " << (NW + 1) << "] : 0xFFFFFFFFFFFFFFFFULL;\n";
-    fl << "      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }\n";
-    fl << "      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[" << p_acc[cell_minrow] << "]) + slot, a_); }\n";
 
     std::ostringstream o;
     o << file_header(cg);
@@ -953,27 +998,28 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     o << "  typedef Params<" << meta.ptrs.size() << ", " << meta.ints.size() << "> P;\n";
     o << "  static constexpr int IV_N = " << iv_n << ", IV_MASK = " << iv_mask << ", PTR_SLOT_HASH = " << p_hash << ", PTR_SLOT_ROW = " << p_row
       << ", PTR_OVERFLOW = " << p_ovf << ";\n";
-    // NWARP as seen by the skeleton = count cells + the nrows cell; the min-row cell sits at index NWARP
-    o << "  static constexpr int NKEYS = " << nkeys << ", G1 = " << G1 << ", NLANE = " << NL << ", NWARP = " << (NW + 1) << ", U = " << U << ";\n";
+    o << "  static constexpr int NKEYS = " << nkeys << ", G1 = " << G1 << ", NLANE = " << NLT << ", NWARP = " << NW << ", U = " << U << ";\n";
     o << "  struct Raw {\n" << raw.str() << "    int pad_;\n  };\n";
     o << "  struct Keys {\n" << keys_s.str() << "    int pad_;\n  };\n";
     o << "  struct Vals {\n" << vals_s.str() << "    int pad_;\n  };\n";
     o << "  __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {\n" << load.str() << "  }\n";
+    o << "  __device__ __forceinline__ static void load2(const P& p, Raw& r) {\n" << load2.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {\n" << ev.str() << "  }\n";
     o << "  __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {\n" << ek.str() << "  }\n";
     o << "  __device__ __forceinline__ static uint64_t hash(const Keys& k) {\n" << hs.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {\n" << eq.str() << "  }\n";
+    o << "  __device__ __forceinline__ static uint64_t fingerprint(const Keys& k) {\n" << fps.str() << "  }\n";
     o << "  __device__ __forceinline__ static void lane_init(unsigned long long* cells) {\n" << li.str() << "  }\n";
-    o << "  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v) {\n" << lu.str() << "  }\n";
+    o << "  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v, const int64_t row) {\n" << lu.str() << "  }\n";
     o << "  __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {\n" << gu.str() << "  }\n";
     o << "  __device__ __forceinline__ static void warp_cells(const Vals& v, const bool in_g, unsigned long long* wcell, const int lane) {\n" << wc.str() << "  }\n";
     o << "  __device__ __forceinline__ static void flush(const P& p, const long long slot, const unsigned long long* lcell, const size_t lstride,\n"
          "                                               const unsigned long long* wcell, const size_t wstride, const int lane) {\n" << fl.str() << "  }\n";
     o << "};\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(256) b200_k(const Prog::P p) { agg_body<Prog>(p); }\n";
-    // the skeleton's shared-memory layout uses NWARP = NW + 1 count cells (+1 min-row cell)
-    meta.NWARP = NW + 1;
-    meta.smem_bytes = 8 * (size_t)G1 + 8 * (size_t)8 * G1 * (meta.NWARP + 1) + 8 * (size_t)8 * G1 * NL * 32;
+    o << "extern \"C\" __global__ void __launch_bounds__(256, " << MINB << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }\n";
+    // shared memory: lane cells, ballot cells, tier-1 slots/ready flags/key values (generous bound for sizeof(Keys))
+    meta.smem_bytes = 8 * (size_t)8 * G1 * NLT * 32 + 8 * (size_t)8 * G1 * std::max(NW, 1) + 16 * (size_t)G1 +
+                      (size_t)G1 * (40 * (size_t)nkeys + 16);
     return o.str();
 }
 
@@ -1044,7 +1090,7 @@ std::vector<char> compile_to_cubin(const std::string &body, std::string *path_ou
         f << full;
     }
     nvrtcProgram prog;
-    if (nvrtcCreateProgram(&prog, full.c_str(), (std::string(name) + ".cu").c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    if (nvrtcCreateProgram(&prog, full.c_str(), (base + ".cu").c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)  // full path: ncu --import-source
         fail("nvrtcCreateProgram failed");
     const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=false", "-default-device"};
     nvrtcResult res = nvrtcCompileProgram(prog, 5, opts);
@@ -1096,7 +1142,7 @@ const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &i
     require_device();
     // runtime "library" API (cudart dlopens the driver itself; the .so has no link-time libcuda dependency)
     B200_CUDA(cudaLibraryLoadData(&c->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-    B200_CUDA(cudaLibraryGetKernel(&c->fn, c->lib, "b200_k"));
+    B200_CUDA(cudaLibraryGetKernel(&c->fn, c->lib, op == B200_OP_AGG ? "b200_agg_k" : "b200_project_k"));
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, (const void *)c->fn) == cudaSuccess) c->regs = fa.numRegs;
     if (c->smem_bytes > 48 * 1024)

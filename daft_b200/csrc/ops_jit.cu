@@ -264,8 +264,8 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
     const Compiled &k = jit::get(B200_OP_AGG, plan, len, in, false);
     cudaStream_t st = ctx().stream;
     const int64_t n = in.num_rows;
-    const int ncells = k.NLANE + k.NWARP + 1;  // lane cells, count cells (+nrows inside NWARP), min row
-    const int cell_nrows = k.NLANE + k.NWARP - 1, cell_minrow = k.NLANE + k.NWARP;
+    const int ncells = k.NLANE + k.NWARP;  // value cells + row count + first row, then ballot count cells
+    const int cell_nrows = k.NLANE - 2, cell_minrow = k.NLANE - 1;
 
     // table capacity: grow on overflow (the group count is unknown up front; the reference's
     // GroupedAggregateSink samples the first morsel for the same reason, grouped_aggregate.rs:205-245)
@@ -283,7 +283,6 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         for (int c = 0; c < ncells; c++) {
             int fillv = 0;
             if (c < k.NLANE && k.lane_cell_ops[c] == jit::C_MIN) fillv = 0xFF;
-            if (c == cell_minrow) fillv = 0xFF;
             fill_u8(as<uint8_t>(acc) + (size_t)c * cap * 8, fillv, (size_t)cap * 8);
         }
         fill_u8(overflow->ptr, 0, 8);
