@@ -335,6 +335,20 @@ __device__ __forceinline__ uint64_t str_pack8(Str a) {
     if (nbits < 64) v &= (1ULL << nbits) - 1ULL;
     return v;
 }
+// first min(len, 4) bytes with 32-bit arithmetic only: one aligned word, a second one only when the value
+// straddles it, one funnel shift (short key columns on the exact-code path need at most 3 bytes)
+__device__ __forceinline__ uint64_t str_pack4(Str a) {
+    if (a.len <= 0) return 0ULL;
+    const uintptr_t addr = (uintptr_t)a.p;
+    const uint32_t *w = (const uint32_t *)(addr & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(addr & 3) * 8u;
+    const uint32_t nb = a.len < 4 ? (uint32_t)a.len : 4u;
+    const uint32_t w0 = w[0];
+    const uint32_t w1 = (sh + nb * 8u > 32u) ? w[1] : 0u;
+    uint32_t v = __funnelshift_r(w0, w1, sh);
+    if (nb < 4u) v &= (1u << (nb * 8u)) - 1u;
+    return (uint64_t)v;
+}
 __device__ __forceinline__ uint64_t hash_str_packed(Str a, uint64_t pk, uint64_t seed) {
     const int64_t len = a.len;
     if (len <= 8) {
@@ -572,18 +586,38 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     unsigned long long tfp[G1];
 #pragma unroll
     for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
-    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
-        const int64_t base = c * chunk;
-        typename Prog::Raw raw[U];
+    // software pipeline: string offsets (load0) are fetched one chunk ahead of everything else
+    typename Prog::Raw raw[U];
+    {
+        const int64_t c0 = (int64_t)blockIdx.x * AGG_WARPS + warp;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int64_t row = base + u * 32 + lane;
-            if (row < n) Prog::load(p, row, raw[u]);
+            const int64_t row = c0 * chunk + u * 32 + lane;
+            if (Prog::PIPE && c0 < nchunks && row < n) Prog::load0(p, row, raw[u]);
         }
+    }
+    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
+        const int64_t base = c * chunk;
 #pragma unroll
-        for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
+        for (int u = 0; u < U; u++) {  // fixed-width columns, and the string prefixes whose offsets arrived last iteration
             const int64_t row = base + u * 32 + lane;
-            if (row < n) Prog::load2(p, raw[u]);
+            if (row < n) {
+                Prog::load(p, row, raw[u]);
+                if (Prog::PIPE) Prog::load2(p, raw[u]);
+            }
+        }
+        if (!Prog::PIPE) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
+                const int64_t row = base + u * 32 + lane;
+                if (row < n) Prog::load2(p, raw[u]);
+            }
+        }
+        typename Prog::Raw nxt[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {  // next chunk's string offsets
+            const int64_t row = (c + total_warps) * chunk + u * 32 + lane;
+            if (Prog::PIPE && c + total_warps < nchunks && row < n) Prog::load0(p, row, nxt[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -592,18 +626,21 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
             typename Prog::Vals vals;
             bool live = row < n;
             if (live) live = Prog::eval(p, raw[u], keys, vals);
-            // tier 1: the CTA's first G1 groups, matched by a fingerprint of the key VALUES (registers only),
-            // then verified once against the published key (no xxh3, no global memory on this path)
+            // tier 1: the CTA's first G1 groups, matched on a 64-bit code of the key VALUES held in registers
+            // (no xxh3, no global memory on this path)
+            // key code: exact (injective, bit 63 clear) when the key tuple is narrow, else fingerprint | bit 63
             unsigned long long fp = 0ULL;
-            if (live) fp = Prog::NKEYS > 0 ? (Prog::fingerprint(keys) | 1ULL) : 1ULL;
+            if (live) fp = Prog::NKEYS > 0 ? Prog::code(keys) : 1ULL;
             int lid = -1;
 #pragma unroll
             for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
-            if (Prog::NKEYS > 0 && live && lid >= 0) {
+            if (Prog::NKEYS > 0 && live && lid >= 0 && (fp >> 63)) {  // only inexact codes need the value check
+                Prog::finish_keys(keys);
                 if (!Prog::keys_equal(keys, s_keys[lid])) lid = -1;
             }
             if (live && lid < 0) {  // rare: first rows of a CTA, or a group beyond tier 1
                 // copies made HERE so that only this rare branch spills the key/value registers to the stack
+                Prog::finish_keys(keys);  // full 8-byte string prefixes for hashing / publishing
                 const typename Prog::Keys kcopy = keys;
                 const typename Prog::Vals vcopy = vals;
                 const long long r = agg_slow_path<Prog>(p, kcopy, vcopy, row, fp, s_slot, s_fp, s_keys);
@@ -620,6 +657,10 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
                     if (__any_sync(FULL_MASK, in_g)) Prog::warp_cells(vals, in_g, my_wcell + g * NW, lane);
                 }
             }
+        }
+        if (Prog::PIPE) {
+#pragma unroll
+            for (int u = 0; u < U; u++) Prog::copy0(raw[u], nxt[u]);
         }
     }
     __syncthreads();

@@ -573,7 +573,7 @@ static std::string gen_project(Reader &r, Ast &ast, Compiled &meta, bool with_ta
     for (uint32_t i = 0; i < nexpr; i++) {
         int id = eg.emit(roots[i]);
         const Node &n = ast.nodes[roots[i]];
-        OutCol oc{names[i], n.dtype, n.nullable || with_take};
+        OutCol oc{names[i], n.dtype, n.nullable || with_take, n.nullable || n.dtype == B200_NULL};
         if (n.dtype == B200_NULL) oc.nullable = true;
         meta.outs.push_back(oc);
         const std::string V = eg.v(id), K = eg.k(id);
@@ -770,7 +770,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         const char *v = getenv(name);
         return v && *v ? atoi(v) : dflt;
     };
-    const int MINB = std::max(1, std::min(8, env_int("B200_AGG_MINB", 3)));
+    const int MINB = std::max(1, std::min(8, env_int("B200_AGG_MINB", 2)));
 
     const int iv_n = cg.int_slot(I_N), iv_mask = cg.int_slot(I_MASK);
     const int p_hash = cg.ptr_slot(P_SLOT_HASH, 0), p_row = cg.ptr_slot(P_SLOT_ROW, 0), p_ovf = cg.ptr_slot(P_OVERFLOW, 0);
@@ -779,12 +779,45 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     std::vector<int> p_acc(NLT + NW);
     for (int i = 0; i < NLT + NW; i++) p_acc[i] = cg.ptr_slot(P_ACC, i);
 
+    // ---- exact key code budget (see `code()` below): bytes per string key, 0 = no exact code
+    int exact_B = 0;
+    bool exact_possible = nkeys > 0;
+    {
+        int bits_fixed = 0, nstr = 0;
+        for (uint32_t i = 0; i < nkeys; i++) {
+            const Node &n = ast.nodes[key_roots[i]];
+            if (is_string(n.dtype)) nstr++;
+            else if (n.dtype == B200_BOOL) bits_fixed += 1;
+            else if (n.dtype != B200_NULL) bits_fixed += 8 * dtype_width(n.dtype);
+            if (n.nullable) bits_fixed += 1;
+        }
+        if (bits_fixed > 62) exact_possible = false;
+        if (exact_possible && nstr) {
+            exact_B = std::min(7, ((62 - bits_fixed) / nstr - 3) / 8);
+            if (exact_B < 1) exact_possible = false;
+        }
+    }
+    // string columns that appear ONLY as bare group keys can be prefetched with the cheap 4-byte pack
+    std::vector<int> key_only_str_cols;
+    if (exact_possible && exact_B >= 1 && exact_B <= 4) {
+        for (uint32_t i = 0; i < nkeys; i++) {
+            const Node &n = ast.nodes[key_roots[i]];
+            if (n.tag == T_COL && is_string(n.dtype)) key_only_str_cols.push_back(n.col);
+        }
+    }
+    auto is_pack4_col = [&](int c) {
+        for (int x : key_only_str_cols)
+            if (x == c) return true;
+        return false;
+    };
+
     // ---- columns referenced anywhere -> Raw struct
     std::vector<int> cols;
     if (filter_root >= 0) collect_cols(ast, filter_root, cols);
     for (int k : key_roots) collect_cols(ast, k, cols);
     for (int v : val_roots) collect_cols(ast, v, cols);
-    std::ostringstream raw, load, load2;
+    std::ostringstream raw, load, load2, load0, copy0;
+    const bool pipe_offsets = env_int("B200_AGG_PIPE", 0) != 0;
     size_t raw_bytes = 0;
     for (int c : cols) {
         const int32_t dt = (*ast.col_dtypes)[c];
@@ -797,9 +830,18 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         }
         if (is_string(dt)) {
             raw << "    int64_t o" << c << "a, o" << c << "b; uint64_t pk" << c << ";\n";
-            load << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
+            // string offsets are fetched one chunk AHEAD (load0), so the dependent byte loads of the current
+            // chunk can be issued together with its numeric loads
+            // (B200_AGG_PIPE=1; measured slower on Q1 at 128 registers/thread, so off by default)
+            if (pipe_offsets) {
+                load0 << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
+                copy0 << "    d.o" << c << "a = s.o" << c << "a; d.o" << c << "b = s.o" << c << "b;\n";
+            } else {
+                load << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
+            }
             // second load phase: the first <= 8 bytes of the value (depends on the offsets of phase one)
-            load2 << "    r.pk" << c << " = str_pack8(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, r.o" << c << "b - r.o" << c << "a});\n";
+            load2 << "    r.pk" << c << " = " << (is_pack4_col(c) ? "str_pack4" : "str_pack8") << "(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c
+                  << "a, r.o" << c << "b - r.o" << c << "a});\n";
             raw_bytes += 24;
         } else if (dt == B200_BOOL) {
             raw << "    bool c" << c << ";\n";
@@ -811,7 +853,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
             raw_bytes += std::max(4, dtype_width(dt));
         }
     }
-    const int U = std::max(1, std::min(8, env_int("B200_AGG_U", 1)));
+    const int U = std::max(1, std::min(8, env_int("B200_AGG_U", 2)));
 
     // ---- Keys / Vals structs
     std::ostringstream keys_s, vals_s;
@@ -898,6 +940,43 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         fps << "    f = (f ^ (k.k" << si << " ? " << bits << " : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;\n";
     }
     fps << "    return f;\n";
+    // Exact key code: when every key is narrow (ints <= 32 bit, bools, short strings) the whole key tuple is packed
+    // injectively into 62 bits -- a tier-1 match on the code then needs no verification at all.  Rows whose strings
+    // exceed their byte budget (and plans with wide keys) fall back to fingerprint | bit63 + one verification.
+    std::ostringstream cds;
+    {
+        const bool possible = exact_possible;
+        const int B = exact_B;
+        if (!possible) {
+            cds << "    return fingerprint(k) | 0x8000000000000000ULL;\n";
+        } else {
+            cds << "    uint64_t c = 0x4000000000000000ULL; bool ex = true;\n";
+            int sh = 0;
+            for (uint32_t i = 0; i < nkeys; i++) {
+                const Node &n = ast.nodes[key_roots[i]];
+                const std::string si = std::to_string(i);
+                if (is_string(n.dtype)) {
+                    const unsigned long long mask = (1ULL << (8 * B)) - 1ULL;
+                    cds << "    { const uint64_t l_ = k.k" << si << " ? (uint64_t)k.v" << si << ".len : 0ULL; ex = ex && (l_ <= " << B << "ULL); c |= (k.p" << si
+                        << " & " << mask << "ULL) << " << sh << "; c |= (l_ & 7ULL) << " << (sh + 8 * B) << "; }\n";
+                    sh += 8 * B + 3;
+                } else if (n.dtype != B200_NULL) {
+                    std::string bits;
+                    int w = n.dtype == B200_BOOL ? 1 : 8 * dtype_width(n.dtype);
+                    if (n.dtype == B200_BOOL) bits = "(uint64_t)k.v" + si;
+                    else if (n.dtype == B200_F32) bits = "(uint64_t)(uint32_t)__float_as_int(k.v" + si + ")";
+                    else bits = std::string("(uint64_t)(") + utype(n.dtype) + ")k.v" + si;
+                    cds << "    c |= (k.k" << si << " ? " << bits << " : 0ULL) << " << sh << ";\n";
+                    sh += w;
+                }
+                if (n.nullable) {
+                    cds << "    c |= (uint64_t)(!k.k" << si << ") << " << sh << ";\n";
+                    sh += 1;
+                }
+            }
+            cds << "    return ex ? c : (fingerprint(k) | 0x8000000000000000ULL);\n";
+        }
+    }
 
     // ---- lane cells: init / update / global update / flush
     std::ostringstream li, lu, gu, wc, fl;
@@ -999,16 +1078,27 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     o << "  static constexpr int IV_N = " << iv_n << ", IV_MASK = " << iv_mask << ", PTR_SLOT_HASH = " << p_hash << ", PTR_SLOT_ROW = " << p_row
       << ", PTR_OVERFLOW = " << p_ovf << ";\n";
     o << "  static constexpr int NKEYS = " << nkeys << ", G1 = " << G1 << ", NLANE = " << NLT << ", NWARP = " << NW << ", U = " << U << ";\n";
+    o << "  static constexpr bool PIPE = " << (pipe_offsets ? "true" : "false") << ";\n";
     o << "  struct Raw {\n" << raw.str() << "    int pad_;\n  };\n";
     o << "  struct Keys {\n" << keys_s.str() << "    int pad_;\n  };\n";
     o << "  struct Vals {\n" << vals_s.str() << "    int pad_;\n  };\n";
     o << "  __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {\n" << load.str() << "  }\n";
     o << "  __device__ __forceinline__ static void load2(const P& p, Raw& r) {\n" << load2.str() << "  }\n";
+    o << "  __device__ __forceinline__ static void load0(const P& p, const int64_t row, Raw& r) {\n" << load0.str() << "  }\n";
+    o << "  __device__ __forceinline__ static void copy0(Raw& d, const Raw& s) {\n" << copy0.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {\n" << ev.str() << "  }\n";
     o << "  __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {\n" << ek.str() << "  }\n";
     o << "  __device__ __forceinline__ static uint64_t hash(const Keys& k) {\n" << hs.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {\n" << eq.str() << "  }\n";
+    {
+        std::ostringstream fk;
+        for (uint32_t i = 0; i < nkeys; i++)
+            if (is_string(ast.nodes[key_roots[i]].dtype))
+                fk << "    k.p" << i << " = k.k" << i << " ? str_pack8(k.v" << i << ") : 0ULL;\n";
+        o << "  __device__ __forceinline__ static void finish_keys(Keys& k) {\n" << fk.str() << "  }\n";
+    }
     o << "  __device__ __forceinline__ static uint64_t fingerprint(const Keys& k) {\n" << fps.str() << "  }\n";
+    o << "  __device__ __forceinline__ static uint64_t code(const Keys& k) {\n" << cds.str() << "  }\n";
     o << "  __device__ __forceinline__ static void lane_init(unsigned long long* cells) {\n" << li.str() << "  }\n";
     o << "  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v, const int64_t row) {\n" << lu.str() << "  }\n";
     o << "  __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {\n" << gu.str() << "  }\n";

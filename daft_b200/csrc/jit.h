@@ -20,7 +20,8 @@ enum IntKind { I_N = 0, I_MASK };
 struct OutCol {
     std::string name;
     int32_t dtype;
-    bool nullable;
+    bool nullable;        // a validity bitmap is produced
+    bool expr_nullable;   // the expression itself can yield nulls (ignoring a take's negative indices)
 };
 
 enum CellOp { C_ADD_F64 = 0, C_ADD_F32, C_ADD_I64, C_MIN, C_MAX };
@@ -81,7 +82,8 @@ double last_timed_kernel_ms();
 }  // namespace jit
 
 // operators built on the JIT (ops_jit.cu)
-Batch *op_project(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n);
+// take_idx != null: evaluate at rows take_idx[i]; take_nonneg promises that no index is negative
+Batch *op_project(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n, bool take_nonneg = false);
 Batch *op_filter(const Batch &in, const uint8_t *plan, size_t len);
 Batch *op_agg(const Batch &in, const uint8_t *plan, size_t len);
 

@@ -20,7 +20,7 @@ static int stream_grid(int64_t n, int threads, int per_sm) {
 // Project (RecordBatch::eval_expression_list, src/daft-recordbatch/src/lib.rs:1603-1631)
 // optional take_idx: evaluate the expressions at rows take_idx[i] (negative -> null row)
 // ------------------------------------------------------------------------------------------------
-Batch *op_project(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n) {
+Batch *op_project(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n, bool take_nonneg) {
     require_device();
     const bool with_take = take_idx != nullptr;
     const Compiled &k = jit::get(B200_OP_PROJECT, plan, len, in, with_take);
@@ -100,6 +100,10 @@ Batch *op_project(const Batch &in, const uint8_t *plan, size_t len, const int64_
     for (size_t i = 0; i < nout; i++) {
         Column &c = out->cols[i];
         if (c.dtype != B200_NULL && c.validity) {
+            if (with_take && take_nonneg && !k.outs[i].expr_nullable) {
+                c.validity.reset();  // every bit is set by construction: skip the count (and its sync)
+                continue;
+            }
             c.null_count = n - count_set_bits(as<uint8_t>(c.validity), n);
             if (c.null_count == 0) c.validity.reset();
         }
@@ -342,7 +346,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
     // ---- output: key columns = key expressions evaluated at each group's first row, then agg columns
     std::unique_ptr<Batch> out;
     if (k.nkeys > 0) {
-        out.reset(op_project(in, k.key_project_plan.data(), k.key_project_plan.size(), as<int64_t>(minrow), ng));
+        out.reset(op_project(in, k.key_project_plan.data(), k.key_project_plan.size(), as<int64_t>(minrow), ng, true));
         // first rows are real rows: drop the "take may produce nulls" pessimism
     } else {
         out = std::make_unique<Batch>();

@@ -218,6 +218,80 @@ void fill_iota(int64_t *out, int64_t n) {
     count_launch();
 }
 
+// ------------------------------------------------------------------------------------------------
+// tiny inputs (post-aggregation results: TPC-H sorts 4..1000 rows): one CTA, rank by comparison, one launch
+// ------------------------------------------------------------------------------------------------
+constexpr int SMALL_SORT_MAX = 2048;
+constexpr int SMALL_SORT_KEYS = 8;
+struct SortKeyDesc {
+    int32_t dtype, desc, nulls_first, _pad;
+    const void *data;
+    const uint8_t *validity;
+    const int64_t *offsets;
+};
+struct SortKeySet {
+    int32_t nkeys, _pad;
+    SortKeyDesc k[SMALL_SORT_KEYS];
+};
+
+// three-way compare of rows i, j under the reference comparator (NaN greatest, nulls by nulls_first)
+__device__ __forceinline__ int small_cmp(const SortKeySet &ks, int64_t i, int64_t j) {
+    for (int q = 0; q < ks.nkeys; q++) {
+        const SortKeyDesc &k = ks.k[q];
+        if (k.dtype == B200_NULL) continue;
+        const bool vi = k.validity == nullptr || bit_at(k.validity, i), vj = k.validity == nullptr || bit_at(k.validity, j);
+        int r = 0;
+        if (vi && vj) {
+            switch (k.dtype) {
+#define CMP_T(T) { const T a = ((const T *)k.data)[i], b = ((const T *)k.data)[j]; r = a < b ? -1 : (a > b ? 1 : 0); } break;
+                case B200_I8: CMP_T(int8_t)
+                case B200_I16: CMP_T(int16_t)
+                case B200_I32: case B200_DATE32: CMP_T(int32_t)
+                case B200_I64: case B200_TIMESTAMP: CMP_T(int64_t)
+                case B200_U8: CMP_T(uint8_t)
+                case B200_U16: CMP_T(uint16_t)
+                case B200_U32: CMP_T(uint32_t)
+                case B200_U64: CMP_T(uint64_t)
+#undef CMP_T
+                case B200_BOOL: r = (int)bit_at((const uint8_t *)k.data, i) - (int)bit_at((const uint8_t *)k.data, j); break;
+                case B200_F32: case B200_F64: {
+                    const double a = k.dtype == B200_F32 ? (double)((const float *)k.data)[i] : ((const double *)k.data)[i];
+                    const double b = k.dtype == B200_F32 ? (double)((const float *)k.data)[j] : ((const double *)k.data)[j];
+                    const bool na = a != a, nb = b != b;
+                    if (na || nb) r = (int)na - (int)nb;
+                    else r = a < b ? -1 : (a > b ? 1 : 0);
+                    break;
+                }
+                case B200_LARGE_UTF8: case B200_LARGE_BINARY: {
+                    const int64_t oa = k.offsets[i], la = k.offsets[i + 1] - oa, ob = k.offsets[j], lb = k.offsets[j + 1] - ob;
+                    const uint8_t *pa = (const uint8_t *)k.data + oa, *pb = (const uint8_t *)k.data + ob;
+                    const int64_t m = la < lb ? la : lb;
+                    for (int64_t t = 0; t < m && r == 0; t++) r = (int)pa[t] - (int)pb[t];
+                    if (r == 0) r = la < lb ? -1 : (la > lb ? 1 : 0);
+                    break;
+                }
+                default: break;
+            }
+            if (k.desc) r = -r;
+        } else if (vi != vj) {
+            r = (!vi) ? (k.nulls_first ? -1 : 1) : (k.nulls_first ? 1 : -1);
+        }
+        if (r) return r;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(1024) small_argsort_kernel(SortKeySet ks, int64_t n, int64_t *__restrict__ out_idx) {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        int64_t rank = 0;
+        for (int64_t j = 0; j < n; j++) {
+            const int c = small_cmp(ks, j, i);
+            rank += (c < 0) || (c == 0 && j < i);  // stable: ties keep row order
+        }
+        out_idx[rank] = i;
+    }
+}
+
 static int sgrid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 8)); }
 
 static int key_bits(int32_t dt) {
@@ -240,6 +314,22 @@ Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uin
     iota_kernel<<<sgrid(n), 256, 0, st>>>(as<int64_t>(idx), n);
     count_launch();
     if (n == 1) return idx;
+    if (n <= SMALL_SORT_MAX && nkeys <= SMALL_SORT_KEYS) {
+        SortKeySet ks;
+        ks.nkeys = nkeys;
+        for (int k = 0; k < nkeys; k++) {
+            const int32_t ci = key_cols[k];
+            if (ci < 0 || ci >= (int32_t)b.cols.size()) fail("argsort: key column index out of range");
+            const Column &c = b.cols[ci];
+            const bool desc = descending && descending[k];
+            ks.k[k] = {c.dtype, desc ? 1 : 0, (nulls_first ? nulls_first[k] != 0 : desc) ? 1 : 0, 0, c.data ? c.data->ptr : nullptr,
+                       c.null_count > 0 ? as<uint8_t>(c.validity) : nullptr, as<int64_t>(c.offsets)};
+        }
+        small_argsort_kernel<<<1, 1024, 0, st>>>(ks, n, as<int64_t>(idx));
+        count_launch();
+        B200_CUDA(cudaStreamSynchronize(st));
+        return idx;
+    }
     Buf keys = dev_alloc((size_t)n * 8);
     for (int k = nkeys - 1; k >= 0; k--) {
         const int32_t ci = key_cols[k];
@@ -279,8 +369,28 @@ Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uin
 }
 
 // group slots ordered by their first row (first-occurrence group order, inline_agg.rs:804-807)
+__global__ void __launch_bounds__(1024) small_sort_pairs_kernel(const unsigned long long *__restrict__ keys,
+                                                                const int64_t *__restrict__ vals, int64_t n,
+                                                                unsigned long long *__restrict__ keys_out, int64_t *__restrict__ vals_out) {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = keys[i];
+        int64_t rank = 0;
+        for (int64_t j = 0; j < n; j++) rank += (keys[j] < k) || (keys[j] == k && j < i);
+        keys_out[rank] = k;
+        vals_out[rank] = vals[i];
+    }
+}
+
 Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng) {
     if (ng <= 1) return slots;
+    if (ng <= SMALL_SORT_MAX) {
+        Buf k2 = dev_alloc((size_t)ng * 8), v2 = dev_alloc((size_t)ng * 8);
+        small_sort_pairs_kernel<<<1, 1024, 0, ctx().stream>>>(as<unsigned long long>(minrow), as<int64_t>(slots), ng,
+                                                             as<unsigned long long>(k2), as<int64_t>(v2));
+        count_launch();
+        B200_CUDA(cudaMemcpyAsync(minrow->ptr, k2->ptr, (size_t)ng * 8, cudaMemcpyDeviceToDevice, ctx().stream));
+        return v2;
+    }
     // minrow < 2^40 in practice; skipped passes make the high bytes free
     Buf keys = minrow;
     radix_sort_pairs(keys, slots, ng, 0, 64, false);
