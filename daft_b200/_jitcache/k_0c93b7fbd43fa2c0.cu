@@ -322,31 +322,36 @@ __device__ __forceinline__ uint64_t ord_u64(uint64_t v) { return v; }
 
 // ---- string helpers ---------------------------------------------------------------------------------
 // first min(len, 8) bytes of a string packed little-endian into a register (zero padded): short keys
-// (TPC-H flags, codes) are then hashed and compared without touching memory again
+// (TPC-H flags, codes) are then hashed and compared without touching memory again.
+// Both packers are branch-free (selects + predicated loads of aligned words that contain bytes of the value, so
+// they never leave the allocation) so that the loads of several rows/columns are all in flight before the
+// first one is consumed.
 __device__ __forceinline__ uint64_t str_pack8(Str a) {
-    if (a.len <= 0) return 0ULL;
-    // one or two aligned 8-byte words (never leaves the allocation: the words contain bytes of the string)
     const uintptr_t addr = (uintptr_t)a.p;
-    const uint64_t *w = (const uint64_t *)(addr & ~(uintptr_t)7);
+    const bool any = a.len > 0;
     const int sh = (int)(addr & 7) * 8;
     const int nbits = (a.len < 8 ? (int)a.len : 8) * 8;
-    uint64_t v = w[0] >> sh;
-    if (sh + nbits > 64) v |= w[1] << (64 - sh);
-    if (nbits < 64) v &= (1ULL << nbits) - 1ULL;
+    const unsigned long long *w = (const unsigned long long *)(addr & ~(uintptr_t)7);
+    unsigned long long w0 = 0ULL, w1 = 0ULL;
+    if (any) w0 = __ldg(w);
+    if (any && sh + nbits > 64) w1 = __ldg(w + 1);
+    unsigned long long v = w0 >> sh;
+    v |= sh ? (w1 << (64 - sh)) : 0ULL;
+    v &= nbits >= 64 ? ~0ULL : ((1ULL << nbits) - 1ULL);
     return v;
 }
-// first min(len, 4) bytes with 32-bit arithmetic only: one aligned word, a second one only when the value
-// straddles it, one funnel shift (short key columns on the exact-code path need at most 3 bytes)
+// first min(len, 4) bytes with 32-bit arithmetic only (short key columns on the exact-code path need <= 3 bytes)
 __device__ __forceinline__ uint64_t str_pack4(Str a) {
-    if (a.len <= 0) return 0ULL;
     const uintptr_t addr = (uintptr_t)a.p;
-    const uint32_t *w = (const uint32_t *)(addr & ~(uintptr_t)3);
+    const bool any = a.len > 0;
     const uint32_t sh = (uint32_t)(addr & 3) * 8u;
     const uint32_t nb = a.len < 4 ? (uint32_t)a.len : 4u;
-    const uint32_t w0 = w[0];
-    const uint32_t w1 = (sh + nb * 8u > 32u) ? w[1] : 0u;
-    uint32_t v = __funnelshift_r(w0, w1, sh);
-    if (nb < 4u) v &= (1u << (nb * 8u)) - 1u;
+    const unsigned int *w = (const unsigned int *)(addr & ~(uintptr_t)3);
+    unsigned int w0 = 0u, w1 = 0u;
+    if (any) w0 = __ldg(w);
+    if (any && sh + nb * 8u > 32u) w1 = __ldg(w + 1);
+    unsigned int v = __funnelshift_r(w0, w1, sh);
+    v &= nb >= 4u ? 0xFFFFFFFFu : ((1u << (nb * 8u)) - 1u);
     return (uint64_t)v;
 }
 __device__ __forceinline__ uint64_t hash_str_packed(Str a, uint64_t pk, uint64_t seed) {
@@ -603,14 +608,14 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
             const int64_t row = base + u * 32 + lane;
             if (row < n) {
                 Prog::load(p, row, raw[u]);
-                if (Prog::PIPE) Prog::load2(p, raw[u]);
+                if (Prog::PIPE) Prog::load2(p, row, raw[u]);
             }
         }
         if (!Prog::PIPE) {
 #pragma unroll
             for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
                 const int64_t row = base + u * 32 + lane;
-                if (row < n) Prog::load2(p, raw[u]);
+                if (row < n) Prog::load2(p, row, raw[u]);
             }
         }
         typename Prog::Raw nxt[U];
@@ -622,26 +627,29 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int64_t row = base + u * 32 + lane;
-            typename Prog::Keys keys;
             typename Prog::Vals vals;
             bool live = row < n;
-            if (live) live = Prog::eval(p, raw[u], keys, vals);
             // tier 1: the CTA's first G1 groups, matched on a 64-bit code of the key VALUES held in registers
             // (no xxh3, no global memory on this path)
             // key code: exact (injective, bit 63 clear) when the key tuple is narrow, else fingerprint | bit 63
             unsigned long long fp = 0ULL;
-            if (live) fp = Prog::NKEYS > 0 ? Prog::code(keys) : 1ULL;
+            {
+                typename Prog::Keys keys;  // dead after the code is formed: the rare paths re-read the keys by row
+                if (live) live = Prog::eval(p, raw[u], keys, vals);
+                if (live) fp = Prog::NKEYS > 0 ? Prog::code(keys) : 1ULL;
+            }
             int lid = -1;
 #pragma unroll
             for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
             if (Prog::NKEYS > 0 && live && lid >= 0 && (fp >> 63)) {  // only inexact codes need the value check
-                Prog::finish_keys(keys);
-                if (!Prog::keys_equal(keys, s_keys[lid])) lid = -1;
+                typename Prog::Keys kv;
+                Prog::eval_keys(p, row, kv);
+                if (!Prog::keys_equal(kv, s_keys[lid])) lid = -1;
             }
             if (live && lid < 0) {  // rare: first rows of a CTA, or a group beyond tier 1
-                // copies made HERE so that only this rare branch spills the key/value registers to the stack
-                Prog::finish_keys(keys);  // full 8-byte string prefixes for hashing / publishing
-                const typename Prog::Keys kcopy = keys;
+                // built HERE so that only this rare branch puts key/value structs on the stack
+                typename Prog::Keys kcopy;
+                Prog::eval_keys(p, row, kcopy);  // full key values (8-byte string prefixes) for hashing / publishing
                 const typename Prog::Vals vcopy = vals;
                 const long long r = agg_slow_path<Prog>(p, kcopy, vcopy, row, fp, s_slot, s_fp, s_keys);
                 if (r >= 0) lid = (int)r;
@@ -678,25 +686,230 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
 using namespace b200;
 using namespace b200::jit;
 struct Prog {
-  typedef Params<13, 1> P;
-  static constexpr int IV_N = 0;
-  static constexpr int PTR_TAKE = 0;
-  __device__ __forceinline__ static void row(const P& p, const int64_t out_row, const int64_t row, const bool active, const int pass) {
-    const bool rowok = active && row >= 0;
+  typedef Params<25, 4> P;
+  static constexpr int IV_N = 0, IV_MASK = 1, PTR_SLOT_HASH = 0, PTR_SLOT_ROW = 1, PTR_OVERFLOW = 2;
+  static constexpr int NKEYS = 2, G1 = 3, NLANE = 10, NWARP = 0, U = 2;
+  static constexpr bool PIPE = false;
+  struct Raw {
+    int64_t o0a, o0b; uint64_t pk0;
+    unsigned int sw0a, sw0b;
+    int64_t o1a, o1b; uint64_t pk1;
+    unsigned int sw1a, sw1b;
+    int64_t c2;
+    double c3;
+    double c4;
+    double c5;
+    double c6;
+    uint64_t c7;
+    uint64_t c8;
+    uint64_t c9;
+    int pad_;
+  };
+  struct Keys {
+    Str v0; bool k0;
+    uint64_t p0;
+    Str v1; bool k1;
+    uint64_t p1;
+    int pad_;
+  };
+  struct Vals {
+    int64_t a0; bool k0;
+    double a1; bool k1;
+    double a2; bool k2;
+    double a3; bool k3;
+    double a4; bool k4;
+    uint64_t a5; bool k5;
+    uint64_t a6; bool k6;
+    uint64_t a7; bool k7;
+    int pad_;
+  };
+  __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {
+    { const int64_t* of_ = (const int64_t*)p.ptr[13]; r.o0a = of_[row]; r.o0b = of_[row + 1]; }
+    { const unsigned long long L_ = (unsigned long long)p.ival[2]; r.sw0a = 0u; r.sw0b = 0u;
+      if (L_) { const uintptr_t a_ = (uintptr_t)p.ptr[14] + (unsigned long long)row * L_; const unsigned int* w_ = (const unsigned int*)(a_ & ~(uintptr_t)3);
+        r.sw0a = __ldg(w_); if ((a_ & 3) + L_ > 4) r.sw0b = __ldg(w_ + 1); } }
+    { const int64_t* of_ = (const int64_t*)p.ptr[15]; r.o1a = of_[row]; r.o1b = of_[row + 1]; }
+    { const unsigned long long L_ = (unsigned long long)p.ival[3]; r.sw1a = 0u; r.sw1b = 0u;
+      if (L_) { const uintptr_t a_ = (uintptr_t)p.ptr[16] + (unsigned long long)row * L_; const unsigned int* w_ = (const unsigned int*)(a_ & ~(uintptr_t)3);
+        r.sw1a = __ldg(w_); if ((a_ & 3) + L_ > 4) r.sw1b = __ldg(w_ + 1); } }
+    r.c2 = ((const int64_t*)p.ptr[17])[row];
+    r.c3 = ((const double*)p.ptr[18])[row];
+    r.c4 = ((const double*)p.ptr[19])[row];
+    r.c5 = ((const double*)p.ptr[20])[row];
+    r.c6 = ((const double*)p.ptr[21])[row];
+    r.c7 = ((const uint64_t*)p.ptr[22])[row];
+    r.c8 = ((const uint64_t*)p.ptr[23])[row];
+    r.c9 = ((const uint64_t*)p.ptr[24])[row];
+  }
+  __device__ __forceinline__ static void load2(const P& p, const int64_t row, Raw& r) {
+    { const unsigned long long L_ = (unsigned long long)p.ival[2]; const long long len_ = r.o0b - r.o0a;
+      if (L_ && (unsigned long long)r.o0a == (unsigned long long)row * L_ && len_ <= (long long)L_) {
+        const unsigned int sh_ = (unsigned int)(((uintptr_t)p.ptr[14] + (unsigned long long)r.o0a) & 3) * 8u;
+        unsigned int v_ = __funnelshift_r(r.sw0a, r.sw0b, sh_); const unsigned int nb_ = len_ > 0 ? (unsigned int)len_ : 0u;
+        v_ &= nb_ >= 4u ? 0xFFFFFFFFu : ((1u << (nb_ * 8u)) - 1u); r.pk0 = (uint64_t)v_;
+      } else r.pk0 = str_pack4(Str{(const uint8_t*)p.ptr[14] + r.o0a, len_}); }
+    { const unsigned long long L_ = (unsigned long long)p.ival[3]; const long long len_ = r.o1b - r.o1a;
+      if (L_ && (unsigned long long)r.o1a == (unsigned long long)row * L_ && len_ <= (long long)L_) {
+        const unsigned int sh_ = (unsigned int)(((uintptr_t)p.ptr[16] + (unsigned long long)r.o1a) & 3) * 8u;
+        unsigned int v_ = __funnelshift_r(r.sw1a, r.sw1b, sh_); const unsigned int nb_ = len_ > 0 ? (unsigned int)len_ : 0u;
+        v_ &= nb_ >= 4u ? 0xFFFFFFFFu : ((1u << (nb_ * 8u)) - 1u); r.pk1 = (uint64_t)v_;
+      } else r.pk1 = str_pack4(Str{(const uint8_t*)p.ptr[16] + r.o1a, len_}); }
+  }
+  __device__ __forceinline__ static void load0(const P& p, const int64_t row, Raw& r) {
+  }
+  __device__ __forceinline__ static void copy0(Raw& d, const Raw& s) {
+  }
+  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {
+    const Str v0{(const uint8_t*)p.ptr[14] + r.o0a, r.o0b - r.o0a};
+    const bool k0 = true;
+    keys.v0 = v0; keys.k0 = k0;
+    keys.p0 = keys.k0 ? r.pk0 : 0ULL;
+    const Str v1{(const uint8_t*)p.ptr[16] + r.o1a, r.o1b - r.o1a};
+    const bool k1 = true;
+    keys.v1 = v1; keys.k1 = k1;
+    keys.p1 = keys.k1 ? r.pk1 : 0ULL;
+    const int64_t v2 = r.c2; const bool k2 = true;
+    vals.a0 = (int64_t)v2; vals.k0 = k2;
+    const double v3 = r.c3; const bool k3 = true;
+    vals.a1 = (double)v3; vals.k1 = k3;
+    const double v4 = r.c4; const bool k4 = true;
+    vals.a2 = (double)v4; vals.k2 = k4;
+    const double v5 = r.c5; const bool k5 = true;
+    vals.a3 = (double)v5; vals.k3 = k5;
+    const double v6 = r.c6; const bool k6 = true;
+    vals.a4 = (double)v6; vals.k4 = k6;
+    const uint64_t v7 = r.c7; const bool k7 = true;
+    vals.a5 = (uint64_t)v7; vals.k5 = k7;
+    const uint64_t v8 = r.c8; const bool k8 = true;
+    vals.a6 = (uint64_t)v8; vals.k6 = k8;
+    const uint64_t v9 = r.c9; const bool k9 = true;
+    vals.a7 = (uint64_t)v9; vals.k7 = k9;
+    return true;
+  }
+  __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {
+    const bool rowok = true;
     const bool k0 = rowok;
     Str v0{(const uint8_t*)0, 0};
-    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[1]; const int64_t a_ = of_[row]; v0.p = (const uint8_t*)p.ptr[2] + a_; v0.len = of_[row + 1] - a_; }
-    // ---- output 0 (large_utf8)
-    { const unsigned m_ = __ballot_sync(FULL_MASK, active && k0); if (pass == 0 && (threadIdx.x & 31) == 0) ((uint32_t*)p.ptr[3])[out_row >> 5] = m_; }
-    if (pass == 0) { if (active) ((int64_t*)p.ptr[4])[out_row] = k0 ? v0.len : 0; }
-    else if (active && k0) { uint8_t* d_ = (uint8_t*)p.ptr[5] + ((const int64_t*)p.ptr[6])[out_row]; for (int64_t j_ = 0; j_ < v0.len; j_++) d_[j_] = v0.p[j_]; }
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[13]; const int64_t a_ = of_[row]; v0.p = (const uint8_t*)p.ptr[14] + a_; v0.len = of_[row + 1] - a_; }
+    keys.v0 = v0; keys.k0 = k0;
+    keys.p0 = keys.k0 ? str_pack8(keys.v0) : 0ULL;
     const bool k1 = rowok;
     Str v1{(const uint8_t*)0, 0};
-    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[7]; const int64_t a_ = of_[row]; v1.p = (const uint8_t*)p.ptr[8] + a_; v1.len = of_[row + 1] - a_; }
-    // ---- output 1 (large_utf8)
-    { const unsigned m_ = __ballot_sync(FULL_MASK, active && k1); if (pass == 0 && (threadIdx.x & 31) == 0) ((uint32_t*)p.ptr[9])[out_row >> 5] = m_; }
-    if (pass == 0) { if (active) ((int64_t*)p.ptr[10])[out_row] = k1 ? v1.len : 0; }
-    else if (active && k1) { uint8_t* d_ = (uint8_t*)p.ptr[11] + ((const int64_t*)p.ptr[12])[out_row]; for (int64_t j_ = 0; j_ < v1.len; j_++) d_[j_] = v1.p[j_]; }
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[15]; const int64_t a_ = of_[row]; v1.p = (const uint8_t*)p.ptr[16] + a_; v1.len = of_[row + 1] - a_; }
+    keys.v1 = v1; keys.k1 = k1;
+    keys.p1 = keys.k1 ? str_pack8(keys.v1) : 0ULL;
+  }
+  __device__ __forceinline__ static uint64_t hash(const Keys& k) {
+    uint64_t h = 0;
+    h = (k.k0 ? hash_str_packed(k.v0, k.p0, 0ULL) : xxh::hash_empty(0ULL));
+    h = (k.k1 ? hash_str_packed(k.v1, k.p1, h) : xxh::hash_empty(h));
+    return h;
+  }
+  __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {
+    return true && (a.k0 == b.k0) && (!a.k0 || str_eq_packed(a.v0, a.p0, b.v0, b.p0)) && (a.k1 == b.k1) && (!a.k1 || str_eq_packed(a.v1, a.p1, b.v1, b.p1));
+  }
+  __device__ __forceinline__ static void finish_keys(Keys& k) {
+    k.p0 = k.k0 ? str_pack8(k.v0) : 0ULL;
+    k.p1 = k.k1 ? str_pack8(k.v1) : 0ULL;
+  }
+  __device__ __forceinline__ static uint64_t fingerprint(const Keys& k) {
+    uint64_t f = 0x9E3779B97F4A7C15ULL;
+    f = (f ^ (k.k0 ? (k.p0 ^ ((uint64_t)k.v0.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    f = (f ^ (k.k1 ? (k.p1 ^ ((uint64_t)k.v1.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    return f;
+  }
+  __device__ __forceinline__ static uint64_t code(const Keys& k) {
+    uint64_t c = 0x4000000000000000ULL; bool ex = true;
+    { const uint64_t l_ = k.k0 ? (uint64_t)k.v0.len : 0ULL; ex = ex && (l_ <= 3ULL); c |= (k.p0 & 16777215ULL) << 0; c |= (l_ & 7ULL) << 24; }
+    { const uint64_t l_ = k.k1 ? (uint64_t)k.v1.len : 0ULL; ex = ex && (l_ <= 3ULL); c |= (k.p1 & 16777215ULL) << 27; c |= (l_ & 7ULL) << 51; }
+    return ex ? c : (fingerprint(k) | 0x8000000000000000ULL);
+  }
+  __device__ __forceinline__ static void lane_init(unsigned long long* cells) {
+    cells[0] = 0ULL;
+    cells[32] = 0ULL;
+    cells[64] = 0ULL;
+    cells[96] = 0ULL;
+    cells[128] = 0ULL;
+    cells[160] = 0ULL;
+    cells[192] = 0ULL;
+    cells[224] = 0ULL;
+    cells[256] = 0ULL;
+    cells[288] = 0xFFFFFFFFFFFFFFFFULL;
+  }
+  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v, const int64_t row) {
+    if (v.k0) cells[0] += (unsigned long long)v.a0;
+    if (v.k1) cells[32] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[32]) + v.a1);
+    if (v.k2) cells[64] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[64]) + v.a2);
+    if (v.k3) cells[96] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[96]) + v.a3);
+    if (v.k4) cells[128] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[128]) + v.a4);
+    if (v.k5) cells[160] += (unsigned long long)v.a5;
+    if (v.k6) cells[192] += (unsigned long long)v.a6;
+    if (v.k7) cells[224] += (unsigned long long)v.a7;
+    cells[256] += 1ULL;
+    if ((unsigned long long)row < cells[288]) cells[288] = (unsigned long long)row;
+  }
+  __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {
+    if (v.k0) atomicAdd(((unsigned long long*)p.ptr[3]) + slot, (unsigned long long)v.a0);
+    if (v.k1) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), v.a1);
+    if (v.k2) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), v.a2);
+    if (v.k3) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), v.a3);
+    if (v.k4) atomicAdd((double*)(((unsigned long long*)p.ptr[7]) + slot), v.a4);
+    if (v.k5) atomicAdd(((unsigned long long*)p.ptr[8]) + slot, (unsigned long long)v.a5);
+    if (v.k6) atomicAdd(((unsigned long long*)p.ptr[9]) + slot, (unsigned long long)v.a6);
+    if (v.k7) atomicAdd(((unsigned long long*)p.ptr[10]) + slot, (unsigned long long)v.a7);
+    atomicAdd(((unsigned long long*)p.ptr[11]) + slot, 1ULL);
+    atomicMin(((unsigned long long*)p.ptr[12]) + slot, (unsigned long long)row);
+  }
+  __device__ __forceinline__ static void warp_cells(const Vals& v, const bool in_g, unsigned long long* wcell, const int lane) {
+  }
+  __device__ __forceinline__ static void flush(const P& p, const long long slot, const unsigned long long* lcell, const size_t lstride,
+                                               const unsigned long long* wcell, const size_t wstride, const int lane) {
+    {
+      unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 0 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[3]) + slot, a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 32 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 64 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 96 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 128 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[7]) + slot), a_);
+    }
+    {
+      unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 160 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[8]) + slot, a_);
+    }
+    {
+      unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 192 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[9]) + slot, a_);
+    }
+    {
+      unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 224 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[10]) + slot, a_);
+    }
+    { unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 256 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[11]) + slot, a_); }
+    { unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 288 + lane]; a_ = t_ < a_ ? t_ : a_; }
+      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }
+      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[12]) + slot, a_); }
   }
 };
-extern "C" __global__ void __launch_bounds__(256) b200_project_k(const __grid_constant__ Prog::P p, int pass) { project_body<Prog>(p, pass); }
+extern "C" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }

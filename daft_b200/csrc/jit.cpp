@@ -840,9 +840,26 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
                 load << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
             }
             // second load phase: the first <= 8 bytes of the value (depends on the offsets of phase one)
-            load2 << "    r.pk" << c << " = " << (is_pack4_col(c) ? "str_pack4" : "str_pack8") << "(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c
-                  << "a, r.o" << c << "b - r.o" << c << "a});\n";
-            raw_bytes += 24;
+            if (is_pack4_col(c)) {
+                // Fixed-length value columns (flags, codes): the host passes L = data_bytes / rows when that divides
+                // evenly.  The value's bytes are then fetched SPECULATIVELY at data + row * L together with the
+                // offsets (one memory round trip instead of two) and used only if the offsets confirm the guess.
+                const int iv = cg.int_slot(I_STRLEN + 1000 * c);
+                raw << "    unsigned int sw" << c << "a, sw" << c << "b;\n";
+                load << "    { const unsigned long long L_ = (unsigned long long)p.ival[" << iv << "]; r.sw" << c << "a = 0u; r.sw" << c << "b = 0u;\n"
+                     << "      if (L_) { const uintptr_t a_ = (uintptr_t)" << cg.P(P_COL_DATA, c) << " + (unsigned long long)row * L_; const unsigned int* w_ = (const unsigned int*)(a_ & ~(uintptr_t)3);\n"
+                     << "        r.sw" << c << "a = __ldg(w_); if ((a_ & 3) + L_ > 4) r.sw" << c << "b = __ldg(w_ + 1); } }\n";
+                load2 << "    { const unsigned long long L_ = (unsigned long long)p.ival[" << iv << "]; const long long len_ = r.o" << c << "b - r.o" << c << "a;\n"
+                      << "      if (L_ && (unsigned long long)r.o" << c << "a == (unsigned long long)row * L_ && len_ <= (long long)L_) {\n"
+                      << "        const unsigned int sh_ = (unsigned int)(((uintptr_t)" << cg.P(P_COL_DATA, c) << " + (unsigned long long)r.o" << c << "a) & 3) * 8u;\n"
+                      << "        unsigned int v_ = __funnelshift_r(r.sw" << c << "a, r.sw" << c << "b, sh_); const unsigned int nb_ = len_ > 0 ? (unsigned int)len_ : 0u;\n"
+                      << "        v_ &= nb_ >= 4u ? 0xFFFFFFFFu : ((1u << (nb_ * 8u)) - 1u); r.pk" << c << " = (uint64_t)v_;\n"
+                      << "      } else r.pk" << c << " = str_pack4(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, len_}); }\n";
+                raw_bytes += 32;
+            } else {
+                load2 << "    r.pk" << c << " = str_pack8(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, r.o" << c << "b - r.o" << c << "a});\n";
+                raw_bytes += 24;
+            }
         } else if (dt == B200_BOOL) {
             raw << "    bool c" << c << ";\n";
             load << "    r.c" << c << " = bit_at((const uint8_t*)" << cg.P(P_COL_DATA, c) << ", row);\n";
@@ -1083,7 +1100,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     o << "  struct Keys {\n" << keys_s.str() << "    int pad_;\n  };\n";
     o << "  struct Vals {\n" << vals_s.str() << "    int pad_;\n  };\n";
     o << "  __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {\n" << load.str() << "  }\n";
-    o << "  __device__ __forceinline__ static void load2(const P& p, Raw& r) {\n" << load2.str() << "  }\n";
+    o << "  __device__ __forceinline__ static void load2(const P& p, const int64_t row, Raw& r) {\n" << load2.str() << "  }\n";
     o << "  __device__ __forceinline__ static void load0(const P& p, const int64_t row, Raw& r) {\n" << load0.str() << "  }\n";
     o << "  __device__ __forceinline__ static void copy0(Raw& d, const Raw& s) {\n" << copy0.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {\n" << ev.str() << "  }\n";

@@ -15,7 +15,7 @@ enum PtrKind {
     P_TAKE, P_SLOT_HASH, P_SLOT_ROW, P_ACC, P_OVERFLOW
 };
 struct PtrSlot { int kind; int index; };
-enum IntKind { I_N = 0, I_MASK };
+enum IntKind { I_N = 0, I_MASK, I_STRLEN /* + 1000 * column: constant value length hint of a string column, 0 = none */ };
 
 struct OutCol {
     std::string name;

@@ -54,31 +54,36 @@ __device__ __forceinline__ uint64_t ord_u64(uint64_t v) { return v; }
 
 // ---- string helpers ---------------------------------------------------------------------------------
 // first min(len, 8) bytes of a string packed little-endian into a register (zero padded): short keys
-// (TPC-H flags, codes) are then hashed and compared without touching memory again
+// (TPC-H flags, codes) are then hashed and compared without touching memory again.
+// Both packers are branch-free (selects + predicated loads of aligned words that contain bytes of the value, so
+// they never leave the allocation) so that the loads of several rows/columns are all in flight before the
+// first one is consumed.
 __device__ __forceinline__ uint64_t str_pack8(Str a) {
-    if (a.len <= 0) return 0ULL;
-    // one or two aligned 8-byte words (never leaves the allocation: the words contain bytes of the string)
     const uintptr_t addr = (uintptr_t)a.p;
-    const uint64_t *w = (const uint64_t *)(addr & ~(uintptr_t)7);
+    const bool any = a.len > 0;
     const int sh = (int)(addr & 7) * 8;
     const int nbits = (a.len < 8 ? (int)a.len : 8) * 8;
-    uint64_t v = w[0] >> sh;
-    if (sh + nbits > 64) v |= w[1] << (64 - sh);
-    if (nbits < 64) v &= (1ULL << nbits) - 1ULL;
+    const unsigned long long *w = (const unsigned long long *)(addr & ~(uintptr_t)7);
+    unsigned long long w0 = 0ULL, w1 = 0ULL;
+    if (any) w0 = __ldg(w);
+    if (any && sh + nbits > 64) w1 = __ldg(w + 1);
+    unsigned long long v = w0 >> sh;
+    v |= sh ? (w1 << (64 - sh)) : 0ULL;
+    v &= nbits >= 64 ? ~0ULL : ((1ULL << nbits) - 1ULL);
     return v;
 }
-// first min(len, 4) bytes with 32-bit arithmetic only: one aligned word, a second one only when the value
-// straddles it, one funnel shift (short key columns on the exact-code path need at most 3 bytes)
+// first min(len, 4) bytes with 32-bit arithmetic only (short key columns on the exact-code path need <= 3 bytes)
 __device__ __forceinline__ uint64_t str_pack4(Str a) {
-    if (a.len <= 0) return 0ULL;
     const uintptr_t addr = (uintptr_t)a.p;
-    const uint32_t *w = (const uint32_t *)(addr & ~(uintptr_t)3);
+    const bool any = a.len > 0;
     const uint32_t sh = (uint32_t)(addr & 3) * 8u;
     const uint32_t nb = a.len < 4 ? (uint32_t)a.len : 4u;
-    const uint32_t w0 = w[0];
-    const uint32_t w1 = (sh + nb * 8u > 32u) ? w[1] : 0u;
-    uint32_t v = __funnelshift_r(w0, w1, sh);
-    if (nb < 4u) v &= (1u << (nb * 8u)) - 1u;
+    const unsigned int *w = (const unsigned int *)(addr & ~(uintptr_t)3);
+    unsigned int w0 = 0u, w1 = 0u;
+    if (any) w0 = __ldg(w);
+    if (any && sh + nb * 8u > 32u) w1 = __ldg(w + 1);
+    unsigned int v = __funnelshift_r(w0, w1, sh);
+    v &= nb >= 4u ? 0xFFFFFFFFu : ((1u << (nb * 8u)) - 1u);
     return (uint64_t)v;
 }
 __device__ __forceinline__ uint64_t hash_str_packed(Str a, uint64_t pk, uint64_t seed) {
@@ -335,14 +340,14 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
             const int64_t row = base + u * 32 + lane;
             if (row < n) {
                 Prog::load(p, row, raw[u]);
-                if (Prog::PIPE) Prog::load2(p, raw[u]);
+                if (Prog::PIPE) Prog::load2(p, row, raw[u]);
             }
         }
         if (!Prog::PIPE) {
 #pragma unroll
             for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
                 const int64_t row = base + u * 32 + lane;
-                if (row < n) Prog::load2(p, raw[u]);
+                if (row < n) Prog::load2(p, row, raw[u]);
             }
         }
         typename Prog::Raw nxt[U];
@@ -354,26 +359,29 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int64_t row = base + u * 32 + lane;
-            typename Prog::Keys keys;
             typename Prog::Vals vals;
             bool live = row < n;
-            if (live) live = Prog::eval(p, raw[u], keys, vals);
             // tier 1: the CTA's first G1 groups, matched on a 64-bit code of the key VALUES held in registers
             // (no xxh3, no global memory on this path)
             // key code: exact (injective, bit 63 clear) when the key tuple is narrow, else fingerprint | bit 63
             unsigned long long fp = 0ULL;
-            if (live) fp = Prog::NKEYS > 0 ? Prog::code(keys) : 1ULL;
+            {
+                typename Prog::Keys keys;  // dead after the code is formed: the rare paths re-read the keys by row
+                if (live) live = Prog::eval(p, raw[u], keys, vals);
+                if (live) fp = Prog::NKEYS > 0 ? Prog::code(keys) : 1ULL;
+            }
             int lid = -1;
 #pragma unroll
             for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
             if (Prog::NKEYS > 0 && live && lid >= 0 && (fp >> 63)) {  // only inexact codes need the value check
-                Prog::finish_keys(keys);
-                if (!Prog::keys_equal(keys, s_keys[lid])) lid = -1;
+                typename Prog::Keys kv;
+                Prog::eval_keys(p, row, kv);
+                if (!Prog::keys_equal(kv, s_keys[lid])) lid = -1;
             }
             if (live && lid < 0) {  // rare: first rows of a CTA, or a group beyond tier 1
-                // copies made HERE so that only this rare branch spills the key/value registers to the stack
-                Prog::finish_keys(keys);  // full 8-byte string prefixes for hashing / publishing
-                const typename Prog::Keys kcopy = keys;
+                // built HERE so that only this rare branch puts key/value structs on the stack
+                typename Prog::Keys kcopy;
+                Prog::eval_keys(p, row, kcopy);  // full key values (8-byte string prefixes) for hashing / publishing
                 const typename Prog::Vals vcopy = vals;
                 const long long r = agg_slow_path<Prog>(p, kcopy, vcopy, row, fp, s_slot, s_fp, s_keys);
                 if (r >= 0) lid = (int)r;

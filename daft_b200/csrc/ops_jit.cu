@@ -307,7 +307,17 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
                     default: fail("agg: unexpected parameter kind");
                 }
             }
-            for (size_t s = 0; s < k.ints.size(); s++) a.ival[s] = k.ints[s] == jit::I_N ? n : (cap - 1);
+            for (size_t s = 0; s < k.ints.size(); s++) {
+                const int kind = k.ints[s] % 1000, idx = k.ints[s] / 1000;
+                if (kind == jit::I_N) a.ival[s] = n;
+                else if (kind == jit::I_MASK) a.ival[s] = cap - 1;
+                else if (kind == jit::I_STRLEN) {
+                    // constant-length hint: bytes divide evenly over the rows (verified per row in the kernel)
+                    const Column &sc = in.cols[idx];
+                    const int64_t L = (sc.length > 0 && sc.data_bytes % sc.length == 0) ? sc.data_bytes / sc.length : 0;
+                    a.ival[s] = (L >= 1 && L <= 4) ? L : 0;
+                }
+            }
             int occ = 0;
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k.fn, 256, k.smem_bytes));
             occ = std::max(1, occ);
