@@ -202,14 +202,23 @@ __global__ void gather_u64(const unsigned long long *__restrict__ src, const int
     if (i < n) out[i] = src[idx[i]];
 }
 
+struct FinalizeDesc {
+    int kind, val_dtype, out_dtype, cnt_is_valid_count, const_zero, _pad;
+    const unsigned long long *cell;
+    const unsigned long long *cnt;
+    void *out;
+    uint32_t *out_valid;
+};
+constexpr int MAX_FINALIZE = 32;
+struct FinalizeSet {
+    int n;
+    FinalizeDesc d[MAX_FINALIZE];
+};
 // cell (8-byte) -> typed output value
-__global__ void finalize_agg(int kind, int32_t val_dtype, int32_t out_dtype, const unsigned long long *__restrict__ cell,
-                             const unsigned long long *__restrict__ cnt, int cnt_is_valid_count, int const_zero,
-                             const int64_t *__restrict__ slots, int64_t ng, void *__restrict__ out,
-                             uint32_t *__restrict__ out_valid) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t g_round = (ng + 31) & ~(int64_t)31;
-    if (i >= g_round) return;
+__device__ __forceinline__ void finalize_one(int kind, int32_t val_dtype, int32_t out_dtype, const unsigned long long *__restrict__ cell,
+                                             const unsigned long long *__restrict__ cnt, int cnt_is_valid_count, int const_zero,
+                                             const int64_t *__restrict__ slots, int64_t ng, void *__restrict__ out,
+                                             uint32_t *__restrict__ out_valid, int64_t i) {
     bool valid = false;
     if (i < ng) {
         const int64_t s = slots[i];
@@ -261,6 +270,15 @@ __global__ void finalize_agg(int kind, int32_t val_dtype, int32_t out_dtype, con
     if (out_valid && (threadIdx.x & 31) == 0) out_valid[i >> 5] = m;
 }
 
+// every aggregate column of the output in ONE launch (grid.y = aggregate)
+__global__ void finalize_agg_all(FinalizeSet fs, const int64_t *__restrict__ slots, int64_t ng) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t g_round = (ng + 31) & ~(int64_t)31;
+    if (i >= g_round) return;
+    const FinalizeDesc &d = fs.d[blockIdx.y];
+    finalize_one(d.kind, d.val_dtype, d.out_dtype, d.cell, d.cnt, d.cnt_is_valid_count, d.const_zero, slots, ng, d.out, d.out_valid, i);
+}
+
 Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng);  // sort.cu
 
 Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *first_rows, int64_t *ngroups) {
@@ -283,12 +301,9 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         slot_hash = dev_alloc_zero((size_t)cap * 8);
         slot_row = dev_alloc((size_t)cap * 8);
         fill_u8(slot_row->ptr, 0xFF, (size_t)cap * 8);
-        acc = dev_alloc((size_t)ncells * cap * 8);
-        for (int c = 0; c < ncells; c++) {
-            int fillv = 0;
-            if (c < k.NLANE && k.lane_cell_ops[c] == jit::C_MIN) fillv = 0xFF;
-            fill_u8(as<uint8_t>(acc) + (size_t)c * cap * 8, fillv, (size_t)cap * 8);
-        }
+        acc = dev_alloc_zero((size_t)ncells * cap * 8);
+        for (int c = 0; c < k.NLANE; c++)
+            if (k.lane_cell_ops[c] == jit::C_MIN) fill_u8(as<uint8_t>(acc) + (size_t)c * cap * 8, 0xFF, (size_t)cap * 8);
         fill_u8(overflow->ptr, 0, 8);
         if (n > 0) {
             LaunchArgs a;
@@ -362,6 +377,17 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         out = std::make_unique<Batch>();
         out->num_rows = ng;
     }
+    FinalizeSet fs;
+    fs.n = 0;
+    std::vector<Column> agg_cols;
+    auto flush_finalize = [&]() {
+        if (fs.n && ng > 0) {
+            dim3 grid((unsigned)((ng + 255) / 256), (unsigned)fs.n);
+            finalize_agg_all<<<grid, 256, 0, st>>>(fs, as<int64_t>(slots), ng);
+            count_launch();
+        }
+        fs.n = 0;
+    };
     for (const auto &ag : k.aggs) {
         Column c;
         c.name = ag.name;
@@ -376,12 +402,12 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         const unsigned long long *cnt = ag.cnt_cell >= 0 ? as<unsigned long long>(acc) + (size_t)(k.NLANE + ag.cnt_cell) * cap : nrows_cell;
         // an ungrouped aggregate over zero rows still yields one row: sums null, counts 0
         const int cnt_is_valid = (ag.kind != jit::AGG_COUNT) ? 1 : 0;
-        if (ng > 0) {
-            finalize_agg<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(ag.kind, ag.val_dtype, ag.out_dtype, cell, cnt, cnt_is_valid,
-                                                                        ag.const_zero ? 1 : 0, as<int64_t>(slots), ng, c.data->ptr,
-                                                                        as<uint32_t>(c.validity));
-            count_launch();
-        }
+        fs.d[fs.n++] = {ag.kind, ag.val_dtype, ag.out_dtype, cnt_is_valid, ag.const_zero ? 1 : 0, 0, cell, cnt, c.data->ptr, as<uint32_t>(c.validity)};
+        agg_cols.push_back(std::move(c));
+        if (fs.n == MAX_FINALIZE) flush_finalize();
+    }
+    flush_finalize();
+    for (auto &c : agg_cols) {
         if (c.validity) {
             c.null_count = ng - count_set_bits(as<uint8_t>(c.validity), ng);
             if (c.null_count == 0) c.validity.reset();

@@ -28,11 +28,12 @@ def _u8(xs: Sequence[Any]):
 
 
 class RecordBatch:
-    __slots__ = ("_h", "_schema", "__weakref__")
+    __slots__ = ("_h", "_schema", "_names", "_dtypes", "__weakref__")
 
     def __init__(self, handle: int, schema: pa.Schema | None = None):
         self._h = ctypes.c_void_p(handle)
         self._schema = schema  # logical Arrow types (e.g. timestamp units) for round-tripping
+        self._names = self._dtypes = None  # batches are immutable: schema queried once
 
     def __del__(self):
         try:
@@ -92,11 +93,20 @@ class RecordBatch:
         _lib.call("b200_batch_describe", self._h, ctypes.c_int32(i), ctypes.byref(d))
         return d
 
+    def _load_schema(self):
+        ds = [self._describe(i) for i in range(self.num_columns())]
+        self._names = [d.name.decode() for d in ds]
+        self._dtypes = [d.dtype for d in ds]
+
     def column_names(self) -> list[str]:
-        return [self._describe(i).name.decode() for i in range(self.num_columns())]
+        if self._names is None:
+            self._load_schema()
+        return list(self._names)
 
     def dtypes(self) -> list[int]:
-        return [self._describe(i).dtype for i in range(self.num_columns())]
+        if self._dtypes is None:
+            self._load_schema()
+        return list(self._dtypes)
 
     def schema(self) -> list[tuple[str, int]]:
         return list(zip(self.column_names(), self.dtypes()))
@@ -123,6 +133,7 @@ class RecordBatch:
         out = self.select_columns(list(range(self.num_columns())))
         for i, n in enumerate(names):
             _lib.call("b200_batch_rename", out._h, ctypes.c_int32(i), n.encode())
+        out._names = out._dtypes = None
         return out
 
     def union(self, other: "RecordBatch") -> "RecordBatch":

@@ -1,0 +1,54 @@
+"""Run under torchrun (one process per GPU): NCCL hash-repartition exchange + all-gather vs the oracle."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import pyarrow as pa
+import torch
+import torch.distributed as dist
+
+import daft_b200
+from daft_b200 import col, distributed
+from helpers import assert_tables_equal, random_table
+from oracle import oracle as O
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    daft_b200.init(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = distributed.Communicator()
+    rng = np.random.default_rng(100 + rank)
+    n = 20000 + 1000 * rank
+    tbl = random_table(rng, n, 0.1)
+    rb = daft_b200.RecordBatch.from_arrow_table(tbl)
+    for keys in (["i64"], ["s", "u8"]):
+        got = comm.exchange_by_hash(rb, [col(k) for k in keys]).to_arrow_table()
+        parts = [None] * world
+        dist.all_gather_object(parts, distributed._to_ipc(tbl))
+        want = pa.concat_tables([O.partition_by_hash(distributed._from_ipc(p), keys, world)[rank] for p in parts])
+        assert_tables_equal(got, want)
+    allg = comm.all_gather(rb).to_arrow_table()
+    parts = [None] * world
+    dist.all_gather_object(parts, distributed._to_ipc(tbl))
+    assert_tables_equal(allg, pa.concat_tables([distributed._from_ipc(p) for p in parts]))
+    # high-cardinality group-by through the exchange == single-table oracle
+    full = pa.concat_tables([distributed._from_ipc(p) for p in parts])
+    mine = comm.exchange_by_hash(rb, [col("i32")]).agg([col("f64").sum().alias("s"), col("i32").count("all").alias("c")], [col("i32")]).to_arrow_table()
+    gathered = distributed.gather_tables(mine).sort_by([("i32", "ascending")])
+    from helpers import oracle_agg
+    want = oracle_agg(full, [col("f64").sum().alias("s"), col("i32").count("all").alias("c")], [col("i32")]).sort_by([("i32", "ascending")])
+    assert_tables_equal(gathered, want, float_rtol=1e-9)
+    dist.barrier()
+    if rank == 0:
+        print(f"exchange ok on {world} GPUs")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
