@@ -189,7 +189,7 @@ def main():
     import pyarrow as pa
 
     import daft_b200
-    from daft_b200 import _lib, tpch
+    from daft_b200 import _lib, distributed, tpch
 
     torch.cuda.set_device(local_rank)
     daft_b200.init(local_rank)
@@ -216,9 +216,7 @@ def main():
         if world == 1:
             return tpch.q1(batch)
         part = tpch.q1_partial(batch).to_arrow_table()
-        gathered = [None] * world
-        dist.all_gather_object(gathered, part)
-        return tpch.q1_final(daft_b200.RecordBatch.from_arrow_table(pa.concat_tables(gathered)))
+        return tpch.q1_final(daft_b200.RecordBatch.from_arrow_table(distributed.gather_tables(part)))
 
     # ---------------- value: inputs resident in HBM ----------------
     L.b200_kernel_timing(1)

@@ -228,8 +228,119 @@ static void export_column(const Column &c, ArrowArray *a, ArrowSchema *s) {
     a->buffers = ap->bufptrs.data();
 }
 
+// ---- small batches: every device buffer is packed into one staging block by ONE kernel and comes back with ONE
+// copy (a 4-row aggregate result has ~20 buffers; 20 tiny cudaMemcpyAsync calls cost more than the query's epilogue)
+struct PackDesc {
+    const uint8_t *src;
+    int64_t dst_off, bytes;
+};
+constexpr int PACK_MAX = 96;
+struct PackSet {
+    int n;
+    PackDesc d[PACK_MAX];
+};
+__global__ void pack_buffers(PackSet ps, uint8_t *__restrict__ dst) {
+    const PackDesc d = ps.d[blockIdx.y];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.bytes; i += (int64_t)gridDim.x * blockDim.x)
+        dst[d.dst_off + i] = d.src[i];
+}
+
+static bool export_batch_packed(const Batch &b, ArrowArray *out_array, ArrowSchema *out_schema) {
+    // plan the layout
+    struct Plan { int col, slot; int64_t off, bytes; const void *src; };
+    std::vector<Plan> plan;
+    int64_t total = 0;
+    auto add = [&](int col, int slot, const void *src, int64_t bytes) {
+        plan.push_back({col, slot, total, bytes, src});
+        total += (bytes + 15) & ~(int64_t)15;
+    };
+    for (size_t ci = 0; ci < b.cols.size(); ci++) {
+        const Column &c = b.cols[ci];
+        const int64_t n = c.length;
+        if (c.dtype == B200_NULL) continue;
+        if (c.null_count > 0) add((int)ci, 0, c.validity->ptr, (n + 7) / 8);
+        const int w = dtype_width(c.dtype);
+        if (w) add((int)ci, 1, c.data ? c.data->ptr : nullptr, n * w);
+        else if (c.dtype == B200_BOOL) add((int)ci, 1, c.data ? c.data->ptr : nullptr, (n + 7) / 8);
+        else {
+            if (!c.offsets) return false;
+            add((int)ci, 1, c.offsets->ptr, (n + 1) * 8);
+            add((int)ci, 2, c.data ? c.data->ptr : nullptr, c.data_bytes);
+        }
+    }
+    if (total > (1 << 20) || plan.size() > PACK_MAX) return false;
+    uint8_t *host = static_cast<uint8_t *>(malloc((size_t)total + 64));
+    if (!host) fail("export: out of host memory");
+    if (total > 0) {
+        Buf stage = dev_alloc((size_t)total);
+        PackSet ps;
+        ps.n = 0;
+        int64_t maxb = 1;
+        for (auto &p : plan)
+            if (p.bytes > 0 && p.src) {
+                ps.d[ps.n++] = {static_cast<const uint8_t *>(p.src), p.off, p.bytes};
+                maxb = std::max(maxb, p.bytes);
+            }
+        if (ps.n) {
+            dim3 grid((unsigned)std::min<int64_t>((maxb + 255) / 256, 64), (unsigned)ps.n);
+            pack_buffers<<<grid, 256, 0, ctx().stream>>>(ps, as<uint8_t>(stage));
+            count_launch();
+        }
+        B200_CUDA(cudaMemcpyAsync(host, stage->ptr, (size_t)total, cudaMemcpyDeviceToHost, ctx().stream));
+        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    auto *ap = new ExportPriv, *sp = new ExportPriv;
+    sp->format = "+s";
+    ap->bufs.push_back(host);  // the parent owns the single block
+    memset(out_schema, 0, sizeof(*out_schema));
+    memset(out_array, 0, sizeof(*out_array));
+    for (size_t ci = 0; ci < b.cols.size(); ci++) {
+        const Column &c = b.cols[ci];
+        auto *ca = static_cast<ArrowArray *>(calloc(1, sizeof(ArrowArray)));
+        auto *cs = static_cast<ArrowSchema *>(calloc(1, sizeof(ArrowSchema)));
+        auto *cap = new ExportPriv, *csp = new ExportPriv;
+        csp->name = c.name;
+        csp->format = format_from_dtype(c.dtype);
+        cs->format = csp->format.c_str();
+        cs->name = csp->name.c_str();
+        cs->flags = 2;
+        cs->release = release_schema;
+        cs->private_data = csp;
+        ca->length = c.length;
+        ca->null_count = c.dtype == B200_NULL ? c.length : c.null_count;
+        ca->release = release_array;
+        ca->private_data = cap;
+        if (c.dtype != B200_NULL) {
+            const int nslots = is_string(c.dtype) ? 3 : 2;
+            cap->bufptrs.assign((size_t)nslots, nullptr);
+            for (auto &p : plan)
+                if (p.col == (int)ci) cap->bufptrs[(size_t)p.slot] = host + p.off;
+            ca->n_buffers = nslots;
+            ca->buffers = cap->bufptrs.data();
+        }
+        ap->children.push_back(ca);
+        sp->schildren.push_back(cs);
+    }
+    out_schema->format = sp->format.c_str();
+    out_schema->name = sp->name.c_str();
+    out_schema->n_children = (int64_t)sp->schildren.size();
+    out_schema->children = sp->schildren.data();
+    out_schema->release = release_schema;
+    out_schema->private_data = sp;
+    out_array->length = b.num_rows;
+    out_array->n_buffers = 1;
+    ap->bufptrs.push_back(nullptr);
+    out_array->buffers = ap->bufptrs.data();
+    out_array->n_children = (int64_t)ap->children.size();
+    out_array->children = ap->children.data();
+    out_array->release = release_array;
+    out_array->private_data = ap;
+    return true;
+}
+
 void export_batch(const Batch &b, ArrowArray *out_array, ArrowSchema *out_schema) {
     require_device();
+    if (b.num_rows <= 65536 && export_batch_packed(b, out_array, out_schema)) return;
     auto *ap = new ExportPriv, *sp = new ExportPriv;
     sp->format = "+s";
     sp->name = "";

@@ -33,14 +33,39 @@ def _from_ipc(b: bytes) -> pa.Table:
     return pa.ipc.open_stream(io.BytesIO(b)).read_all()
 
 
+_SMALL_CAP = 1 << 16  # bytes: partial aggregates are a few hundred bytes
+
+
 def gather_tables(tbl: pa.Table, group=None) -> pa.Table:
     """Every rank receives the concatenation (rank order) of all ranks' small host tables
-    (partial aggregates, top-N candidates).  Works on any torch.distributed backend (nccl or gloo)."""
+    (partial aggregates, top-N candidates).  Works on any torch.distributed backend (nccl or gloo).
+    Small payloads travel in ONE fixed-size all-gather (length-prefixed Arrow IPC), large ones fall back
+    to all_gather_object."""
+    import numpy as np
+    import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return tbl
-    parts = [None] * dist.get_world_size(group)
-    dist.all_gather_object(parts, _to_ipc(tbl), group=group)
+    world = dist.get_world_size(group)
+    payload = _to_ipc(tbl)
+    small = len(payload) + 8 <= _SMALL_CAP
+    use_cuda = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    buf = np.zeros(_SMALL_CAP, dtype=np.uint8)
+    if small:
+        buf[:8] = np.frombuffer(np.int64(len(payload)).tobytes(), dtype=np.uint8)
+        buf[8:8 + len(payload)] = np.frombuffer(payload, dtype=np.uint8)
+    else:
+        buf[:8] = np.frombuffer(np.int64(-1).tobytes(), dtype=np.uint8)
+    mine = torch.from_numpy(buf).to(dev)
+    out = torch.empty(world * _SMALL_CAP, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    host = out.cpu().numpy().reshape(world, _SMALL_CAP)
+    lens = [int(np.frombuffer(host[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(world)]
+    if all(l >= 0 for l in lens):
+        return pa.concat_tables([_from_ipc(host[r, 8:8 + lens[r]].tobytes()) for r in range(world)])
+    parts = [None] * world  # some rank has a large table: every rank takes the slow path together
+    dist.all_gather_object(parts, payload, group=group)
     return pa.concat_tables([_from_ipc(p) for p in parts])
 
 
