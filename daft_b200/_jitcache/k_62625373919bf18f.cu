@@ -491,66 +491,184 @@ __device__ __forceinline__ void project_body(const typename Prog::P &p, int pass
 // fused Filter -> Project -> HashAggregate
 // ======================================================================================================
 // Prog provides (all generated):
-//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_SLOT_HASH, PTR_SLOT_ROW, PTR_OVERFLOW;
-//   NKEYS, G1, NLANE (lane cells incl. row count + first row), NWARP (ballot count cells), U, MINB
-//   struct Raw;  struct Keys;  struct Vals;
-//   load(p,row,Raw&) ; bool eval(p,Raw&,Keys&,Vals&) (false = filtered out) ; eval_keys(p,row,Keys&)
-//   uint64 hash(Keys&) ; bool keys_equal(Keys&,Keys&)
-//   lane_init(cell*) ; lane_update(cell*, Vals&, row) ; global_update(p, slot, Vals&, row)
-//   warp_cells(Vals&, in_group, wcell*, lane) ; flush(...)
+//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_TAG, PTR_MINROW (first row per slot = representative row),
+//   PTR_FLAG (int: 0 ok, 1 table overflow, 2 low-cardinality kernel gave up);
+//   NKEYS, G1, NLANE, NWARP, U;  MODE (0: row-dependent exact 62-bit codes, 1: every row exact 63/64-bit code,
+//   2: never exact);  struct Raw / Keys / Vals;
+//   load / load2 / eval / eval_keys / keys_equal / code / lane_init / lane_update / global_update / warp_cells / flush
+//
+// Group identity is carried by a 64-bit key CODE (see jit.cpp "Exact key code"): when it is exact (injective in
+// the key values) equal codes ARE equal keys; otherwise the code is a fingerprint and a match is confirmed against
+// the key values of the slot's representative row (nulls equal, floats by bit pattern -- the reference's
+// "hash equal AND comparator" rule, src/daft-recordbatch/src/ops/inline_agg.rs:760-784).
 constexpr int AGG_WARPS = 8;
+constexpr unsigned long long AGG_EMPTY = 0xFFFFFFFFFFFFFFFFULL;     // min-row cell of an unclaimed slot
+constexpr unsigned long long AGG_CLAIMING = 0xFFFFFFFFFFFFFFFEULL;  // (MODE 1) slot being published
+constexpr int AGG_PROBE_LIMIT = 1024;
 
+__device__ __forceinline__ uint64_t agg_mix(uint64_t x) {
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ULL;
+    x ^= x >> 32;
+    return x;
+}
+
+// Find or claim the global slot of the group with code `tag`.  Returns the slot, or -1 after flagging overflow.
 template <class Prog>
-__device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, const typename Prog::Keys &k, uint64_t h,
-                                                  int64_t row) {
-    unsigned long long *slot_hash = (unsigned long long *)p.ptr[Prog::PTR_SLOT_HASH];
-    long long *slot_row = (long long *)p.ptr[Prog::PTR_SLOT_ROW];
+__device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, unsigned long long tag, int64_t row) {
+    unsigned long long *slot_tag = (unsigned long long *)p.ptr[Prog::PTR_TAG];
+    unsigned long long *slot_min = (unsigned long long *)p.ptr[Prog::PTR_MINROW];
     const uint64_t mask = (uint64_t)p.ival[Prog::IV_MASK];
-    if (h == 0) h = 1;  // 0 marks an empty slot; equality is decided by the key comparison anyway
-    uint64_t s = h & mask;
-    for (uint64_t probes = 0; probes <= mask; probes++) {
-        unsigned long long cur = slot_hash[s];  // may be a stale 0 from L1: the CAS below re-reads at L2
-        bool mine = false;
-        if (cur == 0) {
-            unsigned long long prev = atomicCAS(&slot_hash[s], 0ULL, (unsigned long long)h);
-            if (prev == 0) {
-                // claimed: publish the representative row (written before anyone can need it below)
-                *((volatile long long *)&slot_row[s]) = (long long)row;
-                __threadfence();
-                mine = true;
+    const bool exact = Prog::MODE == 1 || (Prog::MODE == 0 && !(tag >> 63));
+    uint64_t s = agg_mix(tag) & mask;
+    for (int probes = 0; probes < AGG_PROBE_LIMIT; probes++) {
+        if (Prog::MODE == 1) {
+            // tags may take any value: occupancy lives in the min-row cell (EMPTY -> CLAIMING -> first row)
+            unsigned long long m = *((volatile unsigned long long *)&slot_min[s]);
+            if (m == AGG_EMPTY) {
+                const unsigned long long prev = atomicCAS(&slot_min[s], AGG_EMPTY, AGG_CLAIMING);
+                if (prev == AGG_EMPTY) {
+                    *((volatile unsigned long long *)&slot_tag[s]) = tag;
+                    __threadfence();
+                    atomicMin(&slot_min[s], (unsigned long long)row);  // publishes (row < CLAIMING)
+                    return (long long)s;
+                }
+                m = prev;
             }
-            cur = prev == 0 ? h : prev;
-        }
-        if (mine) return (long long)s;
-        if (cur == h) {
-            long long r = slot_row[s];
-            while (r < 0) r = *((volatile long long *)&slot_row[s]);
-            if (r == row) return (long long)s;
-            typename Prog::Keys other;
-            Prog::eval_keys(p, r, other);
-            if (Prog::keys_equal(k, other)) return (long long)s;
+            while (m == AGG_CLAIMING) m = *((volatile unsigned long long *)&slot_min[s]);
+            if (*((volatile unsigned long long *)&slot_tag[s]) == tag) return (long long)s;
+        } else {
+            // tags are never 0 here (bit 62 or bit 63 is set): one CAS on the tag word claims the slot
+            unsigned long long cur = slot_tag[s];  // a stale 0 from L1 is corrected by the CAS below
+            if (cur == 0ULL) {
+                const unsigned long long prev = atomicCAS(&slot_tag[s], 0ULL, tag);
+                if (prev == 0ULL) return (long long)s;  // claimed; the caller's update publishes the first row
+                cur = prev;
+            }
+            if (cur == tag) {
+                if (exact) return (long long)s;
+                unsigned long long r = *((volatile unsigned long long *)&slot_min[s]);
+                while (r == AGG_EMPTY) r = *((volatile unsigned long long *)&slot_min[s]);  // claimer is about to publish
+                if ((int64_t)r == row) return (long long)s;
+                typename Prog::Keys mine, other;
+                Prog::eval_keys(p, row, mine);
+                Prog::eval_keys(p, (int64_t)r, other);
+                if (Prog::keys_equal(mine, other)) return (long long)s;
+            }
         }
         s = (s + 1) & mask;
     }
-    *((int *)p.ptr[Prog::PTR_OVERFLOW]) = 1;  // table full: host retries with a larger table
+    *((volatile int *)p.ptr[Prog::PTR_FLAG]) = 1;  // table too full: the host retries with a larger one
     return -1;
 }
 
-// Rare path, kept out of line so that its registers (XXH3, CAS loops) do not burden the streaming loop:
+// ---- global kernel: mid / high cardinality -------------------------------------------------------------
+// Tier 2: a per-CTA shared-memory table of (exact code -> cells) absorbs the rows of up to T2 groups with
+// shared-memory atomics and is merged into the global table once per CTA, so a few thousand hot groups do not
+// hammer a handful of L2 addresses.  Rows whose group does not fit (or whose code is inexact) go straight to the
+// global table: one CAS to find/claim the slot, then red.global atomics on its cells.
+template <class Prog>
+__device__ __forceinline__ void agg_body_global(const typename Prog::P &p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int T2 = Prog::T2;
+    unsigned long long *t2_tag = (unsigned long long *)smem_raw;  // 0 = empty (codes are never 0)
+    unsigned long long *t2c = t2_tag + T2;                        // cell c of slot t: t2c[c * T2 + t]
+    for (int t = threadIdx.x; t < T2; t += blockDim.x) {
+        t2_tag[t] = 0ULL;
+        Prog::t2_init(t2c, t);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = p.ival[Prog::IV_N];
+    constexpr int U = Prog::U;
+    const int64_t chunk = 32 * U;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+    volatile int *flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
+    int t2_hits = 0, t2_miss = 0;
+    bool use_t2 = T2 >= 64 && Prog::NKEYS > 0;
+    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
+        if (*flag) break;  // someone hit a full table: stop early, the host will retry
+        const int64_t base = c * chunk;
+        typename Prog::Raw raw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load(p, row, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load2(p, row, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            typename Prog::Vals vals;
+            bool live = row < n;
+            unsigned long long tag = 1ULL;
+            {
+                typename Prog::Keys keys;
+                if (live) live = Prog::eval(p, raw[u], keys, vals);
+                if (live && Prog::NKEYS > 0) tag = Prog::code(keys);
+            }
+            if (!live) continue;
+            bool done = false;
+            if (use_t2 && !(tag >> 63)) {  // exact codes only: equal code == equal key, no verification needed
+                unsigned int t = (unsigned int)(agg_mix(tag) >> 40) & (T2 - 1);
+#pragma unroll 1
+                for (int probes = 0; probes < 8 && !done; probes++) {
+                    unsigned long long cur = ((volatile unsigned long long *)t2_tag)[t];
+                    if (cur == 0ULL) {
+                        const unsigned long long prev = atomicCAS(&t2_tag[t], 0ULL, tag);
+                        cur = prev == 0ULL ? tag : prev;
+                    }
+                    if (cur == tag) {
+                        Prog::t2_update(t2c, (int)t, vals, row);
+                        done = true;
+                    }
+                    t = (t + 1) & (T2 - 1);
+                }
+                if (done) t2_hits++;
+                else if (++t2_miss > 256 && t2_miss > 4 * t2_hits) use_t2 = false;  // high cardinality: stop probing tier 2
+            }
+            if (!done) {
+                const long long slot = Prog::NKEYS > 0 ? agg_find_slot<Prog>(p, tag, row) : 0;
+                if (slot >= 0) Prog::global_update(p, slot, vals, row);
+            }
+        }
+    }
+    __syncthreads();
+    // merge tier 2 into the global table (the slot's first row doubles as its representative row)
+    if (!*flag) {
+        for (int t = threadIdx.x; t < T2; t += blockDim.x) {
+            const unsigned long long tag = t2_tag[t];
+            if (tag == 0ULL) continue;
+            const long long slot = agg_find_slot<Prog>(p, tag, (int64_t)t2c[(Prog::NLANE - 1) * T2 + t]);
+            if (slot >= 0) Prog::t2_flush(p, slot, t2c, t);
+        }
+    }
+}
+
+// Rare path of the low-cardinality kernel, kept out of line so that its registers do not burden the streaming loop:
 // find/claim the group's global slot, try to adopt it into the CTA's tier 1, otherwise update it globally.
 // Returns the tier-1 index (>= 0), -2 when the row was accumulated globally, -1 when the table is full.
 template <class Prog>
-__device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const typename Prog::Keys &keys,
-                                                const typename Prog::Vals &vals, int64_t row, unsigned long long fp,
-                                                long long *s_slot, unsigned long long *s_fp, typename Prog::Keys *s_keys) {
-    const long long slot = agg_find_slot<Prog>(p, keys, Prog::hash(keys), row);
+__device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const typename Prog::Vals &vals, int64_t row,
+                                                unsigned long long tag, long long *s_slot, unsigned long long *s_fp,
+                                                typename Prog::Keys *s_keys) {
+    const long long slot = agg_find_slot<Prog>(p, tag, row);
     if (slot < 0) return -1;
     for (int g = 0; g < Prog::G1; g++) {
         const long long old = (long long)atomicCAS((unsigned long long *)&s_slot[g], (unsigned long long)-1LL, (unsigned long long)slot);
-        if (old == -1) {  // this lane owns entry g: publish the key values, then the fingerprint
+        if (old == -1) {  // this lane owns entry g: publish the key values (for inexact codes), then the code
+            typename Prog::Keys keys;
+            Prog::eval_keys(p, row, keys);
             s_keys[g] = keys;
             __threadfence_block();
-            ((volatile unsigned long long *)s_fp)[g] = fp;
+            ((volatile unsigned long long *)s_fp)[g] = tag;
+            // make sure the slot has a representative row even if every later row of this group stays in tier 1
+            atomicMin(((unsigned long long *)p.ptr[Prog::PTR_MINROW]) + slot, (unsigned long long)row);
             return g;
         }
         if (old == slot) return g;
@@ -559,6 +677,7 @@ __device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const
     return -2;
 }
 
+// ---- low-cardinality kernel: tier 1 in shared memory, gives up (flag 2) when most rows miss it ------------------
 template <class Prog>
 __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -566,7 +685,7 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     // layout: lane cells [W][G1][NL][32] u64 | warp cells [W][G1][NW] u64 | s_fp[G1] | s_slot[G1] | s_keys[G1]
     unsigned long long *s_lcell = (unsigned long long *)smem_raw;
     unsigned long long *s_wcell = s_lcell + (size_t)AGG_WARPS * G1 * NL * 32;
-    unsigned long long *s_fp = s_wcell + AGG_WARPS * G1 * NWS;  // key fingerprint of a published entry, 0 = empty
+    unsigned long long *s_fp = s_wcell + AGG_WARPS * G1 * NWS;  // key code of a published entry, 0 = empty
     long long *s_slot = (long long *)(s_fp + G1);
     typename Prog::Keys *s_keys = (typename Prog::Keys *)(s_slot + G1);
 
@@ -586,52 +705,33 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     const int64_t chunk = 32 * U;
     const int64_t nchunks = (n + chunk - 1) / chunk;
     const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
-    // register copy of the tier-1 fingerprints (entries only ever go from 0 to their final value, so a stale
+    volatile int *flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
+    int slow_rows = 0;  // rows of this lane that missed tier 1
+    // register copy of the tier-1 codes (entries only ever go from 0 to their final value, so a stale
     // copy can only miss an entry -> slow path -> refresh)
     unsigned long long tfp[G1];
 #pragma unroll
     for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
-    // software pipeline: string offsets (load0) are fetched one chunk ahead of everything else
-    typename Prog::Raw raw[U];
-    {
-        const int64_t c0 = (int64_t)blockIdx.x * AGG_WARPS + warp;
+    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
+        if (*flag) break;
+        const int64_t base = c * chunk;
+        typename Prog::Raw raw[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int64_t row = c0 * chunk + u * 32 + lane;
-            if (Prog::PIPE && c0 < nchunks && row < n) Prog::load0(p, row, raw[u]);
-        }
-    }
-    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
-        const int64_t base = c * chunk;
-#pragma unroll
-        for (int u = 0; u < U; u++) {  // fixed-width columns, and the string prefixes whose offsets arrived last iteration
             const int64_t row = base + u * 32 + lane;
-            if (row < n) {
-                Prog::load(p, row, raw[u]);
-                if (Prog::PIPE) Prog::load2(p, row, raw[u]);
-            }
+            if (row < n) Prog::load(p, row, raw[u]);
         }
-        if (!Prog::PIPE) {
 #pragma unroll
-            for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
-                const int64_t row = base + u * 32 + lane;
-                if (row < n) Prog::load2(p, row, raw[u]);
-            }
-        }
-        typename Prog::Raw nxt[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {  // next chunk's string offsets
-            const int64_t row = (c + total_warps) * chunk + u * 32 + lane;
-            if (Prog::PIPE && c + total_warps < nchunks && row < n) Prog::load0(p, row, nxt[u]);
+        for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load2(p, row, raw[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int64_t row = base + u * 32 + lane;
             typename Prog::Vals vals;
             bool live = row < n;
-            // tier 1: the CTA's first G1 groups, matched on a 64-bit code of the key VALUES held in registers
-            // (no xxh3, no global memory on this path)
-            // key code: exact (injective, bit 63 clear) when the key tuple is narrow, else fingerprint | bit 63
+            // tier 1: the CTA's first G1 groups, matched on the 64-bit code of the key VALUES held in registers
             unsigned long long fp = 0ULL;
             {
                 typename Prog::Keys keys;  // dead after the code is formed: the rare paths re-read the keys by row
@@ -641,21 +741,20 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
             int lid = -1;
 #pragma unroll
             for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
-            if (Prog::NKEYS > 0 && live && lid >= 0 && (fp >> 63)) {  // only inexact codes need the value check
-                typename Prog::Keys kv;
+            if (Prog::NKEYS > 0 && Prog::MODE != 1 && live && lid >= 0 && (Prog::MODE == 2 || (fp >> 63))) {
+                typename Prog::Keys kv;  // inexact code: confirm against the published key values
                 Prog::eval_keys(p, row, kv);
                 if (!Prog::keys_equal(kv, s_keys[lid])) lid = -1;
             }
-            if (live && lid < 0) {  // rare: first rows of a CTA, or a group beyond tier 1
-                // built HERE so that only this rare branch puts key/value structs on the stack
-                typename Prog::Keys kcopy;
-                Prog::eval_keys(p, row, kcopy);  // full key values (8-byte string prefixes) for hashing / publishing
+            if (live && lid < 0) {  // rare here: first rows of a CTA, or a group beyond tier 1
                 const typename Prog::Vals vcopy = vals;
-                const long long r = agg_slow_path<Prog>(p, kcopy, vcopy, row, fp, s_slot, s_fp, s_keys);
+                const long long r = agg_slow_path<Prog>(p, vcopy, row, fp, s_slot, s_fp, s_keys);
                 if (r >= 0) lid = (int)r;
                 else live = false;  // accumulated globally (or table overflow)
 #pragma unroll
                 for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
+                // most rows missing tier 1 means the input is not low-cardinality: hand over to the global kernel
+                if (++slow_rows > 64 + G1) *flag = 2;
             }
             if (live) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals, row);
             if (NW > 0) {  // valid / null counts of nullable inputs: one ballot per tier-1 group
@@ -665,10 +764,6 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
                     if (__any_sync(FULL_MASK, in_g)) Prog::warp_cells(vals, in_g, my_wcell + g * NW, lane);
                 }
             }
-        }
-        if (Prog::PIPE) {
-#pragma unroll
-            for (int u = 0; u < U; u++) Prog::copy0(raw[u], nxt[u]);
         }
     }
     __syncthreads();
@@ -686,8 +781,8 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
 using namespace b200;
 using namespace b200::jit;
 struct Prog {
-  typedef Params<19, 4> P;
-  static constexpr int IV_N = 0, IV_MASK = 1, PTR_SLOT_HASH = 0, PTR_SLOT_ROW = 1, PTR_OVERFLOW = 2;
+  typedef Params<18, 4> P;
+  static constexpr int IV_N = 0, IV_MASK = 1, PTR_TAG = 0, PTR_MINROW = 8, PTR_FLAG = 1, MODE = 0;
   static constexpr int NKEYS = 2, G1 = 4, NLANE = 7, NWARP = 0, U = 2;
   static constexpr bool PIPE = false;
   struct Raw {
@@ -718,33 +813,33 @@ struct Prog {
     int pad_;
   };
   __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {
-    r.c6 = ((const int32_t*)p.ptr[10])[row];
-    { const int64_t* of_ = (const int64_t*)p.ptr[11]; r.o4a = of_[row]; r.o4b = of_[row + 1]; }
+    r.c6 = ((const int32_t*)p.ptr[9])[row];
+    { const int64_t* of_ = (const int64_t*)p.ptr[10]; r.o4a = of_[row]; r.o4b = of_[row + 1]; }
     { const unsigned long long L_ = (unsigned long long)p.ival[2]; r.sw4a = 0u; r.sw4b = 0u;
-      if (L_) { const uintptr_t a_ = (uintptr_t)p.ptr[12] + (unsigned long long)row * L_; const unsigned int* w_ = (const unsigned int*)(a_ & ~(uintptr_t)3);
+      if (L_) { const uintptr_t a_ = (uintptr_t)p.ptr[11] + (unsigned long long)row * L_; const unsigned int* w_ = (const unsigned int*)(a_ & ~(uintptr_t)3);
         r.sw4a = __ldg(w_); if ((a_ & 3) + L_ > 4) r.sw4b = __ldg(w_ + 1); } }
-    { const int64_t* of_ = (const int64_t*)p.ptr[13]; r.o5a = of_[row]; r.o5b = of_[row + 1]; }
+    { const int64_t* of_ = (const int64_t*)p.ptr[12]; r.o5a = of_[row]; r.o5b = of_[row + 1]; }
     { const unsigned long long L_ = (unsigned long long)p.ival[3]; r.sw5a = 0u; r.sw5b = 0u;
-      if (L_) { const uintptr_t a_ = (uintptr_t)p.ptr[14] + (unsigned long long)row * L_; const unsigned int* w_ = (const unsigned int*)(a_ & ~(uintptr_t)3);
+      if (L_) { const uintptr_t a_ = (uintptr_t)p.ptr[13] + (unsigned long long)row * L_; const unsigned int* w_ = (const unsigned int*)(a_ & ~(uintptr_t)3);
         r.sw5a = __ldg(w_); if ((a_ & 3) + L_ > 4) r.sw5b = __ldg(w_ + 1); } }
-    r.c0 = ((const int64_t*)p.ptr[15])[row];
-    r.c1 = ((const double*)p.ptr[16])[row];
-    r.c2 = ((const double*)p.ptr[17])[row];
-    r.c3 = ((const double*)p.ptr[18])[row];
+    r.c0 = ((const int64_t*)p.ptr[14])[row];
+    r.c1 = ((const double*)p.ptr[15])[row];
+    r.c2 = ((const double*)p.ptr[16])[row];
+    r.c3 = ((const double*)p.ptr[17])[row];
   }
   __device__ __forceinline__ static void load2(const P& p, const int64_t row, Raw& r) {
     { const unsigned long long L_ = (unsigned long long)p.ival[2]; const long long len_ = r.o4b - r.o4a;
       if (L_ && (unsigned long long)r.o4a == (unsigned long long)row * L_ && len_ <= (long long)L_) {
-        const unsigned int sh_ = (unsigned int)(((uintptr_t)p.ptr[12] + (unsigned long long)r.o4a) & 3) * 8u;
+        const unsigned int sh_ = (unsigned int)(((uintptr_t)p.ptr[11] + (unsigned long long)r.o4a) & 3) * 8u;
         unsigned int v_ = __funnelshift_r(r.sw4a, r.sw4b, sh_); const unsigned int nb_ = len_ > 0 ? (unsigned int)len_ : 0u;
         v_ &= nb_ >= 4u ? 0xFFFFFFFFu : ((1u << (nb_ * 8u)) - 1u); r.pk4 = (uint64_t)v_;
-      } else r.pk4 = str_pack4(Str{(const uint8_t*)p.ptr[12] + r.o4a, len_}); }
+      } else r.pk4 = str_pack4(Str{(const uint8_t*)p.ptr[11] + r.o4a, len_}); }
     { const unsigned long long L_ = (unsigned long long)p.ival[3]; const long long len_ = r.o5b - r.o5a;
       if (L_ && (unsigned long long)r.o5a == (unsigned long long)row * L_ && len_ <= (long long)L_) {
-        const unsigned int sh_ = (unsigned int)(((uintptr_t)p.ptr[14] + (unsigned long long)r.o5a) & 3) * 8u;
+        const unsigned int sh_ = (unsigned int)(((uintptr_t)p.ptr[13] + (unsigned long long)r.o5a) & 3) * 8u;
         unsigned int v_ = __funnelshift_r(r.sw5a, r.sw5b, sh_); const unsigned int nb_ = len_ > 0 ? (unsigned int)len_ : 0u;
         v_ &= nb_ >= 4u ? 0xFFFFFFFFu : ((1u << (nb_ * 8u)) - 1u); r.pk5 = (uint64_t)v_;
-      } else r.pk5 = str_pack4(Str{(const uint8_t*)p.ptr[14] + r.o5a, len_}); }
+      } else r.pk5 = str_pack4(Str{(const uint8_t*)p.ptr[13] + r.o5a, len_}); }
   }
   __device__ __forceinline__ static void load0(const P& p, const int64_t row, Raw& r) {
   }
@@ -756,11 +851,11 @@ struct Prog {
     const bool v2 = v0 <= v1;
     const bool k2 = k0 && k1;
     if (!(k2 && v2)) return false;
-    const Str v3{(const uint8_t*)p.ptr[12] + r.o4a, r.o4b - r.o4a};
+    const Str v3{(const uint8_t*)p.ptr[11] + r.o4a, r.o4b - r.o4a};
     const bool k3 = true;
     keys.v0 = v3; keys.k0 = k3;
     keys.p0 = keys.k0 ? r.pk4 : 0ULL;
-    const Str v4{(const uint8_t*)p.ptr[14] + r.o5a, r.o5b - r.o5a};
+    const Str v4{(const uint8_t*)p.ptr[13] + r.o5a, r.o5b - r.o5a};
     const bool k4 = true;
     keys.v1 = v4; keys.k1 = k4;
     keys.p1 = keys.k1 ? r.pk5 : 0ULL;
@@ -788,20 +883,14 @@ struct Prog {
     const bool rowok = true;
     const bool k3 = rowok;
     Str v3{(const uint8_t*)0, 0};
-    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[11]; const int64_t a_ = of_[row]; v3.p = (const uint8_t*)p.ptr[12] + a_; v3.len = of_[row + 1] - a_; }
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[10]; const int64_t a_ = of_[row]; v3.p = (const uint8_t*)p.ptr[11] + a_; v3.len = of_[row + 1] - a_; }
     keys.v0 = v3; keys.k0 = k3;
     keys.p0 = keys.k0 ? str_pack8(keys.v0) : 0ULL;
     const bool k4 = rowok;
     Str v4{(const uint8_t*)0, 0};
-    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[13]; const int64_t a_ = of_[row]; v4.p = (const uint8_t*)p.ptr[14] + a_; v4.len = of_[row + 1] - a_; }
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[12]; const int64_t a_ = of_[row]; v4.p = (const uint8_t*)p.ptr[13] + a_; v4.len = of_[row + 1] - a_; }
     keys.v1 = v4; keys.k1 = k4;
     keys.p1 = keys.k1 ? str_pack8(keys.v1) : 0ULL;
-  }
-  __device__ __forceinline__ static uint64_t hash(const Keys& k) {
-    uint64_t h = 0;
-    h = (k.k0 ? hash_str_packed(k.v0, k.p0, 0ULL) : xxh::hash_empty(0ULL));
-    h = (k.k1 ? hash_str_packed(k.v1, k.p1, h) : xxh::hash_empty(h));
-    return h;
   }
   __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {
     return true && (a.k0 == b.k0) && (!a.k0 || str_eq_packed(a.v0, a.p0, b.v0, b.p0)) && (a.k1 == b.k1) && (!a.k1 || str_eq_packed(a.v1, a.p1, b.v1, b.p1));
@@ -812,8 +901,8 @@ struct Prog {
   }
   __device__ __forceinline__ static uint64_t fingerprint(const Keys& k) {
     uint64_t f = 0x9E3779B97F4A7C15ULL;
-    f = (f ^ (k.k0 ? (k.p0 ^ ((uint64_t)k.v0.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
-    f = (f ^ (k.k1 ? (k.p1 ^ ((uint64_t)k.v1.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    f = (f ^ (k.k0 ? (((uint64_t)k.v0.len <= 4ULL ? k.p0 : xxh::hash_bytes(k.v0.p, k.v0.len, 0ULL)) ^ ((uint64_t)k.v0.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    f = (f ^ (k.k1 ? (((uint64_t)k.v1.len <= 4ULL ? k.p1 : xxh::hash_bytes(k.v1.p, k.v1.len, 0ULL)) ^ ((uint64_t)k.v1.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
     return f;
   }
   __device__ __forceinline__ static uint64_t code(const Keys& k) {
@@ -841,13 +930,40 @@ struct Prog {
     if ((unsigned long long)row < cells[192]) cells[192] = (unsigned long long)row;
   }
   __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {
-    if (v.k0) atomicAdd(((unsigned long long*)p.ptr[3]) + slot, (unsigned long long)v.a0);
-    if (v.k1) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), v.a1);
-    if (v.k2) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), v.a2);
-    if (v.k3) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), v.a3);
-    if (v.k4) atomicAdd((double*)(((unsigned long long*)p.ptr[7]) + slot), v.a4);
-    atomicAdd(((unsigned long long*)p.ptr[8]) + slot, 1ULL);
-    atomicMin(((unsigned long long*)p.ptr[9]) + slot, (unsigned long long)row);
+    if (v.k0) atomicAdd(((unsigned long long*)p.ptr[2]) + slot, (unsigned long long)v.a0);
+    if (v.k1) atomicAdd((double*)(((unsigned long long*)p.ptr[3]) + slot), v.a1);
+    if (v.k2) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), v.a2);
+    if (v.k3) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), v.a3);
+    if (v.k4) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), v.a4);
+    atomicAdd(((unsigned long long*)p.ptr[7]) + slot, 1ULL);
+    atomicMin(((unsigned long long*)p.ptr[8]) + slot, (unsigned long long)row);
+  }
+  static constexpr int T2 = 1024, NCELLS = 7;
+  __device__ __forceinline__ static void t2_init(unsigned long long* t2c, const int t) {
+    t2c[0 * T2 + t] = 0ULL;
+    t2c[1 * T2 + t] = 0ULL;
+    t2c[2 * T2 + t] = 0ULL;
+    t2c[3 * T2 + t] = 0ULL;
+    t2c[4 * T2 + t] = 0ULL;
+    t2c[5 * T2 + t] = 0ULL; t2c[6 * T2 + t] = 0xFFFFFFFFFFFFFFFFULL;
+  }
+  __device__ __forceinline__ static void t2_update(unsigned long long* t2c, const int t, const Vals& v, const int64_t row) {
+    if (v.k0) atomicAdd((t2c + 0 * T2 + t), (unsigned long long)v.a0);
+    if (v.k1) atomicAdd((double*)(t2c + 1 * T2 + t), v.a1);
+    if (v.k2) atomicAdd((double*)(t2c + 2 * T2 + t), v.a2);
+    if (v.k3) atomicAdd((double*)(t2c + 3 * T2 + t), v.a3);
+    if (v.k4) atomicAdd((double*)(t2c + 4 * T2 + t), v.a4);
+    atomicAdd(t2c + 5 * T2 + t, 1ULL);
+    atomicMin(t2c + 6 * T2 + t, (unsigned long long)row);
+  }
+  __device__ __forceinline__ static void t2_flush(const P& p, const long long slot, const unsigned long long* t2c, const int t) {
+    atomicAdd(((unsigned long long*)p.ptr[2]) + slot, t2c[0 * T2 + t]);
+    atomicAdd((double*)(((unsigned long long*)p.ptr[3]) + slot), __longlong_as_double((long long)t2c[1 * T2 + t]));
+    atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), __longlong_as_double((long long)t2c[2 * T2 + t]));
+    atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), __longlong_as_double((long long)t2c[3 * T2 + t]));
+    atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), __longlong_as_double((long long)t2c[4 * T2 + t]));
+    atomicAdd(((unsigned long long*)p.ptr[7]) + slot, t2c[5 * T2 + t]);
+    atomicMin(((unsigned long long*)p.ptr[8]) + slot, t2c[6 * T2 + t]);
   }
   __device__ __forceinline__ static void warp_cells(const Vals& v, const bool in_g, unsigned long long* wcell, const int lane) {
   }
@@ -856,34 +972,34 @@ struct Prog {
     {
       unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 0 + lane];
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[3]) + slot, a_);
+      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[2]) + slot, a_);
     }
     {
       double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 32 + lane]);
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), a_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[3]) + slot), a_);
     }
     {
       double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 64 + lane]);
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), a_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), a_);
     }
     {
       double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 96 + lane]);
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), a_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), a_);
     }
     {
       double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 128 + lane]);
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[7]) + slot), a_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), a_);
     }
     { unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 160 + lane];
       for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
-      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[8]) + slot, a_); }
+      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[7]) + slot, a_); }
     { unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 192 + lane]; a_ = t_ < a_ ? t_ : a_; }
       for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }
-      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[9]) + slot, a_); }
+      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[8]) + slot, a_); }
   }
 };
-extern "C" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }
+extern "C" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_global<Prog>(p); }

@@ -652,7 +652,7 @@ static std::string ord_of(int32_t dt, const std::string &v) {
 struct LaneCell { int op; std::string child_key; int val_slot; int32_t val_dtype; };
 struct WarpCell { std::string cond_key; int val_slot; bool count_nulls; };
 
-static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
+static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, bool global_variant) {
     CG cg{ast, meta};
     const bool has_filter = r.u8() != 0;
     int filter_root = -1;
@@ -771,9 +771,13 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         return v && *v ? atoi(v) : dflt;
     };
     const int MINB = std::max(1, std::min(8, env_int("B200_AGG_MINB", 2)));
+    // tier-2 of the global kernel: a shared-memory table of (code, cells) absorbing mid-cardinality inputs (budget 96 KB)
+    int t2_slots = 64;
+    while ((size_t)(t2_slots * 2) * 8 * (size_t)(1 + NLT + NW) <= 96 * 1024) t2_slots *= 2;
+    if (env_int("B200_AGG_T2", 1) == 0) t2_slots = 2;
 
     const int iv_n = cg.int_slot(I_N), iv_mask = cg.int_slot(I_MASK);
-    const int p_hash = cg.ptr_slot(P_SLOT_HASH, 0), p_row = cg.ptr_slot(P_SLOT_ROW, 0), p_ovf = cg.ptr_slot(P_OVERFLOW, 0);
+    const int p_hash = cg.ptr_slot(P_SLOT_HASH, 0), p_ovf = cg.ptr_slot(P_OVERFLOW, 0);  // slot tags, status flag
     // global cells: [0,NL) value cells, NL = row count, NL+1 = first row, [NL+2, NL+2+NW) ballot count cells
     const int cell_nrows = NL, cell_minrow = NL + 1;
     std::vector<int> p_acc(NLT + NW);
@@ -782,16 +786,28 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     // ---- exact key code budget (see `code()` below): bytes per string key, 0 = no exact code
     int exact_B = 0;
     bool exact_possible = nkeys > 0;
+    const bool wide_mode = false;  // (MODE 1 of the skeleton is not emitted: see the 64-bit key rule below)
+    int wide_key = -1, wide_avail = 0;  // the one 8-byte integer key whose VALUE decides exactness row by row
     {
-        int bits_fixed = 0, nstr = 0;
+        int bits_fixed = 0, nstr = 0, n64 = 0, idx64 = -1;
         for (uint32_t i = 0; i < nkeys; i++) {
             const Node &n = ast.nodes[key_roots[i]];
             if (is_string(n.dtype)) nstr++;
             else if (n.dtype == B200_BOOL) bits_fixed += 1;
             else if (n.dtype != B200_NULL) bits_fixed += 8 * dtype_width(n.dtype);
             if (n.nullable) bits_fixed += 1;
+            if (n.dtype == B200_I64 || n.dtype == B200_U64 || n.dtype == B200_TIMESTAMP) { n64++; idx64 = (int)i; }
         }
-        if (bits_fixed > 62) exact_possible = false;
+        if (bits_fixed > 62) {
+            exact_possible = false;
+            // Int64 keys (every TPC-H key column) rarely use their top bits: pack the value when it fits the bits
+            // left over by the other keys, otherwise that row takes the fingerprint + verification path
+            if (n64 == 1 && nstr == 0 && bits_fixed - 64 <= 30) {
+                exact_possible = true;
+                wide_key = idx64;
+                wide_avail = 62 - (bits_fixed - 64);
+            }
+        }
         if (exact_possible && nstr) {
             exact_B = std::min(7, ((62 - bits_fixed) / nstr - 3) / 8);
             if (exact_B < 1) exact_possible = false;
@@ -949,7 +965,12 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         const Node &n = ast.nodes[key_roots[i]];
         const std::string si = std::to_string(i);
         std::string bits;
-        if (is_string(n.dtype)) bits = "(k.p" + si + " ^ ((uint64_t)k.v" + si + ".len << 56))";
+        if (is_string(n.dtype)) {
+            // values longer than the packed prefix contribute a hash of ALL their bytes (shared prefixes are common)
+            const bool p4 = n.tag == T_COL && is_pack4_col(n.col);
+            bits = "(((uint64_t)k.v" + si + ".len <= " + (p4 ? "4" : "8") + "ULL ? k.p" + si + " : xxh::hash_bytes(k.v" + si + ".p, k.v" + si +
+                   ".len, 0ULL)) ^ ((uint64_t)k.v" + si + ".len << 56))";
+        }
         else if (n.dtype == B200_F64) bits = "(uint64_t)__double_as_longlong(k.v" + si + ")";
         else if (n.dtype == B200_F32) bits = "(uint64_t)(uint32_t)__float_as_int(k.v" + si + ")";
         else if (n.dtype == B200_NULL) bits = "0ULL";
@@ -964,7 +985,28 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     {
         const bool possible = exact_possible;
         const int B = exact_B;
-        if (!possible) {
+        if (wide_mode) {
+            cds << "    uint64_t c = 0ULL;\n";
+            int sh = 0;
+            for (uint32_t i = 0; i < nkeys; i++) {
+                const Node &n = ast.nodes[key_roots[i]];
+                const std::string si = std::to_string(i);
+                if (n.dtype == B200_NULL) continue;
+                std::string bits;
+                const int w = n.dtype == B200_BOOL ? 1 : 8 * dtype_width(n.dtype);
+                if (n.dtype == B200_BOOL) bits = "(uint64_t)k.v" + si;
+                else if (n.dtype == B200_F32) bits = "(uint64_t)(uint32_t)__float_as_int(k.v" + si + ")";
+                else if (n.dtype == B200_F64) bits = "(uint64_t)__double_as_longlong(k.v" + si + ")";
+                else bits = std::string("(uint64_t)(") + utype(n.dtype) + ")k.v" + si;
+                cds << "    c |= (k.k" << si << " ? " << bits << " : 0ULL) << " << sh << ";\n";
+                sh += w;
+                if (n.nullable) {
+                    cds << "    c |= (uint64_t)(!k.k" << si << ") << " << sh << ";\n";
+                    sh += 1;
+                }
+            }
+            cds << "    return c;\n";
+        } else if (!possible) {
             cds << "    return fingerprint(k) | 0x8000000000000000ULL;\n";
         } else {
             cds << "    uint64_t c = 0x4000000000000000ULL; bool ex = true;\n";
@@ -977,6 +1019,10 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
                     cds << "    { const uint64_t l_ = k.k" << si << " ? (uint64_t)k.v" << si << ".len : 0ULL; ex = ex && (l_ <= " << B << "ULL); c |= (k.p" << si
                         << " & " << mask << "ULL) << " << sh << "; c |= (l_ & 7ULL) << " << (sh + 8 * B) << "; }\n";
                     sh += 8 * B + 3;
+                } else if ((int)i == wide_key) {
+                    cds << "    { const uint64_t v_ = k.k" << si << " ? (uint64_t)k.v" << si << " : 0ULL; ex = ex && ((v_ >> " << wide_avail
+                        << ") == 0ULL); c |= (v_ & " << ((1ULL << wide_avail) - 1ULL) << "ULL) << " << sh << "; }\n";
+                    sh += wide_avail;
                 } else if (n.dtype != B200_NULL) {
                     std::string bits;
                     int w = n.dtype == B200_BOOL ? 1 : 8 * dtype_width(n.dtype);
@@ -997,11 +1043,43 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
 
     // ---- lane cells: init / update / global update / flush
     std::ostringstream li, lu, gu, wc, fl;
+    std::ostringstream su, sfl, sinit;  // tier-2 (shared-memory table of the global kernel): update / flush / init of slot cells
     for (int c = 0; c < NL; c++) {
         const LaneCell &lc = lane_cells[c];
         const std::string cell = "cells[" + std::to_string(c * 32) + "]";
         const std::string val = "v.a" + std::to_string(lc.val_slot), vk = "v.k" + std::to_string(lc.val_slot);
         const std::string gp = "((unsigned long long*)" + std::string("p.ptr[") + std::to_string(p_acc[c]) + "]) + slot";
+        {   // tier-2 cell c of slot t lives at t2c[c * T2 + t]
+            const std::string sp = "(t2c + " + std::to_string(c) + " * T2 + t)";
+            const std::string sv = "t2c[" + std::to_string(c) + " * T2 + t]";
+            switch (lc.op) {
+                case C_ADD_F64:
+                    sinit << "    " << sv << " = 0ULL;\n";
+                    su << "    if (" << vk << ") atomicAdd((double*)" << sp << ", " << val << ");\n";
+                    sfl << "    atomicAdd((double*)(" << gp << "), __longlong_as_double((long long)" << sv << "));\n";
+                    break;
+                case C_ADD_F32:
+                    sinit << "    " << sv << " = 0ULL;\n";
+                    su << "    if (" << vk << ") atomicAdd((float*)" << sp << ", " << val << ");\n";
+                    sfl << "    atomicAdd((float*)(" << gp << "), __int_as_float((int)" << sv << "));\n";
+                    break;
+                case C_ADD_I64:
+                    sinit << "    " << sv << " = 0ULL;\n";
+                    su << "    if (" << vk << ") atomicAdd(" << sp << ", (unsigned long long)" << val << ");\n";
+                    sfl << "    atomicAdd(" << gp << ", " << sv << ");\n";
+                    break;
+                case C_MIN:
+                    sinit << "    " << sv << " = 0xFFFFFFFFFFFFFFFFULL;\n";
+                    su << "    if (" << vk << ") atomicMin(" << sp << ", (unsigned long long)" << ord_of(lc.val_dtype, val) << ");\n";
+                    sfl << "    atomicMin(" << gp << ", " << sv << ");\n";
+                    break;
+                case C_MAX:
+                    sinit << "    " << sv << " = 0ULL;\n";
+                    su << "    if (" << vk << ") atomicMax(" << sp << ", (unsigned long long)" << ord_of(lc.val_dtype, val) << ");\n";
+                    sfl << "    atomicMax(" << gp << ", " << sv << ");\n";
+                    break;
+            }
+        }
         switch (lc.op) {
             case C_ADD_F64:
                 li << "    " << cell << " = 0ULL;\n";
@@ -1068,6 +1146,10 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         lu << "    " << cn << " += 1ULL;\n    if ((unsigned long long)row < " << cm << ") " << cm << " = (unsigned long long)row;\n";
         gu << "    atomicAdd(((unsigned long long*)p.ptr[" << p_acc[cell_nrows] << "]) + slot, 1ULL);\n";
         gu << "    atomicMin(((unsigned long long*)p.ptr[" << p_acc[cell_minrow] << "]) + slot, (unsigned long long)row);\n";
+        sinit << "    t2c[" << NL << " * T2 + t] = 0ULL; t2c[" << (NL + 1) << " * T2 + t] = 0xFFFFFFFFFFFFFFFFULL;\n";
+        su << "    atomicAdd(t2c + " << NL << " * T2 + t, 1ULL);\n    atomicMin(t2c + " << (NL + 1) << " * T2 + t, (unsigned long long)row);\n";
+        sfl << "    atomicAdd(((unsigned long long*)p.ptr[" << p_acc[cell_nrows] << "]) + slot, t2c[" << NL << " * T2 + t]);\n";
+        sfl << "    atomicMin(((unsigned long long*)p.ptr[" << p_acc[cell_minrow] << "]) + slot, t2c[" << (NL + 1) << " * T2 + t]);\n";
         fl << "    { unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + " << NL * 32 << " + lane];\n";
         fl << "      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);\n";
         fl << "      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[" << p_acc[cell_nrows] << "]) + slot, a_); }\n";
@@ -1083,6 +1165,9 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
         const std::string cond = w.count_nulls ? "!" + vk : vk;
         wc << "    { const unsigned m_ = __ballot_sync(FULL_MASK, in_g && " << cond << "); if (lane == 0) wcell[" << c << "] += __popc(m_); }\n";
         gu << "    if (" << cond << ") atomicAdd(((unsigned long long*)p.ptr[" << p_acc[NLT + c] << "]) + slot, 1ULL);\n";
+        sinit << "    t2c[" << (NLT + c) << " * T2 + t] = 0ULL;\n";
+        su << "    if (" << cond << ") atomicAdd(t2c + " << (NLT + c) << " * T2 + t, 1ULL);\n";
+        sfl << "    if (t2c[" << (NLT + c) << " * T2 + t]) atomicAdd(((unsigned long long*)p.ptr[" << p_acc[NLT + c] << "]) + slot, t2c[" << (NLT + c) << " * T2 + t]);\n";
         fl << "    { unsigned long long a_ = lane < AGG_WARPS ? wcell[(size_t)lane * wstride + " << c << "] : 0ULL;\n";
         fl << "      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);\n";
         fl << "      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[" << p_acc[NLT + c] << "]) + slot, a_); }\n";
@@ -1092,8 +1177,8 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     o << file_header(cg);
     o << "struct Prog {\n";
     o << "  typedef Params<" << meta.ptrs.size() << ", " << meta.ints.size() << "> P;\n";
-    o << "  static constexpr int IV_N = " << iv_n << ", IV_MASK = " << iv_mask << ", PTR_SLOT_HASH = " << p_hash << ", PTR_SLOT_ROW = " << p_row
-      << ", PTR_OVERFLOW = " << p_ovf << ";\n";
+    o << "  static constexpr int IV_N = " << iv_n << ", IV_MASK = " << iv_mask << ", PTR_TAG = " << p_hash << ", PTR_MINROW = " << p_acc[cell_minrow]
+      << ", PTR_FLAG = " << p_ovf << ", MODE = " << (wide_mode ? 1 : (exact_possible ? 0 : 2)) << ";\n";
     o << "  static constexpr int NKEYS = " << nkeys << ", G1 = " << G1 << ", NLANE = " << NLT << ", NWARP = " << NW << ", U = " << U << ";\n";
     o << "  static constexpr bool PIPE = " << (pipe_offsets ? "true" : "false") << ";\n";
     o << "  struct Raw {\n" << raw.str() << "    int pad_;\n  };\n";
@@ -1105,7 +1190,6 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     o << "  __device__ __forceinline__ static void copy0(Raw& d, const Raw& s) {\n" << copy0.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {\n" << ev.str() << "  }\n";
     o << "  __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {\n" << ek.str() << "  }\n";
-    o << "  __device__ __forceinline__ static uint64_t hash(const Keys& k) {\n" << hs.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {\n" << eq.str() << "  }\n";
     {
         std::ostringstream fk;
@@ -1119,19 +1203,27 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta) {
     o << "  __device__ __forceinline__ static void lane_init(unsigned long long* cells) {\n" << li.str() << "  }\n";
     o << "  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v, const int64_t row) {\n" << lu.str() << "  }\n";
     o << "  __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {\n" << gu.str() << "  }\n";
+    o << "  static constexpr int T2 = " << t2_slots << ", NCELLS = " << (NLT + NW) << ";\n";
+    o << "  __device__ __forceinline__ static void t2_init(unsigned long long* t2c, const int t) {\n" << sinit.str() << "  }\n";
+    o << "  __device__ __forceinline__ static void t2_update(unsigned long long* t2c, const int t, const Vals& v, const int64_t row) {\n" << su.str() << "  }\n";
+    o << "  __device__ __forceinline__ static void t2_flush(const P& p, const long long slot, const unsigned long long* t2c, const int t) {\n" << sfl.str() << "  }\n";
     o << "  __device__ __forceinline__ static void warp_cells(const Vals& v, const bool in_g, unsigned long long* wcell, const int lane) {\n" << wc.str() << "  }\n";
     o << "  __device__ __forceinline__ static void flush(const P& p, const long long slot, const unsigned long long* lcell, const size_t lstride,\n"
          "                                               const unsigned long long* wcell, const size_t wstride, const int lane) {\n" << fl.str() << "  }\n";
     o << "};\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(256, " << MINB << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }\n";
+    if (global_variant)
+        o << "extern \"C\" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_global<Prog>(p); }\n";
+    else
+        o << "extern \"C\" __global__ void __launch_bounds__(256, " << MINB << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }\n";
     // shared memory: lane cells, ballot cells, tier-1 slots/ready flags/key values (generous bound for sizeof(Keys))
-    meta.smem_bytes = 8 * (size_t)8 * G1 * NLT * 32 + 8 * (size_t)8 * G1 * std::max(NW, 1) + 16 * (size_t)G1 +
-                      (size_t)G1 * (40 * (size_t)nkeys + 16);
+    meta.smem_bytes = global_variant ? 8 * (size_t)t2_slots * (size_t)(1 + NLT + NW)
+                                     : 8 * (size_t)8 * G1 * NLT * 32 + 8 * (size_t)8 * G1 * std::max(NW, 1) + 16 * (size_t)G1 +
+                                           (size_t)G1 * (40 * (size_t)nkeys + 16);
     return o.str();
 }
 
 std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
-                     const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta) {
+                     const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta, int variant) {
     Reader r{plan, plan_len};
     Ast ast;
     ast.col_dtypes = &col_dtypes;
@@ -1142,7 +1234,7 @@ std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::ve
         body = gen_project(r, ast, meta, with_take);
         if (r.pos != r.n) fail("plan: trailing bytes");
     } else if (op == B200_OP_AGG) {
-        body = gen_agg(r, ast, meta);
+        body = gen_agg(r, ast, meta, variant != 0);
     } else {
         fail("jit: unknown op");
     }
@@ -1235,16 +1327,16 @@ static std::string cache_key(int op, const uint8_t *plan, size_t plan_len, const
     return k;
 }
 
-const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &input, bool with_take) {
+const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &input, bool with_take, int variant) {
     std::vector<int32_t> dt;
     std::vector<uint8_t> nl;
     for (auto &c : input.cols) { dt.push_back(c.dtype); nl.push_back(c.nullable() ? 1 : 0); }
     std::lock_guard<std::mutex> g(g_mu);
-    const std::string key = cache_key(op, plan, plan_len, dt, nl, with_take);
+    const std::string key = cache_key(op, plan, plan_len, dt, nl, with_take) + (char)('0' + variant);
     auto it = g_kernels.find(key);
     if (it != g_kernels.end()) return *it->second;
     auto c = std::make_unique<Compiled>();
-    const std::string src = generate(op, plan, plan_len, dt, nl, with_take, *c);
+    const std::string src = generate(op, plan, plan_len, dt, nl, with_take, *c, variant);
     std::vector<char> cubin = compile_to_cubin(src, &c->source_path);
     require_device();
     // runtime "library" API (cudart dlopens the driver itself; the .so has no link-time libcuda dependency)
@@ -1263,11 +1355,15 @@ void precompile(int op, const uint8_t *plan, size_t plan_len, const std::vector<
                 const std::vector<uint8_t> &col_nullable) {
     std::lock_guard<std::mutex> g(g_mu);
     Compiled c;
-    const std::string src = generate(op, plan, plan_len, col_dtypes, col_nullable, false, c);
+    const std::string src = generate(op, plan, plan_len, col_dtypes, col_nullable, false, c, 0);
     compile_to_cubin(src, nullptr);
+    if (op == B200_OP_AGG) {  // the high-cardinality variant of the same plan
+        Compiled cg2;
+        compile_to_cubin(generate(op, plan, plan_len, col_dtypes, col_nullable, false, cg2, 1), nullptr);
+    }
     if (op == B200_OP_AGG && !c.key_project_plan.empty() && c.nkeys > 0) {
         Compiled c2;
-        const std::string src2 = generate(B200_OP_PROJECT, c.key_project_plan.data(), c.key_project_plan.size(), col_dtypes, col_nullable, true, c2);
+        const std::string src2 = generate(B200_OP_PROJECT, c.key_project_plan.data(), c.key_project_plan.size(), col_dtypes, col_nullable, true, c2, 0);
         compile_to_cubin(src2, nullptr);
     }
 }

@@ -59,12 +59,13 @@ struct Compiled {
 };
 
 // Codegen only (no CUDA needed): returns the CUDA source for the plan; fills `meta` (fn stays null).
+// variant (AGG only): 0 = low-cardinality kernel (tier-1 shared-memory cells), 1 = global-table kernel
 std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
-                     const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta);
+                     const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta, int variant = 0);
 // NVRTC -> cubin (cached on disk); works without a GPU.
 std::vector<char> compile_to_cubin(const std::string &source, std::string *path_out);
 // generate + compile + load; cached per (op, plan, dtypes, nullability, take)
-const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &input, bool with_take);
+const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &input, bool with_take, int variant = 0);
 void set_cache_dir(const std::string &dir);
 void precompile(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
                 const std::vector<uint8_t> &col_nullable);

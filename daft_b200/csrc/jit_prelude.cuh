@@ -223,66 +223,184 @@ __device__ __forceinline__ void project_body(const typename Prog::P &p, int pass
 // fused Filter -> Project -> HashAggregate
 // ======================================================================================================
 // Prog provides (all generated):
-//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_SLOT_HASH, PTR_SLOT_ROW, PTR_OVERFLOW;
-//   NKEYS, G1, NLANE (lane cells incl. row count + first row), NWARP (ballot count cells), U, MINB
-//   struct Raw;  struct Keys;  struct Vals;
-//   load(p,row,Raw&) ; bool eval(p,Raw&,Keys&,Vals&) (false = filtered out) ; eval_keys(p,row,Keys&)
-//   uint64 hash(Keys&) ; bool keys_equal(Keys&,Keys&)
-//   lane_init(cell*) ; lane_update(cell*, Vals&, row) ; global_update(p, slot, Vals&, row)
-//   warp_cells(Vals&, in_group, wcell*, lane) ; flush(...)
+//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_TAG, PTR_MINROW (first row per slot = representative row),
+//   PTR_FLAG (int: 0 ok, 1 table overflow, 2 low-cardinality kernel gave up);
+//   NKEYS, G1, NLANE, NWARP, U;  MODE (0: row-dependent exact 62-bit codes, 1: every row exact 63/64-bit code,
+//   2: never exact);  struct Raw / Keys / Vals;
+//   load / load2 / eval / eval_keys / keys_equal / code / lane_init / lane_update / global_update / warp_cells / flush
+//
+// Group identity is carried by a 64-bit key CODE (see jit.cpp "Exact key code"): when it is exact (injective in
+// the key values) equal codes ARE equal keys; otherwise the code is a fingerprint and a match is confirmed against
+// the key values of the slot's representative row (nulls equal, floats by bit pattern -- the reference's
+// "hash equal AND comparator" rule, src/daft-recordbatch/src/ops/inline_agg.rs:760-784).
 constexpr int AGG_WARPS = 8;
+constexpr unsigned long long AGG_EMPTY = 0xFFFFFFFFFFFFFFFFULL;     // min-row cell of an unclaimed slot
+constexpr unsigned long long AGG_CLAIMING = 0xFFFFFFFFFFFFFFFEULL;  // (MODE 1) slot being published
+constexpr int AGG_PROBE_LIMIT = 1024;
 
+__device__ __forceinline__ uint64_t agg_mix(uint64_t x) {
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ULL;
+    x ^= x >> 32;
+    return x;
+}
+
+// Find or claim the global slot of the group with code `tag`.  Returns the slot, or -1 after flagging overflow.
 template <class Prog>
-__device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, const typename Prog::Keys &k, uint64_t h,
-                                                  int64_t row) {
-    unsigned long long *slot_hash = (unsigned long long *)p.ptr[Prog::PTR_SLOT_HASH];
-    long long *slot_row = (long long *)p.ptr[Prog::PTR_SLOT_ROW];
+__device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, unsigned long long tag, int64_t row) {
+    unsigned long long *slot_tag = (unsigned long long *)p.ptr[Prog::PTR_TAG];
+    unsigned long long *slot_min = (unsigned long long *)p.ptr[Prog::PTR_MINROW];
     const uint64_t mask = (uint64_t)p.ival[Prog::IV_MASK];
-    if (h == 0) h = 1;  // 0 marks an empty slot; equality is decided by the key comparison anyway
-    uint64_t s = h & mask;
-    for (uint64_t probes = 0; probes <= mask; probes++) {
-        unsigned long long cur = slot_hash[s];  // may be a stale 0 from L1: the CAS below re-reads at L2
-        bool mine = false;
-        if (cur == 0) {
-            unsigned long long prev = atomicCAS(&slot_hash[s], 0ULL, (unsigned long long)h);
-            if (prev == 0) {
-                // claimed: publish the representative row (written before anyone can need it below)
-                *((volatile long long *)&slot_row[s]) = (long long)row;
-                __threadfence();
-                mine = true;
+    const bool exact = Prog::MODE == 1 || (Prog::MODE == 0 && !(tag >> 63));
+    uint64_t s = agg_mix(tag) & mask;
+    for (int probes = 0; probes < AGG_PROBE_LIMIT; probes++) {
+        if (Prog::MODE == 1) {
+            // tags may take any value: occupancy lives in the min-row cell (EMPTY -> CLAIMING -> first row)
+            unsigned long long m = *((volatile unsigned long long *)&slot_min[s]);
+            if (m == AGG_EMPTY) {
+                const unsigned long long prev = atomicCAS(&slot_min[s], AGG_EMPTY, AGG_CLAIMING);
+                if (prev == AGG_EMPTY) {
+                    *((volatile unsigned long long *)&slot_tag[s]) = tag;
+                    __threadfence();
+                    atomicMin(&slot_min[s], (unsigned long long)row);  // publishes (row < CLAIMING)
+                    return (long long)s;
+                }
+                m = prev;
             }
-            cur = prev == 0 ? h : prev;
-        }
-        if (mine) return (long long)s;
-        if (cur == h) {
-            long long r = slot_row[s];
-            while (r < 0) r = *((volatile long long *)&slot_row[s]);
-            if (r == row) return (long long)s;
-            typename Prog::Keys other;
-            Prog::eval_keys(p, r, other);
-            if (Prog::keys_equal(k, other)) return (long long)s;
+            while (m == AGG_CLAIMING) m = *((volatile unsigned long long *)&slot_min[s]);
+            if (*((volatile unsigned long long *)&slot_tag[s]) == tag) return (long long)s;
+        } else {
+            // tags are never 0 here (bit 62 or bit 63 is set): one CAS on the tag word claims the slot
+            unsigned long long cur = slot_tag[s];  // a stale 0 from L1 is corrected by the CAS below
+            if (cur == 0ULL) {
+                const unsigned long long prev = atomicCAS(&slot_tag[s], 0ULL, tag);
+                if (prev == 0ULL) return (long long)s;  // claimed; the caller's update publishes the first row
+                cur = prev;
+            }
+            if (cur == tag) {
+                if (exact) return (long long)s;
+                unsigned long long r = *((volatile unsigned long long *)&slot_min[s]);
+                while (r == AGG_EMPTY) r = *((volatile unsigned long long *)&slot_min[s]);  // claimer is about to publish
+                if ((int64_t)r == row) return (long long)s;
+                typename Prog::Keys mine, other;
+                Prog::eval_keys(p, row, mine);
+                Prog::eval_keys(p, (int64_t)r, other);
+                if (Prog::keys_equal(mine, other)) return (long long)s;
+            }
         }
         s = (s + 1) & mask;
     }
-    *((int *)p.ptr[Prog::PTR_OVERFLOW]) = 1;  // table full: host retries with a larger table
+    *((volatile int *)p.ptr[Prog::PTR_FLAG]) = 1;  // table too full: the host retries with a larger one
     return -1;
 }
 
-// Rare path, kept out of line so that its registers (XXH3, CAS loops) do not burden the streaming loop:
+// ---- global kernel: mid / high cardinality -------------------------------------------------------------
+// Tier 2: a per-CTA shared-memory table of (exact code -> cells) absorbs the rows of up to T2 groups with
+// shared-memory atomics and is merged into the global table once per CTA, so a few thousand hot groups do not
+// hammer a handful of L2 addresses.  Rows whose group does not fit (or whose code is inexact) go straight to the
+// global table: one CAS to find/claim the slot, then red.global atomics on its cells.
+template <class Prog>
+__device__ __forceinline__ void agg_body_global(const typename Prog::P &p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int T2 = Prog::T2;
+    unsigned long long *t2_tag = (unsigned long long *)smem_raw;  // 0 = empty (codes are never 0)
+    unsigned long long *t2c = t2_tag + T2;                        // cell c of slot t: t2c[c * T2 + t]
+    for (int t = threadIdx.x; t < T2; t += blockDim.x) {
+        t2_tag[t] = 0ULL;
+        Prog::t2_init(t2c, t);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = p.ival[Prog::IV_N];
+    constexpr int U = Prog::U;
+    const int64_t chunk = 32 * U;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+    volatile int *flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
+    int t2_hits = 0, t2_miss = 0;
+    bool use_t2 = T2 >= 64 && Prog::NKEYS > 0;
+    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
+        if (*flag) break;  // someone hit a full table: stop early, the host will retry
+        const int64_t base = c * chunk;
+        typename Prog::Raw raw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load(p, row, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load2(p, row, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            typename Prog::Vals vals;
+            bool live = row < n;
+            unsigned long long tag = 1ULL;
+            {
+                typename Prog::Keys keys;
+                if (live) live = Prog::eval(p, raw[u], keys, vals);
+                if (live && Prog::NKEYS > 0) tag = Prog::code(keys);
+            }
+            if (!live) continue;
+            bool done = false;
+            if (use_t2 && !(tag >> 63)) {  // exact codes only: equal code == equal key, no verification needed
+                unsigned int t = (unsigned int)(agg_mix(tag) >> 40) & (T2 - 1);
+#pragma unroll 1
+                for (int probes = 0; probes < 8 && !done; probes++) {
+                    unsigned long long cur = ((volatile unsigned long long *)t2_tag)[t];
+                    if (cur == 0ULL) {
+                        const unsigned long long prev = atomicCAS(&t2_tag[t], 0ULL, tag);
+                        cur = prev == 0ULL ? tag : prev;
+                    }
+                    if (cur == tag) {
+                        Prog::t2_update(t2c, (int)t, vals, row);
+                        done = true;
+                    }
+                    t = (t + 1) & (T2 - 1);
+                }
+                if (done) t2_hits++;
+                else if (++t2_miss > 256 && t2_miss > 4 * t2_hits) use_t2 = false;  // high cardinality: stop probing tier 2
+            }
+            if (!done) {
+                const long long slot = Prog::NKEYS > 0 ? agg_find_slot<Prog>(p, tag, row) : 0;
+                if (slot >= 0) Prog::global_update(p, slot, vals, row);
+            }
+        }
+    }
+    __syncthreads();
+    // merge tier 2 into the global table (the slot's first row doubles as its representative row)
+    if (!*flag) {
+        for (int t = threadIdx.x; t < T2; t += blockDim.x) {
+            const unsigned long long tag = t2_tag[t];
+            if (tag == 0ULL) continue;
+            const long long slot = agg_find_slot<Prog>(p, tag, (int64_t)t2c[(Prog::NLANE - 1) * T2 + t]);
+            if (slot >= 0) Prog::t2_flush(p, slot, t2c, t);
+        }
+    }
+}
+
+// Rare path of the low-cardinality kernel, kept out of line so that its registers do not burden the streaming loop:
 // find/claim the group's global slot, try to adopt it into the CTA's tier 1, otherwise update it globally.
 // Returns the tier-1 index (>= 0), -2 when the row was accumulated globally, -1 when the table is full.
 template <class Prog>
-__device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const typename Prog::Keys &keys,
-                                                const typename Prog::Vals &vals, int64_t row, unsigned long long fp,
-                                                long long *s_slot, unsigned long long *s_fp, typename Prog::Keys *s_keys) {
-    const long long slot = agg_find_slot<Prog>(p, keys, Prog::hash(keys), row);
+__device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const typename Prog::Vals &vals, int64_t row,
+                                                unsigned long long tag, long long *s_slot, unsigned long long *s_fp,
+                                                typename Prog::Keys *s_keys) {
+    const long long slot = agg_find_slot<Prog>(p, tag, row);
     if (slot < 0) return -1;
     for (int g = 0; g < Prog::G1; g++) {
         const long long old = (long long)atomicCAS((unsigned long long *)&s_slot[g], (unsigned long long)-1LL, (unsigned long long)slot);
-        if (old == -1) {  // this lane owns entry g: publish the key values, then the fingerprint
+        if (old == -1) {  // this lane owns entry g: publish the key values (for inexact codes), then the code
+            typename Prog::Keys keys;
+            Prog::eval_keys(p, row, keys);
             s_keys[g] = keys;
             __threadfence_block();
-            ((volatile unsigned long long *)s_fp)[g] = fp;
+            ((volatile unsigned long long *)s_fp)[g] = tag;
+            // make sure the slot has a representative row even if every later row of this group stays in tier 1
+            atomicMin(((unsigned long long *)p.ptr[Prog::PTR_MINROW]) + slot, (unsigned long long)row);
             return g;
         }
         if (old == slot) return g;
@@ -291,6 +409,7 @@ __device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const
     return -2;
 }
 
+// ---- low-cardinality kernel: tier 1 in shared memory, gives up (flag 2) when most rows miss it ------------------
 template <class Prog>
 __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -298,7 +417,7 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     // layout: lane cells [W][G1][NL][32] u64 | warp cells [W][G1][NW] u64 | s_fp[G1] | s_slot[G1] | s_keys[G1]
     unsigned long long *s_lcell = (unsigned long long *)smem_raw;
     unsigned long long *s_wcell = s_lcell + (size_t)AGG_WARPS * G1 * NL * 32;
-    unsigned long long *s_fp = s_wcell + AGG_WARPS * G1 * NWS;  // key fingerprint of a published entry, 0 = empty
+    unsigned long long *s_fp = s_wcell + AGG_WARPS * G1 * NWS;  // key code of a published entry, 0 = empty
     long long *s_slot = (long long *)(s_fp + G1);
     typename Prog::Keys *s_keys = (typename Prog::Keys *)(s_slot + G1);
 
@@ -318,52 +437,33 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     const int64_t chunk = 32 * U;
     const int64_t nchunks = (n + chunk - 1) / chunk;
     const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
-    // register copy of the tier-1 fingerprints (entries only ever go from 0 to their final value, so a stale
+    volatile int *flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
+    int slow_rows = 0;  // rows of this lane that missed tier 1
+    // register copy of the tier-1 codes (entries only ever go from 0 to their final value, so a stale
     // copy can only miss an entry -> slow path -> refresh)
     unsigned long long tfp[G1];
 #pragma unroll
     for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
-    // software pipeline: string offsets (load0) are fetched one chunk ahead of everything else
-    typename Prog::Raw raw[U];
-    {
-        const int64_t c0 = (int64_t)blockIdx.x * AGG_WARPS + warp;
+    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
+        if (*flag) break;
+        const int64_t base = c * chunk;
+        typename Prog::Raw raw[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int64_t row = c0 * chunk + u * 32 + lane;
-            if (Prog::PIPE && c0 < nchunks && row < n) Prog::load0(p, row, raw[u]);
-        }
-    }
-    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
-        const int64_t base = c * chunk;
-#pragma unroll
-        for (int u = 0; u < U; u++) {  // fixed-width columns, and the string prefixes whose offsets arrived last iteration
             const int64_t row = base + u * 32 + lane;
-            if (row < n) {
-                Prog::load(p, row, raw[u]);
-                if (Prog::PIPE) Prog::load2(p, row, raw[u]);
-            }
+            if (row < n) Prog::load(p, row, raw[u]);
         }
-        if (!Prog::PIPE) {
 #pragma unroll
-            for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
-                const int64_t row = base + u * 32 + lane;
-                if (row < n) Prog::load2(p, row, raw[u]);
-            }
-        }
-        typename Prog::Raw nxt[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {  // next chunk's string offsets
-            const int64_t row = (c + total_warps) * chunk + u * 32 + lane;
-            if (Prog::PIPE && c + total_warps < nchunks && row < n) Prog::load0(p, row, nxt[u]);
+        for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load2(p, row, raw[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int64_t row = base + u * 32 + lane;
             typename Prog::Vals vals;
             bool live = row < n;
-            // tier 1: the CTA's first G1 groups, matched on a 64-bit code of the key VALUES held in registers
-            // (no xxh3, no global memory on this path)
-            // key code: exact (injective, bit 63 clear) when the key tuple is narrow, else fingerprint | bit 63
+            // tier 1: the CTA's first G1 groups, matched on the 64-bit code of the key VALUES held in registers
             unsigned long long fp = 0ULL;
             {
                 typename Prog::Keys keys;  // dead after the code is formed: the rare paths re-read the keys by row
@@ -373,21 +473,20 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
             int lid = -1;
 #pragma unroll
             for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
-            if (Prog::NKEYS > 0 && live && lid >= 0 && (fp >> 63)) {  // only inexact codes need the value check
-                typename Prog::Keys kv;
+            if (Prog::NKEYS > 0 && Prog::MODE != 1 && live && lid >= 0 && (Prog::MODE == 2 || (fp >> 63))) {
+                typename Prog::Keys kv;  // inexact code: confirm against the published key values
                 Prog::eval_keys(p, row, kv);
                 if (!Prog::keys_equal(kv, s_keys[lid])) lid = -1;
             }
-            if (live && lid < 0) {  // rare: first rows of a CTA, or a group beyond tier 1
-                // built HERE so that only this rare branch puts key/value structs on the stack
-                typename Prog::Keys kcopy;
-                Prog::eval_keys(p, row, kcopy);  // full key values (8-byte string prefixes) for hashing / publishing
+            if (live && lid < 0) {  // rare here: first rows of a CTA, or a group beyond tier 1
                 const typename Prog::Vals vcopy = vals;
-                const long long r = agg_slow_path<Prog>(p, kcopy, vcopy, row, fp, s_slot, s_fp, s_keys);
+                const long long r = agg_slow_path<Prog>(p, vcopy, row, fp, s_slot, s_fp, s_keys);
                 if (r >= 0) lid = (int)r;
                 else live = false;  // accumulated globally (or table overflow)
 #pragma unroll
                 for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
+                // most rows missing tier 1 means the input is not low-cardinality: hand over to the global kernel
+                if (++slow_rows > 64 + G1) *flag = 2;
             }
             if (live) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals, row);
             if (NW > 0) {  // valid / null counts of nullable inputs: one ballot per tier-1 group
@@ -397,10 +496,6 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
                     if (__any_sync(FULL_MASK, in_g)) Prog::warp_cells(vals, in_g, my_wcell + g * NW, lane);
                 }
             }
-        }
-        if (Prog::PIPE) {
-#pragma unroll
-            for (int u = 0; u < U; u++) Prog::copy0(raw[u], nxt[u]);
         }
     }
     __syncthreads();

@@ -186,12 +186,12 @@ Batch *op_filter(const Batch &in, const uint8_t *plan, size_t len) {
 // ------------------------------------------------------------------------------------------------
 // fused HashAggregate
 // ------------------------------------------------------------------------------------------------
-__global__ void compact_slots(const unsigned long long *__restrict__ slot_hash, const unsigned long long *__restrict__ nrows,
-                              int64_t cap, int ungrouped, unsigned long long *counter, int64_t *__restrict__ out_slot) {
+__global__ void compact_slots(const unsigned long long *__restrict__ nrows, int64_t cap, int ungrouped, unsigned long long *counter,
+                              int64_t *__restrict__ out_slot) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < cap; i += stride) {
-        bool used = ungrouped ? (i == 0) : (slot_hash[i] != 0 && nrows[i] != 0);
+        const bool used = ungrouped ? (i == 0) : (nrows[i] != 0);  // a slot is a group iff some row was accumulated into it
         if (used) out_slot[atomicAdd(counter, 1ULL)] = i;
     }
 }
@@ -283,28 +283,27 @@ Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng);  // sort.cu
 
 Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *first_rows, int64_t *ngroups) {
     require_device();
-    const Compiled &k = jit::get(B200_OP_AGG, plan, len, in, false);
     cudaStream_t st = ctx().stream;
     const int64_t n = in.num_rows;
-    const int ncells = k.NLANE + k.NWARP;  // value cells + row count + first row, then ballot count cells
-    const int cell_nrows = k.NLANE - 2, cell_minrow = k.NLANE - 1;
-
-    // table capacity: grow on overflow (the group count is unknown up front; the reference's
-    // GroupedAggregateSink samples the first morsel for the same reason, grouped_aggregate.rs:205-245)
-    int64_t cap = 1;
-    if (k.nkeys > 0) {
-        cap = 1 << 16;
-        while (cap < 2 * std::min<int64_t>(n, 1 << 15)) cap <<= 1;
-    }
-    Buf slot_hash, slot_row, acc, overflow = dev_alloc_zero(8);
+    // Strategy (the reference samples the first morsel for the same decision, grouped_aggregate.rs:205-245):
+    // start with the low-cardinality kernel; it raises flag 2 as soon as most rows miss its shared-memory tier, and
+    // the global-table kernel takes over from scratch, growing its table while it reports overflow (flag 1).
+    int variant = 0;
+    const Compiled *kp = &jit::get(B200_OP_AGG, plan, len, in, false, 0);
+    int64_t cap = kp->nkeys > 0 ? (1 << 16) : 1;
+    Buf slot_tag, acc, flag = dev_alloc_zero(8);
+    int ncells = 0, cell_nrows = 0, cell_minrow = 0;
     for (int attempt = 0;; attempt++) {
-        slot_hash = dev_alloc_zero((size_t)cap * 8);
-        slot_row = dev_alloc((size_t)cap * 8);
-        fill_u8(slot_row->ptr, 0xFF, (size_t)cap * 8);
+        const Compiled &k = *kp;
+        ncells = k.NLANE + k.NWARP;  // value cells + row count + first row, then ballot count cells
+        cell_nrows = k.NLANE - 2;
+        cell_minrow = k.NLANE - 1;
+        slot_tag = dev_alloc_zero((size_t)cap * 8);
         acc = dev_alloc_zero((size_t)ncells * cap * 8);
         for (int c = 0; c < k.NLANE; c++)
             if (k.lane_cell_ops[c] == jit::C_MIN) fill_u8(as<uint8_t>(acc) + (size_t)c * cap * 8, 0xFF, (size_t)cap * 8);
-        fill_u8(overflow->ptr, 0, 8);
+        fill_u8(flag->ptr, 0, 8);
+        int status = 0;
         if (n > 0) {
             LaunchArgs a;
             a.ptr.assign(k.ptrs.size(), nullptr);
@@ -315,9 +314,8 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
                     case jit::P_COL_DATA: a.ptr[s] = in.cols[ps.index].data ? in.cols[ps.index].data->ptr : nullptr; break;
                     case jit::P_COL_VALID: a.ptr[s] = in.cols[ps.index].validity ? in.cols[ps.index].validity->ptr : nullptr; break;
                     case jit::P_COL_OFFSETS: a.ptr[s] = in.cols[ps.index].offsets ? in.cols[ps.index].offsets->ptr : nullptr; break;
-                    case jit::P_SLOT_HASH: a.ptr[s] = slot_hash->ptr; break;
-                    case jit::P_SLOT_ROW: a.ptr[s] = slot_row->ptr; break;
-                    case jit::P_OVERFLOW: a.ptr[s] = overflow->ptr; break;
+                    case jit::P_SLOT_HASH: a.ptr[s] = slot_tag->ptr; break;
+                    case jit::P_OVERFLOW: a.ptr[s] = flag->ptr; break;
                     case jit::P_ACC: a.ptr[s] = as<uint8_t>(acc) + (size_t)ps.index * cap * 8; break;
                     default: fail("agg: unexpected parameter kind");
                 }
@@ -336,26 +334,36 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
             int occ = 0;
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k.fn, 256, k.smem_bytes));
             occ = std::max(1, occ);
-            const int64_t chunks = (n + 127) / 128;
+            const int64_t chunks = (n + 63) / 64;
             const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 7) / 8, (int64_t)ctx().sm_count * occ));
             jit::launch(k, a, grid, 256, k.smem_bytes, 0, true);
+            if (k.nkeys > 0) {
+                B200_CUDA(cudaMemcpyAsync(&status, flag->ptr, 4, cudaMemcpyDeviceToHost, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+            }
         }
-        int ovf = 0;
-        if (k.nkeys > 0 && n > 0) {
-            B200_CUDA(cudaMemcpyAsync(&ovf, overflow->ptr, 4, cudaMemcpyDeviceToHost, st));
-            B200_CUDA(cudaStreamSynchronize(st));
+        if (!status) break;
+        if (attempt > 10) fail("agg: hash table overflow after repeated growth");
+        if (variant == 0) {
+            variant = 1;
+            kp = &jit::get(B200_OP_AGG, plan, len, in, false, 1);
+            cap = 1 << 20;
+            while (cap < 2 * std::min<int64_t>(n, (int64_t)1 << 23)) cap <<= 1;
+        } else {
+            cap <<= 3;
         }
-        if (!ovf) break;
-        if (attempt > 12) fail("agg: hash table overflow after repeated growth");
-        cap <<= 2;
+        size_t free_b = 0, total_b = 0;
+        B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if ((size_t)cap * 8 * (size_t)(ncells + 1) > free_b + (size_t)(ncells + 1) * (size_t)(cap >> 3) * 8)
+            fail("agg: the group table would not fit in device memory");
     }
+    const Compiled &k = *kp;
 
     // ---- compact occupied slots, order groups by first occurrence
     const unsigned long long *nrows_cell = as<unsigned long long>(acc) + (size_t)cell_nrows * cap;
     Buf counter = dev_alloc_zero(8);
     Buf slots = dev_alloc((size_t)std::max<int64_t>(cap, 1) * 8);
-    compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(as<unsigned long long>(slot_hash), nrows_cell, cap, k.nkeys == 0,
-                                                             as<unsigned long long>(counter), as<int64_t>(slots));
+    compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(nrows_cell, cap, k.nkeys == 0, as<unsigned long long>(counter), as<int64_t>(slots));
     count_launch();
     const int64_t ng = read_i64(as<int64_t>(counter));
     Buf minrow = dev_alloc((size_t)std::max<int64_t>(ng, 1) * 8);
