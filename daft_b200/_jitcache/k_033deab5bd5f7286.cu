@@ -1,3 +1,271 @@
+// XXH3-64 (seeded, default secret) for sm_100a device code.
+//
+// Replaces xxhash_rust::xxh3::xxh3_64_with_seed as called by the reference at
+// src/daft-core/src/kernels/hashing.rs:164-170.  Bit-exact with the canonical xxHash v0.8
+// XXH3_64bits_withSeed for every input length class; the hot classes for this path (1-3 B flag
+// strings, 4 B dates, 8 B keys, 9-16 B names) are straight-line register code with the secret
+// folded into immediates.  This header is compiled both ahead of time (hash.cu, join.cu, ...)
+// and textually prepended to every JIT-generated kernel.
+
+
+#ifdef __CUDACC_RTC__
+typedef signed char int8_t;
+typedef short int16_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+typedef unsigned long size_t;
+#else
+#include <cstdint>
+#include <cstddef>
+#endif
+
+namespace b200 {
+namespace xxh {
+
+#define B200_HD __host__ __device__ __forceinline__
+
+constexpr uint8_t kSecret[192] = {
+    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+    0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+    0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+    0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
+    0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
+    0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
+    0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
+    0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
+    0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
+    0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
+};
+
+// secret words as compile-time constants (offset must be a constant expression)
+constexpr uint64_t sec64c(int off) {
+    uint64_t v = 0;
+    for (int i = 7; i >= 0; --i) v = (v << 8) | kSecret[off + i];
+    return v;
+}
+constexpr uint32_t sec32c(int off) {
+    uint32_t v = 0;
+    for (int i = 3; i >= 0; --i) v = (v << 8) | kSecret[off + i];
+    return v;
+}
+template <int OFF>
+struct Sec {
+    static constexpr uint64_t v64 = sec64c(OFF);
+};
+constexpr uint32_t kBitflip1to3 = sec32c(0) ^ sec32c(4);
+
+constexpr uint32_t P32_1 = 0x9E3779B1U, P32_2 = 0x85EBCA77U, P32_3 = 0xC2B2AE3DU;
+constexpr uint64_t P64_1 = 0x9E3779B185EBCA87ULL, P64_2 = 0xC2B2AE3D27D4EB4FULL, P64_3 = 0x165667B19E3779F9ULL,
+                   P64_4 = 0x85EBCA77C2B2AE63ULL, P64_5 = 0x27D4EB2F165667C5ULL, PMX1 = 0x165667919E3779F9ULL,
+                   PMX2 = 0x9FB21C651E98DF25ULL;
+
+B200_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+B200_HD uint32_t bswap32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+}
+B200_HD uint64_t bswap64(uint64_t x) {
+    return ((uint64_t)bswap32((uint32_t)x) << 32) | bswap32((uint32_t)(x >> 32));
+}
+B200_HD uint64_t mul128_fold64(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return (a * b) ^ __umul64hi(a, b);
+#else
+    unsigned __int128 p = (unsigned __int128)a * b;
+    return (uint64_t)p ^ (uint64_t)(p >> 64);
+#endif
+}
+B200_HD uint64_t xxh64_avalanche(uint64_t h) {
+    h ^= h >> 33; h *= P64_2; h ^= h >> 29; h *= P64_3; h ^= h >> 32; return h;
+}
+B200_HD uint64_t xxh3_avalanche(uint64_t h) {
+    h ^= h >> 37; h *= PMX1; h ^= h >> 32; return h;
+}
+B200_HD uint64_t rrmxmx(uint64_t h, uint64_t len) {
+    h ^= rotl64(h, 49) ^ rotl64(h, 24);
+    h *= PMX2;
+    h ^= (h >> 35) + len;
+    h *= PMX2;
+    return h ^ (h >> 28);
+}
+
+// ---- fixed-width fast paths (value already in a register) ------------------------------------
+B200_HD uint64_t hash_empty(uint64_t seed) {
+    return xxh64_avalanche(seed ^ (Sec<56>::v64 ^ Sec<64>::v64));
+}
+// len in {1,2,3}: c1 = first byte, c2 = byte[len>>1], c3 = last byte
+B200_HD uint64_t hash_1to3(uint32_t c1, uint32_t c2, uint32_t c3, uint32_t len, uint64_t seed) {
+    uint32_t comb = (c1 << 16) | (c2 << 24) | c3 | (len << 8);
+    uint64_t bitflip = (uint64_t)kBitflip1to3 + seed;
+    return xxh64_avalanche((uint64_t)comb ^ bitflip);
+}
+B200_HD uint64_t hash_u8(uint8_t v, uint64_t seed) { return hash_1to3(v, v, v, 1, seed); }
+B200_HD uint64_t hash_u16(uint16_t v, uint64_t seed) { return hash_1to3(v & 0xff, v >> 8, v >> 8, 2, seed); }
+// len in [4,8]: lo32 = first 4 bytes, hi32 = last 4 bytes
+B200_HD uint64_t hash_4to8(uint32_t first4, uint32_t last4, uint32_t len, uint64_t seed) {
+    seed ^= (uint64_t)bswap32((uint32_t)seed) << 32;
+    uint64_t bitflip = (Sec<8>::v64 ^ Sec<16>::v64) - seed;
+    uint64_t in64 = (uint64_t)last4 + ((uint64_t)first4 << 32);
+    return rrmxmx(in64 ^ bitflip, len);
+}
+B200_HD uint64_t hash_u32(uint32_t v, uint64_t seed) { return hash_4to8(v, v, 4, seed); }
+B200_HD uint64_t hash_u64(uint64_t v, uint64_t seed) { return hash_4to8((uint32_t)v, (uint32_t)(v >> 32), 8, seed); }
+// len in [9,16]: lo = first 8 bytes, hi = last 8 bytes
+B200_HD uint64_t hash_9to16(uint64_t first8, uint64_t last8, uint64_t len, uint64_t seed) {
+    uint64_t bf1 = (Sec<24>::v64 ^ Sec<32>::v64) + seed;
+    uint64_t bf2 = (Sec<40>::v64 ^ Sec<48>::v64) - seed;
+    uint64_t lo = first8 ^ bf1, hi = last8 ^ bf2;
+    uint64_t acc = len + bswap64(lo) + hi + mul128_fold64(lo, hi);
+    return xxh3_avalanche(acc);
+}
+
+// ---- byte-stream path --------------------------------------------------------------------------
+static __device__ const uint8_t d_secret[192] = {
+    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+    0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+    0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+    0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
+    0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
+    0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
+    0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
+    0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
+    0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
+    0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
+};
+
+// Unaligned little-endian loads from global memory, byte granular (never reads past p+width).
+B200_HD uint32_t ld32u(const uint8_t *p) {
+    if ((((uintptr_t)p) & 3) == 0) return *reinterpret_cast<const uint32_t *>(p);
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+B200_HD uint64_t ld64u(const uint8_t *p) {
+    if ((((uintptr_t)p) & 7) == 0) return *reinterpret_cast<const uint64_t *>(p);
+    if ((((uintptr_t)p) & 3) == 0) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+        return (uint64_t)q[0] | ((uint64_t)q[1] << 32);
+    }
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) v = (v << 8) | p[i];
+    return v;
+}
+B200_HD uint64_t sec64(int off) {
+#ifdef __CUDA_ARCH__
+    return ld64u(d_secret + off);
+#else
+    return ld64u(kSecret + off);
+#endif
+}
+
+B200_HD uint64_t mix16(const uint8_t *in, int soff, uint64_t seed) {
+    return mul128_fold64(ld64u(in) ^ (sec64(soff) + seed), ld64u(in + 8) ^ (sec64(soff + 8) - seed));
+}
+
+__host__ __device__ __noinline__ uint64_t hash_long(const uint8_t *in, int64_t len, uint64_t seed) {
+    // secret word i (8-byte granular at byte offset `off`) with the seed folded in:
+    // custom[16j..16j+8) = k + seed, custom[16j+8..16j+16) = k - seed; unaligned offsets straddle words.
+    auto csec = [&](int off) -> uint64_t {
+        if (seed == 0) return sec64(off);
+        uint64_t v = 0;
+        // rebuild byte by byte from the two (or one) derived words it touches
+        int w0 = off >> 3, sh = (off & 7) * 8;
+        uint64_t a = sec64(w0 * 8);
+        a = (w0 & 1) ? a - seed : a + seed;
+        if (sh == 0) return a;
+        uint64_t b = sec64(w0 * 8 + 8);
+        b = ((w0 + 1) & 1) ? b - seed : b + seed;
+        v = (a >> sh) | (b << (64 - sh));
+        return v;
+    };
+    uint64_t acc[8] = {P32_3, P64_1, P64_2, P64_3, P64_4, P32_2, P64_5, P32_1};
+    auto accumulate = [&](const uint8_t *p, int soff) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint64_t dv = ld64u(p + 8 * i);
+            uint64_t dk = dv ^ csec(soff + 8 * i);
+            acc[i ^ 1] += dv;
+            acc[i] += (uint64_t)(uint32_t)dk * (dk >> 32);
+        }
+    };
+    const int64_t block_len = 1024;
+    const int64_t nb_blocks = (len - 1) / block_len;
+    for (int64_t n = 0; n < nb_blocks; n++) {
+        for (int s = 0; s < 16; s++) accumulate(in + n * block_len + s * 64, s * 8);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint64_t a = acc[i];
+            a ^= a >> 47;
+            a ^= csec(128 + 8 * i);
+            a *= P32_1;
+            acc[i] = a;
+        }
+    }
+    const int nb_stripes = (int)(((len - 1) - block_len * nb_blocks) / 64);
+    for (int s = 0; s < nb_stripes; s++) accumulate(in + nb_blocks * block_len + s * 64, s * 8);
+    accumulate(in + len - 64, 192 - 64 - 7);
+    uint64_t r = (uint64_t)len * P64_1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r += mul128_fold64(acc[2 * i] ^ csec(11 + 16 * i), acc[2 * i + 1] ^ csec(11 + 16 * i + 8));
+    return xxh3_avalanche(r);
+}
+
+__host__ __device__ __noinline__ uint64_t hash_17plus(const uint8_t *in, int64_t len, uint64_t seed) {
+    if (len <= 128) {
+        uint64_t acc = (uint64_t)len * P64_1;
+        if (len > 32) {
+            if (len > 64) {
+                if (len > 96) {
+                    acc += mix16(in + 48, 96, seed);
+                    acc += mix16(in + len - 64, 112, seed);
+                }
+                acc += mix16(in + 32, 64, seed);
+                acc += mix16(in + len - 48, 80, seed);
+            }
+            acc += mix16(in + 16, 32, seed);
+            acc += mix16(in + len - 32, 48, seed);
+        }
+        acc += mix16(in, 0, seed);
+        acc += mix16(in + len - 16, 16, seed);
+        return xxh3_avalanche(acc);
+    }
+    if (len <= 240) {
+        uint64_t acc = (uint64_t)len * P64_1;
+        int nb = (int)(len / 16);
+        for (int i = 0; i < 8; i++) acc += mix16(in + 16 * i, 16 * i, seed);
+        acc = xxh3_avalanche(acc);
+        for (int i = 8; i < nb; i++) acc += mix16(in + 16 * i, 16 * (i - 8) + 3, seed);
+        acc += mix16(in + len - 16, 136 - 17, seed);
+        return xxh3_avalanche(acc);
+    }
+    return hash_long(in, len, seed);
+}
+
+// any length, any alignment
+B200_HD uint64_t hash_bytes(const uint8_t *in, int64_t len, uint64_t seed) {
+    if (len <= 16) {
+        if (len == 0) return hash_empty(seed);
+        if (len <= 3) return hash_1to3(in[0], in[len >> 1], in[len - 1], (uint32_t)len, seed);
+        if (len <= 8) return hash_4to8(ld32u(in), ld32u(in + len - 4), (uint32_t)len, seed);
+        return hash_9to16(ld64u(in), ld64u(in + len - 8), (uint64_t)len, seed);
+    }
+    return hash_17plus(in, len, seed);
+}
+
+}  // namespace xxh
+}  // namespace b200
+
 // Device-side skeletons of the JIT-specialised pipeline kernels (sm_100a).
 //
 // The host (jit.cpp) turns a serialised plan (include/daft_b200.h "plan encoding") into a `Prog`
@@ -22,7 +290,7 @@
 //     Low-cardinality aggregates (TPC-H Q1: 4 groups) never leave tier 1; high-cardinality ones
 //     (Q18: one group per order) spread their atomics over millions of addresses.
 //   * first-occurrence group order (inline_agg.rs:804-807) is recovered by tracking min(row) per group.
-#pragma once
+
 
 #define FULL_MASK 0xffffffffu
 
@@ -460,105 +728,43 @@ __device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const
     return -2;
 }
 
-// ---- low-cardinality kernels: tier 1 in shared memory, give up (flag 2) when most rows miss it ------------------
-template <class Prog>
-struct AggTier1 {
-    static constexpr int G1 = Prog::G1, NL = Prog::NLANE, NW = Prog::NWARP, NWS = NW > 0 ? NW : 1;
-    unsigned long long *s_lcell, *s_wcell, *s_fp;
-    long long *s_slot;
-    typename Prog::Keys *s_keys;
-    unsigned long long *my_lcell, *my_wcell;
-    unsigned long long tfp[G1];  // register copy of the tier-1 codes (entries only go 0 -> final value: a stale copy
-                                 // can only miss an entry -> slow path -> refresh)
-    int slow_rows;
-    volatile int *flag;
-
-    static __host__ __device__ constexpr size_t smem_bytes() {
-        return 8 * ((size_t)AGG_WARPS * G1 * NL * 32 + (size_t)AGG_WARPS * G1 * NWS + 2 * (size_t)G1) + (size_t)G1 * sizeof(typename Prog::Keys);
-    }
-    // layout: lane cells [W][G1][NL][32] u64 | warp cells [W][G1][NW] u64 | s_fp[G1] | s_slot[G1] | s_keys[G1]
-    __device__ __forceinline__ void init(unsigned char *smem, const typename Prog::P &p) {
-        s_lcell = (unsigned long long *)smem;
-        s_wcell = s_lcell + (size_t)AGG_WARPS * G1 * NL * 32;
-        s_fp = s_wcell + AGG_WARPS * G1 * NWS;
-        s_slot = (long long *)(s_fp + G1);
-        s_keys = (typename Prog::Keys *)(s_slot + G1);
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (threadIdx.x < G1) {
-            s_slot[threadIdx.x] = Prog::NKEYS == 0 ? 0 : -1;
-            s_fp[threadIdx.x] = Prog::NKEYS == 0 ? 1ULL : 0ULL;
-        }
-        for (int i = threadIdx.x; i < AGG_WARPS * G1 * NWS; i += blockDim.x) s_wcell[i] = 0ULL;
-        my_lcell = s_lcell + (size_t)warp * G1 * NL * 32 + lane;  // cell c of group g: [(g*NL+c)*32]
-        for (int g = 0; g < G1; g++) Prog::lane_init(my_lcell + (size_t)g * NL * 32);
-        my_wcell = s_wcell + (size_t)warp * G1 * NWS;
-        slow_rows = 0;
-        flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
-    }
-    __device__ __forceinline__ void refresh() {
-#pragma unroll
-        for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
-    }
-    // one row: filter + projections + key code -> tier-1 cell update (or the rare slow path)
-    __device__ __forceinline__ void row(const typename Prog::P &p, const typename Prog::Raw &raw, int64_t r, bool live, int lane) {
-        typename Prog::Vals vals;
-        unsigned long long fp = 0ULL;
-        {
-            typename Prog::Keys keys;  // dead after the code is formed: the rare paths re-read the keys by row
-            if (live) live = Prog::eval(p, raw, keys, vals);
-            if (live) fp = Prog::NKEYS > 0 ? Prog::code(keys) : 1ULL;
-        }
-        int lid = -1;
-#pragma unroll
-        for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
-        if (Prog::NKEYS > 0 && Prog::MODE != 1 && live && lid >= 0 && (Prog::MODE == 2 || (fp >> 63))) {
-            typename Prog::Keys kv;  // inexact code: confirm against the published key values
-            Prog::eval_keys(p, r, kv);
-            if (!Prog::keys_equal(kv, s_keys[lid])) lid = -1;
-        }
-        if (live && lid < 0) {  // rare here: first rows of a CTA, or a group beyond tier 1
-            const typename Prog::Vals vcopy = vals;
-            const long long q = agg_slow_path<Prog>(p, vcopy, r, fp, s_slot, s_fp, s_keys);
-            if (q >= 0) lid = (int)q;
-            else live = false;  // accumulated globally (or table overflow)
-            refresh();
-            // most rows missing tier 1 means the input is not low-cardinality: hand over to the global kernel
-            if (++slow_rows > 64 + G1) *flag = 2;
-        }
-        if (live) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals, r);
-        if (NW > 0) {  // valid / null counts of nullable inputs: one ballot per tier-1 group
-#pragma unroll
-            for (int g = 0; g < G1; g++) {
-                const bool in_g = live && lid == g;
-                if (__any_sync(FULL_MASK, in_g)) Prog::warp_cells(vals, in_g, my_wcell + g * NW, lane);
-            }
-        }
-    }
-    // flush: warp w reduces groups w, w+W, ... across all warps' private copies (call after __syncthreads)
-    __device__ __forceinline__ void flush(const typename Prog::P &p, int lane, int warp) {
-        for (int g = warp; g < G1; g += AGG_WARPS) {
-            const long long slot = s_slot[g];
-            if (slot < 0) continue;
-            Prog::flush(p, slot, s_lcell + (size_t)g * NL * 32, (size_t)G1 * NL * 32, s_wcell + g * NWS, (size_t)G1 * NWS, lane);
-        }
-    }
-};
-
+// ---- low-cardinality kernel: tier 1 in shared memory, gives up (flag 2) when most rows miss it ------------------
 template <class Prog>
 __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    AggTier1<Prog> t1;
-    t1.init(smem_raw, p);
-    __syncthreads();
-    t1.refresh();
+    constexpr int G1 = Prog::G1, NL = Prog::NLANE, NW = Prog::NWARP, NWS = NW > 0 ? NW : 1;
+    // layout: lane cells [W][G1][NL][32] u64 | warp cells [W][G1][NW] u64 | s_fp[G1] | s_slot[G1] | s_keys[G1]
+    unsigned long long *s_lcell = (unsigned long long *)smem_raw;
+    unsigned long long *s_wcell = s_lcell + (size_t)AGG_WARPS * G1 * NL * 32;
+    unsigned long long *s_fp = s_wcell + AGG_WARPS * G1 * NWS;  // key code of a published entry, 0 = empty
+    long long *s_slot = (long long *)(s_fp + G1);
+    typename Prog::Keys *s_keys = (typename Prog::Keys *)(s_slot + G1);
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < G1) {
+        s_slot[threadIdx.x] = Prog::NKEYS == 0 ? 0 : -1;
+        s_fp[threadIdx.x] = Prog::NKEYS == 0 ? 1ULL : 0ULL;
+    }
+    for (int i = threadIdx.x; i < AGG_WARPS * G1 * NWS; i += blockDim.x) s_wcell[i] = 0ULL;
+    unsigned long long *my_lcell = s_lcell + (size_t)warp * G1 * NL * 32 + lane;  // cell c of group g: [(g*NL+c)*32]
+    for (int g = 0; g < G1; g++) Prog::lane_init(my_lcell + (size_t)g * NL * 32);
+    unsigned long long *my_wcell = s_wcell + (size_t)warp * G1 * NWS;
+    __syncthreads();
+
     const int64_t n = p.ival[Prog::IV_N];
     constexpr int U = Prog::U;
     const int64_t chunk = 32 * U;
     const int64_t nchunks = (n + chunk - 1) / chunk;
     const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+    volatile int *flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
+    int slow_rows = 0;  // rows of this lane that missed tier 1
+    // register copy of the tier-1 codes (entries only ever go from 0 to their final value, so a stale
+    // copy can only miss an entry -> slow path -> refresh)
+    unsigned long long tfp[G1];
+#pragma unroll
+    for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
     for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
-        if (*t1.flag) break;
+        if (*flag) break;
         const int64_t base = c * chunk;
         typename Prog::Raw raw[U];
 #pragma unroll
@@ -574,114 +780,79 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int64_t row = base + u * 32 + lane;
-            t1.row(p, raw[u], row, row < n, lane);
-        }
-    }
-    __syncthreads();
-    t1.flush(p, lane, warp);
-}
-
-// ---- the same kernel fed by TMA bulk copies ---------------------------------------------------------------------
-// Each warp owns a ring of S stages in shared memory.  Lane 0 issues one cp.async.bulk (UBLKCP) per staged column
-// slice -- R consecutive rows of a fixed-width column, R+2 offsets of a string column, R*L value bytes of a
-// fixed-length string column -- completing on the stage's mbarrier; the warp consumes stage i while the copies of
-// stages i+1 .. i+S-1 are in flight, so HBM latency is covered by shared-memory capacity instead of registers and
-// resident warps.  Tail chunks that cannot be staged (offsets need row t+R+1) use the direct-load path.
-__device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-                 "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
-}
-
-template <class Prog>
-__device__ __forceinline__ void agg_body_staged(const typename Prog::P &p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int R = Prog::STAGE_ROWS, S = Prog::STAGES, SB = Prog::STAGE_BYTES;
-    // layout: stages [W][S][SB] (16 B aligned) | mbarriers [W][S] | tier 1
-    unsigned char *stages = smem_raw;
-    unsigned long long *bars = (unsigned long long *)(stages + (size_t)AGG_WARPS * S * SB);
-    AggTier1<Prog> t1;
-    t1.init((unsigned char *)(bars + AGG_WARPS * S), p);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0)
-        for (int s = 0; s < S; s++) mbar_init(smem_u32(&bars[warp * S + s]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    t1.refresh();
-    const int64_t n = p.ival[Prog::IV_N];
-    const int64_t nchunks = (n + R - 1) / R;
-    const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
-    const int64_t c0 = (int64_t)blockIdx.x * AGG_WARPS + warp;
-    unsigned char *my_stage = stages + (size_t)warp * S * SB;
-    auto stageable = [&](int64_t c) { return c < nchunks && (c + 1) * R < n; };  // offsets copy reads row (c+1)*R + 1
-    if (lane == 0) {
-#pragma unroll 1
-        for (int s = 0; s < S; s++) {
-            const int64_t c = c0 + (int64_t)s * total_warps;
-            if (stageable(c)) Prog::stage_issue(p, smem_u32(my_stage + (size_t)s * SB), smem_u32(&bars[warp * S + s]), c * R);
-        }
-    }
-    int64_t i = 0;
-    for (int64_t c = c0; c < nchunks; c += total_warps, i++) {
-        if (*t1.flag) break;
-        const int s = (int)(i % S);
-        const uint32_t parity = (uint32_t)((i / S) & 1);
-        const int64_t base = c * R;
-        const bool staged = stageable(c);
-        const unsigned char *st = my_stage + (size_t)s * SB;
-        if (staged) mbar_wait(smem_u32(&bars[warp * S + s]), parity);
-#pragma unroll 1
-        for (int j = 0; j < R / 32; j += 2) {  // two rows per lane in flight (ILP), both read from shared memory
-            typename Prog::Raw raw[2];
+            typename Prog::Vals vals;
+            bool live = row < n;
+            // tier 1: the CTA's first G1 groups, matched on the 64-bit code of the key VALUES held in registers
+            unsigned long long fp = 0ULL;
+            {
+                typename Prog::Keys keys;  // dead after the code is formed: the rare paths re-read the keys by row
+                if (live) live = Prog::eval(p, raw[u], keys, vals);
+                if (live) fp = Prog::NKEYS > 0 ? Prog::code(keys) : 1ULL;
+            }
+            int lid = -1;
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int r = (j + u) * 32 + lane;
-                const int64_t row = base + r;
-                if (row < n) {
-                    if (staged) Prog::load_staged(p, st, r, row, raw[u]);
-                    else Prog::load(p, row, raw[u]);
+            for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
+            if (Prog::NKEYS > 0 && Prog::MODE != 1 && live && lid >= 0 && (Prog::MODE == 2 || (fp >> 63))) {
+                typename Prog::Keys kv;  // inexact code: confirm against the published key values
+                Prog::eval_keys(p, row, kv);
+                if (!Prog::keys_equal(kv, s_keys[lid])) lid = -1;
+            }
+            if (live && lid < 0) {  // rare here: first rows of a CTA, or a group beyond tier 1
+                const typename Prog::Vals vcopy = vals;
+                const long long r = agg_slow_path<Prog>(p, vcopy, row, fp, s_slot, s_fp, s_keys);
+                if (r >= 0) lid = (int)r;
+                else live = false;  // accumulated globally (or table overflow)
+#pragma unroll
+                for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
+                // most rows missing tier 1 means the input is not low-cardinality: hand over to the global kernel
+                if (++slow_rows > 64 + G1) *flag = 2;
+            }
+            if (live) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals, row);
+            if (NW > 0) {  // valid / null counts of nullable inputs: one ballot per tier-1 group
+#pragma unroll
+                for (int g = 0; g < G1; g++) {
+                    const bool in_g = live && lid == g;
+                    if (__any_sync(FULL_MASK, in_g)) Prog::warp_cells(vals, in_g, my_wcell + g * NW, lane);
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int64_t row = base + (j + u) * 32 + lane;
-                if (row < n) Prog::load2(p, row, raw[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int64_t row = base + (j + u) * 32 + lane;
-                t1.row(p, raw[u], row, row < n, lane);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {  // refill this stage with the chunk S iterations ahead
-            const int64_t cn = c + (int64_t)S * total_warps;
-            if (stageable(cn)) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                Prog::stage_issue(p, smem_u32(my_stage + (size_t)s * SB), smem_u32(&bars[warp * S + s]), cn * R);
-            }
         }
     }
     __syncthreads();
-    t1.flush(p, lane, warp);
+    // flush tier 1: warp w reduces groups w, w+W, ... across all warps' private copies
+    for (int g = warp; g < G1; g += AGG_WARPS) {
+        const long long slot = s_slot[g];
+        if (slot < 0) continue;
+        Prog::flush(p, slot, s_lcell + (size_t)g * NL * 32, (size_t)G1 * NL * 32, s_wcell + g * NWS, (size_t)G1 * NWS, lane);
+    }
 }
 
 }  // namespace jit
 }  // namespace b200
+
+using namespace b200;
+using namespace b200::jit;
+struct Prog {
+  typedef Params<8, 1> P;
+  static constexpr int IV_N = 0, PTR_COUNTS = 0, PTR_IDX = 7;
+  __device__ __forceinline__ static bool keep(const P& p, const int64_t row) {
+    const bool rowok = true;
+    const bool k0 = rowok;
+    const int32_t v0 = rowok ? ((const int32_t*)p.ptr[1])[row] : (int32_t)0;
+    const int32_t v1 = (int32_t)(10471LL); const bool k1 = true;
+    const bool v2 = v0 <= v1;
+    const bool k2 = k0 && k1;
+    const bool k3 = rowok && bit_at((const uint8_t*)p.ptr[2], row);
+    const double v3 = rowok ? ((const double*)p.ptr[3])[row] : (double)0;
+    const double v4 = __longlong_as_double(4602678819172646912LL); const bool k4 = true;
+    const bool v5 = v3 > v4;
+    const bool k5 = k3 && k4;
+    const bool v6 = (k2 && v2) && (k5 && v5);
+    const bool k6 = (k2 && k5) || (k2 && !v2) || (k5 && !v5);
+    return k6 && v6;
+  }
+  __device__ __forceinline__ static void copy(const P& p, const int64_t src, const int64_t dst) {
+    ((int64_t*)p.ptr[4])[dst] = ((const int64_t*)p.ptr[5])[src];
+    ((int32_t*)p.ptr[6])[dst] = ((const int32_t*)p.ptr[1])[src];
+  }
+};
+extern "C" __global__ void __launch_bounds__(256) b200_filter_k(const __grid_constant__ Prog::P p, int pass) { filter_body<Prog>(p, pass); }

@@ -94,7 +94,6 @@ int b200_precompile(int32_t op, const uint8_t *plan, size_t plan_len, const int3
     return guard(errmsg, [&] {
         std::vector<int32_t> dt(col_dtypes, col_dtypes + ncols);
         std::vector<uint8_t> nl(col_nullable, col_nullable + ncols);
-        if (op == B200_OP_FILTER) fail("precompile: wrap a FILTER predicate as PROJECT(fill_null(pred,false))");
         jit::precompile(op, plan, plan_len, dt, nl);
     });
 }

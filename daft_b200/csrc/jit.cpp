@@ -607,6 +607,47 @@ static std::string gen_project(Reader &r, Ast &ast, Compiled &meta, bool with_ta
     return o.str();
 }
 
+// ---- FILTER (fused compaction) ---------------------------------------------------------------------------
+static std::string gen_filter(Reader &r, Ast &ast, Compiled &meta) {
+    CG cg{ast, meta};
+    const int root = parse_node(r, ast);
+    if (ast.nodes[root].dtype != B200_BOOL && ast.nodes[root].dtype != B200_NULL) fail("filter: predicate must be boolean");
+    const int iv_n = cg.int_slot(I_N);
+    const int p_counts = cg.ptr_slot(P_OUT_LEN, 0);
+    std::ostringstream kb, cp;
+    ExprGen eg{cg, DIRECT, kb, "", {}};
+    kb << "    const bool rowok = true;\n";
+    const int id = eg.emit(root);
+    kb << "    return " << eg.k(id) << " && " << eg.v(id) << ";\n";  // a null predicate drops the row (lib.rs:542-563)
+    // fixed-width columns without nulls are compacted in the kernel; the rest are gathered by the host via row ids
+    bool need_idx = false;
+    const int ncols = (int)ast.col_dtypes->size();
+    for (int c = 0; c < ncols; c++) {
+        const int32_t dt = (*ast.col_dtypes)[c];
+        const int w = dtype_width(dt);
+        OutCol oc{"", dt, false, false};
+        if (w && !(*ast.col_nullable)[c]) {
+            cp << "    ((" << ctype(dt) << "*)" << cg.P(P_OUT_DATA, c) << ")[dst] = ((const " << ctype(dt) << "*)" << cg.P(P_COL_DATA, c) << ")[src];\n";
+            oc.nullable = false;
+        } else {
+            oc.nullable = true;  // marks "host gathers this column"
+            if (dt != B200_NULL) need_idx = true;
+        }
+        meta.outs.push_back(oc);
+    }
+    const int p_idx = need_idx ? cg.ptr_slot(P_TAKE, 0) : -1;
+    std::ostringstream o;
+    o << file_header(cg);
+    o << "struct Prog {\n  typedef Params<" << meta.ptrs.size() << ", " << meta.ints.size() << "> P;\n";
+    o << "  static constexpr int IV_N = " << iv_n << ", PTR_COUNTS = " << p_counts << ", PTR_IDX = " << p_idx << ";\n";
+    o << "  __device__ __forceinline__ static bool keep(const P& p, const int64_t row) {\n" << kb.str() << "  }\n";
+    o << "  __device__ __forceinline__ static void copy(const P& p, const int64_t src, const int64_t dst) {\n" << cp.str() << "  }\n";
+    o << "};\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(256) b200_filter_k(const __grid_constant__ Prog::P p, int pass) { filter_body<Prog>(p, pass); }\n";
+    meta.with_take = need_idx;
+    return o.str();
+}
+
 // ---- AGG -----------------------------------------------------------------------------------------
 static std::string hash_expr(int32_t dt, const std::string &v, const std::string &k, const std::string &seed) {
     // Daft null rules, see hash.cu header
@@ -1233,6 +1274,9 @@ std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::ve
     if (op == B200_OP_PROJECT) {
         body = gen_project(r, ast, meta, with_take);
         if (r.pos != r.n) fail("plan: trailing bytes");
+    } else if (op == B200_OP_FILTER) {
+        body = gen_filter(r, ast, meta);
+        if (r.pos != r.n) fail("plan: trailing bytes");
     } else if (op == B200_OP_AGG) {
         body = gen_agg(r, ast, meta, variant != 0);
     } else {
@@ -1341,7 +1385,7 @@ const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &i
     require_device();
     // runtime "library" API (cudart dlopens the driver itself; the .so has no link-time libcuda dependency)
     B200_CUDA(cudaLibraryLoadData(&c->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-    B200_CUDA(cudaLibraryGetKernel(&c->fn, c->lib, op == B200_OP_AGG ? "b200_agg_k" : "b200_project_k"));
+    B200_CUDA(cudaLibraryGetKernel(&c->fn, c->lib, op == B200_OP_AGG ? "b200_agg_k" : (op == B200_OP_FILTER ? "b200_filter_k" : "b200_project_k")));
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, (const void *)c->fn) == cudaSuccess) c->regs = fa.numRegs;
     if (c->smem_bytes > 48 * 1024)

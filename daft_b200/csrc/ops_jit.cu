@@ -160,27 +160,63 @@ Buf bitmap_select(const uint32_t *words, int64_t n, bool invert, int64_t *count_
 
 Batch *op_filter(const Batch &in, const uint8_t *plan, size_t len) {
     require_device();
-    // wrap the predicate as a one-expression PROJECT plan: fill_null(pred, false) so that null drops the row
-    std::vector<uint8_t> proj;
-    auto put32 = [&](uint32_t v) { proj.insert(proj.end(), (uint8_t *)&v, (uint8_t *)&v + 4); };
-    put32(1);
-    put32(4);
-    proj.insert(proj.end(), {'m', 'a', 's', 'k'});
-    proj.push_back(8);  // FILL_NULL
-    proj.insert(proj.end(), plan, plan + len);
-    proj.push_back(1);  // LIT
-    proj.push_back(B200_BOOL);
-    proj.push_back(0);
-    int64_t z = 0;
-    proj.insert(proj.end(), (uint8_t *)&z, (uint8_t *)&z + 8);
-    std::unique_ptr<Batch> mask(op_project(in, proj.data(), proj.size(), nullptr, 0));
-    const Column &m = mask->cols[0];
-    if (m.dtype != B200_BOOL) fail("filter: predicate must be boolean, got " + std::string(dtype_name(m.dtype)));
+    cudaStream_t st = ctx().stream;
     const int64_t n = in.num_rows;
     if (n == 0) return gather_batch(in, nullptr, 0, false);
-    int64_t total = 0;
-    Buf idx = bitmap_select(as<uint32_t>(m.data), n, false, &total);
-    return gather_batch(in, as<int64_t>(idx), total, false);
+    const Compiled &k = jit::get(B200_OP_FILTER, plan, len, in, false);
+    const int64_t ntiles = (n + 2047) / 2048;
+    Buf counts = dev_alloc((size_t)(ntiles + 1) * 8), offs = dev_alloc((size_t)(ntiles + 1) * 8);
+    auto out = std::make_unique<Batch>();
+    Buf idx;
+    auto fill = [&](LaunchArgs &a, Buf &cnt) {
+        a.ptr.assign(k.ptrs.size(), nullptr);
+        a.ival.assign(k.ints.size(), 0);
+        for (size_t s = 0; s < k.ptrs.size(); s++) {
+            const auto &ps = k.ptrs[s];
+            switch (ps.kind) {
+                case jit::P_COL_DATA: a.ptr[s] = in.cols[ps.index].data ? in.cols[ps.index].data->ptr : nullptr; break;
+                case jit::P_COL_VALID: a.ptr[s] = in.cols[ps.index].validity ? in.cols[ps.index].validity->ptr : nullptr; break;
+                case jit::P_COL_OFFSETS: a.ptr[s] = in.cols[ps.index].offsets ? in.cols[ps.index].offsets->ptr : nullptr; break;
+                case jit::P_OUT_LEN: a.ptr[s] = cnt->ptr; break;
+                case jit::P_OUT_DATA: a.ptr[s] = out->cols.size() > (size_t)ps.index && out->cols[ps.index].data ? out->cols[ps.index].data->ptr : nullptr; break;
+                case jit::P_TAKE: a.ptr[s] = idx ? idx->ptr : nullptr; break;
+                default: fail("filter: unexpected parameter kind");
+            }
+        }
+        for (size_t s = 0; s < k.ints.size(); s++)
+            if (k.ints[s] == jit::I_N) a.ival[s] = n;
+    };
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx().sm_count * 8));
+    {
+        LaunchArgs a;
+        fill(a, counts);
+        jit::launch(k, a, grid, 256, 0, 0, false);
+    }
+    exclusive_scan_i64(as<int64_t>(counts), as<int64_t>(offs), ntiles, as<int64_t>(offs) + ntiles);
+    const int64_t total = read_i64(as<int64_t>(offs) + ntiles);
+    out->num_rows = total;
+    for (size_t c = 0; c < in.cols.size(); c++) {
+        Column oc;
+        oc.name = in.cols[c].name;
+        oc.dtype = in.cols[c].dtype;
+        oc.length = total;
+        if (!k.outs[c].nullable) {  // compacted by the kernel
+            const int w = dtype_width(oc.dtype);
+            oc.data = dev_alloc((size_t)std::max<int64_t>(total, 1) * w);
+            oc.data_bytes = total * w;
+        }
+        out->cols.push_back(std::move(oc));
+    }
+    if (k.with_take) idx = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
+    if (total > 0) {
+        LaunchArgs a;
+        fill(a, offs);
+        jit::launch(k, a, grid, 256, 0, 1, false);
+    }
+    for (size_t c = 0; c < in.cols.size(); c++)
+        if (k.outs[c].nullable) out->cols[c] = gather_column(in.cols[c], as<int64_t>(idx), total, false);
+    B200_CUDA(cudaStreamSynchronize(st));
+    return out.release();
 }
 
 // ------------------------------------------------------------------------------------------------
