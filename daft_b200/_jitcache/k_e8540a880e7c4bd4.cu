@@ -1,0 +1,1065 @@
+// XXH3-64 (seeded, default secret) for sm_100a device code.
+//
+// Replaces xxhash_rust::xxh3::xxh3_64_with_seed as called by the reference at
+// src/daft-core/src/kernels/hashing.rs:164-170.  Bit-exact with the canonical xxHash v0.8
+// XXH3_64bits_withSeed for every input length class; the hot classes for this path (1-3 B flag
+// strings, 4 B dates, 8 B keys, 9-16 B names) are straight-line register code with the secret
+// folded into immediates.  This header is compiled both ahead of time (hash.cu, join.cu, ...)
+// and textually prepended to every JIT-generated kernel.
+
+
+#ifdef __CUDACC_RTC__
+typedef signed char int8_t;
+typedef short int16_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+typedef unsigned long size_t;
+#else
+#include <cstdint>
+#include <cstddef>
+#endif
+
+namespace b200 {
+namespace xxh {
+
+#define B200_HD __host__ __device__ __forceinline__
+
+constexpr uint8_t kSecret[192] = {
+    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+    0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+    0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+    0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
+    0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
+    0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
+    0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
+    0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
+    0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
+    0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
+};
+
+// secret words as compile-time constants (offset must be a constant expression)
+constexpr uint64_t sec64c(int off) {
+    uint64_t v = 0;
+    for (int i = 7; i >= 0; --i) v = (v << 8) | kSecret[off + i];
+    return v;
+}
+constexpr uint32_t sec32c(int off) {
+    uint32_t v = 0;
+    for (int i = 3; i >= 0; --i) v = (v << 8) | kSecret[off + i];
+    return v;
+}
+template <int OFF>
+struct Sec {
+    static constexpr uint64_t v64 = sec64c(OFF);
+};
+constexpr uint32_t kBitflip1to3 = sec32c(0) ^ sec32c(4);
+
+constexpr uint32_t P32_1 = 0x9E3779B1U, P32_2 = 0x85EBCA77U, P32_3 = 0xC2B2AE3DU;
+constexpr uint64_t P64_1 = 0x9E3779B185EBCA87ULL, P64_2 = 0xC2B2AE3D27D4EB4FULL, P64_3 = 0x165667B19E3779F9ULL,
+                   P64_4 = 0x85EBCA77C2B2AE63ULL, P64_5 = 0x27D4EB2F165667C5ULL, PMX1 = 0x165667919E3779F9ULL,
+                   PMX2 = 0x9FB21C651E98DF25ULL;
+
+B200_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+B200_HD uint32_t bswap32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+}
+B200_HD uint64_t bswap64(uint64_t x) {
+    return ((uint64_t)bswap32((uint32_t)x) << 32) | bswap32((uint32_t)(x >> 32));
+}
+B200_HD uint64_t mul128_fold64(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return (a * b) ^ __umul64hi(a, b);
+#else
+    unsigned __int128 p = (unsigned __int128)a * b;
+    return (uint64_t)p ^ (uint64_t)(p >> 64);
+#endif
+}
+B200_HD uint64_t xxh64_avalanche(uint64_t h) {
+    h ^= h >> 33; h *= P64_2; h ^= h >> 29; h *= P64_3; h ^= h >> 32; return h;
+}
+B200_HD uint64_t xxh3_avalanche(uint64_t h) {
+    h ^= h >> 37; h *= PMX1; h ^= h >> 32; return h;
+}
+B200_HD uint64_t rrmxmx(uint64_t h, uint64_t len) {
+    h ^= rotl64(h, 49) ^ rotl64(h, 24);
+    h *= PMX2;
+    h ^= (h >> 35) + len;
+    h *= PMX2;
+    return h ^ (h >> 28);
+}
+
+// ---- fixed-width fast paths (value already in a register) ------------------------------------
+B200_HD uint64_t hash_empty(uint64_t seed) {
+    return xxh64_avalanche(seed ^ (Sec<56>::v64 ^ Sec<64>::v64));
+}
+// len in {1,2,3}: c1 = first byte, c2 = byte[len>>1], c3 = last byte
+B200_HD uint64_t hash_1to3(uint32_t c1, uint32_t c2, uint32_t c3, uint32_t len, uint64_t seed) {
+    uint32_t comb = (c1 << 16) | (c2 << 24) | c3 | (len << 8);
+    uint64_t bitflip = (uint64_t)kBitflip1to3 + seed;
+    return xxh64_avalanche((uint64_t)comb ^ bitflip);
+}
+B200_HD uint64_t hash_u8(uint8_t v, uint64_t seed) { return hash_1to3(v, v, v, 1, seed); }
+B200_HD uint64_t hash_u16(uint16_t v, uint64_t seed) { return hash_1to3(v & 0xff, v >> 8, v >> 8, 2, seed); }
+// len in [4,8]: lo32 = first 4 bytes, hi32 = last 4 bytes
+B200_HD uint64_t hash_4to8(uint32_t first4, uint32_t last4, uint32_t len, uint64_t seed) {
+    seed ^= (uint64_t)bswap32((uint32_t)seed) << 32;
+    uint64_t bitflip = (Sec<8>::v64 ^ Sec<16>::v64) - seed;
+    uint64_t in64 = (uint64_t)last4 + ((uint64_t)first4 << 32);
+    return rrmxmx(in64 ^ bitflip, len);
+}
+B200_HD uint64_t hash_u32(uint32_t v, uint64_t seed) { return hash_4to8(v, v, 4, seed); }
+B200_HD uint64_t hash_u64(uint64_t v, uint64_t seed) { return hash_4to8((uint32_t)v, (uint32_t)(v >> 32), 8, seed); }
+// len in [9,16]: lo = first 8 bytes, hi = last 8 bytes
+B200_HD uint64_t hash_9to16(uint64_t first8, uint64_t last8, uint64_t len, uint64_t seed) {
+    uint64_t bf1 = (Sec<24>::v64 ^ Sec<32>::v64) + seed;
+    uint64_t bf2 = (Sec<40>::v64 ^ Sec<48>::v64) - seed;
+    uint64_t lo = first8 ^ bf1, hi = last8 ^ bf2;
+    uint64_t acc = len + bswap64(lo) + hi + mul128_fold64(lo, hi);
+    return xxh3_avalanche(acc);
+}
+
+// ---- byte-stream path --------------------------------------------------------------------------
+static __device__ const uint8_t d_secret[192] = {
+    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+    0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+    0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+    0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
+    0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
+    0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
+    0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
+    0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
+    0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
+    0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
+};
+
+// Unaligned little-endian loads from global memory, byte granular (never reads past p+width).
+B200_HD uint32_t ld32u(const uint8_t *p) {
+    if ((((uintptr_t)p) & 3) == 0) return *reinterpret_cast<const uint32_t *>(p);
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+B200_HD uint64_t ld64u(const uint8_t *p) {
+    if ((((uintptr_t)p) & 7) == 0) return *reinterpret_cast<const uint64_t *>(p);
+    if ((((uintptr_t)p) & 3) == 0) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+        return (uint64_t)q[0] | ((uint64_t)q[1] << 32);
+    }
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) v = (v << 8) | p[i];
+    return v;
+}
+B200_HD uint64_t sec64(int off) {
+#ifdef __CUDA_ARCH__
+    return ld64u(d_secret + off);
+#else
+    return ld64u(kSecret + off);
+#endif
+}
+
+B200_HD uint64_t mix16(const uint8_t *in, int soff, uint64_t seed) {
+    return mul128_fold64(ld64u(in) ^ (sec64(soff) + seed), ld64u(in + 8) ^ (sec64(soff + 8) - seed));
+}
+
+__host__ __device__ __noinline__ uint64_t hash_long(const uint8_t *in, int64_t len, uint64_t seed) {
+    // secret word i (8-byte granular at byte offset `off`) with the seed folded in:
+    // custom[16j..16j+8) = k + seed, custom[16j+8..16j+16) = k - seed; unaligned offsets straddle words.
+    auto csec = [&](int off) -> uint64_t {
+        if (seed == 0) return sec64(off);
+        uint64_t v = 0;
+        // rebuild byte by byte from the two (or one) derived words it touches
+        int w0 = off >> 3, sh = (off & 7) * 8;
+        uint64_t a = sec64(w0 * 8);
+        a = (w0 & 1) ? a - seed : a + seed;
+        if (sh == 0) return a;
+        uint64_t b = sec64(w0 * 8 + 8);
+        b = ((w0 + 1) & 1) ? b - seed : b + seed;
+        v = (a >> sh) | (b << (64 - sh));
+        return v;
+    };
+    uint64_t acc[8] = {P32_3, P64_1, P64_2, P64_3, P64_4, P32_2, P64_5, P32_1};
+    auto accumulate = [&](const uint8_t *p, int soff) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint64_t dv = ld64u(p + 8 * i);
+            uint64_t dk = dv ^ csec(soff + 8 * i);
+            acc[i ^ 1] += dv;
+            acc[i] += (uint64_t)(uint32_t)dk * (dk >> 32);
+        }
+    };
+    const int64_t block_len = 1024;
+    const int64_t nb_blocks = (len - 1) / block_len;
+    for (int64_t n = 0; n < nb_blocks; n++) {
+        for (int s = 0; s < 16; s++) accumulate(in + n * block_len + s * 64, s * 8);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint64_t a = acc[i];
+            a ^= a >> 47;
+            a ^= csec(128 + 8 * i);
+            a *= P32_1;
+            acc[i] = a;
+        }
+    }
+    const int nb_stripes = (int)(((len - 1) - block_len * nb_blocks) / 64);
+    for (int s = 0; s < nb_stripes; s++) accumulate(in + nb_blocks * block_len + s * 64, s * 8);
+    accumulate(in + len - 64, 192 - 64 - 7);
+    uint64_t r = (uint64_t)len * P64_1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r += mul128_fold64(acc[2 * i] ^ csec(11 + 16 * i), acc[2 * i + 1] ^ csec(11 + 16 * i + 8));
+    return xxh3_avalanche(r);
+}
+
+__host__ __device__ __noinline__ uint64_t hash_17plus(const uint8_t *in, int64_t len, uint64_t seed) {
+    if (len <= 128) {
+        uint64_t acc = (uint64_t)len * P64_1;
+        if (len > 32) {
+            if (len > 64) {
+                if (len > 96) {
+                    acc += mix16(in + 48, 96, seed);
+                    acc += mix16(in + len - 64, 112, seed);
+                }
+                acc += mix16(in + 32, 64, seed);
+                acc += mix16(in + len - 48, 80, seed);
+            }
+            acc += mix16(in + 16, 32, seed);
+            acc += mix16(in + len - 32, 48, seed);
+        }
+        acc += mix16(in, 0, seed);
+        acc += mix16(in + len - 16, 16, seed);
+        return xxh3_avalanche(acc);
+    }
+    if (len <= 240) {
+        uint64_t acc = (uint64_t)len * P64_1;
+        int nb = (int)(len / 16);
+        for (int i = 0; i < 8; i++) acc += mix16(in + 16 * i, 16 * i, seed);
+        acc = xxh3_avalanche(acc);
+        for (int i = 8; i < nb; i++) acc += mix16(in + 16 * i, 16 * (i - 8) + 3, seed);
+        acc += mix16(in + len - 16, 136 - 17, seed);
+        return xxh3_avalanche(acc);
+    }
+    return hash_long(in, len, seed);
+}
+
+// any length, any alignment
+B200_HD uint64_t hash_bytes(const uint8_t *in, int64_t len, uint64_t seed) {
+    if (len <= 16) {
+        if (len == 0) return hash_empty(seed);
+        if (len <= 3) return hash_1to3(in[0], in[len >> 1], in[len - 1], (uint32_t)len, seed);
+        if (len <= 8) return hash_4to8(ld32u(in), ld32u(in + len - 4), (uint32_t)len, seed);
+        return hash_9to16(ld64u(in), ld64u(in + len - 8), (uint64_t)len, seed);
+    }
+    return hash_17plus(in, len, seed);
+}
+
+}  // namespace xxh
+}  // namespace b200
+
+// Device-side skeletons of the JIT-specialised pipeline kernels (sm_100a).
+//
+// The host (jit.cpp) turns a serialised plan (include/daft_b200.h "plan encoding") into a `Prog`
+// struct -- straight-line, fully typed code for the filter / key / aggregate-input expressions --
+// and instantiates one of the hand-written skeletons below with it:
+//
+//   project_body         Filter/Project (a10/a11): one pass, outputs written at HBM speed,
+//                        bitmaps built with warp ballots, strings in a length pass + copy pass.
+//   agg_body             fused Filter -> Project -> HashAggregate (a4/a6/a10/a11): every input
+//                        column is read exactly once; nothing is materialised.
+//
+// Group-by design (agg_body), replacing the hashbrown raw-entry probe + per-accumulator scatter
+// passes of src/daft-recordbatch/src/ops/inline_agg.rs:748-824,556-565:
+//   * global open-addressing table keyed by the XXH3 row hash (same hash_rows as the reference), slot
+//     claimed with one atomicCAS; equal hashes are verified against the claiming row's key values
+//     (nulls equal, floats by bit pattern == the reference's "hash equal AND comparator" rule);
+//   * accumulators are indexed by table slot, three tiers by where the group lives:
+//       tier 1  the first G1 groups a CTA meets: per-lane private shared-memory cells, plain
+//               read-modify-write, zero atomics, zero bank conflicts (cell address = lane);
+//               counts and first-row tracking are done per warp with ballots;
+//       tier 3  every other group: red.global atomics on the slot's cells.
+//     Low-cardinality aggregates (TPC-H Q1: 4 groups) never leave tier 1; high-cardinality ones
+//     (Q18: one group per order) spread their atomics over millions of addresses.
+//   * first-occurrence group order (inline_agg.rs:804-807) is recovered by tracking min(row) per group.
+
+
+#define FULL_MASK 0xffffffffu
+
+namespace b200 {
+namespace jit {
+
+struct Str {
+    const uint8_t *p;
+    int64_t len;
+};
+
+__device__ __forceinline__ bool bit_at(const uint8_t *bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+
+// ---- order-preserving keys for min/max on any numeric type ---------------------------------------
+// floats: all NaN collapse to the largest key (NaN sorts greatest, search_sorted.rs:238-245)
+__device__ __forceinline__ uint64_t ord_f64(double v) {
+    if (v != v) return 0xFFFFFFFFFFFFFFFFULL;
+    uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double unord_f64(uint64_t k) {
+    if (k == 0xFFFFFFFFFFFFFFFFULL) return __longlong_as_double(0x7FF8000000000000LL);
+    uint64_t b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ uint64_t ord_f32(float v) { return ord_f64((double)v); }
+__device__ __forceinline__ uint64_t ord_i64(int64_t v) { return (uint64_t)v ^ 0x8000000000000000ULL; }
+__device__ __forceinline__ uint64_t ord_u64(uint64_t v) { return v; }
+
+// ---- string helpers ---------------------------------------------------------------------------------
+// first min(len, 8) bytes of a string packed little-endian into a register (zero padded): short keys
+// (TPC-H flags, codes) are then hashed and compared without touching memory again.
+// Both packers are branch-free (selects + predicated loads of aligned words that contain bytes of the value, so
+// they never leave the allocation) so that the loads of several rows/columns are all in flight before the
+// first one is consumed.
+__device__ __forceinline__ uint64_t str_pack8(Str a) {
+    const uintptr_t addr = (uintptr_t)a.p;
+    const bool any = a.len > 0;
+    const int sh = (int)(addr & 7) * 8;
+    const int nbits = (a.len < 8 ? (int)a.len : 8) * 8;
+    const unsigned long long *w = (const unsigned long long *)(addr & ~(uintptr_t)7);
+    unsigned long long w0 = 0ULL, w1 = 0ULL;
+    if (any) w0 = __ldg(w);
+    if (any && sh + nbits > 64) w1 = __ldg(w + 1);
+    unsigned long long v = w0 >> sh;
+    v |= sh ? (w1 << (64 - sh)) : 0ULL;
+    v &= nbits >= 64 ? ~0ULL : ((1ULL << nbits) - 1ULL);
+    return v;
+}
+// first min(len, 4) bytes with 32-bit arithmetic only (short key columns on the exact-code path need <= 3 bytes)
+// first L (<= 4) bytes at a shared-memory address, little-endian
+__device__ __forceinline__ uint32_t smem_pack4(const unsigned char *q, const int L) {
+    uint32_t v = q[0];
+    if (L > 1) v |= (uint32_t)q[1] << 8;
+    if (L > 2) v |= (uint32_t)q[2] << 16;
+    if (L > 3) v |= (uint32_t)q[3] << 24;
+    return v;
+}
+__device__ __forceinline__ uint64_t str_pack4(Str a) {
+    const uintptr_t addr = (uintptr_t)a.p;
+    const bool any = a.len > 0;
+    const uint32_t sh = (uint32_t)(addr & 3) * 8u;
+    const uint32_t nb = a.len < 4 ? (uint32_t)a.len : 4u;
+    const unsigned int *w = (const unsigned int *)(addr & ~(uintptr_t)3);
+    unsigned int w0 = 0u, w1 = 0u;
+    if (any) w0 = __ldg(w);
+    if (any && sh + nb * 8u > 32u) w1 = __ldg(w + 1);
+    unsigned int v = __funnelshift_r(w0, w1, sh);
+    v &= nb >= 4u ? 0xFFFFFFFFu : ((1u << (nb * 8u)) - 1u);
+    return (uint64_t)v;
+}
+__device__ __forceinline__ uint64_t hash_str_packed(Str a, uint64_t pk, uint64_t seed) {
+    const int64_t len = a.len;
+    if (len <= 8) {
+        if (len == 0) return xxh::hash_empty(seed);
+        if (len <= 3)
+            return xxh::hash_1to3((uint32_t)(pk & 0xff), (uint32_t)((pk >> (8 * (len >> 1))) & 0xff),
+                                  (uint32_t)((pk >> (8 * (len - 1))) & 0xff), (uint32_t)len, seed);
+        return xxh::hash_4to8((uint32_t)pk, (uint32_t)(pk >> (8 * (len - 4))), (uint32_t)len, seed);
+    }
+    return xxh::hash_bytes(a.p, len, seed);
+}
+__device__ __forceinline__ bool str_eq_packed(Str a, uint64_t pa, Str b, uint64_t pb) {
+    if (a.len != b.len || pa != pb) return false;
+    for (int64_t i = 8; i < a.len; i++)
+        if (a.p[i] != b.p[i]) return false;
+    return true;
+}
+__device__ __forceinline__ bool str_eq(Str a, Str b) {
+    if (a.len != b.len) return false;
+    for (int64_t i = 0; i < a.len; i++)
+        if (a.p[i] != b.p[i]) return false;
+    return true;
+}
+__device__ __forceinline__ int str_cmp(Str a, Str b) {
+    int64_t n = a.len < b.len ? a.len : b.len;
+    for (int64_t i = 0; i < n; i++) {
+        int d = (int)a.p[i] - (int)b.p[i];
+        if (d) return d;
+    }
+    return a.len < b.len ? -1 : (a.len > b.len ? 1 : 0);
+}
+__device__ __forceinline__ bool str_startswith(Str a, Str pat) {
+    if (pat.len > a.len) return false;
+    for (int64_t i = 0; i < pat.len; i++)
+        if (a.p[i] != pat.p[i]) return false;
+    return true;
+}
+__device__ __forceinline__ bool str_endswith(Str a, Str pat) {
+    if (pat.len > a.len) return false;
+    const uint8_t *q = a.p + (a.len - pat.len);
+    for (int64_t i = 0; i < pat.len; i++)
+        if (q[i] != pat.p[i]) return false;
+    return true;
+}
+__device__ __forceinline__ bool str_contains(Str a, Str pat) {
+    if (pat.len == 0) return true;
+    for (int64_t s = 0; s + pat.len <= a.len; s++) {
+        int64_t i = 0;
+        while (i < pat.len && a.p[s + i] == pat.p[i]) i++;
+        if (i == pat.len) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ int64_t str_char_len(Str a) {
+    int64_t c = 0;
+    for (int64_t i = 0; i < a.len; i++) c += (a.p[i] & 0xC0) != 0x80;
+    return c;
+}
+__device__ __forceinline__ Str str_left(Str a, int64_t nchars) {
+    if (nchars <= 0) return Str{a.p, 0};
+    int64_t c = 0, i = 0;
+    for (; i < a.len; i++) {
+        if ((a.p[i] & 0xC0) != 0x80) {
+            if (c == nchars) break;
+            c++;
+        }
+    }
+    return Str{a.p, i};
+}
+
+// ---- civil calendar from days since 1970-01-01 (proleptic Gregorian) --------------------------------
+__device__ __forceinline__ void civil_from_days(int64_t z, int32_t &y, int32_t &m, int32_t &d) {
+    z += 719468;
+    const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+    const uint32_t doe = (uint32_t)(z - era * 146097);
+    const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const int64_t yy = (int64_t)yoe + era * 400;
+    const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const uint32_t mp = (5 * doy + 2) / 153;
+    d = (int32_t)(doy - (153 * mp + 2) / 5 + 1);
+    m = (int32_t)(mp < 10 ? mp + 3 : mp - 9);
+    y = (int32_t)(yy + (m <= 2));
+}
+__device__ __forceinline__ int32_t date_year(int32_t days) { int32_t y, m, d; civil_from_days(days, y, m, d); return y; }
+__device__ __forceinline__ uint32_t date_month(int32_t days) { int32_t y, m, d; civil_from_days(days, y, m, d); return (uint32_t)m; }
+__device__ __forceinline__ uint32_t date_day(int32_t days) { int32_t y, m, d; civil_from_days(days, y, m, d); return (uint32_t)d; }
+__device__ __forceinline__ uint32_t date_dow(int32_t days) {  // Monday = 0
+    int64_t r = ((int64_t)days + 3) % 7;
+    return (uint32_t)(r < 0 ? r + 7 : r);
+}
+
+// ---- integer division helpers (floor semantics; divisor 0 handled by the caller as null) ------------
+template <typename T>
+__device__ __forceinline__ T floor_div_s(T a, T b) {
+    T q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) q--;
+    return q;
+}
+template <typename T>
+__device__ __forceinline__ T floor_mod_s(T a, T b) {
+    T r = a % b;
+    if (r != 0 && ((r < 0) != (b < 0))) r += b;
+    return r;
+}
+
+// ---- kernel parameter block: 8-byte slots the host fills in the order codegen allocated them ---------
+template <int NPTR, int NINT>
+struct Params {
+    void *ptr[NPTR > 0 ? NPTR : 1];
+    long long ival[NINT > 0 ? NINT : 1];
+};
+
+// ======================================================================================================
+// Filter / Project
+// ======================================================================================================
+// Prog provides:
+//   using P = Params<..>;  static constexpr int IV_N (ival slot of the row count), PTR_TAKE (ptr slot of
+//   the optional int64 gather index, -1 if none)
+//   __device__ static void row(const P&, int64_t out_row, int64_t src_row, bool active, int pass)
+// `row` is called by ALL lanes (inactive ones too) because bitmap outputs are built with warp ballots.
+template <class Prog>
+__device__ __forceinline__ void project_body(const typename Prog::P &p, int pass) {
+    const int64_t n = p.ival[Prog::IV_N];
+    const int64_t n_round = (n + 31) & ~(int64_t)31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool active = i < n;
+        int64_t src = i;
+        if (Prog::PTR_TAKE >= 0 && active) src = ((const int64_t *)p.ptr[Prog::PTR_TAKE < 0 ? 0 : Prog::PTR_TAKE])[i];
+        Prog::row(p, i, src, active, pass);
+    }
+}
+
+// ======================================================================================================
+// Filter with in-kernel stable compaction (RecordBatch::filter, src/daft-recordbatch/src/lib.rs:520-570)
+// ======================================================================================================
+// pass 0: kept rows per 2048-row tile -> counts[tile];  (host: exclusive scan)  pass 1: predicate again, every
+// surviving row's fixed-width columns are written straight to their final position (row order preserved: warp
+// ballots give the in-tile rank).  Traffic: predicate columns twice, payload once in + once out -- instead of a
+// mask column, an index column and one index-driven gather per column.
+// Prog: IV_N, PTR_COUNTS (int64 per tile: counts in pass 0, exclusive offsets in pass 1), PTR_IDX (-1 or slot of an
+// int64 row-id output for the columns the host gathers), keep(p,row), copy(p,src,dst)
+constexpr int FILTER_THREADS = 256, FILTER_SUB = 8, FILTER_TILE = FILTER_THREADS * FILTER_SUB;
+
+template <class Prog>
+__device__ __forceinline__ void filter_body(const typename Prog::P &p, int pass) {
+    __shared__ int s_w[FILTER_THREADS / 32];
+    __shared__ long long s_run;
+    const int64_t n = p.ival[Prog::IV_N];
+    const int64_t ntiles = (n + FILTER_TILE - 1) / FILTER_TILE;
+    long long *counts = (long long *)p.ptr[Prog::PTR_COUNTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t tbase = tile * FILTER_TILE;
+        if (threadIdx.x == 0) s_run = pass ? counts[tile] : 0;
+        __syncthreads();
+#pragma unroll 1
+        for (int j = 0; j < FILTER_SUB; j++) {
+            const int64_t row = tbase + (int64_t)j * FILTER_THREADS + threadIdx.x;
+            const bool keep = row < n && Prog::keep(p, row);
+            const unsigned m = __ballot_sync(FULL_MASK, keep);
+            if (lane == 0) s_w[warp] = __popc(m);
+            __syncthreads();
+            int woff = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < FILTER_THREADS / 32; w++) {
+                const int c = s_w[w];
+                woff += w < warp ? c : 0;
+                tot += c;
+            }
+            if (pass && keep) {
+                const int64_t dst = s_run + woff + __popc(m & ((1u << lane) - 1u));
+                Prog::copy(p, row, dst);
+                if (Prog::PTR_IDX >= 0) ((int64_t *)p.ptr[Prog::PTR_IDX < 0 ? 0 : Prog::PTR_IDX])[dst] = row;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_run += tot;
+            __syncthreads();
+        }
+        if (!pass && threadIdx.x == 0) counts[tile] = s_run;
+        __syncthreads();
+    }
+}
+
+// ======================================================================================================
+// fused Filter -> Project -> HashAggregate
+// ======================================================================================================
+// Prog provides (all generated):
+//   using P;  IV_N, IV_MASK (table capacity - 1), PTR_TAG, PTR_MINROW (first row per slot = representative row),
+//   PTR_FLAG (int: 0 ok, 1 table overflow, 2 low-cardinality kernel gave up);
+//   NKEYS, G1, NLANE, NWARP, U;  MODE (0: row-dependent exact 62-bit codes, 1: every row exact 63/64-bit code,
+//   2: never exact);  struct Raw / Keys / Vals;
+//   load / load2 / eval / eval_keys / keys_equal / code / lane_init / lane_update / global_update / warp_cells / flush
+//
+// Group identity is carried by a 64-bit key CODE (see jit.cpp "Exact key code"): when it is exact (injective in
+// the key values) equal codes ARE equal keys; otherwise the code is a fingerprint and a match is confirmed against
+// the key values of the slot's representative row (nulls equal, floats by bit pattern -- the reference's
+// "hash equal AND comparator" rule, src/daft-recordbatch/src/ops/inline_agg.rs:760-784).
+#ifndef B200_AGG_WARPS
+#define B200_AGG_WARPS 8  // warps per CTA of the aggregate kernels (the staged build may ask for 16)
+#endif
+constexpr int AGG_WARPS = B200_AGG_WARPS;
+constexpr unsigned long long AGG_EMPTY = 0xFFFFFFFFFFFFFFFFULL;     // min-row cell of an unclaimed slot
+constexpr unsigned long long AGG_CLAIMING = 0xFFFFFFFFFFFFFFFEULL;  // (MODE 1) slot being published
+constexpr int AGG_PROBE_LIMIT = 1024;
+
+__device__ __forceinline__ uint64_t agg_mix(uint64_t x) {
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ULL;
+    x ^= x >> 32;
+    return x;
+}
+
+// Find or claim the global slot of the group with code `tag`.  Returns the slot, or -1 after flagging overflow.
+template <class Prog>
+__device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, unsigned long long tag, int64_t row) {
+    unsigned long long *slot_tag = (unsigned long long *)p.ptr[Prog::PTR_TAG];
+    unsigned long long *slot_min = (unsigned long long *)p.ptr[Prog::PTR_MINROW];
+    const uint64_t mask = (uint64_t)p.ival[Prog::IV_MASK];
+    const bool exact = Prog::MODE == 1 || (Prog::MODE == 0 && !(tag >> 63));
+    uint64_t s = agg_mix(tag) & mask;
+    for (int probes = 0; probes < AGG_PROBE_LIMIT; probes++) {
+        if (Prog::MODE == 1) {
+            // tags may take any value: occupancy lives in the min-row cell (EMPTY -> CLAIMING -> first row)
+            unsigned long long m = *((volatile unsigned long long *)&slot_min[s]);
+            if (m == AGG_EMPTY) {
+                const unsigned long long prev = atomicCAS(&slot_min[s], AGG_EMPTY, AGG_CLAIMING);
+                if (prev == AGG_EMPTY) {
+                    *((volatile unsigned long long *)&slot_tag[s]) = tag;
+                    __threadfence();
+                    atomicMin(&slot_min[s], (unsigned long long)row);  // publishes (row < CLAIMING)
+                    return (long long)s;
+                }
+                m = prev;
+            }
+            while (m == AGG_CLAIMING) m = *((volatile unsigned long long *)&slot_min[s]);
+            if (*((volatile unsigned long long *)&slot_tag[s]) == tag) return (long long)s;
+        } else {
+            // tags are never 0 here (bit 62 or bit 63 is set): one CAS on the tag word claims the slot
+            unsigned long long cur = slot_tag[s];  // a stale 0 from L1 is corrected by the CAS below
+            if (cur == 0ULL) {
+                const unsigned long long prev = atomicCAS(&slot_tag[s], 0ULL, tag);
+                if (prev == 0ULL) return (long long)s;  // claimed; the caller's update publishes the first row
+                cur = prev;
+            }
+            if (cur == tag) {
+                if (exact) return (long long)s;
+                unsigned long long r = *((volatile unsigned long long *)&slot_min[s]);
+                while (r == AGG_EMPTY) r = *((volatile unsigned long long *)&slot_min[s]);  // claimer is about to publish
+                if ((int64_t)r == row) return (long long)s;
+                typename Prog::Keys mine, other;
+                Prog::eval_keys(p, row, mine);
+                Prog::eval_keys(p, (int64_t)r, other);
+                if (Prog::keys_equal(mine, other)) return (long long)s;
+            }
+        }
+        s = (s + 1) & mask;
+    }
+    *((volatile int *)p.ptr[Prog::PTR_FLAG]) = 1;  // table too full: the host retries with a larger one
+    return -1;
+}
+
+// ---- global kernel: mid / high cardinality -------------------------------------------------------------
+// Tier 2: a per-CTA shared-memory table of (exact code -> cells) absorbs the rows of up to T2 groups with
+// shared-memory atomics and is merged into the global table once per CTA, so a few thousand hot groups do not
+// hammer a handful of L2 addresses.  Rows whose group does not fit (or whose code is inexact) go straight to the
+// global table: one CAS to find/claim the slot, then red.global atomics on its cells.
+template <class Prog>
+__device__ __forceinline__ void agg_body_global(const typename Prog::P &p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int T2 = Prog::T2;
+    unsigned long long *t2_tag = (unsigned long long *)smem_raw;  // 0 = empty (codes are never 0)
+    unsigned long long *t2c = t2_tag + T2;                        // cell c of slot t: t2c[c * T2 + t]
+    for (int t = threadIdx.x; t < T2; t += blockDim.x) {
+        t2_tag[t] = 0ULL;
+        Prog::t2_init(t2c, t);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = p.ival[Prog::IV_N];
+    constexpr int U = Prog::U;
+    const int64_t chunk = 32 * U;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+    volatile int *flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
+    int t2_hits = 0, t2_miss = 0;
+    bool use_t2 = T2 >= 64 && Prog::NKEYS > 0;
+    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
+        if (*flag) break;  // someone hit a full table: stop early, the host will retry
+        const int64_t base = c * chunk;
+        typename Prog::Raw raw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load(p, row, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load2(p, row, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            typename Prog::Vals vals;
+            bool live = row < n;
+            unsigned long long tag = 1ULL;
+            {
+                typename Prog::Keys keys;
+                if (live) live = Prog::eval(p, raw[u], keys, vals);
+                if (live && Prog::NKEYS > 0) tag = Prog::code(keys);
+            }
+            if (!live) continue;
+            bool done = false;
+            if (use_t2 && !(tag >> 63)) {  // exact codes only: equal code == equal key, no verification needed
+                unsigned int t = (unsigned int)(agg_mix(tag) >> 40) & (T2 - 1);
+#pragma unroll 1
+                for (int probes = 0; probes < 8 && !done; probes++) {
+                    unsigned long long cur = ((volatile unsigned long long *)t2_tag)[t];
+                    if (cur == 0ULL) {
+                        const unsigned long long prev = atomicCAS(&t2_tag[t], 0ULL, tag);
+                        cur = prev == 0ULL ? tag : prev;
+                    }
+                    if (cur == tag) {
+                        Prog::t2_update(t2c, (int)t, vals, row);
+                        done = true;
+                    }
+                    t = (t + 1) & (T2 - 1);
+                }
+                if (done) t2_hits++;
+                else if (++t2_miss > 256 && t2_miss > 4 * t2_hits) use_t2 = false;  // high cardinality: stop probing tier 2
+            }
+            if (!done) {
+                const long long slot = Prog::NKEYS > 0 ? agg_find_slot<Prog>(p, tag, row) : 0;
+                if (slot >= 0) Prog::global_update(p, slot, vals, row);
+            }
+        }
+    }
+    __syncthreads();
+    // merge tier 2 into the global table (the slot's first row doubles as its representative row)
+    if (!*flag) {
+        for (int t = threadIdx.x; t < T2; t += blockDim.x) {
+            const unsigned long long tag = t2_tag[t];
+            if (tag == 0ULL) continue;
+            const long long slot = agg_find_slot<Prog>(p, tag, (int64_t)t2c[(Prog::NLANE - 1) * T2 + t]);
+            if (slot >= 0) Prog::t2_flush(p, slot, t2c, t);
+        }
+    }
+}
+
+// Rare path of the low-cardinality kernel, kept out of line so that its registers do not burden the streaming loop:
+// find/claim the group's global slot, try to adopt it into the CTA's tier 1, otherwise update it globally.
+// Returns the tier-1 index (>= 0), -2 when the row was accumulated globally, -1 when the table is full.
+template <class Prog>
+__device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const typename Prog::Vals &vals, int64_t row,
+                                                unsigned long long tag, long long *s_slot, unsigned long long *s_fp,
+                                                typename Prog::Keys *s_keys) {
+    const long long slot = agg_find_slot<Prog>(p, tag, row);
+    if (slot < 0) return -1;
+    for (int g = 0; g < Prog::G1; g++) {
+        const long long old = (long long)atomicCAS((unsigned long long *)&s_slot[g], (unsigned long long)-1LL, (unsigned long long)slot);
+        if (old == -1) {  // this lane owns entry g: publish the key values (for inexact codes), then the code
+            typename Prog::Keys keys;
+            Prog::eval_keys(p, row, keys);
+            s_keys[g] = keys;
+            __threadfence_block();
+            ((volatile unsigned long long *)s_fp)[g] = tag;
+            // make sure the slot has a representative row even if every later row of this group stays in tier 1
+            atomicMin(((unsigned long long *)p.ptr[Prog::PTR_MINROW]) + slot, (unsigned long long)row);
+            return g;
+        }
+        if (old == slot) return g;
+    }
+    Prog::global_update(p, slot, vals, row);
+    return -2;
+}
+
+// ---- low-cardinality kernels: tier 1 in shared memory, give up (flag 2) when most rows miss it ------------------
+template <class Prog>
+struct AggTier1 {
+    static constexpr int G1 = Prog::G1, NL = Prog::NLANE, NW = Prog::NWARP, NWS = NW > 0 ? NW : 1;
+    unsigned long long *s_lcell, *s_wcell, *s_fp;
+    long long *s_slot;
+    typename Prog::Keys *s_keys;
+    unsigned long long *my_lcell, *my_wcell;
+    unsigned long long tfp[G1];  // register copy of the tier-1 codes (entries only go 0 -> final value: a stale copy
+                                 // can only miss an entry -> slow path -> refresh)
+    int slow_rows;
+    volatile int *flag;
+
+    static __host__ __device__ constexpr size_t smem_bytes() {
+        return 8 * ((size_t)AGG_WARPS * G1 * NL * 32 + (size_t)AGG_WARPS * G1 * NWS + 2 * (size_t)G1) + (size_t)G1 * sizeof(typename Prog::Keys);
+    }
+    // layout: lane cells [W][G1][NL][32] u64 | warp cells [W][G1][NW] u64 | s_fp[G1] | s_slot[G1] | s_keys[G1]
+    __device__ __forceinline__ void init(unsigned char *smem, const typename Prog::P &p) {
+        s_lcell = (unsigned long long *)smem;
+        s_wcell = s_lcell + (size_t)AGG_WARPS * G1 * NL * 32;
+        s_fp = s_wcell + AGG_WARPS * G1 * NWS;
+        s_slot = (long long *)(s_fp + G1);
+        s_keys = (typename Prog::Keys *)(s_slot + G1);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (threadIdx.x < G1) {
+            s_slot[threadIdx.x] = Prog::NKEYS == 0 ? 0 : -1;
+            s_fp[threadIdx.x] = Prog::NKEYS == 0 ? 1ULL : 0ULL;
+        }
+        for (int i = threadIdx.x; i < AGG_WARPS * G1 * NWS; i += blockDim.x) s_wcell[i] = 0ULL;
+        my_lcell = s_lcell + (size_t)warp * G1 * NL * 32 + lane;  // cell c of group g: [(g*NL+c)*32]
+        for (int g = 0; g < G1; g++) Prog::lane_init(my_lcell + (size_t)g * NL * 32);
+        my_wcell = s_wcell + (size_t)warp * G1 * NWS;
+        slow_rows = 0;
+        flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
+    }
+    __device__ __forceinline__ void refresh() {
+#pragma unroll
+        for (int g = 0; g < G1; g++) tfp[g] = ((volatile unsigned long long *)s_fp)[g];
+    }
+    // one row: filter + projections + key code -> tier-1 cell update (or the rare slow path)
+    __device__ __forceinline__ void row(const typename Prog::P &p, const typename Prog::Raw &raw, int64_t r, bool live, int lane) {
+        typename Prog::Vals vals;
+        unsigned long long fp = 0ULL;
+        {
+            typename Prog::Keys keys;  // dead after the code is formed: the rare paths re-read the keys by row
+            if (live) live = Prog::eval(p, raw, keys, vals);
+            if (live) fp = Prog::NKEYS > 0 ? Prog::code(keys) : 1ULL;
+        }
+        int lid = -1;
+#pragma unroll
+        for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
+        if (Prog::NKEYS > 0 && Prog::MODE != 1 && live && lid >= 0 && (Prog::MODE == 2 || (fp >> 63))) {
+            typename Prog::Keys kv;  // inexact code: confirm against the published key values
+            Prog::eval_keys(p, r, kv);
+            if (!Prog::keys_equal(kv, s_keys[lid])) lid = -1;
+        }
+        if (live && lid < 0) {  // rare here: first rows of a CTA, or a group beyond tier 1
+            const typename Prog::Vals vcopy = vals;
+            const long long q = agg_slow_path<Prog>(p, vcopy, r, fp, s_slot, s_fp, s_keys);
+            if (q >= 0) lid = (int)q;
+            else live = false;  // accumulated globally (or table overflow)
+            refresh();
+            // most rows missing tier 1 means the input is not low-cardinality: hand over to the global kernel
+            if (++slow_rows > 64 + G1) *flag = 2;
+        }
+        if (live) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals, r);
+        if (NW > 0) {  // valid / null counts of nullable inputs: one ballot per tier-1 group
+#pragma unroll
+            for (int g = 0; g < G1; g++) {
+                const bool in_g = live && lid == g;
+                if (__any_sync(FULL_MASK, in_g)) Prog::warp_cells(vals, in_g, my_wcell + g * NW, lane);
+            }
+        }
+    }
+    // flush: warp w reduces groups w, w+W, ... across all warps' private copies (call after __syncthreads)
+    __device__ __forceinline__ void flush(const typename Prog::P &p, int lane, int warp) {
+        for (int g = warp; g < G1; g += AGG_WARPS) {
+            const long long slot = s_slot[g];
+            if (slot < 0) continue;
+            Prog::flush(p, slot, s_lcell + (size_t)g * NL * 32, (size_t)G1 * NL * 32, s_wcell + g * NWS, (size_t)G1 * NWS, lane);
+        }
+    }
+};
+
+template <class Prog>
+__device__ __forceinline__ void agg_body(const typename Prog::P &p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AggTier1<Prog> t1;
+    t1.init(smem_raw, p);
+    __syncthreads();
+    t1.refresh();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = p.ival[Prog::IV_N];
+    constexpr int U = Prog::U;
+    const int64_t chunk = 32 * U;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
+        if (__any_sync(FULL_MASK, *t1.flag != 0)) break;
+        const int64_t base = c * chunk;
+        typename Prog::Raw raw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load(p, row, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
+            const int64_t row = base + u * 32 + lane;
+            if (row < n) Prog::load2(p, row, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t row = base + u * 32 + lane;
+            t1.row(p, raw[u], row, row < n, lane);
+        }
+    }
+    __syncthreads();
+    t1.flush(p, lane, warp);
+}
+
+// ---- the same kernel fed by TMA bulk copies ---------------------------------------------------------------------
+// The CTA owns a ring of S stages in shared memory.  A stage holds R = blockDim.x * RPL consecutive rows of every
+// column the plan reads: R values of a fixed-width column, R+2 offsets of a string column, R*L value bytes of a
+// fixed-length string column.  Thread 0 issues one cp.async.bulk (UBLKCP) per column slice, completing on the
+// stage's "full" mbarrier; every warp copies its rows from the stage into registers, arrives on the stage's "empty"
+// mbarrier and goes on to aggregate them while the copies of the next S-1 stages are in flight -- HBM latency is
+// covered by shared-memory capacity instead of registers and resident warps.  Copies are kilobytes each: the TMA
+// unit retires roughly one bulk copy per ~46 cycles per SM, so per-warp sized copies (256-512 B) are issue bound.
+// Tail chunks that cannot be staged (the offsets slice needs row base+R+1) use the direct-load path.
+__device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait for a phase; gives up (false) when the kernel has been abandoned (status flag set by any CTA)
+__device__ __forceinline__ bool mbar_wait_or_abort(uint32_t bar, uint32_t parity, volatile int *flag) {
+    while (!mbar_try_wait(bar, parity))
+        if (*flag) return false;
+    return true;
+}
+
+template <class Prog>
+__device__ __forceinline__ void agg_body_staged(const typename Prog::P &p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int R = Prog::STAGE_ROWS, S = Prog::STAGES, SB = Prog::STAGE_BYTES, RPL = Prog::RPL, T = AGG_WARPS * 32;
+    static_assert(R == T * RPL, "stage rows");
+    // layout: stages [S][SB] (16 B aligned) | full barriers [S] | empty barriers [S] | tier 1
+    unsigned char *stages = smem_raw;
+    unsigned long long *full = (unsigned long long *)(stages + (size_t)S * SB);
+    unsigned long long *empty = full + S;
+    AggTier1<Prog> t1;
+    t1.init((unsigned char *)(empty + S), p);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), AGG_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    t1.refresh();
+    const int64_t n = p.ival[Prog::IV_N];
+    const int64_t nchunks = (n + R - 1) / R;
+    const int64_t stride = gridDim.x;
+    auto stageable = [&](int64_t c) { return c < nchunks && (c + 1) * R < n; };  // offsets slice reads row (c+1)*R + 1
+    int64_t issued = 0;  // (thread 0) iterations whose copies have been issued
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (int s = 0; s < S; s++) {
+            const int64_t c = blockIdx.x + (int64_t)s * stride;
+            if (stageable(c)) {
+                Prog::stage_issue(p, smem_u32(stages + (size_t)s * SB), smem_u32(&full[s]), c * R);
+                issued = s + 1;
+            }
+        }
+    }
+    bool aborted = false;
+    int64_t i = 0;
+    for (int64_t c = blockIdx.x; c < nchunks; c += stride, i++) {
+        if (__any_sync(FULL_MASK, *t1.flag != 0)) {
+            aborted = true;
+            break;
+        }
+        if (threadIdx.x == 0 && i > 0) {  // refill the stage every warp finished reading one iteration ago
+            const int64_t j = i - 1 + S, cj = blockIdx.x + j * stride;
+            if (stageable(cj)) {
+                const int sp = (int)((i - 1) % S);
+                if (!mbar_wait_or_abort(smem_u32(&empty[sp]), (uint32_t)(((i - 1) / S) & 1), t1.flag)) {
+                    aborted = true;
+                } else {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    Prog::stage_issue(p, smem_u32(stages + (size_t)sp * SB), smem_u32(&full[sp]), cj * R);
+                    issued = j + 1;
+                }
+            }
+        }
+        if (warp == 0) aborted = __any_sync(FULL_MASK, aborted);  // keep warp 0 convergent with its producer lane
+        if (aborted) break;
+        const int s = (int)(i % S);
+        const int64_t base = c * R;
+        typename Prog::Raw raw[RPL];
+        if (stageable(c)) {
+            const bool landed = mbar_wait_or_abort(smem_u32(&full[s]), (uint32_t)((i / S) & 1), t1.flag);
+            if (!__all_sync(FULL_MASK, landed)) {
+                aborted = true;
+                break;
+            }
+            Prog::load_staged(p, stages + (size_t)s * SB, base, (int)threadIdx.x, raw);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty[s]));
+        } else {
+#pragma unroll
+            for (int u = 0; u < RPL; u++) {
+                const int64_t row = base + u * T + threadIdx.x;
+                if (row < n) Prog::load(p, row, raw[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < RPL; u++) {
+                const int64_t row = base + u * T + threadIdx.x;
+                if (row < n) Prog::load2(p, row, raw[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RPL; u++) {
+            const int64_t row = base + u * T + threadIdx.x;
+            t1.row(p, raw[u], row, row < n, lane);
+        }
+    }
+    if (threadIdx.x == 0 && aborted) {
+        // abandoned: copies already issued must land before the CTA's shared memory is released
+        for (int64_t j = i; j < issued; j++)
+            while (!mbar_try_wait(smem_u32(&full[(int)(j % S)]), (uint32_t)((j / S) & 1))) {
+            }
+    }
+    __syncthreads();
+    t1.flush(p, lane, warp);
+}
+
+}  // namespace jit
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::jit;
+struct Prog {
+  typedef Params<26, 1> P;
+  static constexpr int IV_N = 0;
+  static constexpr int PTR_TAKE = -1;
+  __device__ __forceinline__ static void row(const P& p, const int64_t out_row, const int64_t row, const bool active, const int pass) {
+    const bool rowok = active && row >= 0;
+    const bool k0 = rowok;
+    Str v0{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[0]; const int64_t a_ = of_[row]; v0.p = (const uint8_t*)p.ptr[1] + a_; v0.len = of_[row + 1] - a_; }
+    // ---- output 0 (large_utf8)
+    if (pass == 0) { if (active) ((int64_t*)p.ptr[2])[out_row] = k0 ? v0.len : 0; }
+    else if (active && k0) { uint8_t* d_ = (uint8_t*)p.ptr[3] + ((const int64_t*)p.ptr[4])[out_row]; for (int64_t j_ = 0; j_ < v0.len; j_++) d_[j_] = v0.p[j_]; }
+    const bool k1 = rowok;
+    Str v1{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[5]; const int64_t a_ = of_[row]; v1.p = (const uint8_t*)p.ptr[6] + a_; v1.len = of_[row + 1] - a_; }
+    // ---- output 1 (large_utf8)
+    if (pass == 0) { if (active) ((int64_t*)p.ptr[7])[out_row] = k1 ? v1.len : 0; }
+    else if (active && k1) { uint8_t* d_ = (uint8_t*)p.ptr[8] + ((const int64_t*)p.ptr[9])[out_row]; for (int64_t j_ = 0; j_ < v1.len; j_++) d_[j_] = v1.p[j_]; }
+    const bool k2 = rowok;
+    const int64_t v2 = rowok ? ((const int64_t*)p.ptr[10])[row] : (int64_t)0;
+    // ---- output 2 (int64)
+    if (pass == 0 && active) ((int64_t*)p.ptr[11])[out_row] = k2 ? v2 : (int64_t)0;
+    const bool k3 = rowok;
+    const double v3 = rowok ? ((const double*)p.ptr[12])[row] : (double)0;
+    // ---- output 3 (float64)
+    if (pass == 0 && active) ((double*)p.ptr[13])[out_row] = k3 ? v3 : (double)0;
+    const bool k4 = rowok;
+    const double v4 = rowok ? ((const double*)p.ptr[14])[row] : (double)0;
+    // ---- output 4 (float64)
+    if (pass == 0 && active) ((double*)p.ptr[15])[out_row] = k4 ? v4 : (double)0;
+    const bool k5 = rowok;
+    const double v5 = rowok ? ((const double*)p.ptr[16])[row] : (double)0;
+    // ---- output 5 (float64)
+    if (pass == 0 && active) ((double*)p.ptr[17])[out_row] = k5 ? v5 : (double)0;
+    const double v7 = (double)v2; const bool k7 = k2;
+    const bool k8 = rowok;
+    const uint64_t v8 = rowok ? ((const uint64_t*)p.ptr[18])[row] : (uint64_t)0;
+    const double v9 = (double)v8; const bool k9 = k8;
+    const double v10 = v7 / v9; const bool k10 = k7 && k9;
+    // ---- output 6 (float64)
+    if (pass == 0 && active) ((double*)p.ptr[19])[out_row] = k10 ? v10 : (double)0;
+    const bool k12 = rowok;
+    const uint64_t v12 = rowok ? ((const uint64_t*)p.ptr[20])[row] : (uint64_t)0;
+    const double v13 = (double)v12; const bool k13 = k12;
+    const double v14 = v3 / v13; const bool k14 = k3 && k13;
+    // ---- output 7 (float64)
+    if (pass == 0 && active) ((double*)p.ptr[21])[out_row] = k14 ? v14 : (double)0;
+    const bool k15 = rowok;
+    const double v15 = rowok ? ((const double*)p.ptr[22])[row] : (double)0;
+    const bool k16 = rowok;
+    const uint64_t v16 = rowok ? ((const uint64_t*)p.ptr[23])[row] : (uint64_t)0;
+    const double v17 = (double)v16; const bool k17 = k16;
+    const double v18 = v15 / v17; const bool k18 = k15 && k17;
+    // ---- output 8 (float64)
+    if (pass == 0 && active) ((double*)p.ptr[24])[out_row] = k18 ? v18 : (double)0;
+    // ---- output 9 (uint64)
+    if (pass == 0 && active) ((uint64_t*)p.ptr[25])[out_row] = k8 ? v8 : (uint64_t)0;
+  }
+};
+extern "C" __global__ void __launch_bounds__(256) b200_project_k(const __grid_constant__ Prog::P p, int pass) { project_body<Prog>(p, pass); }

@@ -263,7 +263,7 @@ int b200_sort(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, c
               const uint8_t *nulls_first, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
         Buf idx = op_argsort(*batch, key_cols, nkeys, descending, nulls_first);
-        *out = gather_batch(*batch, as<int64_t>(idx), batch->num_rows, false);
+        *out = gather_batch(*batch, as<int64_t>(idx), batch->num_rows, false, true);
         B200_CUDA(cudaStreamSynchronize(ctx().stream));
     });
 }

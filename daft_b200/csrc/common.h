@@ -105,7 +105,8 @@ int64_t read_i64(const int64_t *dev_ptr);                      // syncs
 void fill_u8(void *ptr, int value, size_t bytes);
 // gather rows of `src` at `idx[n]` (int64, -1 => null row) into a new column
 Column gather_column(const Column &src, const int64_t *idx, int64_t n, bool idx_may_be_negative);
-Batch *gather_batch(const Batch &src, const int64_t *idx, int64_t n, bool idx_may_be_negative);
+// `permutation`: idx holds every source row exactly once (sort): string outputs are sized without a host round trip
+Batch *gather_batch(const Batch &src, const int64_t *idx, int64_t n, bool idx_may_be_negative, bool permutation = false);
 Column slice_column(const Column &src, int64_t start, int64_t end);
 Column concat_columns(const std::vector<const Column *> &cols);
 // any integer column -> int64 index buffer (null -> -1)

@@ -68,7 +68,11 @@ struct Node {
 struct Ast {
     std::vector<Node> nodes;
     const std::vector<int32_t> *col_dtypes;
-    const std::vector<uint8_t> *col_nullable;
+    const std::vector<uint8_t> *col_nullable;  // per column: bit 0 = has nulls, bits 1-3 = fixed string length hint
+    bool nullable(int c) const { return ((*col_nullable)[c] & 1) != 0; }
+    // String columns whose bytes divide evenly over the rows at 1..4 B per value (flags, codes): the aggregate kernel is
+    // specialised for that length and fetches the value speculatively; every row still verifies it against the offsets.
+    int fixed_len(int c) const { return ((*col_nullable)[c] >> 1) & 7; }
 };
 
 static bool is_numeric(int32_t dt) { return is_integer(dt) || is_float(dt); }
@@ -81,7 +85,7 @@ static int parse_node(Reader &r, Ast &a) {
             nd.col = (int)r.u32();
             if (nd.col < 0 || nd.col >= (int)a.col_dtypes->size()) fail("plan: column index out of range");
             nd.dtype = (*a.col_dtypes)[nd.col];
-            nd.nullable = (*a.col_nullable)[nd.col] || nd.dtype == B200_NULL;
+            nd.nullable = a.nullable(nd.col) || nd.dtype == B200_NULL;
             nd.key = "c" + std::to_string(nd.col);
             break;
         }
@@ -312,7 +316,7 @@ struct ExprGen {
         switch (n.tag) {
             case T_COL: {
                 const int c = n.col;
-                const bool nullable = (*cg.ast.col_nullable)[c];
+                const bool nullable = cg.ast.nullable(c);
                 if (access == RAW) {
                     if (n.dtype == B200_NULL) {
                         os << "    const bool " << V << " = false; const bool " << K << " = false;\n";
@@ -626,8 +630,11 @@ static std::string gen_filter(Reader &r, Ast &ast, Compiled &meta) {
         const int32_t dt = (*ast.col_dtypes)[c];
         const int w = dtype_width(dt);
         OutCol oc{"", dt, false, false};
-        if (w && !(*ast.col_nullable)[c]) {
-            cp << "    ((" << ctype(dt) << "*)" << cg.P(P_OUT_DATA, c) << ")[dst] = ((const " << ctype(dt) << "*)" << cg.P(P_COL_DATA, c) << ")[src];\n";
+        if (w && !ast.nullable(c)) {
+            // column-major over the tile's FILTER_SUB rows: all loads of a column in flight, then its stores
+            cp << "    { " << ctype(dt) << " v_[FILTER_SUB];\n"
+               << "#pragma unroll\n      for (int j = 0; j < FILTER_SUB; j++) v_[j] = dst[j] >= 0 ? ((const " << ctype(dt) << "*)" << cg.P(P_COL_DATA, c) << ")[src[j]] : " << zero_of(dt) << ";\n"
+               << "#pragma unroll\n      for (int j = 0; j < FILTER_SUB; j++) if (dst[j] >= 0) ((" << ctype(dt) << "*)" << cg.P(P_OUT_DATA, c) << ")[dst[j]] = v_[j]; }\n";
             oc.nullable = false;
         } else {
             oc.nullable = true;  // marks "host gathers this column"
@@ -641,7 +648,7 @@ static std::string gen_filter(Reader &r, Ast &ast, Compiled &meta) {
     o << "struct Prog {\n  typedef Params<" << meta.ptrs.size() << ", " << meta.ints.size() << "> P;\n";
     o << "  static constexpr int IV_N = " << iv_n << ", PTR_COUNTS = " << p_counts << ", PTR_IDX = " << p_idx << ";\n";
     o << "  __device__ __forceinline__ static bool keep(const P& p, const int64_t row) {\n" << kb.str() << "  }\n";
-    o << "  __device__ __forceinline__ static void copy(const P& p, const int64_t src, const int64_t dst) {\n" << cp.str() << "  }\n";
+    o << "  __device__ __forceinline__ static void copy(const P& p, const int64_t (&src)[FILTER_SUB], const int64_t (&dst)[FILTER_SUB]) {\n" << cp.str() << "  }\n";
     o << "};\n";
     o << "extern \"C\" __global__ void __launch_bounds__(256) b200_filter_k(const __grid_constant__ Prog::P p, int pass) { filter_body<Prog>(p, pass); }\n";
     meta.with_take = need_idx;
@@ -693,7 +700,8 @@ static std::string ord_of(int32_t dt, const std::string &v) {
 struct LaneCell { int op; std::string child_key; int val_slot; int32_t val_dtype; };
 struct WarpCell { std::string cond_key; int val_slot; bool count_nulls; };
 
-static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, bool global_variant) {
+static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
+    const bool global_variant = variant == 1, staged_variant = variant == 2;
     CG cg{ast, meta};
     const bool has_filter = r.u8() != 0;
     int filter_root = -1;
@@ -876,10 +884,52 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, bool global_vari
     std::ostringstream raw, load, load2, load0, copy0;
     const bool pipe_offsets = env_int("B200_AGG_PIPE", 0) != 0;
     size_t raw_bytes = 0;
+    // staged variant: R rows of every fixed-width column / R+2 string offsets / R*L bytes of a fixed-length string
+    // column are bulk-copied into a per-warp shared-memory stage; ld_* = the loader reading that stage
+    const int SW = staged_variant ? (env_int("B200_AGG_STAGE_WARPS", 8) >= 16 ? 16 : 8) : 8;  // warps per CTA
+    const int SRPL = std::max(1, std::min(4, env_int("B200_AGG_STAGE_RPL", 2)));                   // rows per thread per stage
+    const int SR = SW * 32 * SRPL;
+    int SS = std::max(2, std::min(8, env_int("B200_AGG_STAGES", 2)));
+    int stage_off = 0, stage_fixed_tx = 0;
+    std::ostringstream st_issue, st_tx, ld_a, ld_ok, ld_first, ld_b;
+    auto seg = [&](int bytes) {
+        const int o = stage_off;
+        stage_off += (bytes + 15) / 16 * 16;
+        return o;
+    };
     for (int c : cols) {
         const int32_t dt = (*ast.col_dtypes)[c];
-        const bool nullable = (*ast.col_nullable)[c];
+        const bool nullable = ast.nullable(c);
         if (dt == B200_NULL) continue;
+        if (staged_variant) {
+            if (nullable) ld_a << "      r.k" << c << " = bit_at((const uint8_t*)" << cg.P(P_COL_VALID, c) << ", row);\n";
+            if (is_string(dt)) {
+                const int bytes = (SR + 2) * 8, o = seg(bytes);
+                stage_fixed_tx += bytes;
+                st_issue << "    bulk_g2s(dst + " << o << ", (const char*)" << cg.P(P_COL_OFFSETS, c) << " + base * 8, " << bytes << ", bar);\n";
+                ld_a << "      { const int64_t* of_ = (const int64_t*)(st + " << o << "); r.o" << c << "a = of_[rr]; r.o" << c << "b = of_[rr + 1]; }\n";
+                if (is_pack4_col(c) && ast.fixed_len(c) > 0) {
+                    const int L = ast.fixed_len(c);
+                    const int ob = seg(SR * L);
+                    stage_fixed_tx += SR * L;
+                    st_issue << "    bulk_g2s(dst + " << ob << ", (const char*)" << cg.P(P_COL_DATA, c) << " + base * " << L << ", " << SR * L << ", bar);\n";
+                    ld_a << "      ok_ = ok_ && (r.o" << c << "b - r.o" << c << "a == " << L << ") && (r.o" << c << "a == row * " << L << ");\n";
+                    ld_b << "      if (fast_) r.pk" << c << " = (uint64_t)smem_pack4(st + " << ob << " + rr * " << L << ", " << L << ");\n"
+                         << "      else r.pk" << c << " = str_pack4(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, r.o" << c << "b - r.o" << c << "a});\n";
+                } else if (is_pack4_col(c)) {
+                    ld_b << "      r.pk" << c << " = str_pack4(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, r.o" << c << "b - r.o" << c << "a});\n";
+                } else {
+                    ld_b << "      r.pk" << c << " = str_pack8(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, r.o" << c << "b - r.o" << c << "a});\n";
+                }
+            } else if (dt == B200_BOOL) {
+                ld_a << "      r.c" << c << " = bit_at((const uint8_t*)" << cg.P(P_COL_DATA, c) << ", row);\n";
+            } else {
+                const int w = dtype_width(dt), bytes = SR * w, o = seg(bytes);
+                stage_fixed_tx += bytes;
+                st_issue << "    bulk_g2s(dst + " << o << ", (const char*)" << cg.P(P_COL_DATA, c) << " + base * " << w << ", " << bytes << ", bar);\n";
+                ld_a << "      r.c" << c << " = ((const " << ctype(dt) << "*)(st + " << o << "))[rr];\n";
+            }
+        }
         if (nullable) {
             raw << "    bool k" << c << ";\n";
             load << "    r.k" << c << " = bit_at((const uint8_t*)" << cg.P(P_COL_VALID, c) << ", row);\n";
@@ -897,22 +947,26 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, bool global_vari
                 load << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
             }
             // second load phase: the first <= 8 bytes of the value (depends on the offsets of phase one)
-            if (is_pack4_col(c)) {
-                // Fixed-length value columns (flags, codes): the host passes L = data_bytes / rows when that divides
-                // evenly.  The value's bytes are then fetched SPECULATIVELY at data + row * L together with the
-                // offsets (one memory round trip instead of two) and used only if the offsets confirm the guess.
-                const int iv = cg.int_slot(I_STRLEN + 1000 * c);
-                raw << "    unsigned int sw" << c << "a, sw" << c << "b;\n";
-                load << "    { const unsigned long long L_ = (unsigned long long)p.ival[" << iv << "]; r.sw" << c << "a = 0u; r.sw" << c << "b = 0u;\n"
-                     << "      if (L_) { const uintptr_t a_ = (uintptr_t)" << cg.P(P_COL_DATA, c) << " + (unsigned long long)row * L_; const unsigned int* w_ = (const unsigned int*)(a_ & ~(uintptr_t)3);\n"
-                     << "        r.sw" << c << "a = __ldg(w_); if ((a_ & 3) + L_ > 4) r.sw" << c << "b = __ldg(w_ + 1); } }\n";
-                load2 << "    { const unsigned long long L_ = (unsigned long long)p.ival[" << iv << "]; const long long len_ = r.o" << c << "b - r.o" << c << "a;\n"
-                      << "      if (L_ && (unsigned long long)r.o" << c << "a == (unsigned long long)row * L_ && len_ <= (long long)L_) {\n"
-                      << "        const unsigned int sh_ = (unsigned int)(((uintptr_t)" << cg.P(P_COL_DATA, c) << " + (unsigned long long)r.o" << c << "a) & 3) * 8u;\n"
-                      << "        unsigned int v_ = __funnelshift_r(r.sw" << c << "a, r.sw" << c << "b, sh_); const unsigned int nb_ = len_ > 0 ? (unsigned int)len_ : 0u;\n"
-                      << "        v_ &= nb_ >= 4u ? 0xFFFFFFFFu : ((1u << (nb_ * 8u)) - 1u); r.pk" << c << " = (uint64_t)v_;\n"
-                      << "      } else r.pk" << c << " = str_pack4(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, len_}); }\n";
-                raw_bytes += 32;
+            if (is_pack4_col(c) && ast.fixed_len(c) > 0) {
+                // Fixed-length value columns (flags, codes): the kernel is specialised for L = data_bytes / rows.  The
+                // value's bytes are fetched SPECULATIVELY at data + row * L together with the offsets (one memory
+                // round trip instead of two) and used only if the row's offsets confirm the guess.
+                const int L = ast.fixed_len(c);
+                raw << "    unsigned int sw" << c << ";\n";
+                if (L == 1 || L == 2 || L == 4) {
+                    const char *ty = L == 1 ? "uint8_t" : (L == 2 ? "uint16_t" : "uint32_t");
+                    load << "    r.sw" << c << " = ((const " << ty << "*)" << cg.P(P_COL_DATA, c) << ")[row];\n";
+                } else {
+                    load << "    { const uint8_t* q_ = (const uint8_t*)" << cg.P(P_COL_DATA, c) << " + row * 3; r.sw" << c
+                         << " = (unsigned)q_[0] | ((unsigned)q_[1] << 8) | ((unsigned)q_[2] << 16); }\n";
+                }
+                load2 << "    { const long long len_ = r.o" << c << "b - r.o" << c << "a;\n"
+                      << "      if (r.o" << c << "a == row * " << L << " && len_ == " << L << ") r.pk" << c << " = (uint64_t)r.sw" << c << ";\n"
+                      << "      else r.pk" << c << " = str_pack4(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, len_}); }\n";
+                raw_bytes += 28;
+            } else if (is_pack4_col(c)) {
+                load2 << "    r.pk" << c << " = str_pack4(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, r.o" << c << "b - r.o" << c << "a});\n";
+                raw_bytes += 24;
             } else {
                 load2 << "    r.pk" << c << " = str_pack8(Str{(const uint8_t*)" << cg.P(P_COL_DATA, c) << " + r.o" << c << "a, r.o" << c << "b - r.o" << c << "a});\n";
                 raw_bytes += 24;
@@ -928,6 +982,15 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, bool global_vari
         }
     }
     const int U = std::max(1, std::min(8, env_int("B200_AGG_U", 2)));
+    // shared memory of the tier-1 kernels: lane cells, ballot cells, slots / codes / key values (generous sizeof(Keys))
+    const size_t tier1_smem = 8 * (size_t)SW * G1 * NLT * 32 + 8 * (size_t)SW * G1 * std::max(NW, 1) + 16 * (size_t)G1 +
+                              (size_t)G1 * (40 * (size_t)nkeys + 16);
+    bool stage_fits = true;
+    if (staged_variant) {
+        const size_t budget = 227 * 1024 - 1024;
+        while (SS > 2 && tier1_smem + (size_t)SS * (stage_off + 16) > budget) SS--;
+        stage_fits = stage_off > 0 && tier1_smem + (size_t)SS * (stage_off + 16) <= budget;
+    }
 
     // ---- Keys / Vals structs
     std::ostringstream keys_s, vals_s;
@@ -1215,6 +1278,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, bool global_vari
     }
 
     std::ostringstream o;
+    if (SW != 8) o << "#define B200_AGG_WARPS " << SW << "\n";
     o << file_header(cg);
     o << "struct Prog {\n";
     o << "  typedef Params<" << meta.ptrs.size() << ", " << meta.ints.size() << "> P;\n";
@@ -1251,15 +1315,35 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, bool global_vari
     o << "  __device__ __forceinline__ static void warp_cells(const Vals& v, const bool in_g, unsigned long long* wcell, const int lane) {\n" << wc.str() << "  }\n";
     o << "  __device__ __forceinline__ static void flush(const P& p, const long long slot, const unsigned long long* lcell, const size_t lstride,\n"
          "                                               const unsigned long long* wcell, const size_t wstride, const int lane) {\n" << fl.str() << "  }\n";
+    if (staged_variant) {
+        o << "  static constexpr int STAGE_ROWS = " << SR << ", STAGES = " << SS << ", STAGE_BYTES = " << stage_off << ", RPL = " << SRPL << ";\n";
+        o << "  __device__ __forceinline__ static void stage_issue(const P& p, const uint32_t dst, const uint32_t bar, const int64_t base) {\n"
+          << "    uint32_t tx = " << stage_fixed_tx << "u;\n" << st_tx.str() << "    mbar_expect_tx(bar, tx);\n" << st_issue.str() << "  }\n";
+        o << "  __device__ __forceinline__ static void load_staged(const P& p, const unsigned char* st, const int64_t base, const int tid, Raw (&raw)[RPL]) {\n"
+          << "    bool ok_ = true;\n"
+          << "#pragma unroll\n    for (int u = 0; u < RPL; u++) {\n      const int rr = u * " << SW * 32 << " + tid; const int64_t row = base + rr; Raw& r = raw[u];\n"
+          << ld_a.str() << "    }\n"
+          << ld_first.str() << "    const bool fast_ = __all_sync(FULL_MASK, ok_);\n"
+          << "#pragma unroll\n    for (int u = 0; u < RPL; u++) {\n      const int rr = u * " << SW * 32 << " + tid; Raw& r = raw[u];\n"
+          << ld_b.str() << "    }\n  }\n";
+    }
     o << "};\n";
-    if (global_variant)
+    if (staged_variant)
+        o << "extern \"C\" __global__ void __launch_bounds__(" << SW * 32 << ", " << (SW == 16 ? 1 : MINB) << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_staged<Prog>(p); }\n";
+    else if (global_variant)
         o << "extern \"C\" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_global<Prog>(p); }\n";
     else
         o << "extern \"C\" __global__ void __launch_bounds__(256, " << MINB << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }\n";
     // shared memory: lane cells, ballot cells, tier-1 slots/ready flags/key values (generous bound for sizeof(Keys))
     meta.smem_bytes = global_variant ? 8 * (size_t)t2_slots * (size_t)(1 + NLT + NW)
-                                     : 8 * (size_t)8 * G1 * NLT * 32 + 8 * (size_t)8 * G1 * std::max(NW, 1) + 16 * (size_t)G1 +
-                                           (size_t)G1 * (40 * (size_t)nkeys + 16);
+                                     : tier1_smem;
+    meta.block_threads = SW * 32;
+    if (staged_variant) {
+        meta.smem_bytes += (size_t)SS * (size_t)stage_off + (size_t)16 * SS;
+        meta.stage_bytes = stage_fits ? stage_off : 0;  // 0: the host runs the direct-load build instead
+        meta.stage_rows = SR;
+        if (!stage_fits) meta.smem_bytes = 0;
+    }
     return o.str();
 }
 
@@ -1278,7 +1362,7 @@ std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::ve
         body = gen_filter(r, ast, meta);
         if (r.pos != r.n) fail("plan: trailing bytes");
     } else if (op == B200_OP_AGG) {
-        body = gen_agg(r, ast, meta, variant != 0);
+        body = gen_agg(r, ast, meta, variant);
     } else {
         fail("jit: unknown op");
     }
@@ -1316,7 +1400,10 @@ static std::string cache_dir() {
 }
 
 std::vector<char> compile_to_cubin(const std::string &body, std::string *path_out) {
-    const std::string full = join_chunks(kPreludeXxh3_chunks) + "\n" + join_chunks(kPreludeJit_chunks) + "\n" + body;
+    // leading "#define ..." lines of the generated code configure the prelude and go in front of it
+    size_t defs_end = 0;
+    while (body.compare(defs_end, 8, "#define ") == 0) defs_end = body.find('\n', defs_end) + 1;
+    const std::string full = body.substr(0, defs_end) + join_chunks(kPreludeXxh3_chunks) + "\n" + join_chunks(kPreludeJit_chunks) + "\n" + body.substr(defs_end);
     char name[64];
     snprintf(name, sizeof name, "k_%016llx", (unsigned long long)fnv1a(full));
     const std::string base = cache_dir() + "/" + name;
@@ -1374,7 +1461,15 @@ static std::string cache_key(int op, const uint8_t *plan, size_t plan_len, const
 const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &input, bool with_take, int variant) {
     std::vector<int32_t> dt;
     std::vector<uint8_t> nl;
-    for (auto &c : input.cols) { dt.push_back(c.dtype); nl.push_back(c.nullable() ? 1 : 0); }
+    for (auto &c : input.cols) {
+        dt.push_back(c.dtype);
+        uint8_t f = c.nullable() ? 1 : 0;
+        if (op == B200_OP_AGG && is_string(c.dtype) && c.length > 0 && c.data_bytes % c.length == 0) {
+            const int64_t L = c.data_bytes / c.length;  // fixed-length hint (see Ast::fixed_len)
+            if (L >= 1 && L <= 4) f |= (uint8_t)(L << 1);
+        }
+        nl.push_back(f);
+    }
     std::lock_guard<std::mutex> g(g_mu);
     const std::string key = cache_key(op, plan, plan_len, dt, nl, with_take) + (char)('0' + variant);
     auto it = g_kernels.find(key);
@@ -1395,8 +1490,21 @@ const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &i
     return ref;
 }
 
+static void precompile_one(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
+                           const std::vector<uint8_t> &col_nullable);
 void precompile(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
                 const std::vector<uint8_t> &col_nullable) {
+    precompile_one(op, plan, plan_len, col_dtypes, col_nullable);
+    if (op == B200_OP_AGG) {  // and the build specialised for 1-byte string columns (TPC-H flags and codes)
+        std::vector<uint8_t> f = col_nullable;
+        bool any = false;
+        for (size_t i = 0; i < f.size(); i++)
+            if (is_string(col_dtypes[i])) { f[i] |= 1 << 1; any = true; }
+        if (any) precompile_one(op, plan, plan_len, col_dtypes, f);
+    }
+}
+static void precompile_one(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
+                           const std::vector<uint8_t> &col_nullable) {
     std::lock_guard<std::mutex> g(g_mu);
     Compiled c;
     const std::string src = generate(op, plan, plan_len, col_dtypes, col_nullable, false, c, 0);
@@ -1404,6 +1512,8 @@ void precompile(int op, const uint8_t *plan, size_t plan_len, const std::vector<
     if (op == B200_OP_AGG) {  // the high-cardinality variant of the same plan
         Compiled cg2;
         compile_to_cubin(generate(op, plan, plan_len, col_dtypes, col_nullable, false, cg2, 1), nullptr);
+        Compiled cg3;  // and the TMA-staged build of the low-cardinality kernel
+        compile_to_cubin(generate(op, plan, plan_len, col_dtypes, col_nullable, false, cg3, 2), nullptr);
     }
     if (op == B200_OP_AGG && !c.key_project_plan.empty() && c.nkeys > 0) {
         Compiled c2;

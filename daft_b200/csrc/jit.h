@@ -53,13 +53,16 @@ struct Compiled {
     std::vector<int> lane_cell_ops;
     std::vector<AggOut> aggs;
     size_t smem_bytes = 0;
+    int block_threads = 256;
+    int stage_rows = 0, stage_bytes = 0;  // staged agg variant: bytes per shared-memory stage (0 = nothing to stage)
     std::vector<uint8_t> key_project_plan;
     int regs = 0;
     std::string source_path;
 };
 
 // Codegen only (no CUDA needed): returns the CUDA source for the plan; fills `meta` (fn stays null).
-// variant (AGG only): 0 = low-cardinality kernel (tier-1 shared-memory cells), 1 = global-table kernel
+// variant (AGG only): 0 = low-cardinality kernel (tier-1 shared-memory cells), 1 = global-table kernel,
+// 2 = the low-cardinality kernel fed by per-warp TMA bulk copies (cp.async.bulk + mbarrier stages)
 std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
                      const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta, int variant = 0);
 // NVRTC -> cubin (cached on disk); works without a GPU.

@@ -73,6 +73,14 @@ __device__ __forceinline__ uint64_t str_pack8(Str a) {
     return v;
 }
 // first min(len, 4) bytes with 32-bit arithmetic only (short key columns on the exact-code path need <= 3 bytes)
+// first L (<= 4) bytes at a shared-memory address, little-endian
+__device__ __forceinline__ uint32_t smem_pack4(const unsigned char *q, const int L) {
+    uint32_t v = q[0];
+    if (L > 1) v |= (uint32_t)q[1] << 8;
+    if (L > 2) v |= (uint32_t)q[2] << 16;
+    if (L > 3) v |= (uint32_t)q[3] << 24;
+    return v;
+}
 __device__ __forceinline__ uint64_t str_pack4(Str a) {
     const uintptr_t addr = (uintptr_t)a.p;
     const bool any = a.len > 0;
@@ -232,40 +240,69 @@ constexpr int FILTER_THREADS = 256, FILTER_SUB = 8, FILTER_TILE = FILTER_THREADS
 
 template <class Prog>
 __device__ __forceinline__ void filter_body(const typename Prog::P &p, int pass) {
-    __shared__ int s_w[FILTER_THREADS / 32];
-    __shared__ long long s_run;
+    // One tile = FILTER_SUB rows per thread, all evaluated (loads in flight together) before any synchronisation;
+    // the (sub-row, warp) survivor counts are scanned by warp 0, so a tile costs two barriers, not four per 256 rows.
+    constexpr int NWF = FILTER_THREADS / 32, E = FILTER_SUB * NWF;
+    static_assert(E % 32 == 0, "scan layout");
+    __shared__ int s_w[E];
+    __shared__ int s_tot;
     const int64_t n = p.ival[Prog::IV_N];
     const int64_t ntiles = (n + FILTER_TILE - 1) / FILTER_TILE;
     long long *counts = (long long *)p.ptr[Prog::PTR_COUNTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t tbase = tile * FILTER_TILE;
-        if (threadIdx.x == 0) s_run = pass ? counts[tile] : 0;
-        __syncthreads();
-#pragma unroll 1
+        bool keep[FILTER_SUB];
+        unsigned m[FILTER_SUB];
+#pragma unroll
         for (int j = 0; j < FILTER_SUB; j++) {
             const int64_t row = tbase + (int64_t)j * FILTER_THREADS + threadIdx.x;
-            const bool keep = row < n && Prog::keep(p, row);
-            const unsigned m = __ballot_sync(FULL_MASK, keep);
-            if (lane == 0) s_w[warp] = __popc(m);
-            __syncthreads();
-            int woff = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < FILTER_THREADS / 32; w++) {
-                const int c = s_w[w];
-                woff += w < warp ? c : 0;
-                tot += c;
-            }
-            if (pass && keep) {
-                const int64_t dst = s_run + woff + __popc(m & ((1u << lane) - 1u));
-                Prog::copy(p, row, dst);
-                if (Prog::PTR_IDX >= 0) ((int64_t *)p.ptr[Prog::PTR_IDX < 0 ? 0 : Prog::PTR_IDX])[dst] = row;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) s_run += tot;
-            __syncthreads();
+            keep[j] = row < n && Prog::keep(p, row);
         }
-        if (!pass && threadIdx.x == 0) counts[tile] = s_run;
+#pragma unroll
+        for (int j = 0; j < FILTER_SUB; j++) {
+            m[j] = __ballot_sync(FULL_MASK, keep[j]);
+            if (lane == 0) s_w[j * NWF + warp] = __popc(m[j]);
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the E counts, E / 32 consecutive entries per lane
+            int v[E / 32], sum = 0;
+#pragma unroll
+            for (int k = 0; k < E / 32; k++) {
+                v[k] = s_w[lane * (E / 32) + k];
+                sum += v[k];
+            }
+            int x = sum;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(FULL_MASK, x, d);
+                if (lane >= d) x += y;
+            }
+            int run = x - sum;
+#pragma unroll
+            for (int k = 0; k < E / 32; k++) {
+                s_w[lane * (E / 32) + k] = run;
+                run += v[k];
+            }
+            if (lane == 31) s_tot = x;
+        }
+        __syncthreads();
+        if (!pass) {
+            if (threadIdx.x == 0) counts[tile] = s_tot;
+        } else {
+            const int64_t obase = counts[tile];
+            int64_t src[FILTER_SUB], dst[FILTER_SUB];  // dst < 0: row dropped
+#pragma unroll
+            for (int j = 0; j < FILTER_SUB; j++) {
+                src[j] = tbase + (int64_t)j * FILTER_THREADS + threadIdx.x;
+                dst[j] = keep[j] ? obase + s_w[j * NWF + warp] + __popc(m[j] & ((1u << lane) - 1u)) : -1;
+            }
+            Prog::copy(p, src, dst);
+            if (Prog::PTR_IDX >= 0) {
+#pragma unroll
+                for (int j = 0; j < FILTER_SUB; j++)
+                    if (dst[j] >= 0) ((int64_t *)p.ptr[Prog::PTR_IDX < 0 ? 0 : Prog::PTR_IDX])[dst[j]] = src[j];
+            }
+        }
         __syncthreads();
     }
 }
@@ -284,7 +321,10 @@ __device__ __forceinline__ void filter_body(const typename Prog::P &p, int pass)
 // the key values) equal codes ARE equal keys; otherwise the code is a fingerprint and a match is confirmed against
 // the key values of the slot's representative row (nulls equal, floats by bit pattern -- the reference's
 // "hash equal AND comparator" rule, src/daft-recordbatch/src/ops/inline_agg.rs:760-784).
-constexpr int AGG_WARPS = 8;
+#ifndef B200_AGG_WARPS
+#define B200_AGG_WARPS 8  // warps per CTA of the aggregate kernels (the staged build may ask for 16)
+#endif
+constexpr int AGG_WARPS = B200_AGG_WARPS;
 constexpr unsigned long long AGG_EMPTY = 0xFFFFFFFFFFFFFFFFULL;     // min-row cell of an unclaimed slot
 constexpr unsigned long long AGG_CLAIMING = 0xFFFFFFFFFFFFFFFEULL;  // (MODE 1) slot being published
 constexpr int AGG_PROBE_LIMIT = 1024;
@@ -370,8 +410,9 @@ __device__ __forceinline__ void agg_body_global(const typename Prog::P &p) {
     volatile int *flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
     int t2_hits = 0, t2_miss = 0;
     bool use_t2 = T2 >= 64 && Prog::NKEYS > 0;
+    int abandoned = 0;  // status flag as of the previous chunk: its load overlaps this chunk's column loads
     for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
-        if (*flag) break;  // someone hit a full table: stop early, the host will retry
+        if (__any_sync(FULL_MASK, abandoned != 0)) break;  // someone hit a full table: stop early, the host will retry
         const int64_t base = c * chunk;
         typename Prog::Raw raw[U];
 #pragma unroll
@@ -379,6 +420,7 @@ __device__ __forceinline__ void agg_body_global(const typename Prog::P &p) {
             const int64_t row = base + u * 32 + lane;
             if (row < n) Prog::load(p, row, raw[u]);
         }
+        abandoned = *flag;
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int64_t row = base + u * 32 + lane;
@@ -544,6 +586,30 @@ struct AggTier1 {
     }
 };
 
+// one chunk of 32*U rows of a warp; FULL: every row of the chunk exists (no per-row bounds checks or guards)
+template <class Prog, bool FULL>
+__device__ __forceinline__ void agg_chunk(AggTier1<Prog> &t1, const typename Prog::P &p, const int64_t base, const int64_t n, const int lane,
+                                          int &abandoned) {
+    constexpr int U = Prog::U;
+    typename Prog::Raw raw[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int64_t row = base + u * 32 + lane;
+        if (FULL || row < n) Prog::load(p, row, raw[u]);
+    }
+    abandoned = *t1.flag;  // consumed at the next chunk: the load overlaps this chunk's column loads
+#pragma unroll
+    for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
+        const int64_t row = base + u * 32 + lane;
+        if (FULL || row < n) Prog::load2(p, row, raw[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int64_t row = base + u * 32 + lane;
+        t1.row(p, raw[u], row, FULL || row < n, lane);
+    }
+}
+
 template <class Prog>
 __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -553,40 +619,30 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     t1.refresh();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n = p.ival[Prog::IV_N];
-    constexpr int U = Prog::U;
-    const int64_t chunk = 32 * U;
-    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const int64_t chunk = 32 * Prog::U;
+    const int64_t nchunks = (n + chunk - 1) / chunk, nfull = n / chunk;
     const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
-    for (int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp; c < nchunks; c += total_warps) {
-        if (*t1.flag) break;
-        const int64_t base = c * chunk;
-        typename Prog::Raw raw[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int64_t row = base + u * 32 + lane;
-            if (row < n) Prog::load(p, row, raw[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
-            const int64_t row = base + u * 32 + lane;
-            if (row < n) Prog::load2(p, row, raw[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int64_t row = base + u * 32 + lane;
-            t1.row(p, raw[u], row, row < n, lane);
-        }
+    int abandoned = 0;  // status flag as of the previous chunk
+    int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp;
+    for (; c < nfull; c += total_warps) {
+        if (__any_sync(FULL_MASK, abandoned != 0)) break;
+        agg_chunk<Prog, true>(t1, p, c * chunk, n, lane, abandoned);
     }
+    if (c < nchunks && c >= nfull && !__any_sync(FULL_MASK, abandoned != 0))  // the one partial chunk at the end of the input
+        agg_chunk<Prog, false>(t1, p, c * chunk, n, lane, abandoned);
     __syncthreads();
     t1.flush(p, lane, warp);
 }
 
 // ---- the same kernel fed by TMA bulk copies ---------------------------------------------------------------------
-// Each warp owns a ring of S stages in shared memory.  Lane 0 issues one cp.async.bulk (UBLKCP) per staged column
-// slice -- R consecutive rows of a fixed-width column, R+2 offsets of a string column, R*L value bytes of a
-// fixed-length string column -- completing on the stage's mbarrier; the warp consumes stage i while the copies of
-// stages i+1 .. i+S-1 are in flight, so HBM latency is covered by shared-memory capacity instead of registers and
-// resident warps.  Tail chunks that cannot be staged (offsets need row t+R+1) use the direct-load path.
+// The CTA owns a ring of S stages in shared memory.  A stage holds R = blockDim.x * RPL consecutive rows of every
+// column the plan reads: R values of a fixed-width column, R+2 offsets of a string column, R*L value bytes of a
+// fixed-length string column.  Thread 0 issues one cp.async.bulk (UBLKCP) per column slice, completing on the
+// stage's "full" mbarrier; every warp copies its rows from the stage into registers, arrives on the stage's "empty"
+// mbarrier and goes on to aggregate them while the copies of the next S-1 stages are in flight -- HBM latency is
+// covered by shared-memory capacity instead of registers and resident warps.  Copies are kilobytes each: the TMA
+// unit retires roughly one bulk copy per ~46 cycles per SM, so per-warp sized copies (256-512 B) are issue bound.
+// Tail chunks that cannot be staged (the offsets slice needs row base+R+1) use the direct-load path.
 __device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -594,90 +650,130 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
                  "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait for a phase; gives up (false) when the kernel has been abandoned (status flag set by any CTA)
+__device__ __forceinline__ bool mbar_wait_or_abort(uint32_t bar, uint32_t parity, volatile int *flag) {
+    for (int spins = 1; !mbar_try_wait(bar, parity); spins++)
+        if ((spins & 15) == 0 && *flag) return false;  // the flag lives in global memory: poll it rarely
+    return true;
 }
 
 template <class Prog>
 __device__ __forceinline__ void agg_body_staged(const typename Prog::P &p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int R = Prog::STAGE_ROWS, S = Prog::STAGES, SB = Prog::STAGE_BYTES;
-    // layout: stages [W][S][SB] (16 B aligned) | mbarriers [W][S] | tier 1
+    constexpr int R = Prog::STAGE_ROWS, S = Prog::STAGES, SB = Prog::STAGE_BYTES, RPL = Prog::RPL, T = AGG_WARPS * 32;
+    static_assert(R == T * RPL, "stage rows");
+    // layout: stages [S][SB] (16 B aligned) | full barriers [S] | empty barriers [S] | tier 1
     unsigned char *stages = smem_raw;
-    unsigned long long *bars = (unsigned long long *)(stages + (size_t)AGG_WARPS * S * SB);
+    unsigned long long *full = (unsigned long long *)(stages + (size_t)S * SB);
+    unsigned long long *empty = full + S;
     AggTier1<Prog> t1;
-    t1.init((unsigned char *)(bars + AGG_WARPS * S), p);
+    t1.init((unsigned char *)(empty + S), p);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0)
-        for (int s = 0; s < S; s++) mbar_init(smem_u32(&bars[warp * S + s]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), AGG_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     t1.refresh();
     const int64_t n = p.ival[Prog::IV_N];
     const int64_t nchunks = (n + R - 1) / R;
-    const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
-    const int64_t c0 = (int64_t)blockIdx.x * AGG_WARPS + warp;
-    unsigned char *my_stage = stages + (size_t)warp * S * SB;
-    auto stageable = [&](int64_t c) { return c < nchunks && (c + 1) * R < n; };  // offsets copy reads row (c+1)*R + 1
-    if (lane == 0) {
+    const int64_t stride = gridDim.x;
+    auto stageable = [&](int64_t c) { return c < nchunks && (c + 1) * R < n; };  // offsets slice reads row (c+1)*R + 1
+    int64_t issued = 0;  // (thread 0) iterations whose copies have been issued
+    if (threadIdx.x == 0) {
 #pragma unroll 1
         for (int s = 0; s < S; s++) {
-            const int64_t c = c0 + (int64_t)s * total_warps;
-            if (stageable(c)) Prog::stage_issue(p, smem_u32(my_stage + (size_t)s * SB), smem_u32(&bars[warp * S + s]), c * R);
+            const int64_t c = blockIdx.x + (int64_t)s * stride;
+            if (stageable(c)) {
+                Prog::stage_issue(p, smem_u32(stages + (size_t)s * SB), smem_u32(&full[s]), c * R);
+                issued = s + 1;
+            }
         }
     }
+    bool aborted = false;
+    int abandoned = 0;  // status flag as loaded 16 iterations ago
     int64_t i = 0;
-    for (int64_t c = c0; c < nchunks; c += total_warps, i++) {
-        if (*t1.flag) break;
-        const int s = (int)(i % S);
-        const uint32_t parity = (uint32_t)((i / S) & 1);
-        const int64_t base = c * R;
-        const bool staged = stageable(c);
-        const unsigned char *st = my_stage + (size_t)s * SB;
-        if (staged) mbar_wait(smem_u32(&bars[warp * S + s]), parity);
-#pragma unroll 1
-        for (int j = 0; j < R / 32; j += 2) {  // two rows per lane in flight (ILP), both read from shared memory
-            typename Prog::Raw raw[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int r = (j + u) * 32 + lane;
-                const int64_t row = base + r;
-                if (row < n) {
-                    if (staged) Prog::load_staged(p, st, r, row, raw[u]);
-                    else Prog::load(p, row, raw[u]);
+    for (int64_t c = blockIdx.x; c < nchunks; c += stride, i++) {
+        if ((i & 15) == 0) {  // iterations are shorter than a global-memory round trip: look at the flag loaded 16 ago
+            if (__any_sync(FULL_MASK, abandoned != 0)) {
+                aborted = true;
+                break;
+            }
+            abandoned = *t1.flag;
+        }
+        if (threadIdx.x == 0 && i > 0) {  // refill the stage every warp finished reading one iteration ago
+            const int64_t j = i - 1 + S, cj = blockIdx.x + j * stride;
+            if (stageable(cj)) {
+                const int sp = (int)((i - 1) % S);
+                if (!mbar_wait_or_abort(smem_u32(&empty[sp]), (uint32_t)(((i - 1) / S) & 1), t1.flag)) {
+                    aborted = true;
+                } else {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    Prog::stage_issue(p, smem_u32(stages + (size_t)sp * SB), smem_u32(&full[sp]), cj * R);
+                    issued = j + 1;
                 }
             }
+        }
+        if (warp == 0) aborted = __any_sync(FULL_MASK, aborted);  // keep warp 0 convergent with its producer lane
+        if (aborted) break;
+        const int s = (int)(i % S);
+        const int64_t base = c * R;
+        typename Prog::Raw raw[RPL];
+        if (stageable(c)) {
+            const bool landed = mbar_wait_or_abort(smem_u32(&full[s]), (uint32_t)((i / S) & 1), t1.flag);
+            if (!__all_sync(FULL_MASK, landed)) {
+                aborted = true;
+                break;
+            }
+            Prog::load_staged(p, stages + (size_t)s * SB, base, (int)threadIdx.x, raw);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty[s]));
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int64_t row = base + (j + u) * 32 + lane;
+            for (int u = 0; u < RPL; u++) t1.row(p, raw[u], base + u * T + threadIdx.x, true, lane);  // staged chunks are full
+            continue;
+        } else {
+#pragma unroll
+            for (int u = 0; u < RPL; u++) {
+                const int64_t row = base + u * T + threadIdx.x;
+                if (row < n) Prog::load(p, row, raw[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < RPL; u++) {
+                const int64_t row = base + u * T + threadIdx.x;
                 if (row < n) Prog::load2(p, row, raw[u]);
             }
+        }
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int64_t row = base + (j + u) * 32 + lane;
-                t1.row(p, raw[u], row, row < n, lane);
-            }
+        for (int u = 0; u < RPL; u++) {
+            const int64_t row = base + u * T + threadIdx.x;
+            t1.row(p, raw[u], row, row < n, lane);
         }
-        __syncwarp();
-        if (lane == 0) {  // refill this stage with the chunk S iterations ahead
-            const int64_t cn = c + (int64_t)S * total_warps;
-            if (stageable(cn)) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                Prog::stage_issue(p, smem_u32(my_stage + (size_t)s * SB), smem_u32(&bars[warp * S + s]), cn * R);
+    }
+    if (threadIdx.x == 0 && aborted) {
+        // abandoned: copies already issued must land before the CTA's shared memory is released
+        for (int64_t j = i; j < issued; j++)
+            while (!mbar_try_wait(smem_u32(&full[(int)(j % S)]), (uint32_t)((j / S) & 1))) {
             }
-        }
     }
     __syncthreads();
     t1.flush(p, lane, warp);

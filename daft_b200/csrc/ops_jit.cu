@@ -325,9 +325,30 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
     // start with the low-cardinality kernel; it raises flag 2 as soon as most rows miss its shared-memory tier, and
     // the global-table kernel takes over from scratch, growing its table while it reports overflow (flag 1).
     int variant = 0;
-    const Compiled *kp = &jit::get(B200_OP_AGG, plan, len, in, false, 0);
+    const Compiled *kp = nullptr;
+    {
+        // the TMA-staged build of the low-cardinality kernel needs 16-byte aligned column buffers and enough rows to
+        // fill its pipeline; anything else runs the direct-load build
+        const char *e = getenv("B200_AGG_STAGED");
+        if (n >= (1 << 16) && !(e && *e == '0')) {
+            const Compiled &k2 = jit::get(B200_OP_AGG, plan, len, in, false, 2);
+            bool ok = k2.stage_bytes > 0;
+            for (const auto &ps : k2.ptrs) {
+                const void *q = nullptr;
+                if (ps.kind == jit::P_COL_DATA) q = in.cols[ps.index].data ? in.cols[ps.index].data->ptr : nullptr;
+                else if (ps.kind == jit::P_COL_OFFSETS) q = in.cols[ps.index].offsets ? in.cols[ps.index].offsets->ptr : nullptr;
+                if (((uintptr_t)q & 15) != 0) ok = false;
+            }
+            if (ok) {
+                variant = 2;
+                kp = &k2;
+            }
+        }
+        if (!kp) kp = &jit::get(B200_OP_AGG, plan, len, in, false, 0);
+    }
     int64_t cap = kp->nkeys > 0 ? (1 << 16) : 1;
-    Buf slot_tag, acc, flag = dev_alloc_zero(8);
+    Buf slot_tag, acc, slots, flag = dev_alloc_zero(16);  // flag: {int status, pad, u64 group counter}
+    int64_t ng = 0;
     int ncells = 0, cell_nrows = 0, cell_minrow = 0;
     for (int attempt = 0;; attempt++) {
         const Compiled &k = *kp;
@@ -338,7 +359,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         acc = dev_alloc_zero((size_t)ncells * cap * 8);
         for (int c = 0; c < k.NLANE; c++)
             if (k.lane_cell_ops[c] == jit::C_MIN) fill_u8(as<uint8_t>(acc) + (size_t)c * cap * 8, 0xFF, (size_t)cap * 8);
-        fill_u8(flag->ptr, 0, 8);
+        fill_u8(flag->ptr, 0, 16);
         int status = 0;
         if (n > 0) {
             LaunchArgs a;
@@ -357,30 +378,36 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
                 }
             }
             for (size_t s = 0; s < k.ints.size(); s++) {
-                const int kind = k.ints[s] % 1000, idx = k.ints[s] / 1000;
+                const int kind = k.ints[s] % 1000;
                 if (kind == jit::I_N) a.ival[s] = n;
                 else if (kind == jit::I_MASK) a.ival[s] = cap - 1;
-                else if (kind == jit::I_STRLEN) {
-                    // constant-length hint: bytes divide evenly over the rows (verified per row in the kernel)
-                    const Column &sc = in.cols[idx];
-                    const int64_t L = (sc.length > 0 && sc.data_bytes % sc.length == 0) ? sc.data_bytes / sc.length : 0;
-                    a.ival[s] = (L >= 1 && L <= 4) ? L : 0;
-                }
             }
             int occ = 0;
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k.fn, 256, k.smem_bytes));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k.fn, k.block_threads, k.smem_bytes));
             occ = std::max(1, occ);
-            const int64_t chunks = (n + 63) / 64;
-            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 7) / 8, (int64_t)ctx().sm_count * occ));
-            jit::launch(k, a, grid, 256, k.smem_bytes, 0, true);
-            if (k.nkeys > 0) {
-                B200_CUDA(cudaMemcpyAsync(&status, flag->ptr, 4, cudaMemcpyDeviceToHost, st));
-                B200_CUDA(cudaStreamSynchronize(st));
-            }
+            // work units: a 64-row chunk per warp (direct-load builds) or a whole stage per CTA (staged build)
+            const int64_t ctas = variant == 2 ? (n + k.stage_rows - 1) / k.stage_rows : ((n + 63) / 64 + 7) / 8;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)ctx().sm_count * occ));
+            jit::launch(k, a, grid, k.block_threads, k.smem_bytes, 0, true);
+        }
+        // compact the occupied slots right behind the kernel: status flag and group count come back in ONE read
+        // (an ungrouped aggregate has exactly one group and no failure mode: no read at all)
+        slots = dev_alloc((size_t)std::max<int64_t>(cap, 1) * 8);
+        compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(as<unsigned long long>(acc) + (size_t)cell_nrows * cap, cap, k.nkeys == 0,
+                                                              as<unsigned long long>(flag) + 1, as<int64_t>(slots));
+        count_launch();
+        if (k.nkeys > 0) {
+            long long host[2] = {0, 0};
+            B200_CUDA(cudaMemcpyAsync(host, flag->ptr, 16, cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            status = (int)(host[0] & 0xffffffffLL);
+            ng = host[1];
+        } else {
+            ng = 1;
         }
         if (!status) break;
         if (attempt > 10) fail("agg: hash table overflow after repeated growth");
-        if (variant == 0) {
+        if (variant != 1) {
             variant = 1;
             kp = &jit::get(B200_OP_AGG, plan, len, in, false, 1);
             cap = 1 << 20;
@@ -397,11 +424,6 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
 
     // ---- compact occupied slots, order groups by first occurrence
     const unsigned long long *nrows_cell = as<unsigned long long>(acc) + (size_t)cell_nrows * cap;
-    Buf counter = dev_alloc_zero(8);
-    Buf slots = dev_alloc((size_t)std::max<int64_t>(cap, 1) * 8);
-    compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(nrows_cell, cap, k.nkeys == 0, as<unsigned long long>(counter), as<int64_t>(slots));
-    count_launch();
-    const int64_t ng = read_i64(as<int64_t>(counter));
     Buf minrow = dev_alloc((size_t)std::max<int64_t>(ng, 1) * 8);
     if (ng > 0) {
         gather_u64<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(as<unsigned long long>(acc) + (size_t)cell_minrow * cap,

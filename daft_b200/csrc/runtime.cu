@@ -279,10 +279,141 @@ Column gather_column(const Column &src, const int64_t *idx, int64_t n, bool idx_
     return out;
 }
 
-Batch *gather_batch(const Batch &src, const int64_t *idx, int64_t n, bool idx_may_be_negative) {
+// Every fixed-width, never-null column of a batch gathered by ONE launch: the index is read once per row and the
+// per-column copies are independent loads (memory-level parallelism across columns).
+struct GatherDesc {
+    const void *src;
+    void *out;
+    int width;
+};
+constexpr int kGatherMaxCols = 24;
+struct GatherSet {
+    GatherDesc d[kGatherMaxCols];
+};
+__global__ void gather_fixed_multi(const __grid_constant__ GatherSet gs, int ncols, const int64_t *__restrict__ idx, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t j = idx[i];
+#pragma unroll 4
+        for (int c = 0; c < ncols; c++) {
+            const GatherDesc &d = gs.d[c];
+            switch (d.width) {
+                case 1: ((uint8_t *)d.out)[i] = j >= 0 ? ((const uint8_t *)d.src)[j] : (uint8_t)0; break;
+                case 2: ((uint16_t *)d.out)[i] = j >= 0 ? ((const uint16_t *)d.src)[j] : (uint16_t)0; break;
+                case 4: ((uint32_t *)d.out)[i] = j >= 0 ? ((const uint32_t *)d.src)[j] : 0u; break;
+                default: ((uint64_t *)d.out)[i] = j >= 0 ? ((const uint64_t *)d.src)[j] : 0ULL; break;
+            }
+        }
+    }
+}
+
+// String columns of a SMALL permutation gather (n <= 2048, e.g. the sort of an aggregation result): lengths, the
+// offsets scan and the byte copy in one single-block launch per batch (blockIdx.x = string column); the output
+// byte count of a permutation equals the input's, so no host round trip is needed to size the buffer.
+struct GatherStrDesc {
+    const int64_t *src_off;
+    const uint8_t *src;
+    int64_t *out_off;
+    uint8_t *out;
+};
+struct GatherStrSet {
+    GatherStrDesc d[kGatherMaxCols];
+};
+constexpr int kSmallGather = 2048;
+__global__ void __launch_bounds__(1024) gather_str_small(const __grid_constant__ GatherStrSet gs, const int64_t *__restrict__ idx, int n) {
+    __shared__ int64_t s_warp[32];
+    const GatherStrDesc &d = gs.d[blockIdx.x];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // two consecutive rows per thread
+    int64_t len0 = 0, len1 = 0, j0 = -1, j1 = -1;
+    if (2 * t < n) { j0 = idx[2 * t]; len0 = d.src_off[j0 + 1] - d.src_off[j0]; }
+    if (2 * t + 1 < n) { j1 = idx[2 * t + 1]; len1 = d.src_off[j1 + 1] - d.src_off[j1]; }
+    int64_t x = len0 + len1;
+    for (int k = 1; k < 32; k <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, x, k);
+        if (lane >= k) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = s_warp[lane];
+        for (int k = 1; k < 32; k <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, w, k);
+            if (lane >= k) w += y;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int64_t excl = x - (len0 + len1) + (warp ? s_warp[warp - 1] : 0);
+    if (2 * t < n) d.out_off[2 * t] = excl;
+    if (2 * t + 1 < n) d.out_off[2 * t + 1] = excl + len0;
+    if (2 * t == n - 1 || 2 * t + 1 == n - 1) d.out_off[n] = excl + len0 + len1;
+    if (j0 >= 0) {
+        const int64_t s = d.src_off[j0];
+        for (int64_t k = 0; k < len0; k++) d.out[excl + k] = d.src[s + k];
+    }
+    if (j1 >= 0) {
+        const int64_t s = d.src_off[j1];
+        for (int64_t k = 0; k < len1; k++) d.out[excl + len0 + k] = d.src[s + k];
+    }
+}
+
+Batch *gather_batch(const Batch &src, const int64_t *idx, int64_t n, bool idx_may_be_negative, bool permutation) {
     auto out = std::make_unique<Batch>();
     out->num_rows = n;
-    for (auto &c : src.cols) out->cols.push_back(gather_column(c, idx, n, idx_may_be_negative));
+    cudaStream_t st = ctx().stream;
+    // fused paths first; whatever they do not cover goes column by column
+    std::vector<char> done(src.cols.size(), 0);
+    out->cols.resize(src.cols.size());
+    if (n > 0) {
+        GatherSet gs;
+        int nf = 0;
+        GatherStrSet ss;
+        int ns = 0;
+        const bool small_perm = permutation && !idx_may_be_negative && n <= kSmallGather && n == src.num_rows;
+        auto flush_fixed = [&] {
+            if (!nf) return;
+            gather_fixed_multi<<<grid_for(n), 256, 0, st>>>(gs, nf, idx, n);
+            count_launch();
+            nf = 0;
+        };
+        for (size_t c = 0; c < src.cols.size(); c++) {
+            const Column &sc = src.cols[c];
+            const int w = dtype_width(sc.dtype);
+            const bool no_validity = sc.null_count == 0 && !idx_may_be_negative;
+            if (w && no_validity) {
+                Column oc;
+                oc.name = sc.name;
+                oc.dtype = sc.dtype;
+                oc.length = n;
+                oc.data = dev_alloc((size_t)n * w);
+                oc.data_bytes = n * w;
+                gs.d[nf++] = GatherDesc{as<uint8_t>(sc.data), as<uint8_t>(oc.data), w};
+                out->cols[c] = std::move(oc);
+                done[c] = 1;
+                if (nf == kGatherMaxCols) flush_fixed();
+            } else if (is_string(sc.dtype) && no_validity && small_perm && ns < kGatherMaxCols) {
+                Column oc;
+                oc.name = sc.name;
+                oc.dtype = sc.dtype;
+                oc.length = n;
+                oc.offsets = dev_alloc((size_t)(n + 1) * 8);
+                oc.data = dev_alloc((size_t)std::max<int64_t>(sc.data_bytes, 1));
+                oc.data_bytes = sc.data_bytes;
+                ss.d[ns++] = GatherStrDesc{as<int64_t>(sc.offsets), as<uint8_t>(sc.data), as<int64_t>(oc.offsets), as<uint8_t>(oc.data)};
+                out->cols[c] = std::move(oc);
+                done[c] = 1;
+            }
+        }
+        flush_fixed();
+        if (ns) {
+            gather_str_small<<<ns, 1024, 0, st>>>(ss, idx, (int)n);
+            count_launch();
+        }
+    }
+    for (size_t c = 0; c < src.cols.size(); c++)
+        if (!done[c]) out->cols[c] = gather_column(src.cols[c], idx, n, idx_may_be_negative);
     return out.release();
 }
 
