@@ -271,10 +271,10 @@ int b200_top_n(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, 
                const uint8_t *nulls_first, int64_t limit, int64_t offset, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
         // RecordBatch::top_n = argsort then slice (src/daft-recordbatch/src/ops/sort.rs:47-61)
-        Buf idx = op_argsort(*batch, key_cols, nkeys, descending, nulls_first);
         const int64_t n = batch->num_rows;
         const int64_t start = std::min<int64_t>(std::max<int64_t>(offset, 0), n);
         const int64_t end = std::min<int64_t>(n, start + std::max<int64_t>(limit, 0));
+        Buf idx = op_top_indices(*batch, key_cols, nkeys, descending, nulls_first, end);
         *out = gather_batch(*batch, as<int64_t>(idx) + start, end - start, false);
         B200_CUDA(cudaStreamSynchronize(ctx().stream));
     });

@@ -887,7 +887,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     // staged variant: R rows of every fixed-width column / R+2 string offsets / R*L bytes of a fixed-length string
     // column are bulk-copied into a per-warp shared-memory stage; ld_* = the loader reading that stage
     const int SW = staged_variant ? (env_int("B200_AGG_STAGE_WARPS", 8) >= 16 ? 16 : 8) : 8;  // warps per CTA
-    const int SRPL = std::max(1, std::min(4, env_int("B200_AGG_STAGE_RPL", 2)));                   // rows per thread per stage
+    const int SRPL = std::max(1, std::min(4, env_int("B200_AGG_STAGE_RPL", 3)));                   // rows per thread per stage
     const int SR = SW * 32 * SRPL;
     int SS = std::max(2, std::min(8, env_int("B200_AGG_STAGES", 2)));
     int stage_off = 0, stage_fixed_tx = 0;
@@ -987,9 +987,16 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
                               (size_t)G1 * (40 * (size_t)nkeys + 16);
     bool stage_fits = true;
     if (staged_variant) {
-        const size_t budget = 227 * 1024 - 1024;
-        while (SS > 2 && tier1_smem + (size_t)SS * (stage_off + 16) > budget) SS--;
-        stage_fits = stage_off > 0 && tier1_smem + (size_t)SS * (stage_off + 16) <= budget;
+        // Measured on B200 (profiles/r01_agg_variants.md): the TMA build wins when two CTAs with 768-row stages fit on
+        // an SM (ungrouped and narrow plans: +7..35%); with smaller stages or one CTA per SM the direct-load build
+        // is faster (TPC-H Q1), so the plan is then declared "not staged" and the host runs the direct build.
+        const size_t budget = (SW == 16 ? 227 * 1024 : (227 * 1024) / 2) - 1024;
+        if (env_int("B200_AGG_STAGE_FORCE", 0)) {
+            while (SS > 2 && tier1_smem + (size_t)SS * (stage_off + 16) > 226 * 1024) SS--;
+            stage_fits = stage_off > 0 && tier1_smem + (size_t)SS * (stage_off + 16) <= 226 * 1024;
+        } else {
+            stage_fits = stage_off > 0 && tier1_smem + (size_t)SS * (stage_off + 16) <= budget;
+        }
     }
 
     // ---- Keys / Vals structs
@@ -1319,13 +1326,13 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         o << "  static constexpr int STAGE_ROWS = " << SR << ", STAGES = " << SS << ", STAGE_BYTES = " << stage_off << ", RPL = " << SRPL << ";\n";
         o << "  __device__ __forceinline__ static void stage_issue(const P& p, const uint32_t dst, const uint32_t bar, const int64_t base) {\n"
           << "    uint32_t tx = " << stage_fixed_tx << "u;\n" << st_tx.str() << "    mbar_expect_tx(bar, tx);\n" << st_issue.str() << "  }\n";
-        o << "  __device__ __forceinline__ static void load_staged(const P& p, const unsigned char* st, const int64_t base, const int tid, Raw (&raw)[RPL]) {\n"
+        o << "  static constexpr bool LATE = " << (env_int("B200_AGG_STAGE_LATE", 1) ? "true" : "false") << ";\n";
+        // one row (rr = its index inside the stage); the fixed-length string check is a vote of the row's warp
+        o << "  __device__ __forceinline__ static void load_staged(const P& p, const unsigned char* st, const int64_t row, const int rr, Raw& r) {\n"
           << "    bool ok_ = true;\n"
-          << "#pragma unroll\n    for (int u = 0; u < RPL; u++) {\n      const int rr = u * " << SW * 32 << " + tid; const int64_t row = base + rr; Raw& r = raw[u];\n"
-          << ld_a.str() << "    }\n"
-          << ld_first.str() << "    const bool fast_ = __all_sync(FULL_MASK, ok_);\n"
-          << "#pragma unroll\n    for (int u = 0; u < RPL; u++) {\n      const int rr = u * " << SW * 32 << " + tid; Raw& r = raw[u];\n"
-          << ld_b.str() << "    }\n  }\n";
+          << ld_a.str()
+          << "    const bool fast_ = __all_sync(FULL_MASK, ok_);\n"
+          << ld_b.str() << "  }\n";
     }
     o << "};\n";
     if (staged_variant)
@@ -1476,6 +1483,11 @@ const Compiled &get(int op, const uint8_t *plan, size_t plan_len, const Batch &i
     if (it != g_kernels.end()) return *it->second;
     auto c = std::make_unique<Compiled>();
     const std::string src = generate(op, plan, plan_len, dt, nl, with_take, *c, variant);
+    if (op == B200_OP_AGG && variant == 2 && c->stage_bytes == 0) {  // plan not worth staging: nothing to compile
+        auto &none = *c;
+        g_kernels[key] = std::move(c);
+        return none;
+    }
     std::vector<char> cubin = compile_to_cubin(src, &c->source_path);
     require_device();
     // runtime "library" API (cudart dlopens the driver itself; the .so has no link-time libcuda dependency)
@@ -1512,8 +1524,9 @@ static void precompile_one(int op, const uint8_t *plan, size_t plan_len, const s
     if (op == B200_OP_AGG) {  // the high-cardinality variant of the same plan
         Compiled cg2;
         compile_to_cubin(generate(op, plan, plan_len, col_dtypes, col_nullable, false, cg2, 1), nullptr);
-        Compiled cg3;  // and the TMA-staged build of the low-cardinality kernel
-        compile_to_cubin(generate(op, plan, plan_len, col_dtypes, col_nullable, false, cg3, 2), nullptr);
+        Compiled cg3;  // and the TMA-staged build of the low-cardinality kernel (when the plan qualifies)
+        const std::string src3 = generate(op, plan, plan_len, col_dtypes, col_nullable, false, cg3, 2);
+        if (cg3.stage_bytes > 0) compile_to_cubin(src3, nullptr);
     }
     if (op == B200_OP_AGG && !c.key_project_plan.empty() && c.nkeys > 0) {
         Compiled c2;

@@ -738,35 +738,49 @@ __device__ __forceinline__ void agg_body_staged(const typename Prog::P &p) {
         if (aborted) break;
         const int s = (int)(i % S);
         const int64_t base = c * R;
-        typename Prog::Raw raw[RPL];
         if (stageable(c)) {
             const bool landed = mbar_wait_or_abort(smem_u32(&full[s]), (uint32_t)((i / S) & 1), t1.flag);
             if (!__all_sync(FULL_MASK, landed)) {
                 aborted = true;
                 break;
             }
-            Prog::load_staged(p, stages + (size_t)s * SB, base, (int)threadIdx.x, raw);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&empty[s]));
+            const unsigned char *st = stages + (size_t)s * SB;
+            if (Prog::LATE) {
+                // one row at a time straight from the stage (lowest register pressure); the stage is released after
+                // the chunk has been aggregated
 #pragma unroll
-            for (int u = 0; u < RPL; u++) t1.row(p, raw[u], base + u * T + threadIdx.x, true, lane);  // staged chunks are full
-            continue;
-        } else {
+                for (int u = 0; u < RPL; u++) {
+                    typename Prog::Raw r1;
+                    const int rr = u * T + threadIdx.x;
+                    Prog::load_staged(p, st, base + rr, rr, r1);
+                    t1.row(p, r1, base + rr, true, lane);  // staged chunks are full
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&empty[s]));
+            } else {
+                // copy the warp's rows to registers, release the stage at once, then aggregate
+                typename Prog::Raw raw[RPL];
 #pragma unroll
-            for (int u = 0; u < RPL; u++) {
-                const int64_t row = base + u * T + threadIdx.x;
-                if (row < n) Prog::load(p, row, raw[u]);
+                for (int u = 0; u < RPL; u++) {
+                    const int rr = u * T + threadIdx.x;
+                    Prog::load_staged(p, st, base + rr, rr, raw[u]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&empty[s]));
+#pragma unroll
+                for (int u = 0; u < RPL; u++) t1.row(p, raw[u], base + u * T + threadIdx.x, true, lane);
             }
-#pragma unroll
+        } else {  // the unstaged tail of the input: one row at a time, direct loads
+#pragma unroll 1
             for (int u = 0; u < RPL; u++) {
+                typename Prog::Raw r1;
                 const int64_t row = base + u * T + threadIdx.x;
-                if (row < n) Prog::load2(p, row, raw[u]);
+                if (row < n) {
+                    Prog::load(p, row, r1);
+                    Prog::load2(p, row, r1);
+                }
+                t1.row(p, r1, row, row < n, lane);
             }
-        }
-#pragma unroll
-        for (int u = 0; u < RPL; u++) {
-            const int64_t row = base + u * T + threadIdx.x;
-            t1.row(p, raw[u], row, row < n, lane);
         }
     }
     if (threadIdx.x == 0 && aborted) {

@@ -368,6 +368,155 @@ Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uin
     return idx;
 }
 
+// ------------------------------------------------------------------------------------------------
+// top-N by selection (RecordBatch::top_n = sort + slice in the reference, src/daft-recordbatch/src/ops/sort.rs:47-61):
+// instead of sorting all rows, find the rank-K threshold of the FIRST sort key with an MSB-first radix select
+// (11-bit digits, one 8 B/row read per pass), compact the rows at or below the threshold (ties included), and run
+// the full multi-key comparator sort on those few candidates only.
+// ------------------------------------------------------------------------------------------------
+constexpr int SEL_BITS = 11, SEL_BINS = 1 << SEL_BITS;
+
+// 64-bit selection key of row r: ascending order of the key == output order of the first sort key; nulls are
+// folded onto the smallest / greatest value (a monotone coarsening: rows it cannot separate stay candidates)
+__device__ __forceinline__ uint64_t select_key(int32_t dtype, const void *data, const uint8_t *validity, int64_t r, bool desc, bool nulls_first) {
+    if (validity != nullptr && !bit_at(validity, r)) return nulls_first ? 0ULL : 0xFFFFFFFFFFFFFFFFULL;
+    uint64_t k = 0;
+    switch (dtype) {
+        case B200_BOOL: k = bit_at((const uint8_t *)data, r); break;
+        case B200_I8: k = (uint64_t)((int64_t)((const int8_t *)data)[r]) ^ 0x8000000000000000ULL; break;
+        case B200_I16: k = (uint64_t)((int64_t)((const int16_t *)data)[r]) ^ 0x8000000000000000ULL; break;
+        case B200_I32: case B200_DATE32: k = (uint64_t)((int64_t)((const int32_t *)data)[r]) ^ 0x8000000000000000ULL; break;
+        case B200_I64: case B200_TIMESTAMP: k = (uint64_t)(((const int64_t *)data)[r]) ^ 0x8000000000000000ULL; break;
+        case B200_U8: k = ((const uint8_t *)data)[r]; break;
+        case B200_U16: k = ((const uint16_t *)data)[r]; break;
+        case B200_U32: k = ((const uint32_t *)data)[r]; break;
+        case B200_U64: k = ((const uint64_t *)data)[r]; break;
+        case B200_F32: k = ordered_f64((double)((const float *)data)[r]); break;
+        case B200_F64: k = ordered_f64(((const double *)data)[r]); break;
+        default: break;
+    }
+    return desc ? ~k : k;
+}
+
+// histogram of the SEL_BITS-bit digit at `shift` over the rows whose higher bits equal `prefix`
+__global__ void __launch_bounds__(256) select_hist(int32_t dtype, const void *__restrict__ data, const uint8_t *__restrict__ validity, int64_t n,
+                                                   int desc, int nulls_first, uint64_t prefix, int shift, int bits, int first,
+                                                   unsigned long long *__restrict__ hist) {
+    __shared__ unsigned int h[SEL_BINS];
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const uint64_t k = select_key(dtype, data, validity, i, desc != 0, nulls_first != 0);
+        const bool in = first || (k >> (shift + bits)) == prefix;
+        if (in) atomicAdd(&h[(k >> shift) & ((1u << bits) - 1u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x)
+        if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
+}
+
+// row ids (ascending) of the rows with (key >> shift) <= bound
+__global__ void __launch_bounds__(256) select_compact(int32_t dtype, const void *__restrict__ data, const uint8_t *__restrict__ validity, int64_t n,
+                                                      int desc, int nulls_first, uint64_t bound, int shift, unsigned long long *__restrict__ counter,
+                                                      int64_t *__restrict__ out, int64_t cap) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (n + 31) & ~(int64_t)31;
+    const int lane = threadIdx.x & 31;
+    for (; i < n_round; i += stride) {
+        bool take = false;
+        if (i < n) take = (select_key(dtype, data, validity, i, desc != 0, nulls_first != 0) >> shift) <= bound;
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int64_t pos = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+            if (take && pos < cap) out[pos] = i;
+        }
+    }
+}
+
+__global__ void map_indices(const int64_t *__restrict__ cand, const int64_t *__restrict__ local, int64_t n, int64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = cand[local[i]];
+}
+
+// first `k` entries of the argsort (k clamped to the row count)
+Buf op_top_indices(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending, const uint8_t *nulls_first, int64_t k) {
+    require_device();
+    if (nkeys < 1) fail("top_n: need at least one sort key");
+    const int64_t n = b.num_rows;
+    k = std::max<int64_t>(0, std::min(k, n));
+    const int32_t c0 = key_cols[0];
+    if (c0 < 0 || c0 >= (int32_t)b.cols.size()) fail("top_n: key column index out of range");
+    const Column &kc = b.cols[c0];
+    const bool selectable = n > (1 << 16) && k > 0 && k <= n / 16 && !is_string(kc.dtype) && kc.dtype != B200_NULL;
+    if (!selectable) return op_argsort(b, key_cols, nkeys, descending, nulls_first);
+    cudaStream_t st = ctx().stream;
+    const bool desc = descending && descending[0];
+    const bool nf = nulls_first ? nulls_first[0] != 0 : desc;
+    const uint8_t *validity = kc.null_count > 0 ? as<uint8_t>(kc.validity) : nullptr;
+    const void *data = kc.data ? kc.data->ptr : nullptr;
+    const int total_bits = 64;
+    Buf hist = dev_alloc((size_t)SEL_BINS * 8);
+    std::vector<unsigned long long> h(SEL_BINS);
+    uint64_t prefix = 0;
+    int64_t below = 0;          // rows strictly before the selected bucket
+    int64_t bucket = n;         // rows inside it
+    int shift = total_bits;     // bits of the key not yet fixed
+    int64_t rank = k;           // rank of the threshold inside the current bucket (1-based)
+    const int64_t slack = 4096;
+    while (shift > 0 && bucket > slack) {
+        const int bits = std::min(SEL_BITS, shift);
+        const int nshift = shift - bits;
+        fill_u8(hist->ptr, 0, (size_t)SEL_BINS * 8);
+        select_hist<<<sgrid(n), 256, 0, st>>>(kc.dtype, data, validity, n, desc ? 1 : 0, nf ? 1 : 0, prefix, nshift, bits, shift == total_bits ? 1 : 0,
+                                              as<unsigned long long>(hist));
+        count_launch();
+        B200_CUDA(cudaMemcpyAsync(h.data(), hist->ptr, (size_t)SEL_BINS * 8, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        int64_t acc = 0;
+        int d = 0;
+        for (; d < SEL_BINS; d++) {
+            if (acc + (int64_t)h[d] >= rank) break;
+            acc += (int64_t)h[d];
+        }
+        if (d == SEL_BINS) fail("top_n: selection histogram is inconsistent");
+        below += acc;
+        rank -= acc;
+        bucket = (int64_t)h[d];
+        prefix = (prefix << bits) | (uint64_t)d;
+        shift = nshift;
+    }
+    const int64_t ncand = below + bucket;
+    if (ncand > n / 2) return op_argsort(b, key_cols, nkeys, descending, nulls_first);  // massive ties: nothing was saved
+    Buf cand = dev_alloc((size_t)ncand * 8), counter = dev_alloc_zero(8);
+    select_compact<<<sgrid(n), 256, 0, st>>>(kc.dtype, data, validity, n, desc ? 1 : 0, nf ? 1 : 0, prefix, shift, as<unsigned long long>(counter),
+                                             as<int64_t>(cand), ncand);
+    count_launch();
+    if (read_i64(as<int64_t>(counter)) != ncand) fail("top_n: candidate count mismatch");
+    // candidates arrive in arbitrary warp order: ties are unordered in the reference too (unstable sort)
+    Batch keys_only;
+    keys_only.num_rows = n;
+    std::vector<int32_t> kidx(nkeys);
+    for (int i = 0; i < nkeys; i++) {
+        const int32_t ci = key_cols[i];
+        if (ci < 0 || ci >= (int32_t)b.cols.size()) fail("top_n: key column index out of range");
+        keys_only.cols.push_back(b.cols[ci]);
+        kidx[i] = i;
+    }
+    std::unique_ptr<Batch> cb(gather_batch(keys_only, as<int64_t>(cand), ncand, false));
+    Buf local = op_argsort(*cb, kidx.data(), nkeys, descending, nulls_first);
+    Buf out = dev_alloc((size_t)std::max<int64_t>(k, 1) * 8);
+    map_indices<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(as<int64_t>(cand), as<int64_t>(local), k, as<int64_t>(out));
+    count_launch();
+    B200_CUDA(cudaStreamSynchronize(st));
+    return out;
+}
+
 // group slots ordered by their first row (first-occurrence group order, inline_agg.rs:804-807)
 __global__ void __launch_bounds__(1024) small_sort_pairs_kernel(const unsigned long long *__restrict__ keys,
                                                                 const int64_t *__restrict__ vals, int64_t n,

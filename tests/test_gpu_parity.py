@@ -225,6 +225,37 @@ def test_sort_multikey(gpu):
     assert_tables_equal(got, O.sort(tbl, ["i64"], [True], [False]).slice(5, 10))
 
 
+@pytest.mark.parametrize("dtype", ["f64", "i64", "i32", "f32"])
+def test_top_n_selection_path(gpu, dtype):
+    """Large inputs take the radix-select path (sort.cu op_top_indices): same rows as sort + slice
+    (src/daft-recordbatch/src/ops/sort.rs:47-61).  Keys are unique so the expected order is total; a second case
+    has massive ties on the first key and relies on the second key."""
+    rng = np.random.default_rng(11)
+    n = 300_000
+    if dtype.startswith("f"):
+        vals = rng.permutation(n).astype(np.float64) * 0.37 - 40_000.0
+        vals[:7] = np.nan
+        arr = pa.array(vals.astype(np.float32 if dtype == "f32" else np.float64))
+    else:
+        vals = rng.permutation(n).astype(np.int64) * 3 - 400_000
+        arr = pa.array(vals.astype(np.int32 if dtype == "i32" else np.int64))
+    mask = rng.random(n) < 0.001
+    arr = pa.array(arr.to_numpy(zero_copy_only=False), mask=mask, type=arr.type)
+    tie = pa.array((np.arange(n) % 3).astype(np.int64))
+    uniq = pa.array(rng.permutation(n).astype(np.int64))
+    tbl = pa.table({"k": arr, "tie": tie, "u": uniq})
+    c = gpu.col
+    rb = RB(gpu, tbl)
+    for desc, nf, limit, offset in ((False, False, 100, 0), (True, False, 57, 13), (False, True, 500, 0), (True, True, 1000, 250)):
+        got = rb.top_n([c("k"), c("u")], limit, descending=[desc, False], nulls_first=[nf, False], offset=offset).to_arrow_table()
+        want = O.sort(tbl, ["k", "u"], [desc, False], [nf, False]).slice(offset, limit)
+        assert_tables_equal(got, want)
+    # first key has 3 distinct values: the threshold bucket holds a third of the input
+    got = rb.top_n([c("tie"), c("u")], 64, descending=[True, True]).to_arrow_table()
+    want = O.sort(tbl, ["tie", "u"], [True, True], [True, True]).slice(0, 64)
+    assert_tables_equal(got, want)
+
+
 def test_sort_by_expression(gpu):
     tbl = pa.table({"a": [3, 1, 2, None], "b": [1.0, 5.0, -1.0, 0.0]})
     c = gpu.col
