@@ -1,7 +1,4 @@
-// generated by embed.py -- do not edit
-namespace b200 { namespace jit {
-extern const char* const kPreludeXxh3_chunks[] = {
-R"B200RAW(// XXH3-64 (seeded, default secret) for sm_100a device code.
+// XXH3-64 (seeded, default secret) for sm_100a device code.
 //
 // Replaces xxhash_rust::xxh3::xxh3_64_with_seed as called by the reference at
 // src/daft-core/src/kernels/hashing.rs:164-170.  Bit-exact with the canonical xxHash v0.8
@@ -166,8 +163,7 @@ B200_HD uint64_t ld64u(const uint8_t *p) {
 }
 B200_HD uint64_t sec64(int off) {
 #ifdef __CUDA_ARCH__
-    re)B200RAW",
-R"B200RAW(turn ld64u(d_secret + off);
+    return ld64u(d_secret + off);
 #else
     return ld64u(kSecret + off);
 #endif
@@ -269,10 +265,8 @@ B200_HD uint64_t hash_bytes(const uint8_t *in, int64_t len, uint64_t seed) {
 
 }  // namespace xxh
 }  // namespace b200
-)B200RAW",
-nullptr};
-extern const char* const kPreludeJit_chunks[] = {
-R"B200RAW(// Device-side skeletons of the JIT-specialised pipeline kernels (sm_100a).
+
+// Device-side skeletons of the JIT-specialised pipeline kernels (sm_100a).
 //
 // The host (jit.cpp) turns a serialised plan (include/daft_b200.h "plan encoding") into a `Prog`
 // struct -- straight-line, fully typed code for the filter / key / aggregate-input expressions --
@@ -442,8 +436,7 @@ __device__ __forceinline__ Str str_left(Str a, int64_t nchars) {
 __device__ __forceinline__ void civil_from_days(int64_t z, int32_t &y, int32_t &m, int32_t &d) {
     z += 719468;
     const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
-    const uint32_t doe = (uint32_t)(z - era * 1)B200RAW",
-R"B200RAW(46097);
+    const uint32_t doe = (uint32_t)(z - era * 146097);
     const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
     const int64_t yy = (int64_t)yoe + era * 400;
     const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
@@ -598,8 +591,7 @@ __device__ __forceinline__ void filter_body(const typename Prog::P &p, int pass)
 // "hash equal AND comparator" rule, src/daft-recordbatch/src/ops/inline_agg.rs:760-784).
 #ifndef B200_AGG_WARPS
 #define B200_AGG_WARPS 8  // warps per CTA of the aggregate kernels (the staged build may ask for 16)
-)B200RAW",
-R"B200RAW(#endif
+#endif
 constexpr int AGG_WARPS = B200_AGG_WARPS;
 constexpr unsigned long long AGG_EMPTY = 0xFFFFFFFFFFFFFFFFULL;     // min-row cell of an unclaimed slot
 constexpr unsigned long long AGG_CLAIMING = 0xFFFFFFFFFFFFFFFEULL;  // (MODE 1) slot being published
@@ -754,8 +746,7 @@ __device__ __forceinline__ void agg_body_global(const typename Prog::P &p) {
 // Rare path of the low-cardinality kernel, kept out of line so that its registers do not burden the streaming loop:
 // find/claim the group's global slot, try to adopt it into the CTA's tier 1, otherwise update it globally.
 // Returns the tier-1 index (>= 0), -2 when the row was accumulated globally, -1 when the table is full.
-template <class Prog)B200RAW",
-R"B200RAW(>
+template <class Prog>
 __device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const typename Prog::Vals &vals, int64_t row,
                                                 unsigned long long tag, long long *s_slot, unsigned long long *s_fp,
                                                 typename Prog::Keys *s_keys) {
@@ -911,8 +902,7 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
     int abandoned = 0;  // status flag as of the previous chunk
     int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp;
-    f)B200RAW",
-R"B200RAW(or (; c < nfull; c += total_warps) {
+    for (; c < nfull; c += total_warps) {
         if (__any_sync(FULL_MASK, abandoned != 0 || t1.gave_up)) break;
         agg_chunk<Prog, true>(t1, p, c * chunk, n, lane, abandoned);
     }
@@ -1065,8 +1055,7 @@ __device__ __forceinline__ void agg_body_staged(const typename Prog::P &p) {
         } else {  // the unstaged tail of the input: one row at a time, direct loads
 #pragma unroll 1
             for (int u = 0; u < RPL; u++) {
-                ty)B200RAW",
-R"B200RAW(pename Prog::Raw r1;
+                typename Prog::Raw r1;
                 const int64_t row = base + u * T + threadIdx.x;
                 if (row < n) {
                     Prog::load(p, row, r1);
@@ -1088,6 +1077,29 @@ R"B200RAW(pename Prog::Raw r1;
 
 }  // namespace jit
 }  // namespace b200
-)B200RAW",
-nullptr};
-}}
+
+using namespace b200;
+using namespace b200::jit;
+struct Prog {
+  typedef Params<13, 1> P;
+  static constexpr int IV_N = 0;
+  static constexpr int PTR_TAKE = 0;
+  __device__ __forceinline__ static void row(const P& p, const int64_t out_row, const int64_t row, const bool active, const int pass) {
+    const bool rowok = active && row >= 0;
+    const bool k0 = rowok;
+    Str v0{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[1]; const int64_t a_ = of_[row]; v0.p = (const uint8_t*)p.ptr[2] + a_; v0.len = of_[row + 1] - a_; }
+    // ---- output 0 (large_utf8)
+    { const unsigned m_ = __ballot_sync(FULL_MASK, active && k0); if (pass == 0 && (threadIdx.x & 31) == 0) ((uint32_t*)p.ptr[3])[out_row >> 5] = m_; }
+    if (pass == 0) { if (active) ((int64_t*)p.ptr[4])[out_row] = k0 ? v0.len : 0; }
+    else if (active && k0) { uint8_t* d_ = (uint8_t*)p.ptr[5] + ((const int64_t*)p.ptr[6])[out_row]; for (int64_t j_ = 0; j_ < v0.len; j_++) d_[j_] = v0.p[j_]; }
+    const bool k1 = rowok;
+    Str v1{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[7]; const int64_t a_ = of_[row]; v1.p = (const uint8_t*)p.ptr[8] + a_; v1.len = of_[row + 1] - a_; }
+    // ---- output 1 (large_utf8)
+    { const unsigned m_ = __ballot_sync(FULL_MASK, active && k1); if (pass == 0 && (threadIdx.x & 31) == 0) ((uint32_t*)p.ptr[9])[out_row >> 5] = m_; }
+    if (pass == 0) { if (active) ((int64_t*)p.ptr[10])[out_row] = k1 ? v1.len : 0; }
+    else if (active && k1) { uint8_t* d_ = (uint8_t*)p.ptr[11] + ((const int64_t*)p.ptr[12])[out_row]; for (int64_t j_ = 0; j_ < v1.len; j_++) d_[j_] = v1.p[j_]; }
+  }
+};
+extern "C" __global__ void __launch_bounds__(256) b200_project_k(const __grid_constant__ Prog::P p, int pass) { project_body<Prog>(p, pass); }

@@ -1,7 +1,4 @@
-// generated by embed.py -- do not edit
-namespace b200 { namespace jit {
-extern const char* const kPreludeXxh3_chunks[] = {
-R"B200RAW(// XXH3-64 (seeded, default secret) for sm_100a device code.
+// XXH3-64 (seeded, default secret) for sm_100a device code.
 //
 // Replaces xxhash_rust::xxh3::xxh3_64_with_seed as called by the reference at
 // src/daft-core/src/kernels/hashing.rs:164-170.  Bit-exact with the canonical xxHash v0.8
@@ -166,8 +163,7 @@ B200_HD uint64_t ld64u(const uint8_t *p) {
 }
 B200_HD uint64_t sec64(int off) {
 #ifdef __CUDA_ARCH__
-    re)B200RAW",
-R"B200RAW(turn ld64u(d_secret + off);
+    return ld64u(d_secret + off);
 #else
     return ld64u(kSecret + off);
 #endif
@@ -269,10 +265,8 @@ B200_HD uint64_t hash_bytes(const uint8_t *in, int64_t len, uint64_t seed) {
 
 }  // namespace xxh
 }  // namespace b200
-)B200RAW",
-nullptr};
-extern const char* const kPreludeJit_chunks[] = {
-R"B200RAW(// Device-side skeletons of the JIT-specialised pipeline kernels (sm_100a).
+
+// Device-side skeletons of the JIT-specialised pipeline kernels (sm_100a).
 //
 // The host (jit.cpp) turns a serialised plan (include/daft_b200.h "plan encoding") into a `Prog`
 // struct -- straight-line, fully typed code for the filter / key / aggregate-input expressions --
@@ -442,8 +436,7 @@ __device__ __forceinline__ Str str_left(Str a, int64_t nchars) {
 __device__ __forceinline__ void civil_from_days(int64_t z, int32_t &y, int32_t &m, int32_t &d) {
     z += 719468;
     const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
-    const uint32_t doe = (uint32_t)(z - era * 1)B200RAW",
-R"B200RAW(46097);
+    const uint32_t doe = (uint32_t)(z - era * 146097);
     const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
     const int64_t yy = (int64_t)yoe + era * 400;
     const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
@@ -598,8 +591,7 @@ __device__ __forceinline__ void filter_body(const typename Prog::P &p, int pass)
 // "hash equal AND comparator" rule, src/daft-recordbatch/src/ops/inline_agg.rs:760-784).
 #ifndef B200_AGG_WARPS
 #define B200_AGG_WARPS 8  // warps per CTA of the aggregate kernels (the staged build may ask for 16)
-)B200RAW",
-R"B200RAW(#endif
+#endif
 constexpr int AGG_WARPS = B200_AGG_WARPS;
 constexpr unsigned long long AGG_EMPTY = 0xFFFFFFFFFFFFFFFFULL;     // min-row cell of an unclaimed slot
 constexpr unsigned long long AGG_CLAIMING = 0xFFFFFFFFFFFFFFFEULL;  // (MODE 1) slot being published
@@ -754,8 +746,7 @@ __device__ __forceinline__ void agg_body_global(const typename Prog::P &p) {
 // Rare path of the low-cardinality kernel, kept out of line so that its registers do not burden the streaming loop:
 // find/claim the group's global slot, try to adopt it into the CTA's tier 1, otherwise update it globally.
 // Returns the tier-1 index (>= 0), -2 when the row was accumulated globally, -1 when the table is full.
-template <class Prog)B200RAW",
-R"B200RAW(>
+template <class Prog>
 __device__ __noinline__ long long agg_slow_path(const typename Prog::P &p, const typename Prog::Vals &vals, int64_t row,
                                                 unsigned long long tag, long long *s_slot, unsigned long long *s_fp,
                                                 typename Prog::Keys *s_keys) {
@@ -911,8 +902,7 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
     int abandoned = 0;  // status flag as of the previous chunk
     int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp;
-    f)B200RAW",
-R"B200RAW(or (; c < nfull; c += total_warps) {
+    for (; c < nfull; c += total_warps) {
         if (__any_sync(FULL_MASK, abandoned != 0 || t1.gave_up)) break;
         agg_chunk<Prog, true>(t1, p, c * chunk, n, lane, abandoned);
     }
@@ -1065,8 +1055,7 @@ __device__ __forceinline__ void agg_body_staged(const typename Prog::P &p) {
         } else {  // the unstaged tail of the input: one row at a time, direct loads
 #pragma unroll 1
             for (int u = 0; u < RPL; u++) {
-                ty)B200RAW",
-R"B200RAW(pename Prog::Raw r1;
+                typename Prog::Raw r1;
                 const int64_t row = base + u * T + threadIdx.x;
                 if (row < n) {
                     Prog::load(p, row, r1);
@@ -1088,6 +1077,211 @@ R"B200RAW(pename Prog::Raw r1;
 
 }  // namespace jit
 }  // namespace b200
-)B200RAW",
-nullptr};
-}}
+
+using namespace b200;
+using namespace b200::jit;
+struct Prog {
+  typedef Params<18, 2> P;
+  static constexpr int IV_N = 0, IV_MASK = 1, PTR_TAG = 0, PTR_MINROW = 8, PTR_FLAG = 1, MODE = 0;
+  static constexpr int NKEYS = 2, G1 = 4, NLANE = 7, NWARP = 0, U = 2;
+  static constexpr bool PIPE = false;
+  struct Raw {
+    int32_t c6;
+    int64_t o4a, o4b; uint64_t pk4;
+    int64_t o5a, o5b; uint64_t pk5;
+    int64_t c0;
+    double c1;
+    double c2;
+    double c3;
+    int pad_;
+  };
+  struct Keys {
+    Str v0; bool k0;
+    uint64_t p0;
+    Str v1; bool k1;
+    uint64_t p1;
+    int pad_;
+  };
+  struct Vals {
+    int64_t a0; bool k0;
+    double a1; bool k1;
+    double a2; bool k2;
+    double a3; bool k3;
+    double a4; bool k4;
+    int pad_;
+  };
+  __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {
+    r.c6 = ((const int32_t*)p.ptr[9])[row];
+    { const int64_t* of_ = (const int64_t*)p.ptr[10]; r.o4a = of_[row]; r.o4b = of_[row + 1]; }
+    { const int64_t* of_ = (const int64_t*)p.ptr[12]; r.o5a = of_[row]; r.o5b = of_[row + 1]; }
+    r.c0 = ((const int64_t*)p.ptr[14])[row];
+    r.c1 = ((const double*)p.ptr[15])[row];
+    r.c2 = ((const double*)p.ptr[16])[row];
+    r.c3 = ((const double*)p.ptr[17])[row];
+  }
+  __device__ __forceinline__ static void load2(const P& p, const int64_t row, Raw& r) {
+    r.pk4 = str_pack4(Str{(const uint8_t*)p.ptr[11] + r.o4a, r.o4b - r.o4a});
+    r.pk5 = str_pack4(Str{(const uint8_t*)p.ptr[13] + r.o5a, r.o5b - r.o5a});
+  }
+  __device__ __forceinline__ static void load0(const P& p, const int64_t row, Raw& r) {
+  }
+  __device__ __forceinline__ static void copy0(Raw& d, const Raw& s) {
+  }
+  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {
+    const int32_t v0 = r.c6; const bool k0 = true;
+    const int32_t v1 = (int32_t)(10471LL); const bool k1 = true;
+    const bool v2 = v0 <= v1;
+    const bool k2 = k0 && k1;
+    if (!(k2 && v2)) return false;
+    const Str v3{(const uint8_t*)p.ptr[11] + r.o4a, r.o4b - r.o4a};
+    const bool k3 = true;
+    keys.v0 = v3; keys.k0 = k3;
+    keys.p0 = keys.k0 ? r.pk4 : 0ULL;
+    const Str v4{(const uint8_t*)p.ptr[13] + r.o5a, r.o5b - r.o5a};
+    const bool k4 = true;
+    keys.v1 = v4; keys.k1 = k4;
+    keys.p1 = keys.k1 ? r.pk5 : 0ULL;
+    const int64_t v5 = r.c0; const bool k5 = true;
+    vals.a0 = (int64_t)v5; vals.k0 = k5;
+    const double v6 = r.c1; const bool k6 = true;
+    vals.a1 = (double)v6; vals.k1 = k6;
+    const double v8 = __longlong_as_double(4607182418800017408LL); const bool k8 = true;
+    const double v9 = r.c2; const bool k9 = true;
+    const double v10 = v8 - v9;
+    const bool k10 = k8 && k9;
+    const double v11 = v6 * v10;
+    const bool k11 = k6 && k10;
+    vals.a2 = (double)v11; vals.k2 = k11;
+    const double v18 = r.c3; const bool k18 = true;
+    const double v19 = v8 + v18;
+    const bool k19 = k8 && k18;
+    const double v20 = v11 * v19;
+    const bool k20 = k11 && k19;
+    vals.a3 = (double)v20; vals.k3 = k20;
+    vals.a4 = (double)v9; vals.k4 = k9;
+    return true;
+  }
+  __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {
+    const bool rowok = true;
+    const bool k3 = rowok;
+    Str v3{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[10]; const int64_t a_ = of_[row]; v3.p = (const uint8_t*)p.ptr[11] + a_; v3.len = of_[row + 1] - a_; }
+    keys.v0 = v3; keys.k0 = k3;
+    keys.p0 = keys.k0 ? str_pack8(keys.v0) : 0ULL;
+    const bool k4 = rowok;
+    Str v4{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[12]; const int64_t a_ = of_[row]; v4.p = (const uint8_t*)p.ptr[13] + a_; v4.len = of_[row + 1] - a_; }
+    keys.v1 = v4; keys.k1 = k4;
+    keys.p1 = keys.k1 ? str_pack8(keys.v1) : 0ULL;
+  }
+  __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {
+    return true && (a.k0 == b.k0) && (!a.k0 || str_eq_packed(a.v0, a.p0, b.v0, b.p0)) && (a.k1 == b.k1) && (!a.k1 || str_eq_packed(a.v1, a.p1, b.v1, b.p1));
+  }
+  __device__ __forceinline__ static void finish_keys(Keys& k) {
+    k.p0 = k.k0 ? str_pack8(k.v0) : 0ULL;
+    k.p1 = k.k1 ? str_pack8(k.v1) : 0ULL;
+  }
+  __device__ __forceinline__ static uint64_t fingerprint(const Keys& k) {
+    uint64_t f = 0x9E3779B97F4A7C15ULL;
+    f = (f ^ (k.k0 ? (((uint64_t)k.v0.len <= 4ULL ? k.p0 : xxh::hash_bytes(k.v0.p, k.v0.len, 0ULL)) ^ ((uint64_t)k.v0.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    f = (f ^ (k.k1 ? (((uint64_t)k.v1.len <= 4ULL ? k.p1 : xxh::hash_bytes(k.v1.p, k.v1.len, 0ULL)) ^ ((uint64_t)k.v1.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    return f;
+  }
+  __device__ __forceinline__ static uint64_t code(const Keys& k) {
+    uint64_t c = 0x4000000000000000ULL; bool ex = true;
+    { const uint64_t l_ = k.k0 ? (uint64_t)k.v0.len : 0ULL; ex = ex && (l_ <= 3ULL); c |= (k.p0 & 16777215ULL) << 0; c |= (l_ & 7ULL) << 24; }
+    { const uint64_t l_ = k.k1 ? (uint64_t)k.v1.len : 0ULL; ex = ex && (l_ <= 3ULL); c |= (k.p1 & 16777215ULL) << 27; c |= (l_ & 7ULL) << 51; }
+    return ex ? c : (fingerprint(k) | 0x8000000000000000ULL);
+  }
+  __device__ __forceinline__ static void lane_init(unsigned long long* cells) {
+    cells[0] = 0ULL;
+    cells[32] = 0ULL;
+    cells[64] = 0ULL;
+    cells[96] = 0ULL;
+    cells[128] = 0ULL;
+    cells[160] = 0ULL;
+    cells[192] = 0xFFFFFFFFFFFFFFFFULL;
+  }
+  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v, const int64_t row) {
+    if (v.k0) cells[0] += (unsigned long long)v.a0;
+    if (v.k1) cells[32] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[32]) + v.a1);
+    if (v.k2) cells[64] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[64]) + v.a2);
+    if (v.k3) cells[96] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[96]) + v.a3);
+    if (v.k4) cells[128] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[128]) + v.a4);
+    cells[160] += 1ULL;
+    if ((unsigned long long)row < cells[192]) cells[192] = (unsigned long long)row;
+  }
+  __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {
+    if (v.k0) atomicAdd(((unsigned long long*)p.ptr[2]) + slot, (unsigned long long)v.a0);
+    if (v.k1) atomicAdd((double*)(((unsigned long long*)p.ptr[3]) + slot), v.a1);
+    if (v.k2) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), v.a2);
+    if (v.k3) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), v.a3);
+    if (v.k4) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), v.a4);
+    atomicAdd(((unsigned long long*)p.ptr[7]) + slot, 1ULL);
+    atomicMin(((unsigned long long*)p.ptr[8]) + slot, (unsigned long long)row);
+  }
+  static constexpr int T2 = 1024, NCELLS = 7;
+  __device__ __forceinline__ static void t2_init(unsigned long long* t2c, const int t) {
+    t2c[0 * T2 + t] = 0ULL;
+    t2c[1 * T2 + t] = 0ULL;
+    t2c[2 * T2 + t] = 0ULL;
+    t2c[3 * T2 + t] = 0ULL;
+    t2c[4 * T2 + t] = 0ULL;
+    t2c[5 * T2 + t] = 0ULL; t2c[6 * T2 + t] = 0xFFFFFFFFFFFFFFFFULL;
+  }
+  __device__ __forceinline__ static void t2_update(unsigned long long* t2c, const int t, const Vals& v, const int64_t row) {
+    if (v.k0) atomicAdd((t2c + 0 * T2 + t), (unsigned long long)v.a0);
+    if (v.k1) atomicAdd((double*)(t2c + 1 * T2 + t), v.a1);
+    if (v.k2) atomicAdd((double*)(t2c + 2 * T2 + t), v.a2);
+    if (v.k3) atomicAdd((double*)(t2c + 3 * T2 + t), v.a3);
+    if (v.k4) atomicAdd((double*)(t2c + 4 * T2 + t), v.a4);
+    atomicAdd(t2c + 5 * T2 + t, 1ULL);
+    atomicMin(t2c + 6 * T2 + t, (unsigned long long)row);
+  }
+  __device__ __forceinline__ static void t2_flush(const P& p, const long long slot, const unsigned long long* t2c, const int t) {
+    atomicAdd(((unsigned long long*)p.ptr[2]) + slot, t2c[0 * T2 + t]);
+    atomicAdd((double*)(((unsigned long long*)p.ptr[3]) + slot), __longlong_as_double((long long)t2c[1 * T2 + t]));
+    atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), __longlong_as_double((long long)t2c[2 * T2 + t]));
+    atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), __longlong_as_double((long long)t2c[3 * T2 + t]));
+    atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), __longlong_as_double((long long)t2c[4 * T2 + t]));
+    atomicAdd(((unsigned long long*)p.ptr[7]) + slot, t2c[5 * T2 + t]);
+    atomicMin(((unsigned long long*)p.ptr[8]) + slot, t2c[6 * T2 + t]);
+  }
+  __device__ __forceinline__ static void warp_cells(const Vals& v, const bool in_g, unsigned long long* wcell, const int lane) {
+  }
+  __device__ __forceinline__ static void flush(const P& p, const long long slot, const unsigned long long* lcell, const size_t lstride,
+                                               const unsigned long long* wcell, const size_t wstride, const int lane) {
+    {
+      unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 0 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[2]) + slot, a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 32 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[3]) + slot), a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 64 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 96 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 128 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), a_);
+    }
+    { unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 160 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[7]) + slot, a_); }
+    { unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 192 + lane]; a_ = t_ < a_ ? t_ : a_; }
+      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }
+      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[8]) + slot, a_); }
+  }
+};
+extern "C" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_global<Prog>(p); }

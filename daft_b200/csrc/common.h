@@ -55,6 +55,7 @@ using Buf = std::shared_ptr<DevAlloc>;
 Buf dev_alloc(size_t bytes);                    // uninitialised
 Buf dev_alloc_zero(size_t bytes);
 Buf dev_borrow(const void *ptr, size_t bytes);  // non-owning view
+Buf dev_sub(const Buf &parent, size_t offset, size_t bytes);  // view into `parent` that keeps it alive
 template <typename T>
 inline T *as(const Buf &b) { return b ? reinterpret_cast<T *>(b->ptr) : nullptr; }
 

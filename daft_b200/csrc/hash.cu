@@ -60,20 +60,63 @@ __global__ void __launch_bounds__(256) hash_null_kernel(const uint64_t *seed, ui
         out[i] = xxh::hash_empty(seed ? seed[i] : 0);
 }
 
+// 8 bytes at any alignment from three aligned words (reads at most 3 bytes before p and 11 past p + 8: inside the
+// allocation's 16-byte tail slack, see common.h)
+__device__ __forceinline__ uint64_t ld_le8(const uint8_t *p) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8u;
+    const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);
+    return (uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32);
+}
+
+// Strings / binary: HB_U rows per thread, phase 1 = offsets (and seeds) of all rows, phase 2 = the first 8 bytes of
+// all rows (branch-free aligned words), phase 3 = the hashes.  Values up to 8 bytes (flags, codes, short names) are
+// hashed from registers; 9..16 bytes need one more load; longer values take the generic byte reader.
+constexpr int HB_U = 4;
 __global__ void __launch_bounds__(256) hash_bytes_kernel(const int64_t *__restrict__ offsets, const uint8_t *__restrict__ data,
                                                           const uint8_t *__restrict__ validity, const uint64_t *seed,
                                                           uint64_t *out, int64_t n) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t s = seed ? seed[i] : 0;
-        uint64_t h;
-        if (validity && !bit_at(validity, i)) {
-            h = xxh::hash_empty(s);
-        } else {
-            int64_t o = offsets[i], len = offsets[i + 1] - o;
-            h = xxh::hash_bytes(data + o, len, s);
+    const int64_t tile = (int64_t)blockDim.x * HB_U;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
+        int64_t o[HB_U], len[HB_U];
+        uint64_t s[HB_U], first8[HB_U];
+        bool ok[HB_U];
+#pragma unroll
+        for (int u = 0; u < HB_U; u++) {
+            const int64_t i = base + (int64_t)u * blockDim.x + threadIdx.x;
+            o[u] = 0;
+            len[u] = 0;
+            s[u] = 0;
+            ok[u] = false;
+            if (i < n) {
+                o[u] = offsets[i];
+                len[u] = offsets[i + 1] - o[u];
+                s[u] = seed ? seed[i] : 0;
+                ok[u] = !(validity && !bit_at(validity, i));
+            }
         }
-        out[i] = h;
+#pragma unroll
+        for (int u = 0; u < HB_U; u++) first8[u] = (ok[u] && len[u] > 0 && len[u] <= 16) ? ld_le8(data + o[u]) : 0ULL;
+#pragma unroll
+        for (int u = 0; u < HB_U; u++) {
+            const int64_t i = base + (int64_t)u * blockDim.x + threadIdx.x;
+            if (i >= n) continue;
+            const int64_t L = len[u];
+            uint64_t h;
+            if (!ok[u] || L == 0) {
+                h = xxh::hash_empty(s[u]);  // a null string hashes the empty slice WITH the seed (hashing.rs:243-265)
+            } else if (L <= 3) {
+                const uint32_t w = (uint32_t)first8[u];
+                h = xxh::hash_1to3(w & 0xff, (w >> (8 * (unsigned)(L >> 1))) & 0xff, (w >> (8 * (unsigned)(L - 1))) & 0xff, (uint32_t)L, s[u]);
+            } else if (L <= 8) {
+                h = xxh::hash_4to8((uint32_t)first8[u], (uint32_t)(first8[u] >> (8 * (unsigned)(L - 4))), (uint32_t)L, s[u]);
+            } else if (L <= 16) {
+                h = xxh::hash_9to16(first8[u], ld_le8(data + o[u] + L - 8), (uint64_t)L, s[u]);
+            } else {
+                h = xxh::hash_bytes(data + o[u], L, s[u]);
+            }
+            out[i] = h;
+        }
     }
 }
 

@@ -513,6 +513,7 @@ struct AggTier1 {
     unsigned long long tfp[G1];  // register copy of the tier-1 codes (entries only go 0 -> final value: a stale copy
                                  // can only miss an entry -> slow path -> refresh)
     int slow_rows;
+    bool gave_up;  // this lane saw (or raised) the status flag on its slow path: the kernel's result will be discarded
     volatile int *flag;
 
     static __host__ __device__ constexpr size_t smem_bytes() {
@@ -535,6 +536,7 @@ struct AggTier1 {
         for (int g = 0; g < G1; g++) Prog::lane_init(my_lcell + (size_t)g * NL * 32);
         my_wcell = s_wcell + (size_t)warp * G1 * NWS;
         slow_rows = 0;
+        gave_up = false;
         flag = (volatile int *)p.ptr[Prog::PTR_FLAG];
     }
     __device__ __forceinline__ void refresh() {
@@ -559,13 +561,21 @@ struct AggTier1 {
             if (!Prog::keys_equal(kv, s_keys[lid])) lid = -1;
         }
         if (live && lid < 0) {  // rare here: first rows of a CTA, or a group beyond tier 1
-            const typename Prog::Vals vcopy = vals;
-            const long long q = agg_slow_path<Prog>(p, vcopy, r, fp, s_slot, s_fp, s_keys);
-            if (q >= 0) lid = (int)q;
-            else live = false;  // accumulated globally (or table overflow)
-            refresh();
-            // most rows missing tier 1 means the input is not low-cardinality: hand over to the global kernel
-            if (++slow_rows > 64 + G1) *flag = 2;
+            if (*flag) {  // already abandoned by someone: do not spend a table probe on a result that is discarded
+                gave_up = true;
+                live = false;
+            } else {
+                const typename Prog::Vals vcopy = vals;
+                const long long q = agg_slow_path<Prog>(p, vcopy, r, fp, s_slot, s_fp, s_keys);
+                if (q >= 0) lid = (int)q;
+                else live = false;  // accumulated globally (or table overflow)
+                refresh();
+                // most rows missing tier 1 means the input is not low-cardinality: hand over to the global kernel
+                if (++slow_rows > 64 + G1) {
+                    *flag = 2;
+                    gave_up = true;
+                }
+            }
         }
         if (live) Prog::lane_update(my_lcell + (size_t)lid * NL * 32, vals, r);
         if (NW > 0) {  // valid / null counts of nullable inputs: one ballot per tier-1 group
@@ -625,7 +635,7 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     int abandoned = 0;  // status flag as of the previous chunk
     int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp;
     for (; c < nfull; c += total_warps) {
-        if (__any_sync(FULL_MASK, abandoned != 0)) break;
+        if (__any_sync(FULL_MASK, abandoned != 0 || t1.gave_up)) break;
         agg_chunk<Prog, true>(t1, p, c * chunk, n, lane, abandoned);
     }
     if (c < nchunks && c >= nfull && !__any_sync(FULL_MASK, abandoned != 0))  // the one partial chunk at the end of the input
@@ -714,6 +724,10 @@ __device__ __forceinline__ void agg_body_staged(const typename Prog::P &p) {
     int abandoned = 0;  // status flag as loaded 16 iterations ago
     int64_t i = 0;
     for (int64_t c = blockIdx.x; c < nchunks; c += stride, i++) {
+        if (__any_sync(FULL_MASK, t1.gave_up)) {  // (a register: set on the slow path only)
+            aborted = true;
+            break;
+        }
         if ((i & 15) == 0) {  // iterations are shorter than a global-memory round trip: look at the flag loaded 16 ago
             if (__any_sync(FULL_MASK, abandoned != 0)) {
                 aborted = true;

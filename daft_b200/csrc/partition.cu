@@ -56,10 +56,161 @@ Buf partition_permutation(const uint64_t *hashes, int64_t n, int32_t P, std::vec
     return rowid;
 }
 
+// ---- direct scatter for P <= 256 ----------------------------------------------------------------------------------
+// Two passes over the hashes instead of (partition id, row id) pairs + a radix pass + one gather per column:
+// pass 1 counts rows per (partition, CTA chunk); after one exclusive scan, pass 2 recomputes hash % P, ranks the row
+// inside its 256-row step with warp match_any (stable: earlier rows first) and copies every fixed-width never-null
+// column straight to its final position in a buffer that holds all partitions back to back (the per-partition
+// columns are views into it).  Other columns (nullable, Boolean, strings) are gathered through the row-id list the
+// same pass emits.  Traffic per row: 8 B hash twice + payload once in, once out.
+constexpr int PS_THREADS = 256, PS_WARPS = PS_THREADS / 32, PS_MAXP = 256, PS_MAXCOLS = 24;
+struct PartCol {
+    const void *src;
+    void *out;
+    int width;
+};
+struct PartCols {
+    PartCol c[PS_MAXCOLS];
+};
+
+__global__ void __launch_bounds__(PS_THREADS) partition_hist(const uint64_t *__restrict__ hashes, int64_t n, int64_t chunk, uint64_t P,
+                                                             int64_t *__restrict__ hist /* [partition][block] */) {
+    __shared__ unsigned int s_cnt[PS_MAXP];
+    for (int i = threadIdx.x; i < PS_MAXP; i += PS_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
+    for (int64_t i = begin + threadIdx.x; i < end; i += PS_THREADS) atomicAdd(&s_cnt[hashes[i] % P], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)P; i += PS_THREADS) hist[(int64_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
+}
+
+__global__ void __launch_bounds__(PS_THREADS) partition_scatter(const uint64_t *__restrict__ hashes, int64_t n, int64_t chunk, uint64_t P,
+                                                                const int64_t *__restrict__ base /* scanned hist */,
+                                                                const __grid_constant__ PartCols cols, int ncols, int64_t *__restrict__ rowid_out) {
+    __shared__ int64_t s_base[PS_MAXP];                 // next output position per partition for this CTA
+    __shared__ unsigned int s_wcnt[PS_WARPS][PS_MAXP];  // per-warp counts -> exclusive prefix over warps
+    __shared__ unsigned int s_tile[PS_MAXP];
+    const int Pn = (int)P;
+    for (int i = threadIdx.x; i < Pn; i += PS_THREADS) s_base[i] = base[(int64_t)i * gridDim.x + blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
+    for (int64_t t0 = begin; t0 < end; t0 += PS_THREADS) {
+        for (int i = threadIdx.x; i < PS_WARPS * Pn; i += PS_THREADS) s_wcnt[i / Pn][i % Pn] = 0;
+        __syncthreads();
+        const int64_t i = t0 + threadIdx.x;
+        const bool valid = i < end;
+        uint32_t d = 0xFFFFFFFFu;  // out-of-range lanes only match each other
+        if (valid) d = (uint32_t)(hashes[i] % P);
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));  // stable: lower lanes (earlier rows) first
+        if (valid && rank == 0) s_wcnt[warp][d] = __popc(peers);
+        __syncthreads();
+        for (int dd = threadIdx.x; dd < Pn; dd += PS_THREADS) {
+            unsigned int run = 0;
+#pragma unroll
+            for (int w = 0; w < PS_WARPS; w++) {
+                const unsigned int c = s_wcnt[w][dd];
+                s_wcnt[w][dd] = run;
+                run += c;
+            }
+            s_tile[dd] = run;
+        }
+        __syncthreads();
+        if (valid) {
+            const int64_t pos = s_base[d] + (int64_t)s_wcnt[warp][d] + rank;
+            if (rowid_out) rowid_out[pos] = i;
+#pragma unroll 4
+            for (int c = 0; c < ncols; c++) {
+                const PartCol &pc = cols.c[c];
+                switch (pc.width) {
+                    case 1: ((uint8_t *)pc.out)[pos] = ((const uint8_t *)pc.src)[i]; break;
+                    case 2: ((uint16_t *)pc.out)[pos] = ((const uint16_t *)pc.src)[i]; break;
+                    case 4: ((uint32_t *)pc.out)[pos] = ((const uint32_t *)pc.src)[i]; break;
+                    default: ((uint64_t *)pc.out)[pos] = ((const uint64_t *)pc.src)[i]; break;
+                }
+            }
+        }
+        __syncthreads();
+        for (int dd = threadIdx.x; dd < Pn; dd += PS_THREADS) s_base[dd] += s_tile[dd];
+    }
+}
+
+__global__ void pick_strided(const int64_t *__restrict__ src, int64_t stride, int n, int64_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[(int64_t)i * stride];
+}
+
+static std::vector<Batch *> partition_direct(const Batch &b, const uint64_t *hashes, int32_t P) {
+    cudaStream_t st = ctx().stream;
+    const int64_t n = b.num_rows;
+    int64_t nblocks = std::max<int64_t>(1, std::min<int64_t>((n + 2047) / 2048, (int64_t)ctx().sm_count * 16));
+    int64_t chunk = (n + nblocks - 1) / nblocks;
+    chunk = (chunk + PS_THREADS - 1) / PS_THREADS * PS_THREADS;
+    nblocks = (n + chunk - 1) / chunk;
+    Buf hist = dev_alloc((size_t)P * nblocks * 8), base = dev_alloc((size_t)(P * nblocks + 1) * 8), starts = dev_alloc((size_t)(P + 1) * 8);
+    partition_hist<<<(unsigned)nblocks, PS_THREADS, 0, st>>>(hashes, n, chunk, (uint64_t)P, as<int64_t>(hist));
+    count_launch();
+    exclusive_scan_i64(as<int64_t>(hist), as<int64_t>(base), (int64_t)P * nblocks, nullptr);
+    pick_strided<<<(P + 255) / 256, 256, 0, st>>>(as<int64_t>(base), nblocks, P, as<int64_t>(starts));
+    count_launch();
+    std::vector<int64_t> offsets((size_t)P + 1, 0);
+    B200_CUDA(cudaMemcpyAsync(offsets.data(), starts->ptr, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    // columns the kernel places itself vs. columns gathered through the row-id list
+    PartCols pcs;
+    int npc = 0;
+    std::vector<Buf> whole(b.cols.size());
+    bool need_rowid = false;
+    for (size_t c = 0; c < b.cols.size(); c++) {
+        const Column &sc = b.cols[c];
+        const int w = dtype_width(sc.dtype);
+        if (w && sc.null_count == 0 && npc < PS_MAXCOLS) {
+            whole[c] = dev_alloc((size_t)n * w);
+            pcs.c[npc++] = PartCol{sc.data->ptr, whole[c]->ptr, w};
+        } else if (sc.dtype != B200_NULL) {
+            need_rowid = true;
+        }
+    }
+    Buf rowid = need_rowid ? dev_alloc((size_t)n * 8) : Buf();
+    partition_scatter<<<(unsigned)nblocks, PS_THREADS, 0, st>>>(hashes, n, chunk, (uint64_t)P, as<int64_t>(base), pcs, npc, as<int64_t>(rowid));
+    count_launch();
+    B200_CUDA(cudaStreamSynchronize(st));
+    offsets[(size_t)P] = n;
+    std::vector<Batch *> out;
+    try {
+        for (int p = 0; p < P; p++) {
+            const int64_t lo = offsets[p], cnt = offsets[p + 1] - offsets[p];
+            auto pb = std::make_unique<Batch>();
+            pb->num_rows = cnt;
+            for (size_t c = 0; c < b.cols.size(); c++) {
+                const Column &sc = b.cols[c];
+                if (whole[c]) {
+                    const int w = dtype_width(sc.dtype);
+                    Column oc;
+                    oc.name = sc.name;
+                    oc.dtype = sc.dtype;
+                    oc.length = cnt;
+                    oc.data = dev_sub(whole[c], (size_t)lo * w, (size_t)cnt * w);
+                    oc.data_bytes = cnt * w;
+                    pb->cols.push_back(std::move(oc));
+                } else {
+                    pb->cols.push_back(gather_column(sc, as<int64_t>(rowid) + lo, cnt, false));
+                }
+            }
+            out.push_back(pb.release());
+        }
+        B200_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        for (auto *x : out) delete x;
+        throw;
+    }
+    return out;
+}
+
 std::vector<Batch *> op_partition_by_hash(const Batch &b, const int32_t *key_cols, int32_t nkeys, int32_t P) {
     require_device();
     if (P <= 0) fail("Can not partition a Table by 0 partitions");
     Buf h = hash_rows(b, key_cols, nkeys, nullptr);
+    if (P <= PS_MAXP && b.num_rows >= 4096) return partition_direct(b, as<uint64_t>(h), P);
     std::vector<int64_t> offsets;
     Buf perm = partition_permutation(as<uint64_t>(h), b.num_rows, P, offsets);
     std::vector<Batch *> out;

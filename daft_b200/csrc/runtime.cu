@@ -46,6 +46,13 @@ Buf dev_borrow(const void *ptr, size_t bytes) {
     a->owned = false;
     return a;
 }
+Buf dev_sub(const Buf &parent, size_t offset, size_t bytes) {
+    auto *v = new DevAlloc;
+    v->ptr = static_cast<char *>(parent->ptr) + offset;
+    v->bytes = bytes;
+    v->owned = false;
+    return Buf(v, [parent](DevAlloc *p) { delete p; });  // the view keeps its parent allocation alive
+}
 void fill_u8(void *ptr, int value, size_t bytes) {
     if (bytes) B200_CUDA(cudaMemsetAsync(ptr, value, bytes, ctx().stream));
 }

@@ -134,7 +134,8 @@ int b200_batch_import(struct ArrowArray *array, struct ArrowSchema *schema, b200
 /* device -> HOST; out_array/out_schema get this library's release callbacks. */
 int b200_batch_export(const b200_batch *batch, struct ArrowArray *out_array, struct ArrowSchema *out_schema,
                       char **errmsg);
-/* wrap existing DEVICE buffers without copying (borrowed; caller keeps them alive). */
+/* wrap existing DEVICE buffers without copying (borrowed; caller keeps them alive).  String/binary `data` buffers
+ * must be followed by 16 readable bytes: the kernels fetch values with aligned word loads (csrc/common.h). */
 int b200_batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t num_rows, b200_batch **out,
                            char **errmsg);
 int b200_batch_describe(const b200_batch *batch, int32_t col, b200_column_desc *out, char **errmsg);
