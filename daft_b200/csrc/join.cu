@@ -6,14 +6,15 @@
 //
 // Build (all on the device, no sequential step):
 //   1. hash_rows over the build keys (the same XXH3 chain the reference uses);
-//   2. stable radix sort of the build row ids by hash -> rows with equal keys are contiguous and in
-//      INSERTION ORDER (the reference's match-list order, probe_table.rs:178-181);
-//   3. run heads (hash[i] != hash[i-1]) are inserted into an open-addressing table of 32-byte slots
-//      {hash, start, count} with one atomicCAS each (distinct hashes -> no duplicates).
-// Probe (two passes: count -> scan -> write, output rows in probe-row order):
-//   slot lookup by hash, then every candidate row of the run is verified against the probe row's key
-//   values: nulls match only where null_equals_null, floats compare with IEEE == (NaN never matches,
-//   nans_equal=false, probe_table.rs:48-51).
+//   2. stable radix sort of the build row ids by the TOP B bits of the hash (B = ceil(log2 rows): 2-4 byte passes
+//      instead of 8) -> the rows of a bucket are contiguous and in INSERTION ORDER (the reference's match-list order,
+//      probe_table.rs:178-181);
+//   3. a direct-address table of 2^B {start, end} entries: bucket heads / tails write their own position.  No
+//      probing, no CAS, no stored hashes: a probe reads exactly one 16-byte entry.
+// Probe (count -> scan -> write, output rows in probe-row order): bucket = top B bits of the probe row's hash; every
+//   row of the bucket is verified against the probe row's key values: nulls match only where null_equals_null, floats
+//   compare with IEEE == (NaN never matches, nans_equal=false, probe_table.rs:48-51).  The count pass remembers each
+//   probe row's first match, so the write pass repeats the bucket walk only for rows with several matches.
 // Left / right / outer joins mark matched build rows in a bitmap (1 = matched; the reference keeps the
 // complement, src/daft-local-execution/src/join/index_bitmap.rs:5-60) that finalize turns into the
 // unmatched-build-rows output.
@@ -39,11 +40,9 @@ struct KeySet {
     KeyDesc k[MAX_JOIN_KEYS];
 };
 
-struct __align__(32) JoinSlot {
-    unsigned long long hash;  // 0 = empty (hash 0 is remapped to 1; keys are verified anyway)
-    long long start;          // first position in `sorted_rows`
-    long long count;
-    long long pad;
+struct __align__(16) JoinBucket {
+    long long start;  // first position in `sorted_rows`
+    long long end;    // one past the last (start == end == 0: empty bucket)
 };
 
 }  // namespace b200
@@ -58,8 +57,8 @@ struct b200_probe_table {
     std::unique_ptr<b200::Batch> build;                 // concatenated build side (all columns)
     std::vector<int32_t> key_cols;
     b200::Buf sorted_rows;                              // build row ids sorted by hash (stable)
-    b200::Buf slots;                                    // JoinSlot[cap]
-    int64_t cap = 0;
+    b200::Buf slots;                                    // JoinBucket[1 << bits]
+    int bits = 0;                                       // bucket = hash >> (64 - bits)
     int64_t num_rows = 0;
 };
 struct b200_join_state {
@@ -124,104 +123,71 @@ __device__ __forceinline__ bool keys_match(const KeySet &a, int64_t i, const Key
 }
 
 // ---- build ---------------------------------------------------------------------------------------
-__global__ void count_run_heads(const uint64_t *__restrict__ sorted_hash, int64_t n, unsigned long long *__restrict__ nheads) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t c = 0;
-    for (; i < n; i += stride) c += (i == 0 || sorted_hash[i] != sorted_hash[i - 1]);
-    c = block_reduce_sum_i64<256>(c);
-    if (threadIdx.x == 0 && c) atomicAdd(nheads, (unsigned long long)c);
-}
-__global__ void insert_runs(const uint64_t *__restrict__ sorted_hash, int64_t n, JoinSlot *__restrict__ slots, uint64_t mask) {
+__global__ void bucket_bounds(const uint64_t *__restrict__ sorted_hash, int64_t n, int shift, JoinBucket *__restrict__ table) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const uint64_t hraw = sorted_hash[i];
-        if (i != 0 && hraw == sorted_hash[i - 1]) continue;
-        const unsigned long long h = hraw ? hraw : 1ULL;
-        uint64_t s = h & mask;
-        for (;;) {
-            const unsigned long long prev = atomicCAS(&slots[s].hash, 0ULL, h);
-            if (prev == 0ULL) {
-                slots[s].start = i;
-                break;
-            }
-            s = (s + 1) & mask;  // distinct run heads never share a hash, except raw 0 vs raw 1 (verified by keys)
-        }
-    }
-}
-// run length = distance to the next head; heads write their own count (one thread per row, cheap scan-free form)
-__global__ void fill_run_counts(const uint64_t *__restrict__ sorted_hash, int64_t n, JoinSlot *__restrict__ slots, uint64_t mask) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        const uint64_t hraw = sorted_hash[i];
-        const bool last = (i == n - 1) || sorted_hash[i + 1] != hraw;
-        if (!last) continue;
-        // find this run's slot and store end - start
-        const unsigned long long h = hraw ? hraw : 1ULL;
-        uint64_t s = h & mask;
-        for (;;) {
-            if (slots[s].hash == h) {
-                const long long st = slots[s].start;
-                if (sorted_hash[st] == hraw) {  // raw 0 and raw 1 both map to h == 1: pick the right run
-                    slots[s].count = i + 1 - st;
-                    break;
-                }
-            }
-            s = (s + 1) & mask;
-        }
+        const uint64_t b = sorted_hash[i] >> shift;
+        if (i == 0 || (sorted_hash[i - 1] >> shift) != b) table[b].start = i;
+        if (i == n - 1 || (sorted_hash[i + 1] >> shift) != b) table[b].end = i + 1;
     }
 }
 
 // ---- probe -----------------------------------------------------------------------------------------
-// mode 0: count matches per probe row;  mode 1: write pairs at out_off[row]
-template <int MODE>
-__global__ void __launch_bounds__(256) probe_kernel(const uint64_t *__restrict__ probe_hash, int64_t n_probe, KeySet bk, KeySet pk,
-                                                     const JoinSlot *__restrict__ slots, uint64_t mask,
-                                                     const int64_t *__restrict__ sorted_rows, int keep_unmatched_probe,
-                                                     int64_t *__restrict__ counts, const int64_t *__restrict__ out_off,
-                                                     int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build,
-                                                     unsigned int *__restrict__ matched_bits) {
+// counts[i] = matches of probe row i (1 for a kept unmatched row), first[i] = its first matching build row or -1
+__global__ void __launch_bounds__(256) probe_count_kernel(const uint64_t *__restrict__ probe_hash, int64_t n_probe, KeySet bk, KeySet pk,
+                                                           const JoinBucket *__restrict__ table, int shift,
+                                                           const int64_t *__restrict__ sorted_rows, int keep_unmatched_probe,
+                                                           int64_t *__restrict__ counts, int64_t *__restrict__ first) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n_probe; i += stride) {
-        const uint64_t hraw = probe_hash[i];
-        const unsigned long long h = hraw ? hraw : 1ULL;
-        uint64_t s = h & mask;
-        int64_t nmatch = 0;
-        int64_t o = MODE == 1 ? out_off[i] : 0;
-        for (;;) {
-            const JoinSlot e = slots[s];
-            if (e.hash == 0ULL) break;
-            if (e.hash == h) {
-                for (long long t = 0; t < e.count; t++) {
-                    const int64_t br = sorted_rows[e.start + t];
-                    if (keys_match(bk, br, pk, i)) {
-                        if (MODE == 1) {
-                            out_probe[o + nmatch] = i;
-                            out_build[o + nmatch] = br;
-                            if (matched_bits) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
-                        }
-                        nmatch++;
-                    }
-                }
-                // keep scanning only for the raw-0 / raw-1 alias; a second slot with the same h is otherwise impossible
-                if (h != 1ULL) break;
+        const JoinBucket e = table[probe_hash[i] >> shift];
+        int64_t nmatch = 0, f = -1;
+        for (long long t = e.start; t < e.end; t++) {
+            const int64_t br = sorted_rows[t];
+            if (keys_match(bk, br, pk, i)) {
+                if (nmatch == 0) f = br;
+                nmatch++;
             }
-            s = (s + 1) & mask;
         }
-        if (MODE == 0) {
-            counts[i] = (nmatch == 0 && keep_unmatched_probe) ? 1 : nmatch;
-        } else if (nmatch == 0 && keep_unmatched_probe) {
+        counts[i] = (nmatch == 0 && keep_unmatched_probe) ? 1 : nmatch;
+        first[i] = f;
+    }
+}
+__global__ void __launch_bounds__(256) probe_write_kernel(const uint64_t *__restrict__ probe_hash, int64_t n_probe, KeySet bk, KeySet pk,
+                                                           const JoinBucket *__restrict__ table, int shift,
+                                                           const int64_t *__restrict__ sorted_rows, const int64_t *__restrict__ out_off,
+                                                           const int64_t *__restrict__ first, int64_t *__restrict__ out_probe,
+                                                           int64_t *__restrict__ out_build, unsigned int *__restrict__ matched_bits) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n_probe; i += stride) {
+        const int64_t o = out_off[i], cnt = out_off[i + 1] - o;
+        if (cnt == 0) continue;
+        const int64_t f = first[i];
+        if (cnt == 1) {  // one match, or a kept unmatched probe row (f == -1)
             out_probe[o] = i;
-            out_build[o] = -1;
+            out_build[o] = f;
+            if (matched_bits && f >= 0) atomicOr(&matched_bits[f >> 5], 1u << (f & 31));
+            continue;
+        }
+        const JoinBucket e = table[probe_hash[i] >> shift];
+        int64_t w = 0;
+        for (long long t = e.start; t < e.end; t++) {
+            const int64_t br = sorted_rows[t];
+            if (keys_match(bk, br, pk, i)) {
+                out_probe[o + w] = i;
+                out_build[o + w] = br;
+                if (matched_bits) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
+                w++;
+            }
         }
     }
 }
 
 __global__ void exists_kernel(const uint64_t *__restrict__ probe_hash, int64_t n_probe, KeySet bk, KeySet pk,
-                              const JoinSlot *__restrict__ slots, uint64_t mask, const int64_t *__restrict__ sorted_rows,
+                              const JoinBucket *__restrict__ table, int shift, const int64_t *__restrict__ sorted_rows,
                               uint32_t *__restrict__ out_bits) {
     const int64_t n_round = (n_probe + 31) & ~(int64_t)31;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,18 +195,8 @@ __global__ void exists_kernel(const uint64_t *__restrict__ probe_hash, int64_t n
     for (; i < n_round; i += stride) {
         bool found = false;
         if (i < n_probe) {
-            const uint64_t hraw = probe_hash[i];
-            const unsigned long long h = hraw ? hraw : 1ULL;
-            uint64_t s = h & mask;
-            for (;;) {
-                const JoinSlot e = slots[s];
-                if (e.hash == 0ULL) break;
-                if (e.hash == h) {
-                    for (long long t = 0; t < e.count && !found; t++) found = keys_match(bk, sorted_rows[e.start + t], pk, i);
-                    if (found || h != 1ULL) break;
-                }
-                s = (s + 1) & mask;
-            }
+            const JoinBucket e = table[probe_hash[i] >> shift];
+            for (long long t = e.start; t < e.end && !found; t++) found = keys_match(bk, sorted_rows[t], pk, i);
         }
         const unsigned m = __ballot_sync(0xffffffffu, found);
         if ((threadIdx.x & 31) == 0) out_bits[i >> 5] = m;
@@ -297,23 +253,15 @@ void probe_table_build(b200_probe_table *pt) {
     // reference limits (probe_table.rs:22-25,128-129) are 2^36 rows per table; ours is the same order
     Buf hashes = hash_rows(b, pt->key_cols.data(), pt->nkeys, nullptr);
     Buf rows = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
-    int64_t nheads = 0;
+    int bits = 4;
+    while (bits < 40 && ((int64_t)1 << bits) < n) bits++;  // at most one row per bucket on average
+    pt->bits = bits;
+    pt->slots = dev_alloc_zero(((size_t)1 << bits) * sizeof(JoinBucket));
     if (n > 0) {
         fill_iota(as<int64_t>(rows), n);
-        radix_sort_pairs(hashes, rows, n, 0, 64, false);
-        Buf nh = dev_alloc_zero(8);
-        count_run_heads<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), n, as<unsigned long long>(nh));
-        count_launch();
-        nheads = read_i64(as<int64_t>(nh));
-    }
-    int64_t cap = 64;
-    while ((double)cap * 0.7 < (double)nheads) cap <<= 1;
-    pt->cap = cap;
-    pt->slots = dev_alloc_zero((size_t)cap * sizeof(JoinSlot));
-    if (n > 0) {
-        insert_runs<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), n, as<JoinSlot>(pt->slots), (uint64_t)cap - 1);
-        count_launch();
-        fill_run_counts<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), n, as<JoinSlot>(pt->slots), (uint64_t)cap - 1);
+        const int sort_bits = (bits + 7) / 8 * 8;  // whole byte passes over the top of the hash
+        radix_sort_pairs(hashes, rows, n, 64 - sort_bits, 64, false);
+        bucket_bounds<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), n, 64 - bits, as<JoinBucket>(pt->slots));
         count_launch();
     }
     pt->sorted_rows = rows;
@@ -349,8 +297,8 @@ Batch *probe_exists(const b200_probe_table *pt, const Batch &probe, const int32_
     c.data_bytes = (n + 7) / 8;
     if (n > 0) {
         exists_kernel<<<jgrid(n), 256, 0, ctx().stream>>>(as<uint64_t>(h), n, make_keyset(*pt->build, pt->key_cols, pt->nulls_equal),
-                                                           make_keyset(probe, pk, pt->nulls_equal), as<JoinSlot>(pt->slots),
-                                                           (uint64_t)pt->cap - 1, as<int64_t>(pt->sorted_rows), as<uint32_t>(c.data));
+                                                           make_keyset(probe, pk, pt->nulls_equal), as<JoinBucket>(pt->slots),
+                                                           64 - pt->bits, as<int64_t>(pt->sorted_rows), as<uint32_t>(c.data));
         count_launch();
     }
     auto out = std::make_unique<Batch>();
@@ -375,19 +323,18 @@ static void probe_pairs(const b200_probe_table *pt, const Batch &probe, const in
     }
     Buf h = hash_rows(probe, key_cols, pt->nkeys, nullptr);
     const KeySet bk = make_keyset(*pt->build, pt->key_cols, pt->nulls_equal), pks = make_keyset(probe, pk, pt->nulls_equal);
-    Buf counts = dev_alloc((size_t)(n + 1) * 8), offs = dev_alloc((size_t)(n + 1) * 8);
-    probe_kernel<0><<<jgrid(n), 256, 0, st>>>(as<uint64_t>(h), n, bk, pks, as<JoinSlot>(pt->slots), (uint64_t)pt->cap - 1,
-                                               as<int64_t>(pt->sorted_rows), keep_unmatched_probe ? 1 : 0, as<int64_t>(counts), nullptr,
-                                               nullptr, nullptr, nullptr);
+    Buf counts = dev_alloc((size_t)(n + 1) * 8), offs = dev_alloc((size_t)(n + 1) * 8), first = dev_alloc((size_t)n * 8);
+    probe_count_kernel<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(h), n, bk, pks, as<JoinBucket>(pt->slots), 64 - pt->bits,
+                                                 as<int64_t>(pt->sorted_rows), keep_unmatched_probe ? 1 : 0, as<int64_t>(counts), as<int64_t>(first));
     count_launch();
     exclusive_scan_i64(as<int64_t>(counts), as<int64_t>(offs), n, as<int64_t>(offs) + n);
     total = read_i64(as<int64_t>(offs) + n);
     out_probe = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
     out_build = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
     if (total > 0) {
-        probe_kernel<1><<<jgrid(n), 256, 0, st>>>(as<uint64_t>(h), n, bk, pks, as<JoinSlot>(pt->slots), (uint64_t)pt->cap - 1,
-                                                   as<int64_t>(pt->sorted_rows), keep_unmatched_probe ? 1 : 0, nullptr, as<int64_t>(offs),
-                                                   as<int64_t>(out_probe), as<int64_t>(out_build), matched_bits);
+        probe_write_kernel<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(h), n, bk, pks, as<JoinBucket>(pt->slots), 64 - pt->bits,
+                                                     as<int64_t>(pt->sorted_rows), as<int64_t>(offs), as<int64_t>(first), as<int64_t>(out_probe),
+                                                     as<int64_t>(out_build), matched_bits);
         count_launch();
     }
     B200_CUDA(cudaGetLastError());

@@ -79,7 +79,14 @@ __global__ void __launch_bounds__(PS_THREADS) partition_hist(const uint64_t *__r
     for (int i = threadIdx.x; i < PS_MAXP; i += PS_THREADS) s_cnt[i] = 0;
     __syncthreads();
     const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
-    for (int64_t i = begin + threadIdx.x; i < end; i += PS_THREADS) atomicAdd(&s_cnt[hashes[i] % P], 1u);
+    // warp-aggregated: with a handful of partitions every lane would hit the same few shared-memory words
+    const int lane = threadIdx.x & 31;
+    for (int64_t i0 = begin; i0 < end; i0 += PS_THREADS) {
+        const int64_t i = i0 + threadIdx.x;
+        const uint32_t d = i < end ? (uint32_t)(hashes[i] % P) : 0xFFFFFFFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (i < end && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_cnt[d], (unsigned)__popc(peers));
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < (int)P; i += PS_THREADS) hist[(int64_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
 }

@@ -42,36 +42,60 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist(const uint64_t *__restr
     }
 }
 
+// Stable scatter of one 8-bit digit.  A CTA walks its chunk in tiles of RS_THREADS * RS_ITEMS rows; inside a tile
+// warp w owns rows [w * 32 * RS_ITEMS, (w + 1) * 32 * RS_ITEMS) and item j of lane l is row j * 32 + l of that
+// span, so (warp, item, lane) order IS row order.  All keys / values of a thread are loaded up front (memory-level
+// parallelism), ranks inside the warp come from match_any + a warp-private digit counter (no block barrier per
+// item), and the per-digit prefix over the 8 warps costs three block barriers per 2048 rows.
+constexpr int RS_ITEMS = 8;
 template <int BITS>
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint64_t *__restrict__ keys, const int64_t *__restrict__ vals,
                                                              int64_t n, int64_t chunk, int shift, uint32_t xor_mask,
                                                              const int64_t *__restrict__ base /* scanned hist */,
                                                              uint64_t *__restrict__ keys_out, int64_t *__restrict__ vals_out) {
     constexpr int R = 1 << BITS;
+    static_assert(R == RS_THREADS, "one thread per digit in the prefix step");
     __shared__ int64_t s_base[R];                 // next output position per digit for this CTA
     __shared__ unsigned int s_wcnt[RS_WARPS][R];  // per-warp digit counts -> exclusive prefix over warps
-    __shared__ unsigned int s_tile[R];            // digit totals of the current sub-tile
-    for (int i = threadIdx.x; i < R; i += RS_THREADS) s_base[i] = base[(int64_t)i * gridDim.x + blockIdx.x];
+    __shared__ unsigned int s_tile[R];            // digit totals of the current tile
+    s_base[threadIdx.x] = base[(int64_t)threadIdx.x * gridDim.x + blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
-    for (int64_t t0 = begin; t0 < end; t0 += RS_THREADS) {
-        for (int i = threadIdx.x; i < RS_WARPS * R; i += RS_THREADS) (&s_wcnt[0][0])[i] = 0;
-        __syncthreads();
-        const int64_t i = t0 + threadIdx.x;
-        const bool valid = i < end;
-        uint64_t k = 0;
-        int64_t v = 0;
-        uint32_t d = 0xFFFFFFFFu;  // out-of-range lanes only match each other
-        if (valid) {
-            k = keys[i];
-            v = vals[i];
-            d = ((uint32_t)(k >> shift) & (R - 1)) ^ xor_mask;
+    constexpr int TILE = RS_THREADS * RS_ITEMS;
+    for (int64_t t0 = begin; t0 < end; t0 += TILE) {
+#pragma unroll
+        for (int i = 0; i < R / 32; i++) s_wcnt[warp][i * 32 + lane] = 0;
+        __syncwarp();
+        const int64_t wbase = t0 + (int64_t)warp * 32 * RS_ITEMS + lane;
+        uint64_t k[RS_ITEMS];
+        int64_t v[RS_ITEMS];
+        uint32_t d[RS_ITEMS];
+        unsigned short rank[RS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; j++) {
+            const int64_t i = wbase + j * 32;
+            k[j] = 0;
+            v[j] = 0;
+            if (i < end) {
+                k[j] = keys[i];
+                v[j] = vals[i];
+            }
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const int rank = __popc(peers & ((1u << lane) - 1u));  // stable: lower lanes (earlier rows) first
-        if (valid && rank == 0) s_wcnt[warp][d] = __popc(peers);
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; j++) {
+            const bool valid = wbase + j * 32 < end;
+            d[j] = valid ? (((uint32_t)(k[j] >> shift) & (R - 1)) ^ xor_mask) : 0xFFFFFFFFu;  // invalid lanes only match each other
+            const unsigned peers = __match_any_sync(0xffffffffu, d[j]);
+            const int lt = __popc(peers & ((1u << lane) - 1u));  // stable: lower lanes (earlier rows) first
+            const unsigned int before = valid ? s_wcnt[warp][d[j]] : 0u;
+            __syncwarp();
+            if (valid && lt == 0) s_wcnt[warp][d[j]] = before + __popc(peers);
+            __syncwarp();
+            rank[j] = (unsigned short)(before + lt);
+        }
         __syncthreads();
-        for (int dd = threadIdx.x; dd < R; dd += RS_THREADS) {
+        {
+            const int dd = threadIdx.x;
             unsigned int run = 0;
 #pragma unroll
             for (int w = 0; w < RS_WARPS; w++) {
@@ -82,14 +106,17 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint64_t *__re
             s_tile[dd] = run;
         }
         __syncthreads();
-        if (valid) {
-            const int64_t pos = s_base[d] + (int64_t)s_wcnt[warp][d] + rank;
-            keys_out[pos] = k;
-            vals_out[pos] = v;
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; j++) {
+            if (wbase + j * 32 < end) {
+                const int64_t pos = s_base[d[j]] + (int64_t)s_wcnt[warp][d[j]] + rank[j];
+                keys_out[pos] = k[j];
+                vals_out[pos] = v[j];
+            }
         }
         __syncthreads();
-        for (int dd = threadIdx.x; dd < R; dd += RS_THREADS) s_base[dd] += s_tile[dd];
-        // the zero-fill + barrier at the top of the next iteration orders this update before its use
+        s_base[threadIdx.x] += s_tile[threadIdx.x];
+        // the next tile reads s_base only after its own first block barrier
     }
 }
 
@@ -101,7 +128,7 @@ static void radix_pass(const uint64_t *kin, const int64_t *vin, uint64_t *kout, 
     int64_t nblocks = std::min<int64_t>((n + 2047) / 2048, (int64_t)ctx().sm_count * 8);
     nblocks = std::max<int64_t>(nblocks, 1);
     int64_t chunk = (n + nblocks - 1) / nblocks;
-    chunk = (chunk + RS_THREADS - 1) / RS_THREADS * RS_THREADS;
+    chunk = (chunk + RS_THREADS * RS_ITEMS - 1) / (RS_THREADS * RS_ITEMS) * (RS_THREADS * RS_ITEMS);
     nblocks = (n + chunk - 1) / chunk;
     Buf hist = dev_alloc((size_t)R * nblocks * 8), base = dev_alloc((size_t)R * nblocks * 8), totals = dev_alloc_zero((size_t)R * 8);
     const uint32_t xm = invert ? (uint32_t)(R - 1) : 0u;

@@ -83,6 +83,35 @@ def test_hash_string_length_classes(gpu):
     assert got == [xxhash.xxh3_64_intdigest(v, s) for v, s in zip(vals, seeds)]
 
 
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 8])
+def test_hash_fixed_length_strings(gpu, L):
+    """Columns whose bytes divide evenly over the rows take the speculative fixed-length fetch of
+    hash_bytes_kernel (hash.cu); each row still verifies the guess against its offsets.  Cases: truly fixed
+    length, fixed length with nulls (a null slot has length 0, so later rows no longer sit at row * L), and
+    ragged lengths whose total happens to be rows * L."""
+    import xxhash
+    rng = np.random.default_rng(L)
+    n = 4099
+    fixed = [bytes(rng.integers(97, 123, L, dtype=np.uint8)) for _ in range(n)]
+    got = RB(gpu, pa.table({"s": pa.array(fixed, type=pa.large_binary())})).hash_rows([gpu.col("s")]).to_pydict()["hash"]
+    assert got == [xxhash.xxh3_64_intdigest(v) for v in fixed]
+    # ragged, same total: pair up rows (L-1, L+1)
+    ragged = []
+    for i in range(0, n - 1, 2):
+        ragged += [bytes(rng.integers(97, 123, L - 1, dtype=np.uint8)), bytes(rng.integers(97, 123, L + 1, dtype=np.uint8))]
+    ragged.append(bytes(rng.integers(97, 123, L, dtype=np.uint8)))
+    assert sum(map(len, ragged)) == n * L
+    seeds = [int(x) for x in rng.integers(0, 2**63, n, dtype=np.uint64)]
+    seed = RB(gpu, pa.table({"s": pa.array(seeds, type=pa.uint64())}))
+    got = RB(gpu, pa.table({"s": pa.array(ragged, type=pa.large_binary())})).hash_rows([gpu.col("s")], seed=seed).to_pydict()["hash"]
+    assert got == [xxhash.xxh3_64_intdigest(v, s) for v, s in zip(ragged, seeds)]
+    # nulls: oracle rule (null string hashes the empty slice WITH the seed)
+    withnull = [None if i % 7 == 3 else v.decode() for i, v in enumerate(fixed)]
+    col_ = pa.array(withnull, type=pa.large_utf8())
+    got = np.array(RB(gpu, pa.table({"s": col_})).hash_rows([gpu.col("s")]).to_pydict()["hash"], dtype=np.uint64)
+    assert (got == O.hash_column(pa.chunked_array([col_]))).all()
+
+
 def test_hash_null_array(gpu):
     tbl = pa.table({"n": pa.nulls(5)})
     got = RB(gpu, tbl).hash_rows([gpu.col("n")]).to_pydict()["hash"]
