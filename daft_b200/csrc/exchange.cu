@@ -268,9 +268,180 @@ Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, i
     return route_batch(c, *staged, rows);
 }
 
+// ---- small batches (partial aggregates, top-N candidates): ONE fixed-size all-gather ---------------------------------
+// Every rank packs its batch into a slab of SLAB_BYTES: a host-built header (row count, per column null count and
+// data bytes -- all known on the host without a device read) followed by the 16-byte aligned column buffers.  One
+// ncclAllGather moves the slabs, one strided D2H copy brings the W headers back (the only synchronisation), and one
+// kernel assembles the concatenated columns (byte copies, offset rebasing, bit-granular validity concatenation).
+// A rank whose batch does not fit writes rows = -1 and ALL ranks fall through to the general route below.
+constexpr int64_t SLAB_BYTES = 32 * 1024, SLAB_HDR = 2048;
+struct SegDesc {
+    int kind;  // 0 bytes, 1 string offsets (rebase), 2 bits (src == nullptr: all ones)
+    int _pad;
+    const uint8_t *src;
+    uint8_t *dst;
+    int64_t n;         // bytes / offsets entries - 1 / bits
+    int64_t dst_base;  // kind 1: byte base added to the rebased offsets; kind 2: first destination bit; kind 1 dst row via dst pointer
+};
+__global__ void pack_segments(const SegDesc *__restrict__ d) {
+    const SegDesc s = d[blockIdx.x];
+    if (s.kind == 0) {
+        for (int64_t i = threadIdx.x; i < s.n; i += blockDim.x) s.dst[i] = s.src[i];
+    } else if (s.kind == 1) {
+        const int64_t *so = reinterpret_cast<const int64_t *>(s.src);
+        int64_t *dofs = reinterpret_cast<int64_t *>(s.dst);
+        const int64_t first = so[0];
+        for (int64_t i = threadIdx.x; i <= s.n; i += blockDim.x) dofs[i] = so[i] - first + s.dst_base;
+    } else {
+        unsigned int *words = reinterpret_cast<unsigned int *>(s.dst);
+        for (int64_t i = threadIdx.x; i < s.n; i += blockDim.x) {
+            const bool bit = s.src == nullptr || bit_at(s.src, i);
+            const int64_t o = s.dst_base + i;
+            if (bit) atomicOr(&words[o >> 5], 1u << (o & 31));
+        }
+    }
+}
+static void run_segments(const std::vector<SegDesc> &segs) {
+    if (segs.empty()) return;
+    cudaStream_t st = ctx().stream;
+    Buf d = dev_alloc(segs.size() * sizeof(SegDesc));
+    B200_CUDA(cudaMemcpyAsync(d->ptr, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+    pack_segments<<<(unsigned)segs.size(), 256, 0, st>>>(as<SegDesc>(d));
+    count_launch();
+    B200_CUDA(cudaStreamSynchronize(st));  // `segs` (host) and `d` must outlive the copy / kernel
+}
+
+// returns nullptr when some rank's batch does not fit a slab (collective decision)
+static Batch *all_gather_small(b200_comm *c, const Batch &b) {
+    cudaStream_t st = ctx().stream;
+    const int W = c->world;
+    const int nc = (int)b.cols.size();
+    // header: [0] rows (-1 = too big), [1] ncols, then per column {null_count, data_bytes}
+    std::vector<int64_t> hdr(SLAB_HDR / 8, 0);
+    bool fits = 2 + 2 * (int64_t)nc <= SLAB_HDR / 8;
+    int64_t off = SLAB_HDR;
+    struct Part { int64_t valid_off = -1, offs_off = -1, data_off = -1; };
+    std::vector<Part> parts(nc);
+    std::vector<SegDesc> segs;
+    Buf slab = dev_alloc((size_t)SLAB_BYTES), all = dev_alloc((size_t)SLAB_BYTES * W);
+    auto place = [&](int64_t bytes) {
+        const int64_t o = off;
+        off += (bytes + 15) & ~(int64_t)15;
+        return o;
+    };
+    for (int ci = 0; ci < nc && fits; ci++) {
+        const Column &col = b.cols[ci];
+        const int64_t n = col.length;
+        hdr[2 + 2 * ci] = col.null_count;
+        hdr[3 + 2 * ci] = col.data_bytes;
+        if (col.dtype == B200_NULL) continue;
+        if (col.null_count > 0) parts[ci].valid_off = place((n + 7) / 8);
+        if (is_string(col.dtype)) parts[ci].offs_off = place((n + 1) * 8);
+        const int w = dtype_width(col.dtype);
+        const int64_t db = w ? n * w : (col.dtype == B200_BOOL ? (n + 7) / 8 : col.data_bytes);
+        parts[ci].data_off = place(db);
+        if (off > SLAB_BYTES) fits = false;
+        if (!fits) break;
+        uint8_t *base = as<uint8_t>(slab);
+        if (col.null_count > 0) segs.push_back({0, 0, as<uint8_t>(col.validity), base + parts[ci].valid_off, (n + 7) / 8, 0});
+        if (is_string(col.dtype) && col.offsets) segs.push_back({0, 0, as<uint8_t>(col.offsets), base + parts[ci].offs_off, (n + 1) * 8, 0});
+        if (db > 0 && col.data) segs.push_back({0, 0, as<uint8_t>(col.data), base + parts[ci].data_off, db, 0});
+    }
+    hdr[0] = fits ? b.num_rows : -1;
+    hdr[1] = nc;
+    B200_CUDA(cudaMemcpyAsync(slab->ptr, hdr.data(), (size_t)SLAB_HDR, cudaMemcpyHostToDevice, st));
+    if (fits && !segs.empty()) {
+        Buf d = dev_alloc(segs.size() * sizeof(SegDesc));
+        B200_CUDA(cudaMemcpyAsync(d->ptr, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+        pack_segments<<<(unsigned)segs.size(), 256, 0, st>>>(as<SegDesc>(d));
+        count_launch();
+        B200_NCCL(nccl().AllGather(slab->ptr, all->ptr, (size_t)SLAB_BYTES, ncclUint8, c->comm, st));
+        count_launch();
+        // (d is released after the stream-ordered free; the synchronise below covers the host vector)
+    } else {
+        B200_NCCL(nccl().AllGather(slab->ptr, all->ptr, (size_t)SLAB_BYTES, ncclUint8, c->comm, st));
+        count_launch();
+    }
+    std::vector<int64_t> hs((size_t)W * (SLAB_HDR / 8));
+    B200_CUDA(cudaMemcpy2DAsync(hs.data(), (size_t)SLAB_HDR, all->ptr, (size_t)SLAB_BYTES, (size_t)SLAB_HDR, (size_t)W, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < W; r++) {
+        const int64_t *h = &hs[(size_t)r * (SLAB_HDR / 8)];
+        if (h[0] < 0) return nullptr;
+        if (h[1] != nc) fail("all_gather: ranks disagree on the number of columns");
+    }
+    // assemble: every rank walks the same layout rule over each source slab
+    auto out = std::make_unique<Batch>();
+    int64_t total_rows = 0;
+    for (int r = 0; r < W; r++) total_rows += hs[(size_t)r * (SLAB_HDR / 8)];
+    out->num_rows = total_rows;
+    std::vector<int64_t> cursor(W, SLAB_HDR);  // running offset inside each rank's slab
+    std::vector<SegDesc> asm_segs;
+    const uint8_t *allp = as<uint8_t>(all);
+    for (int ci = 0; ci < nc; ci++) {
+        const Column &col = b.cols[ci];
+        Column o;
+        o.name = col.name;
+        o.dtype = col.dtype;
+        o.length = total_rows;
+        if (col.dtype == B200_NULL) {
+            o.null_count = total_rows;
+            out->cols.push_back(std::move(o));
+            continue;
+        }
+        int64_t nulls = 0, dbytes = 0;
+        for (int r = 0; r < W; r++) {
+            nulls += hs[(size_t)r * (SLAB_HDR / 8) + 2 + 2 * ci];
+            dbytes += hs[(size_t)r * (SLAB_HDR / 8) + 3 + 2 * ci];
+        }
+        o.null_count = nulls;
+        const int w = dtype_width(col.dtype);
+        const bool is_bool = col.dtype == B200_BOOL, is_str = is_string(col.dtype);
+        if (nulls > 0) o.validity = dev_alloc_zero((size_t)((total_rows + 31) / 32 + 1) * 4);
+        if (is_str) o.offsets = dev_alloc((size_t)(total_rows + 1) * 8);
+        if (w) {
+            o.data = dev_alloc((size_t)std::max<int64_t>(total_rows * w, 1));
+            o.data_bytes = total_rows * w;
+        } else if (is_bool) {
+            o.data = dev_alloc_zero((size_t)((total_rows + 31) / 32 + 1) * 4);
+            o.data_bytes = (total_rows + 7) / 8;
+        } else {
+            o.data = dev_alloc((size_t)std::max<int64_t>(dbytes, 1));
+            o.data_bytes = dbytes;
+        }
+        int64_t row_base = 0, byte_base = 0;
+        for (int r = 0; r < W; r++) {
+            const int64_t *h = &hs[(size_t)r * (SLAB_HDR / 8)];
+            const int64_t n = h[0], rn = h[2 + 2 * ci], rdb = h[3 + 2 * ci];
+            const uint8_t *sl = allp + (size_t)r * SLAB_BYTES;
+            auto take = [&](int64_t bytes) {
+                const int64_t o2 = cursor[r];
+                cursor[r] += (bytes + 15) & ~(int64_t)15;
+                return sl + o2;
+            };
+            const uint8_t *vsrc = rn > 0 ? take((n + 7) / 8) : nullptr;
+            const uint8_t *osrc = is_str ? take((n + 1) * 8) : nullptr;
+            const int64_t db = w ? n * w : (is_bool ? (n + 7) / 8 : rdb);
+            const uint8_t *dsrc = take(db);
+            if (nulls > 0 && n > 0) asm_segs.push_back({2, 0, vsrc, as<uint8_t>(o.validity), n, row_base});
+            if (is_str) asm_segs.push_back({1, 0, osrc, as<uint8_t>(o.offsets) + (size_t)row_base * 8, n, byte_base});
+            if (w && n > 0) asm_segs.push_back({0, 0, dsrc, as<uint8_t>(o.data) + (size_t)row_base * w, n * w, 0});
+            else if (is_bool && n > 0) asm_segs.push_back({2, 0, dsrc, as<uint8_t>(o.data), n, row_base});
+            else if (is_str && rdb > 0) asm_segs.push_back({0, 0, dsrc, as<uint8_t>(o.data) + (size_t)byte_base, rdb, 0});
+            row_base += n;
+            byte_base += is_str ? rdb : 0;
+        }
+        if (nulls == 0) o.validity.reset();
+        out->cols.push_back(std::move(o));
+    }
+    run_segments(asm_segs);
+    return out.release();
+}
+
 Batch *all_gather_batches(b200_comm *c, const Batch &b) {
     require_device();
     if (!c) fail("null communicator");
+    if (Batch *small = all_gather_small(c, b)) return small;
     const int W = c->world;
     std::vector<int64_t> soff(W, 0), scnt(W, b.num_rows);
     const Route rows = make_route(c, soff, scnt);

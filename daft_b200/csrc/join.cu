@@ -40,9 +40,15 @@ struct KeySet {
     KeyDesc k[MAX_JOIN_KEYS];
 };
 
-struct __align__(16) JoinBucket {
-    long long start;  // first position in `sorted_rows`
-    long long end;    // one past the last (start == end == 0: empty bucket)
+// One 32-byte sector per bucket: besides its span in `sorted_rows` the entry carries the bucket's FIRST row inline --
+// its row id and a tag that is either the key value itself (single integer-like key column without nulls: the
+// match is decided without touching the build side) or the row's full hash (a cheap reject before the key compare).
+// A probe into a one-row bucket (the common case at <= 1 row per bucket) therefore costs one random sector.
+struct __align__(32) JoinBucket {
+    long long start;      // first position in `sorted_rows`
+    long long end;        // one past the last (start == end == 0: empty bucket)
+    long long first_row;  // sorted_rows[start]
+    unsigned long long tag;
 };
 
 }  // namespace b200
@@ -59,6 +65,7 @@ struct b200_probe_table {
     b200::Buf sorted_rows;                              // build row ids sorted by hash (stable)
     b200::Buf slots;                                    // JoinBucket[1 << bits]
     int bits = 0;                                       // bucket = hash >> (64 - bits)
+    int inline_width = 0;                               // > 0: tags are key values of that byte width (see JoinBucket)
     int64_t num_rows = 0;
 };
 struct b200_join_state {
@@ -123,13 +130,49 @@ __device__ __forceinline__ bool keys_match(const KeySet &a, int64_t i, const Key
 }
 
 // ---- build ---------------------------------------------------------------------------------------
-__global__ void bucket_bounds(const uint64_t *__restrict__ sorted_hash, int64_t n, int shift, JoinBucket *__restrict__ table) {
+__device__ __forceinline__ unsigned long long key_bits(const void *data, int width, int64_t r) {
+    switch (width) {
+        case 1: return ((const uint8_t *)data)[r];
+        case 2: return ((const uint16_t *)data)[r];
+        case 4: return ((const uint32_t *)data)[r];
+        default: return ((const uint64_t *)data)[r];
+    }
+}
+__global__ void bucket_bounds(const uint64_t *__restrict__ sorted_hash, const int64_t *__restrict__ sorted_rows, int64_t n, int shift,
+                              const void *__restrict__ key_data, int inline_width, JoinBucket *__restrict__ table) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const uint64_t b = sorted_hash[i] >> shift;
-        if (i == 0 || (sorted_hash[i - 1] >> shift) != b) table[b].start = i;
+        const uint64_t h = sorted_hash[i], b = h >> shift;
+        if (i == 0 || (sorted_hash[i - 1] >> shift) != b) {
+            const int64_t r = sorted_rows[i];
+            table[b].start = i;
+            table[b].first_row = r;
+            table[b].tag = inline_width ? key_bits(key_data, inline_width, r) : h;
+        }
         if (i == n - 1 || (sorted_hash[i + 1] >> shift) != b) table[b].end = i + 1;
+    }
+}
+
+// Walk one bucket for probe row i: calls f(build_row) for every match, in insertion order.
+template <class F>
+__device__ __forceinline__ void bucket_matches(const JoinBucket &e, uint64_t h, const KeySet &bk, const KeySet &pk, int64_t i,
+                                               const int64_t *__restrict__ sorted_rows, int inline_width, F &&f) {
+    if (e.end == e.start) return;
+    if (inline_width) {
+        if (pk.k[0].validity != nullptr && !bit_at(pk.k[0].validity, i)) return;  // build side has no nulls in this mode
+        const unsigned long long v = key_bits(pk.k[0].data, inline_width, i);
+        if (e.tag == v) f(e.first_row);
+        for (long long t = e.start + 1; t < e.end; t++) {
+            const int64_t br = sorted_rows[t];
+            if (key_bits(bk.k[0].data, inline_width, br) == v) f(br);
+        }
+    } else {
+        if (e.tag == h && keys_match(bk, e.first_row, pk, i)) f(e.first_row);
+        for (long long t = e.start + 1; t < e.end; t++) {
+            const int64_t br = sorted_rows[t];
+            if (keys_match(bk, br, pk, i)) f(br);
+        }
     }
 }
 
@@ -137,27 +180,26 @@ __global__ void bucket_bounds(const uint64_t *__restrict__ sorted_hash, int64_t 
 // counts[i] = matches of probe row i (1 for a kept unmatched row), first[i] = its first matching build row or -1
 __global__ void __launch_bounds__(256) probe_count_kernel(const uint64_t *__restrict__ probe_hash, int64_t n_probe, KeySet bk, KeySet pk,
                                                            const JoinBucket *__restrict__ table, int shift,
-                                                           const int64_t *__restrict__ sorted_rows, int keep_unmatched_probe,
+                                                           const int64_t *__restrict__ sorted_rows, int inline_width, int keep_unmatched_probe,
                                                            int64_t *__restrict__ counts, int64_t *__restrict__ first) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n_probe; i += stride) {
-        const JoinBucket e = table[probe_hash[i] >> shift];
+        const uint64_t h = probe_hash[i];
+        const JoinBucket e = table[h >> shift];
         int64_t nmatch = 0, f = -1;
-        for (long long t = e.start; t < e.end; t++) {
-            const int64_t br = sorted_rows[t];
-            if (keys_match(bk, br, pk, i)) {
-                if (nmatch == 0) f = br;
-                nmatch++;
-            }
-        }
+        bucket_matches(e, h, bk, pk, i, sorted_rows, inline_width, [&](int64_t br) {
+            if (nmatch == 0) f = br;
+            nmatch++;
+        });
         counts[i] = (nmatch == 0 && keep_unmatched_probe) ? 1 : nmatch;
         first[i] = f;
     }
 }
 __global__ void __launch_bounds__(256) probe_write_kernel(const uint64_t *__restrict__ probe_hash, int64_t n_probe, KeySet bk, KeySet pk,
                                                            const JoinBucket *__restrict__ table, int shift,
-                                                           const int64_t *__restrict__ sorted_rows, const int64_t *__restrict__ out_off,
+                                                           const int64_t *__restrict__ sorted_rows, int inline_width,
+                                                           const int64_t *__restrict__ out_off,
                                                            const int64_t *__restrict__ first, int64_t *__restrict__ out_probe,
                                                            int64_t *__restrict__ out_build, unsigned int *__restrict__ matched_bits) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,22 +214,20 @@ __global__ void __launch_bounds__(256) probe_write_kernel(const uint64_t *__rest
             if (matched_bits && f >= 0) atomicOr(&matched_bits[f >> 5], 1u << (f & 31));
             continue;
         }
-        const JoinBucket e = table[probe_hash[i] >> shift];
+        const uint64_t h = probe_hash[i];
+        const JoinBucket e = table[h >> shift];
         int64_t w = 0;
-        for (long long t = e.start; t < e.end; t++) {
-            const int64_t br = sorted_rows[t];
-            if (keys_match(bk, br, pk, i)) {
-                out_probe[o + w] = i;
-                out_build[o + w] = br;
-                if (matched_bits) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
-                w++;
-            }
-        }
+        bucket_matches(e, h, bk, pk, i, sorted_rows, inline_width, [&](int64_t br) {
+            out_probe[o + w] = i;
+            out_build[o + w] = br;
+            if (matched_bits) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
+            w++;
+        });
     }
 }
 
 __global__ void exists_kernel(const uint64_t *__restrict__ probe_hash, int64_t n_probe, KeySet bk, KeySet pk,
-                              const JoinBucket *__restrict__ table, int shift, const int64_t *__restrict__ sorted_rows,
+                              const JoinBucket *__restrict__ table, int shift, const int64_t *__restrict__ sorted_rows, int inline_width,
                               uint32_t *__restrict__ out_bits) {
     const int64_t n_round = (n_probe + 31) & ~(int64_t)31;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,8 +235,9 @@ __global__ void exists_kernel(const uint64_t *__restrict__ probe_hash, int64_t n
     for (; i < n_round; i += stride) {
         bool found = false;
         if (i < n_probe) {
-            const JoinBucket e = table[probe_hash[i] >> shift];
-            for (long long t = e.start; t < e.end && !found; t++) found = keys_match(bk, sorted_rows[t], pk, i);
+            const uint64_t h = probe_hash[i];
+            const JoinBucket e = table[h >> shift];
+            bucket_matches(e, h, bk, pk, i, sorted_rows, inline_width, [&](int64_t) { found = true; });
         }
         const unsigned m = __ballot_sync(0xffffffffu, found);
         if ((threadIdx.x & 31) == 0) out_bits[i >> 5] = m;
@@ -261,7 +302,13 @@ void probe_table_build(b200_probe_table *pt) {
         fill_iota(as<int64_t>(rows), n);
         const int sort_bits = (bits + 7) / 8 * 8;  // whole byte passes over the top of the hash
         radix_sort_pairs(hashes, rows, n, 64 - sort_bits, 64, false);
-        bucket_bounds<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), n, 64 - bits, as<JoinBucket>(pt->slots));
+        // inline key tags: one integer-like key column without nulls (floats keep IEEE ==, strings need their bytes)
+        const Column &k0 = b.cols[pt->key_cols[0]];
+        const bool int_like = k0.dtype == B200_I8 || k0.dtype == B200_I16 || k0.dtype == B200_I32 || k0.dtype == B200_I64 || k0.dtype == B200_U8 ||
+                              k0.dtype == B200_U16 || k0.dtype == B200_U32 || k0.dtype == B200_U64 || k0.dtype == B200_DATE32 || k0.dtype == B200_TIMESTAMP;
+        pt->inline_width = (pt->nkeys == 1 && int_like && k0.null_count == 0) ? dtype_width(k0.dtype) : 0;
+        bucket_bounds<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), as<int64_t>(rows), n, 64 - bits, k0.data ? k0.data->ptr : nullptr,
+                                                pt->inline_width, as<JoinBucket>(pt->slots));
         count_launch();
     }
     pt->sorted_rows = rows;
@@ -298,7 +345,7 @@ Batch *probe_exists(const b200_probe_table *pt, const Batch &probe, const int32_
     if (n > 0) {
         exists_kernel<<<jgrid(n), 256, 0, ctx().stream>>>(as<uint64_t>(h), n, make_keyset(*pt->build, pt->key_cols, pt->nulls_equal),
                                                            make_keyset(probe, pk, pt->nulls_equal), as<JoinBucket>(pt->slots),
-                                                           64 - pt->bits, as<int64_t>(pt->sorted_rows), as<uint32_t>(c.data));
+                                                           64 - pt->bits, as<int64_t>(pt->sorted_rows), pt->inline_width, as<uint32_t>(c.data));
         count_launch();
     }
     auto out = std::make_unique<Batch>();
@@ -325,7 +372,8 @@ static void probe_pairs(const b200_probe_table *pt, const Batch &probe, const in
     const KeySet bk = make_keyset(*pt->build, pt->key_cols, pt->nulls_equal), pks = make_keyset(probe, pk, pt->nulls_equal);
     Buf counts = dev_alloc((size_t)(n + 1) * 8), offs = dev_alloc((size_t)(n + 1) * 8), first = dev_alloc((size_t)n * 8);
     probe_count_kernel<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(h), n, bk, pks, as<JoinBucket>(pt->slots), 64 - pt->bits,
-                                                 as<int64_t>(pt->sorted_rows), keep_unmatched_probe ? 1 : 0, as<int64_t>(counts), as<int64_t>(first));
+                                                 as<int64_t>(pt->sorted_rows), pt->inline_width, keep_unmatched_probe ? 1 : 0, as<int64_t>(counts),
+                                                 as<int64_t>(first));
     count_launch();
     exclusive_scan_i64(as<int64_t>(counts), as<int64_t>(offs), n, as<int64_t>(offs) + n);
     total = read_i64(as<int64_t>(offs) + n);
@@ -333,7 +381,8 @@ static void probe_pairs(const b200_probe_table *pt, const Batch &probe, const in
     out_build = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
     if (total > 0) {
         probe_write_kernel<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(h), n, bk, pks, as<JoinBucket>(pt->slots), 64 - pt->bits,
-                                                     as<int64_t>(pt->sorted_rows), as<int64_t>(offs), as<int64_t>(first), as<int64_t>(out_probe),
+                                                     as<int64_t>(pt->sorted_rows), pt->inline_width, as<int64_t>(offs), as<int64_t>(first),
+                                                     as<int64_t>(out_probe),
                                                      as<int64_t>(out_build), matched_bits);
         count_launch();
     }

@@ -177,6 +177,21 @@ class RecordBatch:
         base = len(names)
         return both, [base + i for i in range(len(exprs))]
 
+    # Serialised plan parameters are cached per (expression objects, input schema): an operator instance serialises
+    # its plan node once, not once per batch.  Values keep the expressions alive so the
+    # ids in the key stay unique.
+    _plan_cache: dict = {}
+
+    def _cached_plan(self, kind: str, groups: Sequence[Sequence[Expression] | None], build):
+        key = (kind, tuple(None if g is None else tuple(map(id, g)) for g in groups), tuple(self.column_names()), tuple(self.dtypes()))
+        hit = RecordBatch._plan_cache.get(key)
+        if hit is None:
+            if len(RecordBatch._plan_cache) > 512:
+                RecordBatch._plan_cache.clear()
+            hit = (build(), [list(g) for g in groups if g is not None])
+            RecordBatch._plan_cache[key] = hit
+        return hit[0]
+
     def eval_expression_list(self, exprs: Sequence[Expression]) -> "RecordBatch":
         """RecordBatch::eval_expression_list (src/daft-recordbatch/src/lib.rs:1603-1631)."""
         assert all(isinstance(e, Expression) for e in exprs)
@@ -185,7 +200,7 @@ class RecordBatch:
             if e.name() in seen:
                 raise ValueError(f"duplicate output column name {e.name()!r}")
             seen.add(e.name())
-        plan, _, _ = encode_project(exprs, self.column_names(), self.dtypes())
+        plan = self._cached_plan("project", [exprs], lambda: encode_project(exprs, self.column_names(), self.dtypes())[0])
         out = ctypes.c_void_p()
         _lib.call("b200_eval_expression_list", self._h, plan, ctypes.c_size_t(len(plan)), ctypes.byref(out))
         return RecordBatch._wrap(out)
@@ -195,7 +210,7 @@ class RecordBatch:
         assert all(isinstance(e, Expression) for e in exprs)
         if len(exprs) == 0:
             return self
-        plan = encode_filter(exprs, self.column_names(), self.dtypes())
+        plan = self._cached_plan("filter", [exprs], lambda: encode_filter(exprs, self.column_names(), self.dtypes()))
         out = ctypes.c_void_p()
         _lib.call("b200_filter", self._h, plan, ctypes.c_size_t(len(plan)), ctypes.byref(out))
         return RecordBatch._wrap(out)
@@ -204,7 +219,8 @@ class RecordBatch:
             predicate: Sequence[Expression] | None = None) -> "RecordBatch":
         """RecordBatch::agg (src/daft-recordbatch/src/ops/agg.rs:20-88).  `predicate` fuses the Filter that
         feeds the aggregate into the same kernel (rows failing it are skipped; nothing is materialised)."""
-        plan = encode_agg(to_agg, group_by or [], self.column_names(), self.dtypes(), predicate)
+        plan = self._cached_plan("agg", [to_agg, group_by or [], predicate],
+                                 lambda: encode_agg(to_agg, group_by or [], self.column_names(), self.dtypes(), predicate))
         out = ctypes.c_void_p()
         _lib.call("b200_agg", self._h, plan, ctypes.c_size_t(len(plan)), ctypes.byref(out))
         return RecordBatch._wrap(out)
@@ -286,7 +302,8 @@ class RecordBatch:
         both, idx = self._resolve_keys(sort_keys)
         out = ctypes.c_void_p()
         _lib.call("b200_sort", both._h, _i32(idx), ctypes.c_int32(len(idx)), _u8(desc), _u8(nf), ctypes.byref(out))
-        return RecordBatch._wrap(out).select_columns(list(range(self.num_columns())))
+        res = RecordBatch._wrap(out)
+        return res if both is self else res.select_columns(list(range(self.num_columns())))
 
     def top_n(self, sort_keys: Sequence[Expression], limit: int, descending=None, nulls_first=None, offset: int = 0) -> "RecordBatch":
         desc, nf = self._sort_flags(sort_keys, descending, nulls_first)

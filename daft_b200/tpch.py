@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import datetime
+import functools
 from typing import Sequence
 
 import pyarrow as pa
@@ -61,6 +62,7 @@ def generate_host(table: str, sf: float, columns: Sequence[str] | None = None, r
 # ------------------------------------------------------------------------------------------------
 # Q1 (benchmarking/tpch/answers.py:12-32)
 # ------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
 def q1_exprs():
     disc_price = col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))
     charge = disc_price * (1 + col("L_TAX"))
@@ -79,6 +81,7 @@ def q1_exprs():
     return predicate, group_by, aggs
 
 
+@functools.lru_cache(maxsize=None)
 def q1_partial_exprs():
     """First stage of the two-stage rewrite (src/daft-local-plan/src/agg.rs:107-166): Mean -> Sum + Count."""
     disc_price = col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))
@@ -98,6 +101,7 @@ def q1_partial_exprs():
     return predicate, group_by, aggs
 
 
+@functools.lru_cache(maxsize=None)
 def q1_final_exprs():
     """Second stage + final projection: Sum of partial sums/counts, merge_mean = sum / count
     (src/daft-dsl/src/functions/agg/mod.rs:29-53)."""

@@ -37,6 +37,15 @@ def main():
     parts = [None] * world
     dist.all_gather_object(parts, distributed._to_ipc(tbl))
     assert_tables_equal(allg, pa.concat_tables([distributed._from_ipc(p) for p in parts]))
+    # small batches take the packed single-collective path (exchange.cu all_gather_small): nulls, Booleans, strings,
+    # a rank with zero rows, and a null-typed column
+    for nsmall in (7 + 3 * rank, 0 if rank == world - 1 else 33, 300):
+        small = random_table(np.random.default_rng(7 * rank + nsmall), nsmall, 0.3)
+        small = small.append_column("allnull", pa.nulls(nsmall))
+        got = comm.all_gather(daft_b200.RecordBatch.from_arrow_table(small)).to_arrow_table()
+        sparts = [None] * world
+        dist.all_gather_object(sparts, distributed._to_ipc(small))
+        assert_tables_equal(got, pa.concat_tables([distributed._from_ipc(p) for p in sparts]))
     # high-cardinality group-by through the exchange == single-table oracle
     full = pa.concat_tables([distributed._from_ipc(p) for p in parts])
     mine = comm.exchange_by_hash(rb, [col("i32")]).agg([col("f64").sum().alias("s"), col("i32").count("all").alias("c")], [col("i32")]).to_arrow_table()
