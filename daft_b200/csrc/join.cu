@@ -138,19 +138,40 @@ __device__ __forceinline__ unsigned long long key_bits(const void *data, int wid
         default: return ((const uint64_t *)data)[r];
     }
 }
+// The head row of a bucket (first position whose top bits differ from its predecessor) walks forward to the bucket's
+// end -- buckets hold about one row -- and writes the whole 32-byte entry with two 16-byte stores.  Runs longer than
+// BB_WALK are closed by their tail row instead (it sees no head within BB_WALK positions behind it).
+constexpr int BB_WALK = 32;
 __global__ void bucket_bounds(const uint64_t *__restrict__ sorted_hash, const int64_t *__restrict__ sorted_rows, int64_t n, int shift,
                               const void *__restrict__ key_data, int inline_width, JoinBucket *__restrict__ table) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         const uint64_t h = sorted_hash[i], b = h >> shift;
-        if (i == 0 || (sorted_hash[i - 1] >> shift) != b) {
+        const bool head = i == 0 || (sorted_hash[i - 1] >> shift) != b;
+        if (head) {
+            int64_t j = i + 1;
+            while (j < n && j - i <= BB_WALK && (sorted_hash[j] >> shift) == b) j++;
+            const bool closed = j == n || (sorted_hash[j] >> shift) != b;
             const int64_t r = sorted_rows[i];
-            table[b].start = i;
-            table[b].first_row = r;
-            table[b].tag = inline_width ? key_bits(key_data, inline_width, r) : h;
+            longlong2 lo, hi;
+            lo.x = i;
+            lo.y = closed ? j : 0;  // a long run: the tail row stores `end`
+            hi.x = r;
+            hi.y = (long long)(inline_width ? key_bits(key_data, inline_width, r) : h);
+            longlong2 *e = reinterpret_cast<longlong2 *>(&table[b]);
+            if (closed) e[0] = lo;
+            else table[b].start = i;  // (the tail row owns `end`: no store of ours may overwrite it)
+            e[1] = hi;
+        } else {
+            const bool tail = i == n - 1 || (sorted_hash[i + 1] >> shift) != b;
+            if (tail) {
+                // distance to the head: only runs longer than BB_WALK + 1 rows are closed here
+                int64_t back = 1;
+                while (back <= BB_WALK + 1 && i - back >= 0 && (sorted_hash[i - back] >> shift) == b) back++;
+                if (back > BB_WALK + 1) table[b].end = i + 1;
+            }
         }
-        if (i == n - 1 || (sorted_hash[i + 1] >> shift) != b) table[b].end = i + 1;
     }
 }
 

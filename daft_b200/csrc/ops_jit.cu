@@ -232,6 +232,46 @@ __global__ void compact_slots(const unsigned long long *__restrict__ nrows, int6
     }
 }
 
+// Tier-1 tables (65536 slots) almost always hold a handful of groups: ONE single-CTA launch finds the occupied slots,
+// orders them by first row (first-occurrence group order, inline_agg.rs:804-807) and emits slot ids + first rows.
+// counter[0] = number of groups, or -1 when there are more than SMALL_GROUPS (the host then takes the general path).
+constexpr int SMALL_GROUPS = 1024;
+__global__ void __launch_bounds__(1024) small_groups_epilogue(const unsigned long long *__restrict__ nrows, const unsigned long long *__restrict__ minrow_cell,
+                                                              int64_t cap, int ungrouped, long long *__restrict__ counter,
+                                                              int64_t *__restrict__ out_slot, unsigned long long *__restrict__ out_minrow) {
+    __shared__ int64_t s_slot[SMALL_GROUPS];
+    __shared__ unsigned long long s_min[SMALL_GROUPS];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < cap; i += blockDim.x) {
+        const bool used = ungrouped ? (i == 0) : (nrows[i] != 0);
+        if (used) {
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < SMALL_GROUPS) {
+                s_slot[pos] = i;
+                s_min[pos] = minrow_cell[i];
+            }
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n > SMALL_GROUPS) {
+        if (threadIdx.x == 0) counter[0] = -1;
+        return;
+    }
+    // rank by (first row, slot): first rows of distinct groups are distinct, the slot only breaks the ungrouped / empty tie
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long m = s_min[i];
+        const int64_t sl = s_slot[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) rank += (s_min[j] < m) || (s_min[j] == m && s_slot[j] < sl);
+        out_slot[rank] = sl;
+        out_minrow[rank] = m;
+    }
+    if (threadIdx.x == 0) counter[0] = n;
+}
+
 __global__ void gather_u64(const unsigned long long *__restrict__ src, const int64_t *__restrict__ idx, int64_t n,
                            unsigned long long *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,8 +387,9 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         if (!kp) kp = &jit::get(B200_OP_AGG, plan, len, in, false, 0);
     }
     int64_t cap = kp->nkeys > 0 ? (1 << 16) : 1;
-    Buf slot_tag, acc, slots, flag = dev_alloc_zero(16);  // flag: {int status, pad, u64 group counter}
+    Buf slot_tag, acc, slots, minrow_sorted, flag = dev_alloc_zero(16);  // flag: {int status, pad, u64 group counter}
     int64_t ng = 0;
+    bool small_path = false;  // slots / first rows already ordered by the single-CTA epilogue
     int ncells = 0, cell_nrows = 0, cell_minrow = 0;
     for (int attempt = 0;; attempt++) {
         const Compiled &k = *kp;
@@ -393,8 +434,16 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         // compact the occupied slots right behind the kernel: status flag and group count come back in ONE read
         // (an ungrouped aggregate has exactly one group and no failure mode: no read at all)
         slots = dev_alloc((size_t)std::max<int64_t>(cap, 1) * 8);
-        compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(as<unsigned long long>(acc) + (size_t)cell_nrows * cap, cap, k.nkeys == 0,
-                                                              as<unsigned long long>(flag) + 1, as<int64_t>(slots));
+        const unsigned long long *nrows_c = as<unsigned long long>(acc) + (size_t)cell_nrows * cap;
+        const unsigned long long *minrow_c = as<unsigned long long>(acc) + (size_t)cell_minrow * cap;
+        small_path = cap <= (1 << 16);
+        if (small_path) {
+            minrow_sorted = dev_alloc((size_t)SMALL_GROUPS * 8);
+            small_groups_epilogue<<<1, 1024, 0, st>>>(nrows_c, minrow_c, cap, k.nkeys == 0, as<long long>(flag) + 1, as<int64_t>(slots),
+                                                      as<unsigned long long>(minrow_sorted));
+        } else {
+            compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(nrows_c, cap, k.nkeys == 0, as<unsigned long long>(flag) + 1, as<int64_t>(slots));
+        }
         count_launch();
         if (k.nkeys > 0) {
             long long host[2] = {0, 0};
@@ -402,6 +451,13 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
             B200_CUDA(cudaStreamSynchronize(st));
             status = (int)(host[0] & 0xffffffffLL);
             ng = host[1];
+            if (!status && ng < 0) {  // more groups than the single-CTA epilogue handles: general path on the same table
+                small_path = false;
+                fill_u8(as<uint8_t>(flag) + 8, 0, 8);
+                compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(nrows_c, cap, 0, as<unsigned long long>(flag) + 1, as<int64_t>(slots));
+                count_launch();
+                ng = read_i64(as<int64_t>(flag) + 1);
+            }
         } else {
             ng = 1;
         }
@@ -424,8 +480,8 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
 
     // ---- compact occupied slots, order groups by first occurrence
     const unsigned long long *nrows_cell = as<unsigned long long>(acc) + (size_t)cell_nrows * cap;
-    Buf minrow = dev_alloc((size_t)std::max<int64_t>(ng, 1) * 8);
-    if (ng > 0) {
+    Buf minrow = small_path ? minrow_sorted : dev_alloc((size_t)std::max<int64_t>(ng, 1) * 8);
+    if (ng > 0 && !small_path) {
         gather_u64<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(as<unsigned long long>(acc) + (size_t)cell_minrow * cap,
                                                                   as<int64_t>(slots), ng, as<unsigned long long>(minrow));
         count_launch();

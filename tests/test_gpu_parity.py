@@ -349,6 +349,22 @@ def test_hash_join_matches_oracle(gpu, how, nl, nr, kr):
         assert_tables_equal(got, want)
 
 
+@pytest.mark.parametrize("how", ["inner", "left", "outer", "semi"])
+def test_hash_join_long_duplicate_runs(gpu, how):
+    """Build keys repeated hundreds of times: bucket runs far longer than the head row's forward walk
+    (join.cu bucket_bounds BB_WALK), matches still in build insertion order (probe_table.rs:178-181)."""
+    rng = np.random.default_rng(3)
+    nb, npr = 6000, 400
+    right = pa.table({"k": pa.array(rng.integers(0, 12, nb), type=pa.int64()), "rv": pa.array(np.arange(nb), type=pa.int64())})
+    left = pa.table({"k": pa.array(rng.integers(0, 16, npr), type=pa.int64()), "lv": pa.array(np.arange(npr) * 10, type=pa.int64())})
+    c = gpu.col
+    got = RB(gpu, left).hash_join(RB(gpu, right), [c("k")], [c("k")], how=how).to_arrow_table()
+    want = O.hash_join(left, right, ["k"], ["k"], how)
+    if how == "semi":
+        want = want.select(left.column_names)
+    assert_tables_equal(got, want)
+
+
 def test_join_null_safe_and_float_keys(gpu):
     left = pa.table({"a": pa.array([1, None, 3], type=pa.int64()), "f": pa.array([0.0, float("nan"), 1.5]), "x": [10, 20, 30]})
     right = pa.table({"a": pa.array([None, 1, 1], type=pa.int64()), "f": pa.array([-0.0, float("nan"), 1.5]), "y": [1, 2, 3]})
