@@ -225,7 +225,7 @@ int b200_take(const b200_batch *batch, const b200_batch *indices, b200_batch **o
         const Column &ic = col_at(indices, 0);
         Buf idx = indices_to_i64(ic);
         *out = gather_batch(*batch, as<int64_t>(idx), ic.length, ic.null_count > 0);
-        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+        op_done();
     });
 }
 int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, char **errmsg) {
@@ -243,7 +243,7 @@ int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, c
             for (int i = 0; i < n; i++) cs.push_back(&batches[i]->cols[c]);
             o->cols.push_back(concat_columns(cs));
         }
-        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+        op_done();
         *out = o.release();
     });
 }
@@ -264,7 +264,7 @@ int b200_sort(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, c
     return guard(errmsg, [&] {
         Buf idx = op_argsort(*batch, key_cols, nkeys, descending, nulls_first);
         *out = gather_batch(*batch, as<int64_t>(idx), batch->num_rows, false, true);
-        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+        op_done();
     });
 }
 int b200_top_n(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
@@ -276,7 +276,7 @@ int b200_top_n(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, 
         const int64_t end = std::min<int64_t>(n, start + std::max<int64_t>(limit, 0));
         Buf idx = op_top_indices(*batch, key_cols, nkeys, descending, nulls_first, end);
         *out = gather_batch(*batch, as<int64_t>(idx) + start, end - start, false);
-        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+        op_done();
     });
 }
 

@@ -104,6 +104,10 @@ void exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n, int64_t *tot
 int64_t count_set_bits(const uint8_t *bitmap, int64_t nbits);  // syncs
 int64_t read_i64(const int64_t *dev_ptr);                      // syncs
 void fill_u8(void *ptr, int value, size_t bytes);
+// End of an operator: results are stream-ordered (every buffer of this library lives and dies on ctx().stream), so the
+// host does not wait for the device here -- the next operator's launches queue behind this one's.  Launch errors are
+// still reported; B200_SYNC_OPS=1 restores a blocking wait (debugging).
+void op_done();
 // gather rows of `src` at `idx[n]` (int64, -1 => null row) into a new column
 Column gather_column(const Column &src, const int64_t *idx, int64_t n, bool idx_may_be_negative);
 // `permutation`: idx holds every source row exactly once (sort): string outputs are sized without a host round trip

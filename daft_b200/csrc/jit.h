@@ -57,6 +57,10 @@ struct Compiled {
     int stage_rows = 0, stage_bytes = 0;  // staged agg variant: bytes per shared-memory stage (0 = nothing to stage)
     std::vector<uint8_t> key_project_plan;
     int regs = 0;
+    // (AGG, first-choice build) what the previous run of this plan found: the reference samples every query's first
+    // morsel to choose its strategy (grouped_aggregate.rs:205-245); a plan that needed the global-table kernel last
+    // time starts with it, sized from the group count it saw
+    mutable int64_t last_groups = -1;
     std::string source_path;
 };
 

@@ -333,7 +333,7 @@ void probe_table_build(b200_probe_table *pt) {
         count_launch();
     }
     pt->sorted_rows = rows;
-    B200_CUDA(cudaStreamSynchronize(st));
+    op_done();
     pt->built = true;
 }
 
@@ -372,7 +372,7 @@ Batch *probe_exists(const b200_probe_table *pt, const Batch &probe, const int32_
     auto out = std::make_unique<Batch>();
     out->num_rows = n;
     out->cols.push_back(std::move(c));
-    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    op_done();
     return out.release();
 }
 
@@ -419,7 +419,7 @@ Batch *probe_indices(const b200_probe_table *pt, const Batch &probe, const int32
     out->num_rows = total;
     out->cols.push_back(make_u64_column("probe_idx", pi, total));
     out->cols.push_back(make_u64_column("build_idx", bi, total));
-    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    op_done();
     return out.release();
 }
 
@@ -451,7 +451,7 @@ Batch *hash_join_probe(const b200_probe_table *pt, b200_join_state *st, const Ba
         int64_t total = 0;
         Buf idx = bitmap_select(as<uint32_t>(ex->cols[0].data), n, join_type == B200_JOIN_ANTI, &total);
         Batch *out = gather_batch(probe, as<int64_t>(idx), total, false);
-        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+        op_done();
         return out;
     }
     const bool keep_probe = join_type == B200_JOIN_OUTER || (join_type == B200_JOIN_LEFT && probe_is_left) ||
@@ -473,7 +473,7 @@ Batch *hash_join_probe(const b200_probe_table *pt, b200_join_state *st, const Ba
         append_cols(*out, std::move(pcols));
         append_cols(*out, std::move(bcols));
     }
-    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    op_done();
     return out.release();
 }
 
@@ -496,7 +496,7 @@ Batch *hash_join_finalize(const b200_probe_table *pt, b200_join_state *st, const
         append_cols(*out, std::move(pcols));
         append_cols(*out, std::move(bcols));
     }
-    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    op_done();
     return out.release();
 }
 

@@ -215,7 +215,7 @@ Batch *op_filter(const Batch &in, const uint8_t *plan, size_t len) {
     }
     for (size_t c = 0; c < in.cols.size(); c++)
         if (k.outs[c].nullable) out->cols[c] = gather_column(in.cols[c], as<int64_t>(idx), total, false);
-    B200_CUDA(cudaStreamSynchronize(st));
+    op_done();
     return out.release();
 }
 
@@ -387,6 +387,13 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         if (!kp) kp = &jit::get(B200_OP_AGG, plan, len, in, false, 0);
     }
     int64_t cap = kp->nkeys > 0 ? (1 << 16) : 1;
+    const Compiled *k_first = kp;  // carries the plan's history (the global build is only compiled when needed)
+    if (kp->nkeys > 0 && k_first->last_groups > 64 && n >= (1 << 16)) {  // sticky choice: skip the tier-1 attempt it would abandon again
+        variant = 1;
+        kp = &jit::get(B200_OP_AGG, plan, len, in, false, 1);
+        cap = 1 << 16;
+        while (2 * cap < 3 * k_first->last_groups) cap <<= 1;  // load factor <= 2/3: a larger table only costs DRAM locality
+    }
     Buf slot_tag, acc, slots, minrow_sorted, flag = dev_alloc_zero(16);  // flag: {int status, pad, u64 group counter}
     int64_t ng = 0;
     bool small_path = false;  // slots / first rows already ordered by the single-CTA epilogue
@@ -477,6 +484,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
             fail("agg: the group table would not fit in device memory");
     }
     const Compiled &k = *kp;
+    k_first->last_groups = (variant == 1) ? ng : 0;
 
     // ---- compact occupied slots, order groups by first occurrence
     const unsigned long long *nrows_cell = as<unsigned long long>(acc) + (size_t)cell_nrows * cap;
@@ -536,7 +544,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         }
         out->cols.push_back(std::move(c));
     }
-    B200_CUDA(cudaStreamSynchronize(st));  // `acc` and friends are released after this point
+    op_done();
     if (first_rows) *first_rows = minrow;
     if (ngroups) *ngroups = ng;
     return out.release();

@@ -205,7 +205,7 @@ static std::vector<Batch *> partition_direct(const Batch &b, const uint64_t *has
             }
             out.push_back(pb.release());
         }
-        B200_CUDA(cudaStreamSynchronize(st));
+        op_done();
     } catch (...) {
         for (auto *x : out) delete x;
         throw;
@@ -224,7 +224,7 @@ std::vector<Batch *> op_partition_by_hash(const Batch &b, const int32_t *key_col
     try {
         for (int p = 0; p < P; p++)
             out.push_back(gather_batch(b, as<int64_t>(perm) + offsets[p], offsets[p + 1] - offsets[p], false));
-        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+        op_done();
     } catch (...) {
         for (auto *x : out) delete x;
         throw;
@@ -255,7 +255,7 @@ Batch *op_dedup(const Batch &b, const int32_t *key_cols, int32_t nkeys) {
     int64_t ng = 0;
     std::unique_ptr<Batch> keys(op_agg_first_rows(b, plan.data(), plan.size(), &first, &ng));
     Batch *out = gather_batch(b, as<int64_t>(first), ng, false);
-    B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    op_done();
     return out;
 }
 

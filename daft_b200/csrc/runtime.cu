@@ -53,6 +53,11 @@ Buf dev_sub(const Buf &parent, size_t offset, size_t bytes) {
     v->owned = false;
     return Buf(v, [parent](DevAlloc *p) { delete p; });  // the view keeps its parent allocation alive
 }
+void op_done() {
+    static const bool blocking = [] { const char *e = getenv("B200_SYNC_OPS"); return e && *e == '1'; }();
+    if (blocking) B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    B200_CUDA(cudaPeekAtLastError());
+}
 void fill_u8(void *ptr, int value, size_t bytes) {
     if (bytes) B200_CUDA(cudaMemsetAsync(ptr, value, bytes, ctx().stream));
 }

@@ -380,7 +380,7 @@ Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uin
         }
         small_argsort_kernel<<<1, 1024, 0, st>>>(ks, n, as<int64_t>(idx));
         count_launch();
-        B200_CUDA(cudaStreamSynchronize(st));
+        op_done();
         return idx;
     }
     Buf keys = dev_alloc((size_t)n * 8);
@@ -417,7 +417,7 @@ Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uin
             radix_sort_pairs(keys, idx, n, 0, 8, nf);
         }
     }
-    B200_CUDA(cudaStreamSynchronize(st));
+    op_done();
     return idx;
 }
 
@@ -566,7 +566,7 @@ Buf op_top_indices(const Batch &b, const int32_t *key_cols, int32_t nkeys, const
     Buf out = dev_alloc((size_t)std::max<int64_t>(k, 1) * 8);
     map_indices<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(as<int64_t>(cand), as<int64_t>(local), k, as<int64_t>(out));
     count_launch();
-    B200_CUDA(cudaStreamSynchronize(st));
+    op_done();
     return out;
 }
 
