@@ -1,3 +1,271 @@
+// XXH3-64 (seeded, default secret) for sm_100a device code.
+//
+// Replaces xxhash_rust::xxh3::xxh3_64_with_seed as called by the reference at
+// src/daft-core/src/kernels/hashing.rs:164-170.  Bit-exact with the canonical xxHash v0.8
+// XXH3_64bits_withSeed for every input length class; the hot classes for this path (1-3 B flag
+// strings, 4 B dates, 8 B keys, 9-16 B names) are straight-line register code with the secret
+// folded into immediates.  This header is compiled both ahead of time (hash.cu, join.cu, ...)
+// and textually prepended to every JIT-generated kernel.
+
+
+#ifdef __CUDACC_RTC__
+typedef signed char int8_t;
+typedef short int16_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+typedef unsigned long size_t;
+#else
+#include <cstdint>
+#include <cstddef>
+#endif
+
+namespace b200 {
+namespace xxh {
+
+#define B200_HD __host__ __device__ __forceinline__
+
+constexpr uint8_t kSecret[192] = {
+    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+    0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+    0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+    0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
+    0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
+    0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
+    0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
+    0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
+    0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
+    0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
+};
+
+// secret words as compile-time constants (offset must be a constant expression)
+constexpr uint64_t sec64c(int off) {
+    uint64_t v = 0;
+    for (int i = 7; i >= 0; --i) v = (v << 8) | kSecret[off + i];
+    return v;
+}
+constexpr uint32_t sec32c(int off) {
+    uint32_t v = 0;
+    for (int i = 3; i >= 0; --i) v = (v << 8) | kSecret[off + i];
+    return v;
+}
+template <int OFF>
+struct Sec {
+    static constexpr uint64_t v64 = sec64c(OFF);
+};
+constexpr uint32_t kBitflip1to3 = sec32c(0) ^ sec32c(4);
+
+constexpr uint32_t P32_1 = 0x9E3779B1U, P32_2 = 0x85EBCA77U, P32_3 = 0xC2B2AE3DU;
+constexpr uint64_t P64_1 = 0x9E3779B185EBCA87ULL, P64_2 = 0xC2B2AE3D27D4EB4FULL, P64_3 = 0x165667B19E3779F9ULL,
+                   P64_4 = 0x85EBCA77C2B2AE63ULL, P64_5 = 0x27D4EB2F165667C5ULL, PMX1 = 0x165667919E3779F9ULL,
+                   PMX2 = 0x9FB21C651E98DF25ULL;
+
+B200_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+B200_HD uint32_t bswap32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+}
+B200_HD uint64_t bswap64(uint64_t x) {
+    return ((uint64_t)bswap32((uint32_t)x) << 32) | bswap32((uint32_t)(x >> 32));
+}
+B200_HD uint64_t mul128_fold64(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return (a * b) ^ __umul64hi(a, b);
+#else
+    unsigned __int128 p = (unsigned __int128)a * b;
+    return (uint64_t)p ^ (uint64_t)(p >> 64);
+#endif
+}
+B200_HD uint64_t xxh64_avalanche(uint64_t h) {
+    h ^= h >> 33; h *= P64_2; h ^= h >> 29; h *= P64_3; h ^= h >> 32; return h;
+}
+B200_HD uint64_t xxh3_avalanche(uint64_t h) {
+    h ^= h >> 37; h *= PMX1; h ^= h >> 32; return h;
+}
+B200_HD uint64_t rrmxmx(uint64_t h, uint64_t len) {
+    h ^= rotl64(h, 49) ^ rotl64(h, 24);
+    h *= PMX2;
+    h ^= (h >> 35) + len;
+    h *= PMX2;
+    return h ^ (h >> 28);
+}
+
+// ---- fixed-width fast paths (value already in a register) ------------------------------------
+B200_HD uint64_t hash_empty(uint64_t seed) {
+    return xxh64_avalanche(seed ^ (Sec<56>::v64 ^ Sec<64>::v64));
+}
+// len in {1,2,3}: c1 = first byte, c2 = byte[len>>1], c3 = last byte
+B200_HD uint64_t hash_1to3(uint32_t c1, uint32_t c2, uint32_t c3, uint32_t len, uint64_t seed) {
+    uint32_t comb = (c1 << 16) | (c2 << 24) | c3 | (len << 8);
+    uint64_t bitflip = (uint64_t)kBitflip1to3 + seed;
+    return xxh64_avalanche((uint64_t)comb ^ bitflip);
+}
+B200_HD uint64_t hash_u8(uint8_t v, uint64_t seed) { return hash_1to3(v, v, v, 1, seed); }
+B200_HD uint64_t hash_u16(uint16_t v, uint64_t seed) { return hash_1to3(v & 0xff, v >> 8, v >> 8, 2, seed); }
+// len in [4,8]: lo32 = first 4 bytes, hi32 = last 4 bytes
+B200_HD uint64_t hash_4to8(uint32_t first4, uint32_t last4, uint32_t len, uint64_t seed) {
+    seed ^= (uint64_t)bswap32((uint32_t)seed) << 32;
+    uint64_t bitflip = (Sec<8>::v64 ^ Sec<16>::v64) - seed;
+    uint64_t in64 = (uint64_t)last4 + ((uint64_t)first4 << 32);
+    return rrmxmx(in64 ^ bitflip, len);
+}
+B200_HD uint64_t hash_u32(uint32_t v, uint64_t seed) { return hash_4to8(v, v, 4, seed); }
+B200_HD uint64_t hash_u64(uint64_t v, uint64_t seed) { return hash_4to8((uint32_t)v, (uint32_t)(v >> 32), 8, seed); }
+// len in [9,16]: lo = first 8 bytes, hi = last 8 bytes
+B200_HD uint64_t hash_9to16(uint64_t first8, uint64_t last8, uint64_t len, uint64_t seed) {
+    uint64_t bf1 = (Sec<24>::v64 ^ Sec<32>::v64) + seed;
+    uint64_t bf2 = (Sec<40>::v64 ^ Sec<48>::v64) - seed;
+    uint64_t lo = first8 ^ bf1, hi = last8 ^ bf2;
+    uint64_t acc = len + bswap64(lo) + hi + mul128_fold64(lo, hi);
+    return xxh3_avalanche(acc);
+}
+
+// ---- byte-stream path --------------------------------------------------------------------------
+static __device__ const uint8_t d_secret[192] = {
+    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+    0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+    0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+    0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
+    0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
+    0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
+    0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
+    0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
+    0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
+    0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
+};
+
+// Unaligned little-endian loads from global memory, byte granular (never reads past p+width).
+B200_HD uint32_t ld32u(const uint8_t *p) {
+    if ((((uintptr_t)p) & 3) == 0) return *reinterpret_cast<const uint32_t *>(p);
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+B200_HD uint64_t ld64u(const uint8_t *p) {
+    if ((((uintptr_t)p) & 7) == 0) return *reinterpret_cast<const uint64_t *>(p);
+    if ((((uintptr_t)p) & 3) == 0) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+        return (uint64_t)q[0] | ((uint64_t)q[1] << 32);
+    }
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) v = (v << 8) | p[i];
+    return v;
+}
+B200_HD uint64_t sec64(int off) {
+#ifdef __CUDA_ARCH__
+    return ld64u(d_secret + off);
+#else
+    return ld64u(kSecret + off);
+#endif
+}
+
+B200_HD uint64_t mix16(const uint8_t *in, int soff, uint64_t seed) {
+    return mul128_fold64(ld64u(in) ^ (sec64(soff) + seed), ld64u(in + 8) ^ (sec64(soff + 8) - seed));
+}
+
+__host__ __device__ __noinline__ uint64_t hash_long(const uint8_t *in, int64_t len, uint64_t seed) {
+    // secret word i (8-byte granular at byte offset `off`) with the seed folded in:
+    // custom[16j..16j+8) = k + seed, custom[16j+8..16j+16) = k - seed; unaligned offsets straddle words.
+    auto csec = [&](int off) -> uint64_t {
+        if (seed == 0) return sec64(off);
+        uint64_t v = 0;
+        // rebuild byte by byte from the two (or one) derived words it touches
+        int w0 = off >> 3, sh = (off & 7) * 8;
+        uint64_t a = sec64(w0 * 8);
+        a = (w0 & 1) ? a - seed : a + seed;
+        if (sh == 0) return a;
+        uint64_t b = sec64(w0 * 8 + 8);
+        b = ((w0 + 1) & 1) ? b - seed : b + seed;
+        v = (a >> sh) | (b << (64 - sh));
+        return v;
+    };
+    uint64_t acc[8] = {P32_3, P64_1, P64_2, P64_3, P64_4, P32_2, P64_5, P32_1};
+    auto accumulate = [&](const uint8_t *p, int soff) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint64_t dv = ld64u(p + 8 * i);
+            uint64_t dk = dv ^ csec(soff + 8 * i);
+            acc[i ^ 1] += dv;
+            acc[i] += (uint64_t)(uint32_t)dk * (dk >> 32);
+        }
+    };
+    const int64_t block_len = 1024;
+    const int64_t nb_blocks = (len - 1) / block_len;
+    for (int64_t n = 0; n < nb_blocks; n++) {
+        for (int s = 0; s < 16; s++) accumulate(in + n * block_len + s * 64, s * 8);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint64_t a = acc[i];
+            a ^= a >> 47;
+            a ^= csec(128 + 8 * i);
+            a *= P32_1;
+            acc[i] = a;
+        }
+    }
+    const int nb_stripes = (int)(((len - 1) - block_len * nb_blocks) / 64);
+    for (int s = 0; s < nb_stripes; s++) accumulate(in + nb_blocks * block_len + s * 64, s * 8);
+    accumulate(in + len - 64, 192 - 64 - 7);
+    uint64_t r = (uint64_t)len * P64_1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r += mul128_fold64(acc[2 * i] ^ csec(11 + 16 * i), acc[2 * i + 1] ^ csec(11 + 16 * i + 8));
+    return xxh3_avalanche(r);
+}
+
+__host__ __device__ __noinline__ uint64_t hash_17plus(const uint8_t *in, int64_t len, uint64_t seed) {
+    if (len <= 128) {
+        uint64_t acc = (uint64_t)len * P64_1;
+        if (len > 32) {
+            if (len > 64) {
+                if (len > 96) {
+                    acc += mix16(in + 48, 96, seed);
+                    acc += mix16(in + len - 64, 112, seed);
+                }
+                acc += mix16(in + 32, 64, seed);
+                acc += mix16(in + len - 48, 80, seed);
+            }
+            acc += mix16(in + 16, 32, seed);
+            acc += mix16(in + len - 32, 48, seed);
+        }
+        acc += mix16(in, 0, seed);
+        acc += mix16(in + len - 16, 16, seed);
+        return xxh3_avalanche(acc);
+    }
+    if (len <= 240) {
+        uint64_t acc = (uint64_t)len * P64_1;
+        int nb = (int)(len / 16);
+        for (int i = 0; i < 8; i++) acc += mix16(in + 16 * i, 16 * i, seed);
+        acc = xxh3_avalanche(acc);
+        for (int i = 8; i < nb; i++) acc += mix16(in + 16 * i, 16 * (i - 8) + 3, seed);
+        acc += mix16(in + len - 16, 136 - 17, seed);
+        return xxh3_avalanche(acc);
+    }
+    return hash_long(in, len, seed);
+}
+
+// any length, any alignment
+B200_HD uint64_t hash_bytes(const uint8_t *in, int64_t len, uint64_t seed) {
+    if (len <= 16) {
+        if (len == 0) return hash_empty(seed);
+        if (len <= 3) return hash_1to3(in[0], in[len >> 1], in[len - 1], (uint32_t)len, seed);
+        if (len <= 8) return hash_4to8(ld32u(in), ld32u(in + len - 4), (uint32_t)len, seed);
+        return hash_9to16(ld64u(in), ld64u(in + len - 8), (uint64_t)len, seed);
+    }
+    return hash_17plus(in, len, seed);
+}
+
+}  // namespace xxh
+}  // namespace b200
+
 // Device-side skeletons of the JIT-specialised pipeline kernels (sm_100a).
 //
 // The host (jit.cpp) turns a serialised plan (include/daft_b200.h "plan encoding") into a `Prog`
@@ -22,7 +290,7 @@
 //     Low-cardinality aggregates (TPC-H Q1: 4 groups) never leave tier 1; high-cardinality ones
 //     (Q18: one group per order) spread their atomics over millions of addresses.
 //   * first-occurrence group order (inline_agg.rs:804-807) is recovered by tracking min(row) per group.
-#pragma once
+
 
 #define FULL_MASK 0xffffffffu
 
@@ -336,13 +604,10 @@ __device__ __forceinline__ uint64_t agg_mix(uint64_t x) {
     return x;
 }
 
-// Two layouts of the global table, chosen by the host per launch (ival[IV_RSTRIDE] = words between records):
-//  * records (stride = Prog::ASTRIDE): [code, cell 0, cell 1, ...] padded to whole 32-byte sectors -- everything one
-//    row touches sits in one or two adjacent sectors: for tables larger than L2 (DRAM-bound random access);
-//  * one array per cell (stride = 1): a row's atomics land on different L2 slices and proceed in parallel: for tables
-//    that live in L2 (atomic-throughput bound).  Measured on B200, 50 M rows: 100 k groups 1.6 ms vs 2.3 ms with
-//    records; 10 M groups 9.9 ms vs 6.9 ms with records.
-// All "slot" values handed around are ELEMENT indices (record number * stride): a cell is `cell_base[slot]`.
+// The global table is an array of RECORDS of Prog::ASTRIDE 64-bit words: [code, cell 0, cell 1, ...] (value cells, row
+// count, first row, ballot counts), padded to whole 32-byte sectors -- everything one row touches sits in one or two
+// adjacent sectors instead of one sector per cell array.  All "slot" values handed around are ELEMENT indices
+// (record number * ASTRIDE), so a cell is `cell_base[slot]` with cell_base = table + 1 + cell.
 // Find or claim the record of the group with code `tag`.  Returns its element index, or -1 after flagging overflow.
 template <class Prog>
 __device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, unsigned long long tag, int64_t row) {
@@ -350,10 +615,9 @@ __device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, un
     unsigned long long *slot_min = (unsigned long long *)p.ptr[Prog::PTR_MINROW];
     const uint64_t mask = (uint64_t)p.ival[Prog::IV_MASK];
     const bool exact = Prog::MODE == 1 || (Prog::MODE == 0 && !(tag >> 63));
-    const uint64_t rstride = (uint64_t)p.ival[Prog::IV_RSTRIDE];
     uint64_t rec = agg_mix(tag) & mask;
     for (int probes = 0; probes < AGG_PROBE_LIMIT; probes++) {
-        const uint64_t s = rec * rstride;
+        const uint64_t s = rec * Prog::ASTRIDE;
         // tags are never 0 (bit 62 or bit 63 is set): one CAS on the tag word claims the record
         unsigned long long cur = slot_tag[s];  // a stale 0 from L1 is corrected by the CAS below
         if (cur == 0ULL) {
@@ -801,3 +1065,220 @@ __device__ __forceinline__ void agg_body_staged(const typename Prog::P &p) {
 
 }  // namespace jit
 }  // namespace b200
+
+using namespace b200;
+using namespace b200::jit;
+struct Prog {
+  typedef Params<18, 2> P;
+  static constexpr int IV_N = 0, IV_MASK = 1, PTR_TAG = 0, PTR_MINROW = 8, PTR_FLAG = 1, MODE = 0;
+  static constexpr int ASTRIDE = 8;
+  static constexpr int NKEYS = 2, G1 = 4, NLANE = 7, NWARP = 0, U = 2;
+  static constexpr bool PIPE = false;
+  struct Raw {
+    int32_t c6;
+    int64_t o4a, o4b; uint64_t pk4;
+    unsigned int sw4;
+    int64_t o5a, o5b; uint64_t pk5;
+    unsigned int sw5;
+    int64_t c0;
+    double c1;
+    double c2;
+    double c3;
+    int pad_;
+  };
+  struct Keys {
+    Str v0; bool k0;
+    uint64_t p0;
+    Str v1; bool k1;
+    uint64_t p1;
+    int pad_;
+  };
+  struct Vals {
+    int64_t a0; bool k0;
+    double a1; bool k1;
+    double a2; bool k2;
+    double a3; bool k3;
+    double a4; bool k4;
+    int pad_;
+  };
+  __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {
+    r.c6 = ((const int32_t*)p.ptr[9])[row];
+    { const int64_t* of_ = (const int64_t*)p.ptr[10]; r.o4a = of_[row]; r.o4b = of_[row + 1]; }
+    r.sw4 = ((const uint8_t*)p.ptr[11])[row];
+    { const int64_t* of_ = (const int64_t*)p.ptr[12]; r.o5a = of_[row]; r.o5b = of_[row + 1]; }
+    r.sw5 = ((const uint8_t*)p.ptr[13])[row];
+    r.c0 = ((const int64_t*)p.ptr[14])[row];
+    r.c1 = ((const double*)p.ptr[15])[row];
+    r.c2 = ((const double*)p.ptr[16])[row];
+    r.c3 = ((const double*)p.ptr[17])[row];
+  }
+  __device__ __forceinline__ static void load2(const P& p, const int64_t row, Raw& r) {
+    { const long long len_ = r.o4b - r.o4a;
+      if (r.o4a == row * 1 && len_ == 1) r.pk4 = (uint64_t)r.sw4;
+      else r.pk4 = str_pack4(Str{(const uint8_t*)p.ptr[11] + r.o4a, len_}); }
+    { const long long len_ = r.o5b - r.o5a;
+      if (r.o5a == row * 1 && len_ == 1) r.pk5 = (uint64_t)r.sw5;
+      else r.pk5 = str_pack4(Str{(const uint8_t*)p.ptr[13] + r.o5a, len_}); }
+  }
+  __device__ __forceinline__ static void load0(const P& p, const int64_t row, Raw& r) {
+  }
+  __device__ __forceinline__ static void copy0(Raw& d, const Raw& s) {
+  }
+  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {
+    const int32_t v0 = r.c6; const bool k0 = true;
+    const int32_t v1 = (int32_t)(10471LL); const bool k1 = true;
+    const bool v2 = v0 <= v1;
+    const bool k2 = k0 && k1;
+    if (!(k2 && v2)) return false;
+    const Str v3{(const uint8_t*)p.ptr[11] + r.o4a, r.o4b - r.o4a};
+    const bool k3 = true;
+    keys.v0 = v3; keys.k0 = k3;
+    keys.p0 = keys.k0 ? r.pk4 : 0ULL;
+    const Str v4{(const uint8_t*)p.ptr[13] + r.o5a, r.o5b - r.o5a};
+    const bool k4 = true;
+    keys.v1 = v4; keys.k1 = k4;
+    keys.p1 = keys.k1 ? r.pk5 : 0ULL;
+    const int64_t v5 = r.c0; const bool k5 = true;
+    vals.a0 = (int64_t)v5; vals.k0 = k5;
+    const double v6 = r.c1; const bool k6 = true;
+    vals.a1 = (double)v6; vals.k1 = k6;
+    const double v8 = __longlong_as_double(4607182418800017408LL); const bool k8 = true;
+    const double v9 = r.c2; const bool k9 = true;
+    const double v10 = v8 - v9;
+    const bool k10 = k8 && k9;
+    const double v11 = v6 * v10;
+    const bool k11 = k6 && k10;
+    vals.a2 = (double)v11; vals.k2 = k11;
+    const double v18 = r.c3; const bool k18 = true;
+    const double v19 = v8 + v18;
+    const bool k19 = k8 && k18;
+    const double v20 = v11 * v19;
+    const bool k20 = k11 && k19;
+    vals.a3 = (double)v20; vals.k3 = k20;
+    vals.a4 = (double)v9; vals.k4 = k9;
+    return true;
+  }
+  __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {
+    const bool rowok = true;
+    const bool k3 = rowok;
+    Str v3{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[10]; const int64_t a_ = of_[row]; v3.p = (const uint8_t*)p.ptr[11] + a_; v3.len = of_[row + 1] - a_; }
+    keys.v0 = v3; keys.k0 = k3;
+    keys.p0 = keys.k0 ? str_pack8(keys.v0) : 0ULL;
+    const bool k4 = rowok;
+    Str v4{(const uint8_t*)0, 0};
+    if (rowok) { const int64_t* of_ = (const int64_t*)p.ptr[12]; const int64_t a_ = of_[row]; v4.p = (const uint8_t*)p.ptr[13] + a_; v4.len = of_[row + 1] - a_; }
+    keys.v1 = v4; keys.k1 = k4;
+    keys.p1 = keys.k1 ? str_pack8(keys.v1) : 0ULL;
+  }
+  __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {
+    return true && (a.k0 == b.k0) && (!a.k0 || str_eq_packed(a.v0, a.p0, b.v0, b.p0)) && (a.k1 == b.k1) && (!a.k1 || str_eq_packed(a.v1, a.p1, b.v1, b.p1));
+  }
+  __device__ __forceinline__ static void finish_keys(Keys& k) {
+    k.p0 = k.k0 ? str_pack8(k.v0) : 0ULL;
+    k.p1 = k.k1 ? str_pack8(k.v1) : 0ULL;
+  }
+  __device__ __forceinline__ static uint64_t fingerprint(const Keys& k) {
+    uint64_t f = 0x9E3779B97F4A7C15ULL;
+    f = (f ^ (k.k0 ? (((uint64_t)k.v0.len <= 4ULL ? k.p0 : xxh::hash_bytes(k.v0.p, k.v0.len, 0ULL)) ^ ((uint64_t)k.v0.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    f = (f ^ (k.k1 ? (((uint64_t)k.v1.len <= 4ULL ? k.p1 : xxh::hash_bytes(k.v1.p, k.v1.len, 0ULL)) ^ ((uint64_t)k.v1.len << 56)) : 0xA5A5A5A5A5A5A5A5ULL)) * 0xD6E8FEB86659FD93ULL; f ^= f >> 32;
+    return f;
+  }
+  __device__ __forceinline__ static uint64_t code(const Keys& k) {
+    uint64_t c = 0x4000000000000000ULL; bool ex = true;
+    { const uint64_t l_ = k.k0 ? (uint64_t)k.v0.len : 0ULL; ex = ex && (l_ <= 3ULL); c |= (k.p0 & 16777215ULL) << 0; c |= (l_ & 7ULL) << 24; }
+    { const uint64_t l_ = k.k1 ? (uint64_t)k.v1.len : 0ULL; ex = ex && (l_ <= 3ULL); c |= (k.p1 & 16777215ULL) << 27; c |= (l_ & 7ULL) << 51; }
+    return ex ? c : (fingerprint(k) | 0x8000000000000000ULL);
+  }
+  __device__ __forceinline__ static void lane_init(unsigned long long* cells) {
+    cells[0] = 0ULL;
+    cells[32] = 0ULL;
+    cells[64] = 0ULL;
+    cells[96] = 0ULL;
+    cells[128] = 0ULL;
+    cells[160] = 0ULL;
+    cells[192] = 0xFFFFFFFFFFFFFFFFULL;
+  }
+  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v, const int64_t row) {
+    if (v.k0) cells[0] += (unsigned long long)v.a0;
+    if (v.k1) cells[32] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[32]) + v.a1);
+    if (v.k2) cells[64] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[64]) + v.a2);
+    if (v.k3) cells[96] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[96]) + v.a3);
+    if (v.k4) cells[128] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)cells[128]) + v.a4);
+    cells[160] += 1ULL;
+    if ((unsigned long long)row < cells[192]) cells[192] = (unsigned long long)row;
+  }
+  __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {
+    if (v.k0) atomicAdd(((unsigned long long*)p.ptr[2]) + slot, (unsigned long long)v.a0);
+    if (v.k1) atomicAdd((double*)(((unsigned long long*)p.ptr[3]) + slot), v.a1);
+    if (v.k2) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), v.a2);
+    if (v.k3) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), v.a3);
+    if (v.k4) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), v.a4);
+    atomicAdd(((unsigned long long*)p.ptr[7]) + slot, 1ULL);
+    atomicMin(((unsigned long long*)p.ptr[8]) + slot, (unsigned long long)row);
+  }
+  static constexpr int T2 = 1024, NCELLS = 7;
+  __device__ __forceinline__ static void t2_init(unsigned long long* t2c, const int t) {
+    t2c[0 * T2 + t] = 0ULL;
+    t2c[1 * T2 + t] = 0ULL;
+    t2c[2 * T2 + t] = 0ULL;
+    t2c[3 * T2 + t] = 0ULL;
+    t2c[4 * T2 + t] = 0ULL;
+    t2c[5 * T2 + t] = 0ULL; t2c[6 * T2 + t] = 0xFFFFFFFFFFFFFFFFULL;
+  }
+  __device__ __forceinline__ static void t2_update(unsigned long long* t2c, const int t, const Vals& v, const int64_t row) {
+    if (v.k0) atomicAdd((t2c + 0 * T2 + t), (unsigned long long)v.a0);
+    if (v.k1) atomicAdd((double*)(t2c + 1 * T2 + t), v.a1);
+    if (v.k2) atomicAdd((double*)(t2c + 2 * T2 + t), v.a2);
+    if (v.k3) atomicAdd((double*)(t2c + 3 * T2 + t), v.a3);
+    if (v.k4) atomicAdd((double*)(t2c + 4 * T2 + t), v.a4);
+    atomicAdd(t2c + 5 * T2 + t, 1ULL);
+    atomicMin(t2c + 6 * T2 + t, (unsigned long long)row);
+  }
+  __device__ __forceinline__ static void t2_flush(const P& p, const long long slot, const unsigned long long* t2c, const int t) {
+    atomicAdd(((unsigned long long*)p.ptr[2]) + slot, t2c[0 * T2 + t]);
+    atomicAdd((double*)(((unsigned long long*)p.ptr[3]) + slot), __longlong_as_double((long long)t2c[1 * T2 + t]));
+    atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), __longlong_as_double((long long)t2c[2 * T2 + t]));
+    atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), __longlong_as_double((long long)t2c[3 * T2 + t]));
+    atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), __longlong_as_double((long long)t2c[4 * T2 + t]));
+    atomicAdd(((unsigned long long*)p.ptr[7]) + slot, t2c[5 * T2 + t]);
+    atomicMin(((unsigned long long*)p.ptr[8]) + slot, t2c[6 * T2 + t]);
+  }
+  __device__ __forceinline__ static void warp_cells(const Vals& v, const bool in_g, unsigned long long* wcell, const int lane) {
+  }
+  __device__ __forceinline__ static void flush(const P& p, const long long slot, const unsigned long long* lcell, const size_t lstride,
+                                               const unsigned long long* wcell, const size_t wstride, const int lane) {
+    {
+      unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 0 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd(((unsigned long long*)p.ptr[2]) + slot, a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 32 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[3]) + slot), a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 64 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[4]) + slot), a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 96 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[5]) + slot), a_);
+    }
+    {
+      double a_ = 0.0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += __longlong_as_double((long long)lcell[(size_t)w_ * lstride + 128 + lane]);
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0) atomicAdd((double*)(((unsigned long long*)p.ptr[6]) + slot), a_);
+    }
+    { unsigned long long a_ = 0; for (int w_ = 0; w_ < AGG_WARPS; w_++) a_ += lcell[(size_t)w_ * lstride + 160 + lane];
+      for (int d_ = 16; d_ > 0; d_ >>= 1) a_ += __shfl_xor_sync(FULL_MASK, a_, d_);
+      if (lane == 0 && a_) atomicAdd(((unsigned long long*)p.ptr[7]) + slot, a_); }
+    { unsigned long long a_ = 0xFFFFFFFFFFFFFFFFULL; for (int w_ = 0; w_ < AGG_WARPS; w_++) { unsigned long long t_ = lcell[(size_t)w_ * lstride + 192 + lane]; a_ = t_ < a_ ? t_ : a_; }
+      for (int d_ = 16; d_ > 0; d_ >>= 1) { unsigned long long t_ = __shfl_xor_sync(FULL_MASK, a_, d_); a_ = t_ < a_ ? t_ : a_; }
+      if (lane == 0) atomicMin(((unsigned long long*)p.ptr[8]) + slot, a_); }
+  }
+};
+extern "C" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_global<Prog>(p); }

@@ -808,6 +808,8 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     const int NL = (int)lane_cells.size(), NW = (int)warp_cells.size(), NLT = NL + 2;
     meta.NLANE = NLT;
     meta.NWARP = NW;
+    const int astride = (1 + NLT + NW + 3) / 4 * 4;  // record = code + cells, whole 32-byte sectors
+    meta.astride = astride;
     for (auto &c : lane_cells) meta.lane_cell_ops.push_back(c.op);
     meta.lane_cell_ops.push_back(C_ADD_I64);  // row count
     meta.lane_cell_ops.push_back(C_MIN);      // first row
@@ -825,7 +827,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     while ((size_t)(t2_slots * 2) * 8 * (size_t)(1 + NLT + NW) <= 96 * 1024) t2_slots *= 2;
     if (env_int("B200_AGG_T2", 1) == 0) t2_slots = 2;
 
-    const int iv_n = cg.int_slot(I_N), iv_mask = cg.int_slot(I_MASK);
+    const int iv_n = cg.int_slot(I_N), iv_mask = cg.int_slot(I_MASK), iv_rstride = cg.int_slot(I_RSTRIDE);
     const int p_hash = cg.ptr_slot(P_SLOT_HASH, 0), p_ovf = cg.ptr_slot(P_OVERFLOW, 0);  // slot tags, status flag
     // global cells: [0,NL) value cells, NL = row count, NL+1 = first row, [NL+2, NL+2+NW) ballot count cells
     const int cell_nrows = NL, cell_minrow = NL + 1;
@@ -1291,6 +1293,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     o << "  typedef Params<" << meta.ptrs.size() << ", " << meta.ints.size() << "> P;\n";
     o << "  static constexpr int IV_N = " << iv_n << ", IV_MASK = " << iv_mask << ", PTR_TAG = " << p_hash << ", PTR_MINROW = " << p_acc[cell_minrow]
       << ", PTR_FLAG = " << p_ovf << ", MODE = " << (wide_mode ? 1 : (exact_possible ? 0 : 2)) << ";\n";
+    o << "  static constexpr int ASTRIDE = " << astride << ", IV_RSTRIDE = " << iv_rstride << ";\n";
     o << "  static constexpr int NKEYS = " << nkeys << ", G1 = " << G1 << ", NLANE = " << NLT << ", NWARP = " << NW << ", U = " << U << ";\n";
     o << "  static constexpr bool PIPE = " << (pipe_offsets ? "true" : "false") << ";\n";
     o << "  struct Raw {\n" << raw.str() << "    int pad_;\n  };\n";

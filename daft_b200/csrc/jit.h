@@ -15,7 +15,7 @@ enum PtrKind {
     P_TAKE, P_SLOT_HASH, P_SLOT_ROW, P_ACC, P_OVERFLOW
 };
 struct PtrSlot { int kind; int index; };
-enum IntKind { I_N = 0, I_MASK, I_STRLEN /* + 1000 * column: constant value length hint of a string column, 0 = none */ };
+enum IntKind { I_N = 0, I_MASK, I_STRLEN /* (unused) */, I_RSTRIDE /* words between group-table records: 1 = one array per cell */ };
 
 struct OutCol {
     std::string name;
@@ -50,6 +50,7 @@ struct Compiled {
     // agg
     int nkeys = 0;
     int G1 = 0, NLANE = 0, NWARP = 0;
+    int astride = 1;  // 64-bit words per global-table record (code + cells, padded to 32-byte sectors)
     std::vector<int> lane_cell_ops;
     std::vector<AggOut> aggs;
     size_t smem_bytes = 0;

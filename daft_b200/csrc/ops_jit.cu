@@ -222,13 +222,36 @@ Batch *op_filter(const Batch &in, const uint8_t *plan, size_t len) {
 // ------------------------------------------------------------------------------------------------
 // fused HashAggregate
 // ------------------------------------------------------------------------------------------------
-__global__ void compact_slots(const unsigned long long *__restrict__ nrows, int64_t cap, int ungrouped, unsigned long long *counter,
+// records are `astride` words apart; emitted slot ids are ELEMENT indices (record * astride), see agg_find_slot
+__global__ void compact_slots(const unsigned long long *__restrict__ nrows, int64_t cap, int astride, int ungrouped, unsigned long long *counter,
                               int64_t *__restrict__ out_slot) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < cap; i += stride) {
-        const bool used = ungrouped ? (i == 0) : (nrows[i] != 0);  // a slot is a group iff some row was accumulated into it
-        if (used) out_slot[atomicAdd(counter, 1ULL)] = i;
+    const int64_t cap_round = (cap + 31) & ~(int64_t)31;
+    const int lane = threadIdx.x & 31;
+    for (; i < cap_round; i += stride) {
+        // a record is a group iff some row was accumulated into it; one counter update per warp, not per group
+        const bool used = i < cap && (ungrouped ? (i == 0) : (nrows[i * astride] != 0));
+        const unsigned m = __ballot_sync(0xffffffffu, used);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (used) out_slot[base + __popc(m & ((1u << lane) - 1u))] = i * astride;
+        }
+    }
+}
+// every record starts as [0, identity of cell 0, identity of cell 1, ...] (0 for sums / counts, all ones for minima)
+struct TableInit {
+    unsigned long long word[40];
+};
+__global__ void init_table(unsigned long long *__restrict__ table, int64_t nrecords, int astride, const __grid_constant__ TableInit init) {
+    // one record per thread, 16-byte stores (astride is a multiple of 4 words, records are 32-byte aligned)
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; r < nrecords; r += stride) {
+        ulonglong2 *rec = reinterpret_cast<ulonglong2 *>(table + r * astride);
+        for (int w = 0; w < astride; w += 2) rec[w >> 1] = make_ulonglong2(init.word[w], init.word[w + 1]);
     }
 }
 
@@ -237,7 +260,7 @@ __global__ void compact_slots(const unsigned long long *__restrict__ nrows, int6
 // counter[0] = number of groups, or -1 when there are more than SMALL_GROUPS (the host then takes the general path).
 constexpr int SMALL_GROUPS = 1024;
 __global__ void __launch_bounds__(1024) small_groups_epilogue(const unsigned long long *__restrict__ nrows, const unsigned long long *__restrict__ minrow_cell,
-                                                              int64_t cap, int ungrouped, long long *__restrict__ counter,
+                                                              int64_t cap, int astride, int ungrouped, long long *__restrict__ counter,
                                                               int64_t *__restrict__ out_slot, unsigned long long *__restrict__ out_minrow) {
     __shared__ int64_t s_slot[SMALL_GROUPS];
     __shared__ unsigned long long s_min[SMALL_GROUPS];
@@ -245,12 +268,12 @@ __global__ void __launch_bounds__(1024) small_groups_epilogue(const unsigned lon
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     for (int64_t i = threadIdx.x; i < cap; i += blockDim.x) {
-        const bool used = ungrouped ? (i == 0) : (nrows[i] != 0);
+        const bool used = ungrouped ? (i == 0) : (nrows[i * astride] != 0);
         if (used) {
             const int pos = atomicAdd(&s_n, 1);
             if (pos < SMALL_GROUPS) {
-                s_slot[pos] = i;
-                s_min[pos] = minrow_cell[i];
+                s_slot[pos] = i * astride;
+                s_min[pos] = minrow_cell[i * astride];
             }
         }
     }
@@ -397,16 +420,32 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
     Buf slot_tag, acc, slots, minrow_sorted, flag = dev_alloc_zero(16);  // flag: {int status, pad, u64 group counter}
     int64_t ng = 0;
     bool small_path = false;  // slots / first rows already ordered by the single-CTA epilogue
+    size_t cell_step_final = 1;  // layout of the table the successful attempt used
     int ncells = 0, cell_nrows = 0, cell_minrow = 0;
     for (int attempt = 0;; attempt++) {
         const Compiled &k = *kp;
         ncells = k.NLANE + k.NWARP;  // value cells + row count + first row, then ballot count cells
         cell_nrows = k.NLANE - 2;
         cell_minrow = k.NLANE - 1;
-        slot_tag = dev_alloc_zero((size_t)cap * 8);
-        acc = dev_alloc_zero((size_t)ncells * cap * 8);
-        for (int c = 0; c < k.NLANE; c++)
-            if (k.lane_cell_ops[c] == jit::C_MIN) fill_u8(as<uint8_t>(acc) + (size_t)c * cap * 8, 0xFF, (size_t)cap * 8);
+        // layout: records when the table outgrows L2 (DRAM locality), one array per cell otherwise (parallel L2 atomics)
+        if (k.astride > 40) fail("agg: too many accumulator cells per group");
+        const bool records = (size_t)cap * (size_t)k.astride * 8 > ((size_t)48 << 20);
+        const int astride = records ? k.astride : 1;
+        const size_t cell_step = records ? 1 : (size_t)cap;  // words between the bases of consecutive cell arrays
+        acc = dev_alloc((size_t)cap * k.astride * 8);
+        if (records) {
+            TableInit ti;
+            for (int w = 0; w < 40; w++) ti.word[w] = 0ULL;
+            for (int c = 0; c < k.NLANE; c++)
+                if (k.lane_cell_ops[c] == jit::C_MIN) ti.word[1 + c] = ~0ULL;
+            init_table<<<stream_grid(cap, 256, 8), 256, 0, st>>>(as<unsigned long long>(acc), cap, k.astride, ti);
+            count_launch();
+        } else {
+            fill_u8(acc->ptr, 0, (size_t)cap * (1 + ncells) * 8);
+            for (int c = 0; c < k.NLANE; c++)
+                if (k.lane_cell_ops[c] == jit::C_MIN) fill_u8(as<uint8_t>(acc) + (size_t)(1 + c) * cap * 8, 0xFF, (size_t)cap * 8);
+        }
+        auto cell_base = [&](int c) { return as<unsigned long long>(acc) + (size_t)(1 + c) * cell_step; };
         fill_u8(flag->ptr, 0, 16);
         int status = 0;
         if (n > 0) {
@@ -419,9 +458,9 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
                     case jit::P_COL_DATA: a.ptr[s] = in.cols[ps.index].data ? in.cols[ps.index].data->ptr : nullptr; break;
                     case jit::P_COL_VALID: a.ptr[s] = in.cols[ps.index].validity ? in.cols[ps.index].validity->ptr : nullptr; break;
                     case jit::P_COL_OFFSETS: a.ptr[s] = in.cols[ps.index].offsets ? in.cols[ps.index].offsets->ptr : nullptr; break;
-                    case jit::P_SLOT_HASH: a.ptr[s] = slot_tag->ptr; break;
+                    case jit::P_SLOT_HASH: a.ptr[s] = acc->ptr; break;
                     case jit::P_OVERFLOW: a.ptr[s] = flag->ptr; break;
-                    case jit::P_ACC: a.ptr[s] = as<uint8_t>(acc) + (size_t)ps.index * cap * 8; break;
+                    case jit::P_ACC: a.ptr[s] = cell_base(ps.index); break;
                     default: fail("agg: unexpected parameter kind");
                 }
             }
@@ -429,6 +468,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
                 const int kind = k.ints[s] % 1000;
                 if (kind == jit::I_N) a.ival[s] = n;
                 else if (kind == jit::I_MASK) a.ival[s] = cap - 1;
+                else if (kind == jit::I_RSTRIDE) a.ival[s] = astride;
             }
             int occ = 0;
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k.fn, k.block_threads, k.smem_bytes));
@@ -441,15 +481,16 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         // compact the occupied slots right behind the kernel: status flag and group count come back in ONE read
         // (an ungrouped aggregate has exactly one group and no failure mode: no read at all)
         slots = dev_alloc((size_t)std::max<int64_t>(cap, 1) * 8);
-        const unsigned long long *nrows_c = as<unsigned long long>(acc) + (size_t)cell_nrows * cap;
-        const unsigned long long *minrow_c = as<unsigned long long>(acc) + (size_t)cell_minrow * cap;
+        const unsigned long long *nrows_c = cell_base(cell_nrows);
+        const unsigned long long *minrow_c = cell_base(cell_minrow);
+        cell_step_final = cell_step;
         small_path = cap <= (1 << 16);
         if (small_path) {
             minrow_sorted = dev_alloc((size_t)SMALL_GROUPS * 8);
-            small_groups_epilogue<<<1, 1024, 0, st>>>(nrows_c, minrow_c, cap, k.nkeys == 0, as<long long>(flag) + 1, as<int64_t>(slots),
+            small_groups_epilogue<<<1, 1024, 0, st>>>(nrows_c, minrow_c, cap, astride, k.nkeys == 0, as<long long>(flag) + 1, as<int64_t>(slots),
                                                       as<unsigned long long>(minrow_sorted));
         } else {
-            compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(nrows_c, cap, k.nkeys == 0, as<unsigned long long>(flag) + 1, as<int64_t>(slots));
+            compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(nrows_c, cap, astride, k.nkeys == 0, as<unsigned long long>(flag) + 1, as<int64_t>(slots));
         }
         count_launch();
         if (k.nkeys > 0) {
@@ -461,7 +502,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
             if (!status && ng < 0) {  // more groups than the single-CTA epilogue handles: general path on the same table
                 small_path = false;
                 fill_u8(as<uint8_t>(flag) + 8, 0, 8);
-                compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(nrows_c, cap, 0, as<unsigned long long>(flag) + 1, as<int64_t>(slots));
+                compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(nrows_c, cap, astride, 0, as<unsigned long long>(flag) + 1, as<int64_t>(slots));
                 count_launch();
                 ng = read_i64(as<int64_t>(flag) + 1);
             }
@@ -480,17 +521,18 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         }
         size_t free_b = 0, total_b = 0;
         B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        if ((size_t)cap * 8 * (size_t)(ncells + 1) > free_b + (size_t)(ncells + 1) * (size_t)(cap >> 3) * 8)
+        if ((size_t)cap * 8 * (size_t)(kp->astride + 1) > free_b + (size_t)(kp->astride + 1) * (size_t)(cap >> 3) * 8)
             fail("agg: the group table would not fit in device memory");
     }
     const Compiled &k = *kp;
     k_first->last_groups = (variant == 1) ? ng : 0;
 
     // ---- compact occupied slots, order groups by first occurrence
-    const unsigned long long *nrows_cell = as<unsigned long long>(acc) + (size_t)cell_nrows * cap;
+    auto cell_ptr = [&](int c) { return as<unsigned long long>(acc) + (size_t)(1 + c) * cell_step_final; };
+    const unsigned long long *nrows_cell = cell_ptr(cell_nrows);
     Buf minrow = small_path ? minrow_sorted : dev_alloc((size_t)std::max<int64_t>(ng, 1) * 8);
     if (ng > 0 && !small_path) {
-        gather_u64<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(as<unsigned long long>(acc) + (size_t)cell_minrow * cap,
+        gather_u64<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(cell_ptr(cell_minrow),
                                                                   as<int64_t>(slots), ng, as<unsigned long long>(minrow));
         count_launch();
         if (k.nkeys > 0 && ng > 1) {
@@ -528,8 +570,8 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         c.data_bytes = ng * w;
         const bool may_null = ag.kind != jit::AGG_COUNT && (ag.child_nullable || k.nkeys == 0);
         if (may_null) c.validity = dev_alloc((size_t)((ng + 31) / 32 + 1) * 4);
-        const unsigned long long *cell = ag.lane_cell >= 0 ? as<unsigned long long>(acc) + (size_t)ag.lane_cell * cap : nullptr;
-        const unsigned long long *cnt = ag.cnt_cell >= 0 ? as<unsigned long long>(acc) + (size_t)(k.NLANE + ag.cnt_cell) * cap : nrows_cell;
+        const unsigned long long *cell = ag.lane_cell >= 0 ? cell_ptr(ag.lane_cell) : nullptr;
+        const unsigned long long *cnt = ag.cnt_cell >= 0 ? cell_ptr(k.NLANE + ag.cnt_cell) : nrows_cell;
         // an ungrouped aggregate over zero rows still yields one row: sums null, counts 0
         const int cnt_is_valid = (ag.kind != jit::AGG_COUNT) ? 1 : 0;
         fs.d[fs.n++] = {ag.kind, ag.val_dtype, ag.out_dtype, cnt_is_valid, ag.const_zero ? 1 : 0, 0, cell, cnt, c.data->ptr, as<uint32_t>(c.validity)};
