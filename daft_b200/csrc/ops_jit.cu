@@ -267,13 +267,24 @@ __global__ void __launch_bounds__(1024) small_groups_epilogue(const unsigned lon
     __shared__ int s_n;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < cap; i += blockDim.x) {
-        const bool used = ungrouped ? (i == 0) : (nrows[i * astride] != 0);
-        if (used) {
-            const int pos = atomicAdd(&s_n, 1);
-            if (pos < SMALL_GROUPS) {
-                s_slot[pos] = i * astride;
-                s_min[pos] = minrow_cell[i * astride];
+    // eight independent loads in flight per thread: one CTA scans the 65 536-slot table in a few microseconds
+    for (int64_t i0 = threadIdx.x; i0 < cap; i0 += (int64_t)blockDim.x * 8) {
+        unsigned long long nr[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            nr[u] = (i < cap && !ungrouped) ? nrows[i * astride] : 0ULL;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            const bool used = i < cap && (ungrouped ? (i == 0) : (nr[u] != 0));
+            if (used) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < SMALL_GROUPS) {
+                    s_slot[pos] = i * astride;
+                    s_min[pos] = minrow_cell[i * astride];
+                }
             }
         }
     }
@@ -409,9 +420,12 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         }
         if (!kp) kp = &jit::get(B200_OP_AGG, plan, len, in, false, 0);
     }
-    int64_t cap = kp->nkeys > 0 ? (1 << 16) : 1;
+    // Table behind the tier-1 kernels: on large inputs they only finish when a CTA meets a handful of groups (anything else
+    // is abandoned to the global build), so a small table is enough and keeps its initialisation and the epilogue's scan
+    // cheap; small inputs never reach the abandon threshold and may hold tens of thousands of groups.
+    int64_t cap = kp->nkeys > 0 ? (n >= (1 << 20) ? (1 << 13) : (1 << 16)) : 1;
     const Compiled *k_first = kp;  // carries the plan's history (the global build is only compiled when needed)
-    if (kp->nkeys > 0 && k_first->last_groups > 64 && n >= (1 << 16)) {  // sticky choice: skip the tier-1 attempt it would abandon again
+    if (kp->nkeys > 0 && k_first->last_groups > 0 && n >= (1 << 16)) {  // sticky choice: skip the tier-1 attempt it would abandon again
         variant = 1;
         kp = &jit::get(B200_OP_AGG, plan, len, in, false, 1);
         cap = 1 << 16;
