@@ -114,6 +114,9 @@ int b200_abi_version(void);
 int b200_init(int device_ordinal, char **errmsg);  /* selects the device, creates the library stream + pool */
 void b200_free_string(char *s);
 void *b200_stream(void);                           /* cudaStream_t all operators are enqueued on */
+/* Results are stream-ordered: operator calls return when their work is queued on b200_stream(); a host that reads
+ * device buffers itself (b200_batch_describe) or hands them to another stream waits here first.  b200_batch_export
+ * waits by itself.  (The reference's operators return materialised batches; the equivalent point is the export.) */
 int b200_synchronize(char **errmsg);
 /* number of kernel launches issued by this library since load (bench.py "gpu_launches") */
 int64_t b200_launch_count(void);
