@@ -200,10 +200,35 @@ class RecordBatch:
             if e.name() in seen:
                 raise ValueError(f"duplicate output column name {e.name()!r}")
             seen.add(e.name())
-        plan = self._cached_plan("project", [exprs], lambda: encode_project(exprs, self.column_names(), self.dtypes())[0])
+        # Bare column references (possibly aliased) are zero-copy, as in the reference where Expr::Column evaluates to the
+        # same Series (an Arc clone, src/daft-recordbatch/src/lib.rs:1290-1300): only computed expressions reach the kernel.
+        names = self.column_names()
+
+        def passthrough(e):
+            inner = e
+            while inner.kind == "alias":
+                inner = inner.args[0]
+            return names.index(inner.value) if inner.kind == "col" and inner.value in names else None
+
+        src = [passthrough(e) for e in exprs]
+        computed = [e for e, p in zip(exprs, src) if p is None]
+        if not computed:
+            return self.select_columns(src).rename([e.name() for e in exprs])
+        plan = self._cached_plan("project", [computed], lambda: encode_project(computed, names, self.dtypes())[0])
         out = ctypes.c_void_p()
         _lib.call("b200_eval_expression_list", self._h, plan, ctypes.c_size_t(len(plan)), ctypes.byref(out))
-        return RecordBatch._wrap(out)
+        res = RecordBatch._wrap(out)
+        if len(computed) == len(exprs):
+            return res
+        both = self.union(res)
+        base, k, order = len(names), 0, []
+        for p in src:
+            if p is None:
+                order.append(base + k)
+                k += 1
+            else:
+                order.append(p)
+        return both.select_columns(order).rename([e.name() for e in exprs])
 
     def filter(self, exprs: Sequence[Expression]) -> "RecordBatch":
         """RecordBatch::filter (lib.rs:520-570): conjuncts AND-ed; a null predicate drops the row."""
