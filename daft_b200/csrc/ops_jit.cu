@@ -424,6 +424,10 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
     // is abandoned to the global build), so a small table is enough and keeps its initialisation and the epilogue's scan
     // cheap; small inputs never reach the abandon threshold and may hold tens of thousands of groups.
     int64_t cap = kp->nkeys > 0 ? (n >= (1 << 20) ? (1 << 13) : (1 << 16)) : 1;
+    if (kp->nkeys > 0 && n < (1 << 15)) {  // n rows cannot form more than n groups: merges of partials get a tiny table
+        cap = 64;
+        while (cap < 2 * n) cap <<= 1;
+    }
     const Compiled *k_first = kp;  // carries the plan's history (the global build is only compiled when needed)
     if (kp->nkeys > 0 && k_first->last_groups > 0 && n >= (1 << 16)) {  // sticky choice: skip the tier-1 attempt it would abandon again
         variant = 1;
