@@ -724,13 +724,25 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     const uint32_t naggs = r.u32();
     struct AggIn { int kind, mode; std::string name; int root; };
     std::vector<AggIn> aggs;
+    uint32_t nanyval = 0;
+    std::vector<uint8_t> anyval_bytes;  // [name, node] of every any_value child = the entries of a PROJECT plan
     for (uint32_t i = 0; i < naggs; i++) {
         AggIn a;
         a.kind = r.u8();
         a.mode = r.u8();
+        const size_t start = r.pos;
         a.name = r.str();
         a.root = parse_node(r, ast);
+        if (a.kind == AGG_ANY_VALUE) {
+            nanyval++;
+            anyval_bytes.insert(anyval_bytes.end(), r.p + start, r.p + r.pos);
+        }
         aggs.push_back(a);
+    }
+    if (nanyval) {
+        meta.anyval_project_plan.resize(4);
+        memcpy(meta.anyval_project_plan.data(), &nanyval, 4);
+        meta.anyval_project_plan.insert(meta.anyval_project_plan.end(), anyval_bytes.begin(), anyval_bytes.end());
     }
     if (r.pos != r.n) fail("plan: trailing bytes");
 
@@ -765,6 +777,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         warp_cells.push_back({"", vslot, count_nulls});
         return (int)warp_cells.size() - 1;
     };
+    int anyval_seen = 0;
     for (auto &a : aggs) {
         const Node &c = ast.nodes[a.root];
         AggOut o;
@@ -798,6 +811,15 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
                 o.out_dtype = c.dtype;
                 o.lane_cell = lane_cell(a.kind == AGG_MIN ? C_MIN : C_MAX, vs);
                 if (c.nullable) o.cnt_cell = warp_cell(vs, false);
+                break;
+            }
+            case AGG_ANY_VALUE: {
+                // Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the child at the group's first row; with
+                // ignore_nulls the first NON-NULL row, which needs its own per-group row cell -- only offered where it is the
+                // same thing (children that cannot be null)
+                if (a.mode == 1 && c.nullable) fail("agg: any_value(ignore_nulls=true) over a nullable input is not supported on the device");
+                o.out_dtype = c.dtype;
+                o.proj_index = anyval_seen++;
                 break;
             }
             default: fail("agg: unsupported aggregation kind " + std::to_string(a.kind));
@@ -1530,6 +1552,10 @@ static void precompile_one(int op, const uint8_t *plan, size_t plan_len, const s
         Compiled cg3;  // and the TMA-staged build of the low-cardinality kernel (when the plan qualifies)
         const std::string src3 = generate(op, plan, plan_len, col_dtypes, col_nullable, false, cg3, 2);
         if (cg3.stage_bytes > 0) compile_to_cubin(src3, nullptr);
+    }
+    if (op == B200_OP_AGG && !c.anyval_project_plan.empty()) {
+        Compiled c3;
+        compile_to_cubin(generate(B200_OP_PROJECT, c.anyval_project_plan.data(), c.anyval_project_plan.size(), col_dtypes, col_nullable, true, c3, 0), nullptr);
     }
     if (op == B200_OP_AGG && !c.key_project_plan.empty() && c.nkeys > 0) {
         Compiled c2;

@@ -36,6 +36,7 @@ struct AggOut {
     int cnt_cell = -1;       // warp count cell with #valid (or #null for count-null), -1 => use nrows
     bool child_nullable = false;
     bool const_zero = false; // count(null) over a non-nullable child
+    int proj_index = -1;     // AGG_ANY_VALUE: column of the any-value projection (child evaluated at the group's first row)
 };
 
 struct Compiled {
@@ -57,6 +58,7 @@ struct Compiled {
     int block_threads = 256;
     int stage_rows = 0, stage_bytes = 0;  // staged agg variant: bytes per shared-memory stage (0 = nothing to stage)
     std::vector<uint8_t> key_project_plan;
+    std::vector<uint8_t> anyval_project_plan;  // PROJECT plan of the any_value children (evaluated at the first rows)
     int regs = 0;
     // (AGG, first-choice build) what the previous run of this plan found: the reference samples every query's first
     // morsel to choose its strategy (grouped_aggregate.rs:205-245); a plan that needed the global-table kernel last

@@ -329,7 +329,7 @@ __device__ __forceinline__ void finalize_one(int kind, int32_t val_dtype, int32_
                                              const unsigned long long *__restrict__ cnt, int cnt_is_valid_count, int const_zero,
                                              const int64_t *__restrict__ slots, int64_t ng, void *__restrict__ out,
                                              uint32_t *__restrict__ out_valid, int64_t i) {
-    bool valid = false;
+    bool valid = false, bool_bit = false;
     if (i < ng) {
         const int64_t s = slots[i];
         const unsigned long long c = cell ? cell[s] : 0ULL;
@@ -371,6 +371,7 @@ __device__ __forceinline__ void finalize_one(int kind, int32_t val_dtype, int32_
                     case B200_U8: ((uint8_t *)out)[i] = valid ? (uint8_t)v : 0; break;
                     case B200_U16: ((uint16_t *)out)[i] = valid ? (uint16_t)v : 0; break;
                     case B200_U32: ((uint32_t *)out)[i] = valid ? (uint32_t)v : 0; break;
+                    case B200_BOOL: bool_bit = valid && v != 0; break;  // bool_and / bool_or: a bitmap, written below
                     default: ((unsigned long long *)out)[i] = valid ? v : 0ULL; break;
                 }
             }
@@ -378,6 +379,10 @@ __device__ __forceinline__ void finalize_one(int kind, int32_t val_dtype, int32_
     }
     const unsigned m = __ballot_sync(0xffffffffu, valid);
     if (out_valid && (threadIdx.x & 31) == 0) out_valid[i >> 5] = m;
+    if (out_dtype == B200_BOOL && kind != jit::AGG_COUNT) {
+        const unsigned b = __ballot_sync(0xffffffffu, bool_bit);
+        if ((threadIdx.x & 31) == 0) ((uint32_t *)out)[i >> 5] = b;
+    }
 }
 
 // every aggregate column of the output in ONE launch (grid.y = aggregate)
@@ -567,6 +572,10 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         out = std::make_unique<Batch>();
         out->num_rows = ng;
     }
+    // any_value columns: the child expressions evaluated at the groups' first rows (one projection for all of them)
+    std::unique_ptr<Batch> anyval;
+    if (!k.anyval_project_plan.empty() && ng > 0 && n > 0)
+        anyval.reset(op_project(in, k.anyval_project_plan.data(), k.anyval_project_plan.size(), as<int64_t>(minrow), ng, true));
     FinalizeSet fs;
     fs.n = 0;
     std::vector<Column> agg_cols;
@@ -583,9 +592,31 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         c.name = ag.name;
         c.dtype = ag.out_dtype;
         c.length = ng;
+        if (ag.kind == jit::AGG_ANY_VALUE) {
+            if (anyval) {
+                c = anyval->cols[ag.proj_index];
+                c.name = ag.name;
+            } else {  // no rows at all (ungrouped aggregate over an empty input): null
+                c.null_count = ng;
+                if (c.dtype != B200_NULL) {
+                    c.validity = dev_alloc_zero((size_t)((ng + 31) / 32 + 1) * 4);
+                    const int w0 = dtype_width(c.dtype);
+                    c.data = dev_alloc_zero((size_t)std::max<int64_t>(ng, 1) * std::max(w0, 1) + 8);
+                    c.data_bytes = w0 ? ng * w0 : (c.dtype == B200_BOOL ? (ng + 7) / 8 : 0);
+                    if (is_string(c.dtype)) c.offsets = dev_alloc_zero((size_t)(ng + 1) * 8);
+                }
+            }
+            agg_cols.push_back(std::move(c));
+            continue;
+        }
         const int w = dtype_width(c.dtype);
-        c.data = dev_alloc((size_t)std::max<int64_t>(ng, 1) * w);
-        c.data_bytes = ng * w;
+        if (c.dtype == B200_BOOL) {
+            c.data = dev_alloc((size_t)((ng + 31) / 32 + 1) * 4);
+            c.data_bytes = (ng + 7) / 8;
+        } else {
+            c.data = dev_alloc((size_t)std::max<int64_t>(ng, 1) * w);
+            c.data_bytes = ng * w;
+        }
         const bool may_null = ag.kind != jit::AGG_COUNT && (ag.child_nullable || k.nkeys == 0);
         if (may_null) c.validity = dev_alloc((size_t)((ng + 31) / 32 + 1) * 4);
         const unsigned long long *cell = ag.lane_cell >= 0 ? cell_ptr(ag.lane_cell) : nullptr;

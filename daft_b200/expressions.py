@@ -119,6 +119,11 @@ class Expression:
     def min(self): return self._agg("min")
     def max(self): return self._agg("max")
     def count(self, mode: str = "valid"): return self._agg("count", mode)
+    def any_value(self, ignore_nulls: bool = False):
+        """Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the group's first row, or its first non-null row."""
+        return self._agg("any_value", "ignore_nulls" if ignore_nulls else "first")
+    def bool_and(self): return self._agg("min")   # nulls ignored, all-null group -> null (array/ops/bool_agg.rs:19-60)
+    def bool_or(self): return self._agg("max")
 
     def __repr__(self):
         if self.kind == "col": return f"col({self.value})"
@@ -329,6 +334,7 @@ def encode_agg(to_agg: Sequence[Expression], group_by: Sequence[Expression], nam
             inner = inner.args[0]
         if inner.kind != "agg":
             raise ValueError(f"expected an aggregation expression, got {a!r}")
-        out += struct.pack("<BB", AGG_KINDS[inner.op], COUNT_MODES[inner.value]) + _enc_str(name.encode())
+        mode = {"first": 0, "ignore_nulls": 1}[inner.value] if inner.op == "any_value" else COUNT_MODES[inner.value]
+        out += struct.pack("<BB", AGG_KINDS[inner.op], mode) + _enc_str(name.encode())
         out += encode(bind(inner.args[0], names, dtypes))
     return out

@@ -215,7 +215,10 @@ def agg_sum(arr, gid: np.ndarray, ng: int) -> pa.Array:
 
 
 def agg_minmax(arr, gid: np.ndarray, ng: int, which: str) -> pa.Array:
-    """Min/MaxAccum* (inline_agg.rs:200-298)."""
+    """Min/MaxAccum* (inline_agg.rs:200-298); Boolean = bool_and / bool_or over the valid rows (array/ops/bool_agg.rs:19-60)."""
+    arr0 = normalize(arr)
+    if pa.types.is_boolean(arr0.type):
+        return agg_minmax(arr0.cast(pa.uint8()), gid, ng, which).cast(pa.bool_())
     v = ColView(arr)
     typ = v.arr.type
     code = {DATE32: I32, TIMESTAMP: I64}.get(v.code, v.code)
@@ -278,6 +281,25 @@ def agg(tbl: pa.Table, aggs: Sequence[tuple], group_by: Sequence) -> pa.Table:
             with np.errstate(all="ignore"):
                 q = sn / cn
             r = pa.array(q, mask=(cn == 0))
+        elif kind == "any_value":
+            # Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the first row of each group, or with
+            # ignore_nulls its first non-null row (null when there is none); ungrouped: row 0 / first valid row / null
+            arr_n = normalize(arr)
+            ignore = (a[3] if len(a) > 3 else "first") == "ignore_nulls"
+            valid = np.ones(n, dtype=bool) if arr_n.null_count == 0 else ~np.asarray(arr_n.is_null())
+            if pa.types.is_null(arr_n.type):
+                idx = [None] * ng
+            elif keys:
+                idx = [None] * ng
+                if ignore:
+                    for row in np.flatnonzero(valid)[::-1]:
+                        idx[int(gid[row])] = int(row)
+                else:
+                    idx = [int(x) for x in first]
+            else:
+                cand = np.flatnonzero(valid) if ignore else np.arange(n)
+                idx = [int(cand[0]) if len(cand) else None]
+            r = arr_n.take(pa.array(idx, type=pa.int64()))
         else:
             raise NotImplementedError(kind)
         cols.append(r)

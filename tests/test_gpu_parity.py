@@ -214,6 +214,24 @@ def test_groupby_null_and_nan_keys(gpu):
     assert got.column("n").to_pylist() == [2, 2, 1]
 
 
+@pytest.mark.parametrize("n", [0, 1, 700, 90_000])
+def test_any_value_and_bool_aggs(gpu, n):
+    """any_value = the child at the group's first row (series/ops/agg.rs:353-382); bool_and / bool_or ignore nulls."""
+    rng = np.random.default_rng(n + 3)
+    tbl = random_table(rng, n, 0.2)
+    c = gpu.col
+    aggs = [c("s").any_value().alias("any_s"), c("f64").any_value().alias("any_f"), (c("i32") * 2).any_value().alias("any_e"),
+            c("k").any_value(ignore_nulls=True).alias("any_k"), c("b").bool_and().alias("ba"), c("b").bool_or().alias("bo"),
+            c("i64").sum().alias("sum_i64")]
+    for keys, pred in (([], None), (["u8"], None), (["b", "i8"], [c("i32") > -500]), (["s"], None)):
+        got = RB(gpu, tbl).agg(aggs, [c(k) for k in keys], predicate=pred).to_arrow_table()
+        want = oracle_agg(tbl, aggs, [c(k) for k in keys], pred)
+        assert_tables_equal(got, want)
+    if tbl.column("i32").null_count > 0:  # first NON-NULL row of a nullable input is not offered on the device
+        with pytest.raises(gpu.B200Error, match="ignore_nulls"):
+            RB(gpu, tbl).agg([c("i32").any_value(ignore_nulls=True).alias("x")], [c("u8")])
+
+
 def test_dedup(gpu):
     rng = np.random.default_rng(2)
     tbl = random_table(rng, 3000, 0.2)

@@ -174,3 +174,15 @@ def test_filter_project_oracle_semantics():
     assert E.eval_expression(d, col("d").year()).to_pylist() == [1998, 1970, 1600]
     assert E.eval_expression(d, col("d").month()).to_pylist() == [9, 1, 2]
     assert E.eval_expression(d, col("d").day()).to_pylist() == [2, 1, 29]
+
+
+def test_any_value_and_bool_aggs_semantics():
+    # src/daft-core/src/series/ops/agg.rs:353-382 (first row / first non-null row), array/ops/bool_agg.rs:19-60
+    t = pa.table({"k": [1, 2, 1, 2, 3], "v": pa.array([None, 5, 7, None, None], type=pa.int64()), "s": ["a", "b", "c", "d", "e"],
+                  "b": [True, None, False, True, None]})
+    aggs = [col("v").any_value().alias("a"), col("v").any_value(True).alias("b"), col("s").any_value().alias("c"),
+            col("b").bool_and().alias("ba"), col("b").bool_or().alias("bo")]
+    assert oracle_agg(t, aggs, [col("k")]).to_pydict() == {"k": [1, 2, 3], "a": [None, 5, None], "b": [7, 5, None], "c": ["a", "b", "e"],
+                                                           "ba": [False, True, None], "bo": [True, True, None]}
+    assert oracle_agg(t, aggs[:2], []).to_pydict() == {"a": [None], "b": [5]}
+    assert oracle_agg(t.slice(0, 0), aggs[:1], []).to_pydict() == {"a": [None]}
