@@ -51,7 +51,7 @@ enum Tag { T_COL = 0, T_LIT, T_BINARY, T_UNARY, T_CAST, T_IF_ELSE, T_IS_IN, T_BE
 enum BinOp { B_ADD = 0, B_SUB, B_MUL, B_TRUE_DIV, B_FLOOR_DIV, B_MOD, B_LT, B_LE, B_EQ, B_NE, B_GE, B_GT, B_AND, B_OR,
              B_XOR, B_EQ_NULL_SAFE, B_SHL, B_SHR };
 enum UnOp { U_NOT = 0, U_NEG, U_IS_NULL, U_NOT_NULL, U_ABS };
-enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW };
+enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT };
 
 struct Node {
     int tag = 0, op = 0;
@@ -220,6 +220,7 @@ static int parse_node(Reader &r, Ast &a) {
                 case F_UTF8_LENGTH: nd.dtype = B200_U64; break;
                 case F_STARTSWITH: case F_ENDSWITH: case F_CONTAINS: nd.dtype = B200_BOOL; break;
                 case F_LEFT: nd.dtype = B200_LARGE_UTF8; break;
+                case F_SQRT: nd.dtype = B200_F64; break;  // operand cast to Float64 by the host (IEEE correctly rounded sqrt)
                 default: fail("plan: unknown function");
             }
             break;
@@ -532,6 +533,7 @@ struct ExprGen {
                     case F_ENDSWITH: os << "    const bool " << V << " = str_endswith(" << a << ", " << v(kid[1]) << ");\n"; break;
                     case F_CONTAINS: os << "    const bool " << V << " = str_contains(" << a << ", " << v(kid[1]) << ");\n"; break;
                     case F_LEFT: os << "    const Str " << V << " = str_left(" << a << ", (int64_t)" << v(kid[1]) << ");\n"; break;
+                    case F_SQRT: os << "    const double " << V << " = sqrt((double)" << a << ");\n"; break;
                 }
                 os << "    const bool " << K << " = " << allk << ";\n";
                 break;

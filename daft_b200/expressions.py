@@ -19,7 +19,7 @@ BINOPS = {"add": 0, "sub": 1, "mul": 2, "true_div": 3, "floor_div": 4, "mod": 5,
           "ge": 10, "gt": 11, "and": 12, "or": 13, "xor": 14, "eq_null_safe": 15, "shl": 16, "shr": 17}
 UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
-         "day_of_week": 8}
+         "day_of_week": 8, "sqrt": 9}
 AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
 _CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
@@ -119,6 +119,14 @@ class Expression:
     def min(self): return self._agg("min")
     def max(self): return self._agg("max")
     def count(self, mode: str = "valid"): return self._agg("count", mode)
+    def sqrt(self): return Expression("function", "sqrt", (self,))
+    def stddev(self, ddof: int = 0):
+        """Staged exactly like the reference's plan rewrite (src/daft-local-plan/src/agg.rs:190-226): sum(x), sum(x*x),
+        count(x) over Float64, then sqrt(((sqsum/n) - (sum/n)^2) * n / (n - ddof)), null when n <= ddof."""
+        return self._agg("stddev", int(ddof))
+    def var(self, ddof: int = 1):
+        """src/daft-local-plan/src/agg.rs:227-258: the same staging without the square root."""
+        return self._agg("var", int(ddof))
     def any_value(self, ignore_nulls: bool = False):
         """Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the group's first row, or its first non-null row."""
         return self._agg("any_value", "ignore_nulls" if ignore_nulls else "first")
@@ -244,9 +252,11 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
     if k == "function":
         kids = [bind(x, names, dtypes) for x in e.args]
         out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,
-               "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8}[e.op]
+               "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8, "sqrt": dt.F64}[e.op]
         if e.op == "left":
             kids[1] = _cast(kids[1], dt.I64)
+        if e.op == "sqrt":
+            kids[0] = _cast(kids[0], dt.F64)
         return Bound(T_FUNCTION, out, FUNCS[e.op], kids)
     if k == "agg":
         raise ValueError("aggregation expressions are only valid inside agg()")
@@ -338,3 +348,35 @@ def encode_agg(to_agg: Sequence[Expression], group_by: Sequence[Expression], nam
         out += struct.pack("<BB", AGG_KINDS[inner.op], mode) + _enc_str(name.encode())
         out += encode(bind(inner.args[0], names, dtypes))
     return out
+
+
+def stage_moment_aggs(to_agg: Sequence[Expression]):
+    """stddev / var -> (first-stage aggregations, final projection) as populate_aggregation_stages does
+    (src/daft-local-plan/src/agg.rs:190-258); returns None when the list has neither."""
+    if not any(_agg_inner(a).op in ("stddev", "var") for a in to_agg):
+        return None
+    first, final = [], []
+    for i, a in enumerate(to_agg):
+        inner = _agg_inner(a)
+        if inner.op not in ("stddev", "var"):
+            first.append(a)
+            final.append(col(a.name()))
+            continue
+        x = inner.args[0].cast(dt.F64)
+        s, q, c = f"__sum{i}", f"__sqsum{i}", f"__cnt{i}"
+        first += [x.sum().alias(s), (x * x).sum().alias(q), x.count().alias(c)]
+        n = col(c).cast(dt.F64)
+        mean = col(s) / n
+        pop_var = col(q) / n - mean * mean
+        ddof = lit(float(inner.value))
+        adjusted = pop_var * n / (n - ddof)
+        result = (n <= ddof).if_else(lit(None), adjusted.sqrt() if inner.op == "stddev" else adjusted)
+        final.append(result.alias(a.name()))
+    return first, final
+
+
+def _agg_inner(a: Expression) -> Expression:
+    inner = a
+    while inner.kind == "alias":
+        inner = inner.args[0]
+    return inner

@@ -14,7 +14,7 @@ import pyarrow as pa
 
 from . import _lib
 from . import datatypes as dt
-from .expressions import Expression, col, encode_agg, encode_filter, encode_project
+from .expressions import Expression, col, encode_agg, encode_filter, encode_project, stage_moment_aggs
 
 JOIN_TYPES = {"inner": 0, "left": 1, "right": 2, "outer": 3, "semi": 4, "anti": 5}
 
@@ -244,6 +244,11 @@ class RecordBatch:
             predicate: Sequence[Expression] | None = None) -> "RecordBatch":
         """RecordBatch::agg (src/daft-recordbatch/src/ops/agg.rs:20-88).  `predicate` fuses the Filter that
         feeds the aggregate into the same kernel (rows failing it are skipped; nothing is materialised)."""
+        staged = stage_moment_aggs(to_agg)
+        if staged is not None:  # stddev / var: first-stage sums + counts, then the final projection (agg.rs:190-258)
+            first, final = staged
+            keys = [col(g.name()) for g in (group_by or [])]
+            return self.agg(first, group_by, predicate).eval_expression_list(keys + final)
         plan = self._cached_plan("agg", [to_agg, group_by or [], predicate],
                                  lambda: encode_agg(to_agg, group_by or [], self.column_names(), self.dtypes(), predicate))
         out = ctypes.c_void_p()

@@ -263,7 +263,7 @@ int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begi
  *     15 eq_null_safe 16 shift_left 17 shift_right
  *   unary ops: 0 not 1 negate 2 is_null 3 not_null 4 abs
  *   functions: 0 year 1 month 2 day 3 utf8_length 4 utf8_startswith 5 utf8_endswith 6 utf8_contains
- *              7 utf8_left 8 day_of_week
+ *              7 utf8_left 8 day_of_week 9 sqrt (Float64 operand; IEEE correctly rounded)
  *   Operands of a binary op must already have identical dtypes (the host inserts the supertype
  *   casts the reference decides at plan time); true_div requires F64 operands.
  *

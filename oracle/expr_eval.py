@@ -162,6 +162,9 @@ def _eval(b: Bound, cols, n: int):
             if fn in ("year", "month", "day"):
                 y, m, d = _civil(a)
                 return {"year": y.astype(np.int32), "month": m.astype(np.uint32), "day": d.astype(np.uint32)}[fn], allk
+            if fn == "sqrt":
+                with np.errstate(all="ignore"):
+                    return np.sqrt(a.astype(np.float64)), allk
             if fn == "day_of_week":
                 return ((a.astype(np.int64) + 3) % 7).astype(np.uint32), allk
             if fn == "utf8_length":

@@ -38,6 +38,12 @@ class OracleRecordBatch:
         return OracleRecordBatch(E.filter(self.tbl, exprs) if exprs else self.tbl)
 
     def agg(self, to_agg, group_by=None, predicate=None) -> "OracleRecordBatch":
+        from daft_b200.expressions import col as _col, stage_moment_aggs
+        staged = stage_moment_aggs(to_agg)  # stddev / var: the reference's staged rewrite (src/daft-local-plan/src/agg.rs:190-258)
+        if staged is not None:
+            first, final = staged
+            keys = [_col(g.name()) for g in (group_by or [])]
+            return self.agg(first, group_by, predicate).eval_expression_list(keys + final)
         tbl = E.filter(self.tbl, predicate) if predicate else self.tbl
         specs = []
         for a in to_agg:
