@@ -127,6 +127,10 @@ class Expression:
     def var(self, ddof: int = 1):
         """src/daft-local-plan/src/agg.rs:227-258: the same staging without the square root."""
         return self._agg("var", int(ddof))
+    def count_distinct(self):
+        """Distinct non-null values per group as UInt64 (Series::count_distinct = agg_list + list_count_distinct over a
+        probe table WITHOUT nulls, src/daft-functions-list/src/series.rs:37-40,234-247)."""
+        return self._agg("count_distinct")
     def any_value(self, ignore_nulls: bool = False):
         """Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the group's first row, or its first non-null row."""
         return self._agg("any_value", "ignore_nulls" if ignore_nulls else "first")

@@ -27,6 +27,12 @@ def _u8(xs: Sequence[Any]):
     return (ctypes.c_uint8 * len(xs))(*[1 if x else 0 for x in xs])
 
 
+def _inner(a: Expression) -> Expression:
+    while a.kind == "alias":
+        a = a.args[0]
+    return a
+
+
 class RecordBatch:
     __slots__ = ("_h", "_schema", "_names", "_dtypes", "__weakref__")
 
@@ -244,6 +250,8 @@ class RecordBatch:
             predicate: Sequence[Expression] | None = None) -> "RecordBatch":
         """RecordBatch::agg (src/daft-recordbatch/src/ops/agg.rs:20-88).  `predicate` fuses the Filter that
         feeds the aggregate into the same kernel (rows failing it are skipped; nothing is materialised)."""
+        if any(_inner(a).op == "count_distinct" for a in to_agg):
+            return self._agg_with_count_distinct(to_agg, group_by or [], predicate)
         staged = stage_moment_aggs(to_agg)
         if staged is not None:  # stddev / var: first-stage sums + counts, then the final projection (agg.rs:190-258)
             first, final = staged
@@ -254,6 +262,30 @@ class RecordBatch:
         out = ctypes.c_void_p()
         _lib.call("b200_agg", self._h, plan, ctypes.c_size_t(len(plan)), ctypes.byref(out))
         return RecordBatch._wrap(out)
+
+    def _agg_with_count_distinct(self, to_agg, group_by, predicate) -> "RecordBatch":
+        """count_distinct(x) per group = dedup on (keys, x), then count the non-null x per key.  Dedup keeps first
+        occurrences in row order, so every partial result lists the groups in the same first-occurrence order and the
+        columns are simply placed side by side (the reference builds per-group lists and one probe table per group,
+        src/daft-functions-list/src/series.rs:37-40,234-247)."""
+        base = self.filter(predicate) if predicate else self
+        keys = [g.alias(f"__k{i}") for i, g in enumerate(group_by)]
+        key_cols = [col(f"__k{i}") for i in range(len(group_by))]
+        plain = [a for a in to_agg if _inner(a).op != "count_distinct"]
+        # a count(all) keeps the group list complete even when every other aggregate is a count_distinct
+        parts = base.agg(plain + [col(base.column_names()[0]).count("all").alias("__rows")] if base.num_columns() else plain, group_by)
+        out_cols, pieces = {}, parts
+        for i, a in enumerate(to_agg):
+            if _inner(a).op != "count_distinct":
+                continue
+            x = _inner(a).args[0]
+            pairs = base.eval_expression_list(keys + [x.alias("__x")]).dedup(key_cols + [col("__x")])
+            cnt = pairs.agg([col("__x").count("valid").alias(f"__cd{i}")], key_cols)
+            pieces = pieces.union(cnt.eval_expression_list([col(f"__cd{i}")]))
+            out_cols[i] = f"__cd{i}"
+        final = [col(g.name()) for g in group_by]
+        final += [col(out_cols[i]).alias(a.name()) if i in out_cols else col(a.name()) for i, a in enumerate(to_agg)]
+        return pieces.eval_expression_list(final)
 
     def dedup(self, exprs: Sequence[Expression]) -> "RecordBatch":
         if len(exprs) == 0:

@@ -281,6 +281,14 @@ def agg(tbl: pa.Table, aggs: Sequence[tuple], group_by: Sequence) -> pa.Table:
             with np.errstate(all="ignore"):
                 q = sn / cn
             r = pa.array(q, mask=(cn == 0))
+        elif kind == "count_distinct":
+            # distinct NON-NULL values per group, UInt64 (src/daft-functions-list/src/series.rs:37-40,234-247), by definition
+            vals = normalize(arr).to_pylist()
+            seen = [set() for _ in range(ng)]
+            for g, v in zip(gid.tolist(), vals):
+                if v is not None:
+                    seen[g].add(v)
+            r = pa.array([len(s_) for s_ in seen], type=pa.uint64())
         elif kind == "any_value":
             # Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the first row of each group, or with
             # ignore_nulls its first non-null row (null when there is none); ungrouped: row 0 / first valid row / null

@@ -257,6 +257,21 @@ def test_stddev_var_staged_like_the_reference(gpu, n):
         assert got["v1"][0] == pytest.approx(np.nanvar(x, ddof=1), rel=1e-9)
 
 
+@pytest.mark.parametrize("n", [0, 1, 5000, 80_000])
+def test_count_distinct(gpu, n):
+    """count_distinct = distinct non-null values per group, UInt64 (src/daft-functions-list/src/series.rs:37-40,234-247);
+    the device path is dedup on (keys, value) + count, the oracle counts sets by definition."""
+    rng = np.random.default_rng(n + 11)
+    tbl = random_table(rng, n, 0.15)
+    c = gpu.col
+    aggs = [c("u16").count_distinct().alias("d_u16"), c("s").count_distinct().alias("d_s"), c("i64").sum().alias("sum_i64"),
+            (c("i32") % 10).count_distinct().alias("d_expr"), c("u8").count("all").alias("rows")]
+    for keys, pred in (([], None), (["k"], None), (["b", "i8"], [c("u32") > 3000])):
+        got = RB(gpu, tbl).agg(aggs, [c(k) for k in keys], predicate=pred).to_arrow_table()
+        want = oracle_agg(tbl, aggs, [c(k) for k in keys], pred)
+        assert_tables_equal(got, want)
+
+
 def test_dedup(gpu):
     rng = np.random.default_rng(2)
     tbl = random_table(rng, 3000, 0.2)
