@@ -204,6 +204,26 @@ int b200_partition_by_hash(const b200_batch *batch, const int32_t *key_cols, int
     });
 }
 
+int b200_search_sorted(const b200_batch *sorted, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
+                       b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!sorted || !batch) fail("null batch");
+        Buf pos = op_search_sorted(*sorted, *batch, key_cols, nkeys, descending);
+        auto o = std::make_unique<Batch>();
+        o->num_rows = batch->num_rows;
+        o->cols.push_back(make_u64_column("idx", pos, batch->num_rows));
+        *out = o.release();
+    });
+}
+int b200_partition_by_range(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const b200_batch *boundaries,
+                            const uint8_t *descending, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!batch || !boundaries) fail("null batch");
+        std::vector<Batch *> parts = op_partition_by_range(*batch, key_cols, nkeys, *boundaries, descending);
+        for (size_t i = 0; i < parts.size(); i++) out[i] = parts[i];
+    });
+}
+
 // ---- filter / project / agg -----------------------------------------------------------------------
 int b200_filter(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] { *out = op_filter(*batch, plan, plan_len); });

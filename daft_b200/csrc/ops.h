@@ -27,6 +27,9 @@ Batch *batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t nu
 void radix_sort_pairs(Buf &keys, Buf &vals, int64_t n, int begin_bit, int end_bit, bool descending);
 void fill_iota(int64_t *out, int64_t n);
 Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending, const uint8_t *nulls_first);
+Buf op_search_sorted(const Batch &sorted, const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending);
+std::vector<Batch *> op_partition_by_range(const Batch &b, const int32_t *key_cols, int32_t nkeys, const Batch &boundaries,
+                                           const uint8_t *descending);
 // the first k entries of that argsort, found by selection when k is small (sort.cu)
 Buf op_top_indices(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending, const uint8_t *nulls_first, int64_t k);
 Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng);

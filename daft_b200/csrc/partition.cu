@@ -232,6 +232,28 @@ std::vector<Batch *> op_partition_by_hash(const Batch &b, const int32_t *key_col
     return out;
 }
 
+// RecordBatch::partition_by_range (src/daft-recordbatch/src/ops/partition.rs:88-101): target = search_sorted(boundaries, keys)
+// -> boundaries.len() + 1 partitions, input order preserved inside a partition
+std::vector<Batch *> op_partition_by_range(const Batch &b, const int32_t *key_cols, int32_t nkeys, const Batch &boundaries,
+                                           const uint8_t *descending) {
+    require_device();
+    const int32_t P = (int32_t)boundaries.num_rows + 1;
+    if (boundaries.num_rows == 0) return {new Batch(b)};
+    Buf target = op_search_sorted(boundaries, b, key_cols, nkeys, descending);  // in [0, P): usable as "hash % P"
+    if (P <= PS_MAXP && b.num_rows >= 4096) return partition_direct(b, as<uint64_t>(target), P);
+    std::vector<int64_t> offsets;
+    Buf perm = partition_permutation(as<uint64_t>(target), b.num_rows, P, offsets);
+    std::vector<Batch *> out;
+    try {
+        for (int p = 0; p < P; p++) out.push_back(gather_batch(b, as<int64_t>(perm) + offsets[p], offsets[p + 1] - offsets[p], false));
+        op_done();
+    } catch (...) {
+        for (auto *x : out) delete x;
+        throw;
+    }
+    return out;
+}
+
 // distinct rows over the key columns, first occurrence kept, first-occurrence order
 Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *first_rows, int64_t *ngroups);  // ops_jit.cu
 

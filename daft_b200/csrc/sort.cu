@@ -287,16 +287,18 @@ struct SortKeySet {
     SortKeyDesc k[SMALL_SORT_KEYS];
 };
 
-// three-way compare of rows i, j under the reference comparator (NaN greatest, nulls by nulls_first)
-__device__ __forceinline__ int small_cmp(const SortKeySet &ks, int64_t i, int64_t j) {
-    for (int q = 0; q < ks.nkeys; q++) {
-        const SortKeyDesc &k = ks.k[q];
+// three-way compare of row i of table A with row j of table B under the reference comparator (NaN greatest, nulls by
+// nulls_first); flags and dtypes come from A, both tables have the same key dtypes
+__device__ __forceinline__ int small_cmp2(const SortKeySet &ka, int64_t i, const SortKeySet &kb, int64_t j) {
+    for (int q = 0; q < ka.nkeys; q++) {
+        const SortKeyDesc &k = ka.k[q];
+        const SortKeyDesc &kj = kb.k[q];
         if (k.dtype == B200_NULL) continue;
-        const bool vi = k.validity == nullptr || bit_at(k.validity, i), vj = k.validity == nullptr || bit_at(k.validity, j);
+        const bool vi = k.validity == nullptr || bit_at(k.validity, i), vj = kj.validity == nullptr || bit_at(kj.validity, j);
         int r = 0;
         if (vi && vj) {
             switch (k.dtype) {
-#define CMP_T(T) { const T a = ((const T *)k.data)[i], b = ((const T *)k.data)[j]; r = a < b ? -1 : (a > b ? 1 : 0); } break;
+#define CMP_T(T) { const T a = ((const T *)k.data)[i], b = ((const T *)kj.data)[j]; r = a < b ? -1 : (a > b ? 1 : 0); } break;
                 case B200_I8: CMP_T(int8_t)
                 case B200_I16: CMP_T(int16_t)
                 case B200_I32: case B200_DATE32: CMP_T(int32_t)
@@ -306,18 +308,18 @@ __device__ __forceinline__ int small_cmp(const SortKeySet &ks, int64_t i, int64_
                 case B200_U32: CMP_T(uint32_t)
                 case B200_U64: CMP_T(uint64_t)
 #undef CMP_T
-                case B200_BOOL: r = (int)bit_at((const uint8_t *)k.data, i) - (int)bit_at((const uint8_t *)k.data, j); break;
+                case B200_BOOL: r = (int)bit_at((const uint8_t *)k.data, i) - (int)bit_at((const uint8_t *)kj.data, j); break;
                 case B200_F32: case B200_F64: {
                     const double a = k.dtype == B200_F32 ? (double)((const float *)k.data)[i] : ((const double *)k.data)[i];
-                    const double b = k.dtype == B200_F32 ? (double)((const float *)k.data)[j] : ((const double *)k.data)[j];
+                    const double b = k.dtype == B200_F32 ? (double)((const float *)kj.data)[j] : ((const double *)kj.data)[j];
                     const bool na = a != a, nb = b != b;
                     if (na || nb) r = (int)na - (int)nb;
                     else r = a < b ? -1 : (a > b ? 1 : 0);
                     break;
                 }
                 case B200_LARGE_UTF8: case B200_LARGE_BINARY: {
-                    const int64_t oa = k.offsets[i], la = k.offsets[i + 1] - oa, ob = k.offsets[j], lb = k.offsets[j + 1] - ob;
-                    const uint8_t *pa = (const uint8_t *)k.data + oa, *pb = (const uint8_t *)k.data + ob;
+                    const int64_t oa = k.offsets[i], la = k.offsets[i + 1] - oa, ob = kj.offsets[j], lb = kj.offsets[j + 1] - ob;
+                    const uint8_t *pa = (const uint8_t *)k.data + oa, *pb = (const uint8_t *)kj.data + ob;
                     const int64_t m = la < lb ? la : lb;
                     for (int64_t t = 0; t < m && r == 0; t++) r = (int)pa[t] - (int)pb[t];
                     if (r == 0) r = la < lb ? -1 : (la > lb ? 1 : 0);
@@ -332,6 +334,24 @@ __device__ __forceinline__ int small_cmp(const SortKeySet &ks, int64_t i, int64_
         if (r) return r;
     }
     return 0;
+}
+
+__device__ __forceinline__ int small_cmp(const SortKeySet &ks, int64_t i, int64_t j) { return small_cmp2(ks, i, ks, j); }
+
+// RecordBatch::search_sorted (src/daft-recordbatch/src/ops/search_sorted.rs:13-36, kernels/search_sorted.rs:420-433): for every key
+// row the number of rows of the sorted table that compare <= it (upper bound; nulls_first = descending per column)
+__global__ void search_sorted_kernel(SortKeySet sorted, SortKeySet keys, int64_t nsorted, int64_t nkeys_rows, uint64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nkeys_rows; i += stride) {
+        int64_t left = 0, right = nsorted;
+        while (left < right) {
+            const int64_t mid = left + ((right - left) >> 1);
+            if (small_cmp2(sorted, mid, keys, i) <= 0) left = mid + 1;
+            else right = mid;
+        }
+        out[i] = (uint64_t)left;
+    }
 }
 
 __global__ void __launch_bounds__(1024) small_argsort_kernel(SortKeySet ks, int64_t n, int64_t *__restrict__ out_idx) {
@@ -355,6 +375,45 @@ static int key_bits(int32_t dt) {
         case B200_U32: return 32;
         default: return 64;  // signed ints carry the bias in bit 63; floats use all 64
     }
+}
+
+static SortKeySet make_sort_keyset(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending, const uint8_t *nulls_first) {
+    if (nkeys < 1 || nkeys > SMALL_SORT_KEYS) fail("between 1 and 8 key columns are supported");
+    SortKeySet ks;
+    ks.nkeys = nkeys;
+    for (int k = 0; k < nkeys; k++) {
+        const int32_t ci = key_cols[k];
+        if (ci < 0 || ci >= (int32_t)b.cols.size()) fail("key column index out of range");
+        const Column &c = b.cols[ci];
+        const bool desc = descending && descending[k];
+        ks.k[k] = {c.dtype, desc ? 1 : 0, (nulls_first ? nulls_first[k] != 0 : desc) ? 1 : 0, 0, c.data ? c.data->ptr : nullptr,
+                   c.null_count > 0 ? as<uint8_t>(c.validity) : nullptr, as<int64_t>(c.offsets)};
+    }
+    return ks;
+}
+
+// positions[i] = number of rows of `sorted` (over its first nkeys columns) that compare <= key row i of `b`
+Buf op_search_sorted(const Batch &sorted, const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending) {
+    require_device();
+    if ((int32_t)sorted.cols.size() != nkeys) fail("search_sorted: the sorted table must have exactly the key columns");
+    std::vector<int32_t> bcols(nkeys);
+    for (int k = 0; k < nkeys; k++) {
+        bcols[k] = k;
+        const int32_t ci = key_cols[k];
+        if (ci < 0 || ci >= (int32_t)b.cols.size()) fail("search_sorted: key column index out of range");
+        if (sorted.cols[k].dtype != b.cols[ci].dtype)
+            fail(std::string("Schema Mismatch in search_sorted: data: ") + dtype_name(sorted.cols[k].dtype) + " vs keys: " + dtype_name(b.cols[ci].dtype));
+    }
+    // SortOptions::new(reversed, reversed): nulls first exactly when descending (kernels/search_sorted.rs:401-406)
+    const SortKeySet ks_sorted = make_sort_keyset(sorted, bcols.data(), nkeys, descending, descending);
+    const SortKeySet ks_keys = make_sort_keyset(b, key_cols, nkeys, descending, descending);
+    const int64_t n = b.num_rows;
+    Buf out = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+    if (n > 0) {
+        search_sorted_kernel<<<sgrid(n), 256, 0, ctx().stream>>>(ks_sorted, ks_keys, sorted.num_rows, n, as<uint64_t>(out));
+        count_launch();
+    }
+    return out;
 }
 
 Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending, const uint8_t *nulls_first) {

@@ -317,6 +317,31 @@ class RecordBatch:
         keep = list(range(self.num_columns()))
         return [RecordBatch._wrap(ctypes.c_void_p(h)).select_columns(keep) for h in outs]
 
+    def search_sorted(self, keys: "RecordBatch", descending: Sequence[bool] | bool = False) -> "RecordBatch":
+        """RecordBatch::search_sorted (src/daft-recordbatch/src/ops/search_sorted.rs:13-36): self is the sorted table."""
+        if self.dtypes() != keys.dtypes():
+            raise ValueError(f"Schema Mismatch in search_sorted: data: {self.schema()} vs keys: {keys.schema()}")
+        desc = [descending] * self.num_columns() if isinstance(descending, bool) else list(descending)
+        if len(desc) != self.num_columns():
+            raise ValueError("Mismatch in number of arguments for `descending` in search sorted")
+        out = ctypes.c_void_p()
+        _lib.call("b200_search_sorted", self._h, keys._h, _i32(list(range(self.num_columns()))), ctypes.c_int32(self.num_columns()), _u8(desc),
+                  ctypes.byref(out))
+        return RecordBatch._wrap(out)
+
+    def partition_by_range(self, partition_keys: Sequence[Expression], boundaries: "RecordBatch", descending: Sequence[bool]) -> list["RecordBatch"]:
+        """RecordBatch::partition_by_range (src/daft-recordbatch/src/ops/partition.rs:88-101)."""
+        if not isinstance(boundaries, RecordBatch):
+            raise TypeError(f"Expected a RecordBatch for `boundaries` in partition_by_range but got {type(boundaries)}")
+        if len(boundaries) == 0:
+            return [self]
+        both, idx = self._resolve_keys(partition_keys)
+        nparts = len(boundaries) + 1
+        outs = (ctypes.c_void_p * nparts)()
+        _lib.call("b200_partition_by_range", both._h, _i32(idx), ctypes.c_int32(len(idx)), boundaries._h, _u8(list(descending)), outs)
+        keep = list(range(self.num_columns()))
+        return [RecordBatch._wrap(ctypes.c_void_p(h)).select_columns(keep) for h in outs]
+
     # ---- take / sort ------------------------------------------------------------------------------------
     def take(self, indices: "RecordBatch | Sequence[int] | pa.Array") -> "RecordBatch":
         if not isinstance(indices, RecordBatch):

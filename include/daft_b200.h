@@ -163,6 +163,16 @@ int b200_hash_rows(const b200_batch *batch, const int32_t *key_cols, int32_t nke
 int b200_partition_by_hash(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys,
                            int32_t num_partitions, b200_batch **out, char **errmsg);
 
+/* a12 RepartitionSpec::Range: positions[i] = rows of `sorted` (exactly the key columns, ascending / descending per flag,
+ * nulls first where descending) that compare <= key row i (RecordBatch::search_sorted,
+ * src/daft-recordbatch/src/ops/search_sorted.rs:13-36; src/daft-core/src/kernels/search_sorted.rs:363-433) -> UInt64 column "idx" */
+int b200_search_sorted(const b200_batch *sorted, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys,
+                       const uint8_t *descending, b200_batch **out, char **errmsg);
+/* out[0 .. boundaries.num_rows]: rows whose search_sorted position is p, input order preserved
+ * (RecordBatch::partition_by_range, src/daft-recordbatch/src/ops/partition.rs:88-101); empty boundaries -> out[0] = the batch */
+int b200_partition_by_range(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const b200_batch *boundaries,
+                            const uint8_t *descending, b200_batch **out, char **errmsg);
+
 /* ---- a10/a11: filter / project.  `plan` = serialised expression program (see below). ---- */
 int b200_filter(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg);
 int b200_eval_expression_list(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out,

@@ -426,3 +426,54 @@ def argsort(key_arrs: Sequence, descending=None, nulls_first=None) -> np.ndarray
 def sort(tbl: pa.Table, keys: Sequence[str], descending=None, nulls_first=None) -> pa.Table:
     idx = argsort([tbl.column(k) for k in keys], descending, nulls_first)
     return tbl.take(pa.array(idx, type=pa.int64()))
+
+
+# --------------------------------------------------------------------------- a12 (range repartition)
+def _cmp_values(a, b, descending: bool) -> int:
+    """make_daft_comparator with SortOptions::new(descending, nulls_first=descending)
+    (src/daft-core/src/kernels/search_sorted.rs:401-406): NaN is the greatest float (cmp_float :238-245)."""
+    if a is None or b is None:
+        if a is None and b is None:
+            return 0
+        r = -1 if a is None else 1          # nulls_first == descending: nulls are "largest" ascending, and first descending
+        return r if descending else -r
+    an = isinstance(a, float) and a != a
+    bn = isinstance(b, float) and b != b
+    if an or bn:
+        r = int(an) - int(bn)
+    else:
+        r = -1 if a < b else (1 if a > b else 0)
+    return -r if descending else r
+
+
+def search_sorted(sorted_tbl: pa.Table, keys_tbl: pa.Table, descending: Sequence[bool]) -> np.ndarray:
+    """RecordBatch::search_sorted (src/daft-recordbatch/src/ops/search_sorted.rs:13-36; binary search of
+    src/daft-core/src/kernels/search_sorted.rs:420-433): rows of the sorted table that compare <= each key row."""
+    srows = list(zip(*[normalize(c).to_pylist() for c in sorted_tbl.columns])) if sorted_tbl.num_columns else []
+    krows = list(zip(*[normalize(c).to_pylist() for c in keys_tbl.columns]))
+    out = np.zeros(len(krows), dtype=np.uint64)
+
+    def cmp(sr, kr):
+        for a, b, d in zip(sr, kr, descending):
+            r = _cmp_values(a, b, d)
+            if r:
+                return r
+        return 0
+    for i, kr in enumerate(krows):
+        left, right = 0, len(srows)
+        while left < right:
+            mid = left + ((right - left) >> 1)
+            if cmp(srows[mid], kr) <= 0:
+                left = mid + 1
+            else:
+                right = mid
+        out[i] = left
+    return out
+
+
+def partition_by_range(tbl: pa.Table, keys: Sequence[str], boundaries: pa.Table, descending: Sequence[bool]) -> list[pa.Table]:
+    """RecordBatch::partition_by_range (src/daft-recordbatch/src/ops/partition.rs:88-101)."""
+    if boundaries.num_rows == 0:
+        return [tbl]
+    target = search_sorted(boundaries, tbl.select(list(keys)), descending)
+    return [tbl.filter(pa.array(target == p)) for p in range(boundaries.num_rows + 1)]

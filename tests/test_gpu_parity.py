@@ -272,6 +272,25 @@ def test_count_distinct(gpu, n):
         assert_tables_equal(got, want)
 
 
+@pytest.mark.parametrize("n,nb", [(0, 3), (50, 0), (3000, 7), (20_000, 300)])
+def test_search_sorted_and_partition_by_range(gpu, n, nb):
+    """RecordBatch::search_sorted / partition_by_range (ops/search_sorted.rs:13-36, ops/partition.rs:88-101): upper-bound
+    positions under the sort comparator (NaN greatest, nulls first where descending), stable partitions."""
+    rng = np.random.default_rng(n + nb)
+    tbl = random_table(rng, n, 0.1)
+    c = gpu.col
+    for keys, desc in ((["i32"], [False]), (["f64", "u8"], [True, False]), (["s", "i8"], [False, True])):
+        src = random_table(rng, max(nb * 3, 1), 0.1).select(keys)
+        bounds = O.sort(src, keys, desc, desc).slice(0, nb)   # boundaries are sorted with nulls_first = descending
+        got_pos = RB(gpu, bounds).search_sorted(RB(gpu, tbl.select(keys)), desc).to_pydict()["idx"]
+        assert got_pos == O.search_sorted(bounds, tbl.select(keys), desc).tolist()
+        got = RB(gpu, tbl).partition_by_range([c(k) for k in keys], RB(gpu, bounds), desc)
+        want = O.partition_by_range(tbl, keys, bounds, desc)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert_tables_equal(g.to_arrow_table(), w)
+
+
 def test_dedup(gpu):
     rng = np.random.default_rng(2)
     tbl = random_table(rng, 3000, 0.2)
