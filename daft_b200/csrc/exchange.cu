@@ -308,7 +308,7 @@ static void run_segments(const std::vector<SegDesc> &segs) {
     B200_CUDA(cudaMemcpyAsync(d->ptr, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
     pack_segments<<<(unsigned)segs.size(), 256, 0, st>>>(as<SegDesc>(d));
     count_launch();
-    B200_CUDA(cudaStreamSynchronize(st));  // `segs` (host) and `d` must outlive the copy / kernel
+    // no wait: the pageable-host copy above is staged before cudaMemcpyAsync returns, `d` is freed in stream order
 }
 
 // returns nullptr when some rank's batch does not fit a slab (collective decision)
