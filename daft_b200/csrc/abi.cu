@@ -125,6 +125,13 @@ int b200_batch_describe(const b200_batch *batch, int32_t col, b200_column_desc *
         out->name = c.name.c_str();
     });
 }
+int b200_batch_dtypes(const b200_batch *batch, int32_t *out_dtypes, int32_t n, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!batch || !out_dtypes) fail("null argument");
+        if (n < 0 || n > (int32_t)batch->cols.size()) fail("dtypes: column count out of range");
+        for (int32_t i = 0; i < n; i++) out_dtypes[i] = batch->cols[i].dtype;
+    });
+}
 int64_t b200_batch_num_rows(const b200_batch *batch) { return batch ? batch->num_rows : -1; }
 int32_t b200_batch_num_columns(const b200_batch *batch) { return batch ? (int32_t)batch->cols.size() : -1; }
 int64_t b200_batch_size_bytes(const b200_batch *batch) {

@@ -119,4 +119,4 @@ class Communicator:
         from .recordbatch import RecordBatch
         out = ctypes.c_void_p()
         _lib.call("b200_all_gather", self._h, batch._h, ctypes.byref(out))
-        return RecordBatch._wrap(out)
+        return RecordBatch._wrap(out, like=batch)

@@ -81,8 +81,14 @@ class RecordBatch:
         return RecordBatch.from_arrow_table(pa.table(cols))
 
     @staticmethod
-    def _wrap(handle, like: "RecordBatch | None" = None) -> "RecordBatch":
-        return RecordBatch(handle.value if isinstance(handle, ctypes.c_void_p) else handle, None)
+    def _wrap(handle, like: "RecordBatch | None" = None, names=None, dtypes=None) -> "RecordBatch":
+        """`names` / `dtypes`: the result's schema when the caller already knows it (saves one C call per column)."""
+        rb = RecordBatch(handle.value if isinstance(handle, ctypes.c_void_p) else handle, None)
+        if like is not None:
+            names, dtypes = like._names, like._dtypes
+        if names is not None and dtypes is not None:
+            rb._names, rb._dtypes = list(names), list(dtypes)
+        return rb
 
     # ---- inspection -------------------------------------------------------------------------------
     def __len__(self) -> int:
@@ -133,18 +139,24 @@ class RecordBatch:
     def select_columns(self, idx: Sequence[int]) -> "RecordBatch":
         out = ctypes.c_void_p()
         _lib.call("b200_batch_select", self._h, _i32(idx), ctypes.c_int32(len(idx)), ctypes.byref(out))
+        if self._names is not None:
+            return RecordBatch._wrap(out, names=[self._names[i] for i in idx], dtypes=[self._dtypes[i] for i in idx])
         return RecordBatch._wrap(out)
 
     def rename(self, names: Sequence[str]) -> "RecordBatch":
-        out = self.select_columns(list(range(self.num_columns())))
+        old = self.column_names()
+        out = self.select_columns(list(range(len(old))))
         for i, n in enumerate(names):
-            _lib.call("b200_batch_rename", out._h, ctypes.c_int32(i), n.encode())
-        out._names = out._dtypes = None
+            if n != old[i]:
+                _lib.call("b200_batch_rename", out._h, ctypes.c_int32(i), n.encode())
+        out._names, out._dtypes = list(names), self.dtypes()
         return out
 
     def union(self, other: "RecordBatch") -> "RecordBatch":
         out = ctypes.c_void_p()
         _lib.call("b200_batch_union", self._h, other._h, ctypes.byref(out))
+        if self._names is not None and other._names is not None:
+            return RecordBatch._wrap(out, names=self._names + other._names, dtypes=self._dtypes + other._dtypes)
         return RecordBatch._wrap(out)
 
     def slice(self, start: int, end: int) -> "RecordBatch":
@@ -220,10 +232,10 @@ class RecordBatch:
         computed = [e for e, p in zip(exprs, src) if p is None]
         if not computed:
             return self.select_columns(src).rename([e.name() for e in exprs])
-        plan = self._cached_plan("project", [computed], lambda: encode_project(computed, names, self.dtypes())[0])
+        plan, onames, odt = self._cached_plan("project", [computed], lambda: encode_project(computed, names, self.dtypes()))
         out = ctypes.c_void_p()
         _lib.call("b200_eval_expression_list", self._h, plan, ctypes.c_size_t(len(plan)), ctypes.byref(out))
-        res = RecordBatch._wrap(out)
+        res = RecordBatch._wrap(out, names=onames, dtypes=odt)
         if len(computed) == len(exprs):
             return res
         both = self.union(res)
@@ -261,7 +273,10 @@ class RecordBatch:
                                  lambda: encode_agg(to_agg, group_by or [], self.column_names(), self.dtypes(), predicate))
         out = ctypes.c_void_p()
         _lib.call("b200_agg", self._h, plan, ctypes.c_size_t(len(plan)), ctypes.byref(out))
-        return RecordBatch._wrap(out)
+        onames = [g.name() for g in (group_by or [])] + [a.name() for a in to_agg]
+        odt = (ctypes.c_int32 * len(onames))()
+        _lib.call("b200_batch_dtypes", out, odt, ctypes.c_int32(len(onames)))
+        return RecordBatch._wrap(out, names=onames, dtypes=list(odt))
 
     def _agg_with_count_distinct(self, to_agg, group_by, predicate) -> "RecordBatch":
         """count_distinct(x) per group = dedup on (keys, x), then count the non-null x per key.  Dedup keeps first
@@ -389,7 +404,7 @@ class RecordBatch:
         both, idx = self._resolve_keys(sort_keys)
         out = ctypes.c_void_p()
         _lib.call("b200_sort", both._h, _i32(idx), ctypes.c_int32(len(idx)), _u8(desc), _u8(nf), ctypes.byref(out))
-        res = RecordBatch._wrap(out)
+        res = RecordBatch._wrap(out, like=both)
         return res if both is self else res.select_columns(list(range(self.num_columns())))
 
     def top_n(self, sort_keys: Sequence[Expression], limit: int, descending=None, nulls_first=None, offset: int = 0) -> "RecordBatch":

@@ -142,6 +142,8 @@ int b200_batch_export(const b200_batch *batch, struct ArrowArray *out_array, str
 int b200_batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t num_rows, b200_batch **out,
                            char **errmsg);
 int b200_batch_describe(const b200_batch *batch, int32_t col, b200_column_desc *out, char **errmsg);
+/* dtype codes of the first n columns in one call (hosts that already know the column names skip b200_batch_describe) */
+int b200_batch_dtypes(const b200_batch *batch, int32_t *out_dtypes, int32_t n, char **errmsg);
 int64_t b200_batch_num_rows(const b200_batch *batch);
 int32_t b200_batch_num_columns(const b200_batch *batch);
 int64_t b200_batch_size_bytes(const b200_batch *batch);
