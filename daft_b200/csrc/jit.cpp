@@ -861,7 +861,6 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     // ---- exact key code budget (see `code()` below): bytes per string key, 0 = no exact code
     int exact_B = 0;
     bool exact_possible = nkeys > 0;
-    const bool wide_mode = false;  // (MODE 1 of the skeleton is not emitted: see the 64-bit key rule below)
     int wide_key = -1, wide_avail = 0;  // the one 8-byte integer key whose VALUE decides exactness row by row
     {
         int bits_fixed = 0, nstr = 0, n64 = 0, idx64 = -1;
@@ -907,8 +906,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     if (filter_root >= 0) collect_cols(ast, filter_root, cols);
     for (int k : key_roots) collect_cols(ast, k, cols);
     for (int v : val_roots) collect_cols(ast, v, cols);
-    std::ostringstream raw, load, load2, load0, copy0;
-    const bool pipe_offsets = env_int("B200_AGG_PIPE", 0) != 0;
+    std::ostringstream raw, load, load2;
     size_t raw_bytes = 0;
     // staged variant: R rows of every fixed-width column / R+2 string offsets / R*L bytes of a fixed-length string
     // column are bulk-copied into a per-warp shared-memory stage; ld_* = the loader reading that stage
@@ -917,7 +915,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     const int SR = SW * 32 * SRPL;
     int SS = std::max(2, std::min(8, env_int("B200_AGG_STAGES", 2)));
     int stage_off = 0, stage_fixed_tx = 0;
-    std::ostringstream st_issue, st_tx, ld_a, ld_ok, ld_first, ld_b;
+    std::ostringstream st_issue, ld_a, ld_b;
     auto seg = [&](int bytes) {
         const int o = stage_off;
         stage_off += (bytes + 15) / 16 * 16;
@@ -963,15 +961,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         }
         if (is_string(dt)) {
             raw << "    int64_t o" << c << "a, o" << c << "b; uint64_t pk" << c << ";\n";
-            // string offsets are fetched one chunk AHEAD (load0), so the dependent byte loads of the current
-            // chunk can be issued together with its numeric loads
-            // (B200_AGG_PIPE=1; measured slower on Q1 at 128 registers/thread, so off by default)
-            if (pipe_offsets) {
-                load0 << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
-                copy0 << "    d.o" << c << "a = s.o" << c << "a; d.o" << c << "b = s.o" << c << "b;\n";
-            } else {
-                load << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
-            }
+            load << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
             // second load phase: the first <= 8 bytes of the value (depends on the offsets of phase one)
             if (is_pack4_col(c) && ast.fixed_len(c) > 0) {
                 // Fixed-length value columns (flags, codes): the kernel is specialised for L = data_bytes / rows.  The
@@ -1122,28 +1112,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     {
         const bool possible = exact_possible;
         const int B = exact_B;
-        if (wide_mode) {
-            cds << "    uint64_t c = 0ULL;\n";
-            int sh = 0;
-            for (uint32_t i = 0; i < nkeys; i++) {
-                const Node &n = ast.nodes[key_roots[i]];
-                const std::string si = std::to_string(i);
-                if (n.dtype == B200_NULL) continue;
-                std::string bits;
-                const int w = n.dtype == B200_BOOL ? 1 : 8 * dtype_width(n.dtype);
-                if (n.dtype == B200_BOOL) bits = "(uint64_t)k.v" + si;
-                else if (n.dtype == B200_F32) bits = "(uint64_t)(uint32_t)__float_as_int(k.v" + si + ")";
-                else if (n.dtype == B200_F64) bits = "(uint64_t)__double_as_longlong(k.v" + si + ")";
-                else bits = std::string("(uint64_t)(") + utype(n.dtype) + ")k.v" + si;
-                cds << "    c |= (k.k" << si << " ? " << bits << " : 0ULL) << " << sh << ";\n";
-                sh += w;
-                if (n.nullable) {
-                    cds << "    c |= (uint64_t)(!k.k" << si << ") << " << sh << ";\n";
-                    sh += 1;
-                }
-            }
-            cds << "    return c;\n";
-        } else if (!possible) {
+        if (!possible) {
             cds << "    return fingerprint(k) | 0x8000000000000000ULL;\n";
         } else {
             cds << "    uint64_t c = 0x4000000000000000ULL; bool ex = true;\n";
@@ -1316,17 +1285,14 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     o << "struct Prog {\n";
     o << "  typedef Params<" << meta.ptrs.size() << ", " << meta.ints.size() << "> P;\n";
     o << "  static constexpr int IV_N = " << iv_n << ", IV_MASK = " << iv_mask << ", PTR_TAG = " << p_hash << ", PTR_MINROW = " << p_acc[cell_minrow]
-      << ", PTR_FLAG = " << p_ovf << ", MODE = " << (wide_mode ? 1 : (exact_possible ? 0 : 2)) << ";\n";
+      << ", PTR_FLAG = " << p_ovf << ", MODE = " << (exact_possible ? 0 : 2) << ";\n";
     o << "  static constexpr int ASTRIDE = " << astride << ", IV_RSTRIDE = " << iv_rstride << ";\n";
     o << "  static constexpr int NKEYS = " << nkeys << ", G1 = " << G1 << ", NLANE = " << NLT << ", NWARP = " << NW << ", U = " << U << ";\n";
-    o << "  static constexpr bool PIPE = " << (pipe_offsets ? "true" : "false") << ";\n";
     o << "  struct Raw {\n" << raw.str() << "    int pad_;\n  };\n";
     o << "  struct Keys {\n" << keys_s.str() << "    int pad_;\n  };\n";
     o << "  struct Vals {\n" << vals_s.str() << "    int pad_;\n  };\n";
     o << "  __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {\n" << load.str() << "  }\n";
     o << "  __device__ __forceinline__ static void load2(const P& p, const int64_t row, Raw& r) {\n" << load2.str() << "  }\n";
-    o << "  __device__ __forceinline__ static void load0(const P& p, const int64_t row, Raw& r) {\n" << load0.str() << "  }\n";
-    o << "  __device__ __forceinline__ static void copy0(Raw& d, const Raw& s) {\n" << copy0.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {\n" << ev.str() << "  }\n";
     o << "  __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {\n" << ek.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {\n" << eq.str() << "  }\n";
@@ -1352,7 +1318,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     if (staged_variant) {
         o << "  static constexpr int STAGE_ROWS = " << SR << ", STAGES = " << SS << ", STAGE_BYTES = " << stage_off << ", RPL = " << SRPL << ";\n";
         o << "  __device__ __forceinline__ static void stage_issue(const P& p, const uint32_t dst, const uint32_t bar, const int64_t base) {\n"
-          << "    uint32_t tx = " << stage_fixed_tx << "u;\n" << st_tx.str() << "    mbar_expect_tx(bar, tx);\n" << st_issue.str() << "  }\n";
+          << "    mbar_expect_tx(bar, " << stage_fixed_tx << "u);\n" << st_issue.str() << "  }\n";
         o << "  static constexpr bool LATE = " << (env_int("B200_AGG_STAGE_LATE", 1) ? "true" : "false") << ";\n";
         // one row (rr = its index inside the stage); the fixed-length string check is a vote of the row's warp
         o << "  __device__ __forceinline__ static void load_staged(const P& p, const unsigned char* st, const int64_t row, const int rr, Raw& r) {\n"

@@ -15,7 +15,7 @@ enum PtrKind {
     P_TAKE, P_SLOT_HASH, P_SLOT_ROW, P_ACC, P_OVERFLOW
 };
 struct PtrSlot { int kind; int index; };
-enum IntKind { I_N = 0, I_MASK, I_STRLEN /* (unused) */, I_RSTRIDE /* words between group-table records: 1 = one array per cell */ };
+enum IntKind { I_N = 0, I_MASK, I_RSTRIDE /* words between group-table records: 1 = one array per cell */ };
 
 struct OutCol {
     std::string name;

@@ -4,23 +4,24 @@
 // struct -- straight-line, fully typed code for the filter / key / aggregate-input expressions --
 // and instantiates one of the hand-written skeletons below with it:
 //
-//   project_body         Filter/Project (a10/a11): one pass, outputs written at HBM speed,
-//                        bitmaps built with warp ballots, strings in a length pass + copy pass.
-//   agg_body             fused Filter -> Project -> HashAggregate (a4/a6/a10/a11): every input
-//                        column is read exactly once; nothing is materialised.
+//   project_body         Project (a11): one pass, outputs written at HBM speed, bitmaps built with
+//                        warp ballots, strings in a length pass + copy pass.
+//   filter_body          Filter (a10): count pass + stable compaction pass over 2048-row tiles.
+//   agg_body             fused Filter -> Project -> HashAggregate (a4/a6/a10/a11), low cardinality,
+//                        direct loads: every input column is read exactly once, nothing is materialised.
+//   agg_body_staged      the same kernel fed by cp.async.bulk (TMA) stages + mbarriers.
+//   agg_body_global      mid / high cardinality: shared-memory tier 2 + global open-addressing table.
 //
-// Group-by design (agg_body), replacing the hashbrown raw-entry probe + per-accumulator scatter
-// passes of src/daft-recordbatch/src/ops/inline_agg.rs:748-824,556-565:
-//   * global open-addressing table keyed by the XXH3 row hash (same hash_rows as the reference), slot
-//     claimed with one atomicCAS; equal hashes are verified against the claiming row's key values
-//     (nulls equal, floats by bit pattern == the reference's "hash equal AND comparator" rule);
-//   * accumulators are indexed by table slot, three tiers by where the group lives:
-//       tier 1  the first G1 groups a CTA meets: per-lane private shared-memory cells, plain
-//               read-modify-write, zero atomics, zero bank conflicts (cell address = lane);
-//               counts and first-row tracking are done per warp with ballots;
-//       tier 3  every other group: red.global atomics on the slot's cells.
-//     Low-cardinality aggregates (TPC-H Q1: 4 groups) never leave tier 1; high-cardinality ones
-//     (Q18: one group per order) spread their atomics over millions of addresses.
+// Group-by design, replacing the hashbrown raw-entry probe + per-accumulator scatter passes of
+// src/daft-recordbatch/src/ops/inline_agg.rs:748-824,556-565 (details at each skeleton and in DESIGN.md 3.1):
+//   * a group is identified by a 64-bit key CODE -- an injective packing of the key values when they fit 62 bits
+//     (equal codes ARE equal keys), otherwise a fingerprint confirmed against the key values of the group's first
+//     row (nulls equal, floats by bit pattern == the reference's "hash equal AND comparator" rule);
+//   * tier 1: the first G1 groups a CTA meets live in per-lane private shared-memory cells (plain
+//     read-modify-write, zero atomics, zero bank conflicts); a tier-1 kernel that keeps missing its groups raises
+//     the status flag and the host reruns the plan with the global kernel;
+//   * global kernel: tier 2 = shared-memory table with shared atomics, then red.global atomics on the group's
+//     cells in a table whose layout (records vs one array per cell) the host picks by size;
 //   * first-occurrence group order (inline_agg.rs:804-807) is recovered by tracking min(row) per group.
 #pragma once
 
@@ -313,9 +314,11 @@ __device__ __forceinline__ void filter_body(const typename Prog::P &p, int pass)
 // Prog provides (all generated):
 //   using P;  IV_N, IV_MASK (table capacity - 1), PTR_TAG, PTR_MINROW (first row per slot = representative row),
 //   PTR_FLAG (int: 0 ok, 1 table overflow, 2 low-cardinality kernel gave up);
-//   NKEYS, G1, NLANE, NWARP, U;  MODE (0: row-dependent exact 62-bit codes, 1: every row exact 63/64-bit code,
-//   2: never exact);  struct Raw / Keys / Vals;
-//   load / load2 / eval / eval_keys / keys_equal / code / lane_init / lane_update / global_update / warp_cells / flush
+//   IV_RSTRIDE (words between table records), ASTRIDE (record size);  NKEYS, G1, NLANE, NWARP, U;
+//   MODE (0: row-dependent exact 62-bit codes, 2: never exact);  struct Raw / Keys / Vals;
+//   load / load2 / eval / eval_keys / keys_equal / code / lane_init / lane_update / global_update / warp_cells / flush;
+//   t2_init / t2_update / t2_flush (global build);  STAGE_ROWS / STAGES / STAGE_BYTES / RPL / LATE, stage_issue / load_staged
+//   (TMA build)
 //
 // Group identity is carried by a 64-bit key CODE (see jit.cpp "Exact key code"): when it is exact (injective in
 // the key values) equal codes ARE equal keys; otherwise the code is a fingerprint and a match is confirmed against
@@ -326,7 +329,6 @@ __device__ __forceinline__ void filter_body(const typename Prog::P &p, int pass)
 #endif
 constexpr int AGG_WARPS = B200_AGG_WARPS;
 constexpr unsigned long long AGG_EMPTY = 0xFFFFFFFFFFFFFFFFULL;     // min-row cell of an unclaimed slot
-constexpr unsigned long long AGG_CLAIMING = 0xFFFFFFFFFFFFFFFEULL;  // (MODE 1) slot being published
 constexpr int AGG_PROBE_LIMIT = 1024;
 
 __device__ __forceinline__ uint64_t agg_mix(uint64_t x) {
@@ -349,7 +351,7 @@ __device__ __forceinline__ long long agg_find_slot(const typename Prog::P &p, un
     unsigned long long *slot_tag = (unsigned long long *)p.ptr[Prog::PTR_TAG];
     unsigned long long *slot_min = (unsigned long long *)p.ptr[Prog::PTR_MINROW];
     const uint64_t mask = (uint64_t)p.ival[Prog::IV_MASK];
-    const bool exact = Prog::MODE == 1 || (Prog::MODE == 0 && !(tag >> 63));
+    const bool exact = Prog::MODE == 0 && !(tag >> 63);
     const uint64_t rstride = (uint64_t)p.ival[Prog::IV_RSTRIDE];
     uint64_t rec = agg_mix(tag) & mask;
     for (int probes = 0; probes < AGG_PROBE_LIMIT; probes++) {
@@ -547,7 +549,7 @@ struct AggTier1 {
         int lid = -1;
 #pragma unroll
         for (int g = 0; g < G1; g++) lid = (tfp[g] == fp) ? g : lid;
-        if (Prog::NKEYS > 0 && Prog::MODE != 1 && live && lid >= 0 && (Prog::MODE == 2 || (fp >> 63))) {
+        if (Prog::NKEYS > 0 && live && lid >= 0 && (Prog::MODE == 2 || (fp >> 63))) {
             typename Prog::Keys kv;  // inexact code: confirm against the published key values
             Prog::eval_keys(p, r, kv);
             if (!Prog::keys_equal(kv, s_keys[lid])) lid = -1;
