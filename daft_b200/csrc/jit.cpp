@@ -906,7 +906,22 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     if (filter_root >= 0) collect_cols(ast, filter_root, cols);
     for (int k : key_roots) collect_cols(ast, k, cols);
     for (int v : val_roots) collect_cols(ast, v, cols);
-    std::ostringstream raw, load, load2;
+    std::ostringstream raw, load, load2, pf;
+    const int chunk_rows = 32 * std::max(1, std::min(8, env_int("B200_AGG_U", 2)));
+    // L2 prefetch of the warp's next chunk (jit_prelude.cuh agg_chunk).  Measured on B200 (SF10): plans that read string
+    // columns gain (Q1 0.636 -> 0.571 ms, count-by-flags 0.490 -> 0.449 ms: their 9-11 narrow loads per row are latency
+    // bound), numeric-only plans that already stream at ~6 TB/s lose 10-15% -- so it is on exactly when a string
+    // column is read.  B200_AGG_PREFETCH = 0 off / 1 all columns / 2 string columns only; default: auto.
+    bool reads_strings = false;
+    for (int c : cols) reads_strings = reads_strings || is_string((*ast.col_dtypes)[c]);
+    const int pf_env = env_int("B200_AGG_PREFETCH", -1);
+    const int pf_mode = pf_env >= 0 ? pf_env : (reads_strings ? 1 : 0);
+    bool pf_is_string_col = false;
+    auto pf_span = [&](const std::string &ptr, int bytes_per_row, int extra_bytes) {  // lines of one chunk of a column
+        if (pf_mode == 0 || (pf_mode == 2 && !pf_is_string_col)) return;
+        const int lines = (chunk_rows * bytes_per_row + extra_bytes + 127) / 128;  // chunks start on 64-row boundaries of 256-byte aligned buffers
+        pf << "    if (lane < " << lines << ") prefetch_l2((const char*)" << ptr << " + row0 * " << bytes_per_row << " + lane * 128);\n";
+    };
     size_t raw_bytes = 0;
     // staged variant: R rows of every fixed-width column / R+2 string offsets / R*L bytes of a fixed-length string
     // column are bulk-copied into a per-warp shared-memory stage; ld_* = the loader reading that stage
@@ -962,6 +977,10 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         if (is_string(dt)) {
             raw << "    int64_t o" << c << "a, o" << c << "b; uint64_t pk" << c << ";\n";
             load << "    { const int64_t* of_ = (const int64_t*)" << cg.P(P_COL_OFFSETS, c) << "; r.o" << c << "a = of_[row]; r.o" << c << "b = of_[row + 1]; }\n";
+            pf_is_string_col = true;
+            pf_span(cg.P(P_COL_OFFSETS, c), 8, 8);
+            if (is_pack4_col(c) && ast.fixed_len(c) > 0) pf_span(cg.P(P_COL_DATA, c), ast.fixed_len(c), 0);
+            pf_is_string_col = false;
             // second load phase: the first <= 8 bytes of the value (depends on the offsets of phase one)
             if (is_pack4_col(c) && ast.fixed_len(c) > 0) {
                 // Fixed-length value columns (flags, codes): the kernel is specialised for L = data_bytes / rows.  The
@@ -994,6 +1013,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         } else {
             raw << "    " << ctype(dt) << " c" << c << ";\n";
             load << "    r.c" << c << " = ((const " << ctype(dt) << "*)" << cg.P(P_COL_DATA, c) << ")[row];\n";
+            pf_span(cg.P(P_COL_DATA, c), dtype_width(dt), 0);
             raw_bytes += std::max(4, dtype_width(dt));
         }
     }
@@ -1293,6 +1313,9 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     o << "  struct Vals {\n" << vals_s.str() << "    int pad_;\n  };\n";
     o << "  __device__ __forceinline__ static void load(const P& p, const int64_t row, Raw& r) {\n" << load.str() << "  }\n";
     o << "  __device__ __forceinline__ static void load2(const P& p, const int64_t row, Raw& r) {\n" << load2.str() << "  }\n";
+    o << "  static constexpr bool PREFETCH = " << (pf_mode ? "true" : "false") << ";\n";
+    o << "  static constexpr int PFDIST = " << std::max(1, std::min(8, env_int("B200_AGG_PFDIST", 1))) << ";\n";
+    o << "  __device__ __forceinline__ static void prefetch(const P& p, const int64_t row0, const int lane) {\n" << pf.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {\n" << ev.str() << "  }\n";
     o << "  __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {\n" << ek.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {\n" << eq.str() << "  }\n";

@@ -36,6 +36,7 @@ struct Str {
 };
 
 __device__ __forceinline__ bool bit_at(const uint8_t *bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+__device__ __forceinline__ void prefetch_l2(const void *q) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q)); }
 
 // ---- order-preserving keys for min/max on any numeric type ---------------------------------------
 // floats: all NaN collapse to the largest key (NaN sorts greatest, search_sorted.rs:238-245)
@@ -593,7 +594,7 @@ struct AggTier1 {
 // one chunk of 32*U rows of a warp; FULL: every row of the chunk exists (no per-row bounds checks or guards)
 template <class Prog, bool FULL>
 __device__ __forceinline__ void agg_chunk(AggTier1<Prog> &t1, const typename Prog::P &p, const int64_t base, const int64_t n, const int lane,
-                                          int &abandoned) {
+                                          int &abandoned, const int64_t nextstep) {
     constexpr int U = Prog::U;
     typename Prog::Raw raw[U];
 #pragma unroll
@@ -602,6 +603,12 @@ __device__ __forceinline__ void agg_chunk(AggTier1<Prog> &t1, const typename Pro
         if (FULL || row < n) Prog::load(p, row, raw[u]);
     }
     abandoned = *t1.flag;  // consumed at the next chunk: the load overlaps this chunk's column loads
+    if (FULL && Prog::PREFETCH) {
+        // pull the cache lines of the chunk this warp handles NEXT into L2 (no registers, no scoreboard): when the warp
+        // gets there its loads pay L2 latency instead of HBM latency
+        const int64_t next = base + nextstep * Prog::PFDIST;
+        if (next + 32 * U <= n) Prog::prefetch(p, next, lane);
+    }
 #pragma unroll
     for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
         const int64_t row = base + u * 32 + lane;
@@ -630,10 +637,10 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp;
     for (; c < nfull; c += total_warps) {
         if (__any_sync(FULL_MASK, abandoned != 0 || t1.gave_up)) break;
-        agg_chunk<Prog, true>(t1, p, c * chunk, n, lane, abandoned);
+        agg_chunk<Prog, true>(t1, p, c * chunk, n, lane, abandoned, total_warps * chunk);
     }
     if (c < nchunks && c >= nfull && !__any_sync(FULL_MASK, abandoned != 0))  // the one partial chunk at the end of the input
-        agg_chunk<Prog, false>(t1, p, c * chunk, n, lane, abandoned);
+        agg_chunk<Prog, false>(t1, p, c * chunk, n, lane, abandoned, 0);
     __syncthreads();
     t1.flush(p, lane, warp);
 }
