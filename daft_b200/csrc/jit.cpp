@@ -917,10 +917,16 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     const int pf_env = env_int("B200_AGG_PREFETCH", -1);
     const int pf_mode = pf_env >= 0 ? pf_env : (reads_strings ? 1 : 0);
     bool pf_is_string_col = false;
+    int pf_lines = 0;
     auto pf_span = [&](const std::string &ptr, int bytes_per_row, int extra_bytes) {  // lines of one chunk of a column
         if (pf_mode == 0 || (pf_mode == 2 && !pf_is_string_col)) return;
         const int lines = (chunk_rows * bytes_per_row + extra_bytes + 127) / 128;  // chunks start on 64-row boundaries of 256-byte aligned buffers
-        pf << "    if (lane < " << lines << ") prefetch_l2((const char*)" << ptr << " + row0 * " << bytes_per_row << " + lane * 128);\n";
+        // lanes [pf_lines, pf_lines + lines) own this column's lines (second slot for footprints beyond 32 lines)
+        for (int l = 0; l < lines; l++, pf_lines++) {
+            if (pf_lines >= 64) break;
+            const int slot = pf_lines / 32, ln = pf_lines % 32;
+            pf << "    if (lane == " << ln << ") { f.b" << slot << " = (const char*)" << ptr << " + " << l * 128 << "; f.w" << slot << " = " << bytes_per_row << "; }\n";
+        }
     };
     size_t raw_bytes = 0;
     // staged variant: R rows of every fixed-width column / R+2 string offsets / R*L bytes of a fixed-length string
@@ -1315,7 +1321,9 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     o << "  __device__ __forceinline__ static void load2(const P& p, const int64_t row, Raw& r) {\n" << load2.str() << "  }\n";
     o << "  static constexpr bool PREFETCH = " << (pf_mode ? "true" : "false") << ";\n";
     o << "  static constexpr int PFDIST = " << std::max(1, std::min(8, env_int("B200_AGG_PFDIST", 1))) << ";\n";
-    o << "  __device__ __forceinline__ static void prefetch(const P& p, const int64_t row0, const int lane) {\n" << pf.str() << "  }\n";
+    o << "  static constexpr int PF_LINES = " << pf_lines << ";\n";
+    o << "  __device__ __forceinline__ static void prefetch_setup(const P& p, const int lane, PfLane& f) {\n"
+      << "    f.b0 = nullptr; f.b1 = nullptr; f.w0 = 0; f.w1 = 0;\n" << pf.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool eval(const P& p, const Raw& r, Keys& keys, Vals& vals) {\n" << ev.str() << "  }\n";
     o << "  __device__ __forceinline__ static void eval_keys(const P& p, const int64_t row, Keys& keys) {\n" << ek.str() << "  }\n";
     o << "  __device__ __forceinline__ static bool keys_equal(const Keys& a, const Keys& b) {\n" << eq.str() << "  }\n";

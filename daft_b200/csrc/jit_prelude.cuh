@@ -591,10 +591,16 @@ struct AggTier1 {
     }
 };
 
+// the line(s) of a chunk's footprint a lane prefetches: address = b + first_row_of_chunk * w
+struct PfLane {
+    const char *b0, *b1;
+    int w0, w1;
+};
+
 // one chunk of 32*U rows of a warp; FULL: every row of the chunk exists (no per-row bounds checks or guards)
 template <class Prog, bool FULL>
 __device__ __forceinline__ void agg_chunk(AggTier1<Prog> &t1, const typename Prog::P &p, const int64_t base, const int64_t n, const int lane,
-                                          int &abandoned, const int64_t nextstep) {
+                                          int &abandoned, const int64_t nextstep, const PfLane &pf) {
     constexpr int U = Prog::U;
     typename Prog::Raw raw[U];
 #pragma unroll
@@ -604,10 +610,14 @@ __device__ __forceinline__ void agg_chunk(AggTier1<Prog> &t1, const typename Pro
     }
     abandoned = *t1.flag;  // consumed at the next chunk: the load overlaps this chunk's column loads
     if (FULL && Prog::PREFETCH) {
-        // pull the cache lines of the chunk this warp handles NEXT into L2 (no registers, no scoreboard): when the warp
-        // gets there its loads pay L2 latency instead of HBM latency
+        // pull the cache lines of the chunk this warp handles NEXT into L2 (no scoreboard entry): when the warp gets there
+        // its loads pay L2 latency instead of HBM latency.  Every lane owns one (or two) fixed lines of the chunk's
+        // footprint -- base pointer and bytes-per-row are set up once per kernel -- so a chunk costs two instructions.
         const int64_t next = base + nextstep * Prog::PFDIST;
-        if (next + 32 * U <= n) Prog::prefetch(p, next, lane);
+        if (next + 32 * U <= n) {
+            if (pf.b0) prefetch_l2(pf.b0 + next * pf.w0);
+            if (Prog::PF_LINES > 32 && pf.b1) prefetch_l2(pf.b1 + next * pf.w1);
+        }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {  // dependent loads (string prefixes) of all U rows, issued back to back
@@ -634,13 +644,15 @@ __device__ __forceinline__ void agg_body(const typename Prog::P &p) {
     const int64_t nchunks = (n + chunk - 1) / chunk, nfull = n / chunk;
     const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
     int abandoned = 0;  // status flag as of the previous chunk
+    PfLane pf;
+    Prog::prefetch_setup(p, lane, pf);
     int64_t c = (int64_t)blockIdx.x * AGG_WARPS + warp;
     for (; c < nfull; c += total_warps) {
         if (__any_sync(FULL_MASK, abandoned != 0 || t1.gave_up)) break;
-        agg_chunk<Prog, true>(t1, p, c * chunk, n, lane, abandoned, total_warps * chunk);
+        agg_chunk<Prog, true>(t1, p, c * chunk, n, lane, abandoned, total_warps * chunk, pf);
     }
     if (c < nchunks && c >= nfull && !__any_sync(FULL_MASK, abandoned != 0))  // the one partial chunk at the end of the input
-        agg_chunk<Prog, false>(t1, p, c * chunk, n, lane, abandoned, 0);
+        agg_chunk<Prog, false>(t1, p, c * chunk, n, lane, abandoned, 0, pf);
     __syncthreads();
     t1.flush(p, lane, warp);
 }
