@@ -350,6 +350,14 @@ class RecordBatch:
             raise TypeError(f"Expected a RecordBatch for `boundaries` in partition_by_range but got {type(boundaries)}")
         if len(boundaries) == 0:
             return [self]
+        from .expressions import bind
+        names, dtypes = self.column_names(), self.dtypes()
+        key_schema = [(e.name(), bind(e, names, dtypes).dtype) for e in partition_keys]
+        if key_schema != boundaries.schema():  # names and dtypes first, as RecordBatch::search_sorted does (search_sorted.rs:14-26)
+            raise ValueError(f"Schema Mismatch in search_sorted: data: {boundaries.schema()} vs keys: {key_schema}")
+        if len(descending) != boundaries.num_columns():
+            raise ValueError(f"Mismatch in number of arguments for `descending` in search sorted: num_columns: "
+                             f"{boundaries.num_columns()} vs : descending.len() {len(descending)}")
         both, idx = self._resolve_keys(partition_keys)
         nparts = len(boundaries) + 1
         outs = (ctypes.c_void_p * nparts)()

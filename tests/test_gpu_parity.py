@@ -291,6 +291,25 @@ def test_search_sorted_and_partition_by_range(gpu, n, nb):
             assert_tables_equal(g.to_arrow_table(), w)
 
 
+def test_partition_by_range_reference_literals(gpu):
+    """tests/recordbatch/test_partitioning.py:316-344: multi-column string boundaries and the input validation errors."""
+    c = gpu.col
+    table = RB(gpu, pa.table({"x": ["a", "c", "a", "c"], "y": ["1", "2", "3", "4"]}))
+    bounds = RB(gpu, pa.table({"x": ["b"], "y": ["1"]}))
+    parts = table.partition_by_range([c("x"), c("y")], bounds, [False, False])
+    assert [p.to_pydict() for p in parts] == [{"x": ["a", "a"], "y": ["1", "3"]}, {"x": ["c", "c"], "y": ["2", "4"]}]
+    parts = table.partition_by_range([c("x"), c("y")], bounds, [True, False])
+    assert [p.to_pydict() for p in parts] == [{"x": ["c", "c"], "y": ["2", "4"]}, {"x": ["a", "a"], "y": ["1", "3"]}]
+    data = pa.table({"x": [1, 2, 3], "b": [0, 1, 2]})
+    t, b = RB(gpu, data), RB(gpu, data)
+    with pytest.raises(ValueError, match="Schema Mismatch"):
+        t.partition_by_range([c("x")], b, [False])
+    with pytest.raises(ValueError, match="Mismatch in number of arguments for `descending`"):
+        t.partition_by_range([c("x")], b.eval_expression_list([c("x")]), [False, False])
+    with pytest.raises(ValueError, match="Schema Mismatch"):
+        t.partition_by_range([c("x")], b.eval_expression_list([c("x").alias("y")]), [False])
+
+
 def test_dedup(gpu):
     rng = np.random.default_rng(2)
     tbl = random_table(rng, 3000, 0.2)

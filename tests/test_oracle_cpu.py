@@ -186,3 +186,36 @@ def test_any_value_and_bool_aggs_semantics():
                                                            "ba": [False, True, None], "bo": [True, True, None]}
     assert oracle_agg(t, aggs[:2], []).to_pydict() == {"a": [None], "b": [5]}
     assert oracle_agg(t.slice(0, 0), aggs[:1], []).to_pydict() == {"a": [None]}
+
+
+def test_partition_by_range_reference_cases():
+    # tests/recordbatch/test_partitioning.py:316-328 (literal) and :246-276 (invariants)
+    table = pa.table({"x": ["a", "c", "a", "c"], "y": ["1", "2", "3", "4"]})
+    bounds = pa.table({"x": ["b"], "y": ["1"]})
+    parts = O.partition_by_range(table, ["x", "y"], bounds, [False, False])
+    assert [p.to_pydict() for p in parts] == [{"x": ["a", "a"], "y": ["1", "3"]}, {"x": ["c", "c"], "y": ["2", "4"]}]
+    parts = O.partition_by_range(table, ["x", "y"], bounds, [True, False])
+    assert [p.to_pydict() for p in parts] == [{"x": ["c", "c"], "y": ["2", "4"]}, {"x": ["a", "a"], "y": ["1", "3"]}]
+    for size in (0, 1, 10, 33, 100):
+        for k in (1, 2, 3, 10, 40):
+            for desc in (False, True):
+                tbl = pa.table({"x": np.arange(size, dtype=np.float64), "x_ind": list(range(size))})
+                original = np.linspace(0, size, k)
+                inp = original[1:][::-1] if desc else original[1:]
+                parts = O.partition_by_range(tbl, ["x"], pa.table({"x": inp}), [desc])
+                parts = parts[::-1] if desc else parts
+                assert sum(p.num_rows for p in parts) == size
+                seen = set()
+                for i, p in enumerate(parts):
+                    for x, xi in zip(p.column("x").to_pylist(), p.column("x_ind").to_pylist()):
+                        assert original[i] <= x and (i >= k - 1 or x <= original[i + 1])
+                        assert xi not in seen
+                        seen.add(xi)
+
+
+def test_search_sorted_matches_numpy_searchsorted_right():
+    rng = np.random.default_rng(4)
+    srt = np.sort(rng.integers(0, 50, 40))
+    keys = rng.integers(-5, 60, 500)
+    got = O.search_sorted(pa.table({"a": srt}), pa.table({"a": keys}), [False])
+    assert got.tolist() == np.searchsorted(srt, keys, side="right").tolist()
