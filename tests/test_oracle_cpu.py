@@ -219,3 +219,31 @@ def test_search_sorted_matches_numpy_searchsorted_right():
     keys = rng.integers(-5, 60, 500)
     got = O.search_sorted(pa.table({"a": srt}), pa.table({"a": keys}), [False])
     assert got.tolist() == np.searchsorted(srt, keys, side="right").tolist()
+
+
+def test_any_value_reference_cases():
+    # tests/recordbatch/test_table_aggs.py:333-353: per group, any_value(False) may be null only where the case says so,
+    # any_value(True) must be non-null whenever the group has a non-null value
+    cases = [({"a": [1], "b": ["a"]}, {"a": False}, {"a": False}),
+             ({"a": [None], "b": ["a"]}, {"a": True}, {"a": True}),
+             ({"a": [None, 1], "b": ["a", "a"]}, {"a": True}, {"a": False}),
+             ({"a": [1, None, 2], "b": ["a", "b", "b"]}, {"a": False, "b": True}, {"a": False, "b": False})]
+    for data, expected_nulls, expected_no_nulls in cases:
+        t = pa.table({"a": pa.array(data["a"], type=pa.int64()), "b": data["b"]})
+        for ignore, expected in ((False, expected_nulls), (True, expected_no_nulls)):
+            got = oracle_agg(t, [col("a").any_value(ignore).alias("a")], [col("b")]).to_pydict()
+            assert len(got["b"]) == len(expected)
+            for k, v in zip(got["b"], got["a"]):
+                assert expected[k] or v is not None
+
+
+def test_groupby_null_groups_reference_cases():
+    # tests/recordbatch/test_table_aggs.py:557-603: a null key is a group of its own; all-null keys form one group
+    for typ in (pa.int8(), pa.int32(), pa.int64(), pa.uint16(), pa.float32(), pa.float64(), pa.large_utf8(), pa.bool_()):
+        grp = pa.array([None, None, None], type=typ)
+        t = pa.table({"group": grp, "cookies": [1, 2, 3]})
+        assert oracle_agg(t, [col("cookies").sum().alias("cookies")], [col("group")]).to_pydict() == {"group": [None], "cookies": [6]}
+        vals = ["1", "1", None] if pa.types.is_large_string(typ) else ([True, True, None] if pa.types.is_boolean(typ) else [1, 1, None])
+        t = pa.table({"group": pa.array(vals, type=typ), "cookies": [2, 2, 3]})
+        got = oracle_agg(t, [col("cookies").sum().alias("sum")], [col("group")]).to_pydict()
+        assert got == {"group": [vals[0], None], "sum": [4, 3]}
