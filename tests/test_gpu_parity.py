@@ -461,6 +461,32 @@ def test_hash_join_long_duplicate_runs(gpu, how):
     assert_tables_equal(got, want)
 
 
+@pytest.mark.parametrize("typ", [pa.int64(), pa.float64(), pa.large_utf8()])
+@pytest.mark.parametrize("null_safe", [False, True])
+def test_join_pairs_from_reference_tests(gpu, typ, null_safe):
+    """The literal (left row, right row) pair tables of tests/recordbatch/test_joins.py:59-140, through the C ABI."""
+    from test_oracle_cpu import JOIN_PAIR_CASES
+    c = gpu.col
+    for left, right, pairs, ns_pairs in JOIN_PAIR_CASES:
+        expected = ns_pairs if null_safe else pairs
+
+        def column(vals):
+            if pa.types.is_large_string(typ):
+                return pa.array([None if v is None else str(v) for v in vals], type=typ)
+            return pa.array(vals, type=typ)
+        lt = pa.table({"x": column(left), "x_ind": pa.array(list(range(len(left))), type=pa.int64())})
+        rt = pa.table({"y": column(right), "y_ind": pa.array(list(range(len(right))), type=pa.int64())})
+        kw = {"null_equals_null": [True]} if null_safe else {}
+        res = RB(gpu, lt).hash_join(RB(gpu, rt), [c("x")], [c("y")], how="inner", **kw).to_arrow_table()
+        assert res.column_names == ["x", "x_ind", "y", "y_ind"]
+        got = list(zip(res.column("x_ind").to_pylist(), res.column("y_ind").to_pylist()))
+        assert sorted(got) == sorted(expected)
+        assert res.column("y").to_pylist() == [rt.column("y").to_pylist()[j] for _, j in got]
+        res = RB(gpu, rt).hash_join(RB(gpu, lt), [c("y")], [c("x")], how="inner", **kw).to_arrow_table()
+        assert res.column_names == ["y", "y_ind", "x", "x_ind"]
+        assert sorted(zip(res.column("x_ind").to_pylist(), res.column("y_ind").to_pylist())) == sorted(expected)
+
+
 def test_join_null_safe_and_float_keys(gpu):
     left = pa.table({"a": pa.array([1, None, 3], type=pa.int64()), "f": pa.array([0.0, float("nan"), 1.5]), "x": [10, 20, 30]})
     right = pa.table({"a": pa.array([None, 1, 1], type=pa.int64()), "f": pa.array([-0.0, float("nan"), 1.5]), "y": [1, 2, 3]})

@@ -247,3 +247,39 @@ def test_groupby_null_groups_reference_cases():
         t = pa.table({"group": pa.array(vals, type=typ), "cookies": [2, 2, 3]})
         got = oracle_agg(t, [col("cookies").sum().alias("sum")], [col("group")]).to_pydict()
         assert got == {"group": [vals[0], None], "sum": [4, 3]}
+
+
+JOIN_PAIR_CASES = [  # tests/recordbatch/test_joins.py:59-91: (left, right, expected (left_idx, right_idx) pairs, null-safe pairs)
+    ([0, 1, 2, 3, None], [0, 1, 2, 3, None], [(0, 0), (1, 1), (2, 2), (3, 3)], [(0, 0), (1, 1), (2, 2), (3, 3), (4, 4)]),
+    ([None, None, 3, 1, 2, 0], [0, 1, 2, 3, None], [(5, 0), (3, 1), (4, 2), (2, 3)], [(5, 0), (3, 1), (4, 2), (2, 3), (0, 4), (1, 4)]),
+    ([None, 4, 5, 6, 7], [0, 1, 2, 3, None], [], [(0, 4)]),
+    ([None, 0, 0, 0, 1, None], [0, 1, 2, 3, None], [(1, 0), (2, 0), (3, 0), (4, 1)], [(1, 0), (2, 0), (3, 0), (4, 1), (5, 4), (0, 4)]),
+    ([None, 0, 0, 1, 1, None], [0, 1, 2, 3, None], [(1, 0), (2, 0), (3, 1), (4, 1)], [(1, 0), (2, 0), (3, 1), (4, 1), (5, 4), (0, 4)]),
+    ([None, 0, 0, 1, 1, None], [3, 1, 0, 2, None], [(1, 2), (2, 2), (3, 1), (4, 1)], [(1, 2), (2, 2), (3, 1), (4, 1), (5, 4), (0, 4)]),
+]
+
+
+@pytest.mark.parametrize("typ", [pa.int8(), pa.int32(), pa.int64(), pa.uint8(), pa.uint64(), pa.float32(), pa.float64(), pa.large_utf8()])
+@pytest.mark.parametrize("case", range(len(JOIN_PAIR_CASES)))
+@pytest.mark.parametrize("null_safe", [False, True])
+def test_join_pairs_from_reference_tests(typ, case, null_safe):
+    left, right, pairs, ns_pairs = JOIN_PAIR_CASES[case]
+    expected = ns_pairs if null_safe else pairs
+
+    def column(vals):
+        if pa.types.is_large_string(typ):
+            return pa.array([None if v is None else str(v) for v in vals], type=typ)
+        return pa.array(vals, type=typ)
+    lt = pa.table({"x": column(left), "x_ind": list(range(len(left)))})
+    rt = pa.table({"y": column(right), "y_ind": list(range(len(right)))})
+    kw = {"null_equals_null": [True]} if null_safe else {}
+    res = O.hash_join(lt, rt, ["x"], ["y"], "inner", **kw)
+    assert res.column_names == ["x", "x_ind", "y", "y_ind"]
+    got = list(zip(res.column("x_ind").to_pylist(), res.column("y_ind").to_pylist()))
+    assert sorted(got) == sorted(expected)
+    assert res.column("x").to_pylist() == [lt.column("x").to_pylist()[i] for i, _ in got]
+    assert res.column("y").to_pylist() == [rt.column("y").to_pylist()[j] for _, j in got]
+    # same pairs with the tables swapped (test_joins.py:121-140)
+    res = O.hash_join(rt, lt, ["y"], ["x"], "inner", **kw)
+    assert res.column_names == ["y", "y_ind", "x", "x_ind"]
+    assert sorted(zip(res.column("x_ind").to_pylist(), res.column("y_ind").to_pylist())) == sorted(expected)
