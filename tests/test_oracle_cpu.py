@@ -283,3 +283,30 @@ def test_join_pairs_from_reference_tests(typ, case, null_safe):
     res = O.hash_join(rt, lt, ["y"], ["x"], "inner", **kw)
     assert res.column_names == ["y", "y_ind", "x", "x_ind"]
     assert sorted(zip(res.column("x_ind").to_pylist(), res.column("y_ind").to_pylist())) == sorted(expected)
+
+
+SORT_CASES = [  # tests/recordbatch/test_sorting.py:127-136: (a, b, a_desc, b_desc, expected argsort); nulls_first defaults to descending
+    ([None, 4, 2, 1, 5], [0, 1, 2, 3, None], False, False, [3, 2, 1, 4, 0]),
+    ([None, 4, 2, 1, 5], [0, 1, 2, 3, None], False, True, [3, 2, 1, 4, 0]),
+    ([1, 1, 1, 1, 1], [None, 3, 1, 2, 0], False, False, [4, 2, 3, 1, 0]),
+    ([1, 1, 1, 1, 1], [None, 3, 1, 2, 0], True, False, [4, 2, 3, 1, 0]),
+    ([None, None, None, None, None], [None, 3, 1, 2, 0], False, False, [4, 2, 3, 1, 0]),
+    ([None, None, None, None, None], [None, 3, 1, 2, 0], True, False, [4, 2, 3, 1, 0]),
+    ([None, 4, 2, 1, 5], [None, None, None, None, None], False, False, [3, 2, 1, 4, 0]),
+    ([None, 4, 2, 1, 5], [None, None, None, None, None], False, True, [3, 2, 1, 4, 0]),
+]
+
+
+@pytest.mark.parametrize("sort_typ", [pa.int8(), pa.int64(), pa.uint32(), pa.float32(), pa.float64(), pa.large_utf8()])
+@pytest.mark.parametrize("value_typ", [pa.int64(), pa.float64(), pa.large_utf8()])
+@pytest.mark.parametrize("case", range(len(SORT_CASES)))
+def test_multi_column_argsort_from_reference_tests(sort_typ, value_typ, case):
+    a, b, a_desc, b_desc, expected = SORT_CASES[case]
+
+    def column(vals, typ):
+        if pa.types.is_large_string(typ):
+            return pa.array([None if v is None else str(v) for v in vals], type=typ)
+        return pa.array(vals, type=typ)
+    ca, cb = column(a, sort_typ), column(b, value_typ)
+    assert O.argsort([ca, cb], [a_desc, b_desc], [a_desc, b_desc]).tolist() == expected
+    assert O.argsort([ca, cb], [not a_desc, not b_desc], [not a_desc, not b_desc]).tolist() == expected[::-1]
