@@ -310,3 +310,27 @@ def test_multi_column_argsort_from_reference_tests(sort_typ, value_typ, case):
     ca, cb = column(a, sort_typ), column(b, value_typ)
     assert O.argsort([ca, cb], [a_desc, b_desc], [a_desc, b_desc]).tolist() == expected
     assert O.argsort([ca, cb], [not a_desc, not b_desc], [not a_desc, not b_desc]).tolist() == expected[::-1]
+
+
+def test_global_and_grouped_agg_literals_from_reference_tests():
+    # tests/recordbatch/test_table_aggs.py:356-440 (global) and :475-555 (grouped; results compared after sorting by the keys)
+    for vals, exp in (([], {"count": [0], "sum": [None], "mean": [None], "min": [None], "max": [None]}),
+                      ([None], {"count": [0], "sum": [None], "mean": [None], "min": [None], "max": [None]}),
+                      ([None, None, None], {"count": [0], "sum": [None], "mean": [None], "min": [None], "max": [None]}),
+                      ([None, 3, None, None, 1, 2, 0, None], {"count": [4], "sum": [6], "mean": [1.5], "min": [0], "max": [3]})):
+        t = pa.table({"input": pa.array(vals, type=pa.int32())})
+        x = col("input")
+        got = oracle_agg(t, [x.count().alias("count"), x.sum().alias("sum"), x.mean().alias("mean"), x.min().alias("min"), x.max().alias("max")], [])
+        assert got.to_pydict() == exp
+    values = [("Bob", None), ("Bob", None), ("Bob", 5), ("Bob", 5), (None, None), (None, 5), (None, None), (None, 2),
+              ("Alice", None), ("Alice", None), ("Alice", None), ("Alice", None)]
+    t = pa.table({"name": pa.array([v[0] for v in values], type=pa.large_utf8()), "cookies": pa.array([v[1] for v in values], type=pa.int64())})
+
+    def sorted_result(aggs, groups):
+        r = oracle_agg(t, aggs, [col(g) for g in groups])
+        return O.sort(r, groups, [False] * len(groups), [False] * len(groups)).to_pydict()
+    assert sorted_result([col("cookies").sum().alias("sum"), col("name").count().alias("count")], ["name"]) == \
+        {"name": ["Alice", "Bob", None], "sum": [None, 10, 7], "count": [4, 4, 0]}
+    assert sorted_result([col("name").count().alias("count")], ["cookies"]) == {"cookies": [2, 5, None], "count": [0, 2, 6]}
+    assert sorted_result([col("name").count().alias("count")], ["name", "cookies"]) == \
+        {"name": ["Alice", "Bob", "Bob", None, None, None], "cookies": [None, 5, None, 2, 5, None], "count": [4, 2, 2, 0, 0, 0]}
