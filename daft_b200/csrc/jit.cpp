@@ -512,7 +512,14 @@ struct ExprGen {
                     os << "    const bool " << V << " = str_cmp(" << a << ", " << lo << ") >= 0 && str_cmp(" << a << ", " << hi << ") <= 0;\n";
                 else
                     os << "    const bool " << V << " = " << a << " >= " << lo << " && " << a << " <= " << hi << ";\n";
-                os << "    const bool " << K << " = " << k(kid[0]) << " && " << k(kid[1]) << " && " << k(kid[2]) << ";\n";
+                // value.gte(lower).and(value.lte(upper)) with the Kleene `and` (src/daft-core/src/array/ops/between.rs:30-32):
+                // null unless both comparisons are known, or one of them is known to be false
+                {
+                    const std::string kg = "(" + k(kid[0]) + " && " + k(kid[1]) + ")", kl = "(" + k(kid[0]) + " && " + k(kid[2]) + ")";
+                    const std::string ge = is_string(C.dtype) ? "(str_cmp(" + a + ", " + lo + ") >= 0)" : "(" + a + " >= " + lo + ")";
+                    const std::string le = is_string(C.dtype) ? "(str_cmp(" + a + ", " + hi + ") <= 0)" : "(" + a + " <= " + hi + ")";
+                    os << "    const bool " << K << " = (" << kg << " && " << kl << ") || (" << kg << " && !" << ge << ") || (" << kl << " && !" << le << ");\n";
+                }
                 break;
             }
             case T_FILL_NULL:

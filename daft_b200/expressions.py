@@ -248,7 +248,12 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
     if k == "between":
         c, lo, hi = (bind(x, names, dtypes) for x in e.args)
         st = dt.supertype(dt.supertype(c.dtype, lo.dtype), hi.dtype)
-        return Bound(T_BETWEEN, dt.BOOL, kids=[_cast(c, st), _cast(lo, st), _cast(hi, st)])
+        # value.gte(lower).and(value.lte(upper)) with the Kleene `and` (src/daft-core/src/array/ops/between.rs:30-32): a null
+        # bound makes the row null unless the other comparison is already false (tests/recordbatch/test_between.py:44-48)
+        cv, lov, hiv = _cast(c, st), _cast(lo, st), _cast(hi, st)
+        ge = Bound(T_BINARY, dt.BOOL, BINOPS["ge"], [cv, lov])
+        le = Bound(T_BINARY, dt.BOOL, BINOPS["le"], [cv, hiv])
+        return Bound(T_BINARY, dt.BOOL, BINOPS["and"], [ge, le])
     if k == "fill_null":
         c, f = bind(e.args[0], names, dtypes), bind(e.args[1], names, dtypes)
         st = dt.supertype(c.dtype, f.dtype)

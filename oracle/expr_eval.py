@@ -149,7 +149,10 @@ def _eval(b: Bound, cols, n: int):
             return r, ka
         if b.tag == T_BETWEEN:
             (a, ka), (lo, kl), (hi, kh) = kids
-            return np.asarray((a >= lo) & (a <= hi), dtype=bool), ka & kl & kh
+            # gte(lower) Kleene-and lte(upper) (src/daft-core/src/array/ops/between.rs:30-32, comparison.rs:725-786)
+            ge, le = np.asarray(a >= lo, dtype=bool), np.asarray(a <= hi, dtype=bool)
+            kg, kle = ka & kl, ka & kh
+            return ge & le, (kg & kle) | (kg & ~ge) | (kle & ~le)
         if b.tag == T_FILL_NULL:
             (a, ka), (f, kf) = kids
             return np.where(ka, a, f), ka | kf

@@ -334,3 +334,22 @@ def test_global_and_grouped_agg_literals_from_reference_tests():
     assert sorted_result([col("name").count().alias("count")], ["cookies"]) == {"cookies": [2, 5, None], "count": [0, 2, 6]}
     assert sorted_result([col("name").count().alias("count")], ["name", "cookies"]) == \
         {"name": ["Alice", "Bob", "Bob", None, None, None], "cookies": [None, 5, None, 2, 5, None], "count": [4, 2, 2, 0, 0, 0]}
+
+
+@pytest.mark.parametrize("value,lower,upper,expected", [
+    # tests/recordbatch/test_between.py:20-48 (the non-decimal rows)
+    ([1, 2, 3, 4], 1, 2, [True, True, False, False]), ([1, 2, 3, 4], 1.0, 2.0, [True, True, False, False]),
+    ([1.0, 2.0, 3.0, 4.0], 1.0, 2.0, [True, True, False, False]), ([1.0, 2.0, 3.0, 4.0], 1, 2, [True, True, False, False]),
+    ([1.0, 2.0, 3.0, 4.0], None, 1, [None, False, False, False]), ([1.0, 2.0, 3.0, 4.0], 1, None, [None, None, None, None]),
+    ([1.0, 2.0, 3.0, 4.0], None, None, [None, None, None, None]), ([None, None, None, None], None, None, [None, None, None, None]),
+    ([None, None, None, None], 1, 1, [None, None, None, None]),
+])
+def test_between_null_bounds_from_reference_tests(value, lower, upper, expected):
+    typ = pa.float64() if any(isinstance(v, float) for v in value) else (pa.null() if all(v is None for v in value) else pa.int64())
+    t = pa.table({"value": pa.array(value, type=typ)})
+    got = E.eval_expression_list(t, [col("value").between(lower, upper).alias("value")]).to_pydict()["value"]
+    assert got == expected
+    # the same rows with the bounds as columns (test_between.py:133-146)
+    if lower is not None and upper is not None and typ != pa.null():
+        t2 = t.append_column("lo", pa.array([lower] * 4, type=typ)).append_column("hi", pa.array([upper] * 4, type=typ))
+        assert E.eval_expression_list(t2, [col("value").between(col("lo"), col("hi")).alias("v")]).to_pydict()["v"] == expected
