@@ -353,3 +353,43 @@ def test_between_null_bounds_from_reference_tests(value, lower, upper, expected)
     if lower is not None and upper is not None and typ != pa.null():
         t2 = t.append_column("lo", pa.array([lower] * 4, type=typ)).append_column("hi", pa.array([upper] * 4, type=typ))
         assert E.eval_expression_list(t2, [col("value").between(col("lo"), col("hi")).alias("v")]).to_pydict()["v"] == expected
+
+
+def _eval1(vals, expr, typ=None):
+    t = pa.table({"input": pa.array(vals, type=typ)})
+    return E.eval_expression_list(t, [expr.alias("input")]).to_pydict()["input"]
+
+
+def test_expression_literals_from_reference_tests():
+    c = col("input")
+    # tests/recordbatch/test_is_in.py:20-58, 113-130, 140-146
+    assert _eval1([None, None], c.is_in([None])) == [None, None]
+    assert _eval1([True, False], c.is_in([False])) == [False, True]
+    assert _eval1(["a", "b", "c", "d"], c.is_in(["a", "b"])) == [True, True, False, False]
+    assert _eval1([-1, 2, 3, 4], c.is_in([-1, 2])) == [True, True, False, False]
+    assert _eval1([-1.0, 2.0, 3.0, 4.0], c.is_in([-1.0, 2.0])) == [True, True, False, False]
+    assert _eval1([1, 2, 3, 4], c.is_in([1.0, 2.0])) == [True, True, False, False]
+    assert _eval1([1.0, 2.0, 3.0, 4.0], c.is_in([1, 2])) == [True, True, False, False]
+    for vals in ([True, False, None], ["a", "b", None], [1, 2, None], [1.0, 2.0, None]):
+        assert _eval1(vals, c.is_in([None])) == [False, False, None]
+    assert _eval1([None, None, None], c.is_in([None])) == [None, None, None]
+    assert _eval1([1, 2, 3, 4], c.is_in([])) == [False, False, False, False]
+    # tests/recordbatch/test_fill.py:12-21
+    assert _eval1([None, None, None], c.fill_null("a")) == ["a", "a", "a"]
+    assert _eval1([True, False, None], c.fill_null(False)) == [True, False, False]
+    assert _eval1(["a", "b", None], c.fill_null("b")) == ["a", "b", "b"]
+    assert _eval1([-1, None, 3], c.fill_null(0)) == [-1, 0, 3]
+    assert _eval1([-1.0, None, 3.0], c.fill_null(0.0)) == [-1.0, 0.0, 3.0]
+    assert _eval1([datetime.date(2024, 5, 1), None, datetime.date(2023, 1, 1)], c.fill_null(datetime.date(2022, 1, 1))) == \
+        [datetime.date(2024, 5, 1), datetime.date(2022, 1, 1), datetime.date(2023, 1, 1)]
+    # tests/recordbatch/test_eval.py:28-100: not / is_null / not_null
+    assert _eval1([True, False, None], ~c) == [False, True, None]
+    assert _eval1(["apple", None, "banana"], ~(c != "banana")) == [False, None, True]
+    assert _eval1([True, False, None], c.is_null()) == [False, False, True]
+    assert _eval1(["a", "b", "c"], c.is_null()) == [False, False, False]
+    assert _eval1([None, None], c.is_null()) == [True, True]
+    assert _eval1([True, False, None], c.not_null()) == [True, True, False]
+    assert _eval1([None, None], c.not_null()) == [False, False]
+    # tests/recordbatch/test_when.py:13-20
+    t = pa.table({"predicate": [True, False, True], "if_true": [1, 2, 3], "if_false": [4, 5, 6]})
+    assert E.eval_expression_list(t, [col("predicate").if_else(col("if_true"), col("if_false")).alias("r")]).to_pydict()["r"] == [1, 5, 3]
