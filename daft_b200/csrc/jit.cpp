@@ -403,12 +403,12 @@ struct ExprGen {
                         const bool div = n.op == B_FLOOR_DIV;
                         if (is_float(t)) {
                             if (div) os << "    const " << T << " " << V << " = floor(" << a << " / " << b << ");\n";
-                            else os << "    const " << T << " " << V << " = " << a << " - floor(" << a << " / " << b << ") * " << b << ";\n";
+                            else os << "    const " << T << " " << V << " = fmod" << (t == B200_F32 ? "f" : "") << "(" << a << ", " << b << ");\n";  // Rust `%` on floats
                             os << "    const bool " << K << " = " << ka << " && " << kb << ";\n";
                         } else {
                             os << "    const bool " << K << " = " << ka << " && " << kb << " && (" << b << " != 0);\n";
                             if (is_signed_int(t))
-                                os << "    const " << T << " " << V << " = " << K << " ? " << (div ? "floor_div_s" : "floor_mod_s") << "<" << T << ">(" << a << ", " << b << ") : (" << T << ")0;\n";
+                                os << "    const " << T << " " << V << " = " << K << " ? " << (div ? "trunc_div_s" : "trunc_rem_s") << "<" << T << ">(" << a << ", " << b << ") : (" << T << ")0;\n";
                             else
                                 os << "    const " << T << " " << V << " = " << K << " ? (" << T << ")(" << a << (div ? " / " : " % ") << b << ") : (" << T << ")0;\n";
                         }

@@ -187,18 +187,18 @@ __device__ __forceinline__ uint32_t date_dow(int32_t days) {  // Monday = 0
     return (uint32_t)(r < 0 ? r + 7 : r);
 }
 
-// ---- integer division helpers (floor semantics; divisor 0 handled by the caller as null) ------------
+// ---- integer division helpers ------------------------------------------------------------------------
+// The reference's `//` and `%` on integers are Rust's `/` and `%` (src/daft-core/src/array/ops/arithmetic.rs:245-300,
+// series/ops/arithmetic.rs:456-466): quotient truncated toward zero, remainder with the sign of the dividend
+// (its `pmod` function is the positive modulo).  Divisor 0 is handled by the caller as null (the reference panics);
+// MIN / -1 wraps instead of trapping.
 template <typename T>
-__device__ __forceinline__ T floor_div_s(T a, T b) {
-    T q = a / b;
-    if ((a % b != 0) && ((a < 0) != (b < 0))) q--;
-    return q;
+__device__ __forceinline__ T trunc_div_s(T a, T b) {
+    return b == (T)-1 ? (T)(0ULL - (unsigned long long)a) : (T)(a / b);
 }
 template <typename T>
-__device__ __forceinline__ T floor_mod_s(T a, T b) {
-    T r = a % b;
-    if (r != 0 && ((r < 0) != (b < 0))) r += b;
-    return r;
+__device__ __forceinline__ T trunc_rem_s(T a, T b) {
+    return b == (T)-1 ? (T)0 : (T)(a % b);
 }
 
 // ---- kernel parameter block: 8-byte slots the host fills in the order codegen allocated them ---------

@@ -273,6 +273,10 @@ int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begi
  *   binary ops (src/daft-dsl Operator, evaluated at src/daft-recordbatch/src/lib.rs:1376-1400):
  *     0 add 1 sub 2 mul 3 true_div 4 floor_div 5 mod 6 lt 7 le 8 eq 9 ne 10 ge 11 gt 12 and 13 or 14 xor
  *     15 eq_null_safe 16 shift_left 17 shift_right
+ *     floor_div / mod follow the reference's Rust arithmetic (src/daft-core/src/array/ops/arithmetic.rs:245-300,
+ *     series/ops/arithmetic.rs:456-466): on integers the quotient truncates toward zero and the remainder takes the sign
+ *     of the dividend; on floats floor_div = floor(l / r) and mod = fmod(l, r).  An integer divisor of 0 yields null
+ *     (the reference panics); MIN / -1 wraps.
  *   unary ops: 0 not 1 negate 2 is_null 3 not_null 4 abs
  *   functions: 0 year 1 month 2 day 3 utf8_length 4 utf8_startswith 5 utf8_endswith 6 utf8_contains
  *              7 utf8_left 8 day_of_week 9 sqrt (Float64 operand; IEEE correctly rounded)

@@ -93,12 +93,16 @@ def _eval(b: Bound, cols, n: int):
             if op == "true_div":
                 return a / c, both
             if op in ("floor_div", "mod"):
-                if dt.is_float(t):
-                    q = np.floor(a / c)
-                    return (q if op == "floor_div" else a - q * c), both
-                ok = both & (c != 0)
-                cs = np.where(c == 0, 1, c)
-                r = (a // cs) if op == "floor_div" else (a % cs)
+                # Rust semantics (src/daft-core/src/array/ops/arithmetic.rs:245-300, series/ops/arithmetic.rs:456-466): integer `//` truncates
+                # toward zero, `%` takes the sign of the dividend (floats: fmod); float `//` = floor(l / r).  x // 0, x % 0 on
+                # integers: null here (the reference panics)
+                with np.errstate(all="ignore"):
+                    if dt.is_float(t):
+                        return (np.floor(a / c) if op == "floor_div" else np.fmod(a, c)), both
+                    ok = both & (c != 0)
+                    cs = np.where(c == 0, 1, c)
+                    rem = np.fmod(a, cs)
+                    r = ((a - rem) // cs) if op == "floor_div" else rem
                 return np.where(ok, r, 0).astype(a.dtype), ok
             if op in ("lt", "le", "ge", "gt", "eq", "ne"):
                 f = {"lt": np.less, "le": np.less_equal, "ge": np.greater_equal, "gt": np.greater, "eq": np.equal, "ne": np.not_equal}[op]

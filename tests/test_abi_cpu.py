@@ -57,6 +57,12 @@ def test_codegen_and_nvrtc_offline(tmp_path):
     plan, onames, odt = encode_project([(col("a") + 1).alias("x"), (col("b") * 2.0 > 1).alias("y"), col("s").left(2).alias("z")], names, dts)
     assert onames == ["x", "y", "z"] and odt == [dt.I64, dt.BOOL, dt.LARGE_UTF8]
     _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 0, 1), ctypes.c_int32(3))
+    # `//` and `%` (Rust semantics: trunc_div_s / trunc_rem_s helpers, fmod for floats) must compile for every arithmetic type
+    plan, _, odt = encode_project([(col("a") // 3).alias("q"), (col("a") % -3).alias("r"), (col("b") // 2.0).alias("fq"), (col("b") % 2.0).alias("fr")], names, dts)
+    assert odt == [dt.I64, dt.I64, dt.F64, dt.F64]
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))
+    assert any("trunc_div_s<" in open(os.path.join(tmp_path, f)).read() and "fmod(" in open(os.path.join(tmp_path, f)).read()
+               for f in os.listdir(tmp_path) if f.endswith(".cu"))
     plan = encode_agg([col("b").sum().alias("sb"), col("a").max().alias("ma"), col("a").count().alias("n")], [col("s"), col("a") % 3], names, dts,
                       [col("b") > lit(0.5)])
     _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))

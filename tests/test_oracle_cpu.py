@@ -393,3 +393,28 @@ def test_expression_literals_from_reference_tests():
     # tests/recordbatch/test_when.py:13-20
     t = pa.table({"predicate": [True, False, True], "if_true": [1, 2, 3], "if_false": [4, 5, 6]})
     assert E.eval_expression_list(t, [col("predicate").if_else(col("if_true"), col("if_false")).alias("r")]).to_pydict()["r"] == [1, 5, 3]
+
+
+def test_floor_div_and_mod_follow_rust_semantics():
+    """`//` on integers is Rust `/` (truncates toward zero), `%` is Rust `%` (sign of the dividend; fmod for floats), float
+    `//` is floor(l / r): src/daft-core/src/array/ops/arithmetic.rs:245-300, series/ops/arithmetic.rs:456-466.  The reference's
+    own literals (tests/recordbatch/test_eval.py, tests/expressions/typing) only use non-negative operands, where truncation
+    and floor agree; the signed cases are the rule itself."""
+    a = [-7, 7, -7, -8, 7, 0, 9, None]
+    b = [3, -3, -3, -3, 2, 5, 0, 2]
+    for typ in (pa.int8(), pa.int16(), pa.int32(), pa.int64()):
+        t = pa.table({"a": pa.array(a, type=typ), "b": pa.array(b, type=typ)})
+        out = E.eval_expression_list(t, [(col("a") // col("b")).alias("q"), (col("a") % col("b")).alias("r")]).to_pydict()
+        assert out["q"] == [-2, -2, 2, 2, 3, 0, None, None]  # x // 0 is null here (the reference panics)
+        assert out["r"] == [-1, 1, -1, -2, 1, 0, None, None]
+    # positive operands: the reference's literal cases (floor == trunc)
+    t = pa.table({"a": pa.array([1, 2, 3, 4], type=pa.uint32()), "b": pa.array([1, 2, 2, 3], type=pa.uint32())})
+    out = E.eval_expression_list(t, [(col("a") // col("b")).alias("q"), (col("a") % col("b")).alias("r")]).to_pydict()
+    assert out == {"q": [1, 1, 1, 1], "r": [0, 0, 1, 1]}
+    x = [-7.5, 7.5, -7.0, 1.0, -1.0, 5.5]
+    y = [2.0, -2.0, 3.0, -3.0, -3.0, 2.0]
+    for typ in (pa.float32(), pa.float64()):
+        t = pa.table({"x": pa.array(x, type=typ), "y": pa.array(y, type=typ)})
+        out = E.eval_expression_list(t, [(col("x") // col("y")).alias("q"), (col("x") % col("y")).alias("r")]).to_pydict()
+        assert out["q"] == [-4.0, -4.0, -3.0, -1.0, 0.0, 2.0]
+        assert out["r"] == [-1.5, 1.5, -1.0, 1.0, -1.0, 1.5]
