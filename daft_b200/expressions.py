@@ -225,6 +225,10 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         if op in _ARITH:
             if not dt.is_numeric(st):
                 raise TypeError(f"cannot apply {op} to {dt.NAMES[st]}")
+            if op == "floor_div" and st == dt.F32:
+                # float `//` is (l / r).floor() computed as a Float64 true division, then cast to the supertype
+                # (src/daft-core/src/series/ops/arithmetic.rs:466-469)
+                return _cast(Bound(T_BINARY, dt.F64, BINOPS[op], [_cast(l, dt.F64), _cast(r, dt.F64)]), dt.F32)
             return Bound(T_BINARY, st, BINOPS[op], [l, r])
         raise ValueError(op)
     if k == "unary":

@@ -63,6 +63,10 @@ def test_codegen_and_nvrtc_offline(tmp_path):
     _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))
     assert any("trunc_div_s<" in open(os.path.join(tmp_path, f)).read() and "fmod(" in open(os.path.join(tmp_path, f)).read()
                for f in os.listdir(tmp_path) if f.endswith(".cu"))
+    # Float32 `//` binds as floor(f64(l) / f64(r)) cast back to Float32 (series/ops/arithmetic.rs:466-469)
+    plan, _, odt = encode_project([(col("x") // col("y")).alias("q"), (col("x") % col("y")).alias("r")], ["x", "y"], [dt.F32, dt.F32])
+    assert odt == [dt.F32, dt.F32]
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 2)(dt.F32, dt.F32), (ctypes.c_uint8 * 2)(1, 0), ctypes.c_int32(2))
     plan = encode_agg([col("b").sum().alias("sb"), col("a").max().alias("ma"), col("a").count().alias("n")], [col("s"), col("a") % 3], names, dts,
                       [col("b") > lit(0.5)])
     _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))

@@ -134,7 +134,7 @@ def exprs_under_test(c, lit):
         c("i8").eq_null_safe(c("i8")).alias("e29"), abs(c("i16")).alias("e30"), (c("u64") + 1).alias("e31"),
         lit(7).alias("e32"), lit(None).alias("e33"), (c("f32") + c("f32")).alias("e34"), c("d").alias("e35"),
         (c("b") ^ c("b")).alias("e36"), (c("f64") % c("f32")).alias("e37"), (c("f64") // 7.0).alias("e38"),
-        (c("i32") % c("i8")).alias("e39"),
+        (c("i32") % c("i8")).alias("e39"), (c("f32") // c("i8")).alias("e40"), (c("f32") % c("i8")).alias("e41"),
     ]
 
 
