@@ -7,6 +7,8 @@
 #include "jit.h"
 
 #include <dlfcn.h>
+#include <cmath>
+#include <cstdio>
 #include <nvrtc.h>
 #include <sys/stat.h>
 
@@ -76,6 +78,21 @@ struct Ast {
 };
 
 static bool is_numeric(int32_t dt) { return is_integer(dt) || is_float(dt); }
+
+// Casts go through arrow-rs `cast` with its default CastOptions { safe: true } (src/daft-core/src/array/ops/cast.rs:194-196;
+// arrow-cast 57.3.0, Cargo.lock:298): a value the target integer type cannot hold becomes NULL.  Integer sources use
+// num-traits 0.2.19 NumCast (exact range check), float sources succeed iff the value truncated toward zero is in range
+// (NaN fails).  Date32 / Timestamp cast as their physical Int32 / Int64.
+static bool int_like(int32_t dt) { return is_integer(dt) || dt == B200_DATE32 || dt == B200_TIMESTAMP; }
+static bool int_like_signed(int32_t dt) { return is_signed_int(dt) || dt == B200_DATE32 || dt == B200_TIMESTAMP; }
+static bool cast_can_fail(int32_t src, int32_t dst) {
+    if (!int_like(dst)) return false;
+    if (is_float(src)) return true;
+    if (!int_like(src)) return false;  // bool -> 0 / 1
+    const int bs = 8 * dtype_width(src), bd = 8 * dtype_width(dst);
+    if (int_like_signed(src)) return !int_like_signed(dst) || bs > bd;
+    return int_like_signed(dst) ? bs >= bd : bs > bd;
+}
 
 static int parse_node(Reader &r, Ast &a) {
     Node nd;
@@ -157,7 +174,7 @@ static int parse_node(Reader &r, Ast &a) {
             nd.dtype = r.u8();
             int c = parse_node(r, a);
             nd.kids = {c};
-            nd.nullable = a.nodes[c].nullable;
+            nd.nullable = a.nodes[c].nullable || cast_can_fail(a.nodes[c].dtype, nd.dtype);
             nd.key = "k" + std::to_string(nd.dtype) + "(" + a.nodes[c].key + ")";
             break;
         }
@@ -479,8 +496,27 @@ struct ExprGen {
                     fail("plan: casts between strings and other types are not supported on the device");
                 } else if (n.dtype == B200_BOOL) {
                     os << "    const bool " << V << " = " << a << " != 0; const bool " << K << " = " << ka << ";\n";
-                } else {
+                } else if (!cast_can_fail(C.dtype, n.dtype)) {
                     os << "    const " << T << " " << V << " = (" << T << ")" << a << "; const bool " << K << " = " << ka << ";\n";
+                } else if (is_float(C.dtype)) {
+                    // out-of-range / NaN -> null: the value truncated toward zero must lie in [MIN, MAX] of the target
+                    const int bits = 8 * dtype_width(n.dtype);
+                    const bool sg = int_like_signed(n.dtype);
+                    char lo[64], hi[64];
+                    snprintf(lo, sizeof lo, "%.1f", sg ? -std::ldexp(1.0, bits - 1) : 0.0);
+                    snprintf(hi, sizeof hi, "%.1f", std::ldexp(1.0, sg ? bits - 1 : bits));
+                    const std::string tv = pfx + "t" + std::to_string(id);
+                    os << "    const double " << tv << " = trunc((double)" << a << ");\n";
+                    os << "    const bool " << K << " = " << ka << " && " << tv << " >= " << lo << " && " << tv << " < " << hi << ";\n";
+                    os << "    const " << T << " " << V << " = " << K << " ? (" << T << ")" << a << " : (" << T << ")0;\n";
+                } else {
+                    // narrowing / sign-changing integer cast: null unless the value survives the round trip with its sign
+                    const std::string S = ctype(C.dtype), tv = pfx + "t" + std::to_string(id);
+                    os << "    const " << T << " " << tv << " = (" << T << ")" << a << ";\n";
+                    os << "    const bool " << K << " = " << ka << " && ((" << S << ")" << tv << " == " << a << ") && ("
+                       << (int_like_signed(n.dtype) ? "(" + tv + " < 0)" : std::string("false")) << " == "
+                       << (int_like_signed(C.dtype) ? "(" + a + " < 0)" : std::string("false")) << ");\n";
+                    os << "    const " << T << " " << V << " = " << K << " ? " << tv << " : (" << T << ")0;\n";
                 }
                 break;
             }

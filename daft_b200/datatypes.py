@@ -50,6 +50,16 @@ _WIDTH = {I8: 1, I16: 2, I32: 4, I64: 8, U8: 1, U16: 2, U32: 4, U64: 8, F32: 4, 
 def width(c): return _WIDTH.get(c, 0)
 
 
+def int_like(c): return is_integer(c) or c in (DATE32, TIMESTAMP)
+def int_like_signed(c): return is_signed(c) or c in (DATE32, TIMESTAMP)
+
+
+def int_range(c):
+    """[min, max] of an integer (or integer-backed) dtype."""
+    bits = 8 * width(c)
+    return (-(1 << (bits - 1)), (1 << (bits - 1)) - 1) if int_like_signed(c) else (0, (1 << bits) - 1)
+
+
 def supertype(a: int, b: int) -> int:
     """Common type both operands are cast to before a binary op (the reference decides this at plan
     time: src/daft-core/src/utils/supertype.rs try_get_supertype; restated for the numeric lattice)."""

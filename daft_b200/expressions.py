@@ -189,6 +189,10 @@ def _cast(b: Bound, to: int) -> Bound:
         if dt.is_float(to): v = float(v)
         elif dt.is_integer(to) and isinstance(v, float) and v == int(v): v = int(v)
         elif dt.is_integer(to) and isinstance(v, float): return Bound(T_CAST, to, kids=[b])
+        if dt.is_integer(to) and isinstance(v, int) and not isinstance(v, bool):
+            lo, hi = dt.int_range(to)
+            if not lo <= v <= hi:
+                v = None  # arrow-rs safe cast: a value the target type cannot hold becomes null (array/ops/cast.rs:194-196)
         return Bound(T_LIT, to, value=v)
     return Bound(T_CAST, to, kids=[b])
 

@@ -264,7 +264,8 @@ int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begi
  *     1 LIT      u8 dtype, u8 is_null, (BOOL/ints: i64 | F32/F64: f64 | DATE32/TIMESTAMP: i64 | UTF8/BINARY: str)
  *     2 BINARY   u8 op, node lhs, node rhs
  *     3 UNARY    u8 op, node child
- *     4 CAST     u8 dtype, node child
+ *     4 CAST     u8 dtype, node child   (numeric / bool / date casts; a value the target integer type cannot hold, or a
+ *                NaN / infinite float cast to an integer, is NULL: arrow-rs safe cast, src/daft-core/src/array/ops/cast.rs:194-196)
  *     5 IF_ELSE  node predicate, node if_true, node if_false
  *     6 IS_IN    node child, u32 n, n x node(LIT)
  *     7 BETWEEN  node child, node lower, node upper

@@ -138,6 +138,20 @@ def _eval(b: Bound, cols, n: int):
                 return a, ka
             if b.dtype == dt.BOOL:
                 return a != 0, ka
+            if dt.int_like(b.dtype) and (dt.is_float(src) or dt.int_like(src)):
+                # arrow-rs `cast` with its default CastOptions { safe: true } (src/daft-core/src/array/ops/cast.rs:194-196; arrow-cast
+                # 57.3.0, Cargo.lock:298): a value the target integer type cannot hold becomes null.  Floats convert iff the
+                # value truncated toward zero is in range (num-traits 0.2.19 ToPrimitive; NaN fails).
+                lo, hi = dt.int_range(b.dtype)
+                with np.errstate(all="ignore"):
+                    if dt.is_float(src):
+                        t = np.trunc(a.astype(np.float64))
+                        ok = (t >= float(lo)) & (t < float(hi + 1))
+                        v = np.where(ok, a, 0).astype(_NP[b.dtype])
+                    else:
+                        v = a.astype(_NP[b.dtype])
+                        ok = (v.astype(a.dtype) == a) & ((v < 0) == (a < 0))
+                return np.where(ok, v, 0).astype(_NP[b.dtype]), ka & ok
             return a.astype(_NP[b.dtype]), ka
         if b.tag == T_IF_ELSE:
             (p, kp), (x, kx), (y, ky) = kids

@@ -67,6 +67,15 @@ def test_codegen_and_nvrtc_offline(tmp_path):
     plan, _, odt = encode_project([(col("x") // col("y")).alias("q"), (col("x") % col("y")).alias("r")], ["x", "y"], [dt.F32, dt.F32])
     assert odt == [dt.F32, dt.F32]
     _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 2)(dt.F32, dt.F32), (ctypes.c_uint8 * 2)(1, 0), ctypes.c_int32(2))
+    # narrowing / sign-changing / float -> int casts carry the arrow-rs safe-cast null rule: every source x target pair compiles
+    import pyarrow as pa
+    srcs = {"i8": dt.I8, "i16": dt.I16, "i32": dt.I32, "i64": dt.I64, "u8": dt.U8, "u16": dt.U16, "u32": dt.U32, "u64": dt.U64,
+            "f32": dt.F32, "f64": dt.F64, "d": dt.DATE32, "bo": dt.BOOL}
+    tgts = [pa.int8(), pa.int16(), pa.int32(), pa.int64(), pa.uint8(), pa.uint16(), pa.uint32(), pa.uint64(), pa.float32(), pa.float64()]
+    exprs = [col(n).cast(t).alias(f"{n}_{i}") for n in srcs for i, t in enumerate(tgts)]
+    plan, _, _ = encode_project(exprs, list(srcs), list(srcs.values()))
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * len(srcs))(*srcs.values()),
+              (ctypes.c_uint8 * len(srcs))(*([0] * len(srcs))), ctypes.c_int32(len(srcs)))
     plan = encode_agg([col("b").sum().alias("sb"), col("a").max().alias("ma"), col("a").count().alias("n")], [col("s"), col("a") % 3], names, dts,
                       [col("b") > lit(0.5)])
     _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))

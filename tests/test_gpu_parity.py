@@ -148,6 +148,29 @@ def test_project_matches_oracle(gpu, n, nulls):
     assert_tables_equal(got, want)  # bit-exact, floats included (same op order, no FMA)
 
 
+def test_cast_out_of_range_is_null(gpu):
+    """arrow-rs safe-cast rule (src/daft-core/src/array/ops/cast.rs:194-196): what the target integer type cannot hold is null."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    edge_i = np.array([0, 127, 128, -128, -129, 255, 256, -1, 32767, 32768, -32769, 2**31 - 1, 2**31, -2**31 - 1, 2**32, 2**63 - 1, -2**63], dtype=np.int64)
+    edge_f = np.array([0.9, -0.9, 127.9, 128.0, -128.9, -129.0, np.nan, np.inf, -np.inf, 255.5, 256.0, 2147483647.5, 2147483648.0,
+                       -2147483648.9, 9.3e18, -9.3e18, 1.8e19, 1.9e19, 4294967295.9, 4294967296.0])
+    i64 = np.concatenate([edge_i, rng.integers(-70000, 70000, n), rng.integers(-2**62, 2**62, n)])
+    f64 = np.concatenate([edge_f, rng.standard_normal(n) * 300, rng.standard_normal(n // 2) * 1e10, rng.standard_normal(n) * 1e19])[:len(i64)]
+    assert len(f64) == len(i64)
+    tbl = pa.table({
+        "i64": pa.array(i64, mask=rng.random(len(i64)) < 0.1), "u64": pa.array(i64.view(np.uint64)), "i16": pa.array((i64 & 0xffff).astype(np.uint16).view(np.int16)),
+        "f64": pa.array(f64, mask=rng.random(len(i64)) < 0.1), "f32": pa.array(f64.astype(np.float32)),
+    })
+    c = gpu.col
+    tgts = [pa.int8(), pa.int16(), pa.int32(), pa.int64(), pa.uint8(), pa.uint16(), pa.uint32(), pa.uint64(), pa.float32(), pa.float64()]
+    exprs = [c(nm).cast(t).alias(f"{nm}_{t}") for nm in tbl.column_names for t in tgts]
+    got = RB(gpu, tbl).eval_expression_list(exprs).to_arrow_table()
+    want = E.eval_expression_list(tbl, exprs)
+    assert want.column("i64_int8").null_count > n and want.column("i16_int64").null_count == 0
+    assert_tables_equal(got, want)
+
+
 @pytest.mark.parametrize("n", [0, 5, 1000, 10007])
 def test_filter_matches_oracle(gpu, n):
     rng = np.random.default_rng(n)

@@ -418,3 +418,36 @@ def test_floor_div_and_mod_follow_rust_semantics():
         out = E.eval_expression_list(t, [(col("x") // col("y")).alias("q"), (col("x") % col("y")).alias("r")]).to_pydict()
         assert out["q"] == [-4.0, -4.0, -3.0, -1.0, 0.0, 2.0]
         assert out["r"] == [-1.5, 1.5, -1.0, 1.0, -1.0, 1.5]
+
+
+def test_cast_out_of_range_is_null_like_arrow_rs_safe_cast():
+    """DataArray::cast delegates to arrow::compute::cast with the default CastOptions (safe = true;
+    src/daft-core/src/array/ops/cast.rs:194-196): values the target integer type cannot hold become null, floats truncate
+    toward zero (NaN / inf -> null), widening and int -> float casts never fail."""
+    t = pa.table({
+        "i64": pa.array([0, 127, 128, -128, -129, 2**40, -1, None], type=pa.int64()),
+        "u64": pa.array([0, 2**63 - 1, 2**63, 2**64 - 1, 255, 256, 65535, None], type=pa.uint64()),
+        "f64": pa.array([0.9, -0.9, 127.9, 128.0, -128.9, -129.0, float("nan"), float("inf")], type=pa.float64()),
+        "f32": pa.array([2147483520.0, 2147483648.0, -2147483648.0, -1.0, 255.5, 256.0, 1e20, None], type=pa.float32()),
+    })
+    out = E.eval_expression_list(t, [
+        col("i64").cast(pa.int8()).alias("i64_i8"), col("i64").cast(pa.uint8()).alias("i64_u8"), col("i64").cast(pa.uint64()).alias("i64_u64"),
+        col("i64").cast(pa.int32()).alias("i64_i32"), col("u64").cast(pa.int64()).alias("u64_i64"), col("u64").cast(pa.uint8()).alias("u64_u8"),
+        col("u64").cast(pa.uint16()).alias("u64_u16"), col("f64").cast(pa.int8()).alias("f64_i8"), col("f64").cast(pa.uint8()).alias("f64_u8"),
+        col("f32").cast(pa.int32()).alias("f32_i32"), col("f32").cast(pa.uint8()).alias("f32_u8"), col("i64").cast(pa.float32()).alias("i64_f32"),
+    ]).to_pydict()
+    assert out["i64_i8"] == [0, 127, None, -128, None, None, -1, None]
+    assert out["i64_u8"] == [0, 127, 128, None, None, None, None, None]
+    assert out["i64_u64"] == [0, 127, 128, None, None, 2**40, None, None]
+    assert out["i64_i32"] == [0, 127, 128, -128, -129, None, -1, None]
+    assert out["u64_i64"] == [0, 2**63 - 1, None, None, 255, 256, 65535, None]
+    assert out["u64_u8"] == [0, None, None, None, 255, None, None, None]
+    assert out["u64_u16"] == [0, None, None, None, 255, 256, 65535, None]
+    assert out["f64_i8"] == [0, 0, 127, None, -128, None, None, None]
+    assert out["f64_u8"] == [0, 0, 127, 128, None, None, None, None]
+    assert out["f32_i32"] == [2147483520, None, -2147483648, -1, 255, 256, None, None]
+    assert out["f32_u8"] == [None, None, None, None, 255, None, None, None]
+    assert out["i64_f32"] == [0.0, 127.0, 128.0, -128.0, -129.0, float(np.float32(2**40)), -1.0, None]
+    # a literal that does not fit folds to a null literal
+    out = E.eval_expression_list(t, [lit(300).cast(pa.int8()).alias("x"), lit(-1).cast(pa.uint32()).alias("y"), lit(7).cast(pa.int8()).alias("z")]).to_pydict()
+    assert out == {"x": [None] * 8, "y": [None] * 8, "z": [7] * 8}
