@@ -399,8 +399,27 @@ struct ExprGen {
                 const Node &L = cg.ast.nodes[n.kids[0]];
                 const int32_t t = L.dtype != B200_NULL ? L.dtype : cg.ast.nodes[n.kids[1]].dtype;
                 const std::string a = v(kid[0]), b = v(kid[1]), ka = k(kid[0]), kb = k(kid[1]);
+                // Floats compare by IEEE totalOrder (f_key).  Against a finite non-zero literal the IEEE comparison differs from it
+                // only for a NaN operand, so the hot predicates (`x >= 0.05`) keep the plain compare plus a NaN-sign fix-up and need
+                // no key registers.
+                auto plain_lit = [&](int kidx) {
+                    const Node &q = cg.ast.nodes[n.kids[kidx]];
+                    if (q.tag != T_LIT || q.lit_null || !is_float(q.dtype)) return false;
+                    double d;
+                    memcpy(&d, &q.lit_i, 8);
+                    return d == d && (q.dtype == B200_F32 ? (float)d != 0.0f : d != 0.0);
+                };
                 auto cmp = [&](const char *op) {
                     if (is_string(t)) os << "    const bool " << V << " = str_cmp(" << a << ", " << b << ") " << op << " 0;\n";
+                    else if (is_float(t) && (plain_lit(1) || plain_lit(0))) {
+                        const bool less = op[0] == '<';                       // operator as written: a op b
+                        const bool var_left = plain_lit(1);                   // the non-literal side
+                        const std::string &x = var_left ? a : b;
+                        // a < c holds for a = -NaN; c < b holds for b = +NaN (and symmetrically for > / >=)
+                        const char *fix = (less == var_left) ? "f_negnan(" : "f_posnan(";
+                        os << "    const bool " << V << " = (" << a << " " << op << " " << b << ") || " << fix << x << ");\n";
+                    }
+                    else if (is_float(t)) os << "    const bool " << V << " = f_key(" << a << ") " << op << " f_key(" << b << ");\n";  // IEEE totalOrder
                     else os << "    const bool " << V << " = " << a << " " << op << " " << b << ";\n";
                     os << "    const bool " << K << " = " << ka << " && " << kb << ";\n";
                 };
@@ -438,6 +457,8 @@ struct ExprGen {
                     case B_EQ: case B_NE: case B_EQ_NULL_SAFE: {
                         std::string eq;
                         if (is_string(t)) eq = "str_eq(" + a + ", " + b + ")";
+                        else if (is_float(t) && (plain_lit(0) || plain_lit(1))) eq = "(" + a + " == " + b + ")";  // unique bit pattern
+                        else if (is_float(t)) eq = "(f_key(" + a + ") == f_key(" + b + "))";  // bit equality: NaN == NaN, -0.0 != 0.0
                         else eq = "(" + a + " == " + b + ")";
                         if (n.op == B_EQ_NULL_SAFE) {
                             os << "    const bool " << V << " = (" << ka << " && " << kb << ") ? " << eq << " : (" << ka << " == " << kb << "); const bool " << K << " = true;\n";
@@ -536,6 +557,8 @@ struct ExprGen {
                     if (it2.lit_null || it2.dtype == B200_NULL) continue;
                     if (it2.dtype != C.dtype) fail("plan: is_in item dtype differs from the tested expression");
                     if (is_string(C.dtype)) os << "    " << V << " = " << V << " || str_eq(" << a << ", " << v(kid[i]) << ");\n";
+                    else if (is_float(C.dtype))  // BTreeSet<FloatWrapper>: all NaNs are one element, -0.0 == 0.0 (is_in.rs:44-66)
+                        os << "    " << V << " = " << V << " || (" << a << " == " << v(kid[i]) << ") || (isnan(" << a << ") && isnan(" << v(kid[i]) << "));\n";
                     else os << "    " << V << " = " << V << " || (" << a << " == " << v(kid[i]) << ");\n";
                 }
                 os << "    const bool " << K << " = " << k(kid[0]) << ";\n";
@@ -543,7 +566,9 @@ struct ExprGen {
             }
             case T_BETWEEN: {
                 const Node &C = cg.ast.nodes[n.kids[0]];
-                const std::string a = v(kid[0]), lo = v(kid[1]), hi = v(kid[2]);
+                const bool fk = is_float(C.dtype);  // floats compare by totalOrder, like the comparison operators
+                const std::string a = fk ? "f_key(" + v(kid[0]) + ")" : v(kid[0]), lo = fk ? "f_key(" + v(kid[1]) + ")" : v(kid[1]),
+                                  hi = fk ? "f_key(" + v(kid[2]) + ")" : v(kid[2]);
                 if (is_string(C.dtype))
                     os << "    const bool " << V << " = str_cmp(" << a << ", " << lo << ") >= 0 && str_cmp(" << a << ", " << hi << ") <= 0;\n";
                 else
@@ -1402,8 +1427,15 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
           << ld_b.str() << "  }\n";
     }
     o << "};\n";
+    // Ungrouped staged plans (Q6-shaped scans) whose tier-1 cells and stages fit three times into an SM are compiled for three
+    // resident CTAs: the extra bytes in flight are what the staged build is for, and at 256 threads that needs <= 80 registers
+    // (ptxas otherwise settles a few registers above that and silently drops to two CTAs).
+    int staged_minb = MINB;
+    if (staged_variant && SW == 8 && nkeys == 0 &&
+        3 * (tier1_smem + (size_t)SS * (size_t)stage_off + (size_t)16 * SS + 1024) <= (size_t)227 * 1024)
+        staged_minb = std::max(MINB, 3);
     if (staged_variant)
-        o << "extern \"C\" __global__ void __launch_bounds__(" << SW * 32 << ", " << (SW == 16 ? 1 : MINB) << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_staged<Prog>(p); }\n";
+        o << "extern \"C\" __global__ void __launch_bounds__(" << SW * 32 << ", " << (SW == 16 ? 1 : staged_minb) << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_staged<Prog>(p); }\n";
     else if (global_variant)
         o << "extern \"C\" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_global<Prog>(p); }\n";
     else

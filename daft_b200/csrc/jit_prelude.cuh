@@ -201,6 +201,24 @@ __device__ __forceinline__ T trunc_rem_s(T a, T b) {
     return b == (T)-1 ? (T)0 : (T)(a % b);
 }
 
+// ---- float comparison keys ---------------------------------------------------------------------------
+// The reference compares with the arrow-rs `cmp` kernels (src/daft-core/src/array/ops/comparison.rs:541-603), which order floats
+// by IEEE 754 totalOrder: -NaN < -inf < ... < -0.0 < +0.0 < ... < +inf < +NaN, equality = equal bit patterns.  f_key maps the
+// sign-magnitude pattern to a two's-complement integer with that order (f64::total_cmp); literals fold at compile time.
+__device__ __forceinline__ long long f_key(double x) {
+    const long long b = __double_as_longlong(x);
+    return b ^ (long long)((unsigned long long)(b >> 63) >> 1);
+}
+__device__ __forceinline__ int f_key(float x) {
+    const int b = __float_as_int(x);
+    return b ^ (int)((unsigned)(b >> 31) >> 1);
+}
+
+__device__ __forceinline__ bool f_posnan(double x) { return x != x && __double2hiint(x) >= 0; }
+__device__ __forceinline__ bool f_negnan(double x) { return x != x && __double2hiint(x) < 0; }
+__device__ __forceinline__ bool f_posnan(float x) { return x != x && __float_as_int(x) >= 0; }
+__device__ __forceinline__ bool f_negnan(float x) { return x != x && __float_as_int(x) < 0; }
+
 // ---- kernel parameter block: 8-byte slots the host fills in the order codegen allocated them ---------
 template <int NPTR, int NINT>
 struct Params {

@@ -274,6 +274,9 @@ int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begi
  *   binary ops (src/daft-dsl Operator, evaluated at src/daft-recordbatch/src/lib.rs:1376-1400):
  *     0 add 1 sub 2 mul 3 true_div 4 floor_div 5 mod 6 lt 7 le 8 eq 9 ne 10 ge 11 gt 12 and 13 or 14 xor
  *     15 eq_null_safe 16 shift_left 17 shift_right
+ *     lt..gt / eq / ne / eq_null_safe / BETWEEN on floats use IEEE 754 totalOrder like the arrow-rs `cmp` kernels the reference calls
+ *     (src/daft-core/src/array/ops/comparison.rs:541-603): NaN == NaN, +NaN > +inf, -0.0 < +0.0.  IS_IN on floats follows the
+ *     reference's BTreeSet<FloatWrapper> (is_in.rs:44-66): any NaN matches a NaN item, -0.0 matches 0.0.
  *     floor_div / mod follow the reference's Rust arithmetic (src/daft-core/src/array/ops/arithmetic.rs:245-300,
  *     series/ops/arithmetic.rs:456-466): on integers the quotient truncates toward zero and the remainder takes the sign
  *     of the dividend; on floats floor_div = floor(l / r) and mod = fmod(l, r).  An integer divisor of 0 yields null

@@ -75,6 +75,20 @@ def _civil(days: np.ndarray):
     return y + (m <= 2), m, d
 
 
+def _total_order_key(a: np.ndarray) -> np.ndarray:
+    """Floats compare by IEEE 754 totalOrder, as the arrow-rs `cmp` kernels the reference calls do
+    (src/daft-core/src/array/ops/comparison.rs:541-603 -> arrow::compute::kernels::cmp, arrow-ord 57.3.0): -NaN < -inf < ... <
+    -0.0 < +0.0 < ... < +inf < +NaN, and equality is equality of the bit patterns (NaN == NaN, -0.0 != 0.0).  The key is the
+    sign-magnitude bit pattern mapped to a two's-complement integer with the same order (what f64::total_cmp does)."""
+    if a.dtype == np.float64:
+        bits = a.view(np.int64)
+        return bits ^ ((bits >> 63) & np.int64(0x7FFFFFFFFFFFFFFF))
+    if a.dtype == np.float32:
+        bits = a.view(np.int32)
+        return bits ^ ((bits >> 31) & np.int32(0x7FFFFFFF))
+    return a
+
+
 def _eval(b: Bound, cols, n: int):
     if b.tag == T_COL:
         return cols[b.col]
@@ -106,9 +120,9 @@ def _eval(b: Bound, cols, n: int):
                 return np.where(ok, r, 0).astype(a.dtype), ok
             if op in ("lt", "le", "ge", "gt", "eq", "ne"):
                 f = {"lt": np.less, "le": np.less_equal, "ge": np.greater_equal, "gt": np.greater, "eq": np.equal, "ne": np.not_equal}[op]
-                return np.asarray(f(a, c), dtype=bool), both
+                return np.asarray(f(_total_order_key(a), _total_order_key(c)), dtype=bool), both
             if op == "eq_null_safe":
-                return np.where(both, np.asarray(a == c, dtype=bool), ka == kc), np.ones(n, dtype=bool)
+                return np.where(both, np.asarray(_total_order_key(a) == _total_order_key(c), dtype=bool), ka == kc), np.ones(n, dtype=bool)
             if op == "and":  # Kleene, src/daft-core/src/array/ops/comparison.rs:725-786
                 va, vc = ka & a.astype(bool), kc & c.astype(bool)
                 return va & vc, both | (ka & ~a.astype(bool)) | (kc & ~c.astype(bool))
@@ -164,10 +178,15 @@ def _eval(b: Bound, cols, n: int):
                 if kb.value is None or kb.dtype == dt.NULL:
                     continue
                 r |= np.asarray(a == v, dtype=bool)
+                if dt.is_float(b.kids[0].dtype):
+                    # float membership goes through a BTreeSet<FloatWrapper>: every NaN equals every NaN, -0.0 equals 0.0
+                    # (src/daft-core/src/array/ops/is_in.rs:44-66, src/common/hashable-float-wrapper/src/lib.rs:45-57)
+                    r |= np.isnan(a) & np.isnan(v)
             return r, ka
         if b.tag == T_BETWEEN:
             (a, ka), (lo, kl), (hi, kh) = kids
             # gte(lower) Kleene-and lte(upper) (src/daft-core/src/array/ops/between.rs:30-32, comparison.rs:725-786)
+            a, lo, hi = _total_order_key(a), _total_order_key(lo), _total_order_key(hi)
             ge, le = np.asarray(a >= lo, dtype=bool), np.asarray(a <= hi, dtype=bool)
             kg, kle = ka & kl, ka & kh
             return ge & le, (kg & kle) | (kg & ~ge) | (kle & ~le)

@@ -76,6 +76,11 @@ def test_codegen_and_nvrtc_offline(tmp_path):
     plan, _, _ = encode_project(exprs, list(srcs), list(srcs.values()))
     _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * len(srcs))(*srcs.values()),
               (ctypes.c_uint8 * len(srcs))(*([0] * len(srcs))), ctypes.c_int32(len(srcs)))
+    # float comparisons / between / is_in (totalOrder keys, NaN membership) for both float widths
+    fl = [e for nm in ("x", "y") for e in ((col(nm) <= col("y")).alias(nm + "le"), (col(nm) == 0.0).alias(nm + "eq"), col(nm).between(0.0, 1.0).alias(nm + "bt"),
+                                           col(nm).is_in([float("nan"), 0.5]).alias(nm + "in"), col(nm).eq_null_safe(col("y")).alias(nm + "ens"))]
+    plan, _, _ = encode_project(fl, ["x", "y"], [dt.F32, dt.F64])
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 2)(dt.F32, dt.F64), (ctypes.c_uint8 * 2)(1, 1), ctypes.c_int32(2))
     plan = encode_agg([col("b").sum().alias("sb"), col("a").max().alias("ma"), col("a").count().alias("n")], [col("s"), col("a") % 3], names, dts,
                       [col("b") > lit(0.5)])
     _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))

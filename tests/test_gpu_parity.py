@@ -148,6 +148,30 @@ def test_project_matches_oracle(gpu, n, nulls):
     assert_tables_equal(got, want)  # bit-exact, floats included (same op order, no FMA)
 
 
+def test_float_comparisons_total_order(gpu):
+    """NaN / signed-zero / infinity operands: the comparison operators order floats by IEEE totalOrder (arrow-rs `cmp` kernels,
+    src/daft-core/src/array/ops/comparison.rs:541-603); float is_in treats all NaNs as one element (is_in.rs:44-66)."""
+    rng = np.random.default_rng(11)
+    n = 5000
+    special = np.array([np.nan, -np.nan, 0.0, -0.0, np.inf, -np.inf, 1.0, -1.0, 0.5])
+    x = special[rng.integers(0, len(special), n)]
+    y = special[rng.integers(0, len(special), n)]
+    for typ in (pa.float64(), pa.float32()):
+        tbl = pa.table({"x": pa.array(x, type=typ, mask=rng.random(n) < 0.1), "y": pa.array(y, type=typ, mask=rng.random(n) < 0.1)})
+        c = gpu.col
+        exprs = [(c("x") == c("y")).alias("eq"), (c("x") != c("y")).alias("ne"), (c("x") < c("y")).alias("lt"), (c("x") <= c("y")).alias("le"),
+                 (c("x") > c("y")).alias("gt"), (c("x") >= c("y")).alias("ge"), (c("x") > 0.0).alias("gt0"), (c("x") == 0.0).alias("eq0"),
+                 c("x").between(0.0, float("inf")).alias("bt"), c("x").between(c("y"), 1.0).alias("bt2"), c("x").is_in([float("nan"), 0.0, 0.5]).alias("in"),
+                 c("x").eq_null_safe(c("y")).alias("ens")]
+        got = RB(gpu, tbl).eval_expression_list(exprs).to_arrow_table()
+        want = E.eval_expression_list(tbl, exprs)
+        assert_tables_equal(got, want)
+        for pred in ([c("x") > 0.0], [c("x") <= c("y")], [c("x") == c("y")], [c("x").is_in([float("nan")])]):
+            g, w = RB(gpu, tbl).filter(pred).to_arrow_table(), E.filter(tbl, pred)
+            assert g.num_rows == w.num_rows
+            assert_tables_equal(g, w)
+
+
 def test_cast_out_of_range_is_null(gpu):
     """arrow-rs safe-cast rule (src/daft-core/src/array/ops/cast.rs:194-196): what the target integer type cannot hold is null."""
     rng = np.random.default_rng(5)

@@ -451,3 +451,34 @@ def test_cast_out_of_range_is_null_like_arrow_rs_safe_cast():
     # a literal that does not fit folds to a null literal
     out = E.eval_expression_list(t, [lit(300).cast(pa.int8()).alias("x"), lit(-1).cast(pa.uint32()).alias("y"), lit(7).cast(pa.int8()).alias("z")]).to_pydict()
     assert out == {"x": [None] * 8, "y": [None] * 8, "z": [7] * 8}
+
+
+def test_float_comparisons_use_total_order_like_arrow_rs():
+    """The reference's comparison operators are the arrow-rs `cmp` kernels (src/daft-core/src/array/ops/comparison.rs:541-603),
+    documented to order floats by IEEE 754 totalOrder: NaN == NaN, NaN is greater than +inf, -0.0 < +0.0.  Float `is_in` goes through
+    a BTreeSet<FloatWrapper> instead (is_in.rs:44-66): NaN matches NaN and -0.0 matches 0.0."""
+    nan, inf = float("nan"), float("inf")
+    x = [1.0, nan, -0.0, 0.0, inf, -inf, nan, None]
+    y = [nan, nan, 0.0, -0.0, nan, nan, 1.0, 1.0]
+    for typ in (pa.float32(), pa.float64()):
+        t = pa.table({"x": pa.array(x, type=typ), "y": pa.array(y, type=typ)})
+        out = E.eval_expression_list(t, [
+            (col("x") == col("y")).alias("eq"), (col("x") != col("y")).alias("ne"), (col("x") < col("y")).alias("lt"),
+            (col("x") <= col("y")).alias("le"), (col("x") > col("y")).alias("gt"), (col("x") >= col("y")).alias("ge"),
+            col("x").between(0.0, inf).alias("bt"), col("x").is_in([nan, 0.0]).alias("in"), (col("x") > inf).alias("gt_inf"),
+            col("x").eq_null_safe(col("y")).alias("ens"),
+        ]).to_pydict()
+        assert out["eq"] == [False, True, False, False, False, False, False, None]
+        assert out["ne"] == [True, False, True, True, True, True, True, None]
+        assert out["lt"] == [True, False, True, False, True, True, False, None]
+        assert out["le"] == [True, True, True, False, True, True, False, None]
+        assert out["gt"] == [False, False, False, True, False, False, True, None]
+        assert out["ge"] == [False, True, False, True, False, False, True, None]
+        assert out["bt"] == [True, False, False, True, True, False, False, None]   # -0.0 sorts below the +0.0 bound, NaN above +inf
+        assert out["in"] == [False, True, True, True, False, False, True, None]
+        assert out["gt_inf"] == [False, True, False, False, False, False, True, None]
+        assert out["ens"] == [False, True, False, False, False, False, False, False]
+    # filter keeps the NaN rows for `x > 0` (NaN is the greatest value), drops them for `x < 0`
+    t = pa.table({"x": pa.array([1.0, nan, -1.0, None])})
+    assert E.filter(t, [col("x") > 0.0]).column("x").to_pylist()[0] == 1.0 and E.filter(t, [col("x") > 0.0]).num_rows == 2
+    assert E.filter(t, [col("x") < 0.0]).to_pydict() == {"x": [-1.0]}
