@@ -273,4 +273,6 @@ def filter(tbl: pa.Table, exprs) -> pa.Table:
     for e in exprs[1:]:
         pred = pred & e
     mask = eval_expression(tbl, pred)
+    if not pa.types.is_boolean(mask.type):  # mask.bool()? in mask_filter (lib.rs:543) -> "... BooleanType" ValueError
+        raise ValueError(f"filter predicate must be boolean, got {mask.type}")
     return tbl.filter(pc.fill_null(mask, False))

@@ -482,3 +482,67 @@ def test_float_comparisons_use_total_order_like_arrow_rs():
     t = pa.table({"x": pa.array([1.0, nan, -1.0, None])})
     assert E.filter(t, [col("x") > 0.0]).column("x").to_pylist()[0] == 1.0 and E.filter(t, [col("x") > 0.0]).num_rows == 2
     assert E.filter(t, [col("x") < 0.0]).to_pydict() == {"x": [-1.0]}
+
+
+def test_utf8_and_temporal_literals_from_reference_tests():
+    """tests/recordbatch/utf8/test_left.py, test_length.py, test_compares.py:8-32; tests/series/test_temporal_ops.py:12-95
+    (day / month / year / day_of_week: 0 = Monday, UInt32 / Int32 result types)."""
+    import datetime
+    t = pa.table({"col": pa.array(["foo", None, "barBaz", "quux", "1"], type=pa.large_utf8())})
+    assert E.eval_expression_list(t, [col("col").left(3)]).to_pydict() == {"col": ["foo", None, "bar", "quu", "1"]}
+    t = pa.table({"col": pa.array(["foo", None, "barbaz", "quux", "😉test", ""], type=pa.large_utf8())})
+    out = E.eval_expression_list(t, [col("col").length()])
+    assert out.to_pydict() == {"col": [3, None, 6, 4, 5, 0]} and out.schema.field("col").type == pa.uint64()
+    for fn, data in (("endswith", ["x_foo", "y_foo", "z_bar"]), ("startswith", ["foo_x", "foo_y", "bar_z"]), ("contains", ["x_foo_x", "y_foo_y", "z_bar_z"])):
+        t = pa.table({"col": pa.array(data, type=pa.large_utf8())})
+        assert E.eval_expression_list(t, [getattr(col("col"), fn)("foo")]).to_pydict() == {"col": [True, True, False]}
+        assert E.eval_expression_list(t, [getattr(col("col"), fn)(lit("foo"))]).to_pydict() == {"col": [True, True, False]}
+    # temporal
+    days = [3, 4, 5, None, 6, 7, None, 8, 9]  # 2023-04-03 is a Monday
+    t = pa.table({"d": pa.array([None if d is None else datetime.date(2023, 4, d) for d in days], type=pa.date32())})
+    out = E.eval_expression_list(t, [col("d").day_of_week().alias("dow"), col("d").day().alias("day")])
+    assert out.column("dow").to_pylist() == [0, 1, 2, None, 3, 4, None, 5, 6] and out.schema.field("dow").type == pa.uint32()
+    assert out.column("day").to_pylist() == days and out.schema.field("day").type == pa.uint32()
+    months = list(range(1, 10)) + [None, 11, 12]
+    t = pa.table({"d": pa.array([None if m is None else datetime.date(2023, m, 1) for m in months], type=pa.date32())})
+    out = E.eval_expression_list(t, [col("d").month()])
+    assert out.column("d").to_pylist() == months and out.schema.field("d").type == pa.uint32()
+    years = [1, 1969, 2028, 2027, 2024, None, 2025, None]
+    t = pa.table({"d": pa.array([None if y is None else datetime.date(y, 1, 1) for y in years], type=pa.date32())})
+    out = E.eval_expression_list(t, [col("d").year()])
+    assert out.column("d").to_pylist() == years and out.schema.field("d").type == pa.int32()
+    # tests/recordbatch/test_filter.py:199-222: filter on day_of_week() == 2 keeps the Wednesdays (null days drop out)
+    dd = [None if d is None else datetime.date(2023, 4, d) for d in (8, 5, None, 15, 12, None)]
+    t = pa.table({"days": pa.array(dd, type=pa.date32()), "enum": [0, 1, 2, 3, 4, 5]})
+    assert E.filter(t, [col("days").day_of_week() == 2]).to_pydict() == {"days": [datetime.date(2023, 4, 5), datetime.date(2023, 4, 12)], "enum": [1, 4]}
+
+
+def test_filter_literals_from_reference_tests():
+    """tests/recordbatch/test_filter.py:11-196: all / some / none pass, literal and null predicates, date predicates."""
+    import datetime
+    t = pa.table({"a": [1, 2, 3, 4], "b": [5, 6, 7, 8]})
+    assert E.filter(t, [col("a") < col("b"), col("a") < 5]).to_pydict() == {"a": [1, 2, 3, 4], "b": [5, 6, 7, 8]}
+    assert E.filter(t, [lit(True), lit(True)]).to_pydict() == {"a": [1, 2, 3, 4], "b": [5, 6, 7, 8]}
+    assert E.filter(t, [((col("a") * 4) < col("b")) | (col("b") == 8)]).to_pydict() == {"a": [1, 4], "b": [5, 8]}
+    assert E.filter(t, [(col("b") / col("a")) >= 3]).to_pydict() == {"a": [1, 2], "b": [5, 6]}
+    assert E.filter(t, [col("a") < col("b"), col("a") > 5]).to_pydict() == {"a": [], "b": []}
+    assert E.filter(t, [col("a") < col("b"), lit(False)]).to_pydict() == {"a": [], "b": []}
+    assert E.filter(t, [lit(None).cast(pa.bool_())]).to_pydict() == {"a": [], "b": []}
+    with pytest.raises(ValueError, match="[Bb]oolean"):
+        E.filter(t, [col("a") + 1])
+    from daft_b200 import datatypes as dt
+    from daft_b200.expressions import encode_filter
+    with pytest.raises(ValueError, match="[Bb]oolean"):  # the host mirror refuses before anything reaches the device
+        encode_filter([col("a") + 1], ["a", "b"], [dt.I64, dt.I64])
+
+    def table(dates):
+        return pa.table({"days": pa.array(dates, type=pa.date32()), "enum": [0, 1, 2, 3, 4, 5]})
+    D = datetime.date
+    t = table([D(2023, 1, 5), D(2023, 1, 4), D(2023, 1, 1), None, D(2023, 1, 2), None])
+    assert E.filter(t, [(col("days") > D(2023, 1, 2)) & (col("enum") > 0)]).to_pydict() == {"days": [D(2023, 1, 4)], "enum": [1]}
+    t = table([D(2023, 1, 3), D(2023, 1, 28), None, D(2023, 1, 9), D(2023, 1, 18), None])
+    assert E.filter(t, [col("days").day() > 15]).to_pydict() == {"days": [D(2023, 1, 28), D(2023, 1, 18)], "enum": [1, 4]}
+    t = table([D(2023, 2, 1), D(2023, 6, 1), None, D(2023, 4, 1), D(2023, 11, 1), None])
+    assert E.filter(t, [col("days").month() > 5]).to_pydict() == {"days": [D(2023, 6, 1), D(2023, 11, 1)], "enum": [1, 4]}
+    t = table([D(5, 1, 1), D(4000, 1, 1), D(1, 1, 1), None, D(2022, 1, 1), None])
+    assert E.filter(t, [col("days").year() > 2000]).to_pydict() == {"days": [D(4000, 1, 1), D(2022, 1, 1)], "enum": [1, 4]}
