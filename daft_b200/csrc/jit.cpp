@@ -144,8 +144,10 @@ static int parse_node(Reader &r, Ast &a) {
                     nd.nullable = false;
                     break;
                 case B_AND: case B_OR: case B_XOR:
-                    if (t != B200_BOOL && t != B200_NULL) fail("plan: and/or/xor need boolean operands");
-                    nd.dtype = B200_BOOL;
+                    // booleans: Kleene and / or, xor; integers: bitwise, null if either side is null
+                    // (src/daft-core/src/array/ops/bitwise.rs; tests/recordbatch/test_bitwise.py)
+                    if (t != B200_BOOL && t != B200_NULL && !is_integer(t)) fail("plan: and/or/xor need boolean or integer operands");
+                    nd.dtype = is_integer(t) ? t : B200_BOOL;
                     break;
                 case B_SHL: case B_SHR:
                     if (!is_integer(t)) fail("plan: shift needs integer operands");
@@ -467,16 +469,19 @@ struct ExprGen {
                         }
                         break;
                     }
-                    case B_AND:  // Kleene (src/daft-core/src/array/ops/comparison.rs:725-786)
-                        os << "    const bool " << V << " = (" << ka << " && " << a << ") && (" << kb << " && " << b << ");\n";
-                        os << "    const bool " << K << " = (" << ka << " && " << kb << ") || (" << ka << " && !" << a << ") || (" << kb << " && !" << b << ");\n";
-                        break;
-                    case B_OR:   // comparison.rs:788-841
-                        os << "    const bool " << V << " = (" << ka << " && " << a << ") || (" << kb << " && " << b << ");\n";
-                        os << "    const bool " << K << " = (" << ka << " && " << kb << ") || (" << ka << " && " << a << ") || (" << kb << " && " << b << ");\n";
-                        break;
-                    case B_XOR:
-                        os << "    const bool " << V << " = " << a << " != " << b << "; const bool " << K << " = " << ka << " && " << kb << ";\n";
+                    case B_AND: case B_OR: case B_XOR:
+                        if (is_integer(t)) {  // bitwise; null if either side is null
+                            os << "    const " << T << " " << V << " = (" << T << ")(" << a << (n.op == B_AND ? " & " : (n.op == B_OR ? " | " : " ^ ")) << b
+                               << "); const bool " << K << " = " << ka << " && " << kb << ";\n";
+                        } else if (n.op == B_AND) {  // Kleene (src/daft-core/src/array/ops/comparison.rs:725-786)
+                            os << "    const bool " << V << " = (" << ka << " && " << a << ") && (" << kb << " && " << b << ");\n";
+                            os << "    const bool " << K << " = (" << ka << " && " << kb << ") || (" << ka << " && !" << a << ") || (" << kb << " && !" << b << ");\n";
+                        } else if (n.op == B_OR) {   // comparison.rs:788-841
+                            os << "    const bool " << V << " = (" << ka << " && " << a << ") || (" << kb << " && " << b << ");\n";
+                            os << "    const bool " << K << " = (" << ka << " && " << kb << ") || (" << ka << " && " << a << ") || (" << kb << " && " << b << ");\n";
+                        } else {
+                            os << "    const bool " << V << " = " << a << " != " << b << "; const bool " << K << " = " << ka << " && " << kb << ";\n";
+                        }
                         break;
                     case B_SHL: case B_SHR:
                         os << "    const " << T << " " << V << " = (" << T << ")(" << a << (n.op == B_SHL ? " << " : " >> ") << b << "); const bool " << K << " = " << ka << " && " << kb << ";\n";

@@ -216,8 +216,14 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         if op == "true_div":
             return Bound(T_BINARY, dt.F64, BINOPS[op], [_cast(l, dt.F64), _cast(r, dt.F64)])
         if op in ("and", "or", "xor"):
-            if dt.is_integer(l.dtype) and dt.is_integer(r.dtype):
-                raise NotImplementedError("bitwise and/or/xor on integers")
+            if dt.is_integer(l.dtype) or dt.is_integer(r.dtype):
+                # bitwise on integers: supertype, null if either side is null (src/daft-core/src/array/ops/bitwise.rs)
+                if not all(dt.is_integer(x.dtype) or x.dtype == dt.NULL for x in (l, r)):
+                    raise TypeError(f"cannot apply {op} to {dt.NAMES[l.dtype]} and {dt.NAMES[r.dtype]}")
+                st = dt.supertype(l.dtype, r.dtype)
+                if not dt.is_integer(st):
+                    raise TypeError(f"cannot apply {op} to {dt.NAMES[l.dtype]} and {dt.NAMES[r.dtype]}")
+                return Bound(T_BINARY, st, BINOPS[op], [_cast(l, st), _cast(r, st)])
             return Bound(T_BINARY, dt.BOOL, BINOPS[op], [_cast(l, dt.BOOL) if l.dtype == dt.NULL else l,
                                                           _cast(r, dt.BOOL) if r.dtype == dt.NULL else r])
         if op in ("shl", "shr"):
@@ -237,6 +243,8 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         raise ValueError(op)
     if k == "unary":
         c = bind(e.args[0], names, dtypes)
+        if e.op == "not" and c.dtype not in (dt.BOOL, dt.NULL):
+            raise ValueError(f"cannot apply not to {dt.NAMES[c.dtype]}: expected Boolean")  # tests/recordbatch/test_eval.py:47-51
         if e.op in ("is_null", "not_null", "not"):
             return Bound(T_UNARY, dt.BOOL, UNOPS[e.op], [c])
         return Bound(T_UNARY, c.dtype, UNOPS[e.op], [c])

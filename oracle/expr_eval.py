@@ -123,6 +123,9 @@ def _eval(b: Bound, cols, n: int):
                 return np.asarray(f(_total_order_key(a), _total_order_key(c)), dtype=bool), both
             if op == "eq_null_safe":
                 return np.where(both, np.asarray(_total_order_key(a) == _total_order_key(c), dtype=bool), ka == kc), np.ones(n, dtype=bool)
+            if op in ("and", "or", "xor") and dt.is_integer(t):  # bitwise on integers, null if either side is null (array/ops/bitwise.rs)
+                f = {"and": np.bitwise_and, "or": np.bitwise_or, "xor": np.bitwise_xor}[op]
+                return f(a, c), both
             if op == "and":  # Kleene, src/daft-core/src/array/ops/comparison.rs:725-786
                 va, vc = ka & a.astype(bool), kc & c.astype(bool)
                 return va & vc, both | (ka & ~a.astype(bool)) | (kc & ~c.astype(bool))

@@ -81,6 +81,10 @@ def test_codegen_and_nvrtc_offline(tmp_path):
                                            col(nm).is_in([float("nan"), 0.5]).alias(nm + "in"), col(nm).eq_null_safe(col("y")).alias(nm + "ens"))]
     plan, _, _ = encode_project(fl, ["x", "y"], [dt.F32, dt.F64])
     _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 2)(dt.F32, dt.F64), (ctypes.c_uint8 * 2)(1, 1), ctypes.c_int32(2))
+    # bitwise and / or / xor on integers (mixed widths through the supertype)
+    plan, _, odt = encode_project([(col("p") & col("q")).alias("a"), (col("p") | 3).alias("o"), (col("q") ^ col("q")).alias("x")], ["p", "q"], [dt.I8, dt.U16])
+    assert odt == [dt.I32, dt.I32, dt.U16]
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 2)(dt.I8, dt.U16), (ctypes.c_uint8 * 2)(1, 0), ctypes.c_int32(2))
     plan = encode_agg([col("b").sum().alias("sb"), col("a").max().alias("ma"), col("a").count().alias("n")], [col("s"), col("a") % 3], names, dts,
                       [col("b") > lit(0.5)])
     _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))

@@ -135,6 +135,7 @@ def exprs_under_test(c, lit):
         lit(7).alias("e32"), lit(None).alias("e33"), (c("f32") + c("f32")).alias("e34"), c("d").alias("e35"),
         (c("b") ^ c("b")).alias("e36"), (c("f64") % c("f32")).alias("e37"), (c("f64") // 7.0).alias("e38"),
         (c("i32") % c("i8")).alias("e39"), (c("f32") // c("i8")).alias("e40"), (c("f32") % c("i8")).alias("e41"),
+        (c("i64") & c("i32")).alias("e42"), (c("u8") | c("u16")).alias("e43"), (c("i16") ^ 255).alias("e44"),
     ]
 
 

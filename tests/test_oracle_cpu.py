@@ -546,3 +546,28 @@ def test_filter_literals_from_reference_tests():
     assert E.filter(t, [col("days").month() > 5]).to_pydict() == {"days": [D(2023, 6, 1), D(2023, 11, 1)], "enum": [1, 4]}
     t = table([D(5, 1, 1), D(4000, 1, 1), D(1, 1, 1), None, D(2022, 1, 1), None])
     assert E.filter(t, [col("days").year() > 2000]).to_pydict() == {"days": [D(4000, 1, 1), D(2022, 1, 1)], "enum": [1, 4]}
+
+
+def test_bitwise_and_not_literals_from_reference_tests():
+    """tests/recordbatch/test_bitwise.py:13-71 (and / or / xor on integers: null if either side is null, scalar operands) and
+    tests/recordbatch/test_eval.py:11-51 (arithmetic projection, `~` on a non-boolean column is a ValueError)."""
+    from operator import and_, or_, xor
+    cases = [([0b1100, 0b1010, 0b1001], [0b1010, 0b1100, 0b1001]), ([0b1100, None, 0b1001], [0b1010, 0b1100, None]),
+             ([None, None, None], [0b1010, 0b1100, 0b1001]), ([0b1100, 0b1010, 0b1001], [None, None, None])]
+    for op in (and_, or_, xor):
+        for left, right in cases:
+            t = pa.table({"left": pa.array(left, type=pa.int64()), "right": pa.array(right, type=pa.int64())})
+            want = [op(i, j) if i is not None and j is not None else None for i, j in zip(left, right)]
+            assert E.eval_expression_list(t, [op(col("left"), col("right"))]).to_pydict()["left"] == want
+        for data, scalar in (([0b1100, 0b1010, 0b1001], 0b1010), ([0b1100, None, 0b1001], None)):
+            t = pa.table({"data": pa.array(data, type=pa.int64())})
+            want = [op(d, scalar) if d is not None and scalar is not None else None for d in data]
+            assert E.eval_expression_list(t, [op(col("data"), lit(scalar))]).to_pydict()["data"] == want
+    # mixed widths go through the integer supertype
+    t = pa.table({"a": pa.array([0x7f, -1, 5], type=pa.int8()), "b": pa.array([0x1ff, 0x0f0, None], type=pa.int32())})
+    out = E.eval_expression_list(t, [(col("a") & col("b")).alias("x"), (col("a") ^ col("b")).alias("y")])
+    assert out.to_pydict() == {"x": [0x7f, 0x0f0, None], "y": [0x180, -241, None]} and out.schema.field("x").type == pa.int32()
+    t = pa.table({"a": [1, 2, 3, 4], "b": [5, 6, 7, 8]})
+    assert E.eval_expression_list(t, [col("a") + col("b"), col("b") * 2]).to_pydict() == {"a": [6, 8, 10, 12], "b": [10, 12, 14, 16]}
+    with pytest.raises(ValueError):
+        E.eval_expression_list(pa.table({"input": pa.array([None, 0, 1], type=pa.int64())}), [~col("input")])
