@@ -251,6 +251,7 @@ int b200_take(const b200_batch *batch, const b200_batch *indices, b200_batch **o
         require_device();
         const Column &ic = col_at(indices, 0);
         Buf idx = indices_to_i64(ic);
+        check_take_indices(as<int64_t>(idx), ic.length, batch->num_rows, ic.null_count > 0);
         *out = gather_batch(*batch, as<int64_t>(idx), ic.length, ic.null_count > 0);
         op_done();
     });

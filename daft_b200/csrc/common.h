@@ -116,6 +116,7 @@ Column slice_column(const Column &src, int64_t start, int64_t end);
 Column concat_columns(const std::vector<const Column *> &cols);
 // any integer column -> int64 index buffer (null -> -1)
 Buf indices_to_i64(const Column &c);
+void check_take_indices(const int64_t *idx, int64_t n, int64_t limit, bool null_marked);  // fails on idx >= limit / negative
 Column make_u64_column(const std::string &name, Buf data, int64_t n);
 
 // ---- hashing (hash.cu) -----------------------------------------------------------------------

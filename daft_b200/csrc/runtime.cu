@@ -465,6 +465,32 @@ Buf indices_to_i64(const Column &c) {
     return out;
 }
 
+// Caller-supplied take indices are validated before the gather dereferences them: the reference raises "index out of bounds"
+// (tests/recordbatch/test_take.py:31-34); indices produced inside the library (sort, join, partition) skip this.
+__global__ void check_indices_kernel(const int64_t *__restrict__ idx, int64_t n, int64_t limit, bool allow_negative, int *flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) {
+        const int64_t j = idx[i];
+        bad |= j >= limit || (j < 0 && !allow_negative);
+    }
+    if (bad) *flag = 1;
+}
+
+void check_take_indices(const int64_t *idx, int64_t n, int64_t limit, bool null_marked) {
+    if (n == 0) return;
+    cudaStream_t st = ctx().stream;
+    Buf flag = dev_alloc_zero(sizeof(int));
+    check_indices_kernel<<<grid_for(n), 256, 0, st>>>(idx, n, limit, null_marked, as<int>(flag));
+    count_launch();
+    B200_CUDA(cudaGetLastError());
+    int h = 0;
+    B200_CUDA(cudaMemcpyAsync(&h, as<int>(flag), sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (h) fail("take: index out of bounds (the batch has " + std::to_string(limit) + " rows)");
+}
+
 Column make_u64_column(const std::string &name, Buf data, int64_t n) {
     Column c;
     c.name = name;

@@ -186,7 +186,9 @@ int b200_agg(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200
 int b200_dedup(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out, char **errmsg);
 
 /* ---- take / concat ---- */
-/* indices: column 0 of `indices`, any integer dtype; null index -> null row. */
+/* indices: column 0 of `indices`, any integer dtype; null index -> null row.  An index outside [0, rows) fails with
+ * "index out of bounds" (tests/recordbatch/test_take.py:31-34): the indices are validated on the device before the gather,
+ * which costs one 4-byte read back. */
 int b200_take(const b200_batch *batch, const b200_batch *indices, b200_batch **out, char **errmsg);
 int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, char **errmsg);
 
@@ -274,6 +276,8 @@ int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begi
  *   binary ops (src/daft-dsl Operator, evaluated at src/daft-recordbatch/src/lib.rs:1376-1400):
  *     0 add 1 sub 2 mul 3 true_div 4 floor_div 5 mod 6 lt 7 le 8 eq 9 ne 10 ge 11 gt 12 and 13 or 14 xor
  *     15 eq_null_safe 16 shift_left 17 shift_right
+ *     and / or / xor: Kleene logic on booleans; bitwise on integers (null if either side is null,
+ *     src/daft-core/src/array/ops/bitwise.rs, tests/recordbatch/test_bitwise.py).
  *     lt..gt / eq / ne / eq_null_safe / BETWEEN on floats use IEEE 754 totalOrder like the arrow-rs `cmp` kernels the reference calls
  *     (src/daft-core/src/array/ops/comparison.rs:541-603): NaN == NaN, +NaN > +inf, -0.0 < +0.0.  IS_IN on floats follows the
  *     reference's BTreeSet<FloatWrapper> (is_in.rs:44-66): any NaN matches a NaN item, -0.0 matches 0.0.

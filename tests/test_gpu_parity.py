@@ -466,6 +466,25 @@ def test_take_and_concat_and_slice(gpu):
     assert_tables_equal(got, tbl.slice(17, 333 - 17))
 
 
+def test_take_literals_and_bounds_from_reference_tests(gpu):
+    """tests/recordbatch/test_take.py:15-70: empty take, repeated / reversed indices, out-of-bounds indices are an error."""
+    empty = RB(gpu, pa.table({"a": pa.array([], type=pa.int64())}))
+    assert empty.take(pa.array([], type=pa.int64())).to_pydict() == {"a": []}
+    with pytest.raises(Exception, match="index out of bounds"):
+        empty.take(pa.array([1], type=pa.int64()))
+    rb = RB(gpu, pa.table({"a": [1, 2, 3, 4]}))
+    assert rb.take(pa.array([0, 1], type=pa.int64())).to_pydict() == {"a": [1, 2]}
+    assert rb.take(pa.array([3, 2], type=pa.int64())).to_pydict() == {"a": [4, 3]}
+    assert rb.take(pa.array([3, 2, 2, 2, 3], type=pa.int64())).to_pydict() == {"a": [4, 3, 3, 3, 4]}
+    for typ in (pa.int8(), pa.int16(), pa.int32(), pa.uint8(), pa.uint16(), pa.uint32(), pa.uint64()):
+        assert rb.take(pa.array([3, 0, None], type=typ)).to_pydict() == {"a": [4, 1, None]}
+    for bad in ([4], [0, 1, 2, 3, 4], [-1], [2**40]):
+        with pytest.raises(Exception, match="index out of bounds"):
+            rb.take(pa.array(bad, type=pa.int64()))
+    with pytest.raises(Exception, match="index out of bounds"):
+        rb.take(pa.array([1, None, 7], type=pa.int32()))
+
+
 # ---------------------------------------------------------------------------------------------- join
 def join_tables(rng, nl, nr, key_range, nulls=0.1):
     def keycol(n):

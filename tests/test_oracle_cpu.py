@@ -571,3 +571,49 @@ def test_bitwise_and_not_literals_from_reference_tests():
     assert E.eval_expression_list(t, [col("a") + col("b"), col("b") * 2]).to_pydict() == {"a": [6, 8, 10, 12], "b": [10, 12, 14, 16]}
     with pytest.raises(ValueError):
         E.eval_expression_list(pa.table({"input": pa.array([None, 0, 1], type=pa.int64())}), [~col("input")])
+
+
+_NUMERIC_TYPES = [pa.int8(), pa.int16(), pa.int32(), pa.int64(), pa.uint8(), pa.uint16(), pa.uint32(), pa.uint64(), pa.float32(), pa.float64()]
+
+
+@pytest.mark.parametrize("typ", _NUMERIC_TYPES, ids=str)
+def test_numeric_expression_matrix_from_reference_tests(typ):
+    """tests/recordbatch/numeric/test_numeric.py:44-75: 12 operators x 10 numeric dtypes, with and without nulls; the expected
+    values are Python's own operators on the inputs."""
+    import operator as ops
+    OPS = [ops.add, ops.sub, ops.mul, ops.truediv, ops.floordiv, ops.mod, ops.lt, ops.le, ops.eq, ops.ne, ops.ge, ops.gt]
+    a, b = [5, 6, 7, 8], [1, 2, 3, 4]
+    t = pa.table({"a": a, "b": b})
+    for op in OPS:
+        got = E.eval_expression_list(t, [op(col("a").cast(typ), col("b").cast(typ)).alias("result")])
+        assert got.column_names == ["result"]
+        assert got.column("result").to_pylist() == [op(x, y) for x, y in zip(a, b)], op
+    a, b = [5, 6, None, 8, None], [1, 2, 3, None, None]
+    t = pa.table({"a": pa.array(a, type=pa.int64()), "b": pa.array(b, type=pa.int64())})
+    for op in OPS:
+        got = E.eval_expression_list(t, [op(col("a").cast(typ), col("b").cast(typ)).alias("result")]).column("result").to_pylist()
+        assert got[:2] == [op(x, y) for x, y in zip(a[:2], b[:2])] and got[2:] == [None, None, None], op
+
+
+def test_abs_negate_sqrt_shift_literals_from_reference_tests():
+    """tests/recordbatch/numeric/test_numeric.py:78-96, 186-209, 741-846."""
+    import math
+    t = pa.table({"a": pa.array([None, -1.0, 0, 2, 3, None], type=pa.float64()), "b": pa.array([-1, -2, 3, 4, None, None], type=pa.int64())})
+    out = E.eval_expression_list(t, [abs(col("a")), abs(col("b"))]).to_pydict()
+    assert out == {"a": [None, 1.0, 0.0, 2.0, 3.0, None], "b": [1, 2, 3, 4, None, None]}
+    t = pa.table({"a": pa.array([None, -1, -5, 0, 5, 2, None], type=pa.int64()), "b": pa.array([-1.7, -1.5, -1.3, 0.3, 0.7, None, None])})
+    assert E.eval_expression_list(t, [-col("a"), -col("b")]).to_pydict() == {"a": [None, 1, 5, 0, -5, -2, None], "b": [1.7, 1.5, 1.3, -0.3, -0.7, None, None]}
+    t = pa.table({"a": pa.array([4, 9, None, 16, 25, None], type=pa.int64()), "b": pa.array([2.25, 0.81, None, 1, 10.24, None], type=pa.float64())})
+    out = E.eval_expression_list(t, [col("a").sqrt(), col("b").sqrt()]).to_pydict()
+    assert out["a"] == [2.0, 3.0, None, 4.0, 5.0, None] and out["b"] == [math.sqrt(v) if v is not None else None for v in [2.25, 0.81, None, 1, 10.24, None]]
+    for left, right in (([1, 2, 3], [4, 5, 6]), ([1, 2, None], [4, None, 6])):
+        t = pa.table({"a": pa.array(left, type=pa.int64()), "b": pa.array(right, type=pa.int64())})
+        assert E.eval_expression_list(t, [col("a") << col("b")]).to_pydict()["a"] == [i << j if i is not None and j is not None else None for i, j in zip(left, right)]
+        assert E.eval_expression_list(t, [col("a") >> col("b")]).to_pydict()["a"] == [i >> j if i is not None and j is not None else None for i, j in zip(left, right)]
+    t = pa.table({"a": [1, 2, 4]})
+    assert E.eval_expression_list(t, [col("a") << 1]).to_pydict()["a"] == [2, 4, 8]
+    assert E.eval_expression_list(t, [col("a") >> 1]).to_pydict()["a"] == [0, 1, 2]
+    s = pa.table({"a": pa.array(["a", "b", "c"], type=pa.large_utf8())})
+    for bad in (abs(col("a")), -col("a"), col("a") << col("a"), col("a") >> col("a")):
+        with pytest.raises((ValueError, TypeError)):
+            E.eval_expression_list(s, [bad])
