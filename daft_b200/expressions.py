@@ -370,8 +370,12 @@ def encode_agg(to_agg: Sequence[Expression], group_by: Sequence[Expression], nam
         if inner.kind != "agg":
             raise ValueError(f"expected an aggregation expression, got {a!r}")
         mode = {"first": 0, "ignore_nulls": 1}[inner.value] if inner.op == "any_value" else COUNT_MODES[inner.value]
+        child = bind(inner.args[0], names, dtypes)
+        if inner.op in ("sum", "mean") and not dt.is_numeric(child.dtype):
+            # the reference rejects this when it types the aggregation (tests/recordbatch/test_table_aggs.py:283-286)
+            raise ValueError(f"Expected input to {inner.op}() to be numeric, got {dt.NAMES[child.dtype]}")
         out += struct.pack("<BB", AGG_KINDS[inner.op], mode) + _enc_str(name.encode())
-        out += encode(bind(inner.args[0], names, dtypes))
+        out += encode(child)
     return out
 
 

@@ -173,12 +173,16 @@ class RecordBatch:
 
     @classmethod
     def concat(cls, to_merge: Sequence["RecordBatch"]) -> "RecordBatch":
+        """RecordBatch::concat (error behaviour pinned by tests/recordbatch/test_concat.py:29-73)."""
         if len(to_merge) == 0:
             raise ValueError("Need at least 1 RecordBatch to concat")
+        for t in to_merge:
+            if not isinstance(t, RecordBatch):
+                raise TypeError(f"Expected a RecordBatch for concat, got {type(t).__name__}")
         names = to_merge[0].column_names()
         for t in to_merge[1:]:
             if t.column_names() != names or t.dtypes() != to_merge[0].dtypes():
-                raise ValueError("RecordBatch concat requires all schemas to match")
+                raise ValueError("RecordBatch::concat requires all schemas to match")
         arr = (ctypes.c_void_p * len(to_merge))(*[t._h.value for t in to_merge])
         out = ctypes.c_void_p()
         _lib.call("b200_concat", arr, ctypes.c_int32(len(to_merge)), ctypes.byref(out))

@@ -205,6 +205,8 @@ def agg_sum(arr, gid: np.ndarray, ng: int) -> pa.Array:
     elif pa.types.is_unsigned_integer(t):
         arr = arr.cast(pa.uint64())
     v = ColView(arr)
+    if v.code not in _SUM_FN:
+        raise ValueError(f"Expected input to sum() to be numeric, got {t}")
     fn, npt = _SUM_FN[v.code]
     out = np.zeros(max(ng, 1), dtype=npt)
     ov = np.zeros(max(ng, 1), dtype=np.uint8)

@@ -466,6 +466,24 @@ def test_take_and_concat_and_slice(gpu):
     assert_tables_equal(got, tbl.slice(17, 333 - 17))
 
 
+def test_concat_literals_and_errors_from_reference_tests(gpu):
+    """tests/recordbatch/test_concat.py:8-73."""
+    RBc = gpu.RecordBatch
+    a = RB(gpu, pa.table({"x": [1, 2, 3], "y": pa.array(["a", "b", "c"], type=pa.large_utf8())}))
+    b = RB(gpu, pa.table({"x": [4, 5, 6], "y": pa.array(["d", "e", "f"], type=pa.large_utf8())}))
+    assert RBc.concat([a, b]).to_pydict() == {"x": [1, 2, 3, 4, 5, 6], "y": ["a", "b", "c", "d", "e", "f"]}
+    e = pa.table({"x": pa.array([], type=pa.int64()), "y": pa.array([], type=pa.large_utf8())})
+    assert RBc.concat([RB(gpu, e), RB(gpu, e)]).to_pydict() == {"x": [], "y": []}
+    x = RB(gpu, pa.table({"x": [1, 2, 3]}))
+    with pytest.raises(TypeError, match="Expected a RecordBatch for concat"):
+        RBc.concat([x, []])
+    with pytest.raises(ValueError, match="Need at least 1 RecordBatch"):
+        RBc.concat([])
+    for other in ({"y": [1, 2, 3]}, {"x": [1.0, 2.0, 3.0]}, {"x": [1, 2, 3], "y": [2, 3, 4]}):
+        with pytest.raises(ValueError, match="RecordBatch::concat requires all schemas to match"):
+            RBc.concat([x, RB(gpu, pa.table(other))])
+
+
 def test_take_literals_and_bounds_from_reference_tests(gpu):
     """tests/recordbatch/test_take.py:15-70: empty take, repeated / reversed indices, out-of-bounds indices are an error."""
     empty = RB(gpu, pa.table({"a": pa.array([], type=pa.int64())}))

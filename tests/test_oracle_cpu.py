@@ -617,3 +617,46 @@ def test_abs_negate_sqrt_shift_literals_from_reference_tests():
     for bad in (abs(col("a")), -col("a"), col("a") << col("a"), col("a") >> col("a")):
         with pytest.raises((ValueError, TypeError)):
             E.eval_expression_list(s, [bad])
+
+
+@pytest.mark.parametrize("typ", _NUMERIC_TYPES, ids=str)
+def test_global_agg_dtype_matrix_from_reference_tests(typ):
+    """tests/recordbatch/test_table_aggs.py:25-31,75-86 (count), :105-135 (min / max), :244-266 (sum / mean) over every numeric dtype."""
+    x = col("input")
+    for vals, exp in (([], 0), ([None], 0), ([None, None, None], 0), ([0], 1), ([None, 0, None, 0, None], 2)):
+        t = pa.table({"input": pa.array(vals, type=typ)})
+        got = oracle_agg(t, [x.count().alias("count")], [])
+        assert got.to_pydict() == {"count": [exp]} and got.schema.field("count").type == pa.uint64()
+    for vals, mn, mx in (([], None, None), ([None], None, None), ([None, None, None], None, None), ([5], 5, 5), ([None, 5], 5, 5),
+                         ([None, 1, 21, None, 21, 1, None], 1, 21)):
+        t = pa.table({"input": pa.array(vals, type=typ)})
+        got = oracle_agg(t, [x.min().alias("min"), x.max().alias("max")], [])
+        assert got.to_pydict() == {"min": [mn], "max": [mx]} and got.schema.field("min").type == typ
+    for vals, s, m in (([], None, None), ([None], None, None), ([None, None, None], None, None), ([0], 0, 0.0), ([1], 1, 1.0),
+                       ([None, 3, None, None, 1, 2, 0, None], 6, 1.5)):
+        t = pa.table({"input": pa.array(vals, type=typ)})
+        got = oracle_agg(t, [x.sum().alias("sum"), x.mean().alias("mean")], [])
+        assert got.to_pydict() == {"sum": [s], "mean": [m]}
+        # sum widens to Int64 / UInt64, floats keep their width (inline_agg.rs:424-460); mean is Float64
+        want = pa.int64() if pa.types.is_signed_integer(typ) else pa.uint64() if pa.types.is_unsigned_integer(typ) else typ
+        assert got.schema.field("sum").type == want and got.schema.field("mean").type == pa.float64()
+
+
+def test_sum_upcast_and_bool_minmax_from_reference_tests():
+    """tests/recordbatch/test_table_aggs.py:269-281 (sum of 128 x dtype max / min does not overflow), :160-185 (bool min / max),
+    :283-286 (sum of strings is a ValueError)."""
+    for nptype in (np.uint8, np.uint16, np.uint32, np.int8, np.int16, np.int32):
+        t = pa.table({"maxes": np.full(128, np.iinfo(nptype).max, dtype=nptype), "mins": np.full(128, np.iinfo(nptype).min, dtype=nptype)})
+        got = oracle_agg(t, [col("maxes").sum(), col("mins").sum()], []).to_pydict()
+        assert got == {"maxes": [128 * int(np.iinfo(nptype).max)], "mins": [128 * int(np.iinfo(nptype).min)]}
+    for vals, mn, mx in (([], None, None), ([None], None, None), ([None, None, None], None, None), ([False, True], False, True),
+                         ([None, None, True, None], True, True)):
+        t = pa.table({"input": pa.array(vals, type=pa.bool_())})
+        assert oracle_agg(t, [col("input").min().alias("min"), col("input").max().alias("max")], []).to_pydict() == {"min": [mn], "max": [mx]}
+    with pytest.raises(ValueError):
+        oracle_agg(pa.table({"a": pa.array(["str1", "str2"], type=pa.large_utf8())}), [col("a").sum()], [])
+    from daft_b200 import datatypes as dt
+    from daft_b200.expressions import encode_agg
+    for bad in (col("a").sum(), col("a").mean()):
+        with pytest.raises(ValueError, match="numeric"):  # the host mirror refuses before anything reaches the device
+            encode_agg([bad], [], ["a"], [dt.LARGE_UTF8])
