@@ -53,7 +53,8 @@ enum Tag { T_COL = 0, T_LIT, T_BINARY, T_UNARY, T_CAST, T_IF_ELSE, T_IS_IN, T_BE
 enum BinOp { B_ADD = 0, B_SUB, B_MUL, B_TRUE_DIV, B_FLOOR_DIV, B_MOD, B_LT, B_LE, B_EQ, B_NE, B_GE, B_GT, B_AND, B_OR,
              B_XOR, B_EQ_NULL_SAFE, B_SHL, B_SHR };
 enum UnOp { U_NOT = 0, U_NEG, U_IS_NULL, U_NOT_NULL, U_ABS };
-enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT };
+enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT,
+          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN };
 
 struct Node {
     int tag = 0, op = 0;
@@ -240,6 +241,21 @@ static int parse_node(Reader &r, Ast &a) {
                 case F_STARTSWITH: case F_ENDSWITH: case F_CONTAINS: nd.dtype = B200_BOOL; break;
                 case F_LEFT: nd.dtype = B200_LARGE_UTF8; break;
                 case F_SQRT: nd.dtype = B200_F64; break;  // operand cast to Float64 by the host (IEEE correctly rounded sqrt)
+                case F_IS_NAN: case F_NOT_NAN: case F_IS_INF: {  // src/daft-core/src/array/ops/float.rs:13-110: nulls stay null
+                    if (nd.kids.size() != 1 || !is_float(a.nodes[nd.kids[0]].dtype)) fail("plan: is_nan / not_nan / is_inf need one float operand");
+                    nd.dtype = B200_BOOL;
+                    break;
+                }
+                case F_CEIL: case F_FLOOR: {  // src/daft-functions/src/numeric/ceil.rs:25-38, floor.rs (integers are returned unchanged by the host)
+                    if (nd.kids.size() != 1 || !is_float(a.nodes[nd.kids[0]].dtype)) fail("plan: ceil / floor need one float operand");
+                    nd.dtype = a.nodes[nd.kids[0]].dtype;
+                    break;
+                }
+                case F_SIGN: {  // src/daft-functions/src/numeric/sign.rs:26-42 -> array/ops/sign.rs: signum, 0 / 1 for unsigned integers
+                    if (nd.kids.size() != 1 || !is_numeric(a.nodes[nd.kids[0]].dtype)) fail("plan: sign needs one numeric operand");
+                    nd.dtype = a.nodes[nd.kids[0]].dtype;
+                    break;
+                }
                 default: fail("plan: unknown function");
             }
             break;
@@ -607,6 +623,20 @@ struct ExprGen {
                     case F_CONTAINS: os << "    const bool " << V << " = str_contains(" << a << ", " << v(kid[1]) << ");\n"; break;
                     case F_LEFT: os << "    const Str " << V << " = str_left(" << a << ", (int64_t)" << v(kid[1]) << ");\n"; break;
                     case F_SQRT: os << "    const double " << V << " = sqrt((double)" << a << ");\n"; break;
+                    case F_IS_NAN: os << "    const bool " << V << " = (" << a << " != " << a << ");\n"; break;
+                    case F_NOT_NAN: os << "    const bool " << V << " = (" << a << " == " << a << ");\n"; break;
+                    case F_IS_INF: os << "    const bool " << V << " = (" << a << " - " << a << " != 0) && (" << a << " == " << a << ");\n"; break;
+                    case F_CEIL: os << "    const " << T << " " << V << " = " << (n.dtype == B200_F32 ? "ceilf(" : "ceil(") << a << ");\n"; break;
+                    case F_FLOOR: os << "    const " << T << " " << V << " = " << (n.dtype == B200_F32 ? "floorf(" : "floor(") << a << ");\n"; break;
+                    case F_SIGN:
+                        if (is_float(n.dtype))  // f64::signum: NaN stays NaN, otherwise +-1 with the operand's sign (signum(+-0.0) = +-1.0)
+                            os << "    const " << T << " " << V << " = (" << a << " != " << a << ") ? " << a << " : "
+                               << (n.dtype == B200_F32 ? "copysignf(1.0f, " : "copysign(1.0, ") << a << ");\n";
+                        else if (is_signed_int(n.dtype))
+                            os << "    const " << T << " " << V << " = (" << T << ")((" << a << " > 0) - (" << a << " < 0));\n";
+                        else
+                            os << "    const " << T << " " << V << " = (" << T << ")(" << a << " != 0);\n";
+                        break;
                 }
                 os << "    const bool " << K << " = " << allk << ";\n";
                 break;

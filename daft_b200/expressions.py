@@ -19,7 +19,7 @@ BINOPS = {"add": 0, "sub": 1, "mul": 2, "true_div": 3, "floor_div": 4, "mod": 5,
           "ge": 10, "gt": 11, "and": 12, "or": 13, "xor": 14, "eq_null_safe": 15, "shl": 16, "shr": 17}
 UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
-         "day_of_week": 8, "sqrt": 9}
+         "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15}
 AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
 _CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
@@ -120,6 +120,17 @@ class Expression:
     def max(self): return self._agg("max")
     def count(self, mode: str = "valid"): return self._agg("count", mode)
     def sqrt(self): return Expression("function", "sqrt", (self,))
+    def is_nan(self): return Expression("function", "is_nan", (self,))
+    def not_nan(self): return Expression("function", "not_nan", (self,))
+    def is_inf(self): return Expression("function", "is_inf", (self,))
+    def ceil(self): return Expression("function", "ceil", (self,))
+    def floor(self): return Expression("function", "floor", (self,))
+    def sign(self): return Expression("function", "sign", (self,))
+    def negate(self): return Expression("unary", "neg", (self,))
+
+    def fill_nan(self, fill_value):
+        """input.if_else(fill_value, not_nan(input)) (src/daft-functions/src/float/fill_nan.rs:41-49): nulls stay null."""
+        return Expression("fill_nan", args=(self, _to_expr(fill_value)))
     def stddev(self, ddof: int = 0):
         """Staged exactly like the reference's plan rewrite (src/daft-local-plan/src/agg.rs:190-226): sum(x), sum(x*x),
         count(x) over Float64, then sqrt(((sqsum/n) - (sum/n)^2) * n / (n - ddof)), null when n <= ddof."""
@@ -274,6 +285,28 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         c, f = bind(e.args[0], names, dtypes), bind(e.args[1], names, dtypes)
         st = dt.supertype(c.dtype, f.dtype)
         return Bound(T_FILL_NULL, st, kids=[_cast(c, st), _cast(f, st)])
+    if k == "fill_nan":
+        x, f = (bind(a, names, dtypes) for a in e.args)
+        if x.dtype == dt.NULL:
+            return x
+        if not (dt.is_float(x.dtype) and dt.is_float(f.dtype)):
+            raise TypeError(f"Expects input for fill_nan to be float, but received {dt.NAMES[x.dtype]} and {dt.NAMES[f.dtype]}")
+        st = dt.supertype(x.dtype, f.dtype)
+        x, f = _cast(x, st), _cast(f, st)
+        return Bound(T_IF_ELSE, st, kids=[Bound(T_FUNCTION, dt.BOOL, FUNCS["not_nan"], [x]), x, f])
+    if k == "function" and e.op in ("is_nan", "not_nan", "is_inf", "ceil", "floor", "sign"):
+        c = bind(e.args[0], names, dtypes)
+        if e.op in ("is_nan", "not_nan", "is_inf"):
+            if c.dtype == dt.NULL:  # float.rs:29-40: an all-null boolean column
+                return Bound(T_LIT, dt.BOOL, value=None)
+            if not dt.is_float(c.dtype):
+                raise ValueError(f"Expected input to {e.op} to be float, got {dt.NAMES[c.dtype]}")
+            return Bound(T_FUNCTION, dt.BOOL, FUNCS[e.op], [c])
+        if not dt.is_numeric(c.dtype):
+            raise ValueError(f"Expected input to {e.op} to be numeric, got {dt.NAMES[c.dtype]}")  # test_numeric.py:116-120,141-145,179-183
+        if e.op in ("ceil", "floor") and dt.is_integer(c.dtype):
+            return c  # integers are returned unchanged (src/daft-functions/src/numeric/ceil.rs:25-33, floor.rs)
+        return Bound(T_FUNCTION, c.dtype, FUNCS[e.op], [c])
     if k == "function":
         kids = [bind(x, names, dtypes) for x in e.args]
         out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,

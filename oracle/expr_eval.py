@@ -208,6 +208,15 @@ def _eval(b: Bound, cols, n: int):
             if fn == "sqrt":
                 with np.errstate(all="ignore"):
                     return np.sqrt(a.astype(np.float64)), allk
+            if fn == "is_nan": return np.isnan(a), allk           # array/ops/float.rs:13-110
+            if fn == "not_nan": return ~np.isnan(a), allk
+            if fn == "is_inf": return np.isinf(a), allk
+            if fn == "ceil": return np.ceil(a), allk               # array/ops/ceil.rs
+            if fn == "floor": return np.floor(a), allk
+            if fn == "sign":                                       # array/ops/sign.rs: signum / sign_unsigned
+                if a.dtype.kind == "f":
+                    return np.where(np.isnan(a), a, np.copysign(np.ones_like(a), a)), allk
+                return np.sign(a).astype(a.dtype), allk
             if fn == "day_of_week":
                 return ((a.astype(np.int64) + 3) % 7).astype(np.uint32), allk
             if fn == "utf8_length":

@@ -85,6 +85,15 @@ def test_codegen_and_nvrtc_offline(tmp_path):
     plan, _, odt = encode_project([(col("p") & col("q")).alias("a"), (col("p") | 3).alias("o"), (col("q") ^ col("q")).alias("x")], ["p", "q"], [dt.I8, dt.U16])
     assert odt == [dt.I32, dt.I32, dt.U16]
     _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 2)(dt.I8, dt.U16), (ctypes.c_uint8 * 2)(1, 0), ctypes.c_int32(2))
+    # float predicates, ceil / floor / sign, fill_nan (lowered to if_else(not_nan(x), x, fill))
+    fx = [e for nm in ("x", "y") for e in (col(nm).is_nan().alias(nm + "n"), col(nm).not_nan().alias(nm + "nn"), col(nm).is_inf().alias(nm + "i"),
+                                           col(nm).ceil().alias(nm + "c"), col(nm).floor().alias(nm + "f"), col(nm).sign().alias(nm + "s"),
+                                           col(nm).fill_nan(2.0).alias(nm + "fn"))]
+    fx += [col("p").sign().alias("ps"), col("q").sign().alias("qs"), col("p").ceil().alias("pc")]
+    plan, _, odt = encode_project(fx, ["x", "y", "p", "q"], [dt.F32, dt.F64, dt.I8, dt.U16])
+    assert odt[-3:] == [dt.I8, dt.U16, dt.I8] and odt[3:7] == [dt.F32, dt.F32, dt.F32, dt.F64]
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 4)(dt.F32, dt.F64, dt.I8, dt.U16),
+              (ctypes.c_uint8 * 4)(1, 1, 1, 0), ctypes.c_int32(4))
     plan = encode_agg([col("b").sum().alias("sb"), col("a").max().alias("ma"), col("a").count().alias("n")], [col("s"), col("a") % 3], names, dts,
                       [col("b") > lit(0.5)])
     _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))

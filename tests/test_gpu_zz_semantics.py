@@ -119,3 +119,30 @@ def test_take_literals_and_bounds_from_reference_tests(gpu):
             rb.take(pa.array(bad, type=pa.int64()))
     with pytest.raises(Exception, match="index out of bounds"):
         rb.take(pa.array([1, None, 7], type=pa.int32()))
+
+
+def test_float_predicates_ceil_floor_sign_fill_nan(gpu):
+    """is_nan / not_nan / is_inf, ceil / floor / sign, fill_nan against the oracle over NaN / infinity / signed-zero inputs, plus the
+    reference's literal cases (tests/recordbatch/test_filter.py:223-241, test_fill.py:49-62)."""
+    rng = np.random.default_rng(23)
+    n = 4000
+    special = np.array([np.nan, -np.nan, 0.0, -0.0, np.inf, -np.inf, 1.5, -1.5, 0.5, -0.5, 2.0, 1e300, -1e-300])
+    x = np.where(rng.random(n) < 0.5, special[rng.integers(0, len(special), n)], rng.standard_normal(n) * 100)
+    tbl = pa.table({"f64": pa.array(x, mask=rng.random(n) < 0.1), "f32": pa.array(x.astype(np.float32), mask=rng.random(n) < 0.1),
+                    "i32": pa.array(rng.integers(-5, 5, n).astype(np.int32), mask=rng.random(n) < 0.1), "u16": pa.array(rng.integers(0, 3, n).astype(np.uint16))})
+    c = gpu.col
+    exprs = [e for nm in ("f64", "f32") for e in (c(nm).is_nan().alias(nm + "_nan"), c(nm).not_nan().alias(nm + "_nn"), c(nm).is_inf().alias(nm + "_inf"),
+                                                   c(nm).ceil().alias(nm + "_ceil"), c(nm).floor().alias(nm + "_floor"), c(nm).sign().alias(nm + "_sign"),
+                                                   c(nm).fill_nan(2.0).alias(nm + "_fn"), c(nm).fill_nan(c("f64")).alias(nm + "_fn2"))]
+    exprs += [c("i32").sign().alias("i_sign"), c("u16").sign().alias("u_sign"), c("i32").ceil().alias("i_ceil"), c("u16").floor().alias("u_floor")]
+    got = RB(gpu, tbl).eval_expression_list(exprs).to_arrow_table()
+    want = E.eval_expression_list(tbl, exprs)
+    assert_tables_equal(got, want)
+    nan = float("nan")
+    rb = RB(gpu, pa.table({"a": pa.array([1.0, nan, 3.0, None, nan])}))
+    assert rb.eval_expression_list([c("a").is_nan()]).to_pydict() == {"a": [False, True, False, None, True]}
+    assert rb.eval_expression_list([c("a").not_nan()]).to_pydict() == {"a": [True, False, True, None, False]}
+    assert rb.filter([c("a").not_nan()]).to_pydict() == {"a": [1.0, 3.0]}
+    for typ in (pa.float32(), pa.float64()):
+        rb = RB(gpu, pa.table({"input": pa.array([1.0, None, 3.0, nan], type=typ)}))
+        assert rb.eval_expression_list([c("input").fill_nan(2.0)]).to_pydict() == {"input": [1.0, None, 3.0, 2.0]}

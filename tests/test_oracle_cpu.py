@@ -660,3 +660,42 @@ def test_sum_upcast_and_bool_minmax_from_reference_tests():
     for bad in (col("a").sum(), col("a").mean()):
         with pytest.raises(ValueError, match="numeric"):  # the host mirror refuses before anything reaches the device
             encode_agg([bad], [], ["a"], [dt.LARGE_UTF8])
+
+
+def test_float_predicates_ceil_floor_sign_fill_nan_from_reference_tests():
+    """tests/recordbatch/test_filter.py:223-241 (is_nan / is_inf / not_nan: nulls are not NaNs), tests/recordbatch/numeric/
+    test_numeric.py:98-183 (ceil / floor / sign and their bad inputs), tests/recordbatch/test_fill.py:49-62 (fill_nan)."""
+    import math
+    nan, inf = float("nan"), float("inf")
+    t = pa.table({"a": pa.array([1.0, nan, 3.0, None, nan])})
+    assert E.eval_expression_list(t, [col("a").is_nan()]).to_pydict() == {"a": [False, True, False, None, True]}
+    assert E.eval_expression_list(t, [col("a").not_nan()]).to_pydict() == {"a": [True, False, True, None, False]}
+    t = pa.table({"a": pa.array([-inf, 0.0, None, inf])})
+    assert E.eval_expression_list(t, [col("a").is_inf()]).to_pydict() == {"a": [True, False, None, True]}
+    a, b = [None, -1.0, -0.5, 0, 0.5, 2, None], [-1.7, -1.5, -1.3, 0.3, 0.7, None, None]
+    t = pa.table({"a": pa.array(a, type=pa.float64()), "b": pa.array(b, type=pa.float64())})
+    for fn, pyfn in (("ceil", math.ceil), ("floor", math.floor)):
+        out = E.eval_expression_list(t, [getattr(col("a"), fn)(), getattr(col("b"), fn)()]).to_pydict()
+        assert out == {"a": [pyfn(v) if v is not None else None for v in a], "b": [pyfn(v) if v is not None else None for v in b]}
+
+    def check_sign(v):
+        return -1 if v < 0 else (1 if v > 0 else 0)
+    ai = [None, -1, -5, 0, 5, 2, None]
+    t = pa.table({"a": pa.array(ai, type=pa.int64()), "b": pa.array(b, type=pa.float64()), "u": pa.array([None, 0, 1, 2, 3, 4, 5], type=pa.uint8())})
+    out = E.eval_expression_list(t, [col("a").sign(), col("b").sign(), col("u").sign(), col("a").ceil().alias("ac"), col("u").floor().alias("uf")])
+    assert out.column("a").to_pylist() == [check_sign(v) if v is not None else None for v in ai] and out.schema.field("a").type == pa.int64()
+    assert out.column("b").to_pylist() == [check_sign(v) if v is not None else None for v in b] and out.schema.field("b").type == pa.float64()
+    assert out.column("u").to_pylist() == [None, 0, 1, 1, 1, 1, 1] and out.schema.field("u").type == pa.uint8()
+    assert out.column("ac").to_pylist() == ai and out.column("uf").to_pylist() == [None, 0, 1, 2, 3, 4, 5]  # integers pass through
+    # Rust signum: +-0.0 -> +-1.0, NaN -> NaN (array/ops/sign.rs:10-12)
+    z = E.eval_expression_list(pa.table({"x": pa.array([0.0, -0.0, nan, -inf])}), [col("x").sign()]).column("x").to_pylist()
+    assert z[:2] == [1.0, -1.0] and math.isnan(z[2]) and z[3] == -1.0
+    s = pa.table({"a": pa.array(["a", "b", "c"], type=pa.large_utf8())})
+    for bad in (col("a").ceil(), col("a").floor(), col("a").sign()):
+        with pytest.raises(ValueError, match="to be numeric"):
+            E.eval_expression_list(s, [bad])
+    for typ in (pa.float32(), pa.float64()):
+        t = pa.table({"input": pa.array([1.0, None, 3.0, nan], type=typ)})
+        out = E.eval_expression_list(t, [col("input").fill_nan(2.0)])
+        assert out.to_pydict() == {"input": [1.0, None, 3.0, 2.0]}
+    assert E.eval_expression_list(pa.table({"n": pa.nulls(3)}), [col("n").is_nan()]).to_pydict() == {"n": [None, None, None]}
