@@ -699,3 +699,13 @@ def test_float_predicates_ceil_floor_sign_fill_nan_from_reference_tests():
         out = E.eval_expression_list(t, [col("input").fill_nan(2.0)])
         assert out.to_pydict() == {"input": [1.0, None, 3.0, 2.0]}
     assert E.eval_expression_list(pa.table({"n": pa.nulls(3)}), [col("n").is_nan()]).to_pydict() == {"n": [None, None, None]}
+
+
+@pytest.mark.parametrize("data,typ", [(1, pa.int32()), ("a", pa.large_utf8()), (True, pa.bool_()), (b"Y", pa.large_binary()), (0.5, pa.float64()),
+                                       (None, pa.null()), (2**40, pa.int64())])
+def test_literal_broadcast_from_reference_tests(data, typ):
+    """tests/recordbatch/test_broadcasts.py:10-14: a literal projects to one value per row, named "literal"; Python ints that fit
+    are Int32 literals (src/daft-dsl/src/lit)."""
+    t = pa.table({"x": [1, 2, 3]})
+    out = E.eval_expression_list(t, [col("x"), lit(data)])
+    assert out.to_pydict() == {"x": [1, 2, 3], "literal": [data] * 3} and out.schema.field("literal").type == typ
