@@ -260,7 +260,14 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
             return Bound(T_UNARY, dt.BOOL, UNOPS[e.op], [c])
         return Bound(T_UNARY, c.dtype, UNOPS[e.op], [c])
     if k == "cast":
-        return _cast(bind(e.args[0], names, dtypes), e.dtype)
+        c = bind(e.args[0], names, dtypes)
+        if c.dtype != dt.NULL and c.dtype != e.dtype:
+            if dt.is_string(c.dtype) != dt.is_string(e.dtype):
+                raise NotImplementedError(f"cast {dt.NAMES[c.dtype]} -> {dt.NAMES[e.dtype]}: parsing / formatting casts are not built")
+            if {c.dtype, e.dtype} == {dt.DATE32, dt.TIMESTAMP}:
+                # the reference converts days <-> timestamp units here; a physical integer cast would silently be wrong
+                raise NotImplementedError(f"cast {dt.NAMES[c.dtype]} -> {dt.NAMES[e.dtype]}: temporal unit conversion is not built")
+        return _cast(c, e.dtype)
     if k == "if_else":
         p, a, b = (bind(x, names, dtypes) for x in e.args)
         st = dt.supertype(a.dtype, b.dtype)
