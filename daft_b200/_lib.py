@@ -50,7 +50,7 @@ class ColumnDesc(ctypes.Structure):
 # every symbol include/daft_b200.h declares (tests/test_abi_cpu.py checks the .so exports all of them)
 SYMBOLS = [
     "b200_abi_version", "b200_init", "b200_free_string", "b200_stream", "b200_synchronize", "b200_launch_count",
-    "b200_set_jit_cache_dir", "b200_precompile", "b200_kernel_timing", "b200_last_agg_kernel_ms",
+    "b200_set_jit_cache_dir", "b200_precompile", "b200_jit_describe", "b200_kernel_timing", "b200_last_agg_kernel_ms",
     "b200_batch_import", "b200_batch_export", "b200_batch_from_device", "b200_batch_describe", "b200_batch_num_rows",
     "b200_batch_num_columns", "b200_batch_size_bytes", "b200_batch_free", "b200_batch_select", "b200_batch_rename",
     "b200_batch_union", "b200_batch_slice",

@@ -98,6 +98,29 @@ int b200_precompile(int32_t op, const uint8_t *plan, size_t plan_len, const int3
     });
 }
 
+int b200_jit_describe(int32_t op, const uint8_t *plan, size_t plan_len, const int32_t *col_dtypes, const uint8_t *col_nullable,
+                      int32_t ncols, char **out_text, char **errmsg) {
+    return guard(errmsg, [&] {
+        std::vector<int32_t> dt(col_dtypes, col_dtypes + ncols);
+        std::vector<uint8_t> nl(col_nullable, col_nullable + ncols);
+        jit::Compiled meta;
+        const std::string src = jit::generate(op, plan, plan_len, dt, nl, false, meta, 0);
+        std::string t = "ptrs=";
+        for (size_t i = 0; i < meta.ptrs.size(); i++)
+            t += (i ? "," : "") + std::to_string(meta.ptrs[i].kind) + ":" + std::to_string(meta.ptrs[i].index);
+        t += "\nints=";
+        for (size_t i = 0; i < meta.ints.size(); i++) t += (i ? "," : "") + std::to_string(meta.ints[i]);
+        t += "\nouts=";
+        for (size_t i = 0; i < meta.outs.size(); i++)
+            t += (i ? "," : "") + std::to_string(meta.outs[i].dtype) + ":" + (meta.outs[i].nullable ? "1" : "0");
+        t += "\n---\n" + src;
+        char *m = static_cast<char *>(malloc(t.size() + 1));
+        if (!m) fail("out of memory");
+        memcpy(m, t.c_str(), t.size() + 1);
+        *out_text = m;
+    });
+}
+
 // ---- batches -------------------------------------------------------------------------------------
 int b200_batch_import(struct ArrowArray *array, struct ArrowSchema *schema, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] { *out = import_batch(array, schema); });

@@ -1,0 +1,202 @@
+"""Host emulation of the JIT-generated PROJECT code (test infrastructure).
+
+The projection kernel the library generates for a plan is straight-line, fully typed C++ (`Prog::row`) over a small set
+of helpers in `daft_b200/csrc/jit_prelude.cuh`.  This module asks the library for that source and its parameter layout
+(`b200_jit_describe`, no CUDA involved), compiles the very same text for the host with a shim for the handful of CUDA
+intrinsics it uses, and runs it over Arrow inputs one emulated warp at a time.  Warp ballots -- the only cross-lane
+operation of `row` -- are replayed in two sweeps per warp: sweep 0 records every lane's vote per call site, sweep 1 re-runs
+the (pure, idempotent) row code with the recorded masks, so the bitmaps it stores are the ones a real warp would store.
+
+What this proves: the generated expression code (casts, division, comparisons, null rules, functions) computes what the
+oracle computes.  What it does not: anything about the launch, the memory system or the skeletons around `row`.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pyarrow as pa
+
+from daft_b200 import _lib
+from daft_b200 import datatypes as dt
+from daft_b200.expressions import encode_project
+
+P_COL_DATA, P_COL_VALID, P_COL_OFFSETS, P_OUT_DATA, P_OUT_VALID = 0, 1, 2, 3, 4
+I_N = 0
+
+_NP = {dt.I8: np.int8, dt.I16: np.int16, dt.I32: np.int32, dt.I64: np.int64, dt.U8: np.uint8, dt.U16: np.uint16, dt.U32: np.uint32,
+       dt.U64: np.uint64, dt.F32: np.float32, dt.F64: np.float64, dt.DATE32: np.int32, dt.TIMESTAMP: np.int64}
+
+_SHIM = r"""
+#include <cstdint>
+#include <cstring>
+#include <math.h>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __global__
+#define __launch_bounds__(...)
+#define __grid_constant__
+struct EmuDim3 { unsigned x, y, z; };
+static EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
+static unsigned g_ballots[1 << 14];
+static int g_site, g_phase, g_lane;
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+    const int s = g_site++;
+    if (g_phase == 0) { if (pred) g_ballots[s] |= 1u << g_lane; return 0u; }
+    return g_ballots[s];
+}
+static inline long long __double_as_longlong(double x) { long long b; memcpy(&b, &x, 8); return b; }
+static inline double __longlong_as_double(long long b) { double x; memcpy(&x, &b, 8); return x; }
+static inline int __float_as_int(float x) { int b; memcpy(&b, &x, 4); return b; }
+static inline float __int_as_float(int b) { float x; memcpy(&x, &b, 4); return x; }
+static inline int __double2hiint(double x) { return (int)(__double_as_longlong(x) >> 32); }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
+template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
+"""
+
+_DRIVER = r"""
+extern "C" void emu_run(void **ptrs, int nptr, long long *ints, int nint, long long n) {
+    Prog::P p;
+    for (int i = 0; i < nptr; i++) p.ptr[i] = ptrs[i];
+    for (int i = 0; i < nint; i++) p.ival[i] = ints[i];
+    const long long n_round = (n + 31) & ~31LL;
+    for (long long base = 0; base < n_round; base += 32) {
+        for (int pass = 0; pass < 1; pass++) {
+            memset(g_ballots, 0, sizeof(g_ballots));
+            for (g_phase = 0; g_phase < 2; g_phase++)
+                for (g_lane = 0; g_lane < 32; g_lane++) {
+                    g_site = 0;
+                    threadIdx.x = (unsigned)g_lane;
+                    const long long i = base + g_lane;
+                    Prog::row(p, i, i, i < n, pass);
+                }
+        }
+    }
+}
+"""
+
+
+def _prelude_for_host() -> str:
+    xxh = open(os.path.join(_lib.CSRC, "xxh3.cuh")).read().replace("#pragma once", "")   # prepended to every generated kernel
+    text = xxh + open(os.path.join(_lib.CSRC, "jit_prelude.cuh")).read()
+    cut = text.index("// Filter with in-kernel stable compaction")
+    cut = text.rindex("// ====", 0, cut)
+    text = text[:cut]
+    text = re.sub(r"asm volatile\([^;]*\);", ";", text)   # PTX-only helpers (prefetch) are never reached from Prog::row
+    return text.replace("#pragma once", "") + "\n}  // namespace jit\n}  // namespace b200\n"
+
+
+def describe_project(exprs, names, dtypes, nullable):
+    plan, onames, odt = encode_project(exprs, names, dtypes)
+    out, err = ctypes.c_void_p(), ctypes.c_void_p()
+    n = len(dtypes)
+    rc = _lib.lib().b200_jit_describe(ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * n)(*dtypes),
+                                      (ctypes.c_uint8 * n)(*nullable), ctypes.c_int32(n), ctypes.byref(out), ctypes.byref(err))
+    _lib.check(rc, err)
+    text = ctypes.string_at(out.value).decode()
+    _lib.lib().b200_free_string(out)
+    head, src = text.split("\n---\n", 1)
+    fields = dict(line.split("=", 1) for line in head.split("\n"))
+    ptrs = [tuple(map(int, s.split(":"))) for s in fields["ptrs"].split(",") if s]
+    ints = [int(s) for s in fields["ints"].split(",") if s]
+    outs = [tuple(map(int, s.split(":"))) for s in fields["outs"].split(",") if s]
+    return src, ptrs, ints, outs, onames, odt
+
+
+def _compile(src: str) -> ctypes.CDLL:
+    body = "\n".join(l for l in src.split("\n") if "__global__" not in l)
+    full = _SHIM + _prelude_for_host() + body + _DRIVER
+    tag = hashlib.sha1(full.encode()).hexdigest()[:16]
+    d = os.path.join(tempfile.gettempdir(), "daft_b200_jit_emu")
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, f"emu_{tag}.so")
+    if not os.path.exists(so):
+        cpp = os.path.join(d, f"emu_{tag}.cpp")
+        with open(cpp, "w") as f:
+            f.write(full)
+        # -ffp-contract=off: the device code is compiled with --fmad=false
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", so, cpp])
+    return ctypes.CDLL(so)
+
+
+def _pack_bits(mask: np.ndarray, nwords32: int) -> np.ndarray:
+    out = np.zeros(nwords32 * 4, dtype=np.uint8)
+    packed = np.packbits(mask.astype(np.uint8), bitorder="little")
+    out[:len(packed)] = packed
+    return out
+
+
+def emulate_project(tbl: pa.Table, exprs) -> pa.Table:
+    """eval_expression_list through the generated `Prog::row`, on the host."""
+    tbl = tbl.combine_chunks()
+    n = tbl.num_rows
+    names = tbl.column_names
+    cols = [tbl.column(i).chunk(0) if tbl.column(i).num_chunks else pa.array([], type=tbl.column(i).type) for i in range(len(names))]
+    dtypes = [dt.from_arrow(c.type) for c in cols]
+    nullable = [1 if c.null_count > 0 else 0 for c in cols]
+    src, ptrs, ints, outs, onames, odt = describe_project(exprs, names, dtypes, nullable)
+    lib = _compile(src)
+    nw = max((n + 31) // 32, 1)
+    keep, slots, out_bufs = [], [], {}
+    for kind, idx in ptrs:
+        if kind in (P_COL_DATA, P_COL_VALID, P_COL_OFFSETS):
+            c, code = cols[idx], dtypes[idx]
+            if kind == P_COL_VALID:
+                buf = _pack_bits(np.asarray(c.is_valid()), nw + 1)
+            elif kind == P_COL_OFFSETS:
+                buf = np.frombuffer(c.buffers()[1], dtype=np.int64, count=n + 1 + c.offset)[c.offset:].copy() if n else np.zeros(1, np.int64)
+            elif dt.is_string(code):
+                raw = c.buffers()[2]
+                buf = np.concatenate([np.frombuffer(raw, dtype=np.uint8) if raw is not None else np.zeros(0, np.uint8), np.zeros(16, np.uint8)])
+            elif code == dt.BOOL:
+                buf = _pack_bits(np.asarray(c.fill_null(False)), nw + 1)
+            elif code == dt.NULL:
+                buf = np.zeros(8, np.uint8)
+            else:
+                phys = c.cast(pa.int32()) if code == dt.DATE32 else c.cast(pa.int64()) if code == dt.TIMESTAMP else c
+                buf = np.ascontiguousarray(np.concatenate([np.asarray(phys.fill_null(0)).astype(_NP[code]), np.zeros(4, _NP[code])]))
+        elif kind == P_OUT_VALID:
+            buf = np.zeros(nw, dtype=np.uint32)
+            out_bufs[("valid", idx)] = buf
+        elif kind == P_OUT_DATA:
+            code = outs[idx][0]
+            if code in (dt.BOOL, dt.NULL):
+                buf = np.zeros(nw, dtype=np.uint32)
+            elif dt.is_string(code):
+                raise NotImplementedError("host emulation covers fixed-width and boolean outputs")
+            else:
+                buf = np.zeros(nw * 32, dtype=_NP[code])
+            out_bufs[("data", idx)] = buf
+        else:
+            raise NotImplementedError(f"host emulation: parameter kind {kind}")
+        keep.append(buf)
+        slots.append(buf.ctypes.data)
+    ivals = [n if k == I_N else 0 for k in ints]
+    lib.emu_run((ctypes.c_void_p * max(len(slots), 1))(*slots), ctypes.c_int(len(slots)),
+                (ctypes.c_longlong * max(len(ivals), 1))(*ivals), ctypes.c_int(len(ivals)), ctypes.c_longlong(n))
+    arrays = []
+    for i, (code, nullable_out) in enumerate(outs):
+        valid = np.ones(n, dtype=bool)
+        if ("valid", i) in out_bufs:
+            valid = np.unpackbits(out_bufs[("valid", i)].view(np.uint8), bitorder="little")[:n].astype(bool)
+        mask = None if valid.all() else ~valid
+        if code == dt.NULL:
+            arrays.append(pa.nulls(n))
+        elif code == dt.BOOL:
+            vals = np.unpackbits(out_bufs[("data", i)].view(np.uint8), bitorder="little")[:n].astype(bool)
+            arrays.append(pa.array(vals, type=pa.bool_(), mask=mask))
+        else:
+            vals = out_bufs[("data", i)][:n]
+            arr = pa.array(vals, mask=mask)
+            arrays.append(arr.cast(dt.to_arrow(code)) if arr.type != dt.to_arrow(code) else arr)
+    return pa.table(arrays, names=list(onames))
