@@ -26,7 +26,7 @@ from daft_b200 import _lib
 from daft_b200 import datatypes as dt
 from daft_b200.expressions import encode_project
 
-P_COL_DATA, P_COL_VALID, P_COL_OFFSETS, P_OUT_DATA, P_OUT_VALID = 0, 1, 2, 3, 4
+P_COL_DATA, P_COL_VALID, P_COL_OFFSETS, P_OUT_DATA, P_OUT_VALID, P_OUT_LEN, P_OUT_OFFSETS = 0, 1, 2, 3, 4, 5, 6
 I_N = 0
 
 _NP = {dt.I8: np.int8, dt.I16: np.int16, dt.I32: np.int32, dt.I64: np.int64, dt.U8: np.uint8, dt.U16: np.uint16, dt.U32: np.uint32,
@@ -65,22 +65,20 @@ template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
 """
 
 _DRIVER = r"""
-extern "C" void emu_run(void **ptrs, int nptr, long long *ints, int nint, long long n) {
+extern "C" void emu_run(void **ptrs, int nptr, long long *ints, int nint, long long n, int pass) {
     Prog::P p;
     for (int i = 0; i < nptr; i++) p.ptr[i] = ptrs[i];
     for (int i = 0; i < nint; i++) p.ival[i] = ints[i];
     const long long n_round = (n + 31) & ~31LL;
     for (long long base = 0; base < n_round; base += 32) {
-        for (int pass = 0; pass < 1; pass++) {
-            memset(g_ballots, 0, sizeof(g_ballots));
-            for (g_phase = 0; g_phase < 2; g_phase++)
-                for (g_lane = 0; g_lane < 32; g_lane++) {
-                    g_site = 0;
-                    threadIdx.x = (unsigned)g_lane;
-                    const long long i = base + g_lane;
-                    Prog::row(p, i, i, i < n, pass);
-                }
-        }
+        memset(g_ballots, 0, sizeof(g_ballots));
+        for (g_phase = 0; g_phase < 2; g_phase++)
+            for (g_lane = 0; g_lane < 32; g_lane++) {
+                g_site = 0;
+                threadIdx.x = (unsigned)g_lane;
+                const long long i = base + g_lane;
+                Prog::row(p, i, i, i < n, pass);
+            }
     }
 }
 """
@@ -173,17 +171,37 @@ def emulate_project(tbl: pa.Table, exprs) -> pa.Table:
             if code in (dt.BOOL, dt.NULL):
                 buf = np.zeros(nw, dtype=np.uint32)
             elif dt.is_string(code):
-                raise NotImplementedError("host emulation covers fixed-width and boolean outputs")
+                buf = None   # allocated after pass 0, once the lengths are known
             else:
                 buf = np.zeros(nw * 32, dtype=_NP[code])
             out_bufs[("data", idx)] = buf
+        elif kind == P_OUT_LEN:
+            buf = np.zeros(nw * 32, dtype=np.int64)
+            out_bufs[("len", idx)] = buf
+        elif kind == P_OUT_OFFSETS:
+            buf = np.zeros(nw * 32 + 1, dtype=np.int64)
+            out_bufs[("offsets", idx)] = buf
         else:
             raise NotImplementedError(f"host emulation: parameter kind {kind}")
         keep.append(buf)
-        slots.append(buf.ctypes.data)
+        slots.append(buf.ctypes.data if buf is not None else 0)
     ivals = [n if k == I_N else 0 for k in ints]
-    lib.emu_run((ctypes.c_void_p * max(len(slots), 1))(*slots), ctypes.c_int(len(slots)),
-                (ctypes.c_longlong * max(len(ivals), 1))(*ivals), ctypes.c_int(len(ivals)), ctypes.c_longlong(n))
+
+    def run(pass_):
+        lib.emu_run((ctypes.c_void_p * max(len(slots), 1))(*slots), ctypes.c_int(len(slots)),
+                    (ctypes.c_longlong * max(len(ivals), 1))(*ivals), ctypes.c_int(len(ivals)), ctypes.c_longlong(n), ctypes.c_int(pass_))
+    run(0)
+    string_outs = [i for i, (code, _) in enumerate(outs) if dt.is_string(code)]
+    if string_outs:
+        # the two-pass protocol of op_project: pass 0 wrote one length per row, the host scans them into offsets and
+        # allocates the bytes, pass 1 copies
+        for i in string_outs:
+            lens = out_bufs[("len", i)][:n]
+            out_bufs[("offsets", i)][1:n + 1] = np.cumsum(lens)
+            data = np.zeros(int(lens.sum()) + 16, dtype=np.uint8)
+            out_bufs[("data", i)] = data
+            slots[ptrs.index((P_OUT_DATA, i))] = data.ctypes.data
+        run(1)
     arrays = []
     for i, (code, nullable_out) in enumerate(outs):
         valid = np.ones(n, dtype=bool)
@@ -195,6 +213,12 @@ def emulate_project(tbl: pa.Table, exprs) -> pa.Table:
         elif code == dt.BOOL:
             vals = np.unpackbits(out_bufs[("data", i)].view(np.uint8), bitorder="little")[:n].astype(bool)
             arrays.append(pa.array(vals, type=pa.bool_(), mask=mask))
+        elif dt.is_string(code):
+            off = out_bufs[("offsets", i)][:n + 1]
+            raw = out_bufs[("data", i)].tobytes()
+            items = [raw[off[j]:off[j + 1]] if valid[j] else None for j in range(n)]
+            arrays.append(pa.array([x.decode() if x is not None else None for x in items], type=pa.large_utf8()) if code == dt.LARGE_UTF8
+                          else pa.array(items, type=pa.large_binary()))
         else:
             vals = out_bufs[("data", i)][:n]
             arr = pa.array(vals, mask=mask)

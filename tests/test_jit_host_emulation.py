@@ -56,14 +56,12 @@ class _EmulatedModule:
 
 
 EMU = _EmulatedModule()
-_STRING_OUTPUTS = {"e25", "e26"}   # string-typed outputs (two-pass length / copy protocol) are not emulated
-
 
 @pytest.mark.parametrize("n,nulls", [(0, 0.1), (1, 0.0), (100, 0.3), (4097, 0.1), (4097, 0.0)])
 def test_generated_projection_code_matches_oracle(n, nulls):
     rng = np.random.default_rng(n + 7)
     tbl = random_table(rng, n, nulls)
-    exprs = [e for e in parity.exprs_under_test(EMU.col, EMU.lit) if e.name() not in _STRING_OUTPUTS]
+    exprs = parity.exprs_under_test(EMU.col, EMU.lit)   # string outputs included (two-pass length / copy protocol)
     got = jit_emu.emulate_project(tbl, exprs)
     want = E.eval_expression_list(tbl, exprs)
     assert_tables_equal(got, want)
