@@ -235,6 +235,8 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
                 if not dt.is_integer(st):
                     raise TypeError(f"cannot apply {op} to {dt.NAMES[l.dtype]} and {dt.NAMES[r.dtype]}")
                 return Bound(T_BINARY, st, BINOPS[op], [_cast(l, st), _cast(r, st)])
+            if not all(x.dtype in (dt.BOOL, dt.NULL) for x in (l, r)):
+                raise TypeError(f"cannot apply {op} to {dt.NAMES[l.dtype]} and {dt.NAMES[r.dtype]}: expected Boolean or integer operands")
             return Bound(T_BINARY, dt.BOOL, BINOPS[op], [_cast(l, dt.BOOL) if l.dtype == dt.NULL else l,
                                                           _cast(r, dt.BOOL) if r.dtype == dt.NULL else r])
         if op in ("shl", "shr"):
@@ -318,6 +320,14 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         kids = [bind(x, names, dtypes) for x in e.args]
         out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,
                "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8, "sqrt": dt.F64}[e.op]
+        if e.op in ("utf8_length", "startswith", "endswith", "contains", "left") and not dt.is_string(kids[0].dtype):
+            raise ValueError(f"Expects input to {e.op} to be utf8, but received {dt.NAMES[kids[0].dtype]}")
+        if e.op in ("startswith", "endswith", "contains") and not dt.is_string(kids[1].dtype):
+            raise ValueError(f"Expects pattern of {e.op} to be utf8, but received {dt.NAMES[kids[1].dtype]}")
+        if e.op in ("year", "month", "day", "day_of_week") and kids[0].dtype not in (dt.DATE32,):
+            raise ValueError(f"Expected input to {e.op} to be a date, got {dt.NAMES[kids[0].dtype]}")
+        if e.op == "sqrt" and not dt.is_numeric(kids[0].dtype):
+            raise ValueError(f"Expected input to sqrt to be numeric, got {dt.NAMES[kids[0].dtype]}")
         if e.op == "left":
             kids[1] = _cast(kids[1], dt.I64)
         if e.op == "sqrt":

@@ -142,7 +142,8 @@ def _eval(b: Bound, cols, n: int):
             (a, ka), = kids
             op = _UN[b.op]
             if op == "not": return ~a.astype(bool), ka
-            if op == "neg": return (0 - a).astype(a.dtype), ka
+            if op == "neg":  # Rust `-v` (array/ops/sign.rs:14-16): IEEE negation for floats (-(+0.0) = -0.0), wrapping for integers
+                return (np.negative(a) if a.dtype.kind == "f" else (0 - a).astype(a.dtype)), ka
             if op == "abs": return np.abs(a), ka
             if op == "is_null": return ~ka, np.ones(n, dtype=bool)
             if op == "not_null": return ka.copy(), np.ones(n, dtype=bool)

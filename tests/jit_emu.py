@@ -122,8 +122,11 @@ def _compile(src: str) -> ctypes.CDLL:
         cpp = os.path.join(d, f"emu_{tag}.cpp")
         with open(cpp, "w") as f:
             f.write(full)
-        # -ffp-contract=off: the device code is compiled with --fmad=false
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", so, cpp])
+        # -ffp-contract=off: the device code is compiled with --fmad=false.  -fno-builtin-fmod*: gcc otherwise reasons that
+        # fabs(fmod(x, y)) == fmod(x, y) for non-negative x and drops the fabs, which is visible when libm returns the
+        # negative x86 default NaN for fmod(x, 0).
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w",
+                               "-o", so, cpp])
     return ctypes.CDLL(so)
 
 

@@ -87,3 +87,16 @@ def test_generated_casts_out_of_range_null():
 
 def test_generated_float_predicates_ceil_floor_sign_fill_nan():
     semantics.test_float_predicates_ceil_floor_sign_fill_nan(EMU)
+
+
+@pytest.mark.parametrize("seed", [300, 301])
+def test_random_expression_trees_match_oracle(seed):
+    """Two seeded batches of the expression fuzzer (scripts/fuzz_exprs.py: arithmetic, division, casts, comparisons, Kleene logic,
+    bitwise, if_else, fill_null, between, is_in, float predicates, string and date functions, depth <= 3): one projection of 40
+    random trees each through the generated code, against the oracle.  Longer runs: `python scripts/fuzz_exprs.py 60 40 1000`."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import fuzz_exprs
+    bad = fuzz_exprs.run_batch(seed, 40)
+    assert not bad, bad
