@@ -60,6 +60,22 @@ def int_range(c):
     return (-(1 << (bits - 1)), (1 << (bits - 1)) - 1) if int_like_signed(c) else (0, (1 << bits) - 1)
 
 
+def rem_supertype(a: int, b: int) -> int:
+    """Operand type of `%` (try_integer_widen_for_rem, src/daft-core/src/datatypes/infer_datatype.rs:662-745): Float64 if either side
+    is, else Float32 if either side is, else the integer of the larger width -- UNSIGNED as soon as one side is unsigned (a negative
+    value on the other side then becomes null in the cast, as every out-of-range cast does)."""
+    if is_numeric(a) and is_numeric(b):
+        if F64 in (a, b):
+            return F64
+        if F32 in (a, b):
+            return F32
+        w = max(width(a), width(b))
+        if is_signed(a) and is_signed(b):
+            return {1: I8, 2: I16, 4: I32, 8: I64}[w]
+        return {1: U8, 2: U16, 4: U32, 8: U64}[w]
+    return supertype(a, b)
+
+
 def supertype(a: int, b: int) -> int:
     """Common type both operands are cast to before a binary op (the reference decides this at plan
     time: src/daft-core/src/utils/supertype.rs try_get_supertype; restated for the numeric lattice)."""
@@ -92,6 +108,6 @@ def supertype(a: int, b: int) -> int:
         return F64
     if is_string(a) and is_string(b):
         return LARGE_BINARY if LARGE_BINARY in (a, b) else LARGE_UTF8
-    if {a, b} == {DATE32, TIMESTAMP}:
-        return TIMESTAMP
+    # Date vs Timestamp: the reference compares at Date after a temporal conversion of the timestamp (infer_datatype.rs:132-137); that
+    # conversion is not built, so mixing the two is refused instead of reinterpreting days as microseconds
     raise TypeError(f"no supertype for {NAMES[a]} and {NAMES[b]}")

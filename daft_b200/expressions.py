@@ -177,12 +177,17 @@ def _lit_dtype(v) -> int:
     if isinstance(v, bytes): return dt.LARGE_BINARY
     if isinstance(v, datetime.datetime): return dt.TIMESTAMP
     if isinstance(v, datetime.date): return dt.DATE32
-    raise TypeError(f"unsupported literal {v!r}")
+    raise DaftTypeError(f"unsupported literal {v!r}")
 
 
 # ------------------------------------------------------------------------------------------------
 # binding: names -> indices, dtype inference, supertype casts, encoding
 # ------------------------------------------------------------------------------------------------
+class DaftTypeError(TypeError, ValueError):
+    """Typing errors of the bound expression.  The reference raises DaftError::TypeError, which its Python layer surfaces as
+    ValueError (e.g. tests/series/test_comparisons.py:476-500), so both exception types match."""
+
+
 class Bound:
     """A typed, index-resolved node ready for encoding."""
     __slots__ = ("tag", "op", "dtype", "kids", "col", "value")
@@ -230,24 +235,24 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
             if dt.is_integer(l.dtype) or dt.is_integer(r.dtype):
                 # bitwise on integers: supertype, null if either side is null (src/daft-core/src/array/ops/bitwise.rs)
                 if not all(dt.is_integer(x.dtype) or x.dtype == dt.NULL for x in (l, r)):
-                    raise TypeError(f"cannot apply {op} to {dt.NAMES[l.dtype]} and {dt.NAMES[r.dtype]}")
+                    raise DaftTypeError(f"Cannot perform logical / bitwise {op} on types: {dt.NAMES[l.dtype]}, {dt.NAMES[r.dtype]}")
                 st = dt.supertype(l.dtype, r.dtype)
                 if not dt.is_integer(st):
-                    raise TypeError(f"cannot apply {op} to {dt.NAMES[l.dtype]} and {dt.NAMES[r.dtype]}")
+                    raise DaftTypeError(f"cannot apply {op} to {dt.NAMES[l.dtype]} and {dt.NAMES[r.dtype]}")
                 return Bound(T_BINARY, st, BINOPS[op], [_cast(l, st), _cast(r, st)])
             if not all(x.dtype in (dt.BOOL, dt.NULL) for x in (l, r)):
-                raise TypeError(f"cannot apply {op} to {dt.NAMES[l.dtype]} and {dt.NAMES[r.dtype]}: expected Boolean or integer operands")
+                raise DaftTypeError(f"Cannot perform logical / bitwise {op} on types: {dt.NAMES[l.dtype]}, {dt.NAMES[r.dtype]}")
             return Bound(T_BINARY, dt.BOOL, BINOPS[op], [_cast(l, dt.BOOL) if l.dtype == dt.NULL else l,
                                                           _cast(r, dt.BOOL) if r.dtype == dt.NULL else r])
         if op in ("shl", "shr"):
             return Bound(T_BINARY, l.dtype, BINOPS[op], [l, _cast(r, l.dtype)])
-        st = dt.supertype(l.dtype, r.dtype)
+        st = dt.rem_supertype(l.dtype, r.dtype) if op == "mod" else dt.supertype(l.dtype, r.dtype)
         l, r = _cast(l, st), _cast(r, st)
         if op in _CMP:
             return Bound(T_BINARY, dt.BOOL, BINOPS[op], [l, r])
         if op in _ARITH:
             if not dt.is_numeric(st):
-                raise TypeError(f"cannot apply {op} to {dt.NAMES[st]}")
+                raise DaftTypeError(f"cannot apply {op} to {dt.NAMES[st]}")
             if op == "floor_div" and st == dt.F32:
                 # float `//` is (l / r).floor() computed as a Float64 true division, then cast to the supertype
                 # (src/daft-core/src/series/ops/arithmetic.rs:466-469)
@@ -299,7 +304,7 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         if x.dtype == dt.NULL:
             return x
         if not (dt.is_float(x.dtype) and dt.is_float(f.dtype)):
-            raise TypeError(f"Expects input for fill_nan to be float, but received {dt.NAMES[x.dtype]} and {dt.NAMES[f.dtype]}")
+            raise DaftTypeError(f"Expects input for fill_nan to be float, but received {dt.NAMES[x.dtype]} and {dt.NAMES[f.dtype]}")
         st = dt.supertype(x.dtype, f.dtype)
         x, f = _cast(x, st), _cast(f, st)
         return Bound(T_IF_ELSE, st, kids=[Bound(T_FUNCTION, dt.BOOL, FUNCS["not_nan"], [x]), x, f])

@@ -709,3 +709,60 @@ def test_literal_broadcast_from_reference_tests(data, typ):
     t = pa.table({"x": [1, 2, 3]})
     out = E.eval_expression_list(t, [col("x"), lit(data)])
     assert out.to_pydict() == {"x": [1, 2, 3], "literal": [data] * 3} and out.schema.field("literal").type == typ
+
+
+def test_comparison_literals_from_reference_series_tests():
+    """tests/series/test_comparisons.py:150-181 (every int / float dtype pair), :240-274 (boolean arrays incl. Kleene and / or / xor),
+    :476-500 (logical ops on a boolean and an integer are an error), :502-546 (dates)."""
+    import datetime
+    import itertools
+
+    def six(t):
+        return [E.eval_expression_list(t, [e.alias("r")]).column("r").to_pylist() for e in
+                (col("l") < col("r"), col("l") <= col("r"), col("l") == col("r"), col("l") != col("r"), col("l") >= col("r"), col("l") > col("r"))]
+    want = [[False, True, False, None, None, None], [True, True, False, None, None, None], [True, False, False, None, None, None],
+            [False, True, True, None, None, None], [True, False, True, None, None, None], [False, False, True, None, None, None]]
+    for lt, rt in itertools.product(_NUMERIC_TYPES, repeat=2):
+        t = pa.table({"l": pa.array([1, 2, 3, None, 5, None], type=lt), "r": pa.array([1, 3, 1, 5, None, None], type=rt)})
+        assert six(t) == want, (lt, rt)
+    D = datetime.date
+    t = pa.table({"l": pa.array([D(2023, 1, 1), D(2023, 1, 2), D(2023, 1, 3), None, D(2023, 1, 5), None], type=pa.date32()),
+                  "r": pa.array([D(2023, 1, 1), D(2023, 1, 3), D(2023, 1, 1), D(2023, 1, 5), None, None], type=pa.date32())})
+    assert six(t) == want
+    t = pa.table({"l": pa.array([True, False, True, False, True, False, None, None, None]), "r": pa.array([True, True, False, False, None, None, True, False, None])})
+    assert six(t) == [[False, True, False, False] + [None] * 5, [True, True, False, True] + [None] * 5, [True, False, False, True] + [None] * 5,
+                      [False, True, True, False] + [None] * 5, [True, False, True, True] + [None] * 5, [False, False, True, False] + [None] * 5]
+    ops = E.eval_expression_list(t, [(col("l") & col("r")).alias("and"), (col("l") | col("r")).alias("or"), (col("l") ^ col("r")).alias("xor")]).to_pydict()
+    assert ops["and"] == [True, False, False, False, None, False, None, False, None]
+    assert ops["or"] == [True, True, True, False, True, None, True, None, None]
+    assert ops["xor"] == [False, True, True, False, None, None, None, None, None]
+    t = pa.table({"l": pa.array([False, True, None, None]), "r": pa.array([1, 2, 3, 4], type=pa.int64())})
+    for bad in (col("l") & col("r"), col("l") | col("r"), col("l") ^ col("r"), col("r") & col("l"), col("r") | col("l"), col("r") ^ col("l")):
+        with pytest.raises(ValueError, match="logic"):
+            E.eval_expression_list(t, [bad])
+
+
+def test_arithmetic_matrix_from_reference_series_tests():
+    """tests/series/test_arithmetic.py:30-62 (every numeric dtype pair: + - * / // %) and :332-345 (`%` of any two integer types is an
+    integer: try_integer_widen_for_rem, infer_datatype.rs:662-745, not the numeric supertype)."""
+    import itertools
+    for lt, rt in itertools.product(_NUMERIC_TYPES, repeat=2):
+        t = pa.table({"left": pa.array([1, 2, 3, None, 5, None], type=lt), "right": pa.array([1, 4, 1, 5, None, None], type=rt)})
+        L, R = col("left"), col("right")
+        out = E.eval_expression_list(t, [(L + R).alias("add"), (L - R).alias("sub"), (L * R).alias("mul"), (L / R).alias("div"),
+                                         (L // R).alias("fdiv"), (L % R).alias("mod")])
+        assert out.column("add").to_pylist() == [2, 6, 4, None, None, None], (lt, rt)
+        if pa.types.is_signed_integer(lt) or pa.types.is_signed_integer(rt):
+            assert out.column("sub").to_pylist() == [0, -2, 2, None, None, None], (lt, rt)
+        assert out.column("mul").to_pylist() == [1, 8, 3, None, None, None]
+        assert out.column("div").to_pylist() == [1.0, 0.5, 3.0, None, None, None] and out.schema.field("div").type == pa.float64()
+        assert out.column("fdiv").to_pylist() == [1, 0, 3, None, None, None]
+        assert out.column("mod").to_pylist() == [0, 2, 0, None, None, None]
+        if pa.types.is_integer(lt) and pa.types.is_integer(rt):
+            assert pa.types.is_integer(out.schema.field("mod").type), (lt, rt)
+    # the widening itself: unsigned wins, and a negative operand of an unsigned `%` is null
+    t = pa.table({"a": pa.array([-7, 7, None], type=pa.int8()), "b": pa.array([3, 3, 3], type=pa.uint8()), "c": pa.array([2, 2, 2], type=pa.uint64()),
+                  "f": pa.array([2.0, 2.0, 2.0], type=pa.float32()), "g": pa.array([9, 9, 9], type=pa.int64())})
+    out = E.eval_expression_list(t, [(col("a") % col("b")).alias("ab"), (col("g") % col("c")).alias("gc"), (col("g") % col("f")).alias("gf"), (col("a") % col("g")).alias("ag")])
+    assert [out.schema.field(n).type for n in ("ab", "gc", "gf", "ag")] == [pa.uint8(), pa.uint64(), pa.float32(), pa.int64()]
+    assert out.to_pydict() == {"ab": [None, 1, None], "gc": [1, 1, 1], "gf": [1.0, 1.0, 1.0], "ag": [-7, 7, None]}
