@@ -240,7 +240,12 @@ static int parse_node(Reader &r, Ast &a) {
                 case F_UTF8_LENGTH: nd.dtype = B200_U64; break;
                 case F_STARTSWITH: case F_ENDSWITH: case F_CONTAINS: nd.dtype = B200_BOOL; break;
                 case F_LEFT: nd.dtype = B200_LARGE_UTF8; break;
-                case F_SQRT: nd.dtype = B200_F64; break;  // operand cast to Float64 by the host (IEEE correctly rounded sqrt)
+                case F_SQRT: {  // operand cast by the host to its floating representation (Float32 for 8/16-bit integers and Float32,
+                                // Float64 otherwise: DataType::to_floating_representation, src/daft-schema/src/dtype.rs:756-772)
+                    if (nd.kids.size() != 1 || !is_float(a.nodes[nd.kids[0]].dtype)) fail("plan: sqrt needs one float operand");
+                    nd.dtype = a.nodes[nd.kids[0]].dtype;
+                    break;
+                }
                 case F_IS_NAN: case F_NOT_NAN: case F_IS_INF: {  // src/daft-core/src/array/ops/float.rs:13-110: nulls stay null
                     if (nd.kids.size() != 1 || !is_float(a.nodes[nd.kids[0]].dtype)) fail("plan: is_nan / not_nan / is_inf need one float operand");
                     nd.dtype = B200_BOOL;
@@ -622,7 +627,7 @@ struct ExprGen {
                     case F_ENDSWITH: os << "    const bool " << V << " = str_endswith(" << a << ", " << v(kid[1]) << ");\n"; break;
                     case F_CONTAINS: os << "    const bool " << V << " = str_contains(" << a << ", " << v(kid[1]) << ");\n"; break;
                     case F_LEFT: os << "    const Str " << V << " = str_left(" << a << ", (int64_t)" << v(kid[1]) << ");\n"; break;
-                    case F_SQRT: os << "    const double " << V << " = sqrt((double)" << a << ");\n"; break;
+                    case F_SQRT: os << "    const " << T << " " << V << " = " << (n.dtype == B200_F32 ? "sqrtf(" : "sqrt(") << a << ");\n"; break;  // IEEE correctly rounded
                     case F_IS_NAN: os << "    const bool " << V << " = (" << a << " != " << a << ");\n"; break;
                     case F_NOT_NAN: os << "    const bool " << V << " = (" << a << " == " << a << ");\n"; break;
                     case F_IS_INF: os << "    const bool " << V << " = (" << a << " - " << a << " != 0) && (" << a << " == " << a << ");\n"; break;

@@ -336,7 +336,9 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         if e.op == "left":
             kids[1] = _cast(kids[1], dt.I64)
         if e.op == "sqrt":
-            kids[0] = _cast(kids[0], dt.F64)
+            # computed in the operand's floating representation (src/daft-schema/src/dtype.rs:756-772, numeric/sqrt.rs:27-35)
+            out = dt.F32 if kids[0].dtype in (dt.I8, dt.I16, dt.U8, dt.U16, dt.F32) else dt.F64
+            kids[0] = _cast(kids[0], out)
         return Bound(T_FUNCTION, out, FUNCS[e.op], kids)
     if k == "agg":
         raise ValueError("aggregation expressions are only valid inside agg()")

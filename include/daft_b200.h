@@ -294,7 +294,7 @@ int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begi
  *     (the reference panics); MIN / -1 wraps.
  *   unary ops: 0 not 1 negate 2 is_null 3 not_null 4 abs
  *   functions: 0 year 1 month 2 day 3 utf8_length 4 utf8_startswith 5 utf8_endswith 6 utf8_contains
- *              7 utf8_left 8 day_of_week 9 sqrt (Float64 operand; IEEE correctly rounded)
+ *              7 utf8_left 8 day_of_week 9 sqrt (Float32 / Float64 operand, same type; IEEE correctly rounded)
  *              10 is_nan 11 not_nan 12 is_inf (float operand -> Boolean; nulls stay null, src/daft-core/src/array/ops/float.rs)
  *              13 ceil 14 floor (float operand, same type) 15 sign (numeric operand, same type: signum; 0 / 1 for unsigned)
  *   Operands of a binary op must already have identical dtypes (the host inserts the supertype

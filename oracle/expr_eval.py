@@ -208,7 +208,7 @@ def _eval(b: Bound, cols, n: int):
                 return {"year": y.astype(np.int32), "month": m.astype(np.uint32), "day": d.astype(np.uint32)}[fn], allk
             if fn == "sqrt":
                 with np.errstate(all="ignore"):
-                    return np.sqrt(a.astype(np.float64)), allk
+                    return np.sqrt(a), allk   # `a` is already Float32 / Float64 (the bound plan casts to the floating representation)
             if fn == "is_nan": return np.isnan(a), allk           # array/ops/float.rs:13-110
             if fn == "not_nan": return ~np.isnan(a), allk
             if fn == "is_inf": return np.isinf(a), allk
