@@ -766,3 +766,54 @@ def test_arithmetic_matrix_from_reference_series_tests():
     out = E.eval_expression_list(t, [(col("a") % col("b")).alias("ab"), (col("g") % col("c")).alias("gc"), (col("g") % col("f")).alias("gf"), (col("a") % col("g")).alias("ag")])
     assert [out.schema.field(n).type for n in ("ab", "gc", "gf", "ag")] == [pa.uint8(), pa.uint64(), pa.float32(), pa.int64()]
     assert out.to_pydict() == {"ab": [None, 1, None], "gc": [1, 1, 1], "gf": [1.0, 1.0, 1.0], "ag": [-7, 7, None]}
+
+
+def _rows(t: pa.Table):
+    d = t.to_pydict()
+    return sorted((tuple((k, d[k][i]) for k in d) for i in range(t.num_rows)), key=repr)
+
+
+@pytest.mark.parametrize("null_safe", [True, False])
+def test_multicolumn_join_literals_from_reference_tests(null_safe):
+    """tests/recordbatch/test_joins.py:168-293 (multi-column keys: empty results, no cross product, cross product, all-null keys) and
+    :307-358 (boolean / null key columns with a `right.y` payload name, anti joins)."""
+    S = pa.large_utf8()
+    ne = [null_safe] * 2 if null_safe else None
+    for left in ({"a": [], "b": []}, {"a": ["apple", "banana"], "b": [3, 4]}):
+        for right in ({"x": [], "y": []}, {"x": ["banana", "apple"], "y": [3, 4]}):
+            lt = pa.table({"a": pa.array(left["a"], type=S), "b": pa.array(left["b"], type=pa.int32())})
+            rt = pa.table({"x": pa.array(right["x"], type=S), "y": pa.array(right["y"], type=pa.int32())})
+            assert O.hash_join(lt, rt, ["a", "b"], ["x", "y"], "inner", null_equals_null=ne).to_pydict() == {"a": [], "b": [], "x": [], "y": []}
+    lt = pa.table({"a": pa.array(["apple", "apple", "banana", "banana", "carrot", None], type=S), "b": [1, 2, 2, 2, 3, 3], "c": [1, 2, 3, 4, 5, 5]})
+    rt = pa.table({"x": pa.array(["banana", "carrot", "apple", "banana", "apple", "durian", None], type=S), "y": [1, 3, 2, 1, 3, 6, 3], "z": [1, 2, 3, 4, 5, 6, 6]})
+    exp = [{"a": "apple", "b": 2, "c": 2, "x": "apple", "y": 2, "z": 3}, {"a": "carrot", "b": 3, "c": 5, "x": "carrot", "y": 3, "z": 2}]
+    if null_safe:
+        exp.append({"a": None, "b": 3, "c": 5, "x": None, "y": 3, "z": 6})
+    assert _rows(O.hash_join(lt, rt, ["a", "b"], ["x", "y"], "inner", null_equals_null=ne)) == _rows(pa.Table.from_pylist(exp, schema=pa.schema(
+        [("a", S), ("b", pa.int64()), ("c", pa.int64()), ("x", S), ("y", pa.int64()), ("z", pa.int64())])))
+    lt = pa.table({"a": pa.array(["apple", "apple", "banana", "banana", "banana", None], type=S), "b": [1, 0, 1, 1, 1, 1], "c": [1, 2, 3, 4, 5, 5]})
+    rt = pa.table({"x": pa.array(["apple", "apple", "banana", "banana", "banana", None], type=S), "y": [1, 0, 1, 1, 0, 1], "z": [1, 2, 3, 4, 5, 5]})
+    got = O.hash_join(lt, rt, ["a", "b"], ["x", "y"], "inner", null_equals_null=ne)
+    exp = [("apple", 1, 1, 1), ("apple", 0, 2, 2)] + [("banana", 1, c, z) for c in (3, 4, 5) for z in (3, 4)] + ([(None, 1, 5, 5)] if null_safe else [])
+    assert sorted(zip(*[got.column(n).to_pylist() for n in ("a", "b", "c", "z")]), key=repr) == sorted(exp, key=repr)
+    lt = pa.table({"a": pa.array([None, None], type=pa.int64()), "b": pa.array([None, None], type=S), "c": [1, 2]})
+    rt = pa.table({"x": pa.array([None, None], type=pa.int64()), "y": pa.array([None, None], type=S), "z": [1, 2]})
+    got = O.hash_join(lt, rt, ["a", "b"], ["x", "y"], "inner", null_equals_null=ne)
+    assert sorted(zip(got.column("c").to_pylist(), got.column("z").to_pylist())) == ([(1, 1), (1, 2), (2, 1), (2, 2)] if null_safe else [])
+    # boolean key, same key name on both sides, payload called "right.y"
+    lt = pa.table({"x": pa.array([False, True, None]), "y": [0, 1, 2]})
+    rt = pa.table({"x": pa.array([None, True, False, None]), "right.y": [0, 1, 2, 3]})
+    got = O.hash_join(lt, rt, ["x"], ["x"], "inner", null_equals_null=[True] if null_safe else None)
+    assert got.column_names == ["x", "y", "right.y"]
+    got = O.sort(got, ["x", "right.y"], [False, False], [False, False])
+    assert got.column("y").to_pylist() == ([0, 1, 2, 2] if null_safe else [0, 1])
+    assert got.column("right.y").to_pylist() == ([2, 1, 0, 3] if null_safe else [2, 1])
+    lt = pa.table({"x": pa.array([None, None, None], type=pa.int64()), "y": [0, 1, 2]})
+    rt = pa.table({"x": pa.array([None, None, None, None], type=pa.int64()), "right.y": [0, 1, 2, 3]})
+    got = O.hash_join(lt, rt, ["x"], ["x"], "inner")
+    assert got.column_names == ["x", "y", "right.y"] and got.num_rows == 0
+    # anti joins keep the left schema, whatever the right key is called
+    lt = pa.table({"x": [1, 2, 3, 4], "y": [3, 4, 5, 6]})
+    for rname in ("x", "z"):
+        got = O.hash_join(lt, pa.table({rname: [2, 3, 5]}), ["x"], [rname], "anti")
+        assert got.to_pydict() == {"x": [1, 4], "y": [3, 6]}
