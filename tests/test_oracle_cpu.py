@@ -817,3 +817,31 @@ def test_multicolumn_join_literals_from_reference_tests(null_safe):
     for rname in ("x", "z"):
         got = O.hash_join(lt, pa.table({rname: [2, 3, 5]}), ["x"], [rname], "anti")
         assert got.to_pydict() == {"x": [1, 4], "y": [3, 6]}
+
+
+def test_single_column_boolean_and_string_sort_literals_from_reference_tests():
+    """tests/recordbatch/test_sorting.py:49-125 (single key, every numeric / string dtype, ascending puts nulls last, descending is the exact
+    reverse), :280-350 (boolean first key), :443-462 (two string keys), :465-468 (sorting by a literal keeps the order)."""
+    S = pa.large_utf8()
+    for typ in _NUMERIC_TYPES + [S]:
+        vals = [None, 4, 2, 1, 5]
+        a = pa.array([None if v is None else str(v) for v in vals], type=S) if typ == S else pa.array(vals, type=typ)
+        assert O.argsort([a]).tolist() == [3, 2, 1, 4, 0], typ
+        assert O.argsort([a], [True]).tolist() == [0, 4, 1, 2, 3], typ
+    cases = [([None, True, False, True, False], [0, 1, 2, 3, None], False, False, [2, 4, 1, 3, 0]),
+             ([None, True, False, True, False], [0, 1, 2, 3, None], True, False, [0, 1, 3, 2, 4]),
+             ([True, True, True, True, True], [None, 3, 1, 2, 0], False, False, [4, 2, 3, 1, 0]),
+             ([True, True, True, True, True], [None, 3, 1, 2, 0], True, False, [4, 2, 3, 1, 0]),
+             ([None, None, None, None, None], [None, 3, 1, 2, 0], False, False, [4, 2, 3, 1, 0]),
+             ([None, None, None, None, None], [None, 3, 1, 2, 0], True, False, [4, 2, 3, 1, 0])]
+    for a, b, ad, bd, expected in cases:
+        for typ in _NUMERIC_TYPES + [S]:
+            bb = pa.array([None if v is None else str(v) for v in b], type=S) if typ == S else pa.array(b, type=typ)
+            keys = [pa.array(a, type=pa.bool_()), bb]
+            assert O.argsort(keys, [ad, bd]).tolist() == expected, (a, b, ad, typ)
+            assert O.argsort(keys, [not ad, not bd]).tolist() == expected[::-1], (a, b, ad, typ)
+    t = pa.table({"firstname": pa.array(["bob", "alice", "eve", None, None, "bob", "alice"], type=S), "lastname": pa.array(["a", "a", "a", "bond", None, None, "a"], type=S)})
+    assert O.sort(t, ["firstname", "lastname"]).to_pydict() == {"firstname": ["alice", "alice", "bob", "bob", "eve", None, None],
+                                                                  "lastname": ["a", "a", "a", None, "a", "bond", None]}
+    lit_key = E.eval_expression_list(pa.table({"a": [1, 2, 3, 4, 5]}), [lit(1)]).column("literal")
+    assert O.argsort([lit_key]).tolist() == [0, 1, 2, 3, 4]
