@@ -89,9 +89,10 @@ def test_codegen_and_nvrtc_offline(tmp_path):
     fx = [e for nm in ("x", "y") for e in (col(nm).is_nan().alias(nm + "n"), col(nm).not_nan().alias(nm + "nn"), col(nm).is_inf().alias(nm + "i"),
                                            col(nm).ceil().alias(nm + "c"), col(nm).floor().alias(nm + "f"), col(nm).sign().alias(nm + "s"),
                                            col(nm).fill_nan(2.0).alias(nm + "fn"))]
-    fx += [col("p").sign().alias("ps"), col("q").sign().alias("qs"), col("p").ceil().alias("pc")]
+    fx += [col("p").sign().alias("ps"), col("q").sign().alias("qs"), col("p").ceil().alias("pc"), col("x").sqrt().alias("xsq"),
+           col("y").sqrt().alias("ysq"), col("p").sqrt().alias("psq")]
     plan, _, odt = encode_project(fx, ["x", "y", "p", "q"], [dt.F32, dt.F64, dt.I8, dt.U16])
-    assert odt[-3:] == [dt.I8, dt.U16, dt.I8] and odt[3:7] == [dt.F32, dt.F32, dt.F32, dt.F64]
+    assert odt[-6:] == [dt.I8, dt.U16, dt.I8, dt.F32, dt.F64, dt.F32] and odt[3:7] == [dt.F32, dt.F32, dt.F32, dt.F64]
     _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 4)(dt.F32, dt.F64, dt.I8, dt.U16),
               (ctypes.c_uint8 * 4)(1, 1, 1, 0), ctypes.c_int32(4))
     plan = encode_agg([col("b").sum().alias("sb"), col("a").max().alias("ma"), col("a").count().alias("n")], [col("s"), col("a") % 3], names, dts,
