@@ -134,7 +134,8 @@ def test_float_predicates_ceil_floor_sign_fill_nan(gpu):
     exprs = [e for nm in ("f64", "f32") for e in (c(nm).is_nan().alias(nm + "_nan"), c(nm).not_nan().alias(nm + "_nn"), c(nm).is_inf().alias(nm + "_inf"),
                                                    c(nm).ceil().alias(nm + "_ceil"), c(nm).floor().alias(nm + "_floor"), c(nm).sign().alias(nm + "_sign"),
                                                    c(nm).fill_nan(2.0).alias(nm + "_fn"), c(nm).fill_nan(c("f64")).alias(nm + "_fn2"))]
-    exprs += [c("i32").sign().alias("i_sign"), c("u16").sign().alias("u_sign"), c("i32").ceil().alias("i_ceil"), c("u16").floor().alias("u_floor")]
+    exprs += [c("i32").sign().alias("i_sign"), c("u16").sign().alias("u_sign"), c("i32").ceil().alias("i_ceil"), c("u16").floor().alias("u_floor"),
+              c("f32").sqrt().alias("f32_sqrt"), c("f64").sqrt().alias("f64_sqrt"), c("u16").sqrt().alias("u16_sqrt"), c("i32").sqrt().alias("i32_sqrt")]
     got = RB(gpu, tbl).eval_expression_list(exprs).to_arrow_table()
     want = E.eval_expression_list(tbl, exprs)
     assert_tables_equal(got, want)
