@@ -245,6 +245,8 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
             return Bound(T_BINARY, dt.BOOL, BINOPS[op], [_cast(l, dt.BOOL) if l.dtype == dt.NULL else l,
                                                           _cast(r, dt.BOOL) if r.dtype == dt.NULL else r])
         if op in ("shl", "shr"):
+            if not (dt.is_integer(l.dtype) and dt.is_integer(r.dtype)):  # infer_datatype.rs:494-520, test_numeric.py:773-785
+                raise DaftTypeError(f"Cannot operate shift {'left' if op == 'shl' else 'right'} on types: {dt.NAMES[l.dtype]}, {dt.NAMES[r.dtype]}")
             return Bound(T_BINARY, l.dtype, BINOPS[op], [l, _cast(r, l.dtype)])
         st = dt.rem_supertype(l.dtype, r.dtype) if op == "mod" else dt.supertype(l.dtype, r.dtype)
         l, r = _cast(l, st), _cast(r, st)

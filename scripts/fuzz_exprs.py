@@ -34,7 +34,9 @@ def gen_num(rng, depth):
     if r < 0.32:   # leaves derived from the date / string columns
         return [col("d").year(), col("d").month(), col("d").day(), col("d").day_of_week(), col("s").length(), gen_str(rng, 1).length()][rng.integers(0, 6)]
     a, b = gen_num(rng, depth - 1), gen_num(rng, depth - 1)
-    k = rng.integers(0, 18)
+    k = rng.integers(0, 20)
+    if k == 18: return a << lit(int(rng.integers(0, 8)))
+    if k == 19: return a >> lit(int(rng.integers(0, 8)))
     if k == 13: return a & b
     if k == 14: return a | b
     if k == 15: return a ^ b
