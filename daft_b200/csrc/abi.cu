@@ -113,6 +113,20 @@ int b200_jit_describe(int32_t op, const uint8_t *plan, size_t plan_len, const in
         t += "\nouts=";
         for (size_t i = 0; i < meta.outs.size(); i++)
             t += (i ? "," : "") + std::to_string(meta.outs[i].dtype) + ":" + (meta.outs[i].nullable ? "1" : "0");
+        if (op == B200_OP_AGG) {  // what the host needs to read the group table back (ops_jit.cu op_agg_first_rows)
+            t += "\nnkeys=" + std::to_string(meta.nkeys) + "\nnlane=" + std::to_string(meta.NLANE) + "\nnwarp=" + std::to_string(meta.NWARP) + "\naggs=";
+            for (size_t i = 0; i < meta.aggs.size(); i++) {
+                const jit::AggOut &a = meta.aggs[i];
+                t += (i ? "," : "") + std::to_string(a.kind) + ":" + std::to_string(a.count_mode) + ":" + std::to_string(a.val_dtype) + ":" +
+                     std::to_string(a.out_dtype) + ":" + std::to_string(a.lane_cell) + ":" + std::to_string(a.cnt_cell) + ":" +
+                     (a.child_nullable ? "1" : "0") + ":" + (a.const_zero ? "1" : "0") + ":" + a.name;
+            }
+            t += "\ncellops=";
+            for (size_t i = 0; i < meta.lane_cell_ops.size(); i++) t += (i ? "," : "") + std::to_string(meta.lane_cell_ops[i]);
+            static const char *hex = "0123456789abcdef";
+            t += "\nkeyplan=";
+            for (uint8_t b : meta.key_project_plan) { t += hex[b >> 4]; t += hex[b & 15]; }
+        }
         t += "\n---\n" + src;
         char *m = static_cast<char *>(malloc(t.size() + 1));
         if (!m) fail("out of memory");

@@ -227,3 +227,213 @@ def emulate_project(tbl: pa.Table, exprs) -> pa.Table:
             arr = pa.array(vals, mask=mask)
             arrays.append(arr.cast(dt.to_arrow(code)) if arr.type != dt.to_arrow(code) else arr)
     return pa.table(arrays, names=list(onames))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Aggregate plans: the generated load / eval (filter + key + value expressions) / keys_equal / code / global_update
+# functions, driven row by row on the host.  Group lookup is a plain hash map keyed by Prog::code and confirmed with
+# Prog::keys_equal; the cells are read back the way ops_jit.cu op_agg_first_rows finalises them.
+# ------------------------------------------------------------------------------------------------------------------
+P_SLOT_HASH, P_ACC, P_OVERFLOW = 8, 10, 11
+I_MASK, I_RSTRIDE = 1, 2
+C_ADD_F64, C_ADD_F32, C_ADD_I64, C_MIN, C_MAX = 0, 1, 2, 3, 4
+AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_MEAN = 0, 1, 2, 3, 4
+
+_AGG_SHIM = r"""
+#include <unordered_map>
+#include <vector>
+static inline double atomicAdd(double *p, double v) { const double o = *p; *p = o + v; return o; }
+static inline float atomicAdd(float *p, float v) { const float o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v < o) *p = v; return o; }
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int) { return v; }
+static inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v, int) { return v; }
+static inline double __shfl_xor_sync(unsigned, double v, int) { return v; }
+static inline float __shfl_xor_sync(unsigned, float v, int) { return v; }
+static inline bool __all_sync(unsigned, bool p) { return p; }
+struct PfLaneEmu;
+"""
+
+_AGG_DRIVER = r"""
+extern "C" long long emu_agg(void **ptrs, int nptr, long long *ints, int nint, long long n, long long cap) {
+    Prog::P p;
+    for (int i = 0; i < nptr; i++) p.ptr[i] = ptrs[i];
+    for (int i = 0; i < nint; i++) p.ival[i] = ints[i];
+    std::unordered_multimap<uint64_t, long long> table;
+    std::vector<Prog::Keys> group_keys;
+    long long ngroups = 0;
+    for (long long row = 0; row < n; row++) {
+        Prog::Raw r;
+        Prog::load(p, row, r);
+        Prog::load2(p, row, r);
+        Prog::Keys k;
+        Prog::Vals v;
+        if (!Prog::eval(p, r, k, v)) continue;
+        long long slot = -1;
+        if constexpr (Prog::NKEYS > 0) {
+            const uint64_t code = Prog::code(k);
+            auto range = table.equal_range(code);
+            for (auto it = range.first; it != range.second; ++it)
+                if (Prog::keys_equal(group_keys[it->second], k)) { slot = it->second; break; }
+            if (slot < 0) {
+                if (ngroups >= cap) return -1;
+                slot = ngroups++;
+                group_keys.push_back(k);
+                table.emplace(code, slot);
+            }
+        } else {
+            slot = 0;
+            ngroups = 1;
+        }
+        Prog::global_update(p, slot, v, row);
+    }
+    return ngroups;
+}
+"""
+
+
+def describe_agg(plan: bytes, dtypes, nullable):
+    out, err = ctypes.c_void_p(), ctypes.c_void_p()
+    n = len(dtypes)
+    rc = _lib.lib().b200_jit_describe(ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * n)(*dtypes),
+                                      (ctypes.c_uint8 * n)(*nullable), ctypes.c_int32(n), ctypes.byref(out), ctypes.byref(err))
+    _lib.check(rc, err)
+    text = ctypes.string_at(out.value).decode()
+    _lib.lib().b200_free_string(out)
+    head, src = text.split("\n---\n", 1)
+    f = dict(line.split("=", 1) for line in head.split("\n"))
+    aggs = []
+    for s in f["aggs"].split(","):
+        kind, mode, vdt, odt, lane, cnt, cn, cz, name = s.split(":", 8)
+        aggs.append(dict(kind=int(kind), mode=int(mode), val_dtype=int(vdt), out_dtype=int(odt), lane_cell=int(lane), cnt_cell=int(cnt),
+                         child_nullable=cn == "1", const_zero=cz == "1", name=name))
+    return dict(src=src, ptrs=[tuple(map(int, s.split(":"))) for s in f["ptrs"].split(",") if s], ints=[int(s) for s in f["ints"].split(",") if s],
+                nkeys=int(f["nkeys"]), nlane=int(f["nlane"]), nwarp=int(f["nwarp"]), aggs=aggs, cellops=[int(s) for s in f["cellops"].split(",") if s])
+
+
+def _compile_agg(src: str) -> ctypes.CDLL:
+    lines = src.split("\n")
+    defines = "\n".join(l for l in lines if l.startswith("#define"))     # hoisted in front of the prelude by the library too
+    body = "\n".join(l for l in lines if "__global__" not in l and not l.startswith("#define"))
+    text = open(os.path.join(_lib.CSRC, "jit_prelude.cuh")).read()
+    # the aggregate skeletons are CUDA-only; the generated Prog needs the helpers above them plus PfLane / AGG_WARPS
+    head = _prelude_for_host().rsplit("\n}  // namespace jit", 1)[0]
+    m = re.search(r"struct PfLane \{.*?\};", text, re.S)
+    extra = "#ifndef B200_AGG_WARPS\n#define B200_AGG_WARPS 8\n#endif\nconstexpr int AGG_WARPS = B200_AGG_WARPS;\n" + m.group(0) + "\n"
+    full = _SHIM + _AGG_SHIM + defines + "\n" + head + extra + "\n}  // namespace jit\n}  // namespace b200\n" + body + _AGG_DRIVER
+    tag = hashlib.sha1(full.encode()).hexdigest()[:16]
+    d = os.path.join(tempfile.gettempdir(), "daft_b200_jit_emu")
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, f"emuagg_{tag}.so")
+    if not os.path.exists(so):
+        cpp = os.path.join(d, f"emuagg_{tag}.cpp")
+        with open(cpp, "w") as fh:
+            fh.write(full)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w",
+                               "-o", so, cpp])
+    return ctypes.CDLL(so)
+
+
+def _input_buffer(kind, c, code, n, nw):
+    if kind == P_COL_VALID:
+        return _pack_bits(np.asarray(c.is_valid()), nw + 1)
+    if kind == P_COL_OFFSETS:
+        return np.frombuffer(c.buffers()[1], dtype=np.int64, count=n + 1 + c.offset)[c.offset:].copy() if n else np.zeros(1, np.int64)
+    if dt.is_string(code):
+        raw = c.buffers()[2]
+        return np.concatenate([np.frombuffer(raw, dtype=np.uint8) if raw is not None else np.zeros(0, np.uint8), np.zeros(16, np.uint8)])
+    if code == dt.BOOL:
+        return _pack_bits(np.asarray(c.fill_null(False)), nw + 1)
+    if code == dt.NULL:
+        return np.zeros(8, np.uint8)
+    phys = c.cast(pa.int32()) if code == dt.DATE32 else c.cast(pa.int64()) if code == dt.TIMESTAMP else c
+    return np.ascontiguousarray(np.concatenate([np.asarray(phys.fill_null(0)).astype(_NP[code]), np.zeros(4, _NP[code])]))
+
+
+def _decode_ord(cells: np.ndarray, code: int) -> np.ndarray:
+    """Inverse of the order-preserving min / max keys (jit_prelude.cuh ord_*; ops_jit.cu finalize_one)."""
+    if code in (dt.F32, dt.F64):
+        nan = cells == np.uint64(0xFFFFFFFFFFFFFFFF)
+        bits = np.where(cells >> np.uint64(63) != 0, cells & np.uint64(0x7FFFFFFFFFFFFFFF), ~cells)
+        vals = bits.view(np.float64).copy()
+        vals[nan] = np.nan
+        return vals.astype(_NP[code])
+    if dt.int_like_signed(code):
+        return (cells ^ np.uint64(0x8000000000000000)).view(np.int64).astype(_NP[code])
+    if code == dt.BOOL:
+        return cells != 0
+    return cells.astype(_NP[code])
+
+
+def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None):
+    """(aggregate columns in first-occurrence group order, first row of every group) through the generated aggregate code."""
+    from daft_b200.expressions import encode_agg
+    tbl = tbl.combine_chunks()
+    n = tbl.num_rows
+    names = tbl.column_names
+    cols = [tbl.column(i).chunk(0) if tbl.column(i).num_chunks else pa.array([], type=tbl.column(i).type) for i in range(len(names))]
+    dtypes = [dt.from_arrow(c.type) for c in cols]
+    nullable = [1 if c.null_count > 0 else 0 for c in cols]
+    d = describe_agg(encode_agg(aggs, group_by, names, dtypes, predicate), dtypes, nullable)
+    lib = _compile_agg(d["src"])
+    nw = max((n + 31) // 32, 1)
+    cap = max(n, 1)
+    ncell = d["nlane"] + d["nwarp"]
+    acc = np.zeros((ncell, cap), dtype=np.uint64)
+    for i, op in enumerate(d["cellops"]):
+        if op == C_MIN:
+            acc[i, :] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    keep, slots = [acc], []
+    for kind, idx in d["ptrs"]:
+        if kind in (P_COL_DATA, P_COL_VALID, P_COL_OFFSETS):
+            buf = _input_buffer(kind, cols[idx], dtypes[idx], n, nw)
+            keep.append(buf)
+            slots.append(buf.ctypes.data)
+        elif kind == P_ACC:
+            slots.append(acc[idx].ctypes.data)
+        elif kind in (P_SLOT_HASH, P_OVERFLOW):
+            buf = np.zeros(cap + 8, dtype=np.uint64)
+            keep.append(buf)
+            slots.append(buf.ctypes.data)
+        else:
+            raise NotImplementedError(f"host emulation: aggregate parameter kind {kind}")
+    ivals = [{I_N: n, I_MASK: cap - 1, I_RSTRIDE: 1}[k] for k in d["ints"]]
+    lib.emu_agg.restype = ctypes.c_longlong
+    ng = lib.emu_agg((ctypes.c_void_p * len(slots))(*slots), ctypes.c_int(len(slots)), (ctypes.c_longlong * len(ivals))(*ivals),
+                     ctypes.c_int(len(ivals)), ctypes.c_longlong(n), ctypes.c_longlong(cap))
+    assert ng >= 0
+    if d["nkeys"] == 0:
+        ng = 1   # an ungrouped aggregate always yields one row (sums null, counts 0 over an empty / fully filtered input)
+    nl = d["nlane"]
+    nrows, minrow = acc[nl - 2, :ng], acc[nl - 1, :ng]
+    order = np.argsort(minrow, kind="stable") if d["nkeys"] > 0 else np.arange(ng)
+    arrays, out_names = [], []
+    for a in d["aggs"]:
+        cnt = (acc[nl + a["cnt_cell"], :ng] if a["cnt_cell"] >= 0 else nrows)[order]
+        cell = acc[a["lane_cell"], :ng][order] if a["lane_cell"] >= 0 else None
+        typ = dt.to_arrow(a["out_dtype"])
+        if a["kind"] == AGG_COUNT:
+            arr = pa.array(np.zeros(ng, np.uint64) if a["const_zero"] else cnt, type=pa.uint64())
+        else:
+            valid = cnt > 0
+            may_null = a["child_nullable"] or d["nkeys"] == 0
+            mask = ~valid if may_null and not valid.all() else None
+            if a["kind"] in (AGG_SUM, AGG_MEAN):
+                v = a["val_dtype"]
+                s = cell.view(np.float64) if v == dt.F64 else (cell & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32) if v == dt.F32 \
+                    else cell if v == dt.U64 else cell.view(np.int64)
+                if a["kind"] == AGG_MEAN:
+                    with np.errstate(all="ignore"):
+                        s = np.where(valid, s.astype(np.float64) / np.maximum(cnt, 1).astype(np.float64), 0.0)
+                arr = pa.array(np.where(valid, s, 0).astype(_NP.get(a["out_dtype"], np.float64)), type=typ, mask=mask)
+            else:
+                vals = _decode_ord(cell, a["out_dtype"])
+                if a["out_dtype"] == dt.BOOL:
+                    arr = pa.array(vals & valid, type=pa.bool_(), mask=mask)
+                else:
+                    phys = pa.array(np.where(valid, vals, 0).astype(vals.dtype), mask=mask)
+                    arr = phys.cast(typ) if phys.type != typ else phys
+        arrays.append(arr)
+        out_names.append(a["name"])
+    return pa.table(arrays, names=out_names), minrow[order].astype(np.int64)
