@@ -147,3 +147,14 @@ def test_generated_tpch_q1_q6_match_golden_answers():
     got6 = _EmulatedBatch(li).agg([(col("L_EXTENDEDPRICE") * col("L_DISCOUNT")).sum().alias("revenue")], [], pred).to_pydict()["revenue"][0]
     want6 = golden["q6"]["revenue"][0]
     assert abs(got6 - want6) <= 1e-9 * abs(want6)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_aggregate_plans_match_oracle(seed):
+    """Seeded plans of the aggregate fuzzer (scripts/fuzz_aggs.py: random predicate, 0-3 group keys, 1-6 aggregates over random
+    expression trees) through the generated aggregate code.  Longer runs: `python scripts/fuzz_aggs.py 60 100`."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import fuzz_aggs
+    assert fuzz_aggs.run(seed) is None
