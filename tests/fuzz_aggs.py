@@ -1,7 +1,7 @@
 """Random aggregate plans (predicate + group keys + aggregates over random expressions) through the generated aggregate code on
 the host (tests/jit_emu.py emulate_agg) against the oracle.
 
-    python scripts/fuzz_aggs.py [plans] [seed]
+    python tests/fuzz_aggs.py [plans] [seed]
 """
 import os
 import sys
@@ -12,7 +12,6 @@ import pyarrow as pa
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.join(ROOT, "scripts"))
 
 import fuzz_exprs as F  # noqa: E402
 import jit_emu  # noqa: E402

@@ -1,6 +1,6 @@
 """Random expression trees through the generated projection code on the host (tests/jit_emu.py) against the oracle.
 
-    python scripts/fuzz_exprs.py [batches] [exprs_per_batch] [seed]
+    python tests/fuzz_exprs.py [batches] [exprs_per_batch] [seed]
 
 Every batch is one projection (one g++ compile).  A mismatch prints the expression and the first differing row.
 """

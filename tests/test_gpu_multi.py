@@ -14,7 +14,7 @@ def test_exchange_by_hash_two_ranks():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", os.path.join(ROOT, "scripts", "exchange_check.py")]
+           "--master-port", "29611", os.path.join(ROOT, "tests", "exchange_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "exchange ok on 2 GPUs" in r.stdout

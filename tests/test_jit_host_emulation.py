@@ -105,12 +105,9 @@ def test_generated_float_predicates_ceil_floor_sign_fill_nan():
 
 @pytest.mark.parametrize("seed", [300, 301])
 def test_random_expression_trees_match_oracle(seed):
-    """Two seeded batches of the expression fuzzer (scripts/fuzz_exprs.py: arithmetic, division, casts, comparisons, Kleene logic,
+    """Two seeded batches of the expression fuzzer (tests/fuzz_exprs.py: arithmetic, division, casts, comparisons, Kleene logic,
     bitwise, if_else, fill_null, between, is_in, float predicates, string and date functions, depth <= 3): one projection of 40
-    random trees each through the generated code, against the oracle.  Longer runs: `python scripts/fuzz_exprs.py 60 40 1000`."""
-    import os
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    random trees each through the generated code, against the oracle.  Longer runs: `python tests/fuzz_exprs.py 60 40 1000`."""
     import fuzz_exprs
     bad = fuzz_exprs.run_batch(seed, 40)
     assert not bad, bad
@@ -151,10 +148,7 @@ def test_generated_tpch_q1_q6_match_golden_answers():
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_random_aggregate_plans_match_oracle(seed):
-    """Seeded plans of the aggregate fuzzer (scripts/fuzz_aggs.py: random predicate, 0-3 group keys, 1-6 aggregates over random
-    expression trees) through the generated aggregate code.  Longer runs: `python scripts/fuzz_aggs.py 60 100`."""
-    import os
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    """Seeded plans of the aggregate fuzzer (tests/fuzz_aggs.py: random predicate, 0-3 group keys, 1-6 aggregates over random
+    expression trees) through the generated aggregate code.  Longer runs: `python tests/fuzz_aggs.py 60 100`."""
     import fuzz_aggs
     assert fuzz_aggs.run(seed) is None
