@@ -139,6 +139,16 @@ def test_generated_tpch_q1_q6_match_golden_answers():
     for name, vals in want.items():
         for a, b in zip(got[name], vals):
             assert a == b or abs(a - b) <= 1e-9 * abs(b), (name, a, b)
+    # the two-stage form the multi-GPU path runs: partial aggregate -> final aggregate of the partials -> merge_mean projection
+    predicate, group_by, partial = tpch.q1_partial_exprs()
+    parts = _EmulatedBatch(li.slice(0, 30000)).agg(partial, group_by, predicate).to_arrow_table(), \
+        _EmulatedBatch(li.slice(30000)).agg(partial, group_by, predicate).to_arrow_table()
+    group_by, final, project = tpch.q1_final_exprs()
+    merged = _EmulatedBatch(pa.concat_tables(parts).combine_chunks()).agg(final, group_by).to_arrow_table()
+    two = _EmulatedBatch(merged).eval_expression_list(project).to_arrow_table().sort_by([("L_RETURNFLAG", "ascending"), ("L_LINESTATUS", "ascending")]).to_pydict()
+    for name, vals in want.items():
+        for a, b in zip(two[name], vals):
+            assert a == b or abs(a - b) <= 1e-9 * abs(b), (name, a, b)
     pred = [col("L_SHIPDATE") >= datetime.date(1994, 1, 1), col("L_SHIPDATE") < datetime.date(1995, 1, 1), col("L_DISCOUNT") >= 0.05,
             col("L_DISCOUNT") <= 0.07, col("L_QUANTITY") < 24]
     got6 = _EmulatedBatch(li).agg([(col("L_EXTENDEDPRICE") * col("L_DISCOUNT")).sum().alias("revenue")], [], pred).to_pydict()["revenue"][0]
