@@ -293,10 +293,10 @@ extern "C" long long emu_agg(void **ptrs, int nptr, long long *ints, int nint, l
 """
 
 
-def describe_agg(plan: bytes, dtypes, nullable):
+def describe_agg(plan: bytes, dtypes, nullable, variant: int = 0):
     out, err = ctypes.c_void_p(), ctypes.c_void_p()
     n = len(dtypes)
-    rc = _lib.lib().b200_jit_describe(ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * n)(*dtypes),
+    rc = _lib.lib().b200_jit_describe(ctypes.c_int32(2 | (variant << 8)), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * n)(*dtypes),
                                       (ctypes.c_uint8 * n)(*nullable), ctypes.c_int32(n), ctypes.byref(out), ctypes.byref(err))
     _lib.check(rc, err)
     text = ctypes.string_at(out.value).decode()
@@ -312,7 +312,7 @@ def describe_agg(plan: bytes, dtypes, nullable):
                 nkeys=int(f["nkeys"]), nlane=int(f["nlane"]), nwarp=int(f["nwarp"]), aggs=aggs, cellops=[int(s) for s in f["cellops"].split(",") if s])
 
 
-def _compile_agg(src: str) -> ctypes.CDLL:
+def _compile_agg(src: str, staged: bool = False) -> ctypes.CDLL:
     lines = src.split("\n")
     defines = "\n".join(l for l in lines if l.startswith("#define"))     # hoisted in front of the prelude by the library too
     body = "\n".join(l for l in lines if "__global__" not in l and not l.startswith("#define"))
@@ -321,7 +321,8 @@ def _compile_agg(src: str) -> ctypes.CDLL:
     head = _prelude_for_host().rsplit("\n}  // namespace jit", 1)[0]
     m = re.search(r"struct PfLane \{.*?\};", text, re.S)
     extra = "#ifndef B200_AGG_WARPS\n#define B200_AGG_WARPS 8\n#endif\nconstexpr int AGG_WARPS = B200_AGG_WARPS;\n" + m.group(0) + "\n"
-    full = _SHIM + _AGG_SHIM + defines + "\n" + head + extra + "\n}  // namespace jit\n}  // namespace b200\n" + body + _AGG_DRIVER
+    full = _SHIM + _AGG_SHIM + (_STAGED_SHIM if staged else "") + defines + "\n" + head + extra + "\n}  // namespace jit\n}  // namespace b200\n" + body + \
+        (_STAGED_DRIVER if staged else _AGG_DRIVER)
     tag = hashlib.sha1(full.encode()).hexdigest()[:16]
     d = os.path.join(tempfile.gettempdir(), "daft_b200_jit_emu")
     os.makedirs(d, exist_ok=True)
@@ -366,8 +367,9 @@ def _decode_ord(cells: np.ndarray, code: int) -> np.ndarray:
     return cells.astype(_NP[code])
 
 
-def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None):
-    """(aggregate columns in first-occurrence group order, first row of every group) through the generated aggregate code."""
+def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = False):
+    """(aggregate columns in first-occurrence group order, first row of every group) through the generated aggregate code.
+    staged=True runs the TMA-staged build of an ungrouped plan: full tiles go through stage_issue / load_staged."""
     from daft_b200.expressions import encode_agg
     tbl = tbl.combine_chunks()
     n = tbl.num_rows
@@ -375,8 +377,8 @@ def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None):
     cols = [tbl.column(i).chunk(0) if tbl.column(i).num_chunks else pa.array([], type=tbl.column(i).type) for i in range(len(names))]
     dtypes = [dt.from_arrow(c.type) for c in cols]
     nullable = [1 if c.null_count > 0 else 0 for c in cols]
-    d = describe_agg(encode_agg(aggs, group_by, names, dtypes, predicate), dtypes, nullable)
-    lib = _compile_agg(d["src"])
+    d = describe_agg(encode_agg(aggs, group_by, names, dtypes, predicate), dtypes, nullable, 2 if staged else 0)
+    lib = _compile_agg(d["src"], staged)
     nw = max((n + 31) // 32, 1)
     cap = max(n, 1)
     ncell = d["nlane"] + d["nwarp"]
@@ -399,9 +401,16 @@ def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None):
         else:
             raise NotImplementedError(f"host emulation: aggregate parameter kind {kind}")
     ivals = [{I_N: n, I_MASK: cap - 1, I_RSTRIDE: 1}[k] for k in d["ints"]]
-    lib.emu_agg.restype = ctypes.c_longlong
-    ng = lib.emu_agg((ctypes.c_void_p * len(slots))(*slots), ctypes.c_int(len(slots)), (ctypes.c_longlong * len(ivals))(*ivals),
-                     ctypes.c_int(len(ivals)), ctypes.c_longlong(n), ctypes.c_longlong(cap))
+    if staged:
+        lib.emu_agg_staged.restype = ctypes.c_longlong
+        staged_rows = lib.emu_agg_staged((ctypes.c_void_p * len(slots))(*slots), ctypes.c_int(len(slots)), (ctypes.c_longlong * len(ivals))(*ivals),
+                                         ctypes.c_int(len(ivals)), ctypes.c_longlong(n))
+        assert staged_rows > 0 or n < 4096, "no tile went through the stage"
+        ng = 1
+    else:
+        lib.emu_agg.restype = ctypes.c_longlong
+        ng = lib.emu_agg((ctypes.c_void_p * len(slots))(*slots), ctypes.c_int(len(slots)), (ctypes.c_longlong * len(ivals))(*ivals),
+                         ctypes.c_int(len(ivals)), ctypes.c_longlong(n), ctypes.c_longlong(cap))
     assert ng >= 0
     if d["nkeys"] == 0:
         ng = 1   # an ungrouped aggregate always yields one row (sums null, counts 0 over an empty / fully filtered input)
@@ -437,3 +446,35 @@ def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None):
         arrays.append(arr)
         out_names.append(a["name"])
     return pa.table(arrays, names=out_names), minrow[order].astype(np.int64)
+
+
+# ---- the TMA-staged aggregate build (variant 2): stage_issue copies column slices into a stage, load_staged reads the stage ----
+_STAGED_SHIM = r"""
+static unsigned char g_stage[1 << 20];
+static inline void mbar_expect_tx(uint32_t, uint32_t) {}
+static inline void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t) { memcpy(g_stage + dst, src, bytes); }
+"""
+
+_STAGED_DRIVER = r"""
+extern "C" long long emu_agg_staged(void **ptrs, int nptr, long long *ints, int nint, long long n) {
+    static_assert(Prog::NKEYS == 0, "the staged emulation covers ungrouped plans (what the library stages by default)");
+    Prog::P p;
+    for (int i = 0; i < nptr; i++) p.ptr[i] = ptrs[i];
+    for (int i = 0; i < nint; i++) p.ival[i] = ints[i];
+    long long staged_rows = 0;
+    for (long long base = 0; base < n; base += Prog::STAGE_ROWS) {
+        const bool full = base + Prog::STAGE_ROWS <= n;   // the skeleton stages full tiles and loads the tail directly
+        if (full) { Prog::stage_issue(p, 0u, 0u, base); staged_rows += Prog::STAGE_ROWS; }
+        for (int rr = 0; rr < Prog::STAGE_ROWS && base + rr < n; rr++) {
+            Prog::Raw r;
+            if (full) Prog::load_staged(p, g_stage, base + rr, rr, r);
+            else { Prog::load(p, base + rr, r); Prog::load2(p, base + rr, r); }
+            Prog::Keys k;
+            Prog::Vals v;
+            if (!Prog::eval(p, r, k, v)) continue;
+            Prog::global_update(p, 0, v, base + rr);
+        }
+    }
+    return staged_rows;
+}
+"""

@@ -162,3 +162,26 @@ def test_random_aggregate_plans_match_oracle(seed):
     expression trees) through the generated aggregate code.  Longer runs: `python tests/fuzz_aggs.py 60 100`."""
     import fuzz_aggs
     assert fuzz_aggs.run(seed) is None
+
+
+@pytest.mark.parametrize("nulls", [0.0, 0.2])
+def test_generated_staged_aggregate_build(nulls):
+    """The TMA-staged build of ungrouped plans (what Q6-shaped scans run): stage_issue lays the column slices out in the stage,
+    load_staged reads them back; full 768-row tiles go through the stage, the tail through the direct loads."""
+    import json
+    import os
+    from daft_b200 import tpch
+    rng = np.random.default_rng(41)
+    tbl = random_table(rng, 5000, nulls).drop_columns(["s"])   # string bytes are not staged; keep the fixed-width columns
+    c = col
+    aggs = [c("i64").sum().alias("s"), c("f64").mean().alias("m"), c("u8").max().alias("mx"), c("i32").count().alias("cnt"), (c("f64") * c("f32")).sum().alias("e")]
+    pred = [c("i32") > -500, c("f64") <= 900.0]
+    got, _ = jit_emu.emulate_agg(tbl, aggs, [], pred, staged=True)
+    from helpers import oracle_agg
+    assert_tables_equal(got, oracle_agg(tbl, aggs, [], pred), float_rtol=1e-12)
+    li = tpch.generate_host("lineitem", 0.01, tpch.Q1_COLUMNS)
+    pred = [col("L_SHIPDATE") >= datetime.date(1994, 1, 1), col("L_SHIPDATE") < datetime.date(1995, 1, 1), col("L_DISCOUNT") >= 0.05,
+            col("L_DISCOUNT") <= 0.07, col("L_QUANTITY") < 24]
+    got, _ = jit_emu.emulate_agg(li, [(col("L_EXTENDEDPRICE") * col("L_DISCOUNT")).sum().alias("revenue")], [], pred, staged=True)
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tpch_q1_q6_sf001.json")))
+    assert abs(got.column("revenue")[0].as_py() - golden["q6"]["revenue"][0]) <= 1e-9 * golden["q6"]["revenue"][0]
