@@ -478,3 +478,94 @@ extern "C" long long emu_agg_staged(void **ptrs, int nptr, long long *ints, int 
     return staged_rows;
 }
 """
+
+
+# ---- Filter plans: the generated keep() (predicate) and copy() (column-major compaction of the fixed-width never-null columns) ----
+_FILTER_DRIVER = r"""
+extern "C" long long emu_filter(void **ptrs, int nptr, long long *ints, int nint, long long n, long long *kept_rows) {
+    Prog::P p;
+    for (int i = 0; i < nptr; i++) p.ptr[i] = ptrs[i];
+    for (int i = 0; i < nint; i++) p.ival[i] = ints[i];
+    long long nk = 0;
+    for (long long row = 0; row < n; row++)
+        if (Prog::keep(p, row)) kept_rows[nk++] = row;
+    // the skeleton hands copy() FILTER_SUB (source row, destination row) pairs per thread, destination -1 for dropped rows
+    for (long long base = 0; base < n; base += FILTER_SUB) {
+        int64_t src[FILTER_SUB], dst[FILTER_SUB];
+        for (int j = 0; j < FILTER_SUB; j++) {
+            src[j] = base + j < n ? base + j : 0;
+            dst[j] = -1;
+            if (base + j < n) {
+                // destination = rank of the row among the kept rows (binary search in kept_rows)
+                long long lo = 0, hi = nk;
+                while (lo < hi) { const long long mid = (lo + hi) / 2; if (kept_rows[mid] < base + j) lo = mid + 1; else hi = mid; }
+                if (lo < nk && kept_rows[lo] == base + j) dst[j] = lo;
+            }
+        }
+        Prog::copy(p, src, dst);
+    }
+    return nk;
+}
+"""
+
+
+def emulate_filter(tbl: pa.Table, predicates) -> pa.Table:
+    """RecordBatch::filter through the generated keep() and copy(); columns the kernel does not copy itself (nullable / string /
+    boolean ones, gathered by the host through the row-id list) are taken with pyarrow at the kept rows."""
+    from daft_b200.expressions import encode_filter
+    tbl = tbl.combine_chunks()
+    n = tbl.num_rows
+    names = tbl.column_names
+    cols = [tbl.column(i).chunk(0) if tbl.column(i).num_chunks else pa.array([], type=tbl.column(i).type) for i in range(len(names))]
+    dtypes = [dt.from_arrow(c.type) for c in cols]
+    nullable = [1 if c.null_count > 0 else 0 for c in cols]
+    plan = encode_filter(list(predicates), names, dtypes)
+    out, err = ctypes.c_void_p(), ctypes.c_void_p()
+    rc = _lib.lib().b200_jit_describe(ctypes.c_int32(1), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * len(dtypes))(*dtypes),
+                                      (ctypes.c_uint8 * len(dtypes))(*nullable), ctypes.c_int32(len(dtypes)), ctypes.byref(out), ctypes.byref(err))
+    _lib.check(rc, err)
+    text = ctypes.string_at(out.value).decode()
+    _lib.lib().b200_free_string(out)
+    head, src = text.split("\n---\n", 1)
+    f = dict(line.split("=", 1) for line in head.split("\n"))
+    ptrs = [tuple(map(int, s.split(":"))) for s in f["ptrs"].split(",") if s]
+    ints = [int(s) for s in f["ints"].split(",") if s]
+    body = "\n".join(l for l in src.split("\n") if "__global__" not in l)
+    full = _SHIM + "constexpr int FILTER_SUB = 8;\n" + _prelude_for_host() + body + _FILTER_DRIVER
+    tag = hashlib.sha1(full.encode()).hexdigest()[:16]
+    d = os.path.join(tempfile.gettempdir(), "daft_b200_jit_emu")
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, f"emufilter_{tag}.so")
+    if not os.path.exists(so):
+        cpp = os.path.join(d, f"emufilter_{tag}.cpp")
+        with open(cpp, "w") as fh:
+            fh.write(full)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w",
+                               "-o", so, cpp])
+    lib = ctypes.CDLL(so)
+    nw = max((n + 31) // 32, 1)
+    keep, slots, copied = [], [], {}
+    for kind, idx in ptrs:
+        if kind in (P_COL_DATA, P_COL_VALID, P_COL_OFFSETS):
+            buf = _input_buffer(kind, cols[idx], dtypes[idx], n, nw)
+        elif kind == P_OUT_DATA:
+            buf = np.zeros(max(n, 1) + 8, dtype=_NP[dtypes[idx]])
+            copied[idx] = buf
+        else:   # tile counts / row-id list: written by the skeleton, not by the generated code
+            buf = np.zeros(max(n, 1) + 8, dtype=np.int64)
+        keep.append(buf)
+        slots.append(buf.ctypes.data)
+    ivals = [n if k == I_N else 0 for k in ints]
+    kept = np.zeros(max(n, 1), dtype=np.int64)
+    lib.emu_filter.restype = ctypes.c_longlong
+    nk = lib.emu_filter((ctypes.c_void_p * max(len(slots), 1))(*slots), ctypes.c_int(len(slots)), (ctypes.c_longlong * max(len(ivals), 1))(*ivals),
+                        ctypes.c_int(len(ivals)), ctypes.c_longlong(n), kept.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    rows = pa.array(kept[:nk], type=pa.int64())
+    arrays = []
+    for i, c in enumerate(cols):
+        if i in copied:
+            arr = pa.array(copied[i][:nk])
+            arrays.append(arr.cast(c.type) if arr.type != c.type else arr)
+        else:
+            arrays.append(c.take(rows))
+    return pa.table(arrays, names=names), sorted(copied)

@@ -185,3 +185,17 @@ def test_generated_staged_aggregate_build(nulls):
     got, _ = jit_emu.emulate_agg(li, [(col("L_EXTENDEDPRICE") * col("L_DISCOUNT")).sum().alias("revenue")], [], pred, staged=True)
     golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tpch_q1_q6_sf001.json")))
     assert abs(got.column("revenue")[0].as_py() - golden["q6"]["revenue"][0]) <= 1e-9 * golden["q6"]["revenue"][0]
+
+
+@pytest.mark.parametrize("n,nulls", [(0, 0.1), (5, 0.1), (1000, 0.1), (10007, 0.0), (10007, 0.3)])
+def test_generated_filter_keep_and_copy(n, nulls):
+    """Filter plans proper: the generated keep() and the column-major copy() of the fixed-width never-null columns (the other
+    columns are gathered by the host on the device, with pyarrow here)."""
+    rng = np.random.default_rng(n)
+    tbl = random_table(rng, n, nulls)
+    c = col
+    for pred in ([c("i32") > 0], [c("b")], [c("f64") < 0.0, c("s") != "a"], [c("i64").is_null() | (c("u8") == 3)], [c("i32") > 5000],
+                 [c("d") <= datetime.date(1998, 9, 2)], [c("k") % 3 == 1, c("f32").not_nan()]):
+        got, copied = jit_emu.emulate_filter(tbl, pred)
+        assert_tables_equal(got, E.filter(tbl, pred))
+        assert 13 in copied   # "k" never has nulls: always copied by the generated code
