@@ -7,6 +7,9 @@ intrinsics it uses, and runs it over Arrow inputs one emulated warp at a time.  
 operation of `row` -- are replayed in two sweeps per warp: sweep 0 records every lane's vote per call site, sweep 1 re-runs
 the (pure, idempotent) row code with the recorded masks, so the bitmaps it stores are the ones a real warp would store.
 
+Aggregate plans (emulate_agg: load / eval / keys_equal / code / global_update, the staged build's stage_issue / load_staged) and
+filter plans (emulate_filter: keep / copy) are driven the same way further down.
+
 What this proves: the generated expression code (casts, division, comparisons, null rules, functions) computes what the
 oracle computes.  What it does not: anything about the launch, the memory system or the skeletons around `row`.
 """
