@@ -259,7 +259,9 @@ struct PfLaneEmu;
 """
 
 _AGG_DRIVER = r"""
-extern "C" long long emu_agg(void **ptrs, int nptr, long long *ints, int nint, long long n, long long cap) {
+extern "C" long long emu_agg(void **ptrs, int nptr, long long *ints, int nint, long long n, long long cap, int tier2) {
+    std::vector<unsigned long long> t2c((size_t)Prog::T2 * Prog::NCELLS + 8);
+    std::vector<char> t2_used((size_t)Prog::T2 + 1, 0);
     Prog::P p;
     for (int i = 0; i < nptr; i++) p.ptr[i] = ptrs[i];
     for (int i = 0; i < nint; i++) p.ival[i] = ints[i];
@@ -289,8 +291,20 @@ extern "C" long long emu_agg(void **ptrs, int nptr, long long *ints, int nint, l
             slot = 0;
             ngroups = 1;
         }
+        if (tier2) {
+            // the global build's shared-memory tier: the first T2 groups accumulate in a CTA-local table (t2_update) that is
+            // flushed into the global cells at the end (t2_flush); later groups go straight to the global cells
+            if (slot < Prog::T2) {
+                if (!t2_used[slot]) { Prog::t2_init(t2c.data(), (int)slot); t2_used[slot] = 1; }
+                Prog::t2_update(t2c.data(), (int)slot, v, row);
+                continue;
+            }
+        }
         Prog::global_update(p, slot, v, row);
     }
+    if (tier2)
+        for (long long t = 0; t < Prog::T2 && t < ngroups; t++)
+            if (t2_used[t]) Prog::t2_flush(p, t, t2c.data(), (int)t);
     return ngroups;
 }
 """
@@ -370,7 +384,7 @@ def _decode_ord(cells: np.ndarray, code: int) -> np.ndarray:
     return cells.astype(_NP[code])
 
 
-def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = False):
+def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = False, tier2: bool = False):
     """(aggregate columns in first-occurrence group order, first row of every group) through the generated aggregate code.
     staged=True runs the TMA-staged build of an ungrouped plan: full tiles go through stage_issue / load_staged."""
     from daft_b200.expressions import encode_agg
@@ -380,7 +394,8 @@ def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = Fa
     cols = [tbl.column(i).chunk(0) if tbl.column(i).num_chunks else pa.array([], type=tbl.column(i).type) for i in range(len(names))]
     dtypes = [dt.from_arrow(c.type) for c in cols]
     nullable = [1 if c.null_count > 0 else 0 for c in cols]
-    d = describe_agg(encode_agg(aggs, group_by, names, dtypes, predicate), dtypes, nullable, 2 if staged else 0)
+    # tier2=True: the global-table build, its first T2 groups going through the shared-memory tier (t2_init / t2_update / t2_flush)
+    d = describe_agg(encode_agg(aggs, group_by, names, dtypes, predicate), dtypes, nullable, 2 if staged else 1 if tier2 else 0)
     lib = _compile_agg(d["src"], staged)
     nw = max((n + 31) // 32, 1)
     cap = max(n, 1)
@@ -413,7 +428,7 @@ def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = Fa
     else:
         lib.emu_agg.restype = ctypes.c_longlong
         ng = lib.emu_agg((ctypes.c_void_p * len(slots))(*slots), ctypes.c_int(len(slots)), (ctypes.c_longlong * len(ivals))(*ivals),
-                         ctypes.c_int(len(ivals)), ctypes.c_longlong(n), ctypes.c_longlong(cap))
+                         ctypes.c_int(len(ivals)), ctypes.c_longlong(n), ctypes.c_longlong(cap), ctypes.c_int(1 if tier2 else 0))
     assert ng >= 0
     if d["nkeys"] == 0:
         ng = 1   # an ungrouped aggregate always yields one row (sums null, counts 0 over an empty / fully filtered input)

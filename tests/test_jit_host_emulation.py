@@ -199,3 +199,18 @@ def test_generated_filter_keep_and_copy(n, nulls):
         got, copied = jit_emu.emulate_filter(tbl, pred)
         assert_tables_equal(got, E.filter(tbl, pred))
         assert 13 in copied   # "k" never has nulls: always copied by the generated code
+
+
+def test_generated_global_build_tier2_functions():
+    """The global-table build (mid / high cardinality): groups below T2 accumulate through t2_init / t2_update and are merged with
+    t2_flush, the rest go straight to global_update -- same results as the oracle either way."""
+    from helpers import oracle_agg
+    rng = np.random.default_rng(3)
+    tbl = random_table(rng, 4000, 0.2)
+    c = col
+    aggs = [c("f64").sum().alias("sf"), c("i32").max().alias("mx"), c("i32").min().alias("mn"), c("i64").count().alias("n"), c("u8").mean().alias("avg"),
+            c("f32").sum().alias("s32"), c("b").max().alias("bmax"), c("d").min().alias("dmin"), c("u64").sum().alias("su")]
+    for gb in ([c("k"), c("s")], [c("i32")], [c("u32"), c("b")]):
+        got, first = jit_emu.emulate_agg(tbl, aggs, gb, [c("f64") > -500.0], tier2=True)
+        want = oracle_agg(tbl, aggs, gb, [c("f64") > -500.0])
+        assert_tables_equal(got, want.select([a.name() for a in aggs]), float_rtol=1e-12)
