@@ -105,8 +105,9 @@ int b200_jit_describe(int32_t op, const uint8_t *plan, size_t plan_len, const in
         std::vector<uint8_t> nl(col_nullable, col_nullable + ncols);
         jit::Compiled meta;
         const int variant = (op >> 8) & 0xff;  // aggregate build: 0 direct loads, 1 global table, 2 TMA-staged (jit.h)
+        const bool with_take = ((op >> 16) & 1) != 0;  // projection evaluated at gathered rows (negative index -> null row)
         op &= 0xff;
-        const std::string src = jit::generate(op, plan, plan_len, dt, nl, false, meta, variant);
+        const std::string src = jit::generate(op, plan, plan_len, dt, nl, with_take, meta, variant);
         std::string t = "ptrs=";
         for (size_t i = 0; i < meta.ptrs.size(); i++)
             t += (i ? "," : "") + std::to_string(meta.ptrs[i].kind) + ":" + std::to_string(meta.ptrs[i].index);

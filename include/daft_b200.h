@@ -132,7 +132,8 @@ int b200_precompile(int32_t op, const uint8_t *plan, size_t plan_len, const int3
 /* Code generation only (no CUDA, no compile): the kernel parameter layout and the generated source of a plan, as text
  *   "ptrs=<kind>:<index>,...\nints=<kind>,...\nouts=<dtype>:<nullable>,...\n---\n<CUDA source>"
  * (ptr kinds: 0 column data, 1 column validity, 2 column offsets, 3 output data, 4 output validity, 5 output lengths,
- * 6 output offsets, 7 take indices, ...; see csrc/jit.h).  For aggregate plans bits 8-15 of `op` select the build
+ * 6 output offsets, 7 take indices, ...; see csrc/jit.h).  Bit 16 of `op` asks for the projection build that evaluates at
+ * gathered rows (take indices, negative = null row).  For aggregate plans bits 8-15 of `op` select the build
  * (0 direct loads, 1 global table, 2 TMA-staged) and the text also carries the group-table cell layout
  * (nkeys / nlane / nwarp / aggs / cellops).  Lets tests/test_jit_host_emulation.py run the generated per-row code on the
  * host against the oracle.  *out_text is malloc'd: release with b200_free_string. */

@@ -29,7 +29,7 @@ from daft_b200 import _lib
 from daft_b200 import datatypes as dt
 from daft_b200.expressions import encode_project
 
-P_COL_DATA, P_COL_VALID, P_COL_OFFSETS, P_OUT_DATA, P_OUT_VALID, P_OUT_LEN, P_OUT_OFFSETS = 0, 1, 2, 3, 4, 5, 6
+P_COL_DATA, P_COL_VALID, P_COL_OFFSETS, P_OUT_DATA, P_OUT_VALID, P_OUT_LEN, P_OUT_OFFSETS, P_TAKE = 0, 1, 2, 3, 4, 5, 6, 7
 I_N = 0
 
 _NP = {dt.I8: np.int8, dt.I16: np.int16, dt.I32: np.int32, dt.I64: np.int64, dt.U8: np.uint8, dt.U16: np.uint16, dt.U32: np.uint32,
@@ -69,6 +69,7 @@ template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
 
 _DRIVER = r"""
 extern "C" void emu_run(void **ptrs, int nptr, long long *ints, int nint, long long n, int pass) {
+    const long long *take = Prog::PTR_TAKE >= 0 ? (const long long *)ptrs[Prog::PTR_TAKE < 0 ? 0 : Prog::PTR_TAKE] : nullptr;
     Prog::P p;
     for (int i = 0; i < nptr; i++) p.ptr[i] = ptrs[i];
     for (int i = 0; i < nint; i++) p.ival[i] = ints[i];
@@ -80,7 +81,7 @@ extern "C" void emu_run(void **ptrs, int nptr, long long *ints, int nint, long l
                 g_site = 0;
                 threadIdx.x = (unsigned)g_lane;
                 const long long i = base + g_lane;
-                Prog::row(p, i, i, i < n, pass);
+                Prog::row(p, i, (take && i < n) ? take[i] : i, i < n, pass);   // project_body: src = take[i] when gathering
             }
     }
 }
@@ -97,11 +98,11 @@ def _prelude_for_host() -> str:
     return text.replace("#pragma once", "") + "\n}  // namespace jit\n}  // namespace b200\n"
 
 
-def describe_project(exprs, names, dtypes, nullable):
+def describe_project(exprs, names, dtypes, nullable, with_take: bool = False):
     plan, onames, odt = encode_project(exprs, names, dtypes)
     out, err = ctypes.c_void_p(), ctypes.c_void_p()
     n = len(dtypes)
-    rc = _lib.lib().b200_jit_describe(ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * n)(*dtypes),
+    rc = _lib.lib().b200_jit_describe(ctypes.c_int32((1 << 16) if with_take else 0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * n)(*dtypes),
                                       (ctypes.c_uint8 * n)(*nullable), ctypes.c_int32(n), ctypes.byref(out), ctypes.byref(err))
     _lib.check(rc, err)
     text = ctypes.string_at(out.value).decode()
@@ -140,30 +141,35 @@ def _pack_bits(mask: np.ndarray, nwords32: int) -> np.ndarray:
     return out
 
 
-def emulate_project(tbl: pa.Table, exprs) -> pa.Table:
-    """eval_expression_list through the generated `Prog::row`, on the host."""
+def emulate_project(tbl: pa.Table, exprs, take=None) -> pa.Table:
+    """eval_expression_list through the generated `Prog::row`, on the host.  take: int64 row indices to evaluate at (the
+    gathering build op_project uses for group keys, any_value and join outputs); a negative index yields a null row."""
     tbl = tbl.combine_chunks()
-    n = tbl.num_rows
+    n_in = tbl.num_rows
+    n = n_in if take is None else len(take)
     names = tbl.column_names
     cols = [tbl.column(i).chunk(0) if tbl.column(i).num_chunks else pa.array([], type=tbl.column(i).type) for i in range(len(names))]
     dtypes = [dt.from_arrow(c.type) for c in cols]
     nullable = [1 if c.null_count > 0 else 0 for c in cols]
-    src, ptrs, ints, outs, onames, odt = describe_project(exprs, names, dtypes, nullable)
+    src, ptrs, ints, outs, onames, odt = describe_project(exprs, names, dtypes, nullable, take is not None)
     lib = _compile(src)
     nw = max((n + 31) // 32, 1)
+    nw_in = max((n_in + 31) // 32, 1)
     keep, slots, out_bufs = [], [], {}
     for kind, idx in ptrs:
-        if kind in (P_COL_DATA, P_COL_VALID, P_COL_OFFSETS):
+        if kind == P_TAKE:
+            buf = np.concatenate([np.asarray(take, dtype=np.int64), np.zeros(32, np.int64)])
+        elif kind in (P_COL_DATA, P_COL_VALID, P_COL_OFFSETS):
             c, code = cols[idx], dtypes[idx]
             if kind == P_COL_VALID:
-                buf = _pack_bits(np.asarray(c.is_valid()), nw + 1)
+                buf = _pack_bits(np.asarray(c.is_valid()), nw_in + 1)
             elif kind == P_COL_OFFSETS:
-                buf = np.frombuffer(c.buffers()[1], dtype=np.int64, count=n + 1 + c.offset)[c.offset:].copy() if n else np.zeros(1, np.int64)
+                buf = np.frombuffer(c.buffers()[1], dtype=np.int64, count=n_in + 1 + c.offset)[c.offset:].copy() if n_in else np.zeros(1, np.int64)
             elif dt.is_string(code):
                 raw = c.buffers()[2]
                 buf = np.concatenate([np.frombuffer(raw, dtype=np.uint8) if raw is not None else np.zeros(0, np.uint8), np.zeros(16, np.uint8)])
             elif code == dt.BOOL:
-                buf = _pack_bits(np.asarray(c.fill_null(False)), nw + 1)
+                buf = _pack_bits(np.asarray(c.fill_null(False)), nw_in + 1)
             elif code == dt.NULL:
                 buf = np.zeros(8, np.uint8)
             else:

@@ -56,17 +56,38 @@ class _EmulatedBatch:
         """Aggregate columns through the generated aggregate code (jit_emu.emulate_agg); the key columns are the group-by
         expressions at each group's first row, which is how op_agg_first_rows builds them (a projection at the first rows)."""
         group_by = list(group_by or [])
-        cols, first = jit_emu.emulate_agg(self._t, list(aggs), group_by, predicate)
+        aggs = list(aggs)
+
+        def inner(a):
+            while a.kind == "alias":
+                a = a.args[0]
+            return a
+        # let the library's code generator see the plan as submitted (it refuses what the device does not offer)
+        names = self._t.column_names
+        dts = [daft_b200.datatypes.from_arrow(self._t.schema.field(n).type) for n in names]
+        from daft_b200.expressions import encode_agg
+        jit_emu.describe_agg(encode_agg(aggs, group_by, names, dts, predicate), dts, [1 if self._t.column(n).null_count else 0 for n in names])
+        anyv = [a for a in aggs if inner(a).op == "any_value"]
+        plain = [a for a in aggs if inner(a).op != "any_value"] or [col(self._t.column_names[0]).count("all").alias("__rows")]
+        cols, first = jit_emu.emulate_agg(self._t, plain, group_by, predicate)
+        out = {n: cols.column(n) for n in cols.column_names}
+        if anyv:   # any_value = the child expression at the group's first row: one gathering projection (op_agg_first_rows)
+            at_first = jit_emu.emulate_project(self._t, [inner(a).args[0].alias(a.name()) for a in anyv], take=first) if self._t.num_rows else \
+                pa.table({a.name(): pa.nulls(len(first)) for a in anyv})
+            out.update({n: at_first.column(n) for n in at_first.column_names})
+        ordered = [out[a.name()] for a in aggs]
+        names = [a.name() for a in aggs]
         if not group_by:
-            return _Result(cols)
-        keys = jit_emu.emulate_project(self._t.take(pa.array(first, type=pa.int64())), group_by)
-        return _Result(pa.table(keys.columns + cols.columns, names=keys.column_names + cols.column_names))
+            return _Result(pa.table(ordered, names=names))
+        keys = jit_emu.emulate_project(self._t, group_by, take=first)   # group keys: the same gathering projection
+        return _Result(pa.table(keys.columns + ordered, names=keys.column_names + names))
 
 
 class _EmulatedModule:
     col = staticmethod(daft_b200.col)
     lit = staticmethod(daft_b200.lit)
     RecordBatch = _EmulatedBatch
+    B200Error = daft_b200._lib.B200Error
 
 
 EMU = _EmulatedModule()
@@ -214,3 +235,21 @@ def test_generated_global_build_tier2_functions():
         got, first = jit_emu.emulate_agg(tbl, aggs, gb, [c("f64") > -500.0], tier2=True)
         want = oracle_agg(tbl, aggs, gb, [c("f64") > -500.0])
         assert_tables_equal(got, want.select([a.name() for a in aggs]), float_rtol=1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 700, 5000])
+def test_generated_any_value_and_bool_aggs(n):
+    """any_value (a gathering projection at the groups' first rows) and the boolean min / max aggregates."""
+    parity.test_any_value_and_bool_aggs(EMU, n)
+
+
+def test_generated_gathering_projection_null_rows():
+    """The projection build that evaluates at gathered rows (group keys, any_value, join outputs): a negative index is a row of
+    nulls, so `is_null` turns true there and literals stay valid -- compared with the oracle on the taken table."""
+    rng = np.random.default_rng(5)
+    tbl = random_table(rng, 1000, 0.2)
+    idx = np.where(rng.random(700) < 0.15, -1, rng.integers(0, 1000, 700))
+    exprs = parity.exprs_under_test(EMU.col, EMU.lit)
+    got = jit_emu.emulate_project(tbl, exprs, take=idx)
+    want = E.eval_expression_list(tbl.take(pa.array([None if i < 0 else int(i) for i in idx], type=pa.int64())), exprs)
+    assert_tables_equal(got, want)
