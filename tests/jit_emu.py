@@ -251,15 +251,30 @@ AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_MEAN = 0, 1, 2, 3, 4
 _AGG_SHIM = r"""
 #include <unordered_map>
 #include <vector>
-static inline double atomicAdd(double *p, double v) { const double o = *p; *p = o + v; return o; }
-static inline float atomicAdd(float *p, float v) { const float o = *p; *p = o + v; return o; }
-static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
-static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
-static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v < o) *p = v; return o; }
-static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int) { return v; }
-static inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v, int) { return v; }
-static inline double __shfl_xor_sync(unsigned, double v, int) { return v; }
-static inline float __shfl_xor_sync(unsigned, float v, int) { return v; }
+static bool g_commit = true;   // false while a warp-wide reduction is being replayed to its fixed point (see emu_agg_tier1)
+static inline double atomicAdd(double *p, double v) { const double o = *p; if (g_commit) *p = o + v; return o; }
+static inline float atomicAdd(float *p, float v) { const float o = *p; if (g_commit) *p = o + v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (g_commit) *p = o + v; return o; }
+static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (g_commit && v > o) *p = v; return o; }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (g_commit && v < o) *p = v; return o; }
+// Butterfly shuffles: lanes run one after the other, so a lane cannot see its partner's value of the same step.  The flush is
+// pure, so it is replayed: every replay records each lane's value per shuffle call site and hands out the partner's value of the
+// PREVIOUS replay; after as many replays as there are dependent steps every value is the true one.
+static unsigned long long g_shfl_prev[512][32], g_shfl_cur[512][32];
+static int g_shfl_site;
+template <typename T> static inline T emu_shfl_xor(T v, int d) {
+    const int s = g_shfl_site++;
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    g_shfl_cur[s][g_lane] = bits;
+    T out;
+    memcpy(&out, &g_shfl_prev[s][g_lane ^ d], sizeof(T));
+    return out;
+}
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int d) { return emu_shfl_xor(v, d); }
+static inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v, int d) { return emu_shfl_xor(v, d); }
+static inline double __shfl_xor_sync(unsigned, double v, int d) { return emu_shfl_xor(v, d); }
+static inline float __shfl_xor_sync(unsigned, float v, int d) { return emu_shfl_xor(v, d); }
 static inline bool __all_sync(unsigned, bool p) { return p; }
 struct PfLaneEmu;
 """
@@ -316,6 +331,89 @@ extern "C" long long emu_agg(void **ptrs, int nptr, long long *ints, int nint, l
 """
 
 
+_TIER1_DRIVER = r"""
+// The low-cardinality build's accumulate path: per-lane private cells (lane_init / lane_update), ballot count cells (warp_cells) and
+// the warp-wide flush into the global cells.  One emulated warp processes the rows 32 at a time; the other warps of the CTA keep
+// their freshly initialised cells, which the flush folds in as it would on the device.
+extern "C" long long emu_agg_tier1(void **ptrs, int nptr, long long *ints, int nint, long long n, long long cap) {
+    Prog::P p;
+    for (int i = 0; i < nptr; i++) p.ptr[i] = ptrs[i];
+    for (int i = 0; i < nint; i++) p.ival[i] = ints[i];
+    constexpr int NL = Prog::NLANE, NW = Prog::NWARP > 0 ? Prog::NWARP : 1;
+    const size_t lstride = (size_t)NL * 32, wstride = NW;
+    std::unordered_multimap<uint64_t, long long> table;
+    std::vector<Prog::Keys> group_keys;
+    std::vector<std::vector<unsigned long long>> lcells, wcells;
+    long long ngroups = 0;
+    auto new_group = [&]() {
+        lcells.emplace_back((size_t)AGG_WARPS * lstride);
+        wcells.emplace_back((size_t)AGG_WARPS * wstride, 0ULL);
+        for (int w = 0; w < AGG_WARPS; w++)
+            for (int l = 0; l < 32; l++) Prog::lane_init(lcells.back().data() + (size_t)w * lstride + l);
+        return ngroups++;
+    };
+    if (Prog::NKEYS == 0) new_group();
+    for (long long base = 0; base < n; base += 32) {
+        Prog::Vals vals[32];
+        long long gid[32];
+        for (int l = 0; l < 32; l++) {
+            gid[l] = -1;
+            const long long row = base + l;
+            if (row >= n) continue;
+            Prog::Raw r;
+            Prog::load(p, row, r);
+            Prog::load2(p, row, r);
+            Prog::Keys k;
+            if (!Prog::eval(p, r, k, vals[l])) continue;
+            long long slot = -1;
+            if constexpr (Prog::NKEYS > 0) {
+                const uint64_t code = Prog::code(k);
+                auto range = table.equal_range(code);
+                for (auto it = range.first; it != range.second; ++it)
+                    if (Prog::keys_equal(group_keys[it->second], k)) { slot = it->second; break; }
+                if (slot < 0) {
+                    if (ngroups >= cap) return -1;
+                    slot = new_group();
+                    group_keys.push_back(k);
+                    table.emplace(code, slot);
+                }
+            } else {
+                slot = 0;
+            }
+            gid[l] = slot;
+            Prog::lane_update(lcells[slot].data() + l, vals[l], row);   // warp 0, lane l
+        }
+        for (int l = 0; l < 32; l++) {
+            const long long g = gid[l];
+            if (g < 0) continue;
+            bool first = true;
+            for (int m = 0; m < l; m++) first = first && gid[m] != g;
+            if (!first) continue;
+            memset(g_ballots, 0, sizeof(g_ballots));
+            for (g_phase = 0; g_phase < 2; g_phase++)
+                for (g_lane = 0; g_lane < 32; g_lane++) {
+                    g_site = 0;
+                    Prog::warp_cells(vals[g_lane], gid[g_lane] == g, wcells[g].data(), g_lane);
+                }
+        }
+    }
+    for (long long g = 0; g < ngroups; g++) {
+        memset(g_shfl_prev, 0, sizeof(g_shfl_prev));
+        for (int rep = 0; rep < 8; rep++) {
+            g_commit = rep == 7;
+            for (g_lane = 0; g_lane < 32; g_lane++) {
+                g_shfl_site = 0;
+                Prog::flush(p, g, lcells[g].data(), lstride, wcells[g].data(), wstride, g_lane);
+            }
+            memcpy(g_shfl_prev, g_shfl_cur, sizeof(g_shfl_prev));
+        }
+        g_commit = true;
+    }
+    return ngroups;
+}
+"""
+
+
 def describe_agg(plan: bytes, dtypes, nullable, variant: int = 0):
     out, err = ctypes.c_void_p(), ctypes.c_void_p()
     n = len(dtypes)
@@ -335,7 +433,7 @@ def describe_agg(plan: bytes, dtypes, nullable, variant: int = 0):
                 nkeys=int(f["nkeys"]), nlane=int(f["nlane"]), nwarp=int(f["nwarp"]), aggs=aggs, cellops=[int(s) for s in f["cellops"].split(",") if s])
 
 
-def _compile_agg(src: str, staged: bool = False) -> ctypes.CDLL:
+def _compile_agg(src: str, staged: bool = False, tier1: bool = False) -> ctypes.CDLL:
     lines = src.split("\n")
     defines = "\n".join(l for l in lines if l.startswith("#define"))     # hoisted in front of the prelude by the library too
     body = "\n".join(l for l in lines if "__global__" not in l and not l.startswith("#define"))
@@ -345,7 +443,7 @@ def _compile_agg(src: str, staged: bool = False) -> ctypes.CDLL:
     m = re.search(r"struct PfLane \{.*?\};", text, re.S)
     extra = "#ifndef B200_AGG_WARPS\n#define B200_AGG_WARPS 8\n#endif\nconstexpr int AGG_WARPS = B200_AGG_WARPS;\n" + m.group(0) + "\n"
     full = _SHIM + _AGG_SHIM + (_STAGED_SHIM if staged else "") + defines + "\n" + head + extra + "\n}  // namespace jit\n}  // namespace b200\n" + body + \
-        (_STAGED_DRIVER if staged else _AGG_DRIVER)
+        (_STAGED_DRIVER if staged else _TIER1_DRIVER if tier1 else _AGG_DRIVER)
     tag = hashlib.sha1(full.encode()).hexdigest()[:16]
     d = os.path.join(tempfile.gettempdir(), "daft_b200_jit_emu")
     os.makedirs(d, exist_ok=True)
@@ -390,7 +488,7 @@ def _decode_ord(cells: np.ndarray, code: int) -> np.ndarray:
     return cells.astype(_NP[code])
 
 
-def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = False, tier2: bool = False):
+def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = False, tier2: bool = False, tier1: bool = False):
     """(aggregate columns in first-occurrence group order, first row of every group) through the generated aggregate code.
     staged=True runs the TMA-staged build of an ungrouped plan: full tiles go through stage_issue / load_staged."""
     from daft_b200.expressions import encode_agg
@@ -402,7 +500,8 @@ def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = Fa
     nullable = [1 if c.null_count > 0 else 0 for c in cols]
     # tier2=True: the global-table build, its first T2 groups going through the shared-memory tier (t2_init / t2_update / t2_flush)
     d = describe_agg(encode_agg(aggs, group_by, names, dtypes, predicate), dtypes, nullable, 2 if staged else 1 if tier2 else 0)
-    lib = _compile_agg(d["src"], staged)
+    # tier1=True: the low-cardinality build's own accumulate path (lane_init / lane_update / warp_cells / flush)
+    lib = _compile_agg(d["src"], staged, tier1)
     nw = max((n + 31) // 32, 1)
     cap = max(n, 1)
     ncell = d["nlane"] + d["nwarp"]
@@ -431,6 +530,10 @@ def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = Fa
                                          ctypes.c_int(len(ivals)), ctypes.c_longlong(n))
         assert staged_rows > 0 or n < 4096, "no tile went through the stage"
         ng = 1
+    elif tier1:
+        lib.emu_agg_tier1.restype = ctypes.c_longlong
+        ng = lib.emu_agg_tier1((ctypes.c_void_p * len(slots))(*slots), ctypes.c_int(len(slots)), (ctypes.c_longlong * len(ivals))(*ivals),
+                               ctypes.c_int(len(ivals)), ctypes.c_longlong(n), ctypes.c_longlong(cap))
     else:
         lib.emu_agg.restype = ctypes.c_longlong
         ng = lib.emu_agg((ctypes.c_void_p * len(slots))(*slots), ctypes.c_int(len(slots)), (ctypes.c_longlong * len(ivals))(*ivals),

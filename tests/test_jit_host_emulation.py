@@ -34,6 +34,8 @@ class _Result:
 class _EmulatedBatch:
     """Stands in for daft_b200.RecordBatch: projections (and filter predicates) run through the generated code on the host."""
 
+    AGG_MODE: dict = {}   # which generated accumulate path agg() drives: {} = global_update, {"tier1": True} = lane cells + flush
+
     def __init__(self, tbl):
         self._t = tbl
 
@@ -69,7 +71,7 @@ class _EmulatedBatch:
         jit_emu.describe_agg(encode_agg(aggs, group_by, names, dts, predicate), dts, [1 if self._t.column(n).null_count else 0 for n in names])
         anyv = [a for a in aggs if inner(a).op == "any_value"]
         plain = [a for a in aggs if inner(a).op != "any_value"] or [col(self._t.column_names[0]).count("all").alias("__rows")]
-        cols, first = jit_emu.emulate_agg(self._t, plain, group_by, predicate)
+        cols, first = jit_emu.emulate_agg(self._t, plain, group_by, predicate, **self.AGG_MODE)
         out = {n: cols.column(n) for n in cols.column_names}
         if anyv:   # any_value = the child expression at the group's first row: one gathering projection (op_agg_first_rows)
             at_first = jit_emu.emulate_project(self._t, [inner(a).args[0].alias(a.name()) for a in anyv], take=first) if self._t.num_rows else \
@@ -91,6 +93,17 @@ class _EmulatedModule:
 
 
 EMU = _EmulatedModule()
+
+
+class _EmulatedBatchTier1(_EmulatedBatch):
+    AGG_MODE = {"tier1": True}
+
+
+class _EmulatedModuleTier1(_EmulatedModule):
+    RecordBatch = _EmulatedBatchTier1
+
+
+EMU_T1 = _EmulatedModuleTier1()
 
 @pytest.mark.parametrize("n,nulls", [(0, 0.1), (1, 0.0), (100, 0.3), (4097, 0.1), (4097, 0.0)])
 def test_generated_projection_code_matches_oracle(n, nulls):
@@ -253,3 +266,27 @@ def test_generated_gathering_projection_null_rows():
     got = jit_emu.emulate_project(tbl, exprs, take=idx)
     want = E.eval_expression_list(tbl.take(pa.array([None if i < 0 else int(i) for i in idx], type=pa.int64())), exprs)
     assert_tables_equal(got, want)
+
+
+@pytest.mark.parametrize("n,nulls", [(0, 0.1), (1, 0.0), (1000, 0.2), (5000, 0.3)])
+def test_generated_tier1_accumulate_path_matches_oracle(n, nulls):
+    """The low-cardinality build's own accumulate path -- what the Q1 kernel runs per row: per-lane private cells (lane_init /
+    lane_update), ballot count cells (warp_cells) and the warp-wide butterfly flush into the global cells (shuffles replayed to
+    their fixed point) -- over the group-by matrix of the device parity test, plus the ungrouped / predicate / null-key cases."""
+    parity.test_groupby_inline_aggs(EMU_T1, n, nulls)
+    if n == 1000:
+        parity.test_ungrouped_and_fused_predicate(EMU_T1)
+        parity.test_groupby_null_and_nan_keys(EMU_T1)
+
+
+def test_generated_tier1_tpch_q1_matches_golden_answers():
+    import json
+    import os
+    from daft_b200 import tpch
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tpch_q1_q6_sf001.json")))
+    li = tpch.generate_host("lineitem", 0.01, tpch.Q1_COLUMNS)
+    predicate, group_by, aggs = tpch.q1_exprs()
+    got = _EmulatedBatchTier1(li).agg(aggs, group_by, predicate).to_arrow_table().sort_by([("L_RETURNFLAG", "ascending"), ("L_LINESTATUS", "ascending")]).to_pydict()
+    for name, vals in golden["q1"].items():
+        for a, b in zip(got[name], vals):
+            assert a == b or abs(a - b) <= 1e-9 * abs(b), (name, a, b)
