@@ -19,6 +19,9 @@ int set_err(char **errmsg, const std::string &msg) {
 template <class F>
 int guard(char **errmsg, F &&f) {
     try {
+        // Entry points may be called from any host thread: a new thread's current device is 0, so every call selects the
+        // library's device first (launches and stream-ordered allocations on ctx().stream need it current).
+        if (ctx().ready) cudaSetDevice(ctx().device);
         f();
         return 0;
     } catch (const std::exception &e) {
@@ -31,6 +34,23 @@ const Column &col_at(const Batch *b, int32_t i) {
     if (!b) fail("null batch");
     if (i < 0 || i >= (int32_t)b->cols.size()) fail("column index out of range");
     return b->cols[i];
+}
+// Operators work on plain columns: views (join outputs) are gathered here, on first use, and only the columns asked for.
+Batch plain(const b200_batch *b, const std::vector<int32_t> *cols = nullptr) {
+    if (!b) fail("null batch");
+    return materialize_batch(*b, cols);
+}
+Batch plain_keys(const b200_batch *b, const int32_t *key_cols, int32_t nkeys) {
+    if (!b) fail("null batch");
+    std::vector<int32_t> k(key_cols, key_cols + (nkeys > 0 ? nkeys : 0));
+    return materialize_batch(*b, &k);
+}
+Batch plain_for_plan(const b200_batch *b, int op, const uint8_t *plan, size_t plan_len) {
+    if (!b) fail("null batch");
+    const std::vector<int32_t> cols = jit::referenced_columns(op, plan, plan_len);
+    for (int32_t c : cols)
+        if (c < 0 || c >= (int32_t)b->cols.size()) fail("plan: column index out of range");
+    return materialize_batch(*b, &cols);
 }
 }  // namespace
 
@@ -144,8 +164,7 @@ int b200_batch_import(struct ArrowArray *array, struct ArrowSchema *schema, b200
 }
 int b200_batch_export(const b200_batch *batch, struct ArrowArray *out_array, struct ArrowSchema *out_schema, char **errmsg) {
     return guard(errmsg, [&] {
-        if (!batch) fail("null batch");
-        export_batch(*batch, out_array, out_schema);
+        export_batch(plain(batch), out_array, out_schema);
     });
 }
 int b200_batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t num_rows, b200_batch **out, char **errmsg) {
@@ -153,7 +172,8 @@ int b200_batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t 
 }
 int b200_batch_describe(const b200_batch *batch, int32_t col, b200_column_desc *out, char **errmsg) {
     return guard(errmsg, [&] {
-        const Column &c = col_at(batch, col);
+        const Column c = materialize(col_at(batch, col));
+        if (col_at(batch, col).is_view()) const_cast<b200_batch *>(batch)->cols[col] = c;  // keeps the described pointers alive
         out->dtype = c.dtype;
         out->_reserved = 0;
         out->length = c.length;
@@ -162,7 +182,7 @@ int b200_batch_describe(const b200_batch *batch, int32_t col, b200_column_desc *
         out->offsets = c.offsets ? c.offsets->ptr : nullptr;
         out->data = c.data ? c.data->ptr : nullptr;
         out->data_bytes = c.data_bytes;
-        out->name = c.name.c_str();
+        out->name = batch->cols[col].name.c_str();
     });
 }
 int b200_batch_dtypes(const b200_batch *batch, int32_t *out_dtypes, int32_t n, char **errmsg) {
@@ -177,7 +197,8 @@ int32_t b200_batch_num_columns(const b200_batch *batch) { return batch ? (int32_
 int64_t b200_batch_size_bytes(const b200_batch *batch) {
     if (!batch) return -1;
     int64_t s = 0;
-    for (auto &c : batch->cols) {
+    for (auto &c0 : batch->cols) {
+        const Column &c = c0.is_view() ? *c0.base : c0;  // a view is sized by what it selects from
         s += c.data_bytes;
         if (c.offsets) s += (c.length + 1) * 8;
         if (c.validity) s += (c.length + 7) / 8;
@@ -226,16 +247,16 @@ int b200_hash_rows(const b200_batch *batch, const int32_t *key_cols, int32_t nke
                    char **errmsg) {
     return guard(errmsg, [&] {
         require_device();
-        if (!batch) fail("null batch");
+        const Batch in = plain_keys(batch, key_cols, nkeys);
         const uint64_t *sd = nullptr;
         if (seed) {
-            const Column &s = col_at(seed, 0);
+            const Column s = materialize(col_at(seed, 0));
             if (s.dtype != B200_U64) fail(std::string("seed data type expected to be uint64, got ") + dtype_name(s.dtype));
             if (s.length != batch->num_rows) fail("seed length does not match array length");
             if (s.null_count) fail("seed must not contain nulls");
             sd = as<uint64_t>(s.data);
         }
-        Buf h = hash_rows(*batch, key_cols, nkeys, sd);
+        Buf h = hash_rows(in, key_cols, nkeys, sd);
         auto o = std::make_unique<Batch>();
         o->num_rows = batch->num_rows;
         o->cols.push_back(make_u64_column("hash", h, batch->num_rows));
@@ -245,8 +266,7 @@ int b200_hash_rows(const b200_batch *batch, const int32_t *key_cols, int32_t nke
 int b200_partition_by_hash(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, int32_t num_partitions,
                            b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
-        if (!batch) fail("null batch");
-        std::vector<Batch *> parts = op_partition_by_hash(*batch, key_cols, nkeys, num_partitions);
+        std::vector<Batch *> parts = op_partition_by_hash(plain(batch), key_cols, nkeys, num_partitions);
         for (int i = 0; i < num_partitions; i++) out[i] = parts[i];
     });
 }
@@ -255,7 +275,7 @@ int b200_search_sorted(const b200_batch *sorted, const b200_batch *batch, const 
                        b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
         if (!sorted || !batch) fail("null batch");
-        Buf pos = op_search_sorted(*sorted, *batch, key_cols, nkeys, descending);
+        Buf pos = op_search_sorted(plain(sorted), plain_keys(batch, key_cols, nkeys), key_cols, nkeys, descending);
         auto o = std::make_unique<Batch>();
         o->num_rows = batch->num_rows;
         o->cols.push_back(make_u64_column("idx", pos, batch->num_rows));
@@ -266,33 +286,33 @@ int b200_partition_by_range(const b200_batch *batch, const int32_t *key_cols, in
                             const uint8_t *descending, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
         if (!batch || !boundaries) fail("null batch");
-        std::vector<Batch *> parts = op_partition_by_range(*batch, key_cols, nkeys, *boundaries, descending);
+        std::vector<Batch *> parts = op_partition_by_range(plain(batch), key_cols, nkeys, plain(boundaries), descending);
         for (size_t i = 0; i < parts.size(); i++) out[i] = parts[i];
     });
 }
 
 // ---- filter / project / agg -----------------------------------------------------------------------
 int b200_filter(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = op_filter(*batch, plan, plan_len); });
+    return guard(errmsg, [&] { *out = op_filter(plain(batch), plan, plan_len); });
 }
 int b200_eval_expression_list(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = op_project(*batch, plan, plan_len, nullptr, 0); });
+    return guard(errmsg, [&] { *out = op_project(plain_for_plan(batch, B200_OP_PROJECT, plan, plan_len), plan, plan_len, nullptr, 0); });
 }
 int b200_agg(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = op_agg(*batch, plan, plan_len); });
+    return guard(errmsg, [&] { *out = op_agg(plain_for_plan(batch, B200_OP_AGG, plan, plan_len), plan, plan_len); });
 }
 int b200_dedup(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = op_dedup(*batch, key_cols, nkeys); });
+    return guard(errmsg, [&] { *out = op_dedup(plain(batch), key_cols, nkeys); });
 }
 
 // ---- take / concat ----------------------------------------------------------------------------------
 int b200_take(const b200_batch *batch, const b200_batch *indices, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
         require_device();
-        const Column &ic = col_at(indices, 0);
+        const Column ic = materialize(col_at(indices, 0));
         Buf idx = indices_to_i64(ic);
         check_take_indices(as<int64_t>(idx), ic.length, batch->num_rows, ic.null_count > 0);
-        *out = gather_batch(*batch, as<int64_t>(idx), ic.length, ic.null_count > 0);
+        *out = gather_batch(plain(batch), as<int64_t>(idx), ic.length, ic.null_count > 0);
         op_done();
     });
 }
@@ -302,13 +322,15 @@ int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, c
         if (n < 1) fail("concat: need at least one batch");
         auto o = std::make_unique<Batch>();
         const size_t nc = batches[0]->cols.size();
+        std::vector<Batch> ins;
         for (int i = 0; i < n; i++) {
             if (batches[i]->cols.size() != nc) fail("concat: schema mismatch");
             o->num_rows += batches[i]->num_rows;
+            ins.push_back(plain(batches[i]));
         }
         for (size_t c = 0; c < nc; c++) {
             std::vector<const Column *> cs;
-            for (int i = 0; i < n; i++) cs.push_back(&batches[i]->cols[c]);
+            for (int i = 0; i < n; i++) cs.push_back(&ins[i].cols[c]);
             o->cols.push_back(concat_columns(cs));
         }
         op_done();
@@ -320,7 +342,7 @@ int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, c
 int b200_argsort(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
                  const uint8_t *nulls_first, b200_batch **out_indices, char **errmsg) {
     return guard(errmsg, [&] {
-        Buf idx = op_argsort(*batch, key_cols, nkeys, descending, nulls_first);
+        Buf idx = op_argsort(plain_keys(batch, key_cols, nkeys), key_cols, nkeys, descending, nulls_first);
         auto o = std::make_unique<Batch>();
         o->num_rows = batch->num_rows;
         o->cols.push_back(make_u64_column("indices", idx, batch->num_rows));
@@ -330,8 +352,9 @@ int b200_argsort(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys
 int b200_sort(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
               const uint8_t *nulls_first, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
-        Buf idx = op_argsort(*batch, key_cols, nkeys, descending, nulls_first);
-        *out = gather_batch(*batch, as<int64_t>(idx), batch->num_rows, false, true);
+        const Batch in = plain(batch);
+        Buf idx = op_argsort(in, key_cols, nkeys, descending, nulls_first);
+        *out = gather_batch(in, as<int64_t>(idx), in.num_rows, false, true);
         op_done();
     });
 }
@@ -342,8 +365,9 @@ int b200_top_n(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, 
         const int64_t n = batch->num_rows;
         const int64_t start = std::min<int64_t>(std::max<int64_t>(offset, 0), n);
         const int64_t end = std::min<int64_t>(n, start + std::max<int64_t>(limit, 0));
-        Buf idx = op_top_indices(*batch, key_cols, nkeys, descending, nulls_first, end);
-        *out = gather_batch(*batch, as<int64_t>(idx) + start, end - start, false);
+        const Batch in = plain(batch);
+        Buf idx = op_top_indices(in, key_cols, nkeys, descending, nulls_first, end);
+        *out = gather_batch(in, as<int64_t>(idx) + start, end - start, false);
         op_done();
     });
 }
@@ -378,7 +402,7 @@ int b200_hash_join_probe(const b200_probe_table *pt, b200_join_state *st, const 
 }
 int b200_hash_join_finalize(const b200_probe_table *pt, b200_join_state *st, const b200_batch *probe_schema_like,
                             int32_t build_on_left, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = hash_join_finalize(pt, st, *probe_schema_like, build_on_left != 0); });
+    return guard(errmsg, [&] { *out = hash_join_finalize(pt, st, plain(probe_schema_like), build_on_left != 0); });
 }
 
 // ---- exchange ----------------------------------------------------------------------------------------
@@ -391,10 +415,10 @@ int b200_comm_init(const uint8_t *id128, int32_t rank, int32_t world, b200_comm 
 void b200_comm_free(b200_comm *c) { comm_free(c); }
 int b200_exchange_by_hash(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out,
                           char **errmsg) {
-    return guard(errmsg, [&] { *out = exchange_by_hash(c, *batch, key_cols, nkeys); });
+    return guard(errmsg, [&] { *out = exchange_by_hash(c, plain(batch), key_cols, nkeys); });
 }
 int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = all_gather_batches(c, *batch); });
+    return guard(errmsg, [&] { *out = all_gather_batches(c, plain(batch)); });
 }
 
 // ---- TPC-H generator -----------------------------------------------------------------------------------

@@ -76,15 +76,28 @@ inline bool is_unsigned_int(int32_t dt) { return dt >= B200_U8 && dt <= B200_U64
 inline bool is_integer(int32_t dt) { return is_signed_int(dt) || is_unsigned_int(dt); }
 const char *dtype_name(int32_t dt);
 
+struct Column;
+// A VIEW column is a selection vector over another column: row i of the view is row sel[i] of `base` (a negative
+// index is a null row).  Join outputs are views (late materialisation: a probe chain moves row ids, not payload
+// columns; the reference pipelines morsel-sized intermediates through its probe operators for the same reason,
+// src/daft-local-execution/src/join/inner_join.rs:11-85).  A view is gathered into a plain column the first time an
+// operator needs its values; the result is cached in `state`, which every copy of the view shares.
+struct ViewState;
 struct Column {
     std::string name;
     int32_t dtype = B200_NULL;
     int64_t length = 0;
-    int64_t null_count = 0;  // exact
+    int64_t null_count = 0;  // exact (plain columns)
     Buf validity;            // null when null_count == 0
     Buf offsets;             // strings
     Buf data;
     int64_t data_bytes = 0;
+    // view part (all empty for a plain column)
+    std::shared_ptr<const Column> base;  // a plain column
+    Buf sel;                             // int64[length]
+    bool sel_may_be_negative = false;
+    std::shared_ptr<ViewState> state;
+    bool is_view() const { return (bool)sel; }
     bool nullable() const { return dtype == B200_NULL || null_count > 0; }
 };
 
@@ -118,6 +131,18 @@ Column concat_columns(const std::vector<const Column *> &cols);
 Buf indices_to_i64(const Column &c);
 void check_take_indices(const int64_t *idx, int64_t n, int64_t limit, bool null_marked);  // fails on idx >= limit / negative
 Column make_u64_column(const std::string &name, Buf data, int64_t n);
+
+// ---- views (runtime.cu) ------------------------------------------------------------------------
+// rows idx[0..n) of `src` as view columns (views of views compose their selection vectors: one small gather per
+// distinct selection vector of `src`)
+std::vector<Column> make_view_columns(const Batch &src, const Buf &idx, int64_t n, bool idx_may_be_negative);
+// the plain form of `c` (gathers a view on first use; cached)
+Column materialize(const Column &c);
+// a batch whose columns `cols` (all when null) are plain; view columns sharing a selection vector are gathered together
+Batch materialize_batch(const Batch &b, const std::vector<int32_t> *cols = nullptr);
+inline void require_plain(const Column &c) {
+    if (c.is_view()) fail("internal error: operator reached an unmaterialised view column '" + c.name + "'");
+}
 
 // ---- hashing (hash.cu) -----------------------------------------------------------------------
 // out[i] = xxh3_64(col[i], seed ? seed[i] : 0) with Daft's null rules

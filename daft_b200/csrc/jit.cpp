@@ -12,6 +12,7 @@
 #include <nvrtc.h>
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <fstream>
 #include <functional>
 #include <mutex>
@@ -1491,6 +1492,59 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         if (!stage_fits) meta.smem_bytes = 0;
     }
     return o.str();
+}
+
+// Column indices a plan reads (structure walk only, no typing): operators gather just these when the input holds views.
+static void scan_node(Reader &r, std::vector<int32_t> &cols) {
+    const int tag = r.u8();
+    switch (tag) {
+        case T_COL: cols.push_back((int32_t)r.u32()); break;
+        case T_LIT: {
+            const int dt = r.u8();
+            r.u8();
+            if (is_string(dt)) r.str();
+            else r.i64();
+            break;
+        }
+        case T_BINARY: r.u8(); scan_node(r, cols); scan_node(r, cols); break;
+        case T_UNARY: case T_CAST: r.u8(); scan_node(r, cols); break;
+        case T_IF_ELSE: case T_BETWEEN: scan_node(r, cols); scan_node(r, cols); scan_node(r, cols); break;
+        case T_IS_IN: {
+            scan_node(r, cols);
+            const uint32_t n = r.u32();
+            for (uint32_t i = 0; i < n; i++) scan_node(r, cols);
+            break;
+        }
+        case T_FILL_NULL: scan_node(r, cols); scan_node(r, cols); break;
+        case T_FUNCTION: {
+            r.u8();
+            const int n = r.u8();
+            for (int i = 0; i < n; i++) scan_node(r, cols);
+            break;
+        }
+        default: fail("plan: unknown node tag");
+    }
+}
+std::vector<int32_t> referenced_columns(int op, const uint8_t *plan, size_t plan_len) {
+    Reader r{plan, plan_len};
+    std::vector<int32_t> cols;
+    if (op == B200_OP_PROJECT) {
+        const uint32_t n = r.u32();
+        for (uint32_t i = 0; i < n; i++) { r.str(); scan_node(r, cols); }
+    } else if (op == B200_OP_FILTER) {
+        scan_node(r, cols);
+    } else if (op == B200_OP_AGG) {
+        if (r.u8()) scan_node(r, cols);
+        const uint32_t nk = r.u32();
+        for (uint32_t i = 0; i < nk; i++) { r.str(); scan_node(r, cols); }
+        const uint32_t na = r.u32();
+        for (uint32_t i = 0; i < na; i++) { r.u8(); r.u8(); r.str(); scan_node(r, cols); }
+    } else {
+        fail("jit: unknown op");
+    }
+    std::sort(cols.begin(), cols.end());
+    cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+    return cols;
 }
 
 std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,

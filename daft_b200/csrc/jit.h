@@ -72,6 +72,8 @@ struct Compiled {
 // 2 = the low-cardinality kernel fed by per-warp TMA bulk copies (cp.async.bulk + mbarrier stages)
 std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
                      const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta, int variant = 0);
+// column indices the plan reads
+std::vector<int32_t> referenced_columns(int op, const uint8_t *plan, size_t plan_len);
 // NVRTC -> cubin (cached on disk); works without a GPU.
 std::vector<char> compile_to_cubin(const std::string &source, std::string *path_out);
 // generate + compile + load; cached per (op, plan, dtypes, nullability, take)

@@ -1,5 +1,7 @@
 // Library context, stream-ordered device memory, and the small fixed-function kernels every
 // operator leans on: exclusive scan, bit counting, row gather (take), slice, concat.
+#include <mutex>
+
 #include "common.h"
 #include "kernels.cuh"
 
@@ -231,6 +233,7 @@ static int grid_for(int64_t n, int threads = 256) {
 }
 
 Column gather_column(const Column &src, const int64_t *idx, int64_t n, bool idx_may_be_negative) {
+    require_plain(src);
     cudaStream_t st = ctx().stream;
     Column out;
     out.name = src.name;
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(1024) gather_str_small(const __grid_constant__
 }
 
 Batch *gather_batch(const Batch &src, const int64_t *idx, int64_t n, bool idx_may_be_negative, bool permutation) {
+    for (const Column &c : src.cols) require_plain(c);
     auto out = std::make_unique<Batch>();
     out->num_rows = n;
     cudaStream_t st = ctx().stream;
@@ -427,6 +431,124 @@ Batch *gather_batch(const Batch &src, const int64_t *idx, int64_t n, bool idx_ma
     for (size_t c = 0; c < src.cols.size(); c++)
         if (!done[c]) out->cols[c] = gather_column(src.cols[c], idx, n, idx_may_be_negative);
     return out.release();
+}
+
+// ------------------------------------------------------------------------------------------------
+// views: selection vectors over plain columns (late materialisation of join outputs)
+// ------------------------------------------------------------------------------------------------
+struct ViewState {
+    std::mutex mu;
+    bool done = false;
+    Column plain;
+};
+
+// out[i] = idx[i] >= 0 ? inner[idx[i]] : -1   (selection vector of a view of a view)
+__global__ void compose_sel(const int64_t *__restrict__ inner, const int64_t *__restrict__ idx, int64_t n, int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t j = idx[i];
+        out[i] = j >= 0 ? inner[j] : -1;
+    }
+}
+
+static bool view_done(const Column &c) {
+    if (!c.is_view()) return true;
+    std::lock_guard<std::mutex> g(c.state->mu);
+    return c.state->done;
+}
+
+Column materialize(const Column &c) {
+    if (!c.is_view()) return c;
+    std::lock_guard<std::mutex> g(c.state->mu);
+    if (!c.state->done) {
+        c.state->plain = gather_column(*c.base, as<int64_t>(c.sel), c.length, c.sel_may_be_negative);
+        c.state->done = true;
+    }
+    Column out = c.state->plain;
+    out.name = c.name;
+    return out;
+}
+
+Batch materialize_batch(const Batch &b, const std::vector<int32_t> *cols) {
+    Batch out = b;
+    std::vector<int32_t> all;
+    if (!cols) {
+        for (size_t i = 0; i < b.cols.size(); i++) all.push_back((int32_t)i);
+        cols = &all;
+    }
+    // pending views grouped by selection vector: one fused gather per group
+    std::vector<int32_t> pending;
+    for (int32_t ci : *cols) {
+        if (ci < 0 || ci >= (int32_t)b.cols.size()) fail("column index out of range");
+        if (b.cols[ci].is_view() && !view_done(b.cols[ci])) pending.push_back(ci);
+    }
+    std::vector<char> taken(pending.size(), 0);
+    for (size_t a = 0; a < pending.size(); a++) {
+        if (taken[a]) continue;
+        const Column &ca = b.cols[pending[a]];
+        Batch group;
+        std::vector<size_t> members;
+        for (size_t k = a; k < pending.size(); k++) {
+            const Column &ck = b.cols[pending[k]];
+            if (taken[k] || ck.sel.get() != ca.sel.get() || ck.length != ca.length) continue;
+            bool dup = false;  // the same view listed twice (select of one column under two names)
+            for (size_t m : members) dup |= b.cols[pending[m]].state.get() == ck.state.get();
+            if (dup) continue;
+            taken[k] = 1;
+            members.push_back(k);
+            group.cols.push_back(*ck.base);
+        }
+        bool neg = false;
+        for (size_t m : members) neg |= b.cols[pending[m]].sel_may_be_negative;
+        group.num_rows = group.cols.empty() ? 0 : group.cols[0].length;
+        std::unique_ptr<Batch> g(gather_batch(group, as<int64_t>(ca.sel), ca.length, neg));
+        for (size_t m = 0; m < members.size(); m++) {
+            const Column &cm = b.cols[pending[members[m]]];
+            std::lock_guard<std::mutex> lk(cm.state->mu);
+            if (!cm.state->done) {
+                cm.state->plain = std::move(g->cols[m]);
+                cm.state->done = true;
+            }
+        }
+    }
+    for (int32_t ci : *cols)
+        if (out.cols[ci].is_view()) out.cols[ci] = materialize(b.cols[ci]);
+    return out;
+}
+
+std::vector<Column> make_view_columns(const Batch &src, const Buf &idx, int64_t n, bool idx_may_be_negative) {
+    std::vector<Column> out;
+    std::vector<std::pair<const DevAlloc *, Buf>> composed;  // inner selection vector -> composed vector
+    for (const Column &sc : src.cols) {
+        Column v;
+        v.name = sc.name;
+        v.dtype = sc.dtype;
+        v.length = n;
+        v.state = std::make_shared<ViewState>();
+        if (sc.is_view() && !view_done(sc)) {
+            Buf comp;
+            for (auto &pr : composed)
+                if (pr.first == sc.sel.get()) comp = pr.second;
+            if (!comp) {
+                comp = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+                if (n > 0) {
+                    compose_sel<<<grid_for(n), 256, 0, ctx().stream>>>(as<int64_t>(sc.sel), as<int64_t>(idx), n, as<int64_t>(comp));
+                    count_launch();
+                }
+                composed.emplace_back(sc.sel.get(), comp);
+            }
+            v.base = sc.base;
+            v.sel = comp;
+            v.sel_may_be_negative = idx_may_be_negative || sc.sel_may_be_negative;
+        } else {
+            v.base = std::make_shared<const Column>(materialize(sc));
+            v.sel = idx;
+            v.sel_may_be_negative = idx_may_be_negative;
+        }
+        out.push_back(std::move(v));
+    }
+    return out;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,6 +635,14 @@ __global__ void iota_i64(int64_t *out, int64_t n, int64_t start) {
 Column slice_column(const Column &src, int64_t start, int64_t end) {
     // byte-aligned fixed-width slices without nulls are views; everything else goes through gather
     const int64_t n = end - start;
+    if (src.is_view() && !view_done(src)) {  // a slice of a selection vector
+        Column out = src;
+        out.length = n;
+        out.sel = dev_sub(src.sel, (size_t)start * 8, (size_t)n * 8);
+        out.state = std::make_shared<ViewState>();
+        return out;
+    }
+    if (src.is_view()) return slice_column(materialize(src), start, end);
     int w = dtype_width(src.dtype);
     if (w && src.null_count == 0) {
         Column out = src;
@@ -554,6 +684,7 @@ __global__ void copy_bits(const uint8_t *__restrict__ src, int64_t nbits, uint8_
 }
 
 Column concat_columns(const std::vector<const Column *> &cols) {
+    for (auto *c : cols) require_plain(*c);
     cudaStream_t st = ctx().stream;
     Column out;
     out.name = cols[0]->name;

@@ -173,7 +173,7 @@ B200_HD uint64_t mix16(const uint8_t *in, int soff, uint64_t seed) {
     return mul128_fold64(ld64u(in) ^ (sec64(soff) + seed), ld64u(in + 8) ^ (sec64(soff + 8) - seed));
 }
 
-__host__ __device__ __noinline__ uint64_t hash_long(const uint8_t *in, int64_t len, uint64_t seed) {
+inline __host__ __device__ __noinline__ uint64_t hash_long(const uint8_t *in, int64_t len, uint64_t seed) {
     // secret word i (8-byte granular at byte offset `off`) with the seed folded in:
     // custom[16j..16j+8) = k + seed, custom[16j+8..16j+16) = k - seed; unaligned offsets straddle words.
     auto csec = [&](int off) -> uint64_t {
@@ -221,7 +221,7 @@ __host__ __device__ __noinline__ uint64_t hash_long(const uint8_t *in, int64_t l
     return xxh3_avalanche(r);
 }
 
-__host__ __device__ __noinline__ uint64_t hash_17plus(const uint8_t *in, int64_t len, uint64_t seed) {
+inline __host__ __device__ __noinline__ uint64_t hash_17plus(const uint8_t *in, int64_t len, uint64_t seed) {
     if (len <= 128) {
         uint64_t acc = (uint64_t)len * P64_1;
         if (len > 32) {

@@ -73,8 +73,15 @@ class JoinState:
 
 
 def _with_keys(batch: RecordBatch, on: Sequence[Expression], key_dtypes: Sequence[int]) -> tuple[RecordBatch, list[int]]:
-    """Append the evaluated (and supertype-cast) join key expressions as trailing columns."""
-    exprs = [e.cast(t).alias(f"__key{i}") for i, (e, t) in enumerate(zip(on, key_dtypes))]
+    """Append the evaluated (and supertype-cast) join key expressions as trailing columns.  A key that is a plain
+    column of the right dtype is passed through untouched (zero-copy; it may be a view, which the probe reads through
+    its selection vector), so a chain of joins never gathers its keys."""
+    from .expressions import bind
+    names, dts = batch.column_names(), batch.dtypes()
+    exprs = []
+    for i, (e, t) in enumerate(zip(on, key_dtypes)):
+        same = bind(e, names, dts).dtype == t
+        exprs.append((e if same else e.cast(t)).alias(f"__key{i}"))
     keys = batch.eval_expression_list(exprs)
     base = batch.num_columns()
     return batch.union(keys), [base + i for i in range(len(on))]

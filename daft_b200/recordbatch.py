@@ -429,9 +429,9 @@ class RecordBatch:
 
     # ---- join ---------------------------------------------------------------------------------------------
     def hash_join(self, right: "RecordBatch", left_on: Sequence[Expression], right_on: Sequence[Expression], how: str = "inner",
-                  null_equals_null: Sequence[bool] | None = None) -> "RecordBatch":
+                  null_equals_null: Sequence[bool] | None = None, build_on_left: bool | None = None) -> "RecordBatch":
         """RecordBatch::hash_join (src/daft-recordbatch/src/ops/joins/mod.rs) with the operator-level output
         schema of src/daft-local-execution/src/join/inner_join.rs:50-78: join keys that share a name (taken
         from the left), left non-key columns, right non-key columns (clashing names get a `right.` prefix)."""
         from .join import hash_join  # late import: join.py builds on this class
-        return hash_join(self, right, left_on, right_on, how, null_equals_null)
+        return hash_join(self, right, left_on, right_on, how, null_equals_null, build_on_left)

@@ -161,15 +161,18 @@ Q5_COLUMNS = {
 
 
 def q5(t: dict[str, RecordBatch]) -> RecordBatch:
-    region = t["region"].filter([col("R_NAME") == "ASIA"])
+    """The join order of answers.py:124-143; every join builds on its smaller side, as the reference planner decides
+    (src/daft-local-execution/src/pipeline.rs:1106-1194).  Join outputs are views (selection vectors), so the chain
+    moves row ids only: L_ORDERKEY is read through the first join's selection vector by the second probe, and
+    L_EXTENDEDPRICE / L_DISCOUNT are gathered for the rows that survive all five joins."""
     orders = t["orders"].filter([col("O_ORDERDATE") >= datetime.date(1994, 1, 1), col("O_ORDERDATE") < datetime.date(1995, 1, 1)])
-    j = region.hash_join(t["nation"], [col("R_REGIONKEY")], [col("N_REGIONKEY")])
-    j = j.hash_join(t["supplier"], [col("N_NATIONKEY")], [col("S_NATIONKEY")])
-    # probe the big table against the small build side: lineitem x (asia suppliers)
-    j = t["lineitem"].hash_join(j.eval_expression_list([col("N_NAME"), col("S_SUPPKEY"), col("S_NATIONKEY")]),
-                                [col("L_SUPPKEY")], [col("S_SUPPKEY")])
-    j = j.eval_expression_list([col("N_NAME"), col("L_ORDERKEY"), col("S_NATIONKEY"), col("L_EXTENDEDPRICE"), col("L_DISCOUNT")])
-    j = j.hash_join(orders.eval_expression_list([col("O_ORDERKEY"), col("O_CUSTKEY")]), [col("L_ORDERKEY")], [col("O_ORDERKEY")])
-    j = j.hash_join(t["customer"], [col("O_CUSTKEY"), col("S_NATIONKEY")], [col("C_CUSTKEY"), col("C_NATIONKEY")])
+    region = t["region"].filter([col("R_NAME") == "ASIA"])
+    j = region.hash_join(t["nation"], [col("R_REGIONKEY")], [col("N_REGIONKEY")], build_on_left=True)
+    j = j.hash_join(t["supplier"], [col("N_NATIONKEY")], [col("S_NATIONKEY")], build_on_left=True)
+    j = j.hash_join(t["lineitem"], [col("S_SUPPKEY")], [col("L_SUPPKEY")], build_on_left=True)
+    j = j.eval_expression_list([col("N_NAME"), col("L_EXTENDEDPRICE"), col("L_DISCOUNT"), col("L_ORDERKEY"), col("N_NATIONKEY")])
+    j = j.hash_join(orders, [col("L_ORDERKEY")], [col("O_ORDERKEY")], build_on_left=len(j) < len(orders))
+    j = j.hash_join(t["customer"], [col("O_CUSTKEY"), col("N_NATIONKEY")], [col("C_CUSTKEY"), col("C_NATIONKEY")],
+                    build_on_left=len(j) < len(t["customer"]))
     out = j.agg([(col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))).sum().alias("revenue")], [col("N_NAME")])
     return out.sort([col("revenue")], descending=True)

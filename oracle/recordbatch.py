@@ -61,7 +61,8 @@ class OracleRecordBatch:
         idx = O.argsort([E.eval_expression(self.tbl, k) for k in sort_keys], desc, nf)
         return OracleRecordBatch(self.tbl.take(pa.array(idx, type=pa.int64())))
 
-    def hash_join(self, right: "OracleRecordBatch", left_on, right_on, how="inner", null_equals_null=None) -> "OracleRecordBatch":
+    def hash_join(self, right: "OracleRecordBatch", left_on, right_on, how="inner", null_equals_null=None,
+                  build_on_left=None) -> "OracleRecordBatch":
         lt, rt = self.tbl, right.tbl
         lk, rk = [], []
         for i, (le, re_) in enumerate(zip(left_on, right_on)):
@@ -73,4 +74,4 @@ class OracleRecordBatch:
         new_names = [n if (n in common or n not in lt.column_names) else f"right.{n}" for n in rt.column_names]
         rmap = dict(zip(rt.column_names, new_names))
         rt2 = rt.rename_columns(new_names)
-        return OracleRecordBatch(O.hash_join(lt, rt2, lk, [rmap[k] for k in rk], how, null_equals_null))
+        return OracleRecordBatch(O.hash_join(lt, rt2, lk, [rmap[k] for k in rk], how, null_equals_null, build_on_left))
