@@ -50,16 +50,16 @@ class ColumnDesc(ctypes.Structure):
 # every symbol include/daft_b200.h declares (tests/test_abi_cpu.py checks the .so exports all of them)
 SYMBOLS = [
     "b200_abi_version", "b200_init", "b200_free_string", "b200_stream", "b200_synchronize", "b200_launch_count",
-    "b200_set_jit_cache_dir", "b200_precompile", "b200_jit_describe", "b200_kernel_timing", "b200_last_agg_kernel_ms",
-    "b200_batch_import", "b200_batch_export", "b200_batch_from_device", "b200_batch_describe", "b200_batch_num_rows",
+    "b200_set_jit_cache_dir", "b200_precompile", "b200_jit_describe", "b200_kernel_timing", "b200_last_agg_kernel_ms", "b200_kernel_timing_report",
+    "b200_batch_import", "b200_batch_export", "b200_batch_from_device", "b200_batch_describe", "b200_batch_materialize", "b200_batch_num_rows",
     "b200_batch_num_columns", "b200_batch_size_bytes", "b200_batch_free", "b200_batch_select", "b200_batch_rename",
     "b200_batch_union", "b200_batch_slice",
-    "b200_hash_rows", "b200_partition_by_hash", "b200_search_sorted", "b200_partition_by_range", "b200_batch_dtypes", "b200_filter", "b200_eval_expression_list", "b200_agg", "b200_dedup",
+    "b200_hash_rows", "b200_partition_by_hash", "b200_search_sorted", "b200_partition_by_range", "b200_batch_dtypes", "b200_filter", "b200_eval_expression_list", "b200_agg", "b200_dedup", "b200_groupby_create", "b200_groupby_push", "b200_groupby_finalize", "b200_groupby_free",
     "b200_take", "b200_concat", "b200_argsort", "b200_sort", "b200_top_n",
     "b200_probe_table_create", "b200_probe_table_add", "b200_probe_table_build", "b200_probe_table_num_rows",
     "b200_probe_table_free", "b200_probe_exists", "b200_probe_indices", "b200_join_state_create", "b200_join_state_free",
     "b200_hash_join_probe", "b200_hash_join_finalize",
-    "b200_comm_unique_id", "b200_comm_init", "b200_comm_free", "b200_exchange_by_hash", "b200_all_gather",
+    "b200_comm_unique_id", "b200_comm_init", "b200_comm_free", "b200_exchange_by_hash", "b200_all_gather", "b200_agg_allreduce",
     "b200_tpch_generate", "b200_tpch_num_rows", "b200_tpch_generate_host",
 ]
 
@@ -96,6 +96,7 @@ def lib() -> ctypes.CDLL:
         L.b200_probe_table_free.argtypes = [ctypes.c_void_p]
         L.b200_join_state_free.argtypes = [ctypes.c_void_p]
         L.b200_comm_free.argtypes = [ctypes.c_void_p]
+        L.b200_groupby_free.argtypes = [ctypes.c_void_p]
         L.b200_batch_num_rows.argtypes = [ctypes.c_void_p]
         L.b200_batch_num_columns.argtypes = [ctypes.c_void_p]
         L.b200_batch_size_bytes.argtypes = [ctypes.c_void_p]
@@ -145,3 +146,14 @@ def stream_ptr() -> int:
 
 def synchronize() -> None:
     call("b200_synchronize")
+
+
+def kernel_timing_report() -> dict:
+    """{"kernel": {"launches": n, "ms": total}} since the last report (enable with lib().b200_kernel_timing(1))."""
+    import json
+    out = ctypes.c_void_p()
+    call("b200_kernel_timing_report", ctypes.byref(out))
+    try:
+        return json.loads(ctypes.string_at(out.value).decode())
+    finally:
+        lib().b200_free_string(out)

@@ -96,7 +96,17 @@ int64_t b200_launch_count(void) { return g_launches.load(); }
 // device time of the dominant kernel (the fused aggregate) measured with CUDA events on the launching stream
 int b200_kernel_timing(int enable) {
     jit::enable_kernel_timing(enable != 0);
+    kernel_timing_enable(enable != 0);
     return 0;
+}
+int b200_kernel_timing_report(char **out_json, char **errmsg) {
+    return guard(errmsg, [&] {
+        const std::string t = kernel_timing_report();
+        char *m = static_cast<char *>(malloc(t.size() + 1));
+        if (!m) fail("out of memory");
+        memcpy(m, t.c_str(), t.size() + 1);
+        *out_json = m;
+    });
 }
 double b200_last_agg_kernel_ms(void) {
     try {
@@ -144,6 +154,9 @@ int b200_jit_describe(int32_t op, const uint8_t *plan, size_t plan_len, const in
                      std::to_string(a.out_dtype) + ":" + std::to_string(a.lane_cell) + ":" + std::to_string(a.cnt_cell) + ":" +
                      (a.child_nullable ? "1" : "0") + ":" + (a.const_zero ? "1" : "0") + ":" + a.name;
             }
+            t += "\nnancells=";  // per aggregate: nan_cell:last_cell (float min / max: the NaN-forgetting fold, jit.h AggOut)
+            for (size_t i = 0; i < meta.aggs.size(); i++)
+                t += (i ? "," : "") + std::to_string(meta.aggs[i].nan_cell) + ":" + std::to_string(meta.aggs[i].last_cell);
             t += "\ncellops=";
             for (size_t i = 0; i < meta.lane_cell_ops.size(); i++) t += (i ? "," : "") + std::to_string(meta.lane_cell_ops[i]);
             static const char *hex = "0123456789abcdef";
@@ -172,17 +185,29 @@ int b200_batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t 
 }
 int b200_batch_describe(const b200_batch *batch, int32_t col, b200_column_desc *out, char **errmsg) {
     return guard(errmsg, [&] {
-        const Column c = materialize(col_at(batch, col));
-        if (col_at(batch, col).is_view()) const_cast<b200_batch *>(batch)->cols[col] = c;  // keeps the described pointers alive
+        const Column &c = col_at(batch, col);
         out->dtype = c.dtype;
         out->_reserved = 0;
         out->length = c.length;
+        out->name = c.name.c_str();
+        if (c.is_view()) {  // a join output that nobody has read yet: schema only (b200_batch_materialize gives buffers)
+            out->null_count = -1;
+            out->validity = out->offsets = out->data = nullptr;
+            out->data_bytes = 0;
+            return;
+        }
         out->null_count = c.null_count;
         out->validity = c.validity ? c.validity->ptr : nullptr;
         out->offsets = c.offsets ? c.offsets->ptr : nullptr;
         out->data = c.data ? c.data->ptr : nullptr;
         out->data_bytes = c.data_bytes;
-        out->name = batch->cols[col].name.c_str();
+    });
+}
+int b200_batch_materialize(const b200_batch *batch, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        require_device();
+        *out = new Batch(plain(batch));
+        op_done();
     });
 }
 int b200_batch_dtypes(const b200_batch *batch, int32_t *out_dtypes, int32_t n, char **errmsg) {
@@ -301,6 +326,20 @@ int b200_eval_expression_list(const b200_batch *batch, const uint8_t *plan, size
 int b200_agg(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] { *out = op_agg(plain_for_plan(batch, B200_OP_AGG, plan, plan_len), plan, plan_len); });
 }
+int b200_groupby_create(const uint8_t *partial_plan, size_t partial_len, const uint8_t *final_plan, size_t final_len,
+                        const uint8_t *project_plan, size_t project_len, b200_groupby_state **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = groupby_create(partial_plan, partial_len, final_plan, final_len, project_plan, project_len); });
+}
+int b200_groupby_push(b200_groupby_state *st, const b200_batch *batch, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!batch) fail("null batch");
+        groupby_push(st, *batch);
+    });
+}
+int b200_groupby_finalize(b200_groupby_state *st, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = groupby_finalize(st); });
+}
+void b200_groupby_free(b200_groupby_state *st) { groupby_free(st); }
 int b200_dedup(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] { *out = op_dedup(plain(batch), key_cols, nkeys); });
 }
@@ -416,6 +455,14 @@ void b200_comm_free(b200_comm *c) { comm_free(c); }
 int b200_exchange_by_hash(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out,
                           char **errmsg) {
     return guard(errmsg, [&] { *out = exchange_by_hash(c, plain(batch), key_cols, nkeys); });
+}
+int b200_agg_allreduce(b200_comm *c, const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, int32_t *merged,
+                       char **errmsg) {
+    return guard(errmsg, [&] {
+        Batch *r = op_agg_allreduce(c, plain_for_plan(batch, B200_OP_AGG, plan, plan_len), plan, plan_len);
+        *out = r;
+        *merged = r ? 1 : 0;
+    });
 }
 int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] { *out = all_gather_batches(c, plain(batch)); });

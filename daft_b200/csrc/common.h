@@ -144,6 +144,19 @@ inline void require_plain(const Column &c) {
     if (c.is_view()) fail("internal error: operator reached an unmaterialised view column '" + c.name + "'");
 }
 
+// ---- per-kernel device timing (runtime.cu; bench support) ----------------------------------------
+// While enabled (b200_kernel_timing), a KernelTimer brackets the launches in its scope with CUDA events on the library
+// stream; kernel_timing_report() waits for the stream and returns {"name": {"launches": n, "ms": total}, ...} as JSON
+// text, then forgets the samples.  Disabled = no events, no cost.
+void kernel_timing_enable(bool on);
+bool kernel_timing_enabled();
+std::string kernel_timing_report();
+struct KernelTimer {
+    explicit KernelTimer(const char *name);
+    ~KernelTimer();
+    int slot = -1;
+};
+
 // ---- hashing (hash.cu) -----------------------------------------------------------------------
 // out[i] = xxh3_64(col[i], seed ? seed[i] : 0) with Daft's null rules
 void hash_column(const Column &c, const uint64_t *seed, uint64_t *out);

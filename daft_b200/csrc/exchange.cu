@@ -32,6 +32,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t);
     const char *(*GetErrorString)(ncclResult_t);
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*GroupStart)();
@@ -57,6 +58,7 @@ static NcclApi &nccl() {
         a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
         a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
         a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+        a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
         a.Send = (decltype(a.Send))sym("ncclSend");
         a.Recv = (decltype(a.Recv))sym("ncclRecv");
         a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
@@ -436,6 +438,45 @@ static Batch *all_gather_small(b200_comm *c, const Batch &b) {
     }
     run_segments(asm_segs);
     return out.release();
+}
+
+// ---- low-cardinality aggregates: the group tables themselves are all-reduced ------------------------------------------
+// Every rank ran the same aggregate kernel into a table of the same capacity; a group's slot is a function of its
+// key code (open addressing from the same home slot), so slot s holds the same group on every rank unless two codes
+// collided differently -- which the caller detects from the MIN / MAX of the tag words.  One grouped NCCL launch:
+// tags MAX (+ their non-zero MIN), the status word MAX, and one all-reduce per run of cells with the same operator
+// (f64 sums, 64-bit integer sums, minima, maxima).  Cells listed in `keep_local` (the groups' first rows) stay local.
+void allreduce_agg_table(b200_comm *c, unsigned long long *acc, size_t cap, const std::vector<int> &cell_ops, const std::vector<char> &keep_local,
+                         unsigned long long *tagmin, int *status_flag) {
+    require_device();
+    if (!c) fail("null communicator");
+    cudaStream_t st = ctx().stream;
+    KernelTimer kt("agg_table_allreduce");
+    B200_NCCL(nccl().GroupStart());
+    B200_NCCL(nccl().AllReduce(acc, acc, cap, ncclUint64, ncclMax, c->comm, st));
+    B200_NCCL(nccl().AllReduce(tagmin, tagmin, cap, ncclUint64, ncclMin, c->comm, st));
+    B200_NCCL(nccl().AllReduce(status_flag, status_flag, 1, ncclInt32, ncclMax, c->comm, st));
+    size_t i = 0;
+    while (i < cell_ops.size()) {
+        if (keep_local[i]) {
+            i++;
+            continue;
+        }
+        size_t j = i + 1;
+        while (j < cell_ops.size() && !keep_local[j] && cell_ops[j] == cell_ops[i]) j++;
+        unsigned long long *base = acc + (1 + i) * cap;
+        const size_t count = (j - i) * cap;
+        switch (cell_ops[i]) {
+            case 0: B200_NCCL(nccl().AllReduce(base, base, count, ncclDouble, ncclSum, c->comm, st)); break;   // C_ADD_F64
+            case 2: B200_NCCL(nccl().AllReduce(base, base, count, ncclUint64, ncclSum, c->comm, st)); break;   // C_ADD_I64 (wraps like the kernel)
+            case 3: B200_NCCL(nccl().AllReduce(base, base, count, ncclUint64, ncclMin, c->comm, st)); break;   // C_MIN
+            case 4: B200_NCCL(nccl().AllReduce(base, base, count, ncclUint64, ncclMax, c->comm, st)); break;   // C_MAX
+            default: fail("agg all-reduce: unsupported cell operator");
+        }
+        i = j;
+    }
+    B200_NCCL(nccl().GroupEnd());
+    count_launch();
 }
 
 Batch *all_gather_batches(b200_comm *c, const Batch &b) {

@@ -808,11 +808,14 @@ static std::string ord_of(int32_t dt, const std::string &v) {
     return "ord_i64((int64_t)" + v + ")";
 }
 
-struct LaneCell { int op; std::string child_key; int val_slot; int32_t val_dtype; };
+// flavor: 0 = the value itself; 1 = float min / max candidate (NaN values are skipped); 2 = 1 + row of the last NaN value;
+// 3 = 1 + row of the last valid value (2 and 3 are C_MAX cells over the row number)
+struct LaneCell { int op; std::string child_key; int val_slot; int32_t val_dtype; int flavor; };
 struct WarpCell { std::string cond_key; int val_slot; bool count_nulls; };
 
 static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
-    const bool global_variant = variant == 1, staged_variant = variant == 2;
+    const bool nanfix_variant = variant == 3;  // generated like the global-table build, different kernel body
+    const bool global_variant = variant == 1 || nanfix_variant, staged_variant = variant == 2;
     CG cg{ast, meta};
     const bool has_filter = r.u8() != 0;
     int filter_root = -1;
@@ -876,10 +879,10 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     };
     std::vector<LaneCell> lane_cells;
     std::vector<WarpCell> warp_cells;
-    auto lane_cell = [&](int op, int vslot) {
+    auto lane_cell = [&](int op, int vslot, int flavor = 0) {
         for (size_t i = 0; i < lane_cells.size(); i++)
-            if (lane_cells[i].op == op && lane_cells[i].val_slot == vslot) return (int)i;
-        lane_cells.push_back({op, "", vslot, val_dtypes[vslot]});
+            if (lane_cells[i].op == op && lane_cells[i].val_slot == vslot && lane_cells[i].flavor == flavor) return (int)i;
+        lane_cells.push_back({op, "", vslot, val_dtypes[vslot], flavor});
         return (int)lane_cells.size() - 1;
     };
     auto warp_cell = [&](int vslot, bool count_nulls) {
@@ -920,7 +923,14 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
                 int vs = val_slot(a.root, c.dtype);
                 o.val_dtype = c.dtype;
                 o.out_dtype = c.dtype;
-                o.lane_cell = lane_cell(a.kind == AGG_MIN ? C_MIN : C_MAX, vs);
+                if (is_float(c.dtype)) {  // the reference's NaN-forgetting left fold (AggOut::nan_cell)
+                    o.lane_cell = lane_cell(a.kind == AGG_MIN ? C_MIN : C_MAX, vs, 1);
+                    o.nan_cell = lane_cell(C_MAX, vs, 2);
+                    o.last_cell = lane_cell(C_MAX, vs, 3);
+                    meta.has_nan_fold = true;
+                } else {
+                    o.lane_cell = lane_cell(a.kind == AGG_MIN ? C_MIN : C_MAX, vs);
+                }
                 if (c.nullable) o.cnt_cell = warp_cell(vs, false);
                 break;
             }
@@ -1288,8 +1298,12 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     for (int c = 0; c < NL; c++) {
         const LaneCell &lc = lane_cells[c];
         const std::string cell = "cells[" + std::to_string(c * 32) + "]";
-        const std::string val = "v.a" + std::to_string(lc.val_slot), vk = "v.k" + std::to_string(lc.val_slot);
+        const std::string val = "v.a" + std::to_string(lc.val_slot), vk0 = "v.k" + std::to_string(lc.val_slot);
+        const std::string is_nan = "(" + val + " != " + val + ")";
+        const std::string vk = lc.flavor == 1 ? "(" + vk0 + " && !" + is_nan + ")" : lc.flavor == 2 ? "(" + vk0 + " && " + is_nan + ")" : vk0;
+        const std::string row_ord = "(unsigned long long)(row + 1)";
         const std::string gp = "((unsigned long long*)" + std::string("p.ptr[") + std::to_string(p_acc[c]) + "]) + slot";
+        const std::string ordv = lc.flavor >= 2 ? row_ord : ord_of(lc.val_dtype, val);
         {   // tier-2 cell c of slot t lives at t2c[c * T2 + t]
             const std::string sp = "(t2c + " + std::to_string(c) + " * T2 + t)";
             const std::string sv = "t2c[" + std::to_string(c) + " * T2 + t]";
@@ -1311,12 +1325,12 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
                     break;
                 case C_MIN:
                     sinit << "    " << sv << " = 0xFFFFFFFFFFFFFFFFULL;\n";
-                    su << "    if (" << vk << ") atomicMin(" << sp << ", (unsigned long long)" << ord_of(lc.val_dtype, val) << ");\n";
+                    su << "    if (" << vk << ") atomicMin(" << sp << ", (unsigned long long)" << ordv << ");\n";
                     sfl << "    atomicMin(" << gp << ", " << sv << ");\n";
                     break;
                 case C_MAX:
                     sinit << "    " << sv << " = 0ULL;\n";
-                    su << "    if (" << vk << ") atomicMax(" << sp << ", (unsigned long long)" << ord_of(lc.val_dtype, val) << ");\n";
+                    su << "    if (" << vk << ") atomicMax(" << sp << ", (unsigned long long)" << ordv << ");\n";
                     sfl << "    atomicMax(" << gp << ", " << sv << ");\n";
                     break;
             }
@@ -1339,13 +1353,13 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
                 break;
             case C_MIN:
                 li << "    " << cell << " = 0xFFFFFFFFFFFFFFFFULL;\n";
-                lu << "    if (" << vk << ") { const unsigned long long o_ = " << ord_of(lc.val_dtype, val) << "; if (o_ < " << cell << ") " << cell << " = o_; }\n";
-                gu << "    if (" << vk << ") atomicMin(" << gp << ", (unsigned long long)" << ord_of(lc.val_dtype, val) << ");\n";
+                lu << "    if (" << vk << ") { const unsigned long long o_ = " << ordv << "; if (o_ < " << cell << ") " << cell << " = o_; }\n";
+                gu << "    if (" << vk << ") atomicMin(" << gp << ", (unsigned long long)" << ordv << ");\n";
                 break;
             case C_MAX:
                 li << "    " << cell << " = 0ULL;\n";
-                lu << "    if (" << vk << ") { const unsigned long long o_ = " << ord_of(lc.val_dtype, val) << "; if (o_ > " << cell << ") " << cell << " = o_; }\n";
-                gu << "    if (" << vk << ") atomicMax(" << gp << ", (unsigned long long)" << ord_of(lc.val_dtype, val) << ");\n";
+                lu << "    if (" << vk << ") { const unsigned long long o_ = " << ordv << "; if (o_ > " << cell << ") " << cell << " = o_; }\n";
+                gu << "    if (" << vk << ") atomicMax(" << gp << ", (unsigned long long)" << ordv << ");\n";
                 break;
         }
         // flush: combine the 8 warps' copies for this lane, butterfly over lanes, one atomic per CTA
@@ -1448,6 +1462,18 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     o << "  __device__ __forceinline__ static void lane_init(unsigned long long* cells) {\n" << li.str() << "  }\n";
     o << "  __device__ __forceinline__ static void lane_update(unsigned long long* cells, const Vals& v, const int64_t row) {\n" << lu.str() << "  }\n";
     o << "  __device__ __forceinline__ static void global_update(const P& p, const long long slot, const Vals& v, const int64_t row) {\n" << gu.str() << "  }\n";
+    {   // fix-up pass: re-fold the float min / max candidates over the rows after the group's last NaN
+        std::ostringstream nf;
+        for (const auto &ag : meta.aggs) {
+            if (ag.nan_cell < 0) continue;
+            const LaneCell &lc = lane_cells[ag.lane_cell];
+            const std::string val = "v.a" + std::to_string(lc.val_slot), vk0 = "v.k" + std::to_string(lc.val_slot);
+            nf << "    if (" << vk0 << " && !(" << val << " != " << val << ") && (unsigned long long)(row + 1) > ((const unsigned long long*)p.ptr["
+               << p_acc[ag.nan_cell] << "])[slot]) " << (lc.op == C_MIN ? "atomicMin" : "atomicMax") << "(((unsigned long long*)p.ptr[" << p_acc[ag.lane_cell]
+               << "]) + slot, (unsigned long long)" << ord_of(lc.val_dtype, val) << ");\n";
+        }
+        o << "  __device__ __forceinline__ static void nanfix_update(const P& p, const long long slot, const Vals& v, const int64_t row) {\n" << nf.str() << "  }\n";
+    }
     o << "  static constexpr int T2 = " << t2_slots << ", NCELLS = " << (NLT + NW) << ";\n";
     o << "  __device__ __forceinline__ static void t2_init(unsigned long long* t2c, const int t) {\n" << sinit.str() << "  }\n";
     o << "  __device__ __forceinline__ static void t2_update(unsigned long long* t2c, const int t, const Vals& v, const int64_t row) {\n" << su.str() << "  }\n";
@@ -1477,12 +1503,14 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         staged_minb = std::max(MINB, 3);
     if (staged_variant)
         o << "extern \"C\" __global__ void __launch_bounds__(" << SW * 32 << ", " << (SW == 16 ? 1 : staged_minb) << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_staged<Prog>(p); }\n";
+    else if (nanfix_variant)
+        o << "extern \"C\" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_nanfix<Prog>(p); }\n";
     else if (global_variant)
         o << "extern \"C\" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_global<Prog>(p); }\n";
     else
         o << "extern \"C\" __global__ void __launch_bounds__(256, " << MINB << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }\n";
     // shared memory: lane cells, ballot cells, tier-1 slots/ready flags/key values (generous bound for sizeof(Keys))
-    meta.smem_bytes = global_variant ? 8 * (size_t)t2_slots * (size_t)(1 + NLT + NW)
+    meta.smem_bytes = nanfix_variant ? 0 : global_variant ? 8 * (size_t)t2_slots * (size_t)(1 + NLT + NW)
                                      : tier1_smem;
     meta.block_threads = SW * 32;
     if (staged_variant) {

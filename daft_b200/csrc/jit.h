@@ -6,6 +6,9 @@
 
 #include "common.h"
 
+struct b200_comm;
+struct b200_groupby_state;
+
 namespace b200 {
 namespace jit {
 
@@ -37,6 +40,11 @@ struct AggOut {
     bool child_nullable = false;
     bool const_zero = false; // count(null) over a non-nullable child
     int proj_index = -1;     // AGG_ANY_VALUE: column of the any-value projection (child evaluated at the group's first row)
+    // Float min / max reproduce the reference's left fold `if a < b {a} else {b}` (inline_agg.rs:271-298 == compare_agg.rs
+    // :75-95), which FORGETS everything before a NaN: the result is the min / max of the values after the group's last NaN,
+    // and NaN when the last valid value is one.  lane_cell then folds the non-NaN values only, nan_cell = 1 + row of the
+    // group's last NaN (0: none), last_cell = 1 + row of its last valid value.
+    int nan_cell = -1, last_cell = -1;
 };
 
 struct Compiled {
@@ -54,6 +62,7 @@ struct Compiled {
     int astride = 1;  // 64-bit words per global-table record (code + cells, padded to 32-byte sectors)
     std::vector<int> lane_cell_ops;
     std::vector<AggOut> aggs;
+    bool has_nan_fold = false;  // some aggregate carries nan_cell / last_cell (see AggOut)
     size_t smem_bytes = 0;
     int block_threads = 256;
     int stage_rows = 0, stage_bytes = 0;  // staged agg variant: bytes per shared-memory stage (0 = nothing to stage)
@@ -69,7 +78,8 @@ struct Compiled {
 
 // Codegen only (no CUDA needed): returns the CUDA source for the plan; fills `meta` (fn stays null).
 // variant (AGG only): 0 = low-cardinality kernel (tier-1 shared-memory cells), 1 = global-table kernel,
-// 2 = the low-cardinality kernel fed by per-warp TMA bulk copies (cp.async.bulk + mbarrier stages)
+// 2 = the low-cardinality kernel fed by per-warp TMA bulk copies (cp.async.bulk + mbarrier stages),
+// 3 = the NaN-fold fix-up pass over a finished group table (re-folds float min / max over the rows after each group's last NaN)
 std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
                      const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta, int variant = 0);
 // column indices the plan reads
@@ -99,5 +109,12 @@ double last_timed_kernel_ms();
 Batch *op_project(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n, bool take_nonneg = false);
 Batch *op_filter(const Batch &in, const uint8_t *plan, size_t len);
 Batch *op_agg(const Batch &in, const uint8_t *plan, size_t len);
+// also returns the groups' first rows; `coll`: all-reduce the group table across the communicator's ranks (ops_jit.cu)
+Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *first_rows, int64_t *ngroups, b200_comm *coll = nullptr);
+Batch *op_agg_allreduce(b200_comm *comm, const Batch &in, const uint8_t *plan, size_t len);  // nullptr: use the two-stage plan
+b200_groupby_state *groupby_create(const uint8_t *p1, size_t n1, const uint8_t *p2, size_t n2, const uint8_t *p3, size_t n3);
+void groupby_free(b200_groupby_state *s);
+void groupby_push(b200_groupby_state *s, const Batch &in);
+Batch *groupby_finalize(b200_groupby_state *s);
 
 }  // namespace b200

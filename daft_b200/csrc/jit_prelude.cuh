@@ -488,6 +488,29 @@ __device__ __forceinline__ void agg_body_global(const typename Prog::P &p) {
     }
 }
 
+// ---- NaN-fold fix-up pass (variant 3) --------------------------------------------------------------------
+// Float min / max follow the reference's left fold, which forgets everything before a NaN (jit.h AggOut::nan_cell).
+// The aggregate kernels fold the non-NaN candidates of ALL rows and record each group's last NaN row; when some group
+// has a NaN in the middle of its values the host clears those candidate cells and runs this pass over the same input
+// and the same (finished) table: every row finds its group's record again and re-enters its candidates only if it
+// lies after the group's last NaN.
+template <class Prog>
+__device__ __forceinline__ void agg_body_nanfix(const typename Prog::P &p) {
+    const int64_t n = p.ival[Prog::IV_N];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+        typename Prog::Raw raw;
+        Prog::load(p, row, raw);
+        Prog::load2(p, row, raw);
+        typename Prog::Keys keys;
+        typename Prog::Vals vals;
+        if (!Prog::eval(p, raw, keys, vals)) continue;
+        long long slot = 0;
+        if (Prog::NKEYS > 0) slot = agg_find_slot<Prog>(p, Prog::code(keys), row);
+        if (slot >= 0) Prog::nanfix_update(p, slot, vals, row);
+    }
+}
+
 // Rare path of the low-cardinality kernel, kept out of line so that its registers do not burden the streaming loop:
 // find/claim the group's global slot, try to adopt it into the CTA's tier 1, otherwise update it globally.
 // Returns the tier-1 index (>= 0), -2 when the row was accumulated globally, -1 when the table is full.

@@ -5,24 +5,29 @@
 // GrowableRecordBatch materialisation of src/daft-local-execution/src/join/inner_join.rs:11-85.
 //
 // Build (all on the device, no sequential step):
-//   1. hash_rows over the build keys (the same XXH3 chain the reference uses);
+//   1. row hashes of the build keys: XXH3 hash_rows (the chain the reference uses) in general; a single integer-like
+//      key column without nulls takes a two-multiply mixer instead (the table's hash is internal: the reference's
+//      ProbeTable never exposes it, only the match sets are observable);
 //   2. stable radix sort of the build row ids by the TOP B bits of the hash (B = ceil(log2 rows): 2-4 byte passes
 //      instead of 8) -> the rows of a bucket are contiguous and in INSERTION ORDER (the reference's match-list order,
 //      probe_table.rs:178-181);
-//   3. a direct-address table of 2^B 32-byte entries {start, end, first row, tag}: bucket heads / tails write their own
-//      position.  No probing, no CAS: a probe reads exactly one 32-byte sector;
-//   4. tables that do not fit L2 also get a blocked Bloom filter (one 64-bit word per key, 3 bits, ~8 bits / build row:
-//      it stays L2-resident), so probe rows without a partner never touch the table in DRAM.
-// Probe (two passes over tiles of 1024 probe rows, output rows in probe-row order, matches in build insertion order):
-//   pass 0 counts the matches of every tile, the tile counts are scanned, pass 1 recomputes the matches and writes the
-//   (probe row, build row) pairs at their final positions (block-wide scan inside the tile).  Nothing per probe row is
-//   materialised between the passes: no hash column, no per-row counts / offsets / first-match arrays.
-//   * single integer-like key without build-side nulls: the key is hashed in registers (XXH3 of its 1/2/4/8 bytes, the
-//     value hash_rows would produce) and compared against the tag the bucket carries inline -- one sector per probe;
-//     the probe key may be read THROUGH a selection vector (a view column), so a probe chain never gathers its keys;
-//   * anything else: hash_rows over the key columns, then every bucket row is verified by value: nulls match only where
-//     null_equals_null, floats compare with IEEE == (NaN never matches, nans_equal=false, probe_table.rs:48-51);
-//   * every thread keeps four probe rows in flight (keys, then Bloom words, then bucket sectors: independent loads);
+//   3. a direct-address table of 2^B 32-byte buckets {start, end, row0, row1, tag0, tag1}: the first TWO rows of a bucket
+//      live in the bucket itself (row id + tag = the key value for inline keys, the row hash otherwise), so a probe reads
+//      exactly one 32-byte sector unless its bucket holds three or more rows (8% of the occupied buckets at one row per
+//      bucket).  No probing, no CAS;
+//   4. a blocked Bloom filter (one 64-bit word per key, 2 bits, ~8 bits / build row: L1 / L2 resident), so probe rows
+//      without a partner never touch the table (DRAM sectors for large tables, L2 bandwidth for small ones).
+// Probe (units of 128 probe rows, one warp per unit; output rows in probe-row order, matches in build insertion order):
+//   pass 0 counts the matches of every unit and leaves ONE BIT per probe row ("produces output"); the unit counts are
+//   scanned; pass 1 revisits only the rows whose bit is set, recomputes their matches and writes the (probe row, build
+//   row) pairs at their final positions (warp scan inside the unit).  Nothing else per probe row is materialised between
+//   the passes: no hash column, no per-row counts / offsets / first-match arrays.  Warps never synchronise with each
+//   other and fetch the keys of their next unit while they work on the current one.
+//   * inline keys: the key is hashed in registers and compared against the tags in the bucket; the probe key may be
+//     read THROUGH a selection vector (a view column), so a probe chain never gathers its keys;
+//   * anything else: hash_rows over the key columns, then every candidate row is verified by value: nulls match only
+//     where null_equals_null, floats compare with IEEE == (NaN never matches, nans_equal=false, probe_table.rs:48-51);
+//   * every lane keeps four probe rows in flight (keys, then Bloom words, then bucket sectors: independent loads);
 //   * buckets of 32+ rows (heavy duplicate keys) are walked by the whole warp: 32 build rows per step, matches ranked
 //     with a ballot so insertion order is kept.
 // Join outputs are VIEWS (common.h): both sides' columns become selection vectors over the inputs, so a chain of joins
@@ -35,7 +40,6 @@
 #include "common.h"
 #include "kernels.cuh"
 #include "ops.h"
-#include "xxh3.cuh"
 
 namespace b200 {
 
@@ -53,15 +57,14 @@ struct KeySet {
     KeyDesc k[MAX_JOIN_KEYS];
 };
 
-// One 32-byte sector per bucket: besides its span in `sorted_rows` the entry carries the bucket's FIRST row inline --
-// its row id and a tag that is either the key value itself (single integer-like key column without nulls: the
-// match is decided without touching the build side) or the row's full hash (a cheap reject before the key compare).
-// A probe into a one-row bucket (the common case at <= 1 row per bucket) therefore costs one random sector.
+// One 32-byte sector per bucket: its span in `sorted_rows` plus its first TWO rows inline -- row id and a tag that is
+// either the key value itself (inline keys: the match is decided without touching the build side) or the row's full
+// hash (a cheap reject before the key compare).  Row ids are 32-bit: a probe table holds fewer than 2^32 rows.
 struct __align__(32) JoinBucket {
-    long long start;      // first position in `sorted_rows`
-    long long end;        // one past the last (start == end == 0: empty bucket)
-    long long first_row;  // sorted_rows[start]
-    unsigned long long tag;
+    unsigned int start;  // first position in `sorted_rows`
+    unsigned int end;    // one past the last (start == end: empty bucket)
+    unsigned int row0, row1;
+    unsigned long long tag0, tag1;
 };
 
 }  // namespace b200
@@ -154,6 +157,18 @@ __device__ __forceinline__ unsigned long long key_bits(const void *data, int wid
         default: return ((const uint64_t *)data)[r];
     }
 }
+// hash of an inline key (zero-extended to 64 bits): two multiplies, every output bit depends on every input bit
+__device__ __forceinline__ uint64_t ihash(unsigned long long v) {
+    uint64_t h = v * 0x9E3779B97F4A7C15ULL;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ULL;
+    return h ^ (h >> 29);
+}
+__global__ void hash_inline_keys(const void *__restrict__ data, int width, int64_t n, uint64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = ihash(key_bits(data, width, i));
+}
 // The head row of a bucket (first position whose top bits differ from its predecessor) walks forward to the bucket's
 // end -- buckets hold about one row -- and writes the whole 32-byte entry with two 16-byte stores.  Runs longer than
 // BB_WALK are closed by their tail row instead (it sees no head within BB_WALK positions behind it).
@@ -169,31 +184,41 @@ __global__ void bucket_bounds(const uint64_t *__restrict__ sorted_hash, const in
             int64_t j = i + 1;
             while (j < n && j - i <= BB_WALK && (sorted_hash[j] >> shift) == b) j++;
             const bool closed = j == n || (sorted_hash[j] >> shift) != b;
-            const int64_t r = sorted_rows[i];
-            longlong2 lo, hi;
-            lo.x = i;
-            lo.y = closed ? j : 0;  // a long run: the tail row stores `end`
-            hi.x = r;
-            hi.y = (long long)(inline_width ? key_bits(key_data, inline_width, r) : h);
-            longlong2 *e = reinterpret_cast<longlong2 *>(&table[b]);
-            if (closed) e[0] = lo;
-            else table[b].start = i;  // (the tail row owns `end`: no store of ours may overwrite it)
-            e[1] = hi;
+            const int64_t r0 = sorted_rows[i];
+            const bool two = j - i >= 2;
+            const int64_t r1 = two ? sorted_rows[i + 1] : 0;
+            uint4 lo;
+            lo.x = (unsigned)i;
+            lo.y = closed ? (unsigned)j : (unsigned)i;  // a long run: the tail row stores `end`
+            lo.z = (unsigned)r0;
+            lo.w = (unsigned)r1;
+            ulonglong2 hi;
+            hi.x = inline_width ? key_bits(key_data, inline_width, r0) : h;
+            hi.y = two ? (inline_width ? key_bits(key_data, inline_width, r1) : sorted_hash[i + 1]) : 0ULL;
+            if (closed) {
+                *reinterpret_cast<uint4 *>(&table[b]) = lo;
+            } else {  // (the tail row owns `end`: no store of ours may overwrite it)
+                table[b].start = lo.x;
+                table[b].row0 = lo.z;
+                table[b].row1 = lo.w;
+            }
+            *reinterpret_cast<ulonglong2 *>(&table[b].tag0) = hi;
         } else {
             const bool tail = i == n - 1 || (sorted_hash[i + 1] >> shift) != b;
             if (tail) {
                 // distance to the head: only runs longer than BB_WALK + 1 rows are closed here
                 int64_t back = 1;
                 while (back <= BB_WALK + 1 && i - back >= 0 && (sorted_hash[i - back] >> shift) == b) back++;
-                if (back > BB_WALK + 1) table[b].end = i + 1;
+                if (back > BB_WALK + 1) table[b].end = (unsigned)(i + 1);
             }
         }
     }
 }
 
-// Blocked Bloom filter: word = bits 18.. of the hash, three bit positions from its low 18 bits.
+// Blocked Bloom filter: word = bits 18.. of the hash, two bit positions from its low 10 bits.
+// one bit in each 32-bit half of the word (see bloom_pass)
 __device__ __forceinline__ unsigned long long bloom_need(uint64_t h) {
-    return (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63)) | (1ULL << ((h >> 12) & 63));
+    return (1ULL << (h & 31)) | (1ULL << (32 + ((h >> 5) & 31)));
 }
 __global__ void bloom_build(const uint64_t *__restrict__ hashes, int64_t n, unsigned long long *__restrict__ words, uint64_t mask) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,8 +231,9 @@ __global__ void bloom_build(const uint64_t *__restrict__ hashes, int64_t n, unsi
 
 // ---- probe -----------------------------------------------------------------------------------------
 constexpr int PT = 256;          // threads per CTA
-constexpr int PR = 4;            // probe rows per thread per tile: independent loads in flight
-constexpr int PTILE = PT * PR;   // rows per tile
+constexpr int UR = 4;            // probe rows per lane per step of the count pass: independent loads in flight
+constexpr int CHUNK = 1024;      // probe rows per warp work item = 32 bitmap words = one count
+constexpr int WR = 2;            // hit rows per lane per step of the write pass
 constexpr int LONG_BUCKET = 32;  // buckets at least this long are walked by the whole warp
 
 struct ProbeArgs {
@@ -234,231 +260,368 @@ __device__ __forceinline__ unsigned long long key_w(const void *data, int64_t r)
     if (W == 4) return ((const uint32_t *)data)[r];
     return ((const uint64_t *)data)[r];
 }
+// the probe-side key stream is read once: evict-first, so it does not push the table / Bloom words out of L2
 template <int W>
-__device__ __forceinline__ uint64_t hash_w(unsigned long long v) {  // == hash_rows of the key column (hash.cu hash_value<T>, seed 0)
-    if (W == 1) return xxh::hash_u8((uint8_t)v, 0);
-    if (W == 2) return xxh::hash_u16((uint16_t)v, 0);
-    if (W == 4) return xxh::hash_u32((uint32_t)v, 0);
-    return xxh::hash_u64(v, 0);
+__device__ __forceinline__ unsigned long long key_stream(const void *data, int64_t r) {
+    if (W == 1) return __ldcs((const uint8_t *)data + r);
+    if (W == 2) return __ldcs((const uint16_t *)data + r);
+    if (W == 4) return __ldcs((const uint32_t *)data + r);
+    return __ldcs((const unsigned long long *)data + r);
 }
 __device__ __forceinline__ long long shfl_ll(long long v, int src) {
     const int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffffLL), src), hi = __shfl_sync(0xffffffffu, (int)(v >> 32), src);
     return ((long long)hi << 32) | (unsigned int)lo;
 }
+// Bloom test on a 64-bit word: one bit in each 32-bit half (two 32-bit shifts instead of three 64-bit ones)
+__device__ __forceinline__ bool bloom_pass(unsigned long long w, uint64_t h) {
+    const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
+    return ((lo >> (h & 31)) & (hi >> ((h >> 5) & 31)) & 1u) != 0;
+}
 
-// thread-serial walk of a short bucket: f(build_row) for every match, in insertion order
-template <int W, class F>
-__device__ __forceinline__ void walk_bucket(const ProbeArgs &a, const JoinBucket &e, unsigned long long v, uint64_t h, int64_t i, F &&f) {
+// does build row `br` match probe row `i` (key value `v`)?
+template <int W>
+__device__ __forceinline__ bool row_matches(const ProbeArgs &a, int64_t br, unsigned long long v, int64_t i) {
+    return W ? key_w<W>(a.bkey, br) == v : keys_match(a.bk, br, a.pk, i);
+}
+// matches of the two inline entries: bit 0 = row0, bit 1 = row1
+template <int W>
+__device__ __forceinline__ unsigned inline_matches(const ProbeArgs &a, const JoinBucket &e, unsigned len, unsigned long long v, uint64_t h, int64_t i) {
+    unsigned m = 0;
     if (W) {
-        if (e.tag == v) f(e.first_row);
-        for (long long t = e.start + 1; t < e.end; t++) {
-            const int64_t br = a.sorted_rows[t];
-            if (key_w<W>(a.bkey, br) == v) f(br);
-        }
+        m = (len >= 1 && e.tag0 == v ? 1u : 0u) | (len >= 2 && e.tag1 == v ? 2u : 0u);
     } else {
-        if (e.tag == h && keys_match(a.bk, e.first_row, a.pk, i)) f(e.first_row);
-        for (long long t = e.start + 1; t < e.end; t++) {
-            const int64_t br = a.sorted_rows[t];
-            if (keys_match(a.bk, br, a.pk, i)) f(br);
+        if (len >= 1 && e.tag0 == h && keys_match(a.bk, e.row0, a.pk, i)) m |= 1u;
+        if (len >= 2 && e.tag1 == h && keys_match(a.bk, e.row1, a.pk, i)) m |= 2u;
+    }
+    return m;
+}
+__device__ __forceinline__ JoinBucket load_bucket(const ProbeArgs &a, uint64_t h) {
+    const JoinBucket *b = &a.table[h >> a.shift];
+    const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(b));
+    const ulonglong2 hi = __ldg(reinterpret_cast<const ulonglong2 *>(&b->tag0));
+    JoinBucket e;
+    e.start = lo.x;
+    e.end = lo.y;
+    e.row0 = lo.z;
+    e.row1 = lo.w;
+    e.tag0 = hi.x;
+    e.tag1 = hi.y;
+    return e;
+}
+// matches of probe row i beyond the two inline entries of a short bucket (thread-serial)
+template <int W>
+__device__ __forceinline__ unsigned tail_matches(const ProbeArgs &a, const JoinBucket &e, unsigned long long v, int64_t i) {
+    unsigned c = 0;
+    for (unsigned t = e.start + 2; t < e.end; t++) c += row_matches<W>(a, a.sorted_rows[t], v, i) ? 1u : 0u;
+    return c;
+}
+// matches of ONE probe row (owner lane `src`) in a long bucket, counted by the whole warp
+template <int W>
+__device__ __forceinline__ unsigned warp_count_long(const ProbeArgs &a, unsigned start, unsigned end, unsigned long long v, int64_t i, int lane) {
+    unsigned c = 0;
+    for (unsigned t0 = start; t0 < end; t0 += 32) {
+        const unsigned t = t0 + lane;
+        const bool mt = t < end && row_matches<W>(a, a.sorted_rows[t], v, i);
+        c += __popc(__ballot_sync(0xffffffffu, mt));
+    }
+    return c;
+}
+
+// key (inline: value, generic: row hash) of probe row i; false = the row cannot match (null / negative selection)
+template <int W, bool SEL, bool NULLS>
+__device__ __forceinline__ bool load_key(const ProbeArgs &a, int64_t i, unsigned long long &v) {
+    if (W) {
+        int64_t row = i;
+        if (SEL) {
+            row = __ldcs(a.psel + i);
+            if (row < 0) return false;
         }
+        if (NULLS && !bit_at(a.pvalid, row)) return false;
+        v = key_stream<W>(a.pkey, row);
+        return true;
+    }
+    v = __ldcs(a.phash + i);
+    return true;
+}
+
+// matches of one probe row per lane, any bucket length (kept out of line: the registers of the rare path must not
+// burden the straight-line step); row0 = probe row of lane 0
+template <int W>
+__device__ __noinline__ unsigned count_slow_row(const ProbeArgs &a, JoinBucket e, unsigned long long v, unsigned im, int64_t i, int64_t row0, int lane) {
+    const unsigned len = e.end - e.start;
+    unsigned c = __popc(im);
+    if (len > 2 && len < LONG_BUCKET) c += tail_matches<W>(a, e, v, i);
+    unsigned pending = __ballot_sync(0xffffffffu, len >= LONG_BUCKET);
+    while (pending) {  // long buckets: the whole warp walks them, one owner lane at a time
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const unsigned s = __shfl_sync(0xffffffffu, e.start, src) + 2, en = __shfl_sync(0xffffffffu, e.end, src);
+        const unsigned long long vv = (unsigned long long)shfl_ll((long long)v, src);
+        const unsigned cc = warp_count_long<W>(a, s, en, vv, row0 + src, lane);
+        if (lane == src) c += cc;
+    }
+    return c;
+}
+
+// One step of the count pass: UR rows per lane.  The common case -- every probed bucket holds at most two rows, which
+// live inline -- is straight-line code: hash, Bloom word, (predicated) bucket sector, two tag compares, three ballots.
+// Anything else (a bucket of three or more rows) takes the slow tail for the whole step.
+template <int W, bool FULL, bool KEEP>
+__device__ __forceinline__ long long count_step(const ProbeArgs &a, int64_t base, int64_t n, int lane, const unsigned long long (&v)[UR], const bool (&hit0)[UR],
+                                                uint32_t *__restrict__ bits) {
+    uint64_t h[UR];
+    unsigned long long bw[UR];
+    bool hit[UR];
+#pragma unroll
+    for (int r = 0; r < UR; r++) {
+        h[r] = W ? ihash(v[r]) : v[r];
+        bw[r] = __ldg(a.bloom + ((h[r] >> 18) & a.bloom_mask));  // (a row without a key reads the word of hash(0): harmless)
+    }
+#pragma unroll
+    for (int r = 0; r < UR; r++) hit[r] = hit0[r] && bloom_pass(bw[r], h[r]);
+    JoinBucket e[UR];
+#pragma unroll
+    for (int r = 0; r < UR; r++) {
+        e[r].start = e[r].end = 0;
+        e[r].tag0 = e[r].tag1 = 0;
+        e[r].row0 = e[r].row1 = 0;
+        if (hit[r]) e[r] = load_bucket(a, h[r]);
+    }
+    unsigned im[UR];
+    bool rare = false;
+#pragma unroll
+    for (int r = 0; r < UR; r++) {
+        const unsigned len = e[r].end - e[r].start;
+        im[r] = inline_matches<W>(a, e[r], len, v[r], h[r], base + r * 32 + lane);
+        rare = rare || len > 2;
+    }
+    long long total = 0;
+    if (!__any_sync(0xffffffffu, rare)) {
+#pragma unroll
+        for (int r = 0; r < UR; r++) {
+            const unsigned m0 = __ballot_sync(0xffffffffu, (im[r] & 1u) != 0), m1 = __ballot_sync(0xffffffffu, (im[r] & 2u) != 0);
+            unsigned out = m0 | m1;
+            unsigned extra = 0;
+            if (KEEP) {  // unmatched probe rows produce a null-extended row
+                const unsigned live = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, base + r * 32 + lane < n);
+                extra = __popc(live & ~out);
+                out = live;
+            }
+            if (lane == 0 && (FULL || base + r * 32 < n)) bits[(base >> 5) + r] = out;
+            total += __popc(m0) + __popc(m1) + extra;
+        }
+        return total;
+    }
+    // ---- slow tail: some bucket of this step holds three or more rows
+#pragma unroll
+    for (int r = 0; r < UR; r++) {
+        const int64_t i = base + r * 32 + lane;
+        unsigned c = count_slow_row<W>(a, e[r], v[r], im[r], i, base + r * 32, lane);
+        if (KEEP && c == 0 && (FULL || i < n)) c = 1;
+        const unsigned m = __ballot_sync(0xffffffffu, c > 0);
+        if (lane == 0 && (FULL || base + r * 32 < n)) bits[(base >> 5) + r] = m;
+        unsigned x = c;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        total += x;
+    }
+    return total;
+}
+
+// ---- pass 0: one warp per chunk of 1024 probe rows: 32 "produces output" bitmap words and one output-row count.
+// Eight steps of 4 rows per lane; the keys of the next step are fetched before the current one is processed.
+template <int W, bool SEL, bool NULLS, bool KEEP, bool FULL>
+__device__ __forceinline__ long long count_chunk(const ProbeArgs &a, int64_t cbase, int64_t n, int lane, uint32_t *__restrict__ bits) {
+    constexpr int STEPS = CHUNK / (32 * UR);
+    long long total = 0;
+    unsigned long long nv[UR];
+    bool nh[UR];
+#pragma unroll
+    for (int r = 0; r < UR; r++) {
+        const int64_t i = cbase + r * 32 + lane;
+        nv[r] = 0;
+        nh[r] = (FULL || i < n) && load_key<W, SEL, NULLS>(a, i, nv[r]);
+    }
+#pragma unroll 1
+    for (int step = 0; step < STEPS; step++) {
+        const int64_t base = cbase + (int64_t)step * (32 * UR);
+        unsigned long long v[UR];
+        bool hit[UR];
+#pragma unroll
+        for (int r = 0; r < UR; r++) {
+            v[r] = nv[r];
+            hit[r] = nh[r];
+        }
+        if (step + 1 < STEPS) {
+#pragma unroll
+            for (int r = 0; r < UR; r++) {
+                const int64_t i = base + (32 * UR) + r * 32 + lane;
+                nv[r] = 0;
+                nh[r] = (FULL || i < n) && load_key<W, SEL, NULLS>(a, i, nv[r]);
+            }
+        }
+        total += count_step<W, FULL, KEEP>(a, base, n, lane, v, hit, bits);
+    }
+    return total;
+}
+template <int W, bool SEL, bool NULLS, bool KEEP>
+__global__ void __launch_bounds__(PT, 3) probe_count_kernel(const __grid_constant__ ProbeArgs a, int64_t n, int64_t nchunks, int64_t *__restrict__ chunk_cnt,
+                                                            uint32_t *__restrict__ bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * (PT / 32) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (PT / 32);
+    for (int64_t chunk = gw; chunk < nchunks; chunk += nw) {
+        const int64_t cbase = chunk * CHUNK;
+        const long long total = cbase + CHUNK <= n ? count_chunk<W, SEL, NULLS, KEEP, true>(a, cbase, n, lane, bits)
+                                                   : count_chunk<W, SEL, NULLS, KEEP, false>(a, cbase, n, lane, bits);
+        if (lane == 0) chunk_cnt[chunk] = total;
     }
 }
 
-// MODE 0: tile_cnt[tile] = matches of the tile (kept unmatched probe rows count 1)
-// MODE 1: write (probe row, build row) pairs from tile_off[tile] on
-// MODE 2: out_bits = "probe row has a match" bitmap
-template <int W, int MODE>
-__global__ void __launch_bounds__(PT, 2) probe_kernel(const __grid_constant__ ProbeArgs a, int64_t n, int64_t ntiles, const int64_t *__restrict__ tile_off,
-                                                      int64_t *__restrict__ tile_cnt, int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build,
-                                                      unsigned int *__restrict__ matched_bits, uint32_t *__restrict__ out_bits, int keep_unmatched) {
-    __shared__ long long s_tot[PR][PT / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t base = tile * PTILE;
-        long long o_tile = 0;
-        if (MODE == 1) {
-            o_tile = tile_off[tile];
-            if (tile_off[tile + 1] == o_tile) continue;  // nothing to write for this tile (uniform for the CTA)
-        }
-        JoinBucket e[PR];
-        unsigned long long v[PR];
-        uint64_t h[PR];
-        bool hit[PR];
-        // ---- keys of all rows, then hashes (+ Bloom words), then bucket sectors
+// ---- pass 1: one warp per chunk.  The set bits of the chunk's 32 bitmap words are expanded into a dense list of row
+// offsets (shared memory), so every lane works on a row that produces output: WR rows per lane per step.
+template <int W, bool SEL, bool NULLS>
+__global__ void __launch_bounds__(PT, 3) probe_write_kernel(const __grid_constant__ ProbeArgs a, int64_t n, int64_t nchunks,
+                                                            const int64_t *__restrict__ chunk_off, const uint32_t *__restrict__ bits,
+                                                            int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build,
+                                                            unsigned int *__restrict__ matched_bits) {
+    __shared__ unsigned short s_list[PT / 32][CHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * (PT / 32) + warp, nw = (int64_t)gridDim.x * (PT / 32);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned short *list = s_list[warp];
+    for (int64_t chunk = gw; chunk < nchunks; chunk += nw) {
+        long long o = chunk_off[chunk];
+        if (chunk_off[chunk + 1] == o) continue;  // nothing to write (uniform for the warp)
+        const int64_t cbase = chunk * CHUNK;
+        // ---- dense list of the rows whose bit is set
+        const int64_t word = (cbase >> 5) + lane;
+        unsigned w = (cbase + (int64_t)lane * 32 < n) ? bits[word] : 0u;
+        unsigned pre = __popc(w);
 #pragma unroll
-        for (int r = 0; r < PR; r++) {
-            const int64_t i = base + (int64_t)r * PT + tid;
-            hit[r] = i < n;
-            v[r] = 0;
-            h[r] = 0;
-            if (W) {
-                if (hit[r]) {
-                    const int64_t row = a.psel ? a.psel[i] : i;
-                    hit[r] = row >= 0 && (a.pvalid == nullptr || bit_at(a.pvalid, row));
-                    if (hit[r]) v[r] = key_w<W>(a.pkey, row);
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, pre, d);
+            if (lane >= d) pre += y;
+        }
+        const unsigned hits = __shfl_sync(0xffffffffu, pre, 31);
+        pre -= __popc(w);
+        __syncwarp();
+        while (w) {
+            const int b = __ffs(w) - 1;
+            w &= w - 1;
+            list[pre++] = (unsigned short)(lane * 32 + b);
+        }
+        __syncwarp();
+        // ---- WR hit rows per lane per step, in row order
+        for (unsigned j0 = 0; j0 < hits; j0 += 32 * WR) {
+            unsigned long long v[WR];
+            int64_t row[WR];
+            bool act[WR], hit[WR];
+#pragma unroll
+            for (int r = 0; r < WR; r++) {
+                const unsigned j = j0 + r * 32 + lane;
+                act[r] = j < hits;
+                row[r] = cbase + (act[r] ? list[j] : 0);
+                v[r] = 0;
+                hit[r] = act[r] && load_key<W, SEL, NULLS>(a, row[r], v[r]);
+            }
+            uint64_t h[WR];
+            JoinBucket e[WR];
+#pragma unroll
+            for (int r = 0; r < WR; r++) {
+                h[r] = W ? ihash(v[r]) : v[r];
+                e[r].start = e[r].end = 0;
+                if (hit[r]) e[r] = load_bucket(a, h[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < WR; r++) {
+                const int64_t i = row[r];
+                const unsigned len = e[r].end - e[r].start;
+                const unsigned im = inline_matches<W>(a, e[r], len, v[r], h[r], i);
+                unsigned c = __popc(im);
+                const bool is_long = len >= LONG_BUCKET;
+                if (len > 2 && !is_long) c += tail_matches<W>(a, e[r], v[r], i);
+                unsigned pending = __ballot_sync(0xffffffffu, is_long);
+                while (pending) {
+                    const int src = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    const unsigned s = __shfl_sync(0xffffffffu, e[r].start, src) + 2, en = __shfl_sync(0xffffffffu, e[r].end, src);
+                    const unsigned long long vv = (unsigned long long)shfl_ll((long long)v[r], src);
+                    const unsigned cc = warp_count_long<W>(a, s, en, vv, shfl_ll(i, src), lane);
+                    if (lane == src) c += cc;
                 }
-            } else if (hit[r]) {
-                h[r] = a.phash[i];
-            }
-        }
-        if (W) {
+                const bool unmatched = act[r] && c == 0;  // its bit was set all the same: a kept probe row
+                if (unmatched) c = 1;
+                // exclusive scan of c over the lanes: ballots when no row has two matches
+                long long off;
+                if (__all_sync(0xffffffffu, c <= 1)) {
+                    const unsigned m = __ballot_sync(0xffffffffu, c == 1);
+                    off = o + __popc(m & lt_mask);
+                    o += __popc(m);
+                } else {
+                    long long x = c;
 #pragma unroll
-            for (int r = 0; r < PR; r++) h[r] = hash_w<W>(v[r]);
-        }
-        if (a.bloom) {
-            unsigned long long bw[PR];
-#pragma unroll
-            for (int r = 0; r < PR; r++) bw[r] = hit[r] ? a.bloom[(h[r] >> 18) & a.bloom_mask] : 0ULL;
-#pragma unroll
-            for (int r = 0; r < PR; r++) {
-                const unsigned long long need = bloom_need(h[r]);
-                hit[r] = hit[r] && (bw[r] & need) == need;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < PR; r++) {
-            e[r].start = e[r].end = 0;
-            if (hit[r]) {
-                const longlong2 *q = reinterpret_cast<const longlong2 *>(&a.table[h[r] >> a.shift]);
-                const longlong2 lo = q[0], hi = q[1];
-                e[r].start = lo.x;
-                e[r].end = lo.y;
-                e[r].first_row = hi.x;
-                e[r].tag = (unsigned long long)hi.y;
-            }
-        }
-        // ---- match counts (and the first match, which settles the common one-match case without a second walk)
-        long long cnt[PR], first[PR];
-#pragma unroll
-        for (int r = 0; r < PR; r++) {
-            const int64_t i = base + (int64_t)r * PT + tid;
-            cnt[r] = 0;
-            first[r] = -1;
-            const long long len = e[r].end - e[r].start;
-            if (len > 0 && len < LONG_BUCKET) {
-                long long c = 0, f = -1;
-                walk_bucket<W>(a, e[r], v[r], h[r], i, [&](int64_t br) {
-                    if (c == 0) f = br;
-                    c++;
-                });
-                cnt[r] = c;
-                first[r] = f;
-            }
-            // long buckets: the whole warp walks them, one owner lane at a time
-            unsigned pending = __ballot_sync(0xffffffffu, len >= LONG_BUCKET);
-            while (pending) {
-                const int src = __ffs(pending) - 1;
-                pending &= pending - 1;
-                const long long s = shfl_ll(e[r].start, src), en = shfl_ll(e[r].end, src);
-                const unsigned long long vv = (unsigned long long)shfl_ll((long long)v[r], src);
-                const int64_t ii = base + (int64_t)r * PT + (warp << 5) + src;
-                long long c = 0, f = -1;
-                for (long long t0 = s; t0 < en; t0 += 32) {
-                    const long long t = t0 + lane;
-                    int64_t br = -1;
-                    bool mt = false;
-                    if (t < en) {
-                        br = a.sorted_rows[t];
-                        mt = W ? key_w<W>(a.bkey, br) == vv : keys_match(a.bk, br, a.pk, ii);
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const long long y = shfl_ll(x, max(lane - d, 0));
+                        if (lane >= d) x += y;
                     }
-                    const unsigned mm = __ballot_sync(0xffffffffu, mt);
-                    if (mm) {
-                        const long long fb = shfl_ll(br, __ffs(mm) - 1);
-                        if (c == 0) f = fb;
-                        c += __popc(mm);
+                    off = o + x - c;
+                    o += shfl_ll(x, 31);
+                }
+                if (unmatched) {
+                    out_probe[off] = i;
+                    out_build[off] = -1;
+                } else if (c > 0 && !is_long) {
+                    long long p = off;
+                    if (im & 1u) {
+                        out_probe[p] = i;
+                        out_build[p] = e[r].row0;
+                        if (matched_bits) atomicOr(&matched_bits[e[r].row0 >> 5], 1u << (e[r].row0 & 31));
+                        p++;
+                    }
+                    if (im & 2u) {
+                        out_probe[p] = i;
+                        out_build[p] = e[r].row1;
+                        if (matched_bits) atomicOr(&matched_bits[e[r].row1 >> 5], 1u << (e[r].row1 & 31));
+                        p++;
+                    }
+                    if (len > 2) {
+                        for (unsigned t = e[r].start + 2; t < e[r].end; t++) {
+                            const int64_t br = a.sorted_rows[t];
+                            if (row_matches<W>(a, br, v[r], i)) {
+                                out_probe[p] = i;
+                                out_build[p] = br;
+                                if (matched_bits) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
+                                p++;
+                            }
+                        }
                     }
                 }
-                if (lane == src) {
-                    cnt[r] = c;
-                    first[r] = f;
-                }
-            }
-            if (keep_unmatched && i < n && cnt[r] == 0) cnt[r] = 1;  // first stays -1: a null-extended row
-        }
-        if (MODE == 2) {
-#pragma unroll
-            for (int r = 0; r < PR; r++) {
-                const unsigned m = __ballot_sync(0xffffffffu, cnt[r] > 0);
-                const int64_t w0 = base + (int64_t)r * PT + (warp << 5);
-                if (lane == 0 && w0 < n) out_bits[w0 >> 5] = m;
-            }
-            continue;
-        }
-        // ---- block-wide exclusive scan in row order (r major, thread minor)
-        long long inc[PR];
-#pragma unroll
-        for (int r = 0; r < PR; r++) {
-            long long x = cnt[r];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const long long y = shfl_ll(x, max(lane - d, 0));
-                if (lane >= d) x += y;
-            }
-            inc[r] = x;
-            if (lane == 31) s_tot[r][warp] = x;
-        }
-        __syncthreads();
-        long long run = 0, off[PR];
-#pragma unroll
-        for (int r = 0; r < PR; r++) {
-            long long before = 0, all = 0;
-#pragma unroll
-            for (int w = 0; w < PT / 32; w++) {
-                const long long t = s_tot[r][w];
-                all += t;
-                if (w < warp) before += t;
-            }
-            off[r] = run + before + inc[r] - cnt[r];
-            run += all;
-        }
-        __syncthreads();  // s_tot is reused by the next tile
-        if (MODE == 0) {
-            if (tid == 0) tile_cnt[tile] = run;
-            continue;
-        }
-        // ---- MODE 1: write the pairs
-#pragma unroll
-        for (int r = 0; r < PR; r++) {
-            const int64_t i = base + (int64_t)r * PT + tid;
-            const long long o = o_tile + off[r];
-            const long long len = e[r].end - e[r].start;
-            if (cnt[r] == 1) {  // one match, or a kept unmatched probe row (first == -1)
-                out_probe[o] = i;
-                out_build[o] = first[r];
-                if (matched_bits && first[r] >= 0) atomicOr(&matched_bits[first[r] >> 5], 1u << (first[r] & 31));
-            } else if (cnt[r] > 1 && len < LONG_BUCKET) {
-                long long w = 0;
-                walk_bucket<W>(a, e[r], v[r], h[r], i, [&](int64_t br) {
-                    out_probe[o + w] = i;
-                    out_build[o + w] = br;
-                    if (matched_bits) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
-                    w++;
-                });
-            }
-            unsigned pending = __ballot_sync(0xffffffffu, cnt[r] > 1 && len >= LONG_BUCKET);
-            while (pending) {
-                const int src = __ffs(pending) - 1;
-                pending &= pending - 1;
-                const long long s = shfl_ll(e[r].start, src), en = shfl_ll(e[r].end, src);
-                const unsigned long long vv = (unsigned long long)shfl_ll((long long)v[r], src);
-                const int64_t ii = base + (int64_t)r * PT + (warp << 5) + src;
-                long long oo = shfl_ll(o, src);
-                for (long long t0 = s; t0 < en; t0 += 32) {
-                    const long long t = t0 + lane;
-                    int64_t br = -1;
-                    bool mt = false;
-                    if (t < en) {
-                        br = a.sorted_rows[t];
-                        mt = W ? key_w<W>(a.bkey, br) == vv : keys_match(a.bk, br, a.pk, ii);
+                // long buckets: the whole warp writes them, one owner lane at a time, insertion order kept by ballots
+                pending = __ballot_sync(0xffffffffu, is_long && c > 0 && !unmatched);
+                while (pending) {
+                    const int src = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    const unsigned s = __shfl_sync(0xffffffffu, e[r].start, src), en = __shfl_sync(0xffffffffu, e[r].end, src);
+                    const unsigned long long vv = (unsigned long long)shfl_ll((long long)v[r], src);
+                    const int64_t ii = shfl_ll(i, src);
+                    long long oo = shfl_ll(off, src);
+                    for (unsigned t0 = s; t0 < en; t0 += 32) {
+                        const unsigned t = t0 + lane;
+                        int64_t br = -1;
+                        bool mt = false;
+                        if (t < en) {
+                            br = a.sorted_rows[t];
+                            mt = row_matches<W>(a, br, vv, ii);
+                        }
+                        const unsigned mm = __ballot_sync(0xffffffffu, mt);
+                        if (mt) {
+                            const long long p = oo + __popc(mm & lt_mask);
+                            out_probe[p] = ii;
+                            out_build[p] = br;
+                            if (matched_bits) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
+                        }
+                        oo += __popc(mm);
                     }
-                    const unsigned mm = __ballot_sync(0xffffffffu, mt);
-                    if (mt) {
-                        const long long p = oo + __popc(mm & ((1u << lane) - 1u));
-                        out_probe[p] = ii;
-                        out_build[p] = br;
-                        if (matched_bits) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
-                    }
-                    oo += __popc(mm);
                 }
             }
         }
@@ -493,8 +656,10 @@ void probe_table_build(b200_probe_table *pt) {
     cudaStream_t st = ctx().stream;
     pt->key_cols = pt->pending_keys[0];
     if (pt->pending.size() == 1) {
-        // payload columns may stay views (a join output as build side): only the keys are read here
-        pt->build = std::make_unique<Batch>(materialize_batch(*pt->pending[0], &pt->key_cols));
+        // payload columns of a large build side may stay views (a join output as build side): only the keys are read
+        // here.  A small one is gathered now: every output column then shares the one build-row selection vector.
+        const bool small = pt->pending[0]->num_rows <= ((int64_t)1 << 22);
+        pt->build = std::make_unique<Batch>(materialize_batch(*pt->pending[0], small ? nullptr : &pt->key_cols));
     } else {
         auto b = std::make_unique<Batch>();
         const size_t nc = pt->pending[0]->cols.size();
@@ -516,7 +681,23 @@ void probe_table_build(b200_probe_table *pt) {
     const int64_t n = b.num_rows;
     pt->num_rows = n;
     // reference limits (probe_table.rs:22-25,128-129) are 2^36 rows per table; ours is the same order
-    Buf hashes = hash_rows(b, pt->key_cols.data(), pt->nkeys, nullptr);
+    KernelTimer kt_build("join_build");
+    if (n >= ((int64_t)1 << 32) - 1) fail("join: a probe table holds fewer than 2^32 rows");
+    // inline key tags: one integer-like key column without nulls (floats keep IEEE ==, strings need their bytes)
+    const Column &k0 = b.cols[pt->key_cols[0]];
+    const bool int_like = k0.dtype == B200_I8 || k0.dtype == B200_I16 || k0.dtype == B200_I32 || k0.dtype == B200_I64 || k0.dtype == B200_U8 ||
+                          k0.dtype == B200_U16 || k0.dtype == B200_U32 || k0.dtype == B200_U64 || k0.dtype == B200_DATE32 || k0.dtype == B200_TIMESTAMP;
+    pt->inline_width = (pt->nkeys == 1 && int_like && k0.null_count == 0) ? dtype_width(k0.dtype) : 0;
+    Buf hashes;
+    if (pt->inline_width) {
+        hashes = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+        if (n > 0) {
+            hash_inline_keys<<<jgrid(n), 256, 0, st>>>(k0.data->ptr, pt->inline_width, n, as<uint64_t>(hashes));
+            count_launch();
+        }
+    } else {
+        hashes = hash_rows(b, pt->key_cols.data(), pt->nkeys, nullptr);
+    }
     Buf rows = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
     int bits = 4;
     while (bits < 40 && ((int64_t)1 << bits) < n) bits++;  // at most one row per bucket on average
@@ -526,17 +707,13 @@ void probe_table_build(b200_probe_table *pt) {
         fill_iota(as<int64_t>(rows), n);
         const int sort_bits = (bits + 7) / 8 * 8;  // whole byte passes over the top of the hash
         radix_sort_pairs(hashes, rows, n, 64 - sort_bits, 64, false);
-        // inline key tags: one integer-like key column without nulls (floats keep IEEE ==, strings need their bytes)
-        const Column &k0 = b.cols[pt->key_cols[0]];
-        const bool int_like = k0.dtype == B200_I8 || k0.dtype == B200_I16 || k0.dtype == B200_I32 || k0.dtype == B200_I64 || k0.dtype == B200_U8 ||
-                              k0.dtype == B200_U16 || k0.dtype == B200_U32 || k0.dtype == B200_U64 || k0.dtype == B200_DATE32 || k0.dtype == B200_TIMESTAMP;
-        pt->inline_width = (pt->nkeys == 1 && int_like && k0.null_count == 0) ? dtype_width(k0.dtype) : 0;
         bucket_bounds<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), as<int64_t>(rows), n, 64 - bits, k0.data ? k0.data->ptr : nullptr,
                                                 pt->inline_width, as<JoinBucket>(pt->slots));
         count_launch();
-        // a table that cannot stay in L2 (126 MB) gets the Bloom filter: ~8 bits per build row
+        // Bloom filter, ~8 bits per build row: probe rows without a partner stop at one 8-byte word (L1 / L2 resident)
+        // instead of a 32-byte table sector -- in DRAM for large tables, L2 bandwidth for small ones
         const char *env = getenv("B200_JOIN_BLOOM");
-        const bool want = env ? *env == '1' : (((size_t)1 << bits) * sizeof(JoinBucket) > ((size_t)48 << 20));
+        const bool want = env ? *env != '0' : true;
         if (want) {
             uint64_t words = 1024;
             while ((int64_t)words * 8 < n) words <<= 1;
@@ -545,6 +722,11 @@ void probe_table_build(b200_probe_table *pt) {
             bloom_build<<<jgrid(n), 256, 0, st>>>(as<uint64_t>(hashes), n, as<unsigned long long>(pt->bloom), pt->bloom_mask);
             count_launch();
         }
+    }
+    if (!pt->bloom) {  // the probe kernels always consult the filter: a one-word filter that passes everything
+        pt->bloom = dev_alloc(8);
+        fill_u8(pt->bloom->ptr, 0xFF, 8);
+        pt->bloom_mask = 0;
     }
     pt->sorted_rows = rows;
     op_done();
@@ -600,17 +782,55 @@ static void make_probe_plan(const b200_probe_table *pt, const Batch &probe, cons
     }
 }
 
-template <int MODE>
-static void launch_probe(int width, const ProbeArgs &a, int64_t n, int64_t ntiles, const int64_t *tile_off, int64_t *tile_cnt, int64_t *out_probe,
-                         int64_t *out_build, unsigned int *matched_bits, uint32_t *out_bits, int keep) {
+// kernel variants: key width (0 = generic keys) x selection vector x nullable probe key x kept unmatched probe rows
+template <int W>
+static void launch_count_w(bool sel, bool nulls, bool keep, int grid, cudaStream_t st, const ProbeArgs &a, int64_t n, int64_t nchunks, int64_t *chunk_cnt,
+                           uint32_t *bits) {
+#define B200_COUNT(S, N, K) probe_count_kernel<W, S, N, K><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits)
+    if (sel) {
+        if (nulls) { if (keep) B200_COUNT(true, true, true); else B200_COUNT(true, true, false); }
+        else { if (keep) B200_COUNT(true, false, true); else B200_COUNT(true, false, false); }
+    } else {
+        if (nulls) { if (keep) B200_COUNT(false, true, true); else B200_COUNT(false, true, false); }
+        else { if (keep) B200_COUNT(false, false, true); else B200_COUNT(false, false, false); }
+    }
+#undef B200_COUNT
+}
+static void launch_count(int width, const ProbeArgs &a, int64_t n, int64_t nchunks, int64_t *chunk_cnt, uint32_t *bits, int keep) {
     cudaStream_t st = ctx().stream;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx().sm_count * 2));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nchunks + PT / 32 - 1) / (PT / 32), (int64_t)ctx().sm_count * 3));
+    const bool sel = a.psel != nullptr, nulls = a.pvalid != nullptr;
+    KernelTimer kt("join_probe_count");
     switch (width) {
-        case 1: probe_kernel<1, MODE><<<grid, PT, 0, st>>>(a, n, ntiles, tile_off, tile_cnt, out_probe, out_build, matched_bits, out_bits, keep); break;
-        case 2: probe_kernel<2, MODE><<<grid, PT, 0, st>>>(a, n, ntiles, tile_off, tile_cnt, out_probe, out_build, matched_bits, out_bits, keep); break;
-        case 4: probe_kernel<4, MODE><<<grid, PT, 0, st>>>(a, n, ntiles, tile_off, tile_cnt, out_probe, out_build, matched_bits, out_bits, keep); break;
-        case 8: probe_kernel<8, MODE><<<grid, PT, 0, st>>>(a, n, ntiles, tile_off, tile_cnt, out_probe, out_build, matched_bits, out_bits, keep); break;
-        default: probe_kernel<0, MODE><<<grid, PT, 0, st>>>(a, n, ntiles, tile_off, tile_cnt, out_probe, out_build, matched_bits, out_bits, keep); break;
+        case 1: launch_count_w<1>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
+        case 2: launch_count_w<2>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
+        case 4: launch_count_w<4>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
+        case 8: launch_count_w<8>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
+        default: launch_count_w<0>(false, false, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
+    }
+    count_launch();
+    B200_CUDA(cudaGetLastError());
+}
+template <int W>
+static void launch_write_w(bool sel, bool nulls, int grid, cudaStream_t st, const ProbeArgs &a, int64_t n, int64_t nchunks, const int64_t *chunk_off,
+                           const uint32_t *bits, int64_t *out_probe, int64_t *out_build, unsigned int *matched_bits) {
+#define B200_WRITE(S, N) probe_write_kernel<W, S, N><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits)
+    if (sel) { if (nulls) B200_WRITE(true, true); else B200_WRITE(true, false); }
+    else { if (nulls) B200_WRITE(false, true); else B200_WRITE(false, false); }
+#undef B200_WRITE
+}
+static void launch_write(int width, const ProbeArgs &a, int64_t n, int64_t nchunks, const int64_t *chunk_off, const uint32_t *bits, int64_t *out_probe,
+                         int64_t *out_build, unsigned int *matched_bits) {
+    cudaStream_t st = ctx().stream;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nchunks + PT / 32 - 1) / (PT / 32), (int64_t)ctx().sm_count * 3));
+    const bool sel = a.psel != nullptr, nulls = a.pvalid != nullptr;
+    KernelTimer kt("join_probe_write");
+    switch (width) {
+        case 1: launch_write_w<1>(sel, nulls, grid, st, a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits); break;
+        case 2: launch_write_w<2>(sel, nulls, grid, st, a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits); break;
+        case 4: launch_write_w<4>(sel, nulls, grid, st, a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits); break;
+        case 8: launch_write_w<8>(sel, nulls, grid, st, a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits); break;
+        default: launch_write_w<0>(false, false, grid, st, a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits); break;
     }
     count_launch();
     B200_CUDA(cudaGetLastError());
@@ -624,12 +844,14 @@ Batch *probe_exists(const b200_probe_table *pt, const Batch &probe, const int32_
     c.name = "exists";
     c.dtype = B200_BOOL;
     c.length = n;
-    c.data = dev_alloc((size_t)((n + 31) / 32 + 1) * 4);
+    c.data = dev_alloc_zero((size_t)((n + 31) / 32 + 1) * 4);
     c.data_bytes = (n + 7) / 8;
     if (n > 0) {
         ProbePlan pp;
         make_probe_plan(pt, probe, key_cols, pp);
-        launch_probe<2>(pt->inline_width, pp.args, n, (n + PTILE - 1) / PTILE, nullptr, nullptr, nullptr, nullptr, nullptr, as<uint32_t>(c.data), 0);
+        const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
+        Buf counts = dev_alloc((size_t)(nchunks + 1) * 8);
+        launch_count(pt->inline_width, pp.args, n, nchunks, as<int64_t>(counts), as<uint32_t>(c.data), 0);
     }
     auto out = std::make_unique<Batch>();
     out->num_rows = n;
@@ -651,17 +873,17 @@ static void probe_pairs(const b200_probe_table *pt, const Batch &probe, const in
     }
     ProbePlan pp;
     make_probe_plan(pt, probe, key_cols, pp);
-    const int64_t ntiles = (n + PTILE - 1) / PTILE;
-    Buf counts = dev_alloc((size_t)(ntiles + 1) * 8), offs = dev_alloc((size_t)(ntiles + 1) * 8);
-    const int keep = keep_unmatched_probe ? 1 : 0;
-    launch_probe<0>(pt->inline_width, pp.args, n, ntiles, nullptr, as<int64_t>(counts), nullptr, nullptr, nullptr, nullptr, keep);
-    exclusive_scan_i64(as<int64_t>(counts), as<int64_t>(offs), ntiles, as<int64_t>(offs) + ntiles);
-    total = read_i64(as<int64_t>(offs) + ntiles);
+    const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
+    Buf counts = dev_alloc((size_t)(nchunks + 1) * 8), offs = dev_alloc((size_t)(nchunks + 1) * 8);
+    Buf bits = dev_alloc((size_t)((n + 31) / 32 + 1) * 4);  // one "produces output" bit per probe row, pass 0 -> pass 1
+    launch_count(pt->inline_width, pp.args, n, nchunks, as<int64_t>(counts), as<uint32_t>(bits), keep_unmatched_probe ? 1 : 0);
+    exclusive_scan_i64(as<int64_t>(counts), as<int64_t>(offs), nchunks, as<int64_t>(offs) + nchunks);
+    total = read_i64(as<int64_t>(offs) + nchunks);
     out_probe = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
     out_build = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
     if (total > 0)
-        launch_probe<1>(pt->inline_width, pp.args, n, ntiles, as<int64_t>(offs), nullptr, as<int64_t>(out_probe), as<int64_t>(out_build), matched_bits,
-                        nullptr, keep);
+        launch_write(pt->inline_width, pp.args, n, nchunks, as<int64_t>(offs), as<uint32_t>(bits), as<int64_t>(out_probe), as<int64_t>(out_build),
+                     matched_bits);
 }
 
 Batch *probe_indices(const b200_probe_table *pt, const Batch &probe, const int32_t *key_cols) {

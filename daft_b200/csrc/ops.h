@@ -63,6 +63,8 @@ b200_comm *comm_init(const uint8_t *id128, int32_t rank, int32_t world);
 void comm_free(b200_comm *c);
 Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys);
 Batch *all_gather_batches(b200_comm *c, const Batch &b);
+void allreduce_agg_table(b200_comm *c, unsigned long long *acc, size_t cap, const std::vector<int> &cell_ops, const std::vector<char> &keep_local,
+                         unsigned long long *tagmin, int *status_flag);
 
 // tpch_gen.cu
 Batch *tpch_generate(int32_t table, double sf, int64_t row_begin, int64_t row_end, uint64_t seed, const char *const *columns,

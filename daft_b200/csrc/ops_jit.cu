@@ -1,5 +1,6 @@
 // Host orchestration of the JIT-specialised operators: Project, Filter, fused HashAggregate.
 #include <algorithm>
+#include <mutex>
 
 #include "common.h"
 #include "jit.h"
@@ -259,9 +260,14 @@ __global__ void init_table(unsigned long long *__restrict__ table, int64_t nreco
 // orders them by first row (first-occurrence group order, inline_agg.rs:804-807) and emits slot ids + first rows.
 // counter[0] = number of groups, or -1 when there are more than SMALL_GROUPS (the host then takes the general path).
 constexpr int SMALL_GROUPS = 1024;
+// Collective mode (tags != nullptr: the table was all-reduced across ranks, exchange.cu allreduce_agg_table): a group
+// whose tag differs from the all-reduced non-zero MIN (two keys met in one slot), whose code is inexact (bit 63), or
+// that has no local first row (minrow still empty) cannot be finished from the merged table: status 3.
 __global__ void __launch_bounds__(1024) small_groups_epilogue(const unsigned long long *__restrict__ nrows, const unsigned long long *__restrict__ minrow_cell,
                                                               int64_t cap, int astride, int ungrouped, long long *__restrict__ counter,
-                                                              int64_t *__restrict__ out_slot, unsigned long long *__restrict__ out_minrow) {
+                                                              int64_t *__restrict__ out_slot, unsigned long long *__restrict__ out_minrow,
+                                                              const unsigned long long *__restrict__ tags = nullptr,
+                                                              const unsigned long long *__restrict__ tagmin = nullptr, int *status = nullptr) {
     __shared__ int64_t s_slot[SMALL_GROUPS];
     __shared__ unsigned long long s_min[SMALL_GROUPS];
     __shared__ int s_n;
@@ -281,9 +287,14 @@ __global__ void __launch_bounds__(1024) small_groups_epilogue(const unsigned lon
             const bool used = i < cap && (ungrouped ? (i == 0) : (nr[u] != 0));
             if (used) {
                 const int pos = atomicAdd(&s_n, 1);
+                const unsigned long long mr = minrow_cell[i * astride];
                 if (pos < SMALL_GROUPS) {
                     s_slot[pos] = i * astride;
-                    s_min[pos] = minrow_cell[i * astride];
+                    s_min[pos] = mr;
+                }
+                if (tags && !ungrouped) {
+                    const unsigned long long t = tags[i * astride];
+                    if (t != tagmin[i] || (t >> 63) || mr == ~0ULL) atomicMax(status, 3);
                 }
             }
         }
@@ -318,8 +329,9 @@ struct FinalizeDesc {
     const unsigned long long *cnt;
     void *out;
     uint32_t *out_valid;
+    const unsigned long long *nan_cell, *last_cell;  // float min / max: 1 + row of the group's last NaN / last valid value
 };
-constexpr int MAX_FINALIZE = 32;
+constexpr int MAX_FINALIZE = 24;
 struct FinalizeSet {
     int n;
     FinalizeDesc d[MAX_FINALIZE];
@@ -328,7 +340,8 @@ struct FinalizeSet {
 __device__ __forceinline__ void finalize_one(int kind, int32_t val_dtype, int32_t out_dtype, const unsigned long long *__restrict__ cell,
                                              const unsigned long long *__restrict__ cnt, int cnt_is_valid_count, int const_zero,
                                              const int64_t *__restrict__ slots, int64_t ng, void *__restrict__ out,
-                                             uint32_t *__restrict__ out_valid, int64_t i) {
+                                             uint32_t *__restrict__ out_valid, int64_t i, const unsigned long long *__restrict__ nan_cell,
+                                             const unsigned long long *__restrict__ last_cell) {
     bool valid = false, bool_bit = false;
     if (i < ng) {
         const int64_t s = slots[i];
@@ -351,15 +364,17 @@ __device__ __forceinline__ void finalize_one(int kind, int32_t val_dtype, int32_
                 else ((unsigned long long *)out)[i] = valid ? c : 0ULL;  // f64 bits / i64 / u64
             } else {  // min / max: decode the order-preserving key
                 unsigned long long v = c;
+                // the left fold ends on NaN exactly when the group's last valid value is one (inline_agg.rs:271-298)
+                const bool ends_nan = nan_cell != nullptr && nan_cell[s] != 0ULL && nan_cell[s] == last_cell[s];
                 switch (out_dtype) {
                     case B200_F64: {
-                        double d = (c == 0xFFFFFFFFFFFFFFFFULL) ? __longlong_as_double(0x7FF8000000000000LL)
+                        double d = (ends_nan || c == 0xFFFFFFFFFFFFFFFFULL) ? __longlong_as_double(0x7FF8000000000000LL)
                                                                  : __longlong_as_double((long long)((c >> 63) ? (c & 0x7FFFFFFFFFFFFFFFULL) : ~c));
                         ((double *)out)[i] = valid ? d : 0.0;
                         break;
                     }
                     case B200_F32: {
-                        double d = (c == 0xFFFFFFFFFFFFFFFFULL) ? __longlong_as_double(0x7FF8000000000000LL)
+                        double d = (ends_nan || c == 0xFFFFFFFFFFFFFFFFULL) ? __longlong_as_double(0x7FF8000000000000LL)
                                                                  : __longlong_as_double((long long)((c >> 63) ? (c & 0x7FFFFFFFFFFFFFFFULL) : ~c));
                         ((float *)out)[i] = valid ? (float)d : 0.f;
                         break;
@@ -391,12 +406,45 @@ __global__ void finalize_agg_all(FinalizeSet fs, const int64_t *__restrict__ slo
     const int64_t g_round = (ng + 31) & ~(int64_t)31;
     if (i >= g_round) return;
     const FinalizeDesc &d = fs.d[blockIdx.y];
-    finalize_one(d.kind, d.val_dtype, d.out_dtype, d.cell, d.cnt, d.cnt_is_valid_count, d.const_zero, slots, ng, d.out, d.out_valid, i);
+    finalize_one(d.kind, d.val_dtype, d.out_dtype, d.cell, d.cnt, d.cnt_is_valid_count, d.const_zero, slots, ng, d.out, d.out_valid, i, d.nan_cell,
+                 d.last_cell);
 }
 
 Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng);  // sort.cu
 
-Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *first_rows, int64_t *ngroups) {
+// float min / max, NaN-forgetting fold: does some group have a NaN that is not its last valid value?
+struct NanPairs {
+    int n;
+    const unsigned long long *nan_cell[16], *last_cell[16];
+};
+__global__ void nan_mid_check(const int64_t *__restrict__ slots, int64_t ng, const __grid_constant__ NanPairs np, int *flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ng) return;
+    const int64_t s = slots[i];
+    for (int k = 0; k < np.n; k++) {
+        const unsigned long long a = np.nan_cell[k][s];
+        if (a != 0ULL && a != np.last_cell[k][s]) *flag = 1;
+    }
+}
+__global__ void reset_cell(unsigned long long *__restrict__ cell, int64_t nrecords, int astride, unsigned long long value) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nrecords; i += stride) cell[i * astride] = value;
+}
+
+__global__ void tag_min_prep(const unsigned long long *__restrict__ tags, int64_t cap, unsigned long long *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) {
+        const unsigned long long t = tags[i];
+        out[i] = t == 0ULL ? ~0ULL : t;
+    }
+}
+
+// `coll` != nullptr: the aggregate of a low-cardinality plan over one scan partition per rank -- the group table is
+// all-reduced across the ranks before it is read back, so every rank finishes with the global result and no second
+// aggregation stage runs.  Returns nullptr (on every rank alike: the decision is taken from all-reduced words) when the
+// plan or the data do not allow it; the caller then runs the two-stage plan.
+Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *first_rows, int64_t *ngroups, b200_comm *coll) {
     require_device();
     cudaStream_t st = ctx().stream;
     const int64_t n = in.num_rows;
@@ -433,8 +481,16 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         cap = 64;
         while (cap < 2 * n) cap <<= 1;
     }
+    if (coll) {
+        cap = kp->nkeys > 0 ? (1 << 13) : 1;  // the same table shape on every rank, whatever its row count
+        for (const auto &ag : kp->aggs)
+            if (ag.kind == jit::AGG_ANY_VALUE) return nullptr;  // a first-row value is per rank: two-stage plan
+        for (int op : kp->lane_cell_ops)
+            if (op == jit::C_ADD_F32) return nullptr;
+        if (kp->has_nan_fold) return nullptr;  // float min / max fold in row order: rows are per rank
+    }
     const Compiled *k_first = kp;  // carries the plan's history (the global build is only compiled when needed)
-    if (kp->nkeys > 0 && k_first->last_groups > 0 && n >= (1 << 16)) {  // sticky choice: skip the tier-1 attempt it would abandon again
+    if (!coll && kp->nkeys > 0 && k_first->last_groups > 0 && n >= (1 << 16)) {  // sticky choice: skip the tier-1 attempt it would abandon again
         variant = 1;
         kp = &jit::get(B200_OP_AGG, plan, len, in, false, 1);
         cap = 1 << 16;
@@ -444,6 +500,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
     int64_t ng = 0;
     bool small_path = false;  // slots / first rows already ordered by the single-CTA epilogue
     size_t cell_step_final = 1;  // layout of the table the successful attempt used
+    int astride_final = 1;
     int ncells = 0, cell_nrows = 0, cell_minrow = 0;
     for (int attempt = 0;; attempt++) {
         const Compiled &k = *kp;
@@ -501,17 +558,31 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
             const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)ctx().sm_count * occ));
             jit::launch(k, a, grid, k.block_threads, k.smem_bytes, 0, true);
         }
+        Buf tagmin;
+        if (coll) {  // merge the tables of all ranks (also the status word: every rank takes the same decision below)
+            if (records) fail("agg all-reduce: unexpected record layout");
+            tagmin = dev_alloc((size_t)cap * 8);
+            tag_min_prep<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(as<unsigned long long>(acc), cap, as<unsigned long long>(tagmin));
+            count_launch();
+            std::vector<int> ops(k.lane_cell_ops.begin(), k.lane_cell_ops.end());
+            for (int w = 0; w < k.NWARP; w++) ops.push_back(jit::C_ADD_I64);
+            std::vector<char> keep(ops.size(), 0);
+            keep[(size_t)k.NLANE - 1] = 1;  // first rows index THIS rank's input: they stay local
+            allreduce_agg_table(coll, as<unsigned long long>(acc), (size_t)cap, ops, keep, as<unsigned long long>(tagmin), as<int>(flag));
+        }
         // compact the occupied slots right behind the kernel: status flag and group count come back in ONE read
         // (an ungrouped aggregate has exactly one group and no failure mode: no read at all)
         slots = dev_alloc((size_t)std::max<int64_t>(cap, 1) * 8);
         const unsigned long long *nrows_c = cell_base(cell_nrows);
         const unsigned long long *minrow_c = cell_base(cell_minrow);
         cell_step_final = cell_step;
+        astride_final = astride;
         small_path = cap <= (1 << 16);
         if (small_path) {
             minrow_sorted = dev_alloc((size_t)SMALL_GROUPS * 8);
             small_groups_epilogue<<<1, 1024, 0, st>>>(nrows_c, minrow_c, cap, astride, k.nkeys == 0, as<long long>(flag) + 1, as<int64_t>(slots),
-                                                      as<unsigned long long>(minrow_sorted));
+                                                      as<unsigned long long>(minrow_sorted), coll ? as<unsigned long long>(acc) : nullptr,
+                                                      as<unsigned long long>(tagmin), as<int>(flag));
         } else {
             compact_slots<<<stream_grid(cap, 256, 8), 256, 0, st>>>(nrows_c, cap, astride, k.nkeys == 0, as<unsigned long long>(flag) + 1, as<int64_t>(slots));
         }
@@ -522,6 +593,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
             B200_CUDA(cudaStreamSynchronize(st));
             status = (int)(host[0] & 0xffffffffLL);
             ng = host[1];
+            if (coll && (status || ng < 0)) return nullptr;  // abandoned / overflow / not mergeable: identical on every rank
             if (!status && ng < 0) {  // more groups than the single-CTA epilogue handles: general path on the same table
                 small_path = false;
                 fill_u8(as<uint8_t>(flag) + 8, 0, 8);
@@ -560,6 +632,54 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         count_launch();
         if (k.nkeys > 0 && ng > 1) {
             slots = sort_slots_by_minrow(slots, minrow, ng);  // also permutes `minrow` in place
+        }
+    }
+
+    // ---- float min / max: the reference's fold forgets what came before a NaN (jit.h AggOut::nan_cell).  The kernel
+    // folded the non-NaN candidates of all rows; a group whose last NaN is followed by more values is re-folded over
+    // the rows after that NaN by a second pass over the input (rare: only when such a group exists).
+    if (k.has_nan_fold && ng > 0 && n > 0) {
+        NanPairs np;
+        np.n = 0;
+        for (const auto &ag : k.aggs)
+            if (ag.nan_cell >= 0 && np.n < 16) {
+                np.nan_cell[np.n] = cell_ptr(ag.nan_cell);
+                np.last_cell[np.n] = cell_ptr(ag.last_cell);
+                np.n++;
+            }
+        Buf nflag = dev_alloc_zero(8);
+        nan_mid_check<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(as<int64_t>(slots), ng, np, as<int>(nflag));
+        count_launch();
+        if (read_i64(as<int64_t>(nflag)) != 0) {
+            for (const auto &ag : k.aggs)
+                if (ag.nan_cell >= 0) {
+                    reset_cell<<<stream_grid(cap, 256, 8), 256, 0, st>>>(cell_ptr(ag.lane_cell), cap, astride_final,
+                                                                         k.lane_cell_ops[ag.lane_cell] == jit::C_MIN ? ~0ULL : 0ULL);
+                    count_launch();
+                }
+            const Compiled &k3 = jit::get(B200_OP_AGG, plan, len, in, false, 3);
+            LaunchArgs a;
+            a.ptr.assign(k3.ptrs.size(), nullptr);
+            a.ival.assign(k3.ints.size(), 0);
+            for (size_t s2 = 0; s2 < k3.ptrs.size(); s2++) {
+                const auto &ps = k3.ptrs[s2];
+                switch (ps.kind) {
+                    case jit::P_COL_DATA: a.ptr[s2] = in.cols[ps.index].data ? in.cols[ps.index].data->ptr : nullptr; break;
+                    case jit::P_COL_VALID: a.ptr[s2] = in.cols[ps.index].validity ? in.cols[ps.index].validity->ptr : nullptr; break;
+                    case jit::P_COL_OFFSETS: a.ptr[s2] = in.cols[ps.index].offsets ? in.cols[ps.index].offsets->ptr : nullptr; break;
+                    case jit::P_SLOT_HASH: a.ptr[s2] = acc->ptr; break;
+                    case jit::P_OVERFLOW: a.ptr[s2] = flag->ptr; break;
+                    case jit::P_ACC: a.ptr[s2] = cell_ptr(ps.index); break;
+                    default: fail("agg: unexpected parameter kind");
+                }
+            }
+            for (size_t s2 = 0; s2 < k3.ints.size(); s2++) {
+                const int kind = k3.ints[s2] % 1000;
+                if (kind == jit::I_N) a.ival[s2] = n;
+                else if (kind == jit::I_MASK) a.ival[s2] = cap - 1;
+                else if (kind == jit::I_RSTRIDE) a.ival[s2] = astride_final;
+            }
+            jit::launch(k3, a, stream_grid(n, 256, 8), 256, 0, 0, false);
         }
     }
 
@@ -623,7 +743,8 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         const unsigned long long *cnt = ag.cnt_cell >= 0 ? cell_ptr(k.NLANE + ag.cnt_cell) : nrows_cell;
         // an ungrouped aggregate over zero rows still yields one row: sums null, counts 0
         const int cnt_is_valid = (ag.kind != jit::AGG_COUNT) ? 1 : 0;
-        fs.d[fs.n++] = {ag.kind, ag.val_dtype, ag.out_dtype, cnt_is_valid, ag.const_zero ? 1 : 0, 0, cell, cnt, c.data->ptr, as<uint32_t>(c.validity)};
+        fs.d[fs.n++] = {ag.kind, ag.val_dtype, ag.out_dtype, cnt_is_valid, ag.const_zero ? 1 : 0, 0, cell, cnt, c.data->ptr, as<uint32_t>(c.validity),
+                        ag.nan_cell >= 0 ? cell_ptr(ag.nan_cell) : nullptr, ag.last_cell >= 0 ? cell_ptr(ag.last_cell) : nullptr};
         agg_cols.push_back(std::move(c));
         if (fs.n == MAX_FINALIZE) flush_finalize();
     }
@@ -641,6 +762,65 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
     return out.release();
 }
 
-Batch *op_agg(const Batch &in, const uint8_t *plan, size_t len) { return op_agg_first_rows(in, plan, len, nullptr, nullptr); }
+Batch *op_agg(const Batch &in, const uint8_t *plan, size_t len) { return op_agg_first_rows(in, plan, len, nullptr, nullptr, nullptr); }
+
+}  // namespace b200
+
+// ------------------------------------------------------------------------------------------------
+// GroupedAggregateSink state (src/daft-local-execution/src/sinks/grouped_aggregate.rs:146-488): the planner hands the
+// sink its partial aggregations, final aggregations and final projection; every pushed batch is reduced to a partial
+// result that stays in HBM, finalize merges them.
+// ------------------------------------------------------------------------------------------------
+struct b200_groupby_state {
+    std::vector<uint8_t> partial_plan, final_plan, project_plan;
+    std::vector<std::unique_ptr<b200::Batch>> partials;
+    std::mutex mu;
+};
+
+namespace b200 {
+
+b200_groupby_state *groupby_create(const uint8_t *p1, size_t n1, const uint8_t *p2, size_t n2, const uint8_t *p3, size_t n3) {
+    if (!p1 || !p2 || !p3) fail("groupby: null plan");
+    auto *s = new b200_groupby_state;
+    s->partial_plan.assign(p1, p1 + n1);
+    s->final_plan.assign(p2, p2 + n2);
+    s->project_plan.assign(p3, p3 + n3);
+    return s;
+}
+void groupby_free(b200_groupby_state *s) { delete s; }
+void groupby_push(b200_groupby_state *s, const Batch &in) {
+    if (!s) fail("null groupby state");
+    const std::vector<int32_t> cols = jit::referenced_columns(B200_OP_AGG, s->partial_plan.data(), s->partial_plan.size());
+    std::unique_ptr<Batch> part(op_agg(materialize_batch(in, &cols), s->partial_plan.data(), s->partial_plan.size()));
+    std::lock_guard<std::mutex> g(s->mu);
+    s->partials.push_back(std::move(part));
+}
+Batch *groupby_finalize(b200_groupby_state *s) {
+    if (!s) fail("null groupby state");
+    std::lock_guard<std::mutex> g(s->mu);
+    if (s->partials.empty()) fail("groupby: finalize before any batch was pushed");
+    std::unique_ptr<Batch> all;
+    if (s->partials.size() == 1) {
+        all = std::make_unique<Batch>(*s->partials[0]);
+    } else {
+        all = std::make_unique<Batch>();
+        const size_t nc = s->partials[0]->cols.size();
+        for (auto &p : s->partials) all->num_rows += p->num_rows;
+        for (size_t c = 0; c < nc; c++) {
+            std::vector<const Column *> cs;
+            for (auto &p : s->partials) cs.push_back(&p->cols[c]);
+            all->cols.push_back(concat_columns(cs));
+        }
+    }
+    std::unique_ptr<Batch> merged(op_agg(*all, s->final_plan.data(), s->final_plan.size()));
+    Batch *out = op_project(*merged, s->project_plan.data(), s->project_plan.size(), nullptr, 0);
+    op_done();
+    return out;
+}
+
+Batch *op_agg_allreduce(b200_comm *comm, const Batch &in, const uint8_t *plan, size_t len) {
+    if (!comm) fail("null communicator");
+    return op_agg_first_rows(in, plan, len, nullptr, nullptr, comm);
+}
 
 }  // namespace b200

@@ -255,7 +255,6 @@ std::vector<Batch *> op_partition_by_range(const Batch &b, const int32_t *key_co
 }
 
 // distinct rows over the key columns, first occurrence kept, first-occurrence order
-Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *first_rows, int64_t *ngroups);  // ops_jit.cu
 
 Batch *op_dedup(const Batch &b, const int32_t *key_cols, int32_t nkeys) {
     require_device();

@@ -18,6 +18,80 @@ void require_device() {
     if (!ctx().ready) fail("daft_b200: no CUDA device initialised (call b200_init); there is no CPU fallback");
 }
 
+// ---- per-kernel timing ---------------------------------------------------------------------------
+namespace {
+struct TimedSample {
+    std::string name;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+std::mutex g_timer_mu;
+bool g_timer_on = false;
+std::vector<TimedSample> g_samples;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    B200_CUDA(cudaEventCreate(&e));
+    return e;
+}
+}  // namespace
+void kernel_timing_enable(bool on) {
+    std::lock_guard<std::mutex> g(g_timer_mu);
+    g_timer_on = on;
+}
+bool kernel_timing_enabled() { return g_timer_on; }
+KernelTimer::KernelTimer(const char *name) {
+    if (!g_timer_on) return;
+    std::lock_guard<std::mutex> g(g_timer_mu);
+    if (g_samples.size() >= 65536) return;  // bounded: a forgotten enable must not grow without limit
+    TimedSample s;
+    s.name = name;
+    s.e0 = take_event();
+    s.e1 = take_event();
+    B200_CUDA(cudaEventRecord(s.e0, ctx().stream));
+    slot = (int)g_samples.size();
+    g_samples.push_back(std::move(s));
+}
+KernelTimer::~KernelTimer() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> g(g_timer_mu);
+    if (slot < (int)g_samples.size()) cudaEventRecord(g_samples[slot].e1, ctx().stream);
+}
+std::string kernel_timing_report() {
+    std::lock_guard<std::mutex> g(g_timer_mu);
+    if (ctx().ready) B200_CUDA(cudaStreamSynchronize(ctx().stream));
+    std::vector<std::string> names;
+    std::vector<double> total;
+    std::vector<int64_t> count;
+    for (auto &s : g_samples) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.e0, s.e1) != cudaSuccess) ms = 0.f;
+        size_t k = 0;
+        while (k < names.size() && names[k] != s.name) k++;
+        if (k == names.size()) {
+            names.push_back(s.name);
+            total.push_back(0.0);
+            count.push_back(0);
+        }
+        total[k] += ms;
+        count[k] += 1;
+        g_event_pool.push_back(s.e0);
+        g_event_pool.push_back(s.e1);
+    }
+    g_samples.clear();
+    std::string out = "{";
+    for (size_t k = 0; k < names.size(); k++) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "\"launches\": %lld, \"ms\": %.6f", (long long)count[k], total[k]);
+        out += (k ? ", \"" : "\"") + names[k] + "\": {" + buf + "}";
+    }
+    return out + "}";
+}
+
 const char *dtype_name(int32_t dt) {
     static const char *names[] = {"null", "bool", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32",
                                   "uint64", "float32", "float64", "date32", "timestamp", "large_utf8", "large_binary"};
@@ -376,6 +450,7 @@ __global__ void __launch_bounds__(1024) gather_str_small(const __grid_constant__
 
 Batch *gather_batch(const Batch &src, const int64_t *idx, int64_t n, bool idx_may_be_negative, bool permutation) {
     for (const Column &c : src.cols) require_plain(c);
+    KernelTimer kt("gather_batch");
     auto out = std::make_unique<Batch>();
     out->num_rows = n;
     cudaStream_t st = ctx().stream;
@@ -532,6 +607,7 @@ std::vector<Column> make_view_columns(const Batch &src, const Buf &idx, int64_t 
                 if (pr.first == sc.sel.get()) comp = pr.second;
             if (!comp) {
                 comp = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+                KernelTimer kt("compose_sel");
                 if (n > 0) {
                     compose_sel<<<grid_for(n), 256, 0, ctx().stream>>>(as<int64_t>(sc.sel), as<int64_t>(idx), n, as<int64_t>(comp));
                     count_launch();

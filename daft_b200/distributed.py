@@ -114,6 +114,33 @@ class Communicator:
         _lib.call("b200_exchange_by_hash", self._h, both._h, _i32(idx), ctypes.c_int32(len(idx)), ctypes.byref(out))
         return RecordBatch._wrap(out).select_columns(list(range(batch.num_columns())))
 
+    def agg(self, batch, to_agg: Sequence, group_by: Sequence | None = None, predicate: Sequence | None = None):
+        """HashAggregate over one scan partition per rank; every rank returns the global result.
+        Low-cardinality results take ONE stage: the per-GPU group tables are all-reduced over NVLink
+        (b200_agg_allreduce).  Anything else (decided collectively inside the library) runs the reference's two-stage
+        plan: first-stage aggregate per rank -> all-gather of the partials -> second stage + final projection
+        (populate_aggregation_stages; src/daft-distributed/src/pipeline_node/aggregate.rs:281-340)."""
+        from . import _lib
+        from .aggstages import populate_aggregation_stages
+        from .expressions import _agg_inner, col, encode_agg
+        from .recordbatch import RecordBatch
+        group_by = list(group_by or [])
+        staged_only = any(_agg_inner(a).op in ("stddev", "var", "count_distinct") for a in to_agg)
+        if not staged_only:
+            plan = batch._cached_plan("agg", [to_agg, group_by, predicate],
+                                      lambda: encode_agg(to_agg, group_by, batch.column_names(), batch.dtypes(), predicate))
+            out, merged = ctypes.c_void_p(), ctypes.c_int32(0)
+            _lib.call("b200_agg_allreduce", self._h, batch._h, plan, ctypes.c_size_t(len(plan)), ctypes.byref(out), ctypes.byref(merged))
+            if merged.value:
+                onames = [g.name() for g in group_by] + [a.name() for a in to_agg]
+                odt = (ctypes.c_int32 * len(onames))()
+                _lib.call("b200_batch_dtypes", out, odt, ctypes.c_int32(len(onames)))
+                return RecordBatch._wrap(out, names=onames, dtypes=list(odt))
+        first, second, final = populate_aggregation_stages(to_agg, group_by)
+        partial = batch.agg(first, group_by, predicate)
+        keys = [col(g.name()) for g in group_by]
+        return self.all_gather(partial).agg(second, keys).eval_expression_list(final)
+
     def all_gather(self, batch):
         from . import _lib
         from .recordbatch import RecordBatch

@@ -126,7 +126,9 @@ def hash_join(left: RecordBatch, right: RecordBatch, left_on: Sequence[Expressio
     out = ctypes.c_void_p()
     _lib.call("b200_hash_join_probe", pt._h, st._h if st else None, probe._h, _i32(pkeys), ctypes.c_int32(jt),
               ctypes.c_int32(1 if build_on_left else 0), ctypes.byref(out))
-    joined = RecordBatch._wrap(out)
+    # joined columns: [left_aug..., right_aug...] (the build side comes first iff it is the left side)
+    joined = RecordBatch._wrap(out, names=laug.column_names() + raug.column_names(), dtypes=laug.dtypes() + raug.dtypes()) \
+        if how not in ("semi", "anti") else RecordBatch._wrap(out, like=probe)
     if how in ("semi", "anti"):
         return joined.select_columns(list(range(left.num_columns())))
     if st is not None:

@@ -166,7 +166,7 @@ class RecordBatch:
             raise ValueError(f"invalid slice bounds {start}..{end}")
         out = ctypes.c_void_p()
         _lib.call("b200_batch_slice", self._h, ctypes.c_int64(start), ctypes.c_int64(min(end, len(self))), ctypes.byref(out))
-        return RecordBatch._wrap(out)
+        return RecordBatch._wrap(out, like=self)
 
     def head(self, num: int) -> "RecordBatch":
         return self.slice(0, min(num, len(self)))
@@ -186,7 +186,7 @@ class RecordBatch:
         arr = (ctypes.c_void_p * len(to_merge))(*[t._h.value for t in to_merge])
         out = ctypes.c_void_p()
         _lib.call("b200_concat", arr, ctypes.c_int32(len(to_merge)), ctypes.byref(out))
-        return RecordBatch._wrap(out)
+        return RecordBatch._wrap(out, like=to_merge[0])
 
     # ---- expressions --------------------------------------------------------------------------------
     def _resolve_keys(self, exprs: Sequence[Expression]) -> tuple["RecordBatch", list[int]]:
@@ -260,7 +260,7 @@ class RecordBatch:
         plan = self._cached_plan("filter", [exprs], lambda: encode_filter(exprs, self.column_names(), self.dtypes()))
         out = ctypes.c_void_p()
         _lib.call("b200_filter", self._h, plan, ctypes.c_size_t(len(plan)), ctypes.byref(out))
-        return RecordBatch._wrap(out)
+        return RecordBatch._wrap(out, like=self)
 
     def agg(self, to_agg: Sequence[Expression], group_by: Sequence[Expression] | None = None,
             predicate: Sequence[Expression] | None = None) -> "RecordBatch":
@@ -376,7 +376,7 @@ class RecordBatch:
             indices = RecordBatch.from_arrow_table(pa.table({"idx": arr}))
         out = ctypes.c_void_p()
         _lib.call("b200_take", self._h, indices._h, ctypes.byref(out))
-        return RecordBatch._wrap(out)
+        return RecordBatch._wrap(out, like=self)
 
     @staticmethod
     def _sort_flags(sort_keys, descending, nulls_first):

@@ -136,6 +136,13 @@ def q1_final(partials: RecordBatch) -> RecordBatch:
     return partials.agg(aggs, group_by).eval_expression_list(project).sort([col("L_RETURNFLAG"), col("L_LINESTATUS")])
 
 
+def q1_distributed(lineitem: RecordBatch, comm) -> RecordBatch:
+    """Q1 over one scan partition per rank (distributed.Communicator.agg): the per-GPU group tables are all-reduced over
+    NVLink and every rank finishes with the global answer (src/daft-distributed/src/pipeline_node/aggregate.rs:281-340)."""
+    predicate, group_by, aggs = q1_exprs()
+    return comm.agg(lineitem, aggs, group_by, predicate).sort([col("L_RETURNFLAG"), col("L_LINESTATUS")])
+
+
 # ------------------------------------------------------------------------------------------------
 # Q6 (answers.py:146-155): pure scan + ungrouped aggregate
 # ------------------------------------------------------------------------------------------------

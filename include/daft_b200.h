@@ -124,6 +124,10 @@ int64_t b200_launch_count(void);
  * stream; b200_last_agg_kernel_ms returns the duration of the most recent one (-1 if none). */
 int b200_kernel_timing(int enable);
 double b200_last_agg_kernel_ms(void);
+/* per-kernel device time since the last report, as JSON text {"<kernel>": {"launches": n, "ms": total}, ...} (waits for the
+ * stream; *out_json is malloc'd: release with b200_free_string).  Covers the join probe / build kernels, the radix sort
+ * passes, partition and exchange kernels; the fused aggregate is reported by b200_last_agg_kernel_ms. */
+int b200_kernel_timing_report(char **out_json, char **errmsg);
 /* JIT cache: directory holding generated .cu/.cubin (default <lib dir>/_jitcache) */
 int b200_set_jit_cache_dir(const char *path, char **errmsg);
 /* compile (no launch) the kernels a plan needs -- usable without a GPU (build check) */
@@ -151,7 +155,11 @@ int b200_batch_export(const b200_batch *batch, struct ArrowArray *out_array, str
  * must be followed by 16 readable bytes: the kernels fetch values with aligned word loads (csrc/common.h). */
 int b200_batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t num_rows, b200_batch **out,
                            char **errmsg);
+/* Columns of a join output are VIEWS (row-id selection vectors over the join inputs) until an operator reads them: for
+ * such a column describe reports dtype, length and name only (null_count = -1, pointers NULL).  b200_batch_materialize
+ * returns the same batch with every column gathered into plain Arrow buffers (shared with `batch`: the gather happens once). */
 int b200_batch_describe(const b200_batch *batch, int32_t col, b200_column_desc *out, char **errmsg);
+int b200_batch_materialize(const b200_batch *batch, b200_batch **out, char **errmsg);
 /* dtype codes of the first n columns in one call (hosts that already know the column names skip b200_batch_describe) */
 int b200_batch_dtypes(const b200_batch *batch, int32_t *out_dtypes, int32_t n, char **errmsg);
 int64_t b200_batch_num_rows(const b200_batch *batch);
@@ -192,6 +200,19 @@ int b200_eval_expression_list(const b200_batch *batch, const uint8_t *plan, size
 
 /* ---- a4/a5/a6: grouped / ungrouped aggregate with the filter + projections fused in ---- */
 int b200_agg(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg);
+/* GroupedAggregateSink / AggregateSink state (src/daft-local-execution/src/sinks/grouped_aggregate.rs:146-488,
+ * sinks/aggregate.rs:54-123): make_state -> sink(morsel)* -> finalize.  The three AGG / AGG / PROJECT plans are what the
+ * reference's planner hands the sink (populate_aggregation_stages, src/daft-local-plan/src/agg.rs:13-416): the partial
+ * aggregation run on every pushed batch, the final aggregation over the concatenated partials (its input schema = the
+ * partial plan's output: key columns, then aggregates) and the final projection.  Partials stay in HBM.  push may be
+ * called from several host threads (the reference gives every worker its own state; here one state serialises its
+ * bookkeeping and the kernels queue on the library stream). */
+typedef struct b200_groupby_state b200_groupby_state;
+int b200_groupby_create(const uint8_t *partial_plan, size_t partial_len, const uint8_t *final_plan, size_t final_len,
+                        const uint8_t *project_plan, size_t project_len, b200_groupby_state **out, char **errmsg);
+int b200_groupby_push(b200_groupby_state *st, const b200_batch *batch, char **errmsg);
+int b200_groupby_finalize(b200_groupby_state *st, b200_batch **out, char **errmsg);
+void b200_groupby_free(b200_groupby_state *st);
 /* a13: distinct rows over key columns (first occurrence kept, first-occurrence order) */
 int b200_dedup(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out, char **errmsg);
 
@@ -248,6 +269,14 @@ void b200_comm_free(b200_comm *c);
 /* hash-partition `batch` into `world` pieces and all-to-all them; out = this rank's piece. */
 int b200_exchange_by_hash(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys,
                           b200_batch **out, char **errmsg);
+/* Low-cardinality HashAggregate over one scan partition per rank (the reference's partial aggregate -> gather -> final
+ * aggregate, src/daft-distributed/src/pipeline_node/aggregate.rs:281-340, as ONE stage): every rank runs b200_agg's
+ * kernel, the group tables are all-reduced over NVLink (one grouped NCCL launch), and every rank finishes with the global
+ * result.  `plan` is the single-stage AGG plan (means included).  *merged = 0 (and *out = NULL) on EVERY rank when the
+ * tables cannot be merged slot by slot (more than ~1000 groups, key codes that are not injective, any_value / Float32
+ * sums, a group without a local row): the caller then runs the two-stage plan through b200_all_gather. */
+int b200_agg_allreduce(b200_comm *c, const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out,
+                       int32_t *merged, char **errmsg);
 /* every rank receives the concatenation of all ranks' batches in rank order (broadcast join / partial-agg merge) */
 int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, char **errmsg);
 

@@ -429,6 +429,8 @@ def describe_agg(plan: bytes, dtypes, nullable, variant: int = 0):
         kind, mode, vdt, odt, lane, cnt, cn, cz, name = s.split(":", 8)
         aggs.append(dict(kind=int(kind), mode=int(mode), val_dtype=int(vdt), out_dtype=int(odt), lane_cell=int(lane), cnt_cell=int(cnt),
                          child_nullable=cn == "1", const_zero=cz == "1", name=name))
+    for a, pair in zip(aggs, f.get("nancells", "").split(",")):   # float min / max: the NaN-forgetting fold (jit.h AggOut::nan_cell)
+        a["nan_cell"], a["last_cell"] = (int(x) for x in pair.split(":")) if pair else (-1, -1)
     return dict(src=src, ptrs=[tuple(map(int, s.split(":"))) for s in f["ptrs"].split(",") if s], ints=[int(s) for s in f["ints"].split(",") if s],
                 nkeys=int(f["nkeys"]), nlane=int(f["nlane"]), nwarp=int(f["nwarp"]), aggs=aggs, cellops=[int(s) for s in f["cellops"].split(",") if s])
 
@@ -565,6 +567,12 @@ def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = Fa
                 arr = pa.array(np.where(valid, s, 0).astype(_NP.get(a["out_dtype"], np.float64)), type=typ, mask=mask)
             else:
                 vals = _decode_ord(cell, a["out_dtype"])
+                if a.get("nan_cell", -1) >= 0:
+                    # first pass + finalize only: NaN iff the group's last valid value is one (ops_jit.cu finalize_one); a NaN
+                    # in the MIDDLE of a group needs the device's second pass, which this emulation does not run
+                    nanrow, lastrow = acc[a["nan_cell"], :ng][order], acc[a["last_cell"], :ng][order]
+                    assert not ((nanrow != 0) & (nanrow != lastrow)).any(), "emulation input has a NaN followed by more values in its group"
+                    vals = np.where((nanrow != 0) & (nanrow == lastrow), np.nan, vals).astype(vals.dtype)
                 if a["out_dtype"] == dt.BOOL:
                     arr = pa.array(vals & valid, type=pa.bool_(), mask=mask)
                 else:

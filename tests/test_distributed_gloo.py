@@ -24,14 +24,18 @@ def _worker(rank, world, port, q):
         n = tpch.num_rows("lineitem", 0.01)
         b, e = distributed.shard_rows(n, rank, world)
         shard = tpch.generate_host("lineitem", 0.01, tpch.Q1_COLUMNS, b, e)
-        pred, gb, aggs = tpch.q1_partial_exprs()
-        fgb, faggs, fproj = tpch.q1_final_exprs()
+        # the plan shapes Communicator.agg falls back to: the generic rewrite of the single-stage Q1 aggregation list
+        from daft_b200 import col
+        from daft_b200.aggstages import populate_aggregation_stages
+        pred, gb, aggs = tpch.q1_exprs()
+        first, second, fproj = populate_aggregation_stages(aggs, gb)
+        fgb = [col(g.name()) for g in gb]
 
         def final(parts):
-            merged = oracle_agg(parts, faggs, fgb)
+            merged = oracle_agg(parts, second, fgb)
             return E.eval_expression_list(merged, fproj).sort_by([("L_RETURNFLAG", "ascending"), ("L_LINESTATUS", "ascending")])
 
-        out = distributed.two_stage_aggregate(lambda: oracle_agg(shard, aggs, gb, pred), final)
+        out = distributed.two_stage_aggregate(lambda: oracle_agg(shard, first, gb, pred), final)
         q.put((rank, distributed._to_ipc(out), e - b))
     finally:
         dist.destroy_process_group()

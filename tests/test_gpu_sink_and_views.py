@@ -1,0 +1,104 @@
+"""GroupedAggregateSink over b200_groupby_* (src/daft-local-execution/src/sinks/grouped_aggregate.rs:146-488) and the
+late-materialised (view) outputs of the hash join."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from helpers import assert_tables_equal, oracle_agg, random_table
+
+pytestmark = pytest.mark.gpu
+
+
+def RB(gpu, tbl):
+    return gpu.RecordBatch.from_arrow_table(tbl)
+
+
+@pytest.mark.parametrize("morsel", [700, 4096, 100_000])
+def test_grouped_aggregate_sink_matches_single_batch(gpu, morsel):
+    from daft_b200.aggstages import GroupedAggregateSink
+    rng = np.random.default_rng(morsel)
+    tbl = random_table(rng, 20_000, 0.15)
+    c = gpu.col
+    aggs = [c("i64").sum().alias("sm"), c("f64").mean().alias("m"), c("i32").count("all").alias("ca"), c("i32").count("null").alias("cn"),
+            c("u16").min().alias("lo"), c("i64").max().alias("hi"), c("b").bool_and().alias("ball"), (c("f64") * 2).stddev().alias("sd"),
+            c("i16").var(1).alias("vr"), c("i8").mean().alias("m8")]
+    for gb, pred in (([c("k")], None), ([c("s"), c("u8")], [c("i32") > 0]), ([], None)):
+        sink = GroupedAggregateSink(aggs, gb, pred)
+        for o in range(0, tbl.num_rows, morsel):
+            sink.sink(RB(gpu, tbl.slice(o, morsel)))
+        got = sink.finalize().to_arrow_table()
+        want = oracle_agg_staged(tbl, aggs, gb, pred)
+        assert_tables_equal(got, want, float_rtol=1e-9, sort_by=[g.name() for g in gb] or None)
+
+
+def oracle_agg_staged(tbl, aggs, gb, pred):
+    from oracle.recordbatch import OracleRecordBatch
+    return OracleRecordBatch(tbl).agg(aggs, gb, pred).to_arrow_table()
+
+
+def test_q1_through_the_sink(gpu):
+    from daft_b200 import tpch
+    from daft_b200.aggstages import GroupedAggregateSink
+    pred, gb, aggs = tpch.q1_exprs()
+    host = tpch.generate_host("lineitem", 0.05, tpch.Q1_COLUMNS)
+    sink = GroupedAggregateSink(aggs, gb, pred)
+    for o in range(0, host.num_rows, 131072):
+        sink.sink(RB(gpu, host.slice(o, 131072)))
+    got = sink.finalize().sort([gpu.col("L_RETURNFLAG"), gpu.col("L_LINESTATUS")]).to_arrow_table()
+    want = oracle_agg(host, aggs, gb, pred).sort_by([("L_RETURNFLAG", "ascending"), ("L_LINESTATUS", "ascending")])
+    assert_tables_equal(got, want, float_rtol=1e-9)
+
+
+def test_join_outputs_are_views_until_read(gpu):
+    """b200_batch_describe reports schema only for an unread join output; materialize / any operator gathers it."""
+    import ctypes
+    from daft_b200 import _lib
+    rng = np.random.default_rng(5)
+    left = pa.table({"k": pa.array(rng.integers(0, 50, 2000).astype(np.int64)), "a": pa.array(np.arange(2000)), "s": pa.array([f"row{i}" for i in range(2000)])})
+    right = pa.table({"k": pa.array(np.arange(40, dtype=np.int64)), "b": pa.array(np.arange(40) * 10.0)})
+    c = gpu.col
+    j = RB(gpu, left).hash_join(RB(gpu, right), [c("k")], [c("k")])
+    d = j._describe(1)
+    assert d.length == len(j) and d.null_count == -1 and not d.data          # still a selection vector over `left`
+    plain = ctypes.c_void_p()
+    _lib.call("b200_batch_materialize", j._h, ctypes.byref(plain))
+    pj = gpu.RecordBatch._wrap(plain, like=j)
+    d2 = pj._describe(1)
+    assert d2.null_count == 0 and d2.data
+    from oracle import oracle as O
+    want = O.hash_join(left, right, ["k"], ["k"], "inner")
+    assert_tables_equal(pj.to_arrow_table(), want)
+    assert_tables_equal(j.to_arrow_table(), want)
+    # a chain of joins reads its keys through the selection vectors; slices and filters of views work
+    right2 = pa.table({"a": pa.array(np.arange(0, 2000, 3)), "z": pa.array(np.arange(0, 2000, 3) % 7)})
+    j2 = j.hash_join(RB(gpu, right2), [c("a")], [c("a")])
+    want2 = O.hash_join(want, right2, ["a"], ["a"], "inner")
+    assert_tables_equal(j2.to_arrow_table(), want2)
+    assert_tables_equal(j2.slice(5, 60).to_arrow_table(), want2.slice(5, 55))
+    assert_tables_equal(j2.filter([c("z") == 3]).to_arrow_table(), want2.filter(pa.compute.equal(want2.column("z"), 3)))
+    assert_tables_equal(j2.sort([c("b"), c("a")], descending=[True, False]).to_arrow_table(),
+                        want2.sort_by([("b", "descending"), ("a", "ascending")]))
+
+
+def test_probe_indices_multi_table_build_and_probe_through_view(gpu):
+    """ProbeTableBuilder::add_table twice (probe_table.rs:117-185): build rows are numbered across the added tables in
+    insertion order; probe_indices yields (probe row, build row) in probe order, matches in insertion order."""
+    from daft_b200.join import ProbeTable
+    from oracle import oracle as O
+    rng = np.random.default_rng(8)
+    b1 = pa.table({"k": pa.array(rng.integers(0, 30, 500).astype(np.int64)), "p": pa.array(np.arange(500))})
+    b2 = pa.table({"k": pa.array(rng.integers(0, 30, 300).astype(np.int64)), "p": pa.array(np.arange(300) + 1000)})
+    probe = pa.table({"k": pa.array(rng.integers(0, 40, 1000).astype(np.int64))})
+    pt = ProbeTable(1)
+    pt.add_table(RB(gpu, b1), [0])
+    pt.add_table(RB(gpu, b2), [0])
+    pt.build()
+    assert pt.num_rows() == 800
+    got = pt.probe_indices(RB(gpu, probe), [0]).to_pydict()
+    build = pa.concat_tables([b1, b2])
+    offs, rows = O.join_matches([build.column("k")], [probe.column("k")], None)
+    cnt = np.diff(offs)
+    assert got["probe_idx"] == np.repeat(np.arange(1000), cnt).tolist()
+    assert got["build_idx"] == rows.tolist()
+    ex = pt.probe_exists(RB(gpu, probe), [0]).to_pydict()["exists"]
+    assert ex == (cnt > 0).tolist()
