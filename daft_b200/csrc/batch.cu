@@ -420,6 +420,19 @@ void export_host_columns(std::vector<HostCol> &cols, int64_t num_rows, ArrowArra
     out_array->private_data = ap;
 }
 
+__global__ void rebase_offsets_kernel(const int64_t *__restrict__ src, int64_t n1, int64_t first, int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n1; i += stride) out[i] = src[i] - first;
+}
+static Buf rebase_offsets(const int64_t *src, int64_t n, int64_t first) {
+    Buf out = dev_alloc((size_t)(n + 1) * 8);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 256) / 256, (int64_t)ctx().sm_count * 8));
+    rebase_offsets_kernel<<<grid, 256, 0, ctx().stream>>>(src, n + 1, first, as<int64_t>(out));
+    count_launch();
+    return out;
+}
+
 Batch *batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t num_rows) {
     require_device();
     auto out = std::make_unique<Batch>();
@@ -438,6 +451,21 @@ Batch *batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t nu
         if (d.data) c.data = dev_borrow(d.data, (size_t)d.data_bytes);
         c.data_bytes = d.data_bytes;
         if (is_string(c.dtype) && !d.offsets) fail("from_device: string column without offsets");
+        if (is_string(c.dtype) && d.length > 0) {
+            // A sliced Arrow string array has offsets[0] != 0.  The operators that copy value bytes wholesale (concat, the
+            // packed all-gather, small permutation gathers) take the bytes from `data` + 0: re-base such a column here by
+            // viewing the data buffer from its first referenced byte and shifting the offsets once (one 16-byte read back).
+            int64_t ends[2] = {0, 0};
+            B200_CUDA(cudaMemcpyAsync(&ends[0], d.offsets, 8, cudaMemcpyDeviceToHost, ctx().stream));
+            B200_CUDA(cudaMemcpyAsync(&ends[1], (const int64_t *)d.offsets + d.length, 8, cudaMemcpyDeviceToHost, ctx().stream));
+            B200_CUDA(cudaStreamSynchronize(ctx().stream));
+            if (ends[0] < 0 || ends[1] < ends[0] || ends[1] > d.data_bytes) fail("from_device: string offsets outside the data buffer");
+            if (ends[0] != 0) {
+                c.offsets = rebase_offsets((const int64_t *)d.offsets, d.length, ends[0]);
+                c.data = dev_borrow((const uint8_t *)d.data + ends[0], (size_t)(ends[1] - ends[0]));
+            }
+            c.data_bytes = ends[1] - ends[0];
+        }
         out->cols.push_back(std::move(c));
     }
     return out.release();

@@ -19,6 +19,11 @@
 struct b200_comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // peer-store exchange: every rank owns a receive arena (cudaMalloc, exported over CUDA IPC) that all peers map
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<void *> peer_arena;  // [world]: mapped base of every rank's arena (own entry = arena)
+    int p2p_state = 0;               // 0 untried, 1 usable, -1 unavailable (no IPC / no peer access): NCCL send/recv instead
 };
 
 namespace b200 {
@@ -90,7 +95,16 @@ b200_comm *comm_init(const uint8_t *id128, int32_t rank, int32_t world) {
     c->world = world;
     return c.release();
 }
+static void arena_release(b200_comm *c) {
+    for (int r = 0; r < (int)c->peer_arena.size(); r++)
+        if (r != c->rank && c->peer_arena[r]) cudaIpcCloseMemHandle(c->peer_arena[r]);
+    c->peer_arena.clear();
+    if (c->arena) cudaFree(c->arena);
+    c->arena = nullptr;
+    c->arena_bytes = 0;
+}
 void comm_free(b200_comm *c) {
+    if (c) arena_release(c);
     if (c && c->comm) nccl().CommDestroy(c->comm);
     delete c;
 }
@@ -123,30 +137,41 @@ struct Route {
     int64_t recv_total = 0;
 };
 
-// all ranks learn everybody's send counts: m[src * world + dst]
-static std::vector<int64_t> gather_counts(b200_comm *c, const std::vector<int64_t> &send_cnt) {
+// all ranks learn everybody's send counts, m[src * (world + nextra) + dst], plus `nextra` extra words per rank (the
+// exchange piggybacks each column's null count: validity only travels for columns some rank has nulls in)
+static std::vector<int64_t> gather_counts(b200_comm *c, const std::vector<int64_t> &send_cnt, const std::vector<int64_t> &extra) {
     cudaStream_t st = ctx().stream;
     const int W = c->world;
-    Buf d_in = dev_alloc((size_t)W * 8), d_out = dev_alloc((size_t)W * W * 8);
-    B200_CUDA(cudaMemcpyAsync(d_in->ptr, send_cnt.data(), (size_t)W * 8, cudaMemcpyHostToDevice, st));
-    B200_NCCL(nccl().AllGather(d_in->ptr, d_out->ptr, (size_t)W, ncclInt64, c->comm, st));
-    std::vector<int64_t> m((size_t)W * W);
-    B200_CUDA(cudaMemcpyAsync(m.data(), d_out->ptr, (size_t)W * W * 8, cudaMemcpyDeviceToHost, st));
+    const size_t per = (size_t)W + extra.size();
+    std::vector<int64_t> mine(send_cnt);
+    mine.insert(mine.end(), extra.begin(), extra.end());
+    Buf d_in = dev_alloc(per * 8), d_out = dev_alloc(per * W * 8);
+    B200_CUDA(cudaMemcpyAsync(d_in->ptr, mine.data(), per * 8, cudaMemcpyHostToDevice, st));
+    B200_NCCL(nccl().AllGather(d_in->ptr, d_out->ptr, per, ncclInt64, c->comm, st));
+    std::vector<int64_t> m(per * W);
+    B200_CUDA(cudaMemcpyAsync(m.data(), d_out->ptr, per * W * 8, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return m;
 }
-static Route make_route(b200_comm *c, const std::vector<int64_t> &send_off, const std::vector<int64_t> &send_cnt) {
+static Route make_route(b200_comm *c, const std::vector<int64_t> &send_off, const std::vector<int64_t> &send_cnt,
+                        const std::vector<int64_t> &extra = {}, std::vector<int64_t> *extra_sum = nullptr) {
     const int W = c->world;
     Route r;
     r.send_off = send_off;
     r.send_cnt = send_cnt;
-    const std::vector<int64_t> m = gather_counts(c, send_cnt);
+    const std::vector<int64_t> m = gather_counts(c, send_cnt, extra);
+    const size_t per = (size_t)W + extra.size();
     r.recv_off.assign(W, 0);
     r.recv_cnt.assign(W, 0);
     for (int src = 0; src < W; src++) {
-        r.recv_cnt[src] = m[(size_t)src * W + c->rank];
+        r.recv_cnt[src] = m[(size_t)src * per + c->rank];
         r.recv_off[src] = r.recv_total;
         r.recv_total += r.recv_cnt[src];
+    }
+    if (extra_sum) {
+        extra_sum->assign(extra.size(), 0);
+        for (int src = 0; src < W; src++)
+            for (size_t e = 0; e < extra.size(); e++) (*extra_sum)[e] += m[(size_t)src * per + W + e];
     }
     return r;
 }
@@ -166,13 +191,15 @@ static void move_buffer(b200_comm *c, const Route &r, const void *send, void *re
 }
 
 // `src` columns are already destination-contiguous (rows [row_route.send_off[p], +send_cnt[p]) go to peer p)
-static Batch *route_batch(b200_comm *c, const Batch &src, const Route &rows) {
+// nulls_anywhere[col] = some rank's piece of that column has nulls (null = unknown: validity always travels)
+static Batch *route_batch(b200_comm *c, const Batch &src, const Route &rows, const std::vector<int64_t> *nulls_anywhere) {
     cudaStream_t st = ctx().stream;
     const int W = c->world;
     const int64_t n_out = rows.recv_total, n_in = src.num_rows;
     auto out = std::make_unique<Batch>();
     out->num_rows = n_out;
-    for (const Column &col : src.cols) {
+    for (size_t ci = 0; ci < src.cols.size(); ci++) {
+        const Column &col = src.cols[ci];
         Column o;
         o.name = col.name;
         o.dtype = col.dtype;
@@ -182,8 +209,9 @@ static Batch *route_batch(b200_comm *c, const Batch &src, const Route &rows) {
             out->cols.push_back(std::move(o));
             continue;
         }
-        // validity travels one byte per row (bitmaps cannot be cut at arbitrary bit offsets); any rank may have nulls
-        {
+        // validity travels one byte per row (bitmaps cannot be cut at arbitrary bit offsets) -- only for columns that have
+        // nulls on some rank
+        if (!nulls_anywhere || (*nulls_anywhere)[ci] > 0) {
             Buf sb = dev_alloc((size_t)std::max<int64_t>(n_in, 1)), rb = dev_alloc((size_t)std::max<int64_t>(n_out, 1));
             if (n_in) {
                 bits_to_bytes<<<egrid(n_in), 256, 0, st>>>(col.null_count > 0 ? as<uint8_t>(col.validity) : nullptr, n_in, as<uint8_t>(sb));
@@ -253,21 +281,213 @@ static Batch *route_batch(b200_comm *c, const Batch &src, const Route &rows) {
     return out.release();
 }
 
+// ---- peer-store exchange: partition + all-to-all in ONE kernel over NVLink peer memory --------------------------------
+// Every rank maps every other rank's receive arena (CUDA IPC).  After the count matrix is known, all ranks derive the
+// same receive layout (column c of rank d: a region of recv_total[d] x width bytes, sender s's rows at row offset
+// sum of counts of the senders before it), and the partition kernel writes each row of a fixed-width, never-null column
+// straight into its destination GPU's arena -- the payload crosses NVLink once, tile by tile, while the kernel is still
+// partitioning (partition.cu partition_scatter<PEER>); nothing is staged in local HBM and no send / recv is posted.
+// A one-word NCCL all-reduce closes the step (all writes landed), then each rank copies its columns out of the arena
+// (device-to-device), which frees the arena for the next exchange: the next exchange's count all-gather orders the
+// next writes behind these copies on every rank.
+static bool arena_ensure(b200_comm *c, size_t need) {  // collective: `need` is identical on every rank
+    if (c->p2p_state < 0) return false;
+    if (c->arena && c->arena_bytes >= need) return true;
+    cudaStream_t st = ctx().stream;
+    const int W = c->world;
+    B200_CUDA(cudaStreamSynchronize(st));
+    arena_release(c);
+    size_t bytes = std::max<size_t>(need + need / 4, (size_t)64 << 20);
+    bytes = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc(&c->arena, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        c->arena = nullptr;
+        ok = 0;
+    } else if (cudaIpcGetMemHandle(&mine, c->arena) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    // all-gather {ok, handle}: 8 + 64 bytes per rank
+    constexpr size_t REC = 8 + sizeof(cudaIpcMemHandle_t);
+    std::vector<uint8_t> rec(REC, 0), all(REC * W);
+    memcpy(rec.data(), &ok, sizeof(int));
+    memcpy(rec.data() + 8, &mine, sizeof(mine));
+    Buf d_in = dev_alloc(REC), d_out = dev_alloc(REC * W);
+    B200_CUDA(cudaMemcpyAsync(d_in->ptr, rec.data(), REC, cudaMemcpyHostToDevice, st));
+    B200_NCCL(nccl().AllGather(d_in->ptr, d_out->ptr, REC, ncclUint8, c->comm, st));
+    B200_CUDA(cudaMemcpyAsync(all.data(), d_out->ptr, REC * W, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    bool all_ok = true;
+    for (int r = 0; r < W; r++) {
+        int o = 0;
+        memcpy(&o, all.data() + r * REC, sizeof(int));
+        all_ok = all_ok && o;
+    }
+    int mapped = all_ok ? 1 : 0;
+    if (all_ok) {
+        c->peer_arena.assign(W, nullptr);
+        for (int r = 0; r < W && mapped; r++) {
+            if (r == c->rank) {
+                c->peer_arena[r] = c->arena;
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + r * REC + 8, sizeof(h));
+            if (cudaIpcOpenMemHandle(&c->peer_arena[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                c->peer_arena[r] = nullptr;
+                mapped = 0;
+            }
+        }
+    }
+    // every rank must have mapped every peer: agree with a MIN all-reduce
+    Buf flag = dev_alloc(4);
+    B200_CUDA(cudaMemcpyAsync(flag->ptr, &mapped, 4, cudaMemcpyHostToDevice, st));
+    B200_NCCL(nccl().AllReduce(flag->ptr, flag->ptr, 1, ncclInt32, ncclMin, c->comm, st));
+    B200_CUDA(cudaMemcpyAsync(&mapped, flag->ptr, 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (!mapped) {
+        arena_release(c);
+        c->p2p_state = -1;
+        return false;
+    }
+    c->arena_bytes = bytes;
+    c->p2p_state = 1;
+    return true;
+}
+
+static Batch *route_batch(b200_comm *c, const Batch &src, const Route &rows, const std::vector<int64_t> *nulls_anywhere);
+
+// returns nullptr when the peer path is not available (the caller takes the NCCL route); collective decisions only
+static Batch *exchange_peer_store(b200_comm *c, const Batch &b, const uint64_t *hashes) {
+    const int W = c->world;
+    const char *env = getenv("B200_EXCHANGE_P2P");
+    if ((env && *env == '0') || c->p2p_state < 0 || W > 8 || W < 2) return nullptr;
+    cudaStream_t st = ctx().stream;
+    // columns the kernel can place itself: fixed width, no nulls ON ANY RANK (decided from the gathered null counts)
+    PartitionPlan pl = partition_count(hashes, b.num_rows, W);
+    std::vector<int64_t> scnt(W), soff(W), nulls, nulls_anywhere;
+    for (int p = 0; p < W; p++) {
+        soff[p] = pl.offsets[p];
+        scnt[p] = pl.offsets[p + 1] - pl.offsets[p];
+    }
+    for (const Column &col : b.cols) nulls.push_back(col.null_count);
+    std::vector<int64_t> m = gather_counts(c, scnt, nulls);
+    const size_t per = (size_t)W + nulls.size();
+    nulls_anywhere.assign(nulls.size(), 0);
+    for (int src = 0; src < W; src++)
+        for (size_t e = 0; e < nulls.size(); e++) nulls_anywhere[e] += m[(size_t)src * per + W + e];
+    std::vector<int> peer_cols, other_cols;
+    for (size_t ci = 0; ci < b.cols.size(); ci++) {
+        const Column &col = b.cols[ci];
+        if (dtype_width(col.dtype) && nulls_anywhere[ci] == 0 && peer_cols.size() < 16) peer_cols.push_back((int)ci);
+        else if (col.dtype != B200_NULL) other_cols.push_back((int)ci);
+    }
+    if (peer_cols.empty()) return nullptr;
+    // receive layout of every rank (identical arithmetic everywhere): column regions back to back, 256-byte aligned
+    std::vector<int64_t> recv_total(W, 0);
+    for (int d = 0; d < W; d++)
+        for (int s2 = 0; s2 < W; s2++) recv_total[d] += m[(size_t)s2 * per + d];
+    auto region = [&](int d, size_t k) {  // byte offset of peer column k in rank d's arena
+        size_t off = 0;
+        for (size_t j = 0; j < k; j++) off += ((size_t)recv_total[d] * dtype_width(b.cols[peer_cols[j]].dtype) + 255) & ~(size_t)255;
+        return off;
+    };
+    size_t need = 0;
+    for (int d = 0; d < W; d++) need = std::max(need, region(d, peer_cols.size()));
+    if (!arena_ensure(c, need)) return nullptr;
+    std::vector<std::vector<void *>> dest(peer_cols.size(), std::vector<void *>(W));
+    for (size_t k = 0; k < peer_cols.size(); k++) {
+        const int w = dtype_width(b.cols[peer_cols[k]].dtype);
+        for (int d = 0; d < W; d++) {
+            int64_t before = 0;
+            for (int s2 = 0; s2 < c->rank; s2++) before += m[(size_t)s2 * per + d];
+            dest[k][d] = (uint8_t *)c->peer_arena[d] + region(d, k) + (size_t)before * w;
+        }
+    }
+    Buf rowid;
+    partition_scatter_to_peers(pl, hashes, b, peer_cols, dest, other_cols.empty() ? nullptr : &rowid);
+    // all writes of all ranks have landed once this collective completes
+    Buf bar = dev_alloc_zero(4);
+    B200_NCCL(nccl().AllReduce(bar->ptr, bar->ptr, 1, ncclInt32, ncclSum, c->comm, st));
+    count_launch();
+    const int64_t n_out = recv_total[c->rank];
+    auto out = std::make_unique<Batch>();
+    out->num_rows = n_out;
+    out->cols.resize(b.cols.size());
+    for (size_t k = 0; k < peer_cols.size(); k++) {
+        const Column &col = b.cols[peer_cols[k]];
+        const int w = dtype_width(col.dtype);
+        Column o;
+        o.name = col.name;
+        o.dtype = col.dtype;
+        o.length = n_out;
+        o.data = dev_alloc((size_t)std::max<int64_t>(n_out, 1) * w);
+        o.data_bytes = n_out * w;
+        if (n_out)
+            B200_CUDA(cudaMemcpyAsync(o.data->ptr, (const uint8_t *)c->arena + region(c->rank, k), (size_t)n_out * w, cudaMemcpyDeviceToDevice, st));
+        out->cols[peer_cols[k]] = std::move(o);
+    }
+    for (size_t ci = 0; ci < b.cols.size(); ci++)
+        if (b.cols[ci].dtype == B200_NULL) {
+            Column o = b.cols[ci];
+            o.length = n_out;
+            o.null_count = n_out;
+            out->cols[ci] = std::move(o);
+        }
+    if (!other_cols.empty()) {  // nullable / Boolean / string columns: destination-ordered gather, then the NCCL route
+        Batch rest;
+        rest.num_rows = b.num_rows;
+        for (int ci : other_cols) rest.cols.push_back(gather_column(b.cols[ci], as<int64_t>(rowid), b.num_rows, false));
+        Route rows;
+        rows.send_off = soff;
+        rows.send_cnt = scnt;
+        rows.recv_off.assign(W, 0);
+        rows.recv_cnt.assign(W, 0);
+        for (int src = 0; src < W; src++) {
+            rows.recv_cnt[src] = m[(size_t)src * per + c->rank];
+            rows.recv_off[src] = rows.recv_total;
+            rows.recv_total += rows.recv_cnt[src];
+        }
+        std::vector<int64_t> na;
+        for (int ci : other_cols) na.push_back(nulls_anywhere[ci]);
+        std::unique_ptr<Batch> routed(route_batch(c, rest, rows, &na));
+        for (size_t k = 0; k < other_cols.size(); k++) out->cols[other_cols[k]] = std::move(routed->cols[k]);
+    }
+    B200_CUDA(cudaStreamSynchronize(st));
+    return out.release();
+}
+
 Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys) {
     require_device();
     if (!c) fail("null communicator");
     const int W = c->world;
     Buf h = hash_rows(b, key_cols, nkeys, nullptr);
+    {
+        KernelTimer ktp("exchange_peer_store");
+        if (Batch *direct = exchange_peer_store(c, b, as<uint64_t>(h))) return direct;
+    }
     std::vector<int64_t> offsets;
-    Buf perm = partition_permutation(as<uint64_t>(h), b.num_rows, W, offsets);
-    std::unique_ptr<Batch> staged(gather_batch(b, as<int64_t>(perm), b.num_rows, false));
+    std::unique_ptr<Batch> staged;
+    if (W <= 256 && b.num_rows >= 4096) {  // direct scatter: the payload moves once, straight into destination order
+        staged.reset(partition_staged(b, as<uint64_t>(h), W, offsets));
+    } else {
+        Buf perm = partition_permutation(as<uint64_t>(h), b.num_rows, W, offsets);
+        staged.reset(gather_batch(b, as<int64_t>(perm), b.num_rows, false));
+    }
     std::vector<int64_t> soff(W), scnt(W);
     for (int p = 0; p < W; p++) {
         soff[p] = offsets[p];
         scnt[p] = offsets[p + 1] - offsets[p];
     }
-    const Route rows = make_route(c, soff, scnt);
-    return route_batch(c, *staged, rows);
+    std::vector<int64_t> nulls, nulls_anywhere;
+    for (const Column &col : staged->cols) nulls.push_back(col.null_count);
+    const Route rows = make_route(c, soff, scnt, nulls, &nulls_anywhere);
+    KernelTimer kt("exchange_route");
+    return route_batch(c, *staged, rows, &nulls_anywhere);
 }
 
 // ---- small batches (partial aggregates, top-N candidates): ONE fixed-size all-gather ---------------------------------
@@ -486,7 +706,7 @@ Batch *all_gather_batches(b200_comm *c, const Batch &b) {
     const int W = c->world;
     std::vector<int64_t> soff(W, 0), scnt(W, b.num_rows);
     const Route rows = make_route(c, soff, scnt);
-    return route_batch(c, b, rows);
+    return route_batch(c, b, rows, nullptr);
 }
 
 }  // namespace b200

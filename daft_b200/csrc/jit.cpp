@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <nvrtc.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <fstream>
@@ -1627,6 +1628,10 @@ static std::string cache_dir() {
     return g_cache_dir;
 }
 
+static std::atomic<unsigned long long> &prog_counter() {
+    static std::atomic<unsigned long long> c{0};
+    return c;
+}
 std::vector<char> compile_to_cubin(const std::string &body, std::string *path_out) {
     // leading "#define ..." lines of the generated code configure the prelude and go in front of it
     size_t defs_end = 0;
@@ -1636,16 +1641,29 @@ std::vector<char> compile_to_cubin(const std::string &body, std::string *path_ou
     snprintf(name, sizeof name, "k_%016llx", (unsigned long long)fnv1a(full));
     const std::string base = cache_dir() + "/" + name;
     if (path_out) *path_out = base + ".cu";
+    // Cache file = cubin bytes followed by a 16-byte trailer {magic, FNV-1a of the bytes}: a file another process is
+    // still writing, or one cut short, fails the check and is recompiled instead of being handed to the loader.
+    static const uint64_t kCubinMagic = 0x4232303043554231ULL;  // "B200CUB1"
     {
         std::ifstream f(base + ".cubin", std::ios::binary);
         if (f) {
             std::vector<char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-            if (!buf.empty()) return buf;
+            if (buf.size() > 16) {
+                uint64_t tr[2];
+                memcpy(tr, buf.data() + buf.size() - 16, 16);
+                buf.resize(buf.size() - 16);
+                if (tr[0] == kCubinMagic && tr[1] == fnv1a(std::string(buf.begin(), buf.end()))) return buf;
+            }
         }
     }
-    {
-        std::ofstream f(base + ".cu");
-        f << full;
+    const std::string uniq = "." + std::to_string((long long)getpid()) + "." + std::to_string(prog_counter()++) + ".tmp";
+    {   // several ranks may generate the same plan at once: private temporary names, atomic renames
+        const std::string tmp = base + ".cu" + uniq;
+        {
+            std::ofstream f(tmp);
+            f << full;
+        }
+        if (rename(tmp.c_str(), (base + ".cu").c_str()) != 0) remove(tmp.c_str());
     }
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, full.c_str(), (base + ".cu").c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)  // full path: ncu --import-source
@@ -1666,10 +1684,17 @@ std::vector<char> compile_to_cubin(const std::string &body, std::string *path_ou
     nvrtcGetCUBIN(prog, cubin.data());
     nvrtcDestroyProgram(&prog);
     {
-        std::ofstream f(base + ".cubin.tmp", std::ios::binary);
-        f.write(cubin.data(), (std::streamsize)cubin.size());
+        const std::string tmp = base + ".cubin" + uniq;
+        bool ok;
+        {
+            std::ofstream f(tmp, std::ios::binary);
+            const uint64_t tr[2] = {kCubinMagic, fnv1a(std::string(cubin.begin(), cubin.end()))};
+            f.write(cubin.data(), (std::streamsize)cubin.size());
+            f.write(reinterpret_cast<const char *>(tr), 16);
+            ok = (bool)f;
+        }
+        if (!ok || rename(tmp.c_str(), (base + ".cubin").c_str()) != 0) remove(tmp.c_str());  // the cache is best effort
     }
-    rename((base + ".cubin.tmp").c_str(), (base + ".cubin").c_str());
     return cubin;
 }
 

@@ -40,6 +40,21 @@ Buf bitmap_select(const uint32_t *words, int64_t n, bool invert, int64_t *count_
 // partition.cu
 // stable partition of rows by pid = hash % P: returns row permutation and fills host offsets[P+1]
 Buf partition_permutation(const uint64_t *hashes, int64_t n, int32_t P, std::vector<int64_t> &offsets);
+// every partition of `b` back to back in one batch, P <= 256 (direct scatter: no row-id permutation, no per-column gather)
+// rowid_out != null: columns the scatter cannot place (nullable / Boolean / strings) are left empty and *rowid_out
+// receives the partition-ordered source row ids; otherwise they are gathered into the staged batch
+Batch *partition_staged(const Batch &b, const uint64_t *hashes, int32_t P, std::vector<int64_t> &offsets, Buf *rowid_out = nullptr);
+// the direct scatter in two steps (peer-store exchange): per-partition counts, then rows written straight to per-destination
+// pointers (peer memory)
+struct PartitionPlan {
+    int64_t n = 0, nblocks = 0, chunk = 0;
+    int32_t P = 0;
+    Buf base;                      // scanned (partition, CTA chunk) histogram
+    std::vector<int64_t> offsets;  // rows of partition p = [offsets[p], offsets[p + 1]) in partition order
+};
+PartitionPlan partition_count(const uint64_t *hashes, int64_t n, int32_t P);
+void partition_scatter_to_peers(const PartitionPlan &pl, const uint64_t *hashes, const Batch &b, const std::vector<int> &cols,
+                                const std::vector<std::vector<void *>> &dest_ptrs, Buf *rowid_out);
 std::vector<Batch *> op_partition_by_hash(const Batch &b, const int32_t *key_cols, int32_t nkeys, int32_t P);
 Batch *op_dedup(const Batch &b, const int32_t *key_cols, int32_t nkeys);
 

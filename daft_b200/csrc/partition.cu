@@ -91,9 +91,19 @@ __global__ void __launch_bounds__(PS_THREADS) partition_hist(const uint64_t *__r
     for (int i = threadIdx.x; i < (int)P; i += PS_THREADS) hist[(int64_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
 }
 
+// PEER: partition d is not written behind partition d - 1 in a local buffer but straight into rank d's receive buffer
+// (peer memory over NVLink): column c of the row at position `pos` of partition d goes to dest.out[c][d] + (pos -
+// dest.start[d]) * width, where out[c][d] already points at this sender's slot in rank d's buffer.
+constexpr int PS_MAXPEERS = 8, PS_PEERCOLS = 16;
+struct PeerDest {
+    uint8_t *out[PS_PEERCOLS][PS_MAXPEERS];
+    long long start[PS_MAXPEERS];
+};
+template <bool PEER>
 __global__ void __launch_bounds__(PS_THREADS) partition_scatter(const uint64_t *__restrict__ hashes, int64_t n, int64_t chunk, uint64_t P,
                                                                 const int64_t *__restrict__ base /* scanned hist */,
-                                                                const __grid_constant__ PartCols cols, int ncols, int64_t *__restrict__ rowid_out) {
+                                                                const __grid_constant__ PartCols cols, int ncols, int64_t *__restrict__ rowid_out,
+                                                                const PeerDest *__restrict__ dest) {
     __shared__ int64_t s_base[PS_MAXP];                 // next output position per partition for this CTA
     __shared__ unsigned int s_wcnt[PS_WARPS][PS_MAXP];  // per-warp counts -> exclusive prefix over warps
     __shared__ unsigned int s_tile[PS_MAXP];
@@ -129,17 +139,24 @@ __global__ void __launch_bounds__(PS_THREADS) partition_scatter(const uint64_t *
 #pragma unroll 4
             for (int c = 0; c < ncols; c++) {
                 const PartCol &pc = cols.c[c];
+                void *o = pc.out;
+                int64_t at = pos;
+                if (PEER) {
+                    o = dest->out[c][d];
+                    at = pos - dest->start[d];
+                }
                 switch (pc.width) {
-                    case 1: ((uint8_t *)pc.out)[pos] = ((const uint8_t *)pc.src)[i]; break;
-                    case 2: ((uint16_t *)pc.out)[pos] = ((const uint16_t *)pc.src)[i]; break;
-                    case 4: ((uint32_t *)pc.out)[pos] = ((const uint32_t *)pc.src)[i]; break;
-                    default: ((uint64_t *)pc.out)[pos] = ((const uint64_t *)pc.src)[i]; break;
+                    case 1: ((uint8_t *)o)[at] = ((const uint8_t *)pc.src)[i]; break;
+                    case 2: ((uint16_t *)o)[at] = ((const uint16_t *)pc.src)[i]; break;
+                    case 4: ((uint32_t *)o)[at] = ((const uint32_t *)pc.src)[i]; break;
+                    default: ((uint64_t *)o)[at] = ((const uint64_t *)pc.src)[i]; break;
                 }
             }
         }
         __syncthreads();
         for (int dd = threadIdx.x; dd < Pn; dd += PS_THREADS) s_base[dd] += s_tile[dd];
     }
+    if (PEER) __threadfence_system();  // the rows must be visible to the peer GPUs before this rank signals completion
 }
 
 __global__ void pick_strided(const int64_t *__restrict__ src, int64_t stride, int n, int64_t *__restrict__ out) {
@@ -147,9 +164,11 @@ __global__ void pick_strided(const int64_t *__restrict__ src, int64_t stride, in
     if (i < n) out[i] = src[(int64_t)i * stride];
 }
 
-static std::vector<Batch *> partition_direct(const Batch &b, const uint64_t *hashes, int32_t P) {
+// all partitions back to back in ONE batch (rows of partition p at [offsets[p], offsets[p + 1])): what the exchange sends
+Batch *partition_staged(const Batch &b, const uint64_t *hashes, int32_t P, std::vector<int64_t> &offsets, Buf *rowid_out) {
     cudaStream_t st = ctx().stream;
     const int64_t n = b.num_rows;
+    KernelTimer kt("partition_direct");
     int64_t nblocks = std::max<int64_t>(1, std::min<int64_t>((n + 2047) / 2048, (int64_t)ctx().sm_count * 16));
     int64_t chunk = (n + nblocks - 1) / nblocks;
     chunk = (chunk + PS_THREADS - 1) / PS_THREADS * PS_THREADS;
@@ -160,7 +179,7 @@ static std::vector<Batch *> partition_direct(const Batch &b, const uint64_t *has
     exclusive_scan_i64(as<int64_t>(hist), as<int64_t>(base), (int64_t)P * nblocks, nullptr);
     pick_strided<<<(P + 255) / 256, 256, 0, st>>>(as<int64_t>(base), nblocks, P, as<int64_t>(starts));
     count_launch();
-    std::vector<int64_t> offsets((size_t)P + 1, 0);
+    offsets.assign((size_t)P + 1, 0);
     B200_CUDA(cudaMemcpyAsync(offsets.data(), starts->ptr, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
     // columns the kernel places itself vs. columns gathered through the row-id list
     PartCols pcs;
@@ -178,29 +197,101 @@ static std::vector<Batch *> partition_direct(const Batch &b, const uint64_t *has
         }
     }
     Buf rowid = need_rowid ? dev_alloc((size_t)n * 8) : Buf();
-    partition_scatter<<<(unsigned)nblocks, PS_THREADS, 0, st>>>(hashes, n, chunk, (uint64_t)P, as<int64_t>(base), pcs, npc, as<int64_t>(rowid));
+    partition_scatter<false><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(hashes, n, chunk, (uint64_t)P, as<int64_t>(base), pcs, npc, as<int64_t>(rowid), nullptr);
     count_launch();
     B200_CUDA(cudaStreamSynchronize(st));
     offsets[(size_t)P] = n;
+    auto out = std::make_unique<Batch>();
+    out->num_rows = n;
+    for (size_t c = 0; c < b.cols.size(); c++) {
+        const Column &sc = b.cols[c];
+        if (whole[c]) {
+            Column oc;
+            oc.name = sc.name;
+            oc.dtype = sc.dtype;
+            oc.length = n;
+            oc.data = whole[c];
+            oc.data_bytes = n * dtype_width(sc.dtype);
+            out->cols.push_back(std::move(oc));
+        } else if (rowid_out) {
+            out->cols.push_back(Column());  // the caller gathers these itself, partition by partition (rowid_out)
+        } else {
+            out->cols.push_back(gather_column(sc, as<int64_t>(rowid), n, false));
+        }
+    }
+    if (rowid_out) *rowid_out = rowid;
+    return out.release();
+}
+
+// ---- the same scatter in two steps for the peer-store exchange (exchange.cu): counts first (the ranks agree on the
+// receive layout), then the scatter straight into the peers' buffers
+PartitionPlan partition_count(const uint64_t *hashes, int64_t n, int32_t P) {
+    cudaStream_t st = ctx().stream;
+    PartitionPlan pl;
+    pl.n = n;
+    pl.P = P;
+    int64_t nblocks = std::max<int64_t>(1, std::min<int64_t>((n + 2047) / 2048, (int64_t)ctx().sm_count * 16));
+    int64_t chunk = (n + nblocks - 1) / nblocks;
+    chunk = std::max<int64_t>(PS_THREADS, (chunk + PS_THREADS - 1) / PS_THREADS * PS_THREADS);
+    nblocks = std::max<int64_t>(1, (n + chunk - 1) / chunk);
+    pl.nblocks = nblocks;
+    pl.chunk = chunk;
+    Buf hist = dev_alloc((size_t)P * nblocks * 8), starts = dev_alloc((size_t)(P + 1) * 8);
+    pl.base = dev_alloc((size_t)(P * nblocks + 1) * 8);
+    partition_hist<<<(unsigned)nblocks, PS_THREADS, 0, st>>>(hashes, n, chunk, (uint64_t)P, as<int64_t>(hist));
+    count_launch();
+    exclusive_scan_i64(as<int64_t>(hist), as<int64_t>(pl.base), (int64_t)P * nblocks, nullptr);
+    pick_strided<<<(P + 255) / 256, 256, 0, st>>>(as<int64_t>(pl.base), nblocks, P, as<int64_t>(starts));
+    count_launch();
+    pl.offsets.assign((size_t)P + 1, 0);
+    B200_CUDA(cudaMemcpyAsync(pl.offsets.data(), starts->ptr, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    pl.offsets[(size_t)P] = n;
+    return pl;
+}
+// cols[c] of `b` (fixed width, no nulls) -> dest_ptrs[c][d] (already offset to this sender's slot in rank d's buffer)
+void partition_scatter_to_peers(const PartitionPlan &pl, const uint64_t *hashes, const Batch &b, const std::vector<int> &cols,
+                                const std::vector<std::vector<void *>> &dest_ptrs, Buf *rowid_out) {
+    cudaStream_t st = ctx().stream;
+    if ((int)cols.size() > PS_PEERCOLS || pl.P > PS_MAXPEERS) fail("peer scatter: too many columns / peers");
+    PartCols pcs;
+    PeerDest pd;
+    memset(&pd, 0, sizeof(pd));
+    for (size_t k = 0; k < cols.size(); k++) {
+        const Column &sc = b.cols[cols[k]];
+        pcs.c[k] = PartCol{sc.data->ptr, nullptr, dtype_width(sc.dtype)};
+        for (int d = 0; d < pl.P; d++) pd.out[k][d] = (uint8_t *)dest_ptrs[k][d];
+    }
+    for (int d = 0; d < pl.P; d++) pd.start[d] = pl.offsets[d];
+    Buf dpd = dev_alloc(sizeof(PeerDest));
+    B200_CUDA(cudaMemcpyAsync(dpd->ptr, &pd, sizeof(PeerDest), cudaMemcpyHostToDevice, st));
+    Buf rowid = rowid_out ? dev_alloc((size_t)std::max<int64_t>(pl.n, 1) * 8) : Buf();
+    KernelTimer kt("partition_scatter_peer");
+    partition_scatter<true><<<(unsigned)pl.nblocks, PS_THREADS, 0, st>>>(hashes, pl.n, pl.chunk, (uint64_t)pl.P, as<int64_t>(pl.base), pcs, (int)cols.size(),
+                                                                      as<int64_t>(rowid), as<PeerDest>(dpd));
+    count_launch();
+    B200_CUDA(cudaStreamSynchronize(st));  // `pd` is a stack object; the caller's barrier follows anyway
+    if (rowid_out) *rowid_out = rowid;
+}
+
+static std::vector<Batch *> partition_direct(const Batch &b, const uint64_t *hashes, int32_t P) {
+    std::vector<int64_t> offsets;
+    Buf rowid;
+    std::unique_ptr<Batch> staged(partition_staged(b, hashes, P, offsets, &rowid));
     std::vector<Batch *> out;
     try {
         for (int p = 0; p < P; p++) {
-            const int64_t lo = offsets[p], cnt = offsets[p + 1] - offsets[p];
             auto pb = std::make_unique<Batch>();
-            pb->num_rows = cnt;
+            pb->num_rows = offsets[p + 1] - offsets[p];
             for (size_t c = 0; c < b.cols.size(); c++) {
-                const Column &sc = b.cols[c];
-                if (whole[c]) {
-                    const int w = dtype_width(sc.dtype);
-                    Column oc;
-                    oc.name = sc.name;
-                    oc.dtype = sc.dtype;
-                    oc.length = cnt;
-                    oc.data = dev_sub(whole[c], (size_t)lo * w, (size_t)cnt * w);
-                    oc.data_bytes = cnt * w;
+                const Column &sc = staged->cols[c];
+                if (sc.data || b.cols[c].dtype == B200_NULL) {  // placed by the scatter kernel: a zero-copy slice
+                    Column oc = b.cols[c].dtype == B200_NULL ? b.cols[c] : slice_column(sc, offsets[p], offsets[p + 1]);
+                    oc.length = pb->num_rows;
+                    if (oc.dtype == B200_NULL) oc.null_count = pb->num_rows;
                     pb->cols.push_back(std::move(oc));
                 } else {
-                    pb->cols.push_back(gather_column(sc, as<int64_t>(rowid) + lo, cnt, false));
+                    pb->cols.push_back(gather_column(b.cols[c], as<int64_t>(rowid) + offsets[p], pb->num_rows, false));
                 }
             }
             out.push_back(pb.release());

@@ -268,6 +268,8 @@ class RecordBatch:
         feeds the aggregate into the same kernel (rows failing it are skipped; nothing is materialised)."""
         if any(_inner(a).op == "count_distinct" for a in to_agg):
             return self._agg_with_count_distinct(to_agg, group_by or [], predicate)
+        if any(self._is_string_minmax(a) for a in to_agg):
+            return self._agg_with_string_minmax(to_agg, group_by or [], predicate)
         staged = stage_moment_aggs(to_agg)
         if staged is not None:  # stddev / var: first-stage sums + counts, then the final projection (agg.rs:190-258)
             first, final = staged
@@ -281,6 +283,45 @@ class RecordBatch:
         odt = (ctypes.c_int32 * len(onames))()
         _lib.call("b200_batch_dtypes", out, odt, ctypes.c_int32(len(onames)))
         return RecordBatch._wrap(out, names=onames, dtypes=list(odt))
+
+    def _is_string_minmax(self, a: Expression) -> bool:
+        from .expressions import bind
+        inner = _inner(a)
+        if inner.kind != "agg" or inner.op not in ("min", "max"):
+            return False
+        return dt.is_string(bind(inner.args[0], self.column_names(), self.dtypes()).dtype)
+
+    def _agg_with_string_minmax(self, to_agg, group_by, predicate) -> "RecordBatch":
+        """min / max over Utf8 / Binary (grouped_cmp_utf8, src/daft-core/src/array/ops/compare_agg.rs:99-134: bytewise
+        comparison, nulls ignored, an all-null group gives null).  Composed from the sort and dedup kernels: rows sorted by
+        (keys, value) with nulls last, then the first row of every key group.  The numeric aggregates run in the fused
+        kernel as usual; both results list one row per group and are aligned by sorting on the keys."""
+        base = self.filter(predicate) if predicate else self
+        keys = [g.alias(f"__k{i}") for i, g in enumerate(group_by)]
+        key_cols = [col(f"__k{i}") for i in range(len(group_by))]
+        plain = [a for a in to_agg if not self._is_string_minmax(a)]
+        anchor = col(base.column_names()[0]).count("all").alias("__rows")  # keeps the group list complete
+        main = base.agg(plain + [anchor], keys)
+        if key_cols:
+            main = main.sort(key_cols)
+        pieces = main
+        for i, a in enumerate(to_agg):
+            if not self._is_string_minmax(a):
+                continue
+            inner = _inner(a)
+            vals = base.eval_expression_list(keys + [inner.args[0].alias("__x")])
+            if key_cols:
+                srt = vals.sort(key_cols + [col("__x")], descending=[False] * len(key_cols) + [inner.op == "max"],
+                                nulls_first=[False] * (len(key_cols) + 1))
+                best = srt.dedup(key_cols).sort(key_cols)
+            else:
+                best = vals.sort([col("__x")], descending=[inner.op == "max"], nulls_first=[False]).head(1)
+                if len(best) == 0:  # an ungrouped aggregate over no rows still yields one (null) row
+                    best = vals.agg([col("__x").any_value().alias("__x")], [])
+            pieces = pieces.union(best.eval_expression_list([col("__x").alias(f"__sm{i}")]))
+        final = [col(f"__k{j}").alias(g.name()) for j, g in enumerate(group_by)]
+        final += [col(f"__sm{i}").alias(a.name()) if self._is_string_minmax(a) else col(a.name()) for i, a in enumerate(to_agg)]
+        return pieces.eval_expression_list(final)
 
     def _agg_with_count_distinct(self, to_agg, group_by, predicate) -> "RecordBatch":
         """count_distinct(x) per group = dedup on (keys, x), then count the non-null x per key.  Dedup keeps first

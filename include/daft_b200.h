@@ -151,8 +151,11 @@ int b200_batch_import(struct ArrowArray *array, struct ArrowSchema *schema, b200
 /* device -> HOST; out_array/out_schema get this library's release callbacks. */
 int b200_batch_export(const b200_batch *batch, struct ArrowArray *out_array, struct ArrowSchema *out_schema,
                       char **errmsg);
-/* wrap existing DEVICE buffers without copying (borrowed; caller keeps them alive).  String/binary `data` buffers
- * must be followed by 16 readable bytes: the kernels fetch values with aligned word loads (csrc/common.h). */
+/* wrap existing DEVICE buffers without copying (borrowed; caller keeps them alive).  Requirements on borrowed buffers:
+ * every buffer must be followed by 16 readable bytes (string values are fetched with aligned word loads, validity /
+ * Boolean bitmaps with 32-bit word loads: csrc/common.h) and fixed-width `data` must be aligned to its element size.
+ * String offsets may start anywhere (a sliced Arrow array): they are re-based to 0 here (a shifted copy of the offsets;
+ * the value bytes stay borrowed); offsets that point outside [0, data_bytes] are rejected. */
 int b200_batch_from_device(const b200_column_desc *cols, int32_t ncols, int64_t num_rows, b200_batch **out,
                            char **errmsg);
 /* Columns of a join output are VIEWS (row-id selection vectors over the join inputs) until an operator reads them: for

@@ -221,6 +221,22 @@ def agg_minmax(arr, gid: np.ndarray, ng: int, which: str) -> pa.Array:
     arr0 = normalize(arr)
     if pa.types.is_boolean(arr0.type):
         return agg_minmax(arr0.cast(pa.uint8()), gid, ng, which).cast(pa.bool_())
+    if pa.types.is_large_string(arr0.type) or pa.types.is_large_binary(arr0.type):
+        # grouped_cmp_utf8 / binary (src/daft-core/src/array/ops/compare_agg.rs:99-134 and below): a left fold in row order
+        # with bytewise comparison, nulls skipped, an all-null group -> null
+        best = [None] * ng
+        for g, x in zip(gid.tolist(), arr0.to_pylist()):
+            if x is None:
+                continue
+            xb = x.encode() if isinstance(x, str) else x
+            cur = best[g]
+            if cur is None:
+                best[g] = x
+            else:
+                cb = cur.encode() if isinstance(cur, str) else cur
+                if (xb < cb) if which == "min" else (xb > cb):
+                    best[g] = x
+        return pa.array(best, type=arr0.type)
     v = ColView(arr)
     typ = v.arr.type
     code = {DATE32: I32, TIMESTAMP: I64}.get(v.code, v.code)

@@ -53,6 +53,24 @@ def main():
     from helpers import oracle_agg
     want = oracle_agg(full, [col("f64").sum().alias("s"), col("i32").count("all").alias("c")], [col("i32")]).sort_by([("i32", "ascending")])
     assert_tables_equal(gathered, want, float_rtol=1e-9)
+    # distributed low-cardinality aggregate: the group tables all-reduced (b200_agg_allreduce) == single-table oracle;
+    # plans the table merge cannot carry (any_value, float min / max folds, high cardinality) take the two-stage rewrite
+    from daft_b200 import tpch
+    aggs = [col("i64").sum().alias("s"), col("f64").mean().alias("m"), col("i32").count("null").alias("cn"), col("u16").min().alias("lo"),
+            col("i64").max().alias("hi"), col("i8").mean().alias("m8")]
+    for gb, pred in (([col("k")], None), ([col("b"), col("u8")], [col("i32") > 0]), ([], None), ([col("s")], None), ([col("i32")], None)):
+        got = comm.agg(rb, aggs, gb, pred).to_arrow_table()
+        want = oracle_agg(full, aggs, gb, pred)
+        keys = [g.name() for g in gb]
+        assert_tables_equal(got, want, float_rtol=1e-9, sort_by=keys or None)
+    fl = [col("f64").min().alias("mn"), col("f32").max().alias("mx"), col("s").any_value().alias("av")]
+    got = comm.agg(rb, fl[:2], [col("k")]).to_arrow_table()
+    assert_tables_equal(got, oracle_agg(full, fl[:2], [col("k")]), float_rtol=1e-9, sort_by=["k"])
+    li = tpch.generate("lineitem", 0.1, tpch.Q1_COLUMNS, *distributed.shard_rows(tpch.num_rows("lineitem", 0.1), rank, world))
+    q1 = tpch.q1_distributed(li, comm).to_arrow_table()
+    pred, gb, q1aggs = tpch.q1_exprs()
+    want = oracle_agg(tpch.generate_host("lineitem", 0.1, tpch.Q1_COLUMNS), q1aggs, gb, pred).sort_by([("L_RETURNFLAG", "ascending"), ("L_LINESTATUS", "ascending")])
+    assert_tables_equal(q1, want, float_rtol=1e-9)
     dist.barrier()
     if rank == 0:
         print(f"exchange ok on {world} GPUs")

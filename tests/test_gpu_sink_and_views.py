@@ -102,3 +102,22 @@ def test_probe_indices_multi_table_build_and_probe_through_view(gpu):
     assert got["build_idx"] == rows.tolist()
     ex = pt.probe_exists(RB(gpu, probe), [0]).to_pydict()["exists"]
     assert ex == (cnt > 0).tolist()
+
+
+def test_string_minmax_reference_literals_and_grouped(gpu):
+    """tests/recordbatch/test_table_aggs.py:137-158,188-213 through the C ABI, then grouped string min / max with a
+    numeric aggregate beside them against the oracle (compare_agg.rs:99-134)."""
+    c = gpu.col
+    cases = [([None], None, None), ([None, None, None], None, None), (["abc"], "abc", "abc"), ([None, "abc"], "abc", "abc"),
+             ([None, "aaa", None, "b", "c", "aaa", None], "aaa", "c")]
+    for vals, lo, hi in cases:
+        tbl = pa.table({"input": pa.array(vals, type=pa.large_utf8())})
+        got = RB(gpu, tbl).agg([c("input").min().alias("min"), c("input").max().alias("max")], []).to_pydict()
+        assert got == {"min": [lo], "max": [hi]}, (vals, got)
+    rng = np.random.default_rng(2)
+    tbl = random_table(rng, 5000, 0.2)
+    aggs = [c("s").min().alias("smin"), c("i64").sum().alias("tot"), c("s").max().alias("smax"), c("s").count().alias("n")]
+    for gb in ([c("k")], [c("u8"), c("b")]):
+        got = RB(gpu, tbl).agg(aggs, gb).to_arrow_table()
+        want = oracle_agg(tbl, aggs, gb)
+        assert_tables_equal(got, want, sort_by=[g.name() for g in gb])

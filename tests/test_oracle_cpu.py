@@ -845,3 +845,17 @@ def test_single_column_boolean_and_string_sort_literals_from_reference_tests():
                                                                   "lastname": ["a", "a", "a", None, "a", "bond", None]}
     lit_key = E.eval_expression_list(pa.table({"a": [1, 2, 3, 4, 5]}), [lit(1)]).column("literal")
     assert O.argsort([lit_key]).tolist() == [0, 1, 2, 3, 4]
+
+
+def test_string_and_binary_minmax_literals_from_reference_tests():
+    """tests/recordbatch/test_table_aggs.py:137-158 (strings) and :188-213 (binary): nulls are ignored, an empty or
+    all-null input gives null (grouped_cmp_utf8, src/daft-core/src/array/ops/compare_agg.rs:99-134)."""
+    from daft_b200 import col
+    from helpers import oracle_agg
+    cases = [([], None, None), ([None], None, None), ([None, None, None], None, None), (["abc"], "abc", "abc"), ([None, "abc"], "abc", "abc"),
+             ([None, "aaa", None, "b", "c", "aaa", None], "aaa", "c")]
+    for vals, lo, hi in cases:
+        for typ, conv in ((pa.large_utf8(), lambda x: x), (pa.large_binary(), lambda x: None if x is None else x.encode())):
+            tbl = pa.table({"input": pa.array([conv(v) for v in vals], type=typ)})
+            got = oracle_agg(tbl, [col("input").min().alias("min"), col("input").max().alias("max")], []).to_pydict()
+            assert got == {"min": [conv(lo)], "max": [conv(hi)]}, (vals, got)
