@@ -56,7 +56,7 @@ enum BinOp { B_ADD = 0, B_SUB, B_MUL, B_TRUE_DIV, B_FLOOR_DIV, B_MOD, B_LT, B_LE
              B_XOR, B_EQ_NULL_SAFE, B_SHL, B_SHR };
 enum UnOp { U_NOT = 0, U_NEG, U_IS_NULL, U_NOT_NULL, U_ABS };
 enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT,
-          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN };
+          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ };
 
 struct Node {
     int tag = 0, op = 0;
@@ -261,6 +261,25 @@ static int parse_node(Reader &r, Ast &a) {
                 case F_SIGN: {  // src/daft-functions/src/numeric/sign.rs:26-42 -> array/ops/sign.rs: signum, 0 / 1 for unsigned integers
                     if (nd.kids.size() != 1 || !is_numeric(a.nodes[nd.kids[0]].dtype)) fail("plan: sign needs one numeric operand");
                     nd.dtype = a.nodes[nd.kids[0]].dtype;
+                    break;
+                }
+                case F_ROUND: {  // src/daft-core/src/array/ops/round.rs:14-35: (v * 10^d).round() / 10^d, half away from zero
+                    if (nd.kids.size() != 2 || !is_float(a.nodes[nd.kids[0]].dtype)) fail("plan: round needs a float operand and a decimals literal");
+                    const Node &d = a.nodes[nd.kids[1]];
+                    if (d.tag != T_LIT || d.dtype != B200_I32 || d.lit_null) fail("plan: round decimals must be an Int32 literal");
+                    nd.dtype = a.nodes[nd.kids[0]].dtype;
+                    nd.nullable = a.nodes[nd.kids[0]].nullable;
+                    break;
+                }
+                case F_MATCH_SEQ: {  // utf8 match / like restricted to literal segments in order (flags: 1 = anchored start, 2 = anchored end)
+                    if (nd.kids.size() < 2 || !is_string(a.nodes[nd.kids[0]].dtype)) fail("plan: match needs a string operand");
+                    for (size_t i = 1; i < nd.kids.size(); i++) {
+                        const Node &l = a.nodes[nd.kids[i]];
+                        if (l.tag != T_LIT || l.lit_null || (i == 1 ? l.dtype != B200_I32 : !is_string(l.dtype)))
+                            fail("plan: match takes an Int32 flags literal followed by string literals");
+                    }
+                    nd.dtype = B200_BOOL;
+                    nd.nullable = a.nodes[nd.kids[0]].nullable;
                     break;
                 }
                 default: fail("plan: unknown function");
@@ -635,6 +654,41 @@ struct ExprGen {
                     case F_IS_INF: os << "    const bool " << V << " = (" << a << " - " << a << " != 0) && (" << a << " == " << a << ");\n"; break;
                     case F_CEIL: os << "    const " << T << " " << V << " = " << (n.dtype == B200_F32 ? "ceilf(" : "ceil(") << a << ");\n"; break;
                     case F_FLOOR: os << "    const " << T << " " << V << " = " << (n.dtype == B200_F32 ? "floorf(" : "floor(") << a << ");\n"; break;
+                    case F_ROUND: {
+                        const int64_t dec = cg.ast.nodes[kid[1]].lit_i;
+                        if (dec == 0) {
+                            os << "    const " << T << " " << V << " = " << (n.dtype == B200_F32 ? "roundf(" : "round(") << a << ");\n";
+                        } else {
+                            char mbuf[64];
+                            snprintf(mbuf, sizeof mbuf, "%.17g", std::pow(10.0, (double)dec));
+                            os << "    const " << T << " " << V << " = (" << T << ")(round((double)" << a << " * " << mbuf << ") / " << mbuf << ");\n";
+                        }
+                        allk = k(kid[0]);
+                        break;
+                    }
+                    case F_MATCH_SEQ: {
+                        const int64_t flags = cg.ast.nodes[kid[1]].lit_i;
+                        const size_t nseg = kid.size() - 2;
+                        os << "    bool " << V << " = true;\n    {\n      int64_t pos_ = 0;\n";
+                        for (size_t j = 0; j < nseg; j++) {
+                            const std::string sg = v(kid[2 + j]);
+                            const bool first = j == 0, last = j + 1 == nseg;
+                            if (first && (flags & 1)) {
+                                os << "      if (" << V << ") { " << V << " = str_startswith(" << a << ", " << sg << "); pos_ = " << sg << ".len; }\n";
+                            } else if (last && (flags & 2)) {
+                                os << "      if (" << V << ") { const int64_t f_ = " << a << ".len - " << sg << ".len; " << V << " = f_ >= pos_ && str_endswith(" << a
+                                   << ", " << sg << "); pos_ = f_ + " << sg << ".len; }\n";
+                            } else {
+                                os << "      if (" << V << ") { const int64_t f_ = str_find_from(" << a << ", " << sg << ", pos_); " << V << " = f_ >= 0; pos_ = f_ + " << sg
+                                   << ".len; }\n";
+                            }
+                        }
+                        if (nseg == 1 && (flags & 3) == 3) os << "      " << V << " = " << V << " && " << a << ".len == " << v(kid[2]) << ".len;\n";
+                        if (nseg == 0 && (flags & 3) == 3) os << "      " << V << " = " << a << ".len == 0;\n";
+                        os << "    }\n";
+                        allk = k(kid[0]);
+                        break;
+                    }
                     case F_SIGN:
                         if (is_float(n.dtype))  // f64::signum: NaN stays NaN, otherwise +-1 with the operand's sign (signum(+-0.0) = +-1.0)
                             os << "    const " << T << " " << V << " = (" << a << " != " << a << ") ? " << a << " : "

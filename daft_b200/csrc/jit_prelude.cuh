@@ -149,6 +149,16 @@ __device__ __forceinline__ bool str_contains(Str a, Str pat) {
     }
     return false;
 }
+// first position >= start where `pat` occurs in `a`, -1 if none
+__device__ __forceinline__ int64_t str_find_from(Str a, Str pat, int64_t start) {
+    if (pat.len == 0) return start <= a.len ? start : -1;
+    for (int64_t s = start; s + pat.len <= a.len; s++) {
+        int64_t i = 0;
+        while (i < pat.len && a.p[s + i] == pat.p[i]) i++;
+        if (i == pat.len) return s;
+    }
+    return -1;
+}
 __device__ __forceinline__ int64_t str_char_len(Str a) {
     int64_t c = 0;
     for (int64_t i = 0; i < a.len; i++) c += (a.p[i] & 0xC0) != 0x80;

@@ -84,6 +84,9 @@ struct b200_probe_table {
     int inline_width = 0;                               // > 0: tags are key values of that byte width (see JoinBucket)
     b200::Buf bloom;                                    // 64-bit words, null for L2-resident tables
     uint64_t bloom_mask = 0;
+    // direct-address mode (unique, dense integer keys): row id by key - min, plus one presence bit per key value
+    b200::Buf direct_rows, direct_bits;
+    uint64_t direct_min = 0, direct_range = 0;
     int64_t num_rows = 0;
 };
 struct b200_join_state {
@@ -250,6 +253,9 @@ struct ProbeArgs {
     const int64_t *psel;
     // generic keys: hash_rows column of the probe side + value comparison
     const uint64_t *phash;
+    // direct-address table (unique dense integer keys): presence bitmap + build row by (key - dmin)
+    const unsigned int *dbits, *drows;
+    unsigned long long dmin, drange;
     KeySet bk, pk;
 };
 
@@ -628,6 +634,127 @@ __global__ void __launch_bounds__(PT, 3) probe_write_kernel(const __grid_constan
     }
 }
 
+// ---- direct-address mode -----------------------------------------------------------------------------------------
+// Join keys are very often dense integers with unique build values (every TPC-H foreign key -> primary key join).  When
+// the build keys are unique and their range is at most 32x their count, the table is an array indexed by key - min:
+// one presence BIT per key value (a 1 M-row table: 125 KB, L1 / L2 resident -- the exact filter a Bloom filter
+// approximates) and one 32-bit build row per key value.  No hashing: a probe is a subtract, a range check, a bit test
+// and, for the rows that pass, one 4-byte load.  Same two passes, same outputs as the bucket table.
+__global__ void key_minmax(const void *__restrict__ data, int width, int64_t n, unsigned long long *__restrict__ mm) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long lo = ~0ULL, hi = 0ULL;
+    for (; i < n; i += stride) {
+        const unsigned long long v = key_bits(data, width, i);
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, (unsigned long long)shfl_ll((long long)lo, (threadIdx.x & 31) ^ d));
+        hi = max(hi, (unsigned long long)shfl_ll((long long)hi, (threadIdx.x & 31) ^ d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[0], lo);
+        atomicMax(&mm[1], hi);
+    }
+}
+__global__ void direct_fill(const void *__restrict__ data, int width, int64_t n, unsigned long long dmin, unsigned int *__restrict__ rows,
+                            unsigned int *__restrict__ bits, int *__restrict__ dup) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const unsigned long long idx = key_bits(data, width, i) - dmin;
+        const unsigned int old = atomicMin(&rows[idx], (unsigned int)i);  // the first row of a key wins (insertion order)
+        if (old != 0xFFFFFFFFu) *dup = 1;                                // a second row with this key: not unique
+        atomicOr(&bits[idx >> 5], 1u << (idx & 31));
+    }
+}
+
+template <int W, bool SEL, bool NULLS, bool KEEP>
+__global__ void __launch_bounds__(PT, 4) direct_count_kernel(const __grid_constant__ ProbeArgs a, int64_t n, int64_t nchunks, int64_t *__restrict__ chunk_cnt,
+                                                             uint32_t *__restrict__ bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * (PT / 32) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (PT / 32);
+    constexpr int DR = 8;  // rows per lane per step
+    for (int64_t chunk = gw; chunk < nchunks; chunk += nw) {
+        const int64_t cbase = chunk * CHUNK;
+        const bool full = cbase + CHUNK <= n;
+        unsigned total = 0;
+#pragma unroll 1
+        for (int step = 0; step < CHUNK / (32 * DR); step++) {
+            const int64_t base = cbase + (int64_t)step * (32 * DR);
+            unsigned long long v[DR];
+            bool hit[DR];
+#pragma unroll
+            for (int r = 0; r < DR; r++) {
+                const int64_t i = base + r * 32 + lane;
+                v[r] = 0;
+                hit[r] = (full || i < n) && load_key<W, SEL, NULLS>(a, i, v[r]);
+            }
+            unsigned word[DR];
+#pragma unroll
+            for (int r = 0; r < DR; r++) {
+                const unsigned long long idx = v[r] - a.dmin;
+                hit[r] = hit[r] && idx < a.drange;
+                word[r] = hit[r] ? __ldg(a.dbits + (idx >> 5)) : 0u;
+                hit[r] = hit[r] && ((word[r] >> (idx & 31)) & 1u);
+            }
+#pragma unroll
+            for (int r = 0; r < DR; r++) {
+                unsigned m = __ballot_sync(0xffffffffu, hit[r]);
+                if (KEEP) m = full ? 0xffffffffu : __ballot_sync(0xffffffffu, base + r * 32 + lane < n);
+                if (lane == 0 && (full || base + r * 32 < n)) bits[(base >> 5) + r] = m;
+                total += __popc(m);
+            }
+        }
+        if (lane == 0) chunk_cnt[chunk] = total;
+    }
+}
+
+template <int W, bool SEL, bool NULLS>
+__global__ void __launch_bounds__(PT, 4) direct_write_kernel(const __grid_constant__ ProbeArgs a, int64_t n, int64_t nchunks,
+                                                             const int64_t *__restrict__ chunk_off, const uint32_t *__restrict__ bits,
+                                                             int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build,
+                                                             unsigned int *__restrict__ matched_bits) {
+    __shared__ unsigned short s_list[PT / 32][CHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * (PT / 32) + warp, nw = (int64_t)gridDim.x * (PT / 32);
+    unsigned short *list = s_list[warp];
+    for (int64_t chunk = gw; chunk < nchunks; chunk += nw) {
+        const long long o = chunk_off[chunk];
+        if (chunk_off[chunk + 1] == o) continue;
+        const int64_t cbase = chunk * CHUNK;
+        unsigned w = (cbase + (int64_t)lane * 32 < n) ? bits[(cbase >> 5) + lane] : 0u;
+        unsigned pre = __popc(w);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, pre, d);
+            if (lane >= d) pre += y;
+        }
+        const unsigned hits = __shfl_sync(0xffffffffu, pre, 31);
+        pre -= __popc(w);
+        __syncwarp();
+        while (w) {
+            const int b = __ffs(w) - 1;
+            w &= w - 1;
+            list[pre++] = (unsigned short)(lane * 32 + b);
+        }
+        __syncwarp();
+        for (unsigned j = lane; j < hits; j += 32) {  // row j of the chunk's output: one build row (or none: a kept probe row)
+            const int64_t i = cbase + list[j];
+            unsigned long long v = 0;
+            long long br = -1;
+            if (load_key<W, SEL, NULLS>(a, i, v)) {
+                const unsigned long long idx = v - a.dmin;
+                if (idx < a.drange && ((__ldg(a.dbits + (idx >> 5)) >> (idx & 31)) & 1u)) br = (long long)__ldg(a.drows + idx);
+            }
+            out_probe[o + j] = i;
+            out_build[o + j] = br;
+            if (matched_bits && br >= 0) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
+        }
+    }
+}
+
 // ---- host --------------------------------------------------------------------------------------------
 b200_probe_table *probe_table_create(int32_t nkeys, const uint8_t *null_equals_null, bool track_indices) {
     if (nkeys < 1 || nkeys > MAX_JOIN_KEYS) fail("join: between 1 and 8 key columns are supported");
@@ -688,6 +815,35 @@ void probe_table_build(b200_probe_table *pt) {
     const bool int_like = k0.dtype == B200_I8 || k0.dtype == B200_I16 || k0.dtype == B200_I32 || k0.dtype == B200_I64 || k0.dtype == B200_U8 ||
                           k0.dtype == B200_U16 || k0.dtype == B200_U32 || k0.dtype == B200_U64 || k0.dtype == B200_DATE32 || k0.dtype == B200_TIMESTAMP;
     pt->inline_width = (pt->nkeys == 1 && int_like && k0.null_count == 0) ? dtype_width(k0.dtype) : 0;
+    if (pt->inline_width && n > 0) {  // unique dense integer keys: the direct-address table needs neither hashes nor a sort
+        const char *env = getenv("B200_JOIN_DIRECT");
+        if (!(env && *env == '0')) {
+            Buf mm = dev_alloc(16);
+            const unsigned long long init[2] = {~0ULL, 0ULL};
+            B200_CUDA(cudaMemcpyAsync(mm->ptr, init, 16, cudaMemcpyHostToDevice, st));
+            key_minmax<<<jgrid(n), 256, 0, st>>>(k0.data->ptr, pt->inline_width, n, as<unsigned long long>(mm));
+            count_launch();
+            unsigned long long h[2];
+            B200_CUDA(cudaMemcpyAsync(h, mm->ptr, 16, cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            const unsigned long long range = h[1] - h[0] + 1;
+            if (h[1] >= h[0] && range != 0 && range <= (unsigned long long)std::max<int64_t>(n * 32, 1 << 16) && range <= (1ULL << 31)) {
+                Buf rows = dev_alloc((size_t)range * 4), dbits = dev_alloc_zero((size_t)(range / 32 + 2) * 4), dup = dev_alloc_zero(8);
+                fill_u8(rows->ptr, 0xFF, (size_t)range * 4);
+                direct_fill<<<jgrid(n), 256, 0, st>>>(k0.data->ptr, pt->inline_width, n, h[0], as<unsigned int>(rows), as<unsigned int>(dbits), as<int>(dup));
+                count_launch();
+                if (read_i64(as<int64_t>(dup)) == 0) {
+                    pt->direct_rows = rows;
+                    pt->direct_bits = dbits;
+                    pt->direct_min = h[0];
+                    pt->direct_range = range;
+                    op_done();
+                    pt->built = true;
+                    return;
+                }
+            }
+        }
+    }
     Buf hashes;
     if (pt->inline_width) {
         hashes = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
@@ -762,6 +918,10 @@ static void make_probe_plan(const b200_probe_table *pt, const Batch &probe, cons
     a.bloom = as<unsigned long long>(pt->bloom);
     a.bloom_mask = pt->bloom_mask;
     a.shift = 64 - pt->bits;
+    a.dbits = as<unsigned int>(pt->direct_bits);
+    a.drows = as<unsigned int>(pt->direct_rows);
+    a.dmin = pt->direct_min;
+    a.drange = pt->direct_range;
     if (pt->inline_width) {
         const Column &bk = pt->build->cols[pt->key_cols[0]];
         a.bkey = bk.data ? bk.data->ptr : nullptr;
@@ -786,21 +946,25 @@ static void make_probe_plan(const b200_probe_table *pt, const Batch &probe, cons
 template <int W>
 static void launch_count_w(bool sel, bool nulls, bool keep, int grid, cudaStream_t st, const ProbeArgs &a, int64_t n, int64_t nchunks, int64_t *chunk_cnt,
                            uint32_t *bits) {
-#define B200_COUNT(S, N, K) probe_count_kernel<W, S, N, K><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits)
+#define B200_COUNT(S, N, K)                                                                                   \
+    do {                                                                                                      \
+        if (W != 0 && a.drows) direct_count_kernel<(W ? W : 8), S, N, K><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits); \
+        else probe_count_kernel<W, S, N, K><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits);             \
+    } while (0)
     if (sel) {
-        if (nulls) { if (keep) B200_COUNT(true, true, true); else B200_COUNT(true, true, false); }
-        else { if (keep) B200_COUNT(true, false, true); else B200_COUNT(true, false, false); }
+        if (nulls) { if (keep) { B200_COUNT(true, true, true); } else { B200_COUNT(true, true, false); } }
+        else { if (keep) { B200_COUNT(true, false, true); } else { B200_COUNT(true, false, false); } }
     } else {
-        if (nulls) { if (keep) B200_COUNT(false, true, true); else B200_COUNT(false, true, false); }
-        else { if (keep) B200_COUNT(false, false, true); else B200_COUNT(false, false, false); }
+        if (nulls) { if (keep) { B200_COUNT(false, true, true); } else { B200_COUNT(false, true, false); } }
+        else { if (keep) { B200_COUNT(false, false, true); } else { B200_COUNT(false, false, false); } }
     }
 #undef B200_COUNT
 }
 static void launch_count(int width, const ProbeArgs &a, int64_t n, int64_t nchunks, int64_t *chunk_cnt, uint32_t *bits, int keep) {
     cudaStream_t st = ctx().stream;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nchunks + PT / 32 - 1) / (PT / 32), (int64_t)ctx().sm_count * 3));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nchunks + PT / 32 - 1) / (PT / 32), (int64_t)ctx().sm_count * (a.drows ? 4 : 3)));
     const bool sel = a.psel != nullptr, nulls = a.pvalid != nullptr;
-    KernelTimer kt("join_probe_count");
+    KernelTimer kt(a.drows ? "join_probe_count_direct" : "join_probe_count");
     switch (width) {
         case 1: launch_count_w<1>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
         case 2: launch_count_w<2>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
@@ -814,17 +978,21 @@ static void launch_count(int width, const ProbeArgs &a, int64_t n, int64_t nchun
 template <int W>
 static void launch_write_w(bool sel, bool nulls, int grid, cudaStream_t st, const ProbeArgs &a, int64_t n, int64_t nchunks, const int64_t *chunk_off,
                            const uint32_t *bits, int64_t *out_probe, int64_t *out_build, unsigned int *matched_bits) {
-#define B200_WRITE(S, N) probe_write_kernel<W, S, N><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits)
-    if (sel) { if (nulls) B200_WRITE(true, true); else B200_WRITE(true, false); }
-    else { if (nulls) B200_WRITE(false, true); else B200_WRITE(false, false); }
+#define B200_WRITE(S, N)                                                                                                              \
+    do {                                                                                                                              \
+        if (W != 0 && a.drows) direct_write_kernel<(W ? W : 8), S, N><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits); \
+        else probe_write_kernel<W, S, N><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits);     \
+    } while (0)
+    if (sel) { if (nulls) { B200_WRITE(true, true); } else { B200_WRITE(true, false); } }
+    else { if (nulls) { B200_WRITE(false, true); } else { B200_WRITE(false, false); } }
 #undef B200_WRITE
 }
 static void launch_write(int width, const ProbeArgs &a, int64_t n, int64_t nchunks, const int64_t *chunk_off, const uint32_t *bits, int64_t *out_probe,
                          int64_t *out_build, unsigned int *matched_bits) {
     cudaStream_t st = ctx().stream;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nchunks + PT / 32 - 1) / (PT / 32), (int64_t)ctx().sm_count * 3));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nchunks + PT / 32 - 1) / (PT / 32), (int64_t)ctx().sm_count * (a.drows ? 4 : 3)));
     const bool sel = a.psel != nullptr, nulls = a.pvalid != nullptr;
-    KernelTimer kt("join_probe_write");
+    KernelTimer kt(a.drows ? "join_probe_write_direct" : "join_probe_write");
     switch (width) {
         case 1: launch_write_w<1>(sel, nulls, grid, st, a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits); break;
         case 2: launch_write_w<2>(sel, nulls, grid, st, a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits); break;

@@ -1,5 +1,6 @@
 // Library context, stream-ordered device memory, and the small fixed-function kernels every
 // operator leans on: exclusive scan, bit counting, row gather (take), slice, concat.
+#include <chrono>
 #include <mutex>
 
 #include "common.h"
@@ -107,6 +108,14 @@ Buf dev_alloc(size_t bytes) {
     auto a = std::make_shared<DevAlloc>();
     a->bytes = bytes;
     // +16 B slack: word-granular readers (unaligned string loads, bitmap words) may touch the tail
+    static const bool trace = [] { const char *e = getenv("B200_TRACE_ALLOC"); return e && *e == '1'; }();
+    if (trace) {
+        const auto t0 = std::chrono::steady_clock::now();
+        B200_CUDA(cudaMallocAsync(&a->ptr, bytes + 16, ctx().stream));
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 0.5) fprintf(stderr, "[b200 alloc] %.1f MB took %.2f ms\n", bytes / 1e6, ms);
+        return a;
+    }
     B200_CUDA(cudaMallocAsync(&a->ptr, bytes + 16, ctx().stream));
     return a;
 }

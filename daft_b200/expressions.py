@@ -19,7 +19,8 @@ BINOPS = {"add": 0, "sub": 1, "mul": 2, "true_div": 3, "floor_div": 4, "mod": 5,
           "ge": 10, "gt": 11, "and": 12, "or": 13, "xor": 14, "eq_null_safe": 15, "shl": 16, "shr": 17}
 UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
-         "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15}
+         "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15,
+         "round": 16, "match_seq": 17}
 AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
 _CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
@@ -127,6 +128,16 @@ class Expression:
     def floor(self): return Expression("function", "floor", (self,))
     def sign(self): return Expression("function", "sign", (self,))
     def negate(self): return Expression("unary", "neg", (self,))
+    def round(self, decimals: int = 0):
+        """Float round to `decimals` places, half away from zero: (v * 10^d).round() / 10^d (src/daft-core/src/array/ops/round.rs:14-35)."""
+        return Expression("function", "round", (self, lit(int(decimals), dt.I32)))
+    def match(self, pattern: str):
+        """utf8 `match` (regex search, src/daft-functions-utf8/src/match_.rs) for the patterns TPC-H and ClickBench use: literal
+        segments separated by `.*`, optionally anchored with ^ / $ (".*special.*requests.*").  Anything else is refused."""
+        return Expression("function", "match_seq", (self, *_segments_of_regex(pattern)))
+    def like(self, pattern: str):
+        """SQL LIKE with `%` wildcards (src/daft-functions-utf8/src/like.rs): anchored at both ends; `_` is refused."""
+        return Expression("function", "match_seq", (self, *_segments_of_like(pattern)))
 
     def fill_nan(self, fill_value):
         """input.if_else(fill_value, not_nan(input)) (src/daft-functions/src/float/fill_nan.rs:41-49): nulls stay null."""
@@ -153,6 +164,35 @@ class Expression:
         if self.kind == "lit": return f"lit({self.value!r})"
         if self.kind == "alias": return f"{self.args[0]!r}.alias({self._name})"
         return f"{self.kind}:{self.op}({', '.join(map(repr, self.args))})"
+
+
+def _segments_of_regex(pattern: str):
+    """-> (flags literal, segment literals...): flags bit 0 = anchored at the start, bit 1 = anchored at the end."""
+    start = pattern.startswith("^")
+    end = pattern.endswith("$") and not pattern.endswith("\\$")
+    body = pattern[1 if start else 0:len(pattern) - (1 if end else 0)]
+    parts = body.split(".*")
+    for part in parts:
+        if any(ch in part for ch in ".^$*+?()[]{}|\\"):
+            raise NotImplementedError(f"match: only literal segments separated by '.*' are supported on the device, got {pattern!r}")
+    # a leading / trailing '.*' cancels the anchor on that side
+    if parts and parts[0] == "" and len(parts) > 1:
+        start, parts = False, parts[1:]
+    if parts and parts[-1] == "" and len(parts) > 1:
+        end, parts = False, parts[:-1]
+    segs = [p_ for p_ in parts if p_ != ""]
+    return [lit((1 if start else 0) | (2 if end else 0), dt.I32)] + [lit(x) for x in segs]
+
+
+def _segments_of_like(pattern: str):
+    if "_" in pattern or "\\" in pattern:
+        raise NotImplementedError(f"like: only '%' wildcards are supported on the device, got {pattern!r}")
+    parts = pattern.split("%")
+    start, end = parts[0] != "", parts[-1] != ""
+    if len(parts) == 1:
+        start = end = True
+    segs = [p_ for p_ in parts if p_ != ""]
+    return [lit((1 if start else 0) | (2 if end else 0), dt.I32)] + [lit(x) for x in segs]
 
 
 def col(name: str) -> Expression:
@@ -323,6 +363,18 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         if e.op in ("ceil", "floor") and dt.is_integer(c.dtype):
             return c  # integers are returned unchanged (src/daft-functions/src/numeric/ceil.rs:25-33, floor.rs)
         return Bound(T_FUNCTION, c.dtype, FUNCS[e.op], [c])
+    if k == "function" and e.op == "round":
+        c, d = bind(e.args[0], names, dtypes), bind(e.args[1], names, dtypes)
+        if not dt.is_numeric(c.dtype):
+            raise ValueError(f"Expected input to round to be numeric, got {dt.NAMES[c.dtype]}")
+        if dt.is_integer(c.dtype):
+            return c  # integers are returned unchanged (src/daft-functions/src/numeric/round.rs)
+        return Bound(T_FUNCTION, c.dtype, FUNCS["round"], [c, _cast(d, dt.I32)])
+    if k == "function" and e.op == "match_seq":
+        kids = [bind(x, names, dtypes) for x in e.args]
+        if not dt.is_string(kids[0].dtype):
+            raise ValueError(f"Expects input to match to be utf8, but received {dt.NAMES[kids[0].dtype]}")
+        return Bound(T_FUNCTION, dt.BOOL, FUNCS["match_seq"], [kids[0], _cast(kids[1], dt.I32)] + kids[2:])
     if k == "function":
         kids = [bind(x, names, dtypes) for x in e.args]
         out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,

@@ -332,6 +332,11 @@ int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begi
  *              7 utf8_left 8 day_of_week 9 sqrt (Float32 / Float64 operand, same type; IEEE correctly rounded)
  *              10 is_nan 11 not_nan 12 is_inf (float operand -> Boolean; nulls stay null, src/daft-core/src/array/ops/float.rs)
  *              13 ceil 14 floor (float operand, same type) 15 sign (numeric operand, same type: signum; 0 / 1 for unsigned)
+ *              16 round (float operand, Int32 literal decimals: (v * 10^d).round() / 10^d, half away from zero,
+ *                 src/daft-core/src/array/ops/round.rs:14-35)
+ *              17 match_seq (string operand, Int32 literal flags, then string literals): the operand contains the literals in
+ *                 this order without overlap; flags bit 0 anchors the first at the start, bit 1 the last at the end -- utf8
+ *                 `match` / `like` for patterns made of literal segments and `.*` / `%` (TPC-H Q13 / Q16, ClickBench)
  *   Operands of a binary op must already have identical dtypes (the host inserts the supertype
  *   casts the reference decides at plan time); true_div requires F64 operands.
  *

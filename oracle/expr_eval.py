@@ -218,6 +218,44 @@ def _eval(b: Bound, cols, n: int):
                 if a.dtype.kind == "f":
                     return np.where(np.isnan(a), a, np.copysign(np.ones_like(a), a)), allk
                 return np.sign(a).astype(a.dtype), allk
+            if fn == "round":                                      # array/ops/round.rs:14-35: (v * 10^d).round() / 10^d, half away from zero
+                d = int(kids[1][0][0]) if n else 0
+                x = a.astype(np.float64)
+                with np.errstate(all="ignore"):
+                    y = x if d == 0 else x * (10.0 ** d)
+                    r = np.where(np.isfinite(y), np.copysign(np.floor(np.abs(y) + 0.5), y), y)
+                    # floor(|y| + 0.5) double-rounds when |y| + 0.5 is inexact (0.49999999999999994): f64::round does not
+                    r = np.where(np.abs(y) < 0.5, np.copysign(0.0, y), r)
+                    r = np.where(np.abs(y) >= 2.0 ** 52, y, r)
+                    out = r if d == 0 else r / (10.0 ** d)
+                return out.astype(a.dtype), allk
+            if fn == "match_seq":
+                flags = int(kids[1][0][0]) if n else 0
+                segs = [kids[j][0][0] if n else b"" for j in range(2, len(kids))]
+
+                def hit(x: bytes) -> bool:
+                    pos = 0
+                    for j, sg in enumerate(segs):
+                        last = j == len(segs) - 1
+                        if j == 0 and (flags & 1):
+                            if not x.startswith(sg):
+                                return False
+                            f = 0
+                        elif last and (flags & 2):
+                            f = len(x) - len(sg)
+                            if f < pos or not x.endswith(sg):
+                                return False
+                        else:
+                            f = x.find(sg, pos)
+                            if f < 0:
+                                return False
+                        pos = f + len(sg)
+                    if len(segs) == 1 and (flags & 3) == 3:
+                        return x == segs[0]
+                    if not segs:
+                        return (flags & 3) != 3 or len(x) == 0
+                    return True
+                return np.array([hit(x) for x in a], dtype=bool), allk
             if fn == "day_of_week":
                 return ((a.astype(np.int64) + 3) % 7).astype(np.uint32), allk
             if fn == "utf8_length":

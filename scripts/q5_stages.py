@@ -10,7 +10,7 @@ t = {tb: tpch.generate(tb, sf, cols) for tb, cols in tpch.Q5_COLUMNS.items()}
 _lib.synchronize()
 def stage(name, fn, out):
     _lib.synchronize(); t0 = time.perf_counter(); r = fn(); _lib.synchronize(); out.append((name, round((time.perf_counter() - t0) * 1e3, 3), len(r))); return r
-for rep in range(3):
+for rep in range(int(os.environ.get('Q5_REPS', '3'))):
     out = []
     orders = stage("filter orders", lambda: t["orders"].filter([col("O_ORDERDATE") >= datetime.date(1994, 1, 1), col("O_ORDERDATE") < datetime.date(1995, 1, 1)]), out)
     region = stage("filter region", lambda: t["region"].filter([col("R_NAME") == "ASIA"]), out)

@@ -121,3 +121,28 @@ def test_string_minmax_reference_literals_and_grouped(gpu):
         got = RB(gpu, tbl).agg(aggs, gb).to_arrow_table()
         want = oracle_agg(tbl, aggs, gb)
         assert_tables_equal(got, want, sort_by=[g.name() for g in gb])
+
+
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer", "semi", "anti"])
+@pytest.mark.parametrize("key_type", [pa.int64(), pa.int32(), pa.uint8(), pa.date32()])
+def test_direct_address_table_equals_bucket_table(gpu, how, key_type, monkeypatch):
+    """Unique, dense integer build keys take the direct-address table (join.cu: key - min indexes a presence bitmap and a
+    row-id array); the same join with the mode switched off takes the hashed bucket table; both equal the oracle."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(17)
+    nb = 200 if key_type == pa.uint8() else 5000
+    np_t = {pa.int64(): np.int64, pa.int32(): np.int32, pa.uint8(): np.uint8, pa.date32(): np.int32}[key_type]
+    base = 0 if key_type == pa.uint8() else -700
+    bkeys = (rng.permutation(nb * 3)[:nb] + base).astype(np_t)       # unique, range 3x the count
+    pkeys = (rng.integers(-100, nb * 3 + 100, 20000) + base).astype(np_t) if key_type != pa.uint8() else rng.integers(0, 256, 20000).astype(np_t)
+    mk = (lambda a: pa.array(a).cast(pa.date32())) if key_type == pa.date32() else (lambda a: pa.array(a, type=key_type))
+    right = pa.table({"k": mk(bkeys), "b": pa.array(np.arange(nb) * 1.5)})
+    left = pa.table({"k": pa.array(mk(pkeys).to_pylist(), type=right.column("k").type, mask=rng.random(20000) < 0.05), "a": pa.array(np.arange(20000))})
+    c = gpu.col
+    want = O.hash_join(left, right, ["k"], ["k"], how)
+    if how in ("semi", "anti"):
+        want = want.select(left.column_names)
+    for direct in ("1", "0"):
+        monkeypatch.setenv("B200_JOIN_DIRECT", direct)
+        got = gpu.RecordBatch.from_arrow_table(left).hash_join(gpu.RecordBatch.from_arrow_table(right), [c("k")], [c("k")], how=how).to_arrow_table()
+        assert_tables_equal(got, want)

@@ -14,6 +14,7 @@ import pytest
 import daft_b200
 from daft_b200 import col
 import jit_emu
+from jit_emu import emulate_project
 import test_gpu_parity as parity
 import test_gpu_zz_semantics as semantics
 from helpers import assert_tables_equal, random_table
@@ -290,3 +291,30 @@ def test_generated_tier1_tpch_q1_matches_golden_answers():
     for name, vals in golden["q1"].items():
         for a, b in zip(got[name], vals):
             assert a == b or abs(a - b) <= 1e-9 * abs(b), (name, a, b)
+
+
+def test_generated_round_and_match_patterns():
+    """round (src/daft-core/src/array/ops/round.rs:14-35) and utf8 match / like over literal-segment patterns (the shapes of
+    benchmarking/tpch/answers.py:365,402 and the LIKE predicates of TPC-H Q13 / Q16 / ClickBench) through the generated code."""
+    rng = np.random.default_rng(21)
+    n = 600
+    x = np.concatenate([rng.standard_normal(n - 8) * 1000, [0.5, -0.5, 2.5, 0.125, -0.125, 1e300, np.nan, 0.49999999999999994]])
+    words = ["special requests", "the special packages requests", "requests special", "", "Customer Complaints", "xCustomeryComplaintsz", "special",
+             "specialrequests", "PROMO BRUSHED", "MEDIUM POLISHED TIN", "abc", "ab", "abcabc"]
+    tbl = pa.table({"f64": pa.array(x, mask=rng.random(n) < 0.1), "f32": pa.array(x.astype(np.float32), mask=rng.random(n) < 0.1),
+                    "s": pa.array([words[i] for i in rng.integers(0, len(words), n)], type=pa.large_utf8(), mask=rng.random(n) < 0.1)})
+    exprs = [col("f64").round(2).alias("r2"), col("f64").round(0).alias("r0"), col("f32").round(1).alias("r1f"), col("f64").round(-2).alias("rm2"),
+             col("s").match(".*special.*requests.*").alias("m1"), col("s").match("special").alias("m2"), col("s").match("^special.*requests$").alias("m3"),
+             col("s").like("%Customer%Complaints%").alias("l1"), col("s").like("PROMO%").alias("l2"), col("s").like("%TIN").alias("l3"),
+             col("s").like("abc").alias("l4"), col("s").like("ab%c").alias("l5"), col("s").like("%").alias("l6"), (~col("s").like("MEDIUM POLISHED%")).alias("l7")]
+    got = emulate_project(tbl, exprs)
+    assert_tables_equal(got, E.eval_expression_list(tbl, exprs))
+    d = got.to_pydict()
+    for i, w in enumerate(tbl.column("s").to_pylist()):
+        if w is not None:
+            assert d["m1"][i] == (w.find("special") >= 0 and w.find("requests", w.find("special") + 7) >= 0)
+            assert d["l5"][i] == (w.startswith("ab") and w.endswith("c") and len(w) >= 3)
+    with pytest.raises(NotImplementedError):
+        col("s").match("a+b")
+    with pytest.raises(NotImplementedError):
+        col("s").like("a_c")
