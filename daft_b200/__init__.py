@@ -2,7 +2,8 @@
 filter / project / exchange) as hand-written sm_100a CUDA kernels behind a C ABI.
 
 Public surface: RecordBatch (device-resident), col / lit expressions, ProbeTable, the TPC-H
-generator and query pipelines in daft_b200.tpch, the multi-GPU exchange in daft_b200.exchange.
+generator and query pipelines in daft_b200.tpch, the aggregation stage rewrite and sink in
+daft_b200.aggstages, the multi-GPU communicator (exchange, all-gather, distributed aggregate) in daft_b200.distributed.
 """
 from . import datatypes
 from ._lib import B200Error, init, launch_count, synchronize

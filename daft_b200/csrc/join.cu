@@ -670,40 +670,61 @@ __global__ void direct_fill(const void *__restrict__ data, int width, int64_t n,
     }
 }
 
+// pass 0 also STASHES the build row of every output row, densely per chunk (stash[chunk * CHUNK + j] = build row of the
+// chunk's j-th output row, 0xFFFFFFFF = none): pass 1 then needs neither the keys nor the table again.
 template <int W, bool SEL, bool NULLS, bool KEEP>
 __global__ void __launch_bounds__(PT, 4) direct_count_kernel(const __grid_constant__ ProbeArgs a, int64_t n, int64_t nchunks, int64_t *__restrict__ chunk_cnt,
-                                                             uint32_t *__restrict__ bits) {
+                                                             uint32_t *__restrict__ bits, uint32_t *__restrict__ stash) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * (PT / 32) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (PT / 32);
-    constexpr int DR = 8;  // rows per lane per step
+    const unsigned lt_mask = (1u << lane) - 1u;
+    constexpr int DR = 4;  // rows per lane per step; the keys of the next step are in flight while this one is processed
+    constexpr int STEPS = CHUNK / (32 * DR);
     for (int64_t chunk = gw; chunk < nchunks; chunk += nw) {
         const int64_t cbase = chunk * CHUNK;
         const bool full = cbase + CHUNK <= n;
         unsigned total = 0;
+        unsigned long long nv[DR];
+        bool nh[DR];
+#pragma unroll
+        for (int r = 0; r < DR; r++) {
+            const int64_t i = cbase + r * 32 + lane;
+            nv[r] = 0;
+            nh[r] = (full || i < n) && load_key<W, SEL, NULLS>(a, i, nv[r]);
+        }
 #pragma unroll 1
-        for (int step = 0; step < CHUNK / (32 * DR); step++) {
+        for (int step = 0; step < STEPS; step++) {
             const int64_t base = cbase + (int64_t)step * (32 * DR);
-            unsigned long long v[DR];
+            unsigned long long idx[DR];
             bool hit[DR];
 #pragma unroll
             for (int r = 0; r < DR; r++) {
-                const int64_t i = base + r * 32 + lane;
-                v[r] = 0;
-                hit[r] = (full || i < n) && load_key<W, SEL, NULLS>(a, i, v[r]);
+                idx[r] = nv[r] - a.dmin;
+                hit[r] = nh[r] && idx[r] < a.drange;
+            }
+            if (step + 1 < STEPS) {
+#pragma unroll
+                for (int r = 0; r < DR; r++) {
+                    const int64_t i = base + (32 * DR) + r * 32 + lane;
+                    nv[r] = 0;
+                    nh[r] = (full || i < n) && load_key<W, SEL, NULLS>(a, i, nv[r]);
+                }
             }
             unsigned word[DR];
 #pragma unroll
+            for (int r = 0; r < DR; r++) word[r] = hit[r] ? __ldg(a.dbits + (idx[r] >> 5)) : 0u;
+            unsigned row[DR];
+#pragma unroll
             for (int r = 0; r < DR; r++) {
-                const unsigned long long idx = v[r] - a.dmin;
-                hit[r] = hit[r] && idx < a.drange;
-                word[r] = hit[r] ? __ldg(a.dbits + (idx >> 5)) : 0u;
-                hit[r] = hit[r] && ((word[r] >> (idx & 31)) & 1u);
+                hit[r] = hit[r] && ((word[r] >> (idx[r] & 31)) & 1u);
+                row[r] = hit[r] && stash ? __ldg(a.drows + idx[r]) : 0xFFFFFFFFu;
             }
 #pragma unroll
             for (int r = 0; r < DR; r++) {
                 unsigned m = __ballot_sync(0xffffffffu, hit[r]);
                 if (KEEP) m = full ? 0xffffffffu : __ballot_sync(0xffffffffu, base + r * 32 + lane < n);
                 if (lane == 0 && (full || base + r * 32 < n)) bits[(base >> 5) + r] = m;
+                if (stash && ((m >> lane) & 1u)) stash[cbase + total + __popc(m & lt_mask)] = row[r];
                 total += __popc(m);
             }
         }
@@ -711,9 +732,9 @@ __global__ void __launch_bounds__(PT, 4) direct_count_kernel(const __grid_consta
     }
 }
 
-template <int W, bool SEL, bool NULLS>
-__global__ void __launch_bounds__(PT, 4) direct_write_kernel(const __grid_constant__ ProbeArgs a, int64_t n, int64_t nchunks,
-                                                             const int64_t *__restrict__ chunk_off, const uint32_t *__restrict__ bits,
+// pass 1: probe rows from the bitmap, build rows from the stash -- a pure streaming pass
+__global__ void __launch_bounds__(PT, 4) direct_write_kernel(int64_t n, int64_t nchunks, const int64_t *__restrict__ chunk_off,
+                                                             const uint32_t *__restrict__ bits, const uint32_t *__restrict__ stash,
                                                              int64_t *__restrict__ out_probe, int64_t *__restrict__ out_build,
                                                              unsigned int *__restrict__ matched_bits) {
     __shared__ unsigned short s_list[PT / 32][CHUNK];
@@ -740,15 +761,10 @@ __global__ void __launch_bounds__(PT, 4) direct_write_kernel(const __grid_consta
             list[pre++] = (unsigned short)(lane * 32 + b);
         }
         __syncwarp();
-        for (unsigned j = lane; j < hits; j += 32) {  // row j of the chunk's output: one build row (or none: a kept probe row)
-            const int64_t i = cbase + list[j];
-            unsigned long long v = 0;
-            long long br = -1;
-            if (load_key<W, SEL, NULLS>(a, i, v)) {
-                const unsigned long long idx = v - a.dmin;
-                if (idx < a.drange && ((__ldg(a.dbits + (idx >> 5)) >> (idx & 31)) & 1u)) br = (long long)__ldg(a.drows + idx);
-            }
-            out_probe[o + j] = i;
+        for (unsigned j = lane; j < hits; j += 32) {
+            const unsigned r = stash[cbase + j];
+            const long long br = r == 0xFFFFFFFFu ? -1LL : (long long)r;
+            out_probe[o + j] = cbase + list[j];
             out_build[o + j] = br;
             if (matched_bits && br >= 0) atomicOr(&matched_bits[br >> 5], 1u << (br & 31));
         }
@@ -945,10 +961,10 @@ static void make_probe_plan(const b200_probe_table *pt, const Batch &probe, cons
 // kernel variants: key width (0 = generic keys) x selection vector x nullable probe key x kept unmatched probe rows
 template <int W>
 static void launch_count_w(bool sel, bool nulls, bool keep, int grid, cudaStream_t st, const ProbeArgs &a, int64_t n, int64_t nchunks, int64_t *chunk_cnt,
-                           uint32_t *bits) {
+                           uint32_t *bits, uint32_t *stash) {
 #define B200_COUNT(S, N, K)                                                                                   \
     do {                                                                                                      \
-        if (W != 0 && a.drows) direct_count_kernel<(W ? W : 8), S, N, K><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits); \
+        if (W != 0 && a.drows) direct_count_kernel<(W ? W : 8), S, N, K><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits, stash); \
         else probe_count_kernel<W, S, N, K><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits);             \
     } while (0)
     if (sel) {
@@ -960,17 +976,18 @@ static void launch_count_w(bool sel, bool nulls, bool keep, int grid, cudaStream
     }
 #undef B200_COUNT
 }
-static void launch_count(int width, const ProbeArgs &a, int64_t n, int64_t nchunks, int64_t *chunk_cnt, uint32_t *bits, int keep) {
+// stash (direct-address tables only): room for one 32-bit build row per probe row, filled densely per chunk
+static void launch_count(int width, const ProbeArgs &a, int64_t n, int64_t nchunks, int64_t *chunk_cnt, uint32_t *bits, int keep, uint32_t *stash = nullptr) {
     cudaStream_t st = ctx().stream;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nchunks + PT / 32 - 1) / (PT / 32), (int64_t)ctx().sm_count * (a.drows ? 4 : 3)));
     const bool sel = a.psel != nullptr, nulls = a.pvalid != nullptr;
     KernelTimer kt(a.drows ? "join_probe_count_direct" : "join_probe_count");
     switch (width) {
-        case 1: launch_count_w<1>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
-        case 2: launch_count_w<2>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
-        case 4: launch_count_w<4>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
-        case 8: launch_count_w<8>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
-        default: launch_count_w<0>(false, false, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits); break;
+        case 1: launch_count_w<1>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits, stash); break;
+        case 2: launch_count_w<2>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits, stash); break;
+        case 4: launch_count_w<4>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits, stash); break;
+        case 8: launch_count_w<8>(sel, nulls, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits, stash); break;
+        default: launch_count_w<0>(false, false, keep != 0, grid, st, a, n, nchunks, chunk_cnt, bits, stash); break;
     }
     count_launch();
     B200_CUDA(cudaGetLastError());
@@ -978,18 +995,22 @@ static void launch_count(int width, const ProbeArgs &a, int64_t n, int64_t nchun
 template <int W>
 static void launch_write_w(bool sel, bool nulls, int grid, cudaStream_t st, const ProbeArgs &a, int64_t n, int64_t nchunks, const int64_t *chunk_off,
                            const uint32_t *bits, int64_t *out_probe, int64_t *out_build, unsigned int *matched_bits) {
-#define B200_WRITE(S, N)                                                                                                              \
-    do {                                                                                                                              \
-        if (W != 0 && a.drows) direct_write_kernel<(W ? W : 8), S, N><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits); \
-        else probe_write_kernel<W, S, N><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits);     \
-    } while (0)
+#define B200_WRITE(S, N) probe_write_kernel<W, S, N><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_off, bits, out_probe, out_build, matched_bits)
     if (sel) { if (nulls) { B200_WRITE(true, true); } else { B200_WRITE(true, false); } }
     else { if (nulls) { B200_WRITE(false, true); } else { B200_WRITE(false, false); } }
 #undef B200_WRITE
 }
 static void launch_write(int width, const ProbeArgs &a, int64_t n, int64_t nchunks, const int64_t *chunk_off, const uint32_t *bits, int64_t *out_probe,
-                         int64_t *out_build, unsigned int *matched_bits) {
+                         int64_t *out_build, unsigned int *matched_bits, const uint32_t *stash = nullptr) {
     cudaStream_t st = ctx().stream;
+    if (stash) {
+        const int g = (int)std::max<int64_t>(1, std::min<int64_t>((nchunks + PT / 32 - 1) / (PT / 32), (int64_t)ctx().sm_count * 4));
+        KernelTimer kt("join_probe_write_direct");
+        direct_write_kernel<<<g, PT, 0, st>>>(n, nchunks, chunk_off, bits, stash, out_probe, out_build, matched_bits);
+        count_launch();
+        B200_CUDA(cudaGetLastError());
+        return;
+    }
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nchunks + PT / 32 - 1) / (PT / 32), (int64_t)ctx().sm_count * (a.drows ? 4 : 3)));
     const bool sel = a.psel != nullptr, nulls = a.pvalid != nullptr;
     KernelTimer kt(a.drows ? "join_probe_write_direct" : "join_probe_write");
@@ -1044,14 +1065,15 @@ static void probe_pairs(const b200_probe_table *pt, const Batch &probe, const in
     const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
     Buf counts = dev_alloc((size_t)(nchunks + 1) * 8), offs = dev_alloc((size_t)(nchunks + 1) * 8);
     Buf bits = dev_alloc((size_t)((n + 31) / 32 + 1) * 4);  // one "produces output" bit per probe row, pass 0 -> pass 1
-    launch_count(pt->inline_width, pp.args, n, nchunks, as<int64_t>(counts), as<uint32_t>(bits), keep_unmatched_probe ? 1 : 0);
+    Buf stash = pp.args.drows ? dev_alloc((size_t)nchunks * CHUNK * 4) : Buf();
+    launch_count(pt->inline_width, pp.args, n, nchunks, as<int64_t>(counts), as<uint32_t>(bits), keep_unmatched_probe ? 1 : 0, as<uint32_t>(stash));
     exclusive_scan_i64(as<int64_t>(counts), as<int64_t>(offs), nchunks, as<int64_t>(offs) + nchunks);
     total = read_i64(as<int64_t>(offs) + nchunks);
     out_probe = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
     out_build = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
     if (total > 0)
         launch_write(pt->inline_width, pp.args, n, nchunks, as<int64_t>(offs), as<uint32_t>(bits), as<int64_t>(out_probe), as<int64_t>(out_build),
-                     matched_bits);
+                     matched_bits, as<uint32_t>(stash));
 }
 
 Batch *probe_indices(const b200_probe_table *pt, const Batch &probe, const int32_t *key_cols) {

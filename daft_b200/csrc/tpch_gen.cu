@@ -19,6 +19,35 @@ namespace b200 {
 
 using namespace tpchgen;
 
+// dictionary-valued string columns: lengths of the drawn words, (scan on the host side of the launch), then the bytes
+__global__ void gen_dict_lens(int col, uint64_t seed, int64_t row_begin, int64_t n, const int32_t *__restrict__ dict_off, int64_t *__restrict__ lens) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int k = gen_dict_index(col, seed, row_begin + i);
+        lens[i] = dict_off[k + 1] - dict_off[k];
+    }
+}
+__global__ void gen_dict_bytes(int col, uint64_t seed, int64_t row_begin, int64_t n, const int32_t *__restrict__ dict_off,
+                               const uint8_t *__restrict__ dict_bytes, const int64_t *__restrict__ offsets, uint8_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int k = gen_dict_index(col, seed, row_begin + i);
+        const int32_t b = dict_off[k], len = dict_off[k + 1] - b;
+        const int64_t o = offsets[i];
+        for (int32_t t = 0; t < len; t++) out[o + t] = dict_bytes[b + t];
+    }
+}
+static void dict_tables(int col, std::vector<int32_t> &off, std::string &bytes) {
+    off.assign(1, 0);
+    bytes.clear();
+    for (int k = 0; k < dict_size(col); k++) {
+        bytes += dict_word(col, k);
+        off.push_back((int32_t)bytes.size());
+    }
+}
+
 __global__ void gen_kernel(int col, int kind, uint64_t seed, int64_t row_begin, int64_t n, Scale sc, void *data, int64_t *offsets) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -41,6 +70,7 @@ int64_t tpch_num_rows(int32_t table, double sf) {
         case B200_TPCH_SUPPLIER: return s.n_suppliers;
         case B200_TPCH_NATION: return 25;
         case B200_TPCH_REGION: return 5;
+        case B200_TPCH_PART: return s.n_parts;
     }
     fail("tpch: unknown table");
 }
@@ -93,7 +123,30 @@ Batch *tpch_generate(int32_t table, double sf, int64_t row_begin, int64_t row_en
         c.dtype = kCols[col].dtype;
         c.length = n;
         const int kind = kind_of(col);
-        if (col == N_NAME || col == R_NAME) {
+        if (is_dict_col(col)) {
+            std::vector<int32_t> doff;
+            std::string dbytes;
+            dict_tables(col, doff, dbytes);
+            Buf d_off = dev_alloc(doff.size() * 4), d_bytes = dev_alloc(dbytes.size()), lens = dev_alloc((size_t)(n + 1) * 8);
+            B200_CUDA(cudaMemcpyAsync(d_off->ptr, doff.data(), doff.size() * 4, cudaMemcpyHostToDevice, st));
+            B200_CUDA(cudaMemcpyAsync(d_bytes->ptr, dbytes.data(), dbytes.size(), cudaMemcpyHostToDevice, st));
+            c.offsets = dev_alloc((size_t)(n + 1) * 8);
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 8));
+            if (n) {
+                gen_dict_lens<<<grid, 256, 0, st>>>(col, seed, row_begin, n, as<int32_t>(d_off), as<int64_t>(lens));
+                count_launch();
+            }
+            exclusive_scan_i64(as<int64_t>(lens), as<int64_t>(c.offsets), n, as<int64_t>(c.offsets) + n);
+            const int64_t total = read_i64(as<int64_t>(c.offsets) + n);
+            c.data = dev_alloc((size_t)std::max<int64_t>(total, 1));
+            c.data_bytes = total;
+            if (n) {
+                gen_dict_bytes<<<grid, 256, 0, st>>>(col, seed, row_begin, n, as<int32_t>(d_off), as<uint8_t>(d_bytes), as<int64_t>(c.offsets),
+                                                     as<uint8_t>(c.data));
+                count_launch();
+            }
+            B200_CUDA(cudaStreamSynchronize(st));  // the host dictionary buffers above
+        } else if (col == N_NAME || col == R_NAME) {
             std::vector<int64_t> offs;
             std::string bytes;
             name_column_host(col, row_begin, row_end, offs, bytes);
@@ -139,7 +192,23 @@ void tpch_generate_host(int32_t table, double sf, int64_t row_begin, int64_t row
     for (int col : resolve_columns(table, columns, ncolumns)) {
         HostCol h{kCols[col].name, kCols[col].dtype, n, nullptr, nullptr, 0};
         const int kind = kind_of(col);
-        if (col == N_NAME || col == R_NAME) {
+        if (is_dict_col(col)) {
+            std::vector<std::string> words;
+            for (int k = 0; k < dict_size(col); k++) words.push_back(dict_word(col, k));
+            h.offsets = (int64_t *)malloc((size_t)(n + 1) * 8);
+            int64_t total = 0;
+            for (int64_t i = 0; i < n; i++) {
+                h.offsets[i] = total;
+                total += (int64_t)words[(size_t)gen_dict_index(col, seed, row_begin + i)].size();
+            }
+            h.offsets[n] = total;
+            h.data = malloc((size_t)total + 8);
+            for (int64_t i = 0; i < n; i++) {
+                const std::string &w = words[(size_t)gen_dict_index(col, seed, row_begin + i)];
+                memcpy((uint8_t *)h.data + h.offsets[i], w.data(), w.size());
+            }
+            h.data_bytes = total;
+        } else if (col == N_NAME || col == R_NAME) {
             std::vector<int64_t> offs;
             std::string bytes;
             name_column_host(col, row_begin, row_end, offs, bytes);

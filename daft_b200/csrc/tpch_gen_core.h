@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <string>
 #include <strings.h>
 
 #ifndef B200_I64  // standalone use: the physical dtype codes of include/daft_b200.h
@@ -78,6 +79,9 @@ enum ColId {
     S_SUPPKEY, S_NATIONKEY, S_ACCTBAL,
     N_NATIONKEY, N_REGIONKEY, N_NAME,
     R_REGIONKEY, R_NAME,
+    // dictionary-valued strings (round 2): the generator draws an index, the column holds the dictionary word
+    L_SHIPMODE, O_ORDERPRIORITY, C_MKTSEGMENT,
+    P_PARTKEY, P_SIZE, P_TYPE,
     NUM_COLS
 };
 struct ColInfo { const char *name; int32_t table; int32_t dtype; };
@@ -92,7 +96,36 @@ static const ColInfo kCols[NUM_COLS] = {
     {"S_SUPPKEY", 3, B200_I64}, {"S_NATIONKEY", 3, B200_I64}, {"S_ACCTBAL", 3, B200_F64},
     {"N_NATIONKEY", 4, B200_I64}, {"N_REGIONKEY", 4, B200_I64}, {"N_NAME", 4, B200_LARGE_UTF8},
     {"R_REGIONKEY", 5, B200_I64}, {"R_NAME", 5, B200_LARGE_UTF8},
+    {"L_SHIPMODE", 0, B200_LARGE_UTF8}, {"O_ORDERPRIORITY", 1, B200_LARGE_UTF8}, {"C_MKTSEGMENT", 2, B200_LARGE_UTF8},
+    {"P_PARTKEY", 6, B200_I64}, {"P_SIZE", 6, B200_I64}, {"P_TYPE", 6, B200_LARGE_UTF8},
 };
+// dictionary columns: number of words (TPC-H specification 4.2.2.13: ship modes, order priorities, market segments;
+// P_TYPE = one syllable of each of three lists, 6 x 5 x 5 = 150 combinations)
+static const char *kShipModes[7] = {"REG AIR", "AIR", "RAIL", "SHIP", "TRUCK", "MAIL", "FOB"};
+static const char *kPriorities[5] = {"1-URGENT", "2-HIGH", "3-MEDIUM", "4-NOT SPECIFIED", "5-LOW"};
+static const char *kSegments[5] = {"AUTOMOBILE", "BUILDING", "FURNITURE", "MACHINERY", "HOUSEHOLD"};
+static const char *kTypeS1[6] = {"STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO"};
+static const char *kTypeS2[5] = {"ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED"};
+static const char *kTypeS3[5] = {"TIN", "NICKEL", "BRASS", "STEEL", "COPPER"};
+inline bool is_dict_col(int col) { return col == L_SHIPMODE || col == O_ORDERPRIORITY || col == C_MKTSEGMENT || col == P_TYPE; }
+inline int dict_size(int col) { return col == L_SHIPMODE ? 7 : col == P_TYPE ? 150 : 5; }
+inline std::string dict_word(int col, int k) {
+    switch (col) {
+        case L_SHIPMODE: return kShipModes[k];
+        case O_ORDERPRIORITY: return kPriorities[k];
+        case C_MKTSEGMENT: return kSegments[k];
+        default: return std::string(kTypeS1[k / 25]) + " " + kTypeS2[(k / 5) % 5] + " " + kTypeS3[k % 5];
+    }
+}
+// the dictionary index of a dictionary column's row
+GEN_HD int gen_dict_index(int col, uint64_t seed, int64_t row) {
+    switch (col) {
+        case L_SHIPMODE: return (int)(rnd(seed, 61, (uint64_t)row) % 7);
+        case O_ORDERPRIORITY: return (int)(rnd(seed, 62, (uint64_t)row) % 5);
+        case C_MKTSEGMENT: return (int)(rnd(seed, 63, (uint64_t)row) % 5);
+        default: return (int)(rnd(seed, 64, (uint64_t)row) % 150);
+    }
+}
 static const char *kNations[25] = {"ALGERIA", "ARGENTINA", "BRAZIL", "CANADA", "EGYPT", "ETHIOPIA", "FRANCE", "GERMANY", "INDIA",
                                    "INDONESIA", "IRAN", "IRAQ", "JAPAN", "JORDAN", "KENYA", "MOROCCO", "MOZAMBIQUE", "PERU", "CHINA",
                                    "ROMANIA", "SAUDI ARABIA", "VIETNAM", "RUSSIA", "UNITED KINGDOM", "UNITED STATES"};
@@ -153,6 +186,8 @@ GEN_HD uint64_t gen_value(int col, uint64_t seed, int64_t row, Scale sc) {
         case S_NATIONKEY: v.i = rnd_range(seed, 51, (uint64_t)row, 0, 24); break;
         case S_ACCTBAL: v.d = (double)rnd_range(seed, 52, (uint64_t)row, -99999, 999999) / 100.0; break;
         case N_NATIONKEY: case R_REGIONKEY: v.i = row; break;
+        case P_PARTKEY: v.i = row + 1; break;
+        case P_SIZE: v.i = rnd_range(seed, 65, (uint64_t)row, 1, 50); break;
         default: break;
     }
     return v.u;

@@ -17,7 +17,7 @@ from . import _lib
 from .expressions import col, lit
 from .recordbatch import RecordBatch
 
-TABLES = {"lineitem": 0, "orders": 1, "customer": 2, "supplier": 3, "nation": 4, "region": 5}
+TABLES = {"lineitem": 0, "orders": 1, "customer": 2, "supplier": 3, "nation": 4, "region": 5, "part": 6}
 DEFAULT_SEED = 20260921
 
 Q1_COLUMNS = ["L_QUANTITY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_TAX", "L_RETURNFLAG", "L_LINESTATUS", "L_SHIPDATE"]
@@ -183,3 +183,78 @@ def q5(t: dict[str, RecordBatch]) -> RecordBatch:
                     build_on_left=len(j) < len(t["customer"]))
     out = j.agg([(col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))).sum().alias("revenue")], [col("N_NAME")])
     return out.sort([col("revenue")], descending=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# More of benchmarking/tpch/answers.py, composed from the same operators.  Each follows the reference's DataFrame form
+# (join order, projections, aggregation lists, final sort / limit); joins build on their smaller side as the planner would.
+# ------------------------------------------------------------------------------------------------
+def _when(pred: "Expression", then, otherwise):
+    """daft.functions.when(pred, then).otherwise(x)"""
+    from .expressions import _to_expr
+    return pred.if_else(_to_expr(then), _to_expr(otherwise))
+
+
+QUERY_COLUMNS = {
+    "q3": {"customer": ["C_CUSTKEY", "C_MKTSEGMENT"], "orders": ["O_ORDERKEY", "O_CUSTKEY", "O_ORDERDATE", "O_SHIPPRIORITY"],
+           "lineitem": ["L_ORDERKEY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_SHIPDATE"]},
+    "q4": {"orders": ["O_ORDERKEY", "O_ORDERDATE", "O_ORDERPRIORITY"], "lineitem": ["L_ORDERKEY", "L_COMMITDATE", "L_RECEIPTDATE"]},
+    "q12": {"orders": ["O_ORDERKEY", "O_ORDERPRIORITY"], "lineitem": ["L_ORDERKEY", "L_SHIPMODE", "L_COMMITDATE", "L_RECEIPTDATE", "L_SHIPDATE"]},
+    "q14": {"lineitem": ["L_PARTKEY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_SHIPDATE"], "part": ["P_PARTKEY", "P_TYPE"]},
+    "q18": {"customer": ["C_CUSTKEY"], "orders": ["O_ORDERKEY", "O_CUSTKEY", "O_ORDERDATE", "O_TOTALPRICE"], "lineitem": ["L_ORDERKEY", "L_QUANTITY"]},
+}
+
+
+def q3(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:78-103: BUILDING customers x orders before 1995-03-15 x lineitems shipped after it; revenue per order, top 10."""
+    customer = t["customer"].filter([col("C_MKTSEGMENT") == "BUILDING"])
+    orders = t["orders"].filter([col("O_ORDERDATE") < datetime.date(1995, 3, 15)])
+    lineitem = t["lineitem"].filter([col("L_SHIPDATE") > datetime.date(1995, 3, 15)])
+    j = customer.hash_join(orders, [col("C_CUSTKEY")], [col("O_CUSTKEY")], build_on_left=len(customer) <= len(orders))
+    j = j.eval_expression_list([col("O_ORDERKEY"), col("O_ORDERDATE"), col("O_SHIPPRIORITY")])
+    j = j.hash_join(lineitem, [col("O_ORDERKEY")], [col("L_ORDERKEY")], build_on_left=len(j) <= len(lineitem))
+    j = j.eval_expression_list([col("O_ORDERKEY"), (col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))).alias("volume"), col("O_ORDERDATE"),
+                                col("O_SHIPPRIORITY")])
+    g = j.agg([col("volume").sum().alias("revenue")], [col("O_ORDERKEY"), col("O_ORDERDATE"), col("O_SHIPPRIORITY")])
+    top = g.top_n([col("revenue"), col("O_ORDERDATE")], 10, descending=[True, False])
+    return top.eval_expression_list([col("O_ORDERKEY"), col("revenue"), col("O_ORDERDATE"), col("O_SHIPPRIORITY")])
+
+
+def q4(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:106-124: orders of 1993 Q3 with at least one late lineitem (semi join), counted per priority."""
+    orders = t["orders"].filter([col("O_ORDERDATE") >= datetime.date(1993, 7, 1), col("O_ORDERDATE") < datetime.date(1993, 10, 1)])
+    lineitems = t["lineitem"].filter([col("L_COMMITDATE") < col("L_RECEIPTDATE")])
+    j = orders.hash_join(lineitems, [col("O_ORDERKEY")], [col("L_ORDERKEY")], how="semi")
+    return j.agg([col("O_ORDERKEY").count().alias("order_count")], [col("O_ORDERPRIORITY")]).sort([col("O_ORDERPRIORITY")])
+
+
+def q12(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:373-395: late MAIL / SHIP lineitems received in 1994, high- and low-priority line counts per ship mode."""
+    j = t["orders"].hash_join(t["lineitem"], [col("O_ORDERKEY")], [col("L_ORDERKEY")], build_on_left=True)
+    j = j.filter([col("L_SHIPMODE").is_in(["MAIL", "SHIP"]), col("L_COMMITDATE") < col("L_RECEIPTDATE"), col("L_SHIPDATE") < col("L_COMMITDATE"),
+                  col("L_RECEIPTDATE") >= datetime.date(1994, 1, 1), col("L_RECEIPTDATE") < datetime.date(1995, 1, 1)])
+    urgent = col("O_ORDERPRIORITY").is_in(["1-URGENT", "2-HIGH"])
+    out = j.agg([_when(urgent, 1, 0).sum().alias("high_line_count"), _when(~urgent, 1, 0).sum().alias("low_line_count")], [col("L_SHIPMODE")])
+    return out.sort([col("L_SHIPMODE")])
+
+
+def q14(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:418-436: promotional revenue share of September 1995."""
+    j = t["lineitem"].hash_join(t["part"], [col("L_PARTKEY")], [col("P_PARTKEY")])
+    pred = [col("L_SHIPDATE") >= datetime.date(1995, 9, 1), col("L_SHIPDATE") < datetime.date(1995, 10, 1)]
+    rev = col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))
+    a = j.agg([_when(col("P_TYPE").startswith("PROMO"), rev, 0.0).sum().alias("tmp_1"), rev.sum().alias("tmp_2")], [], predicate=pred)
+    return a.eval_expression_list([(lit(100.00) * (col("tmp_1") / col("tmp_2"))).alias("promo_revenue")])
+
+
+def q18(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:510-528 (the generator has no C_NAME: the group key list is C_CUSTKEY, O_ORDERKEY, O_ORDERDATE, O_TOTALPRICE):
+    orders whose lineitems sum to more than 300 units -- a high-cardinality group-by over all of lineitem -- top 100 by price."""
+    res_1 = t["lineitem"].agg([col("L_QUANTITY").sum().alias("sum_qty")], [col("L_ORDERKEY")]).filter([col("sum_qty") > 300])
+    j = t["orders"].hash_join(res_1, [col("O_ORDERKEY")], [col("L_ORDERKEY")], build_on_left=len(t["orders"]) <= len(res_1))
+    j = j.hash_join(t["customer"], [col("O_CUSTKEY")], [col("C_CUSTKEY")], build_on_left=len(j) <= len(t["customer"]))
+    j = j.eval_expression_list([col("C_CUSTKEY"), col("O_ORDERKEY"), col("O_ORDERDATE"), col("O_TOTALPRICE")])
+    j = j.hash_join(t["lineitem"], [col("O_ORDERKEY")], [col("L_ORDERKEY")], build_on_left=True)
+    g = j.agg([col("L_QUANTITY").sum().alias("sum")], [col("C_CUSTKEY"), col("O_ORDERKEY"), col("O_ORDERDATE"), col("O_TOTALPRICE")])
+    g = g.eval_expression_list([col("C_CUSTKEY"), col("O_ORDERKEY"), col("O_ORDERDATE").alias("O_ORDERDAT"), col("O_TOTALPRICE"), col("sum")])
+    return g.top_n([col("O_TOTALPRICE"), col("O_ORDERDAT")], 100, descending=[True, False])

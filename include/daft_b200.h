@@ -11,9 +11,12 @@
  *     by this library), outputs carry this library's release callbacks;
  *   - stateful objects are opaque handles with explicit *_free (ctx + fini in the
  *     reference's vtables, abi/mod.rs:66,107);
- *   - handles are not thread-safe for concurrent mutation; read-only sharing of a
- *     finished b200_probe_table across probe threads is allowed (Probeable is Send+Sync,
- *     src/daft-recordbatch/src/probeable/mod.rs:33-85).
+ *   - threading: entry points may be called from any host thread (each call makes the library's
+ *     device current).  Concurrent calls are fine for read-only use of handles -- probing one built
+ *     b200_probe_table from many threads (Probeable is Send+Sync,
+ *     src/daft-recordbatch/src/probeable/mod.rs:33-85), reading the same batches, pushing to one
+ *     b200_groupby_state; mutating calls on ONE handle (add/build, rename, free) must not race
+ *     with other calls on it.  All kernels queue on the one library stream.
  *
  * There is NO CPU fallback behind any entry point: without a CUDA device every operator
  * returns an error.
@@ -285,7 +288,7 @@ int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, cha
 
 /* ---- synthetic TPC-H tables generated straight into HBM (bench / tests) ---- */
 typedef enum { B200_TPCH_LINEITEM = 0, B200_TPCH_ORDERS = 1, B200_TPCH_CUSTOMER = 2, B200_TPCH_SUPPLIER = 3,
-               B200_TPCH_NATION = 4, B200_TPCH_REGION = 5 } b200_tpch_table;
+               B200_TPCH_NATION = 4, B200_TPCH_REGION = 5, B200_TPCH_PART = 6 } b200_tpch_table;
 /* rows [row_begin,row_end) of `table` at `scale_factor`; columns selected by name list (NULL = all implemented). */
 int b200_tpch_generate(int32_t table, double scale_factor, int64_t row_begin, int64_t row_end, uint64_t seed,
                        const char *const *columns, int32_t ncolumns, b200_batch **out, char **errmsg);

@@ -61,6 +61,11 @@ class OracleRecordBatch:
         idx = O.argsort([E.eval_expression(self.tbl, k) for k in sort_keys], desc, nf)
         return OracleRecordBatch(self.tbl.take(pa.array(idx, type=pa.int64())))
 
+    def top_n(self, sort_keys, limit: int, descending=None, nulls_first=None, offset: int = 0) -> "OracleRecordBatch":
+        """RecordBatch::top_n = argsort, then slice (src/daft-recordbatch/src/ops/sort.rs:47-61)."""
+        s = self.sort(sort_keys, descending, nulls_first).tbl
+        return OracleRecordBatch(s.slice(offset, limit))
+
     def hash_join(self, right: "OracleRecordBatch", left_on, right_on, how="inner", null_equals_null=None,
                   build_on_left=None) -> "OracleRecordBatch":
         lt, rt = self.tbl, right.tbl

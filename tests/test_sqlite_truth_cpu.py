@@ -37,3 +37,20 @@ def test_q6_oracle_vs_sqlite(world):
     tables, conn = world
     names, rows = ST.run(conn, 6)
     ST.assert_matches(tpch.q6(OracleRecordBatch(tables["lineitem"])).to_arrow_table(), names, rows)
+
+
+# ---- more of answers.py: the oracle twin of every composed query against SQLite on the same tables -------------------
+def _tables(q):
+    sf = 0.05 if q == "q18" else SF   # Q18's `sum(l_quantity) > 300` keeps 0.07% of the seven-line orders: needs more of them
+    return {t: tpch.generate_host(t, sf, c) for t, c in tpch.QUERY_COLUMNS[q].items()}
+
+
+@pytest.mark.parametrize("q", [3, 4, 12, 14, 18])
+def test_composed_queries_oracle_vs_sqlite(q):
+    name = f"q{q}"
+    tables = _tables(name)
+    conn = ST.load(tables)
+    names, rows = ST.run(conn, q)
+    got = getattr(tpch, name)({t: OracleRecordBatch(v) for t, v in tables.items()}).to_arrow_table()
+    assert len(rows) > 0
+    ST.assert_matches(got, names, rows, check_names=False)
