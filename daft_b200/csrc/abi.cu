@@ -296,6 +296,12 @@ int b200_partition_by_hash(const b200_batch *batch, const int32_t *key_cols, int
     });
 }
 
+int b200_partition_by_random(const b200_batch *batch, int32_t num_partitions, uint64_t seed, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        std::vector<Batch *> parts = op_partition_by_random(plain(batch), num_partitions, seed);
+        for (int i = 0; i < num_partitions; i++) out[i] = parts[i];
+    });
+}
 int b200_search_sorted(const b200_batch *sorted, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending,
                        b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
@@ -455,6 +461,13 @@ void b200_comm_free(b200_comm *c) { comm_free(c); }
 int b200_exchange_by_hash(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out,
                           char **errmsg) {
     return guard(errmsg, [&] { *out = exchange_by_hash(c, plain(batch), key_cols, nkeys); });
+}
+int b200_exchange_random(b200_comm *c, const b200_batch *batch, uint64_t seed, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = exchange_random(c, plain(batch), seed); });
+}
+int b200_exchange_by_range(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const b200_batch *boundaries,
+                           const uint8_t *descending, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = exchange_by_range(c, plain(batch), key_cols, nkeys, plain(boundaries), descending); });
 }
 int b200_agg_allreduce(b200_comm *c, const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, int32_t *merged,
                        char **errmsg) {

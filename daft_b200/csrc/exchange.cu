@@ -461,11 +461,9 @@ static Batch *exchange_peer_store(b200_comm *c, const Batch &b, const uint64_t *
     return out.release();
 }
 
-Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys) {
-    require_device();
-    if (!c) fail("null communicator");
+// rows of `b` go to rank targets[i] % world (targets: u64 per row), arriving in (source rank, source row) order
+static Batch *exchange_by_targets(b200_comm *c, const Batch &b, const Buf &h) {
     const int W = c->world;
-    Buf h = hash_rows(b, key_cols, nkeys, nullptr);
     {
         KernelTimer ktp("exchange_peer_store");
         if (Batch *direct = exchange_peer_store(c, b, as<uint64_t>(h))) return direct;
@@ -488,6 +486,29 @@ Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, i
     const Route rows = make_route(c, soff, scnt, nulls, &nulls_anywhere);
     KernelTimer kt("exchange_route");
     return route_batch(c, *staged, rows, &nulls_anywhere);
+}
+
+// RepartitionSpec::Hash: the same hash_rows % world placement as partition_by_hash (a3)
+Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys) {
+    require_device();
+    if (!c) fail("null communicator");
+    return exchange_by_targets(c, b, hash_rows(b, key_cols, nkeys, nullptr));
+}
+// RepartitionSpec::Random (src/daft-local-execution/src/sinks/repartition.rs:169-171): see partition.cu random_targets; the
+// salt makes the draw a function of (seed, rank, row) so that ranks do not all draw the same sequence
+Batch *exchange_random(b200_comm *c, const Batch &b, uint64_t seed) {
+    require_device();
+    if (!c) fail("null communicator");
+    return exchange_by_targets(c, b, random_targets(b.num_rows, c->world, seed, (uint64_t)c->rank << 40));
+}
+// RepartitionSpec::Range (repartition.rs:172-176; the exchange leg of the distributed sort,
+// src/daft-distributed/src/pipeline_node/sort.rs:249-300): target = search_sorted(boundaries, keys); world - 1 boundaries
+Batch *exchange_by_range(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys, const Batch &boundaries, const uint8_t *descending) {
+    require_device();
+    if (!c) fail("null communicator");
+    if (boundaries.num_rows != c->world - 1) fail("exchange_by_range: need exactly world - 1 boundary rows");
+    if (boundaries.num_rows == 0) return new Batch(b);
+    return exchange_by_targets(c, b, op_search_sorted(boundaries, b, key_cols, nkeys, descending));
 }
 
 // ---- small batches (partial aggregates, top-N candidates): ONE fixed-size all-gather ---------------------------------

@@ -55,6 +55,8 @@ struct PartitionPlan {
 PartitionPlan partition_count(const uint64_t *hashes, int64_t n, int32_t P);
 void partition_scatter_to_peers(const PartitionPlan &pl, const uint64_t *hashes, const Batch &b, const std::vector<int> &cols,
                                 const std::vector<std::vector<void *>> &dest_ptrs, Buf *rowid_out);
+Buf random_targets(int64_t n, int32_t P, uint64_t seed, uint64_t salt);  // u64 target per row (RepartitionSpec::Random)
+std::vector<Batch *> op_partition_by_random(const Batch &b, int32_t P, uint64_t seed);
 std::vector<Batch *> op_partition_by_hash(const Batch &b, const int32_t *key_cols, int32_t nkeys, int32_t P);
 Batch *op_dedup(const Batch &b, const int32_t *key_cols, int32_t nkeys);
 
@@ -77,6 +79,8 @@ void comm_unique_id(uint8_t *out128);
 b200_comm *comm_init(const uint8_t *id128, int32_t rank, int32_t world);
 void comm_free(b200_comm *c);
 Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys);
+Batch *exchange_random(b200_comm *c, const Batch &b, uint64_t seed);
+Batch *exchange_by_range(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys, const Batch &boundaries, const uint8_t *descending);
 Batch *all_gather_batches(b200_comm *c, const Batch &b);
 void allreduce_agg_table(b200_comm *c, unsigned long long *acc, size_t cap, const std::vector<int> &cell_ops, const std::vector<char> &keep_local,
                          unsigned long long *tagmin, int *status_flag);

@@ -304,6 +304,53 @@ static std::vector<Batch *> partition_direct(const Batch &b, const uint64_t *has
     return out;
 }
 
+// RepartitionSpec::Random (RecordBatch::partition_by_random, src/daft-recordbatch/src/ops/partition.rs:72-86): a target
+// per row drawn from a seeded generator.  The reference draws from rand::StdRng (a third-party ChaCha12 stream, absent
+// from the reference tree); what its tests pin is conservation and determinism per (seed, input)
+// (tests/recordbatch/test_partitioning.py:124-147,199-214), which a counter-based generator keeps: target(i) =
+// mix64(mix64(seed) ^ (salt + i)) % P -- independent of how the rows are cut into launches or ranks (salt = the row's
+// global position).
+__device__ __forceinline__ uint64_t rnd_mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__global__ void random_targets_kernel(uint64_t seed, uint64_t salt, int64_t n, uint64_t P, uint64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint64_t s = rnd_mix64(seed);
+    for (; i < n; i += stride) out[i] = rnd_mix64(s ^ (salt + (uint64_t)i)) % P;
+}
+Buf random_targets(int64_t n, int32_t P, uint64_t seed, uint64_t salt) {
+    Buf t = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+    if (n > 0) {
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 8));
+        random_targets_kernel<<<grid, 256, 0, ctx().stream>>>(seed, salt, n, (uint64_t)P, as<uint64_t>(t));
+        count_launch();
+    }
+    return t;
+}
+static std::vector<Batch *> partition_by_targets(const Batch &b, const Buf &targets, int32_t P) {
+    if (P <= PS_MAXP && b.num_rows >= 4096) return partition_direct(b, as<uint64_t>(targets), P);
+    std::vector<int64_t> offsets;
+    Buf perm = partition_permutation(as<uint64_t>(targets), b.num_rows, P, offsets);
+    std::vector<Batch *> out;
+    try {
+        for (int p = 0; p < P; p++) out.push_back(gather_batch(b, as<int64_t>(perm) + offsets[p], offsets[p + 1] - offsets[p], false));
+        op_done();
+    } catch (...) {
+        for (auto *x : out) delete x;
+        throw;
+    }
+    return out;
+}
+std::vector<Batch *> op_partition_by_random(const Batch &b, int32_t P, uint64_t seed) {
+    require_device();
+    if (P <= 0) fail("Can not partition a Table by 0 partitions");
+    return partition_by_targets(b, random_targets(b.num_rows, P, seed, 0), P);
+}
+
 std::vector<Batch *> op_partition_by_hash(const Batch &b, const int32_t *key_cols, int32_t nkeys, int32_t P) {
     require_device();
     if (P <= 0) fail("Can not partition a Table by 0 partitions");

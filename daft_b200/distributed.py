@@ -114,6 +114,50 @@ class Communicator:
         _lib.call("b200_exchange_by_hash", self._h, both._h, _i32(idx), ctypes.c_int32(len(idx)), ctypes.byref(out))
         return RecordBatch._wrap(out).select_columns(list(range(batch.num_columns())))
 
+    def exchange_random(self, batch, seed: int = 0):
+        """RepartitionSpec::Random over the ranks (src/daft-local-execution/src/sinks/repartition.rs:169-171)."""
+        from . import _lib
+        from .recordbatch import RecordBatch
+        out = ctypes.c_void_p()
+        _lib.call("b200_exchange_random", self._h, batch._h, ctypes.c_uint64(seed & (2**64 - 1)), ctypes.byref(out))
+        return RecordBatch._wrap(out, like=batch)
+
+    def exchange_by_range(self, batch, exprs: Sequence, boundaries, descending: Sequence[bool]):
+        """RepartitionSpec::Range: rank r receives the rows whose search_sorted position among the world - 1 boundaries is r."""
+        from . import _lib
+        from .recordbatch import RecordBatch, _i32, _u8
+        both, idx = batch._resolve_keys(exprs)
+        out = ctypes.c_void_p()
+        _lib.call("b200_exchange_by_range", self._h, both._h, _i32(idx), ctypes.c_int32(len(idx)), boundaries._h, _u8(list(descending)),
+                  ctypes.byref(out))
+        return RecordBatch._wrap(out).select_columns(list(range(batch.num_columns())))
+
+    def sort(self, batch, sort_keys: Sequence, descending=None, nulls_first=None, sample_size: int = 20):
+        """Distributed sort (src/daft-distributed/src/pipeline_node/sort.rs): every rank samples `sample_size` rows of the sort
+        keys (sample_size_for_sort = 20), the samples are gathered and sorted, RecordBatch::quantiles picks world - 1
+        boundaries, the rows are range-exchanged and each rank sorts its range: rank order == global order."""
+        from .recordbatch import RecordBatch
+        desc, nf = RecordBatch._sort_flags(sort_keys, descending, nulls_first)
+        keys = batch.eval_expression_list([e.alias(f"__sk{i}") for i, e in enumerate(sort_keys)])
+        n = len(keys)
+        step = max(n // max(sample_size, 1), 1)
+        sample = keys.take(pa.array(list(range(0, n, step))[:sample_size], type=pa.int64()))
+        from .expressions import col
+        kcols = [col(f"__sk{i}") for i in range(len(sort_keys))]
+        gathered = self.all_gather(sample).sort(kcols, desc, nf)
+        boundaries = gathered.quantiles(self.world)
+        if len(boundaries) != self.world - 1:   # no sampled rows at all (every rank is empty or nearly so)
+            return self._sort_fallback(batch, sort_keys, desc, nf)
+        both = batch.union(keys)
+        moved = self.exchange_by_range(both, kcols, boundaries, desc)
+        return moved.sort(kcols, desc, nf).select_columns(list(range(batch.num_columns())))
+
+    def _sort_fallback(self, batch, sort_keys, desc, nf):
+        """Tiny inputs: gather everything and keep this rank's contiguous share of the sorted rows."""
+        allb = self.all_gather(batch).sort(sort_keys, desc, nf)
+        b, e = shard_rows(len(allb), self.rank, self.world)
+        return allb.slice(b, e)
+
     def agg(self, batch, to_agg: Sequence, group_by: Sequence | None = None, predicate: Sequence | None = None):
         """HashAggregate over one scan partition per rank; every rank returns the global result.
         Low-cardinality results take ONE stage: the per-GPU group tables are all-reduced over NVLink

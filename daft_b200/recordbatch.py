@@ -377,6 +377,27 @@ class RecordBatch:
         keep = list(range(self.num_columns()))
         return [RecordBatch._wrap(ctypes.c_void_p(h)).select_columns(keep) for h in outs]
 
+    def partition_by_random(self, num_partitions: int, seed: int) -> list["RecordBatch"]:
+        """RecordBatch::partition_by_random (src/daft-recordbatch/src/ops/partition.rs:72-86): deterministic per (seed, input)."""
+        if not isinstance(num_partitions, int):
+            raise TypeError(f"Expected a num_partitions to be int, got {type(num_partitions)}")
+        if not isinstance(seed, int):
+            raise TypeError(f"Expected a seed to be int, got {type(seed)}")
+        if num_partitions <= 0:
+            raise ValueError("Can not partition a Table by 0 partitions" if num_partitions == 0 else "num_partitions must be positive")
+        outs = (ctypes.c_void_p * num_partitions)()
+        _lib.call("b200_partition_by_random", self._h, ctypes.c_int32(num_partitions), ctypes.c_uint64(seed & (2**64 - 1)), outs)
+        return [RecordBatch._wrap(ctypes.c_void_p(h), like=self) for h in outs]
+
+    def quantiles(self, num: int) -> "RecordBatch":
+        """RecordBatch::quantiles (src/daft-recordbatch/src/lib.rs:491-513): rows floor(i / num * len), i = 1..num-1 -- the range
+        boundaries of a distributed sort when `self` is the sorted sample."""
+        n = len(self)
+        if n == 0:
+            return self
+        pts = [min(int((i / num) * n), n - 1) for i in range(1, num)] if num > 0 else []
+        return self.take(pa.array(pts, type=pa.int64()))
+
     def search_sorted(self, keys: "RecordBatch", descending: Sequence[bool] | bool = False) -> "RecordBatch":
         """RecordBatch::search_sorted (src/daft-recordbatch/src/ops/search_sorted.rs:13-36): self is the sorted table."""
         if self.dtypes() != keys.dtypes():

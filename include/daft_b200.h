@@ -189,6 +189,10 @@ int b200_hash_rows(const b200_batch *batch, const int32_t *key_cols, int32_t nke
 int b200_partition_by_hash(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys,
                            int32_t num_partitions, b200_batch **out, char **errmsg);
 
+/* RepartitionSpec::Random (RecordBatch::partition_by_random, src/daft-recordbatch/src/ops/partition.rs:72-86): out[0..P), rows
+ * placed by a seeded counter-based generator; input order kept inside a partition.  Deterministic per (seed, input); the
+ * placement is NOT rand::StdRng's (the reference's tests pin conservation and determinism only). */
+int b200_partition_by_random(const b200_batch *batch, int32_t num_partitions, uint64_t seed, b200_batch **out, char **errmsg);
 /* a12 RepartitionSpec::Range: positions[i] = rows of `sorted` (exactly the key columns, ascending / descending per flag,
  * nulls first where descending) that compare <= key row i (RecordBatch::search_sorted,
  * src/daft-recordbatch/src/ops/search_sorted.rs:13-36; src/daft-core/src/kernels/search_sorted.rs:363-433) -> UInt64 column "idx" */
@@ -275,6 +279,12 @@ void b200_comm_free(b200_comm *c);
 /* hash-partition `batch` into `world` pieces and all-to-all them; out = this rank's piece. */
 int b200_exchange_by_hash(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys,
                           b200_batch **out, char **errmsg);
+/* RepartitionSpec::Random / ::Range over the communicator (src/daft-local-execution/src/sinks/repartition.rs:166-184).  Range:
+ * `boundaries` holds world - 1 rows of the key columns (RecordBatch::quantiles of the gathered samples,
+ * src/daft-distributed/src/pipeline_node/sort.rs:153-188); rank r receives the rows whose search_sorted position is r. */
+int b200_exchange_random(b200_comm *c, const b200_batch *batch, uint64_t seed, b200_batch **out, char **errmsg);
+int b200_exchange_by_range(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys,
+                           const b200_batch *boundaries, const uint8_t *descending, b200_batch **out, char **errmsg);
 /* Low-cardinality HashAggregate over one scan partition per rank (the reference's partial aggregate -> gather -> final
  * aggregate, src/daft-distributed/src/pipeline_node/aggregate.rs:281-340, as ONE stage): every rank runs b200_agg's
  * kernel, the group tables are all-reduced over NVLink (one grouped NCCL launch), and every rank finishes with the global

@@ -71,6 +71,23 @@ def main():
     pred, gb, q1aggs = tpch.q1_exprs()
     want = oracle_agg(tpch.generate_host("lineitem", 0.1, tpch.Q1_COLUMNS), q1aggs, gb, pred).sort_by([("L_RETURNFLAG", "ascending"), ("L_LINESTATUS", "ascending")])
     assert_tables_equal(q1, want, float_rtol=1e-9)
+    # RepartitionSpec::Random and ::Range, and the distributed sort built on the range exchange
+    rnd = comm.exchange_random(rb, 7).to_arrow_table()
+    cnt = torch.tensor([rnd.num_rows], device="cuda")
+    dist.all_reduce(cnt)
+    assert int(cnt.item()) == sum(20000 + 1000 * r for r in range(world))
+    allr = [None] * world
+    dist.all_gather_object(allr, sorted(rnd.column("i64").to_pylist(), key=lambda v: (v is None, v)))
+    assert sorted((v for part_ in allr for v in part_), key=lambda v: (v is None, v)) == sorted(full.column("i64").to_pylist(), key=lambda v: (v is None, v))
+    for keys, desc in ((["i64"], [False]), (["s", "i32"], [True, False])):
+        srt = comm.sort(rb, [col(k) for k in keys], descending=desc).to_arrow_table()
+        pieces = [None] * world
+        dist.all_gather_object(pieces, distributed._to_ipc(srt))
+        got_all = pa.concat_tables([distributed._from_ipc(p) for p in pieces])
+        want_all = full.take(pa.array(O.argsort([full.column(k) for k in keys], desc, desc), type=pa.int64()))
+        assert got_all.num_rows == want_all.num_rows
+        for k in keys:   # rank order == global order on the sort keys (ties between equal keys are free)
+            assert got_all.column(k).to_pylist() == want_all.column(k).to_pylist(), k
     dist.barrier()
     if rank == 0:
         print(f"exchange ok on {world} GPUs")

@@ -146,3 +146,33 @@ def test_direct_address_table_equals_bucket_table(gpu, how, key_type, monkeypatc
         monkeypatch.setenv("B200_JOIN_DIRECT", direct)
         got = gpu.RecordBatch.from_arrow_table(left).hash_join(gpu.RecordBatch.from_arrow_table(right), [c("k")], [c("k")], how=how).to_arrow_table()
         assert_tables_equal(got, want)
+
+
+@pytest.mark.parametrize("size,k", [(0, 3), (4, 3), (10, 1), (33, 10), (5000, 7), (100000, 300)])
+def test_partition_by_random_conserves_rows_and_is_deterministic(gpu, size, k):
+    """tests/recordbatch/test_partitioning.py:124-147,199-214: k partitions, every row exactly once, same split for the same seed."""
+    tbl = pa.table({"x": pa.array(np.arange(size, dtype=np.int64)), "s": pa.array([f"r{i}" for i in range(size)], type=pa.large_utf8())})
+    rb = RB(gpu, tbl)
+    parts = rb.partition_by_random(k, 0)
+    assert len(parts) == k and sum(len(p) for p in parts) == size
+    seen = [v for p in parts for v in p.to_pydict()["x"]]
+    assert sorted(seen) == list(range(size))
+    for p in parts:
+        d = p.to_pydict()
+        assert d["x"] == sorted(d["x"]) and d["s"] == [f"r{i}" for i in d["x"]]      # input order kept, rows intact
+    again = rb.partition_by_random(k, 0)
+    assert all(a.to_pydict() == b.to_pydict() for a, b in zip(parts, again))
+    if size >= 5000:
+        other = rb.partition_by_random(k, 1)
+        assert any(a.to_pydict() != b.to_pydict() for a, b in zip(parts, other))
+        assert max(len(p) for p in parts) < 3 * size / k + 50
+    with pytest.raises(ValueError):
+        rb.partition_by_random(0, 0)
+
+
+def test_quantiles_match_the_reference_rule(gpu):
+    """RecordBatch::quantiles (src/daft-recordbatch/src/lib.rs:491-513): rows floor(i / num * len) for i in 1..num."""
+    tbl = pa.table({"v": pa.array(np.arange(103, dtype=np.int64))})
+    for num in (1, 2, 4, 8, 200):
+        want = [min(int((i / num) * 103), 102) for i in range(1, num)]
+        assert RB(gpu, tbl).quantiles(num).to_pydict()["v"] == want
