@@ -518,15 +518,27 @@ def run_q5(args, stream, barrier, peak, peak_src):
         # (120 M x (8 B row id + 8 B key)), O_CUSTKEY / N_NATIONKEY hashes of the last join (18 M x 8 B)
         roof.update({"kernel": "probe_kernel<*, count> (all three big joins)", "kernel_ms": pc["ms"] / steps,
                      "algorithmic_bytes_per_launch": n_li * 8, "achieved": None, "frac": None})
-    # ---- e2e: host tables (pinned), H2D of all six tables + D2H of the answer inside the timed region
-    host = {t: tpch.generate_host(t, sf, cols) for t, cols in tpch.Q5_COLUMNS.items()}
-    pinned, keep, h2d = {}, [], 0
-    for t, tb in host.items():
-        p, nb, k = pinned_table(tb)
-        pinned[t] = p
-        keep.append(k)
-        h2d += nb
-    del host
+    # ---- host tables: generated once by the CPU engine's generator (the same values as the device generator,
+    # tests/test_cpu_engine.py), page-locked in place, used by the e2e leg AND by the CPU baseline / answer check
+    from oracle import cpu_engine as CE
+    sf_cpu = q5_cpu_sf(sf) if not args.no_cpu_baseline else sf
+    cols = {t: CE.generate_columns(t, sf, c) for t, c in CE.Q5_COLUMNS.items()}
+    rt = torch.cuda.cudart()
+    pinned, h2d, registered = {}, 0, []
+    for t, names in tpch.Q5_COLUMNS.items():
+        if t in cols:
+            arrays = []
+            for c in names:
+                a = cols[t][c][0]
+                if rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0) == 0:
+                    registered.append(a)
+                typ = pa.date32() if a.dtype == np.int32 else (pa.float64() if a.dtype == np.float64 else pa.int64())
+                arrays.append(pa.Array.from_buffers(typ, len(a), [None, pa.py_buffer(a)]))
+                h2d += a.nbytes
+            pinned[t] = pa.table(arrays, names=names)
+        else:
+            pinned[t] = tpch.generate_host(t, sf, names)  # nation, region: a few rows
+            h2d += pinned[t].nbytes
 
     def step_e2e():
         return tpch.q5({t: daft_b200.RecordBatch.from_arrow_table(p) for t, p in pinned.items()}).to_arrow_table()
@@ -534,22 +546,28 @@ def run_q5(args, stream, barrier, peak, peak_src):
     e2e_steps = max(2, min(args.e2e_steps, 5))
     ms_e2e, out = time_steps(step_e2e, e2e_steps, 1, stream, barrier)
     ms_e2e /= e2e_steps
-    del pinned, keep
+    for a in registered:
+        rt.cudaHostUnregister(a.ctypes.data)
     # ---- CPU engine on the same tables: the answer check and the cpu_baseline
     cpu, checks = None, {}
+    checks["q5_e2e_equals_value_leg"] = check_answer(out, result, ["N_NAME"], "q5 e2e vs value")
     if not args.no_cpu_baseline:
-        sf_cpu = q5_cpu_sf(sf)
-        q = cpu_q5_run(sf_cpu, 2, 1)
+        if sf_cpu != sf:   # host RAM too small to run the CPU engine next to the pinned tables: a bounded sample instead
+            del cols, pinned
+            cols = {t: CE.generate_columns(t, sf_cpu, c) for t, c in CE.Q5_COLUMNS.items()}
+        ans, tasks, probes = CE.q5(cols, 0)   # warm-up
+        t0 = time.perf_counter()
+        ans, tasks, probes = CE.q5(cols, 0)
+        dt = time.perf_counter() - t0
+        n_cpu = len(cols["lineitem"]["L_ORDERKEY"][0])
+        threads = os.cpu_count() or 1
         if sf_cpu == sf:
-            checks["q5_answer_vs_cpu_engine"] = check_answer(result, q["answer"], ["N_NAME"], "q5 value leg")
-            checks["q5_e2e_answer_vs_cpu_engine"] = check_answer(out, q["answer"], ["N_NAME"], "q5 e2e leg")
-        else:  # host RAM too small for the full tables: check the GPU path at the CPU engine's scale factor instead
-            small = tpch.q5({t: tpch.generate(t, sf_cpu, cols) for t, cols in tpch.Q5_COLUMNS.items()}).to_arrow_table()
-            checks[f"q5_sf{sf_cpu:g}_answer_vs_cpu_engine"] = check_answer(small, q["answer"], ["N_NAME"], "q5 reduced")
-            checks["q5_e2e_equals_value_leg"] = check_answer(out, result, ["N_NAME"], "q5 e2e vs value")
-        cpu = {"value": q["rows_per_s"], "unit": UNIT, "cores": q["threads"], "kind": "port", "tasks_per_step": q["tasks"],
-               "probe_rows_per_s": q["probe_rows_per_s"],
-               "sample": f"SF{sf_cpu:g} ({q['rows']} lineitem rows) per step, {q['steps']} steps, {q['ms_per_step']:.0f} ms/step, all {q['threads']} host threads",
+            checks["q5_answer_vs_cpu_engine"] = check_answer(result, ans, ["N_NAME"], "q5 value leg")
+        else:
+            small = tpch.q5({t: tpch.generate(t, sf_cpu, c) for t, c in tpch.Q5_COLUMNS.items()}).to_arrow_table()
+            checks[f"q5_sf{sf_cpu:g}_answer_vs_cpu_engine"] = check_answer(small, ans, ["N_NAME"], "q5 reduced")
+        cpu = {"value": n_cpu / dt, "unit": UNIT, "cores": threads, "kind": "port", "tasks_per_step": tasks, "probe_rows_per_s": probes / dt,
+               "sample": f"SF{sf_cpu:g} ({n_cpu} lineitem rows), 1 step after 1 warm-up, {dt * 1e3:.0f} ms/step, all {threads} host threads",
                "note": CPU_NOTE}
     return {"metric": "tpch_q5_join_pipeline_lineitem_rows_per_sec", "value": n_li / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "config": dict(q5_config(sf), rows=rows, compulsory_input_bytes=alg_bytes),

@@ -157,6 +157,8 @@ int b200_jit_describe(int32_t op, const uint8_t *plan, size_t plan_len, const in
             t += "\nnancells=";  // per aggregate: nan_cell:last_cell (float min / max: the NaN-forgetting fold, jit.h AggOut)
             for (size_t i = 0; i < meta.aggs.size(); i++)
                 t += (i ? "," : "") + std::to_string(meta.aggs[i].nan_cell) + ":" + std::to_string(meta.aggs[i].last_cell);
+            t += "\nfirstvalid=";  // per aggregate: any_value(ignore_nulls) over a nullable child keeps the first valid row here
+            for (size_t i = 0; i < meta.aggs.size(); i++) t += (i ? "," : "") + std::to_string(meta.aggs[i].first_valid_cell);
             t += "\ncellops=";
             for (size_t i = 0; i < meta.lane_cell_ops.size(); i++) t += (i ? "," : "") + std::to_string(meta.lane_cell_ops[i]);
             static const char *hex = "0123456789abcdef";

@@ -49,6 +49,7 @@ struct DevAlloc {
     void *ptr = nullptr;
     size_t bytes = 0;
     bool owned = true;
+    size_t cached_bytes = 0;  // > 0: the block belongs to the size-class cache (its rounded size), see runtime.cu
     ~DevAlloc();
 };
 using Buf = std::shared_ptr<DevAlloc>;

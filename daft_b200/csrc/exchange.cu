@@ -365,7 +365,7 @@ static Batch *route_batch(b200_comm *c, const Batch &src, const Route &rows, con
 static Batch *exchange_peer_store(b200_comm *c, const Batch &b, const uint64_t *hashes) {
     const int W = c->world;
     const char *env = getenv("B200_EXCHANGE_P2P");
-    if ((env && *env == '0') || c->p2p_state < 0 || W > 8 || W < 2) return nullptr;
+    if ((env && *env == '0') || c->p2p_state < 0 || W > 8 || W < 2) return nullptr;  // B200_EXCHANGE_P2P=0: NCCL route only
     cudaStream_t st = ctx().stream;
     // columns the kernel can place itself: fixed width, no nulls ON ANY RANK (decided from the gathered null counts)
     PartitionPlan pl = partition_count(hashes, b.num_rows, W);

@@ -864,7 +864,8 @@ static std::string ord_of(int32_t dt, const std::string &v) {
 }
 
 // flavor: 0 = the value itself; 1 = float min / max candidate (NaN values are skipped); 2 = 1 + row of the last NaN value;
-// 3 = 1 + row of the last valid value (2 and 3 are C_MAX cells over the row number)
+// 3 = 1 + row of the last valid value (2 and 3 are C_MAX cells over the row number); 4 = first row with a valid value (C_MIN
+// over the row number: any_value(ignore_nulls))
 struct LaneCell { int op; std::string child_key; int val_slot; int32_t val_dtype; int flavor; };
 struct WarpCell { std::string cond_key; int val_slot; bool count_nulls; };
 
@@ -993,9 +994,12 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
                 // Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the child at the group's first row; with
                 // ignore_nulls the first NON-NULL row, which needs its own per-group row cell -- only offered where it is the
                 // same thing (children that cannot be null)
-                if (a.mode == 1 && c.nullable) fail("agg: any_value(ignore_nulls=true) over a nullable input is not supported on the device");
                 o.out_dtype = c.dtype;
                 o.proj_index = anyval_seen++;
+                if (a.mode == 1 && c.nullable && c.dtype != B200_NULL) {  // the first NON-NULL row of the group: its own row cell
+                    const int vs = val_slot(a.root, c.dtype);
+                    o.first_valid_cell = lane_cell(C_MIN, vs, 4);
+                }
                 break;
             }
             default: fail("agg: unsupported aggregation kind " + std::to_string(a.kind));
@@ -1358,7 +1362,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         const std::string vk = lc.flavor == 1 ? "(" + vk0 + " && !" + is_nan + ")" : lc.flavor == 2 ? "(" + vk0 + " && " + is_nan + ")" : vk0;
         const std::string row_ord = "(unsigned long long)(row + 1)";
         const std::string gp = "((unsigned long long*)" + std::string("p.ptr[") + std::to_string(p_acc[c]) + "]) + slot";
-        const std::string ordv = lc.flavor >= 2 ? row_ord : ord_of(lc.val_dtype, val);
+        const std::string ordv = lc.flavor == 4 ? "(unsigned long long)row" : lc.flavor >= 2 ? row_ord : ord_of(lc.val_dtype, val);
         {   // tier-2 cell c of slot t lives at t2c[c * T2 + t]
             const std::string sp = "(t2c + " + std::to_string(c) + " * T2 + t)";
             const std::string sv = "t2c[" + std::to_string(c) + " * T2 + t]";
@@ -1827,6 +1831,10 @@ static void precompile_one(int op, const uint8_t *plan, size_t plan_len, const s
         Compiled cg3;  // and the TMA-staged build of the low-cardinality kernel (when the plan qualifies)
         const std::string src3 = generate(op, plan, plan_len, col_dtypes, col_nullable, false, cg3, 2);
         if (cg3.stage_bytes > 0) compile_to_cubin(src3, nullptr);
+        if (c.has_nan_fold) {  // the float min / max fix-up pass (variant 3)
+            Compiled cg4;
+            compile_to_cubin(generate(op, plan, plan_len, col_dtypes, col_nullable, false, cg4, 3), nullptr);
+        }
     }
     if (op == B200_OP_AGG && !c.anyval_project_plan.empty()) {
         Compiled c3;

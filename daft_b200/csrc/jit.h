@@ -45,6 +45,8 @@ struct AggOut {
     // and NaN when the last valid value is one.  lane_cell then folds the non-NaN values only, nan_cell = 1 + row of the
     // group's last NaN (0: none), last_cell = 1 + row of its last valid value.
     int nan_cell = -1, last_cell = -1;
+    // any_value(ignore_nulls) over a nullable child: the cell holds the group's first row whose child is valid (all ones: none)
+    int first_valid_cell = -1;
 };
 
 struct Compiled {

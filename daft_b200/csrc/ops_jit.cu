@@ -322,6 +322,14 @@ __global__ void gather_u64(const unsigned long long *__restrict__ src, const int
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = src[idx[i]];
 }
+// take indices from a "first row" cell: all ones (no such row) -> -1 (a null row)
+__global__ void cell_to_take(const unsigned long long *__restrict__ cell, const int64_t *__restrict__ slots, int64_t n, int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned long long r = cell[slots[i]];
+        out[i] = r == ~0ULL ? -1 : (int64_t)r;
+    }
+}
 
 struct FinalizeDesc {
     int kind, val_dtype, out_dtype, cnt_is_valid_count, const_zero, _pad;
@@ -713,7 +721,15 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         c.dtype = ag.out_dtype;
         c.length = ng;
         if (ag.kind == jit::AGG_ANY_VALUE) {
-            if (anyval) {
+            if (anyval && ag.first_valid_cell >= 0 && ng > 0) {
+                // ignore_nulls: the child at the group's first row where it is valid (Series::any_value, series/ops/agg.rs:353-382)
+                Buf idx = dev_alloc((size_t)ng * 8);
+                cell_to_take<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(cell_ptr(ag.first_valid_cell), as<int64_t>(slots), ng, as<int64_t>(idx));
+                count_launch();
+                std::unique_ptr<Batch> av(op_project(in, k.anyval_project_plan.data(), k.anyval_project_plan.size(), as<int64_t>(idx), ng, false));
+                c = av->cols[ag.proj_index];
+                c.name = ag.name;
+            } else if (anyval) {
                 c = anyval->cols[ag.proj_index];
                 c.name = ag.name;
             } else {  // no rows at all (ungrouped aggregate over an empty input): null

@@ -1,6 +1,7 @@
 // Library context, stream-ordered device memory, and the small fixed-function kernels every
 // operator leans on: exclusive scan, bit counting, row gather (take), slice, concat.
 #include <chrono>
+#include <map>
 #include <mutex>
 
 #include "common.h"
@@ -99,8 +100,57 @@ const char *dtype_name(int32_t dt) {
     return (dt >= 0 && dt < 16) ? names[dt] : "?";
 }
 
+// ---- device memory ---------------------------------------------------------------------------------------------
+// Small blocks come straight from the stream-ordered pool (cudaMallocAsync).  Blocks of 1 MB and more go through a
+// size-class cache in front of it: a freed block is parked in the bin of its (rounded) size and handed to the next
+// request of that class.  Everything this library does is ordered on ONE stream, so a parked block may be reused at
+// once -- the next user's kernels queue behind the previous user's.  Without the cache a repeated multi-GB pattern
+// (join tables, selection vectors) makes the CUDA pool re-map physical memory every few iterations: 40 ms stalls on a
+// 10 ms query.  Cached bytes are capped; a failed allocation empties the cache and retries.
+namespace {
+constexpr size_t kCacheMin = (size_t)1 << 20;
+std::mutex g_cache_mu;
+std::map<size_t, std::vector<void *>> g_cache;  // rounded size -> parked blocks
+size_t g_cached_bytes = 0;
+size_t cache_limit() {
+    static const size_t lim = [] {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (size_t)16 << 30;
+        return total_b / 2;
+    }();
+    return lim;
+}
+// size classes: 8 steps per power of two (<= 12.5 % slack)
+size_t size_class(size_t bytes) {
+    size_t p = kCacheMin;
+    while (p < bytes) p <<= 1;
+    const size_t step = p >> 4;  // p / 16: classes at p/2 + k * p/16
+    const size_t lo = p >> 1;
+    if (bytes <= lo) return lo;
+    return lo + (bytes - lo + step - 1) / step * step;
+}
+void cache_trim_locked(size_t keep) {
+    while (g_cached_bytes > keep && !g_cache.empty()) {
+        auto it = std::prev(g_cache.end());  // largest class first
+        void *p = it->second.back();
+        it->second.pop_back();
+        g_cached_bytes -= it->first;
+        if (it->second.empty()) g_cache.erase(it);
+        cudaFreeAsync(p, ctx().stream);
+    }
+}
+}  // namespace
+
 DevAlloc::~DevAlloc() {
-    if (owned && ptr) cudaFreeAsync(ptr, ctx().stream);
+    if (!owned || !ptr) return;
+    if (cached_bytes) {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        g_cache[cached_bytes].push_back(ptr);
+        g_cached_bytes += cached_bytes;
+        if (g_cached_bytes > cache_limit()) cache_trim_locked(cache_limit() / 2);
+        return;
+    }
+    cudaFreeAsync(ptr, ctx().stream);
 }
 
 Buf dev_alloc(size_t bytes) {
@@ -108,15 +158,39 @@ Buf dev_alloc(size_t bytes) {
     auto a = std::make_shared<DevAlloc>();
     a->bytes = bytes;
     // +16 B slack: word-granular readers (unaligned string loads, bitmap words) may touch the tail
+    const size_t want = bytes + 16;
     static const bool trace = [] { const char *e = getenv("B200_TRACE_ALLOC"); return e && *e == '1'; }();
+    static const bool use_cache = [] { const char *e = getenv("B200_ALLOC_CACHE"); return !(e && *e == '0'); }();
+    size_t cls = 0;
+    if (use_cache && want >= kCacheMin) {
+        cls = size_class(want);
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        auto it = g_cache.find(cls);
+        if (it != g_cache.end() && !it->second.empty()) {
+            a->ptr = it->second.back();
+            it->second.pop_back();
+            if (it->second.empty()) g_cache.erase(it);
+            g_cached_bytes -= cls;
+            a->cached_bytes = cls;
+            return a;
+        }
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaError_t e = cudaMallocAsync(&a->ptr, cls ? cls : want, ctx().stream);
+    if (e != cudaSuccess) {  // give the parked blocks back and try once more
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> g(g_cache_mu);
+            cache_trim_locked(0);
+        }
+        B200_CUDA(cudaStreamSynchronize(ctx().stream));
+        B200_CUDA(cudaMallocAsync(&a->ptr, cls ? cls : want, ctx().stream));
+    }
+    a->cached_bytes = cls;
     if (trace) {
-        const auto t0 = std::chrono::steady_clock::now();
-        B200_CUDA(cudaMallocAsync(&a->ptr, bytes + 16, ctx().stream));
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (ms > 0.5) fprintf(stderr, "[b200 alloc] %.1f MB took %.2f ms\n", bytes / 1e6, ms);
-        return a;
     }
-    B200_CUDA(cudaMallocAsync(&a->ptr, bytes + 16, ctx().stream));
     return a;
 }
 Buf dev_alloc_zero(size_t bytes) {

@@ -246,7 +246,7 @@ def emulate_project(tbl: pa.Table, exprs, take=None) -> pa.Table:
 P_SLOT_HASH, P_ACC, P_OVERFLOW = 8, 10, 11
 I_MASK, I_RSTRIDE = 1, 2
 C_ADD_F64, C_ADD_F32, C_ADD_I64, C_MIN, C_MAX = 0, 1, 2, 3, 4
-AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_MEAN = 0, 1, 2, 3, 4
+AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_MEAN, AGG_ANY_VALUE = 0, 1, 2, 3, 4, 5
 
 _AGG_SHIM = r"""
 #include <unordered_map>
@@ -431,6 +431,8 @@ def describe_agg(plan: bytes, dtypes, nullable, variant: int = 0):
                          child_nullable=cn == "1", const_zero=cz == "1", name=name))
     for a, pair in zip(aggs, f.get("nancells", "").split(",")):   # float min / max: the NaN-forgetting fold (jit.h AggOut::nan_cell)
         a["nan_cell"], a["last_cell"] = (int(x) for x in pair.split(":")) if pair else (-1, -1)
+    for a, fv in zip(aggs, f.get("firstvalid", "").split(",")):   # any_value(ignore_nulls): first valid row (jit.h AggOut::first_valid_cell)
+        a["first_valid_cell"] = int(fv) if fv else -1
     return dict(src=src, ptrs=[tuple(map(int, s.split(":"))) for s in f["ptrs"].split(",") if s], ints=[int(s) for s in f["ints"].split(",") if s],
                 nkeys=int(f["nkeys"]), nlane=int(f["nlane"]), nwarp=int(f["nwarp"]), aggs=aggs, cellops=[int(s) for s in f["cellops"].split(",") if s])
 
@@ -490,7 +492,8 @@ def _decode_ord(cells: np.ndarray, code: int) -> np.ndarray:
     return cells.astype(_NP[code])
 
 
-def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = False, tier2: bool = False, tier1: bool = False):
+def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = False, tier2: bool = False, tier1: bool = False,
+                takes_out: dict | None = None):
     """(aggregate columns in first-occurrence group order, first row of every group) through the generated aggregate code.
     staged=True runs the TMA-staged build of an ungrouped plan: full tiles go through stage_issue / load_staged."""
     from daft_b200.expressions import encode_agg
@@ -551,6 +554,13 @@ def emulate_agg(tbl: pa.Table, aggs, group_by, predicate=None, staged: bool = Fa
         cnt = (acc[nl + a["cnt_cell"], :ng] if a["cnt_cell"] >= 0 else nrows)[order]
         cell = acc[a["lane_cell"], :ng][order] if a["lane_cell"] >= 0 else None
         typ = dt.to_arrow(a["out_dtype"])
+        if a["kind"] == AGG_ANY_VALUE:
+            # no output column here: the caller gathers the child at these rows (ops_jit.cu cell_to_take; all ones = no valid row)
+            if takes_out is not None:
+                fv = a.get("first_valid_cell", -1)
+                r = acc[fv, :ng][order] if fv >= 0 else minrow[order]
+                takes_out[a["name"]] = np.where(r == np.uint64(0xFFFFFFFFFFFFFFFF), -1, r.astype(np.int64)).astype(np.int64)
+            continue
         if a["kind"] == AGG_COUNT:
             arr = pa.array(np.zeros(ng, np.uint64) if a["const_zero"] else cnt, type=pa.uint64())
         else:

@@ -227,9 +227,12 @@ def test_any_value_and_bool_aggs(gpu, n):
         got = RB(gpu, tbl).agg(aggs, [c(k) for k in keys], predicate=pred).to_arrow_table()
         want = oracle_agg(tbl, aggs, [c(k) for k in keys], pred)
         assert_tables_equal(got, want)
-    if tbl.column("i32").null_count > 0:  # first NON-NULL row of a nullable input is not offered on the device
-        with pytest.raises(gpu.B200Error, match="ignore_nulls"):
-            RB(gpu, tbl).agg([c("i32").any_value(ignore_nulls=True).alias("x")], [c("u8")])
+    # ignore_nulls over nullable inputs: the child at the group's first row where it is valid, null for an all-null group
+    ign = [c("i32").any_value(ignore_nulls=True).alias("x"), c("s").any_value(ignore_nulls=True).alias("xs"),
+           c("f64").any_value(ignore_nulls=True).alias("xf"), c("b").any_value(ignore_nulls=True).alias("xb"), c("i32").any_value().alias("first")]
+    for keys in ([], ["u8"], ["s"]):
+        got = RB(gpu, tbl).agg(ign, [c(k) for k in keys]).to_arrow_table()
+        assert_tables_equal(got, oracle_agg(tbl, ign, [c(k) for k in keys]))
 
 
 @pytest.mark.parametrize("n", [1, 2, 3000, 120_000])

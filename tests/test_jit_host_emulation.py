@@ -71,13 +71,16 @@ class _EmulatedBatch:
         from daft_b200.expressions import encode_agg
         jit_emu.describe_agg(encode_agg(aggs, group_by, names, dts, predicate), dts, [1 if self._t.column(n).null_count else 0 for n in names])
         anyv = [a for a in aggs if inner(a).op == "any_value"]
+        ign = [a for a in anyv if inner(a).value == "ignore_nulls"]   # these keep a "first valid row" cell in the aggregate kernel
         plain = [a for a in aggs if inner(a).op != "any_value"] or [col(self._t.column_names[0]).count("all").alias("__rows")]
-        cols, first = jit_emu.emulate_agg(self._t, plain, group_by, predicate, **self.AGG_MODE)
+        takes = {}
+        cols, first = jit_emu.emulate_agg(self._t, plain + ign, group_by, predicate, takes_out=takes, **self.AGG_MODE)
         out = {n: cols.column(n) for n in cols.column_names}
-        if anyv:   # any_value = the child expression at the group's first row: one gathering projection (op_agg_first_rows)
-            at_first = jit_emu.emulate_project(self._t, [inner(a).args[0].alias(a.name()) for a in anyv], take=first) if self._t.num_rows else \
-                pa.table({a.name(): pa.nulls(len(first)) for a in anyv})
-            out.update({n: at_first.column(n) for n in at_first.column_names})
+        for a in anyv:   # any_value = the child expression at the group's first (valid) row: a gathering projection (op_agg_first_rows)
+            take = takes.get(a.name(), first)
+            at = jit_emu.emulate_project(self._t, [inner(a).args[0].alias(a.name())], take=take) if self._t.num_rows else \
+                pa.table({a.name(): pa.nulls(len(first))})
+            out[a.name()] = at.column(a.name())
         ordered = [out[a.name()] for a in aggs]
         names = [a.name() for a in aggs]
         if not group_by:
