@@ -490,7 +490,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         while (cap < 2 * n) cap <<= 1;
     }
     if (coll) {
-        cap = kp->nkeys > 0 ? (1 << 13) : 1;  // the same table shape on every rank, whatever its row count
+        cap = kp->nkeys > 0 ? (1 << 11) : 1;  // the same (small: it is all-reduced) table shape on every rank, whatever its row count
         for (const auto &ag : kp->aggs)
             if (ag.kind == jit::AGG_ANY_VALUE) return nullptr;  // a first-row value is per rank: two-stage plan
         for (int op : kp->lane_cell_ops)

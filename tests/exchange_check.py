@@ -56,7 +56,7 @@ def main():
     # distributed low-cardinality aggregate: the group tables all-reduced (b200_agg_allreduce) == single-table oracle;
     # plans the table merge cannot carry (any_value, float min / max folds, high cardinality) take the two-stage rewrite
     from daft_b200 import tpch
-    aggs = [col("i64").sum().alias("s"), col("f64").mean().alias("m"), col("i32").count("null").alias("cn"), col("u16").min().alias("lo"),
+    aggs = [col("i64").sum().alias("sm"), col("f64").mean().alias("m"), col("i32").count("null").alias("cn"), col("u16").min().alias("lo"),
             col("i64").max().alias("hi"), col("i8").mean().alias("m8")]
     for gb, pred in (([col("k")], None), ([col("b"), col("u8")], [col("i32") > 0]), ([], None), ([col("s")], None), ([col("i32")], None)):
         got = comm.agg(rb, aggs, gb, pred).to_arrow_table()
