@@ -40,6 +40,13 @@ Batch plain(const b200_batch *b, const std::vector<int32_t> *cols = nullptr) {
     if (!b) fail("null batch");
     return materialize_batch(*b, cols);
 }
+// operators that move whole rows between buffers (partition, exchange, filter compaction) handle flat columns only
+Batch flat(const b200_batch *b, const char *what) {
+    Batch p = plain(b);
+    for (const Column &c : p.cols)
+        if (c.dtype == B200_LIST) fail(std::string(what) + ": list columns are not supported (column '" + c.name + "')");
+    return p;
+}
 Batch plain_keys(const b200_batch *b, const int32_t *key_cols, int32_t nkeys) {
     if (!b) fail("null batch");
     std::vector<int32_t> k(key_cols, key_cols + (nkeys > 0 ? nkeys : 0));
@@ -216,7 +223,10 @@ int b200_batch_dtypes(const b200_batch *batch, int32_t *out_dtypes, int32_t n, c
     return guard(errmsg, [&] {
         if (!batch || !out_dtypes) fail("null argument");
         if (n < 0 || n > (int32_t)batch->cols.size()) fail("dtypes: column count out of range");
-        for (int32_t i = 0; i < n; i++) out_dtypes[i] = batch->cols[i].dtype;
+        for (int32_t i = 0; i < n; i++) {
+            const Column &c = batch->cols[i];
+            out_dtypes[i] = c.dtype == B200_LIST && c.child ? (B200_LIST | (c.child->dtype << 8)) : c.dtype;
+        }
     });
 }
 int64_t b200_batch_num_rows(const b200_batch *batch) { return batch ? batch->num_rows : -1; }
@@ -293,14 +303,14 @@ int b200_hash_rows(const b200_batch *batch, const int32_t *key_cols, int32_t nke
 int b200_partition_by_hash(const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, int32_t num_partitions,
                            b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
-        std::vector<Batch *> parts = op_partition_by_hash(plain(batch), key_cols, nkeys, num_partitions);
+        std::vector<Batch *> parts = op_partition_by_hash(flat(batch, "partition_by_hash"), key_cols, nkeys, num_partitions);
         for (int i = 0; i < num_partitions; i++) out[i] = parts[i];
     });
 }
 
 int b200_partition_by_random(const b200_batch *batch, int32_t num_partitions, uint64_t seed, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
-        std::vector<Batch *> parts = op_partition_by_random(plain(batch), num_partitions, seed);
+        std::vector<Batch *> parts = op_partition_by_random(flat(batch, "partition_by_random"), num_partitions, seed);
         for (int i = 0; i < num_partitions; i++) out[i] = parts[i];
     });
 }
@@ -319,14 +329,14 @@ int b200_partition_by_range(const b200_batch *batch, const int32_t *key_cols, in
                             const uint8_t *descending, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
         if (!batch || !boundaries) fail("null batch");
-        std::vector<Batch *> parts = op_partition_by_range(plain(batch), key_cols, nkeys, plain(boundaries), descending);
+        std::vector<Batch *> parts = op_partition_by_range(flat(batch, "partition_by_range"), key_cols, nkeys, plain(boundaries), descending);
         for (size_t i = 0; i < parts.size(); i++) out[i] = parts[i];
     });
 }
 
 // ---- filter / project / agg -----------------------------------------------------------------------
 int b200_filter(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = op_filter(plain(batch), plan, plan_len); });
+    return guard(errmsg, [&] { *out = op_filter(flat(batch, "filter"), plan, plan_len); });
 }
 int b200_eval_expression_list(const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] { *out = op_project(plain_for_plan(batch, B200_OP_PROJECT, plan, plan_len), plan, plan_len, nullptr, 0); });
@@ -462,14 +472,14 @@ int b200_comm_init(const uint8_t *id128, int32_t rank, int32_t world, b200_comm 
 void b200_comm_free(b200_comm *c) { comm_free(c); }
 int b200_exchange_by_hash(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, b200_batch **out,
                           char **errmsg) {
-    return guard(errmsg, [&] { *out = exchange_by_hash(c, plain(batch), key_cols, nkeys); });
+    return guard(errmsg, [&] { *out = exchange_by_hash(c, flat(batch, "exchange_by_hash"), key_cols, nkeys); });
 }
 int b200_exchange_random(b200_comm *c, const b200_batch *batch, uint64_t seed, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = exchange_random(c, plain(batch), seed); });
+    return guard(errmsg, [&] { *out = exchange_random(c, flat(batch, "exchange_random"), seed); });
 }
 int b200_exchange_by_range(b200_comm *c, const b200_batch *batch, const int32_t *key_cols, int32_t nkeys, const b200_batch *boundaries,
                            const uint8_t *descending, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = exchange_by_range(c, plain(batch), key_cols, nkeys, plain(boundaries), descending); });
+    return guard(errmsg, [&] { *out = exchange_by_range(c, flat(batch, "exchange_by_range"), key_cols, nkeys, plain(boundaries), descending); });
 }
 int b200_agg_allreduce(b200_comm *c, const b200_batch *batch, const uint8_t *plan, size_t plan_len, b200_batch **out, int32_t *merged,
                        char **errmsg) {
@@ -480,7 +490,7 @@ int b200_agg_allreduce(b200_comm *c, const b200_batch *batch, const uint8_t *pla
     });
 }
 int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, char **errmsg) {
-    return guard(errmsg, [&] { *out = all_gather_batches(c, plain(batch)); });
+    return guard(errmsg, [&] { *out = all_gather_batches(c, flat(batch, "all_gather")); });
 }
 
 // ---- TPC-H generator -----------------------------------------------------------------------------------

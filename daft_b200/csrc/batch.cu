@@ -47,6 +47,7 @@ static const char *format_from_dtype(int32_t dt) {
         case B200_TIMESTAMP: return "tsu:";
         case B200_LARGE_UTF8: return "U";
         case B200_LARGE_BINARY: return "Z";
+        case B200_LIST: return "+L";
     }
     return "n";
 }
@@ -214,6 +215,20 @@ static void export_column(const Column &c, ArrowArray *a, ArrowSchema *s) {
         ap->bufptrs.push_back(host_copy(c.data ? c.data->ptr : nullptr, (size_t)n * w, ap));
     } else if (c.dtype == B200_BOOL) {
         ap->bufptrs.push_back(host_copy(c.data ? c.data->ptr : nullptr, (size_t)((n + 7) / 8), ap));
+    } else if (c.dtype == B200_LIST) {  // Arrow large_list: [validity, int64 offsets] + one child ("item")
+        if (!c.child || !c.offsets) fail("export: list column without offsets / child");
+        ap->bufptrs.push_back(host_copy(c.offsets->ptr, (size_t)(n + 1) * 8, ap));
+        auto *ca = static_cast<ArrowArray *>(calloc(1, sizeof(ArrowArray)));
+        auto *cs = static_cast<ArrowSchema *>(calloc(1, sizeof(ArrowSchema)));
+        Column item = *c.child;
+        item.name = "item";
+        export_column(item, ca, cs);
+        ap->children.push_back(ca);
+        sp->schildren.push_back(cs);
+        a->n_children = 1;
+        a->children = ap->children.data();
+        s->n_children = 1;
+        s->children = sp->schildren.data();
     } else {
         if (c.offsets) {
             ap->bufptrs.push_back(host_copy(c.offsets->ptr, (size_t)(n + 1) * 8, ap));
@@ -258,6 +273,7 @@ static bool export_batch_packed(const Batch &b, ArrowArray *out_array, ArrowSche
         const Column &c = b.cols[ci];
         const int64_t n = c.length;
         if (c.dtype == B200_NULL) continue;
+        if (c.dtype == B200_LIST) return false;  // nested: the general path
         if (c.null_count > 0) add((int)ci, 0, c.validity->ptr, (n + 7) / 8);
         const int w = dtype_width(c.dtype);
         if (w) add((int)ci, 1, c.data ? c.data->ptr : nullptr, n * w);

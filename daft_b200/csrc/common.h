@@ -90,8 +90,9 @@ struct Column {
     int64_t length = 0;
     int64_t null_count = 0;  // exact (plain columns)
     Buf validity;            // null when null_count == 0
-    Buf offsets;             // strings
+    Buf offsets;             // strings, lists
     Buf data;
+    std::shared_ptr<const Column> child;  // B200_LIST: the flat child column the offsets index
     int64_t data_bytes = 0;
     // view part (all empty for a plain column)
     std::shared_ptr<const Column> base;  // a plain column

@@ -105,6 +105,7 @@ static int parse_node(Reader &r, Ast &a) {
             nd.col = (int)r.u32();
             if (nd.col < 0 || nd.col >= (int)a.col_dtypes->size()) fail("plan: column index out of range");
             nd.dtype = (*a.col_dtypes)[nd.col];
+            if (nd.dtype == B200_LIST) fail("plan: expressions cannot read list columns");
             nd.nullable = a.nullable(nd.col) || nd.dtype == B200_NULL;
             nd.key = "c" + std::to_string(nd.col);
             break;
@@ -870,8 +871,9 @@ struct LaneCell { int op; std::string child_key; int val_slot; int32_t val_dtype
 struct WarpCell { std::string cond_key; int val_slot; bool count_nulls; };
 
 static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
-    const bool nanfix_variant = variant == 3;  // generated like the global-table build, different kernel body
-    const bool global_variant = variant == 1 || nanfix_variant, staged_variant = variant == 2;
+    const bool nanfix_variant = variant == 3;   // generated like the global-table build, different kernel body
+    const bool rowslot_variant = variant == 4;  // likewise: writes every row's table slot (list / set / concat aggregates)
+    const bool global_variant = variant == 1 || nanfix_variant || rowslot_variant, staged_variant = variant == 2;
     CG cg{ast, meta};
     const bool has_filter = r.u8() != 0;
     int filter_root = -1;
@@ -894,8 +896,9 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     const uint32_t naggs = r.u32();
     struct AggIn { int kind, mode; std::string name; int root; };
     std::vector<AggIn> aggs;
-    uint32_t nanyval = 0;
+    uint32_t nanyval = 0, nlist = 0;
     std::vector<uint8_t> anyval_bytes;  // [name, node] of every any_value child = the entries of a PROJECT plan
+    std::vector<uint8_t> list_bytes;    // likewise for the list / set / concat children
     for (uint32_t i = 0; i < naggs; i++) {
         AggIn a;
         a.kind = r.u8();
@@ -907,12 +910,21 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
             nanyval++;
             anyval_bytes.insert(anyval_bytes.end(), r.p + start, r.p + r.pos);
         }
+        if (is_list_agg(a.kind)) {
+            nlist++;
+            list_bytes.insert(list_bytes.end(), r.p + start, r.p + r.pos);
+        }
         aggs.push_back(a);
     }
     if (nanyval) {
         meta.anyval_project_plan.resize(4);
         memcpy(meta.anyval_project_plan.data(), &nanyval, 4);
         meta.anyval_project_plan.insert(meta.anyval_project_plan.end(), anyval_bytes.begin(), anyval_bytes.end());
+    }
+    if (nlist) {
+        meta.listagg_project_plan.resize(4);
+        memcpy(meta.listagg_project_plan.data(), &nlist, 4);
+        meta.listagg_project_plan.insert(meta.listagg_project_plan.end(), list_bytes.begin(), list_bytes.end());
     }
     if (r.pos != r.n) fail("plan: trailing bytes");
 
@@ -947,7 +959,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         warp_cells.push_back({"", vslot, count_nulls});
         return (int)warp_cells.size() - 1;
     };
-    int anyval_seen = 0;
+    int anyval_seen = 0, list_seen = 0;
     for (auto &a : aggs) {
         const Node &c = ast.nodes[a.root];
         AggOut o;
@@ -1002,6 +1014,17 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
                 }
                 break;
             }
+            case AGG_LIST: case AGG_SET: case AGG_CONCAT: {
+                // grouped_list / grouped_set / grouped_concat (src/daft-core/src/array/ops/list_agg.rs:30-57, series/ops/agg.rs:
+                // 531-575, array/ops/concat_agg.rs:138-161): no accumulator cell -- the host orders the rows by group after the
+                // table is built (ops_jit.cu build_list_aggs) and gathers the child, evaluated at every row, in that order
+                if (a.kind == AGG_CONCAT && !is_string(c.dtype))
+                    fail(std::string("agg: concat is offered for string columns, got ") + dtype_name(c.dtype));
+                o.val_dtype = c.dtype;
+                o.out_dtype = a.kind == AGG_CONCAT ? c.dtype : B200_LIST;
+                o.proj_index = list_seen++;
+                break;
+            }
             default: fail("agg: unsupported aggregation kind " + std::to_string(a.kind));
         }
         meta.aggs.push_back(o);
@@ -1031,6 +1054,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
 
     const int iv_n = cg.int_slot(I_N), iv_mask = cg.int_slot(I_MASK), iv_rstride = cg.int_slot(I_RSTRIDE);
     const int p_hash = cg.ptr_slot(P_SLOT_HASH, 0), p_ovf = cg.ptr_slot(P_OVERFLOW, 0);  // slot tags, status flag
+    const int p_rowslot = rowslot_variant ? cg.ptr_slot(P_SLOT_ROW, 0) : 0;                // int64 per input row
     // global cells: [0,NL) value cells, NL = row count, NL+1 = first row, [NL+2, NL+2+NW) ballot count cells
     const int cell_nrows = NL, cell_minrow = NL + 1;
     std::vector<int> p_acc(NLT + NW);
@@ -1493,7 +1517,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
     o << "struct Prog {\n";
     o << "  typedef Params<" << meta.ptrs.size() << ", " << meta.ints.size() << "> P;\n";
     o << "  static constexpr int IV_N = " << iv_n << ", IV_MASK = " << iv_mask << ", PTR_TAG = " << p_hash << ", PTR_MINROW = " << p_acc[cell_minrow]
-      << ", PTR_FLAG = " << p_ovf << ", MODE = " << (exact_possible ? 0 : 2) << ";\n";
+      << ", PTR_FLAG = " << p_ovf << ", PTR_ROWSLOT = " << p_rowslot << ", MODE = " << (exact_possible ? 0 : 2) << ";\n";
     o << "  static constexpr int ASTRIDE = " << astride << ", IV_RSTRIDE = " << iv_rstride << ";\n";
     o << "  static constexpr int NKEYS = " << nkeys << ", G1 = " << G1 << ", NLANE = " << NLT << ", NWARP = " << NW << ", U = " << U << ";\n";
     o << "  struct Raw {\n" << raw.str() << "    int pad_;\n  };\n";
@@ -1564,12 +1588,14 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         o << "extern \"C\" __global__ void __launch_bounds__(" << SW * 32 << ", " << (SW == 16 ? 1 : staged_minb) << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_staged<Prog>(p); }\n";
     else if (nanfix_variant)
         o << "extern \"C\" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_nanfix<Prog>(p); }\n";
+    else if (rowslot_variant)
+        o << "extern \"C\" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_rowslot<Prog>(p); }\n";
     else if (global_variant)
         o << "extern \"C\" __global__ void __launch_bounds__(256, 2) b200_agg_k(const __grid_constant__ Prog::P p) { agg_body_global<Prog>(p); }\n";
     else
         o << "extern \"C\" __global__ void __launch_bounds__(256, " << MINB << ") b200_agg_k(const __grid_constant__ Prog::P p) { agg_body<Prog>(p); }\n";
     // shared memory: lane cells, ballot cells, tier-1 slots/ready flags/key values (generous bound for sizeof(Keys))
-    meta.smem_bytes = nanfix_variant ? 0 : global_variant ? 8 * (size_t)t2_slots * (size_t)(1 + NLT + NW)
+    meta.smem_bytes = (nanfix_variant || rowslot_variant) ? 0 : global_variant ? 8 * (size_t)t2_slots * (size_t)(1 + NLT + NW)
                                      : tier1_smem;
     meta.block_threads = SW * 32;
     if (staged_variant) {
@@ -1839,6 +1865,11 @@ static void precompile_one(int op, const uint8_t *plan, size_t plan_len, const s
     if (op == B200_OP_AGG && !c.anyval_project_plan.empty()) {
         Compiled c3;
         compile_to_cubin(generate(B200_OP_PROJECT, c.anyval_project_plan.data(), c.anyval_project_plan.size(), col_dtypes, col_nullable, true, c3, 0), nullptr);
+    }
+    if (op == B200_OP_AGG && !c.listagg_project_plan.empty()) {
+        Compiled c5, c6;
+        compile_to_cubin(generate(op, plan, plan_len, col_dtypes, col_nullable, false, c5, 4), nullptr);
+        compile_to_cubin(generate(B200_OP_PROJECT, c.listagg_project_plan.data(), c.listagg_project_plan.size(), col_dtypes, col_nullable, false, c6, 0), nullptr);
     }
     if (op == B200_OP_AGG && !c.key_project_plan.empty() && c.nkeys > 0) {
         Compiled c2;

@@ -28,7 +28,8 @@ struct OutCol {
 };
 
 enum CellOp { C_ADD_F64 = 0, C_ADD_F32, C_ADD_I64, C_MIN, C_MAX };
-enum AggKind { AGG_COUNT = 0, AGG_SUM, AGG_MIN, AGG_MAX, AGG_MEAN, AGG_ANY_VALUE };
+enum AggKind { AGG_COUNT = 0, AGG_SUM, AGG_MIN, AGG_MAX, AGG_MEAN, AGG_ANY_VALUE, AGG_LIST, AGG_SET, AGG_CONCAT };
+inline bool is_list_agg(int kind) { return kind == AGG_LIST || kind == AGG_SET || kind == AGG_CONCAT; }
 
 struct AggOut {
     std::string name;
@@ -39,7 +40,8 @@ struct AggOut {
     int cnt_cell = -1;       // warp count cell with #valid (or #null for count-null), -1 => use nrows
     bool child_nullable = false;
     bool const_zero = false; // count(null) over a non-nullable child
-    int proj_index = -1;     // AGG_ANY_VALUE: column of the any-value projection (child evaluated at the group's first row)
+    int proj_index = -1;     // AGG_ANY_VALUE: column of the any-value projection (child evaluated at the group's first row);
+                             // AGG_LIST / SET / CONCAT: column of the list projection (child evaluated at every row)
     // Float min / max reproduce the reference's left fold `if a < b {a} else {b}` (inline_agg.rs:271-298 == compare_agg.rs
     // :75-95), which FORGETS everything before a NaN: the result is the min / max of the values after the group's last NaN,
     // and NaN when the last valid value is one.  lane_cell then folds the non-NaN values only, nan_cell = 1 + row of the
@@ -70,6 +72,7 @@ struct Compiled {
     int stage_rows = 0, stage_bytes = 0;  // staged agg variant: bytes per shared-memory stage (0 = nothing to stage)
     std::vector<uint8_t> key_project_plan;
     std::vector<uint8_t> anyval_project_plan;  // PROJECT plan of the any_value children (evaluated at the first rows)
+    std::vector<uint8_t> listagg_project_plan; // PROJECT plan of the list / set / concat children (evaluated at every row)
     int regs = 0;
     // (AGG, first-choice build) what the previous run of this plan found: the reference samples every query's first
     // morsel to choose its strategy (grouped_aggregate.rs:205-245); a plan that needed the global-table kernel last

@@ -521,6 +521,26 @@ __device__ __forceinline__ void agg_body_nanfix(const typename Prog::P &p) {
     }
 }
 
+// ---- row -> group pass (variant 4) ------------------------------------------------------------------------
+// The list / set / concat aggregates need every row's group.  The table is finished when this runs: each row finds its
+// record again (no claims happen) and its element index is written out; rows the predicate drops get -1.
+template <class Prog>
+__device__ __forceinline__ void agg_body_rowslot(const typename Prog::P &p) {
+    const int64_t n = p.ival[Prog::IV_N];
+    long long *out = (long long *)p.ptr[Prog::PTR_ROWSLOT];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+        typename Prog::Raw raw;
+        Prog::load(p, row, raw);
+        Prog::load2(p, row, raw);
+        typename Prog::Keys keys;
+        typename Prog::Vals vals;
+        long long slot = -1;
+        if (Prog::eval(p, raw, keys, vals)) slot = Prog::NKEYS > 0 ? agg_find_slot<Prog>(p, Prog::code(keys), row) : 0;
+        out[row] = slot;
+    }
+}
+
 // Rare path of the low-cardinality kernel, kept out of line so that its registers do not burden the streaming loop:
 // find/claim the group's global slot, try to adopt it into the CTA's tier 1, otherwise update it globally.
 // Returns the tier-1 index (>= 0), -2 when the row was accumulated globally, -1 when the table is full.

@@ -87,6 +87,7 @@ struct b200_probe_table {
     // direct-address mode (unique, dense integer keys): row id by key - min, plus one presence bit per key value
     b200::Buf direct_rows, direct_bits;
     uint64_t direct_min = 0, direct_range = 0;
+    int direct_extra = 0;  // direct table on the FIRST key of a multi-column key: the other nkeys - 1 are compared at the hit
     int64_t num_rows = 0;
 };
 struct b200_join_state {
@@ -256,6 +257,7 @@ struct ProbeArgs {
     // direct-address table (unique dense integer keys): presence bitmap + build row by (key - dmin)
     const unsigned int *dbits, *drows;
     unsigned long long dmin, drange;
+    // generic mode: all keys.  Direct table on a key prefix: the keys AFTER the first (the probe side's gathered plain)
     KeySet bk, pk;
 };
 
@@ -672,7 +674,9 @@ __global__ void direct_fill(const void *__restrict__ data, int width, int64_t n,
 
 // pass 0 also STASHES the build row of every output row, densely per chunk (stash[chunk * CHUNK + j] = build row of the
 // chunk's j-th output row, 0xFFFFFFFF = none): pass 1 then needs neither the keys nor the table again.
-template <int W, bool SEL, bool NULLS, bool KEEP>
+// EXTRA: the table addresses the first column of a multi-column key; a hit still has to agree on the other columns
+// (a.bk / a.pk hold those, the probe side's indexed by the probe row itself).
+template <int W, bool SEL, bool NULLS, bool KEEP, bool EXTRA>
 __global__ void __launch_bounds__(PT, 4) direct_count_kernel(const __grid_constant__ ProbeArgs a, int64_t n, int64_t nchunks, int64_t *__restrict__ chunk_cnt,
                                                              uint32_t *__restrict__ bits, uint32_t *__restrict__ stash) {
     const int lane = threadIdx.x & 31;
@@ -717,7 +721,15 @@ __global__ void __launch_bounds__(PT, 4) direct_count_kernel(const __grid_consta
 #pragma unroll
             for (int r = 0; r < DR; r++) {
                 hit[r] = hit[r] && ((word[r] >> (idx[r] & 31)) & 1u);
-                row[r] = hit[r] && stash ? __ldg(a.drows + idx[r]) : 0xFFFFFFFFu;
+                row[r] = hit[r] && (stash || EXTRA) ? __ldg(a.drows + idx[r]) : 0xFFFFFFFFu;
+            }
+            if (EXTRA) {
+#pragma unroll
+                for (int r = 0; r < DR; r++)
+                    if (hit[r] && !keys_match(a.bk, (int64_t)row[r], a.pk, base + r * 32 + lane)) {
+                        hit[r] = false;
+                        row[r] = 0xFFFFFFFFu;
+                    }
             }
 #pragma unroll
             for (int r = 0; r < DR; r++) {
@@ -831,13 +843,16 @@ void probe_table_build(b200_probe_table *pt) {
     const bool int_like = k0.dtype == B200_I8 || k0.dtype == B200_I16 || k0.dtype == B200_I32 || k0.dtype == B200_I64 || k0.dtype == B200_U8 ||
                           k0.dtype == B200_U16 || k0.dtype == B200_U32 || k0.dtype == B200_U64 || k0.dtype == B200_DATE32 || k0.dtype == B200_TIMESTAMP;
     pt->inline_width = (pt->nkeys == 1 && int_like && k0.null_count == 0) ? dtype_width(k0.dtype) : 0;
-    if (pt->inline_width && n > 0) {  // unique dense integer keys: the direct-address table needs neither hashes nor a sort
+    // a multi-column key whose first column alone is unique and dense (TPC-H Q5: (C_CUSTKEY, C_NATIONKEY)) gets the
+    // direct-address table on that column; the probe compares the remaining columns at the one candidate row
+    const int direct_width = (int_like && k0.null_count == 0) ? dtype_width(k0.dtype) : 0;
+    if (direct_width && n > 0) {  // unique dense integer keys: the direct-address table needs neither hashes nor a sort
         const char *env = getenv("B200_JOIN_DIRECT");
         if (!(env && *env == '0')) {
             Buf mm = dev_alloc(16);
             const unsigned long long init[2] = {~0ULL, 0ULL};
             B200_CUDA(cudaMemcpyAsync(mm->ptr, init, 16, cudaMemcpyHostToDevice, st));
-            key_minmax<<<jgrid(n), 256, 0, st>>>(k0.data->ptr, pt->inline_width, n, as<unsigned long long>(mm));
+            key_minmax<<<jgrid(n), 256, 0, st>>>(k0.data->ptr, direct_width, n, as<unsigned long long>(mm));
             count_launch();
             unsigned long long h[2];
             B200_CUDA(cudaMemcpyAsync(h, mm->ptr, 16, cudaMemcpyDeviceToHost, st));
@@ -846,13 +861,15 @@ void probe_table_build(b200_probe_table *pt) {
             if (h[1] >= h[0] && range != 0 && range <= (unsigned long long)std::max<int64_t>(n * 32, 1 << 16) && range <= (1ULL << 31)) {
                 Buf rows = dev_alloc((size_t)range * 4), dbits = dev_alloc_zero((size_t)(range / 32 + 2) * 4), dup = dev_alloc_zero(8);
                 fill_u8(rows->ptr, 0xFF, (size_t)range * 4);
-                direct_fill<<<jgrid(n), 256, 0, st>>>(k0.data->ptr, pt->inline_width, n, h[0], as<unsigned int>(rows), as<unsigned int>(dbits), as<int>(dup));
+                direct_fill<<<jgrid(n), 256, 0, st>>>(k0.data->ptr, direct_width, n, h[0], as<unsigned int>(rows), as<unsigned int>(dbits), as<int>(dup));
                 count_launch();
                 if (read_i64(as<int64_t>(dup)) == 0) {
                     pt->direct_rows = rows;
                     pt->direct_bits = dbits;
                     pt->direct_min = h[0];
                     pt->direct_range = range;
+                    pt->direct_extra = pt->nkeys - 1;
+                    pt->inline_width = direct_width;
                     op_done();
                     pt->built = true;
                     return;
@@ -948,6 +965,13 @@ static void make_probe_plan(const b200_probe_table *pt, const Batch &probe, cons
         a.pkey = src.data ? src.data->ptr : nullptr;
         a.pvalid = src.null_count > 0 ? as<uint8_t>(src.validity) : nullptr;
         a.psel = pk.is_view() ? as<int64_t>(pk.sel) : nullptr;
+        if (pt->direct_extra > 0) {  // the other key columns, gathered plain: compared at the hits only
+            std::vector<int32_t> rest(key_cols + 1, key_cols + pt->nkeys), brest(pt->key_cols.begin() + 1, pt->key_cols.end());
+            std::vector<uint8_t> ne(pt->nulls_equal.begin() + 1, pt->nulls_equal.end());
+            pp.keys = materialize_batch(probe, &rest);
+            a.bk = make_keyset(*pt->build, brest, ne);
+            a.pk = make_keyset(pp.keys, rest, ne);
+        }
     } else {
         std::vector<int32_t> pk(key_cols, key_cols + pt->nkeys);
         pp.keys = materialize_batch(probe, &pk);
@@ -964,7 +988,8 @@ static void launch_count_w(bool sel, bool nulls, bool keep, int grid, cudaStream
                            uint32_t *bits, uint32_t *stash) {
 #define B200_COUNT(S, N, K)                                                                                   \
     do {                                                                                                      \
-        if (W != 0 && a.drows) direct_count_kernel<(W ? W : 8), S, N, K><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits, stash); \
+        if (W != 0 && a.drows && a.bk.nkeys > 0) direct_count_kernel<(W ? W : 8), S, N, K, true><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits, stash); \
+        else if (W != 0 && a.drows) direct_count_kernel<(W ? W : 8), S, N, K, false><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits, stash); \
         else probe_count_kernel<W, S, N, K><<<grid, PT, 0, st>>>(a, n, nchunks, chunk_cnt, bits);             \
     } while (0)
     if (sel) {

@@ -331,6 +331,83 @@ __global__ void cell_to_take(const unsigned long long *__restrict__ cell, const 
     }
 }
 
+
+// ---- list / set / concat aggregates ----------------------------------------------------------------------------------
+// grouped_list / grouped_set / grouped_concat (src/daft-core/src/array/ops/list_agg.rs:30-57, series/ops/agg.rs:531-575,
+// array/ops/concat_agg.rs:138-161) walk each group's row indices in order.  Here: every row's group comes from a second pass
+// over the finished table (jit_prelude.cuh agg_body_rowslot), a STABLE radix sort by group position puts each group's rows
+// together in row order, and the child values are gathered in that order.
+__global__ void scatter_rank(const int64_t *__restrict__ slots, int64_t ng, unsigned int *__restrict__ rank) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ng) rank[slots[i]] = (unsigned int)i;
+}
+// sort key of a row = position of its group in the output, or `ng` (behind every group) for a row that does not take part:
+// dropped by the predicate, or a null value where nulls do not count (set, concat)
+__global__ void list_sort_keys(const long long *__restrict__ row_slot, const unsigned int *__restrict__ rank, const uint8_t *__restrict__ valid,
+                               int64_t n, unsigned long long ng, unsigned long long *__restrict__ keys) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const long long s = row_slot[i];
+        keys[i] = (s < 0 || (valid && !bit_at(valid, i))) ? ng : (unsigned long long)rank[s];
+    }
+}
+// bounds[g] = first position of the sorted keys holding a key >= g, for g in [0, ng]: list offsets, bounds[ng] = rows taking part
+__global__ void group_bounds(const unsigned long long *__restrict__ keys, int64_t n, long long ng, int64_t *__restrict__ bounds) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i <= n; i += stride) {
+        const long long lo = i == 0 ? 0 : (long long)min(keys[i - 1], (unsigned long long)ng) + 1;
+        const long long hi = i == n ? ng : (long long)min(keys[i], (unsigned long long)ng);
+        for (long long g = lo; g <= hi; g++) bounds[g] = i;
+    }
+}
+__global__ void gather_i64_at(const int64_t *__restrict__ src, const int64_t *__restrict__ idx, int64_t n, int64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+__global__ void group_has_rows(const int64_t *__restrict__ bounds, int64_t ng, uint32_t *__restrict__ validity) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 32 >= ng) return;
+    uint32_t m = 0;
+    for (int b = 0; b < 32 && w * 32 + b < ng; b++)
+        if (bounds[w * 32 + b + 1] > bounds[w * 32 + b]) m |= 1u << b;
+    validity[w] = m;
+}
+
+static void put_u32(std::vector<uint8_t> &v, uint32_t x) { v.insert(v.end(), (uint8_t *)&x, (uint8_t *)&x + 4); }
+static void put_col_entry(std::vector<uint8_t> &v, const char *name, uint32_t col) {
+    put_u32(v, (uint32_t)strlen(name));
+    v.insert(v.end(), name, name + strlen(name));
+    v.push_back(0);  // T_COL
+    put_u32(v, col);
+}
+
+struct RowGroups {
+    Buf row_slot, rank;  // int64 per input row (-1: dropped), group position per table element
+};
+
+// One list-type aggregate over `vals` (the child evaluated at every input row): the rows taking part, ordered by group.
+// Returns the rows (int64[total]), their group positions (the sorted keys) and the ng + 1 offsets.
+static void rows_by_group(const RowGroups &rg, const uint8_t *valid, int64_t n, int64_t ng, Buf &rows, Buf &keys, Buf &bounds, int64_t &total) {
+    cudaStream_t st = ctx().stream;
+    bounds = dev_alloc((size_t)(ng + 2) * 8);
+    keys = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+    rows = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+    if (n > 0) {
+        list_sort_keys<<<stream_grid(n, 256, 8), 256, 0, st>>>(as<long long>(rg.row_slot), as<unsigned int>(rg.rank), valid, n, (unsigned long long)ng,
+                                                               as<unsigned long long>(keys));
+        count_launch();
+        fill_iota(as<int64_t>(rows), n);
+        int bits = 1;
+        while (((int64_t)1 << bits) <= ng) bits++;
+        radix_sort_pairs(keys, rows, n, 0, bits, false);  // LSD passes: stable, so a group's rows stay in row order
+    }
+    group_bounds<<<stream_grid(n + 1, 256, 8), 256, 0, st>>>(as<unsigned long long>(keys), n, (long long)ng, as<int64_t>(bounds));
+    count_launch();
+    total = read_i64(as<int64_t>(bounds) + ng);
+}
+
 struct FinalizeDesc {
     int kind, val_dtype, out_dtype, cnt_is_valid_count, const_zero, _pad;
     const unsigned long long *cell;
@@ -492,7 +569,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
     if (coll) {
         cap = kp->nkeys > 0 ? (1 << 11) : 1;  // the same (small: it is all-reduced) table shape on every rank, whatever its row count
         for (const auto &ag : kp->aggs)
-            if (ag.kind == jit::AGG_ANY_VALUE) return nullptr;  // a first-row value is per rank: two-stage plan
+            if (ag.kind == jit::AGG_ANY_VALUE || jit::is_list_agg(ag.kind)) return nullptr;  // first-row values / row lists are per rank: two-stage plan
         for (int op : kp->lane_cell_ops)
             if (op == jit::C_ADD_F32) return nullptr;
         if (kp->has_nan_fold) return nullptr;  // float min / max fold in row order: rows are per rank
@@ -704,6 +781,127 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
     std::unique_ptr<Batch> anyval;
     if (!k.anyval_project_plan.empty() && ng > 0 && n > 0)
         anyval.reset(op_project(in, k.anyval_project_plan.data(), k.anyval_project_plan.size(), as<int64_t>(minrow), ng, true));
+    // ---- list / set / concat: rows ordered by group, child gathered in that order (see rows_by_group above)
+    std::vector<Column> list_cols;
+    if (!k.listagg_project_plan.empty()) {
+        std::unique_ptr<Batch> vals(op_project(in, k.listagg_project_plan.data(), k.listagg_project_plan.size(), nullptr, 0));
+        RowGroups rg;
+        rg.row_slot = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+        rg.rank = dev_alloc((size_t)std::max<int64_t>(cap, 1) * (size_t)astride_final * 4);
+        if (ng > 0) {
+            scatter_rank<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(as<int64_t>(slots), ng, as<unsigned int>(rg.rank));
+            count_launch();
+        }
+        if (n > 0) {
+            const Compiled &k4 = jit::get(B200_OP_AGG, plan, len, in, false, 4);
+            LaunchArgs a;
+            a.ptr.assign(k4.ptrs.size(), nullptr);
+            a.ival.assign(k4.ints.size(), 0);
+            for (size_t s2 = 0; s2 < k4.ptrs.size(); s2++) {
+                const auto &ps = k4.ptrs[s2];
+                switch (ps.kind) {
+                    case jit::P_COL_DATA: a.ptr[s2] = in.cols[ps.index].data ? in.cols[ps.index].data->ptr : nullptr; break;
+                    case jit::P_COL_VALID: a.ptr[s2] = in.cols[ps.index].validity ? in.cols[ps.index].validity->ptr : nullptr; break;
+                    case jit::P_COL_OFFSETS: a.ptr[s2] = in.cols[ps.index].offsets ? in.cols[ps.index].offsets->ptr : nullptr; break;
+                    case jit::P_SLOT_HASH: a.ptr[s2] = acc->ptr; break;
+                    case jit::P_OVERFLOW: a.ptr[s2] = flag->ptr; break;
+                    case jit::P_ACC: a.ptr[s2] = cell_ptr(ps.index); break;
+                    case jit::P_SLOT_ROW: a.ptr[s2] = rg.row_slot->ptr; break;
+                    default: fail("agg: unexpected parameter kind");
+                }
+            }
+            for (size_t s2 = 0; s2 < k4.ints.size(); s2++) {
+                const int kind = k4.ints[s2] % 1000;
+                if (kind == jit::I_N) a.ival[s2] = n;
+                else if (kind == jit::I_MASK) a.ival[s2] = cap - 1;
+                else if (kind == jit::I_RSTRIDE) a.ival[s2] = astride_final;
+            }
+            jit::launch(k4, a, stream_grid(n, 256, 8), 256, 0, 0, false);
+        }
+        for (const auto &ag : k.aggs) {
+            if (!jit::is_list_agg(ag.kind)) continue;
+            const Column &x = vals->cols[ag.proj_index];
+            const bool skip_nulls = ag.kind != jit::AGG_LIST && x.null_count > 0;
+            Buf rows, gkeys, bounds;
+            int64_t total = 0;
+            if (x.dtype == B200_NULL && ag.kind != jit::AGG_LIST) {  // every value is null: nothing takes part
+                bounds = dev_alloc_zero((size_t)(ng + 2) * 8);
+                rows = dev_alloc(8);
+            } else {
+                rows_by_group(rg, skip_nulls ? as<uint8_t>(x.validity) : nullptr, n, ng, rows, gkeys, bounds, total);
+            }
+            Column ordered = gather_column(x, as<int64_t>(rows), total, false);
+            if (ag.kind == jit::AGG_SET && total > 0) {
+                // distinct values per group in first-occurrence order (deduplicate_indices, series/ops/agg.rs:23-27): the rows are
+                // grouped already, so the first rows of the distinct (group, value) pairs -- ascending positions -- are the answer
+                Batch tmp;
+                tmp.num_rows = total;
+                tmp.cols.push_back(make_u64_column("g", gkeys, total));
+                tmp.cols[0].dtype = B200_I64;
+                tmp.cols.push_back(ordered);
+                std::vector<uint8_t> dp;
+                dp.push_back(0);           // no predicate
+                put_u32(dp, 2);            // keys: (group, value)
+                put_col_entry(dp, "g", 0);
+                put_col_entry(dp, "v", 1);
+                put_u32(dp, 1);            // one aggregate: count(all)
+                dp.push_back((uint8_t)jit::AGG_COUNT);
+                dp.push_back(0);
+                put_col_entry(dp, "n", 0);
+                Buf firsts;
+                int64_t nd = 0;
+                std::unique_ptr<Batch> dd(op_agg_first_rows(tmp, dp.data(), dp.size(), &firsts, &nd, nullptr));
+                Buf g2 = dev_alloc((size_t)std::max<int64_t>(nd, 1) * 8);
+                if (nd > 0) {
+                    gather_i64_at<<<(unsigned)((nd + 255) / 256), 256, 0, st>>>(as<int64_t>(gkeys), as<int64_t>(firsts), nd, as<int64_t>(g2));
+                    count_launch();
+                }
+                group_bounds<<<stream_grid(nd + 1, 256, 8), 256, 0, st>>>(as<unsigned long long>(g2), nd, (long long)ng, as<int64_t>(bounds));
+                count_launch();
+                ordered = gather_column(ordered, as<int64_t>(firsts), nd, false);
+                total = nd;
+            }
+            Column c;
+            c.name = ag.name;
+            c.length = ng;
+            if (ag.kind == jit::AGG_CONCAT) {
+                // the group's valid strings back to back: offsets of the ordered strings at the group boundaries
+                c.dtype = ag.out_dtype;
+                c.offsets = dev_alloc((size_t)(ng + 1) * 8);
+                if (total > 0) {
+                    gather_i64_at<<<(unsigned)((ng + 1 + 255) / 256), 256, 0, st>>>(as<int64_t>(ordered.offsets), as<int64_t>(bounds), ng + 1, as<int64_t>(c.offsets));
+                    count_launch();
+                    c.data = ordered.data;
+                    c.data_bytes = ordered.data_bytes;
+                } else {
+                    fill_u8(c.offsets->ptr, 0, (size_t)(ng + 1) * 8);
+                    c.data = dev_alloc(8);
+                }
+                if (x.null_count > 0 && ng > 0) {  // null where no value of the group is valid (concat_agg.rs:140-151)
+                    c.validity = dev_alloc_zero((size_t)((ng + 31) / 32 + 1) * 4);
+                    group_has_rows<<<(unsigned)(((ng + 31) / 32 + 255) / 256), 256, 0, st>>>(as<int64_t>(bounds), ng, as<uint32_t>(c.validity));
+                    count_launch();
+                    c.null_count = ng - count_set_bits(as<uint8_t>(c.validity), ng);
+                    if (k.nkeys == 0 && total == 0) {
+                        // ungrouped: null only when rows survive the predicate and all of them are null; over no rows at all the
+                        // result is the empty string (concat_agg.rs:117-131 on the filtered column)
+                        Buf r2, k2, b2;
+                        int64_t live = 0;
+                        rows_by_group(rg, nullptr, n, ng, r2, k2, b2, live);
+                        if (live == 0) c.null_count = 0;
+                    }
+                    if (c.null_count == 0) c.validity.reset();
+                }
+            } else {
+                c.dtype = B200_LIST;
+                c.offsets = bounds;
+                ordered.name = "item";
+                c.child = std::make_shared<const Column>(std::move(ordered));
+            }
+            list_cols.push_back(std::move(c));
+        }
+    }
+    size_t list_next = 0;
     FinalizeSet fs;
     fs.n = 0;
     std::vector<Column> agg_cols;
@@ -720,6 +918,10 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         c.name = ag.name;
         c.dtype = ag.out_dtype;
         c.length = ng;
+        if (jit::is_list_agg(ag.kind)) {
+            agg_cols.push_back(std::move(list_cols[list_next++]));
+            continue;
+        }
         if (ag.kind == jit::AGG_ANY_VALUE) {
             if (anyval && ag.first_valid_cell >= 0 && ng > 0) {
                 // ignore_nulls: the child at the group's first row where it is valid (Series::any_value, series/ops/agg.rs:353-382)

@@ -96,8 +96,8 @@ std::string kernel_timing_report() {
 
 const char *dtype_name(int32_t dt) {
     static const char *names[] = {"null", "bool", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32",
-                                  "uint64", "float32", "float64", "date32", "timestamp", "large_utf8", "large_binary"};
-    return (dt >= 0 && dt < 16) ? names[dt] : "?";
+                                  "uint64", "float32", "float64", "date32", "timestamp", "large_utf8", "large_binary", "list"};
+    return (dt >= 0 && dt < 17) ? names[dt] : "?";
 }
 
 // ---- device memory ---------------------------------------------------------------------------------------------
@@ -368,6 +368,19 @@ __global__ void gather_str_len(const int64_t *__restrict__ offsets, const int64_
         len[i] = j >= 0 ? offsets[j + 1] - offsets[j] : 0;
     }
 }
+// list gather: positions of the gathered rows' elements in the flat child (8 lanes per row, like the string copy)
+__global__ void gather_list_child_idx(const int64_t *__restrict__ src_off, const int64_t *__restrict__ idx, int64_t n,
+                                      const int64_t *__restrict__ out_off, int64_t *__restrict__ child_idx) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    const int sub = (int)(t & 7);
+    for (int64_t i = t >> 3; i < n; i += stride) {
+        const int64_t j = idx[i];
+        if (j < 0) continue;
+        const int64_t b = src_off[j], len = src_off[j + 1] - b, o = out_off[i];
+        for (int64_t e = sub; e < len; e += 8) child_idx[o + e] = b + e;
+    }
+}
 // 8 lanes cooperate on one row so that long strings still copy with some parallelism
 __global__ void gather_str_copy(const int64_t *__restrict__ src_off, const uint8_t *__restrict__ src,
                                 const int64_t *__restrict__ idx, int64_t n, const int64_t *__restrict__ out_off,
@@ -445,6 +458,22 @@ Column gather_column(const Column &src, const int64_t *idx, int64_t n, bool idx_
                                                               as<int64_t>(out.offsets), as<uint8_t>(out.data));
             count_launch();
         }
+    } else if (src.dtype == B200_LIST) {
+        if (!src.child) fail("gather: list column without a child");
+        Buf len = dev_alloc((size_t)(n + 1) * 8);
+        out.offsets = dev_alloc((size_t)(n + 1) * 8);
+        if (n) {
+            gather_str_len<<<grid_for(n), 256, 0, st>>>(as<int64_t>(src.offsets), idx, n, as<int64_t>(len));
+            count_launch();
+        }
+        exclusive_scan_i64(as<int64_t>(len), as<int64_t>(out.offsets), n, as<int64_t>(out.offsets) + n);
+        const int64_t total = read_i64(as<int64_t>(out.offsets) + n);
+        Buf cidx = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
+        if (n && total) {
+            gather_list_child_idx<<<grid_for(n * 8), 256, 0, st>>>(as<int64_t>(src.offsets), idx, n, as<int64_t>(out.offsets), as<int64_t>(cidx));
+            count_launch();
+        }
+        out.child = std::make_shared<const Column>(gather_column(*src.child, as<int64_t>(cidx), total, false));
     } else {
         fail(std::string("gather: unsupported dtype ") + dtype_name(src.dtype));
     }
@@ -858,6 +887,7 @@ Column concat_columns(const std::vector<const Column *> &cols) {
     out.length = n;
     out.null_count = nulls;
     if (out.dtype == B200_NULL) return out;
+    if (out.dtype == B200_LIST) fail("concat: list columns are not supported");
     if (nulls > 0) {
         out.validity = dev_alloc_zero(((n + 31) / 32) * 4);
         int64_t pos = 0;

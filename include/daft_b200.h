@@ -91,7 +91,10 @@ typedef enum {
     B200_DATE32 = 12,       /* days since epoch, physical i32 */
     B200_TIMESTAMP = 13,    /* no tz, physical i64 */
     B200_LARGE_UTF8 = 14,   /* i64 offsets -- Daft always holds strings as Large */
-    B200_LARGE_BINARY = 15
+    B200_LARGE_BINARY = 15,
+    B200_LIST = 16          /* i64 offsets + one child column (Daft List): produced by the list / set aggregates.  Where a
+                             * dtype is reported as one int32 (b200_batch_dtypes) the child's code sits in bits 8..15.
+                             * List columns can be exported, selected, sliced by the host; operators do not read them. */
 } b200_dtype;
 
 /* One column as raw DEVICE pointers (Arrow layout).  Used to wrap buffers that already

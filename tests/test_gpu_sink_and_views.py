@@ -148,6 +148,47 @@ def test_direct_address_table_equals_bucket_table(gpu, how, key_type, monkeypatc
         assert_tables_equal(got, want)
 
 
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer", "semi", "anti"])
+@pytest.mark.parametrize("null_eq", [False, True])
+def test_direct_address_table_on_a_key_prefix(gpu, how, null_eq, monkeypatch):
+    """A multi-column key whose FIRST column is unique and dense on the build side (TPC-H Q5: (C_CUSTKEY, C_NATIONKEY)) takes the
+    direct-address table on that column and compares the other columns at the candidate row (nullable string and float
+    columns here); equal to the bucket table and to the oracle, through a view on the probe side as well."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(23)
+    nb, npr = 4000, 30000
+    bk = (rng.permutation(nb * 2)[:nb] + 50).astype(np.int64)
+    b2 = rng.integers(0, 4, nb)
+    right = pa.table({"k": pa.array(bk), "s": pa.array([None if v == 3 else f"n{v}" for v in b2], type=pa.large_utf8()),
+                      "f": pa.array(b2 * 0.5, mask=rng.random(nb) < 0.1), "payload": pa.array(np.arange(nb) * 2.0)})
+    pk = rng.integers(0, nb * 2 + 100, npr).astype(np.int64)
+    lut_s = dict(zip(bk.tolist(), right.column("s").to_pylist()))
+    lut_f = dict(zip(bk.tolist(), right.column("f").to_pylist()))
+    agree = rng.random(npr) < 0.7           # 70 % of the probe rows carry the build row's other columns, the rest something else
+    ps = [lut_s.get(int(k), "zz") if a else "n0" for k, a in zip(pk, agree)]
+    pf = [lut_f.get(int(k), 9.0) if a else 0.5 for k, a in zip(pk, agree)]
+    left = pa.table({"k": pa.array(pk, mask=rng.random(npr) < 0.03), "s": pa.array(ps, type=pa.large_utf8()), "f": pa.array(pf, type=pa.float64()),
+                     "a": pa.array(np.arange(npr))})
+    c = gpu.col
+    keys = ["k", "s", "f"]
+    ne = [null_eq] * 3
+    want = O.hash_join(left, right, keys, keys, how, null_equals_null=ne)
+    if how in ("semi", "anti"):
+        want = want.select(left.column_names)
+    for direct in ("1", "0"):
+        monkeypatch.setenv("B200_JOIN_DIRECT", direct)
+        lb, rb = gpu.RecordBatch.from_arrow_table(left), gpu.RecordBatch.from_arrow_table(right)
+        got = lb.hash_join(rb, [c(k) for k in keys], [c(k) for k in keys], how=how, null_equals_null=ne).to_arrow_table()
+        assert_tables_equal(got, want)
+    if how == "inner":   # probe side = a join output (views over two different bases)
+        monkeypatch.setenv("B200_JOIN_DIRECT", "1")
+        ids = pa.table({"a": pa.array(np.arange(0, npr, 2)), "tag": pa.array(np.arange(0, npr, 2) % 7)})
+        lb = gpu.RecordBatch.from_arrow_table(ids).hash_join(gpu.RecordBatch.from_arrow_table(left), [c("a")], [c("a")])
+        got = lb.hash_join(gpu.RecordBatch.from_arrow_table(right), [c(k) for k in keys], [c(k) for k in keys], null_equals_null=ne).to_arrow_table()
+        lhs = O.hash_join(ids, left, ["a"], ["a"], "inner")
+        assert_tables_equal(got, O.hash_join(lhs, right, keys, keys, "inner", null_equals_null=ne), sort_by=["a"])
+
+
 @pytest.mark.parametrize("size,k", [(0, 3), (4, 3), (10, 1), (33, 10), (5000, 7), (100000, 300)])
 def test_partition_by_random_conserves_rows_and_is_deterministic(gpu, size, k):
     """tests/recordbatch/test_partitioning.py:124-147,199-214: k partitions, every row exactly once, same split for the same seed."""
