@@ -362,7 +362,7 @@ static bool arena_ensure(b200_comm *c, size_t need) {  // collective: `need` is 
 static Batch *route_batch(b200_comm *c, const Batch &src, const Route &rows, const std::vector<int64_t> *nulls_anywhere);
 
 // returns nullptr when the peer path is not available (the caller takes the NCCL route); collective decisions only
-static Batch *exchange_peer_store(b200_comm *c, const Batch &b, const uint64_t *hashes) {
+static Batch *exchange_peer_store(b200_comm *c, const Batch &b, const PartSrc &hashes) {
     const int W = c->world;
     const char *env = getenv("B200_EXCHANGE_P2P");
     if ((env && *env == '0') || c->p2p_state < 0 || W > 8 || W < 2) return nullptr;  // B200_EXCHANGE_P2P=0: NCCL route only
@@ -462,18 +462,19 @@ static Batch *exchange_peer_store(b200_comm *c, const Batch &b, const uint64_t *
 }
 
 // rows of `b` go to rank targets[i] % world (targets: u64 per row), arriving in (source rank, source row) order
-static Batch *exchange_by_targets(b200_comm *c, const Batch &b, const Buf &h) {
+static Batch *exchange_by_targets(b200_comm *c, const Batch &b, const PartSrc &h) {
     const int W = c->world;
     {
         KernelTimer ktp("exchange_peer_store");
-        if (Batch *direct = exchange_peer_store(c, b, as<uint64_t>(h))) return direct;
+        if (Batch *direct = exchange_peer_store(c, b, h)) return direct;
     }
     std::vector<int64_t> offsets;
     std::unique_ptr<Batch> staged;
     if (W <= 256 && b.num_rows >= 4096) {  // direct scatter: the payload moves once, straight into destination order
-        staged.reset(partition_staged(b, as<uint64_t>(h), W, offsets));
+        staged.reset(partition_staged(b, h, W, offsets));
     } else {
-        Buf perm = partition_permutation(as<uint64_t>(h), b.num_rows, W, offsets);
+        if (!h.hashes) fail("exchange: the row-id partition needs a hash column");  // key mode is only chosen for the direct scatter
+        Buf perm = partition_permutation(h.hashes, b.num_rows, W, offsets);
         staged.reset(gather_batch(b, as<int64_t>(perm), b.num_rows, false));
     }
     std::vector<int64_t> soff(W), scnt(W);
@@ -492,14 +493,17 @@ static Batch *exchange_by_targets(b200_comm *c, const Batch &b, const Buf &h) {
 Batch *exchange_by_hash(b200_comm *c, const Batch &b, const int32_t *key_cols, int32_t nkeys) {
     require_device();
     if (!c) fail("null communicator");
-    return exchange_by_targets(c, b, hash_rows(b, key_cols, nkeys, nullptr));
+    return exchange_by_targets(c, b, part_src_for_keys(b, key_cols, nkeys, c->world <= 256 && b.num_rows >= 4096));
 }
 // RepartitionSpec::Random (src/daft-local-execution/src/sinks/repartition.rs:169-171): see partition.cu random_targets; the
 // salt makes the draw a function of (seed, rank, row) so that ranks do not all draw the same sequence
 Batch *exchange_random(b200_comm *c, const Batch &b, uint64_t seed) {
     require_device();
     if (!c) fail("null communicator");
-    return exchange_by_targets(c, b, random_targets(b.num_rows, c->world, seed, (uint64_t)c->rank << 40));
+    PartSrc src;
+    src.keep = random_targets(b.num_rows, c->world, seed, (uint64_t)c->rank << 40);
+    src.hashes = as<uint64_t>(src.keep);
+    return exchange_by_targets(c, b, src);
 }
 // RepartitionSpec::Range (repartition.rs:172-176; the exchange leg of the distributed sort,
 // src/daft-distributed/src/pipeline_node/sort.rs:249-300): target = search_sorted(boundaries, keys); world - 1 boundaries
@@ -508,7 +512,10 @@ Batch *exchange_by_range(b200_comm *c, const Batch &b, const int32_t *key_cols, 
     if (!c) fail("null communicator");
     if (boundaries.num_rows != c->world - 1) fail("exchange_by_range: need exactly world - 1 boundary rows");
     if (boundaries.num_rows == 0) return new Batch(b);
-    return exchange_by_targets(c, b, op_search_sorted(boundaries, b, key_cols, nkeys, descending));
+    PartSrc src;
+    src.keep = op_search_sorted(boundaries, b, key_cols, nkeys, descending);
+    src.hashes = as<uint64_t>(src.keep);
+    return exchange_by_targets(c, b, src);
 }
 
 // ---- small batches (partial aggregates, top-N candidates): ONE fixed-size all-gather ---------------------------------

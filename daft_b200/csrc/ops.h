@@ -43,7 +43,18 @@ Buf partition_permutation(const uint64_t *hashes, int64_t n, int32_t P, std::vec
 // every partition of `b` back to back in one batch, P <= 256 (direct scatter: no row-id permutation, no per-column gather)
 // rowid_out != null: columns the scatter cannot place (nullable / Boolean / strings) are left empty and *rowid_out
 // receives the partition-ordered source row ids; otherwise they are gathered into the staged batch
-Batch *partition_staged(const Batch &b, const uint64_t *hashes, int32_t P, std::vector<int64_t> &offsets, Buf *rowid_out = nullptr);
+// Where a row's partition comes from: a u64 per row (hash_rows output or explicit targets; partition = value % P), or ONE
+// never-null 4- / 8-byte integer key column hashed in registers (XXH3-64 of the value, the same number hash_rows writes) --
+// the hash column is then neither written nor read.
+struct PartSrc {
+    const uint64_t *hashes = nullptr;
+    const void *key = nullptr;
+    int width = 0;  // 4 or 8 with `key`
+    Buf keep;       // owns `hashes` when this object computed them
+};
+// key mode when `key_cols` is one suitable column (and the direct scatter will be used), hash_rows otherwise
+PartSrc part_src_for_keys(const Batch &b, const int32_t *key_cols, int32_t nkeys, bool allow_fused);
+Batch *partition_staged(const Batch &b, const PartSrc &src, int32_t P, std::vector<int64_t> &offsets, Buf *rowid_out = nullptr);
 // the direct scatter in two steps (peer-store exchange): per-partition counts, then rows written straight to per-destination
 // pointers (peer memory)
 struct PartitionPlan {
@@ -52,8 +63,8 @@ struct PartitionPlan {
     Buf base;                      // scanned (partition, CTA chunk) histogram
     std::vector<int64_t> offsets;  // rows of partition p = [offsets[p], offsets[p + 1]) in partition order
 };
-PartitionPlan partition_count(const uint64_t *hashes, int64_t n, int32_t P);
-void partition_scatter_to_peers(const PartitionPlan &pl, const uint64_t *hashes, const Batch &b, const std::vector<int> &cols,
+PartitionPlan partition_count(const PartSrc &src, int64_t n, int32_t P);
+void partition_scatter_to_peers(const PartitionPlan &pl, const PartSrc &src, const Batch &b, const std::vector<int> &cols,
                                 const std::vector<std::vector<void *>> &dest_ptrs, Buf *rowid_out);
 Buf random_targets(int64_t n, int32_t P, uint64_t seed, uint64_t salt);  // u64 target per row (RepartitionSpec::Random)
 std::vector<Batch *> op_partition_by_random(const Batch &b, int32_t P, uint64_t seed);

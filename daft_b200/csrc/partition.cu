@@ -10,6 +10,7 @@
 #include "jit.h"
 #include "kernels.cuh"
 #include "ops.h"
+#include "xxh3.cuh"
 
 namespace b200 {
 
@@ -73,7 +74,44 @@ struct PartCols {
     PartCol c[PS_MAXCOLS];
 };
 
-__global__ void __launch_bounds__(PS_THREADS) partition_hist(const uint64_t *__restrict__ hashes, int64_t n, int64_t chunk, uint64_t P,
+// hash % P without the 64-bit division (about a hundred instructions on the SM): Lemire's fastmod with M = ceil(2^128 / P),
+// a % P = ((M * a mod 2^128) * P) >> 128 -- exact for every 64-bit a and P.
+struct PartKey {
+    const uint64_t *hashes;
+    const void *key;
+    unsigned long long m_lo, m_hi, P;
+};
+__device__ __forceinline__ uint32_t fastmod_u64(uint64_t a, const PartKey &k) {
+    const uint64_t l_lo = k.m_lo * a;
+    const uint64_t l_hi = __umul64hi(k.m_lo, a) + k.m_hi * a;
+    const uint64_t t = __umul64hi(l_lo, k.P);
+    const uint64_t u_lo = l_hi * k.P, u_hi = __umul64hi(l_hi, k.P);
+    return (uint32_t)(u_hi + ((u_lo + t < u_lo) ? 1ULL : 0ULL));
+}
+// W = 0: the u64 per row is given; W = 4 / 8: XXH3-64 of the key value, computed here (xxh3.cuh hash_u32 / hash_u64 are what
+// hash_rows runs for these dtypes, seed 0)
+template <int W>
+__device__ __forceinline__ uint32_t part_of(const PartKey &k, int64_t i) {
+    uint64_t h;
+    if (W == 0) h = __ldg(k.hashes + i);
+    else if (W == 4) h = xxh::hash_u32(__ldg((const uint32_t *)k.key + i), 0);
+    else h = xxh::hash_u64(__ldg((const unsigned long long *)k.key + i), 0);
+    return fastmod_u64(h, k);
+}
+static PartKey make_part_key(const PartSrc &src, int32_t P) {
+    PartKey k;
+    k.hashes = src.hashes;
+    k.key = src.key;
+    k.P = (unsigned long long)P;
+    const unsigned __int128 M = (~(unsigned __int128)0) / (unsigned __int128)P + 1;  // P = 1: wraps to 0, and a % 1 = 0
+    k.m_lo = (unsigned long long)M;
+    k.m_hi = (unsigned long long)(M >> 64);
+    return k;
+}
+
+constexpr int PH_ROWS = 4;  // rows per thread and step of the histogram pass: four independent loads in flight
+template <int W>
+__global__ void __launch_bounds__(PS_THREADS) partition_hist(const __grid_constant__ PartKey key, int64_t n, int64_t chunk,
                                                              int64_t *__restrict__ hist /* [partition][block] */) {
     __shared__ unsigned int s_cnt[PS_MAXP];
     for (int i = threadIdx.x; i < PS_MAXP; i += PS_THREADS) s_cnt[i] = 0;
@@ -81,14 +119,22 @@ __global__ void __launch_bounds__(PS_THREADS) partition_hist(const uint64_t *__r
     const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
     // warp-aggregated: with a handful of partitions every lane would hit the same few shared-memory words
     const int lane = threadIdx.x & 31;
-    for (int64_t i0 = begin; i0 < end; i0 += PS_THREADS) {
-        const int64_t i = i0 + threadIdx.x;
-        const uint32_t d = i < end ? (uint32_t)(hashes[i] % P) : 0xFFFFFFFFu;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (i < end && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_cnt[d], (unsigned)__popc(peers));
+    for (int64_t i0 = begin; i0 < end; i0 += PS_THREADS * PH_ROWS) {
+        uint32_t d[PH_ROWS];
+#pragma unroll
+        for (int r = 0; r < PH_ROWS; r++) {
+            const int64_t i = i0 + r * PS_THREADS + threadIdx.x;
+            d[r] = i < end ? part_of<W>(key, i) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int r = 0; r < PH_ROWS; r++) {
+            const unsigned peers = __match_any_sync(0xffffffffu, d[r]);
+            if (d[r] != 0xFFFFFFFFu && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_cnt[d[r]], (unsigned)__popc(peers));
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (int)P; i += PS_THREADS) hist[(int64_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
+    const int Pn = (int)key.P;
+    for (int i = threadIdx.x; i < Pn; i += PS_THREADS) hist[(int64_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
 }
 
 // PEER: partition d is not written behind partition d - 1 in a local buffer but straight into rank d's receive buffer
@@ -99,15 +145,15 @@ struct PeerDest {
     uint8_t *out[PS_PEERCOLS][PS_MAXPEERS];
     long long start[PS_MAXPEERS];
 };
-template <bool PEER>
-__global__ void __launch_bounds__(PS_THREADS) partition_scatter(const uint64_t *__restrict__ hashes, int64_t n, int64_t chunk, uint64_t P,
+template <bool PEER, int W>
+__global__ void __launch_bounds__(PS_THREADS) partition_scatter(const __grid_constant__ PartKey key, int64_t n, int64_t chunk,
                                                                 const int64_t *__restrict__ base /* scanned hist */,
                                                                 const __grid_constant__ PartCols cols, int ncols, int64_t *__restrict__ rowid_out,
                                                                 const PeerDest *__restrict__ dest) {
     __shared__ int64_t s_base[PS_MAXP];                 // next output position per partition for this CTA
     __shared__ unsigned int s_wcnt[PS_WARPS][PS_MAXP];  // per-warp counts -> exclusive prefix over warps
     __shared__ unsigned int s_tile[PS_MAXP];
-    const int Pn = (int)P;
+    const int Pn = (int)key.P;
     for (int i = threadIdx.x; i < Pn; i += PS_THREADS) s_base[i] = base[(int64_t)i * gridDim.x + blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
@@ -117,7 +163,7 @@ __global__ void __launch_bounds__(PS_THREADS) partition_scatter(const uint64_t *
         const int64_t i = t0 + threadIdx.x;
         const bool valid = i < end;
         uint32_t d = 0xFFFFFFFFu;  // out-of-range lanes only match each other
-        if (valid) d = (uint32_t)(hashes[i] % P);
+        if (valid) d = part_of<W>(key, i);
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const int rank = __popc(peers & ((1u << lane) - 1u));  // stable: lower lanes (earlier rows) first
         if (valid && rank == 0) s_wcnt[warp][d] = __popc(peers);
@@ -159,13 +205,51 @@ __global__ void __launch_bounds__(PS_THREADS) partition_scatter(const uint64_t *
     if (PEER) __threadfence_system();  // the rows must be visible to the peer GPUs before this rank signals completion
 }
 
+static void launch_hist(const PartSrc &src, int32_t P, int64_t n, int64_t chunk, int64_t nblocks, int64_t *hist) {
+    const PartKey k = make_part_key(src, P);
+    cudaStream_t st = ctx().stream;
+    if (src.key && src.width == 8) partition_hist<8><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, hist);
+    else if (src.key && src.width == 4) partition_hist<4><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, hist);
+    else partition_hist<0><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, hist);
+    count_launch();
+}
+template <bool PEER>
+static void launch_scatter(const PartSrc &src, int32_t P, int64_t n, int64_t chunk, int64_t nblocks, const int64_t *base, const PartCols &pcs, int npc,
+                           int64_t *rowid, const PeerDest *dest) {
+    const PartKey k = make_part_key(src, P);
+    cudaStream_t st = ctx().stream;
+    if (src.key && src.width == 8) partition_scatter<PEER, 8><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, base, pcs, npc, rowid, dest);
+    else if (src.key && src.width == 4) partition_scatter<PEER, 4><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, base, pcs, npc, rowid, dest);
+    else partition_scatter<PEER, 0><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, base, pcs, npc, rowid, dest);
+    count_launch();
+}
+// One never-null integer key of 4 or 8 bytes: its XXH3 is a few multiplies, cheaper than writing and re-reading a hash column
+PartSrc part_src_for_keys(const Batch &b, const int32_t *key_cols, int32_t nkeys, bool allow_fused) {
+    PartSrc src;
+    const char *env = getenv("B200_PARTITION_FUSED");
+    if (allow_fused && nkeys == 1 && !(env && *env == '0')) {
+        if (key_cols[0] < 0 || key_cols[0] >= (int32_t)b.cols.size()) fail("partition: key column index out of range");
+        const Column &k = b.cols[key_cols[0]];
+        const bool int_like = is_integer(k.dtype) || k.dtype == B200_DATE32 || k.dtype == B200_TIMESTAMP;
+        const int w = dtype_width(k.dtype);
+        if (int_like && (w == 4 || w == 8) && k.null_count == 0 && !k.is_view() && k.data) {
+            src.key = k.data->ptr;
+            src.width = w;
+            return src;
+        }
+    }
+    src.keep = hash_rows(b, key_cols, nkeys, nullptr);
+    src.hashes = as<uint64_t>(src.keep);
+    return src;
+}
+
 __global__ void pick_strided(const int64_t *__restrict__ src, int64_t stride, int n, int64_t *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = src[(int64_t)i * stride];
 }
 
 // all partitions back to back in ONE batch (rows of partition p at [offsets[p], offsets[p + 1])): what the exchange sends
-Batch *partition_staged(const Batch &b, const uint64_t *hashes, int32_t P, std::vector<int64_t> &offsets, Buf *rowid_out) {
+Batch *partition_staged(const Batch &b, const PartSrc &src, int32_t P, std::vector<int64_t> &offsets, Buf *rowid_out) {
     cudaStream_t st = ctx().stream;
     const int64_t n = b.num_rows;
     KernelTimer kt("partition_direct");
@@ -174,8 +258,7 @@ Batch *partition_staged(const Batch &b, const uint64_t *hashes, int32_t P, std::
     chunk = (chunk + PS_THREADS - 1) / PS_THREADS * PS_THREADS;
     nblocks = (n + chunk - 1) / chunk;
     Buf hist = dev_alloc((size_t)P * nblocks * 8), base = dev_alloc((size_t)(P * nblocks + 1) * 8), starts = dev_alloc((size_t)(P + 1) * 8);
-    partition_hist<<<(unsigned)nblocks, PS_THREADS, 0, st>>>(hashes, n, chunk, (uint64_t)P, as<int64_t>(hist));
-    count_launch();
+    launch_hist(src, P, n, chunk, nblocks, as<int64_t>(hist));
     exclusive_scan_i64(as<int64_t>(hist), as<int64_t>(base), (int64_t)P * nblocks, nullptr);
     pick_strided<<<(P + 255) / 256, 256, 0, st>>>(as<int64_t>(base), nblocks, P, as<int64_t>(starts));
     count_launch();
@@ -197,8 +280,7 @@ Batch *partition_staged(const Batch &b, const uint64_t *hashes, int32_t P, std::
         }
     }
     Buf rowid = need_rowid ? dev_alloc((size_t)n * 8) : Buf();
-    partition_scatter<false><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(hashes, n, chunk, (uint64_t)P, as<int64_t>(base), pcs, npc, as<int64_t>(rowid), nullptr);
-    count_launch();
+    launch_scatter<false>(src, P, n, chunk, nblocks, as<int64_t>(base), pcs, npc, as<int64_t>(rowid), nullptr);
     B200_CUDA(cudaStreamSynchronize(st));
     offsets[(size_t)P] = n;
     auto out = std::make_unique<Batch>();
@@ -225,7 +307,7 @@ Batch *partition_staged(const Batch &b, const uint64_t *hashes, int32_t P, std::
 
 // ---- the same scatter in two steps for the peer-store exchange (exchange.cu): counts first (the ranks agree on the
 // receive layout), then the scatter straight into the peers' buffers
-PartitionPlan partition_count(const uint64_t *hashes, int64_t n, int32_t P) {
+PartitionPlan partition_count(const PartSrc &src, int64_t n, int32_t P) {
     cudaStream_t st = ctx().stream;
     PartitionPlan pl;
     pl.n = n;
@@ -238,8 +320,7 @@ PartitionPlan partition_count(const uint64_t *hashes, int64_t n, int32_t P) {
     pl.chunk = chunk;
     Buf hist = dev_alloc((size_t)P * nblocks * 8), starts = dev_alloc((size_t)(P + 1) * 8);
     pl.base = dev_alloc((size_t)(P * nblocks + 1) * 8);
-    partition_hist<<<(unsigned)nblocks, PS_THREADS, 0, st>>>(hashes, n, chunk, (uint64_t)P, as<int64_t>(hist));
-    count_launch();
+    launch_hist(src, P, n, chunk, nblocks, as<int64_t>(hist));
     exclusive_scan_i64(as<int64_t>(hist), as<int64_t>(pl.base), (int64_t)P * nblocks, nullptr);
     pick_strided<<<(P + 255) / 256, 256, 0, st>>>(as<int64_t>(pl.base), nblocks, P, as<int64_t>(starts));
     count_launch();
@@ -250,7 +331,7 @@ PartitionPlan partition_count(const uint64_t *hashes, int64_t n, int32_t P) {
     return pl;
 }
 // cols[c] of `b` (fixed width, no nulls) -> dest_ptrs[c][d] (already offset to this sender's slot in rank d's buffer)
-void partition_scatter_to_peers(const PartitionPlan &pl, const uint64_t *hashes, const Batch &b, const std::vector<int> &cols,
+void partition_scatter_to_peers(const PartitionPlan &pl, const PartSrc &src, const Batch &b, const std::vector<int> &cols,
                                 const std::vector<std::vector<void *>> &dest_ptrs, Buf *rowid_out) {
     cudaStream_t st = ctx().stream;
     if ((int)cols.size() > PS_PEERCOLS || pl.P > PS_MAXPEERS) fail("peer scatter: too many columns / peers");
@@ -267,17 +348,15 @@ void partition_scatter_to_peers(const PartitionPlan &pl, const uint64_t *hashes,
     B200_CUDA(cudaMemcpyAsync(dpd->ptr, &pd, sizeof(PeerDest), cudaMemcpyHostToDevice, st));
     Buf rowid = rowid_out ? dev_alloc((size_t)std::max<int64_t>(pl.n, 1) * 8) : Buf();
     KernelTimer kt("partition_scatter_peer");
-    partition_scatter<true><<<(unsigned)pl.nblocks, PS_THREADS, 0, st>>>(hashes, pl.n, pl.chunk, (uint64_t)pl.P, as<int64_t>(pl.base), pcs, (int)cols.size(),
-                                                                      as<int64_t>(rowid), as<PeerDest>(dpd));
-    count_launch();
+    launch_scatter<true>(src, pl.P, pl.n, pl.chunk, pl.nblocks, as<int64_t>(pl.base), pcs, (int)cols.size(), as<int64_t>(rowid), as<PeerDest>(dpd));
     B200_CUDA(cudaStreamSynchronize(st));  // `pd` is a stack object; the caller's barrier follows anyway
     if (rowid_out) *rowid_out = rowid;
 }
 
-static std::vector<Batch *> partition_direct(const Batch &b, const uint64_t *hashes, int32_t P) {
+static std::vector<Batch *> partition_direct(const Batch &b, const PartSrc &src, int32_t P) {
     std::vector<int64_t> offsets;
     Buf rowid;
-    std::unique_ptr<Batch> staged(partition_staged(b, hashes, P, offsets, &rowid));
+    std::unique_ptr<Batch> staged(partition_staged(b, src, P, offsets, &rowid));
     std::vector<Batch *> out;
     try {
         for (int p = 0; p < P; p++) {
@@ -332,7 +411,11 @@ Buf random_targets(int64_t n, int32_t P, uint64_t seed, uint64_t salt) {
     return t;
 }
 static std::vector<Batch *> partition_by_targets(const Batch &b, const Buf &targets, int32_t P) {
-    if (P <= PS_MAXP && b.num_rows >= 4096) return partition_direct(b, as<uint64_t>(targets), P);
+    if (P <= PS_MAXP && b.num_rows >= 4096) {
+        PartSrc src;
+        src.hashes = as<uint64_t>(targets);
+        return partition_direct(b, src, P);
+    }
     std::vector<int64_t> offsets;
     Buf perm = partition_permutation(as<uint64_t>(targets), b.num_rows, P, offsets);
     std::vector<Batch *> out;
@@ -354,8 +437,8 @@ std::vector<Batch *> op_partition_by_random(const Batch &b, int32_t P, uint64_t 
 std::vector<Batch *> op_partition_by_hash(const Batch &b, const int32_t *key_cols, int32_t nkeys, int32_t P) {
     require_device();
     if (P <= 0) fail("Can not partition a Table by 0 partitions");
+    if (P <= PS_MAXP && b.num_rows >= 4096) return partition_direct(b, part_src_for_keys(b, key_cols, nkeys, true), P);
     Buf h = hash_rows(b, key_cols, nkeys, nullptr);
-    if (P <= PS_MAXP && b.num_rows >= 4096) return partition_direct(b, as<uint64_t>(h), P);
     std::vector<int64_t> offsets;
     Buf perm = partition_permutation(as<uint64_t>(h), b.num_rows, P, offsets);
     std::vector<Batch *> out;
@@ -378,7 +461,11 @@ std::vector<Batch *> op_partition_by_range(const Batch &b, const int32_t *key_co
     const int32_t P = (int32_t)boundaries.num_rows + 1;
     if (boundaries.num_rows == 0) return {new Batch(b)};
     Buf target = op_search_sorted(boundaries, b, key_cols, nkeys, descending);  // in [0, P): usable as "hash % P"
-    if (P <= PS_MAXP && b.num_rows >= 4096) return partition_direct(b, as<uint64_t>(target), P);
+    if (P <= PS_MAXP && b.num_rows >= 4096) {
+        PartSrc src;
+        src.hashes = as<uint64_t>(target);
+        return partition_direct(b, src, P);
+    }
     std::vector<int64_t> offsets;
     Buf perm = partition_permutation(as<uint64_t>(target), b.num_rows, P, offsets);
     std::vector<Batch *> out;

@@ -175,8 +175,213 @@ static void radix_pass(const uint64_t *kin, const int64_t *vin, uint64_t *kout, 
     B200_CUDA(cudaGetLastError());
 }
 
+// ---- onesweep: one histogram pass for ALL digits, then one pass per digit that reads the pairs once and writes them once.
+// The per-(digit, CTA) histogram + scan of the two-kernel scheme above is replaced by a decoupled look-back inside the
+// scatter: tiles take their index from an atomic counter (so a tile only ever waits for tiles that already run), publish
+// their digit counts, and sum their predecessors' counts until they meet a tile that already knows its inclusive prefix.
+// Traffic per pass: 16 B read + 16 B written per row (+ 1 KB of status words per 2048-row tile) instead of 24 + 16.
+constexpr int OS_MAXPASS = 8;
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_all(const uint64_t *__restrict__ keys, int64_t n, int begin_bit, int npass,
+                                                              unsigned long long *__restrict__ totals /* [npass][256] */) {
+    __shared__ unsigned int s_cnt[OS_MAXPASS][256];
+    for (int i = threadIdx.x; i < OS_MAXPASS * 256; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * RS_THREADS;
+    // whole warps stay in the loop together (the votes below need every lane)
+    for (int64_t i0 = (int64_t)blockIdx.x * RS_THREADS + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+        const int64_t i = i0 + lane;
+        const bool valid = i < n;
+        const uint64_t k = valid ? keys[i] : 0;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        for (int p = 0; p < npass; p++) {
+            const uint32_t d = (uint32_t)(k >> (begin_bit + 8 * p)) & 255u;
+            // high bytes are very often the same for every row: one add per warp instead of 32 colliding ones
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs(vmask) - 1);
+            const bool same = __all_sync(0xffffffffu, !valid || d == d0);
+            if (same) {
+                if (lane == 0) atomicAdd(&s_cnt[p][d0], (unsigned)__popc(vmask));
+            } else if (valid) {
+                atomicAdd(&s_cnt[p][d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * 256; i += RS_THREADS) {
+        const unsigned int c = (&s_cnt[0][0])[i];
+        if (c) atomicAdd(&totals[i], (unsigned long long)c);
+    }
+}
+
+constexpr uint32_t OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_VAL = (1u << 30) - 1;
+__global__ void __launch_bounds__(RS_THREADS) radix_onesweep(const uint64_t *__restrict__ keys, const int64_t *__restrict__ vals, int64_t n, int shift,
+                                                              uint32_t xor_mask, const int64_t *__restrict__ digit_base /* [256] */,
+                                                              unsigned int *__restrict__ tile_counter, volatile uint32_t *__restrict__ status /* [tiles][256] */,
+                                                              uint64_t *__restrict__ keys_out, int64_t *__restrict__ vals_out) {
+    constexpr int R = 256;
+    constexpr int TILE = RS_THREADS * RS_ITEMS;
+    __shared__ int64_t s_base[R];
+    __shared__ unsigned int s_wcnt[RS_WARPS][R];
+    __shared__ unsigned int s_toff[R];
+    __shared__ unsigned int s_wtot[RS_WARPS];
+    __shared__ unsigned int s_tile_id;
+    __shared__ uint64_t s_k[TILE];
+    __shared__ int64_t s_v[TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntiles = (n + TILE - 1) / TILE;
+    for (;;) {
+        __syncthreads();  // the previous tile's s_k / s_v / s_tile_id are no longer read
+        if (threadIdx.x == 0) s_tile_id = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const int64_t tile = s_tile_id;
+        if (tile >= ntiles) break;
+        const int64_t t0 = tile * TILE, end = min(t0 + (int64_t)TILE, n);
+#pragma unroll
+        for (int i = 0; i < R / 32; i++) s_wcnt[warp][i * 32 + lane] = 0;
+        __syncwarp();
+        const int64_t wbase = t0 + (int64_t)warp * 32 * RS_ITEMS + lane;
+        uint64_t k[RS_ITEMS];
+        int64_t v[RS_ITEMS];
+        uint32_t d[RS_ITEMS];
+        unsigned short rank[RS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; j++) {
+            const int64_t i = wbase + j * 32;
+            k[j] = 0;
+            v[j] = 0;
+            if (i < end) {
+                k[j] = keys[i];
+                v[j] = vals[i];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; j++) {
+            const bool valid = wbase + j * 32 < end;
+            d[j] = valid ? (((uint32_t)(k[j] >> shift) & (R - 1)) ^ xor_mask) : 0xFFFFFFFFu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d[j]);
+            const int lt = __popc(peers & ((1u << lane) - 1u));
+            const unsigned int before = valid ? s_wcnt[warp][d[j]] : 0u;
+            __syncwarp();
+            if (valid && lt == 0) s_wcnt[warp][d[j]] = before + __popc(peers);
+            __syncwarp();
+            rank[j] = (unsigned short)(before + lt);
+        }
+        __syncthreads();
+        {
+            const int dd = threadIdx.x;
+            unsigned int run = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) {
+                const unsigned int c = s_wcnt[w][dd];
+                s_wcnt[w][dd] = run;
+                run += c;
+            }
+            // publish this tile's count of digit dd, then sum the predecessors' (decoupled look-back)
+            volatile uint32_t *mine = status + tile * R + dd;
+            if (tile == 0) {
+                *mine = OS_INC | run;
+                s_base[dd] = digit_base[dd];
+            } else {
+                *mine = OS_AGG | run;
+                uint32_t excl = 0;
+                for (int64_t t = tile - 1;; t--) {
+                    uint32_t sv;
+                    do { sv = status[t * R + dd]; } while ((sv >> 30) == 0);
+                    excl += sv & OS_VAL;
+                    if ((sv >> 30) == 2) break;
+                }
+                *mine = OS_INC | (excl + run);
+                s_base[dd] = digit_base[dd] + (int64_t)excl;
+            }
+            // exclusive scan of the digit totals over the 256 digits: where a digit's run starts inside the tile
+            unsigned int x = run;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) s_wtot[warp] = x;
+            __syncthreads();
+            unsigned int wpre = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) wpre += w < warp ? s_wtot[w] : 0u;
+            s_toff[dd] = wpre + x - run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; j++) {
+            if (wbase + j * 32 < end) {
+                const unsigned int lp = s_toff[d[j]] + s_wcnt[warp][d[j]] + rank[j];
+                s_k[lp] = k[j];
+                s_v[lp] = v[j];
+            }
+        }
+        __syncthreads();
+        const int cnt = (int)(end - t0);
+        for (int e = threadIdx.x; e < cnt; e += RS_THREADS) {
+            const uint64_t kk = s_k[e];
+            const uint32_t dd = ((uint32_t)(kk >> shift) & (R - 1)) ^ xor_mask;
+            const int64_t pos = s_base[dd] + (int64_t)(e - (int)s_toff[dd]);
+            keys_out[pos] = kk;
+            vals_out[pos] = s_v[e];
+        }
+    }
+}
+
+static bool radix_sort_onesweep(Buf &keys, Buf &vals, int64_t n, int begin_bit, int end_bit, bool descending) {
+    const int npass = (end_bit - begin_bit + 7) / 8;
+    const char *env = getenv("B200_SORT_ONESWEEP");
+    if ((env && *env == '0') || npass < 1 || npass > OS_MAXPASS || n >= ((int64_t)1 << 30) || n < (1 << 16)) return false;
+    cudaStream_t st = ctx().stream;
+    constexpr int TILE = RS_THREADS * RS_ITEMS;
+    const int64_t ntiles = (n + TILE - 1) / TILE;
+    Buf totals = dev_alloc_zero((size_t)npass * 256 * 8);
+    const int hgrid = (int)std::min<int64_t>((n + RS_THREADS - 1) / RS_THREADS, (int64_t)ctx().sm_count * 8);
+    radix_hist_all<<<hgrid, RS_THREADS, 0, st>>>(as<uint64_t>(keys), n, begin_bit, npass, as<unsigned long long>(totals));
+    count_launch();
+    std::vector<unsigned long long> tot((size_t)npass * 256);
+    B200_CUDA(cudaMemcpyAsync(tot.data(), totals->ptr, tot.size() * 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));  // the only host round trip of the sort
+    // digit bases of every pass that permutes anything (a pass whose digit is constant is the identity)
+    std::vector<int> live;
+    std::vector<int64_t> bases;
+    const uint32_t xm = descending ? 255u : 0u;
+    for (int p = 0; p < npass; p++) {
+        bool constant = false;
+        for (int d = 0; d < 256; d++) constant = constant || tot[(size_t)p * 256 + d] == (unsigned long long)n;
+        if (constant) continue;
+        live.push_back(p);
+        int64_t run = 0;
+        for (int dd = 0; dd < 256; dd++) {  // dd = digit as the kernel sees it (xor-ed for a descending sort)
+            bases.push_back(run);
+            run += (int64_t)tot[(size_t)p * 256 + (dd ^ (int)xm)];
+        }
+    }
+    if (live.empty()) return true;
+    Buf dbase = dev_alloc(bases.size() * 8);
+    B200_CUDA(cudaMemcpyAsync(dbase->ptr, bases.data(), bases.size() * 8, cudaMemcpyHostToDevice, st));
+    Buf k2 = dev_alloc((size_t)n * 8), v2 = dev_alloc((size_t)n * 8);
+    const size_t status_bytes = (size_t)ntiles * 256 * 4 + 256;
+    Buf status = dev_alloc(status_bytes);
+    int occ = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, radix_onesweep, RS_THREADS, 0));
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx().sm_count * std::max(1, occ));
+    for (size_t li = 0; li < live.size(); li++) {
+        fill_u8(status->ptr, 0, status_bytes);  // tile statuses, and the tile counter behind them
+        unsigned int *counter = reinterpret_cast<unsigned int *>(as<uint8_t>(status) + (size_t)ntiles * 256 * 4);
+        radix_onesweep<<<grid, RS_THREADS, 0, st>>>(as<uint64_t>(keys), as<int64_t>(vals), n, begin_bit + 8 * live[li], xm, as<int64_t>(dbase) + li * 256,
+                                                    counter, as<uint32_t>(status), as<uint64_t>(k2), as<int64_t>(v2));
+        count_launch();
+        std::swap(keys, k2);
+        std::swap(vals, v2);
+    }
+    // (`bases` is pageable host memory: cudaMemcpyAsync has staged it before returning, so it may go out of scope here)
+    B200_CUDA(cudaGetLastError());
+    return true;
+}
+
 void radix_sort_pairs(Buf &keys, Buf &vals, int64_t n, int begin_bit, int end_bit, bool descending) {
     if (n <= 1) return;
+    if (radix_sort_onesweep(keys, vals, n, begin_bit, end_bit, descending)) return;
     Buf k2 = dev_alloc((size_t)n * 8), v2 = dev_alloc((size_t)n * 8);
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
         bool skipped = false;

@@ -4,9 +4,10 @@ from __future__ import annotations
 import pyarrow as pa
 
 NULL, BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F32, F64, DATE32, TIMESTAMP, LARGE_UTF8, LARGE_BINARY = range(16)
+LIST = 16   # output of the list / set aggregates; a schema code carries the child's code in bits 8..15 (b200_batch_dtypes)
 
 NAMES = ["null", "bool", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "float32", "float64",
-         "date32", "timestamp", "large_utf8", "large_binary"]
+         "date32", "timestamp", "large_utf8", "large_binary", "list"]
 
 _PA = {
     pa.null(): NULL, pa.bool_(): BOOL, pa.int8(): I8, pa.int16(): I16, pa.int32(): I32, pa.int64(): I64,
@@ -33,6 +34,8 @@ def from_arrow(t: pa.DataType) -> int:
 
 
 def to_arrow(code: int) -> pa.DataType:
+    if code & 0xFF == LIST:
+        return pa.large_list(_TO_PA[(code >> 8) & 0xFF])
     return _TO_PA[code]
 
 

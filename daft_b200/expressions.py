@@ -21,7 +21,7 @@ UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
          "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15,
          "round": 16, "match_seq": 17}
-AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5}
+AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5, "list": 6, "set": 7, "concat": 8}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
 _CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
 _ARITH = ("add", "sub", "mul", "floor_div", "mod")
@@ -156,6 +156,15 @@ class Expression:
     def any_value(self, ignore_nulls: bool = False):
         """Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the group's first row, or its first non-null row."""
         return self._agg("any_value", "ignore_nulls" if ignore_nulls else "first")
+    def agg_list(self):
+        """Each group's values in row order, nulls kept, as a List column (src/daft-core/src/array/ops/list_agg.rs:30-57)."""
+        return self._agg("list", "all")
+    def agg_set(self):
+        """Each group's distinct non-null values in first-occurrence order (src/daft-core/src/series/ops/agg.rs:531-575)."""
+        return self._agg("set", "all")
+    def agg_concat(self):
+        """Each group's non-null strings back to back (src/daft-core/src/array/ops/concat_agg.rs:138-161); List inputs are not built."""
+        return self._agg("concat", "all")
     def bool_and(self): return self._agg("min")   # nulls ignored, all-null group -> null (array/ops/bool_agg.rs:19-60)
     def bool_or(self): return self._agg("max")
 

@@ -326,6 +326,49 @@ def agg(tbl: pa.Table, aggs: Sequence[tuple], group_by: Sequence) -> pa.Table:
                 cand = np.flatnonzero(valid) if ignore else np.arange(n)
                 idx = [int(cand[0]) if len(cand) else None]
             r = arr_n.take(pa.array(idx, type=pa.int64()))
+        elif kind in ("list", "set", "concat"):
+            # grouped_list (src/daft-core/src/array/ops/list_agg.rs:30-57): each group's values in row order, nulls kept;
+            # grouped_set (src/daft-core/src/series/ops/agg.rs:531-575): the group's distinct NON-NULL values in first-occurrence
+            # order (probe table without nulls); grouped_concat over Utf8 (src/daft-core/src/array/ops/concat_agg.rs:138-161): the
+            # valid strings back to back, null when the column has nulls and the group has no valid value.  Ungrouped: one group.
+            arr_n = normalize(arr)
+            vals = arr_n.to_pylist()
+            rows_of = [[] for _ in range(ng)]
+            for row, g in enumerate(gid.tolist()):
+                rows_of[g].append(row)
+            if kind == "list":
+                r = pa.array([[vals[i] for i in rows] for rows in rows_of], type=pa.large_list(arr_n.type))
+            elif kind == "set":
+                out = []
+                for rows in rows_of:
+                    seen, lst = set(), []
+                    for i in rows:
+                        v = vals[i]
+                        if v is None:
+                            continue
+                        # the probe table matches on (XXH3 of the value's bytes, Literal ==): 0.0 and -0.0 hash apart, and a NaN
+                        # equals nothing, itself included (src/daft-core/src/series/mod.rs:85-100)
+                        if isinstance(v, float):
+                            if v != v:
+                                lst.append(v)
+                                continue
+                            k_ = ("f", np.float64(v).tobytes() if pa.types.is_float64(arr_n.type) else np.float32(v).tobytes())
+                        else:
+                            k_ = v
+                        if k_ not in seen:
+                            seen.add(k_)
+                            lst.append(v)
+                    out.append(lst)
+                r = pa.array(out, type=pa.large_list(arr_n.type))
+            else:
+                if not (pa.types.is_large_string(arr_n.type) or pa.types.is_string(arr_n.type)):
+                    raise NotImplementedError("concat over list columns")
+                has_nulls = arr_n.null_count > 0
+                out = []
+                for rows in rows_of:
+                    parts = [vals[i] for i in rows if vals[i] is not None]
+                    out.append(None if (has_nulls and not parts and rows) else "".join(parts))
+                r = pa.array(out, type=pa.large_utf8())
         else:
             raise NotImplementedError(kind)
         cols.append(r)

@@ -98,6 +98,12 @@ def test_codegen_and_nvrtc_offline(tmp_path):
     plan = encode_agg([col("b").sum().alias("sb"), col("a").max().alias("ma"), col("a").count().alias("n")], [col("s"), col("a") % 3], names, dts,
                       [col("b") > lit(0.5)])
     _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))
+    # list / set / concat aggregates: the row -> group pass (variant 4) and the projection of their children
+    plan = encode_agg([col("a").agg_list().alias("l"), (col("b") * 2).agg_set().alias("st"), col("s").agg_concat().alias("cat"), col("a").sum().alias("t")],
+                      [col("s"), col("a") % 3], names, dts, [col("b") > lit(0.5)])
+    _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))
+    plan = encode_agg([col("a").agg_list().alias("l")], [], names, dts)
+    _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(1, 1, 1), ctypes.c_int32(3))
     files = os.listdir(tmp_path)
     assert any(f.endswith(".cubin") for f in files) and any(f.endswith(".cu") for f in files)
     src = open(os.path.join(tmp_path, next(f for f in files if f.endswith(".cu")))).read()

@@ -353,6 +353,30 @@ def test_sort_multikey(gpu):
     assert_tables_equal(got, O.sort(tbl, ["i64"], [True], [False]).slice(5, 10))
 
 
+@pytest.mark.parametrize("n", [70_000, 300_001, 1_500_000])
+def test_sort_onesweep_equals_two_kernel_radix(gpu, n, monkeypatch):
+    """Inputs of 65 536 rows and more take the onesweep passes (one histogram for all digits, decoupled look-back in the scatter,
+    sort.cu radix_onesweep); the per-pass histogram + scan scheme stays for small and huge inputs.  Both are stable LSD sorts, so
+    their argsorts are IDENTICAL, ties included -- and equal to the oracle's stable sort."""
+    rng = np.random.default_rng(n)
+    tbl = pa.table({"a": pa.array(rng.integers(-50, 50, n).astype(np.int64), mask=rng.random(n) < 0.05),        # heavy ties, nulls
+                    "f": pa.array(np.where(rng.random(n) < 0.01, np.nan, rng.standard_normal(n) * 1e6)),            # all 8 bytes live
+                    "u": pa.array(rng.integers(0, 2**32, n).astype(np.uint32)),
+                    "s": pa.array([f"k{v:05d}" for v in rng.integers(0, 3000, n)], type=pa.large_utf8()),
+                    "row": pa.array(np.arange(n))})
+    c = gpu.col
+    for keys, desc in ((["a"], [False]), (["f"], [True]), (["u", "a"], [False, True]), (["s"], [False])):
+        if keys == ["s"] and n > 400_000:
+            continue
+        res = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("B200_SORT_ONESWEEP", mode)
+            res[mode] = RB(gpu, tbl).argsort([c(k) for k in keys], descending=desc).to_pydict()
+        assert res["1"] == res["0"], keys
+        want = O.argsort([tbl.column(k) for k in keys], desc, desc)
+        assert list(res["1"].values())[0] == [int(x) for x in want], keys
+
+
 @pytest.mark.parametrize("dtype", ["f64", "i64", "i32", "f32"])
 def test_top_n_selection_path(gpu, dtype):
     """Large inputs take the radix-select path (sort.cu op_top_indices): same rows as sort + slice
@@ -403,6 +427,30 @@ def test_partition_by_hash(gpu, P):
         assert len(got) == P
         for g, w in zip(got, want):
             assert_tables_equal(g.to_arrow_table(), w)  # placement and in-partition order are exact
+
+
+@pytest.mark.parametrize("P", [1, 2, 7, 8, 200])
+@pytest.mark.parametrize("key_type", [pa.int64(), pa.int32(), pa.uint32(), pa.uint64(), pa.date32()])
+def test_partition_by_hash_fused_key(gpu, P, key_type, monkeypatch):
+    """One never-null 4- / 8-byte integer key: the partition kernels hash the key in registers (no hash column) and take
+    `% P` by multiplication; placement must equal hash_rows % P exactly, fused or not."""
+    rng = np.random.default_rng(P + 5)
+    n = 30000
+    if key_type == pa.date32():
+        key = pa.array(rng.integers(-20000, 60000, n).astype(np.int32)).cast(pa.date32())
+    elif key_type in (pa.uint32(), pa.uint64()):
+        key = pa.array(rng.integers(0, 2**32 - 1 if key_type == pa.uint32() else 2**63, n).astype(np.uint64)).cast(key_type)
+    else:
+        key = pa.array(rng.integers(-2**31, 2**31 - 1, n)).cast(key_type)
+    tbl = pa.table({"key": key, "v": pa.array(np.arange(n, dtype=np.float64)), "s": pa.array([f"s{i % 17}" for i in range(n)], type=pa.large_utf8()),
+                    "w": pa.array(rng.integers(0, 9, n).astype(np.int16), mask=rng.random(n) < 0.1)})
+    want = O.partition_by_hash(tbl, ["key"], P)
+    for fused in ("1", "0"):
+        monkeypatch.setenv("B200_PARTITION_FUSED", fused)
+        got = RB(gpu, tbl).partition_by_hash([gpu.col("key")], P)
+        assert len(got) == P
+        for g, w in zip(got, want):
+            assert_tables_equal(g.to_arrow_table(), w)
 
 
 def test_take_and_concat_and_slice(gpu):
