@@ -451,7 +451,13 @@ def run_exchange(args, rank, world, comm, total_sf, begin, n_rows, stream, barri
     ms, out = time_steps(step, steps, 2, stream, barrier)
     ms = max_over_ranks(ms) / steps
     # un-timed exchange step alone (the collective's own bytes / time)
+    from daft_b200 import _lib
+    L = _lib.lib()
+    L.b200_kernel_timing(1)
+    _lib.kernel_timing_report()
     ms_x, ex = time_steps(lambda: comm.exchange_by_hash(part, gb), steps, 1, stream, barrier)
+    kt = _lib.kernel_timing_report()   # device time of the library's timed regions on this rank (nested: peer_store contains the scatter)
+    L.b200_kernel_timing(0)
     ms_x = max_over_ranks(ms_x) / steps
     # parity (un-timed): placement = hash_rows % world as the reference's partition_by_hash; every key lands on exactly
     # one rank, so the per-rank groups partition the global groups: (groups, rows, sum) must add up to the values of the
@@ -475,7 +481,8 @@ def run_exchange(args, rank, world, comm, total_sf, begin, n_rows, stream, barri
     return {"workload": f"TPC-H SF{total_sf:g} lineitem: sum(L_QUANTITY), count by L_ORDERKEY through exchange_by_hash (hash_rows % {world}) -> local HashAggregate",
             "value": n_all / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "exchange_ms": ms_x,
             "nvlink_bytes_sent_per_gpu": int(sent), "nvlink_GBps_per_gpu_per_direction": sent / (ms_x * 1e-3) / 1e9,
-            "nvlink_peak_GBps_per_direction": 900.0, "groups": tot[2], "parity": parity}
+            "nvlink_peak_GBps_per_direction": 900.0, "groups": tot[2], "parity": parity,
+            "regions_ms_per_step_rank0": {k: round(v["ms"] / (steps + 1), 4) for k, v in kt.items()}}
 
 
 def run_q5(args, stream, barrier, peak, peak_src):

@@ -66,6 +66,10 @@ def populate_aggregation_stages(aggregations: Sequence[Expression], group_by: Se
             ign = inner.value == "ignore_nulls"
             g = first.add(x.any_value(ign))
             final.append(second.add(g.any_value(ign)).alias(out))
+        elif op == "list":           # :286-290: List per partial, Concat of the partial lists
+            final.append(second.add(first.add(x.agg_list()).agg_concat()).alias(out))
+        elif op == "concat":         # :296-301
+            final.append(second.add(first.add(x.agg_concat()).agg_concat()).alias(out))
         elif op in ("stddev", "var"):  # :190-258
             xf = x.cast(dt.F64)
             s = second.add(first.add(xf.sum()).sum())
@@ -78,7 +82,7 @@ def populate_aggregation_stages(aggregations: Sequence[Expression], group_by: Se
             adjusted = pop_var * n / (n - ddof)
             final.append((n <= ddof).if_else(lit(None), adjusted.sqrt() if op == "stddev" else adjusted).alias(out))
         else:
-            raise NotImplementedError(f"two-stage rewrite of {op} (agg.rs: Set / Concat / List / sketches) is not built")
+            raise NotImplementedError(f"two-stage rewrite of {op} (agg.rs: Set needs list_distinct; sketches) is not built")
     return first.exprs, second.exprs, final
 
 

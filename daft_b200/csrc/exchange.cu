@@ -409,7 +409,7 @@ static Batch *exchange_peer_store(b200_comm *c, const Batch &b, const PartSrc &h
         }
     }
     Buf rowid;
-    partition_scatter_to_peers(pl, hashes, b, peer_cols, dest, other_cols.empty() ? nullptr : &rowid);
+    partition_scatter_to_peers(pl, b, peer_cols, dest, other_cols.empty() ? nullptr : &rowid);
     // all writes of all ranks have landed once this collective completes
     Buf bar = dev_alloc_zero(4);
     B200_NCCL(nccl().AllReduce(bar->ptr, bar->ptr, 1, ncclInt32, ncclSum, c->comm, st));
@@ -691,15 +691,62 @@ static Batch *all_gather_small(b200_comm *c, const Batch &b) {
 // ---- low-cardinality aggregates: the group tables themselves are all-reduced ------------------------------------------
 // Every rank ran the same aggregate kernel into a table of the same capacity; a group's slot is a function of its
 // key code (open addressing from the same home slot), so slot s holds the same group on every rank unless two codes
-// collided differently -- which the caller detects from the MIN / MAX of the tag words.  One grouped NCCL launch:
-// tags MAX (+ their non-zero MIN), the status word MAX, and one all-reduce per run of cells with the same operator
-// (f64 sums, 64-bit integer sums, minima, maxima).  Cells listed in `keep_local` (the groups' first rows) stay local.
-void allreduce_agg_table(b200_comm *c, unsigned long long *acc, size_t cap, const std::vector<int> &cell_ops, const std::vector<char> &keep_local,
+// collided differently -- which the caller detects from the MIN / MAX of the tag words.  ONE collective: the tables
+// (status word, tags, cells -- a few hundred KB) are all-gathered, and a merge kernel folds the W copies of every slot in
+// rank order with the cell's own operator (f64 / 64-bit sums, minima, maxima), so every rank computes bit-identical
+// results.  Cells listed in `keep_local` (the groups' first rows) stay local.  (A grouped ncclAllReduce per operator run
+// was six small collectives; at 8 GPUs their latencies added up to more than the table transfer.)
+struct MergeOps {
+    int ncells;
+    signed char op[48];  // jit cell operator, -1 = keep the local value
+};
+__global__ void merge_agg_tables(const unsigned long long *__restrict__ all, int W, size_t words, size_t cap, const __grid_constant__ MergeOps ops,
+                                 unsigned long long *__restrict__ acc, unsigned long long *__restrict__ tagmin, int *__restrict__ status) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) {
+        int st = 0;
+        for (int r = 0; r < W; r++) st = max(st, (int)(all[(size_t)r * words] & 0xffffffffULL));
+        if (st) atomicMax(status, st);
+    }
+    if (s >= cap) return;
+    unsigned long long tmax = 0ULL, tmin = ~0ULL;
+    for (int r = 0; r < W; r++) {
+        const unsigned long long t = all[(size_t)r * words + 2 + s];
+        tmax = max(tmax, t);
+        if (t) tmin = min(tmin, t);
+    }
+    acc[s] = tmax;
+    tagmin[s] = tmin;
+    for (int c = 0; c < ops.ncells; c++) {
+        const int op = ops.op[c];
+        if (op < 0) continue;
+        const size_t at = 2 + (size_t)(1 + c) * cap + s;
+        unsigned long long v = all[at];
+        for (int r = 1; r < W; r++) {
+            const unsigned long long x = all[(size_t)r * words + at];
+            switch (op) {
+                case 0: v = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)v) + __longlong_as_double((long long)x)); break;  // C_ADD_F64
+                case 2: v += x; break;            // C_ADD_I64 (wraps like the kernel)
+                case 3: v = min(v, x); break;     // C_MIN
+                default: v = max(v, x); break;    // C_MAX
+            }
+        }
+        acc[(size_t)(1 + c) * cap + s] = v;
+    }
+}
+__global__ void tag_min_prep(const unsigned long long *__restrict__ tags, size_t cap, unsigned long long *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) {
+        const unsigned long long t = tags[i];
+        out[i] = t == 0ULL ? ~0ULL : t;
+    }
+}
+// the round-2 first version: one grouped launch of an all-reduce per operator run (B200_AGG_MERGE=allreduce)
+static void allreduce_agg_table_grouped(b200_comm *c, unsigned long long *acc, size_t cap, const std::vector<int> &cell_ops, const std::vector<char> &keep_local,
                          unsigned long long *tagmin, int *status_flag) {
     require_device();
     if (!c) fail("null communicator");
     cudaStream_t st = ctx().stream;
-    KernelTimer kt("agg_table_allreduce");
     B200_NCCL(nccl().GroupStart());
     B200_NCCL(nccl().AllReduce(acc, acc, cap, ncclUint64, ncclMax, c->comm, st));
     B200_NCCL(nccl().AllReduce(tagmin, tagmin, cap, ncclUint64, ncclMin, c->comm, st));
@@ -724,6 +771,40 @@ void allreduce_agg_table(b200_comm *c, unsigned long long *acc, size_t cap, cons
         i = j;
     }
     B200_NCCL(nccl().GroupEnd());
+    count_launch();
+}
+
+void allreduce_agg_table(b200_comm *c, unsigned long long *acc, size_t cap, const std::vector<int> &cell_ops, const std::vector<char> &keep_local,
+                         unsigned long long *tagmin, int *status_flag) {
+    require_device();
+    if (!c) fail("null communicator");
+    cudaStream_t st = ctx().stream;
+    KernelTimer kt("agg_table_allreduce");
+    {
+        const char *env = getenv("B200_AGG_MERGE");
+        if (env && !strcmp(env, "allreduce")) {
+            tag_min_prep<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(acc, cap, tagmin);
+            count_launch();
+            allreduce_agg_table_grouped(c, acc, cap, cell_ops, keep_local, tagmin, status_flag);
+            return;
+        }
+    }
+    MergeOps ops;
+    if (cell_ops.size() > sizeof(ops.op)) fail("agg all-reduce: too many cells");
+    ops.ncells = (int)cell_ops.size();
+    for (size_t i = 0; i < cell_ops.size(); i++) {
+        if (!keep_local[i] && cell_ops[i] != 0 && cell_ops[i] != 2 && cell_ops[i] != 3 && cell_ops[i] != 4) fail("agg all-reduce: unsupported cell operator");
+        ops.op[i] = keep_local[i] ? (signed char)-1 : (signed char)cell_ops[i];
+    }
+    const int W = c->world;
+    const size_t words = 2 + (1 + cell_ops.size()) * cap;  // [status, pad, tags[cap], cells[ncells][cap]]
+    Buf mine = dev_alloc(words * 8), all = dev_alloc(words * 8 * (size_t)W);
+    fill_u8(mine->ptr, 0, 16);
+    B200_CUDA(cudaMemcpyAsync(mine->ptr, status_flag, 4, cudaMemcpyDeviceToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(as<unsigned long long>(mine) + 2, acc, (words - 2) * 8, cudaMemcpyDeviceToDevice, st));
+    B200_NCCL(nccl().AllGather(mine->ptr, all->ptr, words, ncclUint64, c->comm, st));
+    count_launch();
+    merge_agg_tables<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(as<unsigned long long>(all), W, words, cap, ops, acc, tagmin, status_flag);
     count_launch();
 }
 

@@ -122,100 +122,6 @@ __global__ void __launch_bounds__(256, MINB) hash_bytes_kernel(const int64_t *__
 }
 
 
-// ---- short strings, staged per warp ---------------------------------------------------------------------------------
-// A warp takes 128 consecutive rows.  Their offsets arrive with coalesced loads (the end of a row is its neighbour's start: a
-// shuffle, not a second load), and when the 128 values span at most 1 KB -- flags, codes, short names: the common key
-// columns -- their bytes are ONE contiguous range of `data`, copied into shared memory with coalesced word loads.  Every row
-// then assembles its first (and last) 8 bytes from shared memory.  The per-row path above costs two offset loads and three
-// unaligned-window word loads per row; this one about 1.3 global loads per row.  Longer spans fall back to the per-row path
-// for that chunk (a warp-uniform branch).
-constexpr int HW_ROWS = 128, HW_SPAN = 1024, HW_WORDS = HW_SPAN / 4 + 8;
-__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
-    const int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffffLL), src), hi = __shfl_sync(0xffffffffu, (int)(v >> 32), src);
-    return ((int64_t)hi << 32) | (unsigned int)lo;
-}
-__device__ __forceinline__ uint64_t lds_le8(const uint32_t *buf, unsigned byte_off) {
-    const uint32_t *w = buf + (byte_off >> 2);
-    const unsigned sh = (byte_off & 3u) * 8u;
-    const uint32_t a = w[0], b = w[1], c = w[2];
-    return (uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32);
-}
-__device__ __forceinline__ uint64_t hash_short(uint64_t first8, uint64_t last8, int64_t L, uint64_t seed) {
-    if (L <= 3) {
-        const uint32_t w = (uint32_t)first8;
-        return xxh::hash_1to3(w & 0xff, (w >> (8 * (unsigned)(L >> 1))) & 0xff, (w >> (8 * (unsigned)(L - 1))) & 0xff, (uint32_t)L, seed);
-    }
-    if (L <= 8) return xxh::hash_4to8((uint32_t)first8, (uint32_t)(first8 >> (8 * (unsigned)(L - 4))), (uint32_t)L, seed);
-    return xxh::hash_9to16(first8, last8, (uint64_t)L, seed);
-}
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) hash_bytes_warp_kernel(const int64_t *__restrict__ offsets, const uint8_t *__restrict__ data,
-                                                                    const uint8_t *__restrict__ validity, const uint64_t *seed, uint64_t *out, int64_t n) {
-    __shared__ uint32_t s_buf[8][HW_WORDS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *buf = s_buf[warp];
-    const int64_t nchunks = (n + HW_ROWS - 1) / HW_ROWS;
-    for (int64_t chunk = (int64_t)blockIdx.x * 8 + warp; chunk < nchunks; chunk += (int64_t)gridDim.x * 8) {
-        const int64_t base = chunk * HW_ROWS;
-        int64_t o[4];
-        int len[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) o[u] = __ldg(offsets + min(base + u * 32 + lane, n));
-        const int64_t o_end = __ldg(offsets + min(base + HW_ROWS, n));
-#pragma unroll
-        for (int u = 0; u < 4; u++) {  // end of row (u, lane) = start of row (u, lane + 1), or of row (u + 1, 0)
-            const int64_t nxt = shfl_i64(o[u], lane + 1);
-            const int64_t first_next = u < 3 ? shfl_i64(o[u < 3 ? u + 1 : 3], 0) : o_end;  // (the index is clamped for the compiler only)
-            len[u] = (int)min((lane < 31 ? nxt : first_next) - o[u], (int64_t)1 << 30);  // anything above 16 only means "long"
-        }
-        const int64_t o0 = shfl_i64(o[0], 0);
-        const int64_t span = o_end - o0;
-        const bool staged = span <= HW_SPAN;
-        unsigned shift0 = 0;
-        if (staged) {
-            const uintptr_t p0 = reinterpret_cast<uintptr_t>(data + o0);
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(p0 & ~(uintptr_t)3);
-            shift0 = (unsigned)(p0 & 3);
-            const int nwords = (int)((shift0 + span + 3) >> 2) + 3;  // + the slack words an 8-byte window may touch (allocation tail slack, common.h)
-            for (int w = lane; w < nwords; w += 32) buf[w] = __ldg(src + w);
-            __syncwarp();
-        }
-        unsigned long_rows = 0;  // values of more than 16 bytes: hashed after the loop, where little else is live across the call
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int64_t i = base + u * 32 + lane;
-            if (i < n) {
-                const uint64_t sd = seed ? seed[i] : 0;
-                const int64_t L = len[u];
-                const bool ok = !(validity && !bit_at(validity, i));
-                uint64_t h;
-                if (!ok || L == 0) {
-                    h = xxh::hash_empty(sd);  // a null string hashes the empty slice WITH the seed (hashing.rs:243-265)
-                } else if (L > 16) {
-                    long_rows |= 1u << u;
-                    continue;
-                } else if (staged) {
-                    const unsigned at = shift0 + (unsigned)(o[u] - o0);
-                    const uint64_t f8 = lds_le8(buf, at);
-                    h = hash_short(f8, L > 8 ? lds_le8(buf, at + (unsigned)L - 8u) : 0ULL, L, sd);
-                } else {
-                    const uint64_t f8 = ld_le8(data + o[u]);
-                    h = hash_short(f8, L > 8 ? ld_le8(data + o[u] + L - 8) : 0ULL, L, sd);
-                }
-                out[i] = h;
-            }
-        }
-        __syncwarp();  // the next chunk refills the buffer
-#pragma unroll 1
-        for (int u = 0; u < 4; u++)
-            if ((long_rows >> u) & 1u) {
-                const int64_t i = base + u * 32 + lane;
-                const int64_t b0 = offsets[i];
-                out[i] = xxh::hash_17plus(data + b0, offsets[i + 1] - b0, seed ? seed[i] : 0);
-            }
-    }
-}
-
 void hash_column(const Column &c, const uint64_t *seed, uint64_t *out) {
     const int64_t n = c.length;
     if (n == 0) return;
@@ -231,16 +137,13 @@ void hash_column(const Column &c, const uint64_t *seed, uint64_t *out) {
             if (c.dtype == B200_BOOL) hash_bool_kernel<<<grid, 256, 0, st>>>(as<uint8_t>(c.data), v, seed, out, n);
             else if (c.dtype == B200_NULL) hash_null_kernel<<<grid, 256, 0, st>>>(seed, out, n);
             else if (is_string(c.dtype))
-                // 4 rows per thread at <= 64 registers (4 CTAs / SM) measured best on B200: 0.80 ms for two 60 M-row flag
-                // columns vs 1.03 ms for one row per thread; a speculative fixed-length fetch cost more in spills than it saved
             {
-                const char *env = getenv("B200_HASH_STAGED");
-                if (env && *env == '0') hash_bytes_kernel<4, 4><<<grid, 256, 0, st>>>(as<int64_t>(c.offsets), as<uint8_t>(c.data), v, seed, out, n);
-                else if (getenv("B200_HASH_MINB3"))
-                    hash_bytes_warp_kernel<3><<<(int)std::min<int64_t>((n + 1023) / 1024, (int64_t)ctx().sm_count * 6), 256, 0, st>>>(
-                        as<int64_t>(c.offsets), as<uint8_t>(c.data), v, seed, out, n);
-                else hash_bytes_warp_kernel<4><<<(int)std::min<int64_t>((n + 1023) / 1024, (int64_t)ctx().sm_count * 8), 256, 0, st>>>(
-                        as<int64_t>(c.offsets), as<uint8_t>(c.data), v, seed, out, n);
+                // 4 rows per thread at <= 64 registers (4 CTAs / SM) measured best on B200: 0.76 ms for two 60 M-row flag columns
+                // vs 1.03 ms for one row per thread.  Tried and slower: staging a warp's 128 values through shared memory with
+                // coalesced loads (0.89 ms), a speculative fixed-length fetch (spills).
+                // The spill bytes ptxas reports for this kernel sit around the out-of-line call for values of more than 16 bytes
+                // (caller-saved registers): every HB_U x MINB shape has them, none executes them on short values.
+                hash_bytes_kernel<4, 4><<<grid, 256, 0, st>>>(as<int64_t>(c.offsets), as<uint8_t>(c.data), v, seed, out, n);
             }
             else fail(std::string("Hash not implemented for type ") + dtype_name(c.dtype));
     }

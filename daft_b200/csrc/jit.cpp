@@ -74,6 +74,7 @@ struct Ast {
     std::vector<Node> nodes;
     const std::vector<int32_t> *col_dtypes;
     const std::vector<uint8_t> *col_nullable;  // per column: bit 0 = has nulls, bits 1-3 = fixed string length hint
+    int list_col_refs = 0;  // references to list columns: only the bare child of a concat aggregate may be one
     bool nullable(int c) const { return ((*col_nullable)[c] & 1) != 0; }
     // String columns whose bytes divide evenly over the rows at 1..4 B per value (flags, codes): the aggregate kernel is
     // specialised for that length and fetches the value speculatively; every row still verifies it against the offsets.
@@ -105,7 +106,7 @@ static int parse_node(Reader &r, Ast &a) {
             nd.col = (int)r.u32();
             if (nd.col < 0 || nd.col >= (int)a.col_dtypes->size()) fail("plan: column index out of range");
             nd.dtype = (*a.col_dtypes)[nd.col];
-            if (nd.dtype == B200_LIST) fail("plan: expressions cannot read list columns");
+            if (nd.dtype == B200_LIST) a.list_col_refs++;  // legal only as the bare child of a concat aggregate (gen_agg checks)
             nd.nullable = a.nullable(nd.col) || nd.dtype == B200_NULL;
             nd.key = "c" + std::to_string(nd.col);
             break;
@@ -736,6 +737,7 @@ static std::string gen_project(Reader &r, Ast &ast, Compiled &meta, bool with_ta
         names.push_back(r.str());
         roots.push_back(parse_node(r, ast));
     }
+    if (ast.list_col_refs) fail("plan: expressions cannot read list columns");
     const int iv_n = cg.int_slot(I_N);
     const int take_slot = with_take ? cg.ptr_slot(P_TAKE, 0) : -1;
     std::ostringstream body;
@@ -782,6 +784,7 @@ static std::string gen_project(Reader &r, Ast &ast, Compiled &meta, bool with_ta
 static std::string gen_filter(Reader &r, Ast &ast, Compiled &meta) {
     CG cg{ast, meta};
     const int root = parse_node(r, ast);
+    if (ast.list_col_refs) fail("plan: expressions cannot read list columns");
     if (ast.nodes[root].dtype != B200_BOOL && ast.nodes[root].dtype != B200_NULL) fail("filter: predicate must be boolean");
     const int iv_n = cg.int_slot(I_N);
     const int p_counts = cg.ptr_slot(P_OUT_LEN, 0);
@@ -910,7 +913,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
             nanyval++;
             anyval_bytes.insert(anyval_bytes.end(), r.p + start, r.p + r.pos);
         }
-        if (is_list_agg(a.kind)) {
+        if (is_list_agg(a.kind) && ast.nodes[a.root].tag != T_COL) {
             nlist++;
             list_bytes.insert(list_bytes.end(), r.p + start, r.p + r.pos);
         }
@@ -959,7 +962,7 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
         warp_cells.push_back({"", vslot, count_nulls});
         return (int)warp_cells.size() - 1;
     };
-    int anyval_seen = 0, list_seen = 0;
+    int anyval_seen = 0, list_seen = 0, legit_list_refs = 0;
     for (auto &a : aggs) {
         const Node &c = ast.nodes[a.root];
         AggOut o;
@@ -1018,17 +1021,24 @@ static std::string gen_agg(Reader &r, Ast &ast, Compiled &meta, int variant) {
                 // grouped_list / grouped_set / grouped_concat (src/daft-core/src/array/ops/list_agg.rs:30-57, series/ops/agg.rs:
                 // 531-575, array/ops/concat_agg.rs:138-161): no accumulator cell -- the host orders the rows by group after the
                 // table is built (ops_jit.cu build_list_aggs) and gathers the child, evaluated at every row, in that order
-                if (a.kind == AGG_CONCAT && !is_string(c.dtype))
-                    fail(std::string("agg: concat is offered for string columns, got ") + dtype_name(c.dtype));
+                if (a.kind == AGG_CONCAT && !is_string(c.dtype) && c.dtype != B200_LIST)
+                    fail(std::string("agg: concat is offered for string and list columns, got ") + dtype_name(c.dtype));
+                if (a.kind != AGG_CONCAT && c.dtype == B200_LIST) fail("agg: list / set of a list column is not supported");
                 o.val_dtype = c.dtype;
                 o.out_dtype = a.kind == AGG_CONCAT ? c.dtype : B200_LIST;
-                o.proj_index = list_seen++;
+                if (c.tag == T_COL) {
+                    o.child_col = c.col;
+                    if (c.dtype == B200_LIST) legit_list_refs++;
+                } else {
+                    o.proj_index = list_seen++;
+                }
                 break;
             }
             default: fail("agg: unsupported aggregation kind " + std::to_string(a.kind));
         }
         meta.aggs.push_back(o);
     }
+    if (ast.list_col_refs != legit_list_refs) fail("plan: expressions cannot read list columns");
     // lane cells = value cells, then the group's row count and its first row; warp cells = ballot counts
     const int NL = (int)lane_cells.size(), NW = (int)warp_cells.size(), NLT = NL + 2;
     meta.NLANE = NLT;

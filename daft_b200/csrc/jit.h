@@ -49,6 +49,7 @@ struct AggOut {
     int nan_cell = -1, last_cell = -1;
     // any_value(ignore_nulls) over a nullable child: the cell holds the group's first row whose child is valid (all ones: none)
     int first_valid_cell = -1;
+    int child_col = -1;      // AGG_LIST / SET / CONCAT over a bare column: the input column itself is gathered (no projection)
 };
 
 struct Compiled {

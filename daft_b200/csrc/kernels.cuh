@@ -27,6 +27,7 @@ __device__ __forceinline__ int64_t block_reduce_sum_i64(int64_t v) {
 
 __device__ __forceinline__ bool bit_at(const uint8_t *bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
 
+
 // streaming loads/stores that do not pollute L1 (data touched once)
 __device__ __forceinline__ uint64_t ldg_stream_u64(const uint64_t *p) {
     uint64_t v;

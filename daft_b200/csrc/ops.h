@@ -61,10 +61,11 @@ struct PartitionPlan {
     int64_t n = 0, nblocks = 0, chunk = 0;
     int32_t P = 0;
     Buf base;                      // scanned (partition, CTA chunk) histogram
+    Buf pid;                       // one byte per row: its partition (written by the count pass, read by the scatter)
     std::vector<int64_t> offsets;  // rows of partition p = [offsets[p], offsets[p + 1]) in partition order
 };
 PartitionPlan partition_count(const PartSrc &src, int64_t n, int32_t P);
-void partition_scatter_to_peers(const PartitionPlan &pl, const PartSrc &src, const Batch &b, const std::vector<int> &cols,
+void partition_scatter_to_peers(const PartitionPlan &pl, const Batch &b, const std::vector<int> &cols,
                                 const std::vector<std::vector<void *>> &dest_ptrs, Buf *rowid_out);
 Buf random_targets(int64_t n, int32_t P, uint64_t seed, uint64_t salt);  // u64 target per row (RepartitionSpec::Random)
 std::vector<Batch *> op_partition_by_random(const Batch &b, int32_t P, uint64_t seed);

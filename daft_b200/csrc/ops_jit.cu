@@ -517,13 +517,6 @@ __global__ void reset_cell(unsigned long long *__restrict__ cell, int64_t nrecor
     for (; i < nrecords; i += stride) cell[i * astride] = value;
 }
 
-__global__ void tag_min_prep(const unsigned long long *__restrict__ tags, int64_t cap, unsigned long long *__restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cap) {
-        const unsigned long long t = tags[i];
-        out[i] = t == 0ULL ? ~0ULL : t;
-    }
-}
 
 // `coll` != nullptr: the aggregate of a low-cardinality plan over one scan partition per rank -- the group table is
 // all-reduced across the ranks before it is read back, so every rank finishes with the global result and no second
@@ -647,8 +640,6 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         if (coll) {  // merge the tables of all ranks (also the status word: every rank takes the same decision below)
             if (records) fail("agg all-reduce: unexpected record layout");
             tagmin = dev_alloc((size_t)cap * 8);
-            tag_min_prep<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(as<unsigned long long>(acc), cap, as<unsigned long long>(tagmin));
-            count_launch();
             std::vector<int> ops(k.lane_cell_ops.begin(), k.lane_cell_ops.end());
             for (int w = 0; w < k.NWARP; w++) ops.push_back(jit::C_ADD_I64);
             std::vector<char> keep(ops.size(), 0);
@@ -783,8 +774,11 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         anyval.reset(op_project(in, k.anyval_project_plan.data(), k.anyval_project_plan.size(), as<int64_t>(minrow), ng, true));
     // ---- list / set / concat: rows ordered by group, child gathered in that order (see rows_by_group above)
     std::vector<Column> list_cols;
-    if (!k.listagg_project_plan.empty()) {
-        std::unique_ptr<Batch> vals(op_project(in, k.listagg_project_plan.data(), k.listagg_project_plan.size(), nullptr, 0));
+    bool any_list_agg = false;
+    for (const auto &ag : k.aggs) any_list_agg = any_list_agg || jit::is_list_agg(ag.kind);
+    if (any_list_agg) {
+        std::unique_ptr<Batch> vals;  // children that are expressions; bare columns are gathered from the input itself
+        if (!k.listagg_project_plan.empty()) vals.reset(op_project(in, k.listagg_project_plan.data(), k.listagg_project_plan.size(), nullptr, 0));
         RowGroups rg;
         rg.row_slot = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
         rg.rank = dev_alloc((size_t)std::max<int64_t>(cap, 1) * (size_t)astride_final * 4);
@@ -820,7 +814,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         }
         for (const auto &ag : k.aggs) {
             if (!jit::is_list_agg(ag.kind)) continue;
-            const Column &x = vals->cols[ag.proj_index];
+            const Column &x = ag.child_col >= 0 ? in.cols[ag.child_col] : vals->cols[ag.proj_index];
             const bool skip_nulls = ag.kind != jit::AGG_LIST && x.null_count > 0;
             Buf rows, gkeys, bounds;
             int64_t total = 0;
@@ -873,9 +867,11 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
                     count_launch();
                     c.data = ordered.data;
                     c.data_bytes = ordered.data_bytes;
+                    c.child = ordered.child;  // concat of lists (concat_agg.rs:68-116): the ordered lists' elements, regrouped
                 } else {
                     fill_u8(c.offsets->ptr, 0, (size_t)(ng + 1) * 8);
-                    c.data = dev_alloc(8);
+                    if (c.dtype == B200_LIST) c.child = std::make_shared<const Column>(gather_column(*x.child, nullptr, 0, false));
+                    else c.data = dev_alloc(8);
                 }
                 if (x.null_count > 0 && ng > 0) {  // null where no value of the group is valid (concat_agg.rs:140-151)
                     c.validity = dev_alloc_zero((size_t)((ng + 31) / 32 + 1) * 4);

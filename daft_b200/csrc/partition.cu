@@ -80,8 +80,10 @@ struct PartKey {
     const uint64_t *hashes;
     const void *key;
     unsigned long long m_lo, m_hi, P;
+    unsigned long long pow2_mask;  // P - 1 when P is a power of two (then hash % P is a mask), else ~0
 };
 __device__ __forceinline__ uint32_t fastmod_u64(uint64_t a, const PartKey &k) {
+    if (k.pow2_mask != ~0ULL) return (uint32_t)(a & k.pow2_mask);
     const uint64_t l_lo = k.m_lo * a;
     const uint64_t l_hi = __umul64hi(k.m_lo, a) + k.m_hi * a;
     const uint64_t t = __umul64hi(l_lo, k.P);
@@ -106,13 +108,15 @@ static PartKey make_part_key(const PartSrc &src, int32_t P) {
     const unsigned __int128 M = (~(unsigned __int128)0) / (unsigned __int128)P + 1;  // P = 1: wraps to 0, and a % 1 = 0
     k.m_lo = (unsigned long long)M;
     k.m_hi = (unsigned long long)(M >> 64);
+    k.pow2_mask = (P & (P - 1)) == 0 ? (unsigned long long)(P - 1) : ~0ULL;
     return k;
 }
 
 constexpr int PH_ROWS = 4;  // rows per thread and step of the histogram pass: four independent loads in flight
+// The pass also leaves every row's partition as ONE byte (P <= 256): the scatter pass reads that instead of hashing again.
 template <int W>
 __global__ void __launch_bounds__(PS_THREADS) partition_hist(const __grid_constant__ PartKey key, int64_t n, int64_t chunk,
-                                                             int64_t *__restrict__ hist /* [partition][block] */) {
+                                                             int64_t *__restrict__ hist /* [partition][block] */, uint8_t *__restrict__ pid) {
     __shared__ unsigned int s_cnt[PS_MAXP];
     for (int i = threadIdx.x; i < PS_MAXP; i += PS_THREADS) s_cnt[i] = 0;
     __syncthreads();
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(PS_THREADS) partition_hist(const __grid_consta
         for (int r = 0; r < PH_ROWS; r++) {
             const int64_t i = i0 + r * PS_THREADS + threadIdx.x;
             d[r] = i < end ? part_of<W>(key, i) : 0xFFFFFFFFu;
+            if (i < end) pid[i] = (uint8_t)d[r];
         }
 #pragma unroll
         for (int r = 0; r < PH_ROWS; r++) {
@@ -145,15 +150,14 @@ struct PeerDest {
     uint8_t *out[PS_PEERCOLS][PS_MAXPEERS];
     long long start[PS_MAXPEERS];
 };
-template <bool PEER, int W>
-__global__ void __launch_bounds__(PS_THREADS) partition_scatter(const __grid_constant__ PartKey key, int64_t n, int64_t chunk,
+template <bool PEER>
+__global__ void __launch_bounds__(PS_THREADS) partition_scatter(const uint8_t *__restrict__ pid, int Pn, int64_t n, int64_t chunk,
                                                                 const int64_t *__restrict__ base /* scanned hist */,
                                                                 const __grid_constant__ PartCols cols, int ncols, int64_t *__restrict__ rowid_out,
                                                                 const PeerDest *__restrict__ dest) {
     __shared__ int64_t s_base[PS_MAXP];                 // next output position per partition for this CTA
     __shared__ unsigned int s_wcnt[PS_WARPS][PS_MAXP];  // per-warp counts -> exclusive prefix over warps
     __shared__ unsigned int s_tile[PS_MAXP];
-    const int Pn = (int)key.P;
     for (int i = threadIdx.x; i < Pn; i += PS_THREADS) s_base[i] = base[(int64_t)i * gridDim.x + blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(PS_THREADS) partition_scatter(const __grid_con
         const int64_t i = t0 + threadIdx.x;
         const bool valid = i < end;
         uint32_t d = 0xFFFFFFFFu;  // out-of-range lanes only match each other
-        if (valid) d = part_of<W>(key, i);
+        if (valid) d = pid[i];
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const int rank = __popc(peers & ((1u << lane) - 1u));  // stable: lower lanes (earlier rows) first
         if (valid && rank == 0) s_wcnt[warp][d] = __popc(peers);
@@ -205,22 +209,123 @@ __global__ void __launch_bounds__(PS_THREADS) partition_scatter(const __grid_con
     if (PEER) __threadfence_system();  // the rows must be visible to the peer GPUs before this rank signals completion
 }
 
-static void launch_hist(const PartSrc &src, int32_t P, int64_t n, int64_t chunk, int64_t nblocks, int64_t *hist) {
+
+// ---- peer scatter, staged through shared memory -------------------------------------------------------------------------
+// The plain scatter above stores each row where it belongs: with W destinations a warp's store touches W short runs.  In
+// local HBM the L2 merges them; over NVLink every run is its own small write packet.  Here a CTA orders a tile of 1024 rows
+// by destination in shared memory first (stable: tile order is row order), so each destination receives ONE contiguous run
+// per column and tile -- 128 rows at W = 8, a 1 KB burst of 8-byte values -- written by consecutive lanes.
+constexpr int PP_ITEMS = 4, PP_TILE = PS_THREADS * PP_ITEMS;
+__global__ void __launch_bounds__(PS_THREADS) partition_scatter_peers_staged(const uint8_t *__restrict__ pid, int Pn, int64_t n, int64_t chunk,
+                                                                            const int64_t *__restrict__ base, const __grid_constant__ PartCols cols,
+                                                                            int ncols, int64_t *__restrict__ rowid_out, const PeerDest *__restrict__ dest) {
+    __shared__ int64_t s_base[PS_MAXPEERS];
+    __shared__ unsigned int s_wcnt[PS_WARPS][PS_MAXPEERS];
+    __shared__ unsigned int s_tile[PS_MAXPEERS], s_toff[PS_MAXPEERS];
+    __shared__ unsigned long long s_val[PP_TILE];
+    __shared__ uint8_t s_dof[PP_TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < Pn) s_base[threadIdx.x] = base[(int64_t)threadIdx.x * gridDim.x + blockIdx.x];
+    const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
+    for (int64_t t0 = begin; t0 < end; t0 += PP_TILE) {
+        if (threadIdx.x < PS_WARPS * PS_MAXPEERS) (&s_wcnt[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t wbase = t0 + (int64_t)warp * 32 * PP_ITEMS + lane;  // (warp, item, lane) order is row order
+        uint32_t d[PP_ITEMS];
+        unsigned short rank[PP_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PP_ITEMS; j++) {
+            const int64_t i = wbase + j * 32;
+            const bool valid = i < end;
+            d[j] = valid ? pid[i] : 0xFFFFFFFFu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d[j]);
+            const int lt = __popc(peers & ((1u << lane) - 1u));
+            const unsigned int before = valid ? s_wcnt[warp][d[j]] : 0u;
+            __syncwarp();
+            if (valid && lt == 0) s_wcnt[warp][d[j]] = before + __popc(peers);
+            __syncwarp();
+            rank[j] = (unsigned short)(before + lt);
+        }
+        __syncthreads();
+        if (threadIdx.x < Pn) {
+            unsigned int run = 0;
+#pragma unroll
+            for (int w = 0; w < PS_WARPS; w++) {
+                const unsigned int c = s_wcnt[w][threadIdx.x];
+                s_wcnt[w][threadIdx.x] = run;
+                run += c;
+            }
+            s_tile[threadIdx.x] = run;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int run = 0;
+            for (int dd = 0; dd < Pn; dd++) {
+                s_toff[dd] = run;
+                run += s_tile[dd];
+            }
+        }
+        __syncthreads();
+        unsigned short lp[PP_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PP_ITEMS; j++) {
+            lp[j] = 0;
+            if (wbase + j * 32 < end) {
+                lp[j] = (unsigned short)(s_toff[d[j]] + s_wcnt[warp][d[j]] + rank[j]);
+                s_dof[lp[j]] = (uint8_t)d[j];
+                if (rowid_out) rowid_out[s_base[d[j]] + (int64_t)(lp[j] - s_toff[d[j]])] = wbase + j * 32;
+            }
+        }
+        const int cnt = (int)min((int64_t)PP_TILE, end - t0);
+        for (int c = 0; c < ncols; c++) {
+            const PartCol &pc = cols.c[c];
+            __syncthreads();  // s_dof complete / the previous column's s_val consumed
+#pragma unroll
+            for (int j = 0; j < PP_ITEMS; j++) {
+                const int64_t i = wbase + j * 32;
+                if (i < end) {
+                    unsigned long long v;
+                    switch (pc.width) {
+                        case 1: v = ((const uint8_t *)pc.src)[i]; break;
+                        case 2: v = ((const uint16_t *)pc.src)[i]; break;
+                        case 4: v = ((const uint32_t *)pc.src)[i]; break;
+                        default: v = ((const unsigned long long *)pc.src)[i]; break;
+                    }
+                    s_val[lp[j]] = v;
+                }
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < cnt; e += PS_THREADS) {
+                const int dd = s_dof[e];
+                const int64_t at = s_base[dd] - dest->start[dd] + (int64_t)(e - (int)s_toff[dd]);
+                uint8_t *o = dest->out[c][dd];
+                const unsigned long long v = s_val[e];
+                switch (pc.width) {
+                    case 1: ((uint8_t *)o)[at] = (uint8_t)v; break;
+                    case 2: ((uint16_t *)o)[at] = (uint16_t)v; break;
+                    case 4: ((uint32_t *)o)[at] = (uint32_t)v; break;
+                    default: ((unsigned long long *)o)[at] = v; break;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < Pn) s_base[threadIdx.x] += s_tile[threadIdx.x];
+    }
+    __threadfence_system();  // the rows must be visible to the peer GPUs before this rank signals completion
+}
+
+static void launch_hist(const PartSrc &src, int32_t P, int64_t n, int64_t chunk, int64_t nblocks, int64_t *hist, uint8_t *pid) {
     const PartKey k = make_part_key(src, P);
     cudaStream_t st = ctx().stream;
-    if (src.key && src.width == 8) partition_hist<8><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, hist);
-    else if (src.key && src.width == 4) partition_hist<4><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, hist);
-    else partition_hist<0><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, hist);
+    if (src.key && src.width == 8) partition_hist<8><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, hist, pid);
+    else if (src.key && src.width == 4) partition_hist<4><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, hist, pid);
+    else partition_hist<0><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, hist, pid);
     count_launch();
 }
 template <bool PEER>
-static void launch_scatter(const PartSrc &src, int32_t P, int64_t n, int64_t chunk, int64_t nblocks, const int64_t *base, const PartCols &pcs, int npc,
+static void launch_scatter(const uint8_t *pid, int32_t P, int64_t n, int64_t chunk, int64_t nblocks, const int64_t *base, const PartCols &pcs, int npc,
                            int64_t *rowid, const PeerDest *dest) {
-    const PartKey k = make_part_key(src, P);
-    cudaStream_t st = ctx().stream;
-    if (src.key && src.width == 8) partition_scatter<PEER, 8><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, base, pcs, npc, rowid, dest);
-    else if (src.key && src.width == 4) partition_scatter<PEER, 4><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, base, pcs, npc, rowid, dest);
-    else partition_scatter<PEER, 0><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(k, n, chunk, base, pcs, npc, rowid, dest);
+    partition_scatter<PEER><<<(unsigned)nblocks, PS_THREADS, 0, ctx().stream>>>(pid, (int)P, n, chunk, base, pcs, npc, rowid, dest);
     count_launch();
 }
 // One never-null integer key of 4 or 8 bytes: its XXH3 is a few multiplies, cheaper than writing and re-reading a hash column
@@ -258,7 +363,8 @@ Batch *partition_staged(const Batch &b, const PartSrc &src, int32_t P, std::vect
     chunk = (chunk + PS_THREADS - 1) / PS_THREADS * PS_THREADS;
     nblocks = (n + chunk - 1) / chunk;
     Buf hist = dev_alloc((size_t)P * nblocks * 8), base = dev_alloc((size_t)(P * nblocks + 1) * 8), starts = dev_alloc((size_t)(P + 1) * 8);
-    launch_hist(src, P, n, chunk, nblocks, as<int64_t>(hist));
+    Buf pid = dev_alloc((size_t)std::max<int64_t>(n, 1));
+    launch_hist(src, P, n, chunk, nblocks, as<int64_t>(hist), as<uint8_t>(pid));
     exclusive_scan_i64(as<int64_t>(hist), as<int64_t>(base), (int64_t)P * nblocks, nullptr);
     pick_strided<<<(P + 255) / 256, 256, 0, st>>>(as<int64_t>(base), nblocks, P, as<int64_t>(starts));
     count_launch();
@@ -280,7 +386,7 @@ Batch *partition_staged(const Batch &b, const PartSrc &src, int32_t P, std::vect
         }
     }
     Buf rowid = need_rowid ? dev_alloc((size_t)n * 8) : Buf();
-    launch_scatter<false>(src, P, n, chunk, nblocks, as<int64_t>(base), pcs, npc, as<int64_t>(rowid), nullptr);
+    launch_scatter<false>(as<uint8_t>(pid), P, n, chunk, nblocks, as<int64_t>(base), pcs, npc, as<int64_t>(rowid), nullptr);
     B200_CUDA(cudaStreamSynchronize(st));
     offsets[(size_t)P] = n;
     auto out = std::make_unique<Batch>();
@@ -320,7 +426,8 @@ PartitionPlan partition_count(const PartSrc &src, int64_t n, int32_t P) {
     pl.chunk = chunk;
     Buf hist = dev_alloc((size_t)P * nblocks * 8), starts = dev_alloc((size_t)(P + 1) * 8);
     pl.base = dev_alloc((size_t)(P * nblocks + 1) * 8);
-    launch_hist(src, P, n, chunk, nblocks, as<int64_t>(hist));
+    pl.pid = dev_alloc((size_t)std::max<int64_t>(n, 1));
+    launch_hist(src, P, n, chunk, nblocks, as<int64_t>(hist), as<uint8_t>(pl.pid));
     exclusive_scan_i64(as<int64_t>(hist), as<int64_t>(pl.base), (int64_t)P * nblocks, nullptr);
     pick_strided<<<(P + 255) / 256, 256, 0, st>>>(as<int64_t>(pl.base), nblocks, P, as<int64_t>(starts));
     count_launch();
@@ -331,7 +438,7 @@ PartitionPlan partition_count(const PartSrc &src, int64_t n, int32_t P) {
     return pl;
 }
 // cols[c] of `b` (fixed width, no nulls) -> dest_ptrs[c][d] (already offset to this sender's slot in rank d's buffer)
-void partition_scatter_to_peers(const PartitionPlan &pl, const PartSrc &src, const Batch &b, const std::vector<int> &cols,
+void partition_scatter_to_peers(const PartitionPlan &pl, const Batch &b, const std::vector<int> &cols,
                                 const std::vector<std::vector<void *>> &dest_ptrs, Buf *rowid_out) {
     cudaStream_t st = ctx().stream;
     if ((int)cols.size() > PS_PEERCOLS || pl.P > PS_MAXPEERS) fail("peer scatter: too many columns / peers");
@@ -348,7 +455,14 @@ void partition_scatter_to_peers(const PartitionPlan &pl, const PartSrc &src, con
     B200_CUDA(cudaMemcpyAsync(dpd->ptr, &pd, sizeof(PeerDest), cudaMemcpyHostToDevice, st));
     Buf rowid = rowid_out ? dev_alloc((size_t)std::max<int64_t>(pl.n, 1) * 8) : Buf();
     KernelTimer kt("partition_scatter_peer");
-    launch_scatter<true>(src, pl.P, pl.n, pl.chunk, pl.nblocks, as<int64_t>(pl.base), pcs, (int)cols.size(), as<int64_t>(rowid), as<PeerDest>(dpd));
+    const char *env = getenv("B200_PEER_SCATTER_STAGED");
+    if (env && *env == '0') {
+        launch_scatter<true>(as<uint8_t>(pl.pid), pl.P, pl.n, pl.chunk, pl.nblocks, as<int64_t>(pl.base), pcs, (int)cols.size(), as<int64_t>(rowid), as<PeerDest>(dpd));
+    } else {
+        partition_scatter_peers_staged<<<(unsigned)pl.nblocks, PS_THREADS, 0, st>>>(as<uint8_t>(pl.pid), (int)pl.P, pl.n, pl.chunk, as<int64_t>(pl.base), pcs,
+                                                                                   (int)cols.size(), as<int64_t>(rowid), as<PeerDest>(dpd));
+        count_launch();
+    }
     B200_CUDA(cudaStreamSynchronize(st));  // `pd` is a stack object; the caller's barrier follows anyway
     if (rowid_out) *rowid_out = rowid;
 }

@@ -360,8 +360,10 @@ int b200_tpch_generate_host(int32_t table, double scale_factor, int64_t row_begi
  *   FILTER  plan := node predicate               (conjuncts already AND-ed, lib.rs:520-541)
  *   AGG     plan := u8 has_filter, [node filter], u32 nkeys, nkeys x (str name, node),
  *                   u32 naggs, naggs x (u8 kind, u8 count_mode, str name, node child)
- *     agg kinds: 0 count 1 sum 2 min 3 max 4 mean 5 any_value;  count modes: 0 all 1 valid 2 null;
- *     any_value mode: 0 first row of the group, 1 ignore_nulls (first non-null row; inputs that cannot be null only);
+ *     agg kinds: 0 count 1 sum 2 min 3 max 4 mean 5 any_value 6 list 7 set 8 concat;  count modes: 0 all 1 valid 2 null;
+ *     any_value mode: 0 first row of the group, 1 ignore_nulls (first non-null row, null for an all-null group);
+ *     list: the group's values in row order, nulls kept (B200_LIST);  set: its distinct non-null values in first-occurrence
+ *     order (B200_LIST);  concat: its non-null strings back to back (string children only);  mode byte 0 for all three;
  *     min / max over Boolean are bool_and / bool_or
  */
 #define B200_OP_PROJECT 0

@@ -133,3 +133,37 @@ def test_list_columns_are_refused_by_row_moving_operators(gpu):
         res.eval_expression_list([c("l").is_null()])
     with pytest.raises(Exception):
         res.partition_by_hash([c("k")], 2)
+
+
+@pytest.mark.parametrize("morsel", [900, 7000])
+def test_list_and_concat_through_the_two_stage_sink(gpu, morsel):
+    """AggExpr::List / Concat across morsels (src/daft-local-plan/src/agg.rs:286-301): a list per morsel, then the CONCAT of the
+    partial lists (concat over a List column, src/daft-core/src/array/ops/concat_agg.rs:68-116) -- pushed in row order the result
+    equals the single-batch aggregate."""
+    from daft_b200.aggstages import GroupedAggregateSink
+    rng = np.random.default_rng(morsel)
+    tbl = random_table(rng, 20_000, 0.2)
+    c = gpu.col
+    aggs = [c("i32").agg_list().alias("l"), c("s").agg_list().alias("ls"), c("s").agg_concat().alias("cat"), c("i64").sum().alias("tot"),
+            c("f64").mean().alias("m")]
+    for gb, pred in (([c("k")], None), ([c("u8"), c("b")], [c("i32") > 0]), ([], None)):
+        sink = GroupedAggregateSink(aggs, gb, pred)
+        for o in range(0, tbl.num_rows, morsel):
+            sink.sink(RB(gpu, tbl.slice(o, morsel)))
+        got = sink.finalize().to_arrow_table()
+        want = oracle_agg(tbl, aggs, gb, pred)
+        assert_tables_equal(got, want, float_rtol=1e-9, sort_by=[g.name() for g in gb] or None)
+
+
+def test_concat_of_list_columns(gpu):
+    """grouped_concat over a List column: null lists are skipped, a group without a valid list is null, empty lists count as valid
+    (concat_agg.rs:68-116 and its tests :170-230)."""
+    c = gpu.col
+    t = pa.table({"g": pa.array([1, 1, 2, 2, 3, 3, 3], type=pa.int64()), "v": pa.array([1, 2, 3, None, None, None, 7], type=pa.int64()),
+                  "p": pa.array([0, 1, 0, 0, 0, 1, 1], type=pa.int64())})
+    lists = RB(gpu, t).agg([c("v").agg_list().alias("l")], [c("g"), c("p")])       # (1,0):[1] (1,1):[2] (2,0):[3,None] (3,0):[None] (3,1):[None,7]
+    got = lists.agg([c("l").agg_concat().alias("all")], [c("g")]).to_pydict()
+    assert got == {"g": [1, 2, 3], "all": [[1, 2], [3, None], [None, None, 7]]}
+    assert lists.agg([c("l").agg_concat().alias("all")], []).to_pydict() == {"all": [[1, 2, 3, None, None, None, 7]]}
+    with pytest.raises(Exception):
+        lists.agg([c("l").agg_list().alias("ll")], [c("g")])

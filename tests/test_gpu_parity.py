@@ -355,9 +355,9 @@ def test_sort_multikey(gpu):
 
 @pytest.mark.parametrize("n", [70_000, 300_001, 1_500_000])
 def test_sort_onesweep_equals_two_kernel_radix(gpu, n, monkeypatch):
-    """Inputs of 65 536 rows and more take the onesweep passes (one histogram for all digits, decoupled look-back in the scatter,
-    sort.cu radix_onesweep); the per-pass histogram + scan scheme stays for small and huge inputs.  Both are stable LSD sorts, so
-    their argsorts are IDENTICAL, ties included -- and equal to the oracle's stable sort."""
+    """The opt-in onesweep passes (B200_SORT_ONESWEEP=1: one histogram for all digits, decoupled look-back in the scatter,
+    sort.cu radix_onesweep) against the default per-pass histogram + scan scheme.  Both are stable LSD sorts, so their argsorts
+    are IDENTICAL, ties included -- and equal to the oracle's stable sort."""
     rng = np.random.default_rng(n)
     tbl = pa.table({"a": pa.array(rng.integers(-50, 50, n).astype(np.int64), mask=rng.random(n) < 0.05),        # heavy ties, nulls
                     "f": pa.array(np.where(rng.random(n) < 0.01, np.nan, rng.standard_normal(n) * 1e6)),            # all 8 bytes live
