@@ -156,7 +156,7 @@ def cpu_q1_run(sf: float, rows_begin: int, rows_end: int, steps: int, warmup: in
         ans, tasks = CE.q1(cols, threads)
     dt = time.perf_counter() - t0
     return {"rows": n, "rows_per_s": n * steps / dt, "ms_per_step": dt / steps * 1e3, "tasks": tasks, "answer": ans, "steps": steps,
-            "threads": threads or (os.cpu_count() or 1)}
+            "threads": threads or CE.usable_threads()}
 
 
 def cpu_q5_run(sf: float, steps: int, warmup: int, threads: int = 0):
@@ -171,13 +171,25 @@ def cpu_q5_run(sf: float, steps: int, warmup: int, threads: int = 0):
         ans, tasks, probes = CE.q5(cols, threads)
     dt = time.perf_counter() - t0
     return {"rows": n, "rows_per_s": n * steps / dt, "probe_rows_per_s": probes * steps / dt, "ms_per_step": dt / steps * 1e3, "tasks": tasks,
-            "answer": ans, "steps": steps, "threads": threads or (os.cpu_count() or 1), "cols": cols}
+            "answer": ans, "steps": steps, "threads": threads or CE.usable_threads(), "cols": cols}
 
 
 def q5_cpu_sf(q5_sf: float) -> float:
     """The CPU engine needs the tables (22.5 GB at SF100) plus its probe tables in host RAM."""
     need_gb = 0.45 * q5_sf + 8
     return q5_sf if host_mem_available_gb() > need_gb else min(q5_sf, 10.0)
+
+
+def host_cpu_info():
+    """What the host gives this process: logical CPUs and the cgroup quota (a box can show 128 CPUs and allow a dozen)."""
+    info = {"logical_cpus": os.cpu_count()}
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            info["cgroup_" + os.path.basename(path)] = open(path).read().strip()
+            break
+        except OSError:
+            pass
+    return info
 
 
 CPU_NOTE = "CPU restatement of the reference algorithm (oracle/cpu_engine.cpp: 131072-row morsels, one worker per host thread, " \
@@ -189,7 +201,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import cpu_engine as CE
-    threads = os.cpu_count() or 1
+    threads = CE.usable_threads()   # CPUs of the affinity mask, capped by the cgroup CPU quota
     n = CE.num_rows("lineitem", args.sf)
     steps, warmup = max(1, args.steps), max(1, args.warmup)
     r = cpu_q1_run(args.sf, 0, n, steps, warmup)
@@ -200,6 +212,7 @@ def run_reference(args):
         "cpu_baseline": {"value": r["rows_per_s"], "unit": UNIT, "cores": threads, "kind": "port", "tasks_per_step": r["tasks"],
                          "sample": f"the whole workload: lineitem SF{args.sf:g} ({n} rows) per step, {steps} steps", "note": CPU_NOTE},
         "e2e": {"value": r["rows_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": host_cpu_info(),
     }
     if not args.no_q5 and args.gpus == 1:
         sf5 = q5_cpu_sf(args.q5_sf)
@@ -567,7 +580,7 @@ def run_q5(args, stream, barrier, peak, peak_src):
         ans, tasks, probes = CE.q5(cols, 0)
         dt = time.perf_counter() - t0
         n_cpu = len(cols["lineitem"]["L_ORDERKEY"][0])
-        threads = os.cpu_count() or 1
+        threads = CE.usable_threads()
         if sf_cpu == sf:
             checks["q5_answer_vs_cpu_engine"] = check_answer(result, ans, ["N_NAME"], "q5 value leg")
         else:

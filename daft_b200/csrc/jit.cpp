@@ -1670,6 +1670,25 @@ std::vector<int32_t> referenced_columns(int op, const uint8_t *plan, size_t plan
     return cols;
 }
 
+std::vector<ProjectEntry> project_entries(const uint8_t *plan, size_t plan_len) {
+    Reader r{plan, plan_len};
+    std::vector<ProjectEntry> out;
+    const uint32_t n = r.u32();
+    for (uint32_t i = 0; i < n; i++) {
+        ProjectEntry e;
+        e.begin = r.pos;
+        e.name = r.str();
+        const size_t node = r.pos;
+        std::vector<int32_t> cols;
+        scan_node(r, cols);
+        e.end = r.pos;
+        if (plan[node] == T_COL && e.end - node == 5) memcpy(&e.bare_col, plan + node + 1, 4);
+        out.push_back(std::move(e));
+    }
+    if (r.pos != r.n) fail("plan: trailing bytes");
+    return out;
+}
+
 std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
                      const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta, int variant) {
     Reader r{plan, plan_len};

@@ -89,6 +89,13 @@ struct Compiled {
 std::string generate(int op, const uint8_t *plan, size_t plan_len, const std::vector<int32_t> &col_dtypes,
                      const std::vector<uint8_t> &col_nullable, bool with_take, Compiled &meta, int variant = 0);
 // column indices the plan reads
+// the expressions of a PROJECT plan: name, byte range of [str name, node] inside the plan, column index when the node is a bare column
+struct ProjectEntry {
+    std::string name;
+    size_t begin = 0, end = 0;
+    int32_t bare_col = -1;
+};
+std::vector<ProjectEntry> project_entries(const uint8_t *plan, size_t plan_len);
 std::vector<int32_t> referenced_columns(int op, const uint8_t *plan, size_t plan_len);
 // NVRTC -> cubin (cached on disk); works without a GPU.
 std::vector<char> compile_to_cubin(const std::string &source, std::string *path_out);

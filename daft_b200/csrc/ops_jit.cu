@@ -21,7 +21,43 @@ static int stream_grid(int64_t n, int threads, int per_sm) {
 // Project (RecordBatch::eval_expression_list, src/daft-recordbatch/src/lib.rs:1603-1631)
 // optional take_idx: evaluate the expressions at rows take_idx[i] (negative -> null row)
 // ------------------------------------------------------------------------------------------------
+static Batch *op_project_flat(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n, bool take_nonneg);
+
+// List columns are not readable by expressions, but a projection may carry them along as bare column references (the final
+// projection of a two-stage list aggregate does): those are passed through -- shared, or gathered with `take` -- and only the
+// other expressions are compiled.
 Batch *op_project(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n, bool take_nonneg) {
+    bool any_list = false;
+    for (const Column &c : in.cols) any_list = any_list || c.dtype == B200_LIST;
+    if (!any_list) return op_project_flat(in, plan, len, take_idx, take_n, take_nonneg);
+    const std::vector<jit::ProjectEntry> ents = jit::project_entries(plan, len);
+    std::vector<uint8_t> rest(4);
+    uint32_t nrest = 0;
+    std::vector<int> where(ents.size(), -1);
+    for (size_t i = 0; i < ents.size(); i++) {
+        const int32_t bc = ents[i].bare_col;
+        if (bc >= 0 && bc < (int32_t)in.cols.size() && in.cols[bc].dtype == B200_LIST) continue;
+        where[i] = (int)nrest++;
+        rest.insert(rest.end(), plan + ents[i].begin, plan + ents[i].end);
+    }
+    memcpy(rest.data(), &nrest, 4);
+    std::unique_ptr<Batch> flat;
+    if (nrest) flat.reset(op_project_flat(in, rest.data(), rest.size(), take_idx, take_n, take_nonneg));
+    auto out = std::make_unique<Batch>();
+    out->num_rows = take_idx ? take_n : in.num_rows;
+    for (size_t i = 0; i < ents.size(); i++) {
+        if (where[i] >= 0) {
+            out->cols.push_back(std::move(flat->cols[(size_t)where[i]]));
+        } else {
+            Column c = take_idx ? gather_column(materialize(in.cols[ents[i].bare_col]), take_idx, take_n, !take_nonneg) : in.cols[ents[i].bare_col];
+            c.name = ents[i].name;
+            out->cols.push_back(std::move(c));
+        }
+    }
+    return out.release();
+}
+
+static Batch *op_project_flat(const Batch &in, const uint8_t *plan, size_t len, const int64_t *take_idx, int64_t take_n, bool take_nonneg) {
     require_device();
     const bool with_take = take_idx != nullptr;
     const Compiled &k = jit::get(B200_OP_PROJECT, plan, len, in, with_take);

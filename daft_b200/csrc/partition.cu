@@ -210,26 +210,28 @@ __global__ void __launch_bounds__(PS_THREADS) partition_scatter(const uint8_t *_
 }
 
 
-// ---- peer scatter, staged through shared memory -------------------------------------------------------------------------
+// ---- scatter staged through shared memory (local partitions and peer stores) -------------------------------------------------------------------------
 // The plain scatter above stores each row where it belongs: with W destinations a warp's store touches W short runs.  In
 // local HBM the L2 merges them; over NVLink every run is its own small write packet.  Here a CTA orders a tile of 1024 rows
 // by destination in shared memory first (stable: tile order is row order), so each destination receives ONE contiguous run
 // per column and tile -- 128 rows at W = 8, a 1 KB burst of 8-byte values -- written by consecutive lanes.
 constexpr int PP_ITEMS = 4, PP_TILE = PS_THREADS * PP_ITEMS;
-__global__ void __launch_bounds__(PS_THREADS) partition_scatter_peers_staged(const uint8_t *__restrict__ pid, int Pn, int64_t n, int64_t chunk,
-                                                                            const int64_t *__restrict__ base, const __grid_constant__ PartCols cols,
-                                                                            int ncols, int64_t *__restrict__ rowid_out, const PeerDest *__restrict__ dest) {
-    __shared__ int64_t s_base[PS_MAXPEERS];
-    __shared__ unsigned int s_wcnt[PS_WARPS][PS_MAXPEERS];
-    __shared__ unsigned int s_tile[PS_MAXPEERS], s_toff[PS_MAXPEERS];
+template <bool PEER>
+__global__ void __launch_bounds__(PS_THREADS) partition_scatter_staged(const uint8_t *__restrict__ pid, int Pn, int64_t n, int64_t chunk,
+                                                                      const int64_t *__restrict__ base, const __grid_constant__ PartCols cols,
+                                                                      int ncols, int64_t *__restrict__ rowid_out, const PeerDest *__restrict__ dest) {
+    static_assert(PS_MAXP == PS_THREADS, "one thread per partition in the prefix step");
+    __shared__ int64_t s_base[PS_MAXP];
+    __shared__ unsigned int s_wcnt[PS_WARPS][PS_MAXP];
+    __shared__ unsigned int s_tile[PS_MAXP], s_toff[PS_MAXP], s_wtot[PS_WARPS];
     __shared__ unsigned long long s_val[PP_TILE];
     __shared__ uint8_t s_dof[PP_TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < Pn) s_base[threadIdx.x] = base[(int64_t)threadIdx.x * gridDim.x + blockIdx.x];
+    s_base[threadIdx.x] = threadIdx.x < Pn ? base[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] : 0;
     const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(begin + chunk, n);
     for (int64_t t0 = begin; t0 < end; t0 += PP_TILE) {
-        if (threadIdx.x < PS_WARPS * PS_MAXPEERS) (&s_wcnt[0][0])[threadIdx.x] = 0;
-        __syncthreads();
+        for (int i = lane; i < Pn; i += 32) s_wcnt[warp][i] = 0;
+        __syncwarp();
         const int64_t wbase = t0 + (int64_t)warp * 32 * PP_ITEMS + lane;  // (warp, item, lane) order is row order
         uint32_t d[PP_ITEMS];
         unsigned short rank[PP_ITEMS];
@@ -247,23 +249,29 @@ __global__ void __launch_bounds__(PS_THREADS) partition_scatter_peers_staged(con
             rank[j] = (unsigned short)(before + lt);
         }
         __syncthreads();
-        if (threadIdx.x < Pn) {
+        {
+            const int dd = threadIdx.x;
             unsigned int run = 0;
+            if (dd < Pn) {
 #pragma unroll
-            for (int w = 0; w < PS_WARPS; w++) {
-                const unsigned int c = s_wcnt[w][threadIdx.x];
-                s_wcnt[w][threadIdx.x] = run;
-                run += c;
+                for (int w = 0; w < PS_WARPS; w++) {
+                    const unsigned int c = s_wcnt[w][dd];
+                    s_wcnt[w][dd] = run;
+                    run += c;
+                }
             }
-            s_tile[threadIdx.x] = run;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned int run = 0;
-            for (int dd = 0; dd < Pn; dd++) {
-                s_toff[dd] = run;
-                run += s_tile[dd];
+            s_tile[dd] = run;
+            unsigned int x = run;  // exclusive scan over the partitions: where a destination's run starts inside the tile
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
             }
+            if (lane == 31) s_wtot[warp] = x;
+            __syncthreads();
+            unsigned int wpre = 0;
+#pragma unroll
+            for (int w = 0; w < PS_WARPS; w++) wpre += w < warp ? s_wtot[w] : 0u;
+            s_toff[dd] = wpre + x - run;
         }
         __syncthreads();
         unsigned short lp[PP_ITEMS];
@@ -297,8 +305,12 @@ __global__ void __launch_bounds__(PS_THREADS) partition_scatter_peers_staged(con
             __syncthreads();
             for (int e = threadIdx.x; e < cnt; e += PS_THREADS) {
                 const int dd = s_dof[e];
-                const int64_t at = s_base[dd] - dest->start[dd] + (int64_t)(e - (int)s_toff[dd]);
-                uint8_t *o = dest->out[c][dd];
+                int64_t at = s_base[dd] + (int64_t)(e - (int)s_toff[dd]);
+                uint8_t *o = (uint8_t *)pc.out;
+                if (PEER) {
+                    at -= dest->start[dd];
+                    o = dest->out[c][dd];
+                }
                 const unsigned long long v = s_val[e];
                 switch (pc.width) {
                     case 1: ((uint8_t *)o)[at] = (uint8_t)v; break;
@@ -309,9 +321,9 @@ __global__ void __launch_bounds__(PS_THREADS) partition_scatter_peers_staged(con
             }
         }
         __syncthreads();
-        if (threadIdx.x < Pn) s_base[threadIdx.x] += s_tile[threadIdx.x];
+        s_base[threadIdx.x] += s_tile[threadIdx.x];
     }
-    __threadfence_system();  // the rows must be visible to the peer GPUs before this rank signals completion
+    if (PEER) __threadfence_system();  // the rows must be visible to the peer GPUs before this rank signals completion
 }
 
 static void launch_hist(const PartSrc &src, int32_t P, int64_t n, int64_t chunk, int64_t nblocks, int64_t *hist, uint8_t *pid) {
@@ -386,7 +398,16 @@ Batch *partition_staged(const Batch &b, const PartSrc &src, int32_t P, std::vect
         }
     }
     Buf rowid = need_rowid ? dev_alloc((size_t)n * 8) : Buf();
-    launch_scatter<false>(as<uint8_t>(pid), P, n, chunk, nblocks, as<int64_t>(base), pcs, npc, as<int64_t>(rowid), nullptr);
+    {
+        const char *env = getenv("B200_SCATTER_STAGED");
+        if (env && *env == '0') {
+            launch_scatter<false>(as<uint8_t>(pid), P, n, chunk, nblocks, as<int64_t>(base), pcs, npc, as<int64_t>(rowid), nullptr);
+        } else {
+            partition_scatter_staged<false><<<(unsigned)nblocks, PS_THREADS, 0, st>>>(as<uint8_t>(pid), (int)P, n, chunk, as<int64_t>(base), pcs, npc,
+                                                                                     as<int64_t>(rowid), nullptr);
+            count_launch();
+        }
+    }
     B200_CUDA(cudaStreamSynchronize(st));
     offsets[(size_t)P] = n;
     auto out = std::make_unique<Batch>();
@@ -459,7 +480,7 @@ void partition_scatter_to_peers(const PartitionPlan &pl, const Batch &b, const s
     if (env && *env == '0') {
         launch_scatter<true>(as<uint8_t>(pl.pid), pl.P, pl.n, pl.chunk, pl.nblocks, as<int64_t>(pl.base), pcs, (int)cols.size(), as<int64_t>(rowid), as<PeerDest>(dpd));
     } else {
-        partition_scatter_peers_staged<<<(unsigned)pl.nblocks, PS_THREADS, 0, st>>>(as<uint8_t>(pl.pid), (int)pl.P, pl.n, pl.chunk, as<int64_t>(pl.base), pcs,
+        partition_scatter_staged<true><<<(unsigned)pl.nblocks, PS_THREADS, 0, st>>>(as<uint8_t>(pl.pid), (int)pl.P, pl.n, pl.chunk, as<int64_t>(pl.base), pcs,
                                                                                    (int)cols.size(), as<int64_t>(rowid), as<PeerDest>(dpd));
         count_launch();
     }

@@ -887,7 +887,6 @@ Column concat_columns(const std::vector<const Column *> &cols) {
     out.length = n;
     out.null_count = nulls;
     if (out.dtype == B200_NULL) return out;
-    if (out.dtype == B200_LIST) fail("concat: list columns are not supported");
     if (nulls > 0) {
         out.validity = dev_alloc_zero(((n + 31) / 32) * 4);
         int64_t pos = 0;
@@ -942,6 +941,25 @@ Column concat_columns(const std::vector<const Column *> &cols) {
         }
         B200_CUDA(cudaMemcpyAsync(as<int64_t>(out.offsets) + n, &bytes, 8, cudaMemcpyHostToDevice, st));
         B200_CUDA(cudaStreamSynchronize(st));  // `bytes` is a stack variable
+    } else if (out.dtype == B200_LIST) {
+        // lists built by this library start at offset 0 and own exactly their child (aggregates, gathers): the parts' offsets
+        // are shifted by the elements before them and the children concatenated
+        out.offsets = dev_alloc((size_t)(n + 1) * 8);
+        int64_t pos = 0, epos = 0;
+        std::vector<const Column *> kids;
+        for (auto *c : cols) {
+            if (!c->child) fail("concat: list column without a child");
+            if (c->length) {
+                shift_offsets<<<grid_for(c->length), 256, 0, st>>>(as<int64_t>(c->offsets), c->length, epos, as<int64_t>(out.offsets) + pos);
+                count_launch();
+            }
+            pos += c->length;
+            epos += c->child->length;
+            kids.push_back(c->child.get());
+        }
+        B200_CUDA(cudaMemcpyAsync(as<int64_t>(out.offsets) + n, &epos, 8, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaStreamSynchronize(st));  // `epos` is a stack variable
+        out.child = std::make_shared<const Column>(concat_columns(kids));
     } else {
         fail(std::string("concat: unsupported dtype ") + dtype_name(out.dtype));
     }

@@ -49,8 +49,11 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist(const uint64_t *__restr
 // item).  The tile is then ordered by digit in shared memory and written out by consecutive threads, so every
 // digit's rows leave as one contiguous, coalesced run instead of 32 scattered 8-byte stores per instruction.
 constexpr int RS_ITEMS = 8;
+#ifndef RS_MINB
+#define RS_MINB 4
+#endif
 template <int BITS>
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint64_t *__restrict__ keys, const int64_t *__restrict__ vals,
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) radix_scatter(const uint64_t *__restrict__ keys, const int64_t *__restrict__ vals,
                                                              int64_t n, int64_t chunk, int shift, uint32_t xor_mask,
                                                              const int64_t *__restrict__ base /* scanned hist */,
                                                              uint64_t *__restrict__ keys_out, int64_t *__restrict__ vals_out) {
@@ -73,18 +76,12 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint64_t *__re
         __syncwarp();
         const int64_t wbase = t0 + (int64_t)warp * 32 * RS_ITEMS + lane;
         uint64_t k[RS_ITEMS];
-        int64_t v[RS_ITEMS];
         uint32_t d[RS_ITEMS];
         unsigned short rank[RS_ITEMS];
 #pragma unroll
         for (int j = 0; j < RS_ITEMS; j++) {
             const int64_t i = wbase + j * 32;
-            k[j] = 0;
-            v[j] = 0;
-            if (i < end) {
-                k[j] = keys[i];
-                v[j] = vals[i];
-            }
+            k[j] = i < end ? keys[i] : 0;
         }
 #pragma unroll
         for (int j = 0; j < RS_ITEMS; j++) {
@@ -126,9 +123,11 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint64_t *__re
 #pragma unroll
         for (int j = 0; j < RS_ITEMS; j++) {
             if (wbase + j * 32 < end) {
+                // the row ids are loaded here, after the ranking: they are only passed through, and holding them in
+                // registers across the ranking costs a resident CTA per SM
                 const unsigned int lp = s_toff[d[j]] + s_wcnt[warp][d[j]] + rank[j];
                 s_k[lp] = k[j];
-                s_v[lp] = v[j];
+                s_v[lp] = vals[wbase + j * 32];
             }
         }
         __syncthreads();

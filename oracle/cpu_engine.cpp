@@ -31,6 +31,9 @@
  */
 #include <algorithm>
 #include <malloc.h>
+#include <sched.h>
+#include <cstring>
+#include <cstdio>
 #include <climits>
 #include <atomic>
 #include <cmath>
@@ -72,11 +75,30 @@ using namespace b200::tpchgen;
 constexpr int64_t MORSEL = 131072;
 enum { T_I64 = 5, T_F64 = 11, T_DATE32 = 12, T_UTF8 = 14 };
 
-int hw_threads(int threads) {
-    if (threads > 0) return threads;
-    const unsigned h = std::thread::hardware_concurrency();
-    return h ? (int)h : 1;
+// Workers the process may actually run: the CPUs of its affinity mask, capped by the cgroup's CFS quota (a container that
+// sees 128 CPUs but is allowed 12 of them spends most of 128 workers' time throttled).
+int usable_threads() {
+    int n = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(n > 0 ? n : CPU_COUNT(&set), CPU_COUNT(&set));
+    if (n < 1) n = 1;
+    long long quota = -1, period = 100000;
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {  // cgroup v2: "<quota|max> <period>"
+        char q[64] = {0};
+        if (fscanf(f, "%63s %lld", q, &period) >= 1 && strcmp(q, "max") != 0) quota = atoll(q);
+        fclose(f);
+    } else if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {  // cgroup v1
+        if (fscanf(g, "%lld", &quota) != 1) quota = -1;
+        fclose(g);
+        if (FILE *h = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+            if (fscanf(h, "%lld", &period) != 1) period = 100000;
+            fclose(h);
+        }
+    }
+    if (quota > 0 && period > 0) n = (int)std::min<long long>(n, std::max<long long>(1, (quota + period - 1) / period));
+    return n;
 }
+int hw_threads(int threads) { return threads > 0 ? threads : usable_threads(); }
 
 // Per-morsel temporaries are megabyte-sized vectors.  glibc serves those with mmap / munmap by default, so every morsel
 // would fault its pages in afresh under the process-wide mm lock -- at 128 workers that lock, not the query, is what
@@ -274,6 +296,8 @@ CPU_EXPORT const char *cpu_tpch_name(int is_region, int64_t row) { return is_reg
 // Q1 (benchmarking/tpch/answers.py:12-32)
 // out_*: up to `cap` groups, sorted by (L_RETURNFLAG, L_LINESTATUS); returns the number of groups
 // =====================================================================================================================
+CPU_EXPORT int cpu_usable_threads() { return usable_threads(); }
+
 CPU_EXPORT int64_t cpu_q1(int64_t n, const int64_t *qty, const double *price, const double *disc, const double *tax, const int64_t *rf_off,
                           const uint8_t *rf, const int64_t *ls_off, const uint8_t *ls, const int32_t *ship, int32_t ship_cutoff, int threads,
                           int64_t cap, char *out_rf, char *out_ls, int64_t *sum_qty, double *sum_base, double *sum_disc_price, double *sum_charge,

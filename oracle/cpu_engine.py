@@ -119,6 +119,11 @@ def _days(d: datetime.date) -> int:
     return (d - _EPOCH).days
 
 
+def usable_threads() -> int:
+    """Workers a query uses by default: CPUs of the affinity mask, capped by the cgroup CPU quota (cpu_engine.cpp usable_threads)."""
+    return int(lib().cpu_usable_threads())
+
+
 def q1(cols: dict[str, tuple], threads: int = 0) -> tuple[pa.Table, int]:
     """TPC-H Q1 over numpy column buffers (generate_columns('lineitem', sf, Q1_COLUMNS)); returns (answer, morsel tasks)."""
     qty, price, disc, tax = cols["L_QUANTITY"][0], cols["L_EXTENDEDPRICE"][0], cols["L_DISCOUNT"][0], cols["L_TAX"][0]
