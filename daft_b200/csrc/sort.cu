@@ -456,6 +456,79 @@ __global__ void make_string_digit(const int64_t *__restrict__ offsets, const uin
         out[i] = d;
     }
 }
+
+// ---- strings: sort by a 7-byte chunk, then refine only the rows that still tie ------------------------------------------
+// A byte-position LSD sort costs one pass over ALL rows per byte of the LONGEST value: one comment of a few hundred bytes and
+// the sort runs hundreds of passes.  Instead: chunk r of a value = its bytes [7r, 7r + 7) as seven 9-bit digits (0 = past the
+// end, byte + 1 otherwise) in one u64, most significant first -- comparing chunks in order is comparing the strings.  Round 0
+// sorts all rows by chunk 0.  A run of equal chunks whose LAST digit is 0 holds equal strings (they all ended inside the
+// chunk); every other run of two or more rows is unresolved.  Round r sorts only the unresolved rows, by (run, chunk r), and
+// writes them back to the positions they occupied -- the runs are contiguous, so the order of everything else stands.
+// Every sort is a stable LSD radix sort, so rows with equal strings keep the order earlier sort keys gave them.
+__global__ void make_string_chunk(const int64_t *__restrict__ offsets, const uint8_t *__restrict__ bytes, const uint8_t *__restrict__ validity,
+                                  const int64_t *__restrict__ rows, int64_t m, int64_t chunk, uint64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) {
+        const int64_t r = rows[i];
+        uint64_t k = 0;
+        if (validity == nullptr || bit_at(validity, r)) {
+            const int64_t o = offsets[r], len = offsets[r + 1] - o, at = chunk * 7;
+#pragma unroll
+            for (int j = 0; j < 7; j++) k = (k << 9) | (at + j < len ? (uint64_t)bytes[o + at + j] + 1 : 0ULL);
+        }
+        out[i] = k;
+    }
+}
+// after a round: head[i] = 1 where a new run starts (run id changes or chunk changes); unresolved[i] = 1 when the row's run
+// has at least two rows and its chunk does not end the string
+__global__ void string_runs(const uint64_t *__restrict__ chunk, const uint64_t *__restrict__ run, int64_t m, int64_t *__restrict__ head,
+                            int64_t *__restrict__ unresolved) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) {
+        const uint64_t c = chunk[i];
+        const bool same_prev = i > 0 && chunk[i - 1] == c && (run == nullptr || run[i - 1] == run[i]);
+        const bool same_next = i + 1 < m && chunk[i + 1] == c && (run == nullptr || run[i + 1] == run[i]);
+        head[i] = same_prev ? 0 : 1;
+        unresolved[i] = ((same_prev || same_next) && (c & 511ULL) != 0) ? 1 : 0;
+    }
+}
+// compaction of the unresolved rows: their position in the full order, their row id and their new run id
+__global__ void string_compact(const int64_t *__restrict__ unresolved, const int64_t *__restrict__ dst, const int64_t *__restrict__ run_scan,
+                               const int64_t *__restrict__ pos_in, const int64_t *__restrict__ rows, int64_t m, int64_t *__restrict__ pos_out,
+                               int64_t *__restrict__ rows_out, uint64_t *__restrict__ run_out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride)
+        if (unresolved[i]) {
+            const int64_t d = dst[i];
+            pos_out[d] = pos_in ? pos_in[i] : i;
+            rows_out[d] = rows[i];
+            run_out[d] = (uint64_t)run_scan[i];
+        }
+}
+__global__ void scatter_rows(const int64_t *__restrict__ pos, const int64_t *__restrict__ rows, int64_t m, int64_t *__restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) idx[pos[i]] = rows[i];
+}
+__global__ void gather_u64_by(const uint64_t *__restrict__ src, const int64_t *__restrict__ at, int64_t m, uint64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) out[i] = src[at[i]];
+}
+
+__global__ void add_i64(const int64_t *__restrict__ a, const int64_t *__restrict__ b, int64_t m, int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) out[i] = a[i] + b[i];
+}
+__global__ void gather_i64_by(const int64_t *__restrict__ src, const int64_t *__restrict__ at, int64_t m, int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) out[i] = src[at[i]];
+}
 __global__ void make_null_flag(const uint8_t *__restrict__ validity, const int64_t *__restrict__ idx, int64_t n, uint64_t *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -663,16 +736,63 @@ Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uin
         if (c.dtype == B200_NULL) continue;  // every row ties
         const uint8_t *validity = c.null_count > 0 ? as<uint8_t>(c.validity) : nullptr;
         if (is_string(c.dtype)) {
-            Buf ml = dev_alloc_zero(8);
-            max_str_len<<<sgrid(n), 256, 0, st>>>(as<int64_t>(c.offsets), c.length, as<unsigned long long>(ml));
+            const int64_t *off = as<int64_t>(c.offsets);
+            const uint8_t *dat = as<uint8_t>(c.data);
+            // round 0: all rows by their first chunk
+            make_string_chunk<<<sgrid(n), 256, 0, st>>>(off, dat, validity, as<int64_t>(idx), n, 0, as<uint64_t>(keys));
             count_launch();
-            const int64_t maxlen = read_i64(as<int64_t>(ml));
-            for (int64_t pos = maxlen - 1; pos >= 0; pos--) {
-                make_string_digit<<<sgrid(n), 256, 0, st>>>(as<int64_t>(c.offsets), as<uint8_t>(c.data), validity, as<int64_t>(idx), n,
-                                                             pos, as<uint64_t>(keys));
+            radix_sort_pairs(keys, idx, n, 0, 63, desc);
+            // refine: the rows still tied after chunk r - 1 are sorted by (run, chunk r) and put back where they were
+            Buf pos, rows, run, chunks = keys;  // of the unresolved subset: position in idx, row id, run id, last sorted chunk
+            int64_t m = n;
+            for (int64_t round = 1; m > 1; round++) {
+                Buf head = dev_alloc((size_t)m * 8), unres = dev_alloc((size_t)m * 8), hscan = dev_alloc((size_t)(m + 1) * 8),
+                    uscan = dev_alloc((size_t)(m + 1) * 8);
+                string_runs<<<sgrid(m), 256, 0, st>>>(as<uint64_t>(chunks), as<uint64_t>(run), m, as<int64_t>(head), as<int64_t>(unres));
                 count_launch();
-                // 9-bit digit = two 8-bit passes over bits [0,16)
-                radix_sort_pairs(keys, idx, n, 0, 16, desc);
+                exclusive_scan_i64(as<int64_t>(head), as<int64_t>(hscan), m, nullptr);
+                exclusive_scan_i64(as<int64_t>(unres), as<int64_t>(uscan), m, as<int64_t>(uscan) + m);
+                const int64_t m2 = read_i64(as<int64_t>(uscan) + m);
+                if (m2 == 0) break;
+                Buf pos2 = dev_alloc((size_t)m2 * 8), rows2 = dev_alloc((size_t)m2 * 8), run2 = dev_alloc((size_t)m2 * 8);
+                // new run id = number of heads up to and including the row's own run head: constant over a run, ascending
+                Buf runid = dev_alloc((size_t)m * 8);
+                add_i64<<<sgrid(m), 256, 0, st>>>(as<int64_t>(hscan), as<int64_t>(head), m, as<int64_t>(runid));
+                count_launch();
+                string_compact<<<sgrid(m), 256, 0, st>>>(as<int64_t>(unres), as<int64_t>(uscan), as<int64_t>(runid), as<int64_t>(pos),
+                                                         round == 1 ? as<int64_t>(idx) : as<int64_t>(rows), m, as<int64_t>(pos2), as<int64_t>(rows2),
+                                                         as<uint64_t>(run2));
+                count_launch();
+                Buf ch2 = dev_alloc((size_t)m2 * 8);
+                make_string_chunk<<<sgrid(m2), 256, 0, st>>>(off, dat, validity, as<int64_t>(rows2), m2, round, as<uint64_t>(ch2));
+                count_launch();
+                // stable sort by (run, chunk): chunk first, then run; the run ids travel as a second payload through an index
+                Buf ord = dev_alloc((size_t)m2 * 8);
+                fill_iota(as<int64_t>(ord), m2);
+                radix_sort_pairs(ch2, ord, m2, 0, 63, desc);
+                Buf run_by = dev_alloc((size_t)m2 * 8);
+                gather_u64_by<<<sgrid(m2), 256, 0, st>>>(as<uint64_t>(run2), as<int64_t>(ord), m2, as<uint64_t>(run_by));
+                count_launch();
+                Buf ord2 = dev_alloc((size_t)m2 * 8);
+                fill_iota(as<int64_t>(ord2), m2);
+                int rbits = 1;
+                while (((int64_t)1 << rbits) <= m && rbits < 63) rbits++;
+                radix_sort_pairs(run_by, ord2, m2, 0, rbits, false);   // ord2[j] = position in the chunk-sorted order
+                // final order of the subset: element j = rows2[ord[ord2[j]]], chunk = ch2[ord2[j]], run = run_by[j]
+                Buf rows_s = dev_alloc((size_t)m2 * 8), ch_s = dev_alloc((size_t)m2 * 8), comp = dev_alloc((size_t)m2 * 8);
+                gather_i64_by<<<sgrid(m2), 256, 0, st>>>(as<int64_t>(ord), as<int64_t>(ord2), m2, as<int64_t>(comp));
+                count_launch();
+                gather_i64_by<<<sgrid(m2), 256, 0, st>>>(as<int64_t>(rows2), as<int64_t>(comp), m2, as<int64_t>(rows_s));
+                count_launch();
+                gather_u64_by<<<sgrid(m2), 256, 0, st>>>(as<uint64_t>(ch2), as<int64_t>(ord2), m2, as<uint64_t>(ch_s));
+                count_launch();
+                scatter_rows<<<sgrid(m2), 256, 0, st>>>(as<int64_t>(pos2), as<int64_t>(rows_s), m2, as<int64_t>(idx));
+                count_launch();
+                pos = pos2;
+                rows = rows_s;
+                run = run_by;
+                chunks = ch_s;
+                m = m2;
             }
         } else {
             make_ordered_keys<<<sgrid(n), 256, 0, st>>>(c.dtype, c.data ? c.data->ptr : nullptr, validity, as<int64_t>(idx), n,

@@ -377,6 +377,30 @@ def test_sort_onesweep_equals_two_kernel_radix(gpu, n, monkeypatch):
         assert list(res["1"].values())[0] == [int(x) for x in want], keys
 
 
+@pytest.mark.parametrize("n", [3000, 60_000])
+def test_sort_long_strings_with_shared_prefixes(gpu, n):
+    """Strings are sorted by 7-byte chunks: round 0 over all rows, later rounds only over the runs that still tie (sort.cu
+    make_string_chunk / string_runs).  Long common prefixes, values that are prefixes of one another, chunk-boundary lengths (6, 7,
+    8, 13, 14, 15 bytes), embedded 0x00 / 0xFF-like code points, duplicates, nulls, one very long value; ascending and descending,
+    alone and as the second key -- the order must equal the oracle's bytewise comparator sort (stable on ties)."""
+    rng = np.random.default_rng(n)
+    stems = ["", "a", "http://example.com/a/long/common/prefix/", "http://example.com/a/long/common/prefix/that/goes/on/and/on/",
+             "abcdef", "abcdefg", "abcdefgh", "abcdefghijklm", "abcdefghijklmn", "abcdefghijklmno", "\x00\x00", "\x00", "zz\u00ff\u0100"]
+    vals = []
+    for i in range(n):
+        stem = stems[rng.integers(0, len(stems))]
+        tail = "".join(chr(97 + int(c)) for c in rng.integers(0, 3, rng.integers(0, 12)))
+        vals.append(stem + tail)
+    vals[n // 2] = "http://example.com/a/long/common/prefix/" + "q" * 700
+    tbl = pa.table({"s": pa.array(vals, type=pa.large_utf8(), mask=rng.random(n) < 0.05), "g": pa.array(rng.integers(0, 4, n).astype(np.int32)),
+                    "row": pa.array(np.arange(n))})
+    c = gpu.col
+    for keys, desc, nf in ((["s"], [False], None), (["s"], [True], [False]), (["g", "s"], [True, False], None), (["s", "g"], [False, True], [True, False])):
+        got = RB(gpu, tbl).argsort([c(k) for k in keys], descending=desc, nulls_first=nf).to_pydict()
+        want = O.argsort([tbl.column(k) for k in keys], desc, nf if nf is not None else desc)
+        assert list(got.values())[0] == [int(x) for x in want], (keys, desc)
+
+
 @pytest.mark.parametrize("dtype", ["f64", "i64", "i32", "f32"])
 def test_top_n_selection_path(gpu, dtype):
     """Large inputs take the radix-select path (sort.cu op_top_indices): same rows as sort + slice
