@@ -3,8 +3,8 @@
 //
 // Every sort key column is first mapped to an order-preserving u64 ("ordered key"): integers are
 // biased, floats are canonicalised (-0.0 -> +0.0, every NaN -> one value above +inf, matching
-// cmp_float at src/daft-core/src/kernels/search_sorted.rs:238-245), strings are sorted byte position
-// by byte position with a 9-bit digit (0 = past the end).  Multi-key sorts run the keys from last to
+// cmp_float at src/daft-core/src/kernels/search_sorted.rs:238-245), strings are sorted by 7-byte
+// chunks of 9-bit digits (0 = past the end), all rows on the first chunk and only the still-tied runs on the later ones.  Multi-key sorts run the keys from last to
 // first; because each pass is stable the result is exactly the stable sort under the reference's
 // comparator (the reference sort is unstable, so any tie order is admissible).
 //
@@ -440,23 +440,6 @@ __global__ void make_ordered_keys(int32_t dtype, const void *__restrict__ data, 
     }
 }
 
-// string digit at byte position `pos`: 0 past the end (or null), byte+1 otherwise
-__global__ void make_string_digit(const int64_t *__restrict__ offsets, const uint8_t *__restrict__ bytes,
-                                  const uint8_t *__restrict__ validity, const int64_t *__restrict__ idx, int64_t n, int64_t pos,
-                                  uint64_t *__restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        const int64_t r = idx[i];
-        uint64_t d = 0;
-        if (validity == nullptr || bit_at(validity, r)) {
-            const int64_t o = offsets[r], len = offsets[r + 1] - o;
-            if (pos < len) d = (uint64_t)bytes[o + pos] + 1;
-        }
-        out[i] = d;
-    }
-}
-
 // ---- strings: sort by a 7-byte chunk, then refine only the rows that still tie ------------------------------------------
 // A byte-position LSD sort costs one pass over ALL rows per byte of the LONGEST value: one comment of a few hundred bytes and
 // the sort runs hundreds of passes.  Instead: chunk r of a value = its bytes [7r, 7r + 7) as seven 9-bit digits (0 = past the
@@ -738,10 +721,16 @@ Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uin
         if (is_string(c.dtype)) {
             const int64_t *off = as<int64_t>(c.offsets);
             const uint8_t *dat = as<uint8_t>(c.data);
+            // values shorter than a chunk leave its low digits zero for every row: the radix passes start above them
+            Buf ml = dev_alloc_zero(8);
+            max_str_len<<<sgrid(n), 256, 0, st>>>(off, c.length, as<unsigned long long>(ml));
+            count_launch();
+            const int64_t maxlen = read_i64(as<int64_t>(ml));
+            const int low_bit = (int)(9 * std::max<int64_t>(0, 7 - maxlen)) / 8 * 8;
             // round 0: all rows by their first chunk
             make_string_chunk<<<sgrid(n), 256, 0, st>>>(off, dat, validity, as<int64_t>(idx), n, 0, as<uint64_t>(keys));
             count_launch();
-            radix_sort_pairs(keys, idx, n, 0, 63, desc);
+            radix_sort_pairs(keys, idx, n, low_bit, 63, desc);
             // refine: the rows still tied after chunk r - 1 are sorted by (run, chunk r) and put back where they were
             Buf pos, rows, run, chunks = keys;  // of the unresolved subset: position in idx, row id, run id, last sorted chunk
             int64_t m = n;
