@@ -859,3 +859,51 @@ def test_string_and_binary_minmax_literals_from_reference_tests():
             tbl = pa.table({"input": pa.array([conv(v) for v in vals], type=typ)})
             got = oracle_agg(tbl, [col("input").min().alias("min"), col("input").max().alias("max")], []).to_pydict()
             assert got == {"min": [conv(lo)], "max": [conv(hi)]}, (vals, got)
+
+
+def test_list_set_concat_literals_from_reference_tests():
+    """The oracle's list / set / concat against the reference's literal expectations: grouped_list with null keys
+    (tests/recordbatch/test_table_aggs.py:811-828), test_table_agg_groupby_cases[0] (:470-490, list + set next to sum / count), the
+    empty input (:902-913) and string_agg with and without nulls (:1077-1130)."""
+    groups = pa.array([None, 1, None, 1, 2, 2], type=pa.int64())
+    vals = pa.array([None, 0, 1, 2, None, 4], type=pa.int64())
+    got = oracle_agg(pa.table({"groups": groups, "input": vals}), [col("input").agg_list().alias("list")], [col("groups")])
+    got = got.sort_by([("groups", "ascending")]).to_pydict()
+    assert got == {"groups": [1, 2, None], "list": [[0, 2], [None, 4], [None, 1]]}
+    assert oracle_agg(pa.table({"input": vals}), [col("input").agg_list().alias("list")], []).to_pydict() == {"list": [[None, 0, 1, 2, None, 4]]}
+
+    values = [("Bob", None), ("Bob", None), ("Bob", 5), ("Bob", 5), (None, None), (None, 5), (None, None), (None, 2),
+              ("Alice", None), ("Alice", None), ("Alice", None), ("Alice", None)]
+    tbl = pa.table({"name": pa.array([v[0] for v in values], type=pa.large_utf8()), "cookies": pa.array([v[1] for v in values], type=pa.int64())})
+    aggs = [col("cookies").sum().alias("sum"), col("name").count().alias("count"), col("cookies").agg_list().alias("list"), col("cookies").agg_set().alias("set")]
+    got = oracle_agg(tbl, aggs, [col("name")]).sort_by([("name", "ascending")]).to_pydict()
+    assert got["name"] == ["Alice", "Bob", None] and got["sum"] == [None, 10, 7] and got["count"] == [4, 4, 0]
+    assert got["list"] == [[None] * 4, [None, None, 5, 5], [None, 5, None, 2]]
+    assert [set(x) for x in got["set"]] == [set(), {5}, {2, 5}]
+
+    empty = pa.table({"col_A": pa.array([], type=pa.int32()), "col_B": pa.array([], type=pa.int64())})
+    assert oracle_agg(empty, [col("col_A").agg_list().alias("list")], [col("col_B")]).to_pydict() == {"col_B": [], "list": []}
+
+    t = pa.table({"a": pa.array(["the", " quick", " brown", " fox"], type=pa.large_utf8()), "b": pa.array([1, 2, 1, 2], type=pa.int64())})
+    assert oracle_agg(t, [col("a").agg_concat()], []).to_pydict() == {"a": ["the quick brown fox"]}
+    assert oracle_agg(t, [col("a").agg_concat()], [col("b")]).to_pydict() == {"b": [1, 2], "a": ["the brown", " quick fox"]}
+    t = pa.table({"a": pa.array(["the", " quick", None, " fox"], type=pa.large_utf8()), "b": pa.array([1, 2, 1, 2], type=pa.int64())})
+    assert oracle_agg(t, [col("a").agg_concat()], []).to_pydict() == {"a": ["the quick fox"]}
+    assert oracle_agg(t, [col("a").agg_concat()], [col("b")]).to_pydict() == {"b": [1, 2], "a": ["the", " quick fox"]}
+    t = pa.table({"a": pa.array([None, None, None, None], type=pa.large_utf8()), "b": pa.array([1, 2, 1, 2], type=pa.int64())})
+    assert oracle_agg(t, [col("a").agg_concat()], []).to_pydict() == {"a": [None]}
+    # set keeps 0.0 and -0.0 apart and never merges NaNs (probe table: hash of the bytes, then Literal ==; series/mod.rs:85-100)
+    f = pa.table({"x": pa.array([0.0, -0.0, float("nan"), 1.5, float("nan"), 1.5, None, 0.0])})
+    s = oracle_agg(f, [col("x").agg_set().alias("s")], []).to_pydict()["s"][0]
+    assert [repr(v) for v in s] == ["0.0", "-0.0", "nan", "1.5", "nan"]
+
+
+def test_two_stage_list_and_concat_rewrite():
+    """populate_aggregation_stages for List / Concat (src/daft-local-plan/src/agg.rs:286-301): list -> concat of the partial lists."""
+    from daft_b200.aggstages import populate_aggregation_stages
+    first, second, final = populate_aggregation_stages([col("v").agg_list().alias("l"), col("s").agg_concat().alias("c"), col("v").sum().alias("t")], [col("k")])
+    assert [e.name() for e in first] == ["__s1_0", "__s1_1", "__s1_2"] and [repr(e) for e in final][0] == "col(k)"
+    ops = lambda es: [e.args[0].op if e.kind == "alias" else e.op for e in es]
+    assert ops(first) == ["list", "concat", "sum"] and ops(second) == ["concat", "concat", "sum"]
+    with pytest.raises(NotImplementedError):
+        populate_aggregation_stages([col("v").agg_set()], [])
