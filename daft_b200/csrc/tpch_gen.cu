@@ -7,8 +7,9 @@
 // Float64 money, Date, Utf8 flags) with a counter-based RNG, so any row range of any table can be
 // produced independently on any GPU (scan partitions = contiguous row ranges).
 // Differences from dbgen, stated: lineitems per order follow a fixed 28-lines-per-7-orders pattern
-// (mean 4, like dbgen's uniform 1..7) instead of a random count; part/supplier keys are independent
-// uniforms; comments/addresses/phones are not generated.
+// (mean 4, like dbgen's uniform 1..7) instead of a random count; O_ORDERSTATUS follows the lines of that pattern;
+// comments draw from a 48-word subset of the text grammar and P_NAME from 32 of the 92 colours; clerk, L_COMMENT,
+// PS_COMMENT, N_COMMENT and R_COMMENT are not generated.  L_SUPPKEY is one of the part's four partsupp suppliers, as in dbgen.
 #include <thread>
 
 #include "common.h"
@@ -38,6 +39,17 @@ __global__ void gen_dict_bytes(int col, uint64_t seed, int64_t row_begin, int64_
         const int64_t o = offsets[i];
         for (int32_t t = 0; t < len; t++) out[o + t] = dict_bytes[b + t];
     }
+}
+// generated strings (names, phones, addresses, comments): the same two passes, the value comes from gen_string
+__global__ void gen_string_lens(int col, uint64_t seed, int64_t row_begin, int64_t n, int64_t *__restrict__ lens) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) lens[i] = gen_string(col, seed, row_begin + i, nullptr);
+}
+__global__ void gen_string_bytes(int col, uint64_t seed, int64_t row_begin, int64_t n, const int64_t *__restrict__ offsets, uint8_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) gen_string(col, seed, row_begin + i, out + offsets[i]);
 }
 static void dict_tables(int col, std::vector<int32_t> &off, std::string &bytes) {
     off.assign(1, 0);
@@ -71,6 +83,7 @@ int64_t tpch_num_rows(int32_t table, double sf) {
         case B200_TPCH_NATION: return 25;
         case B200_TPCH_REGION: return 5;
         case B200_TPCH_PART: return s.n_parts;
+        case B200_TPCH_PARTSUPP: return 4 * s.n_parts;
     }
     fail("tpch: unknown table");
 }
@@ -146,6 +159,22 @@ Batch *tpch_generate(int32_t table, double sf, int64_t row_begin, int64_t row_en
                 count_launch();
             }
             B200_CUDA(cudaStreamSynchronize(st));  // the host dictionary buffers above
+        } else if (is_generated_string(col)) {
+            Buf lens = dev_alloc((size_t)(n + 1) * 8);
+            c.offsets = dev_alloc((size_t)(n + 1) * 8);
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 8));
+            if (n) {
+                gen_string_lens<<<grid, 256, 0, st>>>(col, seed, row_begin, n, as<int64_t>(lens));
+                count_launch();
+            }
+            exclusive_scan_i64(as<int64_t>(lens), as<int64_t>(c.offsets), n, as<int64_t>(c.offsets) + n);
+            const int64_t total = read_i64(as<int64_t>(c.offsets) + n);
+            c.data = dev_alloc((size_t)std::max<int64_t>(total, 1));
+            c.data_bytes = total;
+            if (n) {
+                gen_string_bytes<<<grid, 256, 0, st>>>(col, seed, row_begin, n, as<int64_t>(c.offsets), as<uint8_t>(c.data));
+                count_launch();
+            }
         } else if (col == N_NAME || col == R_NAME) {
             std::vector<int64_t> offs;
             std::string bytes;
@@ -207,6 +236,25 @@ void tpch_generate_host(int32_t table, double sf, int64_t row_begin, int64_t row
                 const std::string &w = words[(size_t)gen_dict_index(col, seed, row_begin + i)];
                 memcpy((uint8_t *)h.data + h.offsets[i], w.data(), w.size());
             }
+            h.data_bytes = total;
+        } else if (is_generated_string(col)) {
+            h.offsets = (int64_t *)malloc((size_t)(n + 1) * 8);
+            int64_t total = 0;
+            for (int64_t i = 0; i < n; i++) {
+                h.offsets[i] = total;
+                total += gen_string(col, seed, row_begin + i, nullptr);
+            }
+            h.offsets[n] = total;
+            h.data = malloc((size_t)total + 8);
+            const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::thread::hardware_concurrency(), n / 65536 + 1));
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++) {
+                const int64_t b = n * t / nt, e = n * (t + 1) / nt;
+                th.emplace_back([=, &h] {
+                    for (int64_t i = b; i < e; i++) gen_string(col, seed, row_begin + i, (uint8_t *)h.data + h.offsets[i]);
+                });
+            }
+            for (auto &x : th) x.join();
             h.data_bytes = total;
         } else if (col == N_NAME || col == R_NAME) {
             std::vector<int64_t> offs;

@@ -70,6 +70,21 @@ GEN_HD int64_t order_key(int64_t oidx) { return (oidx / 8) * 32 + (oidx % 8) + 1
 GEN_HD int32_t order_date(uint64_t seed, int64_t oidx) {
     return (int32_t)rnd_range(seed, 11, (uint64_t)oidx, DAY_1992_01_01, DAY_1998_08_02);
 }
+// the i-th (0..3) supplier of a part: dbgen's PART_SUPP_BRIDGE (specification 4.2.3, PS_SUPPKEY), S = number of suppliers
+GEN_HD int64_t part_supplier(int64_t partkey, int i, int64_t S) { return (partkey + (int64_t)i * (S / 4 + (partkey - 1) / S)) % S + 1; }
+// 'F' / 'O' / 'P' from the ship dates of the order's lines in the 28-line pattern (all shipped / none / some)
+GEN_HD char order_status(uint64_t seed, int64_t oidx) {
+    const int o = (int)(oidx % 7);
+    const int start = o == 0 ? 0 : o == 1 ? 4 : o == 2 ? 5 : o == 3 ? 12 : o == 4 ? 14 : o == 5 ? 20 : 23;
+    const int count = o == 0 ? 4 : o == 1 ? 1 : o == 2 ? 7 : o == 3 ? 2 : o == 4 ? 6 : o == 5 ? 3 : 5;
+    const int32_t odate = order_date(seed, oidx);
+    int open = 0;
+    for (int l = 0; l < count; l++) {
+        const int64_t row = (oidx / 7) * 28 + start + l;
+        open += odate + (int32_t)rnd_range(seed, 21, (uint64_t)row, 1, 121) > DAY_1995_06_17;
+    }
+    return open == 0 ? 'F' : open == count ? 'O' : 'P';
+}
 
 enum ColId {
     L_ORDERKEY = 0, L_PARTKEY, L_SUPPKEY, L_LINENUMBER, L_QUANTITY, L_EXTENDEDPRICE, L_DISCOUNT, L_TAX, L_RETURNFLAG,
@@ -82,6 +97,12 @@ enum ColId {
     // dictionary-valued strings (round 2): the generator draws an index, the column holds the dictionary word
     L_SHIPMODE, O_ORDERPRIORITY, C_MKTSEGMENT,
     P_PARTKEY, P_SIZE, P_TYPE,
+    // the columns the rest of benchmarking/tpch/answers.py reads (Q2, Q7-Q11, Q13, Q15-Q17, Q19-Q22)
+    L_SHIPINSTRUCT, O_ORDERSTATUS, O_COMMENT,
+    C_NAME, C_ADDRESS, C_PHONE, C_COMMENT,
+    S_NAME, S_ADDRESS, S_PHONE, S_COMMENT,
+    P_NAME, P_MFGR, P_BRAND, P_CONTAINER, P_RETAILPRICE,
+    PS_PARTKEY, PS_SUPPKEY, PS_AVAILQTY, PS_SUPPLYCOST,
     NUM_COLS
 };
 struct ColInfo { const char *name; int32_t table; int32_t dtype; };
@@ -98,6 +119,12 @@ static const ColInfo kCols[NUM_COLS] = {
     {"R_REGIONKEY", 5, B200_I64}, {"R_NAME", 5, B200_LARGE_UTF8},
     {"L_SHIPMODE", 0, B200_LARGE_UTF8}, {"O_ORDERPRIORITY", 1, B200_LARGE_UTF8}, {"C_MKTSEGMENT", 2, B200_LARGE_UTF8},
     {"P_PARTKEY", 6, B200_I64}, {"P_SIZE", 6, B200_I64}, {"P_TYPE", 6, B200_LARGE_UTF8},
+    {"L_SHIPINSTRUCT", 0, B200_LARGE_UTF8}, {"O_ORDERSTATUS", 1, B200_LARGE_UTF8}, {"O_COMMENT", 1, B200_LARGE_UTF8},
+    {"C_NAME", 2, B200_LARGE_UTF8}, {"C_ADDRESS", 2, B200_LARGE_UTF8}, {"C_PHONE", 2, B200_LARGE_UTF8}, {"C_COMMENT", 2, B200_LARGE_UTF8},
+    {"S_NAME", 3, B200_LARGE_UTF8}, {"S_ADDRESS", 3, B200_LARGE_UTF8}, {"S_PHONE", 3, B200_LARGE_UTF8}, {"S_COMMENT", 3, B200_LARGE_UTF8},
+    {"P_NAME", 6, B200_LARGE_UTF8}, {"P_MFGR", 6, B200_LARGE_UTF8}, {"P_BRAND", 6, B200_LARGE_UTF8}, {"P_CONTAINER", 6, B200_LARGE_UTF8},
+    {"P_RETAILPRICE", 6, B200_F64},
+    {"PS_PARTKEY", 7, B200_I64}, {"PS_SUPPKEY", 7, B200_I64}, {"PS_AVAILQTY", 7, B200_I64}, {"PS_SUPPLYCOST", 7, B200_F64},
 };
 // dictionary columns: number of words (TPC-H specification 4.2.2.13: ship modes, order priorities, market segments;
 // P_TYPE = one syllable of each of three lists, 6 x 5 x 5 = 150 combinations)
@@ -107,13 +134,33 @@ static const char *kSegments[5] = {"AUTOMOBILE", "BUILDING", "FURNITURE", "MACHI
 static const char *kTypeS1[6] = {"STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO"};
 static const char *kTypeS2[5] = {"ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED"};
 static const char *kTypeS3[5] = {"TIN", "NICKEL", "BRASS", "STEEL", "COPPER"};
-inline bool is_dict_col(int col) { return col == L_SHIPMODE || col == O_ORDERPRIORITY || col == C_MKTSEGMENT || col == P_TYPE; }
-inline int dict_size(int col) { return col == L_SHIPMODE ? 7 : col == P_TYPE ? 150 : 5; }
+static const char *kInstructs[4] = {"DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"};
+// P_CONTAINER = one syllable of each of two lists (5 x 8), P_BRAND = Brand#MN with M the manufacturer (specification 4.2.3)
+static const char *kContS1[5] = {"SM", "LG", "MED", "JUMBO", "WRAP"};
+static const char *kContS2[8] = {"CASE", "BOX", "BAG", "JAR", "PKG", "PACK", "CAN", "DRUM"};
+inline bool is_dict_col(int col) {
+    return col == L_SHIPMODE || col == O_ORDERPRIORITY || col == C_MKTSEGMENT || col == P_TYPE || col == L_SHIPINSTRUCT || col == P_MFGR ||
+           col == P_BRAND || col == P_CONTAINER;
+}
+inline int dict_size(int col) {
+    switch (col) {
+        case L_SHIPMODE: return 7;
+        case P_TYPE: return 150;
+        case L_SHIPINSTRUCT: return 4;
+        case P_BRAND: return 25;
+        case P_CONTAINER: return 40;
+        default: return 5;
+    }
+}
 inline std::string dict_word(int col, int k) {
     switch (col) {
         case L_SHIPMODE: return kShipModes[k];
         case O_ORDERPRIORITY: return kPriorities[k];
         case C_MKTSEGMENT: return kSegments[k];
+        case L_SHIPINSTRUCT: return kInstructs[k];
+        case P_MFGR: return std::string("Manufacturer#") + (char)('1' + k);
+        case P_BRAND: return std::string("Brand#") + (char)('1' + k / 5) + (char)('1' + k % 5);
+        case P_CONTAINER: return std::string(kContS1[k / 8]) + " " + kContS2[k % 8];
         default: return std::string(kTypeS1[k / 25]) + " " + kTypeS2[(k / 5) % 5] + " " + kTypeS3[k % 5];
     }
 }
@@ -123,6 +170,10 @@ GEN_HD int gen_dict_index(int col, uint64_t seed, int64_t row) {
         case L_SHIPMODE: return (int)(rnd(seed, 61, (uint64_t)row) % 7);
         case O_ORDERPRIORITY: return (int)(rnd(seed, 62, (uint64_t)row) % 5);
         case C_MKTSEGMENT: return (int)(rnd(seed, 63, (uint64_t)row) % 5);
+        case L_SHIPINSTRUCT: return (int)(rnd(seed, 66, (uint64_t)row) % 4);
+        case P_BRAND: return (int)(rnd(seed, 67, (uint64_t)row) % 25);
+        case P_MFGR: return (int)(rnd(seed, 67, (uint64_t)row) % 25) / 5;  // the brand's manufacturer
+        case P_CONTAINER: return (int)(rnd(seed, 68, (uint64_t)row) % 40);
         default: return (int)(rnd(seed, 64, (uint64_t)row) % 150);
     }
 }
@@ -145,7 +196,9 @@ GEN_HD uint64_t gen_value(int col, uint64_t seed, int64_t row, Scale sc) {
         switch (col) {
             case L_ORDERKEY: v.i = order_key(oidx); break;
             case L_PARTKEY: v.i = rnd_range(seed, 22, (uint64_t)row, 1, sc.n_parts); break;
-            case L_SUPPKEY: v.i = rnd_range(seed, 23, (uint64_t)row, 1, sc.n_suppliers); break;
+            case L_SUPPKEY:  // one of the part's four suppliers, as dbgen draws it: (L_PARTKEY, L_SUPPKEY) is a partsupp key
+                v.i = part_supplier(rnd_range(seed, 22, (uint64_t)row, 1, sc.n_parts), (int)(rnd(seed, 23, (uint64_t)row) % 4), sc.n_suppliers);
+                break;
             case L_LINENUMBER: v.i = lno; break;
             case L_QUANTITY: v.i = rnd_range(seed, 24, (uint64_t)row, 1, 50); break;
             case L_EXTENDEDPRICE: {
@@ -188,6 +241,16 @@ GEN_HD uint64_t gen_value(int col, uint64_t seed, int64_t row, Scale sc) {
         case N_NATIONKEY: case R_REGIONKEY: v.i = row; break;
         case P_PARTKEY: v.i = row + 1; break;
         case P_SIZE: v.i = rnd_range(seed, 65, (uint64_t)row, 1, 50); break;
+        case P_RETAILPRICE: {
+            const int64_t pk = row + 1;
+            v.d = (double)(90000 + ((pk / 10) % 20001) + 100 * (pk % 1000)) / 100.0;
+            break;
+        }
+        case O_ORDERSTATUS: v.u = (uint64_t)order_status(seed, row); break;
+        case PS_PARTKEY: v.i = row / 4 + 1; break;
+        case PS_SUPPKEY: v.i = part_supplier(row / 4 + 1, (int)(row % 4), sc.n_suppliers); break;
+        case PS_AVAILQTY: v.i = rnd_range(seed, 81, (uint64_t)row, 1, 9999); break;
+        case PS_SUPPLYCOST: v.d = (double)rnd_range(seed, 82, (uint64_t)row, 100, 100000) / 100.0; break;
         default: break;
     }
     return v.u;
@@ -204,6 +267,126 @@ GEN_HD void gen_store(int col, int kind, uint64_t seed, int64_t row, int64_t i, 
     }
 }
 
+// ---- generated strings: names, phones, addresses, comments (a pure function of column, seed and row, like every other value) ----
+// out == nullptr counts only.  The longest value is 117 bytes (C_COMMENT).
+struct StrOut {
+    uint8_t *p;
+    int n;
+};
+GEN_HD void put(StrOut &s, char c) {
+    if (s.p) s.p[s.n] = (uint8_t)c;
+    s.n++;
+}
+GEN_HD void put_str(StrOut &s, const char *w) {
+    while (*w) put(s, *w++);
+}
+GEN_HD void put_num(StrOut &s, int64_t v, int width) {  // zero-padded decimal
+    int64_t p10 = 1;
+    for (int i = 1; i < width; i++) p10 *= 10;
+    for (; p10 > 0; p10 /= 10) put(s, (char)('0' + (v / p10) % 10));
+}
+GEN_HD int c_strlen(const char *w) {
+    int n = 0;
+    while (w[n]) n++;
+    return n;
+}
+// the text grammar's vocabulary (specification 4.2.2.14, a subset): comments are words of this list separated by blanks
+constexpr int kNumWords = 48;
+GEN_HD const char *text_word(int k) {
+    switch (k) {
+        case 0: return "furiously"; case 1: return "special"; case 2: return "requests"; case 3: return "packages";
+        case 4: return "deposits"; case 5: return "accounts"; case 6: return "pending"; case 7: return "ironic";
+        case 8: return "express"; case 9: return "regular"; case 10: return "final"; case 11: return "bold";
+        case 12: return "slyly"; case 13: return "carefully"; case 14: return "blithely"; case 15: return "quickly";
+        case 16: return "foxes"; case 17: return "ideas"; case 18: return "theodolites"; case 19: return "pinto";
+        case 20: return "beans"; case 21: return "instructions"; case 22: return "dependencies"; case 23: return "excuses";
+        case 24: return "platelets"; case 25: return "asymptotes"; case 26: return "courts"; case 27: return "dolphins";
+        case 28: return "sleep"; case 29: return "wake"; case 30: return "are"; case 31: return "cajole";
+        case 32: return "haggle"; case 33: return "nag"; case 34: return "use"; case 35: return "boost";
+        case 36: return "among"; case 37: return "above"; case 38: return "the"; case 39: return "even";
+        case 40: return "unusual"; case 41: return "silent"; case 42: return "daring"; case 43: return "according";
+        case 44: return "to"; case 45: return "after"; case 46: return "never"; default: return "along";
+    }
+}
+// P_NAME: distinct-looking colour words (specification 4.2.3 lists 92; 32 of them here), five per name
+constexpr int kNumColors = 32;
+GEN_HD const char *color_word(int k) {
+    switch (k) {
+        case 0: return "almond"; case 1: return "antique"; case 2: return "aquamarine"; case 3: return "azure";
+        case 4: return "beige"; case 5: return "bisque"; case 6: return "black"; case 7: return "blanched";
+        case 8: return "blue"; case 9: return "blush"; case 10: return "brown"; case 11: return "burlywood";
+        case 12: return "chartreuse"; case 13: return "chocolate"; case 14: return "coral"; case 15: return "cornflower";
+        case 16: return "cream"; case 17: return "cyan"; case 18: return "dark"; case 19: return "dodger";
+        case 20: return "firebrick"; case 21: return "forest"; case 22: return "frosted"; case 23: return "ghost";
+        case 24: return "goldenrod"; case 25: return "green"; case 26: return "honeydew"; case 27: return "hot";
+        case 28: return "indian"; case 29: return "ivory"; case 30: return "khaki"; default: return "lace";
+    }
+}
+GEN_HD void put_text(StrOut &s, uint64_t seed, uint32_t stream, int64_t row, int lo, int hi) {
+    const int target = lo + (int)(rnd(seed, stream, (uint64_t)row * 32) % (uint64_t)(hi - lo + 1));
+    const int begin = s.n;
+    for (int j = 1; j < 32; j++) {
+        const char *w = text_word((int)(rnd(seed, stream, (uint64_t)row * 32 + (uint64_t)j) % kNumWords));
+        if (s.n - begin + c_strlen(w) + 1 > target) break;
+        if (s.n > begin) put(s, ' ');
+        put_str(s, w);
+    }
+}
+GEN_HD void put_phone(StrOut &s, uint64_t seed, uint32_t stream, int64_t row, int64_t nationkey) {
+    const uint64_t r = rnd(seed, stream, (uint64_t)row);
+    put_num(s, nationkey + 10, 2);
+    put(s, '-');
+    put_num(s, 100 + (int64_t)(r % 900), 3);
+    put(s, '-');
+    put_num(s, 100 + (int64_t)((r >> 16) % 900), 3);
+    put(s, '-');
+    put_num(s, 1000 + (int64_t)((r >> 32) % 9000), 4);
+}
+GEN_HD void put_address(StrOut &s, uint64_t seed, uint32_t stream, int64_t row) {
+    const int len = 10 + (int)(rnd(seed, stream, (uint64_t)row * 8) % 31);
+    for (int j = 0; j < len; j++) {
+        const uint64_t r = rnd(seed, stream, (uint64_t)row * 8 + 1 + (uint64_t)(j / 8)) >> (8 * (j % 8));
+        const int k = (int)(r & 63);
+        put(s, k < 26 ? (char)('a' + k) : k < 52 ? (char)('A' + k - 26) : k < 62 ? (char)('0' + k - 52) : k == 62 ? ' ' : ',');
+    }
+}
+inline bool is_generated_string(int col) {
+    return col == O_COMMENT || col == C_NAME || col == C_ADDRESS || col == C_PHONE || col == C_COMMENT || col == S_NAME || col == S_ADDRESS ||
+           col == S_PHONE || col == S_COMMENT || col == P_NAME;
+}
+// writes the value of a generated-string column (out may be nullptr) and returns its length in bytes
+GEN_HD int gen_string(int col, uint64_t seed, int64_t row, uint8_t *out) {
+    StrOut s{out, 0};
+    switch (col) {
+        case C_NAME: put_str(s, "Customer#"); put_num(s, row + 1, 9); break;
+        case S_NAME: put_str(s, "Supplier#"); put_num(s, row + 1, 9); break;
+        case C_PHONE: put_phone(s, seed, 43, row, rnd_range(seed, 41, (uint64_t)row, 0, 24)); break;  // country code = C_NATIONKEY + 10
+        case S_PHONE: put_phone(s, seed, 53, row, rnd_range(seed, 51, (uint64_t)row, 0, 24)); break;
+        case C_ADDRESS: put_address(s, seed, 44, row); break;
+        case S_ADDRESS: put_address(s, seed, 54, row); break;
+        case C_COMMENT: put_text(s, seed, 45, row, 29, 116); break;
+        case O_COMMENT: put_text(s, seed, 33, row, 19, 78); break;
+        case S_COMMENT: {
+            // 5 suppliers in 10 000 complain, 5 recommend (specification 4.2.3: "Customer ... Complaints" / "Customer ... Recommends")
+            const uint64_t r = rnd(seed, 56, (uint64_t)row) % 2000;
+            put_text(s, seed, 55, row, 25, r < 2 ? 60 : 100);
+            if (r < 2) {
+                put_str(s, " Customer ");
+                put_str(s, text_word((int)(rnd(seed, 57, (uint64_t)row) % kNumWords)));
+                put_str(s, r == 0 ? " Complaints" : " Recommends");
+            }
+            break;
+        }
+        case P_NAME:
+            for (int j = 0; j < 5; j++) {
+                if (j) put(s, ' ');
+                put_str(s, color_word((int)(rnd(seed, 69, (uint64_t)row * 8 + (uint64_t)j) % kNumColors)));
+            }
+            break;
+        default: break;
+    }
+    return s.n;
+}
 
 }  // namespace tpchgen
 }  // namespace b200

@@ -17,7 +17,7 @@ from . import _lib
 from .expressions import col, lit
 from .recordbatch import RecordBatch
 
-TABLES = {"lineitem": 0, "orders": 1, "customer": 2, "supplier": 3, "nation": 4, "region": 5, "part": 6}
+TABLES = {"lineitem": 0, "orders": 1, "customer": 2, "supplier": 3, "nation": 4, "region": 5, "part": 6, "partsupp": 7}
 DEFAULT_SEED = 20260921
 
 Q1_COLUMNS = ["L_QUANTITY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_TAX", "L_RETURNFLAG", "L_LINESTATUS", "L_SHIPDATE"]

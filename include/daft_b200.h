@@ -301,7 +301,7 @@ int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, cha
 
 /* ---- synthetic TPC-H tables generated straight into HBM (bench / tests) ---- */
 typedef enum { B200_TPCH_LINEITEM = 0, B200_TPCH_ORDERS = 1, B200_TPCH_CUSTOMER = 2, B200_TPCH_SUPPLIER = 3,
-               B200_TPCH_NATION = 4, B200_TPCH_REGION = 5, B200_TPCH_PART = 6 } b200_tpch_table;
+               B200_TPCH_NATION = 4, B200_TPCH_REGION = 5, B200_TPCH_PART = 6, B200_TPCH_PARTSUPP = 7 } b200_tpch_table;
 /* rows [row_begin,row_end) of `table` at `scale_factor`; columns selected by name list (NULL = all implemented). */
 int b200_tpch_generate(int32_t table, double scale_factor, int64_t row_begin, int64_t row_end, uint64_t seed,
                        const char *const *columns, int32_t ncolumns, b200_batch **out, char **errmsg);
