@@ -258,3 +258,243 @@ def q18(t: dict[str, RecordBatch]) -> RecordBatch:
     g = j.agg([col("L_QUANTITY").sum().alias("sum")], [col("C_CUSTKEY"), col("O_ORDERKEY"), col("O_ORDERDATE"), col("O_TOTALPRICE")])
     g = g.eval_expression_list([col("C_CUSTKEY"), col("O_ORDERKEY"), col("O_ORDERDATE").alias("O_ORDERDAT"), col("O_TOTALPRICE"), col("sum")])
     return g.top_n([col("O_TOTALPRICE"), col("O_ORDERDAT")], 100, descending=[True, False])
+
+
+# ------------------------------------------------------------------------------------------------
+# The rest of answers.py (Q2, Q7-Q11, Q13, Q15-Q17, Q19-Q22).  DataFrame verbs map onto the RecordBatch surface:
+# where -> filter, select / with_column -> eval_expression_list, distinct -> dedup, sort + limit -> top_n,
+# join(on=lit) (the reference's way of writing a cross join with a one-row table) -> hash_join on the literal column.
+# ------------------------------------------------------------------------------------------------
+def _cols(*names: str):
+    return [col(n) for n in names]
+
+
+def _join(left: RecordBatch, right: RecordBatch, left_on: Sequence[str], right_on: Sequence[str], how: str = "inner") -> RecordBatch:
+    """Inner joins build on the smaller side, as the planner decides (pipeline.rs:1106-1194)."""
+    build_on_left = (len(left) <= len(right)) if how == "inner" else None
+    return left.hash_join(right, _cols(*left_on), _cols(*right_on), how=how, build_on_left=build_on_left)
+
+
+def _with_column(rb: RecordBatch, name: str, e) -> RecordBatch:
+    return rb.eval_expression_list(_cols(*rb.column_names()) + [e.alias(name)])
+
+
+def _volume():
+    return col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))
+
+
+QUERY_COLUMNS.update({
+    "q2": {"region": ["R_REGIONKEY", "R_NAME"], "nation": ["N_NATIONKEY", "N_REGIONKEY", "N_NAME"],
+           "supplier": ["S_SUPPKEY", "S_NATIONKEY", "S_ACCTBAL", "S_NAME", "S_ADDRESS", "S_PHONE", "S_COMMENT"],
+           "partsupp": ["PS_PARTKEY", "PS_SUPPKEY", "PS_SUPPLYCOST"], "part": ["P_PARTKEY", "P_SIZE", "P_TYPE", "P_MFGR"]},
+    "q7": {"nation": ["N_NATIONKEY", "N_NAME"], "supplier": ["S_SUPPKEY", "S_NATIONKEY"], "customer": ["C_CUSTKEY", "C_NATIONKEY"],
+           "orders": ["O_ORDERKEY", "O_CUSTKEY"], "lineitem": ["L_ORDERKEY", "L_SUPPKEY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_SHIPDATE"]},
+    "q8": {"region": ["R_REGIONKEY", "R_NAME"], "nation": ["N_NATIONKEY", "N_REGIONKEY", "N_NAME"], "supplier": ["S_SUPPKEY", "S_NATIONKEY"],
+           "customer": ["C_CUSTKEY", "C_NATIONKEY"], "orders": ["O_ORDERKEY", "O_CUSTKEY", "O_ORDERDATE"], "part": ["P_PARTKEY", "P_TYPE"],
+           "lineitem": ["L_ORDERKEY", "L_PARTKEY", "L_SUPPKEY", "L_EXTENDEDPRICE", "L_DISCOUNT"]},
+    "q9": {"nation": ["N_NATIONKEY", "N_NAME"], "supplier": ["S_SUPPKEY", "S_NATIONKEY"], "part": ["P_PARTKEY", "P_NAME"],
+           "partsupp": ["PS_PARTKEY", "PS_SUPPKEY", "PS_SUPPLYCOST"], "orders": ["O_ORDERKEY", "O_ORDERDATE"],
+           "lineitem": ["L_ORDERKEY", "L_PARTKEY", "L_SUPPKEY", "L_QUANTITY", "L_EXTENDEDPRICE", "L_DISCOUNT"]},
+    "q10": {"nation": ["N_NATIONKEY", "N_NAME"], "customer": ["C_CUSTKEY", "C_NATIONKEY", "C_NAME", "C_ACCTBAL", "C_ADDRESS", "C_PHONE", "C_COMMENT"],
+            "orders": ["O_ORDERKEY", "O_CUSTKEY", "O_ORDERDATE"], "lineitem": ["L_ORDERKEY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_RETURNFLAG"]},
+    "q11": {"nation": ["N_NATIONKEY", "N_NAME"], "supplier": ["S_SUPPKEY", "S_NATIONKEY"],
+            "partsupp": ["PS_PARTKEY", "PS_SUPPKEY", "PS_AVAILQTY", "PS_SUPPLYCOST"]},
+    "q13": {"customer": ["C_CUSTKEY"], "orders": ["O_ORDERKEY", "O_CUSTKEY", "O_COMMENT"]},
+    "q15": {"supplier": ["S_SUPPKEY", "S_NAME", "S_ADDRESS", "S_PHONE"], "lineitem": ["L_SUPPKEY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_SHIPDATE"]},
+    "q16": {"part": ["P_PARTKEY", "P_BRAND", "P_TYPE", "P_SIZE"], "partsupp": ["PS_PARTKEY", "PS_SUPPKEY"], "supplier": ["S_SUPPKEY", "S_COMMENT"]},
+    "q17": {"part": ["P_PARTKEY", "P_BRAND", "P_CONTAINER"], "lineitem": ["L_PARTKEY", "L_QUANTITY", "L_EXTENDEDPRICE"]},
+    "q19": {"part": ["P_PARTKEY", "P_BRAND", "P_CONTAINER", "P_SIZE"],
+            "lineitem": ["L_PARTKEY", "L_QUANTITY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_SHIPMODE", "L_SHIPINSTRUCT"]},
+    "q20": {"nation": ["N_NATIONKEY", "N_NAME"], "supplier": ["S_SUPPKEY", "S_NATIONKEY", "S_NAME", "S_ADDRESS"], "part": ["P_PARTKEY", "P_NAME"],
+            "partsupp": ["PS_PARTKEY", "PS_SUPPKEY", "PS_AVAILQTY"], "lineitem": ["L_PARTKEY", "L_SUPPKEY", "L_QUANTITY", "L_SHIPDATE"]},
+    "q21": {"nation": ["N_NATIONKEY", "N_NAME"], "supplier": ["S_SUPPKEY", "S_NATIONKEY", "S_NAME"], "orders": ["O_ORDERKEY", "O_ORDERSTATUS"],
+            "lineitem": ["L_ORDERKEY", "L_SUPPKEY", "L_COMMITDATE", "L_RECEIPTDATE"]},
+    "q22": {"customer": ["C_CUSTKEY", "C_PHONE", "C_ACCTBAL"], "orders": ["O_CUSTKEY"]},
+})
+
+
+def q2(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:35-75: for size-15 BRASS parts, the European supplier(s) with the minimum supply cost; top 100."""
+    europe = t["region"].filter([col("R_NAME") == "EUROPE"])
+    europe = _join(europe, t["nation"], ["R_REGIONKEY"], ["N_REGIONKEY"])
+    europe = _join(europe, t["supplier"], ["N_NATIONKEY"], ["S_NATIONKEY"])
+    europe = _join(europe, t["partsupp"], ["S_SUPPKEY"], ["PS_SUPPKEY"])
+    brass = t["part"].filter([(col("P_SIZE") == 15) & col("P_TYPE").endswith("BRASS")])
+    brass = _join(brass, europe, ["P_PARTKEY"], ["PS_PARTKEY"])
+    min_cost = brass.agg([col("PS_SUPPLYCOST").min().alias("min")], _cols("P_PARTKEY"))
+    j = _join(brass, min_cost, ["P_PARTKEY"], ["P_PARTKEY"]).filter([col("PS_SUPPLYCOST") == col("min")])
+    j = j.eval_expression_list(_cols("S_ACCTBAL", "S_NAME", "N_NAME", "P_PARTKEY", "P_MFGR", "S_ADDRESS", "S_PHONE", "S_COMMENT"))
+    return j.top_n(_cols("S_ACCTBAL", "N_NAME", "S_NAME", "P_PARTKEY"), 100, descending=[True, False, False, False])
+
+
+def q7(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:158-203: revenue shipped between FRANCE and GERMANY (either direction) per year, 1995-1996."""
+    lineitem = t["lineitem"].filter([(col("L_SHIPDATE") >= datetime.date(1995, 1, 1)) & (col("L_SHIPDATE") <= datetime.date(1996, 12, 31))])
+    nation = t["nation"].filter([(col("N_NAME") == "FRANCE") | (col("N_NAME") == "GERMANY")])
+    sup = _join(nation, t["supplier"], ["N_NATIONKEY"], ["S_NATIONKEY"])
+    sup = _join(sup, lineitem, ["S_SUPPKEY"], ["L_SUPPKEY"])
+    sup = sup.eval_expression_list([col("N_NAME").alias("supp_nation")] + _cols("L_ORDERKEY", "L_EXTENDEDPRICE", "L_DISCOUNT", "L_SHIPDATE"))
+    cust = _join(nation, t["customer"], ["N_NATIONKEY"], ["C_NATIONKEY"])
+    cust = _join(cust, t["orders"], ["C_CUSTKEY"], ["O_CUSTKEY"])
+    cust = cust.eval_expression_list([col("N_NAME").alias("cust_nation"), col("O_ORDERKEY")])
+    j = _join(cust, sup, ["O_ORDERKEY"], ["L_ORDERKEY"])
+    j = j.filter([((col("supp_nation") == "FRANCE") & (col("cust_nation") == "GERMANY"))
+                  | ((col("supp_nation") == "GERMANY") & (col("cust_nation") == "FRANCE"))])
+    j = j.eval_expression_list([col("supp_nation"), col("cust_nation"), col("L_SHIPDATE").year().alias("l_year"), _volume().alias("volume")])
+    g = j.agg([col("volume").sum().alias("revenue")], _cols("supp_nation", "cust_nation", "l_year"))
+    return g.sort(_cols("supp_nation", "cust_nation", "l_year"))
+
+
+def q8(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:206-251: BRAZIL's share of the AMERICA market for ECONOMY ANODIZED STEEL, 1995 and 1996."""
+    region = t["region"].filter([col("R_NAME") == "AMERICA"])
+    orders = t["orders"].filter([(col("O_ORDERDATE") <= datetime.date(1996, 12, 31)) & (col("O_ORDERDATE") >= datetime.date(1995, 1, 1))])
+    part = t["part"].filter([col("P_TYPE") == "ECONOMY ANODIZED STEEL"])
+    nat = _join(t["nation"], t["supplier"], ["N_NATIONKEY"], ["S_NATIONKEY"])
+    line = t["lineitem"].eval_expression_list(_cols("L_PARTKEY", "L_SUPPKEY", "L_ORDERKEY") + [_volume().alias("volume")])
+    line = _join(line, part, ["L_PARTKEY"], ["P_PARTKEY"])
+    line = _join(line, nat, ["L_SUPPKEY"], ["S_SUPPKEY"])
+    j = _join(t["nation"], region, ["N_REGIONKEY"], ["R_REGIONKEY"]).eval_expression_list(_cols("N_NATIONKEY"))
+    j = _join(j, t["customer"], ["N_NATIONKEY"], ["C_NATIONKEY"]).eval_expression_list(_cols("C_CUSTKEY"))
+    j = _join(j, orders, ["C_CUSTKEY"], ["O_CUSTKEY"]).eval_expression_list(_cols("O_ORDERKEY", "O_ORDERDATE"))
+    j = _join(j, line, ["O_ORDERKEY"], ["L_ORDERKEY"])
+    j = j.eval_expression_list([col("O_ORDERDATE").year().alias("o_year"), col("volume"),
+                                _when(col("N_NAME") == "BRAZIL", col("volume"), 0.0).alias("case_volume")])
+    g = j.agg([col("case_volume").sum().alias("case_volume_sum"), col("volume").sum().alias("volume_sum")], _cols("o_year"))
+    return g.eval_expression_list([col("o_year"), (col("case_volume_sum") / col("volume_sum")).alias("mkt_share")]).sort(_cols("o_year"))
+
+
+def q9(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:254-284: profit on green parts per supplier nation and year (the two-key partsupp join)."""
+    linepart = _join(t["part"].filter([col("P_NAME").contains("green")]), t["lineitem"], ["P_PARTKEY"], ["L_PARTKEY"])
+    natsup = _join(t["nation"], t["supplier"], ["N_NATIONKEY"], ["S_NATIONKEY"])
+    j = _join(linepart, natsup, ["L_SUPPKEY"], ["S_SUPPKEY"])
+    j = _join(j, t["partsupp"], ["L_SUPPKEY", "P_PARTKEY"], ["PS_SUPPKEY", "PS_PARTKEY"])
+    j = _join(j, t["orders"], ["L_ORDERKEY"], ["O_ORDERKEY"])
+    amount = _volume() - col("PS_SUPPLYCOST") * col("L_QUANTITY")
+    j = j.eval_expression_list([col("N_NAME"), col("O_ORDERDATE").year().alias("o_year"), amount.alias("amount")])
+    return j.agg([col("amount").sum().alias("amount")], _cols("N_NAME", "o_year")).sort(_cols("N_NAME", "o_year"), descending=[False, True])
+
+
+def q10(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:287-335: customers who returned items ordered in 1993 Q4, by lost revenue; top 20."""
+    lineitem = t["lineitem"].filter([col("L_RETURNFLAG") == "R"])
+    orders = t["orders"].filter([(col("O_ORDERDATE") < datetime.date(1994, 1, 1)) & (col("O_ORDERDATE") >= datetime.date(1993, 10, 1))])
+    j = _join(orders, t["customer"], ["O_CUSTKEY"], ["C_CUSTKEY"])
+    j = _join(j, t["nation"], ["C_NATIONKEY"], ["N_NATIONKEY"])
+    j = _join(j, lineitem, ["O_ORDERKEY"], ["L_ORDERKEY"])
+    j = j.eval_expression_list([col("O_CUSTKEY"), col("C_NAME"), _volume().alias("volume")] + _cols("C_ACCTBAL", "N_NAME", "C_ADDRESS", "C_PHONE", "C_COMMENT"))
+    g = j.agg([col("volume").sum().alias("revenue")], _cols("O_CUSTKEY", "C_NAME", "C_ACCTBAL", "C_PHONE", "N_NAME", "C_ADDRESS", "C_COMMENT"))
+    top = g.top_n(_cols("revenue"), 20, descending=[True])
+    return top.eval_expression_list(_cols("O_CUSTKEY", "C_NAME", "revenue", "C_ACCTBAL", "N_NAME", "C_ADDRESS", "C_PHONE", "C_COMMENT"))
+
+
+def q11(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:338-370: GERMANY's stock value per part above 0.01 % of the total (the scalar subquery is a one-row join)."""
+    res_1 = _join(t["partsupp"], t["supplier"], ["PS_SUPPKEY"], ["S_SUPPKEY"])
+    res_1 = _join(res_1, t["nation"], ["S_NATIONKEY"], ["N_NATIONKEY"]).filter([col("N_NAME") == "GERMANY"])
+    value = col("PS_SUPPLYCOST") * col("PS_AVAILQTY")
+    res_2 = res_1.agg([value.sum().alias("tmp")], []).eval_expression_list([(col("tmp") * (0.0001 / 1)).alias("tmp"), lit(1).alias("lit")])
+    g = _with_column(res_1.agg([value.sum().alias("value")], _cols("PS_PARTKEY")), "lit", lit(1))
+    j = _join(g, res_2, ["lit"], ["lit"]).filter([col("value") > col("tmp")])
+    return j.eval_expression_list([col("PS_PARTKEY"), col("value").round(2)]).sort(_cols("value"), descending=True)
+
+
+def q13(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:396-415: distribution of customers by their number of orders that are not special requests (left join)."""
+    orders = t["orders"].filter([~col("O_COMMENT").match(".*special.*requests.*")])
+    j = t["customer"].hash_join(orders, _cols("C_CUSTKEY"), _cols("O_CUSTKEY"), how="left")
+    g = j.agg([col("O_ORDERKEY").count().alias("c_count")], _cols("C_CUSTKEY")).sort(_cols("C_CUSTKEY"))
+    g = g.agg([col("c_count").count().alias("custdist")], _cols("c_count"))
+    return g.sort(_cols("custdist", "c_count"), descending=[True, True])
+
+
+def q15(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:437-459: the supplier(s) with the top revenue of 1996 Q1 (a join on the maximum: a Float64 key)."""
+    li = t["lineitem"].filter([(col("L_SHIPDATE") >= datetime.date(1996, 1, 1)) & (col("L_SHIPDATE") < datetime.date(1996, 4, 1))])
+    revenue = li.agg([_volume().sum().alias("total_revenue")], _cols("L_SUPPKEY"))
+    revenue = revenue.eval_expression_list([col("L_SUPPKEY").alias("supplier_no"), col("total_revenue")])
+    top = revenue.agg([col("total_revenue").max().alias("total_revenue")], [])
+    revenue = _join(revenue, top, ["total_revenue"], ["total_revenue"])
+    j = _join(t["supplier"], revenue, ["S_SUPPKEY"], ["supplier_no"])
+    return j.eval_expression_list(_cols("S_SUPPKEY", "S_NAME", "S_ADDRESS", "S_PHONE", "total_revenue")).sort(_cols("S_SUPPKEY"))
+
+
+def q16(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:462-489: suppliers per (brand, type, size) excluding the ones with complaints (left join + is_null = anti join)."""
+    suppkeys = t["supplier"].filter([col("S_COMMENT").match(".*Customer.*Complaints.*")])
+    suppkeys = suppkeys.eval_expression_list([col("S_SUPPKEY"), col("S_SUPPKEY").alias("PS_SUPPKEY_RIGHT")])
+    j = _join(t["part"], t["partsupp"], ["P_PARTKEY"], ["PS_PARTKEY"])
+    j = j.filter([(col("P_BRAND") != "Brand#45") & ~col("P_TYPE").startswith("MEDIUM POLISHED")
+                  & col("P_SIZE").is_in([49, 14, 23, 45, 19, 3, 36, 9])])
+    j = j.hash_join(suppkeys, _cols("PS_SUPPKEY"), _cols("S_SUPPKEY"), how="left").filter([col("PS_SUPPKEY_RIGHT").is_null()])
+    j = j.eval_expression_list(_cols("P_BRAND", "P_TYPE", "P_SIZE", "PS_SUPPKEY"))
+    j = j.dedup(_cols("P_BRAND", "P_TYPE", "P_SIZE", "PS_SUPPKEY"))
+    g = j.agg([col("PS_SUPPKEY").count().alias("supplier_cnt")], _cols("P_BRAND", "P_TYPE", "P_SIZE"))
+    return g.sort(_cols("supplier_cnt", "P_BRAND", "P_TYPE", "P_SIZE"), descending=[True, False, False, False])
+
+
+def q17(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:492-507: yearly revenue lost if small orders (< 20 % of the part's mean quantity) of Brand#23 MED BOX parts went away."""
+    part = t["part"].filter([(col("P_BRAND") == "Brand#23") & (col("P_CONTAINER") == "MED BOX")])
+    res_1 = part.hash_join(t["lineitem"], _cols("P_PARTKEY"), _cols("L_PARTKEY"), how="left")
+    g = res_1.agg([(0.2 * col("L_QUANTITY")).mean().alias("avg_quantity")], _cols("P_PARTKEY"))
+    g = g.eval_expression_list([col("P_PARTKEY").alias("key"), col("avg_quantity")])
+    j = _join(g, res_1, ["key"], ["P_PARTKEY"]).filter([col("L_QUANTITY") < col("avg_quantity")])
+    return j.agg([(col("L_EXTENDEDPRICE") / 7.0).sum().alias("avg_yearly")], [])
+
+
+def q19(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:531-572: revenue of three brand / container / quantity / size brackets delivered in person by air."""
+    j = _join(t["lineitem"], t["part"], ["L_PARTKEY"], ["P_PARTKEY"])
+
+    def bracket(brand, containers, qlo, qhi, smax):
+        return ((col("P_BRAND") == brand) & col("P_CONTAINER").is_in(containers) & (col("L_QUANTITY") >= qlo) & (col("L_QUANTITY") <= qhi)
+                & (col("P_SIZE") >= 1) & (col("P_SIZE") <= smax) & col("L_SHIPMODE").is_in(["AIR", "AIR REG"])
+                & (col("L_SHIPINSTRUCT") == "DELIVER IN PERSON"))
+    pred = (bracket("Brand#12", ["SM CASE", "SM BOX", "SM PACK", "SM PKG"], 1, 11, 5)
+            | bracket("Brand#23", ["MED BAG", "MED BOX", "MED PKG", "MED PACK"], 10, 20, 10)
+            | bracket("Brand#34", ["LG CASE", "LG BOX", "LG PACK", "LG PKG"], 20, 30, 15))
+    return j.filter([pred]).agg([_volume().sum().alias("revenue")], [])
+
+
+def q20(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:575-611: CANADA's suppliers holding more than half of 1994's shipped quantity of a forest part."""
+    li = t["lineitem"].filter([(col("L_SHIPDATE") >= datetime.date(1994, 1, 1)) & (col("L_SHIPDATE") < datetime.date(1995, 1, 1))])
+    res_1 = li.agg([(col("L_QUANTITY") * 0.5).sum().alias("sum_quantity")], _cols("L_PARTKEY", "L_SUPPKEY"))
+    res_3 = _join(t["supplier"], t["nation"].filter([col("N_NAME") == "CANADA"]), ["S_NATIONKEY"], ["N_NATIONKEY"])
+    j = t["part"].filter([col("P_NAME").startswith("forest")]).eval_expression_list(_cols("P_PARTKEY")).dedup(_cols("P_PARTKEY"))
+    j = _join(j, t["partsupp"], ["P_PARTKEY"], ["PS_PARTKEY"])
+    j = _join(j, res_1, ["PS_SUPPKEY", "P_PARTKEY"], ["L_SUPPKEY", "L_PARTKEY"]).filter([col("PS_AVAILQTY") > col("sum_quantity")])
+    j = j.eval_expression_list(_cols("PS_SUPPKEY")).dedup(_cols("PS_SUPPKEY"))
+    j = _join(j, res_3, ["PS_SUPPKEY"], ["S_SUPPKEY"])
+    return j.eval_expression_list(_cols("S_NAME", "S_ADDRESS")).sort(_cols("S_NAME"))
+
+
+def q21(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:614-648: SAUDI ARABIA's suppliers that were the only late one on a multi-supplier order with status F; top 100.
+    The DataFrame text counts an order's lines (its `.distinct()` is commented out), which equals the SQL's "another supplier
+    exists" only while no order repeats a supplier; the SQL's meaning is used here: distinct suppliers per order."""
+    li = t["lineitem"]
+    late = li.filter([col("L_RECEIPTDATE") > col("L_COMMITDATE")])
+    multi = li.eval_expression_list(_cols("L_SUPPKEY", "L_ORDERKEY")).agg([col("L_SUPPKEY").count_distinct().alias("nunique_col")], _cols("L_ORDERKEY"))
+    res_1 = _join(multi.filter([col("nunique_col") > 1]), late, ["L_ORDERKEY"], ["L_ORDERKEY"])
+    g = res_1.eval_expression_list(_cols("L_SUPPKEY", "L_ORDERKEY")).agg([col("L_SUPPKEY").count_distinct().alias("nunique_col")], _cols("L_ORDERKEY"))
+    j = _join(g, res_1, ["L_ORDERKEY"], ["L_ORDERKEY"])
+    j = _join(j, t["supplier"], ["L_SUPPKEY"], ["S_SUPPKEY"])
+    j = _join(j, t["nation"], ["S_NATIONKEY"], ["N_NATIONKEY"])
+    j = _join(j, t["orders"], ["L_ORDERKEY"], ["O_ORDERKEY"])
+    j = j.filter([(col("nunique_col") == 1) & (col("N_NAME") == "SAUDI ARABIA") & (col("O_ORDERSTATUS") == "F")])
+    g = j.agg([col("O_ORDERKEY").count().alias("numwait")], _cols("S_NAME"))
+    return g.top_n(_cols("numwait", "S_NAME"), 100, descending=[True, False])
+
+
+def q22(t: dict[str, RecordBatch]) -> RecordBatch:
+    """answers.py:651-676: customers of seven country codes with above-average balances and no orders (anti join)."""
+    res_1 = _with_column(t["customer"], "cntrycode", col("C_PHONE").left(2))
+    res_1 = res_1.filter([col("cntrycode").is_in(["13", "31", "23", "29", "30", "18", "17"])]).eval_expression_list(_cols("C_ACCTBAL", "C_CUSTKEY", "cntrycode"))
+    res_2 = _with_column(res_1.filter([col("C_ACCTBAL") > 0]).agg([col("C_ACCTBAL").mean().alias("avg_acctbal")], []), "lit", lit(1))
+    j = res_1.hash_join(t["orders"], _cols("C_CUSTKEY"), _cols("O_CUSTKEY"), how="anti")
+    j = _join(_with_column(j, "lit", lit(1)), res_2, ["lit"], ["lit"]).filter([col("C_ACCTBAL") > col("avg_acctbal")])
+    g = j.agg([col("C_ACCTBAL").count().alias("numcust"), col("C_ACCTBAL").sum().alias("totacctbal")], _cols("cntrycode"))
+    return g.sort(_cols("cntrycode"))

@@ -54,6 +54,15 @@ class OracleRecordBatch:
         keys = [(g.name(), E.eval_expression(tbl, g)) for g in (group_by or [])]
         return OracleRecordBatch(O.agg(tbl, specs, keys))
 
+    def dedup(self, exprs) -> "OracleRecordBatch":
+        """first row of every distinct key, in first-occurrence order (src/daft-recordbatch/src/ops/groups.rs make_groups)"""
+        _, first, _ = O.group_ids([E.eval_expression(self.tbl, e) for e in exprs])
+        import numpy as np
+        return OracleRecordBatch(self.tbl.take(pa.array(np.sort(first.astype(np.int64)))))
+
+    def head(self, num: int) -> "OracleRecordBatch":
+        return OracleRecordBatch(self.tbl.slice(0, num))
+
     def sort(self, sort_keys, descending=None, nulls_first=None) -> "OracleRecordBatch":
         n = len(sort_keys)
         desc = [descending] * n if isinstance(descending, bool) else (descending or [False] * n)

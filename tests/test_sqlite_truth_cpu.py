@@ -54,3 +54,37 @@ def test_composed_queries_oracle_vs_sqlite(q):
     got = getattr(tpch, name)({t: OracleRecordBatch(v) for t, v in tables.items()}).to_arrow_table()
     assert len(rows) > 0
     ST.assert_matches(got, names, rows, check_names=False)
+
+
+# ---- the rest of answers.py: Q2, Q7-Q11, Q13, Q15-Q17, Q19-Q22 (with the queries above: all 22) --------------------------------------
+# scale factors at which every query has rows to disagree on (Q8: a BRAZIL supplier of the part type, Q16: a supplier with
+# complaints, Q20: forest parts with 1994 shipments, Q2 / Q17: a handful of qualifying parts)
+REST_SF = {2: 0.05, 8: 0.05, 16: 0.05, 17: 0.05, 20: 0.05}
+REST = [2, 7, 8, 9, 10, 11, 13, 15, 16, 17, 19, 20, 21, 22]
+
+
+@pytest.mark.parametrize("q", REST)
+def test_remaining_queries_oracle_vs_sqlite(q):
+    name = f"q{q}"
+    sf = REST_SF.get(q, SF)
+    tables = {t: tpch.generate_host(t, sf, c) for t, c in tpch.QUERY_COLUMNS[name].items()}
+    names, rows = ST.run(ST.load(tables), q)
+    got = getattr(tpch, name)({t: OracleRecordBatch(v) for t, v in tables.items()}).to_arrow_table()
+    assert len(rows) > 0
+    ST.assert_matches(got, names, rows, check_names=False, rel=1e-8)   # Q11 rounds its value to cents
+
+
+def test_generated_strings_follow_their_keys():
+    """C_PHONE's country code is C_NATIONKEY + 10, names carry the key, (L_PARTKEY, L_SUPPKEY) is always a partsupp key."""
+    c = tpch.generate_host("customer", 0.01, ["C_CUSTKEY", "C_NATIONKEY", "C_NAME", "C_PHONE"]).to_pydict()
+    for k, n, name, phone in zip(c["C_CUSTKEY"], c["C_NATIONKEY"], c["C_NAME"], c["C_PHONE"]):
+        assert name == f"Customer#{k:09d}" and phone[:2] == f"{n + 10:02d}" and len(phone) == 15
+    ps = tpch.generate_host("partsupp", 0.01).to_pydict()
+    keys = set(zip(ps["PS_PARTKEY"], ps["PS_SUPPKEY"]))
+    assert len(keys) == len(ps["PS_PARTKEY"]) == 4 * tpch.num_rows("part", 0.01)
+    li = tpch.generate_host("lineitem", 0.01, ["L_PARTKEY", "L_SUPPKEY"]).to_pydict()
+    assert all(k in keys for k in zip(li["L_PARTKEY"], li["L_SUPPKEY"]))
+    # any row range is generated independently of the rest
+    whole = tpch.generate_host("orders", 0.01, ["O_ORDERSTATUS", "O_COMMENT"])
+    part = tpch.generate_host("orders", 0.01, ["O_ORDERSTATUS", "O_COMMENT"], 1000, 1500)
+    assert whole.slice(1000, 500).equals(part)
