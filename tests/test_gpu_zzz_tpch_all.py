@@ -28,7 +28,8 @@ def test_remaining_queries_vs_sqlite_and_oracle(gpu, q):
 @pytest.mark.parametrize("table", ["supplier", "customer", "part", "partsupp", "orders", "lineitem"])
 def test_device_generator_matches_host_generator_on_every_column(gpu, table):
     """names / phones / addresses / comments (two-pass generated strings), the new dictionary columns and partsupp"""
-    for rb, re_ in ((0, -1), (777, 1500)):
+    n = tpch.num_rows(table, 0.01)
+    for rb, re_ in ((0, -1), (n // 3 + 1, n - n // 4)):
         host = tpch.generate_host(table, 0.01, None, rb, re_)
         dev = tpch.generate(table, 0.01, None, rb, re_)
         assert_tables_equal(dev.to_arrow_table(), host)
