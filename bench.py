@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-q5", action="store_true", help="skip the config[2] leg")
+    ap.add_argument("--tpch22-sf", type=float, default=10.0, help="scale factor of the all-22-queries leg (N = 1); 0 skips it")
+    ap.add_argument("--tpch22-budget-s", type=float, default=150.0, help="wall-clock budget of that leg; queries not reached are listed as skipped")
     ap.add_argument("--no-exchange", action="store_true", help="N > 1: skip the exchange workload")
     ap.add_argument("--no-e2e", action="store_true", help="kernel sweeps only: skip the host-buffer leg (the line is then not a bench result)")
     return ap.parse_args()
@@ -434,6 +436,17 @@ def main():
         del lineitem
         q5 = run_q5(args, stream, barrier, peak, peak_src)
 
+    # ================================================================================================
+    # config[3] on one GPU: all 22 queries, tables resident in HBM
+    # ================================================================================================
+    tpch22 = None
+    if world == 1 and args.tpch22_sf > 0:
+        try:
+            del lineitem
+        except NameError:
+            pass
+        tpch22 = run_tpch22(args, stream, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -454,6 +467,8 @@ def main():
     }
     if q5 is not None:
         line["q5"] = q5
+    if tpch22 is not None:
+        line["tpch22"] = tpch22
     if exchange is not None:
         line["exchange"] = exchange
         line["exchange_parity"] = exchange["parity"]
@@ -510,6 +525,54 @@ def run_exchange(args, rank, world, comm, total_sf, begin, n_rows, stream, barri
             "nvlink_bytes_sent_per_gpu": int(sent), "nvlink_GBps_per_gpu_per_direction": sent / (ms_x * 1e-3) / 1e9,
             "nvlink_peak_GBps_per_direction": 900.0, "groups": tot[2], "parity": parity,
             "regions_ms_per_step_rank0": {k: round(v["ms"] / (steps + 1), 4) for k, v in kt.items()}}
+
+
+def run_tpch22(args, stream, barrier):
+    """BASELINE metric, first half ("TPC-H total wall-clock sec") at one GPU: each of the 22 queries of benchmarking/tpch/answers.py
+    (daft_b200/tpch.py) over tables generated into HBM at --tpch22-sf, one warm-up (it also JIT-compiles the query's kernels) and
+    two timed runs with CUDA events.  The answers of these compositions are held to SQLite and the oracle at SF 0.01-0.05 by
+    tests/test_gpu_sqlite_truth.py and tests/test_gpu_zzz_tpch_all.py; here only the result's row count is reported.  A query that
+    fails is reported with its error instead of a time, and queries beyond the wall-clock budget are listed as skipped."""
+    import daft_b200
+    from daft_b200 import _lib, tpch
+    sf = args.tpch22_sf
+    t_begin = time.perf_counter()
+    per_query, skipped, failed = {}, [], {}
+    launches = 0
+    for q in range(1, 23):
+        name = f"q{q}"
+        if time.perf_counter() - t_begin > args.tpch22_budget_s:
+            skipped.append(name)
+            continue
+        try:
+            if q in (1, 6):
+                tables = tpch.generate("lineitem", sf, tpch.Q1_COLUMNS)
+            else:
+                cols = tpch.Q5_COLUMNS if q == 5 else tpch.QUERY_COLUMNS[name]
+                tables = {t: tpch.generate(t, sf, c) for t, c in cols.items()}
+            fn = getattr(tpch, name)
+            l0 = daft_b200.launch_count()
+            ms, out = time_steps(lambda: fn(tables), 2, 1, stream, barrier)
+            n_launch = (daft_b200.launch_count() - l0) // 3
+            launches += n_launch * 2
+            per_query[name] = {"ms": ms / 2, "rows": len(out), "launches": int(n_launch)}
+            del tables, out
+        except Exception as e:  # noqa: BLE001 -- the other queries' numbers stand
+            failed[name] = f"{type(e).__name__}: {str(e)[:300]}"
+            try:
+                _lib.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+    total_ms = sum(v["ms"] for v in per_query.values())
+    lineitem_rows = tpch.num_rows("lineitem", sf)
+    return {"metric": "tpch_total_wall_clock_sec", "value": total_ms / 1e3 if not failed and not skipped else None, "unit": "s",
+            "higher_is_better": False, "sum_of_completed_queries_s": total_ms / 1e3, "queries_completed": len(per_query),
+            "queries_failed": failed, "queries_skipped": skipped, "per_query": per_query,
+            "config": {"workload": f"TPC-H SF{sf:g}, all 22 queries of benchmarking/tpch/answers.py, 1 x B200, tables resident in HBM "
+                                   "(generated on the device, only the columns a query reads)", "scale_factor": sf,
+                       "lineitem_rows": lineitem_rows, "timing": "per query: 1 warm-up + 2 timed runs, CUDA events on the library stream"},
+            "gpu_launches": int(launches), "cpu_baseline": None,
+            "note": "no CPU arm for this leg: the CPU engine (oracle/cpu_engine.cpp) implements Q1 and Q5 only"}
 
 
 def run_q5(args, stream, barrier, peak, peak_src):
