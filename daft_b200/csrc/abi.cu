@@ -373,6 +373,30 @@ int b200_take(const b200_batch *batch, const b200_batch *indices, b200_batch **o
         op_done();
     });
 }
+// ---- joins over sorted inputs, cross join ---------------------------------------------------------
+int b200_merge_join_sorted(const b200_batch *left, const int32_t *left_keys, const b200_batch *right, const int32_t *right_keys, int32_t nkeys,
+                           b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!left || !right) fail("null batch");
+        // only the key columns are read here: payload columns stay views and are gathered once, through the output's selection vectors
+        const Batch l = plain_keys(left, left_keys, nkeys), r = plain_keys(right, right_keys, nkeys);
+        *out = op_merge_join_sorted(l, left_keys, r, right_keys, nkeys);
+    });
+}
+int b200_asof_join_sorted(const b200_batch *left, const int32_t *left_keys, const b200_batch *right, const int32_t *right_keys, int32_t nkeys,
+                          b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!left || !right) fail("null batch");
+        const Batch l = plain_keys(left, left_keys, nkeys), r = plain_keys(right, right_keys, nkeys);
+        *out = op_asof_join_sorted(l, left_keys, r, right_keys, nkeys);
+    });
+}
+int b200_cross_join(const b200_batch *left, const b200_batch *right, int32_t outer_loop_left, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!left || !right) fail("null batch");
+        *out = op_cross_join(*left, *right, outer_loop_left != 0);
+    });
+}
 int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
         require_device();

@@ -33,6 +33,10 @@ std::vector<Batch *> op_partition_by_range(const Batch &b, const int32_t *key_co
 // the first k entries of that argsort, found by selection when k is small (sort.cu)
 Buf op_top_indices(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending, const uint8_t *nulls_first, int64_t k);
 Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng);
+// the joins over sorted inputs and the cross join (sort.cu): outputs are [left columns..., right columns...] as views
+Batch *op_merge_join_sorted(const Batch &left, const int32_t *left_keys, const Batch &right, const int32_t *right_keys, int32_t nkeys);
+Batch *op_asof_join_sorted(const Batch &left, const int32_t *left_keys, const Batch &right, const int32_t *right_keys, int32_t nkeys);
+Batch *op_cross_join(const Batch &left, const Batch &right, bool outer_loop_left);
 
 // ops_jit.cu: ascending indices of the set (or, inverted, clear) bits among the first n bits
 Buf bitmap_select(const uint32_t *words, int64_t n, bool invert, int64_t *count_out);

@@ -556,8 +556,8 @@ struct SortKeySet {
 
 // three-way compare of row i of table A with row j of table B under the reference comparator (NaN greatest, nulls by
 // nulls_first); flags and dtypes come from A, both tables have the same key dtypes
-__device__ __forceinline__ int small_cmp2(const SortKeySet &ka, int64_t i, const SortKeySet &kb, int64_t j) {
-    for (int q = 0; q < ka.nkeys; q++) {
+__device__ __forceinline__ int small_cmp_n(const SortKeySet &ka, int64_t i, const SortKeySet &kb, int64_t j, int nk) {
+    for (int q = 0; q < nk; q++) {
         const SortKeyDesc &k = ka.k[q];
         const SortKeyDesc &kj = kb.k[q];
         if (k.dtype == B200_NULL) continue;
@@ -603,6 +603,7 @@ __device__ __forceinline__ int small_cmp2(const SortKeySet &ka, int64_t i, const
     return 0;
 }
 
+__device__ __forceinline__ int small_cmp2(const SortKeySet &ka, int64_t i, const SortKeySet &kb, int64_t j) { return small_cmp_n(ka, i, kb, j, ka.nkeys); }
 __device__ __forceinline__ int small_cmp(const SortKeySet &ks, int64_t i, int64_t j) { return small_cmp2(ks, i, ks, j); }
 
 // RecordBatch::search_sorted (src/daft-recordbatch/src/ops/search_sorted.rs:13-36, kernels/search_sorted.rs:420-433): for every key
@@ -680,6 +681,168 @@ Buf op_search_sorted(const Batch &sorted, const Batch &b, const int32_t *key_col
         search_sorted_kernel<<<sgrid(n), 256, 0, ctx().stream>>>(ks_sorted, ks_keys, sorted.num_rows, n, as<uint64_t>(out));
         count_launch();
     }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sort-merge, asof and cross joins: the joins the reference runs on SORTED inputs, re-composed from the sort,
+// the binary search above and the view gather.  A sequential two-pointer merge (src/daft-recordbatch/src/ops/joins/
+// merge_join.rs:45-330, asof_join.rs:12-160) has no parallel form; on the device every left row binary-searches the sorted
+// right keys on its own (the searched levels of a sorted key column stay in L2), which yields the same matches:
+//   merge join : the run [lo, hi) of right rows whose keys equal the left row's (a null in any key matches nothing),
+//   asof join  : the last right row with the same by-keys and on-key <= the left row's (null on-keys never match).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool any_key_null(const SortKeySet &ks, int64_t i, int nkeys) {
+    for (int q = 0; q < nkeys; q++)
+        if (ks.k[q].dtype == B200_NULL || (ks.k[q].validity != nullptr && !bit_at(ks.k[q].validity, i))) return true;
+    return false;
+}
+// number of rows of `sorted` that compare < (STRICT) or <= row i of `keys`
+template <bool STRICT>
+__device__ __forceinline__ int64_t bound_of(const SortKeySet &sorted, int64_t nsorted, const SortKeySet &keys, int64_t i) {
+    int64_t left = 0, right = nsorted;
+    while (left < right) {
+        const int64_t mid = left + ((right - left) >> 1);
+        const int c = small_cmp2(sorted, mid, keys, i);
+        if (STRICT ? c < 0 : c <= 0) left = mid + 1;
+        else right = mid;
+    }
+    return left;
+}
+__global__ void merge_ranges_kernel(SortKeySet right, SortKeySet left, int64_t nright, int64_t nleft, int64_t *__restrict__ lo,
+                                    int64_t *__restrict__ cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nleft; i += stride) {
+        int64_t b = 0, c = 0;
+        if (!any_key_null(left, i, left.nkeys)) {
+            b = bound_of<true>(right, nright, left, i);
+            c = bound_of<false>(right, nright, left, i) - b;  // right rows with a null key sort last and compare greater
+        }
+        lo[i] = b;
+        cnt[i] = c;
+    }
+}
+// one thread per output pair: the left row owning output position p is found by binary search in the scanned counts
+__global__ void merge_expand_kernel(const int64_t *__restrict__ offs, const int64_t *__restrict__ lo, int64_t nleft, int64_t total,
+                                    int64_t *__restrict__ lidx, int64_t *__restrict__ ridx) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; p < total; p += stride) {
+        int64_t a = 0, b = nleft;  // last i with offs[i] <= p
+        while (b - a > 1) {
+            const int64_t mid = a + ((b - a) >> 1);
+            if (offs[mid] <= p) a = mid;
+            else b = mid;
+        }
+        lidx[p] = a;
+        ridx[p] = lo[a] + (p - offs[a]);
+    }
+}
+__global__ void asof_backward_kernel(SortKeySet right, SortKeySet left, int64_t nright, int64_t nleft, int32_t nby, int64_t *__restrict__ ridx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nleft; i += stride) {
+        int64_t r = -1;
+        if (!any_key_null(left, i, left.nkeys)) {
+            const int64_t cand = bound_of<false>(right, nright, left, i) - 1;  // the last right row <= (by..., on) of the left row
+            if (cand >= 0 && !any_key_null(right, cand, right.nkeys)) {
+                if (nby == 0 || small_cmp_n(right, cand, left, i, nby) == 0) r = cand;   // same by-group?
+            }
+        }
+        ridx[i] = r;
+    }
+}
+__global__ void cross_indices_kernel(int64_t nl, int64_t nr, int outer_left, int64_t *__restrict__ lidx, int64_t *__restrict__ ridx) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, total = nl * nr;
+    for (; p < total; p += stride) {
+        // the outer-loop side repeats each of its rows |inner| times in a row, the inner side repeats as a whole
+        lidx[p] = outer_left ? p / nr : p % nl;
+        ridx[p] = outer_left ? p % nr : p / nl;
+    }
+}
+
+static void check_join_keys(const Batch &l, const int32_t *lk, const Batch &r, const int32_t *rk, int32_t nkeys, const char *what) {
+    if (nkeys < 1) fail(std::string(what) + ": No columns were passed in to join on");
+    for (int k = 0; k < nkeys; k++) {
+        if (lk[k] < 0 || lk[k] >= (int32_t)l.cols.size() || rk[k] < 0 || rk[k] >= (int32_t)r.cols.size()) fail(std::string(what) + ": key column index out of range");
+        if (l.cols[lk[k]].dtype != r.cols[rk[k]].dtype)
+            fail(std::string(what) + ": Types between left and right keys do not match: " + dtype_name(l.cols[lk[k]].dtype) + " vs " + dtype_name(r.cols[rk[k]].dtype));
+    }
+}
+static Batch *joined_views(const Batch &left, const Buf &lidx, const Batch &right, const Buf &ridx, int64_t n, bool right_may_be_null) {
+    auto out = std::make_unique<Batch>();
+    out->num_rows = n;
+    for (Column &c : make_view_columns(left, lidx, n, false)) out->cols.push_back(std::move(c));
+    for (Column &c : make_view_columns(right, ridx, n, right_may_be_null)) out->cols.push_back(std::move(c));
+    return out.release();
+}
+
+// inner join of two batches SORTED ascending (nulls last) on their key columns; output = [left columns..., right columns...] as
+// views, left-major: pairs of one left row are contiguous, in right order
+Batch *op_merge_join_sorted(const Batch &left, const int32_t *left_keys, const Batch &right, const int32_t *right_keys, int32_t nkeys) {
+    require_device();
+    check_join_keys(left, left_keys, right, right_keys, nkeys, "sort_merge_join");
+    std::vector<uint8_t> zeros((size_t)nkeys, 0);
+    const SortKeySet kl = make_sort_keyset(left, left_keys, nkeys, zeros.data(), zeros.data());
+    const SortKeySet kr = make_sort_keyset(right, right_keys, nkeys, zeros.data(), zeros.data());
+    const int64_t nl = left.num_rows, nr = right.num_rows;
+    cudaStream_t st = ctx().stream;
+    int64_t total = 0;
+    Buf lo, offs;
+    if (nl > 0 && nr > 0) {
+        lo = dev_alloc((size_t)nl * 8);
+        Buf cnt = dev_alloc((size_t)nl * 8);
+        offs = dev_alloc((size_t)(nl + 1) * 8);
+        merge_ranges_kernel<<<sgrid(nl), 256, 0, st>>>(kr, kl, nr, nl, as<int64_t>(lo), as<int64_t>(cnt));
+        count_launch();
+        exclusive_scan_i64(as<int64_t>(cnt), as<int64_t>(offs), nl, as<int64_t>(offs) + nl);
+        total = read_i64(as<int64_t>(offs) + nl);
+    }
+    Buf lidx = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8), ridx = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
+    if (total > 0) {
+        merge_expand_kernel<<<sgrid(total), 256, 0, st>>>(as<int64_t>(offs), as<int64_t>(lo), nl, total, as<int64_t>(lidx), as<int64_t>(ridx));
+        count_launch();
+    }
+    Batch *out = joined_views(left, lidx, right, ridx, total, false);
+    op_done();
+    return out;
+}
+
+// backward asof join: keys = by columns..., then the on column (nby = nkeys - 1); `right` SORTED ascending (nulls last) on its keys,
+// `left` in any order.  Output = every left row in its own order with the matched right row (a null row where none matches).
+Batch *op_asof_join_sorted(const Batch &left, const int32_t *left_keys, const Batch &right, const int32_t *right_keys, int32_t nkeys) {
+    require_device();
+    check_join_keys(left, left_keys, right, right_keys, nkeys, "asof_join");
+    std::vector<uint8_t> zeros((size_t)nkeys, 0);
+    const SortKeySet kl = make_sort_keyset(left, left_keys, nkeys, zeros.data(), zeros.data());
+    const SortKeySet kr = make_sort_keyset(right, right_keys, nkeys, zeros.data(), zeros.data());
+    const int64_t nl = left.num_rows;
+    Buf lidx = dev_alloc((size_t)std::max<int64_t>(nl, 1) * 8), ridx = dev_alloc((size_t)std::max<int64_t>(nl, 1) * 8);
+    if (nl > 0) {
+        fill_iota(as<int64_t>(lidx), nl);
+        asof_backward_kernel<<<sgrid(nl), 256, 0, ctx().stream>>>(kr, kl, right.num_rows, nl, nkeys - 1, as<int64_t>(ridx));
+        count_launch();
+    }
+    Batch *out = joined_views(left, lidx, right, ridx, nl, true);
+    op_done();
+    return out;
+}
+
+// RecordBatch::cross_join (src/daft-recordbatch/src/ops/joins/mod.rs:231-284): every pair, the outer-loop side's rows in order
+Batch *op_cross_join(const Batch &left, const Batch &right, bool outer_loop_left) {
+    require_device();
+    const int64_t nl = left.num_rows, nr = right.num_rows;
+    if (nl > 0 && nr > ((int64_t)1 << 40) / nl) fail("cross_join: the result would exceed 2^40 rows");
+    const int64_t total = nl * nr;
+    Buf lidx = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8), ridx = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8);
+    if (total > 0) {
+        cross_indices_kernel<<<sgrid(total), 256, 0, ctx().stream>>>(nl, nr, outer_loop_left ? 1 : 0, as<int64_t>(lidx), as<int64_t>(ridx));
+        count_launch();
+    }
+    Batch *out = joined_views(left, lidx, right, ridx, total, false);
+    op_done();
     return out;
 }
 

@@ -158,3 +158,87 @@ def hash_join(left: RecordBatch, right: RecordBatch, left_on: Sequence[Expressio
             name = n if n not in lnames else f"right.{n}"
             sel.append(col(uniq[rbase + i]).alias(name))
     return joined.eval_expression_list(sel)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Sort-merge, asof and cross joins: RecordBatch::sort_merge_join / asof_join / cross_join of
+# src/daft-recordbatch/src/ops/joins/mod.rs:81-111,154-229,231-284, composed from sort + binary search + view gather
+# (daft_b200/csrc/sort.cu op_merge_join_sorted / op_asof_join_sorted / op_cross_join).
+# ------------------------------------------------------------------------------------------------------------------------
+def _call_join(fn: str, laug: RecordBatch, lkeys, raug: RecordBatch, rkeys) -> RecordBatch:
+    out = ctypes.c_void_p()
+    _lib.call(fn, laug._h, _i32(lkeys), raug._h, _i32(rkeys), ctypes.c_int32(len(lkeys)), ctypes.byref(out))
+    joined = RecordBatch._wrap(out, names=laug.column_names() + raug.column_names(), dtypes=laug.dtypes() + raug.dtypes())
+    return joined.rename([f"c{i}" for i in range(joined.num_columns())])
+
+
+def _key_dtypes(left: RecordBatch, right: RecordBatch, left_on, right_on) -> list[int]:
+    from .expressions import bind
+    lnames, ldt, rnames, rdt = left.column_names(), left.dtypes(), right.column_names(), right.dtypes()
+    return [dt.supertype(bind(le, lnames, ldt).dtype, bind(re_, rnames, rdt).dtype) for le, re_ in zip(left_on, right_on)]
+
+
+def sort_merge_join(left: RecordBatch, right: RecordBatch, left_on: Sequence[Expression], right_on: Sequence[Expression],
+                    is_sorted: bool = False) -> RecordBatch:
+    """Inner join of two batches over their sorted keys.  Both sides are sorted ascending, nulls last, on the join keys unless
+    `is_sorted`; output schema as for the inner hash join (infer_join_schema): same-named keys once, left columns, right
+    columns (`right.` prefix on clashes).  Rows come left-major in key order; a null in any key matches nothing."""
+    if len(left_on) != len(right_on):
+        raise ValueError(f"Mismatch of join on clauses: left: {len(left_on)} vs right: {len(right_on)}")
+    if len(left_on) == 0:
+        raise ValueError("No columns were passed in to join on")
+    kd = _key_dtypes(left, right, left_on, right_on)
+    lnames, rnames = left.column_names(), right.column_names()
+    laug, lkeys = _with_keys(left, left_on, kd)
+    raug, rkeys = _with_keys(right, right_on, kd)
+    if not is_sorted:
+        nk = len(kd)
+        laug = laug.sort([col(f"__key{i}") for i in range(nk)], descending=[False] * nk, nulls_first=[False] * nk)
+        raug = raug.sort([col(f"__key{i}") for i in range(nk)], descending=[False] * nk, nulls_first=[False] * nk)
+    joined = _call_join("b200_merge_join_sorted", laug, lkeys, raug, rkeys)
+    common = [le.name() for le, re_ in zip(left_on, right_on) if le.kind == "col" and re_.kind == "col" and le.name() == re_.name()]
+    rbase = laug.num_columns()
+    sel = [col(f"c{lnames.index(k)}").alias(k) for k in common]
+    sel += [col(f"c{i}").alias(n) for i, n in enumerate(lnames) if n not in common]
+    sel += [col(f"c{rbase + i}").alias(n if n not in lnames else f"right.{n}") for i, n in enumerate(rnames) if n not in common]
+    return joined.eval_expression_list(sel)
+
+
+def asof_join(left: RecordBatch, right: RecordBatch, left_by: Sequence[Expression], right_by: Sequence[Expression],
+              left_on: Expression, right_on: Expression) -> RecordBatch:
+    """Backward asof join (MicroPartition::asof_join, src/daft-micropartition/src/ops/join.rs:127-187): every left row with the
+    last right row of the same by-group whose on-key is <= its own, or nulls.  Output: all left columns, then the right
+    columns except the right by-columns and a right on-column named like the left one (infer_asof_join_schema,
+    src/daft-dsl/src/join.rs:69-120).  Left rows keep their order (the reference emits them per by-group, sorted by the on-key)."""
+    if len(left_by) != len(right_by):
+        raise ValueError(f"Mismatch of asof by-keys: left: {len(left_by)} vs right: {len(right_by)}")
+    lon, ron = list(left_by) + [left_on], list(right_by) + [right_on]
+    kd = _key_dtypes(left, right, lon, ron)
+    lnames, rnames = left.column_names(), right.column_names()
+    drop = {e.name() for e in right_by if e.kind == "col"}
+    if left_on.kind == "col" and right_on.kind == "col" and left_on.name() == right_on.name():
+        drop.add(right_on.name())
+    clash = [n for n in rnames if n not in drop and n in lnames]
+    if clash:
+        raise ValueError(f"asof_join: duplicate output column name(s) {clash}")
+    laug, lkeys = _with_keys(left, lon, kd)
+    raug, rkeys = _with_keys(right, ron, kd)
+    nk = len(kd)
+    raug = raug.sort([col(f"__key{i}") for i in range(nk)], descending=[False] * nk, nulls_first=[False] * nk)
+    joined = _call_join("b200_asof_join_sorted", laug, lkeys, raug, rkeys)
+    rbase = laug.num_columns()
+    sel = [col(f"c{i}").alias(n) for i, n in enumerate(lnames)]
+    sel += [col(f"c{rbase + i}").alias(n) for i, n in enumerate(rnames) if n not in drop]
+    return joined.eval_expression_list(sel)
+
+
+def cross_join(left: RecordBatch, right: RecordBatch, outer_loop_side: str = "left") -> RecordBatch:
+    """Every pair of rows; the outer-loop side's rows stay in order, each repeated len(inner) times in a row."""
+    if outer_loop_side not in ("left", "right"):
+        raise ValueError(f"outer_loop_side must be 'left' or 'right', not {outer_loop_side!r}")
+    clash = [n for n in right.column_names() if n in left.column_names()]
+    if clash:
+        raise ValueError(f"cross_join: duplicate output column name(s) {clash}")
+    out = ctypes.c_void_p()
+    _lib.call("b200_cross_join", left._h, right._h, ctypes.c_int32(1 if outer_loop_side == "left" else 0), ctypes.byref(out))
+    return RecordBatch._wrap(out, names=left.column_names() + right.column_names(), dtypes=left.dtypes() + right.dtypes())

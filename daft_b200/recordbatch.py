@@ -497,3 +497,21 @@ class RecordBatch:
         from the left), left non-key columns, right non-key columns (clashing names get a `right.` prefix)."""
         from .join import hash_join  # late import: join.py builds on this class
         return hash_join(self, right, left_on, right_on, how, null_equals_null, build_on_left)
+
+    def sort_merge_join(self, right: "RecordBatch", left_on: Sequence[Expression], right_on: Sequence[Expression],
+                        is_sorted: bool = False) -> "RecordBatch":
+        """RecordBatch::sort_merge_join (src/daft-recordbatch/src/ops/joins/mod.rs:154-229)."""
+        from .join import sort_merge_join
+        return sort_merge_join(self, right, left_on, right_on, is_sorted)
+
+    def asof_join(self, right: "RecordBatch", left_by: Sequence[Expression], right_by: Sequence[Expression], left_on: Expression,
+                  right_on: Expression) -> "RecordBatch":
+        """MicroPartition::asof_join, strategy backward (src/daft-micropartition/src/ops/join.rs:127-187)."""
+        from .join import asof_join
+        return asof_join(self, right, left_by, right_by, left_on, right_on)
+
+    def cross_join(self, right: "RecordBatch", outer_loop_side: str = "left") -> "RecordBatch":
+        """RecordBatch::cross_join (src/daft-recordbatch/src/ops/joins/mod.rs:231-284)."""
+        from .join import cross_join
+        return cross_join(self, right, outer_loop_side)
+

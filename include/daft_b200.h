@@ -274,6 +274,22 @@ int b200_hash_join_probe(const b200_probe_table *pt, b200_join_state *st /* NULL
 int b200_hash_join_finalize(const b200_probe_table *pt, b200_join_state *st, const b200_batch *probe_schema_like,
                             int32_t build_on_left, b200_batch **out, char **errmsg);
 
+/* ---- joins over SORTED inputs and the cross join ----
+ * RecordBatch::sort_merge_join / asof_join / cross_join (src/daft-recordbatch/src/ops/joins/mod.rs:81-111,154-229,231-284) behind
+ * SortMergeJoin / AsofJoinOperator / CrossJoinOperator (src/daft-local-execution/src/join/{sort_merge_join,asof_join,cross_join}.rs).
+ * Output of all three: [left columns..., right columns...] as views (selection vectors), names unchanged -- the caller applies the
+ * join's output schema.  Key dtypes must match pairwise (cast to the supertype first, ops/joins/mod.rs:22-46).
+ *  merge_join_sorted: inner join; both sides sorted ascending, nulls last, on their keys; a null in any key matches nothing.
+ *  asof_join_sorted : keys = by columns..., then the on column; `right` sorted ascending (nulls last) on them, `left` in any
+ *                     order; every left row appears once, with the last right row of its by-group whose on-key is <= its own
+ *                     (strategy "backward"), or a null row.
+ *  cross_join       : every pair; outer_loop_left != 0 repeats each left row |right| times in a row (JoinSide::Left). */
+int b200_merge_join_sorted(const b200_batch *left, const int32_t *left_keys, const b200_batch *right, const int32_t *right_keys,
+                           int32_t nkeys, b200_batch **out, char **errmsg);
+int b200_asof_join_sorted(const b200_batch *left, const int32_t *left_keys, const b200_batch *right, const int32_t *right_keys,
+                          int32_t nkeys, b200_batch **out, char **errmsg);
+int b200_cross_join(const b200_batch *left, const b200_batch *right, int32_t outer_loop_left, b200_batch **out, char **errmsg);
+
 /* ---- a12: exchange (hash repartition over NCCL; one process per GPU) ---- */
 typedef struct b200_comm b200_comm;
 int b200_comm_unique_id(uint8_t *out128, char **errmsg); /* rank 0: ncclGetUniqueId, 128 bytes */
