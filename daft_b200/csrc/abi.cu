@@ -397,6 +397,24 @@ int b200_cross_join(const b200_batch *left, const b200_batch *right, int32_t out
         *out = op_cross_join(*left, *right, outer_loop_left != 0);
     });
 }
+// ---- window functions over sorted partitions -------------------------------------------------------
+int b200_window_ranks(const b200_batch *sorted, const int32_t *partition_cols, int32_t npartition, const int32_t *order_cols, int32_t norder,
+                      b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!sorted) fail("null batch");
+        std::vector<int32_t> k(partition_cols, partition_cols + (npartition > 0 ? npartition : 0));
+        k.insert(k.end(), order_cols, order_cols + (norder > 0 ? norder : 0));
+        for (int32_t c : k)
+            if (c < 0 || c >= (int32_t)sorted->cols.size()) fail("window: key column index out of range");
+        *out = op_window_ranks(materialize_batch(*sorted, &k), partition_cols, npartition, order_cols, norder);
+    });
+}
+int b200_window_offset(const b200_batch *values, const b200_batch *partition_ids, int64_t offset, b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] {
+        if (!values || !partition_ids) fail("null batch");
+        *out = op_window_offset(*values, materialize(col_at(partition_ids, 0)), offset);
+    });
+}
 int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
         require_device();

@@ -54,6 +54,7 @@ struct DevAlloc {
 };
 using Buf = std::shared_ptr<DevAlloc>;
 Buf dev_alloc(size_t bytes);                    // uninitialised
+size_t dev_available_bytes();  // driver-free + parked cache blocks + unused pool reservation
 Buf dev_alloc_zero(size_t bytes);
 Buf dev_borrow(const void *ptr, size_t bytes);  // non-owning view
 Buf dev_sub(const Buf &parent, size_t offset, size_t bytes);  // view into `parent` that keeps it alive

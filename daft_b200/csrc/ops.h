@@ -37,6 +37,9 @@ Buf sort_slots_by_minrow(Buf slots, Buf minrow, int64_t ng);
 Batch *op_merge_join_sorted(const Batch &left, const int32_t *left_keys, const Batch &right, const int32_t *right_keys, int32_t nkeys);
 Batch *op_asof_join_sorted(const Batch &left, const int32_t *left_keys, const Batch &right, const int32_t *right_keys, int32_t nkeys);
 Batch *op_cross_join(const Batch &left, const Batch &right, bool outer_loop_left);
+// window functions over a batch sorted by (partition keys, order keys) (sort.cu)
+Batch *op_window_ranks(const Batch &sorted, const int32_t *part_cols, int32_t npart, const int32_t *order_cols, int32_t norder);
+Batch *op_window_offset(const Batch &values, const Column &partition_id, int64_t offset);
 
 // ops_jit.cu: ascending indices of the set (or, inverted, clear) bits among the first n bits
 Buf bitmap_select(const uint32_t *words, int64_t n, bool invert, int64_t *count_out);

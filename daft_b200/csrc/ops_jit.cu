@@ -726,8 +726,7 @@ Batch *op_agg_first_rows(const Batch &in, const uint8_t *plan, size_t len, Buf *
         } else {
             cap <<= 3;
         }
-        size_t free_b = 0, total_b = 0;
-        B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t free_b = dev_available_bytes();
         if ((size_t)cap * 8 * (size_t)(kp->astride + 1) > free_b + (size_t)(kp->astride + 1) * (size_t)(cap >> 3) * 8)
             fail("agg: the group table would not fit in device memory");
     }

@@ -193,6 +193,27 @@ Buf dev_alloc(size_t bytes) {
     }
     return a;
 }
+// Bytes an allocation could still obtain: what the driver reports free, plus the blocks parked in the size-class cache (a failed
+// allocation releases them, see dev_alloc) and the part of the stream-ordered pool that is reserved but not in use (the pool hands
+// it out again without asking the driver) -- cudaMemGetInfo alone counts both as used.
+size_t dev_available_bytes() {
+    size_t free_b = 0, total_b = 0;
+    B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t avail = free_b;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        avail += g_cached_bytes;
+    }
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx().device) == cudaSuccess && pool) {
+        uint64_t reserved = 0, used = 0;
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+            avail += (size_t)(reserved - used);
+    }
+    cudaGetLastError();
+    return std::min(avail, total_b);
+}
 Buf dev_alloc_zero(size_t bytes) {
     Buf b = dev_alloc(bytes);
     B200_CUDA(cudaMemsetAsync(b->ptr, 0, bytes + 16, ctx().stream));

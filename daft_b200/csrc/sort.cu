@@ -846,6 +846,130 @@ Batch *op_cross_join(const Batch &left, const Batch &right, bool outer_loop_left
     return out;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Window functions over a batch SORTED by (partition keys, order keys) (RecordBatch::window_row_number / window_rank /
+// window_offset, src/daft-recordbatch/src/ops/window.rs:636-790, which the reference runs per partition batch inside
+// WindowPartitionAndOrderBySink, src/daft-local-execution/src/sinks/window_partition_and_order_by.rs).  Here the whole sorted
+// table goes through segmented passes: boundary flags by comparing neighbours -> inclusive scans give every row its partition
+// id and peer-group id -> the first row of every partition / peer group is scattered by id -> ranks are differences.
+//   row_number = i - first(partition) + 1        rank = first(peer group) - first(partition) + 1
+//   dense_rank = peer group id - peer group id of the partition's first row + 1
+// Keys compare as in the reference's build_multi_array_is_equal(nulls_equal = true, nans_equal = true): null == null.
+// ------------------------------------------------------------------------------------------------
+__global__ void window_flags_kernel(SortKeySet part, SortKeySet order, int64_t n, int64_t *__restrict__ new_part, int64_t *__restrict__ new_peer) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        // small_cmp2 orders null == null as equal and NaN == NaN as equal: the window's notion of "same partition / same peers"
+        const bool np_ = i == 0 || (part.nkeys > 0 && small_cmp2(part, i - 1, part, i) != 0);
+        const bool nq = np_ || (order.nkeys > 0 && small_cmp2(order, i - 1, order, i) != 0);
+        new_part[i] = np_ ? 1 : 0;
+        new_peer[i] = nq ? 1 : 0;
+    }
+}
+// ids are the inclusive scans of the flags minus one; first[id] = the row where the flag is set
+__global__ void window_firsts_kernel(const int64_t *__restrict__ flag_part, const int64_t *__restrict__ excl_part, const int64_t *__restrict__ flag_peer,
+                                     const int64_t *__restrict__ excl_peer, int64_t n, int64_t *__restrict__ first_of_part,
+                                     int64_t *__restrict__ first_of_peer) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        if (flag_part[i]) first_of_part[excl_part[i]] = i;   // exclusive scan at a flagged row = its id
+        if (flag_peer[i]) first_of_peer[excl_peer[i]] = i;
+    }
+}
+__global__ void window_ranks_kernel(const int64_t *__restrict__ flag_part, const int64_t *__restrict__ excl_part, const int64_t *__restrict__ flag_peer,
+                                    const int64_t *__restrict__ excl_peer, const int64_t *__restrict__ first_of_part,
+                                    const int64_t *__restrict__ first_of_peer, int64_t n, uint64_t *__restrict__ row_number,
+                                    uint64_t *__restrict__ rank, uint64_t *__restrict__ dense_rank, int64_t *__restrict__ part_begin,
+                                    int64_t *__restrict__ part_id) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t pid = excl_part[i] + flag_part[i] - 1, gid = excl_peer[i] + flag_peer[i] - 1;
+        const int64_t p0 = first_of_part[pid];
+        const int64_t g0 = excl_peer[p0];   // peer-group id of the partition's first row (that row is flagged: exclusive scan = id)
+        row_number[i] = (uint64_t)(i - p0 + 1);
+        rank[i] = (uint64_t)(first_of_peer[gid] - p0 + 1);
+        dense_rank[i] = (uint64_t)(gid - g0 + 1);
+        part_begin[i] = p0;
+        part_id[i] = pid;
+    }
+}
+// lead / lag: row i reads row i + offset when that row is in the same partition, else -1 (a null row / the default)
+__global__ void window_offset_kernel(const int64_t *__restrict__ part_id, int64_t n, int64_t offset, int64_t *__restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t j = i + offset;
+        idx[i] = (j >= 0 && j < n && part_id[j] == part_id[i]) ? j : -1;
+    }
+}
+
+static Column make_i64_column(const std::string &name, Buf data, int64_t n) {
+    Column c = make_u64_column(name, data, n);
+    c.dtype = B200_I64;
+    return c;
+}
+// `sorted`: ordered by its partition key columns, then its order key columns.  Returns five columns of sorted.num_rows rows:
+// row_number, rank, dense_rank (UInt64), partition_begin (Int64: row index of the partition's first row), partition_id (Int64).
+Batch *op_window_ranks(const Batch &sorted, const int32_t *part_cols, int32_t npart, const int32_t *order_cols, int32_t norder) {
+    require_device();
+    if (npart < 0 || norder < 0 || npart > SMALL_SORT_KEYS || norder > SMALL_SORT_KEYS) fail("window: at most 8 partition and 8 order keys");
+    SortKeySet kp, ko;
+    kp.nkeys = 0;
+    ko.nkeys = 0;
+    if (npart > 0) kp = make_sort_keyset(sorted, part_cols, npart, nullptr, nullptr);
+    if (norder > 0) ko = make_sort_keyset(sorted, order_cols, norder, nullptr, nullptr);
+    const int64_t n = sorted.num_rows;
+    const size_t bytes = (size_t)std::max<int64_t>(n, 1) * 8;
+    Buf rn = dev_alloc(bytes), rk = dev_alloc(bytes), dr = dev_alloc(bytes), pb = dev_alloc(bytes), pid = dev_alloc(bytes);
+    if (n > 0) {
+        cudaStream_t st = ctx().stream;
+        Buf fp = dev_alloc(bytes), fq = dev_alloc(bytes), ep = dev_alloc(bytes + 8), eq = dev_alloc(bytes + 8), first_p = dev_alloc(bytes),
+            first_q = dev_alloc(bytes);
+        window_flags_kernel<<<sgrid(n), 256, 0, st>>>(kp, ko, n, as<int64_t>(fp), as<int64_t>(fq));
+        count_launch();
+        exclusive_scan_i64(as<int64_t>(fp), as<int64_t>(ep), n, nullptr);
+        exclusive_scan_i64(as<int64_t>(fq), as<int64_t>(eq), n, nullptr);
+        window_firsts_kernel<<<sgrid(n), 256, 0, st>>>(as<int64_t>(fp), as<int64_t>(ep), as<int64_t>(fq), as<int64_t>(eq), n, as<int64_t>(first_p),
+                                                       as<int64_t>(first_q));
+        count_launch();
+        window_ranks_kernel<<<sgrid(n), 256, 0, st>>>(as<int64_t>(fp), as<int64_t>(ep), as<int64_t>(fq), as<int64_t>(eq), as<int64_t>(first_p),
+                                                      as<int64_t>(first_q), n, as<uint64_t>(rn), as<uint64_t>(rk), as<uint64_t>(dr), as<int64_t>(pb),
+                                                      as<int64_t>(pid));
+        count_launch();
+    }
+    auto out = std::make_unique<Batch>();
+    out->num_rows = n;
+    out->cols.push_back(make_u64_column("row_number", rn, n));
+    out->cols.push_back(make_u64_column("rank", rk, n));
+    out->cols.push_back(make_u64_column("dense_rank", dr, n));
+    out->cols.push_back(make_i64_column("partition_begin", pb, n));
+    out->cols.push_back(make_i64_column("partition_id", pid, n));
+    op_done();
+    return out.release();
+}
+// rows of `values` (sorted like the batch op_window_ranks saw) shifted by `offset` inside their partitions: views with null rows
+// where the shifted position leaves the partition, plus an Int64 column "__src" holding the source row (-1 = outside)
+Batch *op_window_offset(const Batch &values, const Column &partition_id, int64_t offset) {
+    require_device();
+    require_plain(partition_id);
+    const int64_t n = values.num_rows;
+    if (partition_id.length != n || partition_id.dtype != B200_I64) fail("window_offset: partition ids must be Int64, one per row");
+    Buf idx = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+    if (n > 0) {
+        window_offset_kernel<<<sgrid(n), 256, 0, ctx().stream>>>(as<int64_t>(partition_id.data), n, offset, as<int64_t>(idx));
+        count_launch();
+    }
+    auto out = std::make_unique<Batch>();
+    out->num_rows = n;
+    for (Column &c : make_view_columns(values, idx, n, true)) out->cols.push_back(std::move(c));
+    out->cols.push_back(make_i64_column("__src", idx, n));
+    op_done();
+    return out.release();
+}
+
 Buf op_argsort(const Batch &b, const int32_t *key_cols, int32_t nkeys, const uint8_t *descending, const uint8_t *nulls_first) {
     require_device();
     if (nkeys < 1) fail("argsort: need at least one sort key");

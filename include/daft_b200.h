@@ -290,6 +290,20 @@ int b200_asof_join_sorted(const b200_batch *left, const int32_t *left_keys, cons
                           int32_t nkeys, b200_batch **out, char **errmsg);
 int b200_cross_join(const b200_batch *left, const b200_batch *right, int32_t outer_loop_left, b200_batch **out, char **errmsg);
 
+/* ---- window functions ----
+ * RecordBatch::window_row_number / window_rank / window_offset (src/daft-recordbatch/src/ops/window.rs:636-790) for ALL partitions
+ * of a batch at once: `sorted` is ordered by its partition key columns, then its order key columns (b200_sort), where the
+ * reference hands its kernels one partition at a time (src/daft-local-execution/src/sinks/window_partition_and_order_by.rs).
+ *  window_ranks : five columns, one row per input row: row_number, rank, dense_rank (UInt64), partition_begin (Int64: index of
+ *                 the partition's first row), partition_id (Int64, dense, in sorted order).  Rows are peers when their order
+ *                 keys are equal with null == null and NaN == NaN (build_multi_array_is_equal, window.rs:661-668).
+ *  window_offset: the columns of `values` read at row + offset when that row lies in the same partition (lead: offset > 0,
+ *                 lag: offset < 0), null rows otherwise, plus an Int64 column "__src" = the source row or -1 (the caller puts
+ *                 the default value there, window.rs:706-789). */
+int b200_window_ranks(const b200_batch *sorted, const int32_t *partition_cols, int32_t npartition, const int32_t *order_cols,
+                      int32_t norder, b200_batch **out, char **errmsg);
+int b200_window_offset(const b200_batch *values, const b200_batch *partition_ids, int64_t offset, b200_batch **out, char **errmsg);
+
 /* ---- a12: exchange (hash repartition over NCCL; one process per GPU) ---- */
 typedef struct b200_comm b200_comm;
 int b200_comm_unique_id(uint8_t *out128, char **errmsg); /* rank 0: ncclGetUniqueId, 128 bytes */

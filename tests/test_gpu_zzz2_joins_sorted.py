@@ -70,6 +70,7 @@ def test_asof_join_matches_oracle(gpu, nl, nr, nby):
         d[f"{p}v"] = pa.array(np.arange(n))
         return pa.table(d)
     left, right = tbl(nl, "l", False), tbl(nr, "r", True)
+    right = right.drop_columns([g for g in ("g1", "g2") if g not in by])   # a right column named like a left one is refused (duplicate names)
     c = gpu.col
     got = gpu.RecordBatch.from_arrow_table(left).asof_join(gpu.RecordBatch.from_arrow_table(right), [c(k) for k in by], [c(k) for k in by],
                                                            c("ts"), c("ts")).to_arrow_table()
