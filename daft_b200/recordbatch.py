@@ -515,3 +515,33 @@ class RecordBatch:
         from .join import cross_join
         return cross_join(self, right, outer_loop_side)
 
+    def _window_ranks(self, partition_cols: Sequence[int], order_cols: Sequence[int]) -> "RecordBatch":
+        """b200_window_ranks over this batch, which is sorted by (partition columns, order columns)."""
+        out = ctypes.c_void_p()
+        _lib.call("b200_window_ranks", self._h, _i32(partition_cols), ctypes.c_int32(len(partition_cols)), _i32(order_cols),
+                  ctypes.c_int32(len(order_cols)), ctypes.byref(out))
+        return RecordBatch._wrap(out, names=["__row_number", "__rank", "__dense_rank", "__partition_begin", "__partition_id"],
+                                 dtypes=[dt.U64, dt.U64, dt.U64, dt.I64, dt.I64])
+
+    def _window_offset(self, partition_ids: "RecordBatch", offset: int) -> "RecordBatch":
+        """b200_window_offset: this batch's columns read `offset` rows away inside the partition, plus `__src` (the row read, -1 = none)."""
+        out = ctypes.c_void_p()
+        _lib.call("b200_window_offset", self._h, partition_ids._h, ctypes.c_int64(offset), ctypes.byref(out))
+        return RecordBatch._wrap(out, names=self.column_names() + ["__src"], dtypes=self.dtypes() + [dt.I64])
+
+    def window(self, partition_by: Sequence[Expression], order_by: Sequence[Expression] = (), descending=None, nulls_first=None,
+               functions: Sequence[tuple] = ()) -> "RecordBatch":
+        """row_number / rank / dense_rank / lead / lag / partition aggregates (daft_b200/window.py)."""
+        from .window import window
+        return window(self, partition_by, order_by, descending, nulls_first, functions)
+
+    def pivot(self, group_by: Sequence[Expression], pivot_col: Expression, values_col: Expression, names: Sequence[str]) -> "RecordBatch":
+        """RecordBatch::pivot (src/daft-recordbatch/src/ops/pivot.rs:70-150)."""
+        from .window import pivot
+        return pivot(self, group_by, pivot_col, values_col, names)
+
+    def agg_pivot(self, group_by: Sequence[Expression], pivot_col: Expression, value_col: Expression, agg: str, names: Sequence[str]) -> "RecordBatch":
+        """PivotSink: aggregate per (group, pivot value), then pivot (src/daft-local-execution/src/sinks/pivot.rs)."""
+        from .window import agg_pivot
+        return agg_pivot(self, group_by, pivot_col, value_col, agg, names)
+

@@ -1,0 +1,130 @@
+"""Window functions and pivot on the RecordBatch surface.
+
+The reference runs its window kernels one partition at a time (RecordBatch::window_row_number / window_rank / window_offset /
+window_grouped_agg, src/daft-recordbatch/src/ops/window.rs:16-82,636-790, inside the Window*Sink operators of
+src/daft-local-execution/src/sinks/window_*.rs).  Here ONE sort by (partition keys, order keys) is followed by segmented passes
+over the whole table (daft_b200/csrc/sort.cu op_window_ranks / op_window_offset), and per-partition aggregates are a group-by
+on the dense partition id joined back through the direct-address join table.  Rows come back sorted by (partition keys, order
+keys); the reference emits them partition by partition in hash-partition order, each sorted by the order keys.
+
+pivot follows RecordBatch::pivot (src/daft-recordbatch/src/ops/pivot.rs:70-150) and PivotSink (sinks/pivot.rs).
+"""
+from __future__ import annotations
+
+from typing import Any, Sequence
+
+from . import datatypes as dt
+from .expressions import Expression, _to_expr, col
+from .recordbatch import RecordBatch
+
+RANK_FUNCS = {"row_number": 0, "rank": 1, "dense_rank": 2}
+
+
+def window(batch: RecordBatch, partition_by: Sequence[Expression], order_by: Sequence[Expression] = (),
+           descending: Sequence[bool] | bool | None = None, nulls_first: Sequence[bool] | bool | None = None,
+           functions: Sequence[tuple] = ()) -> RecordBatch:
+    """`functions`: ("row_number" | "rank" | "dense_rank", name), ("offset", name, expr, offset[, default]) -- lead for a positive
+    offset, lag for a negative one -- or ("agg", name, aggregate expression) for an aggregate over the whole partition.
+    Returns the batch's columns plus one column per function, rows ordered by (partition keys, order keys)."""
+    partition_by, order_by = list(partition_by), list(order_by)
+    if not partition_by and not order_by:
+        raise ValueError("window: partition_by and order_by cannot both be empty")
+    n_o = len(order_by)
+    desc = [descending] * n_o if isinstance(descending, bool) else list(descending or [False] * n_o)
+    nf = [nulls_first] * n_o if isinstance(nulls_first, bool) else list(nulls_first if nulls_first is not None else desc)
+    if len(desc) != n_o or len(nf) != n_o:
+        raise ValueError("window: descending / nulls_first must have one entry per order_by expression")
+    base_names = batch.column_names()
+    both, idx = batch._resolve_keys(partition_by + order_by)
+    names = both.column_names()
+    n_p = len(partition_by)
+    keys = [col(names[i]) for i in idx]
+    srt = both.sort(keys, descending=[False] * n_p + desc, nulls_first=[False] * n_p + nf)
+    ranks = srt._window_ranks(idx[:n_p], idx[n_p:])   # __row_number, __rank, __dense_rank, __partition_begin, __partition_id
+    work = srt.union(ranks)
+    result = [col(n) for n in base_names]
+    seen = set(base_names)
+    for f in functions:
+        kind, name = f[0], f[1]
+        if name in seen:
+            raise ValueError(f"window: duplicate output column name {name!r}")
+        seen.add(name)
+        if kind in RANK_FUNCS:
+            result.append(col(f"__{kind}").alias(name))
+        elif kind == "offset":
+            expr, offset = f[2], int(f[3])
+            default = _to_expr(f[4]) if len(f) > 4 and f[4] is not None else None
+            vals = work.eval_expression_list([expr.alias("__v")])
+            if offset == 0:
+                shifted = vals.eval_expression_list([col("__v").alias(f"__w_{name}")])
+            else:
+                sh = vals._window_offset(work.eval_expression_list([col("__partition_id")]), offset)   # columns __v, __src
+                if default is None:
+                    shifted = sh.eval_expression_list([col("__v").alias(f"__w_{name}")])
+                else:
+                    # rows whose shifted position leaves the partition take the default evaluated at that row, cast to the
+                    # value's type (window.rs:720-745); nulls that were read from inside the partition stay null
+                    tmp = work.union(sh.rename([f"__w0_{name}", f"__src_{name}"]))
+                    shifted = tmp.eval_expression_list([(col(f"__src_{name}") >= 0).if_else(col(f"__w0_{name}"), default.cast(vals.dtypes()[0]))
+                                                        .alias(f"__w_{name}")])
+            work = work.union(shifted)
+            result.append(col(f"__w_{name}").alias(name))
+        elif kind == "agg":
+            if not partition_by:
+                raise ValueError("Partition by cannot be empty for window aggregation")
+            g = work.agg([f[2].alias(f"__w_{name}")], [col("__partition_id")])
+            j = work.eval_expression_list([col("__partition_id")]).hash_join(g, [col("__partition_id")], [col("__partition_id")], build_on_left=False)
+            work = work.union(j.eval_expression_list([col(f"__w_{name}")]))
+            result.append(col(f"__w_{name}").alias(name))
+        else:
+            raise ValueError(f"window: unknown function {kind!r}")
+    return work.eval_expression_list(result)
+
+
+def _pivot_literal(name: str, dtype: int) -> Any:
+    if dt.is_string(dtype):
+        return name
+    if dtype == dt.BOOL:
+        return {"true": True, "false": False}[name.lower()]
+    if dt.is_integer(dtype):
+        return int(name)
+    if dt.is_float(dtype):
+        return float(name)
+    raise ValueError(f"pivot: pivot columns of type {dt.NAMES[dtype]} are not supported")
+
+
+def pivot(batch: RecordBatch, group_by: Sequence[Expression], pivot_col: Expression, values_col: Expression, names: Sequence[str]) -> RecordBatch:
+    """One row per distinct group key (first-occurrence order), one column per entry of `names` holding the value of the row whose
+    pivot column spells that name, null where there is none.  Like the reference this assumes (group, pivot value) pairs are
+    unique -- PivotSink aggregates first (agg_pivot)."""
+    group_by = list(group_by)
+    if not group_by:
+        raise ValueError("pivot: group_by cannot be empty")
+    gnames = [g.name() for g in group_by]
+    base = batch.eval_expression_list([g.alias(f"__g{i}") for i, g in enumerate(group_by)] + [pivot_col.alias("__p"), values_col.alias("__v")])
+    gcols = [col(f"__g{i}") for i in range(len(group_by))]
+    pdtype = base.dtypes()[len(group_by)]
+    out = base.eval_expression_list(gcols).dedup(gcols)
+    keys_only = out
+    never = col("__p").is_null() & col("__p").not_null()   # a name the pivot column cannot spell selects no row: an all-null column
+    for i, name in enumerate(names):
+        try:
+            pred = col("__p") == _pivot_literal(name, pdtype)
+        except (ValueError, KeyError):
+            pred = never
+        rows = base.filter([pred]).eval_expression_list(gcols + [col("__v").alias(f"__n{i}")])
+        j = keys_only.hash_join(rows, gcols, gcols, how="left", null_equals_null=[True] * len(gcols))
+        colv = j.eval_expression_list([col(f"__n{i}")])
+        out = out.union(colv)
+    return out.eval_expression_list([col(f"__g{i}").alias(n) for i, n in enumerate(gnames)] + [col(f"__n{i}").alias(n) for i, n in enumerate(names)])
+
+
+def agg_pivot(batch: RecordBatch, group_by: Sequence[Expression], pivot_col: Expression, value_col: Expression, agg: str,
+              names: Sequence[str]) -> RecordBatch:
+    """PivotSink (src/daft-local-execution/src/sinks/pivot.rs): aggregate the value per (group, pivot value), then pivot."""
+    group_by = list(group_by)
+    pre = batch.eval_expression_list([g.alias(f"__g{i}") for i, g in enumerate(group_by)] + [pivot_col.alias("__p"), value_col.alias("__v")])
+    keys = [col(f"__g{i}") for i in range(len(group_by))] + [col("__p")]
+    g = pre.agg([getattr(col("__v"), agg)().alias("__v")], keys)
+    res = pivot(g, [col(f"__g{i}") for i in range(len(group_by))], col("__p"), col("__v"), names)
+    return res.rename([gb.name() for gb in group_by] + list(names))

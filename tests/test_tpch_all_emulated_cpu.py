@@ -48,6 +48,43 @@ class EmulatedQueryBatch(OracleRecordBatch):
             return RecordBatch._agg_with_string_minmax(self, to_agg, group_by or [], predicate)
         return self._new(_EmulatedBatch(self.tbl).agg(list(to_agg), list(group_by or []), predicate).to_arrow_table())
 
+    _resolve_keys = RecordBatch._resolve_keys
+
+    def rename(self, names):
+        return self._new(self.tbl.rename_columns(list(names)))
+
+    def select_columns(self, idx):
+        return self._new(self.tbl.select(list(idx)))
+
+    # the two native window calls (daft_b200/csrc/sort.cu op_window_ranks / op_window_offset), restated in numpy for the host run
+    def _window_ranks(self, partition_cols, order_cols):
+        import numpy as np
+        from oracle import oracle as O
+        n = self.tbl.num_rows
+        rows = lambda cols: list(zip(*[O.normalize(self.tbl.column(c)).to_pylist() for c in cols])) if cols else [()] * n
+        from oracle.window import _same
+        P, Q = rows(list(partition_cols)), rows(list(order_cols))
+        rn, rk, dr, pb, pid = [], [], [], [], []
+        for i in range(n):
+            newp = i == 0 or not all(_same(a, b) for a, b in zip(P[i - 1], P[i]))
+            newq = newp or not all(_same(a, b) for a, b in zip(Q[i - 1], Q[i]))
+            pb.append(i if newp else pb[-1])
+            pid.append((pid[-1] + 1 if pid else 0) if newp else pid[-1])
+            rn.append(i - pb[-1] + 1)
+            rk.append(rn[-1] if newq else rk[-1])
+            dr.append(1 if newp else (dr[-1] + 1 if newq else dr[-1]))
+        return self._new(pa.table({"__row_number": pa.array(rn, pa.uint64()), "__rank": pa.array(rk, pa.uint64()), "__dense_rank": pa.array(dr, pa.uint64()),
+                                   "__partition_begin": pa.array(pb, pa.int64()), "__partition_id": pa.array(pid, pa.int64())}))
+
+    def _window_offset(self, partition_ids, offset):
+        import numpy as np
+        from oracle import oracle as O
+        pid = partition_ids.tbl.column(0).to_pylist()
+        n = len(pid)
+        src = [j if 0 <= (j := i + offset) < n and pid[j] == pid[i] else -1 for i in range(n)]
+        t = O._take_nullable(self.tbl, np.array(src, dtype=np.int64))
+        return self._new(t.append_column("__src", pa.array(src, pa.int64())))
+
     # the oracle's verbs return OracleRecordBatch: re-wrap
     def sort(self, *a, **k): return self._new(super().sort(*a, **k).tbl)
     def top_n(self, *a, **k): return self._new(super().top_n(*a, **k).tbl)

@@ -1,0 +1,92 @@
+"""Window functions and pivot: the host composition of daft_b200/window.py run on the CPU (generated expression / aggregate
+code through the host emulation, joins / sorts / dedup by the oracle, the two native window calls restated in numpy) against
+the oracle's per-partition restatement of the reference kernels (oracle/window.py), which is pinned on the reference's
+literal expectations (tests/window/test_partition_only.py etc., tests/recordbatch/test_pivot.py)."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from daft_b200 import col, window as W
+from helpers import assert_tables_equal
+from oracle import window as OW
+from test_tpch_all_emulated_cpu import EmulatedQueryBatch
+
+
+def _sorted(tbl, keys):
+    return tbl.sort_by([(k, "ascending") for k in keys])
+
+
+def window_table(rng, n, nulls=0.1):
+    return pa.table({
+        "id": np.arange(n),
+        "g": pa.array(np.array([f"p{v}" for v in rng.integers(0, 5, n)], dtype=object), type=pa.large_string(), mask=rng.random(n) < nulls),
+        "h": pa.array(rng.integers(0, 3, n)),
+        "o": pa.array(rng.integers(0, 8, n), mask=rng.random(n) < nulls),
+        "x": pa.array(rng.standard_normal(n).round(3), mask=rng.random(n) < nulls),
+        "s": pa.array(np.array([f"v{v}" for v in rng.integers(0, 50, n)], dtype=object), type=pa.large_string(), mask=rng.random(n) < nulls),
+    })
+
+
+FUNCS = [("row_number", "rn"), ("rank", "rk"), ("dense_rank", "dr"), ("offset", "lead1", col("x"), 1), ("offset", "lag2", col("x"), -2, 0.5),
+         ("offset", "lead_s", col("s"), 3), ("offset", "self", col("h") + 1, 0), ("agg", "psum", col("x").sum()), ("agg", "pcnt", col("o").count()),
+         ("agg", "pmax", col("h").max())]
+
+
+def test_oracle_window_reference_literals():
+    """tests/window/test_order_by_only.py-style expectations: rank ties, dense rank, lead / lag with defaults"""
+    t = pa.table({"k": ["a", "a", "a", "b", "b"], "v": [10, 10, 20, 5, 7]})
+    got = OW.window(t, [col("k")], [col("v")], [False], [False],
+                    [("row_number", "rn"), ("rank", "rk"), ("dense_rank", "dr"), ("offset", "nx", col("v"), 1), ("offset", "pv", col("v"), -1, -1),
+                     ("agg", "tot", col("v").sum())]).to_pydict()
+    assert got["rn"] == [1, 2, 3, 1, 2] and got["rk"] == [1, 1, 3, 1, 2] and got["dr"] == [1, 1, 2, 1, 2]
+    assert got["nx"] == [10, 20, None, 7, None] and got["pv"] == [-1, 10, 10, -1, 5] and got["tot"] == [40, 40, 40, 12, 12]
+
+
+@pytest.mark.parametrize("n", [0, 1, 37, 400])
+@pytest.mark.parametrize("shape", ["partition+order", "order only", "partition only", "two keys desc"])
+def test_window_composition_matches_oracle(n, shape):
+    rng = np.random.default_rng(n + len(shape))
+    tbl = window_table(rng, n)
+    pb, ob, desc, nf = {"partition+order": ([col("g")], [col("o")], [False], [False]), "order only": ([], [col("o"), col("h")], [False, True], [False, True]),
+                        "partition only": ([col("g"), col("h")], [], [], []),
+                        "two keys desc": ([col("h")], [col("o"), col("x")], [True, False], [True, False])}[shape]
+    funcs = [f for f in FUNCS if pb or f[0] != "agg"]
+    got = W.window(EmulatedQueryBatch(tbl), pb, ob, desc, nf, funcs).to_arrow_table()
+    want = OW.window(tbl, pb, ob, desc, nf, funcs)
+    assert got.column_names == want.column_names
+    if ob and n:
+        # ties in the order keys: row_number / lead / lag depend on the (admissible) order of the tied rows, which differs between a
+        # global stable sort and the per-partition sort -- compare those through a tie-free order (the id column appended)
+        ob2, d2, n2 = ob + [col("id")], desc + [False], nf + [False]
+        got = W.window(EmulatedQueryBatch(tbl), pb, ob2, d2, n2, funcs).to_arrow_table()
+        want = OW.window(tbl, pb, ob2, d2, n2, funcs)
+        got_r = W.window(EmulatedQueryBatch(tbl), pb, ob, desc, nf, [("rank", "rk"), ("dense_rank", "dr")]).to_arrow_table()
+        want_r = OW.window(tbl, pb, ob, desc, nf, [("rank", "rk"), ("dense_rank", "dr")])
+        assert_tables_equal(_sorted(got_r, ["id"]), _sorted(want_r, ["id"]))
+        assert_tables_equal(_sorted(got, ["id"]), _sorted(want, ["id"]), float_rtol=1e-12)
+    elif not ob:
+        keep = [c for c in got.column_names if c not in ("rn", "lead1", "lag2", "lead_s")]   # no order: positions inside a partition are arbitrary
+        assert_tables_equal(_sorted(got.select(keep), ["id"]), _sorted(want.select(keep), ["id"]), float_rtol=1e-12)
+
+
+def test_oracle_pivot_reference_literals():
+    """tests/recordbatch/test_pivot.py: missing combinations are null, unknown names give null columns"""
+    t = pa.table({"group": ["A", "A", "B"], "pivot": ["1", "2", "1"], "value": [1, 2, 3]})
+    assert OW.pivot(t, ["group"], "pivot", "value", ["1", "2"]).to_pydict() == {"group": ["A", "B"], "1": [1, 3], "2": [2, None]}
+    assert OW.pivot(t, ["group"], "pivot", "value", ["1", "3"]).to_pydict() == {"group": ["A", "B"], "1": [1, 3], "3": [None, None]}
+
+
+@pytest.mark.parametrize("ptype", ["str", "int", "bool"])
+def test_pivot_composition_matches_oracle(ptype):
+    rng = np.random.default_rng(5)
+    g1, g2 = rng.integers(0, 6, 300), rng.integers(0, 2, 300)
+    pv = {"str": np.array([f"c{v}" for v in rng.integers(0, 4, 300)], dtype=object), "int": rng.integers(0, 4, 300), "bool": rng.integers(0, 2, 300).astype(bool)}[ptype]
+    tbl = pa.table({"g1": pa.array(g1, mask=rng.random(300) < 0.1), "g2": g2, "p": pa.array(pv, type=pa.large_string()) if ptype == "str" else pv,
+                    "v": rng.standard_normal(300)})
+    names = {"str": ["c0", "c3", "zz", "c1"], "int": ["0", "3", "9", "x"], "bool": ["true", "false"]}[ptype]
+    # unique (group, pivot) pairs: aggregate first, as PivotSink does
+    got = W.agg_pivot(EmulatedQueryBatch(tbl), [col("g1"), col("g2")], col("p"), col("v"), "sum", names).to_arrow_table()
+    from oracle import oracle as O
+    pre = O.agg(tbl, [("sum", tbl.column("v"), "v", "valid")], [("g1", tbl.column("g1")), ("g2", tbl.column("g2")), ("p", tbl.column("p"))])
+    want = OW.pivot(pre, ["g1", "g2"], "p", "v", names)
+    assert_tables_equal(got, want, float_rtol=1e-12)
