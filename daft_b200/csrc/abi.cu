@@ -536,6 +536,14 @@ int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, cha
 }
 
 // ---- TPC-H generator -----------------------------------------------------------------------------------
+// ---- Parquet -> HBM scan ----------------------------------------------------------------------------
+int b200_parquet_read(const char *path, const char *const *columns, int32_t ncolumns, int64_t row_group_begin, int64_t row_group_end,
+                      b200_batch **out, char **errmsg) {
+    return guard(errmsg, [&] { *out = parquet_read(path, columns, ncolumns, row_group_begin, row_group_end); });
+}
+int b200_parquet_file_info(const char *path, int64_t *row_groups, int64_t *rows, char **errmsg) {
+    return guard(errmsg, [&] { parquet_file_info(path, row_groups, rows); });
+}
 int b200_tpch_generate(int32_t table, double scale_factor, int64_t row_begin, int64_t row_end, uint64_t seed,
                        const char *const *columns, int32_t ncolumns, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] { *out = tpch_generate(table, scale_factor, row_begin, row_end, seed, columns, ncolumns); });

@@ -104,6 +104,10 @@ Batch *all_gather_batches(b200_comm *c, const Batch &b);
 void allreduce_agg_table(b200_comm *c, unsigned long long *acc, size_t cap, const std::vector<int> &cell_ops, const std::vector<char> &keep_local,
                          unsigned long long *tagmin, int *status_flag);
 
+// parquet.cu: Parquet column chunks decoded on the device into a batch (flat columns; PLAIN / dictionary; Snappy / uncompressed)
+Batch *parquet_read(const char *path, const char *const *columns, int32_t ncolumns, int64_t rg_begin, int64_t rg_end);
+void parquet_file_info(const char *path, int64_t *row_groups, int64_t *rows);
+
 // tpch_gen.cu
 Batch *tpch_generate(int32_t table, double sf, int64_t row_begin, int64_t row_end, uint64_t seed, const char *const *columns,
                      int32_t ncolumns);

@@ -597,6 +597,15 @@ PQ_HD void stage_values(const ScanCtx &c, int32_t pi) {
         idx_width = vals < end ? (int32_t)vals[0] : 0;
         vals += 1;
     }
+    const bool bool_rle = pg.encoding == E_RLE;   // BOOLEAN only (the planner checks): <4-byte length> <hybrid runs of 1-bit values>
+    if (bool_rle) {
+        if (vals + 4 > end && n > 0) {
+            pg.status = PQ_ERR_VALUES;
+            return;
+        }
+        vals += 4;
+        idx_width = 1;
+    }
     HybridReader indices(vals, end, idx_width);
     const uint8_t *dict_data = dict ? page_data(c, c.pages[dict->page]) : nullptr;
     const int32_t *dict_offs = dict && col.is_string ? c.dict_str_offsets + dict->str_off_begin : nullptr;
@@ -640,6 +649,13 @@ PQ_HD void stage_values(const ScanCtx &c, int32_t pi) {
             } else {
                 copy_bytes(col.out_values + r * col.width, dict_data + (int64_t)k * col.width, col.width);
             }
+        } else if (bool_rle) {
+            const int32_t v = indices.next(ok);
+            if (!ok) {
+                pg.status = PQ_ERR_VALUES;
+                return;
+            }
+            col.out_values[r] = (uint8_t)(v & 1);
         } else if (col.is_string) {
             if (pos + 4 > vbytes) {
                 pg.status = PQ_ERR_VALUES;

@@ -329,6 +329,19 @@ int b200_agg_allreduce(b200_comm *c, const b200_batch *batch, const uint8_t *pla
 /* every rank receives the concatenation of all ranks' batches in rank order (broadcast join / partial-agg merge) */
 int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, char **errmsg);
 
+/* ---- Parquet -> HBM scan ----
+ * The reference's scan source (src/daft-local-execution/src/sources/scan_task.rs:33 -> src/daft-parquet/src/read.rs:553
+ * stream_parquet) for a local file: row groups [row_group_begin, row_group_end) (end < 0 = all) of the named columns
+ * (NULL / 0 = every column) as one batch.  The host reads the footer, the column chunks' bytes and the page headers; the
+ * compressed chunks are copied to HBM as they are and every page is decompressed and decoded on the device.
+ * Supported: flat schemas; BOOLEAN, INT32 (incl. DATE, UINT_32), INT64 (incl. TIMESTAMP micros, UINT_64), FLOAT, DOUBLE, BYTE_ARRAY
+ * (String -> LargeUtf8, otherwise LargeBinary); PLAIN and PLAIN_DICTIONARY / RLE_DICTIONARY pages, data pages V1 and V2 (RLE
+ * Booleans); UNCOMPRESSED and SNAPPY.  Anything else is an error naming the column and the feature (no CPU fallback). */
+int b200_parquet_read(const char *path, const char *const *columns, int32_t ncolumns, int64_t row_group_begin,
+                      int64_t row_group_end, b200_batch **out, char **errmsg);
+/* footer only: number of row groups and rows */
+int b200_parquet_file_info(const char *path, int64_t *row_groups, int64_t *rows, char **errmsg);
+
 /* ---- synthetic TPC-H tables generated straight into HBM (bench / tests) ---- */
 typedef enum { B200_TPCH_LINEITEM = 0, B200_TPCH_ORDERS = 1, B200_TPCH_CUSTOMER = 2, B200_TPCH_SUPPLIER = 3,
                B200_TPCH_NATION = 4, B200_TPCH_REGION = 5, B200_TPCH_PART = 6, B200_TPCH_PARTSUPP = 7 } b200_tpch_table;

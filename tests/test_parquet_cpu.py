@@ -1,0 +1,112 @@
+"""The Parquet scan's decoders (daft_b200/csrc/parquet_core.h, the functions the device runs one page per CUDA thread) and its
+planner (parquet_read.h), built for the host (tests/pq_host.cpp) and held to pyarrow's reader on files pyarrow writes:
+dictionary and PLAIN pages, data pages V1 / V2, Snappy and uncompressed, nulls, several row groups, dictionary fallback."""
+import os
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+
+import pq_host
+from daft_b200 import tpch
+from helpers import assert_tables_equal
+
+
+def mixed_table(rng, n, nulls):
+    def m():
+        return rng.random(n) < nulls if nulls else None
+    words = np.array(["", "a", "bb", "promo brushed", "x" * 40, "ünï", "0123456789" * 3], dtype=object)
+    return pa.table({
+        "i32": pa.array(rng.integers(-2**31, 2**31, n).astype(np.int32), mask=m()),
+        "i64": pa.array(rng.integers(-2**62, 2**62, n), mask=m()),
+        "small": pa.array(rng.integers(0, 7, n), mask=m()),                      # dictionary-friendly
+        "u32": pa.array(rng.integers(0, 2**32, n).astype(np.uint32), mask=m()),
+        "u64": pa.array(rng.integers(0, 2**63, n).astype(np.uint64), mask=m()),
+        "f32": pa.array(rng.standard_normal(n).astype(np.float32), mask=m()),
+        "f64": pa.array(rng.standard_normal(n), mask=m()),
+        "b": pa.array(rng.integers(0, 2, n).astype(bool), mask=m()),
+        "d": pa.array(rng.integers(0, 20000, n).astype(np.int32), type=pa.date32(), mask=m()),
+        "ts": pa.array(rng.integers(0, 2**50, n), type=pa.timestamp("us"), mask=m()),
+        "s": pa.array(words[rng.integers(0, len(words), n)], type=pa.large_string(), mask=m()),
+        "u": pa.array(np.array([f"unique-{i}-{'y' * (i % 13)}" for i in range(n)], dtype=object), type=pa.large_string(), mask=m()),   # high cardinality
+        "bin": pa.array([bytes([i % 256]) * (i % 5) for i in range(n)], type=pa.large_binary(), mask=m()),
+    })
+
+
+def expect(tbl):
+    """what pyarrow reads back, in the library's types (large_string / large_binary)"""
+    return tbl
+
+
+@pytest.mark.parametrize("n,nulls", [(0, 0.0), (1, 0.0), (1000, 0.0), (1000, 0.2), (50000, 0.05)])
+@pytest.mark.parametrize("opts", [
+    dict(compression="snappy"), dict(compression="none"), dict(compression="snappy", use_dictionary=False),
+    dict(compression="snappy", data_page_version="2.0"), dict(compression="none", data_page_version="2.0", use_dictionary=False),
+    dict(compression="snappy", data_page_size=4096, row_group_size=7000, dictionary_pagesize_limit=2048),   # many pages, dictionary fallback to PLAIN
+])
+def test_host_build_matches_pyarrow(tmp_path, n, nulls, opts):
+    rng = np.random.default_rng(n + int(nulls * 100))
+    tbl = mixed_table(rng, n, nulls)
+    path = str(tmp_path / "t.parquet")
+    pq.write_table(tbl, path, **opts)
+    want = pq.read_table(path)
+    got = pq_host.read_table(path)
+    assert_tables_equal(got, want.cast(got.schema))
+    assert got.schema.names == tbl.schema.names
+    # a column subset and a row-group range
+    groups, rows = pq_host.row_groups(path)
+    assert rows == n and groups == pq.ParquetFile(path).metadata.num_row_groups
+    if groups > 2:
+        sub = pq_host.read_table(path, ["s", "i64", "b"], (1, groups - 1))
+        pf = pq.ParquetFile(path)
+        want_sub = pa.concat_tables([pf.read_row_group(g, columns=["s", "i64", "b"]) for g in range(1, groups - 1)])
+        assert_tables_equal(sub, want_sub.cast(sub.schema))
+
+
+def test_tpch_tables_round_trip(tmp_path):
+    """the benchmark's own shape: the generated tables written as the reference's data generation writes them (Snappy, dictionary)"""
+    for table in ("lineitem", "orders", "part"):
+        tbl = tpch.generate_host(table, 0.01)
+        path = str(tmp_path / f"{table}.parquet")
+        pq.write_table(tbl, path, compression="snappy", row_group_size=20000)
+        got = pq_host.read_table(path)
+        assert_tables_equal(got, tbl)
+
+
+def test_refusals(tmp_path):
+    path = str(tmp_path / "z.parquet")
+    pq.write_table(pa.table({"a": [1, 2, 3]}), path, compression="zstd")
+    with pytest.raises(ValueError, match="compression codec 6 is not supported"):
+        pq_host.read_table(path)
+    pq.write_table(pa.table({"a": [[1, 2], [3]]}), path)
+    with pytest.raises(ValueError, match="nested"):
+        pq_host.read_table(path)
+    pq.write_table(pa.table({"a": pa.array([1, 2, 3], pa.int8())}), path)
+    with pytest.raises(ValueError, match="8- and 16-bit integers"):
+        pq_host.read_table(path)
+    pq.write_table(pa.table({"a": [1, 2, 3]}), path)
+    with pytest.raises(ValueError, match="no column named 'nope'"):
+        pq_host.read_table(path, ["nope"])
+    with open(path, "wb") as f:
+        f.write(b"not a parquet file at all")
+    with pytest.raises(ValueError, match="PAR1"):
+        pq_host.read_table(path)
+
+
+def test_snappy_decoder_on_adversarial_blocks():
+    """long literals (61+ bytes: extra length bytes), overlapping copies (run-length patterns), 1/2/4-byte offsets"""
+    import ctypes
+    # through a one-column file whose pages compress into each of those element kinds
+    rng = np.random.default_rng(0)
+    cols = {
+        "runs": pa.array(np.repeat(rng.integers(0, 3, 200), 500)),                           # overlapping copies
+        "noise": pa.array(rng.integers(-2**62, 2**62, 100000)),                               # long literals
+        "period": pa.array(np.tile(rng.integers(0, 2**40, 70000 // 7), 7)[:70000]),           # far copies (offsets > 64 KiB)
+    }
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        for name, arr in cols.items():
+            path = os.path.join(d, name + ".parquet")
+            pq.write_table(pa.table({name: arr}), path, compression="snappy", use_dictionary=False, data_page_size=1 << 20)
+            assert_tables_equal(pq_host.read_table(path), pa.table({name: arr}))
