@@ -15,9 +15,13 @@ namespace b200 {
 
 using namespace pq;
 
-__global__ void __launch_bounds__(32) pq_stage_kernel(ScanCtx ctx, int stage, int count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+// One page per WARP, decoded by its lane 0: the stages are data-dependent sequential walks (Snappy elements, run headers), so 32
+// pages in one warp would serialise each other's branches (first version: 149 ms to decompress 58 MB, gpurun_out/r02b_parquet_scan.txt);
+// a warp of its own lets every page run at the speed of one thread, and puts 32 x more warps on the SMs for the same page count.
+constexpr int PQ_WARPS_PER_BLOCK = 4;
+__global__ void __launch_bounds__(32 * PQ_WARPS_PER_BLOCK) pq_stage_kernel(ScanCtx ctx, int stage, int count) {
+    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= count || (threadIdx.x & 31) != 0) return;
     switch (stage) {
         case 0: stage_decompress(ctx, i); break;
         case 1: stage_dictionary(ctx, i); break;
@@ -56,6 +60,21 @@ struct DeviceExec {
         m.ptr = m.buf->ptr;
         return m;
     }
+    // the planner reads the column chunks straight into page-locked memory (kept across scans, grown on demand): no second host copy,
+    // and the copy to HBM runs at PCIe speed instead of through the driver's bounce buffers
+    uint8_t *stage(size_t bytes) {
+        static uint8_t *buf = nullptr;
+        static size_t cap = 0;
+        if (bytes > cap) {
+            if (buf) cudaFreeHost(buf);
+            buf = nullptr;
+            cap = 0;
+            const size_t want = std::max<size_t>(bytes + bytes / 4, (size_t)64 << 20);
+            B200_CUDA(cudaHostAlloc((void **)&buf, want, cudaHostAllocDefault));
+            cap = want;
+        }
+        return buf;
+    }
     void upload(Mem &m, const void *src, size_t bytes) {
         if (bytes) B200_CUDA(cudaMemcpyAsync(m.ptr, src, bytes, cudaMemcpyHostToDevice, ctx().stream));
         B200_CUDA(cudaStreamSynchronize(ctx().stream));   // `src` is pageable host memory owned by the planner
@@ -67,7 +86,7 @@ struct DeviceExec {
     void run(int stage, const ScanCtx &c, int count) {
         if (count <= 0) return;
         KernelTimer t(stage == 0 ? "parquet_decompress" : stage == 1 ? "parquet_dictionary" : stage == 2 ? "parquet_values" : "parquet_string_bytes");
-        pq_stage_kernel<<<(count + 31) / 32, 32, 0, ctx().stream>>>(c, stage, count);
+        pq_stage_kernel<<<(count + PQ_WARPS_PER_BLOCK - 1) / PQ_WARPS_PER_BLOCK, 32 * PQ_WARPS_PER_BLOCK, 0, ctx().stream>>>(c, stage, count);
         count_launch();
         B200_CUDA(cudaGetLastError());
     }

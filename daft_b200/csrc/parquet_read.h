@@ -4,6 +4,7 @@
 //
 //   X::Mem                      a buffer handle with .ptr
 //   X::alloc(bytes)             uninitialised buffer
+//   X::stage(bytes)             host memory the planner reads the file into (page-locked on the device executor)
 //   X::upload(mem, src, bytes)  host -> buffer
 //   X::download(dst, ptr, bytes)
 //   X::run(stage, ctx, count)   stage 0 decompress / 1 dictionary / 2 values / 3 string bytes over `count` pages (dictionaries for 1)
@@ -150,7 +151,16 @@ std::vector<ColumnResult<X>> scan_file(X &x, const std::string &path, const std:
     *rows_out = n_rows;
 
     // ---- read the chunks and walk their page headers ----
-    std::vector<uint8_t> chunks;
+    int64_t chunk_total = 0;
+    for (size_t ci = 0; ci < sel.size(); ci++)
+        for (int64_t g = rg_begin; g < rg_end; g++) {
+            const RowGroupMeta &rg = fm.row_groups[(size_t)g];
+            if ((size_t)sel[ci] >= rg.columns.size()) throw std::runtime_error("parquet: row group has fewer column chunks than the schema has leaves");
+            if (rg.columns[(size_t)sel[ci]].total_compressed < 0) throw std::runtime_error("parquet: negative column chunk size");
+            chunk_total += rg.columns[(size_t)sel[ci]].total_compressed;
+        }
+    uint8_t *chunks = x.stage((size_t)chunk_total + 16);
+    int64_t chunk_used = 0;
     std::vector<PageDesc> pages;
     std::vector<DictDesc> dicts;
     std::vector<ColumnDesc> cols(sel.size());
@@ -173,14 +183,14 @@ std::vector<ColumnResult<X>> scan_file(X &x, const std::string &path, const std:
             if (cm.type != leaf.physical) throw std::runtime_error(where + "chunk type differs from the schema");
             int64_t start = cm.data_page_offset;
             if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
-            const int64_t base = (int64_t)chunks.size();
-            chunks.resize((size_t)(base + cm.total_compressed));
-            fb.read(start, cm.total_compressed, chunks.data() + base);
+            const int64_t base = chunk_used;
+            chunk_used += cm.total_compressed;
+            fb.read(start, cm.total_compressed, chunks + base);
             int64_t pos = 0, seen = 0;
             int32_t cur_dict = -1;
             while (seen < cm.num_values) {
                 if (pos >= cm.total_compressed) throw std::runtime_error(where + "column chunk ends before its value count");
-                const PageHeader h = parse_page_header(chunks.data() + base + pos, (size_t)(cm.total_compressed - pos));
+                const PageHeader h = parse_page_header(chunks + base + pos, (size_t)(cm.total_compressed - pos));
                 pos += (int64_t)h.header_bytes;
                 if (h.compressed_size < 0 || pos + h.compressed_size > cm.total_compressed) throw std::runtime_error(where + "page runs past its column chunk");
                 if (h.type == P_INDEX) {
@@ -247,10 +257,10 @@ std::vector<ColumnResult<X>> scan_file(X &x, const std::string &path, const std:
 
     // ---- buffers ----
     using Mem = typename X::Mem;
-    Mem d_chunks = x.alloc(chunks.size() + 16), d_scratch = x.alloc((size_t)scratch_bytes + 16), d_pages = x.alloc(std::max<size_t>(pages.size(), 1) * sizeof(PageDesc)),
+    Mem d_chunks = x.alloc((size_t)chunk_total + 16), d_scratch = x.alloc((size_t)scratch_bytes + 16), d_pages = x.alloc(std::max<size_t>(pages.size(), 1) * sizeof(PageDesc)),
         d_cols = x.alloc(std::max<size_t>(cols.size(), 1) * sizeof(ColumnDesc)), d_dicts = x.alloc(std::max<size_t>(dicts.size(), 1) * sizeof(DictDesc)),
         d_dict_offs = x.alloc((size_t)(dict_str_entries + 1) * 4);
-    x.upload(d_chunks, chunks.data(), chunks.size());
+    x.upload(d_chunks, chunks, (size_t)chunk_total);
     std::vector<Mem> values(sel.size()), valid(sel.size()), lengths(sel.size()), offsets(sel.size()), ridx(sel.size()), rsrc(sel.size()), bytes(sel.size());
     const size_t nr = (size_t)std::max<int64_t>(n_rows, 1);
     for (size_t ci = 0; ci < sel.size(); ci++) {

@@ -153,6 +153,20 @@ class Expression:
         """Distinct non-null values per group as UInt64 (Series::count_distinct = agg_list + list_count_distinct over a
         probe table WITHOUT nulls, src/daft-functions-list/src/series.rs:37-40,234-247)."""
         return self._agg("count_distinct")
+    def approx_count_distinct(self):
+        """AggExpr::ApproxCountDistinct in ONE stage (src/daft-recordbatch/src/lib.rs:749-758, array/ops/approx_count_distinct.rs:13-40):
+        the number of distinct XXH3 hashes of the non-null values -- an exact distinct count unless two values collide in 64 bits
+        (the HyperLogLog sketch only appears in the reference's two-stage plan).  Runs as count_distinct."""
+        return self._agg("count_distinct")
+    def percentile(self, percentage: float):
+        """Series::percentile (src/daft-core/src/series/ops/agg.rs:269-301, utils/stats.rs:31-59): the exact percentile of the non-null
+        values as Float64, linearly interpolated between the two neighbouring order statistics."""
+        if not 0.0 <= float(percentage) <= 1.0:
+            raise ValueError(f"Provided percentile must be between 0 and 1: {percentage}")
+        return self._agg("percentile", float(percentage))
+    def median(self):
+        """AggExpr::Median = percentile(0.5) (src/daft-recordbatch/src/lib.rs:779)."""
+        return self._agg("percentile", 0.5)
     def any_value(self, ignore_nulls: bool = False):
         """Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the group's first row, or its first non-null row."""
         return self._agg("any_value", "ignore_nulls" if ignore_nulls else "first")

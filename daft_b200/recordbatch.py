@@ -270,6 +270,8 @@ class RecordBatch:
             return self._agg_with_count_distinct(to_agg, group_by or [], predicate)
         if any(self._is_string_minmax(a) for a in to_agg):
             return self._agg_with_string_minmax(to_agg, group_by or [], predicate)
+        if any(_inner(a).op == "percentile" for a in to_agg):
+            return self._agg_with_percentile(to_agg, group_by or [], predicate)
         staged = stage_moment_aggs(to_agg)
         if staged is not None:  # stddev / var: first-stage sums + counts, then the final projection (agg.rs:190-258)
             first, final = staged
@@ -321,6 +323,46 @@ class RecordBatch:
             pieces = pieces.union(best.eval_expression_list([col("__x").alias(f"__sm{i}")]))
         final = [col(f"__k{j}").alias(g.name()) for j, g in enumerate(group_by)]
         final += [col(f"__sm{i}").alias(a.name()) if self._is_string_minmax(a) else col(a.name()) for i, a in enumerate(to_agg)]
+        return pieces.eval_expression_list(final)
+
+    def _agg_with_percentile(self, to_agg, group_by, predicate) -> "RecordBatch":
+        """percentile / median per group (exact_percentile, src/daft-core/src/utils/stats.rs:31-59), composed from the sort-based
+        window kernels: the non-null values of every group are ranked by value (row_number over (keys; value)); with n values
+        rank = p (n - 1), and the answer interpolates between the rows at floor(rank) and ceil(rank) -- found by a filter on the
+        row number, folded with min / max per group -- as (hi - lo) * (rank - floor(rank)) + lo.  The reference fuses that last step
+        (mul_add): results agree to one ulp.  NaNs sort last, as +NaN does under f64::total_cmp.  Groups without a valid value give
+        null (left join back onto the group list, whose order the other aggregates define)."""
+        from .expressions import lit
+        base = self.filter(predicate) if predicate else self
+        # a constant leading key keeps the ungrouped case on the same path (one partition)
+        keys = [lit(1).alias("__k0")] + [g.alias(f"__k{i + 1}") for i, g in enumerate(group_by)]
+        key_cols = [col(f"__k{i}") for i in range(len(keys))]
+        plain = [a for a in to_agg if _inner(a).op != "percentile"]
+        keyed = base.union(base.eval_expression_list(keys)) if base.num_columns() else base.eval_expression_list(keys)
+        main = keyed.agg(plain + [col("__k0").count("all").alias("__rows")], key_cols)
+        if not group_by and len(main) == 0:
+            # an ungrouped aggregate over no rows still yields one row: the other aggregates' empty-input values, null percentiles
+            return base.agg([a if _inner(a).op != "percentile" else _inner(a).args[0].cast(dt.F64).min().alias(a.name()) for a in to_agg], [])
+        group_list = main.eval_expression_list(key_cols)
+        pieces = main
+        for i, a in enumerate(to_agg):
+            inner = _inner(a)
+            if inner.op != "percentile":
+                continue
+            p = float(inner.value)
+            vals = keyed.eval_expression_list(key_cols + [inner.args[0].cast(dt.F64).alias("__x")]).filter([col("__x").not_null()])
+            w = vals.window(key_cols, [col("__x")], functions=[("row_number", "__rn"), ("agg", "__cnt", col("__x").count())])
+            rank = lit(p) * (col("__cnt").cast(dt.F64) - 1.0)
+            pos = col("__rn").cast(dt.F64) - 1.0
+            w = w.eval_expression_list(key_cols + [col("__x"), rank.alias("__rank"), pos.alias("__pos")])
+            kept = w.filter([(col("__pos") == col("__rank").floor()) | (col("__pos") == col("__rank").ceil())])
+            g = kept.agg([col("__x").min().alias("__lo"), col("__x").max().alias("__hi"), col("__rank").max().alias("__r")], key_cols)
+            val = ((col("__hi") - col("__lo")) * (col("__r") - col("__r").floor()) + col("__lo")).alias(f"__pc{i}")
+            g = g.eval_expression_list(key_cols + [val])
+            j = group_list.hash_join(g, key_cols, key_cols, how="left", null_equals_null=[True] * len(key_cols))
+            pieces = pieces.union(j.eval_expression_list([col(f"__pc{i}")]))
+        final = [col(f"__k{j + 1}").alias(g.name()) for j, g in enumerate(group_by)]
+        final += [col(f"__pc{i}").alias(a.name()) if _inner(a).op == "percentile" else col(a.name()) for i, a in enumerate(to_agg)]
         return pieces.eval_expression_list(final)
 
     def _agg_with_count_distinct(self, to_agg, group_by, predicate) -> "RecordBatch":

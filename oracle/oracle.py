@@ -307,6 +307,26 @@ def agg(tbl: pa.Table, aggs: Sequence[tuple], group_by: Sequence) -> pa.Table:
                 if v is not None:
                     seen[g].add(v)
             r = pa.array([len(s_) for s_ in seen], type=pa.uint64())
+        elif kind == "percentile":
+            # exact_percentile (src/daft-core/src/utils/stats.rs:31-59) over the group's non-null values cast to Float64: sort by
+            # f64::total_cmp, rank = p (n - 1), (upper - lower).mul_add(rank - floor(rank), lower)
+            import math
+            p_ = float(a[3])
+            vals = normalize(arr).cast(pa.float64()).to_pylist()
+            per = [[] for _ in range(ng)]
+            for g, v in zip(gid.tolist(), vals):
+                if v is not None:
+                    per[g].append(v)
+            out = []
+            for vs in per:
+                if not vs:
+                    out.append(None)
+                    continue
+                vs.sort(key=lambda v: (2, 0.0) if v != v else (1, v))   # a (positive) NaN is the greatest under total_cmp
+                rank = p_ * (len(vs) - 1)
+                lo, hi = int(math.floor(rank)), int(math.ceil(rank))
+                out.append(vs[lo] if lo == hi else math.fma(vs[hi] - vs[lo], rank - lo, vs[lo]) if hasattr(math, "fma") else (vs[hi] - vs[lo]) * (rank - lo) + vs[lo])
+            r = pa.array(out, type=pa.float64())
         elif kind == "any_value":
             # Series::any_value (src/daft-core/src/series/ops/agg.rs:353-382): the first row of each group, or with
             # ignore_nulls its first non-null row (null when there is none); ungrouped: row 0 / first valid row / null

@@ -19,6 +19,11 @@ struct HostExec {
         m.ptr = m.keep.get();
         return m;
     }
+    std::vector<uint8_t> staging;
+    uint8_t *stage(size_t bytes) {
+        staging.resize(bytes);
+        return staging.data();
+    }
     void upload(Mem &m, const void *src, size_t bytes) {
         if (bytes) memcpy(m.ptr, src, bytes);
     }

@@ -69,3 +69,26 @@ def test_pivot_matches_oracle(gpu, ptype):
     t = pa.table({"group": pa.array(["A", "A", "B"], pa.large_string()), "pivot": pa.array(["1", "2", "1"], pa.large_string()), "value": [1, 2, 3]})
     got = gpu.RecordBatch.from_arrow_table(t).pivot([c("group")], c("pivot"), c("value"), ["1", "2", "3"]).to_arrow_table()
     assert got.to_pydict() == {"group": ["A", "B"], "1": [1, 3], "2": [2, None], "3": [None, None]}
+
+
+@pytest.mark.parametrize("n", [0, 1, 600, 30000])
+def test_percentile_median_and_approx_count_distinct_match_oracle(gpu, n):
+    """exact_percentile (src/daft-core/src/utils/stats.rs:31-59) through the window-based composition; the reference's fused
+    multiply-add in the interpolation allows one ulp"""
+    from helpers import oracle_agg
+    rng = np.random.default_rng(n)
+    tbl = window_table(rng, n, nulls=0.15)
+    c = gpu.col
+    aggs = [c("x").median().alias("med"), c("o").percentile(0.9).alias("p90"), c("x").sum().alias("sx"), c("h").percentile(0.0).alias("p0"),
+            (c("x") * 2 + c("h")).percentile(0.33).alias("pe"), c("s").approx_count_distinct().alias("acd")]
+    rb = gpu.RecordBatch.from_arrow_table(tbl)
+    for gb in ([c("g")], [c("g"), c("h")], []):
+        got = rb.agg(aggs, gb).to_arrow_table()
+        want = oracle_agg(tbl, aggs, gb)
+        keys = [g.name() for g in gb]
+        if keys:
+            assert_tables_equal(_sorted(got, keys), _sorted(want, keys), float_rtol=1e-9)
+        else:
+            assert_tables_equal(got, want, float_rtol=1e-9)
+    with pytest.raises(ValueError, match="between 0 and 1"):
+        c("x").percentile(1.5)

@@ -41,8 +41,8 @@ def test_q1_and_q6_from_parquet(gpu, tmp_path):
     scanned = gpu.read_parquet(path, tpch.Q1_COLUMNS)
     direct = gpu.RecordBatch.from_arrow_table(host)
     assert_tables_equal(scanned.to_arrow_table(), host)
-    assert_tables_equal(tpch.q1(scanned).to_arrow_table(), tpch.q1(direct).to_arrow_table())
-    assert_tables_equal(tpch.q6(scanned).to_arrow_table(), tpch.q6(direct).to_arrow_table())
+    assert_tables_equal(tpch.q1(scanned).to_arrow_table(), tpch.q1(direct).to_arrow_table(), float_rtol=1e-12)   # the group table's atomics add in any order
+    assert_tables_equal(tpch.q6(scanned).to_arrow_table(), tpch.q6(direct).to_arrow_table(), float_rtol=1e-12)
 
 
 def test_read_parquet_refusals(gpu, tmp_path):

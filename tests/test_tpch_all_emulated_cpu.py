@@ -46,9 +46,15 @@ class EmulatedQueryBatch(OracleRecordBatch):
             return RecordBatch._agg_with_count_distinct(self, to_agg, group_by or [], predicate)
         if any(self._is_string_minmax(a) for a in to_agg):
             return RecordBatch._agg_with_string_minmax(self, to_agg, group_by or [], predicate)
+        if any(_inner(a).op == "percentile" for a in to_agg):
+            return RecordBatch._agg_with_percentile(self, to_agg, group_by or [], predicate)
         return self._new(_EmulatedBatch(self.tbl).agg(list(to_agg), list(group_by or []), predicate).to_arrow_table())
 
     _resolve_keys = RecordBatch._resolve_keys
+
+    def window(self, partition_by, order_by=(), descending=None, nulls_first=None, functions=()):
+        from daft_b200.window import window
+        return window(self, partition_by, order_by, descending, nulls_first, functions)
 
     def rename(self, names):
         return self._new(self.tbl.rename_columns(list(names)))

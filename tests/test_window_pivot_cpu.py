@@ -90,3 +90,33 @@ def test_pivot_composition_matches_oracle(ptype):
     pre = O.agg(tbl, [("sum", tbl.column("v"), "v", "valid")], [("g1", tbl.column("g1")), ("g2", tbl.column("g2")), ("p", tbl.column("p"))])
     want = OW.pivot(pre, ["g1", "g2"], "p", "v", names)
     assert_tables_equal(got, want, float_rtol=1e-12)
+
+
+# ---- percentile / median: the window-based composition of RecordBatch._agg_with_percentile against exact_percentile's restatement ----
+def test_oracle_percentile_reference_literals():
+    """tests/recordbatch/test_table_aggs.py percentile cases: interpolation between order statistics, nulls ignored, all-null -> null"""
+    from helpers import oracle_agg
+    t = pa.table({"g": [1, 1, 1, 1, 2, 2, 3], "x": [1.0, 2.0, 3.0, 4.0, 10.0, None, None]})
+    got = oracle_agg(t, [col("x").median().alias("m"), col("x").percentile(0.25).alias("q1"), col("x").percentile(1.0).alias("mx")], [col("g")]).to_pydict()
+    assert got == {"g": [1, 2, 3], "m": [2.5, 10.0, None], "q1": [1.75, 10.0, None], "mx": [4.0, 10.0, None]}
+    got = oracle_agg(t, [col("x").median().alias("m")], []).to_pydict()
+    assert got == {"m": [3.0]}
+
+
+@pytest.mark.parametrize("n", [0, 1, 50, 600])
+def test_percentile_composition_matches_oracle(n):
+    from helpers import oracle_agg
+    rng = np.random.default_rng(n)
+    tbl = window_table(rng, n, nulls=0.15)
+    aggs = [col("x").median().alias("med"), col("o").percentile(0.9).alias("p90"), col("x").sum().alias("sx"), col("h").percentile(0.0).alias("p0"),
+            (col("x") * 2 + col("h")).percentile(0.33).alias("pe")]
+    for gb in ([col("g")], [col("g"), col("h")], []):
+        got = EmulatedQueryBatch(tbl).agg(aggs, gb).to_arrow_table()
+        want = oracle_agg(tbl, aggs, gb)
+        keys = [g.name() for g in gb]
+        if keys:
+            assert_tables_equal(_sorted(got, keys), _sorted(want, keys), float_rtol=1e-12)
+        else:
+            assert_tables_equal(got, want, float_rtol=1e-12)
+    got = EmulatedQueryBatch(tbl).agg([col("x").median().alias("med")], [col("g")], predicate=[col("h") > 0]).to_arrow_table()
+    assert_tables_equal(_sorted(got, ["g"]), _sorted(oracle_agg(tbl, [col("x").median().alias("med")], [col("g")], [col("h") > 0]), ["g"]), float_rtol=1e-12)
