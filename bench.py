@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-q5", action="store_true", help="skip the config[2] leg")
-    ap.add_argument("--tpch22-sf", type=float, default=10.0, help="scale factor of the all-22-queries leg (N = 1); 0 skips it")
+    ap.add_argument("--tpch22-sf", type=float, default=100.0, help="scale factor of the all-22-queries leg (N = 1; BASELINE metric: TPC-H SF100 total wall-clock); 0 skips it")
     ap.add_argument("--tpch22-queries", default="", help="comma-separated query numbers for that leg (default: all 22)")
     ap.add_argument("--tpch22-budget-s", type=float, default=150.0, help="wall-clock budget of that leg; queries not reached are listed as skipped")
     ap.add_argument("--no-exchange", action="store_true", help="N > 1: skip the exchange workload")
