@@ -75,6 +75,18 @@ def two_stage_aggregate(partial: Callable[[], pa.Table], final: Callable[[pa.Tab
     return final(gather_tables(partial(), group))
 
 
+def partitioned_join(left, right, left_on: Sequence[str], right_on: Sequence[str], world: int, rank: int, partition, exchange, join):
+    """The shape of a distributed hash join (src/daft-distributed/src/pipeline_node/join/hash_join.rs, translated from
+    src/daft-logical-plan's HashJoin with both sides repartitioned by hash of the join keys): rows whose keys are equal hash alike, so
+    after both sides are exchanged by hash(keys) % world the local joins partition the global join.  `partition(table, keys, world)`
+    -> world pieces, `exchange(pieces)` -> this rank's rows from every rank, `join(l, r)` the local join.  Written over callables so
+    the world-2 gloo test drives it with the oracle (tests/test_distributed_gloo.py) and Communicator.hash_join with the device
+    primitives.  A null key hashes like any value but matches nothing: where it lands does not matter for inner / semi joins; for
+    left / right / outer / anti joins every row is still emitted exactly once, on the rank its key hashes to."""
+    lp, rp = partition(left, left_on, world), partition(right, right_on, world)
+    return join(exchange(lp), exchange(rp))
+
+
 class Communicator:
     """NCCL communicator owned by libdaftb200 (b200_comm): rank 0 creates the unique id, torch.distributed
     broadcasts it (out-of-band rendezvous only), every rank calls ncclCommInitRank."""
@@ -184,6 +196,26 @@ class Communicator:
         partial = batch.agg(first, group_by, predicate)
         keys = [col(g.name()) for g in group_by]
         return self.all_gather(partial).agg(second, keys).eval_expression_list(final)
+
+    def hash_join(self, left, right, left_on: Sequence, right_on: Sequence, how: str = "inner", broadcast_rows: int = 1 << 16):
+        """Distributed hash join over one scan partition of each side per rank; the union of the ranks' outputs is the global join.
+        A right side of at most `broadcast_rows` rows per rank is broadcast (all-gather, src/daft-distributed/src/pipeline_node/join/
+        broadcast_join.rs) when the join type allows it (inner / left / semi / anti keep every left row where it is); otherwise both
+        sides are exchanged by the hash of their join keys (hash_join.rs) and joined locally.  Join keys are cast to their common
+        supertype BEFORE hashing (ops/joins/mod.rs:22-46): an Int32 and an Int64 of the same value hash differently."""
+        import torch
+        import torch.distributed as dist
+        from . import datatypes as dt
+        from .expressions import bind
+        lnames, ldt, rnames, rdt = left.column_names(), left.dtypes(), right.column_names(), right.dtypes()
+        kd = [dt.supertype(bind(le, lnames, ldt).dtype, bind(re_, rnames, rdt).dtype) for le, re_ in zip(left_on, right_on)]
+        small = torch.tensor([1 if len(right) <= broadcast_rows else 0], device="cuda")
+        dist.all_reduce(small, op=dist.ReduceOp.MIN)     # every rank takes the same route
+        if int(small.item()) and how in ("inner", "left", "semi", "anti"):
+            return left.hash_join(self.all_gather(right), left_on, right_on, how=how)
+        lk = [(e if bind(e, lnames, ldt).dtype == t else e.cast(t)) for e, t in zip(left_on, kd)]
+        rk = [(e if bind(e, rnames, rdt).dtype == t else e.cast(t)) for e, t in zip(right_on, kd)]
+        return self.exchange_by_hash(left, lk).hash_join(self.exchange_by_hash(right, rk), left_on, right_on, how=how)
 
     def all_gather(self, batch):
         from . import _lib

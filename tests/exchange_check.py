@@ -88,6 +88,22 @@ def main():
         assert got_all.num_rows == want_all.num_rows
         for k in keys:   # rank order == global order on the sort keys (ties between equal keys are free)
             assert got_all.column(k).to_pylist() == want_all.column(k).to_pylist(), k
+    # distributed hash join: exchanged by key hash (large right side) and broadcast (small right side) == single-table oracle
+    lt = tbl.select(["i32", "i64", "s"]).rename_columns(["k", "lv", "ls"])
+    rt = random_table(np.random.default_rng(500 + rank), 5000 + 100 * rank, 0.1).select(["i32", "f64"]).rename_columns(["k", "rv"])
+    lparts, rparts = [None] * world, [None] * world
+    dist.all_gather_object(lparts, distributed._to_ipc(lt))
+    dist.all_gather_object(rparts, distributed._to_ipc(rt))
+    lfull, rfull = (pa.concat_tables([distributed._from_ipc(p) for p in ps]) for ps in (lparts, rparts))
+    for how in ("inner", "left", "anti"):
+        for thr in (0, 1 << 20):
+            j = comm.hash_join(daft_b200.RecordBatch.from_arrow_table(lt), daft_b200.RecordBatch.from_arrow_table(rt), [col("k")], [col("k")], how, thr).to_arrow_table()
+            jparts = [None] * world
+            dist.all_gather_object(jparts, distributed._to_ipc(j))
+            got_j = pa.concat_tables([distributed._from_ipc(p) for p in jparts])
+            want_j = O.hash_join(lfull, rfull, ["k"], ["k"], how)
+            order = [(c, "ascending") for c in want_j.column_names]
+            assert_tables_equal(got_j.sort_by(order), want_j.sort_by(order))
     dist.barrier()
     if rank == 0:
         print(f"exchange ok on {world} GPUs")
