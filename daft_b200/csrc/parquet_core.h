@@ -380,8 +380,32 @@ inline const char *pq_error_text(int e) {
 // Decoders (host + device)
 // ------------------------------------------------------------------------------------------------------------------
 PQ_HD uint32_t ld_u32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+// non-overlapping copy: whole words when source and destination share their misalignment (page payloads sit at arbitrary byte
+// offsets, so this is the lucky half of the cases), bytes otherwise
 PQ_HD void copy_bytes(uint8_t *dst, const uint8_t *src, int64_t n) {
-    for (int64_t i = 0; i < n; i++) dst[i] = src[i];
+    int64_t i = 0;
+    const uintptr_t d = (uintptr_t)dst, s = (uintptr_t)src;
+    if (((d ^ s) & 7) == 0) {
+        while (i < n && ((d + (uintptr_t)i) & 7)) {
+            dst[i] = src[i];
+            i++;
+        }
+        for (; i + 8 <= n; i += 8) *(uint64_t *)(dst + i) = *(const uint64_t *)(src + i);
+    } else if (((d ^ s) & 3) == 0) {
+        while (i < n && ((d + (uintptr_t)i) & 3)) {
+            dst[i] = src[i];
+            i++;
+        }
+        for (; i + 4 <= n; i += 4) *(uint32_t *)(dst + i) = *(const uint32_t *)(src + i);
+    }
+    for (; i < n; i++) dst[i] = src[i];
+}
+PQ_HD void fill_bytes(uint8_t *dst, uint8_t v, int64_t n) {
+    int64_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 7)) dst[i++] = v;
+    const uint64_t w = 0x0101010101010101ULL * v;
+    for (; i + 8 <= n; i += 8) *(uint64_t *)(dst + i) = w;
+    for (; i < n; i++) dst[i] = v;
 }
 
 // Snappy raw format: varint uncompressed length, then literal / copy elements.  Returns the number of bytes produced, -1 when corrupt.
@@ -435,7 +459,8 @@ PQ_HD int64_t snappy_decompress(const uint8_t *src, int64_t n, uint8_t *dst, int
                 break;
         }
         if (off == 0 || off > op || op + len > (int64_t)ulen) return -1;
-        for (int64_t i = 0; i < len; i++) dst[op + i] = dst[op + i - off];   // overlapping copies repeat the pattern byte by byte
+        if (off >= len) copy_bytes(dst + op, dst + op - off, len);   // disjoint ranges
+        else for (int64_t i = 0; i < len; i++) dst[op + i] = dst[op + i - off];   // overlapping copies repeat the pattern byte by byte
         op += len;
     }
     return op == (int64_t)ulen ? op : -1;
@@ -581,6 +606,13 @@ PQ_HD void stage_values(const ScanCtx &c, int32_t pi) {
         }
     }
     HybridReader levels(lev, lev_end, 1);
+    // the common page of a nullable column without nulls: ONE run-length run of 1s covering the page -- no per-value level decode
+    bool all_valid = col.max_def == 0;
+    if (!all_valid && lev != nullptr) {
+        HybridReader peek(lev, lev_end, 1);
+        if (peek.next_run() && !peek.packed && peek.run_value == col.max_def && peek.run_left >= n) all_valid = true;
+    }
+    if (all_valid && col.out_valid) fill_bytes(col.out_valid + r0, 1, n);
     // dictionary indices
     const bool by_dict = pg.encoding == E_RLE_DICTIONARY;
     const DictDesc *dict = by_dict && pg.dict >= 0 ? &c.dicts[pg.dict] : nullptr;
@@ -612,15 +644,23 @@ PQ_HD void stage_values(const ScanCtx &c, int32_t pi) {
     int64_t pos = 0;        // PLAIN: byte position inside the values
     int64_t bool_bit = 0;   // PLAIN BOOLEAN: bit position
     const int64_t vbytes = end - vals;
+    if (all_valid && !by_dict && !bool_rle && !col.is_string && col.physical != T_BOOLEAN) {   // PLAIN fixed width, no nulls: one copy
+        if (n * col.width > vbytes) {
+            pg.status = PQ_ERR_VALUES;
+            return;
+        }
+        copy_bytes(col.out_values + r0 * col.width, vals, n * col.width);
+        return;
+    }
     for (int64_t i = 0; i < n; i++) {
         const int64_t r = r0 + i;
         bool ok = true;
-        const bool valid = col.max_def == 0 || levels.next(ok) == col.max_def;
+        const bool valid = all_valid || levels.next(ok) == col.max_def;
         if (!ok) {
             pg.status = PQ_ERR_LEVELS;
             return;
         }
-        if (col.out_valid) col.out_valid[r] = valid ? 1 : 0;
+        if (col.out_valid && !all_valid) col.out_valid[r] = valid ? 1 : 0;
         if (!valid) {
             if (col.is_string) {
                 col.out_lengths[r] = 0;
