@@ -229,21 +229,24 @@ def q4(t: dict[str, RecordBatch]) -> RecordBatch:
 
 
 def q12(t: dict[str, RecordBatch]) -> RecordBatch:
-    """answers.py:373-395: late MAIL / SHIP lineitems received in 1994, high- and low-priority line counts per ship mode."""
-    j = t["orders"].hash_join(t["lineitem"], [col("O_ORDERKEY")], [col("L_ORDERKEY")], build_on_left=True)
-    j = j.filter([col("L_SHIPMODE").is_in(["MAIL", "SHIP"]), col("L_COMMITDATE") < col("L_RECEIPTDATE"), col("L_SHIPDATE") < col("L_COMMITDATE"),
-                  col("L_RECEIPTDATE") >= datetime.date(1994, 1, 1), col("L_RECEIPTDATE") < datetime.date(1995, 1, 1)])
+    """answers.py:373-395: late MAIL / SHIP lineitems received in 1994, high- and low-priority line counts per ship mode.  The
+    DataFrame text filters after the join; every conjunct reads lineitem only, so the reference's optimizer moves the filter below
+    the join (PushDownFilter, src/daft-logical-plan/src/optimization/rules/push_down_filter.rs) -- the plan it executes is this one."""
+    lineitem = t["lineitem"].filter([col("L_SHIPMODE").is_in(["MAIL", "SHIP"]), col("L_COMMITDATE") < col("L_RECEIPTDATE"),
+                                     col("L_SHIPDATE") < col("L_COMMITDATE"), col("L_RECEIPTDATE") >= datetime.date(1994, 1, 1),
+                                     col("L_RECEIPTDATE") < datetime.date(1995, 1, 1)])
+    j = t["orders"].hash_join(lineitem, [col("O_ORDERKEY")], [col("L_ORDERKEY")], build_on_left=len(t["orders"]) <= len(lineitem))
     urgent = col("O_ORDERPRIORITY").is_in(["1-URGENT", "2-HIGH"])
     out = j.agg([_when(urgent, 1, 0).sum().alias("high_line_count"), _when(~urgent, 1, 0).sum().alias("low_line_count")], [col("L_SHIPMODE")])
     return out.sort([col("L_SHIPMODE")])
 
 
 def q14(t: dict[str, RecordBatch]) -> RecordBatch:
-    """answers.py:418-436: promotional revenue share of September 1995."""
-    j = t["lineitem"].hash_join(t["part"], [col("L_PARTKEY")], [col("P_PARTKEY")])
-    pred = [col("L_SHIPDATE") >= datetime.date(1995, 9, 1), col("L_SHIPDATE") < datetime.date(1995, 10, 1)]
+    """answers.py:418-436: promotional revenue share of September 1995 (the ship-date filter below the join, as PushDownFilter puts it)."""
+    lineitem = t["lineitem"].filter([col("L_SHIPDATE") >= datetime.date(1995, 9, 1), col("L_SHIPDATE") < datetime.date(1995, 10, 1)])
+    j = lineitem.hash_join(t["part"], [col("L_PARTKEY")], [col("P_PARTKEY")], build_on_left=len(lineitem) <= len(t["part"]))
     rev = col("L_EXTENDEDPRICE") * (1 - col("L_DISCOUNT"))
-    a = j.agg([_when(col("P_TYPE").startswith("PROMO"), rev, 0.0).sum().alias("tmp_1"), rev.sum().alias("tmp_2")], [], predicate=pred)
+    a = j.agg([_when(col("P_TYPE").startswith("PROMO"), rev, 0.0).sum().alias("tmp_1"), rev.sum().alias("tmp_2")], [])
     return a.eval_expression_list([(lit(100.00) * (col("tmp_1") / col("tmp_2"))).alias("promo_revenue")])
 
 
@@ -445,13 +448,17 @@ def q17(t: dict[str, RecordBatch]) -> RecordBatch:
 
 
 def q19(t: dict[str, RecordBatch]) -> RecordBatch:
-    """answers.py:531-572: revenue of three brand / container / quantity / size brackets delivered in person by air."""
-    j = _join(t["lineitem"], t["part"], ["L_PARTKEY"], ["P_PARTKEY"])
+    """answers.py:531-572: revenue of three brand / container / quantity / size brackets delivered in person by air.  The three
+    OR-ed brackets share the ship-mode, ship-instruction and P_SIZE >= 1 conjuncts: the reference's simplifier factors them out of the
+    OR (simplify_or, src/daft-algebra/src/simplify/boolean.rs:154-260) and PushDownFilter moves each below the join to the side it
+    reads; the rest of the disjunction stays above the join."""
+    lineitem = t["lineitem"].filter([col("L_SHIPMODE").is_in(["AIR", "AIR REG"]), col("L_SHIPINSTRUCT") == "DELIVER IN PERSON"])
+    part = t["part"].filter([col("P_SIZE") >= 1])
+    j = _join(lineitem, part, ["L_PARTKEY"], ["P_PARTKEY"])
 
     def bracket(brand, containers, qlo, qhi, smax):
         return ((col("P_BRAND") == brand) & col("P_CONTAINER").is_in(containers) & (col("L_QUANTITY") >= qlo) & (col("L_QUANTITY") <= qhi)
-                & (col("P_SIZE") >= 1) & (col("P_SIZE") <= smax) & col("L_SHIPMODE").is_in(["AIR", "AIR REG"])
-                & (col("L_SHIPINSTRUCT") == "DELIVER IN PERSON"))
+                & (col("P_SIZE") <= smax))
     pred = (bracket("Brand#12", ["SM CASE", "SM BOX", "SM PACK", "SM PKG"], 1, 11, 5)
             | bracket("Brand#23", ["MED BAG", "MED BOX", "MED PKG", "MED PACK"], 10, 20, 10)
             | bracket("Brand#34", ["LG CASE", "LG BOX", "LG PACK", "LG PKG"], 20, 30, 15))
@@ -474,17 +481,21 @@ def q20(t: dict[str, RecordBatch]) -> RecordBatch:
 def q21(t: dict[str, RecordBatch]) -> RecordBatch:
     """answers.py:614-648: SAUDI ARABIA's suppliers that were the only late one on a multi-supplier order with status F; top 100.
     The DataFrame text counts an order's lines (its `.distinct()` is commented out), which equals the SQL's "another supplier
-    exists" only while no order repeats a supplier; the SQL's meaning is used here: distinct suppliers per order."""
+    exists" only while no order repeats a supplier; the SQL's meaning is used here: distinct suppliers per order.  "More than one
+    distinct supplier" is written min(L_SUPPKEY) != max(L_SUPPKEY) and "exactly one" min == max: the same predicate as
+    count_distinct > 1 / == 1, through the inline min / max accumulators of the fused aggregate kernel instead of a dedup of all
+    of lineitem (at SF100 the count_distinct form spent 893 ms here, profiles/r02_tpch22.md)."""
     li = t["lineitem"]
     late = li.filter([col("L_RECEIPTDATE") > col("L_COMMITDATE")])
-    multi = li.eval_expression_list(_cols("L_SUPPKEY", "L_ORDERKEY")).agg([col("L_SUPPKEY").count_distinct().alias("nunique_col")], _cols("L_ORDERKEY"))
-    res_1 = _join(multi.filter([col("nunique_col") > 1]), late, ["L_ORDERKEY"], ["L_ORDERKEY"])
-    g = res_1.eval_expression_list(_cols("L_SUPPKEY", "L_ORDERKEY")).agg([col("L_SUPPKEY").count_distinct().alias("nunique_col")], _cols("L_ORDERKEY"))
-    j = _join(g, res_1, ["L_ORDERKEY"], ["L_ORDERKEY"])
+    span = [col("L_SUPPKEY").min().alias("lo"), col("L_SUPPKEY").max().alias("hi")]
+    multi = li.eval_expression_list(_cols("L_SUPPKEY", "L_ORDERKEY")).agg(span, _cols("L_ORDERKEY")).filter([col("lo") != col("hi")])
+    res_1 = _join(multi.eval_expression_list(_cols("L_ORDERKEY")), late, ["L_ORDERKEY"], ["L_ORDERKEY"])
+    g = res_1.eval_expression_list(_cols("L_SUPPKEY", "L_ORDERKEY")).agg(span, _cols("L_ORDERKEY")).filter([col("lo") == col("hi")])
+    j = _join(g.eval_expression_list(_cols("L_ORDERKEY")), res_1, ["L_ORDERKEY"], ["L_ORDERKEY"])
     j = _join(j, t["supplier"], ["L_SUPPKEY"], ["S_SUPPKEY"])
     j = _join(j, t["nation"], ["S_NATIONKEY"], ["N_NATIONKEY"])
     j = _join(j, t["orders"], ["L_ORDERKEY"], ["O_ORDERKEY"])
-    j = j.filter([(col("nunique_col") == 1) & (col("N_NAME") == "SAUDI ARABIA") & (col("O_ORDERSTATUS") == "F")])
+    j = j.filter([(col("N_NAME") == "SAUDI ARABIA") & (col("O_ORDERSTATUS") == "F")])
     g = j.agg([col("O_ORDERKEY").count().alias("numwait")], _cols("S_NAME"))
     return g.top_n(_cols("numwait", "S_NAME"), 100, descending=[True, False])
 
