@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--tpch22-sf", type=float, default=100.0, help="scale factor of the all-22-queries leg (N = 1; BASELINE metric: TPC-H SF100 total wall-clock); 0 skips it")
     ap.add_argument("--tpch22-queries", default="", help="comma-separated query numbers for that leg (default: all 22)")
     ap.add_argument("--tpch22-budget-s", type=float, default=150.0, help="wall-clock budget of that leg; queries not reached are listed as skipped")
+    ap.add_argument("--parquet-sf", type=float, default=1.0, help="scale factor of the Parquet -> HBM scan leg (N = 1); 0 skips it")
     ap.add_argument("--no-exchange", action="store_true", help="N > 1: skip the exchange workload")
     ap.add_argument("--no-e2e", action="store_true", help="kernel sweeps only: skip the host-buffer leg (the line is then not a bench result)")
     return ap.parse_args()
@@ -448,6 +449,10 @@ def main():
             pass
         tpch22 = run_tpch22(args, stream, barrier)
 
+    parquet = None
+    if world == 1 and args.parquet_sf > 0:
+        parquet = run_parquet(args, stream, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -470,6 +475,8 @@ def main():
         line["q5"] = q5
     if tpch22 is not None:
         line["tpch22"] = tpch22
+    if parquet is not None:
+        line["parquet_scan"] = parquet
     if exchange is not None:
         line["exchange"] = exchange
         line["exchange_parity"] = exchange["parity"]
@@ -526,6 +533,56 @@ def run_exchange(args, rank, world, comm, total_sf, begin, n_rows, stream, barri
             "nvlink_bytes_sent_per_gpu": int(sent), "nvlink_GBps_per_gpu_per_direction": sent / (ms_x * 1e-3) / 1e9,
             "nvlink_peak_GBps_per_direction": 900.0, "groups": tot[2], "parity": parity,
             "regions_ms_per_step_rank0": {k: round(v["ms"] / (steps + 1), 4) for k, v in kt.items()}}
+
+
+def run_parquet(args, stream, barrier):
+    """SURVEY 8f-1 on the clock: TPC-H lineitem (the 7 Q1 columns) written by pyarrow as the reference's data generation writes it
+    (Snappy, dictionary pages, 1 Mi-row row groups) to local disk, then `read_parquet` -> HBM (footer, page headers and file reads on
+    the host, decompression and decoding on the device) and Q1 over the scanned batch.  Wall clock around synchronised calls (the scan
+    includes host file reads), device stage times from the library's timing registry, the answer compared with Q1 over the generated
+    table, pyarrow's reader on the host cores beside it.  Any failure is reported in place of the numbers."""
+    import tempfile
+    import daft_b200
+    from daft_b200 import _lib, tpch
+    try:
+        import pyarrow.parquet as pq
+        sf = args.parquet_sf
+        host = tpch.generate_host("lineitem", sf, tpch.Q1_COLUMNS)
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "lineitem.parquet")
+            pq.write_table(host, path, compression="snappy", row_group_size=1 << 20)
+            size = os.path.getsize(path)
+            groups, rows = daft_b200.parquet_file_info(path)
+            for _ in range(2):
+                rb = daft_b200.read_parquet(path)
+            L = _lib.lib()
+            L.b200_kernel_timing(1)
+            _lib.kernel_timing_report()
+            steps = 3
+            _lib.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                rb = daft_b200.read_parquet(path)
+            _lib.synchronize()
+            scan_s = (time.perf_counter() - t0) / steps
+            kt = _lib.kernel_timing_report()
+            L.b200_kernel_timing(0)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                ans = tpch.q1(daft_b200.read_parquet(path)).to_arrow_table()
+            e2e_s = (time.perf_counter() - t0) / steps
+            want = tpch.q1(daft_b200.RecordBatch.from_arrow_table(host)).to_arrow_table()
+            check = check_answer(ans, want, ["L_RETURNFLAG", "L_LINESTATUS"], "q1 over the scanned file")
+            pq.read_table(path)
+            t0 = time.perf_counter()
+            pq.read_table(path)
+            pa_s = time.perf_counter() - t0
+        return {"workload": f"TPC-H SF{sf:g} lineitem, Q1 columns: Parquet (Snappy, dictionary, {groups} row groups) on local disk -> HBM -> Q1",
+                "rows": rows, "file_bytes": size, "arrow_bytes": int(host.nbytes), "scan_ms": scan_s * 1e3, "scan_rows_per_s": rows / scan_s,
+                "scan_arrow_GBps": host.nbytes / scan_s / 1e9, "scan_plus_q1_ms": e2e_s * 1e3, "device_stage_ms": {k: v["ms"] / steps for k, v in kt.items()},
+                "answer_vs_generated_table": check, "pyarrow_read_table_ms": pa_s * 1e3, "pyarrow_cpus": os.cpu_count()}
+    except Exception as e:  # noqa: BLE001 -- this leg never takes the bench line down
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
 
 def run_tpch22(args, stream, barrier):
