@@ -7,6 +7,8 @@
 // sequential inside a page; a column chunk of a 1 M-row row group holds tens to hundreds of pages, a scan of many row groups and
 // columns thousands).  Bytes moved per value: the compressed page once in, the decompressed page once out and once in, the value
 // once out -- all in HBM; PCIe carries the compressed bytes only.
+#include <mutex>
+
 #include "common.h"
 #include "ops.h"
 #include "parquet_read.h"
@@ -109,6 +111,9 @@ struct DeviceExec {
 Batch *parquet_read(const char *path, const char *const *columns, int32_t ncolumns, int64_t rg_begin, int64_t rg_end) {
     require_device();
     if (!path) fail("parquet: null path");
+    // scans share the page-locked staging buffer: one at a time (entry points may be called from several host threads)
+    static std::mutex scan_mu;
+    std::lock_guard<std::mutex> scan_lock(scan_mu);
     std::vector<std::string> want;
     for (int i = 0; i < ncolumns; i++) want.push_back(columns[i]);
     DeviceExec x;

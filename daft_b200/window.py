@@ -110,8 +110,11 @@ def pivot(batch: RecordBatch, group_by: Sequence[Expression], pivot_col: Express
     for i, name in enumerate(names):
         try:
             pred = col("__p") == _pivot_literal(name, pdtype)
+            if name == "None" and dt.is_string(pdtype):
+                pred = pred | col("__p").is_null()
         except (ValueError, KeyError):
-            pred = never
+            # the reference matches names against the pivot values' string form, in which a null spells "None" (pivot.rs:24-44)
+            pred = col("__p").is_null() if name == "None" else never
         rows = base.filter([pred]).eval_expression_list(gcols + [col("__v").alias(f"__n{i}")])
         j = keys_only.hash_join(rows, gcols, gcols, how="left", null_equals_null=[True] * len(gcols))
         colv = j.eval_expression_list([col(f"__n{i}")])

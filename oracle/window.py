@@ -109,7 +109,7 @@ def pivot(tbl: pa.Table, group_by: Sequence[str], pivot_col: str, values_col: st
     groups: dict = {}
     for i, k in enumerate(keys):
         groups.setdefault(k, {})
-        s = None if pv[i] is None else (str(pv[i]).lower() if isinstance(pv[i], bool) else str(pv[i]))
+        s = "None" if pv[i] is None else (str(pv[i]).lower() if isinstance(pv[i], bool) else str(pv[i]))   # str_value of a null is "None"
         groups[k][s] = vv[i]
     cols = {g: [k[j] for k in groups] for j, g in enumerate(group_by)}
     out = pa.table({g: pa.array(cols[g], type=tbl.schema.field(g).type) for g in group_by})

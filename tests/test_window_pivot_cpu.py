@@ -120,3 +120,92 @@ def test_percentile_composition_matches_oracle(n):
             assert_tables_equal(got, want, float_rtol=1e-12)
     got = EmulatedQueryBatch(tbl).agg([col("x").median().alias("med")], [col("g")], predicate=[col("h") > 0]).to_arrow_table()
     assert_tables_equal(_sorted(got, ["g"]), _sorted(oracle_agg(tbl, [col("x").median().alias("med")], [col("g")], [col("h") > 0]), ["g"]), float_rtol=1e-12)
+
+
+# ---- the reference's own pivot cases (tests/recordbatch/test_pivot.py:9-125), through the oracle and through the host composition ----
+PIVOT_LITERALS = [
+    ({"group": ["B", "A", "A", "B"], "pivot": [1, 2, 1, 2], "value": [1, 2, 3, 4]}, ["1", "2"], {"group": ["A", "B"], "1": [3, 1], "2": [2, 4]}),              # :27-54
+    ({"group": ["A", "A", "B"], "pivot": [1, 2, 1], "value": [1, 2, 3]}, ["1"], {"group": ["A", "B"], "1": [1, 3]}),                                          # :57-71
+    ({"group": ["A", "A", "B"], "pivot": [1, 2, 1], "value": [1, 2, 3]}, ["1", "2", "3"], {"group": ["A", "B"], "1": [1, 3], "2": [2, None], "3": [None, None]}),  # :74-90
+    ({"group": ["A", None, "B", None], "pivot": [1, 1, 2, 2], "value": [1, 2, 3, 4]}, ["1", "2"],
+     {"group": ["A", "B", None], "1": [1, None, 2], "2": [None, 3, 4]}),                                                                                        # :93-108
+    ({"group": ["A", "A", "B", "B"], "pivot": [1, None, 1, None], "value": [1, 2, 3, 4]}, ["1", "None"], {"group": ["A", "B"], "1": [1, 3], "None": [2, 4]}),    # :111-125
+]
+
+
+@pytest.mark.parametrize("case", range(len(PIVOT_LITERALS)))
+def test_pivot_reference_literals(case):
+    data, names, want = PIVOT_LITERALS[case]
+    tbl = pa.table({"group": pa.array(data["group"], pa.large_string()), "pivot": pa.array(data["pivot"], pa.int64()), "value": pa.array(data["value"], pa.int64())})
+    for got in (OW.pivot(tbl, ["group"], "pivot", "value", names),
+                W.pivot(EmulatedQueryBatch(tbl), [col("group")], col("pivot"), col("value"), names).to_arrow_table()):
+        assert got.sort_by([("group", "ascending")]).to_pydict() == want
+
+
+# ---- the reference's window cases (tests/window/*.py), through the oracle and through the host composition over the emulation twin ----
+def _both(tbl, pb, ob, desc, nf, funcs):
+    a = OW.window(tbl, pb, ob, desc, nf, funcs)
+    b = W.window(EmulatedQueryBatch(tbl), pb, ob, desc, nf, funcs).to_arrow_table()
+    return a, b
+
+
+def test_window_reference_row_number_literals():
+    """tests/window/test_partition_order_by_rank.py:13-50"""
+    tbl = pa.table({"category": pa.array(["A", "A", "A", "B", "B", "B", "C", "C"], pa.large_string()), "sales": [100, 200, 50, 500, 100, 300, 250, 150]})
+    for desc, want in ((False, [2, 3, 1, 3, 1, 2, 2, 1]), (True, [2, 1, 3, 1, 3, 2, 1, 2])):
+        for got in _both(tbl, [col("category")], [col("sales")], [desc], [desc], [("row_number", "rn")]):
+            got = got.sort_by([("category", "ascending"), ("sales", "ascending")]).to_pydict()
+            ref = sorted(zip(tbl.column("category").to_pylist(), tbl.column("sales").to_pylist(), want))
+            assert list(zip(got["category"], got["sales"], got["rn"])) == ref
+
+
+@pytest.mark.parametrize("desc,nulls_first,expected_rank", [(False, False, [1, 2, 1, 2, 1, 2]), (False, True, [2, 1, 2, 1, 2, 1]),
+                                                             (True, False, [1, 2, 1, 2, 1, 2]), (True, True, [2, 1, 2, 1, 2, 1])])
+def test_window_reference_rank_nulls_first_or_last(desc, nulls_first, expected_rank):
+    """tests/window/test_partition_order_by_rank.py:240-277"""
+    tbl = pa.table({"id": [1, 2, 3, 4, 5, 6], "category": pa.array(["A", "A", "B", "B", "C", "C"], pa.large_string()), "value": [10, None, 20, None, 30, None]})
+    for got in _both(tbl, [col("category")], [col("value")], [desc], [nulls_first], [("rank", "rank"), ("dense_rank", "drank")]):
+        got = got.sort_by([("id", "ascending")]).to_pydict()
+        assert got["rank"] == expected_rank and got["drank"] == expected_rank
+
+
+@pytest.mark.parametrize("desc,nulls_first,expected_lead", [
+    (False, False, [2, 3, 4, None, 6, 7, 8, None, 10, 11, 12, None]), (False, True, [2, 3, None, 1, 6, 7, None, 5, 10, 11, None, 9]),
+    (True, False, [4, 1, 2, None, 8, 5, 6, None, 12, 9, 10, None]), (True, True, [None, 1, 2, 3, None, 5, 6, 7, None, 9, 10, 11])])
+def test_window_reference_lead_nulls_first_or_last(desc, nulls_first, expected_lead):
+    """tests/window/test_partition_order_by_lag_lead.py:65-104"""
+    tbl = pa.table({"id": list(range(1, 13)), "category": pa.array(["A"] * 4 + ["B"] * 4 + ["C"] * 4, pa.large_string()), "ts": [1, 2, 3, None] * 3})
+    for got in _both(tbl, [col("category")], [col("ts")], [desc], [nulls_first], [("offset", "lead_value", col("id"), 1)]):
+        assert got.sort_by([("id", "ascending")]).column("lead_value").to_pylist() == expected_lead
+
+
+def test_window_reference_lag_lead_with_column_default():
+    """tests/window/test_partition_order_by_lag_lead.py:153-198: a default that is an expression of the row, offsets beyond the partition"""
+    import random
+    random.seed(45)
+    rows, want = [], []
+    for category in ["A", "B"]:
+        defaults, values = random.sample(range(10, 100), 50), random.sample(range(10, 100), 50)
+        for ts in range(50):
+            rows.append((category, ts, defaults[ts], values[ts]))
+            want.append((category, ts, 2 * defaults[ts] if ts < 10 else values[ts - 10], 2 * defaults[ts] if ts >= 40 else values[ts + 10],
+                         2 * defaults[ts], 2 * defaults[ts], 99 if ts < 15 else values[ts - 15], 99 if ts >= 35 else values[ts + 15]))
+    tbl = pa.table({"category": pa.array([r[0] for r in rows], pa.large_string()), "ts": [r[1] for r in rows], "default": [r[2] for r in rows],
+                    "value": [r[3] for r in rows]})
+    funcs = [("offset", "lag_10", col("value"), -10, 2 * col("default")), ("offset", "lead_10", col("value"), 10, 2 * col("default")),
+             ("offset", "lag_50", col("value"), -50, 2 * col("default")), ("offset", "lead_50", col("value"), 50, 2 * col("default")),
+             ("offset", "lag_15", col("value"), -15, 99), ("offset", "lead_15", col("value"), 15, 99)]
+    for got in _both(tbl, [col("category")], [col("ts")], [False], [False], funcs):
+        got = got.sort_by([("category", "ascending"), ("ts", "ascending")]).to_pydict()
+        assert list(zip(got["category"], got["ts"], got["lag_10"], got["lead_10"], got["lag_50"], got["lead_50"], got["lag_15"], got["lead_15"])) == want
+
+
+def test_window_reference_partition_only_aggregates():
+    """tests/window/test_partition_only.py:14-155,211-245: sum / min / max / mean / count over the partition, null partition keys form a group"""
+    tbl = pa.table({"category": pa.array(["A", "A", "B", None, "B", None, "C"], pa.large_string()), "value": [1, 2, 3, 4, 5, 6, 7]})
+    funcs = [("agg", "s", col("value").sum()), ("agg", "mn", col("value").min()), ("agg", "mx", col("value").max()), ("agg", "m", col("value").mean()),
+             ("agg", "c", col("value").count())]
+    for got in _both(tbl, [col("category")], [], [], [], funcs):
+        got = got.sort_by([("value", "ascending")]).to_pydict()
+        assert got["s"] == [3, 3, 8, 10, 8, 10, 7] and got["mn"] == [1, 1, 3, 4, 3, 4, 7] and got["mx"] == [2, 2, 5, 6, 5, 6, 7]
+        assert got["m"] == [1.5, 1.5, 4.0, 5.0, 4.0, 5.0, 7.0] and got["c"] == [2, 2, 2, 2, 2, 2, 1]
