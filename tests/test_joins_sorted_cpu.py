@@ -101,3 +101,26 @@ def test_oracle_cross_join():
     left, right = pa.table({"a": [1, 2, 3]}), pa.table({"b": ["x", "y"]})
     assert J.cross_join(left, right, "left").to_pydict() == {"a": [1, 1, 2, 2, 3, 3], "b": ["x", "y", "x", "y", "x", "y"]}
     assert J.cross_join(left, right, "right").to_pydict() == {"a": [1, 2, 3, 1, 2, 3], "b": ["x", "x", "x", "y", "y", "y"]}
+
+
+# ---- the reference runs its join pair tables through BOTH strategies (tests/recordbatch/test_joins.py:30-140, join_impl in
+# ("hash_join", "sort_merge_join"), null-safe equality skipped for the sort-merge join): the same literals through the merge restatement ----
+from test_oracle_cpu import JOIN_PAIR_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("typ", [pa.int8(), pa.int64(), pa.uint64(), pa.float32(), pa.float64(), pa.large_utf8()])
+@pytest.mark.parametrize("case", range(len(JOIN_PAIR_CASES)))
+def test_sort_merge_join_pairs_from_reference_tests(typ, case):
+    left, right, pairs, _ = JOIN_PAIR_CASES[case]
+
+    def column(vals):
+        if pa.types.is_large_string(typ):
+            return pa.array([None if v is None else str(v) for v in vals], type=typ)
+        return pa.array(vals, type=typ)
+    lt = pa.table({"x": column(left), "x_ind": list(range(len(left)))})
+    rt = pa.table({"y": column(right), "y_ind": list(range(len(right)))})
+    res = J.sort_merge_join(lt, rt, ["x"], ["y"])
+    assert res.column_names == ["x", "x_ind", "y", "y_ind"]
+    assert sorted(zip(res.column("x_ind").to_pylist(), res.column("y_ind").to_pylist())) == sorted(pairs)
+    res = J.sort_merge_join(rt, lt, ["y"], ["x"])   # tables swapped (test_joins.py:121-140)
+    assert sorted(zip(res.column("x_ind").to_pylist(), res.column("y_ind").to_pylist())) == sorted(pairs)
