@@ -81,6 +81,16 @@ def populate_aggregation_stages(aggregations: Sequence[Expression], group_by: Se
             ddof = lit(float(inner.value))
             adjusted = pop_var * n / (n - ddof)
             final.append((n <= ddof).if_else(lit(None), adjusted.sqrt() if op == "stddev" else adjusted).alias(out))
+        elif op == "skew":           # :302-348
+            xf = x.cast(dt.F64)
+            n = second.add(first.add(xf.count("valid")).sum())
+            s = second.add(first.add(xf.sum()).sum())
+            s2 = second.add(first.add((xf * xf).sum()).sum())
+            s3 = second.add(first.add((xf * xf * xf).sum()).sum())
+            denom_base = (s2 - s * s / n) / n
+            denom = (denom_base * denom_base * denom_base).sqrt()
+            numerator = s3 - lit(3) * s2 * s / n + lit(2) * s * s * s / n / n
+            final.append((numerator / denom / n).alias(out))
         else:
             raise NotImplementedError(f"two-stage rewrite of {op} (agg.rs: Set needs list_distinct; sketches) is not built")
     return first.exprs, second.exprs, final

@@ -181,7 +181,7 @@ class Communicator:
         from .expressions import _agg_inner, col, encode_agg
         from .recordbatch import RecordBatch
         group_by = list(group_by or [])
-        staged_only = any(_agg_inner(a).op in ("stddev", "var", "count_distinct") for a in to_agg)
+        staged_only = any(_agg_inner(a).op in ("stddev", "var", "skew", "count_distinct") for a in to_agg)
         if not staged_only:
             plan = batch._cached_plan("agg", [to_agg, group_by, predicate],
                                       lambda: encode_agg(to_agg, group_by, batch.column_names(), batch.dtypes(), predicate))

@@ -149,6 +149,10 @@ class Expression:
     def var(self, ddof: int = 1):
         """src/daft-local-plan/src/agg.rs:227-258: the same staging without the square root."""
         return self._agg("var", int(ddof))
+    def skew(self):
+        """AggExpr::Skew as the planner stages it (src/daft-local-plan/src/agg.rs:302-348): count, sum, sum of squares and sum of cubes
+        of the Float64 values, then (S3 - 3 S2 S / N + 2 S^3 / N^2) / sqrt(((S2 - S^2 / N) / N)^3) / N."""
+        return self._agg("skew")
     def count_distinct(self):
         """Distinct non-null values per group as UInt64 (Series::count_distinct = agg_list + list_count_distinct over a
         probe table WITHOUT nulls, src/daft-functions-list/src/series.rs:37-40,234-247)."""
@@ -514,14 +518,14 @@ def encode_agg(to_agg: Sequence[Expression], group_by: Sequence[Expression], nam
 
 
 def stage_moment_aggs(to_agg: Sequence[Expression]):
-    """stddev / var -> (first-stage aggregations, final projection) as populate_aggregation_stages does
-    (src/daft-local-plan/src/agg.rs:190-258); returns None when the list has neither."""
-    if not any(_agg_inner(a).op in ("stddev", "var") for a in to_agg):
+    """stddev / var / skew -> (first-stage aggregations, final projection) as populate_aggregation_stages does
+    (src/daft-local-plan/src/agg.rs:190-258, 302-348); returns None when the list has none of them."""
+    if not any(_agg_inner(a).op in ("stddev", "var", "skew") for a in to_agg):
         return None
     first, final = [], []
     for i, a in enumerate(to_agg):
         inner = _agg_inner(a)
-        if inner.op not in ("stddev", "var"):
+        if inner.op not in ("stddev", "var", "skew"):
             first.append(a)
             final.append(col(a.name()))
             continue
@@ -529,6 +533,15 @@ def stage_moment_aggs(to_agg: Sequence[Expression]):
         s, q, c = f"__sum{i}", f"__sqsum{i}", f"__cnt{i}"
         first += [x.sum().alias(s), (x * x).sum().alias(q), x.count().alias(c)]
         n = col(c).cast(dt.F64)
+        if inner.op == "skew":
+            k = f"__cbsum{i}"
+            first.append((x * x * x).sum().alias(k))
+            S, S2, S3 = col(s), col(q), col(k)
+            denom_base = (S2 - S * S / n) / n
+            denom = (denom_base * denom_base * denom_base).sqrt()
+            numerator = S3 - lit(3) * S2 * S / n + lit(2) * S * S * S / n / n
+            final.append((numerator / denom / n).alias(a.name()))
+            continue
         mean = col(s) / n
         pop_var = col(q) / n - mean * mean
         ddof = lit(float(inner.value))

@@ -307,6 +307,25 @@ def agg(tbl: pa.Table, aggs: Sequence[tuple], group_by: Sequence) -> pa.Table:
                 if v is not None:
                     seen[g].add(v)
             r = pa.array([len(s_) for s_ in seen], type=pa.uint64())
+        elif kind == "skew":
+            # calculate_skew (src/daft-core/src/utils/stats.rs:134-147): (m3 / n) / sqrt((m2 / n)^3) around the group's mean; the planner's
+            # staged form (src/daft-local-plan/src/agg.rs:302-348) computes the same quantity from power sums
+            vals = normalize(arr).cast(pa.float64()).to_pylist()
+            per = [[] for _ in range(ng)]
+            for g, v in zip(gid.tolist(), vals):
+                if v is not None:
+                    per[g].append(v)
+            out = []
+            for vs in per:
+                if not vs:
+                    out.append(None)
+                    continue
+                mean = sum(vs) / len(vs)
+                m3 = sum((v - mean) ** 3 for v in vs)
+                m2 = sum((v - mean) ** 2 for v in vs)
+                with np.errstate(all="ignore"):
+                    out.append(float(np.float64(m3 / len(vs)) / np.sqrt(np.float64(m2 / len(vs)) ** 3)))
+            r = pa.array(out, type=pa.float64())
         elif kind == "percentile":
             # exact_percentile (src/daft-core/src/utils/stats.rs:31-59) over the group's non-null values cast to Float64: sort by
             # f64::total_cmp, rank = p (n - 1), (upper - lower).mul_add(rank - floor(rank), lower)

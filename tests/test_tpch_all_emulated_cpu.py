@@ -48,6 +48,11 @@ class EmulatedQueryBatch(OracleRecordBatch):
             return RecordBatch._agg_with_string_minmax(self, to_agg, group_by or [], predicate)
         if any(_inner(a).op == "percentile" for a in to_agg):
             return RecordBatch._agg_with_percentile(self, to_agg, group_by or [], predicate)
+        from daft_b200.expressions import col as _col, stage_moment_aggs
+        staged = stage_moment_aggs(to_agg)   # stddev / var / skew: first-stage sums, then the final projection (as RecordBatch.agg)
+        if staged is not None:
+            first, final = staged
+            return self.agg(first, group_by, predicate).eval_expression_list([_col(g.name()) for g in (group_by or [])] + final)
         return self._new(_EmulatedBatch(self.tbl).agg(list(to_agg), list(group_by or []), predicate).to_arrow_table())
 
     _resolve_keys = RecordBatch._resolve_keys

@@ -209,3 +209,31 @@ def test_window_reference_partition_only_aggregates():
         got = got.sort_by([("value", "ascending")]).to_pydict()
         assert got["s"] == [3, 3, 8, 10, 8, 10, 7] and got["mn"] == [1, 1, 3, 4, 3, 4, 7] and got["mx"] == [2, 2, 5, 6, 5, 6, 7]
         assert got["m"] == [1.5, 1.5, 4.0, 5.0, 4.0, 5.0, 7.0] and got["c"] == [2, 2, 2, 2, 2, 2, 1]
+
+
+# ---- skew: the planner's staged power-sum form (src/daft-local-plan/src/agg.rs:302-348) executed through the generated code,
+# against calculate_skew's definition (src/daft-core/src/utils/stats.rs:134-147) ----
+def test_skew_staged_form_matches_definition():
+    from helpers import oracle_agg
+    from daft_b200.aggstages import populate_aggregation_stages
+    rng = np.random.default_rng(11)
+    n = 2000
+    tbl = pa.table({"g": pa.array(rng.integers(0, 6, n)), "x": pa.array(rng.gamma(2.0, 3.0, n), mask=rng.random(n) < 0.1),
+                    "i": pa.array(rng.integers(-50, 50, n))})
+    aggs = [col("x").skew().alias("sk"), col("i").skew().alias("ski"), col("x").sum().alias("sx")]
+    for gb in ([col("g")], []):
+        want = oracle_agg(tbl, aggs, gb)
+        got = EmulatedQueryBatch(tbl).agg(aggs, gb).to_arrow_table()
+        keys = [g.name() for g in gb]
+        a, b = (_sorted(got, keys), _sorted(want, keys)) if keys else (got, want)
+        assert_tables_equal(a, b, float_rtol=1e-9)
+        # the two-stage rewrite over two morsels: partial power sums, summed, same projection
+        first, second, final = populate_aggregation_stages(aggs, gb)
+        halves = [EmulatedQueryBatch(tbl.slice(0, 900)).agg(first, gb).to_arrow_table(), EmulatedQueryBatch(tbl.slice(900)).agg(first, gb).to_arrow_table()]
+        merged = EmulatedQueryBatch(pa.concat_tables(halves)).agg(second, [col(g.name()) for g in gb]).eval_expression_list(final).to_arrow_table()
+        a = _sorted(merged, keys) if keys else merged
+        assert_tables_equal(a, b, float_rtol=1e-9)
+    # reference literal (tests/recordbatch/test_table_aggs.py skew cases): symmetric data has zero skew, a single value gives NaN, no value null
+    t = pa.table({"g": [1, 1, 1, 2, 3], "x": [1.0, 2.0, 3.0, 5.0, None]})
+    got = EmulatedQueryBatch(t).agg([col("x").skew().alias("sk")], [col("g")]).to_arrow_table().sort_by([("g", "ascending")]).column("sk").to_pylist()
+    assert got[0] == 0.0 and got[1] != got[1] and got[2] is None
