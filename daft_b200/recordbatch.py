@@ -302,7 +302,7 @@ class RecordBatch:
         keys = [g.alias(f"__k{i}") for i, g in enumerate(group_by)]
         key_cols = [col(f"__k{i}") for i in range(len(group_by))]
         plain = [a for a in to_agg if not self._is_string_minmax(a)]
-        anchor = col(base.column_names()[0]).count("all").alias("__rows")  # keeps the group list complete
+        anchor = col(base.column_names()[0]).count("all").alias("__rows_sm")  # keeps the group list complete (its own name: the rewrites nest)
         main = base.agg(plain + [anchor], keys)
         if key_cols:
             main = main.sort(key_cols)
@@ -339,7 +339,7 @@ class RecordBatch:
         key_cols = [col(f"__k{i}") for i in range(len(keys))]
         plain = [a for a in to_agg if _inner(a).op != "percentile"]
         keyed = base.union(base.eval_expression_list(keys)) if base.num_columns() else base.eval_expression_list(keys)
-        main = keyed.agg(plain + [col("__k0").count("all").alias("__rows")], key_cols)
+        main = keyed.agg(plain + [col("__k0").count("all").alias("__rows_pc")], key_cols)
         if not group_by and len(main) == 0:
             # an ungrouped aggregate over no rows still yields one row: the other aggregates' empty-input values, null percentiles
             return base.agg([a if _inner(a).op != "percentile" else _inner(a).args[0].cast(dt.F64).min().alias(a.name()) for a in to_agg], [])
@@ -374,8 +374,9 @@ class RecordBatch:
         keys = [g.alias(f"__k{i}") for i, g in enumerate(group_by)]
         key_cols = [col(f"__k{i}") for i in range(len(group_by))]
         plain = [a for a in to_agg if _inner(a).op != "count_distinct"]
+        nested = any(_inner(a).op == "percentile" or self._is_string_minmax(a) for a in plain)
         # a count(all) keeps the group list complete even when every other aggregate is a count_distinct
-        parts = base.agg(plain + [col(base.column_names()[0]).count("all").alias("__rows")] if base.num_columns() else plain, group_by)
+        parts = base.agg(plain + [col(base.column_names()[0]).count("all").alias("__rows_cd")] if base.num_columns() else plain, group_by)
         out_cols, pieces = {}, parts
         for i, a in enumerate(to_agg):
             if _inner(a).op != "count_distinct":
@@ -383,6 +384,11 @@ class RecordBatch:
             x = _inner(a).args[0]
             pairs = base.eval_expression_list(keys + [x.alias("__x")]).dedup(key_cols + [col("__x")])
             cnt = pairs.agg([col("__x").count("valid").alias(f"__cd{i}")], key_cols)
+            if nested and group_by:
+                # the other aggregates went through a rewrite of their own (string min / max sorts its groups by key): the two group
+                # lists are the same set in different orders -- align this column on the keys instead of placing it side by side
+                glist = parts.eval_expression_list([col(g.name()).alias(f"__k{j}") for j, g in enumerate(group_by)])
+                cnt = glist.hash_join(cnt, key_cols, key_cols, how="left", null_equals_null=[True] * len(key_cols))
             pieces = pieces.union(cnt.eval_expression_list([col(f"__cd{i}")]))
             out_cols[i] = f"__cd{i}"
         final = [col(g.name()) for g in group_by]

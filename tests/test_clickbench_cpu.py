@@ -1,0 +1,162 @@
+"""ClickBench (benchmarking/clickbench/queries.sql) composed on the operator surface (daft_b200/clickbench.py): the oracle twin of every
+built query is held to SQLite running the statement's SQL on the same synthetic `hits` table, and the same query runs with the code the
+library GENERATES for its filters / projections / aggregates executed on the host (the emulation twin).  CPU only: these compositions
+have not been run on the device."""
+import datetime
+import math
+import sqlite3
+
+import pyarrow as pa
+import pytest
+
+from daft_b200 import clickbench as CB
+from oracle.recordbatch import OracleRecordBatch
+from test_tpch_all_emulated_cpu import EmulatedQueryBatch
+
+N = 20000
+J = "CounterID = 62 AND EventDate >= '2013-07-01' AND EventDate <= '2013-07-31'"
+# (SQL without its LIMIT / OFFSET, k, offset, python kwargs); k = None: the whole result is compared
+SQL = {
+    0: ("SELECT COUNT(*) FROM hits", None, 0, {}),
+    1: ("SELECT COUNT(*) FROM hits WHERE AdvEngineID <> 0", None, 0, {}),
+    2: ("SELECT SUM(AdvEngineID), COUNT(*), AVG(ResolutionWidth) FROM hits", None, 0, {}),
+    3: ("SELECT AVG(UserID) FROM hits", None, 0, {}),
+    4: ("SELECT COUNT(DISTINCT UserID) FROM hits", None, 0, {}),
+    5: ("SELECT COUNT(DISTINCT SearchPhrase) FROM hits", None, 0, {}),
+    6: ("SELECT MIN(EventDate), MAX(EventDate) FROM hits", None, 0, {}),
+    7: ("SELECT AdvEngineID, COUNT(*) AS c FROM hits WHERE AdvEngineID <> 0 GROUP BY AdvEngineID ORDER BY c DESC", 10**9, 0, {}),
+    8: ("SELECT RegionID, COUNT(DISTINCT UserID) AS u FROM hits GROUP BY RegionID ORDER BY u DESC", 10, 0, {}),
+    9: ("SELECT RegionID, SUM(AdvEngineID), COUNT(*) AS c, AVG(ResolutionWidth), COUNT(DISTINCT UserID) FROM hits GROUP BY RegionID ORDER BY c DESC", 10, 0, {}),
+    10: ("SELECT MobilePhoneModel, COUNT(DISTINCT UserID) AS u FROM hits WHERE MobilePhoneModel <> '' GROUP BY MobilePhoneModel ORDER BY u DESC", 10, 0, {}),
+    11: ("SELECT MobilePhone, MobilePhoneModel, COUNT(DISTINCT UserID) AS u FROM hits WHERE MobilePhoneModel <> '' GROUP BY MobilePhone, MobilePhoneModel ORDER BY u DESC", 10, 0, {}),
+    12: ("SELECT SearchPhrase, COUNT(*) AS c FROM hits WHERE SearchPhrase <> '' GROUP BY SearchPhrase ORDER BY c DESC", 10, 0, {}),
+    13: ("SELECT SearchPhrase, COUNT(DISTINCT UserID) AS u FROM hits WHERE SearchPhrase <> '' GROUP BY SearchPhrase ORDER BY u DESC", 10, 0, {}),
+    14: ("SELECT SearchEngineID, SearchPhrase, COUNT(*) AS c FROM hits WHERE SearchPhrase <> '' GROUP BY SearchEngineID, SearchPhrase ORDER BY c DESC", 10, 0, {}),
+    15: ("SELECT UserID, COUNT(*) AS c FROM hits GROUP BY UserID ORDER BY c DESC", 10, 0, {}),
+    16: ("SELECT UserID, SearchPhrase, COUNT(*) AS c FROM hits GROUP BY UserID, SearchPhrase ORDER BY c DESC", 10, 0, {}),
+    17: ("SELECT UserID, SearchPhrase, COUNT(*) AS c FROM hits GROUP BY UserID, SearchPhrase", "any10", 0, {}),
+    19: ("SELECT UserID FROM hits WHERE UserID = {uid}", None, 0, "uid"),
+    20: ("SELECT COUNT(*) FROM hits WHERE URL LIKE '%google%'", None, 0, {}),
+    21: ("SELECT SearchPhrase, MIN(URL), COUNT(*) AS c FROM hits WHERE URL LIKE '%google%' AND SearchPhrase <> '' GROUP BY SearchPhrase ORDER BY c DESC", 10, 0, {}),
+    22: ("SELECT SearchPhrase, MIN(URL), MIN(Title), COUNT(*) AS c, COUNT(DISTINCT UserID) FROM hits WHERE Title LIKE '%Google%' AND URL NOT LIKE '%.google.%' "
+         "AND SearchPhrase <> '' GROUP BY SearchPhrase ORDER BY c DESC", 10, 0, {}),
+    23: ("SELECT * FROM hits WHERE URL LIKE '%google%' ORDER BY EventTime", 10, 0, {}),
+    24: ("SELECT SearchPhrase, EventTime FROM hits WHERE SearchPhrase <> '' ORDER BY EventTime", 10, 0, {}),
+    25: ("SELECT SearchPhrase FROM hits WHERE SearchPhrase <> '' ORDER BY SearchPhrase", 10, 0, {}),
+    26: ("SELECT SearchPhrase, EventTime FROM hits WHERE SearchPhrase <> '' ORDER BY EventTime, SearchPhrase", 10, 0, {}),
+    27: ("SELECT CounterID, AVG(length(URL)) AS l, COUNT(*) AS c FROM hits WHERE URL <> '' GROUP BY CounterID HAVING COUNT(*) > 30 ORDER BY l DESC", 25, 0, {"having": 30}),
+    29: ("SELECT " + ", ".join(f"SUM(ResolutionWidth + {i})" for i in range(90)) + " FROM hits", None, 0, {}),
+    30: ("SELECT SearchEngineID, ClientIP, COUNT(*) AS c, SUM(IsRefresh), AVG(ResolutionWidth) FROM hits WHERE SearchPhrase <> '' GROUP BY SearchEngineID, ClientIP ORDER BY c DESC", 10, 0, {}),
+    31: ("SELECT WatchID, ClientIP, COUNT(*) AS c, SUM(IsRefresh), AVG(ResolutionWidth) FROM hits WHERE SearchPhrase <> '' GROUP BY WatchID, ClientIP ORDER BY c DESC", 10, 0, {}),
+    32: ("SELECT WatchID, ClientIP, COUNT(*) AS c, SUM(IsRefresh), AVG(ResolutionWidth) FROM hits GROUP BY WatchID, ClientIP ORDER BY c DESC", 10, 0, {}),
+    33: ("SELECT URL, COUNT(*) AS c FROM hits GROUP BY URL ORDER BY c DESC", 10, 0, {}),
+    34: ("SELECT 1, URL, COUNT(*) AS c FROM hits GROUP BY 1, URL ORDER BY c DESC", 10, 0, {}),
+    35: ("SELECT ClientIP, ClientIP - 1, ClientIP - 2, ClientIP - 3, COUNT(*) AS c FROM hits GROUP BY ClientIP, ClientIP - 1, ClientIP - 2, ClientIP - 3 ORDER BY c DESC", 10, 0, {}),
+    36: (f"SELECT URL, COUNT(*) AS PageViews FROM hits WHERE {J} AND DontCountHits = 0 AND IsRefresh = 0 AND URL <> '' GROUP BY URL ORDER BY PageViews DESC", 10, 0, {}),
+    37: (f"SELECT Title, COUNT(*) AS PageViews FROM hits WHERE {J} AND DontCountHits = 0 AND IsRefresh = 0 AND Title <> '' GROUP BY Title ORDER BY PageViews DESC", 10, 0, {}),
+    38: (f"SELECT URL, COUNT(*) AS PageViews FROM hits WHERE {J} AND IsRefresh = 0 AND IsLink <> 0 AND IsDownload = 0 GROUP BY URL ORDER BY PageViews DESC", 10, 20, {"offset": 20}),
+    40: (f"SELECT URLHash, EventDate, COUNT(*) AS PageViews FROM hits WHERE {J} AND IsRefresh = 0 AND TraficSourceID IN (-1, 6) AND RefererHash = {{rh}} "
+         "GROUP BY URLHash, EventDate ORDER BY PageViews DESC", 10, 5, "rh"),
+    41: (f"SELECT WindowClientWidth, WindowClientHeight, COUNT(*) AS PageViews FROM hits WHERE {J} AND IsRefresh = 0 AND DontCountHits = 0 AND URLHash = {{uh}} "
+         "GROUP BY WindowClientWidth, WindowClientHeight ORDER BY PageViews DESC", 10, 2, "uh"),
+}
+
+
+def _sql_value(v):
+    if isinstance(v, datetime.datetime):
+        return v.strftime("%Y-%m-%d %H:%M:%S")
+    if isinstance(v, datetime.date):
+        return v.isoformat()
+    return v
+
+
+@pytest.fixture(scope="module")
+def world():
+    hits = CB.generate_hits(N)
+    conn = sqlite3.connect(":memory:")
+    conn.execute(f"create table hits ({', '.join(hits.column_names)})")
+    cols = [[_sql_value(v) for v in c.to_pylist()] for c in hits.columns]
+    conn.executemany(f"insert into hits values ({', '.join('?' * hits.num_columns)})", list(zip(*cols)))
+    # constants the benchmark takes from the real dataset: a user id, a referer hash and a URL hash that exist here
+    consts = {"uid": hits.column("UserID")[0].as_py(), "rh": hits.column("RefererHash")[0].as_py(),
+              "uh": conn.execute(f"select URLHash from hits where {J} and IsRefresh = 0 and DontCountHits = 0 group by URLHash order by count(*) desc").fetchone()[0]}
+    return hits, conn, consts
+
+
+def _close(a, b):
+    a, b = _sql_value(a), _sql_value(b)
+    if isinstance(a, float) or isinstance(b, float):
+        return a is not None and b is not None and math.isclose(float(a), float(b), rel_tol=1e-9, abs_tol=1e-9)
+    return a == b
+
+
+def _rows(tbl: pa.Table):
+    return list(zip(*[c.to_pylist() for c in tbl.columns])) if tbl.num_columns else []
+
+
+def _check(q, got: pa.Table, conn, consts, hits):
+    sql, k, offset, extra = SQL[q]
+    if isinstance(extra, str):
+        sql = sql.format(**{extra: consts[extra]})
+    want = conn.execute(sql).fetchall()
+    got_rows = _rows(got)
+    if q in (24, 26):       # the composition returns SearchPhrase only; SQLite also carries the sort key to settle the expected order
+        want = [(r[0],) for r in want]
+    if q == 23:
+        want = [tuple(r) for r in want]
+    if k is None:
+        assert len(got_rows) == len(want), (q, len(got_rows), len(want))
+        for g, w in zip(got_rows, want):
+            assert all(_close(a, b) for a, b in zip(g, w)), (q, g, w)
+        return
+    if k == "any10":        # LIMIT without ORDER BY: any 10 groups
+        assert len(got_rows) == min(10, len(want))
+        for g in got_rows:
+            assert any(all(_close(a, b) for a, b in zip(g, w)) for w in want), (q, g)
+        return
+    expect = want[offset:offset + k]
+    assert len(got_rows) == len(expect), (q, len(got_rows), len(expect))
+    # ties at equal sort keys may come in any order: every returned row must be a row of the full result, without repeats, and the
+    # sequence of sort keys must be the expected one
+    order_col = {7: 1, 8: 1, 9: 2, 10: 1, 11: 2, 12: 1, 13: 1, 14: 2, 15: 1, 16: 2, 21: 2, 22: 3, 27: 1, 30: 2, 31: 2, 32: 2, 33: 1, 34: 2, 35: 4, 36: 1, 37: 1,
+                 38: 1, 40: 2, 41: 2}.get(q)
+    if order_col is not None:
+        assert all(_close(g[order_col], w[order_col]) for g, w in zip(got_rows, expect)), (q, [g[order_col] for g in got_rows], [w[order_col] for w in expect])
+        used = set()
+        for g in got_rows:
+            hit = next((i for i, w in enumerate(want) if i not in used and all(_close(a, b) for a, b in zip(g, w))), None)
+            assert hit is not None, (q, g)
+            used.add(hit)
+    else:                   # ordered by a value column (23-26): ties only between equal keys -> compare the key sequences
+        key = {23: hits.column_names.index("EventTime"), 24: 0, 25: 0, 26: 0}[q]
+        if q in (24, 26):
+            full = conn.execute(sql).fetchall()[offset:offset + k]
+            times = [r[1] for r in full]
+            if q == 24 and len(set(times)) != len(times):
+                return      # equal timestamps: the phrase order among them is free
+        assert [_sql_value(g[key]) for g in got_rows] == [w[key] for w in expect], q
+
+
+@pytest.mark.parametrize("q", sorted(SQL))
+def test_clickbench_oracle_twin_vs_sqlite(world, q):
+    hits, conn, consts = world
+    _, _, _, extra = SQL[q]
+    kw = dict(extra) if isinstance(extra, dict) else {"uid": {"user_id": consts["uid"]}, "rh": {"offset": 5, "referer_hash": consts["rh"]},
+                                                       "uh": {"offset": 2, "url_hash": consts["uh"]}}[extra]
+    got = CB.QUERIES[q](OracleRecordBatch(hits), **kw).to_arrow_table()
+    _check(q, got, conn, consts, hits)
+
+
+@pytest.mark.parametrize("q", sorted(SQL))
+def test_clickbench_plans_through_generated_code(world, q):
+    hits, conn, consts = world
+    _, _, _, extra = SQL[q]
+    kw = dict(extra) if isinstance(extra, dict) else {"uid": {"user_id": consts["uid"]}, "rh": {"offset": 5, "referer_hash": consts["rh"]},
+                                                       "uh": {"offset": 2, "url_hash": consts["uh"]}}[extra]
+    got = CB.QUERIES[q](EmulatedQueryBatch(hits), **kw).to_arrow_table()
+    _check(q, got, conn, consts, hits)
+
+
+def test_every_statement_is_accounted_for():
+    assert sorted(set(CB.QUERIES) | set(CB.NOT_BUILT)) == list(range(43)) and not set(CB.QUERIES) & set(CB.NOT_BUILT)
+    assert sorted(SQL) == sorted(CB.QUERIES)

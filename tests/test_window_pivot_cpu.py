@@ -237,3 +237,24 @@ def test_skew_staged_form_matches_definition():
     t = pa.table({"g": [1, 1, 1, 2, 3], "x": [1.0, 2.0, 3.0, 5.0, None]})
     got = EmulatedQueryBatch(t).agg([col("x").skew().alias("sk")], [col("g")]).to_arrow_table().sort_by([("g", "ascending")]).column("sk").to_pylist()
     assert got[0] == 0.0 and got[1] != got[1] and got[2] is None
+
+
+def test_composite_aggregates_nest_in_one_call():
+    """count_distinct + string min / max + percentile in ONE aggregation list: each is a host-side rewrite, and they nest.  Found by
+    ClickBench Q22 (count_distinct next to MIN(URL)): the string rewrite sorts its groups by key, the count_distinct column was placed
+    side by side in first-occurrence order -> misaligned rows.  The column is now aligned on the keys."""
+    from helpers import oracle_agg
+    rng = np.random.default_rng(3)
+    n = 1500
+    tbl = pa.table({"g": pa.array(rng.integers(0, 40, n)[::-1].copy()), "h": pa.array(rng.integers(0, 3, n)),
+                    "s": pa.array(np.array([f"v{v}" for v in rng.integers(0, 60, n)], dtype=object), type=pa.large_string(), mask=rng.random(n) < 0.1),
+                    "x": pa.array(rng.standard_normal(n), mask=rng.random(n) < 0.1), "u": pa.array(rng.integers(0, 25, n))})
+    aggs = [col("u").count_distinct().alias("cd"), col("s").min().alias("smin"), col("s").max().alias("smax"), col("x").median().alias("med"),
+            col("x").sum().alias("sx"), col("s").count_distinct().alias("cds")]
+    for gb in ([col("g")], [col("g"), col("h")], []):
+        for subset in (aggs, aggs[:2], [aggs[0], aggs[3]], [aggs[1], aggs[3]]):
+            got = EmulatedQueryBatch(tbl).agg(subset, gb).to_arrow_table()
+            want = oracle_agg(tbl, subset, gb)
+            keys = [g.name() for g in gb]
+            a, b = (_sorted(got, keys), _sorted(want, keys)) if keys else (got, want)
+            assert_tables_equal(a, b, float_rtol=1e-12)
