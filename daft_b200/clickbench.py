@@ -2,8 +2,7 @@
 
 The reference runs these 43 statements through `daft.sql` over the `hits` table (`tests/benchmarks/test_clickbench.py:28-66`: EventDate
 cast to Date, EventTime to Timestamp); each lowers to Filter -> Project -> (Hash)Aggregate -> TopN / Sort, which is what the functions
-below compose by hand.  39 of the 43 are expressible with the expressions the device code generator has; not built: Q18
-(`extract(minute ...)`), Q28 (`REGEXP_REPLACE`), Q39 (a CASE producing strings) and Q42 (`DATE_TRUNC('minute', ...)`).
+below compose by hand.  42 of the 43 are built; not built: Q28 (`REGEXP_REPLACE` with a capture group).
 
 `generate_hits` is a synthetic stand-in for the 100 M-row public dataset (no network here): the columns the queries read, with the
 skew that makes them interesting (Zipf-like users / phrases / URLs, mostly-empty SearchPhrase and MobilePhoneModel, a dominant
@@ -127,6 +126,11 @@ def q14(h): return _top(h.agg([_count("c")], [col("SearchEngineID"), col("Search
 def q15(h): return _top(h.agg([_count("c")], [col("UserID")]), "c", 10)
 def q16(h): return _top(h.agg([_count("c")], [col("UserID"), col("SearchPhrase")]), "c", 10)
 def q17(h): return h.agg([_count("c")], [col("UserID"), col("SearchPhrase")]).head(10)
+def q18(h):
+    g = h.eval_expression_list([col("UserID"), col("EventTime").minute().alias("m"), col("SearchPhrase"), col("WatchID")])
+    return _top(g.agg([_count("c")], [col("UserID"), col("m"), col("SearchPhrase")]), "c", 10)
+
+
 def q19(h, user_id: int = 435090932899640449): return h.filter([col("UserID") == user_id]).eval_expression_list([col("UserID")])
 def q20(h): return h.agg([_count("count")], [], predicate=[col("URL").like("%google%")])
 
@@ -200,6 +204,14 @@ def q38(h, offset: int = 1000):
     return _pageviews(h, [col("URL")], [col("IsRefresh") == 0, col("IsLink") != 0, col("IsDownload") == 0], offset=offset)
 
 
+def q39(h, offset: int = 1000):
+    src = ((col("SearchEngineID") == 0) & (col("AdvEngineID") == 0)).if_else(col("Referer"), lit("")).alias("Src")
+    f = h.filter([col("CounterID") == 62] + JULY + [col("IsRefresh") == 0])
+    f = f.eval_expression_list([col("TraficSourceID"), col("SearchEngineID"), col("AdvEngineID"), src, col("URL").alias("Dst"), col("WatchID")])
+    g = f.agg([_count("PageViews")], [col("TraficSourceID"), col("SearchEngineID"), col("AdvEngineID"), col("Src"), col("Dst")])
+    return _top(g, "PageViews", 10, offset=offset)
+
+
 def q40(h, offset: int = 100, referer_hash: int = 3594120000172545465):
     return _pageviews(h, [col("URLHash"), col("EventDate")], [col("IsRefresh") == 0, col("TraficSourceID").is_in([-1, 6]), col("RefererHash") == referer_hash],
                       offset=offset)
@@ -210,5 +222,12 @@ def q41(h, offset: int = 10000, url_hash: int = 2868770270353813622):
                       offset=offset)
 
 
+def q42(h, offset: int = 1000):
+    f = h.filter([col("CounterID") == 62, col("EventDate") >= datetime.date(2013, 7, 14), col("EventDate") <= datetime.date(2013, 7, 15), col("IsRefresh") == 0,
+                  col("DontCountHits") == 0])
+    g = f.eval_expression_list([col("EventTime").truncate("minute").alias("M"), col("WatchID")]).agg([_count("PageViews")], [col("M")])
+    return g.top_n([col("M")], 10, descending=[False], offset=offset)
+
+
 QUERIES = {i: f for i, f in ((int(n[1:]), f) for n, f in list(globals().items()) if n[0] == "q" and n[1:].isdigit())}
-NOT_BUILT = {18: "extract(minute from EventTime)", 28: "REGEXP_REPLACE", 39: "CASE producing strings", 42: "DATE_TRUNC('minute', EventTime)"}
+NOT_BUILT = {28: "REGEXP_REPLACE"}

@@ -56,7 +56,7 @@ enum BinOp { B_ADD = 0, B_SUB, B_MUL, B_TRUE_DIV, B_FLOOR_DIV, B_MOD, B_LT, B_LE
              B_XOR, B_EQ_NULL_SAFE, B_SHL, B_SHR };
 enum UnOp { U_NOT = 0, U_NEG, U_IS_NULL, U_NOT_NULL, U_ABS };
 enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT,
-          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ };
+          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC };
 
 struct Node {
     int tag = 0, op = 0;
@@ -281,6 +281,19 @@ static int parse_node(Reader &r, Ast &a) {
                             fail("plan: match takes an Int32 flags literal followed by string literals");
                     }
                     nd.dtype = B200_BOOL;
+                    nd.nullable = a.nodes[nd.kids[0]].nullable;
+                    break;
+                }
+                case F_HOUR: case F_MINUTE: case F_SECOND: {  // dt.hour() / minute() / second() of a Timestamp(us) (src/daft-functions-temporal): UInt32
+                    if (nd.kids.size() != 1 || a.nodes[nd.kids[0]].dtype != B200_TIMESTAMP) fail("plan: hour / minute / second need one timestamp operand");
+                    nd.dtype = B200_U32;
+                    break;
+                }
+                case F_TS_TRUNC: {  // dt.truncate(interval) relative to the epoch; the interval arrives as an Int64 literal in microseconds
+                    if (nd.kids.size() != 2 || a.nodes[nd.kids[0]].dtype != B200_TIMESTAMP) fail("plan: truncate needs a timestamp operand and an interval literal");
+                    const Node &u = a.nodes[nd.kids[1]];
+                    if (u.tag != T_LIT || u.dtype != B200_I64 || u.lit_null || u.lit_i <= 0) fail("plan: the truncate interval must be a positive Int64 literal (microseconds)");
+                    nd.dtype = B200_TIMESTAMP;
                     nd.nullable = a.nodes[nd.kids[0]].nullable;
                     break;
                 }
@@ -691,6 +704,13 @@ struct ExprGen {
                         allk = k(kid[0]);
                         break;
                     }
+                    case F_HOUR: os << "    const uint32_t " << V << " = ts_hour((int64_t)" << a << ");\n"; break;
+                    case F_MINUTE: os << "    const uint32_t " << V << " = ts_minute((int64_t)" << a << ");\n"; break;
+                    case F_SECOND: os << "    const uint32_t " << V << " = ts_second((int64_t)" << a << ");\n"; break;
+                    case F_TS_TRUNC:
+                        os << "    const int64_t " << V << " = ts_trunc((int64_t)" << a << ", (int64_t)" << cg.ast.nodes[kid[1]].lit_i << "LL);\n";
+                        allk = k(kid[0]);
+                        break;
                     case F_SIGN:
                         if (is_float(n.dtype))  // f64::signum: NaN stays NaN, otherwise +-1 with the operand's sign (signum(+-0.0) = +-1.0)
                             os << "    const " << T << " " << V << " = (" << a << " != " << a << ") ? " << a << " : "

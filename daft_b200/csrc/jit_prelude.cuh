@@ -197,6 +197,16 @@ __device__ __forceinline__ uint32_t date_dow(int32_t days) {  // Monday = 0
     return (uint32_t)(r < 0 ? r + 7 : r);
 }
 
+// ---- time of day of a Timestamp(us); negative instants count back from the epoch (floor semantics, as chrono does) ----
+__device__ __forceinline__ int64_t ts_floor_mod(int64_t a, int64_t m) {
+    const int64_t r = a % m;
+    return r < 0 ? r + m : r;
+}
+__device__ __forceinline__ uint32_t ts_hour(int64_t us) { return (uint32_t)(ts_floor_mod(us, 86400000000LL) / 3600000000LL); }
+__device__ __forceinline__ uint32_t ts_minute(int64_t us) { return (uint32_t)(ts_floor_mod(us, 3600000000LL) / 60000000LL); }
+__device__ __forceinline__ uint32_t ts_second(int64_t us) { return (uint32_t)(ts_floor_mod(us, 60000000LL) / 1000000LL); }
+__device__ __forceinline__ int64_t ts_trunc(int64_t us, int64_t unit) { return us - ts_floor_mod(us, unit); }
+
 // ---- integer division helpers ------------------------------------------------------------------------
 // The reference's `//` and `%` on integers are Rust's `/` and `%` (src/daft-core/src/array/ops/arithmetic.rs:245-300,
 // series/ops/arithmetic.rs:456-466): quotient truncated toward zero, remainder with the sign of the dividend

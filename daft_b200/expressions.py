@@ -20,7 +20,7 @@ BINOPS = {"add": 0, "sub": 1, "mul": 2, "true_div": 3, "floor_div": 4, "mod": 5,
 UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
          "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15,
-         "round": 16, "match_seq": 17}
+         "round": 16, "match_seq": 17, "hour": 18, "minute": 19, "second": 20, "ts_trunc": 21}
 AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5, "list": 6, "set": 7, "concat": 8}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
 _CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
@@ -106,6 +106,16 @@ class Expression:
     def month(self): return Expression("function", "month", (self,))
     def day(self): return Expression("function", "day", (self,))
     def day_of_week(self): return Expression("function", "day_of_week", (self,))
+    def hour(self): return Expression("function", "hour", (self,))       # of a Timestamp; extract(hour / minute / second from ts)
+    def minute(self): return Expression("function", "minute", (self,))
+    def second(self): return Expression("function", "second", (self,))
+    def truncate(self, unit: str):
+        """dt.truncate / DATE_TRUNC to a multiple of `unit` since the epoch: 'second', 'minute', 'hour' or 'day' (calendar units that
+        do not divide the epoch timeline evenly -- week, month, year -- are refused)."""
+        us = {"second": 1_000_000, "minute": 60_000_000, "hour": 3_600_000_000, "day": 86_400_000_000}.get(unit)
+        if us is None:
+            raise ValueError(f"truncate: unsupported unit {unit!r} (second, minute, hour, day)")
+        return Expression("function", "ts_trunc", (self, lit(us, dt.I64)))
     def length(self): return Expression("function", "utf8_length", (self,))
     def startswith(self, pat): return Expression("function", "startswith", (self, _to_expr(pat)))
     def endswith(self, pat): return Expression("function", "endswith", (self, _to_expr(pat)))
@@ -405,7 +415,10 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
     if k == "function":
         kids = [bind(x, names, dtypes) for x in e.args]
         out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,
-               "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8, "sqrt": dt.F64}[e.op]
+               "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8, "sqrt": dt.F64,
+               "hour": dt.U32, "minute": dt.U32, "second": dt.U32, "ts_trunc": dt.TIMESTAMP}[e.op]
+        if e.op in ("hour", "minute", "second", "ts_trunc") and kids[0].dtype != dt.TIMESTAMP:
+            raise ValueError(f"Expected input to {e.op} to be a timestamp, got {dt.NAMES[kids[0].dtype]}")
         if e.op in ("utf8_length", "startswith", "endswith", "contains", "left") and not dt.is_string(kids[0].dtype):
             raise ValueError(f"Expects input to {e.op} to be utf8, but received {dt.NAMES[kids[0].dtype]}")
         if e.op in ("startswith", "endswith", "contains") and not dt.is_string(kids[1].dtype):

@@ -206,6 +206,13 @@ def _eval(b: Bound, cols, n: int):
             if fn in ("year", "month", "day"):
                 y, m, d = _civil(a)
                 return {"year": y.astype(np.int32), "month": m.astype(np.uint32), "day": d.astype(np.uint32)}[fn], allk
+            if fn in ("hour", "minute", "second"):   # time of day of a Timestamp(us), floor semantics for instants before the epoch
+                us = a.astype(np.int64)
+                mod, div = {"hour": (86400000000, 3600000000), "minute": (3600000000, 60000000), "second": (60000000, 1000000)}[fn]
+                return (np.mod(us, mod) // div).astype(np.uint32), allk
+            if fn == "ts_trunc":
+                us, unit = a.astype(np.int64), kids[1][0].astype(np.int64)
+                return us - np.mod(us, unit), kids[0][1]
             if fn == "sqrt":
                 with np.errstate(all="ignore"):
                     return np.sqrt(a), allk   # `a` is already Float32 / Float64 (the bound plan casts to the floating representation)

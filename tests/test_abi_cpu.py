@@ -122,3 +122,23 @@ def test_host_generator_is_deterministic_and_shaped():
     assert tpch.num_rows("lineitem", 10) == 59986052 and tpch.num_rows("lineitem", 100) == 600037902
     n = tpch.generate_host("nation", 1)
     assert n.num_rows == 25 and n.column("N_NAME").to_pylist()[8] == "INDIA"
+
+
+def test_timestamp_parts_and_string_if_else_compile_for_sm100a(tmp_path):
+    """hour / minute / second / truncate of a Timestamp and a CASE that yields strings (ClickBench Q18 / Q39 / Q42): NVRTC -> sm_100a"""
+    _lib.call("b200_set_jit_cache_dir", str(tmp_path).encode())
+    names, dts = ["ts", "s", "k"], [dt.TIMESTAMP, dt.LARGE_UTF8, dt.I16]
+    from daft_b200 import lit
+    exprs = [col("ts").hour().alias("h"), col("ts").minute().alias("m"), col("ts").second().alias("sec"), col("ts").truncate("minute").alias("tm"),
+             (col("k") == 0).if_else(col("s"), lit("")).alias("src")]
+    plan, onames, odt = encode_project(exprs, names, dts)
+    assert odt == [dt.U32, dt.U32, dt.U32, dt.TIMESTAMP, dt.LARGE_UTF8]
+    for nullable in ((0, 0, 0), (1, 1, 1)):
+        _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(*nullable), ctypes.c_int32(3))
+    assert any("ts_minute(" in open(os.path.join(tmp_path, f)).read() for f in os.listdir(tmp_path) if f.endswith(".cu"))
+    # as group-by keys of an aggregate (Q18: GROUP BY UserID, minute, SearchPhrase)
+    from daft_b200.expressions import encode_agg
+    plan = encode_agg([col("k").count("all").alias("c")], [col("ts").minute().alias("m"), col("s")], names, dts)
+    _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(0, 0, 0), ctypes.c_int32(3))
+    with pytest.raises(ValueError, match="to be a timestamp"):
+        encode_project([col("k").minute()], names, dts)

@@ -35,6 +35,7 @@ SQL = {
     15: ("SELECT UserID, COUNT(*) AS c FROM hits GROUP BY UserID ORDER BY c DESC", 10, 0, {}),
     16: ("SELECT UserID, SearchPhrase, COUNT(*) AS c FROM hits GROUP BY UserID, SearchPhrase ORDER BY c DESC", 10, 0, {}),
     17: ("SELECT UserID, SearchPhrase, COUNT(*) AS c FROM hits GROUP BY UserID, SearchPhrase", "any10", 0, {}),
+    18: ("SELECT UserID, CAST(strftime('%M', EventTime) AS INT) AS m, SearchPhrase, COUNT(*) AS c FROM hits GROUP BY UserID, m, SearchPhrase ORDER BY c DESC", 10, 0, {}),
     19: ("SELECT UserID FROM hits WHERE UserID = {uid}", None, 0, "uid"),
     20: ("SELECT COUNT(*) FROM hits WHERE URL LIKE '%google%'", None, 0, {}),
     21: ("SELECT SearchPhrase, MIN(URL), COUNT(*) AS c FROM hits WHERE URL LIKE '%google%' AND SearchPhrase <> '' GROUP BY SearchPhrase ORDER BY c DESC", 10, 0, {}),
@@ -55,10 +56,14 @@ SQL = {
     36: (f"SELECT URL, COUNT(*) AS PageViews FROM hits WHERE {J} AND DontCountHits = 0 AND IsRefresh = 0 AND URL <> '' GROUP BY URL ORDER BY PageViews DESC", 10, 0, {}),
     37: (f"SELECT Title, COUNT(*) AS PageViews FROM hits WHERE {J} AND DontCountHits = 0 AND IsRefresh = 0 AND Title <> '' GROUP BY Title ORDER BY PageViews DESC", 10, 0, {}),
     38: (f"SELECT URL, COUNT(*) AS PageViews FROM hits WHERE {J} AND IsRefresh = 0 AND IsLink <> 0 AND IsDownload = 0 GROUP BY URL ORDER BY PageViews DESC", 10, 20, {"offset": 20}),
+    39: (f"SELECT TraficSourceID, SearchEngineID, AdvEngineID, CASE WHEN (SearchEngineID = 0 AND AdvEngineID = 0) THEN Referer ELSE '' END AS Src, URL AS Dst, "
+         f"COUNT(*) AS PageViews FROM hits WHERE {J} AND IsRefresh = 0 GROUP BY TraficSourceID, SearchEngineID, AdvEngineID, Src, Dst ORDER BY PageViews DESC", 10, 30, {"offset": 30}),
     40: (f"SELECT URLHash, EventDate, COUNT(*) AS PageViews FROM hits WHERE {J} AND IsRefresh = 0 AND TraficSourceID IN (-1, 6) AND RefererHash = {{rh}} "
          "GROUP BY URLHash, EventDate ORDER BY PageViews DESC", 10, 5, "rh"),
     41: (f"SELECT WindowClientWidth, WindowClientHeight, COUNT(*) AS PageViews FROM hits WHERE {J} AND IsRefresh = 0 AND DontCountHits = 0 AND URLHash = {{uh}} "
          "GROUP BY WindowClientWidth, WindowClientHeight ORDER BY PageViews DESC", 10, 2, "uh"),
+    42: ("SELECT strftime('%Y-%m-%d %H:%M:00', EventTime) AS M, COUNT(*) AS PageViews FROM hits WHERE CounterID = 62 AND EventDate >= '2013-07-14' AND "
+         "EventDate <= '2013-07-15' AND IsRefresh = 0 AND DontCountHits = 0 GROUP BY M ORDER BY M", 10, 40, {"offset": 40}),
 }
 
 
@@ -118,7 +123,7 @@ def _check(q, got: pa.Table, conn, consts, hits):
     assert len(got_rows) == len(expect), (q, len(got_rows), len(expect))
     # ties at equal sort keys may come in any order: every returned row must be a row of the full result, without repeats, and the
     # sequence of sort keys must be the expected one
-    order_col = {7: 1, 8: 1, 9: 2, 10: 1, 11: 2, 12: 1, 13: 1, 14: 2, 15: 1, 16: 2, 21: 2, 22: 3, 27: 1, 30: 2, 31: 2, 32: 2, 33: 1, 34: 2, 35: 4, 36: 1, 37: 1,
+    order_col = {7: 1, 8: 1, 9: 2, 10: 1, 11: 2, 12: 1, 13: 1, 14: 2, 15: 1, 16: 2, 18: 3, 39: 5, 42: 0, 21: 2, 22: 3, 27: 1, 30: 2, 31: 2, 32: 2, 33: 1, 34: 2, 35: 4, 36: 1, 37: 1,
                  38: 1, 40: 2, 41: 2}.get(q)
     if order_col is not None:
         assert all(_close(g[order_col], w[order_col]) for g, w in zip(got_rows, expect)), (q, [g[order_col] for g in got_rows], [w[order_col] for w in expect])
