@@ -110,3 +110,27 @@ def test_snappy_decoder_on_adversarial_blocks():
             path = os.path.join(d, name + ".parquet")
             pq.write_table(pa.table({name: arr}), path, compression="snappy", use_dictionary=False, data_page_size=1 << 20)
             assert_tables_equal(pq_host.read_table(path), pa.table({name: arr}))
+
+
+# ---- the reference's own Parquet test assets (tests/assets/parquet-data: written by parquet-cpp, parquet-mr / Databricks Photon, with
+# schema metadata, page statistics, invalid UTF-8): read where the reference tree is present (this container; never on the GPU box) ----
+REF_ASSETS = "/root/reference/tests/assets"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ASSETS), reason="the reference tree is not present")
+@pytest.mark.parametrize("name", ["parquet-data/databricks-generated.parquet", "parquet-data/invalid_utf8.parquet", "parquet-data/mvp.parquet",
+                                  "parquet-data/parquet-with-schema-metadata.parquet", "parquet-data/sampled-tpch-with-stats.parquet"])
+def test_reference_parquet_assets(name):
+    path = os.path.join(REF_ASSETS, name)
+    got = pq_host.read_table(path)
+    want = pq.read_table(path)
+    assert got.equals(want.cast(got.schema)), name
+    assert pq_host.row_groups(path) == (pq.ParquetFile(path).metadata.num_row_groups, want.num_rows)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ASSETS), reason="the reference tree is not present")
+def test_reference_asset_with_nanosecond_timestamps_is_refused_by_name():
+    with pytest.raises(ValueError, match="WARC-Date.*only microsecond timestamps"):
+        pq_host.read_table(os.path.join(REF_ASSETS, "common-crawl-sample.parquet"))
+    got = pq_host.read_table(os.path.join(REF_ASSETS, "common-crawl-sample.parquet"), ["WARC-Record-ID", "WARC-Type"])   # the other columns read fine
+    assert got.equals(pq.read_table(os.path.join(REF_ASSETS, "common-crawl-sample.parquet"), columns=["WARC-Record-ID", "WARC-Type"]).cast(got.schema))
