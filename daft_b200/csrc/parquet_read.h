@@ -11,8 +11,14 @@
 //   X::scan(lengths, offsets, n)      exclusive scan of n int64 lengths into offsets[0..n], returns offsets[n] (the total)
 //   X::pack(bytes01, n, bitmap) -> number of zero bytes; packs one byte per row into an LSB-first bitmap
 #pragma once
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
+#include <thread>
 
 #include "parquet_core.h"
 
@@ -33,24 +39,61 @@
 namespace b200 {
 namespace pq {
 
-struct FileBytes {   // a whole-file view the planner reads ranges from (pread on a descriptor)
-    FILE *f = nullptr;
+struct FileBytes {   // a whole-file view the planner reads ranges from: pread on a descriptor, safe from several threads at once
+    int fd = -1;
     int64_t size = 0;
     explicit FileBytes(const std::string &path) {
-        f = fopen(path.c_str(), "rb");
-        if (!f) throw std::runtime_error("parquet: cannot open " + path);
-        fseek(f, 0, SEEK_END);
-        size = ftell(f);
+        fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("parquet: cannot open " + path);
+        struct stat st;
+        if (::fstat(fd, &st) != 0) {
+            ::close(fd);
+            throw std::runtime_error("parquet: cannot stat " + path);
+        }
+        size = (int64_t)st.st_size;
     }
     ~FileBytes() {
-        if (f) fclose(f);
+        if (fd >= 0) ::close(fd);
     }
+    FileBytes(const FileBytes &) = delete;
+    FileBytes &operator=(const FileBytes &) = delete;
     void read(int64_t off, int64_t n, uint8_t *dst) const {
         if (off < 0 || n < 0 || off + n > size) throw std::runtime_error("parquet: read outside the file");
-        fseek(f, off, SEEK_SET);
-        if (n && fread(dst, 1, (size_t)n, f) != (size_t)n) throw std::runtime_error("parquet: short read");
+        while (n > 0) {
+            const ssize_t got = ::pread(fd, dst, (size_t)n, (off_t)off);
+            if (got <= 0) throw std::runtime_error("parquet: short read");
+            dst += got;
+            off += got;
+            n -= got;
+        }
     }
 };
+// the column chunks' byte ranges, read by a few threads at once (the page cache / NVMe queue wants more than one request in flight)
+struct ChunkRead {
+    int64_t file_off, bytes, dst_off;
+};
+inline void read_chunks(const FileBytes &fb, const std::vector<ChunkRead> &reads, uint8_t *dst) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::min<size_t>(std::min<size_t>(reads.size(), 8), hw ? hw : 1);
+    if (nt <= 1) {
+        for (const ChunkRead &r : reads) fb.read(r.file_off, r.bytes, dst + r.dst_off);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::string> errors(nt);
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([&, t] {
+            try {
+                for (size_t i = next++; i < reads.size(); i = next++) fb.read(reads[i].file_off, reads[i].bytes, dst + reads[i].dst_off);
+            } catch (const std::exception &e) {
+                errors[t] = e.what();
+            }
+        });
+    for (auto &x : th) x.join();
+    for (const std::string &e : errors)
+        if (!e.empty()) throw std::runtime_error(e);
+}
 
 inline FileMeta read_footer(const FileBytes &fb) {
     if (fb.size < 12) throw std::runtime_error("parquet: file too small");
@@ -161,6 +204,20 @@ std::vector<ColumnResult<X>> scan_file(X &x, const std::string &path, const std:
         }
     uint8_t *chunks = x.stage((size_t)chunk_total + 16);
     int64_t chunk_used = 0;
+    {
+        std::vector<ChunkRead> reads;
+        int64_t at = 0;
+        for (size_t ci = 0; ci < sel.size(); ci++)
+            for (int64_t g = rg_begin; g < rg_end; g++) {
+                const ColumnChunkMeta &cm = fm.row_groups[(size_t)g].columns[(size_t)sel[ci]];
+                int64_t start = cm.data_page_offset;
+                if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
+                if (start < 0 || start + cm.total_compressed > fb.size) throw std::runtime_error("parquet: column chunk lies outside the file");
+                reads.push_back({start, cm.total_compressed, at});
+                at += cm.total_compressed;
+            }
+        read_chunks(fb, reads, chunks);
+    }
     std::vector<PageDesc> pages;
     std::vector<DictDesc> dicts;
     std::vector<ColumnDesc> cols(sel.size());
@@ -181,11 +238,8 @@ std::vector<ColumnResult<X>> scan_file(X &x, const std::string &path, const std:
             const std::string where = "parquet: column '" + leaf.name + "': ";
             if (cm.codec != C_UNCOMPRESSED && cm.codec != C_SNAPPY) throw std::runtime_error(where + "compression codec " + std::to_string(cm.codec) + " is not supported (UNCOMPRESSED and SNAPPY are)");
             if (cm.type != leaf.physical) throw std::runtime_error(where + "chunk type differs from the schema");
-            int64_t start = cm.data_page_offset;
-            if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
-            const int64_t base = chunk_used;
+            const int64_t base = chunk_used;   // the bytes are already in the staging buffer (read_chunks above, same order)
             chunk_used += cm.total_compressed;
-            fb.read(start, cm.total_compressed, chunks + base);
             int64_t pos = 0, seen = 0;
             int32_t cur_dict = -1;
             while (seen < cm.num_values) {

@@ -21,7 +21,7 @@ def lib():
         srcs = [os.path.join(_HERE, "pq_host.cpp"), os.path.join(_HERE, "..", "daft_b200", "csrc", "parquet_core.h"),
                 os.path.join(_HERE, "..", "daft_b200", "csrc", "parquet_read.h")]
         if not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fno-strict-aliasing", "-shared", "-fPIC", "-Wall", "-o", _SO, srcs[0]])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fno-strict-aliasing", "-shared", "-fPIC", "-Wall", "-pthread", "-o", _SO, srcs[0]])
         L = ctypes.CDLL(_SO)
         L.pq_host_read.restype = ctypes.c_void_p
         L.pq_host_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong]
