@@ -50,6 +50,12 @@ __global__ void pq_pack_kernel(const uint8_t *__restrict__ bytes01, int64_t n, u
     if (z) atomicAdd(zeros, z);
 }
 
+__global__ void pq_convert_kernel(int kind, const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int64_t n, int64_t factor) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) convert_one(kind, src, dst, i, factor);
+}
+
 namespace {
 struct DeviceExec {
     struct Mem {
@@ -95,6 +101,12 @@ struct DeviceExec {
     int64_t scan(const int64_t *lengths, int64_t *offsets, int64_t n) {
         exclusive_scan_i64(lengths, offsets, n, offsets + n);
         return read_i64(offsets + n);
+    }
+    void convert(int kind, const uint8_t *src, uint8_t *dst, int64_t n, int64_t factor) {
+        if (n <= 0) return;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 8));
+        pq_convert_kernel<<<grid, 256, 0, ctx().stream>>>(kind, src, dst, n, factor);
+        count_launch();
     }
     int64_t pack(const uint8_t *bytes01, int64_t n, uint8_t *bitmap) {
         if (n <= 0) return 0;

@@ -9,7 +9,7 @@
 // The device runs one page per thread through these stages (daft_b200/csrc/parquet.cu) with the compressed column chunks
 // resident in HBM; tests compile the very same header for the host (tests/pq_host.cpp) and hold the result to pyarrow's reader.
 //
-// Supported: flat (non-nested) columns; BOOLEAN, INT32, INT64, FLOAT, DOUBLE, BYTE_ARRAY; PLAIN, PLAIN_DICTIONARY / RLE_DICTIONARY;
+// Supported: flat (non-nested) columns; BOOLEAN, INT32 (also as 8- / 16-bit integers), INT64 (timestamps of any unit), FLOAT, DOUBLE, BYTE_ARRAY; PLAIN, PLAIN_DICTIONARY / RLE_DICTIONARY;
 // data pages V1 and V2; UNCOMPRESSED and SNAPPY.  Everything else is refused with an error that names it.
 #pragma once
 #include <cstdint>
@@ -744,6 +744,28 @@ PQ_HD void stage_string_bytes(const ScanCtx &c, int32_t pi) {
         if (len == 0) continue;
         const uint8_t *src = by_dict ? dict_data + dict_offs[col.row_dict_index[r]] : data + col.row_src[r];
         copy_bytes(col.out_bytes + o, src, len);
+    }
+}
+
+// ---- after the stages: narrow / rescale a column that Parquet stores wider or in another unit than its Arrow type ----
+// INT32 annotated INT(8 | 16): the low bytes of the little-endian value; TIMESTAMP millis -> micros (x 1000) and nanos -> micros
+// (floor division by 1000, the unit the library's Timestamp has).  One value per call: the executors run it over all rows.
+enum ConvKind { CONV_NONE = 0, CONV_LOW8 = 1, CONV_LOW16 = 2, CONV_MUL64 = 3, CONV_FLOORDIV64 = 4 };
+PQ_HD void convert_one(int kind, const uint8_t *src, uint8_t *dst, int64_t i, int64_t factor) {
+    if (kind == CONV_LOW8) {
+        dst[i] = src[4 * i];
+    } else if (kind == CONV_LOW16) {
+        dst[2 * i] = src[4 * i];
+        dst[2 * i + 1] = src[4 * i + 1];
+    } else {
+        int64_t v = ((const int64_t *)src)[i];
+        if (kind == CONV_MUL64) {
+            v *= factor;
+        } else {
+            const int64_t q = v / factor, r = v % factor;
+            v = r < 0 ? q - 1 : q;
+        }
+        ((int64_t *)dst)[i] = v;
     }
 }
 

@@ -10,6 +10,7 @@
 //   X::run(stage, ctx, count)   stage 0 decompress / 1 dictionary / 2 values / 3 string bytes over `count` pages (dictionaries for 1)
 //   X::scan(lengths, offsets, n)      exclusive scan of n int64 lengths into offsets[0..n], returns offsets[n] (the total)
 //   X::pack(bytes01, n, bitmap) -> number of zero bytes; packs one byte per row into an LSB-first bitmap
+//   X::convert(kind, src, dst, n, factor)   convert_one over n rows (narrow INT32 to 8 / 16 bits, rescale timestamps)
 #pragma once
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -24,6 +25,10 @@
 
 #ifndef B200_BOOL  // standalone use (tests/pq_host.cpp): the physical dtype codes of include/daft_b200.h
 #define B200_BOOL 1
+#define B200_I8 2
+#define B200_I16 3
+#define B200_U8 6
+#define B200_U16 7
 #define B200_I32 4
 #define B200_I64 5
 #define B200_U32 8
@@ -111,6 +116,8 @@ struct LeafInfo {
     std::string name;
     int32_t schema_index = 0, dtype = 0, width = 0, max_def = 0, physical = 0;
     bool is_string = false;
+    int32_t conv = CONV_NONE, final_width = 0;   // a conversion pass after the stages (parquet_core.h convert_one)
+    int64_t conv_factor = 1;
 };
 // flat schemas only: the leaves are the root's children, leaf i is column chunk i of every row group
 inline std::vector<LeafInfo> leaves_of(const FileMeta &fm) {
@@ -138,14 +145,29 @@ inline void resolve_leaf(const FileMeta &fm, LeafInfo &l) {
         case T_BOOLEAN: l.dtype = B200_BOOL; l.width = 1; break;
         case T_INT32:
             if (e.is_date) l.dtype = B200_DATE32;
-            else if (e.int_bits == 8 || e.int_bits == 16) throw std::runtime_error(where + "8- and 16-bit integers (stored as INT32) are not supported");
-            else l.dtype = e.int_unsigned ? B200_U32 : B200_I32;
+            else if (e.int_bits == 8) {
+                l.dtype = e.int_unsigned ? B200_U8 : B200_I8;
+                l.conv = CONV_LOW8;
+                l.final_width = 1;
+            } else if (e.int_bits == 16) {
+                l.dtype = e.int_unsigned ? B200_U16 : B200_I16;
+                l.conv = CONV_LOW16;
+                l.final_width = 2;
+            } else l.dtype = e.int_unsigned ? B200_U32 : B200_I32;
             l.width = 4;
             break;
         case T_INT64:
-            if (e.is_timestamp) {
-                if (e.ts_unit != 2) throw std::runtime_error(where + "only microsecond timestamps are supported");
+            if (e.is_timestamp) {   // the library's Timestamp counts microseconds
                 l.dtype = B200_TIMESTAMP;
+                if (e.ts_unit == 1) {
+                    l.conv = CONV_MUL64;
+                    l.conv_factor = 1000;
+                    l.final_width = 8;
+                } else if (e.ts_unit == 3) {
+                    l.conv = CONV_FLOORDIV64;
+                    l.conv_factor = 1000;
+                    l.final_width = 8;
+                } else if (e.ts_unit != 2) throw std::runtime_error(where + "timestamp without a unit");
             } else l.dtype = e.int_unsigned ? B200_U64 : B200_I64;
             l.width = 8;
             break;
@@ -404,6 +426,11 @@ std::vector<ColumnResult<X>> scan_file(X &x, const std::string &path, const std:
             x.pack((const uint8_t *)values[ci].ptr, n_rows, (uint8_t *)bm.ptr);
             r.data = bm;
             r.data_bytes = (n_rows + 7) / 8;
+        } else if (leaf.conv != CONV_NONE) {
+            Mem fin = x.alloc(nr * (size_t)leaf.final_width);
+            x.convert(leaf.conv, (const uint8_t *)values[ci].ptr, (uint8_t *)fin.ptr, n_rows, leaf.conv_factor);
+            r.data = fin;
+            r.data_bytes = n_rows * leaf.final_width;
         } else {
             r.data = values[ci];
             r.data_bytes = n_rows * cols[ci].width;

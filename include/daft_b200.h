@@ -334,7 +334,8 @@ int b200_all_gather(b200_comm *c, const b200_batch *batch, b200_batch **out, cha
  * stream_parquet) for a local file: row groups [row_group_begin, row_group_end) (end < 0 = all) of the named columns
  * (NULL / 0 = every column) as one batch.  The host reads the footer, the column chunks' bytes and the page headers; the
  * compressed chunks are copied to HBM as they are and every page is decompressed and decoded on the device.
- * Supported: flat schemas; BOOLEAN, INT32 (incl. DATE, UINT_32), INT64 (incl. TIMESTAMP micros, UINT_64), FLOAT, DOUBLE, BYTE_ARRAY
+ * Supported: flat schemas; BOOLEAN, INT32 (incl. DATE, INT(8 | 16 | 32) signed and unsigned), INT64 (incl. TIMESTAMP millis / micros / nanos -> the
+ * library's microsecond Timestamp, UINT_64), FLOAT, DOUBLE, BYTE_ARRAY
  * (String -> LargeUtf8, otherwise LargeBinary); PLAIN and PLAIN_DICTIONARY / RLE_DICTIONARY pages, data pages V1 and V2 (RLE
  * Booleans); UNCOMPRESSED and SNAPPY.  Anything else is an error naming the column and the feature (no CPU fallback). */
 int b200_parquet_read(const char *path, const char *const *columns, int32_t ncolumns, int64_t row_group_begin,

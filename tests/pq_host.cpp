@@ -49,6 +49,9 @@ struct HostExec {
         offsets[n] = acc;
         return acc;
     }
+    void convert(int kind, const uint8_t *src, uint8_t *dst, int64_t n, int64_t factor) {
+        for (int64_t i = 0; i < n; i++) convert_one(kind, src, dst, i, factor);
+    }
     int64_t pack(const uint8_t *bytes01, int64_t n, uint8_t *bitmap) {
         int64_t zeros = 0;
         memset(bitmap, 0, (size_t)((n + 7) / 8));
