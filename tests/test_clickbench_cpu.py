@@ -165,3 +165,17 @@ def test_clickbench_plans_through_generated_code(world, q):
 def test_every_statement_is_accounted_for():
     assert sorted(set(CB.QUERIES) | set(CB.NOT_BUILT)) == list(range(43)) and not set(CB.QUERIES) & set(CB.NOT_BUILT)
     assert sorted(SQL) == sorted(CB.QUERIES)
+
+
+def test_hits_table_round_trips_through_the_parquet_scan(world, tmp_path):
+    """the benchmark's input is a Parquet file with SMALLINT (INT32 / INT(16)) columns, dates and timestamps: written by pyarrow, read by
+    the host build of the device decoders (tests/pq_host.cpp)"""
+    import pyarrow.parquet as pq
+    import pq_host
+    from helpers import assert_tables_equal
+    hits, _, _ = world
+    path = str(tmp_path / "hits.parquet")
+    pq.write_table(hits, path, compression="snappy", row_group_size=6000)
+    got = pq_host.read_table(path)
+    assert_tables_equal(got, hits)
+    assert pq_host.row_groups(path) == (4, hits.num_rows)
