@@ -142,3 +142,19 @@ def test_timestamp_parts_and_string_if_else_compile_for_sm100a(tmp_path):
     _lib.call("b200_precompile", ctypes.c_int32(2), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(*dts), (ctypes.c_uint8 * 3)(0, 0, 0), ctypes.c_int32(3))
     with pytest.raises(ValueError, match="to be a timestamp"):
         encode_project([col("k").minute()], names, dts)
+
+
+def test_generated_rust_bindings_cover_every_symbol():
+    """integration/daft_b200_sys.rs (scripts/gen_rust_ffi.py) is the `extern "C"` block the reference's Rust host binds: it must be in step
+    with the header and declare every exported symbol (there is no Rust toolchain here to compile it)"""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fresh = subprocess.check_output([sys.executable, os.path.join(root, "scripts", "gen_rust_ffi.py")]).decode()
+    committed = open(os.path.join(root, "integration", "daft_b200_sys.rs")).read()
+    assert fresh == committed, "run: python scripts/gen_rust_ffi.py > integration/daft_b200_sys.rs"
+    declared = set(re.findall(r"pub fn (b200_[a-z0-9_]+)\(", committed))
+    assert declared == set(_lib.SYMBOLS)
+    assert "pub fn b200_concat(batches: *const *const B200Batch, n: i32, out: *mut *mut B200Batch, errmsg: *mut *mut c_char) -> c_int;" in committed
+    assert "columns: *const *const c_char" in committed and "seed: *const B200Batch" in committed
