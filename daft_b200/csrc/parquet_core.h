@@ -628,6 +628,10 @@ PQ_HD void stage_values(const ScanCtx &c, int32_t pi) {
         }
         idx_width = vals < end ? (int32_t)vals[0] : 0;
         vals += 1;
+        if (idx_width > 32) {   // a corrupt page: dictionary indices are at most 32 bits wide
+            pg.status = PQ_ERR_VALUES;
+            return;
+        }
     }
     const bool bool_rle = pg.encoding == E_RLE;   // BOOLEAN only (the planner checks): <4-byte length> <hybrid runs of 1-bit values>
     if (bool_rle) {

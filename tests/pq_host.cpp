@@ -109,3 +109,15 @@ __attribute__((visibility("default"))) long long pq_host_row_groups(const char *
     }
 }
 }
+
+#ifdef PQ_HOST_MAIN
+// standalone reader for sanitizer runs: g++ -fsanitize=address,undefined -DPQ_HOST_MAIN tests/pq_host.cpp -o pq_asan; ./pq_asan file.parquet
+int main(int argc, char **argv) {
+    if (argc < 2) return 2;
+    HostScan *s = pq_host_read(argv[1], nullptr, 0, 0, -1);
+    if (!s->error.empty()) printf("err %s\n", s->error.c_str());
+    else printf("ok %lld rows %zu columns\n", (long long)s->rows, s->cols.size());
+    pq_host_free(s);
+    return 0;
+}
+#endif
