@@ -204,5 +204,3 @@ def test_corrupted_files_are_refused_not_crashed_on(tmp_path):
             assert str(e).startswith("parquet:"), e
             outcomes["err"] += 1
     assert outcomes["err"] > 10 and outcomes["ok"] > 10, outcomes
-    # a dictionary index width beyond 32 bits (first byte of a dictionary-encoded page's values) is a corrupt page, not a shift count
-    from oracle import oracle as _unused  # noqa: F401  (keeps the import style of the suite)
