@@ -198,3 +198,21 @@ def test_malformed_plans_are_refused_not_crashed_on():
         else:
             _lib.lib().b200_free_string(out)
     assert refused > 100
+
+
+def test_plain_c_host_compiles_links_and_fails_loudly_without_a_device(tmp_path):
+    """examples/c_host.c: the header is C99, every symbol it uses links against the in-tree library, and without a GPU the first
+    call reports that there is no CPU fallback"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "c_host")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", f"-I{root}/include", f"{root}/examples/c_host.c", f"-L{root}/daft_b200", "-ldaftb200",
+                           f"-Wl,-rpath,{root}/daft_b200", "-o", exe])
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([exe, "missing.parquet", "a"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
