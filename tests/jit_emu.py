@@ -119,7 +119,7 @@ def _compile(src: str) -> ctypes.CDLL:
     body = "\n".join(l for l in src.split("\n") if "__global__" not in l)
     full = _SHIM + _prelude_for_host() + body + _DRIVER
     tag = hashlib.sha1(full.encode()).hexdigest()[:16]
-    d = os.path.join(tempfile.gettempdir(), "daft_b200_jit_emu")
+    d = os.path.join(tempfile.gettempdir(), os.environ.get("B200_EMU_DIR", "daft_b200_jit_emu"))
     os.makedirs(d, exist_ok=True)
     so = os.path.join(d, f"emu_{tag}.so")
     if not os.path.exists(so):
@@ -129,7 +129,7 @@ def _compile(src: str) -> ctypes.CDLL:
         # -ffp-contract=off: the device code is compiled with --fmad=false.  -fno-builtin-fmod*: gcc otherwise reasons that
         # fabs(fmod(x, y)) == fmod(x, y) for non-negative x and drops the fabs, which is visible when libm returns the
         # negative x86 default NaN for fmod(x, 0).
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w",
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w", *os.environ.get("B200_EMU_FLAGS", "").split(),
                                "-o", so, cpp])
     return ctypes.CDLL(so)
 
@@ -449,14 +449,14 @@ def _compile_agg(src: str, staged: bool = False, tier1: bool = False) -> ctypes.
     full = _SHIM + _AGG_SHIM + (_STAGED_SHIM if staged else "") + defines + "\n" + head + extra + "\n}  // namespace jit\n}  // namespace b200\n" + body + \
         (_STAGED_DRIVER if staged else _TIER1_DRIVER if tier1 else _AGG_DRIVER)
     tag = hashlib.sha1(full.encode()).hexdigest()[:16]
-    d = os.path.join(tempfile.gettempdir(), "daft_b200_jit_emu")
+    d = os.path.join(tempfile.gettempdir(), os.environ.get("B200_EMU_DIR", "daft_b200_jit_emu"))
     os.makedirs(d, exist_ok=True)
     so = os.path.join(d, f"emuagg_{tag}.so")
     if not os.path.exists(so):
         cpp = os.path.join(d, f"emuagg_{tag}.cpp")
         with open(cpp, "w") as fh:
             fh.write(full)
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w",
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w", *os.environ.get("B200_EMU_FLAGS", "").split(),
                                "-o", so, cpp])
     return ctypes.CDLL(so)
 
@@ -678,14 +678,14 @@ def emulate_filter(tbl: pa.Table, predicates) -> pa.Table:
     body = "\n".join(l for l in src.split("\n") if "__global__" not in l)
     full = _SHIM + "constexpr int FILTER_SUB = 8;\n" + _prelude_for_host() + body + _FILTER_DRIVER
     tag = hashlib.sha1(full.encode()).hexdigest()[:16]
-    d = os.path.join(tempfile.gettempdir(), "daft_b200_jit_emu")
+    d = os.path.join(tempfile.gettempdir(), os.environ.get("B200_EMU_DIR", "daft_b200_jit_emu"))
     os.makedirs(d, exist_ok=True)
     so = os.path.join(d, f"emufilter_{tag}.so")
     if not os.path.exists(so):
         cpp = os.path.join(d, f"emufilter_{tag}.cpp")
         with open(cpp, "w") as fh:
             fh.write(full)
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w",
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w", *os.environ.get("B200_EMU_FLAGS", "").split(),
                                "-o", so, cpp])
     lib = ctypes.CDLL(so)
     nw = max((n + 31) // 32, 1)
