@@ -105,12 +105,11 @@ def test_oracle_cross_join():
 
 # ---- the reference runs its join pair tables through BOTH strategies (tests/recordbatch/test_joins.py:30-140, join_impl in
 # ("hash_join", "sort_merge_join"), null-safe equality skipped for the sort-merge join): the same literals through the merge restatement ----
-from test_oracle_cpu import JOIN_PAIR_CASES  # noqa: E402
-
-
 @pytest.mark.parametrize("typ", [pa.int8(), pa.int64(), pa.uint64(), pa.float32(), pa.float64(), pa.large_utf8()])
-@pytest.mark.parametrize("case", range(len(JOIN_PAIR_CASES)))
+@pytest.mark.parametrize("case", range(6))
 def test_sort_merge_join_pairs_from_reference_tests(typ, case):
+    from test_oracle_cpu import JOIN_PAIR_CASES   # imported here: tests/test_gpu_zzz2_joins_sorted.py imports this module for its tables
+    assert len(JOIN_PAIR_CASES) == 6
     left, right, pairs, _ = JOIN_PAIR_CASES[case]
 
     def column(vals):
