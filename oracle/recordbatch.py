@@ -31,6 +31,16 @@ class OracleRecordBatch:
     def column_names(self):
         return self.tbl.column_names
 
+    def num_columns(self):
+        return self.tbl.num_columns
+
+    def dtypes(self):
+        from daft_b200 import datatypes as dt
+        return [dt.from_arrow(f.type) for f in self.tbl.schema]
+
+    def slice(self, start: int, end: int) -> "OracleRecordBatch":
+        return OracleRecordBatch(self.tbl.slice(start, max(end - start, 0)))
+
     def eval_expression_list(self, exprs: Sequence[Expression]) -> "OracleRecordBatch":
         return OracleRecordBatch(E.eval_expression_list(self.tbl, exprs))
 

@@ -104,6 +104,16 @@ def main():
             want_j = O.hash_join(lfull, rfull, ["k"], ["k"], how)
             order = [(c, "ascending") for c in want_j.column_names]
             assert_tables_equal(got_j.sort_by(order), want_j.sort_by(order))
+    # the distributed planner over the device backend: a few whole queries on sharded scan partitions == the single-GPU answer
+    from daft_b200.distributed_plan import DeviceBackend, Sharded
+    backend = DeviceBackend(comm)
+    for qname, sf in (("q3", 0.05), ("q5", 0.05), ("q12", 0.05), ("q13", 0.05), ("q18", 0.05), ("q21", 0.05)):
+        cols = tpch.Q5_COLUMNS if qname == "q5" else tpch.QUERY_COLUMNS[qname]
+        for thr in (1 << 20, 300):
+            shards = {t: Sharded(tpch.generate(t, sf, c, *distributed.shard_rows(tpch.num_rows(t, sf), rank, world)), backend, gather_rows=thr) for t, c in cols.items()}
+            got_q = getattr(tpch, qname)(shards).to_arrow_table()
+            want_q = getattr(tpch, qname)({t: tpch.generate(t, sf, c) for t, c in cols.items()}).to_arrow_table()
+            assert_tables_equal(got_q, want_q, float_rtol=1e-9)
     dist.barrier()
     if rank == 0:
         print(f"exchange ok on {world} GPUs")

@@ -131,3 +131,103 @@ def test_partitioned_join_world2_gloo():
         want = O.hash_join(left, right, ["O_ORDERKEY"], ["L_ORDERKEY"], how)
         keys = [(c, "ascending") for c in want.column_names]
         assert_tables_equal(got.sort_by(keys), want.sort_by(keys))
+
+
+# ---- all 22 TPC-H queries over two ranks: the distributed planner (daft_b200/distributed_plan.py) with the oracle as the kernels ----
+def _plan_worker(rank, world, port, q, gather_rows):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from daft_b200 import distributed, tpch
+    from daft_b200.distributed_plan import Sharded
+    from oracle import expr_eval as E
+    from oracle import oracle as O
+    from oracle.recordbatch import OracleRecordBatch
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Backend:
+        def __init__(self):
+            self.rank, self.world = rank, world
+            self.calls = {"exchange": 0, "gather": 0}
+
+        def exchange_by_hash(self, batch, key_exprs):
+            self.calls["exchange"] += 1
+            names = [f"__pk{i}" for i in range(len(key_exprs))]
+            keys = E.eval_expression_list(batch.tbl, [e.alias(n) for e, n in zip(key_exprs, names)])
+            aug = batch.tbl
+            for n in names:
+                aug = aug.append_column(n, keys.column(n))
+            pieces = [p.drop_columns(names) for p in O.partition_by_hash(aug, names, world)]
+            mine = None
+            for dst in range(world):
+                parts = [None] * world
+                dist.all_gather_object(parts, distributed._to_ipc(pieces[dst]))
+                if dst == rank:
+                    mine = parts
+            return OracleRecordBatch(pa.concat_tables([distributed._from_ipc(p) for p in mine]))
+
+        def all_gather(self, batch):
+            self.calls["gather"] += 1
+            parts = [None] * world
+            dist.all_gather_object(parts, distributed._to_ipc(batch.tbl))
+            return OracleRecordBatch(pa.concat_tables([distributed._from_ipc(p) for p in parts]))
+
+        def allreduce_sum(self, value):
+            t = torch.tensor([int(value)], dtype=torch.int64)
+            dist.all_reduce(t)
+            return int(t.item())
+    try:
+        backend, out = Backend(), {}
+        sf_of = {2: 0.05, 8: 0.05, 16: 0.05, 17: 0.05, 18: 0.05, 20: 0.05}
+        for qn in range(1, 23):
+            name, sf = f"q{qn}", sf_of.get(qn, 0.01)
+            cols = {"lineitem": tpch.Q1_COLUMNS} if qn in (1, 6) else (tpch.Q5_COLUMNS if qn == 5 else tpch.QUERY_COLUMNS[name])
+            shards = {}
+            for t, c in cols.items():
+                b, e = distributed.shard_rows(tpch.num_rows(t, sf), rank, world)
+                shards[t] = Sharded(OracleRecordBatch(tpch.generate_host(t, sf, c, b, e)), backend, gather_rows=gather_rows)
+            res = getattr(tpch, name)(shards["lineitem"] if qn in (1, 6) else shards).to_arrow_table()
+            out[qn] = distributed._to_ipc(res)
+        out["calls"] = dict(backend.calls)
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("gather_rows", [1 << 20, 300])
+def test_all_22_queries_over_two_ranks_gloo(gather_rows):
+    """config 4's shape on the CPU: every query over two scan partitions per table, joins and aggregates crossing the ranks through the
+    planner's exchanges (gather_rows = 300 forces the repartitioning routes, 2^20 the gather / broadcast routes), against the
+    single-process oracle answer"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from daft_b200 import tpch
+    from daft_b200.distributed import _from_ipc
+    from helpers import assert_tables_equal
+    from oracle.recordbatch import OracleRecordBatch
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() + 31 + gather_rows % 97) % 1000)
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, q, gather_rows)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=800) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    calls = results[0]["calls"]
+    assert calls == results[1]["calls"]                       # both ranks issued the same collectives
+    if gather_rows == 300:
+        assert calls["exchange"] > 40, calls                  # joins and high-cardinality aggregates repartitioned their inputs
+    else:
+        assert calls["gather"] > calls["exchange"], calls     # small inputs: broadcast joins and gathered partials
+    sf_of = {2: 0.05, 8: 0.05, 16: 0.05, 17: 0.05, 18: 0.05, 20: 0.05}
+    for qn in range(1, 23):
+        name, sf = f"q{qn}", sf_of.get(qn, 0.01)
+        cols = {"lineitem": tpch.Q1_COLUMNS} if qn in (1, 6) else (tpch.Q5_COLUMNS if qn == 5 else tpch.QUERY_COLUMNS[name])
+        full = {t: OracleRecordBatch(tpch.generate_host(t, sf, c)) for t, c in cols.items()}
+        want = getattr(tpch, name)(full["lineitem"] if qn in (1, 6) else full).to_arrow_table()
+        for r in range(2):      # every rank ends with the whole answer
+            assert_tables_equal(_from_ipc(results[r][qn]), want, float_rtol=1e-9), (qn, r)
