@@ -134,18 +134,13 @@ def test_partitioned_join_world2_gloo():
 
 
 # ---- all 22 TPC-H queries over two ranks: the distributed planner (daft_b200/distributed_plan.py) with the oracle as the kernels ----
-def _plan_worker(rank, world, port, q, gather_rows):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+def _gloo_oracle_backend(rank, world):
     import torch
     import torch.distributed as dist
-    from daft_b200 import distributed, tpch
-    from daft_b200.distributed_plan import Sharded
+    from daft_b200 import distributed
     from oracle import expr_eval as E
     from oracle import oracle as O
     from oracle.recordbatch import OracleRecordBatch
-    dist.init_process_group("gloo", rank=rank, world_size=world)
 
     class Backend:
         def __init__(self):
@@ -178,8 +173,20 @@ def _plan_worker(rank, world, port, q, gather_rows):
             t = torch.tensor([int(value)], dtype=torch.int64)
             dist.all_reduce(t)
             return int(t.item())
+    return Backend()
+
+
+def _plan_worker(rank, world, port, q, gather_rows):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from daft_b200 import distributed, tpch
+    from daft_b200.distributed_plan import Sharded
+    from oracle.recordbatch import OracleRecordBatch
+    dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        backend, out = Backend(), {}
+        backend, out = _gloo_oracle_backend(rank, world), {}
         sf_of = {2: 0.05, 8: 0.05, 16: 0.05, 17: 0.05, 18: 0.05, 20: 0.05}
         for qn in range(1, 23):
             name, sf = f"q{qn}", sf_of.get(qn, 0.01)
@@ -231,3 +238,67 @@ def test_all_22_queries_over_two_ranks_gloo(gather_rows):
         want = getattr(tpch, name)(full["lineitem"] if qn in (1, 6) else full).to_arrow_table()
         for r in range(2):      # every rank ends with the whole answer
             assert_tables_equal(_from_ipc(results[r][qn]), want, float_rtol=1e-9), (qn, r)
+
+
+# ---- ClickBench over two ranks: count_distinct / string min (composite aggregates), LIKE filters, top-N with offsets ----
+CB_KW = {27: {"having": 30}, 38: {"offset": 20}, 39: {"offset": 30}, 40: {"offset": 5}, 41: {"offset": 2}, 42: {"offset": 40}}
+
+
+def _clickbench_worker(rank, world, port, q, gather_rows):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from daft_b200 import clickbench as CB, distributed
+    from daft_b200.distributed_plan import Sharded
+    from oracle.recordbatch import OracleRecordBatch
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        backend, out = _gloo_oracle_backend(rank, world), {}
+        hits = CB.generate_hits(6000)
+        b, e = distributed.shard_rows(hits.num_rows, rank, world)
+        for qn, fn in sorted(CB.QUERIES.items()):
+            if qn == 17:
+                continue                      # LIMIT without ORDER BY: any ten groups
+            shard = Sharded(OracleRecordBatch(hits.slice(b, e - b)), backend, gather_rows=gather_rows)
+            out[qn] = distributed._to_ipc(fn(shard, **CB_KW.get(qn, {})).to_arrow_table())
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("gather_rows", [1 << 20, 100])
+def test_clickbench_over_two_ranks_gloo(gather_rows):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from daft_b200 import clickbench as CB
+    from daft_b200.distributed import _from_ipc
+    from oracle.recordbatch import OracleRecordBatch
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() + 57 + gather_rows % 89) % 1000)
+    procs = [ctx.Process(target=_clickbench_worker, args=(r, 2, port, q, gather_rows)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=800) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    hits = CB.generate_hits(6000)
+    for qn, fn in sorted(CB.QUERIES.items()):
+        if qn == 17:
+            continue
+        want = fn(OracleRecordBatch(hits), **CB_KW.get(qn, {})).to_arrow_table()
+        got = _from_ipc(results[0][qn])
+        assert got.column_names == want.column_names and got.num_rows == want.num_rows, qn
+        # the sort column decides the order; rows tied on it may come in any order (as between the single-process engines): compare as sets
+        key = lambda r: tuple((0, "") if v is None else (1, round(v, 9)) if isinstance(v, float) else (1, v) for v in r)   # noqa: E731
+        g = sorted(zip(*[c.to_pylist() for c in got.columns]), key=key) if got.num_columns else []
+        w = sorted(zip(*[c.to_pylist() for c in want.columns]), key=key) if want.num_columns else []
+        order_col = {7: "c", 8: "u", 9: "c", 10: "u", 11: "u", 12: "c", 13: "u", 14: "c", 15: "c", 16: "c", 18: "c", 21: "c", 22: "c", 27: "l", 30: "c", 31: "c", 32: "c",
+                     33: "c", 34: "c", 35: "c", 36: "PageViews", 37: "PageViews", 38: "PageViews", 39: "PageViews", 40: "PageViews", 41: "PageViews"}.get(qn)
+        if order_col is None:
+            assert [key(r) for r in g] == [key(r) for r in w], qn
+        else:   # top-N on a tied count: the sequence of sort keys is fixed, the tied rows are not
+            gc, wc = got.column(order_col).to_pylist(), want.column(order_col).to_pylist()
+            assert all(abs(a - b) <= 1e-9 * max(1.0, abs(b)) for a, b in zip(gc, wc)), (qn, gc, wc)
