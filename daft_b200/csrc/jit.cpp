@@ -56,7 +56,7 @@ enum BinOp { B_ADD = 0, B_SUB, B_MUL, B_TRUE_DIV, B_FLOOR_DIV, B_MOD, B_LT, B_LE
              B_XOR, B_EQ_NULL_SAFE, B_SHL, B_SHR };
 enum UnOp { U_NOT = 0, U_NEG, U_IS_NULL, U_NOT_NULL, U_ABS };
 enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT,
-          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC };
+          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC, F_SUBSTR };
 
 struct Node {
     int tag = 0, op = 0;
@@ -295,6 +295,17 @@ static int parse_node(Reader &r, Ast &a) {
                     if (u.tag != T_LIT || u.dtype != B200_I64 || u.lit_null || u.lit_i <= 0) fail("plan: the truncate interval must be a positive Int64 literal (microseconds)");
                     nd.dtype = B200_TIMESTAMP;
                     nd.nullable = a.nodes[nd.kids[0]].nullable;
+                    break;
+                }
+                case F_SUBSTR: {  // utf8 substr(start, length) in characters (src/daft-functions-utf8/src/substr.rs:269-294): null when the value has
+                                  // no character at `start` or the length is 0; a length literal of -1 stands for "to the end"
+                    if (nd.kids.size() != 3 || !is_string(a.nodes[nd.kids[0]].dtype)) fail("plan: substr needs a string operand, a start and a length");
+                    for (int i = 1; i <= 2; i++) {
+                        const Node &l = a.nodes[nd.kids[i]];
+                        if (l.tag != T_LIT || l.dtype != B200_I64 || l.lit_null || l.lit_i < (i == 1 ? 0 : -1)) fail("plan: substr start / length must be Int64 literals (start >= 0, length >= -1)");
+                    }
+                    nd.dtype = a.nodes[nd.kids[0]].dtype;
+                    nd.nullable = true;
                     break;
                 }
                 default: fail("plan: unknown function");
@@ -704,6 +715,12 @@ struct ExprGen {
                         allk = k(kid[0]);
                         break;
                     }
+                    case F_SUBSTR:
+                        os << "    bool " << pfx << "ok" << id << " = false;\n";
+                        os << "    const Str " << V << " = str_substr(" << a << ", (int64_t)" << cg.ast.nodes[kid[1]].lit_i << "LL, (int64_t)" << cg.ast.nodes[kid[2]].lit_i
+                           << "LL, " << pfx << "ok" << id << ");\n";
+                        allk = k(kid[0]) + " && " + pfx + "ok" + std::to_string(id);
+                        break;
                     case F_HOUR: os << "    const uint32_t " << V << " = ts_hour((int64_t)" << a << ");\n"; break;
                     case F_MINUTE: os << "    const uint32_t " << V << " = ts_minute((int64_t)" << a << ");\n"; break;
                     case F_SECOND: os << "    const uint32_t " << V << " = ts_second((int64_t)" << a << ");\n"; break;

@@ -176,6 +176,32 @@ __device__ __forceinline__ Str str_left(Str a, int64_t nchars) {
     return Str{a.p, i};
 }
 
+// utf8 substr in CHARACTERS (src/daft-functions-utf8/src/substr.rs:269-294): the value has no character at `start`, or `nchars` == 0 -> null
+// (ok = false); nchars < 0 = to the end of the value
+__device__ __forceinline__ Str str_substr(Str a, int64_t start, int64_t nchars, bool &ok) {
+    int64_t c = 0, i = 0;
+    for (; i < a.len; i++) {
+        if ((a.p[i] & 0xC0) != 0x80) {
+            if (c == start) break;
+            c++;
+        }
+    }
+    if (i >= a.len || nchars == 0) {
+        ok = false;
+        return Str{a.p, 0};
+    }
+    ok = true;
+    if (nchars < 0) return Str{a.p + i, a.len - i};
+    int64_t j = i, cc = 0;
+    for (; j < a.len; j++) {
+        if ((a.p[j] & 0xC0) != 0x80) {
+            if (cc == nchars) break;
+            cc++;
+        }
+    }
+    return Str{a.p + i, j - i};
+}
+
 // ---- civil calendar from days since 1970-01-01 (proleptic Gregorian) --------------------------------
 __device__ __forceinline__ void civil_from_days(int64_t z, int32_t &y, int32_t &m, int32_t &d) {
     z += 719468;

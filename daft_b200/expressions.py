@@ -20,7 +20,7 @@ BINOPS = {"add": 0, "sub": 1, "mul": 2, "true_div": 3, "floor_div": 4, "mod": 5,
 UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
          "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15,
-         "round": 16, "match_seq": 17, "hour": 18, "minute": 19, "second": 20, "ts_trunc": 21}
+         "round": 16, "match_seq": 17, "hour": 18, "minute": 19, "second": 20, "ts_trunc": 21, "substr": 22}
 AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5, "list": 6, "set": 7, "concat": 8}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
 _CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
@@ -121,6 +121,12 @@ class Expression:
     def endswith(self, pat): return Expression("function", "endswith", (self, _to_expr(pat)))
     def contains(self, pat): return Expression("function", "contains", (self, _to_expr(pat)))
     def left(self, n): return Expression("function", "left", (self, _to_expr(n)))
+    def substr(self, start: int, length: int | None = None):
+        """utf8 substr(start, length) in characters, 0-based (src/daft-functions-utf8/src/substr.rs:269-294): null when the value has no
+        character at `start` or `length` is 0; `length=None` runs to the end.  `start` and `length` are literals."""
+        if int(start) < 0 or (length is not None and int(length) < 0):
+            raise ValueError("substr: start and length must not be negative")
+        return Expression("function", "substr", (self, lit(int(start), dt.I64), lit(-1 if length is None else int(length), dt.I64)))
 
     # ---- aggregations (AggExpr, src/daft-dsl/src/expr/mod.rs) ----
     def _agg(self, kind, mode="valid"): return Expression("agg", kind, (self,), value=mode)
@@ -416,7 +422,11 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         kids = [bind(x, names, dtypes) for x in e.args]
         out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,
                "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8, "sqrt": dt.F64,
-               "hour": dt.U32, "minute": dt.U32, "second": dt.U32, "ts_trunc": dt.TIMESTAMP}[e.op]
+               "hour": dt.U32, "minute": dt.U32, "second": dt.U32, "ts_trunc": dt.TIMESTAMP, "substr": dt.LARGE_UTF8}[e.op]
+        if e.op == "substr":
+            if not dt.is_string(kids[0].dtype):
+                raise ValueError(f"Expects input to substr to be utf8, but received {dt.NAMES[kids[0].dtype]}")
+            out = kids[0].dtype
         if e.op in ("hour", "minute", "second", "ts_trunc") and kids[0].dtype != dt.TIMESTAMP:
             raise ValueError(f"Expected input to {e.op} to be a timestamp, got {dt.NAMES[kids[0].dtype]}")
         if e.op in ("utf8_length", "startswith", "endswith", "contains", "left") and not dt.is_string(kids[0].dtype):

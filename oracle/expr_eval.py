@@ -271,6 +271,15 @@ def _eval(b: Bound, cols, n: int):
             if fn == "startswith": return np.array([x.startswith(p) for x, p in zip(a, pat)], dtype=bool), allk
             if fn == "endswith": return np.array([x.endswith(p) for x, p in zip(a, pat)], dtype=bool), allk
             if fn == "contains": return np.array([p in x for x, p in zip(a, pat)], dtype=bool), allk
+            if fn == "substr":   # substring(), src/daft-functions-utf8/src/substr.rs:269-294
+                start, ln = int(kids[1][0][0]) if len(kids[1][0]) else 0, int(kids[2][0][0]) if len(kids[2][0]) else -1
+                out, ok = [], []
+                for x in a:
+                    chars = x.decode("utf-8", "ignore")
+                    good = start < len(chars) and ln != 0
+                    ok.append(good)
+                    out.append((chars[start:] if ln < 0 else chars[start:start + ln]).encode() if good else b"")
+                return np.array(out, dtype=object), kids[0][1] & np.array(ok, dtype=bool) if n else kids[0][1]
             if fn == "left":
                 return np.array([x.decode("utf-8", "ignore")[:max(int(k), 0)].encode() for x, k in zip(a, pat)], dtype=object), allk
     raise NotImplementedError(b.tag)

@@ -57,3 +57,32 @@ def test_expression_names():
     assert (col("a") * 2).alias("z").name() == "z"
     assert col("a").sum().name() == "a"
     assert col("a").is_in([1, 2]).name() == "a"
+
+
+def test_substr_reference_literal_generated_code_and_nvrtc(tmp_path):
+    """utf8 substr (tests/recordbatch/utf8/test_substr.py:7-10; substring(), src/daft-functions-utf8/src/substr.rs:269-294): oracle == the
+    reference's literal, the generated code on the host == oracle (multi-byte characters, starts past the end, zero lengths), and the
+    kernel compiles for sm_100a"""
+    import ctypes
+    import pyarrow as pa
+    from daft_b200 import _lib, col
+    from daft_b200 import datatypes as dt
+    from daft_b200.expressions import encode_project
+    from jit_emu import emulate_project
+    from oracle import expr_eval as E
+    t = pa.table({"col": pa.array(["foo", None, "barbarbar", "quux", "1", "", "héllo wörld", "日本語テキスト"], pa.large_string())})
+    got = E.eval_expression_list(t, [col("col").substr(0, 5)])
+    assert got.to_pydict() == {"col": ["foo", None, "barba", "quux", "1", None, "héllo", "日本語テキ"]}
+    exprs = [col("col").substr(0, 5).alias("a"), col("col").substr(2).alias("b"), col("col").substr(1, 0).alias("c"), col("col").substr(3, 2).alias("d"),
+             col("col").substr(4, 100).alias("e"), col("col").substr(1, 3).length().alias("n")]
+    assert emulate_project(t, exprs).equals(E.eval_expression_list(t, exprs))
+    _lib.call("b200_set_jit_cache_dir", str(tmp_path).encode())
+    plan, _, odt = encode_project(exprs, ["col"], [dt.LARGE_UTF8])
+    assert odt[:5] == [dt.LARGE_UTF8] * 5
+    for nullable in (0, 1):
+        _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 1)(dt.LARGE_UTF8), (ctypes.c_uint8 * 1)(nullable), ctypes.c_int32(1))
+    import pytest
+    with pytest.raises(ValueError, match="must not be negative"):
+        col("col").substr(-1)
+    with pytest.raises(ValueError, match="to be utf8"):
+        encode_project([col("x").substr(0, 1)], ["x"], [dt.I64])
