@@ -32,7 +32,8 @@ def gen_num(rng, depth):
             return lit([0, 1, -1, 7, 2.5, -0.5, 1000, None][rng.integers(0, 8)])
         return col(NUM[rng.integers(0, len(NUM))])
     if r < 0.32:   # leaves derived from the date / string columns
-        return [col("d").year(), col("d").month(), col("d").day(), col("d").day_of_week(), col("s").length(), gen_str(rng, 1).length()][rng.integers(0, 6)]
+        return [col("d").year(), col("d").month(), col("d").day(), col("d").day_of_week(), col("s").length(), gen_str(rng, 1).length(),
+                col("ts").hour(), col("ts").minute(), col("ts").second(), col("ts").truncate(["second", "minute", "hour", "day"][rng.integers(0, 4)]).minute()][rng.integers(0, 10)]
     a, b = gen_num(rng, depth - 1), gen_num(rng, depth - 1)
     k = rng.integers(0, 20)
     if k == 18: return a << lit(int(rng.integers(0, 8)))
@@ -91,7 +92,8 @@ def gen_str(rng, depth):
     r = rng.random()
     if depth == 0 or r < 0.4:
         return col("s") if rng.random() < 0.8 else lit(["a", "bb", "", "TPC-H", None][rng.integers(0, 5)])
-    k = rng.integers(0, 3)
+    k = rng.integers(0, 4)
+    if k == 3: return gen_str(rng, depth - 1).substr(int(rng.integers(0, 5)), [None, 0, 1, 3, 40][rng.integers(0, 5)])
     if k == 0: return gen_str(rng, depth - 1).left(int(rng.integers(0, 6)))
     if k == 1: return gen_bool(rng, depth - 1).if_else(gen_str(rng, depth - 1), gen_str(rng, depth - 1))
     return gen_str(rng, depth - 1).fill_null(gen_str(rng, depth - 1))
@@ -100,6 +102,9 @@ def gen_str(rng, depth):
 def batch(seed, nexpr, n=600, nulls=0.15):
     rng = np.random.default_rng(seed)
     tbl = random_table(rng, n, nulls)
+    # a timestamp column of its own (random_table is shared with the device tests and stays as it is): instants on both sides of the epoch
+    ts = pa.array(rng.integers(-10**15, 2 * 10**15, n), type=pa.timestamp("us"), mask=rng.random(n) < nulls)
+    tbl = tbl.append_column("ts", ts)
     exprs = []
     while len(exprs) < nexpr:
         u = rng.random()
