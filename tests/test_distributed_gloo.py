@@ -161,13 +161,13 @@ def _gloo_oracle_backend(rank, world):
                 dist.all_gather_object(parts, distributed._to_ipc(pieces[dst]))
                 if dst == rank:
                     mine = parts
-            return OracleRecordBatch(pa.concat_tables([distributed._from_ipc(p) for p in mine]))
+            return batch.__class__(pa.concat_tables([distributed._from_ipc(p) for p in mine]))
 
         def all_gather(self, batch):
             self.calls["gather"] += 1
             parts = [None] * world
             dist.all_gather_object(parts, distributed._to_ipc(batch.tbl))
-            return OracleRecordBatch(pa.concat_tables([distributed._from_ipc(p) for p in parts]))
+            return batch.__class__(pa.concat_tables([distributed._from_ipc(p) for p in parts]))
 
         def allreduce_sum(self, value):
             t = torch.tensor([int(value)], dtype=torch.int64)
@@ -176,7 +176,7 @@ def _gloo_oracle_backend(rank, world):
     return Backend()
 
 
-def _plan_worker(rank, world, port, q, gather_rows):
+def _plan_worker(rank, world, port, q, gather_rows, emulated=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -187,6 +187,9 @@ def _plan_worker(rank, world, port, q, gather_rows):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         backend, out = _gloo_oracle_backend(rank, world), {}
+        Local = OracleRecordBatch
+        if emulated:   # the plans the planner submits (first / second stage aggregates, key casts) through the GENERATED code on the host
+            from test_tpch_all_emulated_cpu import EmulatedQueryBatch as Local
         sf_of = {2: 0.05, 8: 0.05, 16: 0.05, 17: 0.05, 18: 0.05, 20: 0.05}
         for qn in range(1, 23):
             name, sf = f"q{qn}", sf_of.get(qn, 0.01)
@@ -194,7 +197,7 @@ def _plan_worker(rank, world, port, q, gather_rows):
             shards = {}
             for t, c in cols.items():
                 b, e = distributed.shard_rows(tpch.num_rows(t, sf), rank, world)
-                shards[t] = Sharded(OracleRecordBatch(tpch.generate_host(t, sf, c, b, e)), backend, gather_rows=gather_rows)
+                shards[t] = Sharded(Local(tpch.generate_host(t, sf, c, b, e)), backend, gather_rows=gather_rows)
             res = getattr(tpch, name)(shards["lineitem"] if qn in (1, 6) else shards).to_arrow_table()
             out[qn] = distributed._to_ipc(res)
         out["calls"] = dict(backend.calls)
@@ -204,8 +207,8 @@ def _plan_worker(rank, world, port, q, gather_rows):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("gather_rows", [1 << 20, 300])
-def test_all_22_queries_over_two_ranks_gloo(gather_rows):
+@pytest.mark.parametrize("gather_rows,emulated", [(1 << 20, False), (300, False), (300, True), (1 << 20, True)])
+def test_all_22_queries_over_two_ranks_gloo(gather_rows, emulated):
     """config 4's shape on the CPU: every query over two scan partitions per table, joins and aggregates crossing the ranks through the
     planner's exchanges (gather_rows = 300 forces the repartitioning routes, 2^20 the gather / broadcast routes), against the
     single-process oracle answer"""
@@ -216,8 +219,8 @@ def test_all_22_queries_over_two_ranks_gloo(gather_rows):
     from oracle.recordbatch import OracleRecordBatch
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + ((os.getpid() + 31 + gather_rows % 97) % 1000)
-    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, q, gather_rows)) for r in range(2)]
+    port = 29500 + ((os.getpid() + 31 + gather_rows % 97 + (211 if emulated else 0)) % 1000)
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, q, gather_rows, emulated)) for r in range(2)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=800) for _ in procs)
