@@ -40,6 +40,15 @@
  *                                                             src/daft-local-execution/src/join/ (all files)
  *   b200_exchange_*           RepartitionSink + Flight shuffle src/daft-local-execution/src/sinks/repartition.rs:100-370,
  *                                                             src/daft-shuffles/src/ (all files)
+ *   b200_merge_join_sorted / b200_asof_join_sorted / b200_cross_join
+ *                             RecordBatch::sort_merge_join / asof_join / cross_join
+ *                                                             src/daft-recordbatch/src/ops/joins/mod.rs:81-111,154-284
+ *   b200_window_ranks / b200_window_offset
+ *                             RecordBatch::window_row_number / window_rank / window_offset
+ *                                                             src/daft-recordbatch/src/ops/window.rs:636-790
+ *   b200_parquet_read         stream_parquet behind the scan-task source
+ *                                                             src/daft-parquet/src/read.rs:553,
+ *                                                             src/daft-local-execution/src/sources/scan_task.rs:33
  */
 #ifndef DAFT_B200_H
 #define DAFT_B200_H
