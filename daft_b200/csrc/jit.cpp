@@ -56,7 +56,7 @@ enum BinOp { B_ADD = 0, B_SUB, B_MUL, B_TRUE_DIV, B_FLOOR_DIV, B_MOD, B_LT, B_LE
              B_XOR, B_EQ_NULL_SAFE, B_SHL, B_SHR };
 enum UnOp { U_NOT = 0, U_NEG, U_IS_NULL, U_NOT_NULL, U_ABS };
 enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT,
-          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC, F_SUBSTR };
+          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC, F_SUBSTR, F_RX_MATCH, F_RX_EXTRACT, F_RX_REPLACE_GROUP };
 
 struct Node {
     int tag = 0, op = 0;
@@ -306,6 +306,30 @@ static int parse_node(Reader &r, Ast &a) {
                     }
                     nd.dtype = a.nodes[nd.kids[0]].dtype;
                     nd.nullable = true;
+                    break;
+                }
+                case F_RX_MATCH: case F_RX_EXTRACT: case F_RX_REPLACE_GROUP: {
+                    // regular expressions (daft_b200/regex.py compiles the pattern on the host): operand, the VM program as a binary literal,
+                    // the pattern text (kept for diagnostics and the oracle).  match -> Boolean; extract -> the selected group or null
+                    // (src/daft-functions-utf8/src/extract.rs); replace_group -> the group when the (fully anchored) pattern matches,
+                    // the value unchanged when it does not (regexp_replace(x, '^...(g)...$', '\\1'), replace.rs)
+                    if (nd.kids.size() != 3 || !is_string(a.nodes[nd.kids[0]].dtype)) fail("plan: a regex function needs a string operand, a program and a pattern");
+                    const Node &prog = a.nodes[nd.kids[1]];
+                    if (prog.tag != T_LIT || !is_string(prog.dtype) || prog.lit_null || prog.lit_s.size() < 5) fail("plan: the regex program must be a binary literal");
+                    const size_t ninst = (unsigned char)prog.lit_s[0];
+                    if (ninst == 0 || ninst > 64 || prog.lit_s.size() < 1 + 4 * ninst) fail("plan: malformed regex program");
+                    for (size_t i = 0; i < ninst; i++) {   // every jump stays inside the program, every class table inside the literal
+                        const unsigned char *in = (const unsigned char *)prog.lit_s.data() + 1 + 4 * i;
+                        if (in[0] > 9) fail("plan: unknown regex instruction");
+                        if ((in[0] == 4 && (in[1] >= ninst || in[2] >= ninst)) || (in[0] == 5 && in[1] >= ninst)) fail("plan: regex jump out of range");
+                        if (in[0] == 3) {
+                            const size_t off = (size_t)in[1] | ((size_t)in[3] << 8);
+                            if (off >= prog.lit_s.size() || off + 1 + 2 * (size_t)(unsigned char)prog.lit_s[off] > prog.lit_s.size()) fail("plan: regex class table out of range");
+                        }
+                        if (in[0] != 0 && in[0] != 4 && in[0] != 5 && i + 1 >= ninst) fail("plan: regex program runs off its end");
+                    }
+                    nd.dtype = nd.op == F_RX_MATCH ? B200_BOOL : a.nodes[nd.kids[0]].dtype;
+                    nd.nullable = nd.op == F_RX_EXTRACT ? true : a.nodes[nd.kids[0]].nullable;
                     break;
                 }
                 default: fail("plan: unknown function");
@@ -713,6 +737,24 @@ struct ExprGen {
                         if (nseg == 0 && (flags & 3) == 3) os << "      " << V << " = " << a << ".len == 0;\n";
                         os << "    }\n";
                         allk = k(kid[0]);
+                        break;
+                    }
+                    case F_RX_MATCH:
+                        os << "    const bool " << V << " = rx_exec(" << a << ", " << v(kid[1]) << ").matched;\n";
+                        allk = k(kid[0]);
+                        break;
+                    case F_RX_EXTRACT: case F_RX_REPLACE_GROUP: {
+                        const std::string r_ = pfx + "rx" + std::to_string(id);
+                        os << "    const RxResult " << r_ << " = rx_exec(" << a << ", " << v(kid[1]) << ");\n";
+                        if (n.op == F_RX_EXTRACT) {
+                            os << "    const Str " << V << " = (" << r_ << ".matched && " << r_ << ".c0 >= 0) ? Str{" << a << ".p + " << r_ << ".c0, (int64_t)(" << r_ << ".c1 - " << r_
+                               << ".c0)} : Str{" << a << ".p, 0};\n";
+                            allk = k(kid[0]) + " && " + r_ + ".matched && " + r_ + ".c0 >= 0";
+                        } else {
+                            os << "    const Str " << V << " = !" << r_ << ".matched ? " << a << " : (" << r_ << ".c0 >= 0 ? Str{" << a << ".p + " << r_ << ".c0, (int64_t)(" << r_
+                               << ".c1 - " << r_ << ".c0)} : Str{" << a << ".p, 0});\n";
+                            allk = k(kid[0]);
+                        }
                         break;
                     }
                     case F_SUBSTR:

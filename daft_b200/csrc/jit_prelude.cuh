@@ -202,6 +202,132 @@ __device__ __forceinline__ Str str_substr(Str a, int64_t start, int64_t nchars, 
     return Str{a.p + i, j - i};
 }
 
+// ---- regular expressions: a Pike VM over the program daft_b200/regex.py compiles on the host ------------------------
+// Leftmost-first semantics (the `regex` crate's, src/daft-functions-utf8/src/{match_.rs,extract.rs,replace.rs}); O(len x instructions) per
+// value, no backtracking.  Program: [ninst <= 64] [ninst x (op, a, b, c)] [class tables].  Steps over BYTES: `.` and classes that can
+// match a non-ASCII character take a character's first byte, RX_TAIL its continuation bytes; threads never start inside a character.
+enum { RX_MATCH = 0, RX_CHAR, RX_ANY, RX_CLASS, RX_SPLIT, RX_JMP, RX_SAVE, RX_BOL, RX_EOL, RX_TAIL };
+struct RxResult {
+    bool matched;
+    int32_t c0, c1;   // byte span of the selected capture group (-1: it took no part in the match)
+};
+struct RxList {
+    uint64_t added;
+    int n;
+    uint8_t pc[64];
+    int32_t c0[64], c1[64];
+};
+__device__ __forceinline__ void rx_add(RxList &l, const uint8_t *prog, Str s, int pc0, int64_t pos, int32_t a0, int32_t b0) {
+    uint8_t spc[64];
+    int32_t sa[64], sb[64];
+    int sp = 0;
+    spc[0] = (uint8_t)pc0;
+    sa[0] = a0;
+    sb[0] = b0;
+    sp = 1;
+    while (sp > 0) {
+        sp--;
+        int pc = spc[sp];
+        int32_t a = sa[sp], b = sb[sp];
+        for (;;) {
+            if ((l.added >> pc) & 1ULL) break;
+            l.added |= 1ULL << pc;
+            const uint8_t *in = prog + 1 + 4 * pc;
+            const int op = in[0];
+            if (op == RX_JMP) {
+                pc = in[1];
+                continue;
+            }
+            if (op == RX_SPLIT) {
+                spc[sp] = in[2];   // the second branch waits: everything the first one reaches comes before it in the list
+                sa[sp] = a;
+                sb[sp] = b;
+                sp++;
+                pc = in[1];
+                continue;
+            }
+            if (op == RX_SAVE) {
+                if (in[1] == 0) a = (int32_t)pos;
+                else b = (int32_t)pos;
+                pc++;
+                continue;
+            }
+            if (op == RX_BOL) {
+                if (pos == 0) {
+                    pc++;
+                    continue;
+                }
+                break;
+            }
+            if (op == RX_EOL) {
+                if (pos == s.len) {
+                    pc++;
+                    continue;
+                }
+                break;
+            }
+            if (op == RX_TAIL && !(pos < s.len && (s.p[pos] & 0xC0) == 0x80)) {
+                pc++;
+                continue;
+            }
+            l.pc[l.n] = (uint8_t)pc;
+            l.c0[l.n] = a;
+            l.c1[l.n] = b;
+            l.n++;
+            break;
+        }
+    }
+}
+__device__ __forceinline__ RxResult rx_exec(Str s, Str program) {
+    const uint8_t *prog = program.p;
+    RxList lists[2];
+    int cur = 0;
+    lists[0].added = 0;
+    lists[0].n = 0;
+    RxResult res{false, -1, -1};
+    for (int64_t pos = 0; pos <= s.len; pos++) {
+        RxList &cl = lists[cur], &nl = lists[cur ^ 1];
+        if (!res.matched) rx_add(cl, prog, s, 0, pos, -1, -1);   // unanchored search: a fresh thread, behind every running one
+        nl.added = 0;
+        nl.n = 0;
+        for (int t = 0; t < cl.n; t++) {
+            const int pc = cl.pc[t];
+            const uint8_t *in = prog + 1 + 4 * pc;
+            const int op = in[0];
+            if (op == RX_MATCH) {
+                res.matched = true;
+                res.c0 = cl.c0[t];
+                res.c1 = cl.c1[t];
+                break;   // threads behind this one have lower priority
+            }
+            if (pos >= s.len) continue;
+            const uint8_t ch = s.p[pos];
+            const bool cont = (ch & 0xC0) == 0x80;
+            bool ok = false;
+            int next = pc + 1;
+            if (op == RX_CHAR) ok = ch == in[1];
+            else if (op == RX_ANY) ok = ch != 10 && !cont;
+            else if (op == RX_TAIL) {
+                ok = true;   // parked on a continuation byte by rx_add
+                next = pc;
+            } else if (op == RX_CLASS) {
+                if (ch < 128) {
+                    const uint8_t *tab = prog + ((int)in[1] | ((int)in[3] << 8));
+                    bool in_set = false;
+                    for (int k = 0; k < tab[0]; k++) in_set = in_set || (tab[1 + 2 * k] <= ch && ch <= tab[2 + 2 * k]);
+                    ok = in_set != ((in[2] & 1) != 0);
+                } else {
+                    ok = (in[2] & 2) != 0 && !cont;
+                }
+            }
+            if (ok) rx_add(nl, prog, s, next, pos + 1, cl.c0[t], cl.c1[t]);
+        }
+        cur ^= 1;
+        if (lists[cur].n == 0 && res.matched) break;
+    }
+    return res;
+}
+
 // ---- civil calendar from days since 1970-01-01 (proleptic Gregorian) --------------------------------
 __device__ __forceinline__ void civil_from_days(int64_t z, int32_t &y, int32_t &m, int32_t &d) {
     z += 719468;

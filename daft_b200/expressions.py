@@ -20,7 +20,8 @@ BINOPS = {"add": 0, "sub": 1, "mul": 2, "true_div": 3, "floor_div": 4, "mod": 5,
 UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
          "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15,
-         "round": 16, "match_seq": 17, "hour": 18, "minute": 19, "second": 20, "ts_trunc": 21, "substr": 22}
+         "round": 16, "match_seq": 17, "hour": 18, "minute": 19, "second": 20, "ts_trunc": 21, "substr": 22, "rx_match": 23, "rx_extract": 24,
+         "rx_replace_group": 25}
 AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5, "list": 6, "set": 7, "concat": 8}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
 _CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
@@ -148,9 +149,33 @@ class Expression:
         """Float round to `decimals` places, half away from zero: (v * 10^d).round() / 10^d (src/daft-core/src/array/ops/round.rs:14-35)."""
         return Expression("function", "round", (self, lit(int(decimals), dt.I32)))
     def match(self, pattern: str):
-        """utf8 `match` (regex search, src/daft-functions-utf8/src/match_.rs) for the patterns TPC-H and ClickBench use: literal
-        segments separated by `.*`, optionally anchored with ^ / $ (".*special.*requests.*").  Anything else is refused."""
-        return Expression("function", "match_seq", (self, *_segments_of_regex(pattern)))
+        """utf8 `match` (regex search, src/daft-functions-utf8/src/match_.rs).  Literal segments separated by `.*`, optionally anchored with
+        ^ / $ (".*special.*requests.*": the TPC-H shapes) run as substring searches; any other pattern of the supported regex subset
+        (daft_b200/regex.py) runs in the device's Pike VM."""
+        try:
+            return Expression("function", "match_seq", (self, *_segments_of_regex(pattern)))
+        except NotImplementedError:
+            from . import regex
+            return Expression("function", "rx_match", (self, lit(regex.compile_program(pattern, None), dt.LARGE_BINARY), lit(pattern)))
+    def regexp(self, pattern: str):
+        return self.match(pattern)
+    def regexp_extract(self, pattern: str, index: int = 0):
+        """utf8 `extract(pattern, index)` (src/daft-functions-utf8/src/extract.rs): the first match's capture group `index` (0 = the whole
+        match); null when the pattern does not match or the group took no part in the match."""
+        from . import regex
+        return Expression("function", "rx_extract", (self, lit(regex.compile_program(pattern, int(index)), dt.LARGE_BINARY), lit(pattern)), value=int(index))
+    def regexp_replace(self, pattern: str, replacement: str):
+        """utf8 `replace(pattern, replacement, regex=True)` / SQL REGEXP_REPLACE (src/daft-functions-utf8/src/replace.rs) for the form whose
+        result is a slice of the input: a pattern anchored at both ends (a match is then the whole value) replaced by ONE capture group
+        (`\\1`, `$1`, `${1}`), e.g. ClickBench Q28's host extraction.  Values that do not match stay as they are.  Other forms build new
+        strings and are refused."""
+        from . import regex
+        import re as _re
+        m = _re.fullmatch(r"\\(\d)|\$(\d)|\$\{(\d)\}", replacement)
+        if m is None or not regex.is_fully_anchored(pattern):
+            raise NotImplementedError("regexp_replace: only a fully anchored pattern (^...$) replaced by a single group reference is supported on the device")
+        group = int(next(g for g in m.groups() if g is not None))
+        return Expression("function", "rx_replace_group", (self, lit(regex.compile_program(pattern, group), dt.LARGE_BINARY), lit(pattern)), value=group)
     def like(self, pattern: str):
         """SQL LIKE with `%` wildcards (src/daft-functions-utf8/src/like.rs): anchored at both ends; `_` is refused."""
         return Expression("function", "match_seq", (self, *_segments_of_like(pattern)))
@@ -422,7 +447,13 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         kids = [bind(x, names, dtypes) for x in e.args]
         out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,
                "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8, "sqrt": dt.F64,
-               "hour": dt.U32, "minute": dt.U32, "second": dt.U32, "ts_trunc": dt.TIMESTAMP, "substr": dt.LARGE_UTF8}[e.op]
+               "hour": dt.U32, "minute": dt.U32, "second": dt.U32, "ts_trunc": dt.TIMESTAMP, "substr": dt.LARGE_UTF8,
+               "rx_match": dt.BOOL, "rx_extract": dt.LARGE_UTF8, "rx_replace_group": dt.LARGE_UTF8}[e.op]
+        if e.op in ("rx_match", "rx_extract", "rx_replace_group"):
+            if not dt.is_string(kids[0].dtype):
+                raise ValueError(f"Expects input to {e.op} to be utf8, but received {dt.NAMES[kids[0].dtype]}")
+            if e.op != "rx_match":
+                out = kids[0].dtype
         if e.op == "substr":
             if not dt.is_string(kids[0].dtype):
                 raise ValueError(f"Expects input to substr to be utf8, but received {dt.NAMES[kids[0].dtype]}")
@@ -443,7 +474,7 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
             # computed in the operand's floating representation (src/daft-schema/src/dtype.rs:756-772, numeric/sqrt.rs:27-35)
             out = dt.F32 if kids[0].dtype in (dt.I8, dt.I16, dt.U8, dt.U16, dt.F32) else dt.F64
             kids[0] = _cast(kids[0], out)
-        return Bound(T_FUNCTION, out, FUNCS[e.op], kids)
+        return Bound(T_FUNCTION, out, FUNCS[e.op], kids, value=e.value)
     if k == "agg":
         raise ValueError("aggregation expressions are only valid inside agg()")
     raise ValueError(k)

@@ -271,6 +271,28 @@ def _eval(b: Bound, cols, n: int):
             if fn == "startswith": return np.array([x.startswith(p) for x, p in zip(a, pat)], dtype=bool), allk
             if fn == "endswith": return np.array([x.endswith(p) for x, p in zip(a, pat)], dtype=bool), allk
             if fn == "contains": return np.array([p in x for x, p in zip(a, pat)], dtype=bool), allk
+            if fn in ("rx_match", "rx_extract", "rx_replace_group"):
+                # Python's `re` as the restatement of the regex crate's leftmost-first search (daft_b200/regex.py to_python translates the
+                # supported subset: `$` only at the very end, `.` without newline)
+                import re
+                from daft_b200 import regex as _rx
+                pattern = kids[2][0][0].decode() if len(kids[2][0]) else ""
+                rp = re.compile(_rx.to_python(pattern))
+                group = int(b.value) if getattr(b, "value", None) is not None else 0
+                texts = [x.decode("utf-8", "ignore") for x in a]
+                if fn == "rx_match":
+                    return np.array([rp.search(t) is not None for t in texts], dtype=bool), kids[0][1]
+                out, ok = [], []
+                for t in texts:
+                    m = rp.search(t)
+                    if fn == "rx_extract":
+                        good = m is not None and m.span(group) != (-1, -1)
+                        out.append(m.group(group).encode() if good else b"")
+                        ok.append(good)
+                    else:
+                        out.append(t.encode() if m is None else (m.group(group) or "").encode())
+                        ok.append(True)
+                return np.array(out, dtype=object), (kids[0][1] & np.array(ok, dtype=bool)) if n else kids[0][1]
             if fn == "substr":   # substring(), src/daft-functions-utf8/src/substr.rs:269-294
                 start, ln = int(kids[1][0][0]) if len(kids[1][0]) else 0, int(kids[2][0][0]) if len(kids[2][0]) else -1
                 out, ok = [], []

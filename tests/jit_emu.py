@@ -115,6 +115,26 @@ def describe_project(exprs, names, dtypes, nullable, with_take: bool = False):
     return src, ptrs, ints, outs, onames, odt
 
 
+
+def _build_so(so: str, cpp: str, source: str) -> None:
+    """g++ the generated source into `so`.  Several processes may want the same kernel at the same moment (the world-2 gloo tests): each
+    writes under a name of its own and renames into place, so that nobody ever loads a half-written library."""
+    uniq = f".{os.getpid()}.tmp"
+    with open(cpp + uniq, "w") as f:
+        f.write(source)
+    # -ffp-contract=off: the device code is compiled with --fmad=false.  -fno-builtin-fmod*: gcc otherwise reasons that
+    # fabs(fmod(x, y)) == fmod(x, y) for non-negative x and drops the fabs, which is visible when libm returns the
+    # negative x86 default NaN for fmod(x, 0).
+    try:
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w", "-x", "c++",
+                               *os.environ.get("B200_EMU_FLAGS", "").split(), "-o", so + uniq, cpp + uniq])
+        os.replace(so + uniq, so)
+    finally:
+        for leftover in (cpp + uniq, so + uniq):
+            if os.path.exists(leftover):
+                os.remove(leftover)
+
+
 def _compile(src: str) -> ctypes.CDLL:
     body = "\n".join(l for l in src.split("\n") if "__global__" not in l)
     full = _SHIM + _prelude_for_host() + body + _DRIVER
@@ -123,14 +143,7 @@ def _compile(src: str) -> ctypes.CDLL:
     os.makedirs(d, exist_ok=True)
     so = os.path.join(d, f"emu_{tag}.so")
     if not os.path.exists(so):
-        cpp = os.path.join(d, f"emu_{tag}.cpp")
-        with open(cpp, "w") as f:
-            f.write(full)
-        # -ffp-contract=off: the device code is compiled with --fmad=false.  -fno-builtin-fmod*: gcc otherwise reasons that
-        # fabs(fmod(x, y)) == fmod(x, y) for non-negative x and drops the fabs, which is visible when libm returns the
-        # negative x86 default NaN for fmod(x, 0).
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w", *os.environ.get("B200_EMU_FLAGS", "").split(),
-                               "-o", so, cpp])
+        _build_so(so, os.path.join(d, f"emu_{tag}.cpp"), full)
     return ctypes.CDLL(so)
 
 
@@ -453,11 +466,7 @@ def _compile_agg(src: str, staged: bool = False, tier1: bool = False) -> ctypes.
     os.makedirs(d, exist_ok=True)
     so = os.path.join(d, f"emuagg_{tag}.so")
     if not os.path.exists(so):
-        cpp = os.path.join(d, f"emuagg_{tag}.cpp")
-        with open(cpp, "w") as fh:
-            fh.write(full)
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w", *os.environ.get("B200_EMU_FLAGS", "").split(),
-                               "-o", so, cpp])
+        _build_so(so, os.path.join(d, f"emuagg_{tag}.cpp"), full)
     return ctypes.CDLL(so)
 
 
@@ -682,11 +691,7 @@ def emulate_filter(tbl: pa.Table, predicates) -> pa.Table:
     os.makedirs(d, exist_ok=True)
     so = os.path.join(d, f"emufilter_{tag}.so")
     if not os.path.exists(so):
-        cpp = os.path.join(d, f"emufilter_{tag}.cpp")
-        with open(cpp, "w") as fh:
-            fh.write(full)
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-builtin-fmod", "-fno-builtin-fmodf", "-fPIC", "-shared", "-w", *os.environ.get("B200_EMU_FLAGS", "").split(),
-                               "-o", so, cpp])
+        _build_so(so, os.path.join(d, f"emufilter_{tag}.cpp"), full)
     lib = ctypes.CDLL(so)
     nw = max((n + 31) // 32, 1)
     keep, slots, copied = [], [], {}

@@ -244,7 +244,7 @@ def test_all_22_queries_over_two_ranks_gloo(gather_rows, emulated):
 
 
 # ---- ClickBench over two ranks: count_distinct / string min (composite aggregates), LIKE filters, top-N with offsets ----
-CB_KW = {27: {"having": 30}, 38: {"offset": 20}, 39: {"offset": 30}, 40: {"offset": 5}, 41: {"offset": 2}, 42: {"offset": 40}}
+CB_KW = {27: {"having": 30}, 28: {"having": 30}, 38: {"offset": 20}, 39: {"offset": 30}, 40: {"offset": 5}, 41: {"offset": 2}, 42: {"offset": 40}}
 
 
 def _clickbench_worker(rank, world, port, q, gather_rows):
@@ -298,7 +298,7 @@ def test_clickbench_over_two_ranks_gloo(gather_rows):
         key = lambda r: tuple((0, "") if v is None else (1, round(v, 9)) if isinstance(v, float) else (1, v) for v in r)   # noqa: E731
         g = sorted(zip(*[c.to_pylist() for c in got.columns]), key=key) if got.num_columns else []
         w = sorted(zip(*[c.to_pylist() for c in want.columns]), key=key) if want.num_columns else []
-        order_col = {7: "c", 8: "u", 9: "c", 10: "u", 11: "u", 12: "c", 13: "u", 14: "c", 15: "c", 16: "c", 18: "c", 21: "c", 22: "c", 27: "l", 30: "c", 31: "c", 32: "c",
+        order_col = {7: "c", 8: "u", 9: "c", 10: "u", 11: "u", 12: "c", 13: "u", 14: "c", 15: "c", 16: "c", 18: "c", 21: "c", 22: "c", 27: "l", 28: "l", 30: "c", 31: "c", 32: "c",
                      33: "c", 34: "c", 35: "c", 36: "PageViews", 37: "PageViews", 38: "PageViews", 39: "PageViews", 40: "PageViews", 41: "PageViews"}.get(qn)
         if order_col is None:
             assert [key(r) for r in g] == [key(r) for r in w], qn

@@ -317,7 +317,8 @@ def test_generated_round_and_match_patterns():
         if w is not None:
             assert d["m1"][i] == (w.find("special") >= 0 and w.find("requests", w.find("special") + 7) >= 0)
             assert d["l5"][i] == (w.startswith("ab") and w.endswith("c") and len(w) >= 3)
-    with pytest.raises(NotImplementedError):
-        col("s").match("a+b")
+    assert col("s").match("a+b").op == "rx_match"          # beyond literal segments: the regex VM (tests/test_regex_cpu.py)
+    with pytest.raises(ValueError):
+        col("s").match("(?=a)b")                            # outside the supported regex subset
     with pytest.raises(NotImplementedError):
         col("s").like("a_c")
