@@ -56,7 +56,7 @@ enum BinOp { B_ADD = 0, B_SUB, B_MUL, B_TRUE_DIV, B_FLOOR_DIV, B_MOD, B_LT, B_LE
              B_XOR, B_EQ_NULL_SAFE, B_SHL, B_SHR };
 enum UnOp { U_NOT = 0, U_NEG, U_IS_NULL, U_NOT_NULL, U_ABS };
 enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT,
-          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC, F_SUBSTR, F_RX_MATCH, F_RX_EXTRACT, F_RX_REPLACE_GROUP };
+          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC, F_SUBSTR, F_RX_MATCH, F_RX_EXTRACT, F_RX_REPLACE_GROUP, F_TS_DATE };
 
 struct Node {
     int tag = 0, op = 0;
@@ -306,6 +306,11 @@ static int parse_node(Reader &r, Ast &a) {
                     }
                     nd.dtype = a.nodes[nd.kids[0]].dtype;
                     nd.nullable = true;
+                    break;
+                }
+                case F_TS_DATE: {  // dt.date() of a Timestamp(us): days since the epoch, floor semantics
+                    if (nd.kids.size() != 1 || a.nodes[nd.kids[0]].dtype != B200_TIMESTAMP) fail("plan: date() needs one timestamp operand");
+                    nd.dtype = B200_DATE32;
                     break;
                 }
                 case F_RX_MATCH: case F_RX_EXTRACT: case F_RX_REPLACE_GROUP: {
@@ -739,6 +744,7 @@ struct ExprGen {
                         allk = k(kid[0]);
                         break;
                     }
+                    case F_TS_DATE: os << "    const int32_t " << V << " = (int32_t)((" << a << " - ts_floor_mod((int64_t)" << a << ", 86400000000LL)) / 86400000000LL);\n"; break;
                     case F_RX_MATCH:
                         os << "    const bool " << V << " = rx_exec(" << a << ", " << v(kid[1]) << ").matched;\n";
                         allk = k(kid[0]);

@@ -21,7 +21,7 @@ UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
          "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15,
          "round": 16, "match_seq": 17, "hour": 18, "minute": 19, "second": 20, "ts_trunc": 21, "substr": 22, "rx_match": 23, "rx_extract": 24,
-         "rx_replace_group": 25}
+         "rx_replace_group": 25, "ts_date": 26}
 AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5, "list": 6, "set": 7, "concat": 8}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
 _CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
@@ -107,6 +107,7 @@ class Expression:
     def month(self): return Expression("function", "month", (self,))
     def day(self): return Expression("function", "day", (self,))
     def day_of_week(self): return Expression("function", "day_of_week", (self,))
+    def date(self): return Expression("function", "ts_date", (self,))    # dt.date(): the day of a Timestamp(us) as a Date
     def hour(self): return Expression("function", "hour", (self,))       # of a Timestamp; extract(hour / minute / second from ts)
     def minute(self): return Expression("function", "minute", (self,))
     def second(self): return Expression("function", "second", (self,))
@@ -448,7 +449,11 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,
                "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8, "sqrt": dt.F64,
                "hour": dt.U32, "minute": dt.U32, "second": dt.U32, "ts_trunc": dt.TIMESTAMP, "substr": dt.LARGE_UTF8,
-               "rx_match": dt.BOOL, "rx_extract": dt.LARGE_UTF8, "rx_replace_group": dt.LARGE_UTF8}[e.op]
+               "rx_match": dt.BOOL, "rx_extract": dt.LARGE_UTF8, "rx_replace_group": dt.LARGE_UTF8, "ts_date": dt.DATE32}[e.op]
+        if e.op == "ts_date" and kids[0].dtype != dt.TIMESTAMP:
+            raise ValueError(f"Expected input to date to be a timestamp, got {dt.NAMES[kids[0].dtype]}")
+        if e.op in ("year", "month", "day", "day_of_week") and kids[0].dtype == dt.TIMESTAMP:
+            kids[0] = Bound(T_FUNCTION, dt.DATE32, FUNCS["ts_date"], [kids[0]])   # calendar fields of a timestamp = those of its day
         if e.op in ("rx_match", "rx_extract", "rx_replace_group"):
             if not dt.is_string(kids[0].dtype):
                 raise ValueError(f"Expects input to {e.op} to be utf8, but received {dt.NAMES[kids[0].dtype]}")

@@ -210,6 +210,8 @@ def _eval(b: Bound, cols, n: int):
                 us = a.astype(np.int64)
                 mod, div = {"hour": (86400000000, 3600000000), "minute": (3600000000, 60000000), "second": (60000000, 1000000)}[fn]
                 return (np.mod(us, mod) // div).astype(np.uint32), allk
+            if fn == "ts_date":
+                return np.floor_divide(a.astype(np.int64), 86400000000).astype(np.int32), allk
             if fn == "ts_trunc":
                 us, unit = a.astype(np.int64), kids[1][0].astype(np.int64)
                 return us - np.mod(us, unit), kids[0][1]

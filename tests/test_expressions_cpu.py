@@ -86,3 +86,30 @@ def test_substr_reference_literal_generated_code_and_nvrtc(tmp_path):
         col("col").substr(-1)
     with pytest.raises(ValueError, match="to be utf8"):
         encode_project([col("x").substr(0, 1)], ["x"], [dt.I64])
+
+
+def test_calendar_fields_of_timestamps(tmp_path):
+    """dt.date() / year / month / day / day_of_week of a Timestamp(us): oracle == pyarrow's calendar, generated code == oracle (instants on
+    both sides of the epoch, day boundaries), NVRTC for sm_100a"""
+    import ctypes
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from daft_b200 import _lib, col
+    from daft_b200 import datatypes as dt
+    from daft_b200.expressions import encode_project
+    from jit_emu import emulate_project
+    from oracle import expr_eval as E
+    rng = np.random.default_rng(0)
+    us = np.concatenate([rng.integers(-2 * 10**15, 2 * 10**15, 500), np.array([0, -1, 86400000000 - 1, 86400000000, -86400000000, -86400000001])])
+    t = pa.table({"ts": pa.array(us, type=pa.timestamp("us"), mask=rng.random(len(us)) < 0.1)})
+    exprs = [col("ts").date().alias("d"), col("ts").year().alias("y"), col("ts").month().alias("m"), col("ts").day().alias("dd"), col("ts").day_of_week().alias("dow")]
+    want = E.eval_expression_list(t, exprs)
+    assert emulate_project(t, exprs).equals(want)
+    for name, fn in (("y", pc.year), ("m", pc.month), ("dd", pc.day), ("dow", pc.day_of_week)):
+        assert want.column(name).combine_chunks().cast(pa.int64()).equals(fn(t["ts"]).combine_chunks()), name
+    assert want.column("d").combine_chunks().equals(t["ts"].combine_chunks().cast(pa.date32()))
+    _lib.call("b200_set_jit_cache_dir", str(tmp_path).encode())
+    plan, _, odt = encode_project(exprs, ["ts"], [dt.TIMESTAMP])
+    assert odt == [dt.DATE32, dt.I32, dt.U32, dt.U32, dt.U32]
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 1)(dt.TIMESTAMP), (ctypes.c_uint8 * 1)(1), ctypes.c_int32(1))
