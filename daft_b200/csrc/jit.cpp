@@ -56,7 +56,7 @@ enum BinOp { B_ADD = 0, B_SUB, B_MUL, B_TRUE_DIV, B_FLOOR_DIV, B_MOD, B_LT, B_LE
              B_XOR, B_EQ_NULL_SAFE, B_SHL, B_SHR };
 enum UnOp { U_NOT = 0, U_NEG, U_IS_NULL, U_NOT_NULL, U_ABS };
 enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT,
-          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC, F_SUBSTR, F_RX_MATCH, F_RX_EXTRACT, F_RX_REPLACE_GROUP, F_TS_DATE };
+          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC, F_SUBSTR, F_RX_MATCH, F_RX_EXTRACT, F_RX_REPLACE_GROUP, F_TS_DATE, F_EXP, F_LN, F_LOG2, F_LOG10, F_SIN, F_COS, F_TAN, F_CBRT };
 
 struct Node {
     int tag = 0, op = 0;
@@ -306,6 +306,13 @@ static int parse_node(Reader &r, Ast &a) {
                     }
                     nd.dtype = a.nodes[nd.kids[0]].dtype;
                     nd.nullable = true;
+                    break;
+                }
+                case F_EXP: case F_LN: case F_LOG2: case F_LOG10: case F_SIN: case F_COS: case F_TAN: case F_CBRT: {
+                    // unary float math (src/daft-functions/src/numeric/{exp,log,trigonometry,cbrt}.rs) in the operand's floating representation,
+                    // like sqrt; CUDA's libdevice results are within 1-2 ulp of the host's libm: a floating-point tolerance applies
+                    if (nd.kids.size() != 1 || !is_float(a.nodes[nd.kids[0]].dtype)) fail("plan: exp / ln / log2 / log10 / sin / cos / tan / cbrt need one float operand");
+                    nd.dtype = a.nodes[nd.kids[0]].dtype;
                     break;
                 }
                 case F_TS_DATE: {  // dt.date() of a Timestamp(us): days since the epoch, floor semantics
@@ -742,6 +749,11 @@ struct ExprGen {
                         if (nseg == 0 && (flags & 3) == 3) os << "      " << V << " = " << a << ".len == 0;\n";
                         os << "    }\n";
                         allk = k(kid[0]);
+                        break;
+                    }
+                    case F_EXP: case F_LN: case F_LOG2: case F_LOG10: case F_SIN: case F_COS: case F_TAN: case F_CBRT: {
+                        static const char *names[] = {"exp", "log", "log2", "log10", "sin", "cos", "tan", "cbrt"};
+                        os << "    const " << T << " " << V << " = " << names[n.op - F_EXP] << (n.dtype == B200_F32 ? "f(" : "(") << a << ");\n";
                         break;
                     }
                     case F_TS_DATE: os << "    const int32_t " << V << " = (int32_t)((" << a << " - ts_floor_mod((int64_t)" << a << ", 86400000000LL)) / 86400000000LL);\n"; break;

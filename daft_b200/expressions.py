@@ -21,7 +21,8 @@ UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
          "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15,
          "round": 16, "match_seq": 17, "hour": 18, "minute": 19, "second": 20, "ts_trunc": 21, "substr": 22, "rx_match": 23, "rx_extract": 24,
-         "rx_replace_group": 25, "ts_date": 26}
+         "rx_replace_group": 25, "ts_date": 26, "exp": 27, "ln": 28, "log2": 29, "log10": 30, "sin": 31, "cos": 32, "tan": 33, "cbrt": 34}
+_FLOAT_MATH = ("sqrt", "exp", "ln", "log2", "log10", "sin", "cos", "tan", "cbrt")
 AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5, "list": 6, "set": 7, "concat": 8}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
 _CMP = ("lt", "le", "eq", "ne", "ge", "gt", "eq_null_safe")
@@ -139,6 +140,14 @@ class Expression:
     def max(self): return self._agg("max")
     def count(self, mode: str = "valid"): return self._agg("count", mode)
     def sqrt(self): return Expression("function", "sqrt", (self,))
+    def exp(self): return Expression("function", "exp", (self,))
+    def ln(self): return Expression("function", "ln", (self,))
+    def log2(self): return Expression("function", "log2", (self,))
+    def log10(self): return Expression("function", "log10", (self,))
+    def sin(self): return Expression("function", "sin", (self,))
+    def cos(self): return Expression("function", "cos", (self,))
+    def tan(self): return Expression("function", "tan", (self,))
+    def cbrt(self): return Expression("function", "cbrt", (self,))
     def is_nan(self): return Expression("function", "is_nan", (self,))
     def not_nan(self): return Expression("function", "not_nan", (self,))
     def is_inf(self): return Expression("function", "is_inf", (self,))
@@ -449,7 +458,8 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
         out = {"year": dt.I32, "month": dt.U32, "day": dt.U32, "day_of_week": dt.U32, "utf8_length": dt.U64,
                "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8, "sqrt": dt.F64,
                "hour": dt.U32, "minute": dt.U32, "second": dt.U32, "ts_trunc": dt.TIMESTAMP, "substr": dt.LARGE_UTF8,
-               "rx_match": dt.BOOL, "rx_extract": dt.LARGE_UTF8, "rx_replace_group": dt.LARGE_UTF8, "ts_date": dt.DATE32}[e.op]
+               "rx_match": dt.BOOL, "rx_extract": dt.LARGE_UTF8, "rx_replace_group": dt.LARGE_UTF8, "ts_date": dt.DATE32,
+               "exp": dt.F64, "ln": dt.F64, "log2": dt.F64, "log10": dt.F64, "sin": dt.F64, "cos": dt.F64, "tan": dt.F64, "cbrt": dt.F64}[e.op]
         if e.op == "ts_date" and kids[0].dtype != dt.TIMESTAMP:
             raise ValueError(f"Expected input to date to be a timestamp, got {dt.NAMES[kids[0].dtype]}")
         if e.op in ("year", "month", "day", "day_of_week") and kids[0].dtype == dt.TIMESTAMP:
@@ -471,11 +481,11 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
             raise ValueError(f"Expects pattern of {e.op} to be utf8, but received {dt.NAMES[kids[1].dtype]}")
         if e.op in ("year", "month", "day", "day_of_week") and kids[0].dtype not in (dt.DATE32,):
             raise ValueError(f"Expected input to {e.op} to be a date, got {dt.NAMES[kids[0].dtype]}")
-        if e.op == "sqrt" and not dt.is_numeric(kids[0].dtype):
-            raise ValueError(f"Expected input to sqrt to be numeric, got {dt.NAMES[kids[0].dtype]}")
+        if e.op in _FLOAT_MATH and not dt.is_numeric(kids[0].dtype):
+            raise ValueError(f"Expected input to {e.op} to be numeric, got {dt.NAMES[kids[0].dtype]}")
         if e.op == "left":
             kids[1] = _cast(kids[1], dt.I64)
-        if e.op == "sqrt":
+        if e.op in _FLOAT_MATH:
             # computed in the operand's floating representation (src/daft-schema/src/dtype.rs:756-772, numeric/sqrt.rs:27-35)
             out = dt.F32 if kids[0].dtype in (dt.I8, dt.I16, dt.U8, dt.U16, dt.F32) else dt.F64
             kids[0] = _cast(kids[0], out)

@@ -215,6 +215,10 @@ def _eval(b: Bound, cols, n: int):
             if fn == "ts_trunc":
                 us, unit = a.astype(np.int64), kids[1][0].astype(np.int64)
                 return us - np.mod(us, unit), kids[0][1]
+            if fn in ("exp", "ln", "log2", "log10", "sin", "cos", "tan", "cbrt"):
+                f = {"exp": np.exp, "ln": np.log, "log2": np.log2, "log10": np.log10, "sin": np.sin, "cos": np.cos, "tan": np.tan, "cbrt": np.cbrt}[fn]
+                with np.errstate(all="ignore"):
+                    return f(a), allk   # `a` is already Float32 / Float64
             if fn == "sqrt":
                 with np.errstate(all="ignore"):
                     return np.sqrt(a), allk   # `a` is already Float32 / Float64 (the bound plan casts to the floating representation)

@@ -113,3 +113,28 @@ def test_calendar_fields_of_timestamps(tmp_path):
     plan, _, odt = encode_project(exprs, ["ts"], [dt.TIMESTAMP])
     assert odt == [dt.DATE32, dt.I32, dt.U32, dt.U32, dt.U32]
     _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 1)(dt.TIMESTAMP), (ctypes.c_uint8 * 1)(1), ctypes.c_int32(1))
+
+
+def test_unary_float_math(tmp_path):
+    """exp / ln / log2 / log10 / sin / cos / tan / cbrt in the operand's floating representation (Float32 for narrow integers and Float32, as
+    sqrt): the generated code on the host against numpy, to the floating-point tolerance the device's libdevice needs anyway; NVRTC"""
+    import ctypes
+    import numpy as np
+    import pyarrow as pa
+    from daft_b200 import _lib, col
+    from daft_b200 import datatypes as dt
+    from daft_b200.expressions import encode_project
+    from helpers import assert_tables_equal
+    from jit_emu import emulate_project
+    from oracle import expr_eval as E
+    rng = np.random.default_rng(0)
+    t = pa.table({"x": pa.array(rng.standard_normal(1000) * 5, mask=rng.random(1000) < 0.1), "f": pa.array((rng.random(1000) * 10).astype(np.float32)),
+                  "i": pa.array(rng.integers(1, 100, 1000).astype(np.int16))})
+    fns = ("exp", "ln", "log2", "log10", "sin", "cos", "tan", "cbrt")
+    exprs = [getattr(col(c), fn)().alias(f"{fn}_{c}") for fn in fns for c in ("x", "f", "i")]
+    want = E.eval_expression_list(t, exprs)
+    assert [str(f.type) for f in want.schema][:3] == ["double", "float", "float"]
+    assert_tables_equal(emulate_project(t, exprs), want, float_rtol=1e-6)
+    _lib.call("b200_set_jit_cache_dir", str(tmp_path).encode())
+    plan, _, _ = encode_project(exprs, ["x", "f", "i"], [dt.F64, dt.F32, dt.I16])
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(dt.F64, dt.F32, dt.I16), (ctypes.c_uint8 * 3)(1, 0, 0), ctypes.c_int32(3))
