@@ -70,6 +70,8 @@ def gen_bool(rng, depth):
     if k == 16: return gen_bool(rng, depth - 1) ^ gen_bool(rng, depth - 1)
     if k == 17:
         x, pat = gen_str(rng, depth - 1), ["", "a", "TPC", "d", "lo w", "é"][rng.integers(0, 6)]
+        if rng.random() < 0.3:   # the regex VM
+            return x.match([r"a+b?", r"^[a-d]+$", r"\w+ \w+", r"l{2}|c{3}", r"[^a-z ]", r"(TPC|x)-?H", r"^.{0,3}$", r"é|✓"][rng.integers(0, 8)])
         return [x.startswith(pat), x.endswith(pat), x.contains(pat)][rng.integers(0, 3)]
     if k == 18:
         x, y = gen_str(rng, depth - 1), gen_str(rng, depth - 1)
@@ -93,6 +95,9 @@ def gen_str(rng, depth):
     if depth == 0 or r < 0.4:
         return col("s") if rng.random() < 0.8 else lit(["a", "bb", "", "TPC-H", None][rng.integers(0, 5)])
     k = rng.integers(0, 4)
+    if k == 3 and rng.random() < 0.4:
+        pat, ngroups = [(r"(\w+) (\w+)", 2), (r"[a-d]+", 0), (r"(x+)|(y+)", 2), (r"^(.)(.*)$", 2)][rng.integers(0, 4)]
+        return gen_str(rng, depth - 1).regexp_extract(pat, int(rng.integers(0, ngroups + 1)))
     if k == 3: return gen_str(rng, depth - 1).substr(int(rng.integers(0, 5)), [None, 0, 1, 3, 40][rng.integers(0, 5)])
     if k == 0: return gen_str(rng, depth - 1).left(int(rng.integers(0, 6)))
     if k == 1: return gen_bool(rng, depth - 1).if_else(gen_str(rng, depth - 1), gen_str(rng, depth - 1))
