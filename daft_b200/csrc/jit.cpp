@@ -56,7 +56,7 @@ enum BinOp { B_ADD = 0, B_SUB, B_MUL, B_TRUE_DIV, B_FLOOR_DIV, B_MOD, B_LT, B_LE
              B_XOR, B_EQ_NULL_SAFE, B_SHL, B_SHR };
 enum UnOp { U_NOT = 0, U_NEG, U_IS_NULL, U_NOT_NULL, U_ABS };
 enum Fn { F_YEAR = 0, F_MONTH, F_DAY, F_UTF8_LENGTH, F_STARTSWITH, F_ENDSWITH, F_CONTAINS, F_LEFT, F_DOW, F_SQRT,
-          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC, F_SUBSTR, F_RX_MATCH, F_RX_EXTRACT, F_RX_REPLACE_GROUP, F_TS_DATE, F_EXP, F_LN, F_LOG2, F_LOG10, F_SIN, F_COS, F_TAN, F_CBRT };
+          F_IS_NAN, F_NOT_NAN, F_IS_INF, F_CEIL, F_FLOOR, F_SIGN, F_ROUND, F_MATCH_SEQ, F_HOUR, F_MINUTE, F_SECOND, F_TS_TRUNC, F_SUBSTR, F_RX_MATCH, F_RX_EXTRACT, F_RX_REPLACE_GROUP, F_TS_DATE, F_EXP, F_LN, F_LOG2, F_LOG10, F_SIN, F_COS, F_TAN, F_CBRT, F_LSTRIP, F_RSTRIP, F_RIGHT, F_FIND };
 
 struct Node {
     int tag = 0, op = 0;
@@ -313,6 +313,21 @@ static int parse_node(Reader &r, Ast &a) {
                     // like sqrt; CUDA's libdevice results are within 1-2 ulp of the host's libm: a floating-point tolerance applies
                     if (nd.kids.size() != 1 || !is_float(a.nodes[nd.kids[0]].dtype)) fail("plan: exp / ln / log2 / log10 / sin / cos / tan / cbrt need one float operand");
                     nd.dtype = a.nodes[nd.kids[0]].dtype;
+                    break;
+                }
+                case F_LSTRIP: case F_RSTRIP: {
+                    if (nd.kids.size() != 1 || !is_string(a.nodes[nd.kids[0]].dtype)) fail("plan: lstrip / rstrip need one string operand");
+                    nd.dtype = a.nodes[nd.kids[0]].dtype;
+                    break;
+                }
+                case F_RIGHT: {
+                    if (nd.kids.size() != 2 || !is_string(a.nodes[nd.kids[0]].dtype) || a.nodes[nd.kids[1]].dtype != B200_I64) fail("plan: right needs a string and an Int64 count");
+                    nd.dtype = a.nodes[nd.kids[0]].dtype;
+                    break;
+                }
+                case F_FIND: {  // str::find: BYTE index of the first occurrence, -1 when absent (src/daft-functions-utf8/src/find.rs:85)
+                    if (nd.kids.size() != 2 || !is_string(a.nodes[nd.kids[0]].dtype) || !is_string(a.nodes[nd.kids[1]].dtype)) fail("plan: find needs two string operands");
+                    nd.dtype = B200_I64;
                     break;
                 }
                 case F_TS_DATE: {  // dt.date() of a Timestamp(us): days since the epoch, floor semantics
@@ -756,6 +771,10 @@ struct ExprGen {
                         os << "    const " << T << " " << V << " = " << names[n.op - F_EXP] << (n.dtype == B200_F32 ? "f(" : "(") << a << ");\n";
                         break;
                     }
+                    case F_LSTRIP: os << "    const Str " << V << " = str_lstrip(" << a << ");\n"; break;
+                    case F_RSTRIP: os << "    const Str " << V << " = str_rstrip(" << a << ");\n"; break;
+                    case F_RIGHT: os << "    const Str " << V << " = str_right(" << a << ", (int64_t)" << v(kid[1]) << ");\n"; break;
+                    case F_FIND: os << "    const int64_t " << V << " = str_find_from(" << a << ", " << v(kid[1]) << ", 0);\n"; break;
                     case F_TS_DATE: os << "    const int32_t " << V << " = (int32_t)((" << a << " - ts_floor_mod((int64_t)" << a << ", 86400000000LL)) / 86400000000LL);\n"; break;
                     case F_RX_MATCH:
                         os << "    const bool " << V << " = rx_exec(" << a << ", " << v(kid[1]) << ").matched;\n";

@@ -176,6 +176,51 @@ __device__ __forceinline__ Str str_left(Str a, int64_t nchars) {
     return Str{a.p, i};
 }
 
+// ---- lstrip / rstrip / right / find (src/daft-functions-utf8/src/{lstrip,rstrip,right,find}.rs): views into the value ----
+// Rust's trim_start / trim_end remove characters with the Unicode White_Space property
+__device__ __forceinline__ bool uni_is_space(uint32_t c) {
+    return (c >= 9 && c <= 13) || c == 32 || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) || c == 0x2028 || c == 0x2029 ||
+           c == 0x202F || c == 0x205F || c == 0x3000;
+}
+__device__ __forceinline__ uint32_t utf8_decode(const uint8_t *p, int64_t avail, int &w) {
+    const uint32_t b0 = p[0];
+    if (b0 < 0x80 || avail < 2) { w = 1; return b0; }
+    if (b0 < 0xE0) { w = 2; return ((b0 & 0x1F) << 6) | (p[1] & 0x3F); }
+    if (b0 < 0xF0 && avail >= 3) { w = 3; return ((b0 & 0x0F) << 12) | ((uint32_t)(p[1] & 0x3F) << 6) | (p[2] & 0x3F); }
+    if (avail >= 4) { w = 4; return ((b0 & 0x07) << 18) | ((uint32_t)(p[1] & 0x3F) << 12) | ((uint32_t)(p[2] & 0x3F) << 6) | (p[3] & 0x3F); }
+    w = 1;
+    return b0;
+}
+__device__ __forceinline__ Str str_lstrip(Str a) {
+    int64_t i = 0;
+    while (i < a.len) {
+        int w;
+        if (!uni_is_space(utf8_decode(a.p + i, a.len - i, w))) break;
+        i += w;
+    }
+    return Str{a.p + i, a.len - i};
+}
+__device__ __forceinline__ Str str_rstrip(Str a) {
+    int64_t j = a.len;
+    while (j > 0) {
+        int64_t k = j - 1;
+        while (k > 0 && (a.p[k] & 0xC0) == 0x80) k--;
+        int w;
+        if (!uni_is_space(utf8_decode(a.p + k, j - k, w))) break;
+        j = k;
+    }
+    return Str{a.p, j};
+}
+__device__ __forceinline__ Str str_right(Str a, int64_t nchars) {
+    int64_t j = a.len, c = 0;
+    while (j > 0 && c < nchars) {
+        j--;
+        while (j > 0 && (a.p[j] & 0xC0) == 0x80) j--;
+        c++;
+    }
+    return Str{a.p + j, a.len - j};
+}
+
 // utf8 substr in CHARACTERS (src/daft-functions-utf8/src/substr.rs:269-294): the value has no character at `start`, or `nchars` == 0 -> null
 // (ok = false); nchars < 0 = to the end of the value
 __device__ __forceinline__ Str str_substr(Str a, int64_t start, int64_t nchars, bool &ok) {

@@ -21,7 +21,7 @@ UNOPS = {"not": 0, "neg": 1, "is_null": 2, "not_null": 3, "abs": 4}
 FUNCS = {"year": 0, "month": 1, "day": 2, "utf8_length": 3, "startswith": 4, "endswith": 5, "contains": 6, "left": 7,
          "day_of_week": 8, "sqrt": 9, "is_nan": 10, "not_nan": 11, "is_inf": 12, "ceil": 13, "floor": 14, "sign": 15,
          "round": 16, "match_seq": 17, "hour": 18, "minute": 19, "second": 20, "ts_trunc": 21, "substr": 22, "rx_match": 23, "rx_extract": 24,
-         "rx_replace_group": 25, "ts_date": 26, "exp": 27, "ln": 28, "log2": 29, "log10": 30, "sin": 31, "cos": 32, "tan": 33, "cbrt": 34}
+         "rx_replace_group": 25, "ts_date": 26, "exp": 27, "ln": 28, "log2": 29, "log10": 30, "sin": 31, "cos": 32, "tan": 33, "cbrt": 34, "lstrip": 35, "rstrip": 36, "right": 37, "find": 38}
 _FLOAT_MATH = ("sqrt", "exp", "ln", "log2", "log10", "sin", "cos", "tan", "cbrt")
 AGG_KINDS = {"count": 0, "sum": 1, "min": 2, "max": 3, "mean": 4, "any_value": 5, "list": 6, "set": 7, "concat": 8}
 COUNT_MODES = {"all": 0, "valid": 1, "null": 2}
@@ -124,6 +124,10 @@ class Expression:
     def endswith(self, pat): return Expression("function", "endswith", (self, _to_expr(pat)))
     def contains(self, pat): return Expression("function", "contains", (self, _to_expr(pat)))
     def left(self, n): return Expression("function", "left", (self, _to_expr(n)))
+    def right(self, n): return Expression("function", "right", (self, _to_expr(n)))          # the last n characters
+    def lstrip(self): return Expression("function", "lstrip", (self,))                        # Unicode White_Space, as str::trim_start
+    def rstrip(self): return Expression("function", "rstrip", (self,))
+    def find(self, substr): return Expression("function", "find", (self, _to_expr(substr)))   # byte index of the first occurrence, -1 = none
     def substr(self, start: int, length: int | None = None):
         """utf8 substr(start, length) in characters, 0-based (src/daft-functions-utf8/src/substr.rs:269-294): null when the value has no
         character at `start` or `length` is 0; `length=None` runs to the end.  `start` and `length` are literals."""
@@ -459,7 +463,15 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
                "startswith": dt.BOOL, "endswith": dt.BOOL, "contains": dt.BOOL, "left": dt.LARGE_UTF8, "sqrt": dt.F64,
                "hour": dt.U32, "minute": dt.U32, "second": dt.U32, "ts_trunc": dt.TIMESTAMP, "substr": dt.LARGE_UTF8,
                "rx_match": dt.BOOL, "rx_extract": dt.LARGE_UTF8, "rx_replace_group": dt.LARGE_UTF8, "ts_date": dt.DATE32,
-               "exp": dt.F64, "ln": dt.F64, "log2": dt.F64, "log10": dt.F64, "sin": dt.F64, "cos": dt.F64, "tan": dt.F64, "cbrt": dt.F64}[e.op]
+               "exp": dt.F64, "ln": dt.F64, "log2": dt.F64, "log10": dt.F64, "sin": dt.F64, "cos": dt.F64, "tan": dt.F64, "cbrt": dt.F64,
+               "lstrip": dt.LARGE_UTF8, "rstrip": dt.LARGE_UTF8, "right": dt.LARGE_UTF8, "find": dt.I64}[e.op]
+        if e.op in ("lstrip", "rstrip", "right", "find"):
+            if not dt.is_string(kids[0].dtype) or (e.op == "find" and not dt.is_string(kids[1].dtype)):
+                raise ValueError(f"Expects input to {e.op} to be utf8, but received {dt.NAMES[kids[0].dtype]}")
+            if e.op == "right":
+                kids[1] = _cast(kids[1], dt.I64)
+            if e.op != "find":
+                out = kids[0].dtype
         if e.op == "ts_date" and kids[0].dtype != dt.TIMESTAMP:
             raise ValueError(f"Expected input to date to be a timestamp, got {dt.NAMES[kids[0].dtype]}")
         if e.op in ("year", "month", "day", "day_of_week") and kids[0].dtype == dt.TIMESTAMP:

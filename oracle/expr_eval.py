@@ -273,6 +273,10 @@ def _eval(b: Bound, cols, n: int):
                 return ((a.astype(np.int64) + 3) % 7).astype(np.uint32), allk
             if fn == "utf8_length":
                 return np.array([len(x.decode("utf-8", "ignore")) for x in a], dtype=np.uint64), allk
+            if fn in ("lstrip", "rstrip"):   # Rust's trim_start / trim_end: the Unicode White_Space property (not Python's isspace, which adds U+001C..001F)
+                ws = set("\t\n\x0b\x0c\r \x85\xa0\u1680\u2028\u2029\u202f\u205f\u3000") | {chr(c) for c in range(0x2000, 0x200B)}
+                chars = "".join(ws)
+                return np.array([(x.decode().lstrip(chars) if fn == "lstrip" else x.decode().rstrip(chars)).encode() for x in a], dtype=object), allk
             pat = kids[1][0]
             if fn == "startswith": return np.array([x.startswith(p) for x, p in zip(a, pat)], dtype=bool), allk
             if fn == "endswith": return np.array([x.endswith(p) for x, p in zip(a, pat)], dtype=bool), allk
@@ -308,6 +312,10 @@ def _eval(b: Bound, cols, n: int):
                     ok.append(good)
                     out.append((chars[start:] if ln < 0 else chars[start:start + ln]).encode() if good else b"")
                 return np.array(out, dtype=object), kids[0][1] & np.array(ok, dtype=bool) if n else kids[0][1]
+            if fn == "right":
+                return np.array([(x.decode("utf-8", "ignore")[-int(k):] if int(k) > 0 else "").encode() for x, k in zip(a, pat)], dtype=object), allk
+            if fn == "find":
+                return np.array([x.find(p) for x, p in zip(a, pat)], dtype=np.int64), allk
             if fn == "left":
                 return np.array([x.decode("utf-8", "ignore")[:max(int(k), 0)].encode() for x, k in zip(a, pat)], dtype=object), allk
     raise NotImplementedError(b.tag)

@@ -138,3 +138,27 @@ def test_unary_float_math(tmp_path):
     _lib.call("b200_set_jit_cache_dir", str(tmp_path).encode())
     plan, _, _ = encode_project(exprs, ["x", "f", "i"], [dt.F64, dt.F32, dt.I16])
     _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 3)(dt.F64, dt.F32, dt.I16), (ctypes.c_uint8 * 3)(1, 0, 0), ctypes.c_int32(3))
+
+
+def test_lstrip_rstrip_right_find(tmp_path):
+    """utf8 lstrip / rstrip (Rust trim_start / trim_end: the Unicode White_Space property, so U+3000 and U+00A0 go and U+001C stays),
+    right(n) in characters, find() as a BYTE index (str::find): generated code == oracle, NVRTC"""
+    import ctypes
+    import pyarrow as pa
+    from daft_b200 import _lib, col
+    from daft_b200 import datatypes as dt
+    from daft_b200.expressions import encode_project
+    from jit_emu import emulate_project
+    from oracle import expr_eval as E
+    t = pa.table({"s": pa.array(["  foo ", "\t\nbar\r\n", "　日本 ", "", None, "   ", "x", "\x1cabc\x1c", "\xa0nb sp\x85", "héllo wörld", "no-space"], pa.large_string()),
+                  "n": pa.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 100], pa.int64())})
+    exprs = [col("s").lstrip().alias("l"), col("s").rstrip().alias("r"), col("s").lstrip().rstrip().alias("lr"), col("s").right(3).alias("r3"),
+             col("s").right(col("n")).alias("rn"), col("s").find("o").alias("fo"), col("s").find("ö").alias("f2"), col("s").find("").alias("fe")]
+    want = E.eval_expression_list(t, exprs)
+    assert want.column("lr").to_pylist() == ["foo", "bar", "日本", "", None, "", "x", "\x1cabc\x1c", "nb sp", "héllo wörld", "no-space"]
+    assert want.column("fo").to_pylist() == [3, -1, -1, -1, None, -1, -1, -1, -1, 5, 1] and want.column("f2").to_pylist()[9] == 8   # byte index: é is two bytes
+    assert emulate_project(t, exprs).equals(want)
+    _lib.call("b200_set_jit_cache_dir", str(tmp_path).encode())
+    plan, _, odt = encode_project(exprs, ["s", "n"], [dt.LARGE_UTF8, dt.I64])
+    assert odt == [dt.LARGE_UTF8] * 5 + [dt.I64] * 3
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 2)(dt.LARGE_UTF8, dt.I64), (ctypes.c_uint8 * 2)(1, 0), ctypes.c_int32(2))
