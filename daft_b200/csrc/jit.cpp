@@ -90,6 +90,7 @@ static bool is_numeric(int32_t dt) { return is_integer(dt) || is_float(dt); }
 static bool int_like(int32_t dt) { return is_integer(dt) || dt == B200_DATE32 || dt == B200_TIMESTAMP; }
 static bool int_like_signed(int32_t dt) { return is_signed_int(dt) || dt == B200_DATE32 || dt == B200_TIMESTAMP; }
 static bool cast_can_fail(int32_t src, int32_t dst) {
+    if (is_string(src)) return !is_string(dst);  // parsing
     if (!int_like(dst)) return false;
     if (is_float(src)) return true;
     if (!int_like(src)) return false;  // bool -> 0 / 1
@@ -637,8 +638,14 @@ struct ExprGen {
                     os << "    const " << T << " " << V << " = " << zero_of(n.dtype) << "; const bool " << K << " = false;\n";
                 } else if (is_string(C.dtype) && is_string(n.dtype)) {
                     os << "    const Str " << V << " = " << a << "; const bool " << K << " = " << ka << ";\n";
+                } else if (is_string(C.dtype) && is_integer(n.dtype)) {
+                    // trimmed, then [+-]?[0-9]+ in range of the target, else null (str_parse_int in the prelude)
+                    const std::string tv = pfx + "t" + std::to_string(id);
+                    os << "    unsigned long long " << tv << " = 0; const bool " << K << " = " << ka << " && str_parse_int(" << a << ", "
+                       << 8 * dtype_width(n.dtype) << ", " << (is_signed_int(n.dtype) ? "true" : "false") << ", " << tv << ");\n";
+                    os << "    const " << T << " " << V << " = " << K << " ? (" << T << ")" << tv << " : (" << T << ")0;\n";
                 } else if (is_string(C.dtype) || is_string(n.dtype)) {
-                    fail("plan: casts between strings and other types are not supported on the device");
+                    fail("plan: only Utf8 -> integer among the casts between strings and other types is built on the device");
                 } else if (n.dtype == B200_BOOL) {
                     os << "    const bool " << V << " = " << a << " != 0; const bool " << K << " = " << ka << ";\n";
                 } else if (!cast_can_fail(C.dtype, n.dtype)) {

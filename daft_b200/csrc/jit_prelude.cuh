@@ -211,6 +211,31 @@ __device__ __forceinline__ Str str_rstrip(Str a) {
     }
     return Str{a.p, j};
 }
+// Utf8 -> integer cast: the reference trims Unicode whitespace (src/daft-core/src/array/ops/cast.rs:164-173) and hands the value to
+// arrow-cast 57.3.0's string parser (`parser_primitive!`, atoi 2.0 `from_radix_10_signed_checked`): an optional '+' or '-', then decimal
+// digits only, to the end; the last byte must be a digit; a value the target type cannot hold -- or anything else -- is null
+// (tests: cast.rs:2088-2150).  `bits` / `sg`: the target's width and signedness.  An unsigned target accepts "-0".
+__device__ __forceinline__ bool str_parse_int(Str a, int bits, bool sg, unsigned long long &out) {
+    a = str_rstrip(str_lstrip(a));
+    out = 0;
+    if (a.len == 0) return false;
+    int64_t i = 0;
+    bool neg = false;
+    if (a.p[0] == '+' || a.p[0] == '-') { neg = a.p[0] == '-'; i = 1; }
+    if (i == a.len) return false;
+    unsigned long long acc = 0;
+    for (; i < a.len; i++) {
+        const unsigned d = (unsigned)a.p[i] - 48u;
+        if (d > 9u) return false;
+        if (acc > (0xFFFFFFFFFFFFFFFFULL - d) / 10ULL) return false;
+        acc = acc * 10ULL + d;
+    }
+    const unsigned long long pos_max = sg ? ((1ULL << (bits - 1)) - 1ULL) : (bits == 64 ? 0xFFFFFFFFFFFFFFFFULL : ((1ULL << bits) - 1ULL));
+    const unsigned long long neg_max = sg ? (1ULL << (bits - 1)) : 0ULL;
+    if (acc > (neg ? neg_max : pos_max)) return false;
+    out = neg ? (0ULL - acc) : acc;
+    return true;
+}
 __device__ __forceinline__ Str str_right(Str a, int64_t nchars) {
     int64_t j = a.len, c = 0;
     while (j > 0 && c < nchars) {

@@ -8,6 +8,7 @@ validity mask); binary operands are first cast to their supertype; IEEE f64 arit
 from __future__ import annotations
 
 import datetime
+import re
 
 import numpy as np
 import pyarrow as pa
@@ -73,6 +74,25 @@ def _civil(days: np.ndarray):
     d = doy - (153 * mp + 2) // 5 + 1
     m = np.where(mp < 10, mp + 3, mp - 9)
     return y + (m <= 2), m, d
+
+
+_INT_TEXT = re.compile(rb"[+-]?[0-9]+")
+# Rust `char::is_whitespace` (Unicode White_Space), which `str::trim` removes
+_RUST_SPACE = "\t\n\x0b\x0c\r \x85\xa0\u1680\u2000\u2001\u2002\u2003\u2004\u2005\u2006\u2007\u2008\u2009\u200a\u2028\u2029\u202f\u205f\u3000"
+
+
+def _parse_ints(a, ka, to):
+    """Utf8 -> integer: `.trim()` (src/daft-core/src/array/ops/cast.rs:164-173), then arrow-cast 57.3.0's `parser_primitive!` over atoi 2.0
+    `from_radix_10_signed_checked`: optional sign, decimal digits to the end, null when malformed or out of range (cast.rs:2088-2150)."""
+    lo, hi = dt.int_range(to)
+    out, ok = np.zeros(len(a), dtype=_NP[to]), np.zeros(len(a), dtype=bool)
+    for i, (s, k) in enumerate(zip(a, ka)):
+        if not k:
+            continue
+        t = bytes(s).decode("utf-8", "surrogateescape").strip(_RUST_SPACE).encode("utf-8", "surrogateescape")
+        if _INT_TEXT.fullmatch(t) and lo <= int(t) <= hi:
+            out[i], ok[i] = int(t), True
+    return out, ok
 
 
 def _total_order_key(a: np.ndarray) -> np.ndarray:
@@ -154,6 +174,8 @@ def _eval(b: Bound, cols, n: int):
                 return np.zeros(n, dtype=_NP[b.dtype]) if not dt.is_string(b.dtype) else np.array([b""] * n, dtype=object), np.zeros(n, dtype=bool)
             if dt.is_string(b.dtype):
                 return a, ka
+            if dt.is_string(src):
+                return _parse_ints(a, ka, b.dtype)
             if b.dtype == dt.BOOL:
                 return a != 0, ka
             if dt.int_like(b.dtype) and (dt.is_float(src) or dt.int_like(src)):
