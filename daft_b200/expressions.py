@@ -397,9 +397,12 @@ def bind(e: Expression, names: Sequence[str], dtypes: Sequence[int]) -> Bound:
                 # Utf8 -> integer parses on the device (trimmed, [+-]?digits, out of range / malformed -> null: array/ops/cast.rs:164-173)
                 raise NotImplementedError(f"cast {dt.NAMES[c.dtype]} -> {dt.NAMES[e.dtype]}: of the parsing / formatting casts only "
                                           "Utf8 -> integer is built")
-            if {c.dtype, e.dtype} == {dt.DATE32, dt.TIMESTAMP}:
-                # the reference converts days <-> timestamp units here; a physical integer cast would silently be wrong
-                raise NotImplementedError(f"cast {dt.NAMES[c.dtype]} -> {dt.NAMES[e.dtype]}: temporal unit conversion is not built")
+            if c.dtype == dt.DATE32 and e.dtype == dt.TIMESTAMP:
+                # days x microseconds per day, as an Int64 product (src/daft-core/src/array/ops/cast.rs:268-279), then the physical cast
+                us = Bound(T_BINARY, dt.I64, BINOPS["mul"], [_cast(c, dt.I64), Bound(T_LIT, dt.I64, value=86_400_000_000)])
+                return Bound(T_CAST, dt.TIMESTAMP, kids=[us])
+            if c.dtype == dt.TIMESTAMP and e.dtype == dt.DATE32:
+                return Bound(T_FUNCTION, dt.DATE32, FUNCS["ts_date"], [c])   # TimestampArray::cast -> self.date() (cast.rs:347)
         return _cast(c, e.dtype)
     if k == "if_else":
         p, a, b = (bind(x, names, dtypes) for x in e.args)

@@ -208,3 +208,34 @@ def test_cast_utf8_to_integers(tmp_path):
     for bad in (col("s").cast(dt.F64), col("s").cast(dt.DATE32)):
         with pytest.raises(NotImplementedError):
             encode_project([bad], ["s"], [dt.LARGE_UTF8])
+
+
+def test_cast_date_timestamp_units(tmp_path):
+    """Date -> Timestamp(us) multiplies the days by the microseconds of a day (src/daft-core/src/array/ops/cast.rs:268-279); Timestamp -> Date
+    is the day the instant falls on, floored for instants before the epoch (cast.rs:347 -> TimestampArray::date): generated code == oracle,
+    known answers from pyarrow's own casts, NVRTC"""
+    import ctypes
+    import datetime
+    import numpy as np
+    import pyarrow as pa
+    from daft_b200 import _lib, col
+    from daft_b200 import datatypes as dt
+    from daft_b200.expressions import encode_project
+    from jit_emu import emulate_project
+    from oracle import expr_eval as E
+    rng = np.random.default_rng(9)
+    n = 500
+    days = np.concatenate([[0, 1, -1, 19000, -25567], rng.integers(-40000, 40000, n - 5)]).astype(np.int32)
+    us = np.concatenate([[0, -1, 1, 86_400_000_000, -86_400_000_000, -86_400_000_001], rng.integers(-3 * 10**15, 3 * 10**15, n - 6)])
+    t = pa.table({"d": pa.array(days, pa.date32(), mask=rng.random(n) < 0.1), "ts": pa.array(us, pa.timestamp("us"), mask=rng.random(n) < 0.1)})
+    exprs = [col("d").cast(dt.TIMESTAMP).alias("d_ts"), col("ts").cast(dt.DATE32).alias("ts_d"), col("d").cast(dt.TIMESTAMP).cast(dt.DATE32).alias("back"),
+             (col("ts").cast(dt.DATE32) == col("ts").date()).alias("same"), (col("d").cast(dt.TIMESTAMP) < datetime.datetime(2000, 1, 1)).alias("cmp")]
+    want = E.eval_expression_list(t, exprs)
+    assert want.column("d_ts").combine_chunks().equals(t.column("d").combine_chunks().cast(pa.timestamp("us")))
+    assert want.column("ts_d").combine_chunks().equals(t.column("ts").combine_chunks().cast(pa.date32()))   # pyarrow floors as chrono does
+    assert want.column("back").combine_chunks().equals(t.column("d").combine_chunks())
+    assert emulate_project(t, exprs).equals(want)
+    _lib.call("b200_set_jit_cache_dir", str(tmp_path).encode())
+    plan, _, odt = encode_project(exprs, ["d", "ts"], [dt.DATE32, dt.TIMESTAMP])
+    assert odt == [dt.TIMESTAMP, dt.DATE32, dt.DATE32, dt.BOOL, dt.BOOL]
+    _lib.call("b200_precompile", ctypes.c_int32(0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * 2)(dt.DATE32, dt.TIMESTAMP), (ctypes.c_uint8 * 2)(1, 1), ctypes.c_int32(2))
