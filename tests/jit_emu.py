@@ -98,8 +98,26 @@ def _prelude_for_host() -> str:
     return text.replace("#pragma once", "") + "\n}  // namespace jit\n}  // namespace b200\n"
 
 
+_NVRTC_SEEN = set()
+
+
+def _nvrtc_too(op: int, plan: bytes, dtypes, nullable) -> None:
+    """B200_EMU_NVRTC=<dir>: every plan the emulation runs is ALSO compiled by NVRTC for sm_100a (b200_precompile: all the build variants of
+    an aggregate), cubins into <dir> -- a sweep over whole query suites that no kernel the queries need fails to compile for the device."""
+    d = os.environ.get("B200_EMU_NVRTC")
+    key = (op, bytes(plan), tuple(dtypes), tuple(nullable))
+    if not d or key in _NVRTC_SEEN:
+        return
+    _NVRTC_SEEN.add(key)
+    os.makedirs(d, exist_ok=True)
+    _lib.call("b200_set_jit_cache_dir", d.encode())
+    n = len(dtypes)
+    _lib.call("b200_precompile", ctypes.c_int32(op), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * n)(*dtypes), (ctypes.c_uint8 * n)(*nullable), ctypes.c_int32(n))
+
+
 def describe_project(exprs, names, dtypes, nullable, with_take: bool = False):
     plan, onames, odt = encode_project(exprs, names, dtypes)
+    _nvrtc_too(0, plan, dtypes, nullable)
     out, err = ctypes.c_void_p(), ctypes.c_void_p()
     n = len(dtypes)
     rc = _lib.lib().b200_jit_describe(ctypes.c_int32((1 << 16) if with_take else 0), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * n)(*dtypes),
@@ -428,6 +446,7 @@ extern "C" long long emu_agg_tier1(void **ptrs, int nptr, long long *ints, int n
 
 
 def describe_agg(plan: bytes, dtypes, nullable, variant: int = 0):
+    _nvrtc_too(2, plan, dtypes, nullable)
     out, err = ctypes.c_void_p(), ctypes.c_void_p()
     n = len(dtypes)
     rc = _lib.lib().b200_jit_describe(ctypes.c_int32(2 | (variant << 8)), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * n)(*dtypes),
@@ -674,6 +693,7 @@ def emulate_filter(tbl: pa.Table, predicates) -> pa.Table:
     dtypes = [dt.from_arrow(c.type) for c in cols]
     nullable = [1 if c.null_count > 0 else 0 for c in cols]
     plan = encode_filter(list(predicates), names, dtypes)
+    _nvrtc_too(1, plan, dtypes, nullable)
     out, err = ctypes.c_void_p(), ctypes.c_void_p()
     rc = _lib.lib().b200_jit_describe(ctypes.c_int32(1), plan, ctypes.c_size_t(len(plan)), (ctypes.c_int32 * len(dtypes))(*dtypes),
                                       (ctypes.c_uint8 * len(dtypes))(*nullable), ctypes.c_int32(len(dtypes)), ctypes.byref(out), ctypes.byref(err))
