@@ -54,7 +54,7 @@ SYMBOLS = [
     "b200_batch_import", "b200_batch_export", "b200_batch_from_device", "b200_batch_describe", "b200_batch_materialize", "b200_batch_num_rows",
     "b200_batch_num_columns", "b200_batch_size_bytes", "b200_batch_free", "b200_batch_select", "b200_batch_rename",
     "b200_batch_union", "b200_batch_slice",
-    "b200_parquet_read", "b200_parquet_file_info", "b200_merge_join_sorted", "b200_asof_join_sorted", "b200_cross_join", "b200_window_ranks", "b200_window_offset",
+    "b200_parquet_read", "b200_parquet_file_info", "b200_merge_join_sorted", "b200_asof_join_sorted", "b200_cross_join", "b200_window_ranks", "b200_window_offset", "b200_window_frame",
     "b200_hash_rows", "b200_partition_by_hash", "b200_partition_by_random", "b200_exchange_random", "b200_exchange_by_range", "b200_search_sorted", "b200_partition_by_range", "b200_batch_dtypes", "b200_filter", "b200_eval_expression_list", "b200_agg", "b200_dedup", "b200_groupby_create", "b200_groupby_push", "b200_groupby_finalize", "b200_groupby_free",
     "b200_take", "b200_concat", "b200_argsort", "b200_sort", "b200_top_n",
     "b200_probe_table_create", "b200_probe_table_add", "b200_probe_table_build", "b200_probe_table_num_rows",

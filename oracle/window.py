@@ -8,6 +8,9 @@ window_partition_only.rs): partition by value, sort the partition by the order k
 * offset (lead / lag) -- window_offset, :706-789: the value `offset` rows away inside the partition, else the default (cast to the
   value's type) or null
 * partition aggregate -- window_grouped_agg, :16-82: the aggregate per partition broadcast to its rows
+* aggregate over a ROWS frame -- window_agg_dynamic_frame, :299-385: sum / count / mean slide a state over the partition
+  (window_agg_rows_incremental :388-438, update_incremental_state :274-296, ops/window_states/{sum,count,mean}.rs), min / max
+  re-aggregate every frame (window_agg_rows :441-483)
 pivot -- RecordBatch::pivot, src/daft-recordbatch/src/ops/pivot.rs:70-150.
 Small inputs only (pure-Python loops)."""
 from __future__ import annotations
@@ -41,7 +44,7 @@ def window(tbl: pa.Table, partition_by: Sequence, order_by: Sequence, descending
         parts = [np.nonzero(gid == g)[0] for g in range(len(first))]
     else:
         parts = [np.arange(n)] if n else []
-    order, new_cols = [], {f[1]: [] for f in functions}
+    order, new_cols, frame_types = [], {f[1]: [] for f in functions}, {}
     ovals = list(zip(*[O.normalize(c).to_pylist() for c in ocols])) if ocols else [()] * n
     for rows in parts:
         if ocols:
@@ -82,6 +85,9 @@ def window(tbl: pa.Table, partition_by: Sequence, order_by: Sequence, descending
                         if v is not None and vals and isinstance(next((x for x in vals if x is not None), v), float):
                             v = float(v)
                         new_cols[name].append(v)
+            elif kind == "frame":
+                vals, frame_types[name] = frame_agg(sub_tbl, f[2], f[3], f[4], int(f[5]) if len(f) > 5 else 1)
+                new_cols[name] += vals
             elif kind == "agg":
                 from daft_b200.expressions import _agg_inner
                 inner = _agg_inner(f[2])
@@ -94,12 +100,104 @@ def window(tbl: pa.Table, partition_by: Sequence, order_by: Sequence, descending
             typ = pa.uint64()
         elif kind == "offset":
             typ = O.normalize(E.eval_expression(tbl, f[2])).type
+        elif kind == "frame":
+            typ = frame_types.get(name) or frame_agg(tbl.slice(0, 0), f[2], f[3], f[4], 1)[1]
         else:   # the aggregate's output type: what the ungrouped aggregate over the whole table yields
             from daft_b200.expressions import _agg_inner
             inner = _agg_inner(f[2])
             typ = O.agg(tbl, [(inner.op, E.eval_expression(tbl, inner.args[0]), name, inner.value)], []).column(name).type
         out = out.append_column(name, pa.array(new_cols[name], type=typ))
     return out
+
+
+FRAME_ACC = {"int8": "int64", "int16": "int64", "int32": "int64", "int64": "int64", "uint8": "uint64", "uint16": "uint64", "uint32": "uint64",
+             "uint64": "uint64", "float": "float", "double": "double"}   # window_states/sum.rs:137-158
+
+
+def frame_agg_partition(vals: list, op: str, mode, start, end, min_periods: int, acc: str) -> list:
+    """One partition, already in frame order.  `vals`: Python values (None = null) in the accumulate type `acc`.  The state machine of
+    window_agg_rows_incremental: a frame with fewer than min_periods rows leaves the state alone and gives null; otherwise rows
+    [prev_start, start) are removed and rows [prev_end, end) added -- in that order, with `+=` / `-=` on the accumulate type."""
+    m = len(vals)
+    ftype = {"float": np.float32, "double": np.float64}.get(acc)
+
+    def bounds(r):   # calculate_row_frame_bounds, window.rs:136-163
+        fs = 0 if start is None else min(max(r + start, 0), m)
+        fe = m if end is None else min(max(r + 1 + end, 0), m)
+        if fe < fs:
+            raise ValueError("Negative frame size is not allowed")
+        return fs, fe
+    out = []
+    if op in ("min", "max"):   # no incremental state (window_states/mod.rs:47-49): aggregate the slice
+        for r in range(m):
+            fs, fe = bounds(r)
+            live = [v for v in vals[fs:fe] if v is not None] if fe - fs >= min_periods else []
+            out.append((min(live) if op == "min" else max(live)) if live else None)
+        return out
+    total = sm = valid = valid_not_nan = nan = 0
+    if ftype:
+        sm = ftype(0)
+    ps = pe = 0
+    for r in range(m):
+        fs, fe = bounds(r)
+        enough = fe - fs >= min_periods
+        if enough:
+            for lo, hi, sign in ((ps, fs, -1), (pe, fe, 1)):
+                if hi <= lo:
+                    continue
+                total += sign * (hi - lo)
+                for v in vals[lo:hi]:
+                    if v is None:
+                        continue
+                    valid += sign
+                    if op == "count":
+                        continue
+                    if ftype and v != v:
+                        nan += sign
+                    else:
+                        valid_not_nan += sign
+                        with np.errstate(all="ignore"):
+                            sm = (sm + ftype(v) if sign > 0 else sm - ftype(v)) if ftype else sm + sign * v
+            ps, pe = fs, fe
+        if op == "count":
+            out.append(({"all": total, "valid": valid, "null": total - valid}[mode]) if enough else None)
+        elif not enough or valid_not_nan <= 0:
+            out.append(None)
+        elif op == "sum":
+            if ftype:
+                out.append(float("nan") if nan > 0 else float(sm))
+            else:
+                out.append(((sm + 2**63) % 2**64 - 2**63) if acc == "int64" else sm % 2**64)
+        else:   # mean: sum series / count series (mean.rs:75-80)
+            with np.errstate(all="ignore"):
+                out.append(float("nan") if nan > 0 else float(np.float64(sm) / np.float64(valid)))
+    return out
+
+
+def frame_agg(sub_tbl: pa.Table, agg_expr, start, end, min_periods: int):
+    """-> (values, arrow type) of `agg_expr` over the ROWS frame [start, end] (None = unbounded) of every row of one partition"""
+    from daft_b200.expressions import _agg_inner
+    inner = _agg_inner(agg_expr)
+    if inner.op not in ("sum", "count", "mean", "min", "max"):
+        raise NotImplementedError(f"window frame aggregate {inner.op}")
+    child = O.normalize(E.eval_expression(sub_tbl, inner.args[0]))
+    if inner.op == "count":
+        return frame_agg_partition(child.to_pylist(), "count", inner.value or "valid", start, end, min_periods, ""), pa.uint64()
+    if inner.op == "mean":
+        acc, typ = "double", pa.float64()
+        vals = child.cast(pa.float64(), safe=False).to_pylist()   # i64 -> f64 rounds to nearest, as the reference cast does
+    elif inner.op in ("min", "max"):
+        if not (pa.types.is_integer(child.type) or pa.types.is_date32(child.type) or pa.types.is_timestamp(child.type)):
+            raise NotImplementedError("window frame min / max over non-integer values")
+        # plain comparisons of the values themselves (integers, dates, instants): no accumulate type involved
+        return frame_agg_partition(child.to_pylist(), inner.op, None, start, end, min_periods, ""), child.type
+    else:
+        acc = FRAME_ACC.get(str(child.type))
+        if acc is None:
+            raise TypeError(f"Cannot run Sum over type {child.type}")
+        typ = {"int64": pa.int64(), "uint64": pa.uint64(), "float": pa.float32(), "double": pa.float64()}[acc]
+        vals = child.cast(typ).to_pylist()
+    return frame_agg_partition(vals, inner.op, None, start, end, min_periods, acc), typ
 
 
 def pivot(tbl: pa.Table, group_by: Sequence[str], pivot_col: str, values_col: str, names: Sequence[str]) -> pa.Table:

@@ -258,3 +258,107 @@ def test_composite_aggregates_nest_in_one_call():
             keys = [g.name() for g in gb]
             a, b = (_sorted(got, keys), _sorted(want, keys)) if keys else (got, want)
             assert_tables_equal(a, b, float_rtol=1e-12)
+
+
+# ---- aggregates over ROWS frames (RecordBatch::window_agg_dynamic_frame, src/daft-recordbatch/src/ops/window.rs:299-483) ----
+# three parties: a naive "aggregate the slice" expectation (what the reference's own tests compute, tests/window/test_running_agg.py),
+# the oracle's restatement of the sliding state machine, and daft_b200.window's composition running the host build of the device's
+# state machine (tests/wf_host.cpp <- daft_b200/csrc/window_frame_core.h)
+
+def _naive_frames(values, start, end, min_periods, fn):
+    out, m = [], len(values)
+    for r in range(m):
+        fs = 0 if start is None else min(max(r + start, 0), m)
+        fe = m if end is None else min(max(r + 1 + end, 0), m)
+        live = [v for v in values[fs:fe] if v is not None]
+        out.append(fn(live, fe - fs) if fe - fs >= min_periods else None)
+    return out
+
+
+@pytest.mark.parametrize("start,end,min_periods", [(None, 0, 1), (-2, 0, 1), (-2, 0, 3), (-10, -3, 3), (2, 9, 3), (None, 2, 1), (-3, None, 1), (-2, 2, 1),
+                                                   (-1, 1, 1), (-3, 0, 4), (0, 0, 1), (1, 0, 1), (None, None, 1), (5, 7, 1), (-7, -5, 2), (-(2**62), 2**62, 1), (-(2**63), 2**63 - 1, 2)])
+def test_window_frames_reference_running_agg_cases(start, end, min_periods):
+    """tests/window/test_running_agg.py:25-130 (running sum), :270-297 (mean over -2..0 with min_periods 3), :300-395 (negative / positive
+    bounds with min_periods), :398-465 (one unbounded side), :468-560 (centred frames), :563-620 (min_periods 1-4): integer data, so the
+    slice aggregate the reference's tests expect is exact"""
+    import random
+    random.seed(444)
+    cats, ts, vals = [], [], []
+    per = {}
+    for c in ["X", "Y", "Z"]:
+        v = [random.randint(1, 100) if random.random() > 0.1 else None for _ in range({"X": 100, "Y": 37, "Z": 1}[c])]
+        per[c] = v
+        cats += [c] * len(v); ts += list(range(len(v))); vals += v
+    order = list(range(len(vals)))
+    random.shuffle(order)
+    tbl = pa.table({"category": pa.array([cats[i] for i in order], pa.large_string()), "ts": [ts[i] for i in order], "value": pa.array([vals[i] for i in order], pa.int32())})
+    funcs = [("frame", "s", col("value").sum(), start, end, min_periods), ("frame", "m", col("value").mean(), start, end, min_periods),
+             ("frame", "c", col("value").count(), start, end, min_periods), ("frame", "ca", col("value").count("all"), start, end, min_periods),
+             ("frame", "cn", col("value").count("null"), start, end, min_periods), ("frame", "mn", col("value").min(), start, end, min_periods),
+             ("frame", "mx", col("value").max(), start, end, min_periods)]
+    want = {k: [] for k in ("s", "m", "c", "ca", "cn", "mn", "mx")}
+    for c in ["X", "Y", "Z"]:
+        v = per[c]
+        want["s"] += _naive_frames(v, start, end, min_periods, lambda live, size: sum(live) if live else None)
+        want["m"] += _naive_frames(v, start, end, min_periods, lambda live, size: sum(live) / len(live) if live else None)
+        want["c"] += _naive_frames(v, start, end, min_periods, lambda live, size: len(live))
+        want["ca"] += _naive_frames(v, start, end, min_periods, lambda live, size: size)
+        want["cn"] += _naive_frames(v, start, end, min_periods, lambda live, size: size - len(live))
+        want["mn"] += _naive_frames(v, start, end, min_periods, lambda live, size: min(live) if live else None)
+        want["mx"] += _naive_frames(v, start, end, min_periods, lambda live, size: max(live) if live else None)
+    for got in _both(tbl, [col("category")], [col("ts")], [False], [False], funcs):
+        assert [str(got.schema.field(k).type) for k in ("s", "m", "c", "ca", "cn", "mn", "mx")] == ["int64", "double", "uint64", "uint64", "uint64", "int32", "int32"]
+        got = got.sort_by([("category", "ascending"), ("ts", "ascending")]).to_pydict()
+        for k in want:
+            if k == "m":   # the sliding sum of integers held in Float64 is exact here (small values), the division is one rounding
+                assert got[k] == pytest.approx(want[k], rel=1e-15, abs=0) if None not in want[k] else all(
+                    (a is None and b is None) or (a is not None and b is not None and abs(a - b) <= 1e-12 * abs(b)) for a, b in zip(got[k], want[k]))
+            else:
+                assert got[k] == want[k], k
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_window_frames_float_state_machine_is_bit_exact(seed):
+    """floats (NaN, +-inf, nulls, magnitudes 1e-8 .. 1e12): the sliding `+=` / `-=` sequence of the reference's SumWindowState is order
+    dependent -- the host build of the device's state machine must agree with the oracle's restatement bit for bit; every dtype the
+    reference accumulates differently (Int64 / UInt64 wrap, Float32 in Float32); descending order, several partition keys"""
+    rng = np.random.default_rng(seed)
+    n = 300
+    x = rng.standard_normal(n) * 10.0 ** rng.integers(-8, 12, n)
+    x[rng.random(n) < 0.03] = np.nan
+    x[rng.random(n) < 0.02] = np.inf
+    x[rng.random(n) < 0.02] = -np.inf
+    tbl = pa.table({"id": np.arange(n), "g": pa.array(rng.integers(0, 6, n)), "h": pa.array(rng.integers(0, 2, n).astype(np.int8), mask=rng.random(n) < 0.1),
+                    "o": pa.array(rng.integers(0, 40, n)),
+                    "f64": pa.array(x, mask=rng.random(n) < 0.15), "f32": pa.array(x.astype(np.float32), mask=rng.random(n) < 0.15),
+                    "i64": pa.array(rng.integers(-2**62, 2**62, n), mask=rng.random(n) < 0.1), "u64": pa.array(rng.integers(0, 2**64, n, dtype=np.uint64)),
+                    "i8": pa.array(rng.integers(-128, 128, n).astype(np.int8), mask=rng.random(n) < 0.1), "u16": pa.array(rng.integers(0, 65536, n).astype(np.uint16)),
+                    "d": pa.array(rng.integers(0, 20000, n).astype(np.int32), pa.date32(), mask=rng.random(n) < 0.1)})
+    frames = [(None, 0, 1), (-3, 0, 1), (-1, 4, 2), (2, 5, 1), (-6, -2, 3), (None, None, 1), (-2, None, 1), (0, 0, 1)]
+    start, end, mp = frames[seed % len(frames)]
+    start2, end2, mp2 = frames[(seed + 3) % len(frames)]
+    funcs = []
+    for c in ("f64", "f32", "i64", "u64", "i8", "u16"):
+        funcs += [("frame", f"s_{c}", col(c).sum(), start, end, mp), ("frame", f"m_{c}", col(c).mean(), start2, end2, mp2),
+                  ("frame", f"c_{c}", col(c).count(), start, end, mp)]
+    for c in ("i64", "u64", "i8", "u16", "d"):
+        funcs += [("frame", f"mn_{c}", col(c).min(), start2, end2, mp2), ("frame", f"mx_{c}", col(c).max(), start, end, mp)]
+    funcs += [("frame", "expr", (col("f64") * 2.0 + col("i8")).sum(), start, end, mp), ("row_number", "rn")]
+    desc = bool(seed % 2)
+    a, b = _both(tbl, [col("g"), col("h")], [col("o"), col("id")], [desc, False], [desc, False], funcs)
+    assert a.schema.field("s_f32").type == pa.float32() and a.schema.field("s_i8").type == pa.int64() and a.schema.field("s_u16").type == pa.uint64()
+    assert a.schema.field("mn_d").type == pa.date32() and a.schema.field("m_i8").type == pa.float64()
+    assert_tables_equal(_sorted(b, ["id"]), _sorted(a, ["id"]), float_rtol=0.0)
+
+
+def test_window_frames_errors():
+    tbl = pa.table({"g": [1, 1, 2], "o": [1, 2, 3], "x": [1.0, 2.0, 3.0], "s": pa.array(["a", "b", "c"], pa.large_string())})
+    for make in (lambda t: EmulatedQueryBatch(t),):
+        with pytest.raises(ValueError, match="Negative frame size"):
+            W.window(make(tbl), [col("g")], [col("o")], [False], [False], [("frame", "f", col("x").sum(), 3, 1)])
+        with pytest.raises(NotImplementedError):
+            W.window(make(tbl), [col("g")], [col("o")], [False], [False], [("frame", "f", col("x").min(), -1, 0)])   # float min / max over frames
+        with pytest.raises(NotImplementedError):
+            W.window(make(tbl), [col("g")], [col("o")], [False], [False], [("frame", "f", col("x").stddev(), -1, 0)])
+        with pytest.raises(TypeError):
+            W.window(make(tbl), [col("g")], [col("o")], [False], [False], [("frame", "f", col("s").sum(), -1, 0)])
