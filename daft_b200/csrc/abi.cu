@@ -415,14 +415,15 @@ int b200_window_offset(const b200_batch *values, const b200_batch *partition_ids
         *out = op_window_offset(*values, materialize(col_at(partition_ids, 0)), offset);
     });
 }
-int b200_window_frame(const b200_batch *values, const b200_batch *partition_begin, int32_t agg, int32_t has_start, int64_t start,
-                      int32_t has_end, int64_t end, int64_t min_periods, b200_batch **out, char **errmsg) {
+int b200_window_frame(const b200_batch *values, const b200_batch *partition_begin, const b200_batch *order, int32_t agg, int32_t start_kind,
+                      int64_t start, int32_t end_kind, int64_t end, int32_t descending, int64_t min_periods, b200_batch **out, char **errmsg) {
     return guard(errmsg, [&] {
         if (!partition_begin) fail("null batch");
-        Column v;
+        Column v, o;
         if (values) v = materialize(col_at(values, 0));
-        *out = op_window_frame(values ? &v : nullptr, materialize(col_at(partition_begin, 0)), agg, has_start, start, has_end, end, min_periods,
-                               values ? v.name.c_str() : "count");
+        if (order) o = materialize(col_at(order, 0));
+        *out = op_window_frame(values ? &v : nullptr, materialize(col_at(partition_begin, 0)), order ? &o : nullptr, agg, start_kind, start, end_kind, end,
+                               descending, min_periods, values ? v.name.c_str() : "count");
     });
 }
 int b200_concat(const b200_batch *const *batches, int32_t n, b200_batch **out, char **errmsg) {

@@ -40,9 +40,9 @@ Batch *op_cross_join(const Batch &left, const Batch &right, bool outer_loop_left
 // window functions over a batch sorted by (partition keys, order keys) (sort.cu)
 Batch *op_window_ranks(const Batch &sorted, const int32_t *part_cols, int32_t npart, const int32_t *order_cols, int32_t norder);
 Batch *op_window_offset(const Batch &values, const Column &partition_id, int64_t offset);
-// window_frame.cu: an aggregate over a ROWS frame of every partition (values: null for count(*))
-Batch *op_window_frame(const Column *values, const Column &partition_begin, int32_t agg, int32_t has_start, int64_t start, int32_t has_end,
-                       int64_t end, int64_t min_periods, const char *name);
+// window_frame.cu: an aggregate over a ROWS / RANGE frame of every partition (values: null for count(*); order: the ORDER BY column, RANGE only)
+Batch *op_window_frame(const Column *values, const Column &partition_begin, const Column *order, int32_t agg, int32_t start_kind, int64_t start,
+                       int32_t end_kind, int64_t end, int32_t descending, int64_t min_periods, const char *name);
 
 // ops_jit.cu: ascending indices of the set (or, inverted, clear) bits among the first n bits
 Buf bitmap_select(const uint32_t *words, int64_t n, bool invert, int64_t *count_out);

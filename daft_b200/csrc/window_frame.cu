@@ -1,4 +1,4 @@
-// Window aggregates over ROWS frames on the device: the reference's WindowPartitionAndDynamicFrameSink
+// Window aggregates over ROWS and RANGE frames on the device: the reference's WindowPartitionAndDynamicFrameSink
 // (src/daft-local-execution/src/sinks/window_partition_and_dynamic_frame.rs) calls RecordBatch::window_agg_dynamic_frame
 // (src/daft-recordbatch/src/ops/window.rs:299-385) once per partition; here every partition of the sorted batch is walked by its own
 // thread, all of them in one launch, through the state machine of window_frame_core.h (one thread per partition because a sliding
@@ -15,12 +15,12 @@ using namespace wf;
 
 template <typename T>
 __global__ void window_frame_kernel(FrameSpec f, const T *__restrict__ v, const uint8_t *__restrict__ bits, const int64_t *__restrict__ pbegin,
-                                    int64_t n, T *out_t, uint64_t *out_u64, double *out_f64, uint8_t *ok) {
+                                    int64_t n, T *out_t, uint64_t *out_u64, double *out_f64, uint8_t *ok, int *negative_frame) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || pbegin[i] != i) return;   // the first row of a partition works for all of it
     int64_t e = i + 1;
     while (e < n && pbegin[e] == i) e++;
-    frame_partition<T>(f, v, bits, i, e - i, out_t, out_u64, out_f64, ok);
+    if (!frame_partition<T>(f, v, bits, i, e - i, out_t, out_u64, out_f64, ok)) *negative_frame = 1;
 }
 // one byte per row -> LSB-first validity bitmap, one output byte per thread
 __global__ void window_frame_pack_kernel(const uint8_t *__restrict__ ok, int64_t n, uint8_t *__restrict__ bitmap) {
@@ -34,16 +34,24 @@ __global__ void window_frame_pack_kernel(const uint8_t *__restrict__ ok, int64_t
 
 static inline int wf_grid(int64_t n) { return (int)std::max<int64_t>(1, (n + 255) / 256); }
 
-Batch *op_window_frame(const Column *values, const Column &partition_begin, int32_t agg, int32_t has_start, int64_t start, int32_t has_end,
-                       int64_t end, int64_t min_periods, const char *name) {
+Batch *op_window_frame(const Column *values, const Column &partition_begin, const Column *order, int32_t agg, int32_t start_kind, int64_t start,
+                       int32_t end_kind, int64_t end, int32_t descending, int64_t min_periods, const char *name) {
     require_device();
     require_plain(partition_begin);
     const int64_t n = partition_begin.length;
     if (partition_begin.dtype != B200_I64 || partition_begin.null_count > 0) fail("window_frame: partition_begin must be a non-null Int64 column");
     if (agg < WF_SUM || agg > WF_MAX) fail("window_frame: unknown aggregate");
-    if (has_start && has_end && start > end && start - end > 1) fail("Negative frame size is not allowed");   // window.rs:156-160
+    if (start_kind < WF_UNBOUNDED || start_kind > WF_RANGE || end_kind < WF_UNBOUNDED || end_kind > WF_RANGE) fail("window_frame: unknown boundary kind");
+    if (start_kind == WF_ROWS && end_kind == WF_ROWS && start > end && start - end > 1) fail("Negative frame size is not allowed");   // window.rs:156-160
     const bool counts = agg == WF_COUNT_ALL || agg == WF_COUNT_VALID || agg == WF_COUNT_NULL;
-    FrameSpec f{agg, WF_I64, has_start ? 1 : 0, has_end ? 1 : 0, start, end, min_periods};
+    FrameSpec f{agg, WF_I64, start_kind, end_kind, start, end, min_periods, descending ? 1 : 0, nullptr, nullptr};
+    if (start_kind == WF_RANGE || end_kind == WF_RANGE) {
+        if (!order) fail("window_frame: a RANGE frame needs the ORDER BY column");
+        require_plain(*order);
+        if (order->dtype != B200_I64 || order->length != n) fail("window_frame: the ORDER BY column of a RANGE frame must be Int64 (the host casts), one value per row");
+        f.order = as<int64_t>(order->data);
+        f.order_bits = order->null_count > 0 ? as<uint8_t>(order->validity) : nullptr;
+    }
     const uint8_t *bits = nullptr;
     const void *v = nullptr;
     int32_t out_dtype = B200_U64;
@@ -72,23 +80,25 @@ Batch *op_window_frame(const Column *values, const Column &partition_begin, int3
     Buf out = dev_alloc((size_t)std::max<int64_t>(n, 1) * width);
     Buf ok = dev_alloc((size_t)std::max<int64_t>(n, 1));
     Buf bitmap = dev_alloc_zero((size_t)(std::max<int64_t>(n, 1) + 7) / 8 + 8);
+    Buf negative = dev_alloc_zero(8);
     if (n > 0) {
         cudaStream_t st = ctx().stream;
         const int64_t *pb = as<int64_t>(partition_begin.data);
         KernelTimer t("window_frame");
         if (counts || f.vtype == WF_I64)
-            window_frame_kernel<int64_t><<<wf_grid(n), 256, 0, st>>>(f, counts ? nullptr : (const int64_t *)v, bits, pb, n, as<int64_t>(out), as<uint64_t>(out), nullptr, as<uint8_t>(ok));
+            window_frame_kernel<int64_t><<<wf_grid(n), 256, 0, st>>>(f, counts ? nullptr : (const int64_t *)v, bits, pb, n, as<int64_t>(out), as<uint64_t>(out), nullptr, as<uint8_t>(ok), as<int>(negative));
         else if (f.vtype == WF_U64)
-            window_frame_kernel<uint64_t><<<wf_grid(n), 256, 0, st>>>(f, (const uint64_t *)v, bits, pb, n, as<uint64_t>(out), nullptr, nullptr, as<uint8_t>(ok));
+            window_frame_kernel<uint64_t><<<wf_grid(n), 256, 0, st>>>(f, (const uint64_t *)v, bits, pb, n, as<uint64_t>(out), nullptr, nullptr, as<uint8_t>(ok), as<int>(negative));
         else if (f.vtype == WF_F32)
-            window_frame_kernel<float><<<wf_grid(n), 256, 0, st>>>(f, (const float *)v, bits, pb, n, as<float>(out), nullptr, nullptr, as<uint8_t>(ok));
+            window_frame_kernel<float><<<wf_grid(n), 256, 0, st>>>(f, (const float *)v, bits, pb, n, as<float>(out), nullptr, nullptr, as<uint8_t>(ok), as<int>(negative));
         else
-            window_frame_kernel<double><<<wf_grid(n), 256, 0, st>>>(f, (const double *)v, bits, pb, n, as<double>(out), nullptr, as<double>(out), as<uint8_t>(ok));
+            window_frame_kernel<double><<<wf_grid(n), 256, 0, st>>>(f, (const double *)v, bits, pb, n, as<double>(out), nullptr, as<double>(out), as<uint8_t>(ok), as<int>(negative));
         count_launch();
         B200_CUDA(cudaGetLastError());
         window_frame_pack_kernel<<<wf_grid((n + 7) / 8), 256, 0, st>>>(as<uint8_t>(ok), n, as<uint8_t>(bitmap));
         count_launch();
         B200_CUDA(cudaGetLastError());
+        if (read_i64(as<int64_t>(negative)) != 0) fail("Negative frame size is not allowed");   // window.rs:264-268, found by some row's RANGE search
     }
     Column c;
     c.name = name ? name : "window_frame";

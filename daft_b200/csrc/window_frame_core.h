@@ -1,6 +1,6 @@
-// Window aggregates over ROWS frames: RecordBatch::window_agg_dynamic_frame with row offsets
-// (src/daft-recordbatch/src/ops/window.rs:299-385 -> window_agg_rows_incremental :388-438, window_agg_rows :441-483), one partition
-// per call.  The reference slides an aggregate state over the partition -- rows that left the frame are REMOVED from the state, rows
+// Window aggregates over ROWS and RANGE frames: RecordBatch::window_agg_dynamic_frame
+// (src/daft-recordbatch/src/ops/window.rs:299-385 -> window_agg_rows_incremental :388-438, window_agg_rows :441-483,
+// window_agg_range_incremental :486-566, window_agg_range :569-633), one partition per call.  The reference slides an aggregate state over the partition -- rows that left the frame are REMOVED from the state, rows
 // that entered it are ADDED (update_incremental_state, window.rs:274-296; states in ops/window_states/{sum,count,mean}.rs) -- so a
 // float sum is the result of exactly that sequence of `+=` and `-=`; the same sequence runs here, which is why a partition is walked
 // by one thread (partitions run in parallel).  min / max have no incremental state in the reference (window_states/mod.rs:47-49):
@@ -23,11 +23,16 @@ namespace wf {
 enum Agg { WF_SUM = 0, WF_COUNT_ALL = 1, WF_COUNT_VALID = 2, WF_COUNT_NULL = 3, WF_MEAN = 4, WF_MIN = 5, WF_MAX = 6 };
 enum VType { WF_I64 = 0, WF_U64 = 1, WF_F32 = 2, WF_F64 = 3 };
 
+enum Bound { WF_UNBOUNDED = 0, WF_ROWS = 1, WF_RANGE = 2 };
+
 struct FrameSpec {
     int32_t agg, vtype;
-    int32_t has_start, has_end;   // 0: UNBOUNDED PRECEDING / UNBOUNDED FOLLOWING
-    int64_t start, end;           // row offsets relative to the current row (negative = preceding)
+    int32_t has_start, has_end;   // Bound: 0 UNBOUNDED PRECEDING / FOLLOWING, 1 row offset, 2 offset on the ORDER BY value (RANGE)
+    int64_t start, end;           // offsets relative to the current row / the current row's order value (negative = preceding)
     int64_t min_periods;          // frames holding fewer rows give null
+    int32_t descending;           // RANGE frames: the direction the partition is sorted in
+    const int64_t *order;         // RANGE frames: the ORDER BY column as Int64 (sorted batch), its validity bits (null = all valid)
+    const uint8_t *order_bits;
 };
 
 // calculate_row_frame_bounds (window.rs:136-163): usize saturating_add_signed, then min(total_rows)
@@ -35,12 +40,37 @@ WF_HD int64_t clamp_add(int64_t base, int64_t off, int64_t total) {
     if (off < 0) return off < -base ? 0 : base + off;
     return off > total - base ? total : base + off;
 }
-WF_HD void frame_bounds(const FrameSpec &f, int64_t row, int64_t total, int64_t &fs, int64_t &fe) {
-    fs = f.has_start ? clamp_add(row, f.start, total) : 0;
-    fe = f.has_end ? clamp_add(row + 1, f.end, total) : total;
-}
-
 WF_HD bool bit_set(const uint8_t *bits, int64_t i) { return !bits || ((bits[i >> 3] >> (i & 7)) & 1); }
+
+// calculate_range_frame_bounds (window.rs:167-272).  A RANGE boundary is searched FORWARD from where the previous frame's boundary
+// was (`prev`): the first row whose order value v satisfies, ascending, v >= cur + start (frame start) / v > cur + end (frame end);
+// descending, v <= cur + start / v < cur + end.  A comparison with a null on either side is false (`.get(0).unwrap_or(false)`), so
+// null order values are stepped over and a null current value sends both boundaries to the end of the partition.  cur + offset wraps.
+WF_HD int64_t range_search(const FrameSpec &f, int64_t base, int64_t row, int64_t total, int64_t prev, int64_t off, bool is_end) {
+    int64_t idx = prev;
+    if (!bit_set(f.order_bits, base + row)) return idx > total ? idx : total;
+    const int64_t bound = (int64_t)((uint64_t)f.order[base + row] + (uint64_t)off);
+    for (; idx < total; idx++) {
+        if (!bit_set(f.order_bits, base + idx)) continue;
+        const int64_t v = f.order[base + idx];
+        const bool hit = f.descending ? (is_end ? v < bound : v <= bound) : (is_end ? v > bound : v >= bound);
+        if (hit) break;
+    }
+    return idx;
+}
+// -> false when the frame would have a negative size (the reference raises "Negative frame size is not allowed")
+WF_HD bool frame_bounds(const FrameSpec &f, int64_t base, int64_t row, int64_t total, int64_t prev_s, int64_t prev_e, int64_t &fs, int64_t &fe) {
+    // descending + both boundaries RANGE: the reference swaps them (window.rs:507-513)
+    const bool swap = f.descending && f.has_start == WF_RANGE && f.has_end == WF_RANGE;
+    const int64_t so = swap ? f.end : f.start, eo = swap ? f.start : f.end;
+    fs = f.has_start == WF_UNBOUNDED ? 0 : f.has_start == WF_ROWS ? clamp_add(row, f.start, total) : range_search(f, base, row, total, prev_s, so, false);
+    fe = f.has_end == WF_UNBOUNDED ? total : f.has_end == WF_ROWS ? clamp_add(row + 1, f.end, total) : range_search(f, base, row, total, prev_e, eo, true);
+    if (fe < fs) {
+        fe = fs;
+        return false;
+    }
+    return true;
+}
 
 template <typename T> struct Wrap { typedef T U; };
 template <> struct Wrap<int64_t> { typedef uint64_t U; };   // `+=` / `-=` on i64 wrap in the reference's release build
@@ -97,14 +127,19 @@ template <typename T> WF_HD void state_remove(State<T> &s, const T *v, const uin
 
 // One partition: rows [base, base + total) of the sorted batch.  `v` may be null for the counts.  Outputs are indexed like the
 // inputs: out_t (sum / min / max, type T), out_u64 (counts), out_f64 (mean), ok = 1 where the row's result is not null.
+// Returns false when some row's frame had a negative size.
 template <typename T>
-WF_HD void frame_partition(const FrameSpec &f, const T *v, const uint8_t *bits, int64_t base, int64_t total, T *out_t, uint64_t *out_u64,
+WF_HD bool frame_partition(const FrameSpec &f, const T *v, const uint8_t *bits, int64_t base, int64_t total, T *out_t, uint64_t *out_u64,
                            double *out_f64, uint8_t *ok) {
     const uint64_t min_periods = f.min_periods < 0 ? 0 : (uint64_t)f.min_periods;
+    bool fine = true;
     if (f.agg == WF_MIN || f.agg == WF_MAX) {
+        int64_t ps = 0, pe = 0;   // window_agg_range: the search resumes from EVERY previous row's frame (window.rs:609-610)
         for (int64_t row = 0; row < total; row++) {
             int64_t fs, fe;
-            frame_bounds(f, row, total, fs, fe);
+            fine = frame_bounds(f, base, row, total, ps, pe, fs, fe) && fine;
+            ps = fs;
+            pe = fe;
             bool any = false;
             T best = (T)0;
             if (fe >= fs && (uint64_t)(fe - fs) >= min_periods)
@@ -117,15 +152,15 @@ WF_HD void frame_partition(const FrameSpec &f, const T *v, const uint8_t *bits, 
             out_t[base + row] = any ? best : (T)0;
             ok[base + row] = any ? 1 : 0;
         }
-        return;
+        return fine;
     }
     State<T> s;
     s.sum = (T)0;
     s.valid_not_nan = s.nan = s.total = s.valid = 0;
     int64_t prev_s = 0, prev_e = 0;
     for (int64_t row = 0; row < total; row++) {
-        int64_t fs, fe;
-        frame_bounds(f, row, total, fs, fe);
+        int64_t fs, fe;   // the incremental path resumes a RANGE search from the last frame that was large enough (window.rs:525-552)
+        fine = frame_bounds(f, base, row, total, prev_s, prev_e, fs, fe) && fine;
         const bool enough = fe >= fs && (uint64_t)(fe - fs) >= min_periods;
         if (enough) {
             if (fs > prev_s) state_remove(s, v, bits, base, prev_s, fs);
@@ -152,6 +187,7 @@ WF_HD void frame_partition(const FrameSpec &f, const T *v, const uint8_t *bits, 
             default: out_u64[o] = s.total - s.valid; ok[o] = enough; break;
         }
     }
+    return fine;
 }
 
 }  // namespace wf

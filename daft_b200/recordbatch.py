@@ -577,12 +577,16 @@ class RecordBatch:
         _lib.call("b200_window_offset", self._h, partition_ids._h, ctypes.c_int64(offset), ctypes.byref(out))
         return RecordBatch._wrap(out, names=self.column_names() + ["__src"], dtypes=self.dtypes() + [dt.I64])
 
-    def _window_frame(self, partition_begin: "RecordBatch", agg: int, start, end, min_periods: int, out_dtype: int) -> "RecordBatch":
+    def _window_frame(self, partition_begin: "RecordBatch", agg: int, start, end, min_periods: int, out_dtype: int, kind: int = 1,
+                      order: "RecordBatch | None" = None, descending: bool = False) -> "RecordBatch":
         """b200_window_frame: aggregate `agg` (include/daft_b200.h) of this batch's one column -- already in the accumulate type -- over the
-        ROWS frame [start, end] (None = unbounded) of every row; `self` may have no columns for count(*)."""
+        frame [start, end] (None = unbounded) of every row; kind 1: row offsets, 2: offsets on the value of `order` (one Int64 column);
+        `self` may have no columns for count(*)."""
         out = ctypes.c_void_p()
-        _lib.call("b200_window_frame", self._h if self.num_columns() else None, partition_begin._h, ctypes.c_int32(agg), ctypes.c_int32(start is not None),
-                  ctypes.c_int64(start or 0), ctypes.c_int32(end is not None), ctypes.c_int64(end or 0), ctypes.c_int64(min_periods), ctypes.byref(out))
+        _lib.call("b200_window_frame", self._h if self.num_columns() else None, partition_begin._h, order._h if order is not None else None,
+                  ctypes.c_int32(agg), ctypes.c_int32(kind if start is not None else 0), ctypes.c_int64(start or 0),
+                  ctypes.c_int32(kind if end is not None else 0), ctypes.c_int64(end or 0), ctypes.c_int32(bool(descending)), ctypes.c_int64(min_periods),
+                  ctypes.byref(out))
         return RecordBatch._wrap(out, names=[self.column_names()[0] if self.num_columns() else "count"], dtypes=[out_dtype])
 
     def window(self, partition_by: Sequence[Expression], order_by: Sequence[Expression] = (), descending=None, nulls_first=None,

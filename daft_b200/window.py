@@ -26,7 +26,9 @@ def window(batch: RecordBatch, partition_by: Sequence[Expression], order_by: Seq
     """`functions`: ("row_number" | "rank" | "dense_rank", name), ("offset", name, expr, offset[, default]) -- lead for a positive
     offset, lag for a negative one -- ("agg", name, aggregate expression) for an aggregate over the whole partition, or
     ("frame", name, aggregate expression, start, end[, min_periods = 1]) for sum / count / mean / min / max over the ROWS frame
-    [current row + start, current row + end] (None = unbounded on that side; RecordBatch::window_agg_dynamic_frame).
+    [current row + start, current row + end] (None = unbounded on that side; RecordBatch::window_agg_dynamic_frame);
+    ("range_frame", ...) with the same fields takes start / end as integer offsets on the value of the single ORDER BY key (an integer,
+    a Date in days, a Timestamp in microseconds): the frame holds the rows whose key lies in [key + start, key + end].
     Returns the batch's columns plus one column per function, rows ordered by (partition keys, order keys)."""
     partition_by, order_by = list(partition_by), list(order_by)
     if not partition_by and not order_by:
@@ -78,10 +80,15 @@ def window(batch: RecordBatch, partition_by: Sequence[Expression], order_by: Seq
             j = work.eval_expression_list([col("__partition_id")]).hash_join(g, [col("__partition_id")], [col("__partition_id")], build_on_left=False)
             work = work.union(j.eval_expression_list([col(f"__w_{name}")]))
             result.append(col(f"__w_{name}").alias(name))
-        elif kind == "frame":
+        elif kind in ("frame", "range_frame"):
             start, end = f[3], f[4]
             min_periods = int(f[5]) if len(f) > 5 else 1
-            work = work.union(_frame_agg(work, f[2], start, end, min_periods, f"__w_{name}"))
+            order = None
+            if kind == "range_frame":
+                if n_o != 1:   # validate_range_frame_order_by, window.rs:109-116
+                    raise ValueError("Range frame requires exactly one ORDER BY column, multiple columns are not supported")
+                order = (col(names[idx[n_p]]), desc[0])
+            work = work.union(_frame_agg(work, f[2], start, end, min_periods, f"__w_{name}", order))
             result.append(col(f"__w_{name}").alias(name))
         else:
             raise ValueError(f"window: unknown function {kind!r}")
@@ -91,8 +98,9 @@ def window(batch: RecordBatch, partition_by: Sequence[Expression], order_by: Seq
 FRAME_AGGS = {"sum": 0, "count": {"all": 1, "valid": 2, "null": 3}, "mean": 4, "min": 5, "max": 6}
 
 
-def _frame_agg(work: RecordBatch, agg_expr: Expression, start, end, min_periods: int, out_name: str) -> RecordBatch:
-    """One aggregate over a ROWS frame of the sorted, rank-annotated batch `work` -> a one-column batch named `out_name`.
+def _frame_agg(work: RecordBatch, agg_expr: Expression, start, end, min_periods: int, out_name: str, order=None) -> RecordBatch:
+    """One aggregate over a ROWS frame (or, with `order` = (key column, descending), a RANGE frame) of the sorted, rank-annotated batch
+    `work` -> a one-column batch named `out_name`.
     The value is cast to the type the reference's window state accumulates in (window_states/sum.rs:137-158: signed integers as Int64,
     unsigned as UInt64, floats as they are; mean.rs:92-100: Float64); min / max run on the Int64 / UInt64 image of integer-like values
     and are cast back (the reference re-aggregates every frame with the ordinary aggregate, window.rs:441-483)."""
@@ -100,15 +108,23 @@ def _frame_agg(work: RecordBatch, agg_expr: Expression, start, end, min_periods:
     inner = _agg_inner(agg_expr)
     if inner.kind != "agg" or inner.op not in FRAME_AGGS:
         raise NotImplementedError(f"window frame: aggregate {getattr(inner, 'op', inner.kind)!r} is not built (sum, count, mean, min, max are)")
-    if start is not None and end is not None and int(start) > int(end) + 1:
+    if order is None and start is not None and end is not None and int(start) > int(end) + 1:
         raise ValueError("Negative frame size is not allowed")   # window.rs:156-160 (raised there by the first row it happens on)
+    kw = {}
+    if order is not None:
+        key = work.eval_expression_list([order[0].alias("__o")])
+        if not dt.int_like(key.dtypes()[0]) or key.dtypes()[0] == dt.U64:
+            raise NotImplementedError(f"window range frame: ORDER BY key of type {dt.NAMES[key.dtypes()[0]]} is not built (integers below UInt64, Date, Timestamp are)")
+        if key.dtypes()[0] != dt.I64:
+            key = key.eval_expression_list([col("__o").cast(dt.I64).alias("__o")])
+        kw = dict(kind=2, order=key, descending=order[1])
     pb = work.eval_expression_list([col("__partition_begin")])
     vals = work.eval_expression_list([inner.args[0].alias("__v")])
     src = vals.dtypes()[0]
     if inner.op == "count":
         if src == dt.NULL:
             raise NotImplementedError("window frame: count over a Null column is not built")
-        out = vals._window_frame(pb, FRAME_AGGS["count"][inner.value or "valid"], start, end, min_periods, dt.U64)
+        out = vals._window_frame(pb, FRAME_AGGS["count"][inner.value or "valid"], start, end, min_periods, dt.U64, **kw)
         return out.rename([out_name])
     if inner.op == "mean":
         if not (dt.is_integer(src) or dt.is_float(src)):
@@ -127,7 +143,7 @@ def _frame_agg(work: RecordBatch, agg_expr: Expression, start, end, min_periods:
         out_dt, back = acc, (src if src != acc else None)
     if src != acc:
         vals = vals.eval_expression_list([col("__v").cast(acc).alias("__v")])
-    out = vals._window_frame(pb, FRAME_AGGS[inner.op], start, end, min_periods, out_dt).rename([out_name])
+    out = vals._window_frame(pb, FRAME_AGGS[inner.op], start, end, min_periods, out_dt, **kw).rename([out_name])
     if back is not None:
         out = out.eval_expression_list([col(out_name).cast(back).alias(out_name)])
     return out

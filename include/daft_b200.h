@@ -46,8 +46,8 @@
  *   b200_window_ranks / b200_window_offset
  *                             RecordBatch::window_row_number / window_rank / window_offset
  *                                                             src/daft-recordbatch/src/ops/window.rs:636-790
- *   b200_window_frame         RecordBatch::window_agg_dynamic_frame (ROWS frames)
- *                                                             src/daft-recordbatch/src/ops/window.rs:299-483
+ *   b200_window_frame         RecordBatch::window_agg_dynamic_frame (ROWS and RANGE frames)
+ *                                                             src/daft-recordbatch/src/ops/window.rs:299-633
  *   b200_parquet_read         stream_parquet behind the scan-task source
  *                                                             src/daft-parquet/src/read.rs:553,
  *                                                             src/daft-local-execution/src/sources/scan_task.rs:33
@@ -314,17 +314,18 @@ int b200_cross_join(const b200_batch *left, const b200_batch *right, int32_t out
 int b200_window_ranks(const b200_batch *sorted, const int32_t *partition_cols, int32_t npartition, const int32_t *order_cols,
                       int32_t norder, b200_batch **out, char **errmsg);
 int b200_window_offset(const b200_batch *values, const b200_batch *partition_ids, int64_t offset, b200_batch **out, char **errmsg);
-/*  window_frame : one aggregate over a ROWS frame -- RecordBatch::window_agg_dynamic_frame with row offsets (window.rs:299-385,
- *                 388-483; WindowPartitionAndDynamicFrameSink, sinks/window_partition_and_dynamic_frame.rs) -- for every partition
- *                 of the sorted batch.  `values`: one column, already cast to the type the reference accumulates in (Int64 / UInt64 /
- *                 Float32 / Float64: window_states/sum.rs:137-158; Float64 for mean), or NULL for count(*); `partition_begin`: that
- *                 column of b200_window_ranks.  agg: 0 sum, 1 count(all), 2 count(valid), 3 count(null), 4 mean, 5 min, 6 max
- *                 (min / max: Int64 / UInt64 values).  has_start / has_end = 0: UNBOUNDED PRECEDING / FOLLOWING; start / end: row
- *                 offsets from the current row; frames with fewer than min_periods rows give null.  Sums slide exactly as the
- *                 reference's state does (rows leaving the frame are subtracted, rows entering it added), so floats agree bit for bit.
- *                 RANGE frames are not built. */
-int b200_window_frame(const b200_batch *values, const b200_batch *partition_begin, int32_t agg, int32_t has_start, int64_t start,
-                      int32_t has_end, int64_t end, int64_t min_periods, b200_batch **out, char **errmsg);
+/*  window_frame : one aggregate over a ROWS or RANGE frame -- RecordBatch::window_agg_dynamic_frame (window.rs:299-633;
+ *                 WindowPartitionAndDynamicFrameSink, sinks/window_partition_and_dynamic_frame.rs) -- for every partition of the sorted
+ *                 batch.  `values`: one column, already cast to the type the reference accumulates in (Int64 / UInt64 / Float32 /
+ *                 Float64: window_states/sum.rs:137-158; Float64 for mean), or NULL for count(*); `partition_begin`: that column of
+ *                 b200_window_ranks.  agg: 0 sum, 1 count(all), 2 count(valid), 3 count(null), 4 mean, 5 min, 6 max (min / max: Int64 /
+ *                 UInt64 values).  start_kind / end_kind: 0 UNBOUNDED PRECEDING / FOLLOWING, 1 `start` / `end` are row offsets from the
+ *                 current row, 2 they are offsets on the ORDER BY value (RANGE: `order` = that one column as Int64, `descending` its
+ *                 direction; NULL otherwise).  Frames with fewer than min_periods rows give null.  Sums slide exactly as the
+ *                 reference's state does (rows leaving the frame are subtracted, rows entering it added), so floats agree bit for
+ *                 bit.  A frame of negative size fails with the reference's message. */
+int b200_window_frame(const b200_batch *values, const b200_batch *partition_begin, const b200_batch *order, int32_t agg, int32_t start_kind,
+                      int64_t start, int32_t end_kind, int64_t end, int32_t descending, int64_t min_periods, b200_batch **out, char **errmsg);
 
 /* ---- a12: exchange (hash repartition over NCCL; one process per GPU) ---- */
 typedef struct b200_comm b200_comm;

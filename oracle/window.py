@@ -85,8 +85,13 @@ def window(tbl: pa.Table, partition_by: Sequence, order_by: Sequence, descending
                         if v is not None and vals and isinstance(next((x for x in vals if x is not None), v), float):
                             v = float(v)
                         new_cols[name].append(v)
-            elif kind == "frame":
-                vals, frame_types[name] = frame_agg(sub_tbl, f[2], f[3], f[4], int(f[5]) if len(f) > 5 else 1)
+            elif kind in ("frame", "range_frame"):
+                rng_kw = {}
+                if kind == "range_frame":
+                    if len(order_by) != 1:
+                        raise ValueError("Range frame requires exactly one ORDER BY column, multiple columns are not supported")
+                    rng_kw = dict(order=E.eval_expression(sub_tbl, order_by[0]), descending=bool(list(descending)[0]))
+                vals, frame_types[name] = frame_agg(sub_tbl, f[2], f[3], f[4], int(f[5]) if len(f) > 5 else 1, **rng_kw)
                 new_cols[name] += vals
             elif kind == "agg":
                 from daft_b200.expressions import _agg_inner
@@ -100,7 +105,7 @@ def window(tbl: pa.Table, partition_by: Sequence, order_by: Sequence, descending
             typ = pa.uint64()
         elif kind == "offset":
             typ = O.normalize(E.eval_expression(tbl, f[2])).type
-        elif kind == "frame":
+        elif kind in ("frame", "range_frame"):
             typ = frame_types.get(name) or frame_agg(tbl.slice(0, 0), f[2], f[3], f[4], 1)[1]
         else:   # the aggregate's output type: what the ungrouped aggregate over the whole table yields
             from daft_b200.expressions import _agg_inner
@@ -114,23 +119,44 @@ FRAME_ACC = {"int8": "int64", "int16": "int64", "int32": "int64", "int64": "int6
              "uint64": "uint64", "float": "float", "double": "double"}   # window_states/sum.rs:137-158
 
 
-def frame_agg_partition(vals: list, op: str, mode, start, end, min_periods: int, acc: str) -> list:
+def frame_agg_partition(vals: list, op: str, mode, start, end, min_periods: int, acc: str, order=None, descending: bool = False) -> list:
     """One partition, already in frame order.  `vals`: Python values (None = null) in the accumulate type `acc`.  The state machine of
     window_agg_rows_incremental: a frame with fewer than min_periods rows leaves the state alone and gives null; otherwise rows
     [prev_start, start) are removed and rows [prev_end, end) added -- in that order, with `+=` / `-=` on the accumulate type."""
     m = len(vals)
     ftype = {"float": np.float32, "double": np.float64}.get(acc)
 
-    def bounds(r):   # calculate_row_frame_bounds, window.rs:136-163
-        fs = 0 if start is None else min(max(r + start, 0), m)
-        fe = m if end is None else min(max(r + 1 + end, 0), m)
+    def wrap(x):
+        return (x + 2**63) % 2**64 - 2**63
+
+    def bounds(r, ps=0, pe=0):
+        if order is None:   # calculate_row_frame_bounds, window.rs:136-163
+            fs = 0 if start is None else min(max(r + start, 0), m)
+            fe = m if end is None else min(max(r + 1 + end, 0), m)
+        else:
+            # calculate_range_frame_bounds, window.rs:167-272: each boundary is searched forward from the previous frame's; comparisons with
+            # a null are false; descending order with two offsets swaps them (window.rs:507-513)
+            so, eo = (end, start) if descending and start is not None and end is not None else (start, end)
+            cur = order[r]
+            fs, fe = 0, m
+            if start is not None:
+                fs = ps
+                while fs < m and not (cur is not None and order[fs] is not None and
+                                      (order[fs] <= wrap(cur + so) if descending else order[fs] >= wrap(cur + so))):
+                    fs += 1
+            if end is not None:
+                fe = pe
+                while fe < m and not (cur is not None and order[fe] is not None and
+                                      (order[fe] < wrap(cur + eo) if descending else order[fe] > wrap(cur + eo))):
+                    fe += 1
         if fe < fs:
             raise ValueError("Negative frame size is not allowed")
         return fs, fe
     out = []
     if op in ("min", "max"):   # no incremental state (window_states/mod.rs:47-49): aggregate the slice
+        ps = pe = 0
         for r in range(m):
-            fs, fe = bounds(r)
+            fs, fe = ps, pe = bounds(r, ps, pe)   # window_agg_range: the search resumes from every previous row's frame (window.rs:609-610)
             live = [v for v in vals[fs:fe] if v is not None] if fe - fs >= min_periods else []
             out.append((min(live) if op == "min" else max(live)) if live else None)
         return out
@@ -139,7 +165,7 @@ def frame_agg_partition(vals: list, op: str, mode, start, end, min_periods: int,
         sm = ftype(0)
     ps = pe = 0
     for r in range(m):
-        fs, fe = bounds(r)
+        fs, fe = bounds(r, ps, pe)   # ... from the last frame that was large enough (update_incremental_state is skipped otherwise)
         enough = fe - fs >= min_periods
         if enough:
             for lo, hi, sign in ((ps, fs, -1), (pe, fe, 1)):
@@ -174,15 +200,23 @@ def frame_agg_partition(vals: list, op: str, mode, start, end, min_periods: int,
     return out
 
 
-def frame_agg(sub_tbl: pa.Table, agg_expr, start, end, min_periods: int):
-    """-> (values, arrow type) of `agg_expr` over the ROWS frame [start, end] (None = unbounded) of every row of one partition"""
+def frame_agg(sub_tbl: pa.Table, agg_expr, start, end, min_periods: int, order=None, descending: bool = False):
+    """-> (values, arrow type) of `agg_expr` over the ROWS frame [start, end] (None = unbounded) of every row of one partition; with `order`
+    (the partition's single ORDER BY column) a RANGE frame: offsets on the key's integer value (days / microseconds for temporal keys)"""
     from daft_b200.expressions import _agg_inner
     inner = _agg_inner(agg_expr)
+    kw = {}
+    if order is not None:
+        o = O.normalize(order)
+        phys = pa.int32() if pa.types.is_date32(o.type) else pa.int64()
+        if not (pa.types.is_integer(o.type) or pa.types.is_date32(o.type) or pa.types.is_timestamp(o.type)) or pa.types.is_uint64(o.type):
+            raise NotImplementedError("window range frame over a non-integer ORDER BY key")
+        kw = dict(order=(o.cast(phys) if not pa.types.is_integer(o.type) else o).to_pylist(), descending=descending)
     if inner.op not in ("sum", "count", "mean", "min", "max"):
         raise NotImplementedError(f"window frame aggregate {inner.op}")
     child = O.normalize(E.eval_expression(sub_tbl, inner.args[0]))
     if inner.op == "count":
-        return frame_agg_partition(child.to_pylist(), "count", inner.value or "valid", start, end, min_periods, ""), pa.uint64()
+        return frame_agg_partition(child.to_pylist(), "count", inner.value or "valid", start, end, min_periods, "", **kw), pa.uint64()
     if inner.op == "mean":
         acc, typ = "double", pa.float64()
         vals = child.cast(pa.float64(), safe=False).to_pylist()   # i64 -> f64 rounds to nearest, as the reference cast does
@@ -190,14 +224,14 @@ def frame_agg(sub_tbl: pa.Table, agg_expr, start, end, min_periods: int):
         if not (pa.types.is_integer(child.type) or pa.types.is_date32(child.type) or pa.types.is_timestamp(child.type)):
             raise NotImplementedError("window frame min / max over non-integer values")
         # plain comparisons of the values themselves (integers, dates, instants): no accumulate type involved
-        return frame_agg_partition(child.to_pylist(), inner.op, None, start, end, min_periods, ""), child.type
+        return frame_agg_partition(child.to_pylist(), inner.op, None, start, end, min_periods, "", **kw), child.type
     else:
         acc = FRAME_ACC.get(str(child.type))
         if acc is None:
             raise TypeError(f"Cannot run Sum over type {child.type}")
         typ = {"int64": pa.int64(), "uint64": pa.uint64(), "float": pa.float32(), "double": pa.float64()}[acc]
         vals = child.cast(typ).to_pylist()
-    return frame_agg_partition(vals, inner.op, None, start, end, min_periods, acc), typ
+    return frame_agg_partition(vals, inner.op, None, start, end, min_periods, acc, **kw), typ
 
 
 def pivot(tbl: pa.Table, group_by: Sequence[str], pivot_col: str, values_col: str, names: Sequence[str]) -> pa.Table:

@@ -96,14 +96,15 @@ class EmulatedQueryBatch(OracleRecordBatch):
         t = O._take_nullable(self.tbl, np.array(src, dtype=np.int64))
         return self._new(t.append_column("__src", pa.array(src, pa.int64())))
 
-    def _window_frame(self, partition_begin, agg, start, end, min_periods, out_dtype):
+    def _window_frame(self, partition_begin, agg, start, end, min_periods, out_dtype, kind=1, order=None, descending=False):
         """b200_window_frame through the host build of the very state machine the device kernel runs (tests/wf_host.cpp)"""
         import numpy as np
         import wf_host
         vals = self.tbl.column(0).combine_chunks() if self.tbl.num_columns else None
         pb = np.asarray(partition_begin.tbl.column(0).combine_chunks().to_numpy(zero_copy_only=False), dtype=np.int64)
         name = self.tbl.column_names[0] if self.tbl.num_columns else "count"
-        return self._new(pa.table({name: wf_host.run(vals, pb, agg, start, end, min_periods)}))
+        ordv = order.tbl.column(0).combine_chunks() if order is not None else None
+        return self._new(pa.table({name: wf_host.run(vals, pb, agg, start, end, min_periods, kind, ordv, descending)}))
 
     # the oracle's verbs return OracleRecordBatch: re-wrap
     def sort(self, *a, **k): return self._new(super().sort(*a, **k).tbl)

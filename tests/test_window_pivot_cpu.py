@@ -362,3 +362,88 @@ def test_window_frames_errors():
             W.window(make(tbl), [col("g")], [col("o")], [False], [False], [("frame", "f", col("x").stddev(), -1, 0)])
         with pytest.raises(TypeError):
             W.window(make(tbl), [col("g")], [col("o")], [False], [False], [("frame", "f", col("s").sum(), -1, 0)])
+
+
+# ---- RANGE frames (calculate_range_frame_bounds, window.rs:167-272) ----
+
+@pytest.mark.parametrize("start,end,desc,min_periods", [(-2, 2, False, 1), (-2, 2, True, 1), (-5, -1, False, 1), (-5, -1, True, 1), (1, 5, False, 1), (1, 5, True, 1),
+                                                        (None, 1, False, 1), (-1, None, False, 1), (-10000, 10000, False, 1), (-3, 1, False, 3), (0, 0, True, 1),
+                                                        (None, None, True, 1), (-3, 1, True, 2)])
+def test_window_range_frames_reference_cases(start, end, desc, min_periods):
+    """tests/window/test_running_agg.py:826-1370: distinct integer timestamps with gaps; the frame of a row holds the rows whose ts lies in
+    [ts + start, ts + end], in either sort direction (calculate_expected_range, :978-1010)"""
+    import random
+    random.seed(50)
+    cats, tss, vals, want = [], [], [], {k: {} for k in ("s", "m", "mn", "mx", "c")}
+    for c in ["X", "Y"]:
+        stamps = sorted(random.sample(range(100), 30))
+        v = [random.randint(1, 100) for _ in stamps]
+        for t, x in zip(stamps, v):
+            cats.append(c); tss.append(t); vals.append(x)
+            lo = t + start if start is not None else -10**9
+            hi = t + end if end is not None else 10**9
+            live = [y for u, y in zip(stamps, v) if lo <= u <= hi]
+            ok = len(live) >= min_periods
+            want["s"][(c, t)] = sum(live) if ok and live else None
+            want["m"][(c, t)] = sum(live) / len(live) if ok and live else None
+            want["mn"][(c, t)] = min(live) if ok and live else None
+            want["mx"][(c, t)] = max(live) if ok and live else None
+            want["c"][(c, t)] = len(live) if ok else None
+    order = list(range(len(vals)))
+    random.shuffle(order)
+    tbl = pa.table({"category": pa.array([cats[i] for i in order], pa.large_string()), "ts": pa.array([tss[i] for i in order], pa.int32()),
+                    "value": [vals[i] for i in order]})
+    funcs = [("range_frame", "s", col("value").sum(), start, end, min_periods), ("range_frame", "m", col("value").mean(), start, end, min_periods),
+             ("range_frame", "mn", col("value").min(), start, end, min_periods), ("range_frame", "mx", col("value").max(), start, end, min_periods),
+             ("range_frame", "c", col("value").count(), start, end, min_periods)]
+    for got in _both(tbl, [col("category")], [col("ts")], [desc], [desc], funcs):
+        got = got.to_pydict()
+        for k in want:
+            for c, t, x in zip(got["category"], got["ts"], got[k]):
+                w = want[k][(c, t)]
+                assert (x is None and w is None) or (x is not None and w is not None and abs(x - w) <= 1e-12 * abs(w)), (k, c, t, x, w)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_window_range_frames_match_oracle_with_nulls_and_ties(seed):
+    """duplicate and null order keys, nulls first or last, temporal keys (offsets in days / microseconds), float sums: the host build of the
+    device's state machine == the oracle's restatement (which follows the reference's forward searches, including where they resume)"""
+    rng = np.random.default_rng(100 + seed)
+    n = 250
+    tbl = pa.table({"id": np.arange(n), "g": pa.array(rng.integers(0, 5, n)),
+                    "k": pa.array(rng.integers(0, 60, n), mask=rng.random(n) < 0.08),
+                    "d": pa.array(rng.integers(10000, 10100, n).astype(np.int32), pa.date32(), mask=rng.random(n) < 0.05),
+                    "ts": pa.array(rng.integers(0, 50, n) * 1_000_000, pa.timestamp("us")),
+                    "x": pa.array(rng.standard_normal(n) * 10.0 ** rng.integers(-3, 6, n), mask=rng.random(n) < 0.1),
+                    "v": pa.array(rng.integers(-50, 50, n).astype(np.int16), mask=rng.random(n) < 0.1)})
+    key, scale = [("k", 1), ("d", 1), ("ts", 1_000_000)][seed % 3]
+    desc = bool(seed % 2)
+    nulls_first = desc if seed < 4 else not desc   # nulls-first order keys: the reference's min / max path then resumes its searches at the end
+    frames = [(-3, 3, 1), (-5, -1, 2), (1, 4, 1), (None, 2, 1), (-2, None, 1), (0, 0, 1)]
+    a0, b0, mp = frames[seed]
+    sc = lambda o: None if o is None else o * scale
+    funcs = []
+    for name, e in (("x", col("x")), ("v", col("v"))):
+        funcs += [("range_frame", f"s_{name}", e.sum(), sc(a0), sc(b0), mp), ("range_frame", f"m_{name}", e.mean(), sc(a0), sc(b0), mp),
+                  ("range_frame", f"c_{name}", e.count("all"), sc(a0), sc(b0), mp)]
+    funcs += [("range_frame", "mn", col("v").min(), sc(a0), sc(b0), mp), ("range_frame", "mx", col("v").max(), sc(a0), sc(b0), mp), ("frame", "rows", col("v").sum(), -1, 1)]
+    # ties in the key: the frame of a row does not depend on the order of its peers, the sliding float sum does -- break ties by id on both sides
+    pb, ob = [col("g")], [col(key)]
+    a = OW.window(tbl.sort_by([("id", "ascending")]), pb, ob, [desc], [nulls_first], funcs)
+    b = W.window(EmulatedQueryBatch(tbl), pb, ob, [desc], [nulls_first], funcs).to_arrow_table()
+    exact = [c for c in a.column_names if not c.endswith("_x") or c.startswith("c_")]
+    assert_tables_equal(_sorted(b.select(exact), ["id"]), _sorted(a.select(exact), ["id"]), float_rtol=0.0)
+    loose = [c for c in a.column_names if c not in exact] + ["id"]
+    assert_tables_equal(_sorted(b.select(loose), ["id"]), _sorted(a.select(loose), ["id"]), float_rtol=1e-9)
+
+
+def test_window_range_frame_errors():
+    tbl = pa.table({"g": [1, 1, 1], "o": [1, 2, 3], "p": [1.0, 2.0, 3.0], "x": [1.0, 2.0, 3.0]})
+    with pytest.raises(ValueError, match="exactly one ORDER BY"):
+        W.window(EmulatedQueryBatch(tbl), [col("g")], [col("o"), col("x")], [False, False], [False, False], [("range_frame", "f", col("x").sum(), -1, 1)])
+    with pytest.raises(NotImplementedError):
+        W.window(EmulatedQueryBatch(tbl), [col("g")], [col("p")], [False], [False], [("range_frame", "f", col("x").sum(), -1, 1)])
+    for run in (lambda: W.window(EmulatedQueryBatch(tbl), [col("g")], [col("o")], [False], [False], [("range_frame", "f", col("x").sum(), 2, -2)]),
+                lambda: OW.window(tbl, [col("g")], [col("o")], [False], [False], [("range_frame", "f", col("x").sum(), 2, -2)])):
+        with pytest.raises(ValueError, match="Negative frame size"):
+            run()

@@ -28,28 +28,35 @@ def lib():
     return _lib
 
 
-def run(values: pa.Array | None, partition_begin: np.ndarray, agg: int, start, end, min_periods: int) -> pa.Array:
-    """what b200_window_frame returns for the same arguments (values already in the accumulate type)"""
+def _bits(arr: pa.Array):
+    if arr is None or not arr.null_count:
+        return None
+    return np.packbits(np.asarray(arr.is_valid()), bitorder="little")
+
+
+def run(values: pa.Array | None, partition_begin: np.ndarray, agg: int, start, end, min_periods: int, kind: int = 1, order: pa.Array | None = None,
+        descending: bool = False) -> pa.Array:
+    """what b200_window_frame returns for the same arguments (values already in the accumulate type, `order` as Int64 for RANGE frames);
+    `kind`: 1 = start / end are row offsets, 2 = offsets on the order value; None = unbounded on that side"""
     n = len(partition_begin)
     pb = np.ascontiguousarray(partition_begin, dtype=np.int64)
     counts = agg in (1, 2, 3)
-    vt, vbuf, bits = 0, None, None
+    vt, vbuf = 0, None
     out_type = pa.uint64()
-    if values is not None:
-        if values.null_count:
-            bits = np.frombuffer(values.buffers()[0], dtype=np.uint8)
-            if values.offset:
-                mask = np.asarray(values.is_valid())
-                bits = np.packbits(mask, bitorder="little")
+    bits = _bits(values)
     if not counts:
         vt = VTYPE[values.type]
         vbuf = np.ascontiguousarray(values.fill_null(0).to_numpy(zero_copy_only=False))
         out_type = pa.float64() if agg == 4 else values.type
+    obuf = np.ascontiguousarray(order.fill_null(0).to_numpy(zero_copy_only=False), dtype=np.int64) if order is not None else None
+    obits = _bits(order)
     out = np.zeros(max(n, 1), dtype={pa.uint64(): np.uint64, pa.int64(): np.int64, pa.float32(): np.float32, pa.float64(): np.float64}[out_type])
     ok = np.zeros(max(n, 1), dtype=np.uint8)
-    rc = lib().wf_host_run(ctypes.c_int(agg), ctypes.c_int(vt), ctypes.c_int(start is not None), ctypes.c_longlong(start or 0), ctypes.c_int(end is not None),
-                           ctypes.c_longlong(end or 0), ctypes.c_longlong(min_periods), vbuf.ctypes.data_as(ctypes.c_void_p) if vbuf is not None else None,
-                           bits.ctypes.data_as(ctypes.c_void_p) if bits is not None else None, pb.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(n),
-                           out.ctypes.data_as(ctypes.c_void_p), ok.ctypes.data_as(ctypes.c_void_p))
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    rc = lib().wf_host_run(ctypes.c_int(agg), ctypes.c_int(vt), ctypes.c_int(kind if start is not None else 0), ctypes.c_longlong(start or 0),
+                           ctypes.c_int(kind if end is not None else 0), ctypes.c_longlong(end or 0), ctypes.c_int(bool(descending)), ctypes.c_longlong(min_periods),
+                           ptr(vbuf), ptr(bits), ptr(obuf), ptr(obits), ptr(pb), ctypes.c_longlong(n), ptr(out), ptr(ok))
+    if rc == 2:
+        raise ValueError("Negative frame size is not allowed")
     assert rc == 0
     return pa.array(out[:n], type=out_type, mask=ok[:n] == 0)
