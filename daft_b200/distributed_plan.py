@@ -5,7 +5,8 @@
 (src/daft-distributed/src/pipeline_node/*): filters and projections stay local; an aggregate runs its first stage per rank and then either
 gathers the partials (few groups: every rank finishes the same answer, `aggregate.rs:281-340`) or repartitions them by the group keys
 (many groups); a join broadcasts a small side (`join/broadcast_join.rs`) or repartitions both sides by the hash of the join keys
-(`join/hash_join.rs`); top-N / sort / dedup combine local results.  A table is either *sharded* (every rank holds a disjoint part) or
+(`join/hash_join.rs`); top-N / sort / dedup combine local results; a window repartitions by its
+PARTITION BY keys.  A table is either *sharded* (every rank holds a disjoint part) or
 *replicated* (every rank holds all of it, e.g. a gathered aggregate): the state decides which of those is needed.
 
 The communication itself is a small backend object, so the same planner drives
@@ -130,6 +131,19 @@ class Sharded:
         lm = left.backend.exchange_by_hash(left.local, lk)
         rm = left.backend.exchange_by_hash(right.local, rk)
         return left._like(lm.hash_join(rm, left_on, right_on, **kw), False)
+
+    # ---- windows ----
+    def window(self, partition_by, order_by=(), descending=None, nulls_first=None, functions=()) -> "Sharded":
+        """every partition of the window on one rank (repartition by the PARTITION BY keys, as the reference's distributed window node does:
+        src/daft-distributed/src/pipeline_node/window.rs), then the local operator; without partition keys the rows are gathered"""
+        from .window import window
+        args = (list(partition_by), list(order_by), descending, nulls_first, list(functions))
+        if self.replicated:
+            return self._like(window(self.local, *args))
+        if not args[0]:
+            g = self.gathered()
+            return g._like(window(g.local, *args), True)
+        return self._like(window(self.backend.exchange_by_hash(self.local, args[0]), *args), False)
 
     # ---- order ----
     def sort(self, sort_keys, descending=None, nulls_first=None) -> "Sharded":

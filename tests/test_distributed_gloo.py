@@ -305,3 +305,67 @@ def test_clickbench_over_two_ranks_gloo(gather_rows):
         else:   # top-N on a tied count: the sequence of sort keys is fixed, the tied rows are not
             gc, wc = got.column(order_col).to_pylist(), want.column(order_col).to_pylist()
             assert all(abs(a - b) <= 1e-9 * max(1.0, abs(b)) for a, b in zip(gc, wc)), (qn, gc, wc)
+
+
+# ---- windows over two ranks: repartition by the PARTITION BY keys, then the local operator (ranks, lead / lag, ROWS and RANGE frames) ----
+def _window_table():
+    import numpy as np
+    rng = np.random.default_rng(77)
+    n = 600
+    return pa.table({"id": np.arange(n), "g": pa.array(rng.integers(0, 9, n), mask=rng.random(n) < 0.05), "o": pa.array(rng.integers(0, 80, n)),
+                     "x": pa.array(rng.standard_normal(n), mask=rng.random(n) < 0.1), "v": pa.array(rng.integers(-99, 99, n))})
+
+
+def _window_funcs():
+    from daft_b200 import col
+    return [("row_number", "rn"), ("rank", "rk"), ("offset", "lag1", col("v"), -1), ("agg", "tot", col("v").sum()),
+            ("frame", "run", col("x").sum(), None, 0), ("frame", "avg3", col("v").mean(), -2, 0, 3), ("frame", "mx", col("v").max(), -1, 1),
+            ("range_frame", "near", col("v").sum(), -5, 5), ("range_frame", "cnt", col("x").count(), None, 0)]
+
+
+def _window_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from daft_b200 import col, distributed
+    from daft_b200.distributed_plan import Sharded
+    from test_tpch_all_emulated_cpu import EmulatedQueryBatch
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        backend = _gloo_oracle_backend(rank, world)
+        tbl = _window_table()
+        b, e = distributed.shard_rows(tbl.num_rows, rank, world)
+        sh = Sharded(EmulatedQueryBatch(tbl.slice(b, e - b)), backend)
+        res = sh.window([col("g")], [col("o"), col("id")], [False, False], [False, False], [f for f in _window_funcs() if f[0] != "range_frame"])
+        res_r = sh.window([col("g")], [col("o")], [True], [True], [f for f in _window_funcs() if f[0] == "range_frame"] + [("rank", "rk")])
+        q.put((rank, {"w": distributed._to_ipc(res.to_arrow_table()), "r": distributed._to_ipc(res_r.to_arrow_table()), "calls": dict(backend.calls)}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_windows_over_two_ranks_gloo():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from daft_b200 import col
+    from daft_b200.distributed import _from_ipc
+    from helpers import assert_tables_equal
+    from oracle import window as OW
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() + 613) % 1000)
+    procs = [ctx.Process(target=_window_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=500) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0]["calls"]["exchange"] == 2 and results[0]["calls"] == results[1]["calls"]
+    tbl = _window_table()
+    want = OW.window(tbl, [col("g")], [col("o"), col("id")], [False, False], [False, False], [f for f in _window_funcs() if f[0] != "range_frame"])
+    want_r = OW.window(tbl, [col("g")], [col("o")], [True], [True], [f for f in _window_funcs() if f[0] == "range_frame"] + [("rank", "rk")])
+    by_id = lambda t: t.sort_by([("id", "ascending")])
+    for r in range(2):   # every rank gathers the whole answer in to_arrow_table()
+        assert_tables_equal(by_id(_from_ipc(results[r]["w"])), by_id(want), float_rtol=1e-12)
+        assert_tables_equal(by_id(_from_ipc(results[r]["r"])), by_id(want_r), float_rtol=1e-12)
